@@ -1,0 +1,278 @@
+// amg.cu -- the AMG preconditioner: hierarchy construction loop and the V-cycle.
+//   level loop / stopping rules   src/amg.cu:152-421
+//   V-cycle body                  src/cycles/fixed_cycle.cu:25-248
+//   aggregation level             src/aggregation/aggregation_amg_level.cu:237-299, 842-907, 1945-2023
+// The cycle is restructured around fused kernels (see DESIGN.md "V-cycle dataflow"):
+//   * with zero pre-sweeps and a zero initial guess the residual IS b: no SpMV, no copy;
+//   * the prolongation of the coarse correction is folded into the first post-smoothing sweep
+//     (x is read through aggregates[] from xc and never written unsmoothed);
+//   * the last finest-level sweep can carry PCG's <r,z> reduction.
+// Each shortcut produces bit-identical vectors to the unfused sequence (0 + e == e, b - A*0 == b).
+#include "solvers.h"
+#include "dist.h"
+#include <sstream>
+#include <iomanip>
+
+namespace amgxb {
+
+AMGSolver::AMGSolver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc) : Solver(cfg, scope, rsc)
+{
+    algorithm_ = cfg.get_string("algorithm", scope);
+    cycle_name_ = cfg.get_string("cycle", scope);
+    selector_ = cfg.get_string("selector", scope);
+    max_levels_ = cfg.get_int("max_levels", scope);
+    min_coarse_rows_ = cfg.get_int("min_coarse_rows", scope);
+    coarsen_threshold_ = cfg.get_double("coarsen_threshold", scope);
+    presweeps_ = cfg.get_int("presweeps", scope);
+    postsweeps_ = cfg.get_int("postsweeps", scope);
+    finest_sweeps_ = cfg.get_int("finest_sweeps", scope);
+    coarsest_sweeps_ = cfg.get_int("coarsest_sweeps", scope);
+    intensive_smoothing_ = cfg.get_int("intensive_smoothing", scope);
+    error_scaling_ = cfg.get_int("error_scaling", scope);
+    if (cycle_name_ != "V")
+        fatal(AMGX_RC_BAD_CONFIGURATION, "cycle '" + cycle_name_ + "' is outside the scope of the B200 solve-phase engine (V only)");
+    if (error_scaling_ != 0) fatal(AMGX_RC_BAD_CONFIGURATION, "error_scaling != 0 is not supported by this engine");
+    if (algorithm_ != "AGGREGATION" && algorithm_ != "CLASSICAL")
+        fatal(AMGX_RC_BAD_CONFIGURATION, "algorithm '" + algorithm_ + "' is not supported (AGGREGATION, CLASSICAL)");
+    std::string ns;
+    cfg.get_scoped("coarse_solver", scope, coarse_solver_name_, ns);
+    if (coarse_solver_name_ == "DENSE_LU_SOLVER") {
+        dense_lu_num_rows_ = cfg.get_int("dense_lu_num_rows", scope);
+        dense_lu_max_rows_ = cfg.get_int("dense_lu_max_rows", scope);
+        coarse_solver_ = make_dense_lu_solver(cfg, ns, rsc);
+        coarse_solver_->set_name("DENSE_LU_SOLVER");
+    } else if (coarse_solver_name_ != "NOSOLVER") {
+        coarse_solver_ = Solver::allocate(cfg, scope, "coarse_solver", rsc);
+    }
+}
+
+std::unique_ptr<Solver> AMGSolver::make_smoother() { return Solver::allocate(*cfg_, scope_, "smoother", rsc_); }
+
+void AMGSolver::solver_setup(bool reuse)
+{
+    (void)reuse;
+    levels_.clear();
+    if (dense_lu_num_rows_ > 0) min_coarse_rows_ = dense_lu_num_rows_ / A_->by;   // src/amg.cu:1154-1157
+    if (algorithm_ == "AGGREGATION") setup_aggregation();
+    else setup_classical();
+}
+
+// The level-building loop of AMG_Setup::setup (src/amg.cu:201-418), single-partition form.
+void AMGSolver::setup_aggregation()
+{
+    if (selector_ != "SIZE_2")
+        fatal(AMGX_RC_BAD_CONFIGURATION, "aggregation selector '" + selector_ + "' is not supported by this engine (SIZE_2)");
+    cudaStream_t s = stream();
+    AggSetupParams prm;
+    prm.deterministic = cfg_->get_int("determinism_flag", "default");
+    prm.max_iterations = cfg_->get_int("max_matching_iterations", scope_);
+    prm.max_unassigned = cfg_->get_double("max_unassigned_percentage", scope_);
+    prm.two_phase = cfg_->get_int("handshaking_phases", scope_) == 2;
+    prm.edge_weight_component = cfg_->get_int("aggregation_edge_weight_component", scope_);
+    prm.merge_singletons = cfg_->get_int("merge_singletons", scope_) == 1;
+    prm.weight_formula = cfg_->get_int("weight_formula", scope_);
+
+    levels_.emplace_back(new AMGLevel);
+    levels_[0]->A = A_;
+    levels_[0]->index = 0;
+    int num_levels = 1;
+    bool coarse_solver_exists = (bool)coarse_solver_;
+    while (true) {
+        AMGLevel &L = *levels_.back();
+        Matrix &A = *L.A;
+        A.level = num_levels - 1;
+        const int rows = A.n;
+        if (num_levels >= max_levels_ || rows <= min_coarse_rows_) {
+            if (dense_lu_max_rows_ != 0 && rows > dense_lu_max_rows_) { coarse_solver_.reset(); coarse_solver_exists = false; }
+            L.coarsest = true;
+            if (!coarse_solver_exists) { L.smoother = make_smoother(); L.smoother->setup(A, false); }
+            break;
+        }
+        // createCoarseVertices
+        const int n_agg = size2_select(A, prm, L.aggregates, s);
+        L.n_coarse = n_agg;
+        const long long N = (long long)rows * A.by, nextN = (long long)n_agg * A.by;
+        bool built_next = false;
+        if ((double)nextN <= coarsen_threshold_ * (double)N && nextN != N && n_agg >= min_coarse_rows_) {
+            build_restriction(L.aggregates, rows, n_agg, L.R_row_offsets, L.R_column_indices, s);
+            std::unique_ptr<AMGLevel> next(new AMGLevel);
+            next->owned_A.reset(new Matrix);
+            galerkin_aggregation(A, L.aggregates, n_agg, *next->owned_A, s);
+            next->owned_A->compute_diag_and_plan();
+            next->A = next->owned_A.get();
+            next->index = num_levels;
+            const size_t nc = (size_t)n_agg * A.by;
+            L.bc.resize(nc, A.vec_prec);
+            L.xc.resize(nc, A.vec_prec);
+            L.bc.zero(s);
+            L.xc.zero(s);
+            L.r.resize((size_t)A.n_cols * A.by, A.vec_prec);
+            L.r.zero(s);
+            levels_.push_back(std::move(next));
+            built_next = true;
+        } else {
+            L.aggregates.release();
+            L.n_coarse = 0;
+            L.coarsest = true;
+        }
+        AMGLevel &Lcur = *levels_[num_levels - 1];
+        if (!Lcur.coarsest || !coarse_solver_exists) { Lcur.smoother = make_smoother(); Lcur.smoother->setup(*Lcur.A, false); }
+        if (!built_next) break;
+        num_levels++;
+    }
+    if (coarse_solver_) coarse_solver_->setup(*levels_.back()->A, false);
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+void AMGSolver::solve_init(DevVec &b, DevVec &x, bool xIsZero)
+{
+    if (xIsZero && !levels_.empty()) levels_[0]->init_cycle = true;
+}
+
+Status AMGSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
+{
+    cycle(0, b, x, nullptr);
+    levels_[0]->init_cycle = false;
+    return converged(b, x);
+}
+
+bool AMGSolver::solve_fused_dot(DevVec &b, DevVec &x, const ReduceCtx &red, int fin_op, int fin_slot)
+{
+    // one V-cycle with zero initial guess (what Solver::solve does with max_iters == 1 and no
+    // monitoring) whose last finest-level sweep also reduces <b, x>
+    if (max_iters_ != 1 || monitor_residual_ || levels_.empty()) return false;
+    AMGLevel &L0 = *levels_[0];
+    Solver *sm = L0.smoother.get();
+    const bool single = L0.coarsest;
+    int last_sweeps;
+    if (single) last_sweeps = coarse_solver_ ? 0 : coarsest_sweeps_;
+    else last_sweeps = (finest_sweeps_ != -1) ? (postsweeps_ == 0 ? 0 : finest_sweeps_) : postsweeps_;
+    if (!sm || !sm->supports_fusion() || last_sweeps <= 0) return false;
+    SmoothFuse f;
+    f.dot_b_x = true;
+    f.red = red;
+    f.fin_op = fin_op;
+    f.fin_slot = fin_slot;
+    L0.init_cycle = true;
+    cycle(0, b, x, &f);
+    L0.init_cycle = false;
+    num_iters_ = 1;
+    return true;
+}
+
+// FixedCycle::cycle for the V cycle (src/cycles/fixed_cycle.cu:25-248)
+void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse)
+{
+    cudaStream_t s = stream();
+    AMGLevel &L = *levels_[lvl];
+    Matrix &A = *L.A;
+    Solver *sm = L.smoother.get();
+    const bool finest = (lvl == 0);
+    bool x_is_zero = L.init_cycle;
+    L.init_cycle = false;
+
+    // ---- pre-smoothing ----
+    int n_pre;
+    if (L.coarsest && coarse_solver_) n_pre = 0;
+    else if (L.coarsest) n_pre = coarsest_sweeps_;
+    else if (finest && finest_sweeps_ != -1) n_pre = presweeps_ == 0 ? 0 : finest_sweeps_;
+    else {
+        n_pre = presweeps_;
+        if (presweeps_ != 0 && intensive_smoothing_) n_pre = std::max(n_pre + lvl - 2, 0);
+    }
+    if (L.coarsest) {
+        if (n_pre > 0) {
+            SmoothFuse f;
+            const SmoothFuse *pf = nullptr;
+            if (top_fuse && finest) { f = *top_fuse; pf = &f; }
+            sm->smooth(b, x, x_is_zero, n_pre, pf);
+        } else if (x_is_zero) {
+            x.zero(s);
+        }
+        if (coarse_solver_) coarse_solver_->solve(b, x, x_is_zero && n_pre == 0);
+        return;
+    }
+    bool x_virtual_zero = false;   // x holds no data yet and is mathematically zero
+    if (n_pre > 0) sm->smooth(b, x, x_is_zero, n_pre, nullptr);
+    else if (x_is_zero) x_virtual_zero = true;
+
+    // ---- residual + restriction ----
+    const DevVec *rsrc;
+    if (x_virtual_zero) {
+        rsrc = &b;   // r = b - A*0 = b exactly
+    } else {
+        dist_exchange_halo(A, x, s);
+        CsrOpArgs g;
+        g.x = x.ptr();
+        g.b = b.ptr();
+        g.y = L.r.ptr();
+        matrix_apply(A, EPI_RESID, g, s);
+        rsrc = &L.r;
+    }
+    if (algorithm_ == "AGGREGATION") {
+        agg_restrict(L.R_row_offsets.ptr(), L.R_column_indices.ptr(), rsrc->ptr(), L.bc.ptr(), A.vec_prec, L.n_coarse, A.by, s);
+    } else {
+        classical_restrict(L, *rsrc, s);
+    }
+
+    // ---- coarse-grid correction ----
+    levels_[lvl + 1]->init_cycle = true;
+    cycle(lvl + 1, L.bc, L.xc, nullptr);
+
+    // ---- prolongation + post-smoothing ----
+    int n_post;
+    if (finest && finest_sweeps_ != -1) n_post = postsweeps_ == 0 ? 0 : finest_sweeps_;
+    else {
+        n_post = postsweeps_;
+        if (postsweeps_ != 0 && intensive_smoothing_) n_post = std::max(n_post + lvl - 2, 0);
+    }
+    SmoothFuse f;
+    bool have_fuse = false;
+    if (top_fuse && finest && n_post > 0) { f = *top_fuse; have_fuse = true; }
+    if (algorithm_ == "AGGREGATION") {
+        if (x_virtual_zero && n_post > 0 && sm->supports_fusion()) {
+            // x := P xc is read on the fly by the first sweep
+            f.agg = L.aggregates.ptr();
+            f.xc = L.xc.ptr();
+            have_fuse = true;
+        } else {
+            if (x_virtual_zero) x.zero(s);
+            agg_prolong_add(L.aggregates.ptr(), L.xc.ptr(), x.ptr(), A.vec_prec, A.n, A.by, s);
+        }
+    } else {
+        if (x_virtual_zero) x.zero(s);
+        classical_prolong_add(L, x, s);
+    }
+    if (n_post > 0) sm->smooth(b, x, false, n_post, have_fuse ? &f : nullptr);
+}
+
+// print_grid_stats of the reference (src/amg.cu:1231-1350): same table layout
+void AMGSolver::print_grid_stats()
+{
+    std::stringstream ss;
+    const int nl = (int)levels_.size();
+    long long total_rows = 0, total_nnz = 0;
+    for (auto &l : levels_) { total_rows += l->A->n; total_nnz += l->A->nnz + (l->A->has_ext_diag ? l->A->n : 0); }
+    ss << "AMG Grid:\n";
+    ss << "         Number of Levels: " << nl << "\n";
+    ss << "            LVL         ROWS               NNZ  PARTS    SPRSTY       Mem (GB)\n";
+    ss << "         ----------------------------------------------------------------------\n";
+    for (int i = 0; i < nl; i++) {
+        const Matrix &M = *levels_[i]->A;
+        const long long nnz = M.nnz + (M.has_ext_diag ? M.n : 0);
+        const double sp = M.n ? (double)nnz / ((double)M.n * (double)M.n) : 0.0;
+        const double mem = (double)(M.row_ptr.size() * 4 + M.col_idx.size() * 4 + M.values.nbytes()) / (1024.0 * 1024.0 * 1024.0);
+        ss << std::setw(12) << i << "(D)" << std::setw(13) << M.n << std::setw(18) << nnz << std::setw(7) << 1
+           << std::setw(10) << std::setprecision(3) << std::scientific << sp << std::setw(15) << std::setprecision(3) << std::scientific << mem << "\n";
+    }
+    ss << "         ----------------------------------------------------------------------\n";
+    const Matrix &F = *levels_[0]->A;
+    ss << std::fixed << std::setprecision(5);
+    ss << "         Grid Complexity: " << (double)total_rows / std::max(1, F.n) << "\n";
+    ss << "         Operator Complexity: " << (double)total_nnz / std::max(1ll, (long long)F.nnz + (F.has_ext_diag ? F.n : 0)) << "\n";
+    ss << "         Total Memory Usage: " << device_mem_used_gb() << " GB\n";
+    ss << "         ----------------------------------------------------------------------\n";
+    amgx_output(ss.str().c_str(), (int)ss.str().length());
+}
+
+}  // namespace amgxb

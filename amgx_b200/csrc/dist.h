@@ -1,0 +1,62 @@
+// dist.h -- row-partitioned multi-GPU layer (one process per GPU): local renumbering
+// [interior | boundary | halo], per-neighbour send maps (B2L), NCCL halo exchange overlapped with
+// interior work, scalar all-reduces.  Replaces the reference's DistributedManager exchange_halo /
+// global_reduce_sum over MPI (include/distributed/distributed_manager.h:955-1170,
+// src/distributed/comms_mpi_hostbuffer_stream.cu:598-700, 1226-1268) on the solve path.
+// Also hosts the matrix_apply dispatcher and a few block-size helpers used by the solvers.
+#pragma once
+#include "base.h"
+#include "matrix.h"
+#include "kernels.h"
+
+namespace amgxb {
+
+struct ScalarBlock;
+
+struct DistManager {
+    int rank = 0, world = 1;
+    int n_owned = 0, n_interior = 0, n_halo = 0;
+    std::vector<int> neighbors;          // ranks
+    std::vector<int> send_offsets;       // [nn+1]
+    std::vector<int> halo_offsets;       // [nn+1], relative to n_owned
+    DevBuf<int> send_maps;               // B2L maps, concatenated
+    DevVec send_buf;                     // packed boundary values (vec precision, * block dim)
+    DevBuf<int> perm_old_to_new;         // caller (partition) order -> local order, owned rows
+    std::vector<int64_t> halo_global;    // global id of each halo column
+    int64_t global_offset = 0;           // first global row owned by this rank
+    int64_t n_global = 0;
+    cudaEvent_t ev_pack = nullptr, ev_done = nullptr;
+    double *allreduce_buf = nullptr;     // device, 8 doubles
+    ~DistManager();
+};
+
+// ---- halo exchange (no-ops on a single GPU) ----
+void dist_exchange_halo(const Matrix &A, DevVec &x, cudaStream_t s);
+void dist_exchange_halo_coarse(const Matrix &A, const void *xc, cudaStream_t s);   // vector living on the NEXT level
+double dist_reduce_norm(const Matrix &A, double local, int norm_type);             // host value in, global value out
+ReduceCtx dist_wrap_reduce(const Matrix &A, const ReduceCtx &red);
+void dist_allreduce_scalar_fin(const Matrix &A, const ReduceCtx &red, int slot, int fin_op, cudaStream_t s);
+
+// y = op(A, x): scalar matrices go to the CSR tile kernels, 4x4 blocks to the block kernels.
+void matrix_apply(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s);
+
+// ---- block-size > 1 helpers (k_block.cu) ----
+void block_norms(const DevVec &v, int n, int bsize, int norm_type, const ReduceCtx &red, ScalarBlock &sb, std::vector<double> &out, cudaStream_t s);
+void block_jacobi_setup(const Matrix &A, DevVec &dinv, cudaStream_t s);   // dinv <- inverse of diagonal blocks (in place)
+void block_jacobi_zero(const Matrix &A, const DevVec &dinv, const DevVec &b, DevVec &x, double omega, cudaStream_t s);
+void block_jacobi_sweep(const Matrix &A, const DevVec &dinv, const DevVec &b, const DevVec &x, DevVec &xout, double omega, cudaStream_t s);
+void l1_row_norms(const Matrix &A, DevVec &d, cudaStream_t s);
+
+double device_mem_used_gb();
+void block_build_diag(Matrix &A, cudaStream_t s);
+void block_apply(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s);
+void dist_destroy_comm(Resources *rsc);
+void set_print_callback(AMGX_print_callback cb);
+
+class Solver;
+class Config;
+std::unique_ptr<Solver> make_dilu_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);
+
+void release_reduce_scratch(Resources *rsc);
+
+}  // namespace amgxb

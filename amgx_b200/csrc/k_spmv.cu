@@ -1,0 +1,485 @@
+// k_spmv.cu -- the scalar-CSR kernel family of the solve phase for sm_100a:
+//   SpMV, residual, fused (L1-)Jacobi sweep, each optionally fused with a dot / norm reduction and
+//   optionally reading x through the aggregation prolongation.
+//
+// Replaces, on the hot path: Cusparse::bsrmv_internal / csrmv / cusparseSpMV
+// (src/amgx_cusparse.cu:534-600, 983-1103), axmb (src/blas.cu:601-623), BlockJacobiSolver::smooth_1x1
+// (src/solvers/block_jacobi_solver.cu:1286-1319), JacobiL1Solver::smooth_1x1
+// (src/solvers/jacobi_l1_solver.cu:503-519) and the dot that follows the SpMV in PCG
+// (src/solvers/pcg_solver.cu:118-137).
+//
+// Design (see DESIGN.md "CSR tile kernel"):
+//  * persistent CTAs; a tile = TILE_ROWS consecutive rows.  A dedicated producer warp stages the
+//    tile's row_ptr slice, col_idx range and value range into shared memory with TMA 1-D bulk
+//    copies (cp.async.bulk ... mbarrier::complete_tx), STAGES deep, so HBM sees only fully
+//    coalesced 16-byte-aligned bulk reads of the matrix.
+//  * consumers: one thread per row walks its entries in shared memory left to right with an FMA
+//    chain -- the exact per-row order of the reference's csrmv (y = a*x + y) -- gathering x
+//    through L1/L2 (for stencil-like matrices neighbouring rows gather neighbouring x: coalesced).
+//  * rows longer than the stage capacity fall back to a warp-per-row kernel with a shuffle tree.
+//  * reductions: per-thread partial -> warp shuffle -> per-CTA partial -> the last CTA to finish
+//    sums the partials in index order (deterministic) and applies the scalar epilogue (FinOp).
+#include "kernels.h"
+#include <cooperative_groups.h>
+
+namespace amgxb {
+
+long long g_kernel_launches = 0;
+
+namespace {
+
+constexpr int PRODUCER_THREADS = 32;
+constexpr int MAX_STAGES = 4;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <class T> __device__ __forceinline__ T guard_diag(T d);
+template <> __device__ __forceinline__ double guard_diag<double>(double d) { return fabs(d) < 1e-12 ? copysign(1e-12, d) : d; }
+template <> __device__ __forceinline__ float guard_diag<float>(float d) { return fabs((double)d) < 1e-7 ? copysignf((float)1e-7, d) : d; }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// scalar epilogue executed by one thread of the last CTA
+__device__ void apply_fin(double sum, double *scal, int fin_op, int slot, double *host_mirror, int mirror)
+{
+    double out = sum;
+    switch (fin_op) {
+    case FIN_STORE:
+    case FIN_ABS: scal[slot] = sum; break;
+    case FIN_SQRT: out = sqrt(sum); scal[slot] = out; break;
+    case FIN_PCG_ALPHA: {
+        scal[S_DOT] = sum;
+        double a = (sum != 0.0) ? scal[S_RZ] / sum : 0.0;
+        scal[S_ALPHA] = a;
+        scal[S_NEG_ALPHA] = -a;
+        out = a;
+        break;
+    }
+    case FIN_PCG_BETA: {
+        double old = scal[S_RZ];
+        scal[S_RZ_OLD] = old;
+        scal[S_RZ] = sum;
+        double bta = (old != 0.0) ? sum / old : 0.0;
+        scal[S_BETA] = bta;
+        out = sum;
+        break;
+    }
+    }
+    if (mirror && host_mirror) { host_mirror[slot] = out; }
+}
+
+// Block-level deterministic reduction + "last block finalises" pattern.
+// All threads of the CTA must call it; `nthreads` = blockDim.x; smem_red has >= 33 doubles.
+__device__ void block_reduce_finish(double v, double *smem_red, const ReduceCtx &red, int fin_op, int slot, int mirror)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    if (lane == 0) smem_red[warp] = v;
+    __syncthreads();
+    __shared__ bool is_last;
+    if (warp == 0) {
+        double t = (lane < nwarps) ? smem_red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) {
+            red.partials[blockIdx.x] = t;
+            __threadfence();
+            unsigned ticket = atomicAdd(red.counter, 1u);
+            is_last = (ticket == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        // fixed order: thread t sums partials t, t+blockDim, ... then a fixed tree
+        double t = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += ((volatile double *)red.partials)[i];
+        t = warp_sum(t);
+        if (lane == 0) smem_red[warp] = t;
+        __syncthreads();
+        if (warp == 0) {
+            double u = (lane < nwarps) ? smem_red[lane] : 0.0;
+            u = warp_sum(u);
+            if (lane == 0) {
+                apply_fin(u, red.scal, fin_op, slot, red.host_mirror, mirror);
+                *red.counter = 0u;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+template <class MatT, class VecT> struct TileArgs {
+    const int *row_ptr;
+    const int *col;
+    const MatT *val;
+    int n, num_tiles, cap, stages;
+    const VecT *x;
+    const int *agg;
+    const VecT *b;
+    const MatT *d;
+    VecT *y;
+    double omega;
+    ReduceCtx red;
+    int fin_op, fin_slot, mirror;
+};
+
+template <class VecT, bool AGG> __device__ __forceinline__ VecT gather(const VecT *x, const int *agg, int c)
+{
+    if (AGG) return __ldg(x + __ldg(agg + c));
+    return __ldg(x + c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The tile kernel.  blockDim.x = TILE_ROWS + 32 (last warp = producer).
+// shared memory layout: [stages x full mbarrier][stages x empty mbarrier][red scratch 40 doubles]
+//                       then per stage: vals[cap] | cols[cap] | rp[TILE_ROWS+4]
+// ---------------------------------------------------------------------------------------------
+template <class MatT, class VecT, int TILE_ROWS, int EPI, bool AGG>
+__global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(const TileArgs<MatT, VecT> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + MAX_STAGES;
+    double *smem_red = reinterpret_cast<double *>(smem_raw + 2 * MAX_STAGES * sizeof(uint64_t));
+    unsigned char *stage_base = smem_raw + 512;
+    const size_t vals_bytes = (size_t)a.cap * sizeof(MatT);
+    const size_t cols_bytes = (size_t)a.cap * sizeof(int);
+    const size_t rp_bytes = (size_t)(TILE_ROWS + 4) * sizeof(int);
+    const size_t stage_bytes = vals_bytes + cols_bytes + rp_bytes;
+    constexpr int CONSUMER_WARPS = TILE_ROWS / 32;
+    constexpr bool HAS_RED = (EPI == EPI_SPMV_DOT || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc = 0.0;
+    const int my_tiles = (a.num_tiles > (int)blockIdx.x) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid >= TILE_ROWS) {
+        // ------------------------------- producer warp -------------------------------
+        if (tid == TILE_ROWS) {
+            for (int it = 0; it < my_tiles; it++) {
+                const int tile = blockIdx.x + it * gridDim.x;
+                const int s = it % a.stages;
+                const unsigned ph = (unsigned)(it / a.stages) & 1u;
+                if (it >= a.stages) mbar_wait(&empty[s], ph ^ 1u);
+                const int r0 = tile * TILE_ROWS;
+                const int r1 = min(r0 + TILE_ROWS, a.n);
+                const int nz0 = __ldg(a.row_ptr + r0), nz1 = __ldg(a.row_ptr + r1);
+                const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
+                unsigned char *st = stage_base + (size_t)s * stage_bytes;
+                const unsigned rp_copy = (unsigned)(((r1 - r0 + 1 + 3) & ~3) * sizeof(int));
+                const unsigned cnt = (unsigned)(ea - sa);
+                mbar_expect_tx(&full[s], rp_copy + cnt * (unsigned)(sizeof(MatT) + sizeof(int)));
+                tma_bulk_g2s(st + vals_bytes + cols_bytes, a.row_ptr + r0, rp_copy, &full[s]);
+                if (cnt) {
+                    tma_bulk_g2s(st, a.val + sa, cnt * (unsigned)sizeof(MatT), &full[s]);
+                    tma_bulk_g2s(st + vals_bytes, a.col + sa, cnt * (unsigned)sizeof(int), &full[s]);
+                }
+            }
+        }
+    } else {
+        // ------------------------------- consumers: one row per thread -------------------------------
+        for (int it = 0; it < my_tiles; it++) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int s = it % a.stages;
+            const unsigned ph = (unsigned)(it / a.stages) & 1u;
+            const int row = tile * TILE_ROWS + tid;
+            const bool active = row < a.n;
+            // operands that do not depend on the staged tile: issue their loads before waiting
+            VecT bi = 0, xi = 0;
+            MatT di = 1;
+            if (active) {
+                if (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2 || EPI == EPI_JACOBI_L1)
+                    bi = __ldg(a.b + row);
+                if (EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_JACOBI_L1) {
+                    di = __ldg(a.d + row);
+                    xi = gather<VecT, AGG>(a.x, a.agg, row);
+                }
+                if (EPI == EPI_SPMV_DOT) xi = gather<VecT, AGG>(a.x, a.agg, row);
+            }
+            const unsigned char *st = stage_base + (size_t)s * stage_bytes;
+            const MatT *vals = reinterpret_cast<const MatT *>(st);
+            const int *cols = reinterpret_cast<const int *>(st + vals_bytes);
+            const int *rp = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes);
+            mbar_wait(&full[s], ph);
+            if (active) {
+                const int sa = rp[0] & ~3;
+                int k = rp[tid] - sa;
+                const int kend = rp[tid + 1] - sa;
+                VecT sum = 0;
+                // 4 gathers in flight per step; FMA chain strictly left to right
+                for (; k + 4 <= kend; k += 4) {
+                    const int c0 = cols[k], c1 = cols[k + 1], c2 = cols[k + 2], c3 = cols[k + 3];
+                    const VecT x0 = gather<VecT, AGG>(a.x, a.agg, c0), x1 = gather<VecT, AGG>(a.x, a.agg, c1),
+                               x2 = gather<VecT, AGG>(a.x, a.agg, c2), x3 = gather<VecT, AGG>(a.x, a.agg, c3);
+                    sum = fma((VecT)vals[k], x0, sum);
+                    sum = fma((VecT)vals[k + 1], x1, sum);
+                    sum = fma((VecT)vals[k + 2], x2, sum);
+                    sum = fma((VecT)vals[k + 3], x3, sum);
+                }
+                if (k < kend) {
+                    const int c0 = cols[k];
+                    const int c1 = (k + 1 < kend) ? cols[k + 1] : c0;
+                    const int c2 = (k + 2 < kend) ? cols[k + 2] : c0;
+                    const VecT x0 = gather<VecT, AGG>(a.x, a.agg, c0), x1 = gather<VecT, AGG>(a.x, a.agg, c1),
+                               x2 = gather<VecT, AGG>(a.x, a.agg, c2);
+                    sum = fma((VecT)vals[k], x0, sum);
+                    if (k + 1 < kend) sum = fma((VecT)vals[k + 1], x1, sum);
+                    if (k + 2 < kend) sum = fma((VecT)vals[k + 2], x2, sum);
+                }
+                // ---- epilogue ----
+                if (EPI == EPI_SPMV) {
+                    a.y[row] = sum;
+                } else if (EPI == EPI_SPMV_DOT) {
+                    a.y[row] = sum;
+                    acc += (double)sum * (double)xi;
+                } else if (EPI == EPI_RESID) {
+                    a.y[row] = bi - sum;
+                } else if (EPI == EPI_RESID_NRM2) {
+                    const VecT r = bi - sum;
+                    a.y[row] = r;
+                    acc += (double)r * (double)r;
+                } else {
+                    // x + ((b - Ax) * w) * (1/d): d = 1/d; b -= y; b *= w; b*d + x  (one FMA)
+                    MatT dinv = (MatT)1 / guard_diag<MatT>(di);
+                    VecT t = bi - sum;
+                    t = (VecT)(t * a.omega);
+                    const VecT out = fma(t, (VecT)dinv, xi);
+                    a.y[row] = out;
+                    if (EPI == EPI_JACOBI_DOT) acc += (double)bi * (double)out;
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+        }
+    }
+    if (HAS_RED) block_reduce_finish(acc, smem_red, a.red, a.fin_op, a.fin_slot, a.mirror);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fallback: warp per row, lanes stride the row, shuffle-tree reduction (long / irregular rows).
+// ---------------------------------------------------------------------------------------------
+template <class MatT, class VecT, int EPI, bool AGG>
+__global__ void __launch_bounds__(256) csr_vector_kernel(const TileArgs<MatT, VecT> a)
+{
+    __shared__ double smem_red[40];
+    constexpr bool HAS_RED = (EPI == EPI_SPMV_DOT || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2);
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    double acc = 0.0;
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.n; row += gridDim.x * warps_per_block) {
+        const int k0 = __ldg(a.row_ptr + row), k1 = __ldg(a.row_ptr + row + 1);
+        VecT sum = 0;
+        for (int k = k0 + lane; k < k1; k += 32) sum = fma((VecT)__ldg(a.val + k), gather<VecT, AGG>(a.x, a.agg, __ldg(a.col + k)), sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) {
+            if (EPI == EPI_SPMV) {
+                a.y[row] = sum;
+            } else if (EPI == EPI_SPMV_DOT) {
+                a.y[row] = sum;
+                acc += (double)sum * (double)gather<VecT, AGG>(a.x, a.agg, row);
+            } else if (EPI == EPI_RESID) {
+                a.y[row] = a.b[row] - sum;
+            } else if (EPI == EPI_RESID_NRM2) {
+                const VecT r = a.b[row] - sum;
+                a.y[row] = r;
+                acc += (double)r * (double)r;
+            } else {
+                const VecT bi = a.b[row];
+                MatT dinv = (MatT)1 / guard_diag<MatT>(a.d[row]);
+                VecT t = bi - sum;
+                t = (VecT)(t * a.omega);
+                const VecT out = fma(t, (VecT)dinv, gather<VecT, AGG>(a.x, a.agg, row));
+                a.y[row] = out;
+                if (EPI == EPI_JACOBI_DOT) acc += (double)bi * (double)out;
+            }
+        }
+    }
+    if (HAS_RED) block_reduce_finish(acc, smem_red, a.red, a.fin_op, a.fin_slot, a.mirror);
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan construction
+// ---------------------------------------------------------------------------------------------
+__global__ void find_diag_kernel(const int *row_ptr, const int *col, int n, int *diag_idx)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int d = -1;
+        for (int k = row_ptr[i]; k < row_ptr[i + 1]; k++)
+            if (col[k] == i) { d = k; break; }
+        diag_idx[i] = d;
+    }
+}
+
+__global__ void tile_stats_kernel(const int *row_ptr, int n, int tile_rows, int num_tiles, int *max_tile_nnz, int *max_row_nnz)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < num_tiles; t += gridDim.x * blockDim.x) {
+        int r0 = t * tile_rows, r1 = min(r0 + tile_rows, n);
+        int sa = row_ptr[r0] & ~3, ea = (row_ptr[r1] + 3) & ~3;
+        atomicMax(max_tile_nnz, ea - sa);
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicMax(max_row_nnz, row_ptr[i + 1] - row_ptr[i]);
+}
+
+size_t tile_smem_bytes(int cap, int stages, int tile_rows, size_t mat_size)
+{
+    return 512 + (size_t)stages * ((size_t)cap * (mat_size + 4) + (size_t)(tile_rows + 4) * 4);
+}
+
+template <class MatT, class VecT, int TILE_ROWS, int EPI> void launch_tile(const Matrix &A, const TileArgs<MatT, VecT> &ta, int grid, cudaStream_t s)
+{
+    const size_t smem = A.plan.smem_bytes;
+    if (ta.agg) {
+        auto k = csr_tile_kernel<MatT, VecT, TILE_ROWS, EPI, true>;
+        static bool attr_set = false;
+        if (!attr_set) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+        k<<<grid, TILE_ROWS + PRODUCER_THREADS, smem, s>>>(ta);
+    } else {
+        auto k = csr_tile_kernel<MatT, VecT, TILE_ROWS, EPI, false>;
+        static bool attr_set = false;
+        if (!attr_set) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+        k<<<grid, TILE_ROWS + PRODUCER_THREADS, smem, s>>>(ta);
+    }
+}
+
+template <class MatT, class VecT, int EPI> void launch_epi(const Matrix &A, const TileArgs<MatT, VecT> &ta, cudaStream_t s)
+{
+    if (A.plan.use_tiles) {
+        const int grid = csr_max_grid(A);
+        if (A.plan.tile_rows == 256) launch_tile<MatT, VecT, 256, EPI>(A, ta, grid, s);
+        else launch_tile<MatT, VecT, 128, EPI>(A, ta, grid, s);
+    } else {
+        const int grid = csr_max_grid(A);
+        if (ta.agg) csr_vector_kernel<MatT, VecT, EPI, true><<<grid, 256, 0, s>>>(ta);
+        else csr_vector_kernel<MatT, VecT, EPI, false><<<grid, 256, 0, s>>>(ta);
+    }
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+int csr_max_grid(const Matrix &A)
+{
+    const int sms = A.rsc ? A.rsc->num_sms : 148;
+    if (A.plan.use_tiles) {
+        int per_sm = (int)std::min<size_t>(227 * 1024 / std::max<size_t>(A.plan.smem_bytes, 1), (size_t)(2048 / (A.plan.tile_rows + PRODUCER_THREADS)));
+        per_sm = std::max(1, std::min(per_sm, 4));
+        return std::max(1, std::min(A.plan.num_tiles, sms * per_sm));
+    }
+    return std::max(1, std::min(ceil_div(A.n, 8), sms * 8));
+}
+
+void csr_build_plan(Matrix &A, cudaStream_t s)
+{
+    if (A.bs() != 1) { A.plan = TilePlan(); return; }   // block matrices use the block kernels (k_block.cu)
+    A.diag_idx.resize(A.n);
+    if (A.n == 0) { A.plan = TilePlan(); return; }
+    find_diag_kernel<<<std::min(ceil_div(A.n, 256), 4096), 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, A.diag_idx.ptr());
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    const int sms = A.rsc ? A.rsc->num_sms : 148;
+    TilePlan p;
+    // 256-row tiles once there are enough of them to fill the machine, else 128-row tiles
+    p.tile_rows = (ceil_div(A.n, 256) >= 2 * sms) ? 256 : 128;
+    p.num_tiles = ceil_div(A.n, p.tile_rows);
+    DevBuf<int> stats;
+    stats.resize(2);
+    stats.zero(s);
+    tile_stats_kernel<<<std::min(ceil_div(A.n, 256), 1024), 256, 0, s>>>(A.row_ptr.ptr(), A.n, p.tile_rows, p.num_tiles, stats.ptr(), stats.ptr() + 1);
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    std::vector<int> h = stats.to_host(s);
+    p.max_tile_nnz = std::max(4, h[0]);
+    const size_t msz = prec_size(A.mat_prec);
+    p.use_tiles = false;
+    for (int st = MAX_STAGES; st >= 2; st--) {
+        size_t need = tile_smem_bytes(p.max_tile_nnz, st, p.tile_rows, msz);
+        // prefer >= 2 CTAs per SM at full depth, accept 1 CTA per SM at depth 2
+        size_t budget = (st > 2) ? (size_t)110 * 1024 : (size_t)220 * 1024;
+        if (need <= budget) { p.stages = st; p.smem_bytes = need; p.use_tiles = true; break; }
+    }
+    A.plan = p;
+}
+
+void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s)
+{
+    if (A.bs() != 1) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "csr_op: scalar kernel called on a block matrix");
+    if (A.n == 0) return;
+    AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+        TileArgs<MatT, VecT> ta;
+        ta.row_ptr = A.row_ptr.ptr();
+        ta.col = A.col_idx.ptr();
+        ta.val = A.values.as<MatT>();
+        ta.n = A.n;
+        ta.num_tiles = A.plan.num_tiles;
+        ta.cap = A.plan.max_tile_nnz;
+        ta.stages = A.plan.stages;
+        ta.x = (const VecT *)g.x;
+        ta.agg = g.agg;
+        ta.b = (const VecT *)g.b;
+        ta.d = (const MatT *)g.d;
+        ta.y = (VecT *)g.y;
+        ta.omega = g.omega;
+        ta.red = g.red;
+        ta.fin_op = g.fin_op;
+        ta.fin_slot = g.fin_slot;
+        ta.mirror = g.mirror;
+        switch (epi) {
+        case EPI_SPMV: launch_epi<MatT, VecT, EPI_SPMV>(A, ta, s); break;
+        case EPI_RESID: launch_epi<MatT, VecT, EPI_RESID>(A, ta, s); break;
+        case EPI_JACOBI:
+        case EPI_JACOBI_L1: launch_epi<MatT, VecT, EPI_JACOBI>(A, ta, s); break;
+        case EPI_SPMV_DOT: launch_epi<MatT, VecT, EPI_SPMV_DOT>(A, ta, s); break;
+        case EPI_JACOBI_DOT: launch_epi<MatT, VecT, EPI_JACOBI_DOT>(A, ta, s); break;
+        case EPI_RESID_NRM2: launch_epi<MatT, VecT, EPI_RESID_NRM2>(A, ta, s); break;
+        }
+    });
+}
+
+}  // namespace amgxb

@@ -1,0 +1,78 @@
+// matrix.h -- device-resident block-CSR matrix, vectors and resources of the engine.
+// Layout follows the reference's Matrix<TConfig> (include/matrix.h:65-200): row_offsets[n+1],
+// col_indices[nnz], values[nnz*bs] row-major blocks, diag[n] = index of each row's diagonal
+// entry; an external diagonal (AMGX_matrix_upload_all diag_data != NULL) is stored after the
+// off-diagonal values at block index nnz + row (src/matrix.cu:713-721).
+#pragma once
+#include "base.h"
+#include "config.h"
+
+namespace amgxb {
+
+struct DistManager;   // dist.h
+
+struct Resources {
+    std::shared_ptr<Config> cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;       // compute stream of this engine
+    cudaStream_t side_stream = nullptr;  // halo exchange / copies
+    int num_sms = 148;
+    int rank = 0, world = 1;
+    void *nccl_comm = nullptr;           // ncclComm_t when world > 1
+    ~Resources();
+};
+
+// How the scalar-CSR kernels tile a matrix: fixed TILE_ROWS consecutive rows per tile; per tile the
+// col/val ranges are staged into shared memory with TMA bulk copies (k_spmv.cu).
+struct TilePlan {
+    int tile_rows = 0;          // rows per tile (== CTA size)
+    int num_tiles = 0;
+    int max_tile_nnz = 0;       // capacity each smem stage must hold (already padded for alignment)
+    int stages = 0;             // pipeline depth chosen for this matrix
+    size_t smem_bytes = 0;      // dynamic shared memory per CTA
+    bool use_tiles = false;     // false -> generic warp-per-row kernel
+};
+
+struct Matrix {
+    std::shared_ptr<Resources> rsc;
+    int mode = AMGX_mode_dDDI;
+    Prec mat_prec = Prec::F64, vec_prec = Prec::F64;
+    int n = 0;            // owned block rows
+    int n_cols = 0;       // owned + halo block columns (== n on a single GPU)
+    int nnz = 0;          // stored blocks (without external diagonal)
+    int bx = 1, by = 1;
+    bool has_ext_diag = false;
+    bool merged_ext_diag = false;   // scalar matrix uploaded with diag_data: merged into CSR, diagonal first
+    bool dist_pending = false;      // comm maps were supplied; the next upload_all is a local distributed upload
+    bool initialized = false;
+    int level = 0;
+
+    DevBuf<int> row_ptr, col_idx, diag_idx;
+    DevVec values;        // (nnz [+ n if ext diag]) * bx*by scalars of mat_prec
+    TilePlan plan;
+
+    std::shared_ptr<DistManager> dist;   // null on a single GPU
+
+    // colouring (multicolour smoothers)
+    int num_colors = 0;
+    DevBuf<int> row_colors, sorted_rows_by_color;
+    std::vector<int> color_offsets;      // host, [num_colors+1]
+    bool user_coloring = false;
+
+    int bs() const { return bx * by; }
+    cudaStream_t stream() const { return rsc->stream; }
+    void compute_diag_and_plan();        // diag_idx + tile plan (k_spmv.cu / k_setup.cu)
+};
+
+struct Vector {
+    std::shared_ptr<Resources> rsc;
+    int mode = AMGX_mode_dDDI;
+    Prec prec = Prec::F64;
+    int n = 0;            // block entries
+    int block_dim = 1;
+    DevVec data;          // n*block_dim scalars (+ halo tail when bound to a distributed matrix)
+    std::shared_ptr<DistManager> dist;
+    bool user_order = true;   // distributed: data is in the caller's (partition) order
+};
+
+}  // namespace amgxb

@@ -1,0 +1,620 @@
+// solvers.cu -- Solver base class, convergence criteria, Jacobi smoothers, PCG.  See solvers.h.
+#include "solvers.h"
+#include "dist.h"
+#include <cmath>
+#include <algorithm>
+#include <sstream>
+#include <iomanip>
+#include <map>
+#include <mutex>
+
+namespace amgxb {
+
+// ---------------------------------------------------------------------------------------------
+// Convergence  (src/convergence/*.cu)
+// ---------------------------------------------------------------------------------------------
+void Convergence::init(const Config &cfg, const std::string &scope)
+{
+    tolerance = cfg.get_double("tolerance", scope);
+    alt_rel_tolerance = cfg.get_double("alt_rel_tolerance", scope);
+    max_nrm.clear();
+}
+
+Status Convergence::update_and_check(const std::vector<double> &nrm, const std::vector<double> &nrm_ini)
+{
+    const double eps_conv = fp32 ? (double)1.0e-6f : 1.0e-12;   // Epsilon_conv<T>, include/convergence/convergence.h:21-46
+    switch (kind) {
+    case ABSOLUTE: {
+        bool ok = true;
+        for (size_t i = 0; i < nrm.size(); i++) ok = ok && (nrm[i] < tolerance);
+        return ok ? ST_CONVERGED : ST_NOT_CONVERGED;
+    }
+    case RELATIVE_INI: {
+        bool res = true, res_abs = true;
+        const double eps = 1e-20;
+        for (size_t i = 0; i < nrm.size(); i++) {
+            bool conv = (nrm_ini[i] <= eps) ? true : (nrm[i] / nrm_ini[i] <= tolerance);
+            res = res && conv;
+            bool conv_abs = nrm[i] <= std::max(nrm_ini[i] * eps_conv, eps);
+            res_abs = res_abs && conv_abs;
+        }
+        if (res_abs) return ST_CONVERGED;
+        return res ? ST_CONVERGED : ST_NOT_CONVERGED;
+    }
+    case RELATIVE_MAX: {
+        const double eps = fp32 ? 1e-10 : 1e-20;   // AMGX_NUMERICAL_SZERO / DZERO
+        if (max_nrm.empty()) max_nrm = nrm;
+        else for (size_t i = 0; i < nrm.size(); i++) max_nrm[i] = nrm[i] > max_nrm[i] ? nrm[i] : max_nrm[i];
+        bool res = true, res_abs = true;
+        for (size_t i = 0; i < nrm.size(); i++) {
+            bool conv = (max_nrm[i] <= eps) ? true : ((nrm[i] / max_nrm[i]) <= tolerance);
+            res = res && conv;
+            bool conv_abs = nrm[i] <= std::max(max_nrm[i] * eps_conv, 1e-20);
+            res_abs = res_abs && conv_abs;
+        }
+        if (res_abs) return ST_CONVERGED;
+        return res ? ST_CONVERGED : ST_NOT_CONVERGED;
+    }
+    case COMBINED_REL_INI_ABS: {
+        bool res = true, res_abs = true, res_prec = true;
+        const double eps = 1e-20;
+        for (size_t i = 0; i < nrm.size(); i++) {
+            res_abs = res_abs && (nrm[i] < tolerance);
+            res = res && ((nrm_ini[i] <= eps) ? true : (nrm[i] / nrm_ini[i] <= alt_rel_tolerance));
+            res_prec = res_prec && (nrm[i] <= std::max(nrm_ini[i] * eps_conv, eps));
+        }
+        if (res_prec) return ST_CONVERGED;
+        return (res || res_abs) ? ST_CONVERGED : ST_NOT_CONVERGED;
+    }
+    }
+    return ST_NOT_CONVERGED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar block / reduction scratch
+// ---------------------------------------------------------------------------------------------
+void ScalarBlock::create()
+{
+    if (scal) return;
+    AMGXB_CUDA_CHECK(cudaMalloc(&scal, S_COUNT * sizeof(double)));
+    AMGXB_CUDA_CHECK(cudaMemset(scal, 0, S_COUNT * sizeof(double)));
+    AMGXB_CUDA_CHECK(cudaHostAlloc(&host, S_COUNT * sizeof(double), cudaHostAllocMapped));
+    memset(host, 0, S_COUNT * sizeof(double));
+    AMGXB_CUDA_CHECK(cudaHostGetDevicePointer(&host_dev, host, 0));
+}
+void ScalarBlock::destroy()
+{
+    if (scal) cudaFree(scal);
+    if (host) cudaFreeHost(host);
+    scal = host = host_dev = nullptr;
+}
+
+void ReduceScratch::ensure(cudaStream_t s)
+{
+    const size_t need = 148 * 16 + 64;
+    if (partials.size() < need) {
+        partials.resize(need);
+        counter.resize(1);
+        counter.zero(s);
+    }
+}
+
+static std::map<Resources *, std::unique_ptr<ReduceScratch>> g_scratch;
+static std::mutex g_scratch_mu;
+ReduceScratch &reduce_scratch(Resources *rsc)
+{
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    auto &p = g_scratch[rsc];
+    if (!p) p.reset(new ReduceScratch);
+    p->ensure(rsc->stream);
+    return *p;
+}
+void release_reduce_scratch(Resources *rsc)
+{
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    g_scratch.erase(rsc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Solver base
+// ---------------------------------------------------------------------------------------------
+static NormType parse_norm(const std::string &s)
+{
+    if (s == "L1") return NORM_L1;
+    if (s == "L2") return NORM_L2;
+    if (s == "LMAX") return NORM_LMAX;
+    fatal(AMGX_RC_BAD_CONFIGURATION, "norm '" + s + "' is not supported by this engine (L1, L2, LMAX)");
+}
+
+Solver::Solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc) : cfg_(&cfg), scope_(scope), rsc_(std::move(rsc))
+{
+    verbosity_ = cfg.get_int("verbosity_level", scope);
+    monitor_residual_ = cfg.get_int("monitor_residual", scope) != 0;
+    store_res_history_ = cfg.get_int("store_res_history", scope) != 0;
+    obtain_timings_ = cfg.get_int("obtain_timings", scope) != 0;
+    print_solve_stats_ = cfg.get_int("print_solve_stats", scope) != 0;
+    print_grid_stats_ = cfg.get_int("print_grid_stats", scope) != 0;
+    if (cfg.get_string("scaling", scope) != "NONE")
+        fatal(AMGX_RC_BAD_CONFIGURATION, "matrix scaling is outside the solve-phase engine's scope (scaling must be NONE)");
+    monitor_convergence_ = monitor_residual_;
+    if (scope == "default") {   // backward compatibility rule of the reference (solver.cu:52-60)
+        obtain_timings_ = print_solve_stats_ = print_grid_stats_ = store_res_history_ = monitor_residual_ = false;
+        monitor_convergence_ = cfg.get_int("monitor_residual", scope) != 0;
+        monitor_residual_ = monitor_convergence_;
+        store_res_history_ = cfg.get_int("store_res_history", scope) != 0;
+        print_solve_stats_ = cfg.get_int("print_solve_stats", scope) != 0;
+        print_grid_stats_ = cfg.get_int("print_grid_stats", scope) != 0;
+        obtain_timings_ = cfg.get_int("obtain_timings", scope) != 0;
+    }
+    if (print_solve_stats_ && !monitor_residual_)
+        fatal(AMGX_RC_BAD_PARAMETERS, "Cannot print solver information if residual is not monitored (i.e. print_solve_stats=1 and monitor_residual=0) ");
+    if (store_res_history_ && !monitor_residual_)
+        fatal(AMGX_RC_BAD_PARAMETERS, "Cannot store residual information if residual is not monitored (i.e. store_res_history=1 and monitor_residual=0) ");
+    max_iters_ = cfg.get_int("max_iters", scope);
+    norm_type_ = parse_norm(cfg.get_string("norm", scope));
+    use_scalar_norm_ = cfg.get_int("use_scalar_norm", scope) != 0;
+    std::string cv = cfg.get_string("convergence", scope);
+    if (cv == "ABSOLUTE") conv_.kind = Convergence::ABSOLUTE;
+    else if (cv == "RELATIVE_INI" || cv == "RELATIVE_INI_CORE") conv_.kind = Convergence::RELATIVE_INI;
+    else if (cv == "RELATIVE_MAX" || cv == "RELATIVE_MAX_CORE") conv_.kind = Convergence::RELATIVE_MAX;
+    else if (cv == "COMBINED_REL_INI_ABS") conv_.kind = Convergence::COMBINED_REL_INI_ABS;
+    else fatal(AMGX_RC_BAD_CONFIGURATION, "ConvergenceFactory '" + cv + "' has not been registered");
+    if (store_res_history_) res_history_.resize(max_iters_ + 1);
+    sb_.create();
+    for (auto &e : ev_) AMGXB_CUDA_CHECK(cudaEventCreate(&e));
+}
+
+Solver::~Solver()
+{
+    sb_.destroy();
+    for (auto &e : ev_) if (e) cudaEventDestroy(e);
+}
+
+void Solver::set_max_iters(int m)
+{
+    if (store_res_history_ && (size_t)(m + 1) > res_history_.size()) res_history_.resize(m + 1);
+    max_iters_ = m;
+}
+
+const std::vector<double> &Solver::get_residual(int idx) const
+{
+    if (!store_res_history_) fatal(AMGX_RC_BAD_PARAMETERS, "Residual history was not recorded");
+    if (idx < 0 || (size_t)idx >= res_history_.size()) fatal(AMGX_RC_BAD_PARAMETERS, "Invalid iteration index while retrieving residual");
+    return res_history_[idx];
+}
+
+ReduceCtx Solver::red_ctx()
+{
+    ReduceScratch &rs = reduce_scratch(rsc_.get());
+    ReduceCtx c;
+    c.partials = rs.partials.ptr();
+    c.counter = rs.counter.ptr();
+    c.scal = sb_.scal;
+    c.host_mirror = sb_.host_dev;
+    return c;
+}
+
+void Solver::setup(Matrix &A, bool reuse)
+{
+    if (obtain_timings_) AMGXB_CUDA_CHECK(cudaEventRecord(ev_[0], stream()));
+    if (!A.initialized) fatal(AMGX_RC_BAD_PARAMETERS, "Trying to setup from the uninitialized matrix");
+    if (reuse && A_ != &A) fatal(AMGX_RC_UNKNOWN, "Cannot call resetup with a different matrix");
+    A_ = &A;
+    conv_.fp32 = (A.vec_prec == Prec::F32);
+    solver_setup(reuse);
+    if (monitor_residual_ || is_residual_needed()) {
+        r_.resize((size_t)A.n_cols * A.by, A.vec_prec);
+        r_.zero(stream());
+        has_r_ = true;
+    }
+    if (monitor_convergence_) {
+        const int bsize = use_scalar_norm_ ? 1 : A.by;
+        nrm_.assign(bsize, 0.0);
+        nrm_ini_.assign(bsize, 0.0);
+    }
+    if (obtain_timings_) {
+        AMGXB_CUDA_CHECK(cudaEventRecord(ev_[1], stream()));
+        AMGXB_CUDA_CHECK(cudaEventSynchronize(ev_[1]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
+        setup_time_ = ms * 1e-3;
+    }
+    if (verbosity_ > 2 && print_grid_stats_) print_grid_stats();
+    is_setup_ = true;
+}
+
+void Solver::compute_residual(const DevVec &b, DevVec &x)
+{
+    dist_exchange_halo(*A_, x, stream());
+    CsrOpArgs g;
+    g.x = x.ptr();
+    g.b = b.ptr();
+    g.y = r_.ptr();
+    matrix_apply(*A_, EPI_RESID, g, stream());
+}
+
+void Solver::compute_norm_of(const DevVec &v, std::vector<double> &out)
+{
+    const int bsize = use_scalar_norm_ ? 1 : A_->by;
+    out.resize(bsize);
+    ReduceCtx red = red_ctx();
+    const size_t n = vec_len();
+    if (bsize == 1) {
+        if (norm_type_ == NORM_L2) vec_dot(v.ptr(), v.ptr(), v.prec, n, red, A_->dist ? FIN_STORE : FIN_SQRT, S_NRM, 1, stream());
+        else if (norm_type_ == NORM_L1) vec_nrm1(v.ptr(), v.prec, n, red, S_NRM, 1, stream());
+        else vec_nrmmax(v.ptr(), v.prec, n, red, S_NRM, 1, stream());
+        AMGXB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        double val = sb_.host[S_NRM];
+        if (A_->dist) val = dist_reduce_norm(*A_, val, norm_type_);
+        out[0] = val;
+    } else {
+        block_norms(v, A_->n, bsize, (int)norm_type_, red, sb_, out, stream());
+        if (A_->dist) for (auto &o : out) o = dist_reduce_norm(*A_, norm_type_ == NORM_L2 ? o * o : o, norm_type_);
+    }
+}
+
+void Solver::compute_norm() { compute_norm_of(r_, nrm_); }
+
+Status Solver::converged(const DevVec &b, DevVec &x)
+{
+    if (monitor_residual_) compute_residual(b, x);
+    Status st = ST_NOT_CONVERGED;
+    if (monitor_convergence_) {
+        compute_norm();
+        st = converged();
+    }
+    return st;
+}
+
+Status Solver::compute_norm_and_converged()
+{
+    compute_norm();
+    return converged();
+}
+
+static void print_norm(std::stringstream &ss, const std::vector<double> &nrm)
+{
+    for (double v : nrm) ss << std::scientific << std::setprecision(6) << std::setw(15) << v;
+}
+
+// The iteration loop of the reference's Solver::solve (src/solvers/solver.cu:585-970), same order
+// of residual / norm / convergence operations so that iteration counts agree.
+Status Solver::solve(DevVec &b, DevVec &x, bool xIsZero)
+{
+    if (!is_setup_) fatal(AMGX_RC_BAD_CONFIGURATION, "Error, setup must be called before calling solve");
+    if (obtain_timings_) AMGXB_CUDA_CHECK(cudaEventRecord(ev_[2], stream()));
+    if (monitor_residual_ || is_residual_needed()) {
+        if (xIsZero) vec_copy(r_.ptr(), b.ptr(), b.prec, vec_len(), stream());
+        else compute_residual(b, x);
+    }
+    std::vector<double> last_nrm;
+    if (monitor_convergence_) {
+        compute_norm();
+        last_nrm = nrm_ini_ = nrm_;
+    }
+    if (store_res_history_) res_history_[0] = nrm_;
+    const bool pstats = verbosity_ > 2 && print_solve_stats_;
+    if (pstats) {
+        std::stringstream ss;
+        ss << std::setw(15) << "iter" << std::setw(20) << " Mem Usage (GB)" << std::setw(15) << "residual";
+        for (size_t i = 0; i + 1 < nrm_.size(); i++) ss << std::setw(15) << " ";
+        ss << std::setw(15) << "rate";
+        for (size_t i = 0; i + 1 < nrm_.size(); i++) ss << std::setw(15) << " ";
+        ss << std::endl;
+        ss << "         ----------------------------------------------------------------------";
+        for (size_t i = 0; i + 1 < nrm_.size(); i++) ss << "-----------------------";
+        ss << std::endl;
+        ss << std::setw(15) << "Ini";
+        ss << std::setw(20) << device_mem_used_gb();
+        print_norm(ss, nrm_);
+        ss << std::endl;
+        amgx_output(ss.str().c_str(), (int)ss.str().length());
+    }
+    if (monitor_convergence_) {
+        conv_.init(*cfg_, scope_);
+        if (tol_override_) conv_.tolerance = tol_value_;
+        conv_.update_and_check(nrm_, nrm_ini_);
+    }
+    bool done = monitor_convergence_ ? (converged() == ST_CONVERGED) : false;
+    if (max_iters_ == 0) return monitor_convergence_ ? ST_NOT_CONVERGED : ST_CONVERGED;
+    if (!done) solve_init(b, x, xIsZero);
+    Status conv_stat = done ? ST_CONVERGED : ST_NOT_CONVERGED;
+    std::stringstream ss;
+    for (curr_iter_ = 0; curr_iter_ < max_iters_ && !done; ++curr_iter_) {
+        conv_stat = solve_iteration(b, x, xIsZero);
+        xIsZero = false;
+        done = monitor_convergence_ && is_done(conv_stat);
+        if (pstats) {
+            ss.str(std::string());
+            ss << std::setw(15) << curr_iter_;
+            ss << std::setw(20) << device_mem_used_gb();
+            print_norm(ss, nrm_);
+            ss << std::setw(15);
+            for (size_t i = 0; i < last_nrm.size(); i++) ss << std::fixed << std::setprecision(4) << nrm_[i] / last_nrm[i] << std::setw(8);
+            ss << std::endl;
+            amgx_output(ss.str().c_str(), (int)ss.str().length());
+            last_nrm = nrm_;
+        }
+        if (store_res_history_) res_history_[curr_iter_ + 1] = nrm_;
+    }
+    num_iters_ = curr_iter_;
+    if (num_iters_ > 0) solve_finalize(b, x);
+    if (obtain_timings_) {
+        AMGXB_CUDA_CHECK(cudaEventRecord(ev_[3], stream()));
+        AMGXB_CUDA_CHECK(cudaEventSynchronize(ev_[3]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_[2], ev_[3]);
+        solve_time_ = ms * 1e-3;
+    }
+    if (pstats) {
+        ss.str(std::string());
+        ss << "         ----------------------------------------------------------------------";
+        for (size_t i = 0; i + 1 < nrm_.size(); i++) ss << "-----------------------";
+        ss << std::endl;
+        ss << "         Total Iterations: " << num_iters_ << std::endl;
+        ss << "         Avg Convergence Rate: \t\t";
+        const double eps = conv_.fp32 ? 1e-10 : 1e-20;
+        for (size_t i = 0; i < last_nrm.size(); i++)
+            ss << std::fixed << std::setw(15) << ((nrm_ini_[i] > eps) ? pow(last_nrm[i] / nrm_ini_[i], 1.0 / num_iters_) : nrm_ini_[i]);
+        ss << std::endl;
+        ss << "         Final Residual: \t\t" << std::setprecision(6);
+        for (size_t i = 0; i < last_nrm.size(); i++) ss << std::scientific << std::setw(15) << last_nrm[i] << std::fixed;
+        ss << std::endl;
+        ss << "         Total Reduction in Residual: \t" << std::setprecision(6);
+        for (size_t i = 0; i < last_nrm.size(); i++)
+            ss << std::scientific << std::setw(15) << ((nrm_ini_[i] > eps) ? last_nrm[i] / nrm_ini_[i] : nrm_ini_[i]) << std::fixed;
+        ss << std::endl;
+        ss << "         Maximum Memory Usage: \t\t" << std::setprecision(3) << std::setw(15) << device_mem_used_gb() << " GB" << std::endl;
+        ss << "         ----------------------------------------------------------------------";
+        for (size_t i = 0; i + 1 < nrm_.size(); i++) ss << "-----------------------";
+        ss << std::endl;
+        amgx_output(ss.str().c_str(), (int)ss.str().length());
+    }
+    if (verbosity_ > 2 && obtain_timings_) {
+        std::stringstream ts;
+        ts << "Total Time: " << setup_time_ + solve_time_ << std::endl;
+        ts << "    setup: " << setup_time_ << " s\n";
+        ts << "    solve: " << solve_time_ << " s\n";
+        ts << "    solve(per iteration): " << ((num_iters_ == 0) ? num_iters_ : solve_time_ / num_iters_) << " s\n";
+        amgx_output(ts.str().c_str(), (int)ts.str().length());
+    }
+    return conv_stat;
+}
+
+// generic smoother entry: `sweeps` iterations of solve_iteration without monitoring
+void Solver::smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse)
+{
+    if (fuse && (fuse->agg || fuse->dot_b_x)) fatal(AMGX_RC_INTERNAL, "smoother does not support fused sweeps");
+    const int saved = max_iters_;
+    const bool mr = monitor_residual_, mc = monitor_convergence_;
+    set_max_iters(sweeps);
+    set_tolerance(0.0);
+    solve(b, x, xIsZero);
+    max_iters_ = saved;
+    monitor_residual_ = mr;
+    monitor_convergence_ = mc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NOSOLVER
+// ---------------------------------------------------------------------------------------------
+Status NoSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
+{
+    if (xIsZero) x.zero(stream());
+    return converged(b, x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BLOCK_JACOBI / JACOBI_L1
+// ---------------------------------------------------------------------------------------------
+BlockJacobiSolver::BlockJacobiSolver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc) : Solver(cfg, scope, std::move(rsc))
+{
+    weight_ = cfg.get_double("relaxation_factor", scope);
+    if (weight_ == 0) {
+        weight_ = 1.;
+        amgx_printf("Warning, setting weight to 1 instead of estimating largest_eigen_value in Block Jacobi smoother\n");
+    }
+}
+
+void BlockJacobiSolver::compute_d() { extract_diagonal(*A_, dinv_, stream()); }
+
+void BlockJacobiSolver::solver_setup(bool)
+{
+    if (A_->bx != A_->by) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "Unsupported block size for BlockJacobi_Solver");
+    compute_d();
+    if (A_->bs() != 1) block_jacobi_setup(*A_, dinv_, stream());   // invert diagonal blocks (k_block.cu)
+    tmp_.resize((size_t)A_->n_cols * A_->by, A_->vec_prec);
+    tmp_.zero(stream());
+}
+
+void BlockJacobiSolver::smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse)
+{
+    cudaStream_t s = stream();
+    const bool scalar = A_->bs() == 1;
+    if (!scalar && fuse && (fuse->agg || fuse->dot_b_x)) fatal(AMGX_RC_INTERNAL, "block Jacobi: fused sweeps need block size 1");
+    for (int it = 0; it < sweeps; it++) {
+        const bool first = (it == 0), last = (it == sweeps - 1);
+        const bool want_dot = fuse && fuse->dot_b_x && last;
+        const bool via_agg = fuse && fuse->agg && first;
+        if (first && xIsZero && !via_agg) {
+            // x = w * b / d  -- no SpMV
+            if (scalar) jacobi_zero_guess(b.ptr(), dinv_.ptr(), x.ptr(), A_->mat_prec, A_->vec_prec, vec_len(), weight_, s);
+            else block_jacobi_zero(*A_, dinv_, b, x, weight_, s);
+            if (want_dot) vec_dot(b.ptr(), x.ptr(), x.prec, vec_len(), fuse->red, fuse->fin_op, fuse->fin_slot, 0, s);
+            continue;
+        }
+        if (scalar) {
+            CsrOpArgs g;
+            g.b = b.ptr();
+            g.d = dinv_.ptr();
+            g.omega = weight_;
+            if (via_agg) {
+                // input is the prolongated coarse correction; write straight into x
+                dist_exchange_halo_coarse(*A_, fuse->xc, s);
+                g.x = fuse->xc;
+                g.agg = fuse->agg;
+                g.y = x.ptr();
+            } else {
+                dist_exchange_halo(*A_, x, s);
+                g.x = x.ptr();
+                g.y = tmp_.ptr();
+            }
+            if (want_dot) {
+                g.red = fuse->red;
+                g.fin_op = fuse->fin_op;
+                g.fin_slot = fuse->fin_slot;
+                matrix_apply(*A_, EPI_JACOBI_DOT, g, s);
+            } else {
+                matrix_apply(*A_, EPI_JACOBI, g, s);
+            }
+            if (!via_agg) x.swap(tmp_);
+        } else {
+            dist_exchange_halo(*A_, x, s);
+            block_jacobi_sweep(*A_, dinv_, b, x, tmp_, weight_, s);
+            x.swap(tmp_);
+        }
+    }
+}
+
+Status BlockJacobiSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
+{
+    smooth(b, x, xIsZero, 1, nullptr);
+    return converged(b, x);
+}
+
+JacobiL1Solver::JacobiL1Solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc) : BlockJacobiSolver(cfg, scope, std::move(rsc)) {}
+
+void JacobiL1Solver::compute_d()
+{
+    if (A_->bs() != 1) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "Unsupported block size for JacobiL1_Solver");
+    l1_row_norms(*A_, dinv_, stream());
+}
+
+// ---------------------------------------------------------------------------------------------
+// PCG   (src/solvers/pcg_solver.cu)
+// ---------------------------------------------------------------------------------------------
+PCGSolver::PCGSolver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc) : Solver(cfg, scope, rsc)
+{
+    std::string name, ns;
+    cfg.get_scoped("preconditioner", scope, name, ns);
+    if (name != "NOSOLVER") precond_ = Solver::allocate(cfg, scope, "preconditioner", rsc);
+}
+
+void PCGSolver::solver_setup(bool reuse)
+{
+    if (precond_) precond_->setup(*A_, reuse);
+    const size_t N = (size_t)A_->n_cols * A_->by;
+    p_.resize(N, A_->vec_prec);
+    z_.resize(N, A_->vec_prec);
+    Ap_.resize(N, A_->vec_prec);
+    p_.zero(stream());
+    z_.zero(stream());
+    Ap_.zero(stream());
+}
+
+// z = M^-1 r with zero initial guess, then <r,z> finished on the device by fin_op
+void PCGSolver::apply_precond_and_rz(int fin_op)
+{
+    cudaStream_t s = stream();
+    ReduceCtx red = red_ctx();
+    if (A_->dist) red = dist_wrap_reduce(*A_, red);
+    if (!precond_) {
+        vec_copy(z_.ptr(), r_.ptr(), r_.prec, vec_len(), s);
+        vec_dot(r_.ptr(), z_.ptr(), r_.prec, vec_len(), red, A_->dist ? FIN_STORE : fin_op, S_TMP0, 0, s);
+    } else {
+        AMGSolver *amg = dynamic_cast<AMGSolver *>(precond_.get());
+        bool fused = false;
+        if (amg && !A_->dist) fused = amg->solve_fused_dot(r_, z_, red, fin_op, S_TMP0);
+        if (!fused) {
+            precond_->solve(r_, z_, true);
+            vec_dot(r_.ptr(), z_.ptr(), r_.prec, vec_len(), red, A_->dist ? FIN_STORE : fin_op, S_TMP0, 0, s);
+        }
+    }
+    if (A_->dist) dist_allreduce_scalar_fin(*A_, red, S_TMP0, fin_op, s);
+}
+
+void PCGSolver::solve_init(DevVec &b, DevVec &x, bool xIsZero)
+{
+    cudaStream_t s = stream();
+    // rz = <r, z>: FIN_PCG_BETA stores the sum in S_RZ (beta is garbage here and unused)
+    AMGXB_CUDA_CHECK(cudaMemsetAsync(sb_.scal + S_RZ, 0, sizeof(double), s));
+    apply_precond_and_rz(FIN_PCG_BETA);
+    vec_copy(p_.ptr(), z_.ptr(), z_.prec, vec_len(), s);
+}
+
+Status PCGSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
+{
+    cudaStream_t s = stream();
+    ReduceCtx red = red_ctx();
+    Status conv_stat = ST_NOT_CONVERGED;
+    // Ap = A p fused with <Ap, p>; alpha = rz / <Ap,p> on the device
+    dist_exchange_halo(*A_, p_, s);
+    if (A_->bs() == 1 && !A_->dist) {
+        CsrOpArgs g;
+        g.x = p_.ptr();
+        g.y = Ap_.ptr();
+        g.red = red;
+        g.fin_op = FIN_PCG_ALPHA;
+        g.fin_slot = S_DOT;
+        matrix_apply(*A_, EPI_SPMV_DOT, g, s);
+    } else {
+        CsrOpArgs g;
+        g.x = p_.ptr();
+        g.y = Ap_.ptr();
+        matrix_apply(*A_, EPI_SPMV, g, s);
+        vec_dot(Ap_.ptr(), p_.ptr(), p_.prec, vec_len(), red, A_->dist ? FIN_STORE : FIN_PCG_ALPHA, S_TMP0, 0, s);
+        if (A_->dist) dist_allreduce_scalar_fin(*A_, red, S_TMP0, FIN_PCG_ALPHA, s);
+    }
+    // x += alpha p ; r -= alpha Ap ; norm(r) in the same pass
+    if (monitor_convergence_) {
+        const bool scalar_norm = use_scalar_norm_ || A_->by == 1;
+        if (scalar_norm && !A_->dist) {
+            pcg_update_xr(p_.ptr(), Ap_.ptr(), x.ptr(), r_.ptr(), x.prec, vec_len(), red, (int)norm_type_, S_NRM, 1, s);
+            AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+            nrm_.assign(1, sb_.host[S_NRM]);
+        } else {
+            vec_axpy_dev(p_.ptr(), x.ptr(), x.prec, vec_len(), sb_.scal, S_ALPHA, 1.0, s);
+            vec_axpy_dev(Ap_.ptr(), r_.ptr(), x.prec, vec_len(), sb_.scal, S_NEG_ALPHA, 1.0, s);
+            compute_norm();
+        }
+        conv_stat = converged();
+        if (is_done(conv_stat)) return conv_stat;
+    } else {
+        vec_axpy_dev(p_.ptr(), x.ptr(), x.prec, vec_len(), sb_.scal, S_ALPHA, 1.0, s);
+        vec_axpy_dev(Ap_.ptr(), r_.ptr(), x.prec, vec_len(), sb_.scal, S_NEG_ALPHA, 1.0, s);
+    }
+    if (is_last_iter()) return monitor_convergence_ ? ST_NOT_CONVERGED : ST_CONVERGED;
+    // z = M^-1 r ; rz_old = rz ; rz = <r,z> ; beta = rz / rz_old
+    apply_precond_and_rz(FIN_PCG_BETA);
+    // p = z + beta p     (axpby(z, p, p, 1, beta): z*1 + p*beta)
+    vec_axpby_dev(z_.ptr(), p_.ptr(), p_.ptr(), p_.prec, vec_len(), 1.0, sb_.scal, S_BETA, s);
+    return monitor_convergence_ ? ST_NOT_CONVERGED : ST_CONVERGED;
+}
+
+// ---------------------------------------------------------------------------------------------
+// factory  (SolverFactory::allocate, src/solvers/solver.cu:1098-1134)
+// ---------------------------------------------------------------------------------------------
+std::unique_ptr<Solver> Solver::allocate(Config &cfg, const std::string &current_scope, const std::string &solver_type,
+                                         std::shared_ptr<Resources> rsc)
+{
+    std::string name, new_scope;
+    cfg.get_scoped(solver_type, current_scope, name, new_scope);
+    if ((solver_type == "coarse_solver" || solver_type == "smoother" || solver_type == "preconditioner") &&
+        (name == "AMG" || name == "FGMRES" || name == "PCGF" || name == "PBICGSTAB" || name == "PCG") && new_scope == "default")
+        fatal(AMGX_RC_BAD_PARAMETERS, "Solver " + name + " uses an inner solver (i.e. a preconditioner, smoother or coarse_solver) and therefore cannot be used as an inner solver with the default scope due to the possibility of an infinite number of nested solvers. Please use config_version=2, and specify a new scope name for the inner solver. For example: preconditioner(amg_solver) = AMG. \n");
+    std::unique_ptr<Solver> sv;
+    if (name == "PCG") sv.reset(new PCGSolver(cfg, new_scope, rsc));
+    else if (name == "FGMRES") sv.reset(new FGMRESSolver(cfg, new_scope, rsc));
+    else if (name == "AMG") sv.reset(new AMGSolver(cfg, new_scope, rsc));
+    else if (name == "BLOCK_JACOBI") sv.reset(new BlockJacobiSolver(cfg, new_scope, rsc));
+    else if (name == "JACOBI_L1") sv.reset(new JacobiL1Solver(cfg, new_scope, rsc));
+    else if (name == "MULTICOLOR_DILU") sv = make_dilu_solver(cfg, new_scope, rsc);
+    else if (name == "NOSOLVER") sv.reset(new NoSolver(cfg, new_scope, rsc));
+    else
+        fatal(AMGX_RC_BAD_CONFIGURATION, "Solver '" + name + "' is outside the scope of the B200 solve-phase engine "
+              "(supported: PCG, FGMRES, AMG, BLOCK_JACOBI, JACOBI_L1, MULTICOLOR_DILU, NOSOLVER)");
+    sv->set_name(name);
+    return sv;
+}
+
+}  // namespace amgxb

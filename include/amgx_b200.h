@@ -1,0 +1,225 @@
+/*
+ * amgx_b200.h -- C ABI of libamgx_b200.so, the B200-native AMG solve-phase engine.
+ *
+ * Every AMGX_* entry point below has the SAME name, argument list, argument meaning and
+ * return-code behaviour as the reference's C API so that an application (or pyamgx /
+ * AmgXWrapper / AMGX.jl style binding) built against the reference's amgx_c.h can be
+ * re-linked against this library unchanged.  The reference declaration each one replaces is
+ * cited as  [ref: include/amgx_c.h:<line>]  (paths relative to /root/reference).
+ * Numeric values of the enums follow include/amgx_c.h:51-103 and include/amgx_config.h:13-124.
+ *
+ * Plain pointers and sizes only; no C++/torch types cross this boundary.
+ * AMGXB200_* symbols are extensions of this library (multi-GPU bootstrap, introspection,
+ * micro-benchmarks of the hot kernels); a caller of the reference never needs them.
+ */
+#ifndef AMGX_B200_H
+#define AMGX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define AMGX_API __attribute__((visibility("default")))
+
+/* ---- return codes [ref: include/amgx_c.h:51-69] ---- */
+typedef enum {
+    AMGX_RC_OK = 0, AMGX_RC_BAD_PARAMETERS = 1, AMGX_RC_UNKNOWN = 2, AMGX_RC_NOT_SUPPORTED_TARGET = 3,
+    AMGX_RC_NOT_SUPPORTED_BLOCKSIZE = 4, AMGX_RC_CUDA_FAILURE = 5, AMGX_RC_THRUST_FAILURE = 6,
+    AMGX_RC_NO_MEMORY = 7, AMGX_RC_IO_ERROR = 8, AMGX_RC_BAD_MODE = 9, AMGX_RC_CORE = 10,
+    AMGX_RC_PLUGIN = 11, AMGX_RC_BAD_CONFIGURATION = 12, AMGX_RC_NOT_IMPLEMENTED = 13,
+    AMGX_RC_LICENSE_NOT_FOUND = 14, AMGX_RC_INTERNAL = 15
+} AMGX_RC;
+
+/* ---- solve status [ref: include/amgx_c.h:74-80] ---- */
+typedef enum {
+    AMGX_SOLVE_SUCCESS = 0, AMGX_SOLVE_FAILED = 1, AMGX_SOLVE_DIVERGED = 2, AMGX_SOLVE_NOT_CONVERGED = 3
+} AMGX_SOLVE_STATUS;
+
+/* [ref: include/amgx_c.h:85-91] */
+typedef enum {
+    AMGX_GET_PARAMS_DESC_JSON_TO_FILE = 0, AMGX_GET_PARAMS_DESC_JSON_TO_STRING = 1,
+    AMGX_GET_PARAMS_DESC_TEXT_TO_FILE = 2, AMGX_GET_PARAMS_DESC_TEXT_TO_STRING = 3
+} AMGX_GET_PARAMS_DESC_FLAG;
+
+/* [ref: include/amgx_c.h:96-100] */
+typedef enum { AMGX_DIST_PARTITION_VECTOR = 0, AMGX_DIST_PARTITION_OFFSETS = 1 } AMGX_DIST_PARTITION_INFO;
+
+/* ---- modes [ref: include/amgx_config.h:102-124]: mem + 16*vec + 256*mat + 4096*ind ---- */
+typedef enum {
+    AMGX_unset    = -1,
+    AMGX_mode_hDDI = 8192, AMGX_mode_hDFI = 8448, AMGX_mode_hFFI = 8464,
+    AMGX_mode_dDDI = 8193, AMGX_mode_dDFI = 8449, AMGX_mode_dFFI = 8465
+} AMGX_Mode;
+
+/* ---- opaque handles [ref: include/amgx_c.h:105-124] ---- */
+typedef void (*AMGX_print_callback)(const char *msg, int length);
+typedef struct AMGX_config_handle_struct       *AMGX_config_handle;
+typedef struct AMGX_resources_handle_struct    *AMGX_resources_handle;
+typedef struct AMGX_matrix_handle_struct       *AMGX_matrix_handle;
+typedef struct AMGX_vector_handle_struct       *AMGX_vector_handle;
+typedef struct AMGX_solver_handle_struct       *AMGX_solver_handle;
+typedef struct AMGX_distribution_handle_struct *AMGX_distribution_handle;
+
+/* ---- build / init / system [ref: include/amgx_c.h:149-196] ---- */
+AMGX_RC AMGX_API AMGX_get_api_version(int *major, int *minor);                         /* :149 */
+AMGX_RC AMGX_API AMGX_get_build_info_strings(char **version, char **date, char **time);/* :153 */
+AMGX_RC AMGX_API AMGX_get_error_string(AMGX_RC err, char *buf, int buf_len);           /* :158 */
+AMGX_RC AMGX_API AMGX_initialize(void);                                                /* :164 */
+AMGX_RC AMGX_API AMGX_initialize_plugins(void);                                        /* :166 */
+AMGX_RC AMGX_API AMGX_finalize(void);                                                  /* :168 */
+AMGX_RC AMGX_API AMGX_finalize_plugins(void);                                          /* :170 */
+void    AMGX_API AMGX_abort(AMGX_resources_handle rsrc, int err);                      /* :172 */
+AMGX_RC AMGX_API AMGX_pin_memory(void *ptr, unsigned int bytes);                       /* :177 */
+AMGX_RC AMGX_API AMGX_unpin_memory(void *ptr);                                         /* :181 */
+AMGX_RC AMGX_API AMGX_install_signal_handler(void);                                    /* :184 */
+AMGX_RC AMGX_API AMGX_reset_signal_handler(void);                                      /* :186 */
+AMGX_RC AMGX_API AMGX_register_print_callback(AMGX_print_callback func);               /* :188 */
+
+/* ---- config [ref: include/amgx_c.h:192-215] ---- */
+AMGX_RC AMGX_API AMGX_config_create(AMGX_config_handle *cfg, const char *options);
+AMGX_RC AMGX_API AMGX_config_add_parameters(AMGX_config_handle *cfg, const char *options);
+AMGX_RC AMGX_API AMGX_config_create_from_file(AMGX_config_handle *cfg, const char *param_file);
+AMGX_RC AMGX_API AMGX_config_create_from_file_and_string(AMGX_config_handle *cfg, const char *param_file, const char *options);
+AMGX_RC AMGX_API AMGX_config_get_default_number_of_rings(AMGX_config_handle cfg, int *num_import_rings);
+AMGX_RC AMGX_API AMGX_config_destroy(AMGX_config_handle cfg);
+
+/* ---- resources [ref: include/amgx_c.h:218-231].
+ * `comm`: the reference dereferences it as MPI_Comm*.  This image has no MPI; here `comm` is
+ * NULL (single process, single GPU) or a pointer to an AMGXB200_comm (below): rank, world
+ * size and an ncclUniqueId obtained with AMGXB200_get_nccl_unique_id on rank 0 and
+ * broadcast by the launcher (torch.distributed in bench.py / tests). ---- */
+AMGX_RC AMGX_API AMGX_resources_create(AMGX_resources_handle *rsc, AMGX_config_handle cfg, void *comm, int device_num, const int *devices);
+AMGX_RC AMGX_API AMGX_resources_create_simple(AMGX_resources_handle *rsc, AMGX_config_handle cfg);
+AMGX_RC AMGX_API AMGX_resources_destroy(AMGX_resources_handle rsc);
+
+/* ---- distribution [ref: include/amgx_c.h:236-264] ---- */
+AMGX_RC AMGX_API AMGX_distribution_create(AMGX_distribution_handle *dist, AMGX_config_handle cfg);
+AMGX_RC AMGX_API AMGX_distribution_destroy(AMGX_distribution_handle dist);
+AMGX_RC AMGX_API AMGX_distribution_set_partition_data(AMGX_distribution_handle dist, AMGX_DIST_PARTITION_INFO info, const void *partition_data);
+AMGX_RC AMGX_API AMGX_distribution_set_32bit_colindices(AMGX_distribution_handle dist, int use32bit);
+
+/* ---- matrix [ref: include/amgx_c.h:267-343] ---- */
+AMGX_RC AMGX_API AMGX_matrix_create(AMGX_matrix_handle *mtx, AMGX_resources_handle rsc, AMGX_Mode mode);
+AMGX_RC AMGX_API AMGX_matrix_destroy(AMGX_matrix_handle mtx);
+AMGX_RC AMGX_API AMGX_matrix_upload_all(AMGX_matrix_handle mtx, int n, int nnz, int block_dimx, int block_dimy,
+                                        const int *row_ptrs, const int *col_indices, const void *data, const void *diag_data);
+AMGX_RC AMGX_API AMGX_matrix_replace_coefficients(AMGX_matrix_handle mtx, int n, int nnz, const void *data, const void *diag_data);
+AMGX_RC AMGX_API AMGX_matrix_get_size(const AMGX_matrix_handle mtx, int *n, int *block_dimx, int *block_dimy);
+AMGX_RC AMGX_API AMGX_matrix_get_nnz(const AMGX_matrix_handle mtx, int *nnz);
+AMGX_RC AMGX_API AMGX_matrix_download_all(const AMGX_matrix_handle mtx, int *row_ptrs, int *col_indices, void *data, void **diag_data);
+AMGX_RC AMGX_API AMGX_matrix_vector_multiply(AMGX_matrix_handle mtx, AMGX_vector_handle x, AMGX_vector_handle y);
+AMGX_RC AMGX_API AMGX_matrix_set_boundary_separation(AMGX_matrix_handle mtx, int boundary_separation);
+AMGX_RC AMGX_API AMGX_matrix_comm_from_maps(AMGX_matrix_handle mtx, int allocated_halo_depth, int num_import_rings, int max_num_neighbors,
+                                            const int *neighbors, const int *send_ptrs, const int *send_maps, const int *recv_ptrs, const int *recv_maps);
+AMGX_RC AMGX_API AMGX_matrix_comm_from_maps_one_ring(AMGX_matrix_handle mtx, int allocated_halo_depth, int num_neighbors, const int *neighbors,
+                                                     const int *send_sizes, const int **send_maps, const int *recv_sizes, const int **recv_maps);
+
+/* ---- vector [ref: include/amgx_c.h:346-386] ---- */
+AMGX_RC AMGX_API AMGX_vector_create(AMGX_vector_handle *vec, AMGX_resources_handle rsc, AMGX_Mode mode);
+AMGX_RC AMGX_API AMGX_vector_destroy(AMGX_vector_handle vec);
+AMGX_RC AMGX_API AMGX_vector_upload(AMGX_vector_handle vec, int n, int block_dim, const void *data);
+AMGX_RC AMGX_API AMGX_vector_set_zero(AMGX_vector_handle vec, int n, int block_dim);
+AMGX_RC AMGX_API AMGX_vector_set_random(AMGX_vector_handle vec, int n);
+AMGX_RC AMGX_API AMGX_vector_download(const AMGX_vector_handle vec, void *data);
+AMGX_RC AMGX_API AMGX_vector_get_size(const AMGX_vector_handle vec, int *n, int *block_dim);
+AMGX_RC AMGX_API AMGX_vector_bind(AMGX_vector_handle vec, const AMGX_matrix_handle mtx);
+
+/* ---- solver [ref: include/amgx_c.h:389-437] ---- */
+AMGX_RC AMGX_API AMGX_solver_create(AMGX_solver_handle *slv, AMGX_resources_handle rsc, AMGX_Mode mode, const AMGX_config_handle cfg_solver);
+AMGX_RC AMGX_API AMGX_solver_destroy(AMGX_solver_handle slv);
+AMGX_RC AMGX_API AMGX_solver_setup(AMGX_solver_handle slv, AMGX_matrix_handle mtx);                                  /* :398 */
+AMGX_RC AMGX_API AMGX_solver_solve(AMGX_solver_handle slv, AMGX_vector_handle rhs, AMGX_vector_handle sol);          /* :402 */
+AMGX_RC AMGX_API AMGX_solver_solve_with_0_initial_guess(AMGX_solver_handle slv, AMGX_vector_handle rhs, AMGX_vector_handle sol);
+AMGX_RC AMGX_API AMGX_solver_get_iterations_number(AMGX_solver_handle slv, int *n);
+AMGX_RC AMGX_API AMGX_solver_get_iteration_residual(AMGX_solver_handle slv, int it, int idx, double *res);
+AMGX_RC AMGX_API AMGX_solver_get_status(AMGX_solver_handle slv, AMGX_SOLVE_STATUS *st);
+AMGX_RC AMGX_API AMGX_solver_calculate_residual_norm(AMGX_solver_handle solver, AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle x, void *norm_vector);
+AMGX_RC AMGX_API AMGX_solver_resetup(AMGX_solver_handle slv, AMGX_matrix_handle mtx);                                /* :602 */
+AMGX_RC AMGX_API AMGX_solver_register_print_callback(AMGX_print_callback func);                                       /* :599 */
+
+/* ---- utilities [ref: include/amgx_c.h:440-520] ---- */
+AMGX_RC AMGX_API AMGX_read_system(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol, const char *filename);
+AMGX_RC AMGX_API AMGX_write_system(const AMGX_matrix_handle mtx, const AMGX_vector_handle rhs, const AMGX_vector_handle sol, const char *filename);
+AMGX_RC AMGX_API AMGX_generate_distributed_poisson_7pt(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol,
+                                                       int allocated_halo_depth, int num_import_rings, int nx, int ny, int nz, int px, int py, int pz);
+AMGX_RC AMGX_API AMGX_write_parameters_description(char *filename, AMGX_GET_PARAMS_DESC_FLAG mode);
+AMGX_RC AMGX_API AMGX_matrix_attach_coloring(AMGX_matrix_handle mtx, int *row_coloring, int num_rows, int num_colors);
+AMGX_RC AMGX_API AMGX_matrix_attach_geometry(AMGX_matrix_handle mtx, double *geox, double *geoy, double *geoz, int n);
+AMGX_RC AMGX_API AMGX_matrix_upload_all_global(AMGX_matrix_handle mtx, int n_global, int n, int nnz, int block_dimx, int block_dimy,
+                                               const int *row_ptrs, const void *col_indices_global, const void *data, const void *diag_data,
+                                               int allocated_halo_depth, int num_import_rings, const int *partition_vector);
+AMGX_RC AMGX_API AMGX_matrix_upload_all_global_32(AMGX_matrix_handle mtx, int n_global, int n, int nnz, int block_dimx, int block_dimy,
+                                                  const int *row_ptrs, const void *col_indices_global, const void *data, const void *diag_data,
+                                                  int allocated_halo_depth, int num_import_rings, const int *partition_vector);
+AMGX_RC AMGX_API AMGX_matrix_upload_distributed(AMGX_matrix_handle mtx, int n_global, int n, int nnz, int block_dimx, int block_dimy,
+                                                const int *row_ptrs, const void *col_indices_global, const void *data, const void *diag_data,
+                                                AMGX_distribution_handle distribution);
+AMGX_RC AMGX_API AMGX_matrix_check_symmetry(AMGX_matrix_handle mtx, int *structurally_symmetric, int *symmetric);
+AMGX_RC AMGX_API AMGX_matrix_check_diag_dominant(const AMGX_matrix_handle mtx, int *diag_dominant);
+
+/* =====================================================================================
+ * Extensions of this library (not in the reference).
+ * ===================================================================================== */
+
+/* What `void *comm` of AMGX_resources_create points to when world_size > 1. */
+typedef struct {
+    int  rank;
+    int  world_size;
+    char nccl_unique_id[128];   /* bytes of an ncclUniqueId (sizeof == 128) */
+} AMGXB200_comm;
+
+/* rank 0: fill `id` (128 bytes) with a fresh ncclUniqueId to be broadcast to all ranks. */
+AMGX_RC AMGX_API AMGXB200_get_nccl_unique_id(char *id128);
+
+/* Hierarchy introspection after AMGX_solver_setup (used by the parity tests).
+ * level 0 = finest.  Arrays are copied to host buffers supplied by the caller (may be NULL to
+ * query sizes only). */
+AMGX_RC AMGX_API AMGXB200_solver_get_num_levels(AMGX_solver_handle slv, int *num_levels);
+AMGX_RC AMGX_API AMGXB200_solver_get_level_info(AMGX_solver_handle slv, int level, int *n, int *nnz, int *block_dim, int *n_coarse);
+AMGX_RC AMGX_API AMGXB200_solver_get_level_matrix(AMGX_solver_handle slv, int level, int *row_ptrs, int *col_indices, void *values);
+/* aggregation: aggregates[n]; R_row_offsets[n_coarse+1]; R_column_indices[n] */
+AMGX_RC AMGX_API AMGXB200_solver_get_level_aggregates(AMGX_solver_handle slv, int level, int *aggregates, int *R_row_offsets, int *R_column_indices);
+/* classical: P (n x n_coarse) CSR and R (n_coarse x n) CSR; query nnz with NULL arrays */
+AMGX_RC AMGX_API AMGXB200_solver_get_level_P(AMGX_solver_handle slv, int level, int *nnz, int *row_ptrs, int *col_indices, void *values);
+AMGX_RC AMGX_API AMGXB200_solver_get_level_R(AMGX_solver_handle slv, int level, int *nnz, int *row_ptrs, int *col_indices, void *values);
+/* classical: cf_map[n] (coarse index or <0 for fine points) */
+AMGX_RC AMGX_API AMGXB200_solver_get_level_cf_map(AMGX_solver_handle slv, int level, int *cf_map);
+/* smoother data of a level (Jacobi: d[n]; L1: d_L1[n]; DILU: Einv[n*b*b]) and colouring */
+AMGX_RC AMGX_API AMGXB200_solver_get_level_smoother_data(AMGX_solver_handle slv, int level, void *data);
+AMGX_RC AMGX_API AMGXB200_solver_get_level_coloring(AMGX_solver_handle slv, int level, int *num_colors, int *row_colors);
+
+/* Timing of the last solve measured with CUDA events on the solve stream (seconds) and the number
+ * of kernels this library launched in it. */
+AMGX_RC AMGX_API AMGXB200_solver_get_last_solve_stats(AMGX_solver_handle slv, double *solve_seconds, long long *kernel_launches);
+
+/* Hot-kernel micro-benchmarks on an uploaded matrix (device-resident operands).
+ * kind: 0 = SpMV y=A*x, 1 = fused Jacobi sweep x' = x + w*(b-A*x)/d, 2 = SpMV fused with dot.
+ * Runs `reps` launches on the resource stream, returns average milliseconds per launch measured
+ * with CUDA events on that stream, after `warmup` untimed launches. */
+AMGX_RC AMGX_API AMGXB200_bench_kernel(AMGX_matrix_handle mtx, int kind, int warmup, int reps, int flush_l2, double *avg_ms);
+
+/* Partition planner (pure host code, needs no GPU): given this rank's rows of a global CSR
+ * (global column ids, contiguous row partition by offsets[world+1]) computes the local
+ * renumbering [interior | boundary | halo], the per-neighbour send maps (B2L) and the halo
+ * layout.  Arrays are malloc'ed by the library; free with AMGXB200_partition_plan_free. */
+typedef struct {
+    int  n_owned, n_interior, n_halo, num_neighbors;
+    int *neighbors;        /* [num_neighbors] ranks */
+    int *send_offsets;     /* [num_neighbors+1] into send_maps */
+    int *send_maps;        /* local (renumbered) owned row ids to pack for each neighbour */
+    int *halo_offsets;     /* [num_neighbors+1] offsets (relative to n_owned) of each neighbour's halo segment */
+    int64_t *halo_global;  /* [n_halo] global ids of halo columns in local order */
+    int *perm_old_to_new;  /* [n_owned] local row i (partition order) -> renumbered id */
+    int *local_cols;       /* [nnz] column ids in the renumbered local space (halo ids >= n_owned) */
+} AMGXB200_partition_plan;
+AMGX_RC AMGX_API AMGXB200_partition_plan_create(AMGXB200_partition_plan *plan, int rank, int world_size, const int64_t *offsets,
+                                                int n, int nnz, const int *row_ptrs, const int64_t *col_indices_global);
+void    AMGX_API AMGXB200_partition_plan_free(AMGXB200_partition_plan *plan);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* AMGX_B200_H */

@@ -1,0 +1,583 @@
+/*
+ * amg_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, CPU restatement of the reference's algorithms on the AMG solve-phase hot path and of
+ * the setup producers that decide the integer hierarchy.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it; the product (libamgx_b200.so)
+ * never does.  Every function cites the reference file:line it follows (paths under
+ * /root/reference).  The reference's device kernels run one thread per row / entry; here each
+ * "kernel" is a loop with the same per-element arithmetic, and kernels that read and write the same
+ * array concurrently in the reference are evaluated with snapshot semantics (reads see the state
+ * before the kernel) -- the same choice the CUDA engine makes.
+ *
+ * Pinning: validated against outputs of the reference itself (oracle/_ref, generated on a B200 by
+ * tests/golden/make_golden.py and committed under tests/golden/) -- see tests/test_oracle_golden.py.
+ *
+ * Build: gcc -O2 -fPIC -shared -ffp-contract=off -fopenmp amg_oracle.c -o liboracle.so -lm
+ * (-ffp-contract=off: FMAs appear only where written with fma()/fmaf(), mirroring where nvcc
+ * contracts the reference's device expressions.)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------- */
+/* helpers                                                                                     */
+/* ------------------------------------------------------------------------------------------- */
+static double guard_d(double d) /* isNotCloseToZero(d) ? d : epsilon(d): include/solvers/block_common_solver.h:22-100 */
+{
+    return fabs(d) < 1e-12 ? copysign(1e-12, d) : d;
+}
+
+ORC_API int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+ORC_API void orc_set_num_threads(int t)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* SpMV: y = A x.  Per row strictly left to right, y = a*x + y as one FMA per entry -- the order */
+/* of the reference's csrmv kernel (src/amgx_cusparse.cu:983-1024) and of its host loop          */
+/* (src/multiply.cu:753-852).                                                                    */
+/* ------------------------------------------------------------------------------------------- */
+ORC_API void orc_spmv(int n, const int *rp, const int *ci, const double *va, const double *x, double *y)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        double s = 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; k++) s = fma(va[k], x[ci[k]], s);
+        y[i] = s;
+    }
+}
+
+/* r = b - A x : axmb = SpMV then r*(-1) + b*1 (src/blas.cu:601-623) */
+ORC_API void orc_residual(int n, const int *rp, const int *ci, const double *va, const double *x, const double *b, double *r)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        double s = 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; k++) s = fma(va[k], x[ci[k]], s);
+        r[i] = b[i] - s;
+    }
+}
+
+/* Jacobi sweep: x' = x + ((b - A x) * w) * (1/d) with the exact op order of jacobi_postsmooth_functor */
+/* (src/solvers/block_jacobi_solver.cu:32-50): d = 1/d; b = b - y; b = b*w; return b*d + x  (FMA).    */
+/* Same arithmetic for JACOBI_L1 with d = L1 row norm (src/solvers/jacobi_l1_solver.cu:27-44).        */
+ORC_API void orc_jacobi_sweep(int n, const int *rp, const int *ci, const double *va, const double *d, const double *b, const double *x,
+                              double *xout, double omega)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        double s = 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; k++) s = fma(va[k], x[ci[k]], s);
+        double dinv = 1.0 / guard_d(d[i]);
+        double t = b[i] - s;
+        t = t * omega;
+        xout[i] = fma(t, dinv, x[i]);
+    }
+}
+
+/* zero initial guess: x = b*w/d (jacobi_presmooth_functor, block_jacobi_solver.cu:24-30) */
+ORC_API void orc_jacobi_zero(int n, const double *d, const double *b, double *x, double omega)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) x[i] = b[i] * omega / guard_d(d[i]);
+}
+
+/* d_i = A(i,i) -- first matching column (computeDiagonalKernelCSR, src/matrix.cu:101-126) */
+ORC_API void orc_diag_index(int n, const int *rp, const int *ci, int *diag)
+{
+    for (int i = 0; i < n; i++) {
+        int d = -1;
+        for (int k = rp[i]; k < rp[i + 1]; k++)
+            if (ci[k] == i) { d = k; break; }
+        diag[i] = d;
+    }
+}
+ORC_API void orc_extract_diag(int n, const int *rp, const int *ci, const double *va, double *d)
+{
+    for (int i = 0; i < n; i++) {
+        d[i] = 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; k++)
+            if (ci[k] == i) { d[i] = va[k]; break; }
+    }
+}
+/* L1 row norms (compute_d_kernel, src/solvers/jacobi_l1_solver.cu:60-91) */
+ORC_API void orc_l1_norms(int n, const int *rp, const int *ci, const double *va, double *d)
+{
+    for (int i = 0; i < n; i++) {
+        double acc = 0.0;
+        int npd = 0;
+        for (int k = rp[i]; k < rp[i + 1]; k++) {
+            double a = va[k];
+            if (ci[k] == i && a < 0.) npd = 1;
+            acc += fabs(a);
+        }
+        d[i] = npd ? -acc : acc;
+    }
+}
+
+/* level-1 pieces in the reference's order */
+ORC_API double orc_dot(int n, const double *x, const double *y)
+{
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += x[i] * y[i];
+    return s;
+}
+ORC_API double orc_nrm2(int n, const double *x) { return sqrt(orc_dot(n, x, x)); }
+ORC_API double orc_nrm1(int n, const double *x)
+{
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += fabs(x[i]);
+    return s;
+}
+ORC_API double orc_nrmmax(int n, const double *x)
+{
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s = fmax(s, fabs(x[i]));
+    return s;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* SIZE_2 aggregation                                                                          */
+/* ------------------------------------------------------------------------------------------- */
+static unsigned hash_val(unsigned a, unsigned seed) /* include/aggregation/selectors/common_selector.h:19-29 */
+{
+    a ^= seed;
+    a = (a + 0x7ed55d16u) + (a << 12);
+    a = (a ^ 0xc761c23cu) + (a >> 19);
+    a = (a + 0x165667b1u) + (a << 5);
+    a = (a ^ 0xd3a2646cu) + (a << 9);
+    a = (a + 0xfd7046c5u) + (a << 3);
+    a = (a ^ 0xb55a4f09u) + (a >> 16);
+    return a;
+}
+
+/* computeEdgeWeightsBlockDiaCsr_V2 (common_selector.h:63-137), WeightType = float, weight_formula 0/1 */
+ORC_API void orc_edge_weights(int n, const int *rp, const int *ci, const double *va, int weight_formula, float *w)
+{
+    int *diag = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    orc_diag_index(n, rp, ci, diag);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        double aii = diag[i] >= 0 ? va[diag[i]] : 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; k++) {
+            int j = ci[k];
+            if (i == j || j >= n) { w[k] = -1.0f; continue; }
+            double ajj = diag[j] >= 0 ? va[diag[j]] : 0.0;
+            double mx = fabs(aii) > fabs(ajj) ? fabs(aii) : fabs(ajj);
+            float den = (float)mx;
+            double kval = 0.0;
+            int found = 0;
+            for (int kk = rp[j]; kk < rp[j + 1]; kk++)
+                if (ci[kk] == i) { kval = va[kk]; found = 1; break; }
+            float ew = 0.0f;
+            if (found) {
+                if (weight_formula == 0) {
+                    double ssum = fabs(va[k]) + fabs(kval);
+                    double t = 0.5 * ssum;
+                    ew = (float)(t / (double)den);
+                } else {
+                    double rz = va[k] / aii + kval / ajj;
+                    ew = (float)(-0.5 * (double)(float)rz);
+                }
+            }
+            unsigned lo = (unsigned)(i < j ? i : j), hi = (unsigned)(i < j ? j : i);
+            unsigned h = hash_val(lo, hi);
+            float small_fraction = (1e-5f * (float)h) / 4294967296.0f; /* scaling_factor<float>() * hash / (float)UINT_MAX */
+            ew = fmaf(small_fraction, ew, ew);                         /* ed_weight += small_fraction * ed_weight (contracted) */
+            w[k] = ew;
+        }
+    }
+    free(diag);
+}
+
+/* setAggregates_common_sqblocks (src/aggregation/selectors/size2_selector.cu:736-890), one-phase handshake,
+ * deterministic leftover merge, then renumberAndCountAggregates (agg_selector.cu:18-43).  Returns #aggregates. */
+ORC_API int orc_size2_aggregates(int n, const int *rp, const int *ci, const double *va, int max_iterations, double max_unassigned,
+                                 int merge_singletons, int weight_formula, int *agg)
+{
+    if (n == 0) return 0;
+    float *w = (float *)malloc(sizeof(float) * (size_t)(rp[n] > 0 ? rp[n] : 1));
+    int *strongest = (int *)malloc(sizeof(int) * (size_t)n), *merge_to = (int *)malloc(sizeof(int) * (size_t)n);
+    int *cand = (int *)malloc(sizeof(int) * (size_t)n);
+    orc_edge_weights(n, rp, ci, va, weight_formula, w);
+    for (int i = 0; i < n; i++) { agg[i] = -1; strongest[i] = -1; }
+    int unassigned = n, prev, icount = 0;
+    do {
+        /* findStrongestNeighbourBlockDiaCsr_V2 (size2_selector.cu:224-301), phase 1, snapshot reads of agg[] */
+#pragma omp parallel for schedule(static)
+        for (int t = 0; t < n; t++) {
+            merge_to[t] = -1;
+            if (agg[t] != -1) continue;
+            int s_un = -1, s_ag = -1;
+            float m_un = 0.f, m_ag = 0.f;
+            for (int k = rp[t]; k < rp[t + 1]; k++) {
+                int j = ci[k];
+                float wt = w[k];
+                if (j == t || j >= n) continue;
+                if (agg[j] == -1 && (wt > m_un || (wt == m_un && j > s_un))) { m_un = wt; s_un = j; }
+                else if (agg[j] != -1 && (wt > m_ag || (wt == m_ag && j > s_ag))) { m_ag = wt; s_ag = j; }
+            }
+            if (s_un == -1 && s_ag != -1) merge_to[t] = merge_singletons ? agg[s_ag] : t;
+            else if (s_un != -1) strongest[t] = s_un;
+            else strongest[t] = t;
+        }
+        /* matchEdges (size2_selector.cu:302-323) */
+#pragma omp parallel for schedule(static)
+        for (int t = 0; t < n; t++) {
+            if (agg[t] != -1) continue;
+            if (merge_to[t] != -1) { cand[t] = merge_to[t]; continue; }
+            cand[t] = -1;
+            int pm = strongest[t];
+            if (pm < 0) continue;
+            if (merge_to[pm] == -1 && strongest[pm] == t) cand[t] = (pm > t) ? t : pm;
+        }
+        prev = unassigned;
+        unassigned = 0;
+        for (int t = 0; t < n; t++) {
+            if (agg[t] == -1 && cand[t] != -1) agg[t] = cand[t];
+            if (agg[t] == -1) unassigned++;
+        }
+        icount++;
+    } while (!(unassigned == 0 || icount > max_iterations || 1.0 * unassigned / n < max_unassigned || unassigned == prev));
+
+    if (merge_singletons) {
+        /* mergeWithExistingAggregatesBlockDiaCsr_V2 + joinExistingAggregates, deterministic path (:508-566, 424-440) */
+        for (int t = 0; t < n; t++) cand[t] = -1;
+        while (unassigned != 0) {
+#pragma omp parallel for schedule(static)
+            for (int t = 0; t < n; t++) {
+                if (agg[t] != -1) continue;
+                float m_ag = 0.f;
+                int s_ag = -1;
+                for (int k = rp[t]; k < rp[t + 1]; k++) {
+                    float wt = w[k];
+                    int j = ci[k];
+                    if (j == t || j >= n) continue;
+                    if (agg[j] != -1 && (wt > m_ag || (wt == m_ag && j > s_ag))) { m_ag = wt; s_ag = j; }
+                }
+                cand[t] = (s_ag != -1) ? agg[s_ag] : t;
+            }
+            unassigned = 0;
+            for (int t = 0; t < n; t++) {
+                if (agg[t] == -1 && cand[t] != -1) agg[t] = cand[t];
+                if (agg[t] == -1) unassigned++;
+            }
+        }
+    } else {
+        for (int t = 0; t < n; t++)
+            if (agg[t] == -1) agg[t] = t;
+    }
+    /* renumber: mark used labels, exclusive scan, relabel */
+    int *scratch = (int *)calloc((size_t)n + 1, sizeof(int));
+    for (int t = 0; t < n; t++) scratch[agg[t]] = 1;
+    int run = 0;
+    for (int t = 0; t <= n; t++) { int v = scratch[t]; scratch[t] = run; run += v; }
+    for (int t = 0; t < n; t++) agg[t] = scratch[agg[t]];
+    int nagg = scratch[n];
+    free(scratch); free(w); free(strongest); free(merge_to); free(cand);
+    return nagg;
+}
+
+/* computeRestrictionOperator_common (src/aggregation/aggregation_amg_level.cu:237-299): stable sort of rows by aggregate */
+ORC_API void orc_restriction(int n, int nagg, const int *agg, int *Rp, int *Rc)
+{
+    for (int I = 0; I <= nagg; I++) Rp[I] = 0;
+    for (int i = 0; i < n; i++) Rp[agg[i] + 1]++;
+    for (int I = 0; I < nagg; I++) Rp[I + 1] += Rp[I];
+    int *pos = (int *)malloc(sizeof(int) * (size_t)(nagg > 0 ? nagg : 1));
+    for (int I = 0; I < nagg; I++) pos[I] = Rp[I];
+    for (int i = 0; i < n; i++) Rc[pos[agg[i]]++] = i;
+    free(pos);
+}
+
+/* Galerkin product for piecewise-constant P: Ac(I,J) = sum_{i in I} sum_{j in J} a_ij
+ * (LowDegCoarseAGenerator::computeAOperator, low_deg_coarse_A_generator.cu:1135-1320).  Entries of one coarse
+ * coefficient are summed fine-row ascending, in-row order; coarse rows are emitted with ascending columns
+ * (the reference emits hash-table order -- compare after sorting).  Two calls: counts, then fill. */
+ORC_API int orc_galerkin_count(int n, const int *rp, const int *ci, const int *agg, int nagg, const int *Rp, const int *Rc, int *rpc)
+{
+    int *mark = (int *)malloc(sizeof(int) * (size_t)(nagg > 0 ? nagg : 1));
+    for (int I = 0; I < nagg; I++) mark[I] = -1;
+    int total = 0;
+    rpc[0] = 0;
+    for (int I = 0; I < nagg; I++) {
+        int cnt = 0;
+        for (int q = Rp[I]; q < Rp[I + 1]; q++) {
+            int i = Rc[q];
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                int J = agg[ci[k]];
+                if (mark[J] != I) { mark[J] = I; cnt++; }
+            }
+        }
+        total += cnt;
+        rpc[I + 1] = total;
+    }
+    free(mark);
+    (void)n;
+    return total;
+}
+static int cmp_int(const void *a, const void *b) { return (*(const int *)a > *(const int *)b) - (*(const int *)a < *(const int *)b); }
+ORC_API void orc_galerkin_fill(int n, const int *rp, const int *ci, const double *va, const int *agg, int nagg, const int *Rp, const int *Rc,
+                               const int *rpc, int *cic, double *vac)
+{
+    int *slot = (int *)malloc(sizeof(int) * (size_t)(nagg > 0 ? nagg : 1));
+    for (int I = 0; I < nagg; I++) slot[I] = -1;
+    (void)n;
+    for (int I = 0; I < nagg; I++) {
+        int base = rpc[I], cnt = 0;
+        /* collect distinct coarse columns */
+        for (int q = Rp[I]; q < Rp[I + 1]; q++) {
+            int i = Rc[q];
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                int J = agg[ci[k]];
+                if (slot[J] < base || slot[J] >= base + cnt || cic[slot[J]] != J) { cic[base + cnt] = J; slot[J] = base + cnt; cnt++; }
+            }
+        }
+        qsort(cic + base, (size_t)cnt, sizeof(int), cmp_int);
+        for (int p = 0; p < cnt; p++) { slot[cic[base + p]] = base + p; vac[base + p] = 0.0; }
+        int *first = (int *)calloc((size_t)(cnt > 0 ? cnt : 1), sizeof(int));
+        for (int q = Rp[I]; q < Rp[I + 1]; q++) {
+            int i = Rc[q];
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                int p = slot[agg[ci[k]]];
+                if (!first[p - base]) { vac[p] = va[k]; first[p - base] = 1; }
+                else vac[p] = vac[p] + va[k];
+            }
+        }
+        free(first);
+    }
+    free(slot);
+}
+
+/* restrictResidualKernel / prolongateAndApplyCorrectionKernel (aggregation_amg_level.cu:91-111, 156-181) */
+ORC_API void orc_restrict(int nagg, const int *Rp, const int *Rc, const double *r, double *rc)
+{
+#pragma omp parallel for schedule(static)
+    for (int I = 0; I < nagg; I++) {
+        double t = 0.0;
+        for (int j = Rp[I]; j < Rp[I + 1]; j++) t = t + r[Rc[j]];
+        rc[I] = t;
+    }
+}
+ORC_API void orc_prolong_add(int n, const int *agg, const double *e, double *x)
+{
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) x[i] = x[i] + e[agg[i]];
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* hierarchy + V-cycle + PCG, composed exactly like the reference (unfused)                    */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n, nnz, nagg, coarsest;
+    int *rp, *ci, *agg, *Rp, *Rc;
+    double *va, *d;          /* d: smoother diagonal (Jacobi: a_ii, L1: row norms) */
+    double *bc, *xc, *r, *tmp;
+    int own;
+} orc_level;
+
+typedef struct {
+    int num_levels;
+    orc_level *lv;
+    int presweeps, postsweeps, coarsest_sweeps, finest_sweeps, smoother; /* smoother: 0 BLOCK_JACOBI, 1 JACOBI_L1 */
+    double omega;
+} orc_amg;
+
+ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double *va, int max_levels, int min_coarse_rows, double coarsen_threshold,
+                               int presweeps, int postsweeps, int coarsest_sweeps, int finest_sweeps, int smoother, double omega,
+                               int max_iterations, double max_unassigned, int merge_singletons, int weight_formula)
+{
+    /* AMG_Setup::setup level loop (src/amg.cu:201-418), single partition, coarse_solver = NOSOLVER */
+    orc_amg *a = (orc_amg *)calloc(1, sizeof(orc_amg));
+    a->lv = (orc_level *)calloc((size_t)(max_levels > 0 ? max_levels : 1) + 1, sizeof(orc_level));
+    a->presweeps = presweeps; a->postsweeps = postsweeps; a->coarsest_sweeps = coarsest_sweeps; a->finest_sweeps = finest_sweeps;
+    a->smoother = smoother; a->omega = omega;
+    orc_level *L = &a->lv[0];
+    L->n = n; L->nnz = rp[n]; L->rp = (int *)rp; L->ci = (int *)ci; L->va = (double *)va; L->own = 0;
+    int num_levels = 1;
+    for (;;) {
+        L = &a->lv[num_levels - 1];
+        L->d = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
+        if (smoother == 0) orc_extract_diag(L->n, L->rp, L->ci, L->va, L->d);
+        else orc_l1_norms(L->n, L->rp, L->ci, L->va, L->d);
+        L->tmp = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
+        if (num_levels >= max_levels || L->n <= min_coarse_rows) { L->coarsest = 1; break; }
+        L->agg = (int *)malloc(sizeof(int) * (size_t)L->n);
+        int nagg = orc_size2_aggregates(L->n, L->rp, L->ci, L->va, max_iterations, max_unassigned, merge_singletons, weight_formula, L->agg);
+        if ((double)nagg <= coarsen_threshold * (double)L->n && nagg != L->n && nagg >= min_coarse_rows) {
+            L->nagg = nagg;
+            L->Rp = (int *)malloc(sizeof(int) * ((size_t)nagg + 1));
+            L->Rc = (int *)malloc(sizeof(int) * (size_t)L->n);
+            orc_restriction(L->n, nagg, L->agg, L->Rp, L->Rc);
+            orc_level *N = &a->lv[num_levels];
+            N->n = nagg;
+            N->rp = (int *)malloc(sizeof(int) * ((size_t)nagg + 1));
+            N->nnz = orc_galerkin_count(L->n, L->rp, L->ci, L->agg, nagg, L->Rp, L->Rc, N->rp);
+            N->ci = (int *)malloc(sizeof(int) * (size_t)(N->nnz > 0 ? N->nnz : 1));
+            N->va = (double *)malloc(sizeof(double) * (size_t)(N->nnz > 0 ? N->nnz : 1));
+            orc_galerkin_fill(L->n, L->rp, L->ci, L->va, L->agg, nagg, L->Rp, L->Rc, N->rp, N->ci, N->va);
+            N->own = 1;
+            L->bc = (double *)calloc((size_t)nagg, sizeof(double));
+            L->xc = (double *)calloc((size_t)nagg, sizeof(double));
+            L->r = (double *)calloc((size_t)L->n, sizeof(double));
+            num_levels++;
+        } else {
+            free(L->agg); L->agg = NULL; L->coarsest = 1;
+            break;
+        }
+    }
+    a->num_levels = num_levels;
+    return a;
+}
+
+ORC_API void orc_amg_free(orc_amg *a)
+{
+    if (!a) return;
+    for (int l = 0; l < a->num_levels; l++) {
+        orc_level *L = &a->lv[l];
+        if (L->own) { free(L->rp); free(L->ci); free(L->va); }
+        free(L->agg); free(L->Rp); free(L->Rc); free(L->d); free(L->bc); free(L->xc); free(L->r); free(L->tmp);
+    }
+    free(a->lv);
+    free(a);
+}
+
+ORC_API int orc_amg_num_levels(const orc_amg *a) { return a->num_levels; }
+ORC_API void orc_amg_level_sizes(const orc_amg *a, int l, int *n, int *nnz, int *nagg)
+{
+    *n = a->lv[l].n; *nnz = a->lv[l].nnz; *nagg = a->lv[l].nagg;
+}
+ORC_API void orc_amg_level_arrays(const orc_amg *a, int l, int *rp, int *ci, double *va, int *agg, int *Rp, int *Rc, double *d)
+{
+    const orc_level *L = &a->lv[l];
+    if (rp) memcpy(rp, L->rp, sizeof(int) * ((size_t)L->n + 1));
+    if (ci) memcpy(ci, L->ci, sizeof(int) * (size_t)L->nnz);
+    if (va) memcpy(va, L->va, sizeof(double) * (size_t)L->nnz);
+    if (agg && L->agg) memcpy(agg, L->agg, sizeof(int) * (size_t)L->n);
+    if (Rp && L->Rp) memcpy(Rp, L->Rp, sizeof(int) * ((size_t)L->nagg + 1));
+    if (Rc && L->Rc) memcpy(Rc, L->Rc, sizeof(int) * (size_t)L->n);
+    if (d) memcpy(d, L->d, sizeof(double) * (size_t)L->n);
+}
+
+/* smoother->solve(b, x, xIsZero) with max_iters = sweeps (Solver::solve loop without monitoring) */
+static void smooth(const orc_amg *a, orc_level *L, const double *b, double *x, int x_is_zero, int sweeps)
+{
+    for (int it = 0; it < sweeps; it++) {
+        if (it == 0 && x_is_zero) { orc_jacobi_zero(L->n, L->d, b, x, a->omega); continue; }
+        orc_jacobi_sweep(L->n, L->rp, L->ci, L->va, L->d, b, x, L->tmp, a->omega);
+        memcpy(x, L->tmp, sizeof(double) * (size_t)L->n);
+    }
+}
+
+/* FixedCycle::cycle, V cycle (src/cycles/fixed_cycle.cu:25-248) */
+static void vcycle(const orc_amg *a, int l, const double *b, double *x, int x_is_zero)
+{
+    orc_level *L = &a->lv[l];
+    int finest = (l == 0);
+    int n_pre;
+    if (L->coarsest) n_pre = a->coarsest_sweeps;
+    else if (finest && a->finest_sweeps != -1) n_pre = a->presweeps == 0 ? 0 : a->finest_sweeps;
+    else n_pre = a->presweeps;
+    if (n_pre > 0) smooth(a, L, b, x, x_is_zero, n_pre);
+    else if (x_is_zero) memset(x, 0, sizeof(double) * (size_t)L->n);
+    if (L->coarsest) return;
+    orc_residual(L->n, L->rp, L->ci, L->va, x, b, L->r);          /* axmb */
+    orc_restrict(L->nagg, L->Rp, L->Rc, L->r, L->bc);             /* restrictResidual */
+    vcycle(a, l + 1, L->bc, L->xc, 1);                            /* next level, initial guess zero */
+    orc_prolong_add(L->n, L->agg, L->xc, x);                      /* prolongateAndApplyCorrection */
+    int n_post;
+    if (finest && a->finest_sweeps != -1) n_post = a->postsweeps == 0 ? 0 : a->finest_sweeps;
+    else n_post = a->postsweeps;
+    if (n_post > 0) smooth(a, L, b, x, 0, n_post);
+}
+
+ORC_API void orc_amg_vcycle(const orc_amg *a, const double *b, double *x, int x_is_zero) { vcycle(a, 0, b, x, x_is_zero); }
+
+/* RELATIVE_INI criterion (src/convergence/relative_ini.cu:22-45) */
+static int conv_relative_ini(double nrm, double nrm_ini, double tol)
+{
+    const double eps = 1e-20;
+    int conv = (nrm_ini <= eps) ? 1 : (nrm / nrm_ini <= tol);
+    double thr = nrm_ini * 1.0e-12;
+    if (thr < eps) thr = eps;
+    int conv_abs = nrm <= thr;
+    return conv_abs || conv;
+}
+
+static double norm_of(int n, const double *r, int norm_type)
+{
+    return norm_type == 0 ? orc_nrm1(n, r) : norm_type == 1 ? orc_nrm2(n, r) : orc_nrmmax(n, r);
+}
+
+/* Preconditioned CG: Solver::solve loop (src/solvers/solver.cu:585-970) around PCG_Solver::solve_init /
+ * solve_iteration (src/solvers/pcg_solver.cu:77-190).  precond: 0 none, 1 one AMG V-cycle (zero guess),
+ * 2 one Jacobi sweep (zero guess: z = w r/d).  RELATIVE_INI convergence.  res_hist[0..iters].  Returns iterations. */
+ORC_API int orc_pcg(int n, const int *rp, const int *ci, const double *va, const orc_amg *amg, int precond, double jac_omega, const double *b,
+                    double *x, int x_is_zero, double tol, int max_iters, int norm_type, double *res_hist, int *converged_out)
+{
+    double *r = (double *)malloc(sizeof(double) * (size_t)n), *z = (double *)calloc((size_t)n, sizeof(double));
+    double *p = (double *)malloc(sizeof(double) * (size_t)n), *Ap = (double *)malloc(sizeof(double) * (size_t)n);
+    double *dj = NULL;
+    if (precond == 2) { dj = (double *)malloc(sizeof(double) * (size_t)n); orc_extract_diag(n, rp, ci, va, dj); }
+    if (x_is_zero) memcpy(r, b, sizeof(double) * (size_t)n);
+    else orc_residual(n, rp, ci, va, x, b, r);
+    double nrm = norm_of(n, r, norm_type), nrm_ini = nrm;
+    res_hist[0] = nrm;
+    int done = conv_relative_ini(nrm, nrm_ini, tol), it = 0, conv = done;
+    if (max_iters == 0) { conv = 0; goto finish; }
+    if (!done) {
+        /* solve_init */
+        if (precond == 1) orc_amg_vcycle(amg, r, z, 1);
+        else if (precond == 2) orc_jacobi_zero(n, dj, r, z, jac_omega);
+        else memcpy(z, r, sizeof(double) * (size_t)n);
+        memcpy(p, z, sizeof(double) * (size_t)n);
+    }
+    {
+        double rz = done ? 0.0 : orc_dot(n, r, z);
+        for (it = 0; it < max_iters && !done; it++) {
+            orc_spmv(n, rp, ci, va, p, Ap);
+            double dApp = orc_dot(n, Ap, p);
+            double alpha = 0.0;
+            if (dApp != 0.0) alpha = rz / dApp;
+            for (int i = 0; i < n; i++) x[i] = fma(alpha, p[i], x[i]);       /* axpy(p, x, alpha)   */
+            for (int i = 0; i < n; i++) r[i] = fma(-alpha, Ap[i], r[i]);     /* axpy(Ap, r, -alpha) */
+            nrm = norm_of(n, r, norm_type);
+            res_hist[it + 1] = nrm;
+            if (conv_relative_ini(nrm, nrm_ini, tol)) { done = 1; conv = 1; it++; break; }
+            if (it == max_iters - 1) { it++; break; }
+            if (precond == 1) orc_amg_vcycle(amg, r, z, 1);
+            else if (precond == 2) orc_jacobi_zero(n, dj, r, z, jac_omega);
+            else memcpy(z, r, sizeof(double) * (size_t)n);
+            double rz_old = rz;
+            rz = orc_dot(n, r, z);
+            double beta = 0.0;
+            if (rz_old != 0.0) beta = rz / rz_old;
+            for (int i = 0; i < n; i++) p[i] = z[i] * 1.0 + p[i] * beta;     /* axpby(z, p, p, 1, beta) */
+        }
+    }
+finish:
+    if (converged_out) *converged_out = conv;
+    free(r); free(z); free(p); free(Ap); free(dj);
+    return it;
+}

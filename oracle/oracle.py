@@ -1,0 +1,195 @@
+"""ctypes binding of the CPU oracle (oracle/amg_oracle.c).  TEST INFRASTRUCTURE: may be imported only
+by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", str(_HERE), "liboracle.so"], check=True)
+    return _HERE / "liboracle.so"
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        p = _HERE / "liboracle.so"
+        if not p.exists() or p.stat().st_mtime < (_HERE / "amg_oracle.c").stat().st_mtime:
+            build()
+        _lib = C.CDLL(str(p))
+        _lib.orc_dot.restype = C.c_double
+        _lib.orc_nrm2.restype = C.c_double
+        _lib.orc_nrm1.restype = C.c_double
+        _lib.orc_nrmmax.restype = C.c_double
+        _lib.orc_amg_setup.restype = C.c_void_p
+    return _lib
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def set_num_threads(t: int):
+    lib().orc_set_num_threads(C.c_int(t))
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
+
+
+def spmv(rp, ci, va, x):
+    rp, ci, va, x = _i(rp), _i(ci), _d(va), _d(x)
+    n = rp.shape[0] - 1
+    y = np.empty(n)
+    lib().orc_spmv(n, _p(rp), _p(ci), _p(va), _p(x), _p(y))
+    return y
+
+
+def residual(rp, ci, va, x, b):
+    rp, ci, va, x, b = _i(rp), _i(ci), _d(va), _d(x), _d(b)
+    n = rp.shape[0] - 1
+    r = np.empty(n)
+    lib().orc_residual(n, _p(rp), _p(ci), _p(va), _p(x), _p(b), _p(r))
+    return r
+
+
+def extract_diag(rp, ci, va):
+    rp, ci, va = _i(rp), _i(ci), _d(va)
+    n = rp.shape[0] - 1
+    d = np.empty(n)
+    lib().orc_extract_diag(n, _p(rp), _p(ci), _p(va), _p(d))
+    return d
+
+
+def l1_norms(rp, ci, va):
+    rp, ci, va = _i(rp), _i(ci), _d(va)
+    n = rp.shape[0] - 1
+    d = np.empty(n)
+    lib().orc_l1_norms(n, _p(rp), _p(ci), _p(va), _p(d))
+    return d
+
+
+def jacobi_sweep(rp, ci, va, d, b, x, omega):
+    rp, ci, va, d, b, x = _i(rp), _i(ci), _d(va), _d(d), _d(b), _d(x)
+    n = rp.shape[0] - 1
+    out = np.empty(n)
+    lib().orc_jacobi_sweep(n, _p(rp), _p(ci), _p(va), _p(d), _p(b), _p(x), _p(out), C.c_double(omega))
+    return out
+
+
+def jacobi_zero(d, b, omega):
+    d, b = _d(d), _d(b)
+    x = np.empty_like(b)
+    lib().orc_jacobi_zero(b.shape[0], _p(d), _p(b), _p(x), C.c_double(omega))
+    return x
+
+
+def edge_weights(rp, ci, va, weight_formula=0):
+    rp, ci, va = _i(rp), _i(ci), _d(va)
+    n = rp.shape[0] - 1
+    w = np.empty(ci.shape[0], np.float32)
+    lib().orc_edge_weights(n, _p(rp), _p(ci), _p(va), weight_formula, _p(w))
+    return w
+
+
+def size2_aggregates(rp, ci, va, max_iterations=15, max_unassigned=0.05, merge_singletons=1, weight_formula=0):
+    rp, ci, va = _i(rp), _i(ci), _d(va)
+    n = rp.shape[0] - 1
+    agg = np.empty(n, np.int32)
+    nagg = lib().orc_size2_aggregates(n, _p(rp), _p(ci), _p(va), max_iterations, C.c_double(max_unassigned), merge_singletons, weight_formula, _p(agg))
+    return agg, nagg
+
+
+def restriction(agg, nagg):
+    agg = _i(agg)
+    n = agg.shape[0]
+    Rp = np.empty(nagg + 1, np.int32)
+    Rc = np.empty(n, np.int32)
+    lib().orc_restriction(n, nagg, _p(agg), _p(Rp), _p(Rc))
+    return Rp, Rc
+
+
+def galerkin(rp, ci, va, agg, nagg):
+    rp, ci, va, agg = _i(rp), _i(ci), _d(va), _i(agg)
+    n = rp.shape[0] - 1
+    Rp, Rc = restriction(agg, nagg)
+    rpc = np.empty(nagg + 1, np.int32)
+    nnzc = lib().orc_galerkin_count(n, _p(rp), _p(ci), _p(agg), nagg, _p(Rp), _p(Rc), _p(rpc))
+    cic = np.empty(nnzc, np.int32)
+    vac = np.empty(nnzc)
+    lib().orc_galerkin_fill(n, _p(rp), _p(ci), _p(va), _p(agg), nagg, _p(Rp), _p(Rc), _p(rpc), _p(cic), _p(vac))
+    return rpc, cic, vac
+
+
+class AMG:
+    """Aggregation hierarchy + V-cycle exactly as the reference composes them (unfused)."""
+
+    def __init__(self, rp, ci, va, max_levels=100, min_coarse_rows=2, coarsen_threshold=1.0, presweeps=1, postsweeps=1, coarsest_sweeps=2,
+                 finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, max_iterations=15, max_unassigned=0.05, merge_singletons=1, weight_formula=0):
+        self.rp, self.ci, self.va = _i(rp), _i(ci), _d(va)
+        self.n = self.rp.shape[0] - 1
+        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1}[smoother]
+        self.h = C.c_void_p(lib().orc_amg_setup(self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold),
+                                                presweeps, postsweeps, coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), max_iterations,
+                                                C.c_double(max_unassigned), merge_singletons, weight_formula))
+
+    def num_levels(self):
+        return lib().orc_amg_num_levels(self.h)
+
+    def level(self, l):
+        n, nnz, nagg = C.c_int(), C.c_int(), C.c_int()
+        lib().orc_amg_level_sizes(self.h, l, C.byref(n), C.byref(nnz), C.byref(nagg))
+        n, nnz, nagg = n.value, nnz.value, nagg.value
+        rp = np.empty(n + 1, np.int32)
+        ci = np.empty(nnz, np.int32)
+        va = np.empty(nnz)
+        d = np.empty(n)
+        agg = np.empty(n, np.int32) if nagg else None
+        Rp = np.empty(nagg + 1, np.int32) if nagg else None
+        Rc = np.empty(n, np.int32) if nagg else None
+        lib().orc_amg_level_arrays(self.h, l, _p(rp), _p(ci), _p(va), _p(agg) if nagg else None, _p(Rp) if nagg else None, _p(Rc) if nagg else None, _p(d))
+        return dict(n=n, nnz=nnz, n_coarse=nagg, row_ptr=rp, col_idx=ci, values=va, aggregates=agg, R_row_offsets=Rp, R_column_indices=Rc, d=d)
+
+    def vcycle(self, b, x=None):
+        b = _d(b)
+        zero = x is None
+        x = np.zeros(self.n) if zero else _d(x).copy()
+        lib().orc_amg_vcycle(self.h, _p(b), _p(x), int(zero))
+        return x
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_amg_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def pcg(rp, ci, va, b, amg: AMG | None = None, jacobi_omega: float | None = None, x0=None, tol=1e-6, max_iters=100, norm="L2"):
+    rp, ci, va, b = _i(rp), _i(ci), _d(va), _d(b)
+    n = rp.shape[0] - 1
+    zero = x0 is None
+    x = np.zeros(n) if zero else _d(x0).copy()
+    hist = np.zeros(max_iters + 1)
+    conv = C.c_int()
+    precond = 1 if amg is not None else (2 if jacobi_omega is not None else 0)
+    nt = {"L1": 0, "L2": 1, "LMAX": 2}[norm]
+    it = lib().orc_pcg(n, _p(rp), _p(ci), _p(va), amg.h if amg is not None else None, precond, C.c_double(jacobi_omega or 0.0), _p(b), _p(x),
+                       int(zero), C.c_double(tol), max_iters, nt, _p(hist), C.byref(conv))
+    return x, it, hist[: it + 1].copy(), bool(conv.value)

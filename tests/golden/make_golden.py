@@ -1,0 +1,91 @@
+"""Generate golden vectors by running the UNMODIFIED reference on a B200 (gpurun):
+
+    gpurun -- 'python tests/golden/make_golden.py'
+
+For every case it writes the system, runs oracle/_ref/ref_dump (reference's own C API + a dump of its
+internal hierarchy) with a JSON config in the reference's format, and stores a compressed fixture in
+gpurun_out/golden/<case>.npz; copy those to tests/golden/ and commit them.  Nothing here touches
+/root/reference (it does not exist on the GPU box): the reference is the prebuilt oracle/_ref/."""
+from __future__ import annotations
+
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from amgx_b200 import gallery  # noqa: E402
+from tests.golden.refdump_io import read_dump, write_system  # noqa: E402
+
+OUT = ROOT / "gpurun_out" / "golden"
+REF = ROOT / "oracle" / "_ref" / "ref_dump"
+
+
+def cfg_pcg_agg(tol=1e-10, max_iters=60, pre=0, post=3, omega=0.8, coarsest=2):
+    return {"config_version": 2, "determinism_flag": 1, "solver": {
+        "scope": "main", "solver": "PCG", "max_iters": max_iters, "monitor_residual": 1, "store_res_history": 1,
+        "convergence": "RELATIVE_INI", "tolerance": tol, "norm": "L2", "print_solve_stats": 0, "obtain_timings": 0,
+        "preconditioner": {"scope": "amg", "solver": "AMG", "algorithm": "AGGREGATION", "selector": "SIZE_2", "cycle": "V",
+                           "max_levels": 50, "presweeps": pre, "postsweeps": post, "coarsest_sweeps": coarsest, "coarse_solver": "NOSOLVER",
+                           "max_iters": 1, "monitor_residual": 0, "print_grid_stats": 1,
+                           "smoother": {"scope": "jacobi", "solver": "BLOCK_JACOBI", "relaxation_factor": omega, "monitor_residual": 0}}}}
+
+
+def cfg_pcg_jacobi(tol=1e-8, max_iters=40):
+    return {"config_version": 2, "solver": {
+        "scope": "main", "solver": "PCG", "max_iters": max_iters, "monitor_residual": 1, "store_res_history": 1,
+        "convergence": "RELATIVE_INI", "tolerance": tol, "norm": "L2",
+        "preconditioner": {"scope": "jacobi", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "max_iters": 1, "monitor_residual": 0}}}
+
+
+def cfg_amg_agg_standalone(tol=1e-8, max_iters=40, pre=1, post=1, norm="L1"):
+    return {"config_version": 2, "determinism_flag": 1, "solver": {
+        "scope": "main", "solver": "AMG", "algorithm": "AGGREGATION", "selector": "SIZE_2", "cycle": "V", "max_levels": 50,
+        "presweeps": pre, "postsweeps": post, "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER", "max_iters": max_iters,
+        "monitor_residual": 1, "store_res_history": 1, "convergence": "RELATIVE_INI", "tolerance": tol, "norm": norm,
+        "smoother": {"scope": "jacobi", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "monitor_residual": 0}}}
+
+
+def cases():
+    ex = np.load(ROOT / "tests" / "golden" / "example_matrix_12x12.npz")
+    yield "example12_pcg_jacobi", (ex["row_ptr"], ex["col_idx"], ex["values"]), cfg_pcg_jacobi(), None
+    for n in (6, 10, 16):
+        yield f"poisson{n}_pcg_agg_jacobi", gallery.poisson7pt(n), cfg_pcg_agg(), None
+    yield "poisson12x10x7_pcg_agg_jacobi", gallery.poisson7pt(12, 10, 7), cfg_pcg_agg(), None
+    yield "poisson10_sorted_pcg_agg_jacobi", gallery.poisson7pt_sorted(10), cfg_pcg_agg(), None
+    yield "poisson12_pcg_agg_jacobi_pre2", gallery.poisson7pt(12), cfg_pcg_agg(pre=2, post=2, omega=0.7), None
+    yield "poisson12_amg_standalone_L1", gallery.poisson7pt(12), cfg_amg_agg_standalone(), None
+    yield "banded3000_pcg_agg_jacobi", gallery.random_banded(3000, sigma=40.0), cfg_pcg_agg(max_iters=80), None
+    yield "poisson8_pcg_jacobi", gallery.poisson7pt(8), cfg_pcg_jacobi(tol=1e-10, max_iters=80), None
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    only = sys.argv[1:] or None
+    for name, (rp, ci, va), cfg, x0 in cases():
+        if only and name not in only:
+            continue
+        n = rp.shape[0] - 1
+        rhs = np.ones(n)
+        sysf, cfgf, outf = OUT / f"{name}.sys", OUT / f"{name}.json", OUT / f"{name}.bin"
+        write_system(sysf, rp, ci, va, rhs, x0=x0)
+        cfgf.write_text(json.dumps(cfg, indent=1))
+        r = subprocess.run([str(REF), str(sysf), str(cfgf), str(outf)], capture_output=True, text=True)
+        if r.returncode != 0:
+            print(f"[{name}] ref_dump FAILED rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
+            continue
+        d = read_dump(outf)
+        d["config_json"] = json.dumps(cfg)
+        d["sys_row_ptr"], d["sys_col_idx"], d["sys_values"], d["sys_rhs"] = rp, ci, va, rhs
+        np.savez_compressed(OUT / f"{name}.npz", **{k: v for k, v in d.items()})
+        print(f"[{name}] n={n} status={d['status'][0]} iters={d['iterations'][0]} levels={d.get('num_levels', [0])[0]} "
+              f"res0={d['res_history'][0]:.6e} resN={d['res_history'][-1]:.6e}")
+        for f in (sysf, outf):
+            f.unlink()
+
+
+if __name__ == "__main__":
+    main()
