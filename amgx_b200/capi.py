@@ -65,6 +65,8 @@ def _declare(lib):
         "AMGX_get_api_version": [ip, ip],
         "AMGX_get_error_string": [i, C.c_char_p, i],
         "AMGX_register_print_callback": [vp],
+        "AMGX_pin_memory": [vp, C.c_uint],
+        "AMGX_unpin_memory": [vp],
         "AMGX_config_create": [C.POINTER(vp), C.c_char_p],
         "AMGX_config_add_parameters": [C.POINTER(vp), C.c_char_p],
         "AMGX_config_create_from_file": [C.POINTER(vp), C.c_char_p],

@@ -254,7 +254,9 @@ AMGX_RC AMGX_config_get_default_number_of_rings(AMGX_config_handle cfg, int *num
     std::string alg_s = h->cfg->get_string("algorithm", ss);
     h->cfg->get_scoped("preconditioner", ss, pv, ps);
     std::string alg_p = h->cfg->get_string("algorithm", ps);
-    *num_import_rings = ((sv == "AMG" && alg_s == "CLASSICAL") || (pv == "AMG" && alg_p == "CLASSICAL")) ? 2 : 1;
+    if (sv == "AMG") *num_import_rings = (alg_s == "CLASSICAL") ? 2 : 1;
+    else if (pv == "AMG") *num_import_rings = (alg_p == "CLASSICAL") ? 2 : 1;
+    else *num_import_rings = 1;
     API_END(nullptr)
 }
 

@@ -270,19 +270,28 @@ int size2_select(const Matrix &A, const AggSetupParams &prm, DevBuf<int> &aggreg
     count_launch();
     AMGXB_LAUNCH_CHECK();
 
-    int num_unassigned = n, prev = n, icount = 0;
+    // The reference builds this loop with EXPERIMENTAL_ITERATIVE_MATCHING (size2_selector.cu:22, 808-847): the count of
+    // unaggregated rows is taken after even iterations only and consumed one iteration later, so the loop runs an even
+    // number of handshake steps and the exit test (and the merge phase's first test) see a one-step-stale count.
+    int num_unassigned = n, prev = n, icount = 0, sflag = 1, pending = n;
     do {
         find_strongest_kernel<<<g, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), w.ptr(), n, aggregates.ptr(), strongest.ptr(), merge_to.ptr(),
                                                 prm.merge_singletons);
         match_edges_kernel<<<g, 256, 0, s>>>(n, aggregates.ptr(), strongest.ptr(), merge_to.ptr());
-        counter.zero(s);
-        count_unaggregated_kernel<<<g, 256, 0, s>>>(n, aggregates.ptr(), counter.ptr());
-        count_launch(3);
-        AMGXB_LAUNCH_CHECK();
-        prev = num_unassigned;
-        num_unassigned = read_scalar(counter.ptr(), s);
+        count_launch(2);
+        sflag = (icount & 1);
+        if (sflag == 0) {
+            counter.zero(s);
+            count_unaggregated_kernel<<<g, 256, 0, s>>>(n, aggregates.ptr(), counter.ptr());
+            count_launch();
+            AMGXB_LAUNCH_CHECK();
+            pending = read_scalar(counter.ptr(), s);
+        } else {
+            prev = num_unassigned;
+            num_unassigned = pending;
+        }
         icount++;
-    } while (!(num_unassigned == 0 || icount > prm.max_iterations || 1.0 * num_unassigned / n < prm.max_unassigned || num_unassigned == prev));
+    } while (sflag == 0 || !(num_unassigned == 0 || icount > prm.max_iterations || 1.0 * num_unassigned / n < prm.max_unassigned || num_unassigned == prev));
 
     if (prm.merge_singletons) {
         cand.resize(n);

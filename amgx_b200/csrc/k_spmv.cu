@@ -376,13 +376,13 @@ template <class MatT, class VecT, int TILE_ROWS, int EPI> void launch_tile(const
     const size_t smem = A.plan.smem_bytes;
     if (ta.agg) {
         auto k = csr_tile_kernel<MatT, VecT, TILE_ROWS, EPI, true>;
-        static bool attr_set = false;
-        if (!attr_set) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+        static size_t attr_bytes = 0;   // opt in to exactly what this kernel needs (static smem counts against the 227 KB cap)
+        if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
         k<<<grid, TILE_ROWS + PRODUCER_THREADS, smem, s>>>(ta);
     } else {
         auto k = csr_tile_kernel<MatT, VecT, TILE_ROWS, EPI, false>;
-        static bool attr_set = false;
-        if (!attr_set) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+        static size_t attr_bytes = 0;   // opt in to exactly what this kernel needs (static smem counts against the 227 KB cap)
+        if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
         k<<<grid, TILE_ROWS + PRODUCER_THREADS, smem, s>>>(ta);
     }
 }
@@ -441,7 +441,7 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
     for (int st = MAX_STAGES; st >= 2; st--) {
         size_t need = tile_smem_bytes(p.max_tile_nnz, st, p.tile_rows, msz);
         // prefer >= 2 CTAs per SM at full depth, accept 1 CTA per SM at depth 2
-        size_t budget = (st > 2) ? (size_t)110 * 1024 : (size_t)220 * 1024;
+        size_t budget = (st > 2) ? (size_t)110 * 1024 : (size_t)216 * 1024;
         if (need <= budget) { p.stages = st; p.smem_bytes = need; p.use_tiles = true; break; }
     }
     A.plan = p;

@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- solve-phase benchmark of the B200 AMG engine (contract: see README / DESIGN.md).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n NX]
+
+Workload (BASELINE.json configs[1]): 3-D 7-point Poisson 256^3, fp64, aggregation AMG (SIZE_2) V-cycle
+preconditioned CG, BLOCK_JACOBI(0.8) 0+3 sweeps -- the reference's PCG_AGGREGATION_JACOBI.json.
+A "step" is one AMGX_solver_solve (zero initial guess, b = 1, RELATIVE_INI 1e-6, max 100 iterations);
+metric = outer Krylov iterations (one V-cycle each) per second, whole job.
+  value : solves with b/x already resident in HBM, timed by CUDA events recorded by the library on its
+          solve stream (AMGXB200_solver_get_last_solve_stats), max over ranks.
+  e2e   : the same solve through the C-ABI with HOST buffers: AMGX_vector_upload(rhs) from pinned host
+          memory + AMGX_vector_set_zero + AMGX_solver_solve + AMGX_vector_download(sol), wall clock
+          around the synchronous calls.
+  roofline : fine-level CSR SpMV kernel (the kernel family every sweep / residual / Krylov product runs),
+          algorithmic bytes nnz*(8+4)+rows*4 per launch / CUDA-event time per launch, against the
+          measured HBM copy peak in MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference : the CPU oracle port of the reference algorithm (the reference's
+          own host path has no SIZE_2 aggregation: src/aggregation/selectors/size2_selector.cu:630-643
+          throws) on all host threads, on a bounded sample of the same workload.
+N > 1: the matrix is row-partitioned (z-slabs) over the ranks, one process per GPU, NCCL halo exchange;
+weak scaling (each rank owns an NX^3 / 1 slab: global grid NX x NX x (NX*N)).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CONFIG = ROOT / "amgx_b200" / "configs" / "PCG_AGGREGATION_JACOBI.json"
+METRIC = "solve_phase_vcycle_iterations_per_sec"
+UNIT = "iterations/s"
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_baseline(nx_sample: int, nx_full: int, iters: int):
+    """CPU port (oracle) of the same solver on all host threads, bounded sample."""
+    from amgx_b200 import gallery
+    from oracle import oracle as orc
+    cores = orc.num_threads()
+    rp, ci, va = gallery.poisson7pt(nx_sample)
+    n = rp.shape[0] - 1
+    t0 = time.time()
+    amg = orc.AMG(rp, ci, va, max_levels=50, presweeps=0, postsweeps=3, omega=0.8)
+    t_setup = time.time() - t0
+    t0 = time.time()
+    _, it, hist, _ = orc.pcg(rp, ci, va, np.ones(n), amg=amg, tol=1e-30, max_iters=iters)
+    dt = time.time() - t0
+    scale = (nx_sample ** 3) / float(nx_full ** 3)
+    return {"value": it / dt * scale, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle PCG+aggregation-AMG on 7-pt Poisson {nx_sample}^3 ({n} rows), {it} iterations in {dt:.2f} s "
+                      f"(setup {t_setup:.1f} s untimed); iterations/s scaled by rows ratio {scale:.4g} to {nx_full}^3",
+            "measured_iters_per_s_on_sample": it / dt}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    nx_sample = min(args.n, 96)
+    per_step_iters = 6
+    for _ in range(args.warmup):
+        pass  # the oracle is deterministic CPU code: warm-up would only repeat the sample
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3))):
+        base = oracle_baseline(nx_sample, args.n, per_step_iters)
+        vals.append(base["value"])
+    v = float(np.median(vals))
+    base["value"] = v
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"7-pt Poisson {args.n}^3 fp64, PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI)", "grid": args.n},
+           "cpu_baseline": base,
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "reference has no CPU implementation of SIZE_2 aggregation (size2_selector.cu:630-643 throws); this is the oracle port"}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="grid points per dimension (per rank for --gpus > 1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from amgx_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    capi.initialize()
+    capi.register_print_callback(None)
+    cfg = capi.Config(file=str(CONFIG))
+    comm = None
+    if distributed:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = capi.AMGXB200_comm(rank, world, bytes(idt.cpu().numpy().tobytes()))
+    rsc = capi.Resources(cfg, device=local_rank, comm=comm) if (distributed or local_rank) else capi.Resources(cfg)
+    A, b, x = capi.Matrix(rsc), capi.Vector(rsc), capi.Vector(rsc)
+    nx = args.n
+    t0 = time.time()
+    A.generate_poisson7(b, x, nx, nx, nx, 1, 1, world)     # z-slabs: global grid nx * nx * (nx*world)
+    n, _, _ = A.get_size()
+    nnz = A.get_nnz()
+    slv = capi.Solver(rsc, cfg)
+    slv.setup(A)
+    t_setup = time.time() - t0
+    if distributed:
+        b.bind(A)
+        x.bind(A)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    def one_solve():
+        x.set_zero(n)
+        slv.solve(b, x, zero_initial_guess=True)
+        s, k = slv.last_solve_stats()
+        return s, k, slv.iterations_number
+
+    for _ in range(args.warmup):
+        one_solve()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    tot_s, tot_k, tot_it = 0.0, 0, 0
+    for _ in range(args.steps):
+        s, k, it = one_solve()
+        tot_s += s
+        tot_k += k
+        tot_it += it
+    sync_all()
+    clocks = sampler.stop()
+    if distributed:
+        t = torch.tensor([tot_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_s = float(t.item())
+    value = tot_it / tot_s
+    status = slv.status
+    hist = slv.residual_history() if rank == 0 else []
+
+    # ---- end to end through the C-ABI with host buffers ----
+    hb = np.ones(n)
+    hx = np.zeros(n)
+    lib = capi.load_library()
+    lib.AMGX_pin_memory(hb.ctypes.data, hb.nbytes)
+    lib.AMGX_pin_memory(hx.ctypes.data, hx.nbytes)
+
+    def one_e2e():
+        b.upload(hb)
+        x.set_zero(n)
+        slv.solve(b, x, zero_initial_guess=True)
+        x.download(hx)
+        return slv.iterations_number
+
+    one_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    e_it = 0
+    for _ in range(args.steps):
+        e_it += one_e2e()
+    torch.cuda.synchronize()
+    e_dt = time.perf_counter() - t0
+    if distributed:
+        t = torch.tensor([e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_dt = float(t.item())
+    lib.AMGX_unpin_memory(hb.ctypes.data)
+    lib.AMGX_unpin_memory(hx.ctypes.data)
+
+    # ---- roofline of the dominant kernel (fine-level CSR SpMV) ----
+    roof = None
+    if not distributed:
+        peak, peak_src = measured_peak()
+        ms = A.bench_kernel(0, warmup=3, reps=20, flush_l2=False)      # operands (1.47 GB at 256^3) >> 126 MB L2
+        ms_j = A.bench_kernel(1, warmup=3, reps=20, flush_l2=False)
+        byt = nnz * 12 + n * 4
+        roof = {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": byt / ms / 1e6 / peak, "traffic": None,
+                "kernel": "csr_tile_kernel<EPI_SPMV> (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt, "peak_source": peak_src,
+                "fused_jacobi_sweep": {"ms_per_launch": ms_j, "algorithmic_bytes": byt + 4 * n * 8, "achieved": (byt + 4 * n * 8) / ms_j / 1e6,
+                                       "frac": (byt + 4 * n * 8) / ms_j / 1e6 / peak}}
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and not distributed:
+        cpu = oracle_baseline(min(nx, 96), nx, 6)
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": f"7-pt Poisson {nx}x{nx}x{nx * world} fp64, PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI.json)",
+                          "rows": n * world, "nnz_per_rank": nnz, "iterations_per_step": tot_it / args.steps, "solve_status": status,
+                          "l2": "inputs larger than L2 (matrix alone %.2f GB per rank)" % (nnz * 12 / 1e9), "setup_seconds": t_setup,
+                          "parallelism": f"row-partition x{world}" if distributed else "single GPU"},
+               "e2e": {"value": e_it / e_dt, "unit": UNIT, "h2d_bytes_per_step": int(hb.nbytes), "d2h_bytes_per_step": int(hx.nbytes),
+                       "ms_per_step": e_dt / args.steps * 1e3},
+               "gpu_launches": int(tot_k), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+               "final_relative_residual": (hist[-1] / hist[0]) if hist else None}
+        print(json.dumps(out), flush=True)
+    for o in (slv, x, b, A, rsc, cfg):
+        o.destroy()
+    capi.finalize()
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -222,7 +222,10 @@ ORC_API int orc_size2_aggregates(int n, const int *rp, const int *ci, const doub
     int *cand = (int *)malloc(sizeof(int) * (size_t)n);
     orc_edge_weights(n, rp, ci, va, weight_formula, w);
     for (int i = 0; i < n; i++) { agg[i] = -1; strongest[i] = -1; }
-    int unassigned = n, prev, icount = 0;
+    /* The reference compiles this loop with EXPERIMENTAL_ITERATIVE_MATCHING (size2_selector.cu:22, 808-847): the
+     * unaggregated count is taken after EVEN iterations only and consumed one iteration later, so the loop always
+     * runs an even number of handshake steps and its exit test sees a count that is one step stale. */
+    int unassigned = n, prev = n, icount = 0, s = 1, pending = n;
     do {
         /* findStrongestNeighbourBlockDiaCsr_V2 (size2_selector.cu:224-301), phase 1, snapshot reads of agg[] */
 #pragma omp parallel for schedule(static)
@@ -252,14 +255,16 @@ ORC_API int orc_size2_aggregates(int n, const int *rp, const int *ci, const doub
             if (pm < 0) continue;
             if (merge_to[pm] == -1 && strongest[pm] == t) cand[t] = (pm > t) ? t : pm;
         }
-        prev = unassigned;
-        unassigned = 0;
+        int now = 0;
         for (int t = 0; t < n; t++) {
             if (agg[t] == -1 && cand[t] != -1) agg[t] = cand[t];
-            if (agg[t] == -1) unassigned++;
+            if (agg[t] == -1) now++;
         }
+        s = (icount & 1);
+        if (s == 0) pending = now;
+        else { prev = unassigned; unassigned = pending; }
         icount++;
-    } while (!(unassigned == 0 || icount > max_iterations || 1.0 * unassigned / n < max_unassigned || unassigned == prev));
+    } while (s == 0 || !(unassigned == 0 || icount > max_iterations || 1.0 * unassigned / n < max_unassigned || unassigned == prev));
 
     if (merge_singletons) {
         /* mergeWithExistingAggregatesBlockDiaCsr_V2 + joinExistingAggregates, deterministic path (:508-566, 424-440) */
