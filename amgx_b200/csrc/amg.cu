@@ -230,13 +230,15 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse)
     bool have_fuse = false;
     if (top_fuse && finest && n_post > 0) { f = *top_fuse; have_fuse = true; }
     if (algorithm_ == "AGGREGATION") {
-        if (x_virtual_zero && n_post > 0 && sm->supports_fusion()) {
+        static const bool fuse_prolong = getenv("AMGXB_FUSE_PROLONG") ? atoi(getenv("AMGXB_FUSE_PROLONG")) != 0 : false;
+        if (x_virtual_zero && n_post > 0 && sm->supports_fusion() && fuse_prolong && !A.dist) {
             // x := P xc is read on the fly by the first sweep
             f.agg = L.aggregates.ptr();
             f.xc = L.xc.ptr();
             have_fuse = true;
+        } else if (x_virtual_zero) {
+            agg_prolong_set(L.aggregates.ptr(), L.xc.ptr(), x.ptr(), A.vec_prec, A.n, A.by, s);   // x = 0 + P xc
         } else {
-            if (x_virtual_zero) x.zero(s);
             agg_prolong_add(L.aggregates.ptr(), L.xc.ptr(), x.ptr(), A.vec_prec, A.n, A.by, s);
         }
     } else {

@@ -40,7 +40,27 @@ template <class VecT> __global__ void prolong_kernel(const int *__restrict__ agg
     }
 }
 
+template <class VecT> __global__ void prolong_set_kernel(const int *__restrict__ agg, const VecT *__restrict__ e, VecT *__restrict__ x, int n, int bsize)
+{
+    const long long total = (long long)n * bsize;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / bsize), m = (int)(t % bsize);
+        x[t] = __ldg(e + (size_t)agg[i] * bsize + m);   // 0 + e == e: identical to zero-fill followed by prolongateAndApplyCorrection
+    }
+}
+
 }  // namespace
+
+void agg_prolong_set(const int *aggregates, const void *e, void *x, Prec p, int n, int bsize, cudaStream_t s)
+{
+    if (n == 0) return;
+    AMGXB_DISPATCH_VEC(p, {
+        int grid = std::min(ceil_div((long long)n * bsize, 256), 148 * 16);
+        prolong_set_kernel<VecT><<<grid, 256, 0, s>>>(aggregates, (const VecT *)e, (VecT *)x, n, bsize);
+    });
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+}
 
 void agg_restrict(const int *Rp, const int *Rc, const void *r, void *rc, Prec p, int n_agg, int bsize, cudaStream_t s)
 {

@@ -97,6 +97,7 @@ int  blas_max_grid();
 // -------------------------------------------------------------------------------------------
 void agg_restrict(const int *R_row_offsets, const int *R_col, const void *r, void *rc, Prec p, int n_agg, int bsize, cudaStream_t s);
 void agg_prolong_add(const int *aggregates, const void *e, void *x, Prec p, int n, int bsize, cudaStream_t s);
+void agg_prolong_set(const int *aggregates, const void *e, void *x, Prec p, int n, int bsize, cudaStream_t s);   // x = P e (x was zero)
 
 // -------------------------------------------------------------------------------------------
 // Aggregation setup (k_setup_agg.cu): SIZE_2 selector, R pattern, Galerkin product

@@ -163,20 +163,49 @@ int main(int argc, char **argv)
     int reps = argc > 5 ? atoi(argv[5]) : 1;
     AMGX_Mode mode = mode_s == "dDDI" ? AMGX_mode_dDDI : mode_s == "dDFI" ? AMGX_mode_dDFI : mode_s == "dFFI" ? AMGX_mode_dFFI : AMGX_mode_hDDI;
     const bool mat32 = (mode == AMGX_mode_dDFI || mode == AMGX_mode_dFFI), vec32 = (mode == AMGX_mode_dFFI);
-    FILE *f = fopen(argv[1], "rb");
-    if (!f) { perror("system"); return 1; }
-    int hdr[6];
-    if (fread(hdr, 4, 6, f) != 6) return 1;
-    const int n = hdr[0], nnz = hdr[1], bx = hdr[2], by = hdr[3], has_diag = hdr[4], has_x0 = hdr[5];
-    std::vector<int> rp(n + 1), ci(nnz);
-    std::vector<double> va((size_t)nnz * bx * by), dg, rhs((size_t)n * by), x0((size_t)n * bx, 0.0);
-    fread(rp.data(), 4, n + 1, f);
-    fread(ci.data(), 4, nnz, f);
-    fread(va.data(), 8, va.size(), f);
-    if (has_diag) { dg.resize((size_t)n * bx * by); fread(dg.data(), 8, dg.size(), f); }
-    fread(rhs.data(), 8, rhs.size(), f);
-    if (has_x0) fread(x0.data(), 8, x0.size(), f);
-    fclose(f);
+    int n = 0, nnz = 0, bx = 1, by = 1, has_diag = 0, has_x0 = 0;
+    std::vector<int> rp, ci;
+    std::vector<double> va, dg, rhs, x0;
+    bool dump_levels = true;
+    if (!strncmp(argv[1], "poisson:", 8)) {
+        // generated 7-point Poisson nx^3 (diagonal first, then -1 for i-1,i+1,j-1,j+1,k-1,k+1), b = 1, x0 = 0; timing runs: no hierarchy dump
+        const int nx = atoi(argv[1] + 8);
+        dump_levels = nx <= 64;
+        n = nx * nx * nx;
+        rp.resize((size_t)n + 1);
+        ci.reserve((size_t)n * 7);
+        va.reserve((size_t)n * 7);
+        for (int r = 0; r < n; r++) {
+            const int i = r % nx, j = (r / nx) % nx, k = r / (nx * nx);
+            rp[r] = (int)ci.size();
+            ci.push_back(r); va.push_back(6.0);
+            if (i > 0) { ci.push_back(r - 1); va.push_back(-1.0); }
+            if (i < nx - 1) { ci.push_back(r + 1); va.push_back(-1.0); }
+            if (j > 0) { ci.push_back(r - nx); va.push_back(-1.0); }
+            if (j < nx - 1) { ci.push_back(r + nx); va.push_back(-1.0); }
+            if (k > 0) { ci.push_back(r - nx * nx); va.push_back(-1.0); }
+            if (k < nx - 1) { ci.push_back(r + nx * nx); va.push_back(-1.0); }
+        }
+        rp[n] = (int)ci.size();
+        nnz = (int)ci.size();
+        rhs.assign((size_t)n, 1.0);
+        x0.assign((size_t)n, 0.0);
+    } else {
+        FILE *f = fopen(argv[1], "rb");
+        if (!f) { perror("system"); return 1; }
+        int hdr[6];
+        if (fread(hdr, 4, 6, f) != 6) return 1;
+        n = hdr[0]; nnz = hdr[1]; bx = hdr[2]; by = hdr[3]; has_diag = hdr[4]; has_x0 = hdr[5];
+        rp.resize(n + 1); ci.resize(nnz);
+        va.resize((size_t)nnz * bx * by); rhs.resize((size_t)n * by); x0.assign((size_t)n * bx, 0.0);
+        fread(rp.data(), 4, n + 1, f);
+        fread(ci.data(), 4, nnz, f);
+        fread(va.data(), 8, va.size(), f);
+        if (has_diag) { dg.resize((size_t)n * bx * by); fread(dg.data(), 8, dg.size(), f); }
+        fread(rhs.data(), 8, rhs.size(), f);
+        if (has_x0) fread(x0.data(), 8, x0.size(), f);
+        fclose(f);
+    }
     std::vector<float> vaf, dgf, rhsf, x0f;
     if (mat32) { vaf.assign(va.begin(), va.end()); dgf.assign(dg.begin(), dg.end()); }
     if (vec32) { rhsf.assign(rhs.begin(), rhs.end()); x0f.assign(x0.begin(), x0.end()); }
@@ -238,7 +267,8 @@ int main(int argc, char **argv)
         }
     }
     rec("res_history", 'd', hist.data(), hist.size(), 8);
-    if (vec32) {
+    if (!dump_levels) {
+    } else if (vec32) {
         std::vector<float> xs((size_t)n * bx);
         CK(AMGX_vector_download(x, xs.data()));
         rec("solution", 'f', xs.data(), xs.size(), 4);
@@ -248,7 +278,7 @@ int main(int argc, char **argv)
         rec("solution", 'd', xs.data(), xs.size(), 8);
     }
     // one SpMV through the public API: y = A * rhs
-    {
+    if (dump_levels) {
         AMGX_vector_handle y;
         CK(AMGX_vector_create(&y, rsrc, mode));
         CK(AMGX_vector_set_zero(y, n, by));
@@ -257,7 +287,8 @@ int main(int argc, char **argv)
         else { std::vector<double> ys((size_t)n * by); CK(AMGX_vector_download(y, ys.data())); rec("spmv_A_rhs", 'd', ys.data(), ys.size(), 8); }
         AMGX_vector_destroy(y);
     }
-    if (mode == AMGX_mode_dDDI) dump_hierarchy<AMGX_mode_dDDI>(solver);
+    if (!dump_levels) { /* timing run */ }
+    else if (mode == AMGX_mode_dDDI) dump_hierarchy<AMGX_mode_dDDI>(solver);
     else if (mode == AMGX_mode_dDFI) dump_hierarchy<AMGX_mode_dDFI>(solver);
     else if (mode == AMGX_mode_dFFI) dump_hierarchy<AMGX_mode_dFFI>(solver);
     rec("log", 'i', nullptr, 0, 4);

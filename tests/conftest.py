@@ -27,4 +27,5 @@ def amgx():
 def oracle():
     from oracle import oracle as o
     o.lib()
+    o.set_num_threads(1)   # small inputs: OpenMP fork/join on a 64-core box costs more than the loops
     return o
