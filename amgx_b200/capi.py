@@ -30,7 +30,13 @@ class AMGXError(RuntimeError):
 
 
 class AMGXB200_comm(C.Structure):
-    _fields_ = [("rank", C.c_int), ("world_size", C.c_int), ("nccl_unique_id", C.c_char * 128)]
+    _fields_ = [("rank", C.c_int), ("world_size", C.c_int), ("nccl_unique_id", C.c_ubyte * 128)]
+
+    def __init__(self, rank: int, world_size: int, unique_id: bytes):
+        super().__init__()
+        assert len(unique_id) == 128
+        self.rank, self.world_size = rank, world_size
+        C.memmove(C.addressof(self) + 8, unique_id, 128)   # raw copy: the id contains NUL bytes
 
 
 class PartitionPlan(C.Structure):

@@ -82,8 +82,10 @@ void AMGSolver::setup_aggregation()
         Matrix &A = *L.A;
         A.level = num_levels - 1;
         const int rows = A.n;
-        if (num_levels >= max_levels_ || rows <= min_coarse_rows_) {
-            if (dense_lu_max_rows_ != 0 && rows > dense_lu_max_rows_) { coarse_solver_.reset(); coarse_solver_exists = false; }
+        // stopping rules use the minimum / the sum over the partitions (src/amg.cu:186-200, 282-356)
+        const long long min_part_rows = dist_allreduce_ll(A, rows, 1);
+        if (num_levels >= max_levels_ || min_part_rows <= min_coarse_rows_) {
+            if (dense_lu_max_rows_ != 0 && min_part_rows > dense_lu_max_rows_) { coarse_solver_.reset(); coarse_solver_exists = false; }
             L.coarsest = true;
             if (!coarse_solver_exists) { L.smoother = make_smoother(); L.smoother->setup(A, false); }
             break;
@@ -91,17 +93,26 @@ void AMGSolver::setup_aggregation()
         // createCoarseVertices
         const int n_agg = size2_select(A, prm, L.aggregates, s);
         L.n_coarse = n_agg;
-        const long long N = (long long)rows * A.by, nextN = (long long)n_agg * A.by;
+        const long long N = dist_allreduce_ll(A, rows, 0) * A.by, nextN = dist_allreduce_ll(A, n_agg, 0) * A.by;
+        const long long min_part_next = dist_allreduce_ll(A, n_agg, 1);
         bool built_next = false;
-        if ((double)nextN <= coarsen_threshold_ * (double)N && nextN != N && n_agg >= min_coarse_rows_) {
+        if ((double)nextN <= coarsen_threshold_ * (double)N && nextN != N && min_part_next >= min_coarse_rows_) {
+            std::shared_ptr<DistManager> cdist;
+            int n_int_c = 0;
+            if (A.dist) cdist = dist_coarsen(A, L.aggregates, n_agg, &n_int_c);   // relabels aggregates, appends halo aggregates
             build_restriction(L.aggregates, rows, n_agg, L.R_row_offsets, L.R_column_indices, s);
             std::unique_ptr<AMGLevel> next(new AMGLevel);
             next->owned_A.reset(new Matrix);
             galerkin_aggregation(A, L.aggregates, n_agg, *next->owned_A, s);
+            if (cdist) {
+                next->owned_A->dist = cdist;
+                next->owned_A->n_cols = n_agg + cdist->n_halo;
+                next->owned_A->split_row = n_int_c;
+            }
             next->owned_A->compute_diag_and_plan();
             next->A = next->owned_A.get();
             next->index = num_levels;
-            const size_t nc = (size_t)n_agg * A.by;
+            const size_t nc = (size_t)next->A->n_cols * A.by;
             L.bc.resize(nc, A.vec_prec);
             L.xc.resize(nc, A.vec_prec);
             L.bc.zero(s);
@@ -227,25 +238,29 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse)
         if (postsweeps_ != 0 && intensive_smoothing_) n_post = std::max(n_post + lvl - 2, 0);
     }
     SmoothFuse f;
-    bool have_fuse = false;
+    bool have_fuse = false, in_alt = false;
     if (top_fuse && finest && n_post > 0) { f = *top_fuse; have_fuse = true; }
     if (algorithm_ == "AGGREGATION") {
         static const bool fuse_prolong = getenv("AMGXB_FUSE_PROLONG") ? atoi(getenv("AMGXB_FUSE_PROLONG")) != 0 : false;
+        // where the smoother wants its initial iterate so that n_post sweeps end in x without a copy
+        void *xin = (n_post > 0) ? sm->smooth_input(x, n_post) : x.ptr();
+        in_alt = (xin != x.ptr());
         if (x_virtual_zero && n_post > 0 && sm->supports_fusion() && fuse_prolong && !A.dist) {
             // x := P xc is read on the fly by the first sweep
             f.agg = L.aggregates.ptr();
             f.xc = L.xc.ptr();
             have_fuse = true;
+            in_alt = false;
         } else if (x_virtual_zero) {
-            agg_prolong_set(L.aggregates.ptr(), L.xc.ptr(), x.ptr(), A.vec_prec, A.n, A.by, s);   // x = 0 + P xc
+            agg_prolong_set(L.aggregates.ptr(), L.xc.ptr(), xin, A.vec_prec, A.n, A.by, s);               // x = 0 + P xc
         } else {
-            agg_prolong_add(L.aggregates.ptr(), L.xc.ptr(), x.ptr(), A.vec_prec, A.n, A.by, s);
+            agg_prolong_add(L.aggregates.ptr(), L.xc.ptr(), x.ptr(), xin, A.vec_prec, A.n, A.by, s);      // xin = x + P xc
         }
     } else {
         if (x_virtual_zero) x.zero(s);
         classical_prolong_add(L, x, s);
     }
-    if (n_post > 0) sm->smooth(b, x, false, n_post, have_fuse ? &f : nullptr);
+    if (n_post > 0) sm->smooth(b, x, false, n_post, have_fuse ? &f : nullptr, in_alt);
 }
 
 // print_grid_stats of the reference (src/amg.cu:1231-1350): same table layout

@@ -1,30 +1,565 @@
-// dist.cu -- multi-GPU layer.  (single-GPU behaviour: every exchange is a no-op)
+// dist.cu -- multi-GPU layer: NCCL bootstrap, distributed matrix construction (from the host partition
+// plan), halo exchange overlapped with interior rows, scalar all-reduces, distributed vectors.
+// See dist.h for what it replaces in the reference.  Single-GPU matrices (A.dist == null) make every
+// entry point here a no-op.
 #include "solvers.h"
 #include "dist.h"
 #include "capi_internal.h"
+#include <nccl.h>
+#include <algorithm>
+#include <numeric>
+
 namespace amgxb {
+
+#define AMGXB_NCCL_CHECK(expr)                                                                    \
+    do {                                                                                          \
+        ncclResult_t _r = (expr);                                                                 \
+        if (_r != ncclSuccess) {                                                                  \
+            char _b[512];                                                                         \
+            snprintf(_b, sizeof(_b), "NCCL error %s at %s:%d", ncclGetErrorString(_r), __FILE__, __LINE__); \
+            throw ::amgxb::Error(AMGX_RC_CORE, _b);                                               \
+        }                                                                                         \
+    } while (0)
+
 DistManager::~DistManager()
 {
     if (ev_pack) cudaEventDestroy(ev_pack);
     if (ev_done) cudaEventDestroy(ev_done);
     if (allreduce_buf) cudaFree(allreduce_buf);
 }
-void dist_destroy_comm(Resources *) {}
-void dist_exchange_halo(const Matrix &A, DevVec &, cudaStream_t) { if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "distributed halo exchange"); }
-void dist_exchange_halo_coarse(const Matrix &A, const void *, cudaStream_t) { if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "distributed halo exchange"); }
-double dist_reduce_norm(const Matrix &, double local, int) { return local; }
+
+void dist_get_unique_id(char *id128)
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    AMGXB_NCCL_CHECK(ncclGetUniqueId(&id));
+    memcpy(id128, &id, 128);
+}
+
+void dist_init_comm(Resources *rsc, const AMGXB200_comm *comm)
+{
+    ncclUniqueId id;
+    memcpy(&id, comm->nccl_unique_id, 128);
+    ncclComm_t c;
+    AMGXB_NCCL_CHECK(ncclCommInitRank(&c, comm->world_size, id, comm->rank));
+    rsc->nccl_comm = c;
+    rsc->rank = comm->rank;
+    rsc->world = comm->world_size;
+}
+
+void dist_destroy_comm(Resources *rsc)
+{
+    if (rsc->nccl_comm) {
+        ncclCommDestroy((ncclComm_t)rsc->nccl_comm);
+        rsc->nccl_comm = nullptr;
+    }
+}
+
+static ncclComm_t comm_of(const Matrix &A) { return (ncclComm_t)A.rsc->nccl_comm; }
+
+// ---------------------------------------------------------------------------------------------
+// small host-visible collectives used at setup time
+// ---------------------------------------------------------------------------------------------
+static void ensure_scratch(DistManager &m)
+{
+    if (!m.allreduce_buf) {
+        AMGXB_CUDA_CHECK(cudaMalloc(&m.allreduce_buf, 64 * sizeof(double)));
+        AMGXB_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_pack, cudaEventDisableTiming));
+        AMGXB_CUDA_CHECK(cudaEventCreateWithFlags(&m.ev_done, cudaEventDisableTiming));
+    }
+}
+
+long long dist_allreduce_ll(const Matrix &A, long long v, int op /*0 sum, 1 min, 2 max*/)
+{
+    if (!A.dist) return v;
+    DistManager &m = *A.dist;
+    ensure_scratch(m);
+    cudaStream_t s = A.stream();
+    long long *buf = reinterpret_cast<long long *>(m.allreduce_buf);
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(buf, &v, sizeof(v), cudaMemcpyHostToDevice, s));
+    AMGXB_NCCL_CHECK(ncclAllReduce(buf, buf, 1, ncclInt64, op == 0 ? ncclSum : op == 1 ? ncclMin : ncclMax, comm_of(A), s));
+    long long out;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&out, buf, sizeof(out), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// halo exchange
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <class T> __global__ void pack_kernel(const int *__restrict__ map, int count, int bsize, const T *__restrict__ x, T *__restrict__ buf)
+{
+    const long long total = (long long)count * bsize;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / bsize), c = (int)(t % bsize);
+        buf[t] = x[(size_t)map[k] * bsize + c];
+    }
+}
+__global__ void sqrt_mirror_kernel(double *scal, int slot, int do_sqrt, double *host_mirror)
+{
+    double v = scal[slot];
+    if (do_sqrt) v = sqrt(v);
+    scal[slot] = v;
+    if (host_mirror) host_mirror[slot] = v;
+    __threadfence_system();
+}
+__global__ void fin_kernel(double *scal, int slot, int fin_op)
+{
+    const double sum = scal[slot];
+    if (fin_op == FIN_PCG_ALPHA) {
+        scal[S_DOT] = sum;
+        const double a = (sum != 0.0) ? scal[S_RZ] / sum : 0.0;
+        scal[S_ALPHA] = a;
+        scal[S_NEG_ALPHA] = -a;
+    } else if (fin_op == FIN_PCG_BETA) {
+        const double old = scal[S_RZ];
+        scal[S_RZ_OLD] = old;
+        scal[S_RZ] = sum;
+        scal[S_BETA] = (old != 0.0) ? sum / old : 0.0;
+    } else if (fin_op == FIN_SQRT) {
+        scal[slot] = sqrt(sum);
+    }
+}
+}  // namespace
+
+// Start the exchange of x's halo: pack boundary values (compute stream), then send/recv on the side
+// stream.  matrix_apply waits for it only before the rows that read halo columns.
+template <class T> static void exchange_typed(const Matrix &A, T *x, int bsize, cudaStream_t s, ncclDataType_t dt)
+{
+    DistManager &m = *A.dist;
+    ensure_scratch(m);
+    const int nn = (int)m.neighbors.size();
+    if (nn == 0) return;
+    const int total_send = m.send_offsets[nn];
+    const size_t need = (size_t)total_send * bsize * sizeof(T);
+    if (m.send_buf.b.bytes < need) m.send_buf.b.resize(need);
+    T *buf = (T *)m.send_buf.b.p;
+    if (total_send) {
+        const int grid = std::min(ceil_div((long long)total_send * bsize, 256), 148 * 8);
+        pack_kernel<T><<<grid, 256, 0, s>>>(m.send_maps.ptr(), total_send, bsize, x, buf);
+        count_launch();
+        AMGXB_LAUNCH_CHECK();
+    }
+    cudaStream_t side = A.rsc->side_stream;
+    AMGXB_CUDA_CHECK(cudaEventRecord(m.ev_pack, s));
+    AMGXB_CUDA_CHECK(cudaStreamWaitEvent(side, m.ev_pack, 0));
+    AMGXB_NCCL_CHECK(ncclGroupStart());
+    for (int q = 0; q < nn; q++) {
+        const int sc = m.send_offsets[q + 1] - m.send_offsets[q], rc = m.halo_offsets[q + 1] - m.halo_offsets[q];
+        if (sc) AMGXB_NCCL_CHECK(ncclSend(buf + (size_t)m.send_offsets[q] * bsize, (size_t)sc * bsize, dt, m.neighbors[q], comm_of(A), side));
+        if (rc) AMGXB_NCCL_CHECK(ncclRecv(x + ((size_t)m.n_owned + m.halo_offsets[q]) * bsize, (size_t)rc * bsize, dt, m.neighbors[q], comm_of(A), side));
+    }
+    AMGXB_NCCL_CHECK(ncclGroupEnd());
+    AMGXB_CUDA_CHECK(cudaEventRecord(m.ev_done, side));
+    m.exchange_pending = true;
+}
+
+void dist_exchange_halo_ptr(const Matrix &A, void *x, Prec prec, cudaStream_t s)
+{
+    if (!A.dist) return;
+    if (A.dist->exchange_pending) dist_wait_halo(A, s);
+    const int bsize = A.bx;
+    if (prec == Prec::F64) exchange_typed<double>(A, (double *)x, bsize, s, ncclDouble);
+    else exchange_typed<float>(A, (float *)x, bsize, s, ncclFloat);
+}
+
+void dist_exchange_halo(const Matrix &A, DevVec &x, cudaStream_t s) { dist_exchange_halo_ptr(A, x.ptr(), x.prec, s); }
+
+void dist_wait_halo(const Matrix &A, cudaStream_t s)
+{
+    if (!A.dist || !A.dist->exchange_pending) return;
+    AMGXB_CUDA_CHECK(cudaStreamWaitEvent(s, A.dist->ev_done, 0));
+    A.dist->exchange_pending = false;
+}
+
+void dist_exchange_int(const Matrix &A, int *x, cudaStream_t s)
+{
+    if (!A.dist) return;
+    exchange_typed<int>(A, x, 1, s, ncclInt32);
+    dist_wait_halo(A, s);
+}
+
+void dist_exchange_halo_coarse(const Matrix &, const void *, cudaStream_t) {}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
 ReduceCtx dist_wrap_reduce(const Matrix &, const ReduceCtx &red) { return red; }
-void dist_allreduce_scalar_fin(const Matrix &, const ReduceCtx &, int, int, cudaStream_t) {}
+
+// scal[slot] holds this rank's partial sum: all-reduce it in place on the compute stream, then apply the
+// scalar epilogue on the device.
+void dist_allreduce_scalar_fin(const Matrix &A, const ReduceCtx &red, int slot, int fin_op, cudaStream_t s)
+{
+    if (!A.dist) return;
+    AMGXB_NCCL_CHECK(ncclAllReduce(red.scal + slot, red.scal + slot, 1, ncclDouble, ncclSum, comm_of(A), s));
+    if (fin_op != FIN_STORE) {
+        fin_kernel<<<1, 1, 0, s>>>(red.scal, slot, fin_op);
+        count_launch();
+        AMGXB_LAUNCH_CHECK();
+    }
 }
-namespace amgxb {
-void dist_get_unique_id(char *) { fatal(AMGX_RC_NOT_IMPLEMENTED, "NCCL bootstrap"); }
-void dist_init_comm(Resources *, const AMGXB200_comm *) { fatal(AMGX_RC_NOT_IMPLEMENTED, "multi-GPU resources"); }
-void dist_upload_local(Matrix &, int, int, int, int, const int *, const int *, const void *, const void *) { fatal(AMGX_RC_NOT_IMPLEMENTED, "distributed upload"); }
-void dist_prepare_vector(const Matrix &A, Vector &v) { if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "distributed vectors"); (void)v; }
-void dist_download_vector(const Vector &, void *) { fatal(AMGX_RC_NOT_IMPLEMENTED, "distributed vectors"); }
-void dist_generate_poisson7(Matrix &, int, int, int, int, int, int) { fatal(AMGX_RC_NOT_IMPLEMENTED, "distributed generator"); }
-void dist_upload_global(Matrix &, int, int, int, int, int, const int *, const void *, bool, const void *, const void *, int, const void *) { fatal(AMGX_RC_NOT_IMPLEMENTED, "distributed upload"); }
-void dist_comm_from_maps_one_ring(Matrix &, int, const int *, const int *, const int **, const int *, const int **) { fatal(AMGX_RC_NOT_IMPLEMENTED, "comm_from_maps"); }
-void partition_plan_create(AMGXB200_partition_plan *, int, int, const int64_t *, int, int, const int *, const int64_t *) { fatal(AMGX_RC_NOT_IMPLEMENTED, "partition planner"); }
+
+// norm of a distributed vector: scal[slot] holds the local sum (L1), sum of squares (L2) or max (LMAX)
+void dist_allreduce_norm(const Matrix &A, const ReduceCtx &red, int slot, int norm_type, cudaStream_t s)
+{
+    if (!A.dist) return;
+    AMGXB_NCCL_CHECK(ncclAllReduce(red.scal + slot, red.scal + slot, 1, ncclDouble, norm_type == 2 ? ncclMax : ncclSum, comm_of(A), s));
+    sqrt_mirror_kernel<<<1, 1, 0, s>>>(red.scal, slot, norm_type == 1, red.host_mirror);
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+}
+
+double dist_reduce_norm(const Matrix &, double local, int) { return local; }
+
+// ---------------------------------------------------------------------------------------------
+// y = op(A, x) with the halo exchange overlapped: rows [0, split) first, wait, rows [split, n)
+// ---------------------------------------------------------------------------------------------
+void matrix_apply(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s)
+{
+    if (A.bs() != 1) {
+        if (A.dist) dist_wait_halo(A, s);
+        block_apply(A, epi, args, s);
+        return;
+    }
+    if (A.has_ext_diag) fatal(AMGX_RC_INTERNAL, "scalar matrix with external diagonal must be merged at upload");
+    if (!A.dist) { csr_op(A, epi, args, s, 0); return; }
+    if (A.plan.split > 0 && A.dist->exchange_pending) {
+        csr_op(A, epi, args, s, 1);
+        dist_wait_halo(A, s);
+        csr_op(A, epi, args, s, 2);
+    } else {
+        dist_wait_halo(A, s);
+        csr_op(A, epi, args, s, 0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// building a distributed matrix from this rank's rows (global column ids)
+// ---------------------------------------------------------------------------------------------
+static std::shared_ptr<DistManager> manager_from_plan(Matrix &A, const AMGXB200_partition_plan &pl, const int64_t *offsets)
+{
+    auto m = std::make_shared<DistManager>();
+    m->rank = A.rsc->rank;
+    m->world = A.rsc->world;
+    m->n_owned = pl.n_owned;
+    m->n_interior = pl.n_interior;
+    m->n_halo = pl.n_halo;
+    m->neighbors.assign(pl.neighbors, pl.neighbors + pl.num_neighbors);
+    m->send_offsets.assign(pl.send_offsets, pl.send_offsets + pl.num_neighbors + 1);
+    m->halo_offsets.assign(pl.halo_offsets, pl.halo_offsets + pl.num_neighbors + 1);
+    m->send_maps.from_any(pl.send_maps, (size_t)m->send_offsets.back(), A.stream());
+    m->perm_old_to_new.from_any(pl.perm_old_to_new, (size_t)pl.n_owned, A.stream());
+    m->halo_global.assign(pl.halo_global, pl.halo_global + pl.n_halo);
+    m->global_offset = offsets[m->rank];
+    m->n_global = offsets[m->world];
+    return m;
+}
+
+// verify the structural-symmetry assumption of the planner: what I send to q must be what q expects
+static void verify_plan(const Matrix &A)
+{
+    DistManager &m = *A.dist;
+    const int nn = (int)m.neighbors.size();
+    if (nn == 0) return;
+    ensure_scratch(m);
+    cudaStream_t s = A.stream();
+    DevBuf<int> sendc, recvc;
+    std::vector<int> hs(nn), hr(nn, -1);
+    for (int q = 0; q < nn; q++) hs[q] = m.send_offsets[q + 1] - m.send_offsets[q];
+    sendc.from_any(hs.data(), nn, s);
+    recvc.resize(nn);
+    AMGXB_NCCL_CHECK(ncclGroupStart());
+    for (int q = 0; q < nn; q++) {
+        AMGXB_NCCL_CHECK(ncclSend(sendc.ptr() + q, 1, ncclInt32, m.neighbors[q], comm_of(A), s));
+        AMGXB_NCCL_CHECK(ncclRecv(recvc.ptr() + q, 1, ncclInt32, m.neighbors[q], comm_of(A), s));
+    }
+    AMGXB_NCCL_CHECK(ncclGroupEnd());
+    hr = recvc.to_host(s);
+    for (int q = 0; q < nn; q++)
+        if (hr[q] != m.halo_offsets[q + 1] - m.halo_offsets[q])
+            fatal(AMGX_RC_BAD_PARAMETERS, "distributed matrix is not structurally symmetric across partitions (send/halo size mismatch)");
+}
+
+// host arrays: rp[n+1], global cols[nnz], values (mat precision, nnz*bs), optional external diagonal
+void dist_build_matrix(Matrix &A, const int64_t *offsets, int n, int nnz, int bx, int by, const int *rp, const int64_t *cols, const void *vals,
+                       const void *diag)
+{
+    if (bx != by) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "rectangular blocks are not supported");
+    if (diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "distributed upload with an external diagonal");
+    AMGXB200_partition_plan pl;
+    memset(&pl, 0, sizeof(pl));
+    partition_plan_create(&pl, A.rsc->rank, A.rsc->world, offsets, n, nnz, rp, cols);
+    // permute rows into the local order
+    std::vector<int> inv(n);
+    for (int i = 0; i < n; i++) inv[pl.perm_old_to_new[i]] = i;
+    const size_t bs = (size_t)bx * by, msz = prec_size(A.mat_prec);
+    std::vector<int> rp2(n + 1), ci2(std::max(nnz, 1));
+    std::vector<char> va2(std::max<size_t>((size_t)nnz * bs * msz, 1));
+    size_t o = 0;
+    for (int p = 0; p < n; p++) {
+        const int i = inv[p];
+        rp2[p] = (int)o;
+        const int len = rp[i + 1] - rp[i];
+        memcpy(&ci2[o], pl.local_cols + rp[i], sizeof(int) * len);
+        memcpy(&va2[o * bs * msz], (const char *)vals + (size_t)rp[i] * bs * msz, (size_t)len * bs * msz);
+        o += len;
+    }
+    rp2[n] = (int)o;
+    cudaStream_t s = A.stream();
+    A.initialized = false;
+    A.n = n;
+    A.n_cols = n + pl.n_halo;
+    A.split_row = pl.n_interior;
+    A.nnz = nnz;
+    A.bx = bx;
+    A.by = by;
+    A.has_ext_diag = A.merged_ext_diag = false;
+    A.row_ptr.from_any(rp2.data(), n + 1, s);
+    A.col_idx.from_any(ci2.data(), nnz, s);
+    A.values.resize((size_t)nnz * bs, A.mat_prec);
+    if (nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(A.values.ptr(), va2.data(), (size_t)nnz * bs * msz, cudaMemcpyHostToDevice, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    A.dist = manager_from_plan(A, pl, offsets);
+    AMGXB200_partition_plan_free(&pl);
+    verify_plan(A);
+    A.compute_diag_and_plan();
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+void dist_upload_global(Matrix &A, int n_global, int n, int nnz, int bx, int by, const int *row_ptrs, const void *cols_global, bool cols32,
+                        const void *data, const void *diag_data, int partition_info, const void *partition_data)
+{
+    const int world = A.rsc->world, rank = A.rsc->rank;
+    std::vector<int64_t> offsets(world + 1, 0);
+    if (partition_info == AMGX_DIST_PARTITION_OFFSETS) {
+        if (!partition_data) fatal(AMGX_RC_BAD_PARAMETERS, "partition offsets missing");
+        for (int r = 0; r <= world; r++) offsets[r] = cols32 ? (int64_t)((const int *)partition_data)[r] : ((const int64_t *)partition_data)[r];
+    } else {
+        // partition vector: only contiguous, rank-ordered partitions are supported (the layout OFFSETS describes)
+        if (!partition_data) {
+            // default of the reference: equal contiguous blocks
+            for (int r = 0; r <= world; r++) offsets[r] = (int64_t)n_global * r / world;
+        } else {
+            const int *pv = (const int *)partition_data;
+            std::vector<int64_t> cnt(world, 0);
+            for (int g = 0; g < n_global; g++) {
+                if (pv[g] < 0 || pv[g] >= world || (g > 0 && pv[g] < pv[g - 1]))
+                    fatal(AMGX_RC_NOT_IMPLEMENTED, "only contiguous, rank-ordered partition vectors are supported by this engine");
+                cnt[pv[g]]++;
+            }
+            for (int r = 0; r < world; r++) offsets[r + 1] = offsets[r] + cnt[r];
+        }
+    }
+    if (offsets[world] != n_global || offsets[rank + 1] - offsets[rank] != n) fatal(AMGX_RC_BAD_PARAMETERS, "partition does not match n / n_global");
+    // bring everything to the host
+    const size_t bs = (size_t)bx * by, msz = prec_size(A.mat_prec);
+    std::vector<int> rp(n + 1);
+    AMGXB_CUDA_CHECK(cudaMemcpy(rp.data(), row_ptrs, sizeof(int) * (n + 1), cudaMemcpyDefault));
+    std::vector<int64_t> cols(std::max(nnz, 1));
+    if (cols32) {
+        std::vector<int> c32(std::max(nnz, 1));
+        if (nnz) AMGXB_CUDA_CHECK(cudaMemcpy(c32.data(), cols_global, sizeof(int) * nnz, cudaMemcpyDefault));
+        for (int k = 0; k < nnz; k++) cols[k] = c32[k];
+    } else if (nnz) AMGXB_CUDA_CHECK(cudaMemcpy(cols.data(), cols_global, sizeof(int64_t) * nnz, cudaMemcpyDefault));
+    std::vector<char> vals(std::max<size_t>((size_t)nnz * bs * msz, 1));
+    if (nnz) AMGXB_CUDA_CHECK(cudaMemcpy(vals.data(), data, (size_t)nnz * bs * msz, cudaMemcpyDefault));
+    if (world == 1) {
+        std::vector<int> c32(std::max(nnz, 1));
+        for (int k = 0; k < nnz; k++) c32[k] = (int)cols[k];
+        upload_matrix(A, n, nnz, bx, by, rp.data(), c32.data(), vals.data(), diag_data);
+        return;
+    }
+    dist_build_matrix(A, offsets.data(), n, nnz, bx, by, rp.data(), cols.data(), vals.data(), diag_data);
+}
+
+void dist_upload_local(Matrix &, int, int, int, int, const int *, const int *, const void *, const void *)
+{
+    fatal(AMGX_RC_NOT_IMPLEMENTED, "upload with user-supplied comm maps");
+}
+void dist_comm_from_maps_one_ring(Matrix &, int, const int *, const int *, const int **, const int *, const int **)
+{
+    fatal(AMGX_RC_NOT_IMPLEMENTED, "AMGX_matrix_comm_from_maps_one_ring: use AMGX_matrix_upload_distributed / _all_global");
+}
+
+// 7-point Poisson on a px*py*pz process grid, each rank an nx*ny*nz box (the reference's generator
+// semantics: nx,ny,nz are PER RANK, src/amgx_c.cu:1690-1735).  Global numbering is rank-major: rank r owns
+// global rows [r*nloc, (r+1)*nloc), local lexicographic order inside the box.
+void dist_generate_poisson7(Matrix &A, int nx, int ny, int nz, int px, int py, int pz)
+{
+    const int world = A.rsc->world, rank = A.rsc->rank;
+    const long long nloc = (long long)nx * ny * nz;
+    if (nloc * 7 >= (1ll << 31)) fatal(AMGX_RC_BAD_PARAMETERS, "local grid too large for 32-bit indices");
+    const int rx = rank % px, ry = (rank / px) % py, rz = rank / (px * py);
+    std::vector<int64_t> offsets(world + 1);
+    for (int r = 0; r <= world; r++) offsets[r] = nloc * r;
+    std::vector<int> rp((size_t)nloc + 1);
+    std::vector<int64_t> cols;
+    std::vector<double> vals;
+    cols.reserve((size_t)nloc * 7);
+    vals.reserve((size_t)nloc * 7);
+    auto gid = [&](int qx, int qy, int qz, int i, int j, int k) -> int64_t {
+        const int q = qx + px * (qy + py * qz);
+        return nloc * q + i + (long long)nx * (j + (long long)ny * k);
+    };
+    for (int k = 0; k < nz; k++)
+        for (int j = 0; j < ny; j++)
+            for (int i = 0; i < nx; i++) {
+                const size_t r = i + (size_t)nx * (j + (size_t)ny * k);
+                rp[r] = (int)cols.size();
+                cols.push_back(gid(rx, ry, rz, i, j, k)); vals.push_back(6.0);
+                if (i > 0) { cols.push_back(gid(rx, ry, rz, i - 1, j, k)); vals.push_back(-1.0); }
+                else if (rx > 0) { cols.push_back(gid(rx - 1, ry, rz, nx - 1, j, k)); vals.push_back(-1.0); }
+                if (i < nx - 1) { cols.push_back(gid(rx, ry, rz, i + 1, j, k)); vals.push_back(-1.0); }
+                else if (rx < px - 1) { cols.push_back(gid(rx + 1, ry, rz, 0, j, k)); vals.push_back(-1.0); }
+                if (j > 0) { cols.push_back(gid(rx, ry, rz, i, j - 1, k)); vals.push_back(-1.0); }
+                else if (ry > 0) { cols.push_back(gid(rx, ry - 1, rz, i, ny - 1, k)); vals.push_back(-1.0); }
+                if (j < ny - 1) { cols.push_back(gid(rx, ry, rz, i, j + 1, k)); vals.push_back(-1.0); }
+                else if (ry < py - 1) { cols.push_back(gid(rx, ry + 1, rz, i, 0, k)); vals.push_back(-1.0); }
+                if (k > 0) { cols.push_back(gid(rx, ry, rz, i, j, k - 1)); vals.push_back(-1.0); }
+                else if (rz > 0) { cols.push_back(gid(rx, ry, rz - 1, i, j, nz - 1)); vals.push_back(-1.0); }
+                if (k < nz - 1) { cols.push_back(gid(rx, ry, rz, i, j, k + 1)); vals.push_back(-1.0); }
+                else if (rz < pz - 1) { cols.push_back(gid(rx, ry, rz + 1, i, j, 0)); vals.push_back(-1.0); }
+            }
+    rp[nloc] = (int)cols.size();
+    const int nnz = (int)cols.size();
+    if (A.mat_prec == Prec::F64) dist_build_matrix(A, offsets.data(), (int)nloc, nnz, 1, 1, rp.data(), cols.data(), vals.data(), nullptr);
+    else {
+        std::vector<float> vf(vals.begin(), vals.end());
+        dist_build_matrix(A, offsets.data(), (int)nloc, nnz, 1, 1, rp.data(), cols.data(), vf.data(), nullptr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// distributed vectors: the caller's order (partition order) <-> local order [interior|boundary|halo]
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <class T> __global__ void permute_kernel(const int *__restrict__ perm, int n, int bsize, const T *__restrict__ in, T *__restrict__ out, int forward)
+{
+    const long long total = (long long)n * bsize;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / bsize), c = (int)(t % bsize);
+        if (forward) out[(size_t)perm[i] * bsize + c] = in[t];      // out[new] = in[old]
+        else out[t] = in[(size_t)perm[i] * bsize + c];             // out[old] = in[new]
+    }
+}
+}  // namespace
+
+void dist_prepare_vector(const Matrix &A, Vector &v)
+{
+    if (!A.dist) return;
+    DistManager &m = *A.dist;
+    const int bd = std::max(1, v.block_dim);
+    const size_t need = (size_t)(m.n_owned + m.n_halo) * bd;
+    cudaStream_t s = A.stream();
+    if (v.dist.get() == &m && !v.user_order && v.data.n >= need) return;
+    if (v.n != m.n_owned) fatal(AMGX_RC_BAD_PARAMETERS, "distributed vector size does not match the matrix partition");
+    if (v.user_order) {
+        DevVec nv;
+        nv.resize(need, v.prec);
+        nv.zero(s);
+        const int grid = std::min(ceil_div((long long)m.n_owned * bd, 256), 148 * 8);
+        if (v.prec == Prec::F64) permute_kernel<double><<<grid, 256, 0, s>>>(m.perm_old_to_new.ptr(), m.n_owned, bd, v.data.as<double>(), nv.as<double>(), 1);
+        else permute_kernel<float><<<grid, 256, 0, s>>>(m.perm_old_to_new.ptr(), m.n_owned, bd, v.data.as<float>(), nv.as<float>(), 1);
+        count_launch();
+        AMGXB_LAUNCH_CHECK();
+        AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+        v.data.swap(nv);
+    } else if (v.data.n < need) {
+        DevVec nv;
+        nv.resize(need, v.prec);
+        nv.zero(s);
+        AMGXB_CUDA_CHECK(cudaMemcpyAsync(nv.ptr(), v.data.ptr(), (size_t)m.n_owned * bd * prec_size(v.prec), cudaMemcpyDeviceToDevice, s));
+        AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+        v.data.swap(nv);
+    }
+    v.dist = A.dist;
+    v.user_order = false;
+}
+
+void dist_download_vector(const Vector &v, void *data)
+{
+    DistManager &m = *v.dist;
+    const int bd = std::max(1, v.block_dim);
+    cudaStream_t s = v.rsc->stream;
+    DevVec tmp;
+    tmp.resize((size_t)m.n_owned * bd, v.prec);
+    const int grid = std::min(ceil_div((long long)m.n_owned * bd, 256), 148 * 8);
+    if (v.prec == Prec::F64) permute_kernel<double><<<grid, 256, 0, s>>>(m.perm_old_to_new.ptr(), m.n_owned, bd, v.data.as<double>(), tmp.as<double>(), 0);
+    else permute_kernel<float><<<grid, 256, 0, s>>>(m.perm_old_to_new.ptr(), m.n_owned, bd, v.data.as<float>(), tmp.as<float>(), 0);
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(data, tmp.ptr(), tmp.nbytes(), cudaMemcpyDefault, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+// ---------------------------------------------------------------------------------------------
+// coarse-level communication pattern of an aggregation level (setup time, host bookkeeping).
+// In: aggregates[n_owned] with ids 0..n_agg-1.  Out: aggregates[n_cols] -- owned part relabelled so
+// that aggregates containing a boundary row come last (coarse rows [0, n_interior_c) then reference no
+// halo column), halo part = local ids (n_agg + k) of the neighbours' aggregates -- and the coarse manager.
+// Replaces the reference's setNeighborAggregates / createRenumbering bookkeeping
+// (src/aggregation/aggregation_amg_level.cu:1720-1870).
+// ---------------------------------------------------------------------------------------------
+std::shared_ptr<DistManager> dist_coarsen(const Matrix &A, DevBuf<int> &aggregates, int n_agg, int *n_interior_c)
+{
+    DistManager &m = *A.dist;
+    cudaStream_t s = A.stream();
+    const int n = m.n_owned, nn = (int)m.neighbors.size();
+    std::vector<int> h(n);
+    if (n) AMGXB_CUDA_CHECK(cudaMemcpyAsync(h.data(), aggregates.ptr(), sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<char> bnd(std::max(n_agg, 1), 0);
+    for (int i = m.n_interior; i < n; i++) bnd[h[i]] = 1;
+    std::vector<int> newid(std::max(n_agg, 1));
+    int c = 0;
+    for (int I = 0; I < n_agg; I++) if (!bnd[I]) newid[I] = c++;
+    *n_interior_c = c;
+    for (int I = 0; I < n_agg; I++) if (bnd[I]) newid[I] = c++;
+    for (int i = 0; i < n; i++) h[i] = newid[h[i]];
+    DevBuf<int> ext;
+    ext.resize((size_t)n + m.n_halo);
+    ext.zero(s);
+    if (n) AMGXB_CUDA_CHECK(cudaMemcpyAsync(ext.ptr(), h.data(), sizeof(int) * n, cudaMemcpyHostToDevice, s));
+    dist_exchange_int(A, ext.ptr(), s);
+    std::vector<int> hh(std::max(m.n_halo, 1));
+    if (m.n_halo) AMGXB_CUDA_CHECK(cudaMemcpyAsync(hh.data(), ext.ptr() + n, sizeof(int) * m.n_halo, cudaMemcpyDeviceToHost, s));
+    std::vector<int> smap = m.send_maps.to_host(s);
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    auto cm = std::make_shared<DistManager>();
+    cm->rank = m.rank;
+    cm->world = m.world;
+    cm->n_owned = n_agg;
+    cm->n_interior = *n_interior_c;
+    cm->neighbors = m.neighbors;
+    cm->halo_offsets.assign(1, 0);
+    cm->send_offsets.assign(1, 0);
+    std::vector<int> csend;
+    for (int q = 0; q < nn; q++) {
+        // coarse halo from q: unique remote coarse ids, ascending
+        std::vector<int> u(hh.begin() + m.halo_offsets[q], hh.begin() + m.halo_offsets[q + 1]);
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        const int base = n_agg + cm->halo_offsets.back();
+        for (int k = m.halo_offsets[q]; k < m.halo_offsets[q + 1]; k++)
+            hh[k] = base + (int)(std::lower_bound(u.begin(), u.end(), hh[k]) - u.begin());
+        cm->halo_offsets.push_back(cm->halo_offsets.back() + (int)u.size());
+        // coarse send map to q: unique aggregates of the fine rows q needs, ascending
+        std::vector<int> sq;
+        for (int k = m.send_offsets[q]; k < m.send_offsets[q + 1]; k++) sq.push_back(h[smap[k]]);
+        std::sort(sq.begin(), sq.end());
+        sq.erase(std::unique(sq.begin(), sq.end()), sq.end());
+        csend.insert(csend.end(), sq.begin(), sq.end());
+        cm->send_offsets.push_back((int)csend.size());
+    }
+    cm->n_halo = cm->halo_offsets.back();
+    cm->send_maps.from_any(csend.data(), csend.size(), s);
+    if (m.n_halo) AMGXB_CUDA_CHECK(cudaMemcpyAsync(ext.ptr() + n, hh.data(), sizeof(int) * m.n_halo, cudaMemcpyHostToDevice, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    aggregates.swap(ext);
+    return cm;
+}
+
 void attach_user_coloring(Matrix &, const int *, int, int) { fatal(AMGX_RC_NOT_IMPLEMENTED, "attach_coloring"); }
-}
+
+}  // namespace amgxb

@@ -26,13 +26,21 @@ struct DistManager {
     int64_t global_offset = 0;           // first global row owned by this rank
     int64_t n_global = 0;
     cudaEvent_t ev_pack = nullptr, ev_done = nullptr;
-    double *allreduce_buf = nullptr;     // device, 8 doubles
+    double *allreduce_buf = nullptr;     // device scratch for setup-time collectives
+    bool exchange_pending = false;       // a halo exchange is in flight on the side stream
+    DevBuf<int> halo_int;                // scratch for integer halo exchanges
     ~DistManager();
 };
 
 // ---- halo exchange (no-ops on a single GPU) ----
 void dist_exchange_halo(const Matrix &A, DevVec &x, cudaStream_t s);
+void dist_exchange_halo_ptr(const Matrix &A, void *x, Prec prec, cudaStream_t s);
 void dist_exchange_halo_coarse(const Matrix &A, const void *xc, cudaStream_t s);   // vector living on the NEXT level
+void dist_wait_halo(const Matrix &A, cudaStream_t s);                              // make `s` wait for the exchange in flight
+void dist_exchange_int(const Matrix &A, int *x, cudaStream_t s);                   // blocking (stream-ordered) int exchange, x has n_cols entries
+long long dist_allreduce_ll(const Matrix &A, long long v, int op);                 // host value, op: 0 sum, 1 min, 2 max
+std::shared_ptr<DistManager> dist_coarsen(const Matrix &A, DevBuf<int> &aggregates, int n_agg, int *n_interior_c);
+void dist_allreduce_norm(const Matrix &A, const ReduceCtx &red, int slot, int norm_type, cudaStream_t s);
 double dist_reduce_norm(const Matrix &A, double local, int norm_type);             // host value in, global value out
 ReduceCtx dist_wrap_reduce(const Matrix &A, const ReduceCtx &red);
 void dist_allreduce_scalar_fin(const Matrix &A, const ReduceCtx &red, int slot, int fin_op, cudaStream_t s);
@@ -43,8 +51,8 @@ void matrix_apply(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream
 // ---- block-size > 1 helpers (k_block.cu) ----
 void block_norms(const DevVec &v, int n, int bsize, int norm_type, const ReduceCtx &red, ScalarBlock &sb, std::vector<double> &out, cudaStream_t s);
 void block_jacobi_setup(const Matrix &A, DevVec &dinv, cudaStream_t s);   // dinv <- inverse of diagonal blocks (in place)
-void block_jacobi_zero(const Matrix &A, const DevVec &dinv, const DevVec &b, DevVec &x, double omega, cudaStream_t s);
-void block_jacobi_sweep(const Matrix &A, const DevVec &dinv, const DevVec &b, const DevVec &x, DevVec &xout, double omega, cudaStream_t s);
+void block_jacobi_zero(const Matrix &A, const DevVec &dinv, const DevVec &b, void *x, double omega, cudaStream_t s);
+void block_jacobi_sweep(const Matrix &A, const DevVec &dinv, const DevVec &b, const void *x, void *xout, double omega, cudaStream_t s);
 void l1_row_norms(const Matrix &A, DevVec &d, cudaStream_t s);
 
 double device_mem_used_gb();

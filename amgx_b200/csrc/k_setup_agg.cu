@@ -381,7 +381,7 @@ void galerkin_aggregation(const Matrix &A, const DevBuf<int> &aggregates, int n_
     galerkin_keys_kernel<<<grid_for(n), 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), aggregates.ptr(), n, keys.ptr(), idx.ptr());
     count_launch();
     int bits = 1;
-    while ((1ll << bits) < (long long)n_agg) bits++;
+    while ((1ll << bits) < (long long)n_agg) bits++;   // row part of the key; the column part (incl. halo aggregates) uses the low 32 bits
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.ptr(), keys_sorted.ptr(), idx.ptr(), idx_sorted.ptr(), nnz, 0, 32 + bits, s);
     DevBytes tmp;

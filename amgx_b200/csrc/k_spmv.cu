@@ -147,7 +147,8 @@ template <class MatT, class VecT> struct TileArgs {
     const int *row_ptr;
     const int *col;
     const MatT *val;
-    int n, num_tiles, cap, stages;
+    int n, num_tiles, cap, stages;   // n = end row of the segment
+    int row0;                        // first row of the segment (multiple of 4)
     const VecT *x;
     const int *agg;
     const VecT *b;
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
                 const int s = it % a.stages;
                 const unsigned ph = (unsigned)(it / a.stages) & 1u;
                 if (it >= a.stages) mbar_wait(&empty[s], ph ^ 1u);
-                const int r0 = tile * TILE_ROWS;
+                const int r0 = a.row0 + tile * TILE_ROWS;
                 const int r1 = min(r0 + TILE_ROWS, a.n);
                 const int nz0 = __ldg(a.row_ptr + r0), nz1 = __ldg(a.row_ptr + r1);
                 const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
             const int tile = blockIdx.x + it * gridDim.x;
             const int s = it % a.stages;
             const unsigned ph = (unsigned)(it / a.stages) & 1u;
-            const int row = tile * TILE_ROWS + tid;
+            const int row = a.row0 + tile * TILE_ROWS + tid;
             const bool active = row < a.n;
             // operands that do not depend on the staged tile: issue their loads before waiting
             VecT bi = 0, xi = 0;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256) csr_vector_kernel(const TileArgs<MatT, Ve
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     double acc = 0.0;
-    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.n; row += gridDim.x * warps_per_block) {
+    for (int row = a.row0 + blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.n; row += gridDim.x * warps_per_block) {
         const int k0 = __ldg(a.row_ptr + row), k1 = __ldg(a.row_ptr + row + 1);
         VecT sum = 0;
         for (int k = k0 + lane; k < k1; k += 32) sum = fma((VecT)__ldg(a.val + k), gather<VecT, AGG>(a.x, a.agg, __ldg(a.col + k)), sum);
@@ -355,10 +356,10 @@ __global__ void find_diag_kernel(const int *row_ptr, const int *col, int n, int 
     }
 }
 
-__global__ void tile_stats_kernel(const int *row_ptr, int n, int tile_rows, int num_tiles, int *max_tile_nnz, int *max_row_nnz)
+__global__ void tile_stats_kernel(const int *row_ptr, int row0, int n, int tile_rows, int num_tiles, int *max_tile_nnz, int *max_row_nnz)
 {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < num_tiles; t += gridDim.x * blockDim.x) {
-        int r0 = t * tile_rows, r1 = min(r0 + tile_rows, n);
+        int r0 = row0 + t * tile_rows, r1 = min(r0 + tile_rows, n);
         int sa = row_ptr[r0] & ~3, ea = (row_ptr[r1] + 3) & ~3;
         atomicMax(max_tile_nnz, ea - sa);
     }
@@ -390,11 +391,11 @@ template <class MatT, class VecT, int TILE_ROWS, int EPI> void launch_tile(const
 template <class MatT, class VecT, int EPI> void launch_epi(const Matrix &A, const TileArgs<MatT, VecT> &ta, cudaStream_t s)
 {
     if (A.plan.use_tiles) {
-        const int grid = csr_max_grid(A);
+        const int grid = std::max(1, std::min(csr_max_grid(A), ta.num_tiles));
         if (A.plan.tile_rows == 256) launch_tile<MatT, VecT, 256, EPI>(A, ta, grid, s);
         else launch_tile<MatT, VecT, 128, EPI>(A, ta, grid, s);
     } else {
-        const int grid = csr_max_grid(A);
+        const int grid = std::max(1, std::min(csr_max_grid(A), ceil_div(ta.n - ta.row0, 8)));
         if (ta.agg) csr_vector_kernel<MatT, VecT, EPI, true><<<grid, 256, 0, s>>>(ta);
         else csr_vector_kernel<MatT, VecT, EPI, false><<<grid, 256, 0, s>>>(ta);
     }
@@ -431,8 +432,14 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
     DevBuf<int> stats;
     stats.resize(2);
     stats.zero(s);
-    tile_stats_kernel<<<std::min(ceil_div(A.n, 256), 1024), 256, 0, s>>>(A.row_ptr.ptr(), A.n, p.tile_rows, p.num_tiles, stats.ptr(), stats.ptr() + 1);
+    tile_stats_kernel<<<std::min(ceil_div(A.n, 256), 1024), 256, 0, s>>>(A.row_ptr.ptr(), 0, A.n, p.tile_rows, p.num_tiles, stats.ptr(), stats.ptr() + 1);
     count_launch();
+    p.split = (A.split_row / 4) * 4;   // distributed: rows [0, split) never touch halo columns
+    if (p.split > 0 && p.split < A.n) {
+        tile_stats_kernel<<<std::min(ceil_div(A.n, 256), 1024), 256, 0, s>>>(A.row_ptr.ptr(), 0, p.split, p.tile_rows, ceil_div(p.split, p.tile_rows), stats.ptr(), stats.ptr() + 1);
+        tile_stats_kernel<<<std::min(ceil_div(A.n, 256), 1024), 256, 0, s>>>(A.row_ptr.ptr(), p.split, A.n, p.tile_rows, ceil_div(A.n - p.split, p.tile_rows), stats.ptr(), stats.ptr() + 1);
+        count_launch(2);
+    } else p.split = 0;
     AMGXB_LAUNCH_CHECK();
     std::vector<int> h = stats.to_host(s);
     p.max_tile_nnz = std::max(4, h[0]);
@@ -447,17 +454,22 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
     A.plan = p;
 }
 
-void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s)
+void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int segment)
 {
     if (A.bs() != 1) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "csr_op: scalar kernel called on a block matrix");
     if (A.n == 0) return;
+    // segment 0: all rows; 1: rows [0, split) (no halo columns); 2: rows [split, n)
+    const int row0 = (segment == 2) ? A.plan.split : 0;
+    const int row1 = (segment == 1) ? A.plan.split : A.n;
+    if (row1 <= row0) return;
     AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
         TileArgs<MatT, VecT> ta;
         ta.row_ptr = A.row_ptr.ptr();
         ta.col = A.col_idx.ptr();
         ta.val = A.values.as<MatT>();
-        ta.n = A.n;
-        ta.num_tiles = A.plan.num_tiles;
+        ta.n = row1;
+        ta.row0 = row0;
+        ta.num_tiles = ceil_div(row1 - row0, std::max(1, A.plan.tile_rows));
         ta.cap = A.plan.max_tile_nnz;
         ta.stages = A.plan.stages;
         ta.x = (const VecT *)g.x;

@@ -31,12 +31,12 @@ template <class VecT> __global__ void restrict_block_kernel(const int *__restric
     }
 }
 
-template <class VecT> __global__ void prolong_kernel(const int *__restrict__ agg, const VecT *__restrict__ e, VecT *__restrict__ x, int n, int bsize)
+template <class VecT> __global__ void prolong_kernel(const int *__restrict__ agg, const VecT *__restrict__ e, const VecT *x, VecT *xout, int n, int bsize)
 {
     const long long total = (long long)n * bsize;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(t / bsize), m = (int)(t % bsize);
-        x[t] = x[t] + __ldg(e + (size_t)agg[i] * bsize + m);   // alpha == 1
+        xout[t] = x[t] + __ldg(e + (size_t)agg[i] * bsize + m);   // alpha == 1
     }
 }
 
@@ -78,12 +78,12 @@ void agg_restrict(const int *Rp, const int *Rc, const void *r, void *rc, Prec p,
     AMGXB_LAUNCH_CHECK();
 }
 
-void agg_prolong_add(const int *aggregates, const void *e, void *x, Prec p, int n, int bsize, cudaStream_t s)
+void agg_prolong_add(const int *aggregates, const void *e, const void *x, void *xout, Prec p, int n, int bsize, cudaStream_t s)
 {
     if (n == 0) return;
     AMGXB_DISPATCH_VEC(p, {
         int grid = std::min(ceil_div((long long)n * bsize, 256), 148 * 16);
-        prolong_kernel<VecT><<<grid, 256, 0, s>>>(aggregates, (const VecT *)e, (VecT *)x, n, bsize);
+        prolong_kernel<VecT><<<grid, 256, 0, s>>>(aggregates, (const VecT *)e, (const VecT *)x, (VecT *)xout, n, bsize);
     });
     count_launch();
     AMGXB_LAUNCH_CHECK();

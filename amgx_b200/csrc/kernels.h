@@ -62,7 +62,7 @@ struct CsrOpArgs {
     int mirror = 0;               // write final value to red.host_mirror[fin_slot]
 };
 
-void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s);
+void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s, int segment = 0);
 // Build diag_idx and the tile plan of A (called once per matrix at upload / level creation).
 void csr_build_plan(Matrix &A, cudaStream_t s);
 int  csr_max_grid(const Matrix &A);     // number of CTAs csr_op launches (partials sizing)
@@ -96,7 +96,7 @@ int  blas_max_grid();
 // Aggregation transfer operators (k_transfer.cu)
 // -------------------------------------------------------------------------------------------
 void agg_restrict(const int *R_row_offsets, const int *R_col, const void *r, void *rc, Prec p, int n_agg, int bsize, cudaStream_t s);
-void agg_prolong_add(const int *aggregates, const void *e, void *x, Prec p, int n, int bsize, cudaStream_t s);
+void agg_prolong_add(const int *aggregates, const void *e, const void *x, void *xout, Prec p, int n, int bsize, cudaStream_t s);   // xout = x + P e
 void agg_prolong_set(const int *aggregates, const void *e, void *x, Prec p, int n, int bsize, cudaStream_t s);   // x = P e (x was zero)
 
 // -------------------------------------------------------------------------------------------

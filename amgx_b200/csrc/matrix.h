@@ -31,6 +31,7 @@ struct TilePlan {
     int stages = 0;             // pipeline depth chosen for this matrix
     size_t smem_bytes = 0;      // dynamic shared memory per CTA
     bool use_tiles = false;     // false -> generic warp-per-row kernel
+    int split = 0;              // distributed: first row (multiple of 4) of the segment that reads halo columns
 };
 
 struct Matrix {
@@ -39,6 +40,7 @@ struct Matrix {
     Prec mat_prec = Prec::F64, vec_prec = Prec::F64;
     int n = 0;            // owned block rows
     int n_cols = 0;       // owned + halo block columns (== n on a single GPU)
+    int split_row = 0;    // distributed: number of interior rows (rows [0, split_row) reference no halo column)
     int nnz = 0;          // stored blocks (without external diagonal)
     int bx = 1, by = 1;
     bool has_ext_diag = false;

@@ -46,16 +46,6 @@ void Matrix::compute_diag_and_plan()
     initialized = true;
 }
 
-void matrix_apply(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s)
-{
-    if (A.bs() == 1) {
-        if (A.has_ext_diag) fatal(AMGX_RC_INTERNAL, "scalar matrix with external diagonal must be merged at upload");
-        csr_op(A, epi, args, s);
-    } else {
-        block_apply(A, epi, args, s);
-    }
-}
-
 namespace {
 template <class MatT, class VecT> __global__ void l1_kernel(int n, const int *__restrict__ rp, const int *__restrict__ col, const MatT *__restrict__ val, MatT *__restrict__ d)
 {

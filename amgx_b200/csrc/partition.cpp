@@ -1,0 +1,114 @@
+// partition.cpp -- pure host partition planner (no CUDA calls): local renumbering of a row-partitioned
+// matrix into [interior | boundary | halo], per-neighbour send maps (the reference's B2L maps) and halo
+// layout.  Replaces, for contiguous row partitions, what DistributedManager / DistributedArranger derive
+// in the reference (include/distributed/distributed_manager.h:940-952, include/vector.h:10-28,
+// src/distributed/distributed_arranger.cu).  Exposed through AMGXB200_partition_plan_create so that the
+// CPU (gloo) tests can exercise it without a GPU.
+//
+// Conventions:
+//  * rank r owns global rows [offsets[r], offsets[r+1]).
+//  * halo columns are grouped by owning rank (ascending), inside a group sorted by global id; the k-th
+//    halo column gets local id n_owned + k.
+//  * boundary rows = owned rows with at least one halo column; they are renumbered after the interior
+//    rows (both groups keep their relative order), so rows [0, n_interior) never touch remote data and can
+//    be processed while the halo exchange is in flight.
+//  * send map for neighbour q = my rows (renumbered ids) that q needs, in ascending GLOBAL id order.  The
+//    matrix pattern is assumed structurally symmetric across partitions (row i references a column of q
+//    <=> q references row i), which makes the send side derivable locally; the engine verifies the
+//    neighbours' halo sizes against these maps when the communicator is built.
+#include "capi_internal.h"
+#include <algorithm>
+#include <numeric>
+
+namespace amgxb {
+
+static int owner_of(int64_t g, const int64_t *offsets, int world)
+{
+    const int64_t *p = std::upper_bound(offsets, offsets + world + 1, g);
+    return (int)(p - offsets) - 1;
+}
+
+template <class T> static T *dup(const std::vector<T> &v)
+{
+    T *p = (T *)malloc(sizeof(T) * std::max<size_t>(v.size(), 1));
+    if (!p) fatal(AMGX_RC_NO_MEMORY, "partition plan: out of host memory");
+    if (!v.empty()) memcpy(p, v.data(), sizeof(T) * v.size());
+    return p;
+}
+
+void partition_plan_create(AMGXB200_partition_plan *plan, int rank, int world, const int64_t *offsets, int n, int nnz, const int *row_ptrs,
+                           const int64_t *cols)
+{
+    if (world < 1 || rank < 0 || rank >= world || !offsets || n < 0 || !row_ptrs) fatal(AMGX_RC_BAD_PARAMETERS, "partition plan: bad arguments");
+    const int64_t lo = offsets[rank], hi = offsets[rank + 1];
+    if (hi - lo != n) fatal(AMGX_RC_BAD_PARAMETERS, "partition plan: n does not match the partition offsets");
+    if (row_ptrs[n] != nnz) fatal(AMGX_RC_BAD_PARAMETERS, "partition plan: nnz does not match row_ptrs");
+    const int64_t n_global = offsets[world];
+    // ---- halo columns: unique (owner, global id) ----
+    std::vector<int64_t> halo;
+    std::vector<char> is_boundary(n, 0);
+    for (int i = 0; i < n; i++)
+        for (int k = row_ptrs[i]; k < row_ptrs[i + 1]; k++) {
+            const int64_t g = cols[k];
+            if (g < 0 || g >= n_global) fatal(AMGX_RC_BAD_PARAMETERS, "partition plan: column index out of range");
+            if (g < lo || g >= hi) { halo.push_back(g); is_boundary[i] = 1; }
+        }
+    std::sort(halo.begin(), halo.end());     // global order == (owner, id) order for contiguous partitions
+    halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+    std::vector<int> neighbors, halo_offsets{0};
+    for (size_t k = 0; k < halo.size(); k++) {
+        const int o = owner_of(halo[k], offsets, world);
+        if (neighbors.empty() || neighbors.back() != o) {
+            if (!neighbors.empty()) halo_offsets.push_back((int)k);
+            neighbors.push_back(o);
+        }
+    }
+    halo_offsets.push_back((int)halo.size());
+    if (neighbors.empty()) halo_offsets = {0};
+    // ---- renumber owned rows: interior first, then boundary ----
+    std::vector<int> perm(n);
+    int n_interior = 0;
+    for (int i = 0; i < n; i++) if (!is_boundary[i]) perm[i] = n_interior++;
+    int nb = n_interior;
+    for (int i = 0; i < n; i++) if (is_boundary[i]) perm[i] = nb++;
+    // ---- send maps: rows that reference a column of neighbour q, ascending global id ----
+    const int nn = (int)neighbors.size();
+    std::vector<int> nb_index(world, -1);
+    for (int q = 0; q < nn; q++) nb_index[neighbors[q]] = q;
+    std::vector<std::vector<int>> sends(nn);
+    std::vector<int> last_mark(nn, -1);
+    for (int i = 0; i < n; i++) {
+        if (!is_boundary[i]) continue;
+        for (int k = row_ptrs[i]; k < row_ptrs[i + 1]; k++) {
+            const int64_t g = cols[k];
+            if (g >= lo && g < hi) continue;
+            const int q = nb_index[owner_of(g, offsets, world)];
+            if (last_mark[q] != i) { last_mark[q] = i; sends[q].push_back(perm[i]); }
+        }
+    }
+    std::vector<int> send_offsets{0}, send_maps;
+    for (int q = 0; q < nn; q++) {
+        send_maps.insert(send_maps.end(), sends[q].begin(), sends[q].end());
+        send_offsets.push_back((int)send_maps.size());
+    }
+    // ---- local column ids ----
+    std::vector<int> local_cols(std::max(nnz, 1));
+    for (int k = 0; k < nnz; k++) {
+        const int64_t g = cols[k];
+        if (g >= lo && g < hi) local_cols[k] = perm[(int)(g - lo)];
+        else local_cols[k] = n + (int)(std::lower_bound(halo.begin(), halo.end(), g) - halo.begin());
+    }
+    plan->n_owned = n;
+    plan->n_interior = n_interior;
+    plan->n_halo = (int)halo.size();
+    plan->num_neighbors = nn;
+    plan->neighbors = dup(neighbors);
+    plan->send_offsets = dup(send_offsets);
+    plan->send_maps = dup(send_maps);
+    plan->halo_offsets = dup(halo_offsets);
+    plan->halo_global = dup(halo);
+    plan->perm_old_to_new = dup(perm);
+    plan->local_cols = dup(local_cols);
+}
+
+}  // namespace amgxb

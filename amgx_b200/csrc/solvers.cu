@@ -115,6 +115,24 @@ void release_reduce_scratch(Resources *rsc)
     g_scratch.erase(rsc);
 }
 
+void GraphSegment::reset()
+{
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr;
+    graph = nullptr;
+    uses = 0;
+    launches = 0;
+    key0 = key1 = nullptr;
+    failed = false;
+}
+
+bool graphs_enabled()
+{
+    static const bool on = getenv("AMGXB_GRAPHS") ? atoi(getenv("AMGXB_GRAPHS")) != 0 : true;
+    return on;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Solver base
 // ---------------------------------------------------------------------------------------------
@@ -138,13 +156,8 @@ Solver::Solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources>
         fatal(AMGX_RC_BAD_CONFIGURATION, "matrix scaling is outside the solve-phase engine's scope (scaling must be NONE)");
     monitor_convergence_ = monitor_residual_;
     if (scope == "default") {   // backward compatibility rule of the reference (solver.cu:52-60)
-        obtain_timings_ = print_solve_stats_ = print_grid_stats_ = store_res_history_ = monitor_residual_ = false;
-        monitor_convergence_ = cfg.get_int("monitor_residual", scope) != 0;
-        monitor_residual_ = monitor_convergence_;
-        store_res_history_ = cfg.get_int("store_res_history", scope) != 0;
-        print_solve_stats_ = cfg.get_int("print_solve_stats", scope) != 0;
-        print_grid_stats_ = cfg.get_int("print_grid_stats", scope) != 0;
-        obtain_timings_ = cfg.get_int("obtain_timings", scope) != 0;
+        // the reference zeroes the print parameters of the default scope after reading the monitoring flags
+        print_solve_stats_ = print_grid_stats_ = false;
     }
     if (print_solve_stats_ && !monitor_residual_)
         fatal(AMGX_RC_BAD_PARAMETERS, "Cannot print solver information if residual is not monitored (i.e. print_solve_stats=1 and monitor_residual=0) ");
@@ -233,23 +246,34 @@ void Solver::compute_residual(const DevVec &b, DevVec &x)
     matrix_apply(*A_, EPI_RESID, g, stream());
 }
 
+void Solver::enqueue_norm(const DevVec &v)
+{
+    ReduceCtx red = red_ctx();
+    const size_t n = vec_len();
+    const bool d = (bool)A_->dist;
+    if (norm_type_ == NORM_L2) vec_dot(v.ptr(), v.ptr(), v.prec, n, red, d ? FIN_STORE : FIN_SQRT, S_NRM, d ? 0 : 1, stream());
+    else if (norm_type_ == NORM_L1) vec_nrm1(v.ptr(), v.prec, n, red, S_NRM, d ? 0 : 1, stream());
+    else vec_nrmmax(v.ptr(), v.prec, n, red, S_NRM, d ? 0 : 1, stream());
+    if (d) dist_allreduce_norm(*A_, red, S_NRM, (int)norm_type_, stream());
+}
+
+void Solver::read_norm(std::vector<double> &out)
+{
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    out.assign(1, sb_.host[S_NRM]);
+}
+
 void Solver::compute_norm_of(const DevVec &v, std::vector<double> &out)
 {
     const int bsize = use_scalar_norm_ ? 1 : A_->by;
-    out.resize(bsize);
-    ReduceCtx red = red_ctx();
-    const size_t n = vec_len();
     if (bsize == 1) {
-        if (norm_type_ == NORM_L2) vec_dot(v.ptr(), v.ptr(), v.prec, n, red, A_->dist ? FIN_STORE : FIN_SQRT, S_NRM, 1, stream());
-        else if (norm_type_ == NORM_L1) vec_nrm1(v.ptr(), v.prec, n, red, S_NRM, 1, stream());
-        else vec_nrmmax(v.ptr(), v.prec, n, red, S_NRM, 1, stream());
-        AMGXB_CUDA_CHECK(cudaStreamSynchronize(stream()));
-        double val = sb_.host[S_NRM];
-        if (A_->dist) val = dist_reduce_norm(*A_, val, norm_type_);
-        out[0] = val;
+        enqueue_norm(v);
+        read_norm(out);
     } else {
+        if (A_->dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "block norms on distributed matrices");
+        out.resize(bsize);
+        ReduceCtx red = red_ctx();
         block_norms(v, A_->n, bsize, (int)norm_type_, red, sb_, out, stream());
-        if (A_->dist) for (auto &o : out) o = dist_reduce_norm(*A_, norm_type_ == NORM_L2 ? o * o : o, norm_type_);
     }
 }
 
@@ -382,8 +406,9 @@ Status Solver::solve(DevVec &b, DevVec &x, bool xIsZero)
 }
 
 // generic smoother entry: `sweeps` iterations of solve_iteration without monitoring
-void Solver::smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse)
+void Solver::smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse, bool input_in_alt)
 {
+    if (input_in_alt) fatal(AMGX_RC_INTERNAL, "smoother has no alternate input buffer");
     if (fuse && (fuse->agg || fuse->dot_b_x)) fatal(AMGX_RC_INTERNAL, "smoother does not support fused sweeps");
     const int saved = max_iters_;
     const bool mr = monitor_residual_, mc = monitor_convergence_;
@@ -427,37 +452,53 @@ void BlockJacobiSolver::solver_setup(bool)
     tmp_.zero(stream());
 }
 
-void BlockJacobiSolver::smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse)
+void BlockJacobiSolver::smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse, bool input_in_alt)
 {
+    // `sweeps` Jacobi iterations ending in x's own buffer, no buffer swaps: the iterates ping-pong between x and
+    // tmp_, and the FIRST write goes wherever an even number of hops remains.
     cudaStream_t s = stream();
     const bool scalar = A_->bs() == 1;
+    if (sweeps <= 0) return;
     if (!scalar && fuse && (fuse->agg || fuse->dot_b_x)) fatal(AMGX_RC_INTERNAL, "block Jacobi: fused sweeps need block size 1");
-    for (int it = 0; it < sweeps; it++) {
-        const bool first = (it == 0), last = (it == sweeps - 1);
-        const bool want_dot = fuse && fuse->dot_b_x && last;
-        const bool via_agg = fuse && fuse->agg && first;
-        if (first && xIsZero && !via_agg) {
-            // x = w * b / d  -- no SpMV
-            if (scalar) jacobi_zero_guess(b.ptr(), dinv_.ptr(), x.ptr(), A_->mat_prec, A_->vec_prec, vec_len(), weight_, s);
-            else block_jacobi_zero(*A_, dinv_, b, x, weight_, s);
-            if (want_dot) vec_dot(b.ptr(), x.ptr(), x.prec, vec_len(), fuse->red, fuse->fin_op, fuse->fin_slot, 0, s);
-            continue;
+    const bool via_agg = fuse && fuse->agg;
+    void *xp = x.ptr(), *tp = tmp_.ptr();
+    void *cur;
+    int m;   // number of SpMV sweeps still to run
+    if (xIsZero && !via_agg) {
+        m = sweeps - 1;
+        cur = (m & 1) ? tp : xp;
+        if (scalar) jacobi_zero_guess(b.ptr(), dinv_.ptr(), cur, A_->mat_prec, A_->vec_prec, vec_len(), weight_, s);   // x = w b / d, no SpMV
+        else block_jacobi_zero(*A_, dinv_, b, cur, weight_, s);
+        if (m == 0 && fuse && fuse->dot_b_x) vec_dot(b.ptr(), cur, x.prec, vec_len(), fuse->red, fuse->fin_op, fuse->fin_slot, 0, s);
+    } else {
+        m = sweeps;
+        if (via_agg) cur = nullptr;   // first sweep reads P xc on the fly
+        else if (m & 1) {
+            if (!input_in_alt) vec_copy(tp, xp, x.prec, vec_len(), s);
+            cur = tp;
+        } else {
+            if (input_in_alt) fatal(AMGX_RC_INTERNAL, "Jacobi: alternate input with an even sweep count");
+            cur = xp;
         }
+    }
+    for (int it = 0; it < m; it++) {
+        const bool last = (it == m - 1);
+        const bool want_dot = fuse && fuse->dot_b_x && last;
+        void *out;
+        if (cur == nullptr) out = (m & 1) ? xp : tp;   // agg-fused first sweep: choose so that the last write is x
+        else out = (cur == xp) ? tp : xp;
         if (scalar) {
             CsrOpArgs g;
             g.b = b.ptr();
             g.d = dinv_.ptr();
             g.omega = weight_;
-            if (via_agg) {
-                // input is the prolongated coarse correction; write straight into x
-                dist_exchange_halo_coarse(*A_, fuse->xc, s);
+            g.y = out;
+            if (cur == nullptr) {
                 g.x = fuse->xc;
                 g.agg = fuse->agg;
-                g.y = x.ptr();
             } else {
-                dist_exchange_halo(*A_, x, s);
-                g.x = x.ptr();
-                g.y = tmp_.ptr();
+                dist_exchange_halo_ptr(*A_, cur, x.prec, s);
+                g.x = cur;
             }
             if (want_dot) {
                 g.red = fuse->red;
@@ -467,13 +508,13 @@ void BlockJacobiSolver::smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, c
             } else {
                 matrix_apply(*A_, EPI_JACOBI, g, s);
             }
-            if (!via_agg) x.swap(tmp_);
         } else {
-            dist_exchange_halo(*A_, x, s);
-            block_jacobi_sweep(*A_, dinv_, b, x, tmp_, weight_, s);
-            x.swap(tmp_);
+            dist_exchange_halo_ptr(*A_, cur, x.prec, s);
+            block_jacobi_sweep(*A_, dinv_, b, cur, out, weight_, s);
         }
+        cur = out;
     }
+    if (cur != xp) fatal(AMGX_RC_INTERNAL, "Jacobi ping-pong did not end in x");
 }
 
 Status BlockJacobiSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
@@ -502,6 +543,8 @@ PCGSolver::PCGSolver(Config &cfg, const std::string &scope, std::shared_ptr<Reso
 
 void PCGSolver::solver_setup(bool reuse)
 {
+    segA_.reset();
+    segB_.reset();
     if (precond_) precond_->setup(*A_, reuse);
     const size_t N = (size_t)A_->n_cols * A_->by;
     p_.resize(N, A_->vec_prec);
@@ -542,12 +585,12 @@ void PCGSolver::solve_init(DevVec &b, DevVec &x, bool xIsZero)
     vec_copy(p_.ptr(), z_.ptr(), z_.prec, vec_len(), s);
 }
 
-Status PCGSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
+// Segment A of an iteration: Ap = A p, alpha, x += alpha p, r -= alpha Ap, ||r|| (everything up to the host's
+// convergence check).  Segment B: z = M^-1 r, rz, beta, p = z + beta p.  Each is one CUDA graph after warm-up.
+void PCGSolver::enqueue_A(DevVec &x)
 {
     cudaStream_t s = stream();
     ReduceCtx red = red_ctx();
-    Status conv_stat = ST_NOT_CONVERGED;
-    // Ap = A p fused with <Ap, p>; alpha = rz / <Ap,p> on the device
     dist_exchange_halo(*A_, p_, s);
     if (A_->bs() == 1 && !A_->dist) {
         CsrOpArgs g;
@@ -556,7 +599,7 @@ Status PCGSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
         g.red = red;
         g.fin_op = FIN_PCG_ALPHA;
         g.fin_slot = S_DOT;
-        matrix_apply(*A_, EPI_SPMV_DOT, g, s);
+        matrix_apply(*A_, EPI_SPMV_DOT, g, s);      // Ap = A p fused with <Ap,p>; alpha = rz / <Ap,p> on the device
     } else {
         CsrOpArgs g;
         g.x = p_.ptr();
@@ -565,29 +608,35 @@ Status PCGSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
         vec_dot(Ap_.ptr(), p_.ptr(), p_.prec, vec_len(), red, A_->dist ? FIN_STORE : FIN_PCG_ALPHA, S_TMP0, 0, s);
         if (A_->dist) dist_allreduce_scalar_fin(*A_, red, S_TMP0, FIN_PCG_ALPHA, s);
     }
-    // x += alpha p ; r -= alpha Ap ; norm(r) in the same pass
-    if (monitor_convergence_) {
-        const bool scalar_norm = use_scalar_norm_ || A_->by == 1;
-        if (scalar_norm && !A_->dist) {
-            pcg_update_xr(p_.ptr(), Ap_.ptr(), x.ptr(), r_.ptr(), x.prec, vec_len(), red, (int)norm_type_, S_NRM, 1, s);
-            AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
-            nrm_.assign(1, sb_.host[S_NRM]);
-        } else {
-            vec_axpy_dev(p_.ptr(), x.ptr(), x.prec, vec_len(), sb_.scal, S_ALPHA, 1.0, s);
-            vec_axpy_dev(Ap_.ptr(), r_.ptr(), x.prec, vec_len(), sb_.scal, S_NEG_ALPHA, 1.0, s);
-            compute_norm();
-        }
-        conv_stat = converged();
-        if (is_done(conv_stat)) return conv_stat;
+    const bool scalar_norm = use_scalar_norm_ || A_->by == 1;
+    if (monitor_convergence_ && scalar_norm && !A_->dist) {
+        pcg_update_xr(p_.ptr(), Ap_.ptr(), x.ptr(), r_.ptr(), x.prec, vec_len(), red, (int)norm_type_, S_NRM, 1, s);   // one pass
     } else {
         vec_axpy_dev(p_.ptr(), x.ptr(), x.prec, vec_len(), sb_.scal, S_ALPHA, 1.0, s);
         vec_axpy_dev(Ap_.ptr(), r_.ptr(), x.prec, vec_len(), sb_.scal, S_NEG_ALPHA, 1.0, s);
+        if (monitor_convergence_ && scalar_norm) enqueue_norm(r_);
+    }
+}
+
+void PCGSolver::enqueue_B()
+{
+    apply_precond_and_rz(FIN_PCG_BETA);                                                         // z = M^-1 r ; rz ; beta
+    vec_axpby_dev(z_.ptr(), p_.ptr(), p_.ptr(), p_.prec, vec_len(), 1.0, sb_.scal, S_BETA, stream());   // p = z*1 + p*beta
+}
+
+Status PCGSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
+{
+    Status conv_stat = ST_NOT_CONVERGED;
+    run_segment(segA_, x.ptr(), r_.ptr(), [&] { enqueue_A(x); });
+    if (monitor_convergence_) {
+        const bool scalar_norm = use_scalar_norm_ || A_->by == 1;
+        if (scalar_norm) read_norm(nrm_);
+        else compute_norm();
+        conv_stat = converged();
+        if (is_done(conv_stat)) return conv_stat;
     }
     if (is_last_iter()) return monitor_convergence_ ? ST_NOT_CONVERGED : ST_CONVERGED;
-    // z = M^-1 r ; rz_old = rz ; rz = <r,z> ; beta = rz / rz_old
-    apply_precond_and_rz(FIN_PCG_BETA);
-    // p = z + beta p     (axpby(z, p, p, 1, beta): z*1 + p*beta)
-    vec_axpby_dev(z_.ptr(), p_.ptr(), p_.ptr(), p_.prec, vec_len(), 1.0, sb_.scal, S_BETA, s);
+    run_segment(segB_, z_.ptr(), r_.ptr(), [&] { enqueue_B(); });
     return monitor_convergence_ ? ST_NOT_CONVERGED : ST_CONVERGED;
 }
 

@@ -60,6 +60,21 @@ struct SmoothFuse {
     ReduceCtx red;
 };
 
+// A stretch of stream work between two host synchronisation points, replayed as a CUDA graph once its
+// pointers have been seen twice (first use runs eagerly: lazy allocations, function attributes; second use is
+// captured; later uses replay).  Kernel, memcpy/memset, NCCL and cross-stream event nodes are all captured.
+struct GraphSegment {
+    cudaGraphExec_t exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    long long launches = 0;
+    int uses = 0;
+    const void *key0 = nullptr, *key1 = nullptr;
+    bool failed = false;
+    void reset();
+    ~GraphSegment() { reset(); }
+};
+bool graphs_enabled();
+
 class Solver {
 public:
     Solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);
@@ -83,7 +98,12 @@ public:
     // smoother entry used by the cycles: `sweeps` iterations with no residual monitoring
     // (the reference: smoother->setTolerance(0); set_max_iters(n); solve(b, x, xIsZero),
     //  src/cycles/fixed_cycle.cu:97-102)
-    virtual void smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse);
+    // `input_in_alt`: the caller placed the initial x in smooth_input(x, sweeps) instead of x (see below).
+    virtual void smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse, bool input_in_alt = false);
+    // Out-of-place smoothers ping-pong between x and a private buffer.  To end in x without a copy and without
+    // swapping buffers (pointer stability is what makes the cycle capturable in a CUDA graph) the producer of
+    // the initial x (prolongation) writes it where an odd/even number of sweeps needs it.
+    virtual void *smooth_input(DevVec &x, int sweeps) { (void)sweeps; return x.ptr(); }
     virtual bool supports_fusion() const { return false; }
     virtual bool is_coloring_needed() const { return false; }
     virtual void print_grid_stats() {}
@@ -104,6 +124,9 @@ protected:
     void compute_residual(const DevVec &b, DevVec &x);            // r_ = b - A x
     void compute_norm();                                          // nrm_ from r_ (host sync)
     void compute_norm_of(const DevVec &v, std::vector<double> &out);
+    void enqueue_norm(const DevVec &v);                           // scalar norm of v -> host mirror, no sync
+    void read_norm(std::vector<double> &out);                     // sync + read what enqueue_norm produced
+    template <class F> void run_segment(GraphSegment &g, const void *k0, const void *k1, F &&body);
     Status converged() { return conv_.update_and_check(nrm_, nrm_ini_); }
     Status converged(const DevVec &b, DevVec &x);                 // residual + norm + check when monitoring
     Status compute_norm_and_converged();
@@ -149,7 +172,8 @@ protected:
 class BlockJacobiSolver : public Solver {
 public:
     BlockJacobiSolver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);
-    void smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse) override;
+    void smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse, bool input_in_alt = false) override;
+    void *smooth_input(DevVec &x, int sweeps) override { return (sweeps & 1) ? tmp_.ptr() : x.ptr(); }
     bool supports_fusion() const override { return A_ && A_->bs() == 1; }
     const DevVec *smoother_data() const override { return &dinv_; }
 protected:
@@ -181,6 +205,9 @@ protected:
     void apply_precond_and_rz(int fin_op);   // z = M^-1 r ; <r,z> -> scalars through fin_op
     std::unique_ptr<Solver> precond_;
     DevVec p_, z_, Ap_;
+    GraphSegment segA_, segB_;
+    void enqueue_A(DevVec &x);
+    void enqueue_B();
 };
 
 class FGMRESSolver : public Solver {
@@ -246,6 +273,49 @@ protected:
     double coarsen_threshold_ = 1.0;
     std::unique_ptr<Solver> coarse_solver_;
 };
+
+template <class F> void Solver::run_segment(GraphSegment &g, const void *k0, const void *k1, F &&body)
+{
+    if (!graphs_enabled() || g.failed) { body(); return; }
+    if (g.exec && (g.key0 != k0 || g.key1 != k1)) g.reset();
+    if (g.uses == 0 || g.key0 != k0 || g.key1 != k1) {   // first sight of these pointers: eager
+        g.key0 = k0;
+        g.key1 = k1;
+        g.uses = 1;
+        body();
+        return;
+    }
+    cudaStream_t s = stream();
+    if (!g.exec) {
+        const long long l0 = g_kernel_launches;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); g.failed = true; body(); return; }
+        bool ok = true;
+        try { body(); } catch (...) { ok = false; }
+        cudaGraph_t gr = nullptr;
+        cudaError_t e = cudaStreamEndCapture(s, &gr);
+        if (!ok || e != cudaSuccess || !gr) {
+            cudaGetLastError();
+            if (gr) cudaGraphDestroy(gr);
+            g.failed = true;
+            g_kernel_launches = l0;
+            body();   // the captured work never ran: run it eagerly
+            return;
+        }
+        g.launches = g_kernel_launches - l0;
+        g_kernel_launches = l0;
+        g.graph = gr;
+        if (cudaGraphInstantiate(&g.exec, gr, 0) != cudaSuccess) {
+            cudaGetLastError();
+            g.exec = nullptr;
+            g.failed = true;
+            body();
+            return;
+        }
+    }
+    AMGXB_CUDA_CHECK(cudaGraphLaunch(g.exec, s));
+    g_kernel_launches += g.launches;
+    g.uses++;
+}
 
 // pieces implemented in other translation units
 std::unique_ptr<Solver> make_dense_lu_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);   // dense_lu.cu

@@ -4,8 +4,8 @@
 namespace amgxb {
 void block_norms(const DevVec &, int, int, int, const ReduceCtx &, ScalarBlock &, std::vector<double> &, cudaStream_t) { fatal(AMGX_RC_NOT_IMPLEMENTED, "block norms"); }
 void block_jacobi_setup(const Matrix &, DevVec &, cudaStream_t) { fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "block Jacobi"); }
-void block_jacobi_zero(const Matrix &, const DevVec &, const DevVec &, DevVec &, double, cudaStream_t) { fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "block Jacobi"); }
-void block_jacobi_sweep(const Matrix &, const DevVec &, const DevVec &, const DevVec &, DevVec &, double, cudaStream_t) { fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "block Jacobi"); }
+void block_jacobi_zero(const Matrix &, const DevVec &, const DevVec &, void *, double, cudaStream_t) { fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "block Jacobi"); }
+void block_jacobi_sweep(const Matrix &, const DevVec &, const DevVec &, const void *, void *, double, cudaStream_t) { fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "block Jacobi"); }
 void block_build_diag(Matrix &, cudaStream_t) { fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "block matrices"); }
 void block_apply(const Matrix &, CsrEpi, const CsrOpArgs &, cudaStream_t) { fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "block SpMV"); }
 std::unique_ptr<Solver> make_dilu_solver(Config &, const std::string &, std::shared_ptr<Resources>) { fatal(AMGX_RC_NOT_IMPLEMENTED, "MULTICOLOR_DILU"); }

@@ -1,0 +1,91 @@
+"""Worker for the CPU (gloo) multi-process test of the host-side partition logic: each rank owns a z-slab of a
+7-pt Poisson problem, plans its partition through the C-ABI planner (pure host code), exchanges halos over
+gloo exactly as the engine does over NCCL (pack by send map -> send/recv -> halo tail) and checks that the
+distributed SpMV equals the global one bit for bit."""
+import ctypes as C
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from amgx_b200 import capi, gallery  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    orc.set_num_threads(1)
+    nx, ny, nzl = 7, 5, 4
+    nz = nzl * world
+    rp, ci, va = gallery.poisson7pt(nx, ny, nz)
+    n_global = rp.shape[0] - 1
+    offsets = np.array([nx * ny * nzl * r for r in range(world + 1)], np.int64)
+    lo, hi = int(offsets[rank]), int(offsets[rank + 1])
+    lrp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+    lci = ci[rp[lo]:rp[hi]].astype(np.int64)
+    lva = va[rp[lo]:rp[hi]]
+    lib = capi.load_library()
+    plan = capi.PartitionPlan()
+    rc = lib.AMGXB200_partition_plan_create(C.byref(plan), rank, world, offsets.ctypes.data, hi - lo, lci.shape[0], lrp.ctypes.data, lci.ctypes.data)
+    assert rc == 0, rc
+    n, nh, nn, n_int = plan.n_owned, plan.n_halo, plan.num_neighbors, plan.n_interior
+    neighbors = np.ctypeslib.as_array(plan.neighbors, (nn,)).copy()
+    send_off = np.ctypeslib.as_array(plan.send_offsets, (nn + 1,)).copy()
+    send_maps = np.ctypeslib.as_array(plan.send_maps, (max(send_off[-1], 1),)).copy()[: send_off[-1]]
+    halo_off = np.ctypeslib.as_array(plan.halo_offsets, (nn + 1,)).copy()
+    perm = np.ctypeslib.as_array(plan.perm_old_to_new, (n,)).copy()
+    lcols = np.ctypeslib.as_array(plan.local_cols, (lci.shape[0],)).copy()
+    halo_global = np.ctypeslib.as_array(plan.halo_global, (max(nh, 1),)).copy()[:nh]
+    lib.AMGXB200_partition_plan_free(C.byref(plan))
+    # structure checks
+    expected_nb = [r for r in (rank - 1, rank + 1) if 0 <= r < world]
+    assert list(neighbors) == expected_nb, (neighbors, expected_nb)
+    assert nh == nx * ny * len(expected_nb) and n_int == n - nx * ny * len(expected_nb)
+    assert sorted(perm) == list(range(n)) and np.all(np.sort(perm[: 0]) == [])
+    # local matrix in the renumbered row order
+    inv = np.argsort(perm)
+    rows_len = np.diff(lrp)[inv]
+    nrp = np.zeros(n + 1, np.int32)
+    np.cumsum(rows_len, out=nrp[1:])
+    nci = np.concatenate([lcols[lrp[i]:lrp[i + 1]] for i in inv]).astype(np.int32)
+    nva = np.concatenate([lva[lrp[i]:lrp[i + 1]] for i in inv])
+    assert nci[: nrp[n_int]].max(initial=-1) < n           # interior rows never touch the halo
+    # distributed x: owned part permuted, halo tail received from the neighbours
+    xg = np.random.default_rng(42).standard_normal(n_global)
+    x = np.zeros(n + nh)
+    x[perm] = xg[lo:hi]
+    reqs, bufs = [], []
+    for q, nb in enumerate(neighbors):
+        sb = torch.from_numpy(x[send_maps[send_off[q]:send_off[q + 1]]].copy())
+        rb = torch.empty(int(halo_off[q + 1] - halo_off[q]), dtype=torch.float64)
+        reqs.append(dist.isend(sb, int(nb)))
+        reqs.append(dist.irecv(rb, int(nb)))
+        bufs.append((q, sb, rb))
+    for r in reqs:
+        r.wait()
+    for q, _, rb in bufs:
+        x[n + halo_off[q]: n + halo_off[q + 1]] = rb.numpy()
+    assert np.array_equal(x[n:], xg[halo_global])                  # halo values are the right global entries
+    y = np.empty(n)
+    orc.lib().orc_spmv(n, nrp.ctypes.data_as(C.c_void_p), nci.ctypes.data_as(C.c_void_p), nva.ctypes.data_as(C.c_void_p),
+                       x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p))
+    yg = orc.spmv(rp, ci, va, xg)
+    assert np.array_equal(y[perm], yg[lo:hi]), "distributed SpMV differs from the global one"
+    # global dot through all-reduce == sum of local dots (order differs: tolerance)
+    t = torch.tensor([float(np.dot(y, y))], dtype=torch.float64)
+    dist.all_reduce(t)
+    assert abs(t.item() - float(np.dot(yg, yg))) <= 1e-12 * float(np.dot(yg, yg))
+    dist.barrier()
+    if rank == 0:
+        print("DIST_CPU_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,17 @@
+"""CPU, world_size 2 and 3 over gloo: host-side logic of the multi-GPU path (partition planner + halo protocol)."""
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partition_plan_and_halo_protocol(world):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29511 + world), str(ROOT / "tests" / "dist_cpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DIST_CPU_OK" in r.stdout
