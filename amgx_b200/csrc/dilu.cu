@@ -1,0 +1,357 @@
+// dilu.cu -- MULTICOLOR_DILU smoother: per-colour setup of Einv, forward and backward sweeps, block sizes 1 and 4.
+//   setup    DILU_setup_1x1_kernel / DILU_setup_NxN_kernel   src/solvers/multicolor_dilu_solver.cu:643-812, 362-640
+//   forward  DILU_forward_1x1_kernel / _4x4_                 :1763-1901, 1585-1759
+//   backward DILU_backward_1x1_kernel / _4x4_ / _skip        :2772-2915, 2604-2768
+//   host     solve_iteration / smooth_NxN / computeEinv_NxN  :3773-3851, 4021-4242, 3890-4019
+// Formulas (single partition, boundary_coloring = SYNC_COLORS):
+//   E_i     = A_ii - sum_{colour(j) < colour(i), j != i} A_ij Einv_j A_ji ;  Einv_i = E_i^{-1} (0 stays 0 for 1x1)
+//   forward (colour c ascending):  delta_i = Einv_i ( b_i - sum_j A_ij (x_j + [c != 0 and colour(j) < c] delta_j) )
+//   backward (colour c descending): Delta_i = delta_i - Einv_i sum_{[c != 0 and colour(j) > c]} A_ij Delta_j ;  x_i += w Delta_i
+//   (the "c != 0" guards are the reference's; the last colour uses the cheap Delta = delta shortcut).
+// The 1x1 kernels keep the reference's work decomposition (8 lanes per row, per-lane FMA accumulation, xor-butterfly
+// reduction; setup: 32 lanes per row) so that their sums associate exactly like the reference's.
+#include "solvers.h"
+#include "dist.h"
+
+namespace amgxb {
+
+void color_matrix_min_max(Matrix &A, double max_uncolored_fraction, cudaStream_t s);   // coloring.cu
+
+namespace {
+
+constexpr int NTPR = 8;   // lanes per row in the 1x1 sweeps
+
+template <class MatT, class VecT>
+__global__ void dilu_setup_1x1(const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ diag, const MatT *__restrict__ va,
+                               MatT *Einv, const int *__restrict__ rows, const int *__restrict__ colors, int nrows, int color)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nrows; it += warps_per_grid) {
+        const int i = rows[it];
+        VecT e_out = 0;
+        if (color != 0) {
+            const int k1 = rp[i + 1];
+            for (int k0 = rp[i]; k0 < k1; k0 += 32) {
+                const int k = k0 + lane;
+                if (k < k1) {
+                    const int j = ci[k];
+                    if (j != i && colors[j] < color) {
+                        MatT a_ji = 0;
+                        for (int kk = rp[j]; kk < rp[j + 1]; kk++)
+                            if (ci[kk] == i) { a_ji = va[kk]; break; }   // first match, as the reference's search order yields
+                        e_out += (VecT)(a_ji * Einv[j]) * (VecT)va[k];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) e_out += __shfl_xor_sync(0xffffffffu, e_out, m);
+        if (lane == 0) {
+            const int d = diag[i];
+            MatT res = (d >= 0 ? va[d] : (MatT)0) - (MatT)e_out;
+            if (res != (MatT)0) res = (MatT)1 / res;
+            Einv[i] = res;
+        }
+    }
+}
+
+template <class MatT, class VecT>
+__global__ void dilu_forward_1x1(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, const VecT *x,
+                                 const VecT *__restrict__ b, VecT *delta, const int *__restrict__ rows, int nrows, int color,
+                                 const int *__restrict__ colors, const MatT *__restrict__ Einv, int n_owned)
+{
+    const int l = threadIdx.x % NTPR;
+    const int rows_per_grid = gridDim.x * (blockDim.x / NTPR);
+    for (int it = blockIdx.x * (blockDim.x / NTPR) + threadIdx.x / NTPR; __any_sync(0xffffffffu, it < nrows); it += rows_per_grid) {
+        const bool act = it < nrows;
+        const int i = act ? rows[it] : 0;
+        VecT acc = 0;
+        if (act && l == 0) acc = b[i];
+        if (act) {
+            const int k1 = rp[i + 1];
+            for (int k = rp[i] + l; k < k1; k += NTPR) {
+                const int j = ci[k];
+                VecT xx = x[j];
+                if (color != 0 && j < n_owned && colors[j] < color) xx += delta[j];
+                acc -= (VecT)va[k] * xx;
+            }
+        }
+#pragma unroll
+        for (int m = NTPR / 2; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (act && l == 0) delta[i] = (VecT)Einv[i] * acc;
+    }
+}
+
+template <class MatT, class VecT>
+__global__ void dilu_backward_1x1(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, VecT *x, double weight,
+                                  const int *__restrict__ rows, const int *__restrict__ colors, const MatT *__restrict__ Einv,
+                                  const VecT *__restrict__ delta, VecT *Delta, int nrows, int color, int n_owned)
+{
+    const int l = threadIdx.x % NTPR;
+    const int rows_per_grid = gridDim.x * (blockDim.x / NTPR);
+    for (int it = blockIdx.x * (blockDim.x / NTPR) + threadIdx.x / NTPR; __any_sync(0xffffffffu, it < nrows); it += rows_per_grid) {
+        const bool act = it < nrows;
+        const int i = act ? rows[it] : 0;
+        VecT acc = 0;
+        if (act) {
+            const int k1 = rp[i + 1];
+            for (int k = rp[i] + l; k < k1; k += NTPR) {
+                const int j = ci[k];
+                const bool valid = color != 0 && j < n_owned && colors[j] > color;
+                if (valid) acc += (VecT)va[k] * Delta[j];
+            }
+        }
+#pragma unroll
+        for (int m = NTPR / 2; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+        if (act && l == 0) {
+            const VecT v = delta[i] - (VecT)Einv[i] * acc;
+            x[i] += (VecT)(weight * v);
+            Delta[i] = v;
+        }
+    }
+}
+
+template <class VecT> __global__ void dilu_backward_skip(VecT *x, double weight, const int *__restrict__ rows, const VecT *__restrict__ delta, VecT *Delta, int nrows, int bs)
+{
+    const long long total = (long long)nrows * bs;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = rows[(int)(t / bs)], c = (int)(t % bs);
+        const size_t idx = (size_t)i * bs + c;
+        const VecT v = delta[idx];
+        x[idx] = x[idx] + (VecT)(weight * v);
+        Delta[idx] = v;
+    }
+}
+
+// ------------------------------------------ 4x4 blocks ------------------------------------------
+// In-place Gauss-Jordan without pivoting, the operation order of the reference's lock-step 16-thread version
+// (multicolor_dilu_solver.cu:586-633; include/solvers/block_common_solver.h:106-137).
+template <class T> __device__ __forceinline__ T guard0(T d);
+template <> __device__ __forceinline__ double guard0<double>(double d) { return fabs(d) < 1e-12 ? copysign(1e-12, d) : d; }
+template <> __device__ __forceinline__ float guard0<float>(float d) { return fabs((double)d) < 1e-7 ? copysignf((float)1e-7, d) : d; }
+
+template <class T> __device__ void invert4x4(T *A)
+{
+    for (int row = 0; row < 4; row++) {
+        const T diag = (T)1 / guard0<T>(A[row * 4 + row]);
+        for (int j = 0; j < 4; j++) if (j != row) A[row * 4 + j] *= diag;
+        for (int i = 0; i < 4; i++) if (i != row)
+            for (int j = 0; j < 4; j++) if (j != row) A[i * 4 + j] -= A[i * 4 + row] * A[row * 4 + j];
+        for (int j = 0; j < 4; j++) A[j * 4 + row] = (j == row) ? diag : -A[j * 4 + row] * diag;
+    }
+}
+
+template <class MatT, class VecT>
+__global__ void dilu_setup_4x4(const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ diag, const MatT *__restrict__ va,
+                               MatT *Einv, const int *__restrict__ rows, const int *__restrict__ colors, int nrows, int color)
+{
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nrows; it += gridDim.x * blockDim.x) {
+        const int i = rows[it];
+        VecT E[16];
+        const int d = diag[i];
+        for (int m = 0; m < 16; m++) E[m] = d >= 0 ? (VecT)va[(size_t)d * 16 + m] : (VecT)0;
+        if (color != 0) {
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                const int j = ci[k];
+                if (j == i || colors[j] >= color) continue;
+                int kji = -1;
+                for (int kk = rp[j]; kk < rp[j + 1]; kk++)
+                    if (ci[kk] == i) { kji = kk; break; }
+                VecT T[16];
+                for (int r = 0; r < 4; r++)
+                    for (int c = 0; c < 4; c++) {
+                        VecT t = 0;
+                        for (int m = 0; m < 4; m++) t += (VecT)va[(size_t)k * 16 + r * 4 + m] * (VecT)Einv[(size_t)j * 16 + m * 4 + c];
+                        T[r * 4 + c] = t;
+                    }
+                if (kji >= 0)
+                    for (int r = 0; r < 4; r++)
+                        for (int c = 0; c < 4; c++)
+                            for (int m = 0; m < 4; m++) E[r * 4 + c] -= T[r * 4 + m] * (VecT)va[(size_t)kji * 16 + m * 4 + c];
+            }
+        }
+        invert4x4<VecT>(E);
+        for (int m = 0; m < 16; m++) Einv[(size_t)i * 16 + m] = (MatT)E[m];
+    }
+}
+
+// quad per block row: thread r of the quad owns component r
+template <class MatT, class VecT, bool BACKWARD>
+__global__ void dilu_sweep_4x4(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, VecT *x, const VecT *__restrict__ b,
+                               VecT *delta, VecT *Delta, double weight, const int *__restrict__ rows, int nrows, int color,
+                               const int *__restrict__ colors, const MatT *__restrict__ Einv, int n_owned)
+{
+    const int r = threadIdx.x & 3;
+    const unsigned qmask = 0xFu << ((threadIdx.x & 31) & ~3);
+    const int quads_per_grid = gridDim.x * (blockDim.x >> 2);
+    for (int it = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); __any_sync(0xffffffffu, it < nrows); it += quads_per_grid) {
+        const bool act = it < nrows;
+        const int i = act ? rows[it] : 0;
+        VecT acc = 0;
+        if (act) {
+            if (!BACKWARD) acc = b[(size_t)i * 4 + r];
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                const int j = ci[k];
+                const MatT *a = va + (size_t)k * 16 + r * 4;
+                if (!BACKWARD) {
+                    const bool valid = color != 0 && j < n_owned && colors[j] < color;
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        VecT xx = x[(size_t)j * 4 + m];
+                        if (valid) xx += delta[(size_t)j * 4 + m];
+                        acc -= (VecT)a[m] * xx;
+                    }
+                } else {
+                    const bool valid = color != 0 && j < n_owned && colors[j] > color;
+                    if (valid) {
+#pragma unroll
+                        for (int m = 0; m < 4; m++) acc += (VecT)a[m] * Delta[(size_t)j * 4 + m];
+                    }
+                }
+            }
+        }
+        // y = Einv_i * acc (4x4 mat-vec across the quad)
+        VecT y = 0;
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const VecT am = __shfl_sync(0xffffffffu, acc, ((threadIdx.x & 31) & ~3) + m);
+            if (act) y += (VecT)Einv[(size_t)i * 16 + r * 4 + m] * am;
+        }
+        (void)qmask;
+        if (act) {
+            const size_t idx = (size_t)i * 4 + r;
+            if (!BACKWARD) delta[idx] = y;
+            else {
+                const VecT v = delta[idx] - y;
+                x[idx] += (VecT)(weight * v);
+                Delta[idx] = v;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+class MulticolorDILUSolver : public Solver {
+public:
+    MulticolorDILUSolver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc) : Solver(cfg, scope, std::move(rsc))
+    {
+        weight_ = cfg.get_double("relaxation_factor", scope);
+        if (weight_ == 0) {
+            weight_ = 1.;
+            amgx_printf("Warning, setting weight to 1 instead of estimating largest_eigen_value in Multicolor DILU smoother\n");
+        }
+        const std::string scheme = cfg.get_string("matrix_coloring_scheme", scope);
+        if (scheme != "MIN_MAX") fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_coloring_scheme '" + scheme + "' is not supported by this engine (MIN_MAX, or AMGX_matrix_attach_coloring)");
+        if (cfg.get_int("coloring_level", scope) != 1) fatal(AMGX_RC_BAD_CONFIGURATION, "MULTICOLOR_DILU: coloring_level must be 1");
+        if (cfg.get_int("reorder_cols_by_color", scope) != 0 || cfg.get_int("insert_diag_while_reordering", scope) != 0)
+            fatal(AMGX_RC_NOT_IMPLEMENTED, "reorder_cols_by_color / insert_diag_while_reordering");
+        uncolored_fraction_ = cfg.get_int("determinism_flag", "default") ? 0.0 : cfg.get_double("max_uncolored_percentage", scope);
+    }
+    bool is_coloring_needed() const override { return true; }
+    const DevVec *smoother_data() const override { return &Einv_; }
+    void smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse, bool input_in_alt = false) override
+    {
+        if (input_in_alt || (fuse && (fuse->agg || fuse->dot_b_x))) fatal(AMGX_RC_INTERNAL, "DILU does not support fused sweeps");
+        for (int it = 0; it < sweeps; it++) sweep(b, x, xIsZero && it == 0);
+    }
+
+protected:
+    void solver_setup(bool) override
+    {
+        Matrix &A = *A_;
+        if (A.bx != A.by) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "DILU implemented only for squared blocks");
+        if (A.bs() != 1 && A.bx != 4) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "Multicolor-DILU: block sizes 1 and 4 are enabled in this engine");
+        if (A.has_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "Multicolor-DILU with an external diagonal");
+        if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "Multicolor-DILU on distributed matrices");
+        cudaStream_t s = stream();
+        if (A.num_colors == 0) color_matrix_min_max(A, uncolored_fraction_, s);
+        const size_t bs = A.bs();
+        Einv_.resize((size_t)A.n_cols * bs, A.mat_prec);
+        Einv_.zero(s);
+        delta_.resize((size_t)A.n_cols * A.by, A.vec_prec);
+        Delta_.resize((size_t)A.n_cols * A.by, A.vec_prec);
+        delta_.zero(s);
+        Delta_.zero(s);
+        for (int c = 0; c < A.num_colors; c++) {
+            const int off = A.color_offsets[c], cnt = A.color_offsets[c + 1] - off;
+            if (cnt == 0) continue;
+            AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+                if (bs == 1) {
+                    const int grid = std::min(4096, ceil_div(cnt, 4));
+                    dilu_setup_1x1<MatT, VecT><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.diag_idx.ptr(), A.values.as<MatT>(), Einv_.as<MatT>(),
+                                                                    A.sorted_rows_by_color.ptr() + off, A.row_colors.ptr(), cnt, c);
+                } else {
+                    const int grid = std::min(4096, ceil_div(cnt, 128));
+                    dilu_setup_4x4<MatT, VecT><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.diag_idx.ptr(), A.values.as<MatT>(), Einv_.as<MatT>(),
+                                                                    A.sorted_rows_by_color.ptr() + off, A.row_colors.ptr(), cnt, c);
+                }
+            });
+            count_launch();
+            AMGXB_LAUNCH_CHECK();
+        }
+    }
+
+    void sweep(DevVec &b, DevVec &x, bool xIsZero)
+    {
+        Matrix &A = *A_;
+        cudaStream_t s = stream();
+        if (xIsZero) x.zero(s);
+        const int nc = A.num_colors;
+        const size_t bs = A.bs();
+        AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+            for (int c = 0; c < nc; c++) {
+                const int off = A.color_offsets[c], cnt = A.color_offsets[c + 1] - off;
+                if (cnt == 0) continue;
+                if (bs == 1) {
+                    const int grid = std::min(4096, ceil_div(cnt, 128 / NTPR));
+                    dilu_forward_1x1<MatT, VecT><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
+                                                                      A.sorted_rows_by_color.ptr() + off, cnt, c, A.row_colors.ptr(), Einv_.as<MatT>(), A.n);
+                } else {
+                    const int grid = std::min(4096, ceil_div(cnt, 32));
+                    dilu_sweep_4x4<MatT, VecT, false><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
+                                                                           Delta_.as<VecT>(), weight_, A.sorted_rows_by_color.ptr() + off, cnt, c, A.row_colors.ptr(),
+                                                                           Einv_.as<MatT>(), A.n);
+                }
+                count_launch();
+            }
+            for (int c = nc - 1; c >= 0; c--) {
+                const int off = A.color_offsets[c], cnt = A.color_offsets[c + 1] - off;
+                if (cnt == 0) continue;
+                if (c == nc - 1) {
+                    const int grid = std::min(4096, ceil_div((long long)cnt * bs, 128));
+                    dilu_backward_skip<VecT><<<grid, 128, 0, s>>>(x.as<VecT>(), weight_, A.sorted_rows_by_color.ptr() + off, delta_.as<VecT>(), Delta_.as<VecT>(), cnt, A.by);
+                } else if (bs == 1) {
+                    const int grid = std::min(4096, ceil_div(cnt, 128 / NTPR));
+                    dilu_backward_1x1<MatT, VecT><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), weight_,
+                                                                       A.sorted_rows_by_color.ptr() + off, A.row_colors.ptr(), Einv_.as<MatT>(), delta_.as<VecT>(),
+                                                                       Delta_.as<VecT>(), cnt, c, A.n);
+                } else {
+                    const int grid = std::min(4096, ceil_div(cnt, 32));
+                    dilu_sweep_4x4<MatT, VecT, true><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
+                                                                          Delta_.as<VecT>(), weight_, A.sorted_rows_by_color.ptr() + off, cnt, c, A.row_colors.ptr(),
+                                                                          Einv_.as<MatT>(), A.n);
+                }
+                count_launch();
+            }
+        });
+        AMGXB_LAUNCH_CHECK();
+    }
+
+    Status solve_iteration(DevVec &b, DevVec &x, bool xIsZero) override
+    {
+        sweep(b, x, xIsZero);
+        return converged(b, x);
+    }
+
+    double weight_ = 0.9, uncolored_fraction_ = 0.15;
+    DevVec Einv_, delta_, Delta_;
+};
+
+std::unique_ptr<Solver> make_dilu_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc)
+{
+    return std::unique_ptr<Solver>(new MulticolorDILUSolver(cfg, scope, std::move(rsc)));
+}
+
+}  // namespace amgxb

@@ -560,6 +560,5 @@ std::shared_ptr<DistManager> dist_coarsen(const Matrix &A, DevBuf<int> &aggregat
     return cm;
 }
 
-void attach_user_coloring(Matrix &, const int *, int, int) { fatal(AMGX_RC_NOT_IMPLEMENTED, "attach_coloring"); }
 
 }  // namespace amgxb

@@ -213,6 +213,7 @@ protected:
 class FGMRESSolver : public Solver {
 public:
     FGMRESSolver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);
+    ~FGMRESSolver() override;
     void print_grid_stats() override { if (precond_) precond_->print_grid_stats(); }
     Solver *preconditioner() { return precond_.get(); }
 protected:
@@ -228,6 +229,7 @@ protected:
     double beta_ = 0;
     bool update_x_every_iteration_ = false, update_r_every_iteration_ = false;
     double &H(int i, int j) { return H_[(size_t)i * (R_ + 1) + j]; }   // (R+2) x (R+1) storage
+    double *hs_dev_ = nullptr, *hs_host_ = nullptr, *hs_host_dev_ = nullptr;   // Hessenberg column on device + pinned mirror
 };
 
 // ------------------------------------------------------------------------------------------

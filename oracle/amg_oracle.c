@@ -400,14 +400,26 @@ typedef struct {
     double *va, *d;          /* d: smoother diagonal (Jacobi: a_ii, L1: row norms) */
     double *bc, *xc, *r, *tmp;
     int own;
+    /* MULTICOLOR_DILU smoother data */
+    int num_colors, *colors, *sorted_rows, *color_offsets;
+    double *Einv, *delta, *Delta;
 } orc_level;
 
 typedef struct {
     int num_levels;
     orc_level *lv;
-    int presweeps, postsweeps, coarsest_sweeps, finest_sweeps, smoother; /* smoother: 0 BLOCK_JACOBI, 1 JACOBI_L1 */
-    double omega;
+    int presweeps, postsweeps, coarsest_sweeps, finest_sweeps, smoother; /* smoother: 0 BLOCK_JACOBI, 1 JACOBI_L1, 2 MULTICOLOR_DILU */
+    double omega, uncolored_fraction;
 } orc_amg;
+
+ORC_API int orc_color_min_max(int n, const int *rp, const int *ci, double max_uncolored_fraction, int *colors);
+ORC_API void orc_color_arrays(int n, int num_colors, const int *colors, int *sorted_rows, int *offsets);
+ORC_API void orc_dilu_setup_1x1(int n, const int *rp, const int *ci, const double *va, int num_colors, const int *colors, const int *sorted_rows,
+                                const int *offsets, double *Einv);
+ORC_API void orc_dilu_sweep_1x1(int n, const int *rp, const int *ci, const double *va, int num_colors, const int *colors, const int *sorted_rows,
+                                const int *offsets, const double *Einv, const double *b, double *x, double weight, double *delta, double *Delta);
+static double g_uncolored_fraction = 0.15;
+ORC_API void orc_set_uncolored_fraction(double f) { g_uncolored_fraction = f; }
 
 ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double *va, int max_levels, int min_coarse_rows, double coarsen_threshold,
                                int presweeps, int postsweeps, int coarsest_sweeps, int finest_sweeps, int smoother, double omega,
@@ -424,8 +436,20 @@ ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double
     for (;;) {
         L = &a->lv[num_levels - 1];
         L->d = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
-        if (smoother == 0) orc_extract_diag(L->n, L->rp, L->ci, L->va, L->d);
-        else orc_l1_norms(L->n, L->rp, L->ci, L->va, L->d);
+        if (smoother == 1) orc_l1_norms(L->n, L->rp, L->ci, L->va, L->d);
+        else orc_extract_diag(L->n, L->rp, L->ci, L->va, L->d);
+        if (smoother == 2) {
+            const size_t nn = (size_t)(L->n > 0 ? L->n : 1);
+            L->colors = (int *)malloc(sizeof(int) * nn);
+            L->sorted_rows = (int *)malloc(sizeof(int) * nn);
+            L->num_colors = orc_color_min_max(L->n, L->rp, L->ci, g_uncolored_fraction, L->colors);
+            L->color_offsets = (int *)malloc(sizeof(int) * ((size_t)L->num_colors + 1));
+            orc_color_arrays(L->n, L->num_colors, L->colors, L->sorted_rows, L->color_offsets);
+            L->Einv = (double *)calloc(nn, sizeof(double));
+            L->delta = (double *)calloc(nn, sizeof(double));
+            L->Delta = (double *)calloc(nn, sizeof(double));
+            orc_dilu_setup_1x1(L->n, L->rp, L->ci, L->va, L->num_colors, L->colors, L->sorted_rows, L->color_offsets, L->Einv);
+        }
         L->tmp = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
         if (num_levels >= max_levels || L->n <= min_coarse_rows) { L->coarsest = 1; break; }
         L->agg = (int *)malloc(sizeof(int) * (size_t)L->n);
@@ -463,6 +487,7 @@ ORC_API void orc_amg_free(orc_amg *a)
         orc_level *L = &a->lv[l];
         if (L->own) { free(L->rp); free(L->ci); free(L->va); }
         free(L->agg); free(L->Rp); free(L->Rc); free(L->d); free(L->bc); free(L->xc); free(L->r); free(L->tmp);
+        free(L->colors); free(L->sorted_rows); free(L->color_offsets); free(L->Einv); free(L->delta); free(L->Delta);
     }
     free(a->lv);
     free(a);
@@ -472,6 +497,14 @@ ORC_API int orc_amg_num_levels(const orc_amg *a) { return a->num_levels; }
 ORC_API void orc_amg_level_sizes(const orc_amg *a, int l, int *n, int *nnz, int *nagg)
 {
     *n = a->lv[l].n; *nnz = a->lv[l].nnz; *nagg = a->lv[l].nagg;
+}
+ORC_API int orc_amg_level_dilu(const orc_amg *a, int l, int *colors, double *Einv)
+{
+    const orc_level *L = &a->lv[l];
+    if (!L->colors) return 0;
+    if (colors) memcpy(colors, L->colors, sizeof(int) * (size_t)L->n);
+    if (Einv) memcpy(Einv, L->Einv, sizeof(double) * (size_t)L->n);
+    return L->num_colors;
 }
 ORC_API void orc_amg_level_arrays(const orc_amg *a, int l, int *rp, int *ci, double *va, int *agg, int *Rp, int *Rc, double *d)
 {
@@ -488,6 +521,13 @@ ORC_API void orc_amg_level_arrays(const orc_amg *a, int l, int *rp, int *ci, dou
 /* smoother->solve(b, x, xIsZero) with max_iters = sweeps (Solver::solve loop without monitoring) */
 static void smooth(const orc_amg *a, orc_level *L, const double *b, double *x, int x_is_zero, int sweeps)
 {
+    if (a->smoother == 2) {
+        for (int it = 0; it < sweeps; it++) {
+            if (it == 0 && x_is_zero) memset(x, 0, sizeof(double) * (size_t)L->n);
+            orc_dilu_sweep_1x1(L->n, L->rp, L->ci, L->va, L->num_colors, L->colors, L->sorted_rows, L->color_offsets, L->Einv, b, x, a->omega, L->delta, L->Delta);
+        }
+        return;
+    }
     for (int it = 0; it < sweeps; it++) {
         if (it == 0 && x_is_zero) { orc_jacobi_zero(L->n, L->d, b, x, a->omega); continue; }
         orc_jacobi_sweep(L->n, L->rp, L->ci, L->va, L->d, b, x, L->tmp, a->omega);
@@ -584,5 +624,393 @@ ORC_API int orc_pcg(int n, const int *rp, const int *ci, const double *va, const
 finish:
     if (converged_out) *converged_out = conv;
     free(r); free(z); free(p); free(Ap); free(dj);
+    return it;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* FGMRES(m): FGMRES_Solver::solve_iteration (src/solvers/fgmres_solver.cu:406-569) inside the   */
+/* Solver::solve loop, scalar L2 norm (convergence estimate |s[m+1]|), krylov_dim == restart.   */
+/* precond: 0 none, 1 AMG V-cycle (zero guess), 2 Jacobi zero-guess sweep.                      */
+/* ------------------------------------------------------------------------------------------- */
+static void gen_rot(double dx, double dy, double *cs, double *sn)
+{
+    if (dy < 0.0) { *cs = 1.0; *sn = 0.0; }
+    else if (fabs(dy) > fabs(dx)) { double t = dx / dy; *sn = 1.0 / sqrt(1.0 + t * t); *cs = t * *sn; }
+    else { double t = dy / dx; *cs = 1.0 / sqrt(1.0 + t * t); *sn = t * *cs; }
+}
+
+ORC_API int orc_fgmres(int n, const int *rp, const int *ci, const double *va, const orc_amg *amg, int precond, double jac_omega, const double *b,
+                       double *x, int x_is_zero, double tol, int max_iters, int restart, double *res_hist, int *converged_out)
+{
+    const int R = restart;
+    double **V = (double **)malloc(sizeof(double *) * (size_t)(R + 1)), **Z = (double **)malloc(sizeof(double *) * (size_t)R);
+    for (int i = 0; i <= R; i++) V[i] = (double *)calloc((size_t)n, sizeof(double));
+    for (int i = 0; i < R; i++) Z[i] = (double *)calloc((size_t)n, sizeof(double));
+    double *H = (double *)calloc((size_t)(R + 2) * (R + 1), sizeof(double));
+    double *s = (double *)calloc((size_t)R + 2, sizeof(double)), *cs = (double *)calloc((size_t)R + 1, sizeof(double)), *sn = (double *)calloc((size_t)R + 1, sizeof(double));
+    double *r = (double *)malloc(sizeof(double) * (size_t)n), *dj = NULL;
+#define HH(i, j) H[(size_t)(i) * (R + 1) + (j)]
+    if (precond == 2) { dj = (double *)malloc(sizeof(double) * (size_t)n); orc_extract_diag(n, rp, ci, va, dj); }
+    /* Solver::solve: initial residual + norm */
+    if (x_is_zero) memcpy(r, b, sizeof(double) * (size_t)n);
+    else orc_residual(n, rp, ci, va, x, b, r);
+    double nrm = orc_nrm2(n, r), nrm_ini = nrm, beta = 0.0;
+    res_hist[0] = nrm;
+    int done = conv_relative_ini(nrm, nrm_ini, tol), it = 0, conv = done;
+    if (max_iters == 0) { conv = 0; goto fin; }
+    for (it = 0; it < max_iters && !done; it++) {
+        const int m = it % R;
+        if (m == 0) {
+            orc_residual(n, rp, ci, va, x, b, V[0]);
+            beta = orc_nrm2(n, V[0]);
+            if (it == 0 && conv_relative_ini(beta, nrm_ini, tol)) { res_hist[it + 1] = beta; conv = 1; it++; break; }
+            { const double a = 1.0 / beta; for (int i = 0; i < n; i++) V[0][i] = V[0][i] * a; }
+            for (int i = 0; i < R + 2; i++) s[i] = 0.0;
+            s[0] = beta;
+        }
+        if (precond == 1) orc_amg_vcycle(amg, V[m], Z[m], 1);
+        else if (precond == 2) orc_jacobi_zero(n, dj, V[m], Z[m], jac_omega);
+        else memcpy(Z[m], V[m], sizeof(double) * (size_t)n);
+        orc_spmv(n, rp, ci, va, Z[m], V[m + 1]);
+        for (int i = 0; i <= m; i++) {
+            const double h = orc_dot(n, V[i], V[m + 1]);
+            HH(i, m) = h;
+            for (int k = 0; k < n; k++) V[m + 1][k] = fma(-h, V[i][k], V[m + 1][k]);
+        }
+        HH(m + 1, m) = orc_nrm2(n, V[m + 1]);
+        { const double a = 1.0 / HH(m + 1, m); for (int k = 0; k < n; k++) V[m + 1][k] = V[m + 1][k] * a; }
+        for (int k = 0; k < m; k++) {
+            const double t = cs[k] * HH(k, m) + sn[k] * HH(k + 1, m);
+            HH(k + 1, m) = -sn[k] * HH(k, m) + cs[k] * HH(k + 1, m);
+            HH(k, m) = t;
+        }
+        gen_rot(HH(m, m), HH(m + 1, m), &cs[m], &sn[m]);
+        HH(m, m) = cs[m] * HH(m, m) + sn[m] * HH(m + 1, m);
+        HH(m + 1, m) = 0.0;
+        { const double t = cs[m] * s[m]; s[m + 1] = -sn[m] * s[m]; s[m] = t; }
+        beta = fabs(s[m + 1]);
+        res_hist[it + 1] = beta;
+        const int cv = conv_relative_ini(beta, nrm_ini, tol);
+        if (m == R - 1 || it == max_iters - 1 || cv) {
+            for (int j = m; j >= 0; j--) {
+                s[j] /= HH(j, j);
+                for (int k = j - 1; k >= 0; k--) s[k] -= HH(k, j) * s[j];
+            }
+            for (int j = 0; j <= m; j++) for (int k = 0; k < n; k++) x[k] = fma(s[j], Z[j][k], x[k]);
+        }
+        if (cv) { conv = 1; done = 1; it++; break; }
+    }
+fin:
+    if (converged_out) *converged_out = conv;
+    for (int i = 0; i <= R; i++) free(V[i]);
+    for (int i = 0; i < R; i++) free(Z[i]);
+    free(V); free(Z); free(H); free(s); free(cs); free(sn); free(r); free(dj);
+#undef HH
+    return it;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* MIN_MAX colouring, one ring (src/matrix_coloring/min_max.cu:103-160, 380-420).  Signed hash     */
+/* comparison; a pass colours local maxima `c` and local minima `c+1`; repeat while more than       */
+/* max_uncolored_fraction*n rows are uncoloured (0 with determinism_flag).  Returns num_colors.     */
+/* ------------------------------------------------------------------------------------------- */
+ORC_API int orc_color_min_max(int n, const int *rp, const int *ci, double max_uncolored_fraction, int *colors)
+{
+    int *snap = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) colors[i] = 0;
+    const int max_uncolored = (int)(max_uncolored_fraction * (double)n);
+    int num_colors = 1;
+    for (int num_uncolored = n; num_uncolored > max_uncolored;) {
+        memcpy(snap, colors, sizeof(int) * (size_t)n);
+        for (int i = 0; i < n; i++) {
+            if (snap[i] != 0) continue;
+            const int hash_i = (int)hash_val((unsigned)i, 0);
+            int max_i = 1, min_i = 1;
+            for (int r = rp[i]; r < rp[i + 1]; r++) {
+                const int j = ci[r];
+                if (j >= n) continue;
+                const int hash_j = (int)hash_val((unsigned)j, 0);
+                const int cj = snap[j];
+                if (hash_j > hash_i && (cj == 0 || cj == num_colors)) max_i = 0;
+                if (hash_j < hash_i && (cj == 0 || cj == num_colors + 1)) min_i = 0;
+            }
+            if (max_i) colors[i] = num_colors;
+            else if (min_i) colors[i] = num_colors + 1;
+        }
+        num_colors += 2;
+        num_uncolored = 0;
+        for (int i = 0; i < n; i++) num_uncolored += (colors[i] == 0);
+    }
+    int mx = 0;
+    for (int i = 0; i < n; i++) if (colors[i] > mx) mx = colors[i];
+    free(snap);
+    return mx + 1;
+}
+
+/* createColorArrays (src/matrix_coloring/matrix_coloring.cu:230-281): rows stably sorted by colour */
+ORC_API void orc_color_arrays(int n, int num_colors, const int *colors, int *sorted_rows, int *offsets)
+{
+    for (int c = 0; c <= num_colors; c++) offsets[c] = 0;
+    for (int i = 0; i < n; i++) offsets[colors[i] + 1]++;
+    for (int c = 0; c < num_colors; c++) offsets[c + 1] += offsets[c];
+    int *pos = (int *)malloc(sizeof(int) * (size_t)(num_colors > 0 ? num_colors : 1));
+    for (int c = 0; c < num_colors; c++) pos[c] = offsets[c];
+    for (int i = 0; i < n; i++) sorted_rows[pos[colors[i]]++] = i;
+    free(pos);
+}
+
+/* butterfly reduction over `w` lanes: v[l] += v[l ^ m] for m = w/2 .. 1 (all lanes end with the same sum) */
+static double butterfly(double *v, int w)
+{
+    double t[32];
+    for (int m = w / 2; m > 0; m >>= 1) {
+        for (int l = 0; l < w; l++) t[l] = v[l] + v[l ^ m];
+        for (int l = 0; l < w; l++) v[l] = t[l];
+    }
+    return v[0];
+}
+
+/* DILU_setup_1x1_kernel (src/solvers/multicolor_dilu_solver.cu:643-812): colour by colour;
+ * lane (k - row_begin) % 32 accumulates e += (a_ji*Einv_j)*a_ij with one FMA, then a 32-lane butterfly. */
+ORC_API void orc_dilu_setup_1x1(int n, const int *rp, const int *ci, const double *va, int num_colors, const int *colors, const int *sorted_rows,
+                                const int *offsets, double *Einv)
+{
+    int *diag = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    orc_diag_index(n, rp, ci, diag);
+    for (int i = 0; i < n; i++) Einv[i] = 0.0;
+    for (int c = 0; c < num_colors; c++)
+        for (int q = offsets[c]; q < offsets[c + 1]; q++) {
+            const int i = sorted_rows[q];
+            double lane[32];
+            for (int l = 0; l < 32; l++) lane[l] = 0.0;
+            if (c != 0)
+                for (int k = rp[i]; k < rp[i + 1]; k++) {
+                    const int j = ci[k];
+                    if (j == i || colors[j] >= c) continue;
+                    double a_ji = 0.0;
+                    for (int kk = rp[j]; kk < rp[j + 1]; kk++)
+                        if (ci[kk] == i) { a_ji = va[kk]; break; }
+                    const int l = (k - rp[i]) % 32;
+                    lane[l] = fma(a_ji * Einv[j], va[k], lane[l]);
+                }
+            const double e_out = butterfly(lane, 32);
+            double res = (diag[i] >= 0 ? va[diag[i]] : 0.0) - e_out;
+            if (res != 0.0) res = 1.0 / res;
+            Einv[i] = res;
+        }
+    free(diag);
+}
+
+/* one DILU sweep, 1x1 (forward :1763-1901, backward :2772-2881, last colour :2885-2915), 8 lanes per row */
+ORC_API void orc_dilu_sweep_1x1(int n, const int *rp, const int *ci, const double *va, int num_colors, const int *colors, const int *sorted_rows,
+                                const int *offsets, const double *Einv, const double *b, double *x, double weight, double *delta, double *Delta)
+{
+    for (int c = 0; c < num_colors; c++)
+        for (int q = offsets[c]; q < offsets[c + 1]; q++) {
+            const int i = sorted_rows[q];
+            double lane[8];
+            for (int l = 0; l < 8; l++) lane[l] = 0.0;
+            lane[0] = b[i];
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                const int j = ci[k], l = (k - rp[i]) % 8;
+                double xx = x[j];
+                if (c != 0 && j < n && colors[j] < c) xx += delta[j];
+                lane[l] = fma(-va[k], xx, lane[l]);
+            }
+            delta[i] = Einv[i] * butterfly(lane, 8);
+        }
+    for (int c = num_colors - 1; c >= 0; c--)
+        for (int q = offsets[c]; q < offsets[c + 1]; q++) {
+            const int i = sorted_rows[q];
+            if (c == num_colors - 1) {
+                const double v = delta[i];
+                x[i] = fma(weight, v, x[i]);
+                Delta[i] = v;
+                continue;
+            }
+            double lane[8];
+            for (int l = 0; l < 8; l++) lane[l] = 0.0;
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                const int j = ci[k], l = (k - rp[i]) % 8;
+                if (c != 0 && j < n && colors[j] > c) lane[l] = fma(va[k], Delta[j], lane[l]);
+            }
+            const double v = fma(-Einv[i], butterfly(lane, 8), delta[i]);   /* delta - Einv*acc, contracted on the device */
+            x[i] = fma(weight, v, x[i]);
+            Delta[i] = v;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* 4x4 block kernels (values fp64 here; the fp32-matrix mode is checked with a tolerance)        */
+/* ------------------------------------------------------------------------------------------- */
+ORC_API void orc_bspmv4(int n, const int *rp, const int *ci, const double *va, const double *x, double *y)
+{
+    for (int i = 0; i < n; i++)
+        for (int r = 0; r < 4; r++) {
+            double s = 0.0;
+            for (int k = rp[i]; k < rp[i + 1]; k++)
+                for (int m = 0; m < 4; m++) s = fma(va[(size_t)k * 16 + r * 4 + m], x[(size_t)ci[k] * 4 + m], s);
+            y[(size_t)i * 4 + r] = s;
+        }
+}
+
+/* Gauss-Jordan without pivoting, order of compute_block_inverse_row_major (block_common_solver.h:106-137) */
+ORC_API void orc_invert4x4(double *A)
+{
+    for (int row = 0; row < 4; row++) {
+        const double diag = 1.0 / guard_d(A[row * 4 + row]);
+        for (int j = 0; j < 4; j++) if (j != row) A[row * 4 + j] = A[row * 4 + j] * diag;
+        for (int i = 0; i < 4; i++) if (i != row)
+            for (int j = 0; j < 4; j++) if (j != row) A[i * 4 + j] = fma(-A[i * 4 + row], A[row * 4 + j], A[i * 4 + j]);
+        for (int j = 0; j < 4; j++) A[j * 4 + row] = (j == row) ? diag : -(A[j * 4 + row] * diag);
+    }
+}
+
+ORC_API void orc_bjacobi4_dinv(int n, const int *rp, const int *ci, const double *va, double *dinv)
+{
+    for (int i = 0; i < n; i++) {
+        for (int m = 0; m < 16; m++) dinv[(size_t)i * 16 + m] = 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; k++)
+            if (ci[k] == i) { memcpy(dinv + (size_t)i * 16, va + (size_t)k * 16, sizeof(double) * 16); break; }
+        orc_invert4x4(dinv + (size_t)i * 16);
+    }
+}
+
+/* jacobiSmooth4by4BlockDiaCsrKernel_NAIVE_tex_readDinv2 (block_jacobi_solver.cu:665-739) */
+ORC_API void orc_bjacobi4_sweep(int n, const int *rp, const int *ci, const double *va, const double *dinv, const double *b, const double *x,
+                                double *xout, double weight)
+{
+    for (int i = 0; i < n; i++) {
+        double bm[4];
+        for (int r = 0; r < 4; r++) {
+            double acc = b[(size_t)i * 4 + r];
+            for (int k = rp[i]; k < rp[i + 1]; k++)
+                if (ci[k] == i) { for (int m = 0; m < 4; m++) acc = fma(-va[(size_t)k * 16 + r * 4 + m], x[(size_t)i * 4 + m], acc); break; }
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                if (ci[k] == i) continue;
+                for (int m = 0; m < 4; m++) acc = fma(-va[(size_t)k * 16 + r * 4 + m], x[(size_t)ci[k] * 4 + m], acc);
+            }
+            bm[r] = acc;
+        }
+        for (int r = 0; r < 4; r++) {
+            double t = 0.0;
+            for (int m = 0; m < 4; m++) t = fma(dinv[(size_t)i * 16 + r * 4 + m], bm[m], t);
+            xout[(size_t)i * 4 + r] = fma(t, weight, x[(size_t)i * 4 + r]);
+        }
+    }
+}
+
+ORC_API void orc_bjacobi4_zero(int n, const double *dinv, const double *b, double *x, double weight)
+{
+    for (int i = 0; i < n; i++)
+        for (int r = 0; r < 4; r++) {
+            double t = 0.0;
+            for (int m = 0; m < 4; m++) t = fma(dinv[(size_t)i * 16 + r * 4 + m], b[(size_t)i * 4 + m], t);
+            x[(size_t)i * 4 + r] = t * weight;
+        }
+}
+
+/* DILU 4x4: setup (:362-640) and one sweep (:1585-1759, 2604-2768) -- plain formulas, tolerance-checked */
+ORC_API void orc_dilu_setup_4x4(int n, const int *rp, const int *ci, const double *va, int num_colors, const int *colors, const int *sorted_rows,
+                                const int *offsets, double *Einv)
+{
+    for (size_t t = 0; t < (size_t)n * 16; t++) Einv[t] = 0.0;
+    for (int c = 0; c < num_colors; c++)
+        for (int q = offsets[c]; q < offsets[c + 1]; q++) {
+            const int i = sorted_rows[q];
+            double E[16];
+            for (int m = 0; m < 16; m++) E[m] = 0.0;
+            for (int k = rp[i]; k < rp[i + 1]; k++) if (ci[k] == i) { memcpy(E, va + (size_t)k * 16, sizeof(E)); break; }
+            if (c != 0)
+                for (int k = rp[i]; k < rp[i + 1]; k++) {
+                    const int j = ci[k];
+                    if (j == i || colors[j] >= c) continue;
+                    int kji = -1;
+                    for (int kk = rp[j]; kk < rp[j + 1]; kk++) if (ci[kk] == i) { kji = kk; break; }
+                    double T[16];
+                    for (int r = 0; r < 4; r++)
+                        for (int cc = 0; cc < 4; cc++) {
+                            double t = 0.0;
+                            for (int m = 0; m < 4; m++) t += va[(size_t)k * 16 + r * 4 + m] * Einv[(size_t)j * 16 + m * 4 + cc];
+                            T[r * 4 + cc] = t;
+                        }
+                    if (kji >= 0)
+                        for (int r = 0; r < 4; r++)
+                            for (int cc = 0; cc < 4; cc++)
+                                for (int m = 0; m < 4; m++) E[r * 4 + cc] -= T[r * 4 + m] * va[(size_t)kji * 16 + m * 4 + cc];
+                }
+            orc_invert4x4(E);
+            memcpy(Einv + (size_t)i * 16, E, sizeof(E));
+        }
+}
+
+ORC_API void orc_dilu_sweep_4x4(int n, const int *rp, const int *ci, const double *va, int num_colors, const int *colors, const int *sorted_rows,
+                                const int *offsets, const double *Einv, const double *b, double *x, double weight, double *delta, double *Delta)
+{
+    for (int c = 0; c < num_colors; c++)
+        for (int q = offsets[c]; q < offsets[c + 1]; q++) {
+            const int i = sorted_rows[q];
+            double acc[4];
+            for (int r = 0; r < 4; r++) {
+                acc[r] = b[(size_t)i * 4 + r];
+                for (int k = rp[i]; k < rp[i + 1]; k++) {
+                    const int j = ci[k];
+                    const int valid = c != 0 && j < n && colors[j] < c;
+                    for (int m = 0; m < 4; m++) {
+                        double xx = x[(size_t)j * 4 + m];
+                        if (valid) xx += delta[(size_t)j * 4 + m];
+                        acc[r] -= va[(size_t)k * 16 + r * 4 + m] * xx;
+                    }
+                }
+            }
+            for (int r = 0; r < 4; r++) {
+                double y = 0.0;
+                for (int m = 0; m < 4; m++) y += Einv[(size_t)i * 16 + r * 4 + m] * acc[m];
+                delta[(size_t)i * 4 + r] = y;
+            }
+        }
+    for (int c = num_colors - 1; c >= 0; c--)
+        for (int q = offsets[c]; q < offsets[c + 1]; q++) {
+            const int i = sorted_rows[q];
+            double acc[4] = {0, 0, 0, 0};
+            if (c != num_colors - 1)
+                for (int r = 0; r < 4; r++)
+                    for (int k = rp[i]; k < rp[i + 1]; k++) {
+                        const int j = ci[k];
+                        if (!(c != 0 && j < n && colors[j] > c)) continue;
+                        for (int m = 0; m < 4; m++) acc[r] += va[(size_t)k * 16 + r * 4 + m] * Delta[(size_t)j * 4 + m];
+                    }
+            for (int r = 0; r < 4; r++) {
+                double y = 0.0;
+                for (int m = 0; m < 4; m++) y += Einv[(size_t)i * 16 + r * 4 + m] * acc[m];
+                const double v = delta[(size_t)i * 4 + r] - y;
+                x[(size_t)i * 4 + r] += weight * v;
+                Delta[(size_t)i * 4 + r] = v;
+            }
+        }
+}
+
+/* AMG as the outer solver: Solver::solve loop (src/solvers/solver.cu:585-970) around
+ * AlgebraicMultigrid_Solver::solve_iteration (one V-cycle, then residual + norm + RELATIVE_INI check). */
+ORC_API int orc_amg_solve(const orc_amg *amg, int n, const int *rp, const int *ci, const double *va, const double *b, double *x, int x_is_zero,
+                          double tol, int max_iters, int norm_type, double *res_hist, int *converged_out)
+{
+    double *r = (double *)malloc(sizeof(double) * (size_t)n);
+    if (x_is_zero) memcpy(r, b, sizeof(double) * (size_t)n);
+    else orc_residual(n, rp, ci, va, x, b, r);
+    double nrm = norm_of(n, r, norm_type), nrm_ini = nrm;
+    res_hist[0] = nrm;
+    int done = conv_relative_ini(nrm, nrm_ini, tol), conv = done, it = 0;
+    if (max_iters == 0) conv = 0;
+    else
+        for (it = 0; it < max_iters && !done; it++) {
+            orc_amg_vcycle(amg, b, x, x_is_zero && it == 0);
+            orc_residual(n, rp, ci, va, x, b, r);
+            nrm = norm_of(n, r, norm_type);
+            res_hist[it + 1] = nrm;
+            if (conv_relative_ini(nrm, nrm_ini, tol)) { done = 1; conv = 1; it++; break; }
+        }
+    if (converged_out) *converged_out = conv;
+    free(r);
     return it;
 }

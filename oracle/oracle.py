@@ -143,7 +143,7 @@ class AMG:
                  finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, max_iterations=15, max_unassigned=0.05, merge_singletons=1, weight_formula=0):
         self.rp, self.ci, self.va = _i(rp), _i(ci), _d(va)
         self.n = self.rp.shape[0] - 1
-        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1}[smoother]
+        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2}[smoother]
         self.h = C.c_void_p(lib().orc_amg_setup(self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold),
                                                 presweeps, postsweeps, coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), max_iterations,
                                                 C.c_double(max_unassigned), merge_singletons, weight_formula))
@@ -193,3 +193,88 @@ def pcg(rp, ci, va, b, amg: AMG | None = None, jacobi_omega: float | None = None
     it = lib().orc_pcg(n, _p(rp), _p(ci), _p(va), amg.h if amg is not None else None, precond, C.c_double(jacobi_omega or 0.0), _p(b), _p(x),
                        int(zero), C.c_double(tol), max_iters, nt, _p(hist), C.byref(conv))
     return x, it, hist[: it + 1].copy(), bool(conv.value)
+
+
+def fgmres(rp, ci, va, b, amg: AMG | None = None, jacobi_omega: float | None = None, x0=None, tol=1e-6, max_iters=100, restart=20):
+    rp, ci, va, b = _i(rp), _i(ci), _d(va), _d(b)
+    n = rp.shape[0] - 1
+    zero = x0 is None
+    x = np.zeros(n) if zero else _d(x0).copy()
+    hist = np.zeros(max_iters + 1)
+    conv = C.c_int()
+    precond = 1 if amg is not None else (2 if jacobi_omega is not None else 0)
+    it = lib().orc_fgmres(n, _p(rp), _p(ci), _p(va), amg.h if amg is not None else None, precond, C.c_double(jacobi_omega or 0.0), _p(b), _p(x),
+                          int(zero), C.c_double(tol), max_iters, restart, _p(hist), C.byref(conv))
+    return x, it, hist[: it + 1].copy(), bool(conv.value)
+
+
+def set_uncolored_fraction(f: float):
+    lib().orc_set_uncolored_fraction(C.c_double(f))
+
+
+def amg_solve(amg: AMG, b, x0=None, tol=1e-6, max_iters=100, norm="L2"):
+    b = _d(b)
+    zero = x0 is None
+    x = np.zeros(amg.n) if zero else _d(x0).copy()
+    hist = np.zeros(max_iters + 1)
+    conv = C.c_int()
+    nt = {"L1": 0, "L2": 1, "LMAX": 2}[norm]
+    it = lib().orc_amg_solve(amg.h, amg.n, _p(amg.rp), _p(amg.ci), _p(amg.va), _p(b), _p(x), int(zero), C.c_double(tol), max_iters, nt, _p(hist), C.byref(conv))
+    return x, it, hist[: it + 1].copy(), bool(conv.value)
+
+
+def amg_level_dilu(amg: AMG, l: int):
+    n = amg.level(l)["n"]
+    colors = np.empty(n, np.int32)
+    einv = np.empty(n)
+    nc = lib().orc_amg_level_dilu(amg.h, l, _p(colors), _p(einv))
+    return nc, colors, einv
+
+
+def color_min_max(rp, ci, max_uncolored_fraction=0.15):
+    rp, ci = _i(rp), _i(ci)
+    n = rp.shape[0] - 1
+    colors = np.empty(n, np.int32)
+    nc = lib().orc_color_min_max(n, _p(rp), _p(ci), C.c_double(max_uncolored_fraction), _p(colors))
+    sorted_rows = np.empty(n, np.int32)
+    offsets = np.empty(nc + 1, np.int32)
+    lib().orc_color_arrays(n, nc, _p(colors), _p(sorted_rows), _p(offsets))
+    return nc, colors, sorted_rows, offsets
+
+
+def bspmv4(rp, ci, va, x):
+    rp, ci, va, x = _i(rp), _i(ci), _d(va), _d(x)
+    n = rp.shape[0] - 1
+    y = np.empty(n * 4)
+    lib().orc_bspmv4(n, _p(rp), _p(ci), _p(va), _p(x), _p(y))
+    return y
+
+
+def bjacobi4_dinv(rp, ci, va):
+    rp, ci, va = _i(rp), _i(ci), _d(va)
+    n = rp.shape[0] - 1
+    d = np.empty(n * 16)
+    lib().orc_bjacobi4_dinv(n, _p(rp), _p(ci), _p(va), _p(d))
+    return d
+
+
+def bjacobi4_sweep(rp, ci, va, dinv, b, x, weight):
+    rp, ci, va, dinv, b, x = _i(rp), _i(ci), _d(va), _d(dinv), _d(b), _d(x)
+    n = rp.shape[0] - 1
+    out = np.empty(n * 4)
+    lib().orc_bjacobi4_sweep(n, _p(rp), _p(ci), _p(va), _p(dinv), _p(b), _p(x), _p(out), C.c_double(weight))
+    return out
+
+
+def dilu4(rp, ci, va, b, x, weight, max_uncolored_fraction=0.15, sweeps=1):
+    """colour (on the block graph), set up Einv and run `sweeps` DILU sweeps on a 4x4 block matrix; returns (x, Einv, colors)"""
+    rp, ci, va, b = _i(rp), _i(ci), _d(va), _d(b)
+    n = rp.shape[0] - 1
+    nc, colors, srows, offs = color_min_max(rp, ci, max_uncolored_fraction)
+    einv = np.empty(n * 16)
+    lib().orc_dilu_setup_4x4(n, _p(rp), _p(ci), _p(va), nc, _p(colors), _p(srows), _p(offs), _p(einv))
+    x = _d(x).copy()
+    delta, Delta = np.zeros(n * 4), np.zeros(n * 4)
+    for _ in range(sweeps):
+        lib().orc_dilu_sweep_4x4(n, _p(rp), _p(ci), _p(va), nc, _p(colors), _p(srows), _p(offs), _p(einv), _p(b), _p(x), C.c_double(weight), _p(delta), _p(Delta))
+    return x, einv, colors

@@ -49,6 +49,32 @@ def cfg_amg_agg_standalone(tol=1e-8, max_iters=40, pre=1, post=1, norm="L1"):
         "smoother": {"scope": "jacobi", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "monitor_residual": 0}}}
 
 
+def cfg_fgmres_agg(tol=1e-10, max_iters=60, restart=10, precond=True):
+    c = {"config_version": 2, "determinism_flag": 1, "solver": {
+        "scope": "main", "solver": "FGMRES", "max_iters": max_iters, "gmres_n_restart": restart, "monitor_residual": 1, "store_res_history": 1,
+        "convergence": "RELATIVE_INI", "tolerance": tol, "norm": "L2",
+        "preconditioner": {"scope": "amg", "solver": "AMG", "algorithm": "AGGREGATION", "selector": "SIZE_2", "cycle": "V",
+                           "max_levels": 50, "presweeps": 1, "postsweeps": 2, "coarse_solver": "NOSOLVER",
+                           "max_iters": 1, "monitor_residual": 0,
+                           "smoother": {"scope": "jacobi", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.75, "monitor_residual": 0}}}}
+    if not precond:
+        c["solver"]["preconditioner"] = {"scope": "nop", "solver": "NOSOLVER"}
+    return c
+
+
+def cfg_amg_dilu(tol=1e-8, max_iters=40, norm="L1", determinism=0):
+    return {"config_version": 2, "determinism_flag": determinism, "solver": {
+        "scope": "main", "solver": "AMG", "algorithm": "AGGREGATION", "selector": "SIZE_2", "cycle": "V", "max_levels": 50,
+        "matrix_coloring_scheme": "MIN_MAX", "max_uncolored_percentage": 0.15, "smoother": "MULTICOLOR_DILU", "relaxation_factor": 0.9,
+        "presweeps": 1, "postsweeps": 1, "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER", "max_iters": max_iters,
+        "monitor_residual": 1, "store_res_history": 1, "convergence": "RELATIVE_INI", "tolerance": tol, "norm": norm}}
+
+
+def cfg_pcg_agg_block(tol=1e-8, max_iters=60):
+    c = cfg_pcg_agg(tol=tol, max_iters=max_iters, pre=1, post=1, omega=0.9)
+    return c
+
+
 def cases():
     ex = np.load(ROOT / "tests" / "golden" / "example_matrix_12x12.npz")
     yield "example12_pcg_jacobi", (ex["row_ptr"], ex["col_idx"], ex["values"]), cfg_pcg_jacobi(), None
@@ -60,26 +86,36 @@ def cases():
     yield "poisson12_amg_standalone_L1", gallery.poisson7pt(12), cfg_amg_agg_standalone(), None
     yield "banded3000_pcg_agg_jacobi", gallery.random_banded(3000, sigma=40.0), cfg_pcg_agg(max_iters=80), None
     yield "poisson8_pcg_jacobi", gallery.poisson7pt(8), cfg_pcg_jacobi(tol=1e-10, max_iters=80), None
+    yield "poisson12_amg_dilu", gallery.poisson7pt(12), cfg_amg_dilu(), None
+    yield "poisson9_amg_dilu_det", gallery.poisson7pt(9), cfg_amg_dilu(determinism=1, norm="L2"), None
+    yield "block4_6x5x4_pcg_agg_bjacobi", gallery.block_elasticity(6, 5, 4), cfg_pcg_agg_block(), (4, "dDDI")
+    yield "block4_6x5x4_amg_dilu", gallery.block_elasticity(6, 5, 4), cfg_amg_dilu(tol=1e-8, max_iters=30, norm="L2"), (4, "dDDI")
+    yield "block4_6x5x4_amg_dilu_dDFI", gallery.block_elasticity(6, 5, 4), cfg_amg_dilu(tol=1e-5, max_iters=30, norm="L2"), (4, "dDFI")
+    yield "poisson10_fgmres_agg_jacobi", gallery.poisson7pt(10), cfg_fgmres_agg(restart=5), None
+    yield "poisson8_fgmres_noprec", gallery.poisson7pt(8), cfg_fgmres_agg(restart=12, max_iters=70, tol=1e-8, precond=False), None
+    yield "banded3000_fgmres_agg_jacobi", gallery.random_banded(3000, sigma=40.0), cfg_fgmres_agg(restart=8, max_iters=40), None
 
 
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     only = sys.argv[1:] or None
-    for name, (rp, ci, va), cfg, x0 in cases():
+    for name, (rp, ci, va), cfg, extra in cases():
         if only and name not in only:
             continue
+        bs, mode = extra if extra else (1, "dDDI")
         n = rp.shape[0] - 1
-        rhs = np.ones(n)
+        rhs = np.ones(n * bs)
         sysf, cfgf, outf = OUT / f"{name}.sys", OUT / f"{name}.json", OUT / f"{name}.bin"
-        write_system(sysf, rp, ci, va, rhs, x0=x0)
+        write_system(sysf, rp, ci, va, rhs, block=(bs, bs))
         cfgf.write_text(json.dumps(cfg, indent=1))
-        r = subprocess.run([str(REF), str(sysf), str(cfgf), str(outf)], capture_output=True, text=True)
+        r = subprocess.run([str(REF), str(sysf), str(cfgf), str(outf), mode], capture_output=True, text=True)
         if r.returncode != 0:
             print(f"[{name}] ref_dump FAILED rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
             continue
         d = read_dump(outf)
         d["config_json"] = json.dumps(cfg)
         d["sys_row_ptr"], d["sys_col_idx"], d["sys_values"], d["sys_rhs"] = rp, ci, va, rhs
+        d["sys_block"], d["sys_mode"] = np.array([bs]), mode
         np.savez_compressed(OUT / f"{name}.npz", **{k: v for k, v in d.items()})
         print(f"[{name}] n={n} status={d['status'][0]} iters={d['iterations'][0]} levels={d.get('num_levels', [0])[0]} "
               f"res0={d['res_history'][0]:.6e} resN={d['res_history'][-1]:.6e}")
