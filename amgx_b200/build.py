@@ -22,6 +22,10 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "--extended-lambda", "-Xcompiler", "
           "-DAMGXB200_BUILD", "-w"]
 
 
+# translation units whose arithmetic must match the CPU oracle bit for bit: no implicit FMA contraction
+EXTRA = {"classical.cu": ["-fmad=false"], "spgemm.cu": ["-fmad=false"]}
+
+
 def _nccl_flags():
     """Prefer the system NCCL (headers + libnccl.so); fall back to torch's bundled one."""
     inc, libs = [], []
@@ -58,7 +62,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     for src in sources():
         obj = OBJ / (src.stem + ".o")
         if force or _needs(obj, src, hm):
-            cmd = [NVCC, *ARCH, *COMMON, *inc, "-c", str(src), "-o", str(obj)]
+            cmd = [NVCC, *ARCH, *COMMON, *EXTRA.get(src.name, []), *inc, "-c", str(src), "-o", str(obj)]
             if src.suffix == ".cpp":
                 cmd = [NVCC, *ARCH, *COMMON, "-x", "cu", *inc, "-c", str(src), "-o", str(obj)]
             jobs.append((src, cmd))

@@ -257,8 +257,9 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse)
             agg_prolong_add(L.aggregates.ptr(), L.xc.ptr(), x.ptr(), xin, A.vec_prec, A.n, A.by, s);      // xin = x + P xc
         }
     } else {
-        if (x_virtual_zero) x.zero(s);
-        classical_prolong_add(L, x, s);
+        void *xin = (n_post > 0) ? sm->smooth_input(x, n_post) : x.ptr();
+        in_alt = (xin != x.ptr());
+        classical_prolong_add(L, x_virtual_zero ? nullptr : x.ptr(), xin, s);   // xin = x + P xc  (0 + P xc == P xc exactly)
     }
     if (n_post > 0) sm->smooth(b, x, false, n_post, have_fuse ? &f : nullptr, in_alt);
 }

@@ -1,0 +1,938 @@
+// classical.cu -- classical (Ruge-Stueben) AMG: setup producers and transfer operators of a classical level.
+//   strength AHAT + PMIS weights       src/classical/strength/strength_base.cu:185-330
+//   PMIS                               src/classical/selectors/pmis.cu:221-266, 370-466, 468-622
+//   aggressive PMIS (S2 second pass)   src/classical/selectors/aggressive_pmis.cu:22-150, selector.cu:116-230, 427-580, 942-1004, 1057-1070
+//   D2 "extended+i" interpolation      src/classical/interpolators/distance2.cu:600-716, 1178-1362, 1562-1796
+//   MULTIPASS interpolation            src/classical/interpolators/multipass.cu:94-147, 244-287, 1057-1206, 1538-1720
+//   truncation (interp_max_elements)   src/truncate.cu:352-456, 78-92, 783-862
+//   R = P^T, A_c = R A P               src/classical/classical_amg_level.cu:440-468, 501-586
+//   restrict / prolongate              src/classical/classical_amg_level.cu:590-644, 851-913
+// Order conventions (shared with oracle/classical_oracle.inc.c): the coarse sets of a row are kept
+// sorted by column instead of the reference's hash-table slot order, sums run left to right in storage order, and a
+// product is rounded before it is added (this file is compiled with -fmad=false).  Selection arrays are bit-comparable
+// with the reference; weights agree to rounding; ties among equal weights in the max-elements truncation follow
+// storage order.
+#include "solvers.h"
+#include "dist.h"
+#include <cub/cub.cuh>
+#include <climits>
+
+namespace amgxb {
+
+void spgemm_csr(int m, const DevBuf<int> &arp, const DevBuf<int> &aci, const DevVec &ava, const DevBuf<int> &brp, const DevBuf<int> &bci, const DevVec &bva,
+                DevBuf<int> &crp, DevBuf<int> &cci, DevVec &cva, int *c_nnz, cudaStream_t s);
+
+namespace {
+
+constexpr int COARSE = -1, FINE = -2, STRONG_FINE = -3, UNASSIGNED = -4;
+typedef unsigned char u8;
+typedef long long i64;
+
+inline int grid_for(i64 n) { return (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, 148 * 16)); }
+#define ROW_LOOP(i, n) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += gridDim.x * blockDim.x)
+
+__host__ __device__ inline float cla_hash(int i)   // ourHash, strength_base.cu:41-55
+{
+    unsigned a = (unsigned)i;
+    a = (a + 0x7ed55d16u) + (a << 12);
+    a = (a ^ 0xc761c23cu) + (a >> 19);
+    a = (a + 0x165667b1u) + (a << 5);
+    a = (a ^ 0xd3a2646cu) + (a << 9);
+    a = (a + 0xfd7046c5u) + (a << 3);
+    a = (a ^ 0xb55a4f09u) + (a >> 16);
+    return (float)(a ^ 0x4a51e590u) / (float)UINT_MAX;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// strength of connection
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void strength_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va, double alpha, double max_row_sum,
+                                int compute_row_sum, u8 *__restrict__ s_con, int *cnt)
+{
+    ROW_LOOP(row, n) {
+        double diag = 0, minv = 0, maxv = 0, sum = 0, dsum = 0;
+        const int r0 = rp[row], r1 = rp[row + 1];
+        for (int j = r0; j < r1; j++) {
+            const double v = va[j];
+            if (ci[j] == row) diag = v;
+            else { minv = fmin(minv, v); maxv = fmax(maxv, v); }
+            sum += v;
+            if (ci[j] == row && v != 0) dsum = v;
+        }
+        const double row_sum = compute_row_sum ? fabs(sum / dsum) : -1.0;
+        const double thr = ((diag < 0) ? maxv : minv) * alpha;
+        for (int j = r0; j < r1; j++) {
+            bool strong = false;
+            if (!(compute_row_sum && row_sum > max_row_sum)) strong = ci[j] != row && ((diag < 0) ? va[j] > thr : va[j] < thr);
+            s_con[j] = strong;
+            if (strong && ci[j] < n) atomicAdd(&cnt[ci[j]], 1);
+        }
+    }
+}
+__global__ void pattern_count_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, int *cnt)   // computeWeightsKernel
+{
+    ROW_LOOP(i, n)
+        for (int j = rp[i]; j < rp[i + 1]; j++)
+            if (ci[j] != i) atomicAdd(&cnt[ci[j]], 1);
+}
+__global__ void weights_kernel(int n, const int *__restrict__ cnt, float *w) { ROW_LOOP(i, n) w[i] = (float)cnt[i] + cla_hash(i); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// PMIS
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pmis_init_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, float *w, int *cf, int init)
+{
+    ROW_LOOP(i, n) {
+        const int r0 = rp[i], numj = rp[i + 1] - r0;
+        int c;
+        if (numj == 0) c = FINE;
+        else if (numj == 1 && ci[r0] == i) c = FINE;
+        else if (w[i] < 1) c = FINE;
+        else c = UNASSIGNED;
+        bool isolated = true;
+        for (int j = r0; j < r0 + numj; j++)
+            if (!s_con || s_con[j]) { isolated = false; break; }
+        if (isolated) { c = (init == 3) ? COARSE : STRONG_FINE; w[i] = 0.f; }
+        cf[i] = c;
+    }
+}
+__global__ void pmis_mark_coarse_kernel(int n, const float *__restrict__ w, const int *__restrict__ cf_in, int *cf_out, int *mark)
+{
+    ROW_LOOP(i, n) {
+        const int in = cf_in[i], un = (in == UNASSIGNED);
+        mark[i] = un;
+        cf_out[i] = (w[i] > 1.f) ? (un ? COARSE : in) : in;
+    }
+}
+__global__ void pmis_unmark_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, const float *__restrict__ w,
+                                   int *cf_out, const int *__restrict__ mark)
+{
+    ROW_LOOP(i, n) {
+        if (mark[i] <= 0) continue;
+        const float wr = w[i];
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            if (s_con && !s_con[j]) continue;
+            const int jc = ci[j];
+            if (jc >= n) continue;
+            const float wc = w[jc];
+            if (mark[jc] && wc > 1.0f) {
+                if (wr > wc) cf_out[jc] = UNASSIGNED;        // every write stores UNASSIGNED: the interleaving does not matter
+                else if (wc > wr) cf_out[i] = UNASSIGNED;
+            }
+        }
+    }
+}
+__global__ void pmis_mark_fine_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, const int *__restrict__ cf_in,
+                                      int *cf_out, int *num_unassigned)
+{
+    int un = 0;
+    ROW_LOOP(i, n) {
+        const int in = cf_in[i];
+        bool fine = false;
+        if (in == UNASSIGNED)
+            for (int j = rp[i]; !fine && j < rp[i + 1]; j++) {
+                if (s_con && !s_con[j]) continue;
+                if (ci[j] < n) fine = cf_in[ci[j]] == COARSE;
+            }
+        const int out = fine ? FINE : in;
+        cf_out[i] = out;
+        un += (out == UNASSIGNED);
+    }
+    un = __reduce_add_sync(0xffffffffu, un);
+    if ((threadIdx.x & 31) == 0 && un) atomicAdd(num_unassigned, un);
+}
+
+void pmis(int n, const int *rp, const int *ci, const u8 *s_con, float *w, int *cf, int init, cudaStream_t s)
+{
+    if (n == 0) return;
+    DevBuf<int> scratch, mark, cnt;
+    scratch.resize(n);
+    mark.resize(n);
+    mark.zero(s);
+    cnt.resize(1);
+    const int g = grid_for(n);
+    pmis_init_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, w, cf, init);
+    count_launch();
+    int iter = 0, num_unassigned;
+    do {
+        if (iter || !init) {
+            pmis_mark_coarse_kernel<<<g, 256, 0, s>>>(n, w, cf, scratch.ptr(), mark.ptr());
+            pmis_unmark_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, w, scratch.ptr(), mark.ptr());
+            count_launch(2);
+        } else {
+            AMGXB_CUDA_CHECK(cudaMemcpyAsync(scratch.ptr(), cf, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+        }
+        cnt.zero(s);
+        pmis_mark_fine_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, scratch.ptr(), cf, cnt.ptr());
+        count_launch();
+        AMGXB_LAUNCH_CHECK();
+        num_unassigned = cnt.to_host(s)[0];
+        iter++;
+        if (iter > 10000) fatal(AMGX_RC_INTERNAL, "PMIS did not terminate");
+    } while (num_unassigned != 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// scans / renumbering
+// ---------------------------------------------------------------------------------------------------------------
+template <class T> void exclusive_scan(const T *in, T *out, size_t count, cudaStream_t s)
+{
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, count, s);
+    DevBytes tmp;
+    tmp.resize(tb);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, count, s);
+    count_launch();
+}
+__global__ void flag_coarse_kernel(int n, const int *__restrict__ cf, int *flag) { ROW_LOOP(i, n) flag[i] = (cf[i] == COARSE); if (blockIdx.x == 0 && threadIdx.x == 0) flag[n] = 0; }
+__global__ void assign_coarse_kernel(int n, int *cf, const int *__restrict__ scan) { ROW_LOOP(i, n) if (cf[i] == COARSE) cf[i] = scan[i]; }
+
+int renumber_coarse(int n, int *cf, cudaStream_t s)   // renumberAndCountCoarsePoints
+{
+    if (n == 0) return 0;
+    DevBuf<int> flag, scan;
+    flag.resize((size_t)n + 1);
+    scan.resize((size_t)n + 1);
+    flag_coarse_kernel<<<grid_for(n), 256, 0, s>>>(n, cf, flag.ptr());
+    exclusive_scan(flag.ptr(), scan.ptr(), (size_t)n + 1, s);
+    assign_coarse_kernel<<<grid_for(n), 256, 0, s>>>(n, cf, scan.ptr());
+    count_launch(2);
+    int nc = 0;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&nc, scan.ptr() + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    return nc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sorted coarse sets (thread per row; segments live in global memory)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ inline int insert_sorted(int *a, int m, int key)
+{
+    int lo = 0, hi = m;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    if (lo < m && a[lo] == key) return m;
+    for (int k = m; k > lo; k--) a[k] = a[k - 1];
+    a[lo] = key;
+    return m + 1;
+}
+__device__ inline int find_sorted(const int *a, int m, int key)
+{
+    int lo = 0, hi = m;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return (lo < m && a[lo] == key) ? lo : -1;
+}
+// which rows own a distance-two set: mode 0 = coarse rows (S2), mode 1 = FINE rows (D2; coarse rows get 1 slot)
+__device__ inline int chat_role(int cfv, int mode)
+{
+    if (mode == 0) return cfv >= 0 ? 2 : 0;
+    if (cfv >= 0) return 1;
+    return cfv == STRONG_FINE ? 0 : 2;
+}
+__global__ void chat_upper_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, const int *__restrict__ cf,
+                                  int mode, i64 *ub)
+{
+    ROW_LOOP(i, n) {
+        const int role = chat_role(cf[i], mode);
+        i64 count = 0;
+        if (role == 1) count = 1;
+        else if (role == 2)
+            for (int j = rp[i]; j < rp[i + 1]; j++) {
+                const int c = ci[j];
+                if (c == i || !s_con[j]) continue;
+                const int cc = cf[c];
+                if (cc == FINE) {
+                    for (int jj = rp[c]; jj < rp[c + 1]; jj++) {
+                        const int c2 = ci[jj];
+                        if (c2 != c && s_con[jj]) { const int c3 = cf[c2]; if (c3 != FINE && c3 != STRONG_FINE) count++; }
+                    }
+                } else if (cc != STRONG_FINE) count++;
+            }
+        ub[i] = count;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ub[n] = 0;
+}
+__global__ void chat_fill_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, const int *__restrict__ cf,
+                                 int mode, const i64 *__restrict__ off, int *chat, int *len)
+{
+    ROW_LOOP(i, n) {
+        const int role = chat_role(cf[i], mode);
+        int *out = chat + off[i];
+        int m = 0;
+        if (role == 1) { out[0] = i; m = 1; }
+        else if (role == 2)
+            for (int j = rp[i]; j < rp[i + 1]; j++) {
+                const int c = ci[j];
+                if (c == i || !s_con[j]) continue;
+                const int cc = cf[c];
+                if (cc == FINE) {
+                    for (int jj = rp[c]; jj < rp[c + 1]; jj++) {
+                        const int c2 = ci[jj];
+                        if (c2 != c && s_con[jj]) { const int c3 = cf[c2]; if (c3 != FINE && c3 != STRONG_FINE) m = insert_sorted(out, m, c2); }
+                    }
+                } else if (cc != STRONG_FINE) m = insert_sorted(out, m, c);
+            }
+        len[i] = m;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) len[n] = 0;
+}
+// S2: row of coarse point cf[i] <- its set mapped to coarse ids
+__global__ void s2_compact_kernel(int n, const int *__restrict__ cf, const i64 *__restrict__ off, const int *__restrict__ chat, const int *__restrict__ len,
+                                  const int *__restrict__ s2_rp, int *s2_ci)
+{
+    ROW_LOOP(i, n) {
+        const int c = cf[i];
+        if (c < 0) continue;
+        const int *src = chat + off[i];
+        int *dst = s2_ci + s2_rp[c];
+        for (int k = 0; k < len[i]; k++) dst[k] = cf[src[k]];
+    }
+}
+__global__ void s2_len_kernel(int n, const int *__restrict__ cf, const int *__restrict__ len, int *s2_len, int nc)
+{
+    ROW_LOOP(i, n) if (cf[i] >= 0) s2_len[cf[i]] = len[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) s2_len[nc] = 0;
+}
+__global__ void correct_cf_kernel(int n, int *cf, const int *__restrict__ scanned, const int *__restrict__ cf2)
+{
+    ROW_LOOP(i, n) if (cf[i] == COARSE) { const int c2 = cf2[scanned[i]]; cf[i] = (c2 == STRONG_FINE) ? COARSE : c2; }
+}
+__global__ void copy_segments_int_kernel(int n, const i64 *__restrict__ off, const int *__restrict__ len, const int *__restrict__ dst_rp, const int *__restrict__ src, int *dst)
+{
+    ROW_LOOP(i, n) { const int *a = src + off[i]; int *b = dst + dst_rp[i]; for (int k = 0; k < len[i]; k++) b[k] = a[k]; }
+}
+__global__ void copy_segments_val_kernel(int n, const i64 *__restrict__ off, const int *__restrict__ len, const int *__restrict__ dst_rp, const double *__restrict__ src, double *dst)
+{
+    ROW_LOOP(i, n) { const double *a = src + off[i]; double *b = dst + dst_rp[i]; for (int k = 0; k < len[i]; k++) b[k] = a[k]; }
+}
+
+void aggressive_pmis(int n, const int *rp, const int *ci, const u8 *s_con, float *w, int *cf, cudaStream_t s)
+{
+    pmis(n, rp, ci, s_con, w, cf, 0, s);
+    DevBuf<int> scanned;
+    scanned.resize(n);
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(scanned.ptr(), cf, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    const int nc = renumber_coarse(n, scanned.ptr(), s);
+    if (nc == 0) return;
+    // S2 = distance-two strength graph among the coarse points (createS2)
+    DevBuf<i64> ub, off;
+    ub.resize((size_t)n + 1);
+    off.resize((size_t)n + 1);
+    const int g = grid_for(n);
+    chat_upper_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, scanned.ptr(), 0, ub.ptr());
+    exclusive_scan(ub.ptr(), off.ptr(), (size_t)n + 1, s);
+    i64 total = 0;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&total, off.ptr() + n, sizeof(i64), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    ub.release();
+    DevBuf<int> chat, len, s2_len, s2_rp, s2_ci;
+    chat.resize((size_t)std::max<i64>(total, 1));
+    len.resize((size_t)n + 1);
+    chat_fill_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, scanned.ptr(), 0, off.ptr(), chat.ptr(), len.ptr());
+    s2_len.resize((size_t)nc + 1);
+    s2_rp.resize((size_t)nc + 1);
+    s2_len_kernel<<<g, 256, 0, s>>>(n, scanned.ptr(), len.ptr(), s2_len.ptr(), nc);
+    exclusive_scan(s2_len.ptr(), s2_rp.ptr(), (size_t)nc + 1, s);
+    int s2_nnz = 0;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&s2_nnz, s2_rp.ptr() + nc, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    s2_ci.resize((size_t)std::max(s2_nnz, 1));
+    s2_compact_kernel<<<g, 256, 0, s>>>(n, scanned.ptr(), off.ptr(), chat.ptr(), len.ptr(), s2_rp.ptr(), s2_ci.ptr());
+    count_launch(4);
+    chat.release();
+    off.release();
+    // weights on S2 (Strength_All::computeWeights), PMIS with cf_map_init = 3, correctCfMap
+    DevBuf<int> cnt, cf2;
+    DevBuf<float> w2;
+    cnt.resize(nc);
+    cnt.zero(s);
+    w2.resize(nc);
+    cf2.resize(nc);
+    pattern_count_kernel<<<grid_for(nc), 256, 0, s>>>(nc, s2_rp.ptr(), s2_ci.ptr(), cnt.ptr());
+    weights_kernel<<<grid_for(nc), 256, 0, s>>>(nc, cnt.ptr(), w2.ptr());
+    count_launch(2);
+    pmis(nc, s2_rp.ptr(), s2_ci.ptr(), nullptr, w2.ptr(), cf2.ptr(), 3, s);
+    correct_cf_kernel<<<g, 256, 0, s>>>(n, cf, scanned.ptr(), cf2.ptr());
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// D2 interpolation
+// ---------------------------------------------------------------------------------------------------------------
+__device__ inline bool cla_sign(double x) { return x >= 0.0; }
+
+__global__ void diag_value_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va, double *d)
+{
+    ROW_LOOP(i, n) { double v = 0; for (int j = rp[i]; j < rp[i + 1]; j++) if (ci[j] == i) { v = va[j]; break; } d[i] = v; }
+}
+
+// P's structure already holds, for each row, its sorted coarse set as FINE-GRID ids in p_ci; the kernel computes the
+// weights in place and finally rewrites the ids as coarse ids.
+__global__ void d2_weights_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va, const int *__restrict__ cf,
+                                  const u8 *__restrict__ s_con, const double *__restrict__ diag, const int *__restrict__ p_rp, int *p_ci, double *p_va)
+{
+    ROW_LOOP(i, n) {
+        const int p0 = p_rp[i], m = p_rp[i + 1] - p0;
+        int *ch = p_ci + p0;
+        double *val = p_va + p0;
+        const int cfi = cf[i];
+        if (cfi >= 0) { ch[0] = cfi; val[0] = 1.0; continue; }
+        if (cfi == STRONG_FINE) continue;
+        for (int k = 0; k < m; k++) val[k] = 0.0;
+        const bool sign_i = cla_sign(diag[i]);
+        double weak = 0.0;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            const int c = ci[j];
+            const double a = va[j];
+            const bool offd = (c != i);
+            const bool strong = offd && s_con[j];
+            const int p = find_sorted(ch, m, c);
+            if (p >= 0) val[p] += a;
+            const int cfc = cf[c];
+            if (offd && !strong && p < 0 && cfc != STRONG_FINE) weak += a;
+            if (strong && cfc == FINE) {
+                double bottom = 0.0;
+                for (int jj = rp[c]; jj < rp[c + 1]; jj++) {
+                    const int l = ci[jj];
+                    const bool needed = (l == i) || find_sorted(ch, m, l) >= 0;
+                    const double b = needed ? va[jj] : 0.0;
+                    if (sign_i != cla_sign(b)) bottom += b;
+                }
+                const double inner = (bottom != 0.0) ? a / bottom : a;
+                const double dk = diag[c];
+                double aki = 0.0;
+                for (int jj = rp[c]; jj < rp[c + 1]; jj++) {
+                    const int l = ci[jj];
+                    double b = va[jj];
+                    if (cla_sign(dk) == cla_sign(b)) b = 0.0;
+                    if (l == i) aki = b;
+                    const int q = find_sorted(ch, m, l);
+                    if (q >= 0) { const double t = b * inner; val[q] += t; }
+                }
+                const double t = aki * inner;
+                weak += t;
+            }
+        }
+        weak += diag[i];
+        const double scale = -1.0 / weak;
+        for (int k = 0; k < m; k++) { val[k] = scale * val[k]; ch[k] = cf[ch[k]]; }
+    }
+}
+
+struct Csr {   // plain device CSR (fp64 values)
+    int n = 0, nc = 0, nnz = 0;
+    DevBuf<int> rp, ci;
+    DevVec va;
+};
+
+void interp_d2(const Matrix &A, const int *cf, const u8 *s_con, int nc, Csr &P, cudaStream_t s)
+{
+    const int n = A.n;
+    const int *rp = A.row_ptr.ptr(), *ci = A.col_idx.ptr();
+    const double *va = A.values.as<double>();
+    const int g = grid_for(n);
+    DevBuf<i64> ub, off;
+    ub.resize((size_t)n + 1);
+    off.resize((size_t)n + 1);
+    chat_upper_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, cf, 1, ub.ptr());
+    exclusive_scan(ub.ptr(), off.ptr(), (size_t)n + 1, s);
+    i64 total = 0;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&total, off.ptr() + n, sizeof(i64), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    ub.release();
+    DevBuf<int> chat, len;
+    chat.resize((size_t)std::max<i64>(total, 1));
+    len.resize((size_t)n + 1);
+    chat_fill_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, cf, 1, off.ptr(), chat.ptr(), len.ptr());
+    P.n = n;
+    P.nc = nc;
+    P.rp.resize((size_t)n + 1);
+    exclusive_scan(len.ptr(), P.rp.ptr(), (size_t)n + 1, s);
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&P.nnz, P.rp.ptr() + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    P.ci.resize((size_t)std::max(P.nnz, 1));
+    P.va.resize((size_t)std::max(P.nnz, 1), Prec::F64);
+    copy_segments_int_kernel<<<g, 256, 0, s>>>(n, off.ptr(), len.ptr(), P.rp.ptr(), chat.ptr(), P.ci.ptr());
+    chat.release();
+    DevVec diag;
+    diag.resize((size_t)std::max(n, 1), Prec::F64);
+    diag_value_kernel<<<g, 256, 0, s>>>(n, rp, ci, va, diag.as<double>());
+    d2_weights_kernel<<<g, 256, 0, s>>>(n, rp, ci, va, cf, s_con, diag.as<double>(), P.rp.ptr(), P.ci.ptr(), P.va.as<double>());
+    count_launch(5);
+    AMGXB_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MULTIPASS interpolation
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void mp_init_assigned_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, const int *__restrict__ cf,
+                                        int *assigned, i64 *ub, int *counters)
+{
+    int un = 0, sf = 0;
+    ROW_LOOP(i, n) {
+        int a = -1;
+        i64 u = 0;
+        const int cfi = cf[i];
+        if (cfi >= 0) { a = 0; u = 1; }
+        else if (cfi == FINE) {
+            int cc = 0;
+            for (int j = rp[i]; j < rp[i + 1]; j++) if (ci[j] != i && s_con[j] && cf[ci[j]] >= 0) cc++;
+            if (cc) { a = 1; u = cc; }
+        }
+        assigned[i] = a;
+        ub[i] = u;
+        un += (a < 0);
+        sf += (cfi == STRONG_FINE);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ub[n] = 0;
+    un = __reduce_add_sync(0xffffffffu, un);
+    sf = __reduce_add_sync(0xffffffffu, sf);
+    if ((threadIdx.x & 31) == 0) { if (un) atomicAdd(&counters[0], un); if (sf) atomicAdd(&counters[1], sf); }
+}
+// assigned[i] = pass if a strong neighbour was assigned in pass-1.  Concurrent writes store `pass`, which no reader
+// of this launch tests for (readers compare with pass-1): the result is independent of the interleaving.
+__global__ void mp_fill_assigned_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, int *assigned, int pass,
+                                        int *num_unassigned)
+{
+    int un = 0;
+    ROW_LOOP(i, n) {
+        int a = ((volatile int *)assigned)[i];
+        if (a == -1) {
+            for (int j = rp[i]; j < rp[i + 1]; j++)
+                if (ci[j] != i && s_con[j] && ((volatile int *)assigned)[ci[j]] == pass - 1) { a = pass; break; }
+            if (a == pass) assigned[i] = pass;
+        }
+        un += (a < 0);
+    }
+    un = __reduce_add_sync(0xffffffffu, un);
+    if ((threadIdx.x & 31) == 0 && un) atomicAdd(num_unassigned, un);
+}
+__global__ void mp_upper_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, const int *__restrict__ assigned,
+                                i64 *ub, int pass)
+{
+    ROW_LOOP(i, n) {
+        if (assigned[i] != pass) continue;
+        i64 c = 0;
+        for (int j = rp[i]; j < rp[i + 1]; j++) if (ci[j] != i && s_con[j] && assigned[ci[j]] == pass - 1) c += ub[ci[j]];
+        ub[i] = c;
+    }
+}
+__global__ void mp_first_pass_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va, const int *__restrict__ cf,
+                                     const u8 *__restrict__ s_con, const int *__restrict__ assigned, const double *__restrict__ diag,
+                                     const i64 *__restrict__ off, int *cols, double *vals, int *len)
+{
+    ROW_LOOP(i, n) {
+        int *pc = cols + off[i];
+        double *pv = vals + off[i];
+        const int a = assigned[i];
+        int m = 0;
+        if (a == 0) { pc[0] = cf[i]; pv[0] = 1.0; m = 1; }
+        else if (a == 1) {
+            double sum_N = 0.0, sum_C = 0.0;
+            for (int j = rp[i]; j < rp[i + 1]; j++) {
+                const int c = ci[j];
+                if (c == i) continue;
+                const double v = va[j];
+                if (cf[c] != STRONG_FINE) sum_N += v;
+                if (s_con[j] && assigned[c] == 0) { sum_C += v; pc[m] = cf[c]; pv[m] = v; m++; }
+            }
+            const double sd = sum_C * diag[i];
+            const double div = (fabs(sd) == 0.0) ? 1.0 : sd;
+            const double alfa = -sum_N / div;
+            for (int k = 0; k < m; k++) pv[k] *= alfa;
+        }
+        len[i] = m;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) len[n] = 0;
+}
+__global__ void mp_pass_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va, const int *__restrict__ cf,
+                               const u8 *__restrict__ s_con, const int *__restrict__ assigned, const double *__restrict__ diag, const i64 *__restrict__ off,
+                               int *cols, double *vals, int *len, int pass)
+{
+    ROW_LOOP(i, n) {
+        if (assigned[i] != pass) continue;
+        int *pc = cols + off[i];
+        double *pv = vals + off[i];
+        int m = 0;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            const int k = ci[j];
+            if (k == i || !s_con[j] || assigned[k] != pass - 1) continue;
+            const int *kc = cols + off[k];
+            for (int q = 0; q < len[k]; q++) m = insert_sorted(pc, m, kc[q]);
+        }
+        for (int q = 0; q < m; q++) pv[q] = 0.0;
+        double sum_N = 0.0, sum_C = 0.0;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            const int k = ci[j];
+            if (k == i) continue;
+            const double a = va[j];
+            const bool sa = s_con[j] && assigned[k] == pass - 1;
+            if (!sa) { if (cf[k] != STRONG_FINE) sum_N += a; continue; }
+            const int *kc = cols + off[k];
+            const double *kv = vals + off[k];
+            for (int q = 0; q < len[k]; q++) {
+                const double tmp = kv[q] * a;
+                sum_C += tmp;
+                sum_N += tmp;
+                pv[find_sorted(pc, m, kc[q])] += tmp;
+            }
+        }
+        const double sd = sum_C * diag[i];
+        const double div = (fabs(sd) == 0.0) ? 1.0 : sd;
+        const double alfa = -sum_N / div;
+        for (int q = 0; q < m; q++) pv[q] = alfa * pv[q];
+        len[i] = m;
+    }
+}
+
+void interp_multipass(const Matrix &A, const int *cf, const u8 *s_con, int nc, Csr &P, cudaStream_t s)
+{
+    const int n = A.n;
+    const int *rp = A.row_ptr.ptr(), *ci = A.col_idx.ptr();
+    const double *va = A.values.as<double>();
+    const int g = grid_for(n);
+    DevBuf<int> assigned, counters, len;
+    DevBuf<i64> ub, off;
+    assigned.resize(std::max(n, 1));
+    ub.resize((size_t)n + 1);
+    off.resize((size_t)n + 1);
+    counters.resize(2);
+    counters.zero(s);
+    mp_init_assigned_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, cf, assigned.ptr(), ub.ptr(), counters.ptr());
+    count_launch();
+    std::vector<int> h = counters.to_host(s);
+    const int num_sf = h[1];
+    int remaining = h[0] - num_sf;
+    int pass = 2;
+    while (remaining && pass < 10) {
+        counters.zero(s);
+        mp_fill_assigned_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, assigned.ptr(), pass, counters.ptr());
+        count_launch();
+        remaining = counters.to_host(s)[0] - num_sf;
+        pass++;
+    }
+    const int num_passes = pass;
+    for (int p = 2; p < num_passes; p++) { mp_upper_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, assigned.ptr(), ub.ptr(), p); count_launch(); }
+    exclusive_scan(ub.ptr(), off.ptr(), (size_t)n + 1, s);
+    i64 total = 0;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&total, off.ptr() + n, sizeof(i64), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    ub.release();
+    DevBuf<int> cols;
+    DevVec vals, diag;
+    cols.resize((size_t)std::max<i64>(total, 1));
+    vals.resize((size_t)std::max<i64>(total, 1), Prec::F64);
+    len.resize((size_t)n + 1);
+    diag.resize((size_t)std::max(n, 1), Prec::F64);
+    diag_value_kernel<<<g, 256, 0, s>>>(n, rp, ci, va, diag.as<double>());
+    mp_first_pass_kernel<<<g, 256, 0, s>>>(n, rp, ci, va, cf, s_con, assigned.ptr(), diag.as<double>(), off.ptr(), cols.ptr(), vals.as<double>(), len.ptr());
+    count_launch(2);
+    for (int p = 2; p < num_passes; p++) {
+        mp_pass_kernel<<<g, 256, 0, s>>>(n, rp, ci, va, cf, s_con, assigned.ptr(), diag.as<double>(), off.ptr(), cols.ptr(), vals.as<double>(), len.ptr(), p);
+        count_launch();
+    }
+    P.n = n;
+    P.nc = nc;
+    P.rp.resize((size_t)n + 1);
+    exclusive_scan(len.ptr(), P.rp.ptr(), (size_t)n + 1, s);
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&P.nnz, P.rp.ptr() + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    P.ci.resize((size_t)std::max(P.nnz, 1));
+    P.va.resize((size_t)std::max(P.nnz, 1), Prec::F64);
+    copy_segments_int_kernel<<<g, 256, 0, s>>>(n, off.ptr(), len.ptr(), P.rp.ptr(), cols.ptr(), P.ci.ptr());
+    copy_segments_val_kernel<<<g, 256, 0, s>>>(n, off.ptr(), len.ptr(), P.rp.ptr(), vals.as<double>(), P.va.as<double>());
+    count_launch(2);
+    AMGXB_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// truncation to the max_elmts largest |weights| per row + rescaling to the original row sum
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void trunc_len_kernel(int n, const int *__restrict__ rp, int max_elmts, int *len)
+{
+    ROW_LOOP(i, n) len[i] = min(rp[i + 1] - rp[i], max_elmts);
+    if (blockIdx.x == 0 && threadIdx.x == 0) len[n] = 0;
+}
+__global__ void truncate_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va, const int *__restrict__ nrp,
+                                int *nci, double *nva, int max_elmts)
+{
+    ROW_LOOP(i, n) {
+        const int s = rp[i], e = rp[i + 1], rl = e - s;
+        int oc[32];
+        double ov[32];
+        double orig = 0.0;
+        for (int j = s; j < e; j++) orig += va[j];
+        int m;
+        if (rl <= max_elmts) {
+            m = rl;
+            for (int j = 0; j < m; j++) { oc[j] = ci[s + j]; ov[j] = va[s + j]; }
+        } else {
+            m = max_elmts;
+            for (int j = 0; j < m; j++) { oc[j] = ci[s + j]; ov[j] = va[s + j]; }
+            int nn = m;
+            do {
+                int newn = 0;
+                for (int q = 1; q < nn; q++)
+                    if (fabs(ov[q - 1]) < fabs(ov[q])) {
+                        const double tv = ov[q - 1]; const int ti = oc[q - 1];
+                        ov[q - 1] = ov[q]; oc[q - 1] = oc[q]; ov[q] = tv; oc[q] = ti;
+                        newn = q;
+                    }
+                nn = newn;
+            } while (nn > 0);
+            for (int j = s + m; j < e; j++) {
+                const double v = va[j];
+                for (int q = 0; q < m; q++)
+                    if (fabs(v) > fabs(ov[q])) {
+                        for (int k = m - 1; k > q; k--) { ov[k] = ov[k - 1]; oc[k] = oc[k - 1]; }
+                        ov[q] = v; oc[q] = ci[j];
+                        break;
+                    }
+            }
+        }
+        double nsum = 0.0;
+        for (int j = 0; j < m; j++) nsum += ov[j];
+        const double mult = (fabs(nsum) == 0.0) ? 1.0 : orig / nsum;
+        int *dc = nci + nrp[i];
+        double *dv = nva + nrp[i];
+        for (int j = 0; j < m; j++) { dc[j] = oc[j]; dv[j] = ov[j] * mult; }
+    }
+}
+void truncate_max_elements(Csr &P, int max_elmts, cudaStream_t s)
+{
+    if (max_elmts > 32) fatal(AMGX_RC_BAD_PARAMETERS, "Matrix truncation to > 32 elements not supported");   // truncate.cu:786-789
+    const int n = P.n;
+    if (n == 0) return;
+    DevBuf<int> len, nrp, nci;
+    DevVec nva;
+    len.resize((size_t)n + 1);
+    nrp.resize((size_t)n + 1);
+    trunc_len_kernel<<<grid_for(n), 256, 0, s>>>(n, P.rp.ptr(), max_elmts, len.ptr());
+    exclusive_scan(len.ptr(), nrp.ptr(), (size_t)n + 1, s);
+    int nnz = 0;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&nnz, nrp.ptr() + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    nci.resize((size_t)std::max(nnz, 1));
+    nva.resize((size_t)std::max(nnz, 1), Prec::F64);
+    truncate_kernel<<<grid_for(n), 256, 0, s>>>(n, P.rp.ptr(), P.ci.ptr(), P.va.as<double>(), nrp.ptr(), nci.ptr(), nva.as<double>(), max_elmts);
+    count_launch(2);
+    AMGXB_LAUNCH_CHECK();
+    P.rp.swap(nrp);
+    P.ci.swap(nci);
+    P.va.swap(nva);
+    P.nnz = nnz;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// transpose (stable: rows of R list the fine rows in ascending order)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void expand_rows_kernel(int n, const int *__restrict__ rp, int *row_of) { ROW_LOOP(i, n) for (int k = rp[i]; k < rp[i + 1]; k++) row_of[k] = i; }
+__global__ void iota_kernel(int n, int *v) { ROW_LOOP(i, n) v[i] = i; }
+__global__ void gather_transpose_kernel(int nnz, const int *__restrict__ perm, const int *__restrict__ row_of, const double *__restrict__ va, int *rci, double *rva)
+{
+    ROW_LOOP(q, nnz) { const int e = perm[q]; rci[q] = row_of[e]; rva[q] = va[e]; }
+}
+__global__ void offsets_from_sorted_kernel(int nnz, const int *__restrict__ keys, int n_keys, int *offsets)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p <= nnz; p += gridDim.x * blockDim.x) {
+        const int prev = (p == 0) ? -1 : keys[p - 1];
+        const int cur = (p == nnz) ? n_keys : keys[p];
+        for (int I = prev + 1; I <= cur; I++) offsets[I] = p;
+    }
+}
+void transpose_csr(const Csr &P, Csr &R, cudaStream_t s)
+{
+    R.n = P.nc;
+    R.nc = P.n;
+    R.nnz = P.nnz;
+    R.rp.resize((size_t)R.n + 1);
+    R.ci.resize((size_t)std::max(P.nnz, 1));
+    R.va.resize((size_t)std::max(P.nnz, 1), Prec::F64);
+    if (P.nnz == 0) { R.rp.zero(s); return; }
+    DevBuf<int> row_of, idx, keys_out, perm;
+    row_of.resize(P.nnz);
+    idx.resize(P.nnz);
+    keys_out.resize(P.nnz);
+    perm.resize(P.nnz);
+    expand_rows_kernel<<<grid_for(P.n), 256, 0, s>>>(P.n, P.rp.ptr(), row_of.ptr());
+    iota_kernel<<<grid_for(P.nnz), 256, 0, s>>>(P.nnz, idx.ptr());
+    int bits = 1;
+    while ((1ll << bits) < (i64)P.nc + 1) bits++;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, P.ci.ptr(), keys_out.ptr(), idx.ptr(), perm.ptr(), P.nnz, 0, bits, s);
+    DevBytes tmp;
+    tmp.resize(tb);
+    cub::DeviceRadixSort::SortPairs(tmp.p, tb, P.ci.ptr(), keys_out.ptr(), idx.ptr(), perm.ptr(), P.nnz, 0, bits, s);
+    gather_transpose_kernel<<<grid_for(P.nnz), 256, 0, s>>>(P.nnz, perm.ptr(), row_of.ptr(), P.va.as<double>(), R.ci.ptr(), R.va.as<double>());
+    offsets_from_sorted_kernel<<<grid_for((i64)P.nnz + 1), 256, 0, s>>>(P.nnz, keys_out.ptr(), R.n, R.rp.ptr());
+    count_launch(5);
+    AMGXB_LAUNCH_CHECK();
+}
+
+std::unique_ptr<Matrix> to_matrix(Csr &C, const Matrix &like, cudaStream_t s)
+{
+    std::unique_ptr<Matrix> M(new Matrix);
+    M->rsc = like.rsc;
+    M->mode = like.mode;
+    M->mat_prec = like.mat_prec;
+    M->vec_prec = like.vec_prec;
+    M->n = C.n;
+    M->n_cols = C.nc;
+    M->nnz = C.nnz;
+    M->row_ptr.swap(C.rp);
+    M->col_idx.swap(C.ci);
+    M->values.swap(C.va);
+    M->values.n = (size_t)C.nnz;
+    (void)s;
+    return M;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// level construction
+// ---------------------------------------------------------------------------------------------------------------
+struct ClassicalParams {
+    double strength_threshold, max_row_sum;
+    int max_elmts, aggressive_levels;
+    bool d2, aggressive_multipass;
+};
+
+// createCoarseVertices: strength + C/F splitting; returns the number of coarse points, cf_map renumbered
+static int classical_select(const Matrix &A, const ClassicalParams &prm, int level, DevBuf<u8> &s_con, DevBuf<int> &cf, cudaStream_t s)
+{
+    const int n = A.n;
+    s_con.resize((size_t)std::max(A.nnz, 1));
+    cf.resize((size_t)std::max(n, 1));
+    DevBuf<int> cnt;
+    DevBuf<float> w;
+    cnt.resize(std::max(n, 1));
+    cnt.zero(s);
+    w.resize(std::max(n, 1));
+    const int compute_row_sum = (prm.max_row_sum < 1.0 && n > 0) ? 1 : 0;
+    strength_kernel<<<grid_for(n), 256, 0, s>>>(n, A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<double>(), prm.strength_threshold, prm.max_row_sum,
+                                                  compute_row_sum, s_con.ptr(), cnt.ptr());
+    weights_kernel<<<grid_for(n), 256, 0, s>>>(n, cnt.ptr(), w.ptr());
+    count_launch(2);
+    AMGXB_LAUNCH_CHECK();
+    if (level < prm.aggressive_levels) aggressive_pmis(n, A.row_ptr.ptr(), A.col_idx.ptr(), s_con.ptr(), w.ptr(), cf.ptr(), s);
+    else pmis(n, A.row_ptr.ptr(), A.col_idx.ptr(), s_con.ptr(), w.ptr(), cf.ptr(), 0, s);
+    return renumber_coarse(n, cf.ptr(), s);
+}
+
+void AMGSolver::setup_classical()
+{
+    cudaStream_t s = stream();
+    if (A_->dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "classical AMG on a distributed matrix is not implemented (use AGGREGATION)");
+    if (A_->bs() != 1) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "Unsupported block size for strong connections");   // strength_base.cu:672-681
+    if (A_->mat_prec != Prec::F64 || A_->vec_prec != Prec::F64) fatal(AMGX_RC_BAD_MODE, "classical AMG setup needs mode dDDI");
+    ClassicalParams prm;
+    prm.strength_threshold = cfg_->get_double("strength_threshold", scope_);
+    prm.max_row_sum = cfg_->get_double("max_row_sum", scope_);
+    prm.max_elmts = cfg_->get_int("interp_max_elements", scope_);
+    prm.aggressive_levels = cfg_->get_int("aggressive_levels", scope_);
+    const std::string strength = cfg_->get_string("strength", scope_), interp = cfg_->get_string("interpolator", scope_);
+    const std::string agg_sel = cfg_->get_string("aggressive_selector", scope_), agg_int = cfg_->get_string("aggressive_interpolator", scope_);
+    if (strength != "AHAT") fatal(AMGX_RC_BAD_CONFIGURATION, "strength '" + strength + "' is not supported by this engine (AHAT)");
+    if (selector_ != "PMIS") fatal(AMGX_RC_BAD_CONFIGURATION, "classical selector '" + selector_ + "' is not supported by this engine (PMIS)");
+    if (interp != "D2" && interp != "MULTIPASS") fatal(AMGX_RC_BAD_CONFIGURATION, "interpolator '" + interp + "' is not supported by this engine (D2, MULTIPASS)");
+    if (prm.aggressive_levels > 0) {
+        if (agg_sel != "DEFAULT" && agg_sel != "PMIS") fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_selector '" + agg_sel + "' is not supported (PMIS)");
+        if (agg_int != "MULTIPASS") fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_interpolator '" + agg_int + "' is not supported (MULTIPASS)");
+    }
+    prm.d2 = (interp == "D2");
+    prm.aggressive_multipass = true;
+
+    levels_.emplace_back(new AMGLevel);
+    levels_[0]->A = A_;
+    levels_[0]->index = 0;
+    int num_levels = 1;
+    bool coarse_solver_exists = (bool)coarse_solver_;
+    while (true) {     // AMG_Setup::setup level loop (src/amg.cu:201-418)
+        AMGLevel &L = *levels_.back();
+        Matrix &A = *L.A;
+        A.level = num_levels - 1;
+        const int rows = A.n;
+        if (num_levels >= max_levels_ || rows <= min_coarse_rows_) {
+            if (dense_lu_max_rows_ != 0 && rows > dense_lu_max_rows_) { coarse_solver_.reset(); coarse_solver_exists = false; }
+            L.coarsest = true;
+            if (!coarse_solver_exists) { L.smoother = make_smoother(); L.smoother->setup(A, false); }
+            break;
+        }
+        DevBuf<u8> s_con;
+        const int lvl = num_levels - 1;
+        const int nc = classical_select(A, prm, lvl, s_con, L.cf_map, s);
+        L.n_coarse = nc;
+        bool built_next = false;
+        if ((double)nc <= coarsen_threshold_ * (double)rows && nc != rows && nc >= min_coarse_rows_) {
+            Csr P, R;
+            if (lvl < prm.aggressive_levels || !prm.d2) interp_multipass(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
+            else interp_d2(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
+            s_con.release();
+            if (prm.max_elmts > 0 && P.n > 0) truncate_max_elements(P, prm.max_elmts, s);
+            transpose_csr(P, R, s);
+            // A_c = R (A P)
+            Csr AP;
+            AP.n = rows;
+            AP.nc = nc;
+            spgemm_csr(rows, A.row_ptr, A.col_idx, A.values, P.rp, P.ci, P.va, AP.rp, AP.ci, AP.va, &AP.nnz, s);
+            std::unique_ptr<AMGLevel> next(new AMGLevel);
+            next->owned_A.reset(new Matrix);
+            Matrix &Ac = *next->owned_A;
+            Ac.rsc = A.rsc;
+            Ac.mode = A.mode;
+            Ac.mat_prec = A.mat_prec;
+            Ac.vec_prec = A.vec_prec;
+            Ac.n = nc;
+            Ac.n_cols = nc;
+            spgemm_csr(nc, R.rp, R.ci, R.va, AP.rp, AP.ci, AP.va, Ac.row_ptr, Ac.col_idx, Ac.values, &Ac.nnz, s);
+            Ac.values.n = (size_t)Ac.nnz;
+            AP.rp.release(); AP.ci.release(); AP.va.b.release();
+            Ac.compute_diag_and_plan();
+            L.P = to_matrix(P, A, s);
+            L.R = to_matrix(R, A, s);
+            csr_build_plan(*L.P, s);
+            csr_build_plan(*L.R, s);
+            next->A = next->owned_A.get();
+            next->index = num_levels;
+            L.bc.resize((size_t)nc, A.vec_prec);
+            L.xc.resize((size_t)nc, A.vec_prec);
+            L.bc.zero(s);
+            L.xc.zero(s);
+            L.r.resize((size_t)A.n_cols, A.vec_prec);
+            L.r.zero(s);
+            levels_.push_back(std::move(next));
+            built_next = true;
+        } else {
+            L.cf_map.release();
+            L.n_coarse = 0;
+            L.coarsest = true;
+        }
+        AMGLevel &Lcur = *levels_[num_levels - 1];
+        if (!Lcur.coarsest || !coarse_solver_exists) { Lcur.smoother = make_smoother(); Lcur.smoother->setup(*Lcur.A, false); }
+        if (!built_next) break;
+        num_levels++;
+    }
+    if (coarse_solver_) coarse_solver_->setup(*levels_.back()->A, false);
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+// rr = R r  (Classical_AMG_Level_Base::restrictResidual, classical_amg_level.cu:590-644)
+void classical_restrict(AMGLevel &L, const DevVec &r, cudaStream_t s)
+{
+    CsrOpArgs g;
+    g.x = r.ptr();
+    g.y = L.bc.ptr();
+    csr_op(*L.R, EPI_SPMV, g, s, 0);
+}
+// xout = x + P e  (prolongateAndApplyCorrection: multiply(P, e, tmp); axpby(x, tmp, x, 1, 1); classical_amg_level.cu:851-913)
+void classical_prolong_add(AMGLevel &L, const void *x, void *xout, cudaStream_t s)
+{
+    CsrOpArgs g;
+    g.x = L.xc.ptr();
+    g.b = x;
+    g.y = xout;
+    csr_op(*L.P, x ? EPI_ADD : EPI_SPMV, g, s, 0);
+}
+
+}  // namespace amgxb

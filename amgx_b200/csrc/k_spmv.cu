@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
             VecT bi = 0, xi = 0;
             MatT di = 1;
             if (active) {
-                if (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2 || EPI == EPI_JACOBI_L1)
+                if (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2 || EPI == EPI_JACOBI_L1 || EPI == EPI_ADD)
                     bi = __ldg(a.b + row);
                 if (EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_JACOBI_L1) {
                     di = __ldg(a.d + row);
@@ -279,6 +279,8 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
                     acc += (double)sum * (double)xi;
                 } else if (EPI == EPI_RESID) {
                     a.y[row] = bi - sum;
+                } else if (EPI == EPI_ADD) {
+                    a.y[row] = bi + sum;
                 } else if (EPI == EPI_RESID_NRM2) {
                     const VecT r = bi - sum;
                     a.y[row] = r;
@@ -325,6 +327,8 @@ __global__ void __launch_bounds__(256) csr_vector_kernel(const TileArgs<MatT, Ve
                 acc += (double)sum * (double)gather<VecT, AGG>(a.x, a.agg, row);
             } else if (EPI == EPI_RESID) {
                 a.y[row] = a.b[row] - sum;
+            } else if (EPI == EPI_ADD) {
+                a.y[row] = a.b[row] + sum;
             } else if (EPI == EPI_RESID_NRM2) {
                 const VecT r = a.b[row] - sum;
                 a.y[row] = r;
@@ -485,6 +489,7 @@ void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int
         switch (epi) {
         case EPI_SPMV: launch_epi<MatT, VecT, EPI_SPMV>(A, ta, s); break;
         case EPI_RESID: launch_epi<MatT, VecT, EPI_RESID>(A, ta, s); break;
+        case EPI_ADD: launch_epi<MatT, VecT, EPI_ADD>(A, ta, s); break;
         case EPI_JACOBI:
         case EPI_JACOBI_L1: launch_epi<MatT, VecT, EPI_JACOBI>(A, ta, s); break;
         case EPI_SPMV_DOT: launch_epi<MatT, VecT, EPI_SPMV_DOT>(A, ta, s); break;

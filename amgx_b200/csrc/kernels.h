@@ -46,6 +46,7 @@ enum CsrEpi : int {
     EPI_JACOBI_DOT = 4,  // EPI_JACOBI and reduce sum_i b_i * y_i           (PCG: <r,z> on the last sweep)
     EPI_RESID_NRM2 = 5,  // EPI_RESID and reduce sum_i y_i^2
     EPI_JACOBI_L1 = 6,   // same arithmetic as EPI_JACOBI with d = L1 row norm (jacobi_l1_solver.cu:27-44)
+    EPI_ADD = 7,         // y_i = b_i + (A x)_i   (classical prolongation x + P e, classical_amg_level.cu:884-910)
 };
 
 struct CsrOpArgs {

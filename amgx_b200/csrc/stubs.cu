@@ -3,7 +3,4 @@
 #include "dist.h"
 namespace amgxb {
 std::unique_ptr<Solver> make_dense_lu_solver(Config &, const std::string &, std::shared_ptr<Resources>) { fatal(AMGX_RC_NOT_IMPLEMENTED, "DENSE_LU_SOLVER: set coarse_solver=NOSOLVER"); }
-void classical_restrict(AMGLevel &, const DevVec &, cudaStream_t) { fatal(AMGX_RC_NOT_IMPLEMENTED, "classical AMG"); }
-void classical_prolong_add(AMGLevel &, DevVec &, cudaStream_t) { fatal(AMGX_RC_NOT_IMPLEMENTED, "classical AMG"); }
-void AMGSolver::setup_classical() { fatal(AMGX_RC_NOT_IMPLEMENTED, "classical AMG"); }
 }

@@ -403,6 +403,9 @@ typedef struct {
     /* MULTICOLOR_DILU smoother data */
     int num_colors, *colors, *sorted_rows, *color_offsets;
     double *Einv, *delta, *Delta;
+    /* classical AMG: explicit P (n x nagg) and R = P^T, C/F map of the level */
+    int *Pp, *Pc, *Rtp, *Rtc, *cf;
+    double *Pv, *Rtv;
 } orc_level;
 
 typedef struct {
@@ -412,6 +415,8 @@ typedef struct {
     double omega, uncolored_fraction;
 } orc_amg;
 
+#include "classical_oracle.inc.c"
+
 ORC_API int orc_color_min_max(int n, const int *rp, const int *ci, double max_uncolored_fraction, int *colors);
 ORC_API void orc_color_arrays(int n, int num_colors, const int *colors, int *sorted_rows, int *offsets);
 ORC_API void orc_dilu_setup_1x1(int n, const int *rp, const int *ci, const double *va, int num_colors, const int *colors, const int *sorted_rows,
@@ -420,6 +425,25 @@ ORC_API void orc_dilu_sweep_1x1(int n, const int *rp, const int *ci, const doubl
                                 const int *offsets, const double *Einv, const double *b, double *x, double weight, double *delta, double *Delta);
 static double g_uncolored_fraction = 0.15;
 ORC_API void orc_set_uncolored_fraction(double f) { g_uncolored_fraction = f; }
+
+static void level_smoother_setup(orc_level *L, int smoother)
+{
+    L->d = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
+    if (smoother == 1) orc_l1_norms(L->n, L->rp, L->ci, L->va, L->d);
+    else orc_extract_diag(L->n, L->rp, L->ci, L->va, L->d);
+    if (smoother == 2) {
+        const size_t nn = (size_t)(L->n > 0 ? L->n : 1);
+        L->colors = (int *)malloc(sizeof(int) * nn);
+        L->sorted_rows = (int *)malloc(sizeof(int) * nn);
+        L->num_colors = orc_color_min_max(L->n, L->rp, L->ci, g_uncolored_fraction, L->colors);
+        L->color_offsets = (int *)malloc(sizeof(int) * ((size_t)L->num_colors + 1));
+        orc_color_arrays(L->n, L->num_colors, L->colors, L->sorted_rows, L->color_offsets);
+        L->Einv = (double *)calloc(nn, sizeof(double));
+        L->delta = (double *)calloc(nn, sizeof(double));
+        L->Delta = (double *)calloc(nn, sizeof(double));
+        orc_dilu_setup_1x1(L->n, L->rp, L->ci, L->va, L->num_colors, L->colors, L->sorted_rows, L->color_offsets, L->Einv);
+    }
+}
 
 ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double *va, int max_levels, int min_coarse_rows, double coarsen_threshold,
                                int presweeps, int postsweeps, int coarsest_sweeps, int finest_sweeps, int smoother, double omega,
@@ -435,21 +459,7 @@ ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double
     int num_levels = 1;
     for (;;) {
         L = &a->lv[num_levels - 1];
-        L->d = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
-        if (smoother == 1) orc_l1_norms(L->n, L->rp, L->ci, L->va, L->d);
-        else orc_extract_diag(L->n, L->rp, L->ci, L->va, L->d);
-        if (smoother == 2) {
-            const size_t nn = (size_t)(L->n > 0 ? L->n : 1);
-            L->colors = (int *)malloc(sizeof(int) * nn);
-            L->sorted_rows = (int *)malloc(sizeof(int) * nn);
-            L->num_colors = orc_color_min_max(L->n, L->rp, L->ci, g_uncolored_fraction, L->colors);
-            L->color_offsets = (int *)malloc(sizeof(int) * ((size_t)L->num_colors + 1));
-            orc_color_arrays(L->n, L->num_colors, L->colors, L->sorted_rows, L->color_offsets);
-            L->Einv = (double *)calloc(nn, sizeof(double));
-            L->delta = (double *)calloc(nn, sizeof(double));
-            L->Delta = (double *)calloc(nn, sizeof(double));
-            orc_dilu_setup_1x1(L->n, L->rp, L->ci, L->va, L->num_colors, L->colors, L->sorted_rows, L->color_offsets, L->Einv);
-        }
+        level_smoother_setup(L, smoother);
         L->tmp = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
         if (num_levels >= max_levels || L->n <= min_coarse_rows) { L->coarsest = 1; break; }
         L->agg = (int *)malloc(sizeof(int) * (size_t)L->n);
@@ -480,6 +490,77 @@ ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double
     return a;
 }
 
+
+/* AMG_Setup::setup level loop with Classical_AMG_Level::createCoarseVertices / createCoarseMatrices
+ * (src/classical/classical_amg_level.cu:213-299, 344-435).  interp / aggressive_interp: 0 = D2, 1 = MULTIPASS. */
+ORC_API orc_amg *orc_amg_setup_classical(int n, const int *rp, const int *ci, const double *va, int max_levels, int min_coarse_rows, double coarsen_threshold,
+                                         int presweeps, int postsweeps, int coarsest_sweeps, int finest_sweeps, int smoother, double omega,
+                                         double strength_threshold, double max_row_sum, int interp, int aggressive_levels, int aggressive_interp,
+                                         int max_elmts)
+{
+    orc_amg *a = (orc_amg *)calloc(1, sizeof(orc_amg));
+    a->lv = (orc_level *)calloc((size_t)(max_levels > 0 ? max_levels : 1) + 1, sizeof(orc_level));
+    a->presweeps = presweeps; a->postsweeps = postsweeps; a->coarsest_sweeps = coarsest_sweeps; a->finest_sweeps = finest_sweeps;
+    a->smoother = smoother; a->omega = omega;
+    orc_level *L = &a->lv[0];
+    L->n = n; L->nnz = rp[n]; L->rp = (int *)rp; L->ci = (int *)ci; L->va = (double *)va; L->own = 0;
+    int num_levels = 1;
+    for (;;) {
+        L = &a->lv[num_levels - 1];
+        level_smoother_setup(L, smoother);
+        L->tmp = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
+        if (num_levels >= max_levels || L->n <= min_coarse_rows) { L->coarsest = 1; break; }
+        const int lvl = num_levels - 1;
+        unsigned char *s_con = (unsigned char *)calloc((size_t)(L->nnz > 0 ? L->nnz : 1), 1);
+        float *w = (float *)calloc((size_t)(L->n > 0 ? L->n : 1), sizeof(float));
+        int *cf = (int *)calloc((size_t)(L->n > 0 ? L->n : 1), sizeof(int));
+        orc_cla_strength(L->n, L->rp, L->ci, L->va, strength_threshold, max_row_sum, s_con, w);
+        if (lvl < aggressive_levels) orc_cla_aggressive_pmis(L->n, L->rp, L->ci, s_con, w, cf);
+        else orc_cla_pmis(L->n, L->rp, L->ci, s_con, w, cf, 0);
+        const int nc = orc_cla_renumber(L->n, cf);
+        free(w);
+        if ((double)nc <= coarsen_threshold * (double)L->n && nc != L->n && nc >= min_coarse_rows) {
+            cla_csr P, R, AP, Ac;
+            const int which = (lvl < aggressive_levels) ? aggressive_interp : interp;
+            if (which == 1) cla_interp_multipass(L->n, L->rp, L->ci, L->va, cf, s_con, nc, &P);
+            else cla_interp_d2(L->n, L->rp, L->ci, L->va, cf, s_con, nc, &P);
+            if (max_elmts > 0 && L->n > 0) cla_truncate(&P, max_elmts);
+            cla_transpose(&P, &R);
+            cla_spgemm(L->n, L->rp, L->ci, L->va, P.rp, P.ci, P.va, nc, &AP);
+            cla_spgemm(nc, R.rp, R.ci, R.va, AP.rp, AP.ci, AP.va, nc, &Ac);
+            cla_csr_free(&AP);
+            L->nagg = nc;
+            L->Pp = P.rp; L->Pc = P.ci; L->Pv = P.va;
+            L->Rtp = R.rp; L->Rtc = R.ci; L->Rtv = R.va;
+            L->cf = cf;
+            orc_level *N = &a->lv[num_levels];
+            N->n = nc; N->nnz = Ac.nnz; N->rp = Ac.rp; N->ci = Ac.ci; N->va = Ac.va; N->own = 1;
+            L->bc = (double *)calloc((size_t)nc, sizeof(double));
+            L->xc = (double *)calloc((size_t)nc, sizeof(double));
+            L->r = (double *)calloc((size_t)L->n, sizeof(double));
+            free(s_con);
+            num_levels++;
+        } else {
+            free(s_con); free(cf);
+            L->coarsest = 1;
+            break;
+        }
+    }
+    a->num_levels = num_levels;
+    return a;
+}
+ORC_API int orc_amg_level_classical(const orc_amg *a, int l, int *cf, int *Pp, int *Pc, double *Pv, int *pnnz)
+{
+    const orc_level *L = &a->lv[l];
+    if (!L->Pp) return 0;
+    if (pnnz) *pnnz = L->Pp[L->n];
+    if (cf) memcpy(cf, L->cf, sizeof(int) * (size_t)L->n);
+    if (Pp) memcpy(Pp, L->Pp, sizeof(int) * ((size_t)L->n + 1));
+    if (Pc) memcpy(Pc, L->Pc, sizeof(int) * (size_t)L->Pp[L->n]);
+    if (Pv) memcpy(Pv, L->Pv, sizeof(double) * (size_t)L->Pp[L->n]);
+    return 1;
+}
+
 ORC_API void orc_amg_free(orc_amg *a)
 {
     if (!a) return;
@@ -488,6 +569,7 @@ ORC_API void orc_amg_free(orc_amg *a)
         if (L->own) { free(L->rp); free(L->ci); free(L->va); }
         free(L->agg); free(L->Rp); free(L->Rc); free(L->d); free(L->bc); free(L->xc); free(L->r); free(L->tmp);
         free(L->colors); free(L->sorted_rows); free(L->color_offsets); free(L->Einv); free(L->delta); free(L->Delta);
+        free(L->Pp); free(L->Pc); free(L->Pv); free(L->Rtp); free(L->Rtc); free(L->Rtv); free(L->cf);
     }
     free(a->lv);
     free(a);
@@ -548,9 +630,13 @@ static void vcycle(const orc_amg *a, int l, const double *b, double *x, int x_is
     else if (x_is_zero) memset(x, 0, sizeof(double) * (size_t)L->n);
     if (L->coarsest) return;
     orc_residual(L->n, L->rp, L->ci, L->va, x, b, L->r);          /* axmb */
-    orc_restrict(L->nagg, L->Rp, L->Rc, L->r, L->bc);             /* restrictResidual */
+    if (L->Pp) cla_spmv(L->nagg, L->Rtp, L->Rtc, L->Rtv, L->r, L->bc);   /* classical: rr = R r (classical_amg_level.cu:620-627) */
+    else orc_restrict(L->nagg, L->Rp, L->Rc, L->r, L->bc);        /* restrictResidual */
     vcycle(a, l + 1, L->bc, L->xc, 1);                            /* next level, initial guess zero */
-    orc_prolong_add(L->n, L->agg, L->xc, x);                      /* prolongateAndApplyCorrection */
+    if (L->Pp) {                                                  /* classical: tmp = P e; x = x + tmp (classical_amg_level.cu:884-910) */
+        cla_spmv(L->n, L->Pp, L->Pc, L->Pv, L->xc, L->tmp);
+        for (int i = 0; i < L->n; i++) x[i] = x[i] + L->tmp[i];
+    } else orc_prolong_add(L->n, L->agg, L->xc, x);               /* prolongateAndApplyCorrection */
     int n_post;
     if (finest && a->finest_sweeps != -1) n_post = a->postsweeps == 0 ? 0 : a->finest_sweeps;
     else n_post = a->postsweeps;

@@ -21,7 +21,7 @@ def lib():
     global _lib
     if _lib is None:
         p = _HERE / "liboracle.so"
-        if not p.exists() or p.stat().st_mtime < (_HERE / "amg_oracle.c").stat().st_mtime:
+        if not p.exists() or p.stat().st_mtime < max((_HERE / "amg_oracle.c").stat().st_mtime, (_HERE / "classical_oracle.inc.c").stat().st_mtime):
             build()
         _lib = C.CDLL(str(p))
         _lib.orc_dot.restype = C.c_double
@@ -29,6 +29,9 @@ def lib():
         _lib.orc_nrm1.restype = C.c_double
         _lib.orc_nrmmax.restype = C.c_double
         _lib.orc_amg_setup.restype = C.c_void_p
+        _lib.orc_amg_setup_classical.restype = C.c_void_p
+        _lib.orc_cla_interpolate.restype = C.c_void_p
+        _lib.orc_cla_galerkin.restype = C.c_void_p
     return _lib
 
 
@@ -278,3 +281,95 @@ def dilu4(rp, ci, va, b, x, weight, max_uncolored_fraction=0.15, sweeps=1):
     for _ in range(sweeps):
         lib().orc_dilu_sweep_4x4(n, _p(rp), _p(ci), _p(va), nc, _p(colors), _p(srows), _p(offs), _p(einv), _p(b), _p(x), C.c_double(weight), _p(delta), _p(Delta))
     return x, einv, colors
+
+
+# ---------------------------------------------------------------------------------------------------
+# classical (Ruge-Stueben) AMG: strength, PMIS / aggressive PMIS, D2 / MULTIPASS, truncation, RAP
+# ---------------------------------------------------------------------------------------------------
+COARSE, FINE, STRONG_FINE, UNASSIGNED = -1, -2, -3, -4
+
+
+def cla_strength(rp, ci, va, strength_threshold=0.25, max_row_sum=1.1):
+    rp, ci, va = _i(rp), _i(ci), _d(va)
+    n = rp.shape[0] - 1
+    s_con = np.zeros(ci.shape[0], np.uint8)
+    w = np.zeros(n, np.float32)
+    lib().orc_cla_strength(n, _p(rp), _p(ci), _p(va), C.c_double(strength_threshold), C.c_double(max_row_sum), _p(s_con), _p(w))
+    return s_con, w
+
+
+def cla_pmis(rp, ci, s_con, weights, aggressive=False):
+    """returns the C/F map with COARSE = -1 (not yet renumbered) -- weights is not modified"""
+    rp, ci = _i(rp), _i(ci)
+    n = rp.shape[0] - 1
+    s_con = np.ascontiguousarray(s_con, np.uint8)
+    w = np.ascontiguousarray(weights, np.float32).copy()
+    cf = np.zeros(n, np.int32)
+    if aggressive:
+        lib().orc_cla_aggressive_pmis(n, _p(rp), _p(ci), _p(s_con), _p(w), _p(cf))
+    else:
+        lib().orc_cla_pmis(n, _p(rp), _p(ci), _p(s_con), _p(w), _p(cf), 0)
+    return cf
+
+
+def cla_renumber(cf):
+    cf = _i(cf).copy()
+    nc = lib().orc_cla_renumber(cf.shape[0], _p(cf))
+    return cf, nc
+
+
+def _cla_take(h):
+    n, nc, nnz = C.c_int(), C.c_int(), C.c_int()
+    lib().orc_cla_matrix_sizes(h, C.byref(n), C.byref(nc), C.byref(nnz))
+    rp = np.empty(n.value + 1, np.int32)
+    ci = np.empty(nnz.value, np.int32)
+    va = np.empty(nnz.value)
+    lib().orc_cla_matrix_get(h, _p(rp), _p(ci), _p(va))
+    return rp, ci, va, nc.value
+
+
+def cla_interpolate(rp, ci, va, cf_renumbered, s_con, nc, interpolator="D2", max_elements=-1):
+    rp, ci, va, cf = _i(rp), _i(ci), _d(va), _i(cf_renumbered)
+    s_con = np.ascontiguousarray(s_con, np.uint8)
+    n = rp.shape[0] - 1
+    h = C.c_void_p(lib().orc_cla_interpolate(n, _p(rp), _p(ci), _p(va), _p(cf), _p(s_con), nc, {"D2": 0, "MULTIPASS": 1}[interpolator], max_elements))
+    out = _cla_take(h)
+    lib().orc_cla_matrix_free(h)
+    return out[:3]
+
+
+class ClassicalAMG(AMG):
+    """Classical hierarchy (PMIS / aggressive PMIS, D2 / MULTIPASS, truncation, R = P^T, RAP) + the same V-cycle."""
+
+    def __init__(self, rp, ci, va, max_levels=100, min_coarse_rows=2, coarsen_threshold=1.0, presweeps=1, postsweeps=1, coarsest_sweeps=2,
+                 finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, strength_threshold=0.25, max_row_sum=1.1, interpolator="D1",
+                 aggressive_levels=0, aggressive_interpolator="MULTIPASS", interp_max_elements=-1):
+        self.rp, self.ci, self.va = _i(rp), _i(ci), _d(va)
+        self.n = self.rp.shape[0] - 1
+        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2}[smoother]
+        im = {"D2": 0, "MULTIPASS": 1}
+        self.h = C.c_void_p(lib().orc_amg_setup_classical(
+            self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold), presweeps, postsweeps,
+            coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), C.c_double(strength_threshold), C.c_double(max_row_sum), im[interpolator],
+            aggressive_levels, im[aggressive_interpolator], interp_max_elements))
+
+    def level(self, l):
+        d = super().level_plain(l) if hasattr(super(), "level_plain") else None
+        n, nnz, nc = C.c_int(), C.c_int(), C.c_int()
+        lib().orc_amg_level_sizes(self.h, l, C.byref(n), C.byref(nnz), C.byref(nc))
+        n, nnz, nc = n.value, nnz.value, nc.value
+        rp = np.empty(n + 1, np.int32)
+        ci = np.empty(nnz, np.int32)
+        va = np.empty(nnz)
+        dd = np.empty(n)
+        lib().orc_amg_level_arrays(self.h, l, _p(rp), _p(ci), _p(va), None, None, None, _p(dd))
+        out = dict(n=n, nnz=nnz, n_coarse=nc, row_ptr=rp, col_idx=ci, values=va, d=dd)
+        pnnz = C.c_int()
+        if lib().orc_amg_level_classical(self.h, l, None, None, None, None, C.byref(pnnz)):
+            cf = np.empty(n, np.int32)
+            Pp = np.empty(n + 1, np.int32)
+            Pc = np.empty(pnnz.value, np.int32)
+            Pv = np.empty(pnnz.value)
+            lib().orc_amg_level_classical(self.h, l, _p(cf), _p(Pp), _p(Pc), _p(Pv), None)
+            out.update(cf_map=cf, P_row_offsets=Pp, P_col_indices=Pc, P_values=Pv)
+        return out

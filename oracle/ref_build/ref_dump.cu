@@ -40,6 +40,10 @@
 #include <solvers/multicolor_dilu_solver.h>
 #include <aggregation/aggregation_amg_level.h>
 #include <classical/classical_amg_level.h>
+#include <classical/strength/strength.h>
+#include <classical/selectors/selector.h>
+#include <classical/interpolators/interpolator.h>
+#include <truncate.h>
 #include <matrix_coloring/matrix_coloring.h>
 #include <amgx_c_common.h>
 #include <amgx_c_wrappers.inl>
@@ -143,6 +147,74 @@ template <AMGX_Mode CASE> static void dump_hierarchy(AMGX_solver_handle slv)
         lvl = lvl->getNextLevel(cusp::device_memory());
         li++;
     }
+}
+
+
+// Classical AMG stage dump (level 0): runs the reference's own strength / selector / interpolator / truncation objects
+// on the uploaded matrix, outside the solver, so that the C/F map (which the level discards) and the untruncated P can
+// be pinned.  Enabled by REFDUMP_CLASSICAL="strength_threshold,max_row_sum,interp_max_elements".
+template <AMGX_Mode CASE> static void dump_classical_stages(AMGX_matrix_handle mtx, double theta, double max_row_sum, int max_elmts)
+{
+    typedef typename TemplateMode<CASE>::Type TConfig;
+    typedef Vector<typename TConfig::template setVecPrec<AMGX_vecInt>::Type> IVector;
+    typedef Vector<typename TConfig::template setVecPrec<AMGX_vecBool>::Type> BVector;
+    typedef Vector<typename TConfig::template setVecPrec<AMGX_vecFloat>::Type> FVector;
+    Matrix<TConfig> &A = *get_mode_object_from<CASE, Matrix, AMGX_matrix_handle>(mtx);
+    const int n = A.get_num_rows(), nnz = A.get_num_nz();
+    auto dump_csr = [&](Matrix<TConfig> &M, const std::string &pfx) {
+        int mn = M.get_num_rows(), mnnz = M.get_num_nz();
+        int info[3] = {mn, mnnz, (int)M.get_num_cols()};
+        rec(pfx + "info", 'i', info, 3, 4);
+        rec_ivec(pfx + "row_offsets", M.row_offsets, mn + 1);
+        rec_ivec(pfx + "col_indices", M.col_indices, mnnz);
+        rec_dvec(pfx + "values", M.values, mnnz);
+    };
+    char buf[256];
+    snprintf(buf, sizeof(buf), "strength_threshold=%.17g, max_row_sum=%.17g, strength=AHAT", theta, max_row_sum);
+    AMG_Config c;
+    c.parseParameterString(buf);
+    Strength<TConfig> *st = StrengthFactory<TConfig>::allocate(c, "default");
+    for (int aggressive = 0; aggressive < 2; aggressive++) {
+        const std::string pfx = aggressive ? "stage.aggr." : "stage.pmis.";
+        AMG_Config cs;
+        cs.parseParameterString(aggressive ? "selector=AGGRESSIVE_PMIS" : "selector=PMIS");
+        classical::Selector<TConfig> *sel = classical::SelectorFactory<TConfig>::allocate(cs, "default");
+        BVector s_con(nnz);
+        FVector w(n);
+        IVector cf(n), scratch(n);
+        thrust_wrapper::fill<TConfig::memSpace>(s_con.begin(), s_con.end(), false);
+        thrust_wrapper::fill<TConfig::memSpace>(w.begin(), w.end(), 0.0f);
+        thrust_wrapper::fill<TConfig::memSpace>(cf.begin(), cf.end(), 0);
+        thrust_wrapper::fill<TConfig::memSpace>(scratch.begin(), scratch.end(), 0);
+        st->computeStrongConnectionsAndWeights(A, s_con, w, max_row_sum);
+        if (!aggressive) {
+            std::vector<char> hb(nnz);
+            cudaMemcpy(hb.data(), s_con.raw(), nnz, cudaMemcpyDefault);
+            std::vector<int> hi(hb.begin(), hb.end());
+            rec("stage.s_con", 'i', hi.data(), nnz, 4);
+            rec_dvec("stage.weights", w, n);
+        }
+        sel->markCoarseFinePoints(A, w, s_con, cf, scratch);
+        rec_ivec(pfx + "cf_map", cf, n);
+        int nc = 0;
+        sel->renumberAndCountCoarsePoints(cf, nc, n);
+        rec(pfx + "num_coarse", 'i', &nc, 1, 4);
+        AMG_Config ci;
+        ci.parseParameterString(aggressive ? "interpolator=MULTIPASS" : "interpolator=D2");
+        Interpolator<TConfig> *ip = InterpolatorFactory<TConfig>::allocate(ci, "default");
+        Matrix<TConfig> P;
+        ip->generateInterpolationMatrix(A, cf, s_con, scratch, P);
+        cudaDeviceSynchronize();
+        dump_csr(P, pfx + "P.");
+        if (max_elmts > 0) {
+            Truncate<TConfig>::truncateByMaxElements(P, max_elmts);
+            cudaDeviceSynchronize();
+            dump_csr(P, pfx + "Ptrunc.");
+        }
+        delete ip;
+        delete sel;
+    }
+    delete st;
 }
 
 #define CK(x)                                                                   \
@@ -291,6 +363,12 @@ int main(int argc, char **argv)
     else if (mode == AMGX_mode_dDDI) dump_hierarchy<AMGX_mode_dDDI>(solver);
     else if (mode == AMGX_mode_dDFI) dump_hierarchy<AMGX_mode_dDFI>(solver);
     else if (mode == AMGX_mode_dFFI) dump_hierarchy<AMGX_mode_dFFI>(solver);
+    if (dump_levels && mode == AMGX_mode_dDDI && getenv("REFDUMP_CLASSICAL")) {
+        double th = 0.25, mrs = 1.1;
+        int me = -1;
+        sscanf(getenv("REFDUMP_CLASSICAL"), "%lf,%lf,%d", &th, &mrs, &me);
+        dump_classical_stages<AMGX_mode_dDDI>(A, th, mrs, me);
+    }
     rec("log", 'i', nullptr, 0, 4);
     {
         uint32_t nl = 8;

@@ -9,6 +9,7 @@ gpurun_out/golden/<case>.npz; copy those to tests/golden/ and commit them.  Noth
 from __future__ import annotations
 
 import json
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -70,6 +71,19 @@ def cfg_amg_dilu(tol=1e-8, max_iters=40, norm="L1", determinism=0):
         "monitor_residual": 1, "store_res_history": 1, "convergence": "RELATIVE_INI", "tolerance": tol, "norm": norm}}
 
 
+def cfg_fgmres_classical(tol=1e-10, max_iters=60, restart=20, interpolator="D2", aggressive_levels=1, max_elements=4, strength_threshold=0.25,
+                         max_row_sum=0.9, pre=2, post=2):
+    """src/configs/FGMRES_CLASSICAL_AGGRESSIVE_PMIS.json (BASELINE config 3) with a tighter tolerance"""
+    amg = {"scope": "amg_solver", "solver": "AMG", "algorithm": "CLASSICAL", "selector": "PMIS", "interpolator": interpolator,
+           "aggressive_levels": aggressive_levels, "interp_max_elements": max_elements, "max_row_sum": max_row_sum,
+           "strength_threshold": strength_threshold, "cycle": "V", "max_levels": 50, "min_coarse_rows": 2, "presweeps": pre, "postsweeps": post,
+           "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER", "max_iters": 1, "monitor_residual": 0, "print_grid_stats": 1,
+           "smoother": {"scope": "jacobi", "solver": "JACOBI_L1", "relaxation_factor": 1, "monitor_residual": 0}}
+    return {"config_version": 2, "solver": {
+        "scope": "main", "solver": "FGMRES", "max_iters": max_iters, "gmres_n_restart": restart, "monitor_residual": 1, "store_res_history": 1,
+        "convergence": "RELATIVE_INI", "tolerance": tol, "norm": "L2", "preconditioner": amg}}
+
+
 def cfg_pcg_agg_block(tol=1e-8, max_iters=60):
     c = cfg_pcg_agg(tol=tol, max_iters=max_iters, pre=1, post=1, omega=0.9)
     return c
@@ -94,6 +108,11 @@ def cases():
     yield "poisson10_fgmres_agg_jacobi", gallery.poisson7pt(10), cfg_fgmres_agg(restart=5), None
     yield "poisson8_fgmres_noprec", gallery.poisson7pt(8), cfg_fgmres_agg(restart=12, max_iters=70, tol=1e-8, precond=False), None
     yield "banded3000_fgmres_agg_jacobi", gallery.random_banded(3000, sigma=40.0), cfg_fgmres_agg(restart=8, max_iters=40), None
+    # classical AMG (config 3 family); the third entry asks ref_dump for the level-0 stage dump (strength, C/F maps, P before truncation)
+    yield "poisson12_fgmres_classical_aggr", gallery.poisson7pt(12), cfg_fgmres_classical(), (1, "dDDI", "0.25,0.9,4")
+    yield "poisson16x12x9_fgmres_classical_aggr", gallery.poisson7pt(16, 12, 9), cfg_fgmres_classical(), (1, "dDDI", "0.25,0.9,4")
+    yield "poisson12_sorted_fgmres_classical_d2", gallery.poisson7pt_sorted(12), cfg_fgmres_classical(aggressive_levels=0, max_elements=-1), (1, "dDDI", "0.25,0.9,-1")
+    yield "banded3000_fgmres_classical_d2_trunc", gallery.random_banded(3000, sigma=40.0), cfg_fgmres_classical(aggressive_levels=0, max_iters=40), (1, "dDDI", "0.25,0.9,4")
 
 
 def main():
@@ -102,13 +121,16 @@ def main():
     for name, (rp, ci, va), cfg, extra in cases():
         if only and name not in only:
             continue
-        bs, mode = extra if extra else (1, "dDDI")
+        bs, mode = (extra[0], extra[1]) if extra else (1, "dDDI")
+        env = dict(os.environ)
+        if extra and len(extra) > 2:
+            env["REFDUMP_CLASSICAL"] = extra[2]
         n = rp.shape[0] - 1
         rhs = np.ones(n * bs)
         sysf, cfgf, outf = OUT / f"{name}.sys", OUT / f"{name}.json", OUT / f"{name}.bin"
         write_system(sysf, rp, ci, va, rhs, block=(bs, bs))
         cfgf.write_text(json.dumps(cfg, indent=1))
-        r = subprocess.run([str(REF), str(sysf), str(cfgf), str(outf), mode], capture_output=True, text=True)
+        r = subprocess.run([str(REF), str(sysf), str(cfgf), str(outf), mode], capture_output=True, text=True, env=env)
         if r.returncode != 0:
             print(f"[{name}] ref_dump FAILED rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
             continue

@@ -1,0 +1,166 @@
+"""GPU: classical AMG (BASELINE config 3: FGMRES + PMIS / aggressive PMIS + D2 / MULTIPASS + truncation + JACOBI_L1)
+of the CUDA engine through the C-ABI, against the CPU oracle (every level bit for bit: C/F map, P, Galerkin
+operator) and against the reference's golden vectors (iteration counts; residual history within 1e-12 where no
+tie among equal interpolation weights is broken differently -- see tests/test_oracle_classical.py)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from amgx_b200 import gallery
+from tests.golden.make_golden import cfg_fgmres_classical
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+TIE_FREE = ["poisson12_fgmres_classical_aggr", "poisson12_sorted_fgmres_classical_d2", "banded3000_fgmres_classical_d2_trunc"]
+
+
+def solve(amgx, cfgd, rp, ci, va, rhs):
+    cfg = amgx.Config(cfgd)
+    rsc = amgx.Resources(cfg)
+    n = rp.shape[0] - 1
+    A = amgx.Matrix(rsc).upload(rp, ci, va)
+    b = amgx.Vector(rsc).upload(rhs)
+    x = amgx.Vector(rsc).set_zero(n)
+    slv = amgx.Solver(rsc, cfg)
+    slv.setup(A)
+    slv.solve(b, x, zero_initial_guess=True)
+    out = dict(hist=slv.residual_history(), iters=slv.iterations_number, status=slv.status, x=x.download(), nl=slv.num_levels())
+    out["levels"] = []
+    for l in range(out["nl"]):
+        L = dict(A=slv.level_matrix(l), info=slv.level_info(l), d=slv.level_smoother_data(l))
+        if l < out["nl"] - 1:
+            L["cf"] = slv.level_cf_map(l)
+            L["P"] = slv.level_P(l)
+            L["R"] = slv.level_R(l)
+        out["levels"].append(L)
+    for o in (slv, x, b, A, rsc, cfg):
+        o.destroy()
+    return out
+
+
+def oracle_amg(oracle, rp, ci, va, a):
+    return oracle.ClassicalAMG(rp, ci, va, max_levels=a["max_levels"], min_coarse_rows=a["min_coarse_rows"], presweeps=a["presweeps"],
+                               postsweeps=a["postsweeps"], coarsest_sweeps=a["coarsest_sweeps"], smoother=a["smoother"]["solver"],
+                               omega=a["smoother"]["relaxation_factor"], strength_threshold=a["strength_threshold"], max_row_sum=a["max_row_sum"],
+                               interpolator=a["interpolator"], aggressive_levels=a["aggressive_levels"], interp_max_elements=a["interp_max_elements"])
+
+
+SYSTEMS = {
+    "poisson14_aggr_trunc4": (lambda: gallery.poisson7pt(14), dict()),
+    "poisson20x9x13_d2_trunc4": (lambda: gallery.poisson7pt(20, 9, 13), dict(aggressive_levels=0)),
+    "poisson12s_d2_notrunc": (lambda: gallery.poisson7pt_sorted(12), dict(aggressive_levels=0, max_elements=-1)),
+    "banded4000_d2_trunc6": (lambda: gallery.random_banded(4000, sigma=40.0, seed=5), dict(aggressive_levels=0, max_elements=6, max_iters=40)),
+    "poisson30_multipass_2aggr": (lambda: gallery.poisson7pt(30), dict(interpolator="MULTIPASS", aggressive_levels=2, tol=1e-8)),
+    "poisson24_strict_threshold": (lambda: gallery.poisson7pt(24), dict(strength_threshold=0.5, max_row_sum=1.1, tol=1e-8)),
+}
+
+
+@pytest.mark.parametrize("name", list(SYSTEMS))
+def test_classical_hierarchy_bit_exact_vs_oracle(amgx, oracle, name):
+    gen, kw = SYSTEMS[name]
+    rp, ci, va = gen()
+    n = rp.shape[0] - 1
+    cfgd = cfg_fgmres_classical(**kw)
+    a = cfgd["solver"]["preconditioner"]
+    g = solve(amgx, cfgd, rp, ci, va, np.ones(n))
+    o = oracle_amg(oracle, rp, ci, va, a)
+    assert g["nl"] == o.num_levels() and g["nl"] >= 3
+    for l in range(g["nl"]):
+        L, G = o.level(l), g["levels"][l]
+        assert np.array_equal(G["A"][0], L["row_ptr"]) and np.array_equal(G["A"][1], L["col_idx"]), f"level {l} pattern"
+        assert np.array_equal(G["A"][2], L["values"]), f"level {l} values (bit-exact)"
+        assert np.array_equal(G["d"], L["d"]), f"level {l} L1 norms"
+        if l < g["nl"] - 1:
+            assert np.array_equal(G["cf"], L["cf_map"]), f"level {l} C/F map"
+            assert np.array_equal(G["P"][0], L["P_row_offsets"]) and np.array_equal(G["P"][1], L["P_col_indices"]), f"level {l} P pattern"
+            assert np.array_equal(G["P"][2], L["P_values"]), f"level {l} P values (bit-exact)"
+            nc = o.level(l + 1)["n"]
+            P = sp.csr_matrix((G["P"][2], G["P"][1], G["P"][0]), shape=(L["n"], nc))
+            R = sp.csr_matrix((G["R"][2], G["R"][1], G["R"][0]), shape=(nc, L["n"]))
+            assert (R - P.T).nnz == 0, f"level {l}: R != P^T"
+            assert R.has_sorted_indices   # rows of R ascend (stable transpose)
+    s = cfgd["solver"]
+    xo, ito, histo, convo = oracle.fgmres(rp, ci, va, np.ones(n), amg=o, tol=s["tolerance"], max_iters=s["max_iters"], restart=s["gmres_n_restart"])
+    assert g["iters"] == ito and g["status"] == 0 and convo
+    assert np.max(np.abs(g["hist"] - histo) / histo[0]) < 1e-12
+    A = gallery.to_scipy(rp, ci, va)
+    assert np.linalg.norm(np.ones(n) - A @ g["x"]) <= 1.01 * s["tolerance"] * np.sqrt(n) + 1e-13
+
+
+@pytest.mark.parametrize("name", TIE_FREE)
+def test_classical_matches_reference_golden(amgx, name):
+    d = np.load(GOLD / f"{name}.npz")
+    cfgd = json.loads(str(d["config_json"]))
+    g = solve(amgx, cfgd, d["sys_row_ptr"], d["sys_col_idx"], d["sys_values"], d["sys_rhs"])
+    nl = int(d["num_levels"][0])
+    assert g["nl"] == nl
+    for l in range(nl):
+        info = d[f"L{l}.info"]
+        assert (g["levels"][l]["info"]["n"], g["levels"][l]["info"]["nnz"]) == (info[0], info[1])
+        A1 = sp.csr_matrix((g["levels"][l]["A"][2], g["levels"][l]["A"][1], g["levels"][l]["A"][0]), shape=(info[0], info[0]))
+        A2 = sp.csr_matrix((d[f"L{l}.values"][: info[1]], d[f"L{l}.col_indices"], d[f"L{l}.row_offsets"]), shape=(info[0], info[0]))
+        A1.sort_indices()
+        A2.sort_indices()
+        assert np.array_equal(A1.indices, A2.indices) and np.allclose(A1.data, A2.data, rtol=1e-12, atol=1e-14)
+    ref = d["res_history"]
+    assert g["iters"] == int(d["iterations"][0]) and g["status"] == int(d["status"][0])
+    assert np.max(np.abs(g["hist"] - ref) / ref[0]) < 1e-12
+    assert np.allclose(g["x"], d["solution"], rtol=0, atol=1e-10 * np.abs(d["solution"]).max())
+
+
+def test_classical_tie_case_same_iterations(amgx):
+    d = np.load(GOLD / "poisson16x12x9_fgmres_classical_aggr.npz")
+    cfgd = json.loads(str(d["config_json"]))
+    g = solve(amgx, cfgd, d["sys_row_ptr"], d["sys_col_idx"], d["sys_values"], d["sys_rhs"])
+    assert g["iters"] == int(d["iterations"][0])
+    assert [L["info"]["n"] for L in g["levels"]] == [int(d[f"L{l}.info"][0]) for l in range(g["nl"])]
+    assert np.max(np.abs(g["hist"] - d["res_history"]) / d["res_history"][0]) < 1e-3
+
+
+def test_classical_full_size_properties(amgx):
+    """96^3 (885 k rows): transfer operators and the Galerkin operator checked through properties that do not need the oracle."""
+    rp, ci, va = gallery.poisson7pt(96)
+    n = rp.shape[0] - 1
+    cfgd = cfg_fgmres_classical(tol=1e-8, max_iters=100, restart=50)
+    g = solve(amgx, cfgd, rp, ci, va, np.ones(n))
+    assert g["status"] == 0 and g["iters"] < 60
+    A = gallery.to_scipy(rp, ci, va)
+    assert np.linalg.norm(np.ones(n) - A @ g["x"]) <= 1.01e-8 * np.sqrt(n)
+    L0 = g["levels"][0]
+    nc = g["levels"][1]["info"]["n"]
+    P = sp.csr_matrix((L0["P"][2], L0["P"][1], L0["P"][0]), shape=(n, nc))
+    R = sp.csr_matrix((L0["R"][2], L0["R"][1], L0["R"][0]), shape=(nc, n))
+    assert (R - P.T).nnz == 0
+    assert np.diff(L0["P"][0]).max() <= 4
+    cf = L0["cf"]
+    coarse = cf >= 0
+    assert coarse.sum() == nc and np.array_equal(cf[coarse], np.arange(nc))
+    # coarse rows interpolate from themselves with weight one
+    rows = np.nonzero(coarse)[0]
+    assert np.array_equal(L0["P"][1][L0["P"][0][rows]], cf[rows]) and np.all(L0["P"][2][L0["P"][0][rows]] == 1.0)
+    # Galerkin: A_c == P^T A P (independent scipy product), columns sorted
+    Ac = sp.csr_matrix((g["levels"][1]["A"][2], g["levels"][1]["A"][1], g["levels"][1]["A"][0]), shape=(nc, nc))
+    ref = (P.T @ A @ P).tocsr()
+    ref.sort_indices()
+    assert Ac.has_sorted_indices
+    assert abs(Ac - ref).max() <= 1e-12 * abs(ref).max()
+    assert abs(Ac - Ac.T).max() <= 1e-12 * abs(ref).max()
+
+
+def test_classical_unsupported_options_fail_loudly(amgx):
+    rp, ci, va = gallery.poisson7pt(6)
+    n = rp.shape[0] - 1
+    for kw, key in ((dict(interpolator="D1"), "interpolator"),):
+        cfgd = cfg_fgmres_classical(**kw)
+        cfg = amgx.Config(cfgd)
+        rsc = amgx.Resources(cfg)
+        A = amgx.Matrix(rsc).upload(rp, ci, va)
+        slv = amgx.Solver(rsc, cfg)
+        with pytest.raises(amgx.AMGXError) as e:
+            slv.setup(A)
+        assert key in str(e.value)
+        for o in (slv, A, rsc, cfg):
+            o.destroy()
