@@ -22,7 +22,7 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "--extended-lambda", "-Xcompiler", "
           "-DAMGXB200_BUILD", "-w"]
 
 
-# translation units whose arithmetic must match the CPU oracle bit for bit: no implicit FMA contraction
+# translation units whose arithmetic must be reproducible bit for bit by a sequential CPU restatement: no implicit FMA contraction
 EXTRA = {"classical.cu": ["-fmad=false"], "spgemm.cu": ["-fmad=false"]}
 
 

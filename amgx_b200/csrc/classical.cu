@@ -7,7 +7,7 @@
 //   truncation (interp_max_elements)   src/truncate.cu:352-456, 78-92, 783-862
 //   R = P^T, A_c = R A P               src/classical/classical_amg_level.cu:440-468, 501-586
 //   restrict / prolongate              src/classical/classical_amg_level.cu:590-644, 851-913
-// Order conventions (shared with oracle/classical_oracle.inc.c): the coarse sets of a row are kept
+// Order conventions (see DESIGN.md "classical setup"): the coarse sets of a row are kept
 // sorted by column instead of the reference's hash-table slot order, sums run left to right in storage order, and a
 // product is rounded before it is added (this file is compiled with -fmad=false).  Selection arrays are bit-comparable
 // with the reference; weights agree to rounding; ties among equal weights in the max-elements truncation follow

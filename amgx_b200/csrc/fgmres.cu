@@ -4,8 +4,7 @@
 //   * the MGS coefficients h(i,m) = <V_i, V_{m+1}> never travel to the host inside the chain: each dot leaves its
 //     value in device memory, the following axpy reads it there; the whole Hessenberg column is mirrored to pinned
 //     host memory and read after ONE synchronisation per iteration (the reference synchronises m+2 times);
-//   * Krylov vectors are allocated up front (HBM is 180 GB); the DQGMRES fallback (gmres_krylov_dim < restart) is
-//     not implemented.
+//   * the DQGMRES fallback (gmres_krylov_dim < restart) is not implemented.
 #include "solvers.h"
 #include "dist.h"
 #include <cmath>
@@ -46,8 +45,11 @@ void FGMRESSolver::solver_setup(bool reuse)
     const size_t N = (size_t)A_->n_cols * A_->by;
     V_.resize(kmax + 1);
     Z_.resize(kmax);
-    for (auto &v : V_) { v.resize(N, A_->vec_prec); v.zero(stream()); }
-    for (auto &z : Z_) { z.resize(N, A_->vec_prec); z.zero(stream()); }
+    // Krylov vectors are allocated when an iteration first needs them (gmres_n_restart = 100 in the shipped classical
+    // config would otherwise reserve 201 vectors; a solve that converges in 25 iterations touches 51)
+    for (auto &v : V_) { v.resize(0, A_->vec_prec); }
+    for (auto &z : Z_) { z.resize(0, A_->vec_prec); }
+    krylov_len_ = N;
     if (!hs_dev_) {
         AMGXB_CUDA_CHECK(cudaMalloc(&hs_dev_, (R_ + 8) * sizeof(double)));
         AMGXB_CUDA_CHECK(cudaHostAlloc(&hs_host_, (R_ + 8) * sizeof(double), cudaHostAllocMapped));
@@ -81,6 +83,10 @@ Status FGMRESSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
         if (!A_->dist) return;
         dist_allreduce_norm(*A_, red, slot, is_norm ? 1 : 0, s);
     };
+    auto need = [&](DevVec &v) { if (v.n != krylov_len_) { v.resize(krylov_len_, vp); v.zero(s); } };
+    need(V_[m]);
+    need(V_[m + 1]);
+    need(Z_[m]);
     if (m == 0) {
         // r0 = b - A x ; beta = ||r0||
         dist_exchange_halo(*A_, x, s);
@@ -114,13 +120,21 @@ Status FGMRESSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
         matrix_apply(*A_, EPI_SPMV, g, s);
     }
     // modified Gram-Schmidt, coefficients stay on the device
-    for (int i = 0; i <= m; i++) {
-        vec_dot(V_[i].ptr(), V_[m + 1].ptr(), vp, n, red, FIN_STORE, i, A_->dist ? 0 : 1, s);
-        dist_fin(i, false);
-        vec_axpy_dev(V_[i].ptr(), V_[m + 1].ptr(), vp, n, hs_dev_, i, -1.0, s);
+    if (!A_->dist) {
+        // single GPU: the update w -= h_i v_i and the next coefficient <v_{i+1}, w> (finally ||w||) share one pass over w
+        vec_dot(V_[0].ptr(), V_[m + 1].ptr(), vp, n, red, FIN_STORE, 0, 1, s);
+        for (int i = 0; i < m; i++)
+            vec_axpy_dot_dev(V_[i].ptr(), V_[m + 1].ptr(), V_[i + 1].ptr(), vp, n, hs_dev_, i, -1.0, red, FIN_STORE, i + 1, 1, s);
+        vec_axpy_dot_dev(V_[m].ptr(), V_[m + 1].ptr(), nullptr, vp, n, hs_dev_, m, -1.0, red, FIN_SQRT, m + 1, 1, s);
+    } else {
+        for (int i = 0; i <= m; i++) {
+            vec_dot(V_[i].ptr(), V_[m + 1].ptr(), vp, n, red, FIN_STORE, i, 0, s);
+            dist_fin(i, false);
+            vec_axpy_dev(V_[i].ptr(), V_[m + 1].ptr(), vp, n, hs_dev_, i, -1.0, s);
+        }
+        vec_dot(V_[m + 1].ptr(), V_[m + 1].ptr(), vp, n, red, FIN_STORE, m + 1, 0, s);
+        dist_fin(m + 1, true);
     }
-    vec_dot(V_[m + 1].ptr(), V_[m + 1].ptr(), vp, n, red, A_->dist ? FIN_STORE : FIN_SQRT, m + 1, A_->dist ? 0 : 1, s);
-    dist_fin(m + 1, true);
     vec_scal_dev_inv(V_[m + 1].ptr(), vp, n, hs_dev_, m + 1, s);
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));    // the one host sync of the iteration
     for (int i = 0; i <= m + 1; i++) H(i, m) = hs_host_[i];

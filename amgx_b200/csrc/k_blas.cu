@@ -174,6 +174,23 @@ void vec_axpy_dev(const void *x, void *y, Prec p, size_t n, const double *scal, 
     });
 }
 
+// y += sign*scal[slot]*x and, in the same pass, <z, y_new> (z == nullptr: <y_new, y_new>).  Element arithmetic and the
+// reduction tree are those of vec_axpy_dev followed by vec_dot, so the fused chain reproduces the unfused one bit for bit.
+void vec_axpy_dot_dev(const void *x, void *y, const void *z, Prec p, size_t n, const double *scal, int slot, double sign, const ReduceCtx &red, int fin_op,
+                      int fin_slot, int mirror, cudaStream_t s)
+{
+    AMGXB_DISPATCH_VEC(p, {
+        const VecT *X = (const VecT *)x; VecT *Y = (VecT *)y; const VecT *Z = (const VecT *)z;
+        launch_reduce<false>(n, [=] __device__(size_t i) {
+            const VecT aa = (VecT)(sign * scal[slot]);
+            const VecT yn = fma(aa, X[i], Y[i]);
+            Y[i] = yn;
+            const VecT zz = Z ? Z[i] : yn;
+            return (double)zz * (double)yn;
+        }, red, fin_op, fin_slot, mirror, s);
+    });
+}
+
 void vec_axpby_dev(const void *x, const void *y, void *out, Prec p, size_t n, double a, const double *scal, int slot_b, cudaStream_t s)
 {
     AMGXB_DISPATCH_VEC(p, {

@@ -80,6 +80,9 @@ void vec_axpy(const void *x, void *y, Prec p, size_t n, double a, cudaStream_t s
 void vec_scal(void *x, Prec p, size_t n, double a, cudaStream_t s);
 // device-scalar variants: a = sign * scal[slot]
 void vec_axpy_dev(const void *x, void *y, Prec p, size_t n, const double *scal, int slot, double sign, cudaStream_t s);
+// fused MGS step: y += sign*scal[slot]*x ; scal[fin_slot] = fin(<z, y>)  (z == nullptr: <y, y>)
+void vec_axpy_dot_dev(const void *x, void *y, const void *z, Prec p, size_t n, const double *scal, int slot, double sign, const ReduceCtx &red, int fin_op,
+                      int fin_slot, int mirror, cudaStream_t s);
 void vec_axpby_dev(const void *x, const void *y, void *out, Prec p, size_t n, double a, const double *scal, int slot_b, cudaStream_t s);
 void vec_scal_dev_inv(void *x, Prec p, size_t n, const double *scal, int slot, cudaStream_t s);  // x *= 1/scal[slot]
 // reductions -> red.scal[fin_slot] through fin_op

@@ -227,6 +227,7 @@ protected:
     std::vector<DevVec> V_, Z_;
     std::vector<double> H_, s_, cs_, sn_, gamma_;
     double beta_ = 0;
+    size_t krylov_len_ = 0;
     bool update_x_every_iteration_ = false, update_r_every_iteration_ = false;
     double &H(int i, int j) { return H_[(size_t)i * (R_ + 1) + j]; }   // (R+2) x (R+1) storage
     double *hs_dev_ = nullptr, *hs_host_ = nullptr, *hs_host_dev_ = nullptr;   // Hessenberg column on device + pinned mirror

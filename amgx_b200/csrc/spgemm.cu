@@ -2,7 +2,7 @@
 //   reference: CSR_Multiply::csr_galerkin_product (src/csr_multiply.cu, src/csr_multiply_detail.cu; called from
 //   src/classical/classical_amg_level.cu:581-583) -- a hash SpGEMM whose per-entry sums arrive through atomics in an
 //   unspecified order and whose output columns are left in hash order (spmm_no_sort, src/core.cu:507).
-// This engine fixes the order instead (so that the CPU oracle reproduces every bit):
+// This engine fixes the order instead (so that a sequential CPU restatement reproduces every bit):
 //   * one warp per output row; A's row is walked left to right; for each a_ik the lanes take the entries of row k of
 //     B (their columns are distinct), so every column receives its contributions in the storage order of A's row;
 //   * a product is rounded before it is added (this translation unit is compiled with -fmad=false);
