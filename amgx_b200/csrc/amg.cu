@@ -142,7 +142,14 @@ void AMGSolver::solve_init(DevVec &b, DevVec &x, bool xIsZero)
 
 Status AMGSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
 {
-    cycle(0, b, x, nullptr);
+    // As the main solver (monitored, many iterations on the same b / x) the cycle is replayed as a CUDA graph; as a
+    // preconditioner the caller owns the graph (PCG) or hands in a different vector pair every iteration (FGMRES).
+    if (monitor_residual_ && max_iters_ > 2 && !A_->dist) {
+        const bool zero = levels_[0]->init_cycle;
+        run_segment(zero ? seg_cycle_zero_ : seg_cycle_, b.ptr(), x.ptr(), [&] { levels_[0]->init_cycle = zero; cycle(0, b, x, nullptr); });
+    } else {
+        cycle(0, b, x, nullptr);
+    }
     levels_[0]->init_cycle = false;
     return converged(b, x);
 }

@@ -3,7 +3,7 @@
 //   forward  DILU_forward_1x1_kernel / _4x4_                 :1763-1901, 1585-1759
 //   backward DILU_backward_1x1_kernel / _4x4_ / _skip        :2772-2915, 2604-2768
 //   host     solve_iteration / smooth_NxN / computeEinv_NxN  :3773-3851, 4021-4242, 3890-4019
-// Formulas (single partition, boundary_coloring = SYNC_COLORS):
+// Formulas (boundary_coloring = SYNC_COLORS; j ranges over OWNED columns in the colour-restricted sums):
 //   E_i     = A_ii - sum_{colour(j) < colour(i), j != i} A_ij Einv_j A_ji ;  Einv_i = E_i^{-1} (0 stays 0 for 1x1)
 //   forward (colour c ascending):  delta_i = Einv_i ( b_i - sum_j A_ij (x_j + [c != 0 and colour(j) < c] delta_j) )
 //   backward (colour c descending): Delta_i = delta_i - Einv_i sum_{[c != 0 and colour(j) > c]} A_ij Delta_j ;  x_i += w Delta_i
@@ -23,7 +23,7 @@ constexpr int NTPR = 8;   // lanes per row in the 1x1 sweeps
 
 template <class MatT, class VecT>
 __global__ void dilu_setup_1x1(const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ diag, const MatT *__restrict__ va,
-                               MatT *Einv, const int *__restrict__ rows, const int *__restrict__ colors, int nrows, int color)
+                               MatT *Einv, const int *__restrict__ rows, const int *__restrict__ colors, int nrows, int color, int n_owned)
 {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
@@ -36,7 +36,7 @@ __global__ void dilu_setup_1x1(const int *__restrict__ rp, const int *__restrict
                 const int k = k0 + lane;
                 if (k < k1) {
                     const int j = ci[k];
-                    if (j != i && colors[j] < color) {
+                    if (j != i && j < n_owned && colors[j] < color) {
                         MatT a_ji = 0;
                         for (int kk = rp[j]; kk < rp[j + 1]; kk++)
                             if (ci[kk] == i) { a_ji = va[kk]; break; }   // first match, as the reference's search order yields
@@ -144,7 +144,7 @@ template <class T> __device__ void invert4x4(T *A)
 
 template <class MatT, class VecT>
 __global__ void dilu_setup_4x4(const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ diag, const MatT *__restrict__ va,
-                               MatT *Einv, const int *__restrict__ rows, const int *__restrict__ colors, int nrows, int color)
+                               MatT *Einv, const int *__restrict__ rows, const int *__restrict__ colors, int nrows, int color, int n_owned)
 {
     for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < nrows; it += gridDim.x * blockDim.x) {
         const int i = rows[it];
@@ -154,7 +154,7 @@ __global__ void dilu_setup_4x4(const int *__restrict__ rp, const int *__restrict
         if (color != 0) {
             for (int k = rp[i]; k < rp[i + 1]; k++) {
                 const int j = ci[k];
-                if (j == i || colors[j] >= color) continue;
+                if (j == i || j >= n_owned || colors[j] >= color) continue;
                 int kji = -1;
                 for (int kk = rp[j]; kk < rp[j + 1]; kk++)
                     if (ci[kk] == i) { kji = kk; break; }
@@ -176,50 +176,51 @@ __global__ void dilu_setup_4x4(const int *__restrict__ rp, const int *__restrict
     }
 }
 
-// quad per block row: thread r of the quad owns component r
+// One warp per block row: quad q (lanes 4q..4q+3) takes the blocks q, q+8, ... of the row, thread r of a quad owns
+// component r; the eight partial 4-vectors are combined with an xor butterfly over the quads.  (A single quad walking
+// a 30..60-block coarse row serially is a pure latency chain: ~0.5 us per block.)
 template <class MatT, class VecT, bool BACKWARD>
-__global__ void dilu_sweep_4x4(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, VecT *x, const VecT *__restrict__ b,
-                               VecT *delta, VecT *Delta, double weight, const int *__restrict__ rows, int nrows, int color,
-                               const int *__restrict__ colors, const MatT *__restrict__ Einv, int n_owned)
+__global__ void __launch_bounds__(128) dilu_sweep_4x4(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, VecT *x,
+                                                      const VecT *__restrict__ b, VecT *delta, VecT *Delta, double weight, const int *__restrict__ rows, int nrows,
+                                                      int color, const int *__restrict__ colors, const MatT *__restrict__ Einv, int n_owned)
 {
-    const int r = threadIdx.x & 3;
-    const unsigned qmask = 0xFu << ((threadIdx.x & 31) & ~3);
-    const int quads_per_grid = gridDim.x * (blockDim.x >> 2);
-    for (int it = blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); __any_sync(0xffffffffu, it < nrows); it += quads_per_grid) {
-        const bool act = it < nrows;
-        const int i = act ? rows[it] : 0;
+    const int lane = threadIdx.x & 31;
+    const int r = lane & 3, q = lane >> 2;
+    const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nrows; it += warps_per_grid) {
+        const int i = rows[it];
         VecT acc = 0;
-        if (act) {
-            if (!BACKWARD) acc = b[(size_t)i * 4 + r];
-            for (int k = rp[i]; k < rp[i + 1]; k++) {
-                const int j = ci[k];
-                const MatT *a = va + (size_t)k * 16 + r * 4;
-                if (!BACKWARD) {
-                    const bool valid = color != 0 && j < n_owned && colors[j] < color;
+        if (!BACKWARD && q == 0) acc = b[(size_t)i * 4 + r];
+        const int k1 = rp[i + 1];
+        for (int k = rp[i] + q; k < k1; k += 8) {
+            const int j = ci[k];
+            const MatT *a = va + (size_t)k * 16 + r * 4;
+            if (!BACKWARD) {
+                const bool valid = color != 0 && j < n_owned && colors[j] < color;
 #pragma unroll
-                    for (int m = 0; m < 4; m++) {
-                        VecT xx = x[(size_t)j * 4 + m];
-                        if (valid) xx += delta[(size_t)j * 4 + m];
-                        acc -= (VecT)a[m] * xx;
-                    }
-                } else {
-                    const bool valid = color != 0 && j < n_owned && colors[j] > color;
-                    if (valid) {
+                for (int m = 0; m < 4; m++) {
+                    VecT xx = x[(size_t)j * 4 + m];
+                    if (valid) xx += delta[(size_t)j * 4 + m];
+                    acc -= (VecT)a[m] * xx;
+                }
+            } else {
+                const bool valid = color != 0 && j < n_owned && colors[j] > color;
+                if (valid) {
 #pragma unroll
-                        for (int m = 0; m < 4; m++) acc += (VecT)a[m] * Delta[(size_t)j * 4 + m];
-                    }
+                    for (int m = 0; m < 4; m++) acc += (VecT)a[m] * Delta[(size_t)j * 4 + m];
                 }
             }
         }
-        // y = Einv_i * acc (4x4 mat-vec across the quad)
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        // y = Einv_i * acc (4x4 mat-vec inside quad 0; every quad holds the full acc)
         VecT y = 0;
 #pragma unroll
         for (int m = 0; m < 4; m++) {
-            const VecT am = __shfl_sync(0xffffffffu, acc, ((threadIdx.x & 31) & ~3) + m);
-            if (act) y += (VecT)Einv[(size_t)i * 16 + r * 4 + m] * am;
+            const VecT am = __shfl_sync(0xffffffffu, acc, m);
+            y += (VecT)Einv[(size_t)i * 16 + r * 4 + m] * am;
         }
-        (void)qmask;
-        if (act) {
+        if (q == 0) {
             const size_t idx = (size_t)i * 4 + r;
             if (!BACKWARD) delta[idx] = y;
             else {
@@ -264,7 +265,6 @@ protected:
         if (A.bx != A.by) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "DILU implemented only for squared blocks");
         if (A.bs() != 1 && A.bx != 4) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "Multicolor-DILU: block sizes 1 and 4 are enabled in this engine");
         if (A.has_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "Multicolor-DILU with an external diagonal");
-        if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "Multicolor-DILU on distributed matrices");
         cudaStream_t s = stream();
         if (A.num_colors == 0) color_matrix_min_max(A, uncolored_fraction_, s);
         const size_t bs = A.bs();
@@ -281,11 +281,11 @@ protected:
                 if (bs == 1) {
                     const int grid = std::min(4096, ceil_div(cnt, 4));
                     dilu_setup_1x1<MatT, VecT><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.diag_idx.ptr(), A.values.as<MatT>(), Einv_.as<MatT>(),
-                                                                    A.sorted_rows_by_color.ptr() + off, A.row_colors.ptr(), cnt, c);
+                                                                    A.sorted_rows_by_color.ptr() + off, A.row_colors.ptr(), cnt, c, A.n);
                 } else {
                     const int grid = std::min(4096, ceil_div(cnt, 128));
                     dilu_setup_4x4<MatT, VecT><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.diag_idx.ptr(), A.values.as<MatT>(), Einv_.as<MatT>(),
-                                                                    A.sorted_rows_by_color.ptr() + off, A.row_colors.ptr(), cnt, c);
+                                                                    A.sorted_rows_by_color.ptr() + off, A.row_colors.ptr(), cnt, c, A.n);
                 }
             });
             count_launch();
@@ -298,6 +298,14 @@ protected:
         Matrix &A = *A_;
         cudaStream_t s = stream();
         if (xIsZero) x.zero(s);
+        else if (A.dist) {
+            // row-partitioned: halo values of x are frozen for the sweep (the forward pass reads them in b - A x); the
+            // coloured corrections couple owned rows only -- the reference's SYNC_COLORS forward predicate
+            // (a_col_id < boundary_index, multicolor_dilu_solver.cu:1848-1858).  Halo Delta is never formed: the sweep
+            // is x += w M^-1 (b - A x) with M the DILU factorisation of this rank's diagonal block.
+            dist_exchange_halo(A, x, s);
+            dist_wait_halo(A, s);
+        }
         const int nc = A.num_colors;
         const size_t bs = A.bs();
         AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
@@ -309,7 +317,7 @@ protected:
                     dilu_forward_1x1<MatT, VecT><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
                                                                       A.sorted_rows_by_color.ptr() + off, cnt, c, A.row_colors.ptr(), Einv_.as<MatT>(), A.n);
                 } else {
-                    const int grid = std::min(4096, ceil_div(cnt, 32));
+                    const int grid = std::min(148 * 16, ceil_div(cnt, 4));
                     dilu_sweep_4x4<MatT, VecT, false><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
                                                                            Delta_.as<VecT>(), weight_, A.sorted_rows_by_color.ptr() + off, cnt, c, A.row_colors.ptr(),
                                                                            Einv_.as<MatT>(), A.n);
@@ -328,7 +336,7 @@ protected:
                                                                        A.sorted_rows_by_color.ptr() + off, A.row_colors.ptr(), Einv_.as<MatT>(), delta_.as<VecT>(),
                                                                        Delta_.as<VecT>(), cnt, c, A.n);
                 } else {
-                    const int grid = std::min(4096, ceil_div(cnt, 32));
+                    const int grid = std::min(148 * 16, ceil_div(cnt, 4));
                     dilu_sweep_4x4<MatT, VecT, true><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
                                                                           Delta_.as<VecT>(), weight_, A.sorted_rows_by_color.ptr() + off, cnt, c, A.row_colors.ptr(),
                                                                           Einv_.as<MatT>(), A.n);

@@ -212,6 +212,20 @@ void dist_allreduce_norm(const Matrix &A, const ReduceCtx &red, int slot, int no
 
 double dist_reduce_norm(const Matrix &, double local, int) { return local; }
 
+// host values in, globally reduced values out (op 0: sum, 2: max); used by the per-component block norms
+void dist_allreduce_host(const Matrix &A, double *vals, int count, int op)
+{
+    if (!A.dist || count <= 0) return;
+    DistManager &m = *A.dist;
+    ensure_scratch(m);
+    if (count > 32) fatal(AMGX_RC_INTERNAL, "dist_allreduce_host: at most 32 values");
+    cudaStream_t s = A.stream();
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(m.allreduce_buf, vals, sizeof(double) * count, cudaMemcpyHostToDevice, s));
+    AMGXB_NCCL_CHECK(ncclAllReduce(m.allreduce_buf, m.allreduce_buf, count, ncclDouble, op == 2 ? ncclMax : ncclSum, comm_of(A), s));
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(vals, m.allreduce_buf, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
 // ---------------------------------------------------------------------------------------------
 // y = op(A, x) with the halo exchange overlapped: rows [0, split) first, wait, rows [split, n)
 // ---------------------------------------------------------------------------------------------

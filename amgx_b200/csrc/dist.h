@@ -41,7 +41,8 @@ void dist_exchange_int(const Matrix &A, int *x, cudaStream_t s);                
 long long dist_allreduce_ll(const Matrix &A, long long v, int op);                 // host value, op: 0 sum, 1 min, 2 max
 std::shared_ptr<DistManager> dist_coarsen(const Matrix &A, DevBuf<int> &aggregates, int n_agg, int *n_interior_c);
 void dist_allreduce_norm(const Matrix &A, const ReduceCtx &red, int slot, int norm_type, cudaStream_t s);
-double dist_reduce_norm(const Matrix &A, double local, int norm_type);             // host value in, global value out
+double dist_reduce_norm(const Matrix &A, double local, int norm_type);
+void dist_allreduce_host(const Matrix &A, double *vals, int count, int op);      // op 0 sum, 2 max             // host value in, global value out
 ReduceCtx dist_wrap_reduce(const Matrix &A, const ReduceCtx &red);
 void dist_allreduce_scalar_fin(const Matrix &A, const ReduceCtx &red, int slot, int fin_op, cudaStream_t s);
 
@@ -49,7 +50,8 @@ void dist_allreduce_scalar_fin(const Matrix &A, const ReduceCtx &red, int slot, 
 void matrix_apply(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s);
 
 // ---- block-size > 1 helpers (k_block.cu) ----
-void block_norms(const DevVec &v, int n, int bsize, int norm_type, const ReduceCtx &red, ScalarBlock &sb, std::vector<double> &out, cudaStream_t s);
+void block_norms(const DevVec &v, int n, int bsize, int norm_type, const ReduceCtx &red, ScalarBlock &sb, std::vector<double> &out, cudaStream_t s,
+                 const Matrix *dist_of = nullptr);   // dist_of: reduce over the ranks of this matrix
 void block_jacobi_setup(const Matrix &A, DevVec &dinv, cudaStream_t s);   // dinv <- inverse of diagonal blocks (in place)
 void block_jacobi_zero(const Matrix &A, const DevVec &dinv, const DevVec &b, void *x, double omega, cudaStream_t s);
 void block_jacobi_sweep(const Matrix &A, const DevVec &dinv, const DevVec &b, const void *x, void *xout, double omega, cudaStream_t s);

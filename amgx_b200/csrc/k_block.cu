@@ -236,12 +236,17 @@ void block_jacobi_sweep(const Matrix &A, const DevVec &dinv, const DevVec &b, co
     block_apply(A, EPI_JACOBI, g, s);
 }
 
-void block_norms(const DevVec &v, int n, int bsize, int norm_type, const ReduceCtx &red, ScalarBlock &sb, std::vector<double> &out, cudaStream_t s)
+void block_norms(const DevVec &v, int n, int bsize, int norm_type, const ReduceCtx &red, ScalarBlock &sb, std::vector<double> &out, cudaStream_t s,
+                 const Matrix *dist_of)
 {
     if (bsize > 8) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "block norms support block sizes up to 8");
     const int grid = std::max(1, std::min(ceil_div(n, 256), 256));
-    DevBuf<double> part;
-    part.resize((size_t)grid * 8);
+    static DevBuf<double> part;          // one process drives one device: a single cached partials buffer (no cudaMalloc per norm)
+    static double *hpart = nullptr;      // pinned landing zone
+    if (part.size() < (size_t)256 * 8) {
+        part.resize((size_t)256 * 8);
+        AMGXB_CUDA_CHECK(cudaHostAlloc(&hpart, sizeof(double) * 256 * 8, cudaHostAllocDefault));
+    }
     AMGXB_DISPATCH_VEC(v.prec, {
         if (norm_type == 1) block_norm_kernel<VecT, 1><<<grid, 256, 0, s>>>(v.as<VecT>(), n, bsize, part.ptr());
         else if (norm_type == 0) block_norm_kernel<VecT, 0><<<grid, 256, 0, s>>>(v.as<VecT>(), n, bsize, part.ptr());
@@ -249,13 +254,16 @@ void block_norms(const DevVec &v, int n, int bsize, int norm_type, const ReduceC
     });
     count_launch();
     AMGXB_LAUNCH_CHECK();
-    std::vector<double> h = part.to_host(s);
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(hpart, part.ptr(), sizeof(double) * (size_t)grid * 8, cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    const double *h = hpart;
     out.assign(bsize, 0.0);
     for (int b = 0; b < grid; b++)
         for (int c = 0; c < bsize; c++) {
             if (norm_type == 2) out[c] = std::max(out[c], h[(size_t)b * 8 + c]);
             else out[c] += h[(size_t)b * 8 + c];
         }
+    if (dist_of && dist_of->dist) dist_allreduce_host(*dist_of, out.data(), bsize, norm_type == 2 ? 2 : 0);
     if (norm_type == 1) for (auto &o : out) o = std::sqrt(o);
     (void)red; (void)sb;
 }

@@ -270,10 +270,9 @@ void Solver::compute_norm_of(const DevVec &v, std::vector<double> &out)
         enqueue_norm(v);
         read_norm(out);
     } else {
-        if (A_->dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "block norms on distributed matrices");
         out.resize(bsize);
         ReduceCtx red = red_ctx();
-        block_norms(v, A_->n, bsize, (int)norm_type_, red, sb_, out, stream());
+        block_norms(v, A_->n, bsize, (int)norm_type_, red, sb_, out, stream(), A_);
     }
 }
 

@@ -275,6 +275,7 @@ protected:
     int intensive_smoothing_ = 0, error_scaling_ = 0, dense_lu_num_rows_ = 0, dense_lu_max_rows_ = 0;
     double coarsen_threshold_ = 1.0;
     std::unique_ptr<Solver> coarse_solver_;
+    GraphSegment seg_cycle_, seg_cycle_zero_;   // stand-alone AMG solver: the V-cycle between two convergence checks
 };
 
 template <class F> void Solver::run_segment(GraphSegment &g, const void *k0, const void *k1, F &&body)

@@ -34,6 +34,44 @@ def poisson7pt(nx: int, ny: int | None = None, nz: int | None = None, dtype=np.f
     return rp.astype(np.int32), col, val
 
 
+def poisson7pt_slab(nx: int, ny: int, nz: int, k0: int, k1: int, dtype=np.float64):
+    """Rows of poisson7pt(nx, ny, nz) whose z index lies in [k0, k1): local row_ptr, GLOBAL (int64) columns, values.
+    Used by the multi-GPU drivers: every rank builds only its own slab."""
+    n_loc = nx * ny * (k1 - k0)
+    r = np.arange(nx * ny * k0, nx * ny * k1, dtype=np.int64)
+    i = r % nx
+    j = (r // nx) % ny
+    k = r // (nx * ny)
+    masks = [np.ones(n_loc, bool), i > 0, i < nx - 1, j > 0, j < ny - 1, k > 0, k < nz - 1]
+    offs = [0, -1, 1, -nx, nx, -nx * ny, nx * ny]
+    cnt = np.zeros(n_loc, np.int64)
+    for m in masks:
+        cnt += m
+    rp = np.zeros(n_loc + 1, np.int64)
+    np.cumsum(cnt, out=rp[1:])
+    nnz = int(rp[-1])
+    col = np.empty(nnz, np.int64)
+    val = np.empty(nnz, dtype)
+    pos = rp[:-1].copy()
+    for m, o in zip(masks, offs):
+        idx = pos[m]
+        col[idx] = r[m] + o
+        val[idx] = 6.0 if o == 0 else -1.0
+        pos[m] += 1
+    return rp.astype(np.int32), col, val
+
+
+def block_elasticity_slab(nx: int, ny: int, nz: int, k0: int, k1: int, dtype=np.float64):
+    """Rows [k0, k1) (z slabs) of block_elasticity(nx, ny, nz) with GLOBAL block columns."""
+    rp, col, val = poisson7pt_slab(nx, ny, nz, k0, k1)
+    S = np.array([[0, 1, 0, 1], [1, 0, 1, 0], [0, 1, 0, 1], [1, 0, 1, 0]], dtype=np.float64)
+    I4 = np.eye(4)
+    off = -(I4 + 0.1 * S)
+    dia = 6.6 * I4 + 0.6 * S
+    vals = np.where((val > 0)[:, None, None], dia[None], off[None]).astype(dtype)
+    return rp, col, np.ascontiguousarray(vals.reshape(-1))
+
+
 def poisson7pt_sorted(nx: int, ny: int | None = None, nz: int | None = None, dtype=np.float64):
     """Same matrix with ascending column order inside each row (cusp gallery order)."""
     rp, col, val = poisson7pt(nx, ny, nz, dtype)

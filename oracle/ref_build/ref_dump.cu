@@ -238,7 +238,7 @@ int main(int argc, char **argv)
     int n = 0, nnz = 0, bx = 1, by = 1, has_diag = 0, has_x0 = 0;
     std::vector<int> rp, ci;
     std::vector<double> va, dg, rhs, x0;
-    bool dump_levels = true;
+    bool dump_levels = getenv("REFDUMP_NO_LEVELS") == nullptr;   // timing runs on large systems skip the hierarchy dump
     if (!strncmp(argv[1], "poisson:", 8)) {
         // generated 7-point Poisson nx^3 (diagonal first, then -1 for i-1,i+1,j-1,j+1,k-1,k+1), b = 1, x0 = 0; timing runs: no hierarchy dump
         const int nx = atoi(argv[1] + 8);

@@ -16,6 +16,67 @@ from amgx_b200 import capi, gallery  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
 
+def block_dilu_section(rank, world, rsc, lib):
+    """4x4 blocks, multicolour DILU smoother, row-partitioned: AMG stand-alone and PCG + AMG must converge to the
+    solution of the global system (checked with an independent scipy residual), in dDDI and dDFI."""
+    import ctypes as C
+    import scipy.sparse as sp
+    nx, ny, nzl = 10, 9, 5
+    nz = nzl * world
+    rpg, cig, vag = gallery.block_elasticity(nx, ny, nz)
+    ng = rpg.shape[0] - 1
+    Ag = sp.bsr_matrix((vag.reshape(-1, 4, 4), cig, rpg), shape=(4 * ng, 4 * ng)).tocsr()
+    offsets = np.array([nx * ny * nzl * r for r in range(world + 1)], np.int64)
+    lo, hi = int(offsets[rank]), int(offsets[rank + 1])
+    amg = {"scope": "amg", "solver": "AMG", "algorithm": "AGGREGATION", "selector": "SIZE_2", "cycle": "V", "max_levels": 50,
+           "matrix_coloring_scheme": "MIN_MAX", "max_uncolored_percentage": 0.15, "smoother": "MULTICOLOR_DILU", "relaxation_factor": 0.9,
+           "presweeps": 1, "postsweeps": 1, "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER"}
+    for mode, tol in (("dDDI", 1e-8), ("dDFI", 1e-5)):
+        lrp, lci, lva = gallery.block_elasticity_slab(nx, ny, nz, nzl * rank, nzl * (rank + 1), dtype=np.float32 if mode == "dDFI" else np.float64)
+        assert np.array_equal(lci, cig[rpg[lo]:rpg[hi]].astype(np.int64))
+        for outer in ("AMG", "PCG"):
+            if outer == "AMG":
+                cfgd = {"config_version": 2, "solver": dict(amg, scope="main", max_iters=60, monitor_residual=1, store_res_history=1,
+                                                            convergence="RELATIVE_INI", tolerance=tol, norm="L2")}
+            else:
+                cfgd = {"config_version": 2, "solver": {"scope": "main", "solver": "PCG", "max_iters": 60, "monitor_residual": 1, "store_res_history": 1,
+                                                        "convergence": "RELATIVE_INI", "tolerance": tol, "norm": "L2",
+                                                        "preconditioner": dict(amg, max_iters=1, monitor_residual=0)}}
+            cfg = capi.Config(cfgd)
+            A = capi.Matrix(rsc, mode)
+            dh = C.c_void_p()
+            assert lib.AMGX_distribution_create(C.byref(dh), cfg.h) == 0
+            assert lib.AMGX_distribution_set_partition_data(dh, 1, offsets.ctypes.data) == 0
+            rc = lib.AMGX_matrix_upload_distributed(A.h, ng, hi - lo, lci.shape[0], 4, 4, lrp.ctypes.data, lci.ctypes.data, lva.ctypes.data, None, dh)
+            assert rc == 0, rc
+            lib.AMGX_distribution_destroy(dh)
+            b, x = capi.Vector(rsc, mode), capi.Vector(rsc, mode)
+            b.bind(A)
+            x.bind(A)
+            b.upload(np.ones((hi - lo) * 4), block_dim=4)
+            x.set_zero(hi - lo, 4)
+            slv = capi.Solver(rsc, cfg, mode)
+            slv.setup(A)
+            slv.solve(b, x, zero_initial_guess=True)
+            assert slv.status == "success", (mode, outer, slv.status, slv.iterations_number)
+            hist = np.atleast_2d(slv.residual_history())
+            xs = x.download()
+            parts = [torch.zeros(int(offsets[r + 1] - offsets[r]) * 4, dtype=torch.float64, device="cuda") for r in range(world)]
+            dist.all_gather(parts, torch.from_numpy(np.asarray(xs, np.float64)).cuda())
+            xfull = torch.cat(parts).cpu().numpy()
+            res = np.ones(4 * ng) - Ag @ xfull
+            # per-component L2 norms of the true residual meet the tolerance the solver reported
+            rn = np.array([np.linalg.norm(res[c::4]) for c in range(4)])
+            r0 = np.array([np.linalg.norm(np.ones(ng))] * 4)
+            assert np.all(rn <= 1.05 * tol * r0 + (1e-4 if mode == "dDFI" else 1e-10)), (mode, outer, rn / r0)
+            if rank == 0:
+                print(f"DIST_BLOCK_DILU_OK world={world} mode={mode} outer={outer} levels={slv.num_levels()} iters={slv.iterations_number} "
+                      f"colors={slv.level_coloring(0)[0]} max_rel={np.max(rn / r0):.2e}", flush=True)
+            for o in (slv, x, b, A, cfg):
+                o.destroy()
+    dist.barrier()
+
+
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -84,8 +145,11 @@ def main():
     dist.barrier()
     if rank == 0:
         print(f"DIST_GPU_OK world={world} levels={nl} iters={its} final_rel={hist[-1] / hist[0]:.3e}")
-    for o in (slv, sol, b, y, x, A, rsc, cfg):
+    for o in (slv, sol, b, y, x, A):
         o.destroy()
+    block_dilu_section(rank, world, rsc, lib)
+    rsc.destroy()
+    cfg.destroy()
     capi.finalize()
     dist.destroy_process_group()
 

@@ -26,3 +26,4 @@ def test_distributed_spmv_and_solve(world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_GPU_OK" in r.stdout
+    assert r.stdout.count("DIST_BLOCK_DILU_OK") == 4, r.stdout[-3000:]
