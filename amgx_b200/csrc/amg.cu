@@ -77,6 +77,9 @@ void AMGSolver::setup_aggregation()
     levels_[0]->index = 0;
     int num_levels = 1;
     bool coarse_solver_exists = (bool)coarse_solver_;
+    // replicated coarse tail (dist.cu): EXPERIMENTAL, off by default -- on 4 and 8 ranks it slowed convergence (86 vs 51 iterations at
+    // 96^3 per GPU), cause not yet found; 2 ranks are fine (76 vs 77) and gain 10 %.  AMGXB_TAIL_ROWS=<global rows> enables it.
+    static const long long tail_rows = getenv("AMGXB_TAIL_ROWS") ? atoll(getenv("AMGXB_TAIL_ROWS")) : 0;
     while (true) {
         AMGLevel &L = *levels_.back();
         Matrix &A = *L.A;
@@ -110,6 +113,14 @@ void AMGSolver::setup_aggregation()
                 next->owned_A->split_row = n_int_c;
             }
             next->owned_A->compute_diag_and_plan();
+            if (cdist && tail_rows > 0 && nextN <= tail_rows) {
+                // small enough: replicate the whole level on every rank and stop exchanging halos below here
+                std::unique_ptr<Matrix> G = dist_gather_matrix(*next->owned_A, L.tail_counts, L.tail_offs);
+                G->compute_diag_and_plan();
+                L.tail_gather = true;
+                L.tail_off = L.tail_offs[A.dist->rank];
+                next->owned_A = std::move(G);
+            }
             next->A = next->owned_A.get();
             next->index = num_levels;
             const size_t nc = (size_t)next->A->n_cols * A.by;
@@ -228,7 +239,9 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse)
         rsrc = &L.r;
     }
     if (algorithm_ == "AGGREGATION") {
-        agg_restrict(L.R_row_offsets.ptr(), L.R_column_indices.ptr(), rsrc->ptr(), L.bc.ptr(), A.vec_prec, L.n_coarse, A.by, s);
+        const size_t tail_bytes = (size_t)L.tail_off * A.by * prec_size(A.vec_prec);
+        agg_restrict(L.R_row_offsets.ptr(), L.R_column_indices.ptr(), rsrc->ptr(), (char *)L.bc.ptr() + tail_bytes, A.vec_prec, L.n_coarse, A.by, s);
+        if (L.tail_gather) dist_allgatherv_inplace(A, L.bc.ptr(), A.vec_prec, A.by, L.tail_counts, L.tail_offs, s);
     } else {
         classical_restrict(L, *rsrc, s);
     }
@@ -255,13 +268,13 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse)
         if (x_virtual_zero && n_post > 0 && sm->supports_fusion() && fuse_prolong && !A.dist) {
             // x := P xc is read on the fly by the first sweep
             f.agg = L.aggregates.ptr();
-            f.xc = L.xc.ptr();
+            f.xc = (const char *)L.xc.ptr() + (size_t)L.tail_off * A.by * prec_size(A.vec_prec);
             have_fuse = true;
             in_alt = false;
         } else if (x_virtual_zero) {
-            agg_prolong_set(L.aggregates.ptr(), L.xc.ptr(), xin, A.vec_prec, A.n, A.by, s);               // x = 0 + P xc
+            agg_prolong_set(L.aggregates.ptr(), (const char *)L.xc.ptr() + (size_t)L.tail_off * A.by * prec_size(A.vec_prec), xin, A.vec_prec, A.n, A.by, s);               // x = 0 + P xc
         } else {
-            agg_prolong_add(L.aggregates.ptr(), L.xc.ptr(), x.ptr(), xin, A.vec_prec, A.n, A.by, s);      // xin = x + P xc
+            agg_prolong_add(L.aggregates.ptr(), (const char *)L.xc.ptr() + (size_t)L.tail_off * A.by * prec_size(A.vec_prec), x.ptr(), xin, A.vec_prec, A.n, A.by, s);      // xin = x + P xc
         }
     } else {
         void *xin = (n_post > 0) ? sm->smooth_input(x, n_post) : x.ptr();

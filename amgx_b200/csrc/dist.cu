@@ -241,7 +241,15 @@ void matrix_apply(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream
     if (A.plan.split > 0 && A.dist->exchange_pending) {
         csr_op(A, epi, args, s, 1);
         dist_wait_halo(A, s);
-        csr_op(A, epi, args, s, 2);
+        if (epi == EPI_SPMV_DOT || epi == EPI_JACOBI_DOT || epi == EPI_RESID_NRM2) {
+            // the two row segments each finish a partial sum: the second one adds to the first (stream order)
+            if (args.fin_op != FIN_STORE) fatal(AMGX_RC_INTERNAL, "distributed fused reduction must use FIN_STORE + all-reduce");
+            CsrOpArgs a2 = args;
+            a2.fin_op = FIN_ADD;
+            csr_op(A, epi, a2, s, 2);
+        } else {
+            csr_op(A, epi, args, s, 2);
+        }
     } else {
         dist_wait_halo(A, s);
         csr_op(A, epi, args, s, 0);
@@ -574,5 +582,109 @@ std::shared_ptr<DistManager> dist_coarsen(const Matrix &A, DevBuf<int> &aggregat
     return cm;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Replicated coarse tail: once a level is small, every rank assembles the WHOLE level (rows of rank r occupy the
+// global range [offs[r], offs[r] + counts[r]) in r's local order) and the rest of the hierarchy is built and cycled
+// redundantly on every GPU -- no halo exchange below this level.  The reference's analogue is consolidation
+// (amg_consolidation_flag, src/amg.cu:225-270) onto fewer ranks; with NVSwitch an all-gather of a small vector is
+// cheaper than keeping ~15 latency-bound levels distributed.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void iota_off_kernel(int n, int off, int *v) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = off + i; }
+}
+
+std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &counts, std::vector<int> &offs)
+{
+    DistManager &m = *A.dist;
+    cudaStream_t s = A.stream();
+    const int world = m.world, rank = m.rank;
+    const size_t bs = (size_t)A.bs(), msz = prec_size(A.mat_prec);
+    // sizes of every rank
+    DevBuf<int> sz_send, sz_recv;
+    sz_send.resize(2);
+    sz_recv.resize((size_t)2 * world);
+    const int mine[2] = {A.n, A.nnz};
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(sz_send.ptr(), mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+    AMGXB_NCCL_CHECK(ncclAllGather(sz_send.ptr(), sz_recv.ptr(), 2, ncclInt32, comm_of(A), s));
+    std::vector<int> sz = sz_recv.to_host(s);
+    counts.assign(world, 0);
+    offs.assign(world + 1, 0);
+    std::vector<long long> nnz_off(world + 1, 0);
+    int n_max = 0, nnz_max = 0;
+    for (int r = 0; r < world; r++) {
+        counts[r] = sz[2 * r];
+        offs[r + 1] = offs[r] + counts[r];
+        nnz_off[r + 1] = nnz_off[r] + sz[2 * r + 1];
+        n_max = std::max(n_max, sz[2 * r]);
+        nnz_max = std::max(nnz_max, sz[2 * r + 1]);
+    }
+    const int N = offs[world];
+    const long long NNZ = nnz_off[world];
+    if (NNZ > 0x7fffffffll) fatal(AMGX_RC_INTERNAL, "gathered level too large");
+    // global ids of the local columns (owned: offset + local index; halo: asked from the owner)
+    DevBuf<int> gid;
+    gid.resize((size_t)std::max(A.n_cols, 1));
+    iota_off_kernel<<<std::max(1, std::min(ceil_div(A.n_cols, 256), 1024)), 256, 0, s>>>(A.n_cols, offs[rank], gid.ptr());
+    count_launch();
+    dist_exchange_int(A, gid.ptr(), s);
+    std::vector<int> h_gid = gid.to_host(s), h_rp = A.row_ptr.to_host(s), h_ci = A.col_idx.to_host(s);
+    // padded all-gather of row lengths, global columns and values
+    std::vector<int> len_pad((size_t)std::max(n_max, 1), 0), col_pad((size_t)std::max(nnz_max, 1), 0);
+    for (int i = 0; i < A.n; i++) len_pad[i] = h_rp[i + 1] - h_rp[i];
+    for (int k = 0; k < A.nnz; k++) col_pad[k] = h_gid[h_ci[k]];
+    DevBuf<int> d_len, d_col, r_len, r_col;
+    DevBytes d_val, r_val;
+    d_len.from_any(len_pad.data(), len_pad.size(), s);
+    d_col.from_any(col_pad.data(), col_pad.size(), s);
+    r_len.resize(len_pad.size() * world);
+    r_col.resize(col_pad.size() * world);
+    const size_t val_pad = (size_t)std::max(nnz_max, 1) * bs * msz;
+    d_val.resize(val_pad);
+    r_val.resize(val_pad * world);
+    AMGXB_CUDA_CHECK(cudaMemsetAsync(d_val.p, 0, val_pad, s));
+    if (A.nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(d_val.p, A.values.ptr(), (size_t)A.nnz * bs * msz, cudaMemcpyDeviceToDevice, s));
+    AMGXB_NCCL_CHECK(ncclGroupStart());
+    AMGXB_NCCL_CHECK(ncclAllGather(d_len.ptr(), r_len.ptr(), len_pad.size(), ncclInt32, comm_of(A), s));
+    AMGXB_NCCL_CHECK(ncclAllGather(d_col.ptr(), r_col.ptr(), col_pad.size(), ncclInt32, comm_of(A), s));
+    AMGXB_NCCL_CHECK(ncclAllGather(d_val.p, r_val.p, val_pad, ncclChar, comm_of(A), s));
+    AMGXB_NCCL_CHECK(ncclGroupEnd());
+    std::vector<int> all_len = r_len.to_host(s), all_col = r_col.to_host(s);
+    std::vector<char> all_val(val_pad * world);
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(all_val.data(), r_val.p, all_val.size(), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<int> g_rp((size_t)N + 1, 0), g_ci((size_t)std::max<long long>(NNZ, 1));
+    std::vector<char> g_va((size_t)std::max<long long>(NNZ, 1) * bs * msz);
+    for (int r = 0; r < world; r++) {
+        for (int i = 0; i < counts[r]; i++) g_rp[(size_t)offs[r] + i + 1] = all_len[(size_t)r * len_pad.size() + i];
+        const int nz = sz[2 * r + 1];
+        if (nz) {
+            memcpy(&g_ci[(size_t)nnz_off[r]], &all_col[(size_t)r * col_pad.size()], sizeof(int) * (size_t)nz);
+            memcpy(&g_va[(size_t)nnz_off[r] * bs * msz], &all_val[(size_t)r * val_pad], (size_t)nz * bs * msz);
+        }
+    }
+    for (int i = 0; i < N; i++) g_rp[i + 1] += g_rp[i];
+    std::unique_ptr<Matrix> G(new Matrix);
+    G->rsc = A.rsc;
+    G->mode = A.mode;
+    G->mat_prec = A.mat_prec;
+    G->vec_prec = A.vec_prec;
+    upload_matrix(*G, N, (int)NNZ, A.bx, A.by, g_rp.data(), g_ci.data(), g_va.data(), nullptr);
+    return G;
+}
+
+// v (global length offs[world], block dim bsize): every rank contributes its slice [offs[rank], +counts[rank]) in place
+void dist_allgatherv_inplace(const Matrix &A, void *v, Prec prec, int bsize, const std::vector<int> &counts, const std::vector<int> &offs, cudaStream_t s)
+{
+    const size_t esz = prec_size(prec);
+    const ncclDataType_t dt = prec == Prec::F64 ? ncclDouble : ncclFloat;
+    AMGXB_NCCL_CHECK(ncclGroupStart());
+    for (int r = 0; r < (int)counts.size(); r++) {
+        if (counts[r] == 0) continue;
+        char *p = (char *)v + (size_t)offs[r] * bsize * esz;
+        AMGXB_NCCL_CHECK(ncclBroadcast(p, p, (size_t)counts[r] * bsize, dt, r, comm_of(A), s));
+    }
+    AMGXB_NCCL_CHECK(ncclGroupEnd());
+}
 
 }  // namespace amgxb

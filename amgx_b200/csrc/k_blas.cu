@@ -31,6 +31,7 @@ __device__ void fin_apply(double sum, double *scal, int fin_op, int slot, double
     double out = sum;
     switch (fin_op) {
     case FIN_SQRT: out = sqrt(sum); scal[slot] = out; break;
+    case FIN_ADD: out = scal[slot] + sum; scal[slot] = out; break;
     case FIN_PCG_ALPHA: {
         scal[S_DOT] = sum;
         double a = (sum != 0.0) ? scal[S_RZ] / sum : 0.0;
@@ -233,7 +234,7 @@ void vec_nrmmax(const void *x, Prec p, size_t n, const ReduceCtx &red, int fin_s
 
 // norm_type: 0 = L1, 1 = L2, 2 = LMAX
 void pcg_update_xr(const void *p, const void *Ap, void *x, void *r, Prec pr, size_t n, const ReduceCtx &red, int norm_type,
-                   int fin_slot, int mirror, cudaStream_t s)
+                   int fin_slot, int mirror, cudaStream_t s, bool partial)
 {
     const double *scal = red.scal;
     AMGXB_DISPATCH_VEC(pr, {
@@ -244,7 +245,7 @@ void pcg_update_xr(const void *p, const void *Ap, void *x, void *r, Prec pr, siz
                 X[i] = fma(a, P[i], X[i]);
                 const VecT rn = fma(na, AP[i], R[i]);
                 R[i] = rn;
-                return (double)rn * (double)rn; }, red, FIN_SQRT, fin_slot, mirror, s);
+                return (double)rn * (double)rn; }, red, partial ? FIN_STORE : FIN_SQRT, fin_slot, mirror, s);
         } else if (norm_type == 0) {
             launch_reduce<false>(n, [=] __device__(size_t i) {
                 const VecT a = (VecT)scal[S_ALPHA], na = (VecT)scal[S_NEG_ALPHA];

@@ -82,6 +82,7 @@ __device__ void apply_fin(double sum, double *scal, int fin_op, int slot, double
     case FIN_STORE:
     case FIN_ABS: scal[slot] = sum; break;
     case FIN_SQRT: out = sqrt(sum); scal[slot] = out; break;
+    case FIN_ADD: out = scal[slot] + sum; scal[slot] = out; break;
     case FIN_PCG_ALPHA: {
         scal[S_DOT] = sum;
         double a = (sum != 0.0) ? scal[S_RZ] / sum : 0.0;

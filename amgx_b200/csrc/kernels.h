@@ -23,6 +23,7 @@ enum FinOp : int {
     FIN_PCG_ALPHA = 2,  // S_DOT = sum; S_ALPHA = S_DOT != 0 ? S_RZ / S_DOT : 0; S_NEG_ALPHA = -S_ALPHA   (pcg_solver.cu:128-137)
     FIN_PCG_BETA = 3,   // S_RZ_OLD = S_RZ; S_RZ = sum; S_BETA = S_RZ_OLD != 0 ? S_RZ / S_RZ_OLD : 0        (pcg_solver.cu:172-182)
     FIN_ABS = 4,        // scal[slot] = sum (L1 norm; identical to STORE, kept for readability)
+    FIN_ADD = 5,        // scal[slot] += sum  (second row segment of a distributed matrix: interior + boundary partials)
 };
 
 struct ReduceCtx {          // one per solver; buffers sized for the largest grid we launch
@@ -91,7 +92,7 @@ void vec_nrm1(const void *x, Prec p, size_t n, const ReduceCtx &red, int fin_slo
 void vec_nrmmax(const void *x, Prec p, size_t n, const ReduceCtx &red, int fin_slot, int mirror, cudaStream_t s);
 // PCG fused update: x += alpha p ; r -= alpha Ap ; nrm = ||r||_2 (or L1 / LMAX)  -- alpha = scal[S_ALPHA]
 void pcg_update_xr(const void *p, const void *Ap, void *x, void *r, Prec pr, size_t n, const ReduceCtx &red, int norm_type,
-                   int fin_slot, int mirror, cudaStream_t s);
+                   int fin_slot, int mirror, cudaStream_t s, bool partial = false);   // partial: leave the un-finalised sum (distributed)
 // Jacobi with zero initial guess: x = b*w/d   (block_jacobi_solver.cu:24-30)
 void jacobi_zero_guess(const void *b, const void *d, void *x, Prec matp, Prec vecp, size_t n, double omega, cudaStream_t s);
 int  blas_max_grid();

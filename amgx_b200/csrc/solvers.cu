@@ -127,6 +127,13 @@ void GraphSegment::reset()
     failed = false;
 }
 
+// distributed PCG: fuse <Ap,p>, <r,z> and ||r|| into the producing kernels (AMGXB_DIST_FUSE=0 falls back to separate dot kernels)
+static bool dist_fuse()
+{
+    static const bool on = getenv("AMGXB_DIST_FUSE") ? atoi(getenv("AMGXB_DIST_FUSE")) != 0 : true;
+    return on;
+}
+
 bool graphs_enabled()
 {
     static const bool on = getenv("AMGXB_GRAPHS") ? atoi(getenv("AMGXB_GRAPHS")) != 0 : true;
@@ -566,7 +573,7 @@ void PCGSolver::apply_precond_and_rz(int fin_op)
     } else {
         AMGSolver *amg = dynamic_cast<AMGSolver *>(precond_.get());
         bool fused = false;
-        if (amg && !A_->dist) fused = amg->solve_fused_dot(r_, z_, red, fin_op, S_TMP0);
+        if (amg && (!A_->dist || dist_fuse())) fused = amg->solve_fused_dot(r_, z_, red, A_->dist ? FIN_STORE : fin_op, S_TMP0);
         if (!fused) {
             precond_->solve(r_, z_, true);
             vec_dot(r_.ptr(), z_.ptr(), r_.prec, vec_len(), red, A_->dist ? FIN_STORE : fin_op, S_TMP0, 0, s);
@@ -591,14 +598,15 @@ void PCGSolver::enqueue_A(DevVec &x)
     cudaStream_t s = stream();
     ReduceCtx red = red_ctx();
     dist_exchange_halo(*A_, p_, s);
-    if (A_->bs() == 1 && !A_->dist) {
+    if (A_->bs() == 1 && (!A_->dist || dist_fuse())) {
         CsrOpArgs g;
         g.x = p_.ptr();
         g.y = Ap_.ptr();
         g.red = red;
-        g.fin_op = FIN_PCG_ALPHA;
-        g.fin_slot = S_DOT;
+        g.fin_op = A_->dist ? FIN_STORE : FIN_PCG_ALPHA;
+        g.fin_slot = A_->dist ? S_TMP0 : S_DOT;
         matrix_apply(*A_, EPI_SPMV_DOT, g, s);      // Ap = A p fused with <Ap,p>; alpha = rz / <Ap,p> on the device
+        if (A_->dist) dist_allreduce_scalar_fin(*A_, red, S_TMP0, FIN_PCG_ALPHA, s);   // partial sums of the ranks, then alpha
     } else {
         CsrOpArgs g;
         g.x = p_.ptr();
@@ -608,8 +616,10 @@ void PCGSolver::enqueue_A(DevVec &x)
         if (A_->dist) dist_allreduce_scalar_fin(*A_, red, S_TMP0, FIN_PCG_ALPHA, s);
     }
     const bool scalar_norm = use_scalar_norm_ || A_->by == 1;
-    if (monitor_convergence_ && scalar_norm && !A_->dist) {
-        pcg_update_xr(p_.ptr(), Ap_.ptr(), x.ptr(), r_.ptr(), x.prec, vec_len(), red, (int)norm_type_, S_NRM, 1, s);   // one pass
+    if (monitor_convergence_ && scalar_norm && (!A_->dist || dist_fuse())) {
+        const bool d = (bool)A_->dist;
+        pcg_update_xr(p_.ptr(), Ap_.ptr(), x.ptr(), r_.ptr(), x.prec, vec_len(), red, (int)norm_type_, S_NRM, d ? 0 : 1, s, d);   // one pass
+        if (d) dist_allreduce_norm(*A_, red, S_NRM, (int)norm_type_, s);
     } else {
         vec_axpy_dev(p_.ptr(), x.ptr(), x.prec, vec_len(), sb_.scal, S_ALPHA, 1.0, s);
         vec_axpy_dev(Ap_.ptr(), r_.ptr(), x.prec, vec_len(), sb_.scal, S_NEG_ALPHA, 1.0, s);

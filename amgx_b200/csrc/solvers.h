@@ -251,6 +251,10 @@ struct AMGLevel {
     // cycle work vectors (sized for the NEXT level: bc, xc) and residual of this level
     DevVec bc, xc, r;
     bool init_cycle = false;
+    // distributed hierarchy: the NEXT level is replicated on every rank (dist.cu, "replicated coarse tail")
+    bool tail_gather = false;
+    int tail_off = 0;
+    std::vector<int> tail_counts, tail_offs;
 };
 
 class AMGSolver : public Solver {

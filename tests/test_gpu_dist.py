@@ -17,13 +17,18 @@ def _ngpu():
         return 0
 
 
+@pytest.mark.parametrize("tail_rows", ["0", "131072", "600"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_distributed_spmv_and_solve(world):
+def test_distributed_spmv_and_solve(world, tail_rows):
+    """tail_rows: global size below which a level is replicated on every rank (0: the whole hierarchy stays distributed;
+    600: the switch happens in the middle of the hierarchy)"""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
+    import os
+    env = dict(os.environ, AMGXB_TAIL_ROWS=tail_rows)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29611 + world), str(ROOT / "tests" / "dist_gpu_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT), env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_GPU_OK" in r.stdout
     assert r.stdout.count("DIST_BLOCK_DILU_OK") == 4, r.stdout[-3000:]
