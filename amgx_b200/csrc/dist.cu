@@ -4,6 +4,7 @@
 // entry point here a no-op.
 #include "solvers.h"
 #include "dist.h"
+#include <cmath>
 #include "capi_internal.h"
 #include <nccl.h>
 #include <algorithm>
@@ -670,6 +671,59 @@ std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &co
     G->mat_prec = A.mat_prec;
     G->vec_prec = A.vec_prec;
     upload_matrix(*G, N, (int)NNZ, A.bx, A.by, g_rp.data(), g_ci.data(), g_va.data(), nullptr);
+    if (getenv("AMGXB_TAIL_CHECK") && bs == 1 && A.vec_prec == Prec::F64) {
+        // self-check: y = A x through the distributed operator must equal the owned slice of G x for x(g) = sin(1 + 0.37 g);
+        // and an all-gather of the owned global ids must reproduce 0..N-1
+        std::vector<double> xg((size_t)N), xl((size_t)A.n_cols);
+        for (int g = 0; g < N; g++) xg[g] = std::sin(1.0 + 0.37 * g);
+        for (int c = 0; c < A.n_cols; c++) xl[c] = xg[h_gid[c]];
+        DevVec dx, dy, gx, gy;
+        dx.resize((size_t)A.n_cols, Prec::F64); dy.resize((size_t)A.n_cols, Prec::F64);
+        gx.resize((size_t)N, Prec::F64); gy.resize((size_t)N, Prec::F64);
+        AMGXB_CUDA_CHECK(cudaMemcpyAsync(dx.ptr(), xl.data(), sizeof(double) * xl.size(), cudaMemcpyHostToDevice, s));
+        AMGXB_CUDA_CHECK(cudaMemcpyAsync(gx.ptr(), xg.data(), sizeof(double) * xg.size(), cudaMemcpyHostToDevice, s));
+        CsrOpArgs a1, a2;
+        a1.x = dx.ptr(); a1.y = dy.ptr();
+        csr_op(A, EPI_SPMV, a1, s, 0);
+        a2.x = gx.ptr(); a2.y = gy.ptr();
+        csr_op(*G, EPI_SPMV, a2, s, 0);
+        std::vector<double> y1((size_t)A.n_cols), y2((size_t)N);
+        AMGXB_CUDA_CHECK(cudaMemcpyAsync(y1.data(), dy.ptr(), sizeof(double) * y1.size(), cudaMemcpyDeviceToHost, s));
+        AMGXB_CUDA_CHECK(cudaMemcpyAsync(y2.data(), gy.ptr(), sizeof(double) * y2.size(), cudaMemcpyDeviceToHost, s));
+        AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+        double md = 0, mx = 0;
+        for (int i = 0; i < A.n; i++) { md = std::max(md, std::fabs(y1[i] - y2[(size_t)offs[rank] + i])); mx = std::max(mx, std::fabs(y1[i])); }
+        // symmetry of G and row sums
+        double asym = 0;
+        {
+            std::vector<double> va((size_t)NNZ);
+            memcpy(va.data(), g_va.data(), sizeof(double) * (size_t)NNZ);
+            for (int i = 0; i < N && i < 4000; i++)
+                for (int k = g_rp[i]; k < g_rp[i + 1]; k++) {
+                    const int j = g_ci[k];
+                    double aji = 0; bool f = false;
+                    for (int kk = g_rp[j]; kk < g_rp[j + 1]; kk++) if (g_ci[kk] == i) { aji = va[kk]; f = true; break; }
+                    asym = std::max(asym, f ? std::fabs(aji - va[k]) : 1e30);
+                }
+        }
+        // all-gather check
+        DevVec tv;
+        tv.resize((size_t)N, Prec::F64);
+        tv.zero(s);
+        std::vector<double> mine_v((size_t)A.n);
+        for (int i = 0; i < A.n; i++) mine_v[i] = offs[rank] + i;
+        AMGXB_CUDA_CHECK(cudaMemcpyAsync((double *)tv.ptr() + offs[rank], mine_v.data(), sizeof(double) * mine_v.size(), cudaMemcpyHostToDevice, s));
+        dist_allgatherv_inplace(A, tv.ptr(), Prec::F64, 1, counts, offs, s);
+        std::vector<double> tvh((size_t)N);
+        AMGXB_CUDA_CHECK(cudaMemcpyAsync(tvh.data(), tv.ptr(), sizeof(double) * tvh.size(), cudaMemcpyDeviceToHost, s));
+        AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+        int bad = 0;
+        for (int g = 0; g < N; g++) bad += (tvh[g] != (double)g);
+        unsigned long long cks = 1469598103934665603ull;
+        for (long long k = 0; k < NNZ; k++) cks = (cks ^ (unsigned)g_ci[k]) * 1099511628211ull;
+        fprintf(stderr, "[tail-check rank %d/%d] N=%d NNZ=%lld n_owned=%d n_halo=%d nbrs=%d | max|A x - (G x)_slice| = %.3e (max|y| %.3e) | asym(G) = %.3e | allgatherv mismatches = %d | cks %llx\n",
+                rank, world, N, NNZ, A.n, m.n_halo, (int)m.neighbors.size(), md, mx, asym, bad, cks);
+    }
     return G;
 }
 
