@@ -7,11 +7,11 @@
 //   truncation (interp_max_elements)   src/truncate.cu:352-456, 78-92, 783-862
 //   R = P^T, A_c = R A P               src/classical/classical_amg_level.cu:440-468, 501-586
 //   restrict / prolongate              src/classical/classical_amg_level.cu:590-644, 851-913
-// Order conventions (see DESIGN.md "classical setup"): the coarse sets of a row are kept
-// sorted by column instead of the reference's hash-table slot order, sums run left to right in storage order, and a
-// product is rounded before it is added (this file is compiled with -fmad=false).  Selection arrays are bit-comparable
-// with the reference; weights agree to rounding; ties among equal weights in the max-elements truncation follow
-// storage order.
+// Order conventions (see DESIGN.md "classical setup"): rows of P are emitted in the reference's own order (its
+// hash-table slot order, emulated: it decides which of several equal weights the max-elements truncation keeps); sums
+// run left to right in storage order and a product is rounded before it is added (this file is compiled with
+// -fmad=false).  Selection arrays, the pattern and the row order of P are bit-comparable with the reference on the
+// finest level; weights agree to rounding.
 #include "solvers.h"
 #include "dist.h"
 #include <cub/cub.cuh>
@@ -275,6 +275,138 @@ __global__ void chat_fill_kernel(int n, const int *__restrict__ rp, const int *_
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) len[n] = 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The reference's row order.  A row of P leaves the reference in the slot order of its Hash_set / Hash_map
+// (include/hash_containers_detail.inl): 128 shared-memory slots, slot = ((key ^ c[f]) + c[4+f]) & 127 for the first of
+// four hash functions whose slot is free or already holds the key; a warp inserts up to 32 keys at once and when
+// several lanes race for one empty slot the lowest lane wins (this rule reproduces every row of the reference dumps);
+// keys that lose all four rounds go to a global-memory table (same functions, mask gmem_size-1) stored after the
+// shared-memory part.  The max-elements truncation keeps the FIRST of several equal weights, so this order decides
+// which coarse points survive on symmetric stencils.  Sequential emulation, one thread per row: a "step" is one
+// warp-wide insert, lanes visited in ascending order inside every hash round.
+// ---------------------------------------------------------------------------------------------------------------
+__constant__ unsigned c_cla_hash_keys[8] = {3499211612u, 581869302u, 3890346734u, 3586334585u, 545404204u, 4161255391u, 3922919429u, 949333985u};
+constexpr int SS_SLOTS = 128, SS_OVF = 64;
+struct SlotSet {
+    int tab[SS_SLOTS];
+    int ovf_slot[SS_OVF], ovf_key[SS_OVF];
+    int n_ovf, gmem_mask;
+    __device__ void clear(int gmem_size) { for (int s = 0; s < SS_SLOTS; s++) tab[s] = -1; n_ovf = 0; gmem_mask = gmem_size - 1; }
+    __device__ static unsigned hash(int key, int f) { return ((unsigned)key ^ c_cla_hash_keys[f]) + c_cla_hash_keys[4 + f]; }
+    __device__ void insert_step(int *keys)   // keys[0..31]: key of each lane or -1; destroyed
+    {
+        for (int f = 0; f < 4; f++) {
+            bool any = false;
+            for (int l = 0; l < 32; l++) {
+                const int k = keys[l];
+                if (k == -1) continue;
+                const int s = (int)(hash(k, f) & (SS_SLOTS - 1));
+                const int t = tab[s];
+                if (t == -1) { tab[s] = k; keys[l] = -1; }
+                else if (t == k) keys[l] = -1;
+                else any = true;
+            }
+            if (!any) return;
+        }
+        for (int f = 0; f < 4; f++) {
+            bool any = false;
+            for (int l = 0; l < 32; l++) {
+                const int k = keys[l];
+                if (k == -1) continue;
+                const int s = (int)(hash(k, f) & (unsigned)gmem_mask);
+                int q = -1;
+                for (int t = 0; t < n_ovf; t++) if (ovf_slot[t] == s) { q = t; break; }
+                if (q < 0) {
+                    if (n_ovf < SS_OVF) { ovf_slot[n_ovf] = s; ovf_key[n_ovf] = k; n_ovf++; }
+                    keys[l] = -1;
+                } else if (ovf_key[q] == k) keys[l] = -1;
+                else any = true;
+            }
+            if (!any) return;
+        }
+    }
+    __device__ int store(int *out) const   // shared-memory slots ascending, then global-memory slots ascending
+    {
+        int m = 0;
+        for (int s = 0; s < SS_SLOTS; s++) if (tab[s] != -1) out[m++] = tab[s];
+        int last = -1;
+        for (int t = 0; t < n_ovf; t++) {       // selection by ascending slot (slots are distinct)
+            int best = -1;
+            for (int u = 0; u < n_ovf; u++) if (ovf_slot[u] > last && (best < 0 || ovf_slot[u] < ovf_slot[best])) best = u;
+            out[m++] = ovf_key[best];
+            last = ovf_slot[best];
+        }
+        return m;
+    }
+};
+__device__ inline int find_linear(const int *a, int m, int key) { for (int k = 0; k < m; k++) if (a[k] == key) return k; return -1; }
+
+// distance2::compute_c_hat_kernel (distance2.cu:848-1170): coarse set of the FINE rows in the reference's order.
+// wide == 0: the 8-lanes-per-row variant (average nnz per row < 16), four rows of B in flight; wide == 1: 32 lanes per row of B.
+__global__ void chat_fill_ref_order_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, const int *__restrict__ cf,
+                                           int wide, const i64 *__restrict__ off, int *chat, int *len)
+{
+    ROW_LOOP(i, n) {
+        const int cfi = cf[i];
+        int *out = chat + off[i];
+        if (cfi >= 0) { out[0] = i; len[i] = 1; continue; }
+        if (cfi == STRONG_FINE) { len[i] = 0; continue; }
+        SlotSet h;
+        h.clear(512);                       // gmem_size of the reference on sm >= 7 (distance2.cu:1912-1914)
+        int keys[32], fines[32];
+        const int r1 = rp[i + 1];
+        for (int c0 = rp[i]; c0 < r1; c0 += 32) {
+            int nf = 0;
+            for (int l = 0; l < 32; l++) {
+                keys[l] = -1;
+                const int k = c0 + l;
+                if (k >= r1) continue;
+                const int c = ci[k];
+                if (c == i || !s_con[k]) continue;
+                const int cc = cf[c];
+                if (cc == FINE) fines[nf++] = c;
+                else if (cc != STRONG_FINE) keys[l] = c;
+            }
+            h.insert_step(keys);
+            if (!wide) {
+                for (int g0 = 0; g0 < nf; g0 += 4)
+                    for (int t = 0;; t++) {
+                        bool any = false;
+                        for (int l = 0; l < 32; l++) {
+                            keys[l] = -1;
+                            const int gi = l >> 3, m = l & 7;
+                            if (g0 + gi >= nf) continue;
+                            const int b = fines[g0 + gi], k = rp[b] + m + 8 * t;
+                            if (k >= rp[b + 1]) continue;
+                            any = true;
+                            const int c = ci[k];
+                            if (c != b && s_con[k]) { const int cc = cf[c]; if (cc != FINE && cc != STRONG_FINE) keys[l] = c; }
+                        }
+                        if (!any) break;
+                        h.insert_step(keys);
+                    }
+            } else {
+                for (int g = 0; g < nf; g++) {
+                    const int b = fines[g], b1 = rp[b + 1];
+                    for (int k0 = rp[b]; k0 < b1; k0 += 32) {
+                        for (int l = 0; l < 32; l++) {
+                            keys[l] = -1;
+                            const int k = k0 + l;
+                            if (k >= b1) continue;
+                            const int c = ci[k];
+                            if (c != b && s_con[k]) { const int cc = cf[c]; if (cc != FINE && cc != STRONG_FINE) keys[l] = c; }
+                        }
+                        h.insert_step(keys);
+                    }
+                }
+            }
+        }
+        len[i] = h.store(out);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) len[n] = 0;
+}
+
 // S2: row of coarse point cf[i] <- its set mapped to coarse ids
 __global__ void s2_compact_kernel(int n, const int *__restrict__ cf, const i64 *__restrict__ off, const int *__restrict__ chat, const int *__restrict__ len,
                                   const int *__restrict__ s2_rp, int *s2_ci)
@@ -366,7 +498,7 @@ __global__ void diag_value_kernel(int n, const int *__restrict__ rp, const int *
     ROW_LOOP(i, n) { double v = 0; for (int j = rp[i]; j < rp[i + 1]; j++) if (ci[j] == i) { v = va[j]; break; } d[i] = v; }
 }
 
-// P's structure already holds, for each row, its sorted coarse set as FINE-GRID ids in p_ci; the kernel computes the
+// P's structure already holds, for each row, its coarse set (reference order) as FINE-GRID ids in p_ci; the kernel computes the
 // weights in place and finally rewrites the ids as coarse ids.
 __global__ void d2_weights_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va, const int *__restrict__ cf,
                                   const u8 *__restrict__ s_con, const double *__restrict__ diag, const int *__restrict__ p_rp, int *p_ci, double *p_va)
@@ -386,7 +518,7 @@ __global__ void d2_weights_kernel(int n, const int *__restrict__ rp, const int *
             const double a = va[j];
             const bool offd = (c != i);
             const bool strong = offd && s_con[j];
-            const int p = find_sorted(ch, m, c);
+            const int p = find_linear(ch, m, c);
             if (p >= 0) val[p] += a;
             const int cfc = cf[c];
             if (offd && !strong && p < 0 && cfc != STRONG_FINE) weak += a;
@@ -394,7 +526,7 @@ __global__ void d2_weights_kernel(int n, const int *__restrict__ rp, const int *
                 double bottom = 0.0;
                 for (int jj = rp[c]; jj < rp[c + 1]; jj++) {
                     const int l = ci[jj];
-                    const bool needed = (l == i) || find_sorted(ch, m, l) >= 0;
+                    const bool needed = (l == i) || find_linear(ch, m, l) >= 0;
                     const double b = needed ? va[jj] : 0.0;
                     if (sign_i != cla_sign(b)) bottom += b;
                 }
@@ -406,7 +538,7 @@ __global__ void d2_weights_kernel(int n, const int *__restrict__ rp, const int *
                     double b = va[jj];
                     if (cla_sign(dk) == cla_sign(b)) b = 0.0;
                     if (l == i) aki = b;
-                    const int q = find_sorted(ch, m, l);
+                    const int q = find_linear(ch, m, l);
                     if (q >= 0) { const double t = b * inner; val[q] += t; }
                 }
                 const double t = aki * inner;
@@ -443,7 +575,8 @@ void interp_d2(const Matrix &A, const int *cf, const u8 *s_con, int nc, Csr &P, 
     DevBuf<int> chat, len;
     chat.resize((size_t)std::max<i64>(total, 1));
     len.resize((size_t)n + 1);
-    chat_fill_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, cf, 1, off.ptr(), chat.ptr(), len.ptr());
+    const int wide = !(n > 0 && A.nnz / n < 16);   // kernel variant the reference picks (distance2.cu:1921-1945)
+    chat_fill_ref_order_kernel<<<g, 128, 0, s>>>(n, rp, ci, s_con, cf, wide, off.ptr(), chat.ptr(), len.ptr());
     P.n = n;
     P.nc = nc;
     P.rp.resize((size_t)n + 1);
@@ -553,13 +686,33 @@ __global__ void mp_pass_kernel(int n, const int *__restrict__ rp, const int *__r
         if (assigned[i] != pass) continue;
         int *pc = cols + off[i];
         double *pv = vals + off[i];
-        int m = 0;
-        for (int j = rp[i]; j < rp[i + 1]; j++) {
-            const int k = ci[j];
-            if (k == i || !s_con[j] || assigned[k] != pass - 1) continue;
-            const int *kc = cols + off[k];
-            for (int q = 0; q < len[k]; q++) m = insert_sorted(pc, m, kc[q]);
+        // multipass::compute_c_hat_kernel<8,...> (multipass.cu:762-905): union of the coarse sets of the strong neighbours
+        // assigned in the previous pass, four neighbours in flight, 8 lanes each; keys = coarse ids; reference order
+        SlotSet h;
+        h.clear(2048);
+        int keys[32], nb[32];
+        const int r1 = rp[i + 1];
+        for (int c0 = rp[i]; c0 < r1; c0 += 32) {
+            int nn = 0;
+            const int c1 = min(c0 + 32, r1);
+            for (int j = c0; j < c1; j++) if (ci[j] != i && s_con[j] && assigned[ci[j]] == pass - 1) nb[nn++] = ci[j];
+            for (int g0 = 0; g0 < nn; g0 += 4)
+                for (int t = 0;; t++) {
+                    bool any = false;
+                    for (int l = 0; l < 32; l++) {
+                        keys[l] = -1;
+                        const int gi = l >> 3, mm = l & 7;
+                        if (g0 + gi >= nn) continue;
+                        const int b = nb[g0 + gi], idx = mm + 8 * t;
+                        if (idx >= len[b]) continue;
+                        any = true;
+                        keys[l] = cols[off[b] + idx];
+                    }
+                    if (!any) break;
+                    h.insert_step(keys);
+                }
         }
+        const int m = h.store(pc);
         for (int q = 0; q < m; q++) pv[q] = 0.0;
         double sum_N = 0.0, sum_C = 0.0;
         for (int j = rp[i]; j < rp[i + 1]; j++) {
@@ -574,7 +727,7 @@ __global__ void mp_pass_kernel(int n, const int *__restrict__ rp, const int *__r
                 const double tmp = kv[q] * a;
                 sum_C += tmp;
                 sum_N += tmp;
-                pv[find_sorted(pc, m, kc[q])] += tmp;
+                pv[find_linear(pc, m, kc[q])] += tmp;
             }
         }
         const double sd = sum_C * diag[i];

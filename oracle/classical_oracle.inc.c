@@ -13,13 +13,14 @@
  *   R = P^T, A_c = R A P                         src/classical/classical_amg_level.cu:440-468, 501-586
  *   restriction / prolongation                   src/classical/classical_amg_level.cu:590-644, 851-913
  *
- * Where the reference's device kernels leave an order unspecified (hash-table slot order of a row of
- * P, the order of atomicAdd contributions, lane-partial sums) this restatement fixes ONE order --
- * the same one the CUDA engine uses: sets are kept sorted by column, sums run left to right in
- * storage order, products are rounded before they are added (no FMA).  Consequences, stated in
- * selection arrays (strong connections, C/F maps) are comparable bit for bit with the
- * reference; interpolation weights agree to rounding; the choice among EQUAL weights made by the
- * max-elements truncation follows storage order and can differ from the reference's hash order.
+ * Row order of P: the reference's (hash-table slot order, emulated below -- it decides which of several EQUAL
+ * weights the max-elements truncation keeps).  Where the reference leaves the order of floating-point
+ * contributions to atomics and lane-partial sums, this restatement fixes ONE order -- the same one the CUDA
+ * engine uses: sums run left to right in storage order, products are rounded before they are added (no FMA).
+ * Consequences, stated in DESIGN.md: selection arrays (strong connections, C/F maps), the pattern AND the row
+ * order of P on the finest level are comparable bit for bit with the reference; interpolation weights agree to
+ * rounding.  On coarser levels the reference's A has hash-ordered columns (its SpGEMM), ours ascending ones, so
+ * the emulated insertion sequence -- and with it the choice among equal weights -- can differ there.
  */
 #include <limits.h>
 
@@ -165,6 +166,123 @@ static int cla_find_sorted(const int *a, int m, int key)
     return (lo < m && a[lo] == key) ? lo : -1;
 }
 
+
+/* ---- the reference's row order --------------------------------------------------------------------------------
+ * A row of P leaves the reference in the slot order of its Hash_set / Hash_map (include/hash_containers_detail.inl):
+ * 128 shared-memory slots, slot = ((key ^ c[f]) + c[4+f]) & 127 for the first of four hash functions f whose slot is
+ * free or already holds the key; a warp inserts up to 32 keys at once and, when several lanes race for the same empty
+ * slot, the LOWEST lane wins (observed: this rule reproduces every row of the reference dumps, tests/golden/
+ * *classical*.npz); keys that lose all four rounds go to a global-memory table (same functions, mask gmem_size-1) and
+ * are stored after the shared-memory ones.  The max-elements truncation keeps the FIRST of several equal weights, so
+ * this order decides which coarse points survive on symmetric stencils.  The emulation below is sequential: one
+ * "step" = one warp-wide insert call, lanes visited in ascending order inside every hash round. */
+static const unsigned cla_hash_keys[8] = {3499211612u, 581869302u, 3890346734u, 3586334585u, 545404204u, 4161255391u, 3922919429u, 949333985u};
+#define CLA_SLOTS 128
+#define CLA_OVF 64
+typedef struct { int tab[CLA_SLOTS]; int ovf_slot[CLA_OVF], ovf_key[CLA_OVF], n_ovf, gmem_mask, failed; } cla_slotset;
+static void cla_ss_clear(cla_slotset *h, int gmem_size) { for (int s = 0; s < CLA_SLOTS; s++) h->tab[s] = -1; h->n_ovf = 0; h->gmem_mask = gmem_size - 1; h->failed = 0; }
+static unsigned cla_ss_hash(int key, int f) { return ((unsigned)key ^ cla_hash_keys[f]) + cla_hash_keys[4 + f]; }
+static void cla_ss_insert_step(cla_slotset *h, int *keys, int cnt)   /* keys[l] = key of lane l or -1; destroyed */
+{
+    for (int f = 0; f < 4; f++) {
+        int any = 0;
+        for (int l = 0; l < cnt; l++) {
+            const int k = keys[l];
+            if (k == -1) continue;
+            const int s = (int)(cla_ss_hash(k, f) & (CLA_SLOTS - 1));
+            if (h->tab[s] == -1) { h->tab[s] = k; keys[l] = -1; }
+            else if (h->tab[s] == k) keys[l] = -1;
+            else any = 1;
+        }
+        if (!any) return;
+    }
+    for (int f = 0; f < 4; f++) {
+        int any = 0;
+        for (int l = 0; l < cnt; l++) {
+            const int k = keys[l];
+            if (k == -1) continue;
+            const int s = (int)(cla_ss_hash(k, f) & (unsigned)h->gmem_mask);
+            int q = -1;
+            for (int t = 0; t < h->n_ovf; t++) if (h->ovf_slot[t] == s) { q = t; break; }
+            if (q < 0) {
+                if (h->n_ovf < CLA_OVF) { h->ovf_slot[h->n_ovf] = s; h->ovf_key[h->n_ovf] = k; h->n_ovf++; keys[l] = -1; }
+                else { h->failed = 1; keys[l] = -1; }
+            } else if (h->ovf_key[q] == k) keys[l] = -1;
+            else any = 1;
+        }
+        if (!any) return;
+    }
+    h->failed = 1;   /* the reference would double its global table and retry (status = 1); not emulated */
+}
+static int cla_ss_store(const cla_slotset *h, int *out)   /* shared-memory slots ascending, then global-memory slots ascending */
+{
+    int m = 0;
+    for (int s = 0; s < CLA_SLOTS; s++) if (h->tab[s] != -1) out[m++] = h->tab[s];
+    int idx[CLA_OVF];
+    for (int t = 0; t < h->n_ovf; t++) idx[t] = t;
+    for (int a = 1; a < h->n_ovf; a++) { const int v = idx[a]; int b = a - 1; while (b >= 0 && h->ovf_slot[idx[b]] > h->ovf_slot[v]) { idx[b + 1] = idx[b]; b--; } idx[b + 1] = v; }
+    for (int t = 0; t < h->n_ovf; t++) out[m++] = h->ovf_key[idx[t]];
+    return m;
+}
+static int cla_find_linear(const int *a, int m, int key) { for (int k = 0; k < m; k++) if (a[k] == key) return k; return -1; }
+
+/* distance2::compute_c_hat_kernel (distance2.cu:848-1170): insertion sequence of a FINE row.  wide == 0: the
+ * 8-lanes-per-row variant (avg nnz per row < 16), four rows of B in flight; wide == 1: one row of B per step, 32 lanes. */
+static int cla_c_hat_fill_ref_order(int i, const int *rp, const int *ci, const unsigned char *s_con, const int *cf, int wide, int gmem_size, int *out)
+{
+    cla_slotset h;
+    cla_ss_clear(&h, gmem_size);
+    int keys[32], fines[32];
+    for (int c0 = rp[i]; c0 < rp[i + 1]; c0 += 32) {
+        int nf = 0;
+        const int c1 = (c0 + 32 < rp[i + 1]) ? c0 + 32 : rp[i + 1];
+        for (int l = 0; l < 32; l++) {
+            keys[l] = -1;
+            const int k = c0 + l;
+            if (k >= c1) continue;
+            const int c = ci[k];
+            if (c == i || !s_con[k]) continue;
+            if (cf[c] == CLA_FINE) fines[nf++] = c;
+            else if (cf[c] != CLA_STRONG_FINE) keys[l] = c;
+        }
+        cla_ss_insert_step(&h, keys, 32);
+        if (!wide) {
+            for (int g0 = 0; g0 < nf; g0 += 4) {
+                for (int t = 0;; t++) {
+                    int any = 0;
+                    for (int l = 0; l < 32; l++) {
+                        keys[l] = -1;
+                        const int gi = l >> 3, m = l & 7;
+                        if (g0 + gi >= nf) continue;
+                        const int b = fines[g0 + gi], k = rp[b] + m + 8 * t;
+                        if (k >= rp[b + 1]) continue;
+                        any = 1;
+                        const int c = ci[k];
+                        if (c != b && s_con[k] && cf[c] != CLA_FINE && cf[c] != CLA_STRONG_FINE) keys[l] = c;
+                    }
+                    if (!any) break;
+                    cla_ss_insert_step(&h, keys, 32);
+                }
+            }
+        } else {
+            for (int g = 0; g < nf; g++) {
+                const int b = fines[g];
+                for (int k0 = rp[b]; k0 < rp[b + 1]; k0 += 32) {
+                    for (int l = 0; l < 32; l++) {
+                        keys[l] = -1;
+                        const int k = k0 + l;
+                        if (k >= rp[b + 1]) continue;
+                        const int c = ci[k];
+                        if (c != b && s_con[k] && cf[c] != CLA_FINE && cf[c] != CLA_STRONG_FINE) keys[l] = c;
+                    }
+                    cla_ss_insert_step(&h, keys, 32);
+                }
+            }
+        }
+    }
+    return cla_ss_store(&h, out);
+}
+
 /* The distance-two coarse set of row i: strong coarse neighbours plus strong coarse neighbours of its
  * strong FINE neighbours (estimate_c_hat_size_kernel / compute_c_hat_kernel of selector.cu and
  * distance2.cu share this rule).  `cf` holds coarse ids >= 0, FINE, STRONG_FINE.  Fine-grid ids, sorted. */
@@ -239,6 +357,7 @@ static void cla_interp_d2(int n, const int *rp, const int *ci, const double *va,
 {
     double *diag = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
     cla_diag(n, rp, ci, va, diag);
+    const int wide = !(n > 0 && rp[n] / n < 16);     /* kernel variant picked by the reference: avg nnz per row < 16 -> 8 lanes per row */
     int *prp = (int *)calloc((size_t)n + 1, sizeof(int));
     long long ub = 0;
     for (int i = 0; i < n; i++) ub += (cf[i] >= 0) ? 1 : (cf[i] == CLA_STRONG_FINE ? 0 : cla_c_hat_upper(i, rp, ci, s_con, cf));
@@ -251,7 +370,7 @@ static void cla_interp_d2(int n, const int *rp, const int *ci, const double *va,
         if (cf[i] == CLA_STRONG_FINE) continue;
         int *ch = chat + pos;
         double *val = pv + pos;
-        const int m = cla_c_hat_fill(i, rp, ci, s_con, cf, ch);
+        const int m = cla_c_hat_fill_ref_order(i, rp, ci, s_con, cf, wide, 512, ch);   /* gmem_size 512: distance2.cu:1912-1914 (sm >= 7) */
         for (int k = 0; k < m; k++) val[k] = 0.0;
         const int sign_i = cla_sign(diag[i]);
         double weak = 0.0;
@@ -260,7 +379,7 @@ static void cla_interp_d2(int n, const int *rp, const int *ci, const double *va,
             const double a = va[j];
             const int offd = (c != i);
             const int strong = offd && s_con[j];
-            const int p = cla_find_sorted(ch, m, c);
+            const int p = cla_find_linear(ch, m, c);
             if (p >= 0) val[p] += a;
             if (offd && !strong && p < 0 && cf[c] != CLA_STRONG_FINE) weak += a;
             if (strong && cf[c] == CLA_FINE) {
@@ -268,7 +387,7 @@ static void cla_interp_d2(int n, const int *rp, const int *ci, const double *va,
                 double bottom = 0.0;
                 for (int jj = rp[c]; jj < rp[c + 1]; jj++) {
                     const int l = ci[jj];
-                    const int needed = (l == i) || cla_find_sorted(ch, m, l) >= 0;
+                    const int needed = (l == i) || cla_find_linear(ch, m, l) >= 0;
                     const double b = needed ? va[jj] : 0.0;
                     if (sign_i != cla_sign(b)) bottom += b;
                 }
@@ -281,7 +400,7 @@ static void cla_interp_d2(int n, const int *rp, const int *ci, const double *va,
                     double b = va[jj];
                     if (cla_sign(dk) == cla_sign(b)) b = 0.0;
                     if (l == i) aki = b;
-                    const int q = cla_find_sorted(ch, m, l);
+                    const int q = cla_find_linear(ch, m, l);
                     if (q >= 0) { const double t = b * inner; val[q] += t; }
                 }
                 { const double t = aki * inner; weak += t; }
@@ -370,12 +489,32 @@ static void cla_interp_multipass(int n, const int *rp, const int *ci, const doub
             if (assigned[i] != p) continue;
             int *pc = cols + off[i];
             double *pvv = vals + off[i];
-            int m = 0;
-            for (int j = rp[i]; j < rp[i + 1]; j++) {
-                const int k = ci[j];
-                if (k == i || !s_con[j] || assigned[k] != p - 1) continue;
-                for (int q = 0; q < len[k]; q++) m = cla_insert_sorted(pc, m, cols[off[k] + q]);
+            /* multipass::compute_c_hat_kernel<8,...> (multipass.cu:762-905): union of the coarse sets of the strong
+             * neighbours assigned in the previous pass, four neighbours in flight, 8 lanes each; keys = coarse ids */
+            cla_slotset h;
+            cla_ss_clear(&h, 2048);
+            int keys[32], nb[32];
+            for (int c0 = rp[i]; c0 < rp[i + 1]; c0 += 32) {
+                int nn = 0;
+                const int c1 = (c0 + 32 < rp[i + 1]) ? c0 + 32 : rp[i + 1];
+                for (int j = c0; j < c1; j++) if (ci[j] != i && s_con[j] && assigned[ci[j]] == p - 1) nb[nn++] = ci[j];
+                for (int g0 = 0; g0 < nn; g0 += 4)
+                    for (int t = 0;; t++) {
+                        int any = 0;
+                        for (int l = 0; l < 32; l++) {
+                            keys[l] = -1;
+                            const int gi = l >> 3, mm = l & 7;
+                            if (g0 + gi >= nn) continue;
+                            const int b = nb[g0 + gi], idx = mm + 8 * t;
+                            if (idx >= len[b]) continue;
+                            any = 1;
+                            keys[l] = cols[off[b] + idx];
+                        }
+                        if (!any) break;
+                        cla_ss_insert_step(&h, keys, 32);
+                    }
             }
+            const int m = cla_ss_store(&h, pc);
             for (int q = 0; q < m; q++) pvv[q] = 0.0;
             double sum_N = 0.0, sum_C = 0.0;
             for (int j = rp[i]; j < rp[i + 1]; j++) {
@@ -387,7 +526,7 @@ static void cla_interp_multipass(int n, const int *rp, const int *ci, const doub
                     const double tmp = vals[off[k] + q] * va[j];
                     sum_C += tmp;
                     sum_N += tmp;
-                    pvv[cla_find_sorted(pc, m, cols[off[k] + q])] += tmp;
+                    pvv[cla_find_linear(pc, m, cols[off[k] + q])] += tmp;
                 }
             }
             const double sd = sum_C * diag[i];
