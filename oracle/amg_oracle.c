@@ -406,6 +406,9 @@ typedef struct {
     /* classical AMG: explicit P (n x nagg) and R = P^T, C/F map of the level */
     int *Pp, *Pc, *Rtp, *Rtc, *cf;
     double *Pv, *Rtv;
+    /* DENSE_LU_SOLVER on the coarsest level: column-major LU factors + pivots */
+    double *lu;
+    int *ipiv;
 } orc_level;
 
 typedef struct {
@@ -413,6 +416,7 @@ typedef struct {
     orc_level *lv;
     int presweeps, postsweeps, coarsest_sweeps, finest_sweeps, smoother; /* smoother: 0 BLOCK_JACOBI, 1 JACOBI_L1, 2 MULTICOLOR_DILU */
     double omega, uncolored_fraction;
+    int dense_lu;            /* coarse_solver = DENSE_LU_SOLVER */
 } orc_amg;
 
 #include "classical_oracle.inc.c"
@@ -570,6 +574,7 @@ ORC_API void orc_amg_free(orc_amg *a)
         free(L->agg); free(L->Rp); free(L->Rc); free(L->d); free(L->bc); free(L->xc); free(L->r); free(L->tmp);
         free(L->colors); free(L->sorted_rows); free(L->color_offsets); free(L->Einv); free(L->delta); free(L->Delta);
         free(L->Pp); free(L->Pc); free(L->Pv); free(L->Rtp); free(L->Rtc); free(L->Rtv); free(L->cf);
+        free(L->lu); free(L->ipiv);
     }
     free(a->lv);
     free(a);
@@ -600,6 +605,53 @@ ORC_API void orc_amg_level_arrays(const orc_amg *a, int l, int *rp, int *ci, dou
     if (d) memcpy(d, L->d, sizeof(double) * (size_t)L->n);
 }
 
+
+/* ------------------------------------------------------------------------------------------- */
+/* DENSE_LU_SOLVER (src/solvers/dense_lu_solver.cu:745-985): dense copy of the coarsest matrix,   */
+/* LU with partial pivoting (cuSOLVER getrf in the reference), x = A^-1 b (getrs).  Right-looking */
+/* elimination, pivot = first entry of largest magnitude, multipliers scaled by the reciprocal    */
+/* pivot, one FMA per update -- the order of the engine's single-CTA kernels.                     */
+/* ------------------------------------------------------------------------------------------- */
+ORC_API void orc_dense_lu_factor(int n, double *a, int lda, int *ipiv)
+{
+    for (int k = 0; k < n; k++) {
+        int p = k;
+        double best = fabs(a[(size_t)k + (size_t)k * lda]);
+        for (int i = k + 1; i < n; i++) { const double v = fabs(a[(size_t)i + (size_t)k * lda]); if (v > best) { best = v; p = i; } }
+        ipiv[k] = p;
+        if (p != k)
+            for (int j = 0; j < n; j++) { const double t = a[(size_t)k + (size_t)j * lda]; a[(size_t)k + (size_t)j * lda] = a[(size_t)p + (size_t)j * lda]; a[(size_t)p + (size_t)j * lda] = t; }
+        const double piv = a[(size_t)k + (size_t)k * lda];
+        if (piv != 0.0) { const double r = 1.0 / piv; for (int i = k + 1; i < n; i++) a[(size_t)i + (size_t)k * lda] *= r; }
+        for (int j = k + 1; j < n; j++)
+            for (int i = k + 1; i < n; i++)
+                a[(size_t)i + (size_t)j * lda] = fma(-a[(size_t)i + (size_t)k * lda], a[(size_t)k + (size_t)j * lda], a[(size_t)i + (size_t)j * lda]);
+    }
+}
+ORC_API void orc_dense_lu_solve(int n, const double *lu, int lda, const int *ipiv, const double *rhs, double *x)
+{
+    for (int i = 0; i < n; i++) x[i] = rhs[i];
+    for (int k = 0; k < n; k++) { const int p = ipiv[k]; if (p != k) { const double t = x[k]; x[k] = x[p]; x[p] = t; } }
+    for (int k = 0; k < n - 1; k++) { const double xk = x[k]; for (int i = k + 1; i < n; i++) x[i] = fma(-lu[(size_t)i + (size_t)k * lda], xk, x[i]); }
+    for (int k = n - 1; k >= 0; k--) {
+        x[k] = x[k] / lu[(size_t)k + (size_t)k * lda];
+        const double xk = x[k];
+        for (int i = 0; i < k; i++) x[i] = fma(-lu[(size_t)i + (size_t)k * lda], xk, x[i]);
+    }
+}
+/* call after a setup: turn the coarsest level into a direct solve */
+ORC_API void orc_amg_enable_dense_lu(orc_amg *a)
+{
+    orc_level *L = &a->lv[a->num_levels - 1];
+    const int n = L->n;
+    L->lu = (double *)calloc((size_t)(n > 0 ? n : 1) * (size_t)(n > 0 ? n : 1), sizeof(double));
+    L->ipiv = (int *)calloc((size_t)(n > 0 ? n : 1), sizeof(int));
+    for (int i = 0; i < n; i++)
+        for (int k = L->rp[i]; k < L->rp[i + 1]; k++) L->lu[(size_t)i + (size_t)L->ci[k] * n] = L->va[k];   /* csr_to_dense (last duplicate wins, as the scatter does) */
+    orc_dense_lu_factor(n, L->lu, n, L->ipiv);
+    a->dense_lu = 1;
+}
+
 /* smoother->solve(b, x, xIsZero) with max_iters = sweeps (Solver::solve loop without monitoring) */
 static void smooth(const orc_amg *a, orc_level *L, const double *b, double *x, int x_is_zero, int sweeps)
 {
@@ -623,11 +675,13 @@ static void vcycle(const orc_amg *a, int l, const double *b, double *x, int x_is
     orc_level *L = &a->lv[l];
     int finest = (l == 0);
     int n_pre;
-    if (L->coarsest) n_pre = a->coarsest_sweeps;
+    if (L->coarsest && a->dense_lu) n_pre = 0;                    /* coarsest level with a coarse solver (fixed_cycle.cu:75-78) */
+    else if (L->coarsest) n_pre = a->coarsest_sweeps;
     else if (finest && a->finest_sweeps != -1) n_pre = a->presweeps == 0 ? 0 : a->finest_sweeps;
     else n_pre = a->presweeps;
     if (n_pre > 0) smooth(a, L, b, x, x_is_zero, n_pre);
     else if (x_is_zero) memset(x, 0, sizeof(double) * (size_t)L->n);
+    if (L->coarsest && a->dense_lu) { orc_dense_lu_solve(L->n, L->lu, L->n, L->ipiv, b, x); return; }   /* launchCoarseSolver */
     if (L->coarsest) return;
     orc_residual(L->n, L->rp, L->ci, L->va, x, b, L->r);          /* axmb */
     if (L->Pp) cla_spmv(L->nagg, L->Rtp, L->Rtc, L->Rtv, L->r, L->bc);   /* classical: rr = R r (classical_amg_level.cu:620-627) */

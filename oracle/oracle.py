@@ -143,13 +143,18 @@ class AMG:
     """Aggregation hierarchy + V-cycle exactly as the reference composes them (unfused)."""
 
     def __init__(self, rp, ci, va, max_levels=100, min_coarse_rows=2, coarsen_threshold=1.0, presweeps=1, postsweeps=1, coarsest_sweeps=2,
-                 finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, max_iterations=15, max_unassigned=0.05, merge_singletons=1, weight_formula=0):
+                 finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, max_iterations=15, max_unassigned=0.05, merge_singletons=1, weight_formula=0,
+                 coarse_solver="NOSOLVER", dense_lu_num_rows=128):
         self.rp, self.ci, self.va = _i(rp), _i(ci), _d(va)
+        if coarse_solver == "DENSE_LU_SOLVER":
+            min_coarse_rows = dense_lu_num_rows          # src/amg.cu:1154-1157
         self.n = self.rp.shape[0] - 1
         sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2}[smoother]
         self.h = C.c_void_p(lib().orc_amg_setup(self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold),
                                                 presweeps, postsweeps, coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), max_iterations,
                                                 C.c_double(max_unassigned), merge_singletons, weight_formula))
+        if coarse_solver == "DENSE_LU_SOLVER":
+            lib().orc_amg_enable_dense_lu(self.h)
 
     def num_levels(self):
         return lib().orc_amg_num_levels(self.h)
@@ -343,8 +348,10 @@ class ClassicalAMG(AMG):
 
     def __init__(self, rp, ci, va, max_levels=100, min_coarse_rows=2, coarsen_threshold=1.0, presweeps=1, postsweeps=1, coarsest_sweeps=2,
                  finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, strength_threshold=0.25, max_row_sum=1.1, interpolator="D1",
-                 aggressive_levels=0, aggressive_interpolator="MULTIPASS", interp_max_elements=-1):
+                 aggressive_levels=0, aggressive_interpolator="MULTIPASS", interp_max_elements=-1, coarse_solver="NOSOLVER", dense_lu_num_rows=128):
         self.rp, self.ci, self.va = _i(rp), _i(ci), _d(va)
+        if coarse_solver == "DENSE_LU_SOLVER":
+            min_coarse_rows = dense_lu_num_rows
         self.n = self.rp.shape[0] - 1
         sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2}[smoother]
         im = {"D2": 0, "MULTIPASS": 1}
@@ -352,6 +359,8 @@ class ClassicalAMG(AMG):
             self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold), presweeps, postsweeps,
             coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), C.c_double(strength_threshold), C.c_double(max_row_sum), im[interpolator],
             aggressive_levels, im[aggressive_interpolator], interp_max_elements))
+        if coarse_solver == "DENSE_LU_SOLVER":
+            lib().orc_amg_enable_dense_lu(self.h)
 
     def level(self, l):
         d = super().level_plain(l) if hasattr(super(), "level_plain") else None
@@ -373,3 +382,15 @@ class ClassicalAMG(AMG):
             lib().orc_amg_level_classical(self.h, l, _p(cf), _p(Pp), _p(Pc), _p(Pv), None)
             out.update(cf_map=cf, P_row_offsets=Pp, P_col_indices=Pc, P_values=Pv)
         return out
+
+
+def dense_lu_solve(A_dense, rhs):
+    """LU with partial pivoting exactly as the engine's coarse solver orders it; returns (x, lu, ipiv)"""
+    a = np.asfortranarray(np.array(A_dense, dtype=np.float64))
+    n = a.shape[0]
+    ipiv = np.zeros(n, np.int32)
+    lib().orc_dense_lu_factor(n, _p(a), n, _p(ipiv))
+    x = np.zeros(n)
+    b = _d(rhs)
+    lib().orc_dense_lu_solve(n, _p(a), n, _p(ipiv), _p(b), _p(x))
+    return x, a, ipiv
