@@ -77,9 +77,6 @@ void AMGSolver::setup_aggregation()
     levels_[0]->index = 0;
     int num_levels = 1;
     bool coarse_solver_exists = (bool)coarse_solver_;
-    // replicated coarse tail (dist.cu): EXPERIMENTAL, off by default -- on 4 and 8 ranks it slowed convergence (86 vs 51 iterations at
-    // 96^3 per GPU), cause not yet found; 2 ranks are fine (76 vs 77) and gain 10 %.  AMGXB_TAIL_ROWS=<global rows> enables it.
-    static const long long tail_rows = getenv("AMGXB_TAIL_ROWS") ? atoll(getenv("AMGXB_TAIL_ROWS")) : 0;
     while (true) {
         AMGLevel &L = *levels_.back();
         Matrix &A = *L.A;
@@ -113,14 +110,6 @@ void AMGSolver::setup_aggregation()
                 next->owned_A->split_row = n_int_c;
             }
             next->owned_A->compute_diag_and_plan();
-            if (cdist && tail_rows > 0 && nextN <= tail_rows) {
-                // small enough: replicate the whole level on every rank and stop exchanging halos below here
-                std::unique_ptr<Matrix> G = dist_gather_matrix(*next->owned_A, L.tail_counts, L.tail_offs);
-                G->compute_diag_and_plan();
-                L.tail_gather = true;
-                L.tail_off = L.tail_offs[A.dist->rank];
-                next->owned_A = std::move(G);
-            }
             next->A = next->owned_A.get();
             next->index = num_levels;
             const size_t nc = (size_t)next->A->n_cols * A.by;
@@ -142,8 +131,89 @@ void AMGSolver::setup_aggregation()
         if (!built_next) break;
         num_levels++;
     }
+    // replicated coarse tail, off by default (AMGXB_TAIL_ROWS=<global rows> enables it)
+    static const long long tail_rows = getenv("AMGXB_TAIL_ROWS") ? atoll(getenv("AMGXB_TAIL_ROWS")) : 0;
+    if (tail_rows > 0 && levels_[0]->A->dist) replicate_tail(tail_rows);
     if (coarse_solver_) coarse_solver_->setup(*levels_.back()->A, false);
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+namespace {
+__global__ void add_offset_kernel(int n, const int *__restrict__ in, int off, int *out)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i] + off;
+}
+}  // namespace
+
+// Replicated coarse tail.  The hierarchy has been built distributed (aggregates never cross partitions).  From the first
+// level whose GLOBAL size is <= tail_rows on, every rank assembles the whole level -- matrix (dist_gather_matrix) and
+// aggregates (local ids shifted by the owner's offset on the next level) -- and the rest of the V-cycle runs
+// redundantly on every GPU: the same operators, the same aggregates, the same per-row arithmetic as the distributed
+// cycle (rows keep their column order, an aggregate keeps its fine rows in ascending order), but no halo exchange below
+// the switch; the level above all-gathers its restricted residual instead.
+// History: a first version re-aggregated the gathered level globally (SIZE_2 on the assembled matrix).  That was exact
+// as an operator but a worse preconditioner on slab-stacked domains: 96x96x384 needs 85 PCG iterations with one global
+// SIZE_2 hierarchy and 51 with four per-slab hierarchies (CPU restatement and 4-GPU runs agree), so the tail now keeps
+// the partitioned aggregates.  NOT yet run on a device in this form (no GPU minutes left in round 1): off by default.
+void AMGSolver::replicate_tail(long long tail_rows)
+{
+    cudaStream_t s = stream();
+    const int nl = (int)levels_.size();
+    int t = -1;
+    for (int l = 1; l < nl; l++) {
+        Matrix &A = *levels_[l]->A;
+        if (!A.dist) return;
+        if (dist_allreduce_ll(A, A.n, 0) * A.by <= tail_rows) { t = l; break; }
+    }
+    if (t < 0) return;
+    const int rank = levels_[t]->A->dist->rank;
+    std::vector<std::vector<int>> counts(nl), offs(nl);
+    std::vector<std::unique_ptr<Matrix>> G(nl);
+    for (int l = t; l < nl; l++) G[l] = dist_gather_matrix(*levels_[l]->A, counts[l], offs[l]);
+    // global aggregates + restriction patterns (needs the still-distributed matrices for the communicator)
+    for (int l = t; l + 1 < nl; l++) {
+        AMGLevel &L = *levels_[l];
+        const int Nl = offs[l].back(), Nnext = offs[l + 1].back();
+        DevBuf<int> ag;
+        ag.resize((size_t)std::max(Nl, 1));
+        ag.zero(s);
+        if (L.A->n) add_offset_kernel<<<std::max(1, std::min(ceil_div(L.A->n, 256), 1024)), 256, 0, s>>>(L.A->n, L.aggregates.ptr(), offs[l + 1][rank], ag.ptr() + offs[l][rank]);
+        count_launch();
+        dist_allgatherv_int_inplace(*L.A, ag.ptr(), counts[l], offs[l], s);
+        L.aggregates.swap(ag);
+        L.n_coarse = Nnext;
+        build_restriction(L.aggregates, Nl, Nnext, L.R_row_offsets, L.R_column_indices, s);
+    }
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    // swap in the assembled operators, resize the cycle vectors, rebuild the smoothers
+    for (int l = t; l < nl; l++) {
+        AMGLevel &L = *levels_[l];
+        const int by = L.A->by;
+        const Prec vp = L.A->vec_prec;
+        L.owned_A = std::move(G[l]);
+        L.A = L.owned_A.get();
+        L.A->level = l;
+        if (l + 1 < nl) {
+            const size_t nc = (size_t)offs[l + 1].back() * by;
+            L.bc.resize(nc, vp);
+            L.xc.resize(nc, vp);
+            L.bc.zero(s);
+            L.xc.zero(s);
+            L.r.resize((size_t)L.A->n_cols * by, vp);
+            L.r.zero(s);
+        }
+        if (L.smoother) { L.smoother = make_smoother(); L.smoother->setup(*L.A, false); }
+    }
+    AMGLevel &U = *levels_[t - 1];
+    const int by = U.A->by;
+    U.tail_gather = true;
+    U.tail_counts = counts[t];
+    U.tail_offs = offs[t];
+    U.tail_off = offs[t][rank];
+    U.bc.resize((size_t)offs[t].back() * by, U.A->vec_prec);
+    U.xc.resize((size_t)offs[t].back() * by, U.A->vec_prec);
+    U.bc.zero(s);
+    U.xc.zero(s);
 }
 
 void AMGSolver::solve_init(DevVec &b, DevVec &x, bool xIsZero)

@@ -727,6 +727,16 @@ std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &co
     return G;
 }
 
+void dist_allgatherv_int_inplace(const Matrix &A, int *v, const std::vector<int> &counts, const std::vector<int> &offs, cudaStream_t s)
+{
+    AMGXB_NCCL_CHECK(ncclGroupStart());
+    for (int r = 0; r < (int)counts.size(); r++) {
+        if (counts[r] == 0) continue;
+        AMGXB_NCCL_CHECK(ncclBroadcast(v + offs[r], v + offs[r], (size_t)counts[r], ncclInt32, r, comm_of(A), s));
+    }
+    AMGXB_NCCL_CHECK(ncclGroupEnd());
+}
+
 // v (global length offs[world], block dim bsize): every rank contributes its slice [offs[rank], +counts[rank]) in place
 void dist_allgatherv_inplace(const Matrix &A, void *v, Prec prec, int bsize, const std::vector<int> &counts, const std::vector<int> &offs, cudaStream_t s)
 {

@@ -41,6 +41,7 @@ void dist_exchange_int(const Matrix &A, int *x, cudaStream_t s);                
 long long dist_allreduce_ll(const Matrix &A, long long v, int op);                 // host value, op: 0 sum, 1 min, 2 max
 // replicated coarse tail
 std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &counts, std::vector<int> &offs);
+void dist_allgatherv_int_inplace(const Matrix &A, int *v, const std::vector<int> &counts, const std::vector<int> &offs, cudaStream_t s);
 void dist_allgatherv_inplace(const Matrix &A, void *v, Prec prec, int bsize, const std::vector<int> &counts, const std::vector<int> &offs, cudaStream_t s);
 std::shared_ptr<DistManager> dist_coarsen(const Matrix &A, DevBuf<int> &aggregates, int n_agg, int *n_interior_c);
 void dist_allreduce_norm(const Matrix &A, const ReduceCtx &red, int slot, int norm_type, cudaStream_t s);

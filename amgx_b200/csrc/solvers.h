@@ -272,6 +272,7 @@ protected:
     void cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse);
     void setup_aggregation();
     void setup_classical();
+    void replicate_tail(long long tail_rows);   // distributed hierarchy: assemble the small levels on every rank (amg.cu)
     std::unique_ptr<Solver> make_smoother();
     std::vector<std::unique_ptr<AMGLevel>> levels_;
     std::string algorithm_, cycle_name_, selector_, coarse_solver_name_;
