@@ -37,6 +37,9 @@ def test_reference_example_links_against_our_library(built_lib, tmp_path):
     nm = subprocess.run(["nm", "-D", "--undefined-only", str(tmp_path / "amgx_capi_ref")], capture_output=True, text=True).stdout
     used = sorted({l.split()[-1] for l in nm.splitlines() if " AMGX_" in l})
     assert len(used) >= 30 and "AMGX_solver_solve" in used and "AMGX_read_system" in used
+    # the part of the reference's program that needs no device runs here: initialize, callbacks, version / build strings, finalize
+    run = subprocess.run([str(tmp_path / "amgx_capi_ref"), "--version"], capture_output=True, text=True)
+    assert run.returncode == 0 and "amgx api version: 1.0" in run.stdout and "amgx build version:" in run.stdout
 
 
 def test_example_fails_loudly_without_a_gpu(built_lib, tmp_path):
