@@ -29,8 +29,10 @@ AMGSolver::AMGSolver(Config &cfg, const std::string &scope, std::shared_ptr<Reso
     coarsest_sweeps_ = cfg.get_int("coarsest_sweeps", scope);
     intensive_smoothing_ = cfg.get_int("intensive_smoothing", scope);
     error_scaling_ = cfg.get_int("error_scaling", scope);
-    if (cycle_name_ != "V")
-        fatal(AMGX_RC_BAD_CONFIGURATION, "cycle '" + cycle_name_ + "' is outside the scope of the B200 solve-phase engine (V only)");
+    if (cycle_name_ == "V") cycle_type_ = CYC_V;
+    else if (cycle_name_ == "W") cycle_type_ = CYC_W;
+    else if (cycle_name_ == "F") cycle_type_ = CYC_F;
+    else fatal(AMGX_RC_BAD_CONFIGURATION, "cycle '" + cycle_name_ + "' is outside the scope of the B200 solve-phase engine (V, W, F)");
     if (error_scaling_ != 0) fatal(AMGX_RC_BAD_CONFIGURATION, "error_scaling != 0 is not supported by this engine");
     if (algorithm_ != "AGGREGATION" && algorithm_ != "CLASSICAL")
         fatal(AMGX_RC_BAD_CONFIGURATION, "algorithm '" + algorithm_ + "' is not supported (AGGREGATION, CLASSICAL)");
@@ -259,9 +261,10 @@ bool AMGSolver::solve_fused_dot(DevVec &b, DevVec &x, const ReduceCtx &red, int 
     return true;
 }
 
-// FixedCycle::cycle for the V cycle (src/cycles/fixed_cycle.cu:25-248)
-void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse)
+// FixedCycle::cycle (src/cycles/fixed_cycle.cu:25-248) with the V / W / F dispatchers
+void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse, int type)
 {
+    if (type < 0) type = cycle_type_;
     cudaStream_t s = stream();
     AMGLevel &L = *levels_[lvl];
     Matrix &A = *L.A;
@@ -317,8 +320,19 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse)
     }
 
     // ---- coarse-grid correction ----
+    // V: one cycle on the next level; W: two W cycles; F: a W cycle then a V cycle (src/cycles/{v,w,f}_cycle.cu).  When the
+    // next level is the coarsest a single fixed cycle is launched whatever the type (fixed_cycle.cu:169-179).  The second
+    // visit continues from the xc the first one left (its init flag has been cleared).
     levels_[lvl + 1]->init_cycle = true;
-    cycle(lvl + 1, L.bc, L.xc, nullptr);
+    if (type == CYC_V || levels_[lvl + 1]->coarsest) {
+        cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_V);
+    } else if (type == CYC_W) {
+        cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_W);
+        cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_W);
+    } else {
+        cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_W);
+        cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_V);
+    }
 
     // ---- prolongation + post-smoothing ----
     int n_post;

@@ -269,7 +269,9 @@ protected:
     void solver_setup(bool reuse) override;
     void solve_init(DevVec &b, DevVec &x, bool xIsZero) override;
     Status solve_iteration(DevVec &b, DevVec &x, bool xIsZero) override;
-    void cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse);
+    enum CycleType { CYC_V = 0, CYC_W = 1, CYC_F = 2 };
+    void cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse, int type = -1);   // type -1: the configured cycle
+    int cycle_type_ = CYC_V;
     void setup_aggregation();
     void setup_classical();
     void replicate_tail(long long tail_rows);   // distributed hierarchy: assemble the small levels on every rank (amg.cu)

@@ -417,6 +417,7 @@ typedef struct {
     int presweeps, postsweeps, coarsest_sweeps, finest_sweeps, smoother; /* smoother: 0 BLOCK_JACOBI, 1 JACOBI_L1, 2 MULTICOLOR_DILU */
     double omega, uncolored_fraction;
     int dense_lu;            /* coarse_solver = DENSE_LU_SOLVER */
+    int cycle;               /* 0 V, 1 W, 2 F (src/cycles/{v,w,f}_cycle.cu) */
 } orc_amg;
 
 #include "classical_oracle.inc.c"
@@ -670,7 +671,9 @@ static void smooth(const orc_amg *a, orc_level *L, const double *b, double *x, i
 }
 
 /* FixedCycle::cycle, V cycle (src/cycles/fixed_cycle.cu:25-248) */
-static void vcycle(const orc_amg *a, int l, const double *b, double *x, int x_is_zero)
+static void vcycle_t(const orc_amg *a, int l, const double *b, double *x, int x_is_zero, int type);
+static void vcycle(const orc_amg *a, int l, const double *b, double *x, int x_is_zero) { vcycle_t(a, l, b, x, x_is_zero, a->cycle); }
+static void vcycle_t(const orc_amg *a, int l, const double *b, double *x, int x_is_zero, int type)
 {
     orc_level *L = &a->lv[l];
     int finest = (l == 0);
@@ -686,7 +689,11 @@ static void vcycle(const orc_amg *a, int l, const double *b, double *x, int x_is
     orc_residual(L->n, L->rp, L->ci, L->va, x, b, L->r);          /* axmb */
     if (L->Pp) cla_spmv(L->nagg, L->Rtp, L->Rtc, L->Rtv, L->r, L->bc);   /* classical: rr = R r (classical_amg_level.cu:620-627) */
     else orc_restrict(L->nagg, L->Rp, L->Rc, L->r, L->bc);        /* restrictResidual */
-    vcycle(a, l + 1, L->bc, L->xc, 1);                            /* next level, initial guess zero */
+    /* next level, initial guess zero; W: two W cycles, F: a W then a V cycle; a single fixed cycle when the next level is
+     * the coarsest (fixed_cycle.cu:169-179); the second visit continues from the first one's xc */
+    if (type == 0 || a->lv[l + 1].coarsest) vcycle_t(a, l + 1, L->bc, L->xc, 1, 0);
+    else if (type == 1) { vcycle_t(a, l + 1, L->bc, L->xc, 1, 1); vcycle_t(a, l + 1, L->bc, L->xc, 0, 1); }
+    else { vcycle_t(a, l + 1, L->bc, L->xc, 1, 1); vcycle_t(a, l + 1, L->bc, L->xc, 0, 0); }
     if (L->Pp) {                                                  /* classical: tmp = P e; x = x + tmp (classical_amg_level.cu:884-910) */
         cla_spmv(L->n, L->Pp, L->Pc, L->Pv, L->xc, L->tmp);
         for (int i = 0; i < L->n; i++) x[i] = x[i] + L->tmp[i];
@@ -698,6 +705,7 @@ static void vcycle(const orc_amg *a, int l, const double *b, double *x, int x_is
 }
 
 ORC_API void orc_amg_vcycle(const orc_amg *a, const double *b, double *x, int x_is_zero) { vcycle(a, 0, b, x, x_is_zero); }
+ORC_API void orc_amg_set_cycle(orc_amg *a, int type) { a->cycle = type; }
 
 /* RELATIVE_INI criterion (src/convergence/relative_ini.cu:22-45) */
 static int conv_relative_ini(double nrm, double nrm_ini, double tol)

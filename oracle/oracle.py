@@ -156,6 +156,10 @@ class AMG:
         if coarse_solver == "DENSE_LU_SOLVER":
             lib().orc_amg_enable_dense_lu(self.h)
 
+    def set_cycle(self, name: str):
+        lib().orc_amg_set_cycle(self.h, {"V": 0, "W": 1, "F": 2}[name])
+        return self
+
     def num_levels(self):
         return lib().orc_amg_num_levels(self.h)
 

@@ -2,8 +2,8 @@
 # First GPU call of the next round: everything that was written after round 1 ran out of GPU minutes.
 #   gpurun --gpus 2 --timeout 1500 -- 'bash tools/validate_next_round.sh'
 mkdir -p gpurun_out
-echo "== unvalidated: DENSE_LU_SOLVER"
-AMGXB_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_gpu_dense_lu.py -x -q -m gpu 2>&1 | tail -6
+echo "== unvalidated: DENSE_LU_SOLVER, W/F cycles"
+AMGXB_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_gpu_dense_lu.py tests/test_gpu_cycles.py -q -m gpu 2>&1 | tail -6
 echo "== full gpu suite"
 timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 echo "== replicated tail (partitioned aggregates), 2 GPUs: iterations must equal the tail-off run"
