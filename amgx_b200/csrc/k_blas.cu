@@ -167,6 +167,16 @@ void vec_scal(void *x, Prec p, size_t n, double a, cudaStream_t s)
     AMGXB_DISPATCH_VEC(p, { VecT *X = (VecT *)x; VecT aa = (VecT)a; launch_map(n, [=] __device__(size_t i) { X[i] = X[i] * aa; }, s); });
 }
 
+// out = x*a + y*b + z*c, the expression of the reference's AXPBYPCZ functor (src/blas.cu:107-124)
+void vec_axpbypcz(const void *x, const void *y, const void *z, void *out, Prec p, size_t n, double a, double b, double c, cudaStream_t s)
+{
+    AMGXB_DISPATCH_VEC(p, {
+        const VecT *X = (const VecT *)x; const VecT *Y = (const VecT *)y; const VecT *Z = (const VecT *)z; VecT *O = (VecT *)out;
+        const VecT aa = (VecT)a, bb = (VecT)b, cc = (VecT)c;
+        launch_map(n, [=] __device__(size_t i) { O[i] = X[i] * aa + Y[i] * bb + Z[i] * cc; }, s);
+    });
+}
+
 void vec_axpy_dev(const void *x, void *y, Prec p, size_t n, const double *scal, int slot, double sign, cudaStream_t s)
 {
     AMGXB_DISPATCH_VEC(p, {

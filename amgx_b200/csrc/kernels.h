@@ -78,6 +78,7 @@ void vec_copy(void *dst, const void *src, Prec p, size_t n, cudaStream_t s);
 // y = a*x + b*y style updates with host scalars (exact reference op order: x*a + y*b)
 void vec_axpby(const void *x, const void *y, void *out, Prec p, size_t n, double a, double b, cudaStream_t s);
 void vec_axpy(const void *x, void *y, Prec p, size_t n, double a, cudaStream_t s);          // y = a*x + y
+void vec_axpbypcz(const void *x, const void *y, const void *z, void *out, Prec p, size_t n, double a, double b, double c, cudaStream_t s);   // out = x*a + y*b + z*c
 void vec_scal(void *x, Prec p, size_t n, double a, cudaStream_t s);
 // device-scalar variants: a = sign * scal[slot]
 void vec_axpy_dev(const void *x, void *y, Prec p, size_t n, const double *scal, int slot, double sign, cudaStream_t s);

@@ -1162,3 +1162,5 @@ ORC_API int orc_amg_solve(const orc_amg *amg, int n, const int *rp, const int *c
     free(r);
     return it;
 }
+
+#include "krylov_oracle.inc.c"

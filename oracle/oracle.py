@@ -21,7 +21,7 @@ def lib():
     global _lib
     if _lib is None:
         p = _HERE / "liboracle.so"
-        if not p.exists() or p.stat().st_mtime < max((_HERE / "amg_oracle.c").stat().st_mtime, (_HERE / "classical_oracle.inc.c").stat().st_mtime):
+        if not p.exists() or p.stat().st_mtime < max(f.stat().st_mtime for f in list(_HERE.glob("*.c"))):
             build()
         _lib = C.CDLL(str(p))
         _lib.orc_dot.restype = C.c_double
@@ -217,6 +217,22 @@ def fgmres(rp, ci, va, b, amg: AMG | None = None, jacobi_omega: float | None = N
     precond = 1 if amg is not None else (2 if jacobi_omega is not None else 0)
     it = lib().orc_fgmres(n, _p(rp), _p(ci), _p(va), amg.h if amg is not None else None, precond, C.c_double(jacobi_omega or 0.0), _p(b), _p(x),
                           int(zero), C.c_double(tol), max_iters, restart, _p(hist), C.byref(conv))
+    return x, it, hist[: it + 1].copy(), bool(conv.value)
+
+
+def krylov(kind, rp, ci, va, b, amg: AMG | None = None, jacobi_omega: float | None = None, x0=None, tol=1e-6, max_iters=100, restart=20, norm="L2"):
+    """CG / PCGF / PBICGSTAB / GMRES restatements (oracle/krylov_oracle.inc.c); same return convention as pcg()"""
+    rp, ci, va, b = _i(rp), _i(ci), _d(va), _d(b)
+    n = rp.shape[0] - 1
+    zero = x0 is None
+    x = np.zeros(n) if zero else _d(x0).copy()
+    hist = np.zeros(max_iters + 1)
+    conv = C.c_int()
+    precond = 1 if amg is not None else (2 if jacobi_omega is not None else 0)
+    nt = {"L1": 0, "L2": 1, "LMAX": 2}[norm]
+    k = {"CG": 0, "PCGF": 1, "PBICGSTAB": 2, "GMRES": 3}[kind]
+    it = lib().orc_krylov(k, n, _p(rp), _p(ci), _p(va), amg.h if amg is not None else None, precond, C.c_double(jacobi_omega or 0.0), _p(b), _p(x),
+                          int(zero), C.c_double(tol), max_iters, restart, nt, _p(hist), C.byref(conv))
     return x, it, hist[: it + 1].copy(), bool(conv.value)
 
 

@@ -1,0 +1,57 @@
+"""GPU: CG / PCGF / PBICGSTAB / GMRES of the engine (csrc/krylov_extra.cu) against their CPU restatements: same iteration count,
+residual history to 1e-12 relative.  Written after this round's GPU minutes were spent: opt-in until validated on a device."""
+import numpy as np
+import pytest
+
+from amgx_b200 import gallery
+from tests._gpu_util import JACOBI, NOPREC, UNVALIDATED, amg_agg_cfg, outer_cfg, run_engine
+
+pytestmark = [pytest.mark.gpu, UNVALIDATED]
+
+
+@pytest.mark.parametrize("kind", ["CG", "PCGF", "PBICGSTAB", "GMRES"])
+@pytest.mark.parametrize("precond", ["none", "jacobi", "amg"])
+def test_krylov_matches_oracle(amgx, oracle, kind, precond):
+    rp, ci, va = gallery.poisson7pt(14, 11, 9)
+    n = rp.shape[0] - 1
+    b = np.random.default_rng(4).standard_normal(n)
+    pc = {"none": NOPREC, "jacobi": JACOBI, "amg": amg_agg_cfg()}[precond]
+    kw = {}
+    if precond == "jacobi":
+        kw["jacobi_omega"] = 0.8
+    if precond == "amg":
+        kw["amg"] = oracle.AMG(rp, ci, va, max_levels=50, presweeps=1, postsweeps=1, omega=0.8)
+    extra = {"gmres_n_restart": 7} if kind == "GMRES" else {}
+    x, it, status, hist = run_engine(amgx, outer_cfg(kind, pc, tol=1e-9, max_iters=150, **extra), rp, ci, va, b)
+    xo, ito, histo, convo = oracle.krylov(kind, rp, ci, va, b, tol=1e-9, max_iters=150, restart=7, **kw)
+    assert convo and status == "success" and it == ito
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+    assert np.max(np.abs(x - xo)) <= 1e-9 * np.max(np.abs(xo))
+
+
+@pytest.mark.parametrize("kind", ["CG", "PCGF", "PBICGSTAB", "GMRES"])
+def test_krylov_nonzero_guess_and_iteration_cap(amgx, oracle, kind):
+    rp, ci, va = gallery.random_banded(3000, sigma=40.0)
+    if kind in ("CG", "PCGF"):   # symmetric operator for the CG family
+        A = gallery.to_scipy(rp, ci, va)
+        A = ((A + A.T) * 0.5).tocsr()
+        A.sort_indices()
+        rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data
+    n = rp.shape[0] - 1
+    rng = np.random.default_rng(8)
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    x, it, status, hist = run_engine(amgx, outer_cfg(kind, JACOBI, tol=1e-14, max_iters=6, gmres_n_restart=4), rp, ci, va, b, x0=x0)
+    xo, ito, histo, convo = oracle.krylov(kind, rp, ci, va, b, jacobi_omega=0.8, x0=x0, tol=1e-14, max_iters=6, restart=4)
+    assert it == ito == 6 and status == "not_converged" and not convo
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+
+
+def test_gmres_single_iteration_and_bad_norm(amgx, oracle):
+    rp, ci, va = gallery.poisson7pt(9)
+    n = rp.shape[0] - 1
+    b = np.ones(n)
+    x, it, status, hist = run_engine(amgx, outer_cfg("GMRES", JACOBI, tol=1e-12, max_iters=1), rp, ci, va, b)
+    xo, ito, histo, convo = oracle.krylov("GMRES", rp, ci, va, b, jacobi_omega=0.8, tol=1e-12, max_iters=1)
+    assert it == ito == 1 and np.max(np.abs(hist - histo) / histo[0]) < 1e-12 and np.allclose(x, xo, rtol=1e-12)
+    with pytest.raises(Exception):
+        run_engine(amgx, outer_cfg("GMRES", NOPREC, norm="L1"), rp, ci, va, b)
