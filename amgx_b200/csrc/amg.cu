@@ -32,8 +32,18 @@ AMGSolver::AMGSolver(Config &cfg, const std::string &scope, std::shared_ptr<Reso
     if (cycle_name_ == "V") cycle_type_ = CYC_V;
     else if (cycle_name_ == "W") cycle_type_ = CYC_W;
     else if (cycle_name_ == "F") cycle_type_ = CYC_F;
-    else fatal(AMGX_RC_BAD_CONFIGURATION, "cycle '" + cycle_name_ + "' is outside the scope of the B200 solve-phase engine (V, W, F)");
-    if (error_scaling_ != 0) fatal(AMGX_RC_BAD_CONFIGURATION, "error_scaling != 0 is not supported by this engine");
+    else if (cycle_name_ == "CG") cycle_type_ = CYC_CG;
+    else if (cycle_name_ == "CGF") cycle_type_ = CYC_CGF;
+    else fatal(AMGX_RC_BAD_CONFIGURATION, "CycleFactory '" + cycle_name_ + "' has not been registered");
+    cycle_iters_ = cfg.get_int("cycle_iters", scope);
+    scaling_smoother_steps_ = cfg.get_int("scaling_smoother_steps", scope);
+    reuse_scale_ = cfg.get_int("reuse_scale", scope);
+    // allowed values of the reference's parameter registry: 0, 2, 3 (src/core.cu:437-441)
+    if (error_scaling_ != 0 && error_scaling_ != 2 && error_scaling_ != 3)
+        fatal(AMGX_RC_BAD_CONFIGURATION, "error_scaling must be 0, 2 or 3");
+    if ((cycle_type_ == CYC_CG || cycle_type_ == CYC_CGF) && cycle_iters_ < 1) fatal(AMGX_RC_BAD_CONFIGURATION, "cycle_iters must be >= 1");
+    // host scalars inside the cycle (CG / CGF) or a launch sequence that differs between cycles (reuse_scale): no graph capture around us
+    if (cycle_type_ == CYC_CG || cycle_type_ == CYC_CGF || (error_scaling_ >= 2 && reuse_scale_ > 0)) inhibit_.set();
     if (algorithm_ != "AGGREGATION" && algorithm_ != "CLASSICAL")
         fatal(AMGX_RC_BAD_CONFIGURATION, "algorithm '" + algorithm_ + "' is not supported (AGGREGATION, CLASSICAL)");
     std::string ns;
@@ -329,9 +339,11 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse,
     } else if (type == CYC_W) {
         cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_W);
         cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_W);
-    } else {
+    } else if (type == CYC_F) {
         cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_W);
         cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_V);
+    } else {
+        cg_cycle_dispatch(lvl + 1, L.bc, L.xc, type == CYC_CGF);
     }
 
     // ---- prolongation + post-smoothing ----
@@ -344,7 +356,11 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse,
     SmoothFuse f;
     bool have_fuse = false, in_alt = false;
     if (top_fuse && finest && n_post > 0) { f = *top_fuse; have_fuse = true; }
-    if (algorithm_ == "AGGREGATION") {
+    if (algorithm_ == "AGGREGATION" && error_scaling_ >= 2) {
+        // x += lambda * (smoothed P xc), lambda from the residual the restriction was computed from (b itself when x is still zero)
+        if (x_virtual_zero) x.zero(s);
+        scaled_correction(L, *rsrc, x);
+    } else if (algorithm_ == "AGGREGATION") {
         static const bool fuse_prolong = getenv("AMGXB_FUSE_PROLONG") ? atoi(getenv("AMGXB_FUSE_PROLONG")) != 0 : false;
         // where the smoother wants its initial iterate so that n_post sweeps end in x without a copy
         void *xin = (n_post > 0) ? sm->smooth_input(x, n_post) : x.ptr();
@@ -366,6 +382,121 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse,
         classical_prolong_add(L, x_virtual_zero ? nullptr : x.ptr(), xin, s);   // xin = x + P xc  (0 + P xc == P xc exactly)
     }
     if (n_post > 0) sm->smooth(b, x, false, n_post, have_fuse ? &f : nullptr, in_alt);
+}
+
+double AMGSolver::host_dot(const DevVec &x, const DevVec &y, size_t n)
+{
+    cudaStream_t s = stream();
+    ReduceCtx red = red_ctx();
+    vec_dot(x.ptr(), y.ptr(), x.prec, n, red, FIN_STORE, S_TMP0, 0, s);
+    double h = 0;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&h, red.scal + S_TMP0, sizeof(double), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    return h;
+}
+
+// CG_CycleDispatcher / CG_Flex_CycleDispatcher::dispatch (src/cycles/cg_cycle.cu:18-101, cg_flex_cycle.cu:18-103): cycle_iters
+// iterations of (flexible) PCG on level `lvl`, preconditioned by one CG(F) fixed cycle of that level started from zero.  The
+// recurrence scalars live on the host as in the reference (dotc).
+void AMGSolver::cg_cycle_dispatch(int lvl, DevVec &b, DevVec &x, bool flex)
+{
+    cudaStream_t s = stream();
+    AMGLevel &L = *levels_[lvl];
+    Matrix &A = *L.A;
+    if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "CG / CGF cycles on a distributed matrix");
+    const size_t n = (size_t)A.n * A.by, N = (size_t)A.n_cols * A.by;
+    const Prec vp = A.vec_prec;
+    const int type = flex ? CYC_CGF : CYC_CG;
+    for (DevVec *v : {&L.cg_y, &L.cg_z, &L.cg_r, &L.cg_p, &L.cg_d})
+        if (v->n != N) { v->resize(N, vp); v->zero(s); }
+    DevVec &y = L.cg_y, &z = L.cg_z, &r = L.cg_r, &p = L.cg_p, &d = L.cg_d;
+    auto apply = [&](DevVec &in, DevVec &out) {
+        CsrOpArgs g;
+        g.x = in.ptr();
+        g.y = out.ptr();
+        matrix_apply(A, EPI_SPMV, g, s);
+    };
+    if (L.init_cycle) {
+        x.zero(s);
+        L.init_cycle = false;
+    }
+    apply(x, y);                                                   // y = A x
+    vec_axpby(b.ptr(), y.ptr(), r.ptr(), vp, n, 1.0, -1.0, s);     // r = b - y
+    L.init_cycle = true;
+    cycle(lvl, r, z, nullptr, type);                               // z = M r
+    vec_copy(p.ptr(), z.ptr(), vp, n, s);
+    double rz = flex ? 0.0 : host_dot(r, z, n);
+    int k = 0;
+    while (true) {
+        apply(p, y);
+        if (flex) rz = host_dot(r, z, n);
+        const double alpha = rz / host_dot(y, p, n);
+        vec_axpy(p.ptr(), x.ptr(), vp, n, alpha, s);
+        if (++k == cycle_iters_) break;
+        if (flex) vec_copy(d.ptr(), r.ptr(), vp, n, s);
+        vec_axpy(y.ptr(), r.ptr(), vp, n, alpha * -1.0, s);
+        if (flex) vec_axpby(r.ptr(), d.ptr(), d.ptr(), vp, n, 1.0, -1.0, s);
+        L.init_cycle = true;
+        cycle(lvl, r, z, nullptr, type);
+        double beta;
+        if (flex) beta = host_dot(z, d, n) / rz;
+        else {
+            const double rz_old = rz;
+            rz = host_dot(r, z, n);
+            beta = rz / rz_old;
+        }
+        vec_axpby(z.ptr(), p.ptr(), p.ptr(), vp, n, 1.0, beta, s);
+    }
+}
+
+// prolongateAndApplyCorrection with error_scaling = 2 (lambda = <r, A e> / <A e, A e>) or 3 (lambda = <r, e> / <e, A e>), e = P xc
+// smoothed scaling_smoother_steps times against the residual (aggregation_amg_level.cu:700-824).  The two inner products and the
+// clamped quotient stay on the device; the scale is kept for reuse_scale further corrections.
+void AMGSolver::scaled_correction(AMGLevel &L, const DevVec &rf, DevVec &x)
+{
+    cudaStream_t s = stream();
+    Matrix &A = *L.A;
+    const size_t n = (size_t)A.n * A.by, N = (size_t)A.n_cols * A.by;
+    const Prec vp = A.vec_prec;
+    if (L.ef.n != N) {
+        L.ef.resize(N, vp);
+        L.ef.zero(s);
+        L.Aef.resize(N, vp);
+        L.Aef.zero(s);
+        L.scale.resize(1);
+        L.scale.zero(s);
+        L.scale_counter = 0;
+    }
+    const char *xc = (const char *)L.xc.ptr() + (size_t)L.tail_off * A.by * prec_size(vp);
+    agg_prolong_set(L.aggregates.ptr(), xc, L.ef.ptr(), vp, A.n, A.by, s);      // ef = P xc
+    if (L.scale_counter > 0) {
+        vec_axpy_dev(L.ef.ptr(), x.ptr(), vp, n, L.scale.ptr(), 0, 1.0, s);
+        L.scale_counter--;
+        return;
+    }
+    if (scaling_smoother_steps_ > 0) L.smoother->smooth(const_cast<DevVec &>(rf), L.ef, false, scaling_smoother_steps_, nullptr);
+    dist_exchange_halo(A, L.ef, s);
+    {
+        CsrOpArgs g;
+        g.x = L.ef.ptr();
+        g.y = L.Aef.ptr();
+        matrix_apply(A, EPI_SPMV, g, s);
+    }
+    ReduceCtx red = red_ctx();
+    if (error_scaling_ == 2) {
+        vec_dot(rf.ptr(), L.Aef.ptr(), vp, n, red, FIN_STORE, S_TMP0, 0, s);
+        vec_dot(L.Aef.ptr(), L.Aef.ptr(), vp, n, red, FIN_STORE, S_TMP1, 0, s);
+    } else {
+        vec_dot(rf.ptr(), L.ef.ptr(), vp, n, red, FIN_STORE, S_TMP0, 0, s);
+        vec_dot(L.ef.ptr(), L.Aef.ptr(), vp, n, red, FIN_STORE, S_TMP1, 0, s);
+    }
+    if (A.dist) {
+        dist_allreduce_scalar_fin(A, red, S_TMP0, FIN_STORE, s);
+        dist_allreduce_scalar_fin(A, red, S_TMP1, FIN_STORE, s);
+    }
+    scalar_error_scale(red.scal, S_TMP0, S_TMP1, L.scale.ptr(), s);
+    vec_axpy_dev(L.ef.ptr(), x.ptr(), vp, n, L.scale.ptr(), 0, 1.0, s);        // x += lambda e
+    L.scale_counter = reuse_scale_;
 }
 
 // print_grid_stats of the reference (src/amg.cu:1231-1350): same table layout

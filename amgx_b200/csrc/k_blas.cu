@@ -177,6 +177,20 @@ void vec_axpbypcz(const void *x, const void *y, const void *z, void *out, Prec p
     });
 }
 
+// scale of the coarse-grid correction, error_scaling = 2, 3: out[0] = clamp(scal[nom] / scal[den]) exactly as
+// aggregation_amg_level.cu:797-817 words it (|den| == 0 -> 1; |alpha| < .3 -> sign * .3; |alpha| > 10 -> sign * 10)
+void scalar_error_scale(const double *scal, int slot_nom, int slot_den, double *out, cudaStream_t s)
+{
+    launch_map(1, [=] __device__(size_t) {
+        double nom = scal[slot_nom], den = scal[slot_den];
+        if (fabs(den) == 0.0) nom = den = 1.0;
+        double alpha = nom / den;
+        if (fabs(alpha) < .3) alpha = (alpha / fabs(alpha)) * .3;
+        if (fabs(alpha) > 10) alpha = (alpha / fabs(alpha)) * 10.;
+        out[0] = alpha;
+    }, s);
+}
+
 void vec_axpy_dev(const void *x, void *y, Prec p, size_t n, const double *scal, int slot, double sign, cudaStream_t s)
 {
     AMGXB_DISPATCH_VEC(p, {

@@ -1,5 +1,6 @@
 // solvers.cu -- Solver base class, convergence criteria, Jacobi smoothers, PCG.  See solvers.h.
 #include "solvers.h"
+#include <atomic>
 #include "dist.h"
 #include <cmath>
 #include <algorithm>
@@ -134,10 +135,14 @@ static bool dist_fuse()
     return on;
 }
 
+static std::atomic<int> g_graph_inhibit{0};
+void GraphInhibit::set() { if (!on) { on = true; g_graph_inhibit++; } }
+GraphInhibit::~GraphInhibit() { if (on) g_graph_inhibit--; }
+
 bool graphs_enabled()
 {
     static const bool on = getenv("AMGXB_GRAPHS") ? atoi(getenv("AMGXB_GRAPHS")) != 0 : true;
-    return on;
+    return on && g_graph_inhibit.load() == 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -74,6 +74,13 @@ struct GraphSegment {
     ~GraphSegment() { reset(); }
 };
 bool graphs_enabled();
+// Solvers that synchronise with the host inside what an enclosing solver would capture (CG / CGF cycles) or whose launch
+// sequence changes from one invocation to the next (reuse_scale) hold one of these for their lifetime.
+struct GraphInhibit {
+    bool on = false;
+    void set();
+    ~GraphInhibit();
+};
 
 class Solver {
 public:
@@ -251,6 +258,12 @@ struct AMGLevel {
     // cycle work vectors (sized for the NEXT level: bc, xc) and residual of this level
     DevVec bc, xc, r;
     bool init_cycle = false;
+    // CG / CGF cycles: work vectors of the CG iterations run ON this level (src/cycles/cg_cycle.cu:25-40)
+    DevVec cg_y, cg_z, cg_r, cg_p, cg_d;
+    // error_scaling 2 / 3 (aggregation): prolongated correction, A * correction, the scale (device) and its reuse counter
+    DevVec ef, Aef;
+    DevBuf<double> scale;
+    int scale_counter = 0;
     // distributed hierarchy: the NEXT level is replicated on every rank (dist.cu, "replicated coarse tail")
     bool tail_gather = false;
     int tail_off = 0;
@@ -269,7 +282,12 @@ protected:
     void solver_setup(bool reuse) override;
     void solve_init(DevVec &b, DevVec &x, bool xIsZero) override;
     Status solve_iteration(DevVec &b, DevVec &x, bool xIsZero) override;
-    enum CycleType { CYC_V = 0, CYC_W = 1, CYC_F = 2 };
+    enum CycleType { CYC_V = 0, CYC_W = 1, CYC_F = 2, CYC_CG = 3, CYC_CGF = 4 };
+    void cg_cycle_dispatch(int lvl, DevVec &b, DevVec &x, bool flex);               // CG(F)_CycleDispatcher::dispatch
+    void scaled_correction(AMGLevel &L, const DevVec &rf, DevVec &x);              // x += lambda * smoothed(P xc)
+    double host_dot(const DevVec &x, const DevVec &y, size_t n);
+    int cycle_iters_ = 2, scaling_smoother_steps_ = 2, reuse_scale_ = 0;
+    GraphInhibit inhibit_;
     void cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse, int type = -1);   // type -1: the configured cycle
     int cycle_type_ = CYC_V;
     void setup_aggregation();

@@ -409,6 +409,9 @@ typedef struct {
     /* DENSE_LU_SOLVER on the coarsest level: column-major LU factors + pivots */
     double *lu;
     int *ipiv;
+    /* error scaling: last computed scale and how many more corrections reuse it */
+    double scale;
+    int scale_counter;
 } orc_level;
 
 typedef struct {
@@ -417,7 +420,10 @@ typedef struct {
     int presweeps, postsweeps, coarsest_sweeps, finest_sweeps, smoother; /* smoother: 0 BLOCK_JACOBI, 1 JACOBI_L1, 2 MULTICOLOR_DILU */
     double omega, uncolored_fraction;
     int dense_lu;            /* coarse_solver = DENSE_LU_SOLVER */
-    int cycle;               /* 0 V, 1 W, 2 F (src/cycles/{v,w,f}_cycle.cu) */
+    int cycle;               /* 0 V, 1 W, 2 F, 3 CG, 4 CGF (src/cycles/{v,w,f,cg,cg_flex}_cycle.cu) */
+    int cycle_iters;         /* CG / CGF cycles: CG iterations per visit of a level (default 2, src/core.cu:435) */
+    /* error_scaling = 2, 3 on aggregation levels (src/aggregation/aggregation_amg_level.cu:700-824) */
+    int error_scaling, scaling_smoother_steps, reuse_scale;
 } orc_amg;
 
 #include "classical_oracle.inc.c"
@@ -456,6 +462,7 @@ ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double
 {
     /* AMG_Setup::setup level loop (src/amg.cu:201-418), single partition, coarse_solver = NOSOLVER */
     orc_amg *a = (orc_amg *)calloc(1, sizeof(orc_amg));
+    a->cycle_iters = 2; a->scaling_smoother_steps = 2;
     a->lv = (orc_level *)calloc((size_t)(max_levels > 0 ? max_levels : 1) + 1, sizeof(orc_level));
     a->presweeps = presweeps; a->postsweeps = postsweeps; a->coarsest_sweeps = coarsest_sweeps; a->finest_sweeps = finest_sweeps;
     a->smoother = smoother; a->omega = omega;
@@ -504,6 +511,7 @@ ORC_API orc_amg *orc_amg_setup_classical(int n, const int *rp, const int *ci, co
                                          int max_elmts)
 {
     orc_amg *a = (orc_amg *)calloc(1, sizeof(orc_amg));
+    a->cycle_iters = 2; a->scaling_smoother_steps = 2;
     a->lv = (orc_level *)calloc((size_t)(max_levels > 0 ? max_levels : 1) + 1, sizeof(orc_level));
     a->presweeps = presweeps; a->postsweeps = postsweeps; a->coarsest_sweeps = coarsest_sweeps; a->finest_sweeps = finest_sweeps;
     a->smoother = smoother; a->omega = omega;
@@ -672,6 +680,69 @@ static void smooth(const orc_amg *a, orc_level *L, const double *b, double *x, i
 
 /* FixedCycle::cycle, V cycle (src/cycles/fixed_cycle.cu:25-248) */
 static void vcycle_t(const orc_amg *a, int l, const double *b, double *x, int x_is_zero, int type);
+
+/* CG_CycleDispatcher / CG_Flex_CycleDispatcher::dispatch (src/cycles/cg_cycle.cu:18-101, cg_flex_cycle.cu:18-103): cycle_iters
+ * iterations of (flexible) PCG on level l, preconditioned by one CG(F) fixed cycle of that level with zero initial guess.
+ * x_is_zero = the level's init-cycle flag. */
+static void cg_cycle_dispatch(const orc_amg *a, int l, const double *b, double *x, int flex)
+{
+    const orc_level *L = &a->lv[l];
+    const int n = L->n, type = flex ? 4 : 3;
+    const size_t nb = sizeof(double) * (size_t)(n > 0 ? n : 1);
+    double *y = (double *)malloc(nb), *z = (double *)malloc(nb), *r = (double *)malloc(nb), *p = (double *)malloc(nb), *d = (double *)malloc(nb);
+    memset(x, 0, sizeof(double) * (size_t)n);                     /* the dispatcher is always entered with the init flag set */
+    orc_spmv(n, L->rp, L->ci, L->va, x, y);
+    for (int i = 0; i < n; i++) r[i] = b[i] * 1.0 + y[i] * -1.0;  /* axpby(b, y, r, 1, -1) */
+    vcycle_t(a, l, r, z, 1, type);
+    memcpy(p, z, nb);
+    double rz = flex ? 0.0 : orc_dot(n, r, z);
+    int k = 0;
+    for (;;) {
+        orc_spmv(n, L->rp, L->ci, L->va, p, y);
+        if (flex) rz = orc_dot(n, r, z);
+        const double alpha = rz / orc_dot(n, y, p);
+        for (int i = 0; i < n; i++) x[i] = fma(alpha, p[i], x[i]);
+        if (++k == a->cycle_iters) break;
+        if (flex) memcpy(d, r, nb);
+        { const double ma = alpha * -1.0; for (int i = 0; i < n; i++) r[i] = fma(ma, y[i], r[i]); }
+        if (flex) for (int i = 0; i < n; i++) d[i] = r[i] * 1.0 + d[i] * -1.0;
+        vcycle_t(a, l, r, z, 1, type);
+        double beta;
+        if (flex) beta = orc_dot(n, z, d) / rz;
+        else { const double rz_old = rz; rz = orc_dot(n, r, z); beta = rz / rz_old; }
+        for (int i = 0; i < n; i++) p[i] = z[i] * 1.0 + p[i] * beta;
+    }
+    free(y); free(z); free(r); free(p); free(d);
+}
+
+/* prolongateAndApplyCorrection with error_scaling = 2 (minimise the residual 2-norm) or 3 (minimise the error A-norm):
+ * aggregation_amg_level.cu:700-824.  L->r holds the residual the restriction was computed from. */
+static void smooth(const orc_amg *a, orc_level *L, const double *b, double *x, int x_is_zero, int sweeps);
+static void scaled_correction(orc_amg *a, orc_level *L, double *x)
+{
+    const int n = L->n;
+    if (L->scale_counter > 0) {
+        for (int i = 0; i < n; i++) x[i] = fma(L->scale, L->xc[L->agg[i]], x[i]);
+        L->scale_counter--;
+        return;
+    }
+    double *ef = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1)), *Aef = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; i++) ef[i] = L->xc[L->agg[i]];         /* prolongateVector */
+    if (a->scaling_smoother_steps > 0) smooth(a, L, L->r, ef, 0, a->scaling_smoother_steps);   /* smooth the correction with rhs = residual */
+    orc_spmv(n, L->rp, L->ci, L->va, ef, Aef);
+    double nom, den;
+    if (a->error_scaling == 2) { nom = orc_dot(n, L->r, Aef); den = orc_dot(n, Aef, Aef); }
+    else { nom = orc_dot(n, L->r, ef); den = orc_dot(n, ef, Aef); }
+    if (fabs(den) == 0.0) nom = den = 1.0;
+    double alpha = nom / den;
+    if (fabs(alpha) < .3) alpha = (alpha / fabs(alpha)) * .3;
+    if (fabs(alpha) > 10) alpha = (alpha / fabs(alpha)) * 10.;
+    for (int i = 0; i < n; i++) x[i] = fma(alpha, ef[i], x[i]);   /* applyCorrection */
+    L->scale_counter = a->reuse_scale;
+    L->scale = alpha;
+    free(ef); free(Aef);
+}
+
 static void vcycle(const orc_amg *a, int l, const double *b, double *x, int x_is_zero) { vcycle_t(a, l, b, x, x_is_zero, a->cycle); }
 static void vcycle_t(const orc_amg *a, int l, const double *b, double *x, int x_is_zero, int type)
 {
@@ -693,11 +764,13 @@ static void vcycle_t(const orc_amg *a, int l, const double *b, double *x, int x_
      * the coarsest (fixed_cycle.cu:169-179); the second visit continues from the first one's xc */
     if (type == 0 || a->lv[l + 1].coarsest) vcycle_t(a, l + 1, L->bc, L->xc, 1, 0);
     else if (type == 1) { vcycle_t(a, l + 1, L->bc, L->xc, 1, 1); vcycle_t(a, l + 1, L->bc, L->xc, 0, 1); }
-    else { vcycle_t(a, l + 1, L->bc, L->xc, 1, 1); vcycle_t(a, l + 1, L->bc, L->xc, 0, 0); }
+    else if (type == 2) { vcycle_t(a, l + 1, L->bc, L->xc, 1, 1); vcycle_t(a, l + 1, L->bc, L->xc, 0, 0); }
+    else cg_cycle_dispatch(a, l + 1, L->bc, L->xc, type == 4);
     if (L->Pp) {                                                  /* classical: tmp = P e; x = x + tmp (classical_amg_level.cu:884-910) */
         cla_spmv(L->n, L->Pp, L->Pc, L->Pv, L->xc, L->tmp);
         for (int i = 0; i < L->n; i++) x[i] = x[i] + L->tmp[i];
-    } else orc_prolong_add(L->n, L->agg, L->xc, x);               /* prolongateAndApplyCorrection */
+    } else if (a->error_scaling >= 2) scaled_correction((orc_amg *)a, L, x);
+    else orc_prolong_add(L->n, L->agg, L->xc, x);               /* prolongateAndApplyCorrection */
     int n_post;
     if (finest && a->finest_sweeps != -1) n_post = a->postsweeps == 0 ? 0 : a->finest_sweeps;
     else n_post = a->postsweeps;
@@ -706,6 +779,12 @@ static void vcycle_t(const orc_amg *a, int l, const double *b, double *x, int x_
 
 ORC_API void orc_amg_vcycle(const orc_amg *a, const double *b, double *x, int x_is_zero) { vcycle(a, 0, b, x, x_is_zero); }
 ORC_API void orc_amg_set_cycle(orc_amg *a, int type) { a->cycle = type; }
+ORC_API void orc_amg_set_cycle_iters(orc_amg *a, int iters) { a->cycle_iters = iters; }
+ORC_API void orc_amg_set_error_scaling(orc_amg *a, int error_scaling, int scaling_smoother_steps, int reuse_scale)
+{
+    a->error_scaling = error_scaling; a->scaling_smoother_steps = scaling_smoother_steps; a->reuse_scale = reuse_scale;
+    for (int l = 0; l < a->num_levels; l++) { a->lv[l].scale = 0.0; a->lv[l].scale_counter = 0; }
+}
 
 /* RELATIVE_INI criterion (src/convergence/relative_ini.cu:22-45) */
 static int conv_relative_ini(double nrm, double nrm_ini, double tol)

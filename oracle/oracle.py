@@ -157,7 +157,16 @@ class AMG:
             lib().orc_amg_enable_dense_lu(self.h)
 
     def set_cycle(self, name: str):
-        lib().orc_amg_set_cycle(self.h, {"V": 0, "W": 1, "F": 2}[name])
+        lib().orc_amg_set_cycle(self.h, {"V": 0, "W": 1, "F": 2, "CG": 3, "CGF": 4}[name])
+        return self
+
+    def set_cycle_iters(self, iters: int):
+        lib().orc_amg_set_cycle_iters(self.h, iters)
+        return self
+
+    def set_error_scaling(self, error_scaling: int, scaling_smoother_steps: int = 2, reuse_scale: int = 0):
+        """aggregation levels only (the classical level ignores error_scaling in the reference too)"""
+        lib().orc_amg_set_error_scaling(self.h, error_scaling, scaling_smoother_steps, reuse_scale)
         return self
 
     def num_levels(self):

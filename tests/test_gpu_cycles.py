@@ -39,3 +39,51 @@ def test_pcg_amg_cycle_matches_oracle(amgx, oracle, cyc, grid):
     assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
     for obj in (slv, x, b, A, rsc, cfg):
         obj.destroy()
+
+
+@pytest.mark.parametrize("cyc,iters,outer", [("CG", 2, "PCGF"), ("CGF", 2, "PCGF"), ("CG", 3, "FGMRES"), ("CGF", 1, "PCG")])
+def test_cg_cycles_match_oracle(amgx, oracle, cyc, iters, outer):
+    from tests._gpu_util import amg_agg_cfg, outer_cfg, run_engine
+    rp, ci, va = gallery.poisson7pt(15, 12, 10)
+    n = rp.shape[0] - 1
+    b = np.ones(n)
+    cfgd = outer_cfg(outer, amg_agg_cfg(cycle=cyc, cycle_iters=iters), tol=1e-9, max_iters=60, gmres_n_restart=10)
+    x, it, status, hist = run_engine(amgx, cfgd, rp, ci, va, b)
+    o = oracle.AMG(rp, ci, va, max_levels=50, presweeps=1, postsweeps=1, omega=0.8).set_cycle(cyc).set_cycle_iters(iters)
+    if outer == "PCG":
+        xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, amg=o, tol=1e-9, max_iters=60)
+    elif outer == "FGMRES":
+        xo, ito, histo, convo = oracle.fgmres(rp, ci, va, b, amg=o, tol=1e-9, max_iters=60, restart=10)
+    else:
+        xo, ito, histo, convo = oracle.krylov(outer, rp, ci, va, b, amg=o, tol=1e-9, max_iters=60)
+    assert convo and status == "success" and it == ito
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-11      # host dots of nearly-cancelling quantities: one digit of slack
+
+
+@pytest.mark.parametrize("es,steps,reuse", [(2, 2, 0), (3, 2, 0), (3, 0, 0), (3, 2, 2)])
+def test_error_scaling_matches_oracle(amgx, oracle, es, steps, reuse):
+    from tests._gpu_util import amg_agg_cfg, outer_cfg, run_engine
+    rp, ci, va = gallery.poisson7pt(16, 13, 9)
+    n = rp.shape[0] - 1
+    b = np.ones(n)
+    amg = amg_agg_cfg(error_scaling=es, scaling_smoother_steps=steps, reuse_scale=reuse)
+    x, it, status, hist = run_engine(amgx, outer_cfg("PCG", amg, tol=1e-9, max_iters=80), rp, ci, va, b)
+    o = oracle.AMG(rp, ci, va, max_levels=50, presweeps=1, postsweeps=1, omega=0.8).set_error_scaling(es, steps, reuse)
+    xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, amg=o, tol=1e-9, max_iters=80)
+    assert convo and status == "success" and it == ito
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+
+
+def test_error_scaling_standalone_amg_zero_presweeps(amgx, oracle):
+    """presweeps = 0: the residual the scale is computed from is b itself (the engine never forms r)"""
+    from tests._gpu_util import amg_agg_cfg, run_engine
+    rp, ci, va = gallery.poisson7pt(12)
+    n = rp.shape[0] - 1
+    b = np.ones(n)
+    amg = amg_agg_cfg(pre=0, post=2, error_scaling=3)
+    amg.update(scope="main", max_iters=40, monitor_residual=1, store_res_history=1, convergence="RELATIVE_INI", tolerance=1e-8, norm="L2")
+    x, it, status, hist = run_engine(amgx, {"config_version": 2, "determinism_flag": 1, "solver": amg}, rp, ci, va, b)
+    o = oracle.AMG(rp, ci, va, max_levels=50, presweeps=0, postsweeps=2, omega=0.8).set_error_scaling(3)
+    xo, ito, histo, convo = oracle.amg_solve(o, b, tol=1e-8, max_iters=40)
+    assert convo and status == "success" and it == ito
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12

@@ -44,3 +44,156 @@ def test_w_cycle_on_three_levels_is_two_coarse_visits(oracle):
         res[cyc] = np.linalg.norm(b - gallery.to_scipy(rp, ci, va) @ x)
     assert np.isclose(res["W"], res["F"], rtol=1e-14)      # on 3 levels the W and the V visit of level 1 are the same fixed cycle
     assert res["W"] < res["V"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CG / CGF cycles and error scaling: the C restatement against an independent numpy multilevel implementation
+# built from the oracle's own level arrays (matrices, aggregates)
+# ---------------------------------------------------------------------------------------------------------------
+class NumpyAMG:
+    """fixed_cycle.cu + cg_cycle.cu / cg_flex_cycle.cu + aggregation error scaling, dense numpy, Jacobi smoother"""
+
+    def __init__(self, amg, pre, post, omega, coarsest_sweeps=2, cycle="V", cycle_iters=2, error_scaling=0, steps=2):
+        self.lv = [amg.level(l) for l in range(amg.num_levels())]
+        for L in self.lv:
+            L["A"] = gallery.to_scipy(L["row_ptr"], L["col_idx"], L["values"])
+        self.pre, self.post, self.omega, self.cs = pre, post, omega, coarsest_sweeps
+        self.cycle, self.iters, self.es, self.steps = cycle, cycle_iters, error_scaling, steps
+
+    def smooth(self, L, b, x, zero, sweeps):
+        for it in range(sweeps):
+            if it == 0 and zero:
+                x = self.omega * b / L["d"]
+            else:
+                x = x + self.omega * (b - L["A"] @ x) / L["d"]
+        return x
+
+    def fixed(self, l, b, x, zero, typ):
+        L = self.lv[l]
+        last = l == len(self.lv) - 1
+        npre = self.cs if last else self.pre
+        if npre > 0:
+            x = self.smooth(L, b, x, zero, npre)
+        elif zero:
+            x = np.zeros_like(b)
+        if last:
+            return x
+        r = b - L["A"] @ x
+        agg = L["aggregates"]
+        bc = np.zeros(L["n_coarse"])
+        np.add.at(bc, agg, r)
+        nxt_last = l + 1 == len(self.lv) - 1
+        if typ == "V" or nxt_last:
+            xc = self.fixed(l + 1, bc, None, True, "V")
+        elif typ == "W":
+            xc = self.fixed(l + 1, bc, None, True, "W")
+            xc = self.fixed(l + 1, bc, xc, False, "W")
+        elif typ == "F":
+            xc = self.fixed(l + 1, bc, None, True, "W")
+            xc = self.fixed(l + 1, bc, xc, False, "V")
+        else:
+            xc = self.cg(l + 1, bc, typ == "CGF")
+        e = xc[agg]
+        if self.es >= 2:
+            if self.steps > 0:
+                e = self.smooth(L, r, e, False, self.steps)
+            Ae = L["A"] @ e
+            nom, den = (r @ Ae, Ae @ Ae) if self.es == 2 else (r @ e, e @ Ae)
+            lam = nom / den if den != 0 else 1.0
+            lam = np.sign(lam) * min(max(abs(lam), 0.3), 10.0)
+            x = x + lam * e
+        else:
+            x = x + e
+        if self.post > 0:
+            x = self.smooth(L, b, x, False, self.post)
+        return x
+
+    def cg(self, l, b, flex):
+        A = self.lv[l]["A"]
+        typ = "CGF" if flex else "CG"
+        x = np.zeros_like(b)
+        r = b - A @ x
+        z = self.fixed(l, r, None, True, typ)
+        p = z.copy()
+        rz = r @ z
+        k = 0
+        while True:
+            y = A @ p
+            if flex:
+                rz = r @ z
+            alpha = rz / (y @ p)
+            x = x + alpha * p
+            k += 1
+            if k == self.iters:
+                return x
+            d = r.copy()
+            r = r - alpha * y
+            d = r - d
+            z = self.fixed(l, r, None, True, typ)
+            if flex:
+                beta = (z @ d) / rz
+            else:
+                rz_old, rz = rz, r @ z
+                beta = rz / rz_old
+            p = z + beta * p
+
+    def vcycle(self, b):
+        return self.fixed(0, b, None, True, self.cycle)
+
+
+@pytest.mark.parametrize("cyc,iters", [("V", 2), ("W", 2), ("F", 2), ("CG", 1), ("CG", 2), ("CG", 3), ("CGF", 2), ("CGF", 3)])
+def test_cycles_match_numpy_multilevel(oracle, cyc, iters):
+    rp, ci, va = gallery.poisson7pt(11, 9, 8)
+    n = rp.shape[0] - 1
+    b = np.random.default_rng(5).standard_normal(n)
+    amg = oracle.AMG(rp, ci, va, max_levels=5, presweeps=1, postsweeps=2, omega=0.8).set_cycle(cyc).set_cycle_iters(iters)
+    assert amg.num_levels() == 5
+    x = amg.vcycle(b)
+    ref = NumpyAMG(amg, 1, 2, 0.8, cycle=cyc, cycle_iters=iters).vcycle(b)
+    assert np.max(np.abs(x - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("es", [2, 3])
+@pytest.mark.parametrize("steps", [0, 2])
+def test_error_scaling_matches_numpy_multilevel(oracle, es, steps):
+    rp, ci, va = gallery.poisson7pt(12, 10, 7)
+    n = rp.shape[0] - 1
+    b = np.random.default_rng(6).standard_normal(n)
+    amg = oracle.AMG(rp, ci, va, max_levels=6, presweeps=1, postsweeps=1, omega=0.8).set_error_scaling(es, steps, 0)
+    x = amg.vcycle(b)
+    ref = NumpyAMG(amg, 1, 1, 0.8, error_scaling=es, steps=steps).vcycle(b)
+    assert np.max(np.abs(x - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_error_scaling_reuse_scale_skips_recomputation(oracle):
+    """reuse_scale = k: the next k corrections of a level use the stored scale on the raw (unsmoothed) prolongation"""
+    rp, ci, va = gallery.poisson7pt(10)
+    n = rp.shape[0] - 1
+    b = np.ones(n)
+    a0 = oracle.AMG(rp, ci, va, max_levels=2, presweeps=1, postsweeps=1, omega=0.8).set_error_scaling(3, 2, 0)
+    a1 = oracle.AMG(rp, ci, va, max_levels=2, presweeps=1, postsweeps=1, omega=0.8).set_error_scaling(3, 2, 1)
+    x0, x1 = a0.vcycle(b), a1.vcycle(b)
+    assert np.array_equal(x0, x1)                       # first cycle computes the scale either way
+    A = gallery.to_scipy(rp, ci, va)
+    r = b - A @ x0
+    y0, y1 = a0.vcycle(r), a1.vcycle(r)                 # second cycle: a1 reuses
+    assert not np.array_equal(y0, y1)
+    z0, z1 = a0.vcycle(r), a1.vcycle(r)                 # third: a1 recomputes -> same as a0 again
+    assert np.array_equal(z0, y0) and np.array_equal(z1, y0)
+
+
+def test_cg_cycles_and_error_scaling_accelerate_pcg(oracle):
+    rp, ci, va = gallery.poisson7pt(18)
+    n = rp.shape[0] - 1
+    its = {}
+    for name, f in {"V": lambda a: a, "CG": lambda a: a.set_cycle("CG"), "CGF": lambda a: a.set_cycle("CGF"),
+                    "ES3": lambda a: a.set_error_scaling(3)}.items():
+        amg = f(oracle.AMG(rp, ci, va, max_levels=50, presweeps=1, postsweeps=1, omega=0.8))
+        # a CG cycle is not a fixed linear operator: flexible PCG around it
+        if name.startswith("CG"):
+            x, it, hist, conv = oracle.krylov("PCGF", rp, ci, va, np.ones(n), amg=amg, tol=1e-8, max_iters=100)
+        else:
+            x, it, hist, conv = oracle.pcg(rp, ci, va, np.ones(n), amg=amg, tol=1e-8, max_iters=100)
+        assert conv
+        its[name] = it
+    assert its["CG"] < its["V"] and its["CGF"] < its["V"] and its["ES3"] < its["V"]
