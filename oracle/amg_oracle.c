@@ -417,7 +417,8 @@ typedef struct {
 typedef struct {
     int num_levels;
     orc_level *lv;
-    int presweeps, postsweeps, coarsest_sweeps, finest_sweeps, smoother; /* smoother: 0 BLOCK_JACOBI, 1 JACOBI_L1, 2 MULTICOLOR_DILU */
+    int presweeps, postsweeps, coarsest_sweeps, finest_sweeps, smoother; /* smoother: 0 BLOCK_JACOBI, 1 JACOBI_L1, 2 MULTICOLOR_DILU, 3 MULTICOLOR_GS */
+    int symmetric_gs;        /* MULTICOLOR_GS: symmetric_GS = 1 sweeps the colours up, then down */
     double omega, uncolored_fraction;
     int dense_lu;            /* coarse_solver = DENSE_LU_SOLVER */
     int cycle;               /* 0 V, 1 W, 2 F, 3 CG, 4 CGF (src/cycles/{v,w,f,cg,cg_flex}_cycle.cu) */
@@ -442,7 +443,7 @@ static void level_smoother_setup(orc_level *L, int smoother)
     L->d = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
     if (smoother == 1) orc_l1_norms(L->n, L->rp, L->ci, L->va, L->d);
     else orc_extract_diag(L->n, L->rp, L->ci, L->va, L->d);
-    if (smoother == 2) {
+    if (smoother == 2 || smoother == 3) {
         const size_t nn = (size_t)(L->n > 0 ? L->n : 1);
         L->colors = (int *)malloc(sizeof(int) * nn);
         L->sorted_rows = (int *)malloc(sizeof(int) * nn);
@@ -452,7 +453,7 @@ static void level_smoother_setup(orc_level *L, int smoother)
         L->Einv = (double *)calloc(nn, sizeof(double));
         L->delta = (double *)calloc(nn, sizeof(double));
         L->Delta = (double *)calloc(nn, sizeof(double));
-        orc_dilu_setup_1x1(L->n, L->rp, L->ci, L->va, L->num_colors, L->colors, L->sorted_rows, L->color_offsets, L->Einv);
+        if (smoother == 2) orc_dilu_setup_1x1(L->n, L->rp, L->ci, L->va, L->num_colors, L->colors, L->sorted_rows, L->color_offsets, L->Einv);
     }
 }
 
@@ -661,9 +662,47 @@ ORC_API void orc_amg_enable_dense_lu(orc_amg *a)
     a->dense_lu = 1;
 }
 
+static double butterfly(double *v, int w);
+/* MULTICOLOR_GS, scalar: multicolorGSSmoothCsrKernel_nPerRow (src/solvers/multicolor_gauss_seidel_solver.cu:496-551) colour by
+ * colour, in place; N = 4 lanes per row, 32 when nnz/rows > 20 or nnz/colours < 500000 (:1004-1013); lane (k - row_begin) % N
+ * accumulates -a_ik x_k with one FMA, shuffle-down tree, lane 0: x_i += w (sum + b_i) / a_ii.  symmetric: colours up, then down. */
+ORC_API void orc_gs_sweep(int n, const int *rp, const int *ci, const double *va, int num_colors, const int *sorted_rows, const int *offsets,
+                          const double *b, double *x, double weight, int symmetric)
+{
+    const int nnz = rp[n];
+    int N = 4;
+    if (n > 0 && nnz / n > 20) N = 32;
+    if (num_colors > 0 && nnz / num_colors < 500000) N = 32;
+    for (int pass = 0; pass < (symmetric ? 2 : 1); pass++)
+        for (int cc = 0; cc < num_colors; cc++) {
+            const int c = pass == 0 ? cc : num_colors - 1 - cc;
+            for (int q = offsets[c]; q < offsets[c + 1]; q++) {
+                const int i = sorted_rows[q];
+                double lane[32], dia = 0.0;
+                for (int l = 0; l < 32; l++) lane[l] = 0.0;
+                int found = 0;
+                for (int k = rp[i]; k < rp[i + 1]; k++) {
+                    lane[(k - rp[i]) % N] = fma(-va[k], x[ci[k]], lane[(k - rp[i]) % N]);
+                    if (!found && ci[k] == i) { dia = va[k]; found = 1; }
+                }
+                double acc = butterfly(lane, N);       /* lane 0 of the shuffle-down tree holds the same association */
+                acc += b[i];
+                acc /= guard_d(dia);
+                x[i] = fma(weight, acc, x[i]);
+            }
+        }
+}
+
 /* smoother->solve(b, x, xIsZero) with max_iters = sweeps (Solver::solve loop without monitoring) */
 static void smooth(const orc_amg *a, orc_level *L, const double *b, double *x, int x_is_zero, int sweeps)
 {
+    if (a->smoother == 3) {
+        for (int it = 0; it < sweeps; it++) {
+            if (it == 0 && x_is_zero) memset(x, 0, sizeof(double) * (size_t)L->n);
+            orc_gs_sweep(L->n, L->rp, L->ci, L->va, L->num_colors, L->sorted_rows, L->color_offsets, b, x, a->omega, a->symmetric_gs);
+        }
+        return;
+    }
     if (a->smoother == 2) {
         for (int it = 0; it < sweeps; it++) {
             if (it == 0 && x_is_zero) memset(x, 0, sizeof(double) * (size_t)L->n);
@@ -780,6 +819,7 @@ static void vcycle_t(const orc_amg *a, int l, const double *b, double *x, int x_
 ORC_API void orc_amg_vcycle(const orc_amg *a, const double *b, double *x, int x_is_zero) { vcycle(a, 0, b, x, x_is_zero); }
 ORC_API void orc_amg_set_cycle(orc_amg *a, int type) { a->cycle = type; }
 ORC_API void orc_amg_set_cycle_iters(orc_amg *a, int iters) { a->cycle_iters = iters; }
+ORC_API void orc_amg_set_symmetric_gs(orc_amg *a, int sym) { a->symmetric_gs = sym; }
 ORC_API void orc_amg_set_error_scaling(orc_amg *a, int error_scaling, int scaling_smoother_steps, int reuse_scale)
 {
     a->error_scaling = error_scaling; a->scaling_smoother_steps = scaling_smoother_steps; a->reuse_scale = reuse_scale;

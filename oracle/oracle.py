@@ -149,7 +149,7 @@ class AMG:
         if coarse_solver == "DENSE_LU_SOLVER":
             min_coarse_rows = dense_lu_num_rows          # src/amg.cu:1154-1157
         self.n = self.rp.shape[0] - 1
-        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2}[smoother]
+        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2, "MULTICOLOR_GS": 3}[smoother]
         self.h = C.c_void_p(lib().orc_amg_setup(self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold),
                                                 presweeps, postsweeps, coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), max_iterations,
                                                 C.c_double(max_unassigned), merge_singletons, weight_formula))
@@ -158,6 +158,10 @@ class AMG:
 
     def set_cycle(self, name: str):
         lib().orc_amg_set_cycle(self.h, {"V": 0, "W": 1, "F": 2, "CG": 3, "CGF": 4}[name])
+        return self
+
+    def set_symmetric_gs(self, sym: bool = True):
+        lib().orc_amg_set_symmetric_gs(self.h, int(sym))
         return self
 
     def set_cycle_iters(self, iters: int):
@@ -266,6 +270,16 @@ def amg_level_dilu(amg: AMG, l: int):
     einv = np.empty(n)
     nc = lib().orc_amg_level_dilu(amg.h, l, _p(colors), _p(einv))
     return nc, colors, einv
+
+
+def gs_sweep(rp, ci, va, b, x, weight, symmetric=False, max_uncolored_fraction=0.0):
+    """one MULTICOLOR_GS sweep (colours from MIN_MAX); returns the new x"""
+    rp, ci, va, b = _i(rp), _i(ci), _d(va), _d(b)
+    n = rp.shape[0] - 1
+    nc, colors, srows, offs = color_min_max(rp, ci, max_uncolored_fraction)
+    x = _d(x).copy()
+    lib().orc_gs_sweep(n, _p(rp), _p(ci), _p(va), nc, _p(srows), _p(offs), _p(b), _p(x), C.c_double(weight), int(symmetric))
+    return x
 
 
 def color_min_max(rp, ci, max_uncolored_fraction=0.15):
@@ -382,7 +396,7 @@ class ClassicalAMG(AMG):
         if coarse_solver == "DENSE_LU_SOLVER":
             min_coarse_rows = dense_lu_num_rows
         self.n = self.rp.shape[0] - 1
-        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2}[smoother]
+        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2, "MULTICOLOR_GS": 3}[smoother]
         im = {"D2": 0, "MULTIPASS": 1}
         self.h = C.c_void_p(lib().orc_amg_setup_classical(
             self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold), presweeps, postsweeps,
