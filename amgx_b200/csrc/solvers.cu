@@ -673,6 +673,8 @@ std::unique_ptr<Solver> Solver::allocate(Config &cfg, const std::string &current
     else if (name == "JACOBI_L1") sv.reset(new JacobiL1Solver(cfg, new_scope, rsc));
     else if (name == "MULTICOLOR_DILU") sv = make_dilu_solver(cfg, new_scope, rsc);
     else if (name == "MULTICOLOR_GS") sv = make_gs_solver(cfg, new_scope, rsc);
+    else if (name == "CHEBYSHEV") sv = make_chebyshev_solver(cfg, new_scope, rsc);
+    else if (name == "CHEBYSHEV_POLY") sv = make_chebyshev_poly_solver(cfg, new_scope, rsc);
     else if (name == "CG") sv = make_cg_solver(cfg, new_scope, rsc);
     else if (name == "PCGF") sv = make_pcgf_solver(cfg, new_scope, rsc);
     else if (name == "PBICGSTAB") sv = make_pbicgstab_solver(cfg, new_scope, rsc);
@@ -681,7 +683,7 @@ std::unique_ptr<Solver> Solver::allocate(Config &cfg, const std::string &current
     else if (name == "NOSOLVER") sv.reset(new NoSolver(cfg, new_scope, rsc));
     else
         fatal(AMGX_RC_BAD_CONFIGURATION, "Solver '" + name + "' is outside the scope of the B200 solve-phase engine "
-              "(supported: PCG, PCGF, CG, PBICGSTAB, GMRES, FGMRES, AMG, BLOCK_JACOBI, JACOBI_L1, MULTICOLOR_DILU, MULTICOLOR_GS, DENSE_LU_SOLVER, NOSOLVER)");
+              "(supported: PCG, PCGF, CG, PBICGSTAB, GMRES, FGMRES, AMG, BLOCK_JACOBI, JACOBI_L1, MULTICOLOR_DILU, MULTICOLOR_GS, CHEBYSHEV, CHEBYSHEV_POLY, DENSE_LU_SOLVER, NOSOLVER)");
     sv->set_name(name);
     return sv;
 }

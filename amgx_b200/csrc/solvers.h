@@ -350,6 +350,8 @@ template <class F> void Solver::run_segment(GraphSegment &g, const void *k0, con
 std::unique_ptr<Solver> make_cg_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);         // krylov_extra.cu
 std::unique_ptr<Solver> make_pcgf_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);
 std::unique_ptr<Solver> make_pbicgstab_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);
+std::unique_ptr<Solver> make_chebyshev_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);     // cheby.cu
+std::unique_ptr<Solver> make_chebyshev_poly_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);
 std::unique_ptr<Solver> make_gs_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);            // gs.cu
 std::unique_ptr<Solver> make_gmres_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);
 std::unique_ptr<Solver> make_dense_lu_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc);   // dense_lu.cu

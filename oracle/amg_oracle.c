@@ -409,6 +409,8 @@ typedef struct {
     /* DENSE_LU_SOLVER on the coarsest level: column-major LU factors + pivots */
     double *lu;
     int *ipiv;
+    /* Chebyshev smoothers: spectrum bounds, work vectors, damped-root step lengths */
+    double lmax, lmin, *cheb_p, *cheb_z, *cheb_r, tau[10];
     /* error scaling: last computed scale and how many more corrections reuse it */
     double scale;
     int scale_counter;
@@ -419,6 +421,9 @@ typedef struct {
     orc_level *lv;
     int presweeps, postsweeps, coarsest_sweeps, finest_sweeps, smoother; /* smoother: 0 BLOCK_JACOBI, 1 JACOBI_L1, 2 MULTICOLOR_DILU, 3 MULTICOLOR_GS */
     int symmetric_gs;        /* MULTICOLOR_GS: symmetric_GS = 1 sweeps the colours up, then down */
+    /* smoother 4 CHEBYSHEV (src/solvers/cheb_solver.cu), 5 CHEBYSHEV_POLY (src/solvers/chebyshev_poly.cu) */
+    int cheb_order, cheb_mode, cheb_precond;   /* cheb_precond: 0 none, 1 BLOCK_JACOBI, 2 JACOBI_L1 (one zero-guess sweep, weight cheb_inner_omega) */
+    double cheb_inner_omega, cheb_user_max, cheb_user_min;
     double omega, uncolored_fraction;
     int dense_lu;            /* coarse_solver = DENSE_LU_SOLVER */
     int cycle;               /* 0 V, 1 W, 2 F, 3 CG, 4 CGF (src/cycles/{v,w,f,cg,cg_flex}_cycle.cu) */
@@ -438,11 +443,26 @@ ORC_API void orc_dilu_sweep_1x1(int n, const int *rp, const int *ci, const doubl
 static double g_uncolored_fraction = 0.15;
 ORC_API void orc_set_uncolored_fraction(double f) { g_uncolored_fraction = f; }
 
+static int g_cheb_precond = 0;       /* read by level_smoother_setup for smoother 4: which diagonal the inner Jacobi uses */
 static void level_smoother_setup(orc_level *L, int smoother)
 {
     L->d = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
-    if (smoother == 1) orc_l1_norms(L->n, L->rp, L->ci, L->va, L->d);
+    if (smoother == 1 || (smoother == 4 && g_cheb_precond == 2)) orc_l1_norms(L->n, L->rp, L->ci, L->va, L->d);
     else orc_extract_diag(L->n, L->rp, L->ci, L->va, L->d);
+    if (smoother == 4 || smoother == 5) {
+        const size_t nn = (size_t)(L->n > 0 ? L->n : 1);
+        L->cheb_p = (double *)calloc(nn, sizeof(double));
+        L->cheb_z = (double *)calloc(nn, sizeof(double));
+        L->cheb_r = (double *)calloc(nn, sizeof(double));
+        double lam = 0.0;                 /* getLambdaEstimate + max_element: max_i sum_j |a_ij| */
+        for (int i = 0; i < L->n; i++) {
+            double cur = 0.0;
+            for (int k = L->rp[i]; k < L->rp[i + 1]; k++) cur += fabs(L->va[k]);
+            if (cur > lam) lam = cur;
+        }
+        L->lmax = lam;                    /* the preconditioned variants are filled in by orc_amg_set_chebyshev */
+        L->lmin = lam * 0.125;
+    }
     if (smoother == 2 || smoother == 3) {
         const size_t nn = (size_t)(L->n > 0 ? L->n : 1);
         L->colors = (int *)malloc(sizeof(int) * nn);
@@ -696,6 +716,45 @@ ORC_API void orc_gs_sweep(int n, const int *rp, const int *ci, const double *va,
 /* smoother->solve(b, x, xIsZero) with max_iters = sweeps (Solver::solve loop without monitoring) */
 static void smooth(const orc_amg *a, orc_level *L, const double *b, double *x, int x_is_zero, int sweeps)
 {
+    if (a->smoother == 4) {
+        /* Chebyshev_Solver inside Solver::solve: r = b (x "is zero": x itself is NOT cleared, as in the reference) or b - A x;
+         * solve_init: z = M^-1 r, p = z; every iteration runs cheb_order steps (cheb_solver.cu:243-330) */
+        const int n = L->n;
+        double *p = L->cheb_p, *z = L->cheb_z, *r = L->cheb_r;
+        if (x_is_zero) memcpy(r, b, sizeof(double) * (size_t)n);
+        else orc_residual(n, L->rp, L->ci, L->va, x, b, r);
+#define CHEB_PRECOND() do { if (a->cheb_precond) orc_jacobi_zero(n, L->d, r, z, a->cheb_inner_omega); else memcpy(z, r, sizeof(double) * (size_t)n); } while (0)
+        CHEB_PRECOND();
+        memcpy(p, z, sizeof(double) * (size_t)n);
+        double gamma = 0., beta = 0.;
+        int first = 0;
+        const double ca = (L->lmax + L->lmin) / 2, cc = (L->lmax - L->lmin) / 2;
+        for (int it = 0; it < sweeps; it++)
+            for (int i = 0; i < a->cheb_order; i++) {
+                CHEB_PRECOND();
+                if (first == 0) { gamma = 1. / ca; first = 1; }
+                else {
+                    beta = cc * cc * gamma * gamma / 4.;
+                    if (gamma != 0.0 && (ca - (beta / gamma)) != 0.0) gamma = 1. / (ca - beta / gamma);
+                    for (int k = 0; k < n; k++) p[k] = z[k] * 1.0 + p[k] * beta;
+                }
+                for (int k = 0; k < n; k++) x[k] = fma(gamma, p[k], x[k]);
+                orc_residual(n, L->rp, L->ci, L->va, x, b, r);
+            }
+#undef CHEB_PRECOND
+        return;
+    }
+    if (a->smoother == 5) {
+        /* ChebyshevPolySolver::smooth_1x1 (chebyshev_poly.cu:288-312): x = x + tau_i (b - A x); x is read as it is */
+        const int n = L->n;
+        int order = a->cheb_order < 1 ? 1 : (a->cheb_order > 10 ? 10 : a->cheb_order);
+        for (int it = 0; it < sweeps; it++)
+            for (int i = 0; i < order; i++) {
+                orc_residual(n, L->rp, L->ci, L->va, x, b, L->cheb_r);
+                for (int k = 0; k < n; k++) x[k] = fma(L->tau[i], L->cheb_r[k], x[k]);
+            }
+        return;
+    }
     if (a->smoother == 3) {
         for (int it = 0; it < sweeps; it++) {
             if (it == 0 && x_is_zero) memset(x, 0, sizeof(double) * (size_t)L->n);
@@ -820,6 +879,29 @@ ORC_API void orc_amg_vcycle(const orc_amg *a, const double *b, double *x, int x_
 ORC_API void orc_amg_set_cycle(orc_amg *a, int type) { a->cycle = type; }
 ORC_API void orc_amg_set_cycle_iters(orc_amg *a, int iters) { a->cycle_iters = iters; }
 ORC_API void orc_amg_set_symmetric_gs(orc_amg *a, int sym) { a->symmetric_gs = sym; }
+/* call BEFORE the setup: which diagonal the inner Jacobi of smoother 4 uses (0 none / 1 a_ii / 2 L1 row norm) */
+ORC_API void orc_set_chebyshev_precond(int precond) { g_cheb_precond = precond; }
+/* call AFTER a setup with smoother 4 or 5: spectrum bounds per chebyshev_lambda_estimate_mode (cheb_solver.cu:186-213) and the
+ * damped-root step lengths of CHEBYSHEV_POLY (chebyshev_poly.cu:63-74, 199-208) */
+ORC_API void orc_amg_set_chebyshev(orc_amg *a, int order, int mode, int precond, double inner_omega, double user_max, double user_min)
+{
+    a->cheb_order = order; a->cheb_mode = mode; a->cheb_precond = precond; a->cheb_inner_omega = inner_omega;
+    a->cheb_user_max = user_max; a->cheb_user_min = user_min;
+    for (int l = 0; l < a->num_levels; l++) {
+        orc_level *L = &a->lv[l];
+        if (a->smoother == 4 && precond) {
+            if (mode == 2) { L->lmax = 0.9; L->lmin = L->lmax * 0.125; }
+            else { L->lmax = user_max; L->lmin = user_min; }
+        }
+        if (a->smoother == 5) {
+            const int m = order < 1 ? 1 : (order > 10 ? 10 : order);
+            const double lambda = L->lmax, beta = M_PI / (4 * (double)m + 2);
+            for (int i = 0; i < m; i++)
+                L->tau[i] = (cos(beta) * cos(beta) / (cos(beta * (2 * i + 1)) * cos(beta * (2 * i + 1)) - sin(beta) * sin(beta))) / lambda;
+        }
+    }
+}
+ORC_API void orc_amg_level_lambda(const orc_amg *a, int l, double *lmax, double *lmin) { *lmax = a->lv[l].lmax; *lmin = a->lv[l].lmin; }
 ORC_API void orc_amg_set_error_scaling(orc_amg *a, int error_scaling, int scaling_smoother_steps, int reuse_scale)
 {
     a->error_scaling = error_scaling; a->scaling_smoother_steps = scaling_smoother_steps; a->reuse_scale = reuse_scale;

@@ -139,6 +139,14 @@ def galerkin(rp, ci, va, agg, nagg):
     return rpc, cic, vac
 
 
+SMOOTHERS = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2, "MULTICOLOR_GS": 3, "CHEBYSHEV": 4, "CHEBYSHEV_POLY": 5}
+
+
+def set_chebyshev_precond(name):
+    """which inner Jacobi the CHEBYSHEV smoother of the NEXT setup uses: None, "BLOCK_JACOBI" or "JACOBI_L1"""
+    lib().orc_set_chebyshev_precond({None: 0, "BLOCK_JACOBI": 1, "JACOBI_L1": 2}[name])
+
+
 class AMG:
     """Aggregation hierarchy + V-cycle exactly as the reference composes them (unfused)."""
 
@@ -149,7 +157,7 @@ class AMG:
         if coarse_solver == "DENSE_LU_SOLVER":
             min_coarse_rows = dense_lu_num_rows          # src/amg.cu:1154-1157
         self.n = self.rp.shape[0] - 1
-        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2, "MULTICOLOR_GS": 3}[smoother]
+        sm = SMOOTHERS[smoother]
         self.h = C.c_void_p(lib().orc_amg_setup(self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold),
                                                 presweeps, postsweeps, coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), max_iterations,
                                                 C.c_double(max_unassigned), merge_singletons, weight_formula))
@@ -159,6 +167,17 @@ class AMG:
     def set_cycle(self, name: str):
         lib().orc_amg_set_cycle(self.h, {"V": 0, "W": 1, "F": 2, "CG": 3, "CGF": 4}[name])
         return self
+
+    def set_chebyshev(self, order=5, mode=2, precond=None, inner_omega=0.9, user_max=1.0, user_min=0.125):
+        """smoother CHEBYSHEV / CHEBYSHEV_POLY parameters; `precond` must match set_chebyshev_precond() at setup time"""
+        lib().orc_amg_set_chebyshev(self.h, order, mode, {None: 0, "BLOCK_JACOBI": 1, "JACOBI_L1": 2}[precond], C.c_double(inner_omega),
+                                    C.c_double(user_max), C.c_double(user_min))
+        return self
+
+    def level_lambda(self, l):
+        a, b = C.c_double(), C.c_double()
+        lib().orc_amg_level_lambda(self.h, l, C.byref(a), C.byref(b))
+        return a.value, b.value
 
     def set_symmetric_gs(self, sym: bool = True):
         lib().orc_amg_set_symmetric_gs(self.h, int(sym))
@@ -396,7 +415,7 @@ class ClassicalAMG(AMG):
         if coarse_solver == "DENSE_LU_SOLVER":
             min_coarse_rows = dense_lu_num_rows
         self.n = self.rp.shape[0] - 1
-        sm = {"BLOCK_JACOBI": 0, "JACOBI_L1": 1, "MULTICOLOR_DILU": 2, "MULTICOLOR_GS": 3}[smoother]
+        sm = SMOOTHERS[smoother]
         im = {"D2": 0, "MULTIPASS": 1}
         self.h = C.c_void_p(lib().orc_amg_setup_classical(
             self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold), presweeps, postsweeps,

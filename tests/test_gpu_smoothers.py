@@ -60,3 +60,69 @@ def test_amg_gs_matches_oracle(amgx, oracle, sym):
         oracle.set_uncolored_fraction(0.15)
     assert convo and status == "success" and it == ito
     assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+
+
+def _cheb_amg(precond, order, mode=2, coarsest=0, **extra):
+    sm = {"scope": "cheb", "solver": "CHEBYSHEV", "max_iters": 1, "chebyshev_polynomial_order": order, "chebyshev_lambda_estimate_mode": mode,
+          "monitor_residual": 0}
+    if precond:
+        sm["preconditioner"] = {"scope": "inner", "solver": precond, "max_iters": 1, "relaxation_factor": 0.9, "monitor_residual": 0}
+    else:
+        sm["preconditioner"] = {"scope": "inner", "solver": "NOSOLVER"}
+    sm.update(extra)
+    d = amg_agg_cfg(pre=0, post=1, error_scaling=3, coarsest_sweeps=coarsest)
+    d["smoother"] = sm
+    return d
+
+
+@pytest.mark.parametrize("precond,order,mode", [(None, 2, 2), ("JACOBI_L1", 4, 2), ("BLOCK_JACOBI", 3, 3)])
+def test_amg_chebyshev_matches_oracle(amgx, oracle, precond, order, mode):
+    rp, ci, va = gallery.poisson7pt(15, 13, 10)
+    n = rp.shape[0] - 1
+    b = np.ones(n)
+    amg = _cheb_amg(precond, order, mode, cheby_max_lambda=0.95, cheby_min_lambda=0.1)
+    x, it, status, hist = run_engine(amgx, outer_cfg("PCG", amg, tol=1e-9, max_iters=80), rp, ci, va, b)
+    oracle.set_chebyshev_precond(precond)
+    try:
+        o = oracle.AMG(rp, ci, va, max_levels=50, presweeps=0, postsweeps=1, coarsest_sweeps=0, smoother="CHEBYSHEV")
+    finally:
+        oracle.set_chebyshev_precond(None)
+    o.set_chebyshev(order=order, mode=mode, precond=precond, inner_omega=0.9, user_max=0.95, user_min=0.1).set_error_scaling(3)
+    xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, amg=o, tol=1e-9, max_iters=80)
+    assert convo and status == "success" and it == ito
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+
+
+def test_chebyshev_stale_x_on_the_coarsest_level_matches_oracle(amgx, oracle):
+    """coarsest_sweeps > 0 with a Chebyshev smoother: the reference (and therefore engine and oracle) adds to whatever xc holds"""
+    rp, ci, va = gallery.poisson7pt(10)
+    n = rp.shape[0] - 1
+    b = np.ones(n)
+    amg = _cheb_amg(None, 2, coarsest=1)
+    amg.update(scope="main", max_iters=6, monitor_residual=1, store_res_history=1, convergence="RELATIVE_INI", tolerance=1e-30, norm="L2")
+    x, it, status, hist = run_engine(amgx, {"config_version": 2, "determinism_flag": 1, "solver": amg}, rp, ci, va, b)
+    o = oracle.AMG(rp, ci, va, max_levels=50, presweeps=0, postsweeps=1, coarsest_sweeps=1, smoother="CHEBYSHEV")
+    o.set_chebyshev(order=2, mode=2).set_error_scaling(3)
+    xo, ito, histo, convo = oracle.amg_solve(o, b, tol=1e-30, max_iters=6)
+    assert it == ito == 6
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_amg_chebyshev_poly_matches_oracle(amgx, oracle, order):
+    rp, ci, va = gallery.poisson7pt(14, 12, 11)
+    n = rp.shape[0] - 1
+    b = np.ones(n)
+    amg = amg_agg_cfg(pre=0, post=3, coarsest_sweeps=0)
+    amg["smoother"] = {"scope": "cp", "solver": "CHEBYSHEV_POLY", "chebyshev_polynomial_order": order, "max_iters": 1, "monitor_residual": 0}
+    x, it, status, hist = run_engine(amgx, outer_cfg("PCG", amg, tol=1e-9, max_iters=80), rp, ci, va, b)
+    o = oracle.AMG(rp, ci, va, max_levels=50, presweeps=0, postsweeps=3, coarsest_sweeps=0, smoother="CHEBYSHEV_POLY").set_chebyshev(order=order)
+    xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, amg=o, tol=1e-9, max_iters=80)
+    assert convo and status == "success" and it == ito
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+
+
+def test_chebyshev_eigensolver_modes_fail_loudly(amgx):
+    rp, ci, va = gallery.poisson7pt(5)
+    with pytest.raises(Exception):
+        run_engine(amgx, outer_cfg("PCG", _cheb_amg(None, 2, mode=0)), rp, ci, va, np.ones(125))
