@@ -369,6 +369,9 @@ class Solver:
     def setup(self, A: Matrix):
         _ck(self.lib.AMGX_solver_setup(self.h, A.h), "AMGX_solver_setup")
 
+    def resetup(self, A: Matrix):
+        _ck(self.lib.AMGX_solver_resetup(self.h, A.h), "AMGX_solver_resetup")
+
     def solve(self, b: Vector, x: Vector, zero_initial_guess: bool = False):
         f = self.lib.AMGX_solver_solve_with_0_initial_guess if zero_initial_guess else self.lib.AMGX_solver_solve
         _ck(f(self.h, b.h, x.h), "AMGX_solver_solve")

@@ -62,7 +62,23 @@ std::unique_ptr<Solver> AMGSolver::make_smoother() { return Solver::allocate(*cf
 
 void AMGSolver::solver_setup(bool reuse)
 {
-    (void)reuse;
+    // AMGX_solver_resetup with structure_reuse_levels = k: the aggregates (hence R and P) of the first k-1 coarsenings are
+    // kept and only the Galerkin values, the smoothers and everything below are recomputed (src/amg.cu:229-272: a level is
+    // rebuilt when structure_reuse_levels <= its 1-based index; -1 keeps the structure of every level).
+    reuse_aggregates_.clear();
+    reuse_n_coarse_.clear();
+    const int reuse_levels = cfg_->get_int("structure_reuse_levels", scope_);
+    if (reuse && reuse_levels != 0 && algorithm_ == "AGGREGATION" && !levels_.empty() && !A_->dist) {
+        for (size_t l = 0; l + 1 < levels_.size(); l++) {
+            if (reuse_levels != -1 && reuse_levels <= (int)l + 1) break;
+            if (levels_[l]->n_coarse <= 0 || (l == 0 && levels_[0]->A->n != A_->n)) break;
+            reuse_aggregates_.emplace_back();
+            reuse_aggregates_.back().swap(levels_[l]->aggregates);
+            reuse_n_coarse_.push_back(levels_[l]->n_coarse);
+        }
+    } else if (reuse && reuse_levels != 0 && algorithm_ != "AGGREGATION") {
+        amgx_printf("Warning: structure_reuse_levels is honoured for AGGREGATION hierarchies only; the classical hierarchy is rebuilt\n");
+    }
     levels_.clear();
     if (dense_lu_num_rows_ > 0) min_coarse_rows_ = dense_lu_num_rows_ / A_->by;   // src/amg.cu:1154-1157
     if (algorithm_ == "AGGREGATION") setup_aggregation();
@@ -103,7 +119,14 @@ void AMGSolver::setup_aggregation()
             break;
         }
         // createCoarseVertices
-        const int n_agg = size2_select(A, prm, L.aggregates, s);
+        int n_agg;
+        const size_t li = (size_t)num_levels - 1;
+        if (li < reuse_aggregates_.size() && (int)reuse_aggregates_[li].size() >= rows) {
+            L.aggregates.swap(reuse_aggregates_[li]);       // structure reuse: keep the previous setup's aggregates
+            n_agg = reuse_n_coarse_[li];
+        } else {
+            n_agg = size2_select(A, prm, L.aggregates, s);
+        }
         L.n_coarse = n_agg;
         const long long N = dist_allreduce_ll(A, rows, 0) * A.by, nextN = dist_allreduce_ll(A, n_agg, 0) * A.by;
         const long long min_part_next = dist_allreduce_ll(A, n_agg, 1);

@@ -724,7 +724,7 @@ static AMGX_RC solver_setup_impl(AMGX_solver_handle slv, AMGX_matrix_handle mtx,
 }
 
 AMGX_RC AMGX_solver_setup(AMGX_solver_handle slv, AMGX_matrix_handle mtx) { return solver_setup_impl(slv, mtx, false); }
-AMGX_RC AMGX_solver_resetup(AMGX_solver_handle slv, AMGX_matrix_handle mtx) { return solver_setup_impl(slv, mtx, false); }
+AMGX_RC AMGX_solver_resetup(AMGX_solver_handle slv, AMGX_matrix_handle mtx) { return solver_setup_impl(slv, mtx, true); }
 
 static AMGX_RC solver_solve_impl(AMGX_solver_handle slv, AMGX_vector_handle rhs, AMGX_vector_handle sol, bool xIsZero)
 {

@@ -288,6 +288,8 @@ protected:
     double host_dot(const DevVec &x, const DevVec &y, size_t n);
     int cycle_iters_ = 2, scaling_smoother_steps_ = 2, reuse_scale_ = 0;
     GraphInhibit inhibit_;
+    std::vector<DevBuf<int>> reuse_aggregates_;     // resetup with structure_reuse_levels: aggregates carried over, per level
+    std::vector<int> reuse_n_coarse_;
     void cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse, int type = -1);   // type -1: the configured cycle
     int cycle_type_ = CYC_V;
     void setup_aggregation();

@@ -477,6 +477,12 @@ static void level_smoother_setup(orc_level *L, int smoother)
     }
 }
 
+/* AMGX_solver_resetup with structure_reuse_levels: the NEXT orc_amg_setup takes the aggregates of `from` for every coarsening
+ * whose 1-based level index is < reuse_levels (all of them for -1), src/amg.cu:229-272; cleared by that setup. */
+static const orc_amg *g_reuse_from = NULL;
+static int g_reuse_levels = 0;
+ORC_API void orc_amg_reuse_structure(const orc_amg *from, int reuse_levels) { g_reuse_from = from; g_reuse_levels = reuse_levels; }
+
 ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double *va, int max_levels, int min_coarse_rows, double coarsen_threshold,
                                int presweeps, int postsweeps, int coarsest_sweeps, int finest_sweeps, int smoother, double omega,
                                int max_iterations, double max_unassigned, int merge_singletons, int weight_formula)
@@ -496,7 +502,15 @@ ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double
         L->tmp = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
         if (num_levels >= max_levels || L->n <= min_coarse_rows) { L->coarsest = 1; break; }
         L->agg = (int *)malloc(sizeof(int) * (size_t)L->n);
-        int nagg = orc_size2_aggregates(L->n, L->rp, L->ci, L->va, max_iterations, max_unassigned, merge_singletons, weight_formula, L->agg);
+        int nagg;
+        if (g_reuse_from && g_reuse_levels != 0 && (g_reuse_levels == -1 || g_reuse_levels > num_levels) && num_levels < g_reuse_from->num_levels &&
+            g_reuse_from->lv[num_levels - 1].agg && g_reuse_from->lv[num_levels - 1].n == L->n) {
+            memcpy(L->agg, g_reuse_from->lv[num_levels - 1].agg, sizeof(int) * (size_t)L->n);
+            nagg = g_reuse_from->lv[num_levels - 1].nagg;
+        } else {
+            g_reuse_levels = 0;   /* the chain of reused levels ends at the first rebuilt one */
+            nagg = orc_size2_aggregates(L->n, L->rp, L->ci, L->va, max_iterations, max_unassigned, merge_singletons, weight_formula, L->agg);
+        }
         if ((double)nagg <= coarsen_threshold * (double)L->n && nagg != L->n && nagg >= min_coarse_rows) {
             L->nagg = nagg;
             L->Rp = (int *)malloc(sizeof(int) * ((size_t)nagg + 1));
@@ -520,6 +534,7 @@ ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double
         }
     }
     a->num_levels = num_levels;
+    g_reuse_from = NULL; g_reuse_levels = 0;
     return a;
 }
 

@@ -152,8 +152,10 @@ class AMG:
 
     def __init__(self, rp, ci, va, max_levels=100, min_coarse_rows=2, coarsen_threshold=1.0, presweeps=1, postsweeps=1, coarsest_sweeps=2,
                  finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, max_iterations=15, max_unassigned=0.05, merge_singletons=1, weight_formula=0,
-                 coarse_solver="NOSOLVER", dense_lu_num_rows=128):
+                 coarse_solver="NOSOLVER", dense_lu_num_rows=128, reuse_from=None, structure_reuse_levels=0):
         self.rp, self.ci, self.va = _i(rp), _i(ci), _d(va)
+        if reuse_from is not None:                       # AMGX_solver_resetup with structure_reuse_levels
+            lib().orc_amg_reuse_structure(reuse_from.h, structure_reuse_levels)
         if coarse_solver == "DENSE_LU_SOLVER":
             min_coarse_rows = dense_lu_num_rows          # src/amg.cu:1154-1157
         self.n = self.rp.shape[0] - 1

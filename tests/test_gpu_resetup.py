@@ -1,0 +1,52 @@
+"""GPU: AMGX_matrix_replace_coefficients + AMGX_solver_resetup with structure_reuse_levels (aggregation hierarchies) against the CPU
+restatement.  Written after this round's GPU minutes were spent: opt-in until validated on a device."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from amgx_b200 import gallery
+from tests._gpu_util import UNVALIDATED, amg_agg_cfg, outer_cfg
+
+pytestmark = [pytest.mark.gpu, UNVALIDATED]
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, -1])
+def test_resetup_structure_reuse_matches_oracle(amgx, oracle, k):
+    rp, ci, va = gallery.poisson7pt(12, 10, 9)
+    n = rp.shape[0] - 1
+    A = gallery.to_scipy(rp, ci, va)
+    A.sort_indices()
+    D = 1.0 + 3.0 * np.random.default_rng(9).random(n)
+    B = (sp.diags(D) @ A @ sp.diags(D)).tocsr()
+    B.sort_indices()
+    rp, ci, va, vb = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy(), B.data.copy()
+    b = np.ones(n)
+    cfg = amgx.Config(outer_cfg("PCG", amg_agg_cfg(structure_reuse_levels=k), tol=1e-9, max_iters=80))
+    rsc = amgx.Resources(cfg)
+    M = amgx.Matrix(rsc).upload(rp, ci, va)
+    bv = amgx.Vector(rsc).upload(b)
+    xv = amgx.Vector(rsc).set_zero(n)
+    slv = amgx.Solver(rsc, cfg)
+    try:
+        slv.setup(M)
+        slv.solve(bv, xv, zero_initial_guess=True)
+        kw = dict(max_levels=50, presweeps=1, postsweeps=1, omega=0.8)
+        first = oracle.AMG(rp, ci, va, **kw)
+        xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, amg=first, tol=1e-9, max_iters=80)
+        assert slv.iterations_number == ito
+        M.replace_coefficients(vb)
+        slv.resetup(M)
+        xv.set_zero(n)
+        slv.solve(bv, xv, zero_initial_guess=True)
+        re = oracle.AMG(rp, ci, vb, reuse_from=first, structure_reuse_levels=k, **kw)
+        xo, ito, histo, convo = oracle.pcg(rp, ci, vb, b, amg=re, tol=1e-9, max_iters=80)
+        assert slv.num_levels() == re.num_levels()
+        for l in range(re.num_levels() - 1):
+            agg, _, _ = slv.level_aggregates(l)
+            assert np.array_equal(agg, re.level(l)["aggregates"]), f"aggregates differ on level {l}"
+        hist = np.array(slv.residual_history()).ravel()
+        assert convo and slv.status == "success" and slv.iterations_number == ito
+        assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+    finally:
+        for obj in (slv, xv, bv, M, rsc, cfg):
+            obj.destroy()

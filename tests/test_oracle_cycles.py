@@ -197,3 +197,43 @@ def test_cg_cycles_and_error_scaling_accelerate_pcg(oracle):
         assert conv
         its[name] = it
     assert its["CG"] < its["V"] and its["CGF"] < its["V"] and its["ES3"] < its["V"]
+
+
+def test_structure_reuse_keeps_aggregates_and_recomputes_values(oracle):
+    """resetup with structure_reuse_levels = k: coarsenings 1 .. k-1 keep their aggregates, the Galerkin values follow the new matrix"""
+    rp, ci, va = gallery.poisson7pt(10, 9, 8)
+    n = rp.shape[0] - 1
+    rng = np.random.default_rng(9)
+    A = gallery.to_scipy(rp, ci, va)
+    # a symmetric positive perturbation of the coefficients that changes the strongest-neighbour choices of SIZE_2
+    D = 1.0 + 3.0 * rng.random(n)
+    import scipy.sparse as sp
+    B = (sp.diags(D) @ A @ sp.diags(D)).tocsr()
+    B.sort_indices()
+    A.sort_indices()
+    assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+    rp, ci, va, vb = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy(), B.data.copy()
+    kw = dict(max_levels=50, presweeps=1, postsweeps=1, omega=0.8)
+    first = oracle.AMG(rp, ci, va, **kw)
+    fresh = oracle.AMG(rp, ci, vb, **kw)
+    assert not np.array_equal(first.level(0)["aggregates"], fresh.level(0)["aggregates"])
+    for k in (0, 1, 2, 3, -1):
+        re = oracle.AMG(rp, ci, vb, reuse_from=first, structure_reuse_levels=k, **kw)
+        kept = re.num_levels() - 1 if k == -1 else max(0, min(k - 1, re.num_levels() - 1))
+        for l in range(kept):
+            assert np.array_equal(re.level(l)["aggregates"], first.level(l)["aggregates"])
+            # values are the Galerkin product of the NEW fine matrix with the OLD aggregates
+            Ll, Ln = re.level(l), re.level(l + 1)
+            Al = gallery.to_scipy(Ll["row_ptr"], Ll["col_idx"], Ll["values"])
+            P = sp.csr_matrix((np.ones(Ll["n"]), (np.arange(Ll["n"]), Ll["aggregates"])), shape=(Ll["n"], Ll["n_coarse"]))
+            Ac = (P.T @ Al @ P).toarray()
+            got = gallery.to_scipy(Ln["row_ptr"], Ln["col_idx"], Ln["values"]).toarray()
+            assert np.allclose(got, Ac, rtol=1e-13, atol=1e-13)
+        if kept == 0:
+            assert np.array_equal(re.level(0)["aggregates"], fresh.level(0)["aggregates"])
+        elif kept < re.num_levels() - 1:
+            # the first rebuilt coarsening is SIZE_2 on the (new) matrix of that level, not the old aggregates
+            ref = oracle.size2_aggregates(re.level(kept)["row_ptr"], re.level(kept)["col_idx"], re.level(kept)["values"])[0]
+            assert np.array_equal(re.level(kept)["aggregates"], ref)
+        x, it, hist, conv = oracle.pcg(rp, ci, vb, np.ones(n), amg=re, tol=1e-8, max_iters=100)
+        assert conv
