@@ -1,0 +1,97 @@
+"""Case list for the components written after round 1 ran out of GPU minutes (no reference golden yet).  One definition drives
+three runs: the reference (make_golden.py -> tests/golden/r2_<name>.npz), the CPU oracle (tests/oracle_from_config.py) and the
+engine (tests/test_golden_round2.py).  Configs are in the reference's JSON format."""
+from __future__ import annotations
+
+import numpy as np
+
+from amgx_b200 import gallery
+
+
+def _outer(solver, precond, tol=1e-9, max_iters=80, **extra):
+    s = {"scope": "main", "solver": solver, "max_iters": max_iters, "monitor_residual": 1, "store_res_history": 1, "convergence": "RELATIVE_INI",
+         "tolerance": tol, "norm": "L2", "preconditioner": precond}
+    s.update(extra)
+    return {"config_version": 2, "determinism_flag": 1, "solver": s}
+
+
+def _agg(smoother=None, **extra):
+    d = {"scope": "amg", "solver": "AMG", "algorithm": "AGGREGATION", "selector": "SIZE_2", "cycle": "V", "max_levels": 50, "presweeps": 1,
+         "postsweeps": 1, "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER", "max_iters": 1, "monitor_residual": 0, "print_grid_stats": 1,
+         "smoother": smoother or {"scope": "jac", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "monitor_residual": 0}}
+    d.update(extra)
+    return d
+
+
+def _standalone(amg, tol=1e-8, max_iters=60):
+    a = dict(amg)
+    a.update(scope="main", max_iters=max_iters, monitor_residual=1, store_res_history=1, convergence="RELATIVE_INI", tolerance=tol, norm="L2")
+    return {"config_version": 2, "determinism_flag": 1, "solver": a}
+
+
+NOP = {"scope": "nop", "solver": "NOSOLVER"}
+JAC = {"scope": "pj", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "max_iters": 1, "monitor_residual": 0}
+GS = lambda sym: {"scope": "gs", "solver": "MULTICOLOR_GS", "relaxation_factor": 0.9, "symmetric_GS": sym, "matrix_coloring_scheme": "MIN_MAX",
+                  "monitor_residual": 0}
+CHEB = lambda inner, order, mode=2, **kw: dict({"scope": "cheb", "solver": "CHEBYSHEV", "max_iters": 1, "monitor_residual": 0,
+                                               "chebyshev_polynomial_order": order, "chebyshev_lambda_estimate_mode": mode,
+                                               "preconditioner": ({"scope": "inner", "solver": inner, "max_iters": 1, "relaxation_factor": 0.9,
+                                                                   "monitor_residual": 0} if inner else {"scope": "inner", "solver": "NOSOLVER"})}, **kw)
+CHEBP = lambda order: {"scope": "cp", "solver": "CHEBYSHEV_POLY", "max_iters": 1, "monitor_residual": 0, "chebyshev_polynomial_order": order}
+
+
+def sym_banded(n, sigma):
+    import scipy.sparse as sp  # noqa: F401
+    rp, ci, va = gallery.random_banded(n, sigma=sigma)
+    A = gallery.to_scipy(rp, ci, va)
+    A = (A + A.T).tocsr()
+    A.sort_indices()
+    return A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+
+
+def cases():
+    """yields (name, (row_ptr, col_idx, values), config dict)"""
+    P = lambda *g: gallery.poisson7pt(*g)
+    # Krylov drivers
+    for kind in ("CG", "PCGF", "PBICGSTAB", "GMRES"):
+        extra = {"gmres_n_restart": 7} if kind == "GMRES" else {}
+        yield f"poisson12_{kind.lower()}_noprec", P(12), _outer(kind, NOP, max_iters=150, **extra)
+        if kind != "CG":
+            yield f"poisson12_{kind.lower()}_jacobi", P(12), _outer(kind, JAC, max_iters=150, **extra)
+            yield f"poisson14x11x9_{kind.lower()}_agg", P(14, 11, 9), _outer(kind, _agg(), **extra)
+    yield "banded3000_pbicgstab_agg", gallery.random_banded(3000, sigma=40.0), _outer("PBICGSTAB", _agg())
+    yield "banded3000_gmres_agg", gallery.random_banded(3000, sigma=40.0), _outer("GMRES", _agg(), gmres_n_restart=10)
+    yield "poisson9_gmres_one_iteration", P(9), _outer("GMRES", JAC, max_iters=1)
+    # cycles
+    for cyc in ("W", "F"):
+        yield f"poisson16_pcg_agg_{cyc}", P(16), _outer("PCG", _agg(cycle=cyc))
+    yield "poisson15x12x10_pcgf_agg_CG", P(15, 12, 10), _outer("PCGF", _agg(cycle="CG"))
+    yield "poisson15x12x10_pcgf_agg_CGF", P(15, 12, 10), _outer("PCGF", _agg(cycle="CGF"))
+    yield "poisson12_fgmres_agg_CG3", P(12), _outer("FGMRES", _agg(cycle="CG", cycle_iters=3), gmres_n_restart=10)
+    yield "poisson12_amg_classical_CG", P(12), _standalone(
+        {"solver": "AMG", "algorithm": "CLASSICAL", "selector": "PMIS", "interpolator": "D2", "cycle": "CG", "max_levels": 50, "presweeps": 1,
+         "postsweeps": 1, "coarse_solver": "NOSOLVER", "print_grid_stats": 1,
+         "smoother": {"scope": "jac", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "monitor_residual": 0}})
+    # error scaling
+    for es, steps, reuse in ((2, 2, 0), (3, 2, 0), (3, 0, 0), (3, 2, 2)):
+        yield f"poisson16x13x9_pcg_agg_es{es}_s{steps}_r{reuse}", P(16, 13, 9), _outer(
+            "PCG", _agg(error_scaling=es, scaling_smoother_steps=steps, reuse_scale=reuse))
+    yield "poisson12_amg_agg_es3_pre0", P(12), _standalone(_agg(presweeps=0, postsweeps=2, error_scaling=3))
+    # smoothers
+    for sym in (0, 1):
+        yield f"poisson16x14x11_amg_gs_sym{sym}", P(16, 14, 11), _standalone(_agg(GS(sym), matrix_coloring_scheme="MIN_MAX"))
+    yield "symbanded3000_fgmres_agg_gs", sym_banded(3000, 40.0), _outer("FGMRES", _agg(GS(0), matrix_coloring_scheme="MIN_MAX"), gmres_n_restart=20)
+    yield "poisson15x13x10_pcg_agg_cheb2", P(15, 13, 10), _outer("PCG", _agg(CHEB(None, 2), presweeps=0, coarsest_sweeps=0, error_scaling=3))
+    yield "poisson15x13x10_pcg_agg_cheb4_l1", P(15, 13, 10), _outer("PCG", _agg(CHEB("JACOBI_L1", 4), presweeps=0, coarsest_sweeps=0, error_scaling=3))
+    yield "poisson15x13x10_pcg_agg_cheb3_user", P(15, 13, 10), _outer(
+        "PCG", _agg(CHEB("BLOCK_JACOBI", 3, 3, cheby_max_lambda=1.85, cheby_min_lambda=0.2), presweeps=0, coarsest_sweeps=0, error_scaling=3))
+    yield "poisson10_amg_agg_cheb2_coarsest1", P(10), _standalone(_agg(CHEB(None, 2), presweeps=0, coarsest_sweeps=1, error_scaling=3), tol=1e-30, max_iters=6)
+    for order in (2, 4):
+        yield f"poisson14x12x11_pcg_agg_chebpoly{order}", P(14, 12, 11), _outer("PCG", _agg(CHEBP(order), presweeps=0, postsweeps=3, coarsest_sweeps=0))
+    # dense LU coarse solver
+    for rows in (32, 128):
+        yield f"poisson12_pcg_agg_denselu{rows}", P(12), _outer("PCG", _agg(coarse_solver="DENSE_LU_SOLVER", dense_lu_num_rows=rows))
+
+
+def case_dict():
+    return {name: (mat, cfg) for name, mat, cfg in cases()}

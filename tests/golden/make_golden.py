@@ -1,6 +1,7 @@
 """Generate golden vectors by running the UNMODIFIED reference on a B200 (gpurun):
 
-    gpurun -- 'python tests/golden/make_golden.py'
+    gpurun -- 'python tests/golden/make_golden.py'          # everything
+    gpurun -- 'python tests/golden/make_golden.py r2'       # only the round-2 cases (tests/golden/cases_round2.py)
 
 For every case it writes the system, runs oracle/_ref/ref_dump (reference's own C API + a dump of its
 internal hierarchy) with a JSON config in the reference's format, and stores a compressed fixture in
@@ -115,10 +116,20 @@ def cases():
     yield "banded3000_fgmres_classical_d2_trunc", gallery.random_banded(3000, sigma=40.0), cfg_fgmres_classical(aggressive_levels=0, max_iters=40), (1, "dDDI", "0.25,0.9,4")
 
 
+def all_cases():
+    yield from cases()
+    # components written after round 1's GPU minutes were spent: same definitions the oracle / engine tests use
+    from tests.golden.cases_round2 import cases as cases_r2
+    for name, mat, cfg in cases_r2():
+        yield "r2_" + name, mat, cfg, None
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     only = sys.argv[1:] or None
-    for name, (rp, ci, va), cfg, extra in cases():
+    if only == ["r2"]:
+        only = ["r2_" + n for n, _, _ in __import__("tests.golden.cases_round2", fromlist=["cases"]).cases()]
+    for name, (rp, ci, va), cfg, extra in all_cases():
         if only and name not in only:
             continue
         bs, mode = (extra[0], extra[1]) if extra else (1, "dDDI")
