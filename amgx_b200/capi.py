@@ -131,6 +131,7 @@ def _declare(lib):
         "AMGXB200_solver_get_last_solve_stats": [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
         "AMGXB200_bench_kernel": [vp, i, i, i, i, C.POINTER(C.c_double)],
         "AMGXB200_partition_plan_create": [C.POINTER(PartitionPlan), i, i, vp, i, i, vp, vp],
+        "AMGXB200_partition_vector_to_contiguous": [i, i, vp, vp, vp],
     }
     for name, args in sig.items():
         f = getattr(lib, name)

@@ -207,6 +207,15 @@ AMGX_RC AMGXB200_partition_plan_create(AMGXB200_partition_plan *plan, int rank, 
     API3_END
 }
 
+AMGX_RC AMGXB200_partition_vector_to_contiguous(int n_global, int world_size, const int *partition_vector, int64_t *offsets, int64_t *new_global)
+{
+    API3_BEGIN
+    if (!partition_vector || !offsets || n_global < 0 || world_size < 1) fatal(AMGX_RC_BAD_PARAMETERS, "partition_vector_to_contiguous: bad arguments");
+    if (!partition_vector_to_contiguous(n_global, world_size, partition_vector, offsets, new_global))
+        fatal(AMGX_RC_BAD_PARAMETERS, "partition vector names a rank outside [0, world_size)");
+    API3_END
+}
+
 void AMGXB200_partition_plan_free(AMGXB200_partition_plan *plan)
 {
     if (!plan) return;

@@ -354,7 +354,7 @@ void dist_upload_global(Matrix &A, int n_global, int n, int nnz, int bx, int by,
                         const void *data, const void *diag_data, int partition_info, const void *partition_data)
 {
     const int world = A.rsc->world, rank = A.rsc->rank;
-    std::vector<int64_t> offsets(world + 1, 0);
+    std::vector<int64_t> offsets(world + 1, 0), new_global;   // new_global: non-contiguous partition vector -> contiguous ids
     if (partition_info == AMGX_DIST_PARTITION_OFFSETS) {
         if (!partition_data) fatal(AMGX_RC_BAD_PARAMETERS, "partition offsets missing");
         for (int r = 0; r <= world; r++) offsets[r] = cols32 ? (int64_t)((const int *)partition_data)[r] : ((const int64_t *)partition_data)[r];
@@ -364,14 +364,15 @@ void dist_upload_global(Matrix &A, int n_global, int n, int nnz, int bx, int by,
             // default of the reference: equal contiguous blocks
             for (int r = 0; r <= world; r++) offsets[r] = (int64_t)n_global * r / world;
         } else {
+            // any partition vector: rank r's rows are renumbered to [offsets[r], offsets[r+1]) in increasing global id, the
+            // reference's ipartition_map (loadDistributedMatrixPartitionVec); callers pass their rows in that order
             const int *pv = (const int *)partition_data;
-            std::vector<int64_t> cnt(world, 0);
-            for (int g = 0; g < n_global; g++) {
-                if (pv[g] < 0 || pv[g] >= world || (g > 0 && pv[g] < pv[g - 1]))
-                    fatal(AMGX_RC_NOT_IMPLEMENTED, "only contiguous, rank-ordered partition vectors are supported by this engine");
-                cnt[pv[g]]++;
-            }
-            for (int r = 0; r < world; r++) offsets[r + 1] = offsets[r] + cnt[r];
+            new_global.resize((size_t)std::max(n_global, 1));
+            if (!partition_vector_to_contiguous(n_global, world, pv, offsets.data(), new_global.data()))
+                fatal(AMGX_RC_BAD_PARAMETERS, "partition vector names a rank outside [0, number of ranks)");
+            bool identity = true;
+            for (int g = 0; g < n_global && identity; g++) identity = (new_global[g] == g);
+            if (identity) new_global.clear();
         }
     }
     if (offsets[world] != n_global || offsets[rank + 1] - offsets[rank] != n) fatal(AMGX_RC_BAD_PARAMETERS, "partition does not match n / n_global");
@@ -385,6 +386,11 @@ void dist_upload_global(Matrix &A, int n_global, int n, int nnz, int bx, int by,
         if (nnz) AMGXB_CUDA_CHECK(cudaMemcpy(c32.data(), cols_global, sizeof(int) * nnz, cudaMemcpyDefault));
         for (int k = 0; k < nnz; k++) cols[k] = c32[k];
     } else if (nnz) AMGXB_CUDA_CHECK(cudaMemcpy(cols.data(), cols_global, sizeof(int64_t) * nnz, cudaMemcpyDefault));
+    if (!new_global.empty())
+        for (int k = 0; k < nnz; k++) {
+            if (cols[k] < 0 || cols[k] >= n_global) fatal(AMGX_RC_BAD_PARAMETERS, "global column index out of range");
+            cols[k] = new_global[cols[k]];
+        }
     std::vector<char> vals(std::max<size_t>((size_t)nnz * bs * msz, 1));
     if (nnz) AMGXB_CUDA_CHECK(cudaMemcpy(vals.data(), data, (size_t)nnz * bs * msz, cudaMemcpyDefault));
     if (world == 1) {

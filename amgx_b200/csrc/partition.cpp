@@ -111,4 +111,23 @@ void partition_plan_create(AMGXB200_partition_plan *plan, int rank, int world, c
     plan->local_cols = dup(local_cols);
 }
 
+// Arbitrary partition vector -> contiguous partition (DistributedManager::loadDistributedMatrixPartitionVec,
+// src/distributed/distributed_manager.cu:1133-1203): rank r's rows become global ids [offsets[r], offsets[r+1]) in increasing
+// order of their original global id; new_global[g] = offsets[pv[g]] + #{g' < g : pv[g'] == pv[g]} (the reference's
+// ipartition_map).  offsets has world+1 entries, new_global n_global.  Returns false on an out-of-range rank id.
+bool partition_vector_to_contiguous(int n_global, int world, const int *pv, int64_t *offsets, int64_t *new_global)
+{
+    std::vector<int64_t> cnt((size_t)world + 1, 0);
+    for (int g = 0; g < n_global; g++) {
+        if (pv[g] < 0 || pv[g] >= world) return false;
+        cnt[(size_t)pv[g] + 1]++;
+    }
+    for (int r = 0; r < world; r++) cnt[r + 1] += cnt[r];
+    for (int r = 0; r <= world; r++) offsets[r] = cnt[r];
+    std::vector<int64_t> next(cnt.begin(), cnt.end() - 1);
+    if (new_global)
+        for (int g = 0; g < n_global; g++) new_global[g] = next[pv[g]]++;
+    return true;
+}
+
 }  // namespace amgxb

@@ -218,6 +218,10 @@ typedef struct {
 AMGX_RC AMGX_API AMGXB200_partition_plan_create(AMGXB200_partition_plan *plan, int rank, int world_size, const int64_t *offsets,
                                                 int n, int nnz, const int *row_ptrs, const int64_t *col_indices_global);
 void    AMGX_API AMGXB200_partition_plan_free(AMGXB200_partition_plan *plan);
+/* Arbitrary partition vector (AMGX_DIST_PARTITION_VECTOR, include/amgx_c.h:241-259) -> the contiguous numbering the engine works
+ * in, exactly the reference's ipartition_map (src/distributed/distributed_manager.cu:1175-1203): offsets[world_size+1],
+ * new_global[n_global] (may be NULL).  Pure host code. */
+AMGX_RC AMGX_API AMGXB200_partition_vector_to_contiguous(int n_global, int world_size, const int *partition_vector, int64_t *offsets, int64_t *new_global);
 
 #if defined(__cplusplus)
 }

@@ -25,12 +25,14 @@ def main():
     nz = nzl * world
     rp, ci, va = gallery.poisson7pt(nx, ny, nz)
     n_global = rp.shape[0] - 1
+    lib = capi.load_library()
+    if os.environ.get("AMGXB_TEST_PARTITION") == "vector":
+        return partition_vector_case(lib, rank, world, rp, ci, va)
     offsets = np.array([nx * ny * nzl * r for r in range(world + 1)], np.int64)
     lo, hi = int(offsets[rank]), int(offsets[rank + 1])
     lrp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
     lci = ci[rp[lo]:rp[hi]].astype(np.int64)
     lva = va[rp[lo]:rp[hi]]
-    lib = capi.load_library()
     plan = capi.PartitionPlan()
     rc = lib.AMGXB200_partition_plan_create(C.byref(plan), rank, world, offsets.ctypes.data, hi - lo, lci.shape[0], lrp.ctypes.data, lci.ctypes.data)
     assert rc == 0, rc
@@ -81,6 +83,74 @@ def main():
     t = torch.tensor([float(np.dot(y, y))], dtype=torch.float64)
     dist.all_reduce(t)
     assert abs(t.item() - float(np.dot(yg, yg))) <= 1e-12 * float(np.dot(yg, yg))
+    dist.barrier()
+    if rank == 0:
+        print("DIST_CPU_OK")
+    dist.destroy_process_group()
+
+
+def partition_vector_case(lib, rank, world, rp, ci, va):
+    """an arbitrary (scattered) partition vector: rows are renumbered into the contiguous layout of the reference's ipartition_map
+    (AMGXB200_partition_vector_to_contiguous), then planned / exchanged / multiplied exactly like a contiguous partition"""
+    n_global = rp.shape[0] - 1
+    pv = np.random.default_rng(7).integers(0, world, n_global).astype(np.int32)      # same on every rank
+    offsets = np.zeros(world + 1, np.int64)
+    new_global = np.zeros(n_global, np.int64)
+    rc = lib.AMGXB200_partition_vector_to_contiguous(n_global, world, pv.ctypes.data, offsets.ctypes.data, new_global.ctypes.data)
+    assert rc == 0, rc
+    # the map is a permutation that sends rank r's rows, in increasing global id, onto [offsets[r], offsets[r+1])
+    assert sorted(new_global) == list(range(n_global))
+    for r in range(world):
+        mine_r = np.nonzero(pv == r)[0]
+        assert np.array_equal(new_global[mine_r], np.arange(offsets[r], offsets[r + 1]))
+    bad = pv.copy()
+    bad[3] = world
+    assert lib.AMGXB200_partition_vector_to_contiguous(n_global, world, bad.ctypes.data, offsets.copy().ctypes.data, None) != 0
+    mine = np.nonzero(pv == rank)[0]                     # my rows, increasing global id: the order callers upload them in
+    n = mine.shape[0]
+    lens = (rp[mine + 1] - rp[mine]).astype(np.int32)
+    lrp = np.zeros(n + 1, np.int32)
+    np.cumsum(lens, out=lrp[1:])
+    lci = np.concatenate([new_global[ci[rp[g]:rp[g + 1]]] for g in mine]).astype(np.int64)
+    lva = np.concatenate([va[rp[g]:rp[g + 1]] for g in mine])
+    plan = capi.PartitionPlan()
+    rc = lib.AMGXB200_partition_plan_create(C.byref(plan), rank, world, offsets.ctypes.data, n, lci.shape[0], lrp.ctypes.data, lci.ctypes.data)
+    assert rc == 0, rc
+    nh, nn = plan.n_halo, plan.num_neighbors
+    neighbors = np.ctypeslib.as_array(plan.neighbors, (max(nn, 1),)).copy()[:nn]
+    send_off = np.ctypeslib.as_array(plan.send_offsets, (nn + 1,)).copy()
+    send_maps = np.ctypeslib.as_array(plan.send_maps, (max(send_off[-1], 1),)).copy()[: send_off[-1]]
+    halo_off = np.ctypeslib.as_array(plan.halo_offsets, (nn + 1,)).copy()
+    perm = np.ctypeslib.as_array(plan.perm_old_to_new, (max(n, 1),)).copy()[:n]
+    lcols = np.ctypeslib.as_array(plan.local_cols, (max(lci.shape[0], 1),)).copy()[: lci.shape[0]]
+    halo_global = np.ctypeslib.as_array(plan.halo_global, (max(nh, 1),)).copy()[:nh]
+    lib.AMGXB200_partition_plan_free(C.byref(plan))
+    inv = np.argsort(perm)
+    nrp = np.zeros(n + 1, np.int32)
+    np.cumsum(np.diff(lrp)[inv], out=nrp[1:])
+    nci = np.concatenate([lcols[lrp[i]:lrp[i + 1]] for i in inv]).astype(np.int32)
+    nva = np.concatenate([lva[lrp[i]:lrp[i + 1]] for i in inv])
+    xg = np.random.default_rng(42).standard_normal(n_global)        # indexed by ORIGINAL global id
+    x = np.zeros(n + nh)
+    x[perm] = xg[mine]
+    reqs, bufs = [], []
+    for q, nb in enumerate(neighbors):
+        sb = torch.from_numpy(x[send_maps[send_off[q]:send_off[q + 1]]].copy())
+        rb = torch.empty(int(halo_off[q + 1] - halo_off[q]), dtype=torch.float64)
+        reqs.append(dist.isend(sb, int(nb)))
+        reqs.append(dist.irecv(rb, int(nb)))
+        bufs.append((q, rb))
+    for r in reqs:
+        r.wait()
+    for q, rb in bufs:
+        x[n + halo_off[q]: n + halo_off[q + 1]] = rb.numpy()
+    old_of_new = np.argsort(new_global)                              # contiguous id -> original global id
+    assert np.array_equal(x[n:], xg[old_of_new[halo_global]])
+    y = np.empty(n)
+    orc.lib().orc_spmv(n, nrp.ctypes.data_as(C.c_void_p), nci.ctypes.data_as(C.c_void_p), nva.ctypes.data_as(C.c_void_p),
+                       x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p))
+    yg = orc.spmv(rp, ci, va, xg)
+    assert np.array_equal(y[perm], yg[mine]), "distributed SpMV (partition vector) differs from the global one"
     dist.barrier()
     if rank == 0:
         print("DIST_CPU_OK")

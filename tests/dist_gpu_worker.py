@@ -77,6 +77,59 @@ def block_dilu_section(rank, world, rsc, lib):
     dist.barrier()
 
 
+def partition_vector_section(rank, world, rsc, lib, cfg):
+    """AMGX_matrix_upload_all_global with a scattered (non-contiguous) partition vector: SpMV bit-exact vs the global product and the
+    solve converges to the global solution.  Opt-in (AMGXB_RUN_UNVALIDATED=1) until validated on a device."""
+    import ctypes as C
+    nx, ny, nz = 14, 11, 5 * world
+    rp, ci, va = gallery.poisson7pt(nx, ny, nz)
+    ng = rp.shape[0] - 1
+    # planes are dealt to the ranks in a shuffled order: contiguous chunks, but rank ids neither sorted nor one block per rank
+    plane_owner = np.random.default_rng(3).permutation(np.repeat(np.arange(world), 5))
+    pv = np.repeat(plane_owner, nx * ny).astype(np.int32)
+    mine = np.nonzero(pv == rank)[0]
+    n = mine.shape[0]
+    lens = (rp[mine + 1] - rp[mine]).astype(np.int32)
+    lrp = np.zeros(n + 1, np.int32)
+    np.cumsum(lens, out=lrp[1:])
+    lci = np.concatenate([ci[rp[g]:rp[g + 1]] for g in mine]).astype(np.int64)
+    lva = np.concatenate([va[rp[g]:rp[g + 1]] for g in mine])
+    A = capi.Matrix(rsc)
+    rc = lib.AMGX_matrix_upload_all_global(A.h, ng, n, lci.shape[0], 1, 1, lrp.ctypes.data, lci.ctypes.data, lva.ctypes.data, None, 1, 1, pv.ctypes.data)
+    assert rc == 0, rc
+    xg = np.random.default_rng(12).standard_normal(ng)
+    x, y = capi.Vector(rsc), capi.Vector(rsc)
+    x.bind(A)
+    y.bind(A)
+    x.upload(xg[mine])
+    y.set_zero(n)
+    A.multiply(x, y)
+    assert np.array_equal(y.download(), orc.spmv(rp, ci, va, xg)[mine]), "partition-vector SpMV differs from the global one"
+    b, sol = capi.Vector(rsc), capi.Vector(rsc)
+    b.bind(A)
+    sol.bind(A)
+    b.upload(np.ones(n))
+    sol.set_zero(n)
+    slv = capi.Solver(rsc, cfg)
+    slv.setup(A)
+    slv.solve(b, sol)
+    assert slv.status == "success", slv.status
+    counts = [int(np.count_nonzero(pv == r)) for r in range(world)]
+    parts = [torch.zeros(c, dtype=torch.float64, device="cuda") for c in counts]
+    dist.all_gather(parts, torch.from_numpy(sol.download()).cuda())
+    xfull = np.zeros(ng)
+    for r in range(world):
+        xfull[pv == r] = parts[r].cpu().numpy()
+    res = np.ones(ng) - gallery.to_scipy(rp, ci, va) @ xfull
+    hist = slv.residual_history()
+    assert abs(np.linalg.norm(res) - hist[-1]) <= 1e-9 * hist[0], (np.linalg.norm(res), hist[-1])
+    if rank == 0:
+        print(f"DIST_PARTITION_VECTOR_OK world={world} iters={slv.iterations_number}", flush=True)
+    for o in (slv, sol, b, y, x, A):
+        o.destroy()
+    dist.barrier()
+
+
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -148,6 +201,8 @@ def main():
     for o in (slv, sol, b, y, x, A):
         o.destroy()
     block_dilu_section(rank, world, rsc, lib)
+    if os.environ.get("AMGXB_RUN_UNVALIDATED") == "1":
+        partition_vector_section(rank, world, rsc, lib, cfg)
     rsc.destroy()
     cfg.destroy()
     capi.finalize()

@@ -25,6 +25,8 @@ def test_distributed_spmv_and_solve(world, tail_rows):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     import os
+    if tail_rows != "0" and os.environ.get("AMGXB_RUN_UNVALIDATED") != "1":
+        pytest.skip("replicated coarse tail (partitioned aggregates) not yet validated on a device (AMGXB_RUN_UNVALIDATED=1)")
     env = dict(os.environ, AMGXB_TAIL_ROWS=tail_rows)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29611 + world), str(ROOT / "tests" / "dist_gpu_worker.py")]
@@ -32,3 +34,5 @@ def test_distributed_spmv_and_solve(world, tail_rows):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_GPU_OK" in r.stdout
     assert r.stdout.count("DIST_BLOCK_DILU_OK") == 4, r.stdout[-3000:]
+    if os.environ.get("AMGXB_RUN_UNVALIDATED") == "1":
+        assert "DIST_PARTITION_VECTOR_OK" in r.stdout, r.stdout[-3000:]
