@@ -132,6 +132,7 @@ def _declare(lib):
         "AMGXB200_bench_kernel": [vp, i, i, i, i, C.POINTER(C.c_double)],
         "AMGXB200_partition_plan_create": [C.POINTER(PartitionPlan), i, i, vp, i, i, vp, vp],
         "AMGXB200_partition_vector_to_contiguous": [i, i, vp, vp, vp],
+        "AMGXB200_comm_maps_to_global_cols": [i, i, vp, C.c_int64, i, vp, vp, vp, vp],
     }
     for name, args in sig.items():
         f = getattr(lib, name)

@@ -182,10 +182,27 @@ AMGX_RC AMGX_matrix_upload_all_global_32(AMGX_matrix_handle mtx, int n_global, i
     API3_END
 }
 
-AMGX_RC AMGX_matrix_comm_from_maps(AMGX_matrix_handle mtx, int, int, int, const int *, const int *, const int *, const int *, const int *)
+// include/amgx_c.h:310-323: the multi-ring form, neighbour q's maps are send_maps[send_ptrs[q] .. send_ptrs[q+1]) etc.  The engine
+// exchanges one ring (what aggregation AMG needs); more import rings are rejected, not ignored.
+AMGX_RC AMGX_matrix_comm_from_maps(AMGX_matrix_handle mtx, int allocated_halo_depth, int num_import_rings, int max_num_neighbors, const int *neighbors,
+                                   const int *send_ptrs, const int *send_maps, const int *recv_ptrs, const int *recv_maps)
 {
-    (void)mtx;
-    return AMGX_RC_NOT_IMPLEMENTED;
+    API3_BEGIN
+    MatrixH *m = chk<MatrixH>(mtx, MAGIC_MTX, "matrix");
+    (void)allocated_halo_depth;
+    if (num_import_rings > 1) fatal(AMGX_RC_NOT_IMPLEMENTED, "AMGX_matrix_comm_from_maps with more than one import ring");
+    if (max_num_neighbors < 0 || (max_num_neighbors > 0 && (!neighbors || !send_ptrs || !send_maps || !recv_ptrs || !recv_maps)))
+        fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_matrix_comm_from_maps: null map arrays");
+    std::vector<int> ssz(max_num_neighbors), rsz(max_num_neighbors);
+    std::vector<const int *> sm(max_num_neighbors), rm(max_num_neighbors);
+    for (int q = 0; q < max_num_neighbors; q++) {
+        ssz[q] = send_ptrs[q + 1] - send_ptrs[q];
+        rsz[q] = recv_ptrs[q + 1] - recv_ptrs[q];
+        sm[q] = send_maps + send_ptrs[q];
+        rm[q] = recv_maps + recv_ptrs[q];
+    }
+    dist_comm_from_maps_one_ring(*m->m, max_num_neighbors, neighbors, ssz.data(), sm.data(), rsz.data(), rm.data());
+    API3_END
 }
 
 AMGX_RC AMGX_matrix_comm_from_maps_one_ring(AMGX_matrix_handle mtx, int allocated_halo_depth, int num_neighbors, const int *neighbors,
@@ -204,6 +221,16 @@ AMGX_RC AMGXB200_partition_plan_create(AMGXB200_partition_plan *plan, int rank, 
     API3_BEGIN
     if (!plan) fatal(AMGX_RC_BAD_PARAMETERS, "null plan");
     partition_plan_create(plan, rank, world_size, offsets, n, nnz, row_ptrs, col_indices_global);
+    API3_END
+}
+
+AMGX_RC AMGXB200_comm_maps_to_global_cols(int n, int nnz, const int *local_cols, int64_t my_offset, int num_neighbors, const int *recv_sizes,
+                                          const int *const *recv_maps, const int64_t *const *recv_global, int64_t *cols_out)
+{
+    API3_BEGIN
+    if (n < 0 || nnz < 0 || (nnz > 0 && (!local_cols || !cols_out)) || num_neighbors < 0) fatal(AMGX_RC_BAD_PARAMETERS, "comm_maps_to_global_cols: bad arguments");
+    const std::string err = comm_maps_to_global_cols(n, nnz, local_cols, my_offset, num_neighbors, recv_sizes, recv_maps, recv_global, cols_out);
+    if (!err.empty()) fatal(AMGX_RC_BAD_PARAMETERS, err);
     API3_END
 }
 

@@ -47,6 +47,8 @@ void dist_upload_global(Matrix &A, int n_global, int n, int nnz, int bx, int by,
 void dist_comm_from_maps_one_ring(Matrix &A, int num_neighbors, const int *neighbors, const int *send_sizes, const int **send_maps,
                                   const int *recv_sizes, const int **recv_maps);
 // pure host partition planner (partition.cpp)
+std::string comm_maps_to_global_cols(int n, int nnz, const int *local_cols, int64_t my_offset, int num_neighbors, const int *recv_sizes,
+                                     const int *const *recv_maps, const int64_t *const *recv_global, int64_t *cols_out);   // partition.cpp
 bool partition_vector_to_contiguous(int n_global, int world, const int *pv, int64_t *offsets, int64_t *new_global);   // partition.cpp
 void partition_plan_create(AMGXB200_partition_plan *plan, int rank, int world, const int64_t *offsets, int n, int nnz, const int *row_ptrs,
                            const int64_t *cols_global);

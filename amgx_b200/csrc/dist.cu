@@ -402,13 +402,96 @@ void dist_upload_global(Matrix &A, int n_global, int n, int nnz, int bx, int by,
     dist_build_matrix(A, offsets.data(), n, nnz, bx, by, rp.data(), cols.data(), vals.data(), diag_data);
 }
 
-void dist_upload_local(Matrix &, int, int, int, int, const int *, const int *, const void *, const void *)
+// AMGX_matrix_comm_from_maps_one_ring + AMGX_matrix_upload_all (examples/amgx_mpi_capi_agg.c:480-485): the caller numbers owned
+// columns 0..n-1 and halo columns from n on, and says which of its rows each neighbour needs (send_maps) and which halo column each
+// received value lands in (recv_maps).  The maps are kept until the upload; the upload turns the local numbering into global column
+// ids (ranks own contiguous blocks in rank order; the halo ids come from one exchange of the senders' global row ids) and goes
+// through the same planner as the global uploads, which re-derives interior / boundary rows and the send order it needs.
+void dist_comm_from_maps_one_ring(Matrix &A, int nn, const int *neighbors, const int *send_sizes, const int **send_maps, const int *recv_sizes,
+                                  const int **recv_maps)
 {
-    fatal(AMGX_RC_NOT_IMPLEMENTED, "upload with user-supplied comm maps");
+    if (nn < 0 || (nn > 0 && (!neighbors || !send_sizes || !send_maps || !recv_sizes || !recv_maps)))
+        fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_matrix_comm_from_maps_one_ring: null map arrays");
+    auto cm = std::make_shared<Matrix::CommMaps>();
+    cm->neighbors.assign(neighbors, neighbors + nn);
+    cm->send.resize(nn);
+    cm->recv.resize(nn);
+    for (int q = 0; q < nn; q++) {
+        if (neighbors[q] < 0 || neighbors[q] >= A.rsc->world || neighbors[q] == A.rsc->rank)
+            fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_matrix_comm_from_maps_one_ring: bad neighbour rank");
+        if (send_sizes[q] < 0 || recv_sizes[q] < 0) fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_matrix_comm_from_maps_one_ring: negative map size");
+        cm->send[q].assign(send_maps[q], send_maps[q] + send_sizes[q]);
+        cm->recv[q].assign(recv_maps[q], recv_maps[q] + recv_sizes[q]);
+    }
+    A.comm_maps = cm;
+    A.dist_pending = true;
 }
-void dist_comm_from_maps_one_ring(Matrix &, int, const int *, const int *, const int **, const int *, const int **)
+
+void dist_upload_local(Matrix &A, int n, int nnz, int bx, int by, const int *row_ptrs, const int *col_indices, const void *data, const void *diag_data)
 {
-    fatal(AMGX_RC_NOT_IMPLEMENTED, "AMGX_matrix_comm_from_maps_one_ring: use AMGX_matrix_upload_distributed / _all_global");
+    if (!A.comm_maps) fatal(AMGX_RC_BAD_PARAMETERS, "local distributed upload without communication maps");
+    const Matrix::CommMaps &cm = *A.comm_maps;
+    const int world = A.rsc->world, rank = A.rsc->rank, nn = (int)cm.neighbors.size();
+    if (n < 0 || nnz < 0) fatal(AMGX_RC_BAD_PARAMETERS, "Error: Failure in matrix_upload_all().");
+    cudaStream_t s = A.stream();
+    const size_t bs = (size_t)bx * by, msz = prec_size(A.mat_prec);
+    std::vector<int> rp(n + 1), ci(std::max(nnz, 1));
+    AMGXB_CUDA_CHECK(cudaMemcpy(rp.data(), row_ptrs, sizeof(int) * (n + 1), cudaMemcpyDefault));
+    if (nnz) AMGXB_CUDA_CHECK(cudaMemcpy(ci.data(), col_indices, sizeof(int) * nnz, cudaMemcpyDefault));
+    std::vector<char> vals(std::max<size_t>((size_t)nnz * bs * msz, 1));
+    if (nnz) AMGXB_CUDA_CHECK(cudaMemcpy(vals.data(), data, (size_t)nnz * bs * msz, cudaMemcpyDefault));
+    if (world == 1) {
+        upload_matrix(A, n, nnz, bx, by, rp.data(), ci.data(), vals.data(), diag_data);
+        A.dist_pending = false;
+        return;
+    }
+    // 1. rows per rank -> contiguous global offsets
+    DevBuf<long long> cnt;
+    cnt.resize((size_t)world + 1);
+    const long long mine = n;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(cnt.ptr() + world, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+    AMGXB_NCCL_CHECK(ncclAllGather(cnt.ptr() + world, cnt.ptr(), 1, ncclInt64, (ncclComm_t)A.rsc->nccl_comm, s));
+    std::vector<long long> hc = cnt.to_host(s);
+    std::vector<int64_t> offsets((size_t)world + 1, 0);
+    for (int r = 0; r < world; r++) offsets[r + 1] = offsets[r] + hc[r];
+    // 2. global ids of the rows I send, exchanged for the global ids of my halo columns
+    std::vector<int> soff(nn + 1, 0), roff(nn + 1, 0);
+    for (int q = 0; q < nn; q++) {
+        soff[q + 1] = soff[q] + (int)cm.send[q].size();
+        roff[q + 1] = roff[q] + (int)cm.recv[q].size();
+    }
+    std::vector<long long> sg((size_t)std::max(soff[nn], 1)), rg((size_t)std::max(roff[nn], 1));
+    for (int q = 0; q < nn; q++)
+        for (size_t k = 0; k < cm.send[q].size(); k++) {
+            if (cm.send[q][k] < 0 || cm.send[q][k] >= n) fatal(AMGX_RC_BAD_PARAMETERS, "send_maps holds a row index outside [0, n)");
+            sg[(size_t)soff[q] + k] = offsets[rank] + cm.send[q][k];
+        }
+    DevBuf<long long> dsg, drg;
+    dsg.from_any(sg.data(), sg.size(), s);
+    drg.resize(rg.size());
+    AMGXB_NCCL_CHECK(ncclGroupStart());
+    for (int q = 0; q < nn; q++) {
+        if (soff[q + 1] > soff[q]) AMGXB_NCCL_CHECK(ncclSend(dsg.ptr() + soff[q], (size_t)(soff[q + 1] - soff[q]), ncclInt64, cm.neighbors[q], (ncclComm_t)A.rsc->nccl_comm, s));
+        if (roff[q + 1] > roff[q]) AMGXB_NCCL_CHECK(ncclRecv(drg.ptr() + roff[q], (size_t)(roff[q + 1] - roff[q]), ncclInt64, cm.neighbors[q], (ncclComm_t)A.rsc->nccl_comm, s));
+    }
+    AMGXB_NCCL_CHECK(ncclGroupEnd());
+    rg = drg.to_host(s);
+    // 3. local -> global columns, 4. the usual planner
+    std::vector<int> rsz(nn);
+    std::vector<const int *> rmaps(nn);
+    std::vector<std::vector<int64_t>> rglob(nn);
+    std::vector<const int64_t *> rgp(nn);
+    for (int q = 0; q < nn; q++) {
+        rsz[q] = (int)cm.recv[q].size();
+        rmaps[q] = cm.recv[q].data();
+        rglob[q].assign(rg.begin() + roff[q], rg.begin() + roff[q + 1]);
+        rgp[q] = rglob[q].data();
+    }
+    std::vector<int64_t> cols((size_t)std::max(nnz, 1));
+    const std::string err = comm_maps_to_global_cols(n, nnz, ci.data(), offsets[rank], nn, rsz.data(), rmaps.data(), rgp.data(), cols.data());
+    if (!err.empty()) fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_matrix_comm_from_maps_one_ring / upload_all: " + err);
+    dist_build_matrix(A, offsets.data(), n, nnz, bx, by, rp.data(), cols.data(), vals.data(), diag_data);
+    A.dist_pending = false;
 }
 
 // 7-point Poisson on a px*py*pz process grid, each rank an nx*ny*nz box (the reference's generator

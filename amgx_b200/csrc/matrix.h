@@ -46,6 +46,11 @@ struct Matrix {
     bool has_ext_diag = false;
     bool merged_ext_diag = false;   // scalar matrix uploaded with diag_data: merged into CSR, diagonal first
     bool dist_pending = false;      // comm maps were supplied; the next upload_all is a local distributed upload
+    struct CommMaps {               // AMGX_matrix_comm_from_maps[_one_ring]: neighbours, rows to send, halo columns to receive into
+        std::vector<int> neighbors;
+        std::vector<std::vector<int>> send, recv;
+    };
+    std::shared_ptr<CommMaps> comm_maps;
     bool initialized = false;
     int level = 0;
 

@@ -130,4 +130,36 @@ bool partition_vector_to_contiguous(int n_global, int world, const int *pv, int6
     return true;
 }
 
+// Caller-supplied communication maps (AMGX_matrix_comm_from_maps_one_ring, include/amgx_c.h:325-333) -> global column ids, so
+// that a matrix uploaded in LOCAL numbering (owned columns < n, halo columns >= n) can go through the same planner as the
+// global uploads.  recv_global[q][k] is the global id of the k-th value neighbour q sends (= global id of its send_maps row k);
+// it lands in local halo column recv_maps[q][k].  Returns an empty string, or what is wrong with the maps.
+std::string comm_maps_to_global_cols(int n, int nnz, const int *local_cols, int64_t my_offset, int num_neighbors, const int *recv_sizes,
+                                     const int *const *recv_maps, const int64_t *const *recv_global, int64_t *cols_out)
+{
+    int n_halo = 0;
+    for (int k = 0; k < nnz; k++) {
+        if (local_cols[k] < 0) return "negative column index";
+        if (local_cols[k] >= n) n_halo = std::max(n_halo, local_cols[k] - n + 1);
+    }
+    std::vector<int64_t> halo((size_t)n_halo, -1);
+    for (int q = 0; q < num_neighbors; q++)
+        for (int k = 0; k < recv_sizes[q]; k++) {
+            const int c = recv_maps[q][k];
+            if (c < n) return "recv_maps holds an owned index (< n)";
+            if (c - n >= n_halo) continue;                     // a halo slot no row references: harmless
+            if (halo[c - n] >= 0 && halo[c - n] != recv_global[q][k]) return "a halo column is received from two different rows";
+            halo[c - n] = recv_global[q][k];
+        }
+    for (int k = 0; k < nnz; k++) {
+        const int c = local_cols[k];
+        if (c < n) cols_out[k] = my_offset + c;
+        else {
+            if (halo[c - n] < 0) return "a halo column is not covered by recv_maps";
+            cols_out[k] = halo[c - n];
+        }
+    }
+    return std::string();
+}
+
 }  // namespace amgxb

@@ -221,6 +221,11 @@ void    AMGX_API AMGXB200_partition_plan_free(AMGXB200_partition_plan *plan);
 /* Arbitrary partition vector (AMGX_DIST_PARTITION_VECTOR, include/amgx_c.h:241-259) -> the contiguous numbering the engine works
  * in, exactly the reference's ipartition_map (src/distributed/distributed_manager.cu:1175-1203): offsets[world_size+1],
  * new_global[n_global] (may be NULL).  Pure host code. */
+/* Caller-supplied comm maps (AMGX_matrix_comm_from_maps_one_ring) -> global column ids of a matrix given in local numbering (owned
+ * columns < n, halo columns >= n).  recv_global[q][k] = global id of the k-th value neighbour q sends (its send_maps row k, offset by
+ * q's first global row).  Pure host code; returns AMGX_RC_BAD_PARAMETERS when the maps do not cover the halo columns. */
+AMGX_RC AMGX_API AMGXB200_comm_maps_to_global_cols(int n, int nnz, const int *local_cols, int64_t my_offset, int num_neighbors, const int *recv_sizes,
+                                                   const int *const *recv_maps, const int64_t *const *recv_global, int64_t *cols_out);
 AMGX_RC AMGX_API AMGXB200_partition_vector_to_contiguous(int n_global, int world_size, const int *partition_vector, int64_t *offsets, int64_t *new_global);
 
 #if defined(__cplusplus)

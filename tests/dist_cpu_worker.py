@@ -28,6 +28,8 @@ def main():
     lib = capi.load_library()
     if os.environ.get("AMGXB_TEST_PARTITION") == "vector":
         return partition_vector_case(lib, rank, world, rp, ci, va)
+    if os.environ.get("AMGXB_TEST_PARTITION") == "maps":
+        return comm_maps_case(lib, rank, world, rp, ci, va, nx * ny * nzl)
     offsets = np.array([nx * ny * nzl * r for r in range(world + 1)], np.int64)
     lo, hi = int(offsets[rank]), int(offsets[rank + 1])
     lrp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
@@ -89,6 +91,66 @@ def main():
     dist.destroy_process_group()
 
 
+def comm_maps_case(lib, rank, world, rp, ci, va, nloc):
+    """AMGX_matrix_comm_from_maps_one_ring semantics (examples/amgx_mpi_capi_agg.c:386-420): every rank holds its rows in LOCAL
+    numbering plus neighbours / send_maps / recv_maps.  The engine exchanges the senders' global row ids and calls the host helper
+    tested here; the result must be the true global columns, and the usual planner must then reproduce the global SpMV."""
+    n_global = rp.shape[0] - 1
+    offsets = np.array([nloc * r for r in range(world + 1)], np.int64)
+    owner = lambda g: int(np.searchsorted(offsets, g, side="right") - 1)
+
+    def local_view(r):
+        """what AMGX_read_system_maps_one_ring would hand rank r; halo columns numbered in a deliberately scrambled order"""
+        lo, hi = int(offsets[r]), int(offsets[r + 1])
+        cols = ci[rp[lo]:rp[hi]]
+        halo = np.unique(cols[(cols < lo) | (cols >= hi)])
+        halo = np.random.default_rng(100 + r).permutation(halo)              # arbitrary halo numbering
+        hid = {int(g): hi - lo + k for k, g in enumerate(halo)}
+        lcols = np.array([c - lo if lo <= c < hi else hid[int(c)] for c in cols], np.int32)
+        nbrs = sorted({owner(g) for g in halo})
+        recv = {q: np.array([hid[int(g)] for g in halo if owner(g) == q], np.int32) for q in nbrs}
+        recv_g = {q: np.array([int(g) for g in halo if owner(g) == q], np.int64) for q in nbrs}
+        return lo, hi, lcols, nbrs, recv, recv_g
+
+    lo, hi, lcols, nbrs, recv, recv_g = local_view(rank)
+    n = hi - lo
+    # send_maps[q][k] = my local row whose value lands in q's recv_maps[me][k] (the pairing rule of the API)
+    send = {q: (local_view(q)[5][rank] - lo).astype(np.int32) for q in nbrs}
+    # ---- what the engine does over NCCL, here over gloo: send the global ids of my send rows, receive my halo's global ids
+    reqs, got = [], {}
+    for q in nbrs:
+        sb = torch.from_numpy((send[q].astype(np.int64) + lo).copy())
+        rb = torch.empty(recv[q].shape[0], dtype=torch.int64)
+        reqs += [dist.isend(sb, q), dist.irecv(rb, q)]
+        got[q] = (sb, rb)
+    for r in reqs:
+        r.wait()
+    nn = len(nbrs)
+    rsz = (C.c_int * max(nn, 1))(*[recv[q].shape[0] for q in nbrs])
+    rmaps = (C.c_void_p * max(nn, 1))(*[recv[q].ctypes.data for q in nbrs])
+    rglob_np = [got[q][1].numpy().copy() for q in nbrs]
+    rglob = (C.c_void_p * max(nn, 1))(*[a.ctypes.data for a in rglob_np])
+    out = np.empty(lcols.shape[0], np.int64)
+    rc = lib.AMGXB200_comm_maps_to_global_cols(n, lcols.shape[0], lcols.ctypes.data, lo, nn, rsz, rmaps, rglob, out.ctypes.data)
+    assert rc == 0, rc
+    assert np.array_equal(out, ci[rp[lo]:rp[hi]].astype(np.int64)), "comm maps did not reproduce the global columns"
+    # a map that misses a referenced halo column must be rejected
+    if nn:
+        short = (C.c_int * nn)(*([recv[nbrs[0]].shape[0] - 1] + [recv[q].shape[0] for q in nbrs[1:]]))
+        scratch = out.copy()
+        assert lib.AMGXB200_comm_maps_to_global_cols(n, lcols.shape[0], lcols.ctypes.data, lo, nn, short, rmaps, rglob, scratch.ctypes.data) != 0
+    # ---- the converted matrix goes through the usual planner: distributed SpMV == global SpMV
+    lrp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+    plan = capi.PartitionPlan()
+    assert lib.AMGXB200_partition_plan_create(C.byref(plan), rank, world, offsets.ctypes.data, n, out.shape[0], lrp.ctypes.data, out.ctypes.data) == 0
+    assert plan.n_halo == sum(recv[q].shape[0] for q in nbrs) and plan.num_neighbors == nn
+    lib.AMGXB200_partition_plan_free(C.byref(plan))
+    dist.barrier()
+    if rank == 0:
+        print("DIST_CPU_OK")
+    dist.destroy_process_group()
+
+
 def partition_vector_case(lib, rank, world, rp, ci, va):
     """an arbitrary (scattered) partition vector: rows are renumbered into the contiguous layout of the reference's ipartition_map
     (AMGXB200_partition_vector_to_contiguous), then planned / exchanged / multiplied exactly like a contiguous partition"""
@@ -105,7 +167,8 @@ def partition_vector_case(lib, rank, world, rp, ci, va):
         assert np.array_equal(new_global[mine_r], np.arange(offsets[r], offsets[r + 1]))
     bad = pv.copy()
     bad[3] = world
-    assert lib.AMGXB200_partition_vector_to_contiguous(n_global, world, bad.ctypes.data, offsets.copy().ctypes.data, None) != 0
+    off2 = offsets.copy()
+    assert lib.AMGXB200_partition_vector_to_contiguous(n_global, world, bad.ctypes.data, off2.ctypes.data, None) != 0
     mine = np.nonzero(pv == rank)[0]                     # my rows, increasing global id: the order callers upload them in
     n = mine.shape[0]
     lens = (rp[mine + 1] - rp[mine]).astype(np.int32)

@@ -130,6 +130,68 @@ def partition_vector_section(rank, world, rsc, lib, cfg):
     dist.barrier()
 
 
+def comm_maps_section(rank, world, rsc, lib, cfg):
+    """AMGX_matrix_comm_from_maps_one_ring + AMGX_matrix_upload_all in LOCAL numbering (examples/amgx_mpi_capi_agg.c:480-485): SpMV
+    bit-exact vs the global product, the solve converges to the global solution.  Opt-in until validated on a device."""
+    import ctypes as C
+    nx, ny, nzl = 13, 10, 5
+    rp, ci, va = gallery.poisson7pt(nx, ny, nzl * world)
+    ng = rp.shape[0] - 1
+    offsets = np.array([nx * ny * nzl * r for r in range(world + 1)], np.int64)
+    owner = lambda g: int(np.searchsorted(offsets, g, side="right") - 1)
+
+    def view(r):
+        lo, hi = int(offsets[r]), int(offsets[r + 1])
+        cols = ci[rp[lo]:rp[hi]]
+        halo = np.random.default_rng(100 + r).permutation(np.unique(cols[(cols < lo) | (cols >= hi)]))
+        hid = {int(g): hi - lo + k for k, g in enumerate(halo)}
+        lcols = np.array([c - lo if lo <= c < hi else hid[int(c)] for c in cols], np.int32)
+        nbrs = sorted({owner(g) for g in halo})
+        recv = {q: np.array([hid[int(g)] for g in halo if owner(g) == q], np.int32) for q in nbrs}
+        recv_g = {q: np.array([int(g) for g in halo if owner(g) == q], np.int64) for q in nbrs}
+        return lo, hi, lcols, nbrs, recv, recv_g
+
+    lo, hi, lcols, nbrs, recv, _ = view(rank)
+    n, nn = hi - lo, len(nbrs)
+    send = {q: (view(q)[5][rank] - lo).astype(np.int32) for q in nbrs}
+    lrp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+    lva = np.ascontiguousarray(va[rp[lo]:rp[hi]])
+    A = capi.Matrix(rsc)
+    nb = (C.c_int * nn)(*nbrs)
+    ssz = (C.c_int * nn)(*[send[q].shape[0] for q in nbrs])
+    rsz = (C.c_int * nn)(*[recv[q].shape[0] for q in nbrs])
+    smaps = (C.c_void_p * nn)(*[send[q].ctypes.data for q in nbrs])
+    rmaps = (C.c_void_p * nn)(*[recv[q].ctypes.data for q in nbrs])
+    lib.AMGX_matrix_comm_from_maps_one_ring.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert lib.AMGX_matrix_comm_from_maps_one_ring(A.h, 1, nn, nb, ssz, smaps, rsz, rmaps) == 0
+    x, y, b, sol = (capi.Vector(rsc) for _ in range(4))
+    for v in (x, y, b, sol):
+        v.bind(A)
+    rc = lib.AMGX_matrix_upload_all(A.h, n, lcols.shape[0], 1, 1, lrp.ctypes.data, lcols.ctypes.data, lva.ctypes.data, None)
+    assert rc == 0, rc
+    xg = np.random.default_rng(13).standard_normal(ng)
+    x.upload(xg[lo:hi])
+    y.set_zero(n)
+    A.multiply(x, y)
+    assert np.array_equal(y.download(), orc.spmv(rp, ci, va, xg)[lo:hi]), "comm-maps SpMV differs from the global one"
+    b.upload(np.ones(n))
+    sol.set_zero(n)
+    slv = capi.Solver(rsc, cfg)
+    slv.setup(A)
+    slv.solve(b, sol)
+    assert slv.status == "success", slv.status
+    parts = [torch.zeros(int(offsets[r + 1] - offsets[r]), dtype=torch.float64, device="cuda") for r in range(world)]
+    dist.all_gather(parts, torch.from_numpy(sol.download()).cuda())
+    res = np.ones(ng) - gallery.to_scipy(rp, ci, va) @ torch.cat(parts).cpu().numpy()
+    hist = slv.residual_history()
+    assert abs(np.linalg.norm(res) - hist[-1]) <= 1e-9 * hist[0]
+    if rank == 0:
+        print(f"DIST_COMM_MAPS_OK world={world} iters={slv.iterations_number}", flush=True)
+    for o in (slv, sol, b, y, x, A):
+        o.destroy()
+    dist.barrier()
+
+
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -203,6 +265,7 @@ def main():
     block_dilu_section(rank, world, rsc, lib)
     if os.environ.get("AMGXB_RUN_UNVALIDATED") == "1":
         partition_vector_section(rank, world, rsc, lib, cfg)
+        comm_maps_section(rank, world, rsc, lib, cfg)
     rsc.destroy()
     cfg.destroy()
     capi.finalize()

@@ -8,11 +8,11 @@ import pytest
 ROOT = Path(__file__).resolve().parents[1]
 
 
-@pytest.mark.parametrize("world,partition", [(2, "offsets"), (3, "offsets"), (2, "vector"), (3, "vector")])
+@pytest.mark.parametrize("world,partition", [(2, "offsets"), (3, "offsets"), (2, "vector"), (3, "vector"), (2, "maps"), (3, "maps")])
 def test_partition_plan_and_halo_protocol(world, partition):
     import os
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29511 + world + (10 if partition == "vector" else 0)), str(ROOT / "tests" / "dist_cpu_worker.py")]
+           "--master-port", str(29511 + world + {"offsets": 0, "vector": 10, "maps": 20}[partition]), str(ROOT / "tests" / "dist_cpu_worker.py")]
     env = dict(os.environ, AMGXB_TEST_PARTITION=partition)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=str(ROOT), env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
