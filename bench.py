@@ -286,7 +286,13 @@ def main():
         ms = A.bench_kernel(0, warmup=3, reps=20, flush_l2=False)      # operands (1.47 GB at 256^3) >> 126 MB L2
         ms_j = A.bench_kernel(1, warmup=3, reps=20, flush_l2=False)
         byt = nnz * 12 + n * 4
-        roof = {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": byt / ms / 1e6 / peak, "traffic": None,
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of the same workload (never measured here:
+        # a number taken under a profiler is not a bench value, but the byte counters are deterministic for a given grid)
+        traffic = None
+        tf = ROOT / "profiles" / f"r01_ncu_traffic_spmv_{nx}.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text())["traffic_bytes_per_launch"]
+        roof = {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": byt / ms / 1e6 / peak, "traffic": traffic,
                 "kernel": "csr_tile_kernel<EPI_SPMV> (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt, "peak_source": peak_src,
                 "fused_jacobi_sweep": {"ms_per_launch": ms_j, "algorithmic_bytes": byt + 4 * n * 8, "achieved": (byt + 4 * n * 8) / ms_j / 1e6,
                                        "frac": (byt + 4 * n * 8) / ms_j / 1e6 / peak}}
