@@ -13,6 +13,7 @@
 // -fmad=false).  Selection arrays, the pattern and the row order of P are bit-comparable with the reference on the
 // finest level; weights agree to rounding.
 #include "solvers.h"
+#include <queue>
 #include "dist.h"
 #include <cub/cub.cuh>
 #include <climits>
@@ -96,6 +97,19 @@ __global__ void pmis_init_kernel(int n, const int *__restrict__ rp, const int *_
         cf[i] = c;
     }
 }
+// initialMarkingCfInitKernel (pmis.cu:316-360): cf already holds a C/F splitting (HMIS: the Ruge-Stueben first pass); its F points
+// are reconsidered, its C points and strong-F points stand
+__global__ void pmis_init_from_cf_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, float *w, int *cf, int *mark)
+{
+    ROW_LOOP(i, n) {
+        const int r0 = rp[i], numj = rp[i + 1] - r0, in = cf[i];
+        if (numj == 0) cf[i] = FINE;
+        else if (numj == 1 && ci[r0] == i) cf[i] = FINE;
+        else if (w[i] < 1) cf[i] = FINE;
+        else if (in == STRONG_FINE) w[i] = 0.f;
+        else if (in == FINE) { cf[i] = UNASSIGNED; mark[i] = 1; }
+    }
+}
 __global__ void pmis_mark_coarse_kernel(int n, const float *__restrict__ w, const int *__restrict__ cf_in, int *cf_out, int *mark)
 {
     ROW_LOOP(i, n) {
@@ -151,7 +165,8 @@ void pmis(int n, const int *rp, const int *ci, const u8 *s_con, float *w, int *c
     mark.zero(s);
     cnt.resize(1);
     const int g = grid_for(n);
-    pmis_init_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, w, cf, init);
+    if (init == 1) pmis_init_from_cf_kernel<<<g, 256, 0, s>>>(n, rp, ci, w, cf, mark.ptr());
+    else pmis_init_kernel<<<g, 256, 0, s>>>(n, rp, ci, s_con, w, cf, init);
     count_launch();
     int iter = 0, num_unassigned;
     do {
@@ -170,6 +185,110 @@ void pmis(int n, const int *rp, const int *ci, const u8 *s_con, float *w, int *c
         iter++;
         if (iter > 10000) fatal(AMGX_RC_INTERNAL, "PMIS did not terminate");
     } while (num_unassigned != 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// HMIS = first pass of Ruge-Stueben coarsening, then PMIS on what it left fine.  The reference runs the first pass on the HOST
+// (RS_Selector<host>, src/classical/selectors/rs.cu:36-262: "it's a sequential algorithm", :275) after copying matrix, strength
+// flags and maps back (hmis.cu:58-88); so does this engine.  The reference keeps (measure, row) pairs in a std::set and always takes
+// the largest measure, smallest row among equals; here a priority queue with lazy deletion gives the same sequence.
+// ---------------------------------------------------------------------------------------------------------------
+static void rs_first_pass_host(int n, const std::vector<int> &rp, const std::vector<int> &ci, const std::vector<u8> *s_con, std::vector<int> &cf)
+{
+    auto strong = [&](int k) { return (!s_con || (*s_con)[k]) && ci[k] < n; };
+    std::vector<int> stp((size_t)n + 1, 0), stc((size_t)std::max(rp[n], 1));
+    for (int k = 0; k < rp[n]; k++) if (strong(k)) stp[ci[k] + 1]++;
+    for (int i = 0; i < n; i++) stp[i + 1] += stp[i];
+    {
+        std::vector<int> fill(stp.begin(), stp.end() - 1);
+        for (int i = 0; i < n; i++) for (int k = rp[i]; k < rp[i + 1]; k++) if (strong(k)) stc[fill[ci[k]]++] = i;
+    }
+    std::vector<int> iw(n);
+    std::vector<char> in_set(n, 0);
+    struct Ent { int w, i; };
+    struct Later { bool operator()(const Ent &a, const Ent &b) const { return a.w < b.w || (a.w == b.w && a.i > b.i); } };   // top(): max w, min i
+    std::priority_queue<Ent, std::vector<Ent>, Later> pq;
+    auto erase = [&](int i) { in_set[i] = 0; };
+    auto insert = [&](int i) { in_set[i] = 1; pq.push(Ent{iw[i], i}); };
+    for (int i = 0; i < n; i++) iw[i] = stp[i + 1] - stp[i];
+    cf.assign((size_t)std::max(n, 1), 0);
+    int num_left = 0;
+    for (int j = 0; j < n; j++) {
+        bool isolated = true;
+        for (int k = rp[j]; k < rp[j + 1] && isolated; k++) isolated = !strong(k);
+        if (isolated) { cf[j] = STRONG_FINE; iw[j] = 0; }
+        else { cf[j] = UNASSIGNED; num_left++; }
+    }
+    for (int j = 0; j < n; j++) {
+        if (cf[j] == STRONG_FINE) continue;
+        if (iw[j] > 0) { insert(j); continue; }
+        cf[j] = FINE;
+        for (int k = rp[j]; k < rp[j + 1]; k++) {
+            if (!strong(k)) continue;
+            const int nb = ci[k];
+            if (cf[nb] == STRONG_FINE) continue;
+            if (nb < j) { if (iw[nb] > 0) erase(nb); ++iw[nb]; insert(nb); }
+            else ++iw[nb];
+        }
+        --num_left;
+    }
+    auto bump_unassigned_neighbours = [&](int row) {
+        for (int k = rp[row]; k < rp[row + 1]; k++) {
+            if (!strong(k)) continue;
+            const int d2 = ci[k];
+            if (cf[d2] == UNASSIGNED) { erase(d2); ++iw[d2]; insert(d2); }
+        }
+    };
+    while (num_left > 0) {
+        int index = -1;
+        while (!pq.empty()) {
+            const Ent t = pq.top();
+            pq.pop();
+            if (in_set[t.i] && iw[t.i] == t.w) { index = t.i; break; }
+        }
+        if (index < 0) break;
+        cf[index] = COARSE;
+        iw[index] = 0;
+        --num_left;
+        erase(index);
+        for (int j = stp[index]; j < stp[index + 1]; j++) {
+            const int nb = stc[j];
+            if (cf[nb] != UNASSIGNED) continue;
+            cf[nb] = FINE;
+            erase(nb);
+            --num_left;
+            bump_unassigned_neighbours(nb);
+        }
+        for (int j = rp[index]; j < rp[index + 1]; j++) {
+            if (!strong(j)) continue;
+            const int nb = ci[j];
+            if (cf[nb] != UNASSIGNED) continue;
+            erase(nb);
+            const int wgt = --iw[nb];
+            if (wgt > 0) { insert(nb); continue; }
+            cf[nb] = FINE;
+            --num_left;
+            bump_unassigned_neighbours(nb);
+        }
+    }
+}
+
+void hmis(int n, const int *rp, const int *ci, int nnz, const u8 *s_con, float *w, int *cf, cudaStream_t s)
+{
+    if (n == 0) return;
+    std::vector<int> hrp((size_t)n + 1), hci((size_t)std::max(nnz, 1)), hcf;
+    std::vector<u8> hs;
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(hrp.data(), rp, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, s));
+    if (nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(hci.data(), ci, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost, s));
+    if (s_con) {
+        hs.resize((size_t)std::max(nnz, 1));
+        if (nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(hs.data(), s_con, (size_t)nnz, cudaMemcpyDeviceToHost, s));
+    }
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    rs_first_pass_host(n, hrp, hci, s_con ? &hs : nullptr, hcf);
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(cf, hcf.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    pmis(n, rp, ci, s_con, w, cf, 1, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -437,9 +556,12 @@ __global__ void copy_segments_val_kernel(int n, const i64 *__restrict__ off, con
     ROW_LOOP(i, n) { const double *a = src + off[i]; double *b = dst + dst_rp[i]; for (int k = 0; k < len[i]; k++) b[k] = a[k]; }
 }
 
-void aggressive_pmis(int n, const int *rp, const int *ci, const u8 *s_con, float *w, int *cf, cudaStream_t s)
+// Aggressive_PMIS / Aggressive_HMIS selectors: the same two passes, with the plain selector of the same name on A and on S2
+// (aggressive_pmis.cu:40,132; aggressive_hmis.cu:41,131 -- HMIS ignores the cf_map_init = 3 it is handed, hmis.cu:58-88)
+void aggressive_pmis(int n, const int *rp, const int *ci, int nnz, const u8 *s_con, float *w, int *cf, bool use_hmis, cudaStream_t s)
 {
-    pmis(n, rp, ci, s_con, w, cf, 0, s);
+    if (use_hmis) hmis(n, rp, ci, nnz, s_con, w, cf, s);
+    else pmis(n, rp, ci, s_con, w, cf, 0, s);
     DevBuf<int> scanned;
     scanned.resize(n);
     AMGXB_CUDA_CHECK(cudaMemcpyAsync(scanned.ptr(), cf, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, s));
@@ -482,7 +604,8 @@ void aggressive_pmis(int n, const int *rp, const int *ci, const u8 *s_con, float
     pattern_count_kernel<<<grid_for(nc), 256, 0, s>>>(nc, s2_rp.ptr(), s2_ci.ptr(), cnt.ptr());
     weights_kernel<<<grid_for(nc), 256, 0, s>>>(nc, cnt.ptr(), w2.ptr());
     count_launch(2);
-    pmis(nc, s2_rp.ptr(), s2_ci.ptr(), nullptr, w2.ptr(), cf2.ptr(), 3, s);
+    if (use_hmis) hmis(nc, s2_rp.ptr(), s2_ci.ptr(), s2_nnz, nullptr, w2.ptr(), cf2.ptr(), s);
+    else pmis(nc, s2_rp.ptr(), s2_ci.ptr(), nullptr, w2.ptr(), cf2.ptr(), 3, s);
     correct_cf_kernel<<<g, 256, 0, s>>>(n, cf, scanned.ptr(), cf2.ptr());
     count_launch();
     AMGXB_LAUNCH_CHECK();
@@ -948,7 +1071,7 @@ std::unique_ptr<Matrix> to_matrix(Csr &C, const Matrix &like, cudaStream_t s)
 struct ClassicalParams {
     double strength_threshold, max_row_sum;
     int max_elmts, aggressive_levels;
-    bool d2, aggressive_multipass;
+    bool d2, aggressive_multipass, hmis = false, aggressive_hmis = false;
 };
 
 // createCoarseVertices: strength + C/F splitting; returns the number of coarse points, cf_map renumbered
@@ -968,7 +1091,8 @@ static int classical_select(const Matrix &A, const ClassicalParams &prm, int lev
     weights_kernel<<<grid_for(n), 256, 0, s>>>(n, cnt.ptr(), w.ptr());
     count_launch(2);
     AMGXB_LAUNCH_CHECK();
-    if (level < prm.aggressive_levels) aggressive_pmis(n, A.row_ptr.ptr(), A.col_idx.ptr(), s_con.ptr(), w.ptr(), cf.ptr(), s);
+    if (level < prm.aggressive_levels) aggressive_pmis(n, A.row_ptr.ptr(), A.col_idx.ptr(), A.nnz, s_con.ptr(), w.ptr(), cf.ptr(), prm.aggressive_hmis, s);
+    else if (prm.hmis) hmis(n, A.row_ptr.ptr(), A.col_idx.ptr(), A.nnz, s_con.ptr(), w.ptr(), cf.ptr(), s);
     else pmis(n, A.row_ptr.ptr(), A.col_idx.ptr(), s_con.ptr(), w.ptr(), cf.ptr(), 0, s);
     return renumber_coarse(n, cf.ptr(), s);
 }
@@ -987,10 +1111,14 @@ void AMGSolver::setup_classical()
     const std::string strength = cfg_->get_string("strength", scope_), interp = cfg_->get_string("interpolator", scope_);
     const std::string agg_sel = cfg_->get_string("aggressive_selector", scope_), agg_int = cfg_->get_string("aggressive_interpolator", scope_);
     if (strength != "AHAT") fatal(AMGX_RC_BAD_CONFIGURATION, "strength '" + strength + "' is not supported by this engine (AHAT)");
-    if (selector_ != "PMIS") fatal(AMGX_RC_BAD_CONFIGURATION, "classical selector '" + selector_ + "' is not supported by this engine (PMIS)");
+    if (selector_ != "PMIS" && selector_ != "HMIS")
+        fatal(AMGX_RC_BAD_CONFIGURATION, "classical selector '" + selector_ + "' is not supported by this engine (PMIS, HMIS)");
+    prm.hmis = (selector_ == "HMIS");
     if (interp != "D2" && interp != "MULTIPASS") fatal(AMGX_RC_BAD_CONFIGURATION, "interpolator '" + interp + "' is not supported by this engine (D2, MULTIPASS)");
     if (prm.aggressive_levels > 0) {
-        if (agg_sel != "DEFAULT" && agg_sel != "PMIS") fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_selector '" + agg_sel + "' is not supported (PMIS)");
+        if (agg_sel != "DEFAULT" && agg_sel != "PMIS" && agg_sel != "HMIS")
+            fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_selector '" + agg_sel + "' is not supported (DEFAULT, PMIS, HMIS)");
+        prm.aggressive_hmis = (agg_sel == "HMIS") || (agg_sel == "DEFAULT" && prm.hmis);   // classical_amg_level.cu:132-147
         if (agg_int != "MULTIPASS") fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_interpolator '" + agg_int + "' is not supported (MULTIPASS)");
     }
     prm.d2 = (interp == "D2");

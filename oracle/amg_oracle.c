@@ -565,6 +565,7 @@ ORC_API orc_amg *orc_amg_setup_classical(int n, const int *rp, const int *ci, co
         int *cf = (int *)calloc((size_t)(L->n > 0 ? L->n : 1), sizeof(int));
         orc_cla_strength(L->n, L->rp, L->ci, L->va, strength_threshold, max_row_sum, s_con, w);
         if (lvl < aggressive_levels) orc_cla_aggressive_pmis(L->n, L->rp, L->ci, s_con, w, cf);
+        else if (g_cla_selector == 1) orc_cla_hmis(L->n, L->rp, L->ci, s_con, w, cf);
         else orc_cla_pmis(L->n, L->rp, L->ci, s_con, w, cf, 0);
         const int nc = orc_cla_renumber(L->n, cf);
         free(w);

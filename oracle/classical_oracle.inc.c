@@ -88,7 +88,15 @@ ORC_API void orc_cla_pmis(int n, const int *rp, const int *ci, const unsigned ch
 {
     int *scratch = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
     int *mark = (int *)calloc((size_t)(n > 0 ? n : 1), sizeof(int));
-    for (int i = 0; i < n; i++) {   /* initialMarkingKernel / initialMarkingCFInit3Kernel */
+    for (int i = 0; init == 1 && i < n; i++) {   /* initialMarkingCfInitKernel (pmis.cu:316-360): cf comes from a previous pass (HMIS) */
+        const int numj = rp[i + 1] - rp[i];
+        if (numj == 0) cf[i] = CLA_FINE;
+        else if (numj == 1 && ci[rp[i]] == i) cf[i] = CLA_FINE;
+        else if (w[i] < 1) cf[i] = CLA_FINE;
+        else if (cf[i] == CLA_STRONG_FINE) w[i] = 0.f;
+        else if (cf[i] == CLA_FINE) { cf[i] = CLA_UNASSIGNED; mark[i] = 1; }
+    }
+    for (int i = 0; init != 1 && i < n; i++) {   /* initialMarkingKernel / initialMarkingCFInit3Kernel */
         const int numj = rp[i + 1] - rp[i];
         if (numj == 0) cf[i] = CLA_FINE;
         else if (numj == 1 && ci[rp[i]] == i) cf[i] = CLA_FINE;
@@ -140,6 +148,132 @@ ORC_API void orc_cla_pmis(int n, const int *rp, const int *ci, const unsigned ch
     free(scratch);
     free(mark);
 }
+
+/* RS_Selector<host>::markCoarseFinePoints_1x1 (src/classical/selectors/rs.cu:36-262): first pass of Ruge-Stueben coarsening,
+ * sequential.  The reference keeps (weight, row) pairs in a std::set ordered by weight then by DEcreasing row, and always takes
+ * rbegin(): the largest weight, the SMALLEST row among equals.  Here: a binary heap of (weight, row) with lazy deletion; a row
+ * is in the set iff in_set[row], always with weight == iw[row] (the invariant of the reference's erase / insert pairs). */
+typedef struct { int w, i; } rs_ent;
+static int rs_before(rs_ent a, rs_ent b) { return a.w > b.w || (a.w == b.w && a.i < b.i); }   /* a leaves the heap before b */
+typedef struct { rs_ent *e; int n, cap; } rs_heap;
+static void rs_push(rs_heap *h, int w, int i)
+{
+    if (h->n == h->cap) { h->cap = h->cap ? 2 * h->cap : 1024; h->e = (rs_ent *)realloc(h->e, sizeof(rs_ent) * (size_t)h->cap); }
+    int k = h->n++;
+    rs_ent x = {w, i};
+    while (k > 0) {
+        const int p = (k - 1) / 2;
+        if (!rs_before(x, h->e[p])) break;
+        h->e[k] = h->e[p];
+        k = p;
+    }
+    h->e[k] = x;
+}
+static rs_ent rs_pop(rs_heap *h)
+{
+    const rs_ent top = h->e[0], x = h->e[--h->n];
+    int k = 0;
+    for (;;) {
+        int c = 2 * k + 1;
+        if (c >= h->n) break;
+        if (c + 1 < h->n && rs_before(h->e[c + 1], h->e[c])) c++;
+        if (!rs_before(h->e[c], x)) break;
+        h->e[k] = h->e[c];
+        k = c;
+    }
+    if (h->n > 0) h->e[k] = x;
+    return top;
+}
+ORC_API void orc_cla_rs(int n, const int *rp, const int *ci, const unsigned char *s_con, int *cf, int init)
+{
+#define RS_STRONG(k) ((!s_con || s_con[k]) && ci[k] < n)
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    int *stp = (int *)calloc((size_t)n + 2, sizeof(int)), *stc = (int *)malloc(sizeof(int) * (size_t)(rp[n] > 0 ? rp[n] : 1));
+    for (int k = 0; k < rp[n]; k++) if (RS_STRONG(k)) stp[ci[k] + 1]++;
+    for (int i = 0; i < n; i++) stp[i + 1] += stp[i];
+    int *fillp = (int *)malloc(sizeof(int) * nn);
+    for (int i = 0; i < n; i++) fillp[i] = stp[i];
+    for (int i = 0; i < n; i++) for (int k = rp[i]; k < rp[i + 1]; k++) if (RS_STRONG(k)) stc[fillp[ci[k]]++] = i;   /* S^T, rows ascending */
+    int *iw = (int *)malloc(sizeof(int) * nn);
+    char *in_set = (char *)calloc(nn, 1);
+    rs_heap h = {NULL, 0, 0};
+#define RS_ERASE(i) (in_set[i] = 0)
+#define RS_INSERT(i) do { in_set[i] = 1; rs_push(&h, iw[i], (i)); } while (0)
+    for (int i = 0; i < n; i++) iw[i] = stp[i + 1] - stp[i];
+    int num_left = 0;
+    for (int j = 0; j < n; j++) {
+        int isolated = 1;
+        for (int k = rp[j]; k < rp[j + 1]; k++) if (RS_STRONG(k)) { isolated = 0; break; }
+        if (isolated) { cf[j] = (init == 3) ? CLA_COARSE : CLA_STRONG_FINE; iw[j] = 0; }
+        else { cf[j] = CLA_UNASSIGNED; num_left++; }
+    }
+    for (int j = 0; j < n; j++) {
+        if (cf[j] == CLA_STRONG_FINE) continue;
+        if (iw[j] > 0) { RS_INSERT(j); continue; }
+        cf[j] = CLA_FINE;                                     /* nobody depends on j */
+        for (int k = rp[j]; k < rp[j + 1]; k++) {
+            if (!RS_STRONG(k)) continue;
+            const int nb = ci[k];
+            if (cf[nb] == CLA_STRONG_FINE) continue;
+            if (nb < j) { if (iw[nb] > 0) RS_ERASE(nb); ++iw[nb]; RS_INSERT(nb); }
+            else ++iw[nb];
+        }
+        --num_left;
+    }
+    while (num_left > 0) {
+        int index = -1;
+        while (h.n > 0) {                                     /* rbegin(): skip entries erased or re-weighted since they were pushed */
+            const rs_ent t = rs_pop(&h);
+            if (in_set[t.i] && iw[t.i] == t.w) { index = t.i; break; }
+        }
+        if (index < 0) break;                                 /* the reference would dereference an empty set here */
+        cf[index] = CLA_COARSE;
+        iw[index] = 0;
+        --num_left;
+        RS_ERASE(index);
+        for (int j = stp[index]; j < stp[index + 1]; j++) {   /* rows that strongly depend on the new C point become F */
+            const int nb = stc[j];
+            if (cf[nb] != CLA_UNASSIGNED) continue;
+            cf[nb] = CLA_FINE;
+            RS_ERASE(nb);
+            --num_left;
+            for (int k = rp[nb]; k < rp[nb + 1]; k++) {
+                if (!RS_STRONG(k)) continue;
+                const int d2 = ci[k];
+                if (cf[d2] == CLA_UNASSIGNED) { RS_ERASE(d2); ++iw[d2]; RS_INSERT(d2); }
+            }
+        }
+        for (int j = rp[index]; j < rp[index + 1]; j++) {     /* points the new C point depends on lose one unit of measure */
+            if (!RS_STRONG(j)) continue;
+            const int nb = ci[j];
+            if (cf[nb] != CLA_UNASSIGNED) continue;
+            RS_ERASE(nb);
+            const int wgt = --iw[nb];
+            if (wgt > 0) { RS_INSERT(nb); continue; }
+            cf[nb] = CLA_FINE;
+            --num_left;
+            for (int k = rp[nb]; k < rp[nb + 1]; k++) {
+                if (!RS_STRONG(k)) continue;
+                const int d2 = ci[k];
+                if (cf[d2] == CLA_UNASSIGNED) { RS_ERASE(d2); ++iw[d2]; RS_INSERT(d2); }
+            }
+        }
+    }
+#undef RS_STRONG
+#undef RS_ERASE
+#undef RS_INSERT
+    free(stp); free(stc); free(fillp); free(iw); free(in_set); free(h.e);
+}
+
+/* HMIS_Selector<device>::markCoarseFinePoints_1x1 (src/classical/selectors/hmis.cu:58-88): Ruge-Stueben first pass on the host
+ * (always with cf_map_init = 0), then PMIS with cf_map_init = 1, whatever cf_map_init the caller asked for */
+ORC_API void orc_cla_hmis(int n, const int *rp, const int *ci, const unsigned char *s_con, float *w, int *cf)
+{
+    orc_cla_rs(n, rp, ci, s_con, cf, 0);
+    orc_cla_pmis(n, rp, ci, s_con, w, cf, 1);
+}
+static int g_cla_selector = 0;       /* 0 PMIS, 1 HMIS: selector of the NEXT classical setup (and of its aggressive levels) */
+ORC_API void orc_set_classical_selector(int sel) { g_cla_selector = sel; }
 
 /* renumberAndCountCoarsePoints: COARSE -> 0,1,2,... in row order */
 ORC_API int orc_cla_renumber(int n, int *cf)
@@ -316,7 +450,9 @@ static int cla_c_hat_fill(int i, const int *rp, const int *ci, const unsigned ch
 /* Aggressive_PMIS_Selector::markCoarseFinePoints: PMIS, S2 among the coarse points, PMIS on S2, correctCfMap */
 ORC_API void orc_cla_aggressive_pmis(int n, const int *rp, const int *ci, const unsigned char *s_con, float *w, int *cf)
 {
-    orc_cla_pmis(n, rp, ci, s_con, w, cf, 0);
+    /* Aggressive_PMIS / Aggressive_HMIS selectors differ only in the selector applied to A and to S2 (aggressive_hmis.cu:41,131) */
+    if (g_cla_selector == 1) orc_cla_hmis(n, rp, ci, s_con, w, cf);
+    else orc_cla_pmis(n, rp, ci, s_con, w, cf, 0);
     int *scanned = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
     memcpy(scanned, cf, sizeof(int) * (size_t)n);
     const int nc = orc_cla_renumber(n, scanned);
@@ -336,7 +472,8 @@ ORC_API void orc_cla_aggressive_pmis(int n, const int *rp, const int *ci, const 
     float *w2 = (float *)malloc(sizeof(float) * (size_t)nc);
     int *cf2 = (int *)malloc(sizeof(int) * (size_t)nc);
     cla_weights_pattern(nc, s2p, s2c, w2);
-    orc_cla_pmis(nc, s2p, s2c, NULL, w2, cf2, 3);
+    if (g_cla_selector == 1) orc_cla_hmis(nc, s2p, s2c, NULL, w2, cf2);
+    else orc_cla_pmis(nc, s2p, s2c, NULL, w2, cf2, 3);
     for (int i = 0; i < n; i++)      /* correctCfMapKernel */
         if (cf[i] == CLA_COARSE) { const int c2 = cf2[scanned[i]]; cf[i] = (c2 == CLA_STRONG_FINE) ? CLA_COARSE : c2; }
     free(scanned); free(s2p); free(s2c); free(w2); free(cf2);

@@ -381,6 +381,31 @@ def cla_pmis(rp, ci, s_con, weights, aggressive=False):
     return cf
 
 
+def cla_rs(rp, ci, s_con, init=0):
+    """Ruge-Stueben first pass (the host algorithm HMIS starts from); returns the C/F map"""
+    rp, ci = _i(rp), _i(ci)
+    n = rp.shape[0] - 1
+    s_con = np.ascontiguousarray(s_con, np.uint8)
+    cf = np.zeros(n, np.int32)
+    lib().orc_cla_rs(n, _p(rp), _p(ci), _p(s_con), _p(cf), init)
+    return cf
+
+
+def cla_hmis(rp, ci, s_con, weights):
+    rp, ci = _i(rp), _i(ci)
+    n = rp.shape[0] - 1
+    s_con = np.ascontiguousarray(s_con, np.uint8)
+    w = np.ascontiguousarray(weights, np.float32).copy()
+    cf = np.zeros(n, np.int32)
+    lib().orc_cla_hmis(n, _p(rp), _p(ci), _p(s_con), _p(w), _p(cf))
+    return cf
+
+
+def set_classical_selector(name):
+    """selector of the NEXT ClassicalAMG setups: "PMIS" (default) or "HMIS"""
+    lib().orc_set_classical_selector({"PMIS": 0, "HMIS": 1}[name])
+
+
 def cla_renumber(cf):
     cf = _i(cf).copy()
     nc = lib().orc_cla_renumber(cf.shape[0], _p(cf))
@@ -412,17 +437,20 @@ class ClassicalAMG(AMG):
 
     def __init__(self, rp, ci, va, max_levels=100, min_coarse_rows=2, coarsen_threshold=1.0, presweeps=1, postsweeps=1, coarsest_sweeps=2,
                  finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, strength_threshold=0.25, max_row_sum=1.1, interpolator="D1",
-                 aggressive_levels=0, aggressive_interpolator="MULTIPASS", interp_max_elements=-1, coarse_solver="NOSOLVER", dense_lu_num_rows=128):
+                 aggressive_levels=0, aggressive_interpolator="MULTIPASS", interp_max_elements=-1, coarse_solver="NOSOLVER", dense_lu_num_rows=128,
+                 selector="PMIS"):
         self.rp, self.ci, self.va = _i(rp), _i(ci), _d(va)
         if coarse_solver == "DENSE_LU_SOLVER":
             min_coarse_rows = dense_lu_num_rows
         self.n = self.rp.shape[0] - 1
         sm = SMOOTHERS[smoother]
         im = {"D2": 0, "MULTIPASS": 1}
+        set_classical_selector(selector)
         self.h = C.c_void_p(lib().orc_amg_setup_classical(
             self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold), presweeps, postsweeps,
             coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), C.c_double(strength_threshold), C.c_double(max_row_sum), im[interpolator],
             aggressive_levels, im[aggressive_interpolator], interp_max_elements))
+        set_classical_selector("PMIS")
         if coarse_solver == "DENSE_LU_SOLVER":
             lib().orc_amg_enable_dense_lu(self.h)
 

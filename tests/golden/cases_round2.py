@@ -88,6 +88,16 @@ def cases():
     yield "poisson10_amg_agg_cheb2_coarsest1", P(10), _standalone(_agg(CHEB(None, 2), presweeps=0, coarsest_sweeps=1, error_scaling=3), tol=1e-30, max_iters=6)
     for order in (2, 4):
         yield f"poisson14x12x11_pcg_agg_chebpoly{order}", P(14, 12, 11), _outer("PCG", _agg(CHEBP(order), presweeps=0, postsweeps=3, coarsest_sweeps=0))
+    # HMIS selector (the two shipped HMIS configs: FGMRES_CLASSICAL_AGGRESSIVE_HMIS.json, AMG_CLASSICAL_L1_AGGRESSIVE_HMIS.json)
+    cla = lambda **kw: dict({"scope": "amg", "solver": "AMG", "algorithm": "CLASSICAL", "selector": "HMIS", "interpolator": "D2", "aggressive_levels": 1,
+                             "interp_max_elements": 4, "max_row_sum": 0.9, "strength_threshold": 0.25, "cycle": "V", "max_levels": 50, "min_coarse_rows": 2,
+                             "presweeps": 2, "postsweeps": 2, "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER", "max_iters": 1, "monitor_residual": 0,
+                             "print_grid_stats": 1,
+                             "smoother": {"scope": "jl1", "solver": "JACOBI_L1", "relaxation_factor": 1, "monitor_residual": 0}}, **kw)
+    yield "poisson14_fgmres_classical_hmis_aggr", P(14), _outer("FGMRES", cla(), tol=1e-10, max_iters=60, gmres_n_restart=20)
+    yield "poisson16x12x9_fgmres_classical_hmis", P(16, 12, 9), _outer("FGMRES", cla(aggressive_levels=0), tol=1e-10, max_iters=60, gmres_n_restart=20)
+    yield "banded3000_fgmres_classical_hmis", gallery.random_banded(3000, sigma=40.0), _outer("FGMRES", cla(aggressive_levels=0), tol=1e-10, max_iters=40,
+                                                                                                gmres_n_restart=20)
     # dense LU coarse solver
     for rows in (32, 128):
         yield f"poisson12_pcg_agg_denselu{rows}", P(12), _outer("PCG", _agg(coarse_solver="DENSE_LU_SOLVER", dense_lu_num_rows=rows))

@@ -47,8 +47,8 @@ def build_amg(oracle, a, rp, ci, va, determinism=0):
             assert a.get("selector", "SIZE_2") == "SIZE_2"
             amg = oracle.AMG(rp, ci, va, **kw)
         else:
-            assert _get(a, "selector") == "PMIS"
-            amg = oracle.ClassicalAMG(rp, ci, va, strength_threshold=_get(a, "strength_threshold"), max_row_sum=_get(a, "max_row_sum"),
+            assert _get(a, "selector") in ("PMIS", "HMIS")
+            amg = oracle.ClassicalAMG(rp, ci, va, selector=_get(a, "selector"), strength_threshold=_get(a, "strength_threshold"), max_row_sum=_get(a, "max_row_sum"),
                                       interpolator=_get(a, "interpolator"), aggressive_levels=_get(a, "aggressive_levels"),
                                       aggressive_interpolator=_get(a, "aggressive_interpolator"), interp_max_elements=_get(a, "interp_max_elements"), **kw)
     finally:

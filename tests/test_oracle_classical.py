@@ -12,6 +12,8 @@ from pathlib import Path
 
 import numpy as np
 import pytest
+
+from amgx_b200 import gallery
 import scipy.sparse as sp
 
 GOLD = Path(__file__).parent / "golden"
@@ -150,3 +152,135 @@ def test_classical_vcycle_reduces_error(oracle):
     P = sp.csr_matrix((L0["P_values"], L0["P_col_indices"], L0["P_row_offsets"]), shape=(n, amg.level(1)["n"]))
     rs = np.asarray(P.sum(axis=1)).ravel()
     assert rs.max() <= 1.0 + 1e-12 and rs.min() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# HMIS = Ruge-Stueben first pass on the host + PMIS(cf_map_init = 1)   (parity unpinned: no reference golden yet)
+# ---------------------------------------------------------------------------------------------------------------
+def python_rs(rp, ci, s_con):
+    """rs.cu:36-262 with a sorted container standing in for the std::set (largest weight first, smallest row among equals)"""
+    from sortedcontainers import SortedList
+    n = rp.shape[0] - 1
+    COARSE, FINE, STRONG_FINE, UNASSIGNED = -1, -2, -3, -4
+    strong = [[int(ci[k]) for k in range(rp[i], rp[i + 1]) if s_con[k] and ci[k] < n] for i in range(n)]
+    st = [[] for _ in range(n)]
+    for i in range(n):
+        for j in strong[i]:
+            st[j].append(i)
+    iw = [len(st[i]) for i in range(n)]
+    cf = [0] * n
+    S = SortedList(key=lambda p: (p[0], -p[1]))
+    left = 0
+    for j in range(n):
+        if not strong[j]:
+            cf[j], iw[j] = STRONG_FINE, 0
+        else:
+            cf[j] = UNASSIGNED
+            left += 1
+    for j in range(n):
+        if cf[j] == STRONG_FINE:
+            continue
+        if iw[j] > 0:
+            S.add((iw[j], j))
+            continue
+        cf[j] = FINE
+        for nb in strong[j]:
+            if cf[nb] == STRONG_FINE:
+                continue
+            if nb < j:
+                if iw[nb] > 0:
+                    S.discard((iw[nb], nb))
+                iw[nb] += 1
+                S.add((iw[nb], nb))
+            else:
+                iw[nb] += 1
+        left -= 1
+
+    def bump(d2):
+        S.discard((iw[d2], d2))
+        iw[d2] += 1
+        S.add((iw[d2], d2))
+
+    while left > 0 and S:
+        w, index = S[-1]
+        cf[index] = COARSE
+        iw[index] = 0
+        left -= 1
+        S.discard((w, index))
+        for nb in st[index]:
+            if cf[nb] == UNASSIGNED:
+                cf[nb] = FINE
+                S.discard((iw[nb], nb))
+                left -= 1
+                for d2 in strong[nb]:
+                    if cf[d2] == UNASSIGNED:
+                        bump(d2)
+        for nb in strong[index]:
+            if cf[nb] == UNASSIGNED:
+                S.discard((iw[nb], nb))
+                iw[nb] -= 1
+                if iw[nb] > 0:
+                    S.add((iw[nb], nb))
+                else:
+                    cf[nb] = FINE
+                    left -= 1
+                    for d2 in strong[nb]:
+                        if cf[d2] == UNASSIGNED:
+                            bump(d2)
+    return np.array(cf, np.int32)
+
+
+@pytest.mark.parametrize("mat", ["poisson", "poisson_aniso", "banded"])
+def test_rs_first_pass_matches_python_restatement(oracle, mat):
+    if mat == "poisson":
+        rp, ci, va = gallery.poisson7pt(9, 8, 7)
+    elif mat == "poisson_aniso":
+        rp, ci, va = gallery.poisson7pt(12, 5, 3)
+        va = va.copy()
+        va[np.abs(ci - np.repeat(np.arange(rp.shape[0] - 1), np.diff(rp))) == 1] *= 10.0     # strong coupling along x only
+    else:
+        rp, ci, va = gallery.random_banded(1500, sigma=25.0)
+    s_con, w = oracle.cla_strength(rp, ci, va, 0.25, 1.1)
+    cf = oracle.cla_rs(rp, ci, s_con)
+    ref = python_rs(rp, ci, s_con)
+    assert np.array_equal(cf, ref)
+    assert not np.any(cf == oracle.UNASSIGNED)
+    # every F point that has strong connections depends strongly on at least one C point, or feeds none (RS first pass)
+    n = rp.shape[0] - 1
+    assert np.count_nonzero(cf == oracle.COARSE) > 0
+
+
+@pytest.mark.parametrize("mat", ["poisson", "banded"])
+def test_hmis_is_a_valid_and_sparser_coarsening(oracle, mat):
+    rp, ci, va = gallery.poisson7pt(10, 9, 8) if mat == "poisson" else gallery.random_banded(2000, sigma=25.0)
+    n = rp.shape[0] - 1
+    s_con, w = oracle.cla_strength(rp, ci, va, 0.25, 1.1)
+    cf_h = oracle.cla_hmis(rp, ci, s_con, w)
+    cf_p = oracle.cla_pmis(rp, ci, s_con, w)
+    assert not np.any(cf_h == oracle.UNASSIGNED)
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    strong = s_con.astype(bool) & (ci < n)
+    # every FINE point has a strong COARSE neighbour (it can be interpolated)
+    has_c = np.zeros(n, bool)
+    np.logical_or.at(has_c, rows[strong], cf_h[ci[strong]] == oracle.COARSE)
+    assert np.all(has_c[cf_h == oracle.FINE])
+    # the RS first pass survives: its C points stay C (PMIS with cf_map_init = 1 only reconsiders F points)
+    cf_rs = oracle.cla_rs(rp, ci, s_con)
+    assert np.all(cf_h[cf_rs == oracle.COARSE] == oracle.COARSE)
+    nc_h, nc_p = np.count_nonzero(cf_h == oracle.COARSE), np.count_nonzero(cf_p == oracle.COARSE)
+    assert 0 < nc_h < n and nc_h != nc_p
+
+
+@pytest.mark.parametrize("aggressive", [0, 1])
+def test_classical_amg_with_hmis_converges(oracle, aggressive):
+    rp, ci, va = gallery.poisson7pt(14, 12, 10)
+    n = rp.shape[0] - 1
+    kw = dict(max_levels=50, presweeps=2, postsweeps=2, smoother="JACOBI_L1", omega=1.0, strength_threshold=0.25, max_row_sum=0.9,
+              interpolator="D2", aggressive_levels=aggressive, interp_max_elements=4)
+    h = oracle.ClassicalAMG(rp, ci, va, selector="HMIS", **kw)
+    p = oracle.ClassicalAMG(rp, ci, va, selector="PMIS", **kw)
+    assert h.level(0)["n_coarse"] != p.level(0)["n_coarse"] or not np.array_equal(h.level(0)["cf_map"], p.level(0)["cf_map"])
+    x, it, hist, conv = oracle.fgmres(rp, ci, va, np.ones(n), amg=h, tol=1e-8, max_iters=60, restart=20)
+    assert conv and it < 30
+    A = gallery.to_scipy(rp, ci, va)
+    assert np.linalg.norm(np.ones(n) - A @ x) <= 1e-7 * np.sqrt(n)

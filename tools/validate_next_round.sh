@@ -7,9 +7,9 @@
 mkdir -p gpurun_out
 echo "== full gpu suite (validated components)"
 timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-echo "== unvalidated: DENSE_LU, W/F/CG/CGF cycles, error_scaling, CG/PCGF/PBICGSTAB/GMRES, MULTICOLOR_GS, CHEBYSHEV(_POLY), resetup"
+echo "== unvalidated: DENSE_LU, W/F/CG/CGF cycles, error_scaling, CG/PCGF/PBICGSTAB/GMRES, MULTICOLOR_GS, CHEBYSHEV(_POLY), resetup, HMIS, partition vectors, comm maps, replicated tail"
 AMGXB_RUN_UNVALIDATED=1 timeout 1200 python -m pytest tests/test_gpu_dense_lu.py tests/test_gpu_cycles.py tests/test_gpu_krylov.py tests/test_gpu_smoothers.py \
-    tests/test_gpu_resetup.py tests/test_golden_round2.py -q -m gpu 2>&1 | tail -30 | tee gpurun_out/unvalidated.log
+    tests/test_gpu_resetup.py tests/test_golden_round2.py tests/test_gpu_classical.py tests/test_gpu_dist.py -q -m gpu 2>&1 | tail -30 | tee gpurun_out/unvalidated.log
 echo "== reference goldens for the round-2 cases"
 timeout 900 python tests/golden/make_golden.py r2 2>&1 | tail -40 | tee gpurun_out/make_golden_r2.log
 echo "== replicated tail (partitioned aggregates), 2 GPUs: iterations must equal the tail-off run"
