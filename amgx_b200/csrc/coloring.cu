@@ -46,6 +46,39 @@ __global__ void color_rows_kernel(const int *__restrict__ rp, const int *__restr
     }
 }
 
+// PARALLEL_GREEDY, coloring_level 1 (src/matrix_coloring/parallel_greedy.cu:148-215): an uncoloured row whose (signed) hash beats
+// every uncoloured neighbour takes the smallest colour >= 1 none of its neighbours holds.  The reference updates the colours in
+// place, so whether a row sees a neighbour coloured earlier in the SAME launch depends on scheduling and its colouring is not
+// reproducible run to run; this is the synchronous form of the same rule (every row reads the colours of the previous launch):
+// always a proper colouring, reproducible, and what the reference produces whenever no such same-launch propagation happens.
+__global__ void pg_color_kernel(const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ colors_in, int *colors_out, int n, int *max_color)
+{
+    int mc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int c = colors_in[i];
+        if (c == 0) {
+            const int hash_i = (int)hash_function((unsigned)i, 0);
+            unsigned long long used = 0ull;
+            bool max_row = true;
+            for (int r = rp[i]; r < rp[i + 1]; r++) {
+                const int j = ci[r];
+                if (j >= n || j == i) continue;
+                const int cj = colors_in[j];
+                if (cj > 0 && cj <= 64) used |= 1ull << (64 - cj);
+                max_row &= (hash_i > (int)hash_function((unsigned)j, 0) || cj != 0);
+            }
+            if (max_row) {
+                const unsigned long long free_mask = ~used;
+                if (free_mask != 0ull) c = 64 - (63 - __clzll((long long)free_mask));      // 64 - bfind(~used)
+            }
+        }
+        colors_out[i] = c;
+        mc = max(mc, c);
+    }
+    for (int o = 16; o > 0; o >>= 1) mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    if ((threadIdx.x & 31) == 0 && mc) atomicMax(max_color, mc);
+}
+
 __global__ void count_zero_kernel(int n, const int *__restrict__ v, int *count, int *maxv)
 {
     int c = 0, m = 0;
@@ -114,6 +147,53 @@ void color_matrix_min_max(Matrix &A, double max_uncolored_fraction, cudaStream_t
     count_launch();
     A.num_colors = cnt.to_host(s)[1] + 1;
     build_color_arrays(A, s);
+}
+
+// Parallel_Greedy_Matrix_Coloring::colorMatrix (parallel_greedy.cu:665-790), coloring_level 1: launches until the number of
+// uncoloured rows counted BEFORE a launch is <= max_uncolored (that launch still colours), stops progressing, or 64 colours are in use
+void color_matrix_parallel_greedy(Matrix &A, double max_uncolored_fraction, cudaStream_t s)
+{
+    if (A.user_coloring) return;
+    const int n = A.n;
+    A.row_colors.resize(std::max(A.n_cols, n));
+    A.row_colors.zero(s);
+    DevBuf<int> next, cnt;
+    next.resize(std::max(A.n_cols, n));
+    next.zero(s);
+    cnt.resize(2);
+    const int max_uncolored = (int)(max_uncolored_fraction * (double)n);
+    int prev_uncolored = 0, max_color = 0;
+    for (int iter = 0; n > 0; iter++) {
+        cnt.zero(s);
+        count_zero_kernel<<<grid_for(n), 256, 0, s>>>(n, A.row_colors.ptr(), cnt.ptr(), cnt.ptr() + 1);      // uncoloured before this launch
+        pg_color_kernel<<<grid_for(n), 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.row_colors.ptr(), next.ptr(), n, cnt.ptr() + 1);
+        count_launch(2);
+        AMGXB_LAUNCH_CHECK();
+        A.row_colors.swap(next);
+        const std::vector<int> h = cnt.to_host(s);
+        const int num_uncolored = h[0];
+        max_color = h[1];
+        if (max_color + 1 >= 64 || prev_uncolored == num_uncolored || num_uncolored <= max_uncolored) break;
+        prev_uncolored = num_uncolored;
+        if (iter > 100000) fatal(AMGX_RC_INTERNAL, "PARALLEL_GREEDY colouring did not terminate");
+    }
+    if (max_color + 1 >= 64) {
+        cnt.zero(s);
+        count_zero_kernel<<<grid_for(n), 256, 0, s>>>(n, A.row_colors.ptr(), cnt.ptr(), cnt.ptr() + 1);
+        count_launch();
+        if (cnt.to_host(s)[0] > max_uncolored)
+            fatal(AMGX_RC_NOT_IMPLEMENTED, "PARALLEL_GREEDY colouring needs more than 63 colours (the reference's max-colour fallback is not implemented); use MIN_MAX");
+    }
+    A.num_colors = max_color + 1;
+    build_color_arrays(A, s);
+}
+
+// matrix_coloring_scheme dispatcher used by the multicolour smoothers
+void color_matrix(Matrix &A, const std::string &scheme, double max_uncolored_fraction, cudaStream_t s)
+{
+    if (scheme == "MIN_MAX") color_matrix_min_max(A, max_uncolored_fraction, s);
+    else if (scheme == "PARALLEL_GREEDY") color_matrix_parallel_greedy(A, max_uncolored_fraction, s);
+    else fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_coloring_scheme '" + scheme + "' is not supported by this engine (MIN_MAX, PARALLEL_GREEDY, or AMGX_matrix_attach_coloring)");
 }
 
 void attach_user_coloring(Matrix &A, const int *row_coloring, int num_rows, int num_colors)

@@ -15,7 +15,7 @@
 
 namespace amgxb {
 
-void color_matrix_min_max(Matrix &A, double max_uncolored_fraction, cudaStream_t s);   // coloring.cu
+void color_matrix(Matrix &A, const std::string &scheme, double max_uncolored_fraction, cudaStream_t s);   // coloring.cu
 
 namespace {
 
@@ -243,8 +243,9 @@ public:
             weight_ = 1.;
             amgx_printf("Warning, setting weight to 1 instead of estimating largest_eigen_value in Multicolor DILU smoother\n");
         }
-        const std::string scheme = cfg.get_string("matrix_coloring_scheme", scope);
-        if (scheme != "MIN_MAX") fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_coloring_scheme '" + scheme + "' is not supported by this engine (MIN_MAX, or AMGX_matrix_attach_coloring)");
+        scheme_ = cfg.get_string("matrix_coloring_scheme", scope);
+        if (scheme_ != "MIN_MAX" && scheme_ != "PARALLEL_GREEDY")
+            fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_coloring_scheme '" + scheme_ + "' is not supported by this engine (MIN_MAX, PARALLEL_GREEDY, or AMGX_matrix_attach_coloring)");
         if (cfg.get_int("coloring_level", scope) != 1) fatal(AMGX_RC_BAD_CONFIGURATION, "MULTICOLOR_DILU: coloring_level must be 1");
         if (cfg.get_int("reorder_cols_by_color", scope) != 0 || cfg.get_int("insert_diag_while_reordering", scope) != 0)
             fatal(AMGX_RC_NOT_IMPLEMENTED, "reorder_cols_by_color / insert_diag_while_reordering");
@@ -266,7 +267,7 @@ protected:
         if (A.bs() != 1 && A.bx != 4) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "Multicolor-DILU: block sizes 1 and 4 are enabled in this engine");
         if (A.has_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "Multicolor-DILU with an external diagonal");
         cudaStream_t s = stream();
-        if (A.num_colors == 0) color_matrix_min_max(A, uncolored_fraction_, s);
+        if (A.num_colors == 0) color_matrix(A, scheme_, uncolored_fraction_, s);
         const size_t bs = A.bs();
         Einv_.resize((size_t)A.n_cols * bs, A.mat_prec);
         Einv_.zero(s);
@@ -354,6 +355,7 @@ protected:
     }
 
     double weight_ = 0.9, uncolored_fraction_ = 0.15;
+    std::string scheme_ = "MIN_MAX";
     DevVec Einv_, delta_, Delta_;
 };
 

@@ -12,7 +12,7 @@
 
 namespace amgxb {
 
-void color_matrix_min_max(Matrix &A, double max_uncolored_fraction, cudaStream_t s);   // coloring.cu
+void color_matrix(Matrix &A, const std::string &scheme, double max_uncolored_fraction, cudaStream_t s);   // coloring.cu
 
 namespace {
 
@@ -58,8 +58,9 @@ public:
             weight_ = 1.;
             amgx_printf("Warning, setting weight to 1 instead of estimating largest_eigen_value in Multicolor GaussSeidel smoother\n");
         }
-        const std::string scheme = cfg.get_string("matrix_coloring_scheme", scope);
-        if (scheme != "MIN_MAX") fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_coloring_scheme '" + scheme + "' is not supported by this engine (MIN_MAX, or AMGX_matrix_attach_coloring)");
+        scheme_ = cfg.get_string("matrix_coloring_scheme", scope);
+        if (scheme_ != "MIN_MAX" && scheme_ != "PARALLEL_GREEDY")
+            fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_coloring_scheme '" + scheme_ + "' is not supported by this engine (MIN_MAX, PARALLEL_GREEDY, or AMGX_matrix_attach_coloring)");
         if (cfg.get_int("coloring_level", scope) < 1)
             fatal(AMGX_RC_NOT_IMPLEMENTED, "Matrix must be colored to use multicolor gauss-seidel solver. Try setting: coloring_level=1 in the configuration file");
         if (cfg.get_int("coloring_level", scope) != 1) fatal(AMGX_RC_BAD_CONFIGURATION, "MULTICOLOR_GS: coloring_level must be 1");
@@ -82,7 +83,7 @@ protected:
         if (A.bs() != 1) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "MULTICOLOR_GS: scalar matrices only in this engine");
         if (A.has_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "MULTICOLOR_GS with an external diagonal");
         if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "MULTICOLOR_GS on a distributed matrix");
-        if (A.num_colors == 0) color_matrix_min_max(A, uncolored_fraction_, stream());
+        if (A.num_colors == 0) color_matrix(A, scheme_, uncolored_fraction_, stream());
         // KernelMethod::DEFAULT selection (multicolor_gauss_seidel_solver.cu:1004-1013)
         lanes_ = 4;
         if (A.n > 0 && A.nnz / A.n > 20) lanes_ = 32;
@@ -124,6 +125,7 @@ protected:
     }
 
     double weight_ = 0.9, uncolored_fraction_ = 0.15;
+    std::string scheme_ = "MIN_MAX";
     bool sym_ = false;
     int lanes_ = 4;
 };

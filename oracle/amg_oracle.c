@@ -435,6 +435,8 @@ typedef struct {
 #include "classical_oracle.inc.c"
 
 ORC_API int orc_color_min_max(int n, const int *rp, const int *ci, double max_uncolored_fraction, int *colors);
+ORC_API int orc_color_parallel_greedy(int n, const int *rp, const int *ci, double max_uncolored_fraction, int *colors);
+static int g_coloring_scheme;
 ORC_API void orc_color_arrays(int n, int num_colors, const int *colors, int *sorted_rows, int *offsets);
 ORC_API void orc_dilu_setup_1x1(int n, const int *rp, const int *ci, const double *va, int num_colors, const int *colors, const int *sorted_rows,
                                 const int *offsets, double *Einv);
@@ -467,7 +469,8 @@ static void level_smoother_setup(orc_level *L, int smoother)
         const size_t nn = (size_t)(L->n > 0 ? L->n : 1);
         L->colors = (int *)malloc(sizeof(int) * nn);
         L->sorted_rows = (int *)malloc(sizeof(int) * nn);
-        L->num_colors = orc_color_min_max(L->n, L->rp, L->ci, g_uncolored_fraction, L->colors);
+        L->num_colors = g_coloring_scheme == 1 ? orc_color_parallel_greedy(L->n, L->rp, L->ci, g_uncolored_fraction, L->colors)
+                                               : orc_color_min_max(L->n, L->rp, L->ci, g_uncolored_fraction, L->colors);
         L->color_offsets = (int *)malloc(sizeof(int) * ((size_t)L->num_colors + 1));
         orc_color_arrays(L->n, L->num_colors, L->colors, L->sorted_rows, L->color_offsets);
         L->Einv = (double *)calloc(nn, sizeof(double));
@@ -1113,6 +1116,51 @@ ORC_API int orc_color_min_max(int n, const int *rp, const int *ci, double max_un
 }
 
 /* createColorArrays (src/matrix_coloring/matrix_coloring.cu:230-281): rows stably sorted by colour */
+/* PARALLEL_GREEDY, coloring_level 1 (src/matrix_coloring/parallel_greedy.cu:148-215, 665-790) in its synchronous form: every launch
+ * reads the colours of the previous one (the reference updates in place and is not reproducible run to run; see csrc/coloring.cu).
+ * Colours start at 1, 0 = uncoloured; stops when the count taken BEFORE a launch is <= max_uncolored, does not change, or 64 colours
+ * are in use.  Returns num_colors = max colour + 1. */
+ORC_API int orc_color_parallel_greedy(int n, const int *rp, const int *ci, double max_uncolored_fraction, int *colors)
+{
+    int *next = (int *)calloc((size_t)(n > 0 ? n : 1), sizeof(int));
+    for (int i = 0; i < n; i++) colors[i] = 0;
+    const int max_uncolored = (int)(max_uncolored_fraction * (double)n);
+    int prev = 0, maxc = 0;
+    while (n > 0) {
+        int num_uncolored = 0;
+        for (int i = 0; i < n; i++) num_uncolored += (colors[i] == 0);
+        for (int i = 0; i < n; i++) {
+            int c = colors[i];
+            if (c == 0) {
+                const int hi = (int)hash_val((unsigned)i, 0);
+                unsigned long long used = 0ull;
+                int max_row = 1;
+                for (int r = rp[i]; r < rp[i + 1]; r++) {
+                    const int j = ci[r];
+                    if (j >= n || j == i) continue;
+                    const int cj = colors[j];
+                    if (cj > 0 && cj <= 64) used |= 1ull << (64 - cj);
+                    max_row &= (hi > (int)hash_val((unsigned)j, 0) || cj != 0);
+                }
+                if (max_row && ~used != 0ull) {
+                    int p = 63;
+                    while (!((~used >> p) & 1ull)) p--;          /* bfind(~used) */
+                    c = 64 - p;
+                }
+            }
+            next[i] = c;
+            if (c > maxc) maxc = c;
+        }
+        memcpy(colors, next, sizeof(int) * (size_t)n);
+        if (maxc + 1 >= 64 || prev == num_uncolored || num_uncolored <= max_uncolored) break;
+        prev = num_uncolored;
+    }
+    free(next);
+    return maxc + 1;
+}
+static int g_coloring_scheme = 0;    /* 0 MIN_MAX, 1 PARALLEL_GREEDY: scheme of the multicolour smoothers of the NEXT setups */
+ORC_API void orc_set_coloring_scheme(int scheme) { g_coloring_scheme = scheme; }
+
 ORC_API void orc_color_arrays(int n, int num_colors, const int *colors, int *sorted_rows, int *offsets)
 {
     for (int c = 0; c <= num_colors; c++) offsets[c] = 0;

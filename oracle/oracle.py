@@ -303,6 +303,22 @@ def gs_sweep(rp, ci, va, b, x, weight, symmetric=False, max_uncolored_fraction=0
     return x
 
 
+def set_coloring_scheme(name):
+    """matrix_coloring_scheme of the multicolour smoothers of the NEXT setups: "MIN_MAX" (default) or "PARALLEL_GREEDY"""
+    lib().orc_set_coloring_scheme({"MIN_MAX": 0, "PARALLEL_GREEDY": 1}[name])
+
+
+def color_parallel_greedy(rp, ci, max_uncolored_fraction=0.0):
+    rp, ci = _i(rp), _i(ci)
+    n = rp.shape[0] - 1
+    colors = np.empty(n, np.int32)
+    nc = lib().orc_color_parallel_greedy(n, _p(rp), _p(ci), C.c_double(max_uncolored_fraction), _p(colors))
+    sorted_rows = np.empty(n, np.int32)
+    offsets = np.empty(nc + 1, np.int32)
+    lib().orc_color_arrays(n, nc, _p(colors), _p(sorted_rows), _p(offsets))
+    return nc, colors, sorted_rows, offsets
+
+
 def color_min_max(rp, ci, max_uncolored_fraction=0.15):
     rp, ci = _i(rp), _i(ci)
     n = rp.shape[0] - 1

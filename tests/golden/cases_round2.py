@@ -98,6 +98,15 @@ def cases():
     yield "poisson16x12x9_fgmres_classical_hmis", P(16, 12, 9), _outer("FGMRES", cla(aggressive_levels=0), tol=1e-10, max_iters=60, gmres_n_restart=20)
     yield "banded3000_fgmres_classical_hmis", gallery.random_banded(3000, sigma=40.0), _outer("FGMRES", cla(aggressive_levels=0), tol=1e-10, max_iters=40,
                                                                                                 gmres_n_restart=20)
+    # PARALLEL_GREEDY colouring: the shipped FGMRES_AGGREGATION.json / FGMRES_AGGREGATION_DILU.json preconditioner (DILU, 0 + 3 sweeps,
+    # DENSE_LU coarse solver, min_coarse_rows 32).  The reference's in-place colouring kernel is not reproducible run to run
+    # (csrc/coloring.cu), so these goldens are compared loosely: see REFERENCE_NONDETERMINISTIC in tests/test_golden_round2.py
+    dilu_pg = {"scope": "dilu", "solver": "MULTICOLOR_DILU", "relaxation_factor": 0.75, "matrix_coloring_scheme": "PARALLEL_GREEDY", "monitor_residual": 0}
+    fa = _agg(dilu_pg, presweeps=0, postsweeps=3, coarse_solver="DENSE_LU_SOLVER", dense_lu_num_rows=128, min_coarse_rows=32,
+              matrix_coloring_scheme="PARALLEL_GREEDY")
+    yield "poisson16_fgmres_agg_dilu_pgreedy", P(16), _outer("FGMRES", fa, tol=1e-8, max_iters=60, gmres_n_restart=10)
+    yield "symbanded3000_fgmres_agg_dilu_pgreedy", sym_banded(3000, 40.0), _outer("FGMRES", fa, tol=1e-8, max_iters=60, gmres_n_restart=10)
+    yield "poisson14_amg_gs_pgreedy", P(14), _standalone(_agg(dict(GS(1), matrix_coloring_scheme="PARALLEL_GREEDY"), matrix_coloring_scheme="PARALLEL_GREEDY"))
     # dense LU coarse solver
     for rows in (32, 128):
         yield f"poisson12_pcg_agg_denselu{rows}", P(12), _outer("PCG", _agg(coarse_solver="DENSE_LU_SOLVER", dense_lu_num_rows=rows))

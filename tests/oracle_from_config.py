@@ -40,8 +40,10 @@ def build_amg(oracle, a, rp, ci, va, determinism=0):
         pc = _sub(sm, "preconditioner", "NOSOLVER")
         inner = None if pc["solver"] == "NOSOLVER" else pc["solver"]
     uncol = 0.0 if determinism else sm.get("max_uncolored_percentage", a.get("max_uncolored_percentage", DEFAULTS["max_uncolored_percentage"]))
+    scheme = sm.get("matrix_coloring_scheme", a.get("matrix_coloring_scheme", "MIN_MAX"))
     oracle.set_chebyshev_precond(inner)
     oracle.set_uncolored_fraction(uncol)
+    oracle.set_coloring_scheme(scheme)
     try:
         if _get(a, "algorithm") == "AGGREGATION":
             assert a.get("selector", "SIZE_2") == "SIZE_2"
@@ -54,6 +56,7 @@ def build_amg(oracle, a, rp, ci, va, determinism=0):
     finally:
         oracle.set_chebyshev_precond(None)
         oracle.set_uncolored_fraction(0.15)
+        oracle.set_coloring_scheme("MIN_MAX")
     amg.set_cycle(_get(a, "cycle")).set_cycle_iters(_get(a, "cycle_iters"))
     if _get(a, "algorithm") == "AGGREGATION":
         amg.set_error_scaling(_get(a, "error_scaling"), _get(a, "scaling_smoother_steps"), _get(a, "reuse_scale"))

@@ -17,6 +17,9 @@ GOLD = Path(__file__).parent / "golden"
 CASES = case_dict()
 # cases that do not (and must not) converge: a single GMRES iteration, the stale-x Chebyshev on the coarsest level
 NOT_CONVERGING = {"poisson9_gmres_one_iteration", "poisson10_amg_agg_cheb2_coarsest1"}
+# PARALLEL_GREEDY: the reference colours in place and racily, engine and oracle synchronously -- same rule, possibly another valid
+# colouring, hence another (equally good) smoother: the golden is compared on convergence and iteration count within 2
+REFERENCE_NONDETERMINISTIC = {"poisson16_fgmres_agg_dilu_pgreedy", "symbanded3000_fgmres_agg_dilu_pgreedy", "poisson14_amg_gs_pgreedy"}
 # host-side dots of nearly cancelling quantities inside the cycle: one digit of slack
 TOL = {"poisson15x12x10_pcgf_agg_CG": 1e-11, "poisson15x12x10_pcgf_agg_CGF": 1e-11, "poisson12_fgmres_agg_CG3": 1e-11, "poisson12_amg_classical_CG": 1e-11}
 
@@ -39,6 +42,9 @@ def test_oracle_matches_reference_golden(oracle, name):
     cfg = json.loads(str(d["config_json"]))
     x, it, hist, conv, amg = run_oracle(oracle, cfg, d["sys_row_ptr"], d["sys_col_idx"], d["sys_values"], d["sys_rhs"])
     href = d["res_history"]
+    if name in REFERENCE_NONDETERMINISTIC:
+        assert conv == (int(d["status"][0]) == 0) and abs(it - int(d["iterations"][0])) <= 2
+        return
     assert it == int(d["iterations"][0]) and conv == (int(d["status"][0]) == 0)
     assert np.max(np.abs(hist - href) / href[0]) < TOL.get(name, 1e-12)
     if amg is not None:
@@ -59,5 +65,8 @@ def test_engine_matches_oracle_and_golden(amgx, oracle, name):
     f = GOLD / f"r2_{name}.npz"
     if f.exists():
         d = np.load(f)
+        if name in REFERENCE_NONDETERMINISTIC:
+            assert abs(it - int(d["iterations"][0])) <= 2
+            return
         assert it == int(d["iterations"][0])
         assert np.max(np.abs(hist - d["res_history"]) / d["res_history"][0]) < TOL.get(name, 1e-12)

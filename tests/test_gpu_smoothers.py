@@ -126,3 +126,42 @@ def test_chebyshev_eigensolver_modes_fail_loudly(amgx):
     rp, ci, va = gallery.poisson7pt(5)
     with pytest.raises(Exception):
         run_engine(amgx, outer_cfg("PCG", _cheb_amg(None, 2, mode=0)), rp, ci, va, np.ones(125))
+
+
+@pytest.mark.parametrize("mat", ["poisson", "banded"])
+def test_parallel_greedy_colouring_bit_exact(amgx, oracle, mat):
+    """integer work: the engine's colours on every level of a DILU hierarchy == the restatement's; solve history to 1e-12"""
+    rp, ci, va = gallery.poisson7pt(15, 11, 9) if mat == "poisson" else sym_banded(6000, 50.0)
+    n = rp.shape[0] - 1
+    amg = amg_agg_cfg(pre=0, post=3, omega=0.75, smoother="MULTICOLOR_DILU", matrix_coloring_scheme="PARALLEL_GREEDY")
+    amg["smoother"]["matrix_coloring_scheme"] = "PARALLEL_GREEDY"
+    amg.update(scope="main", max_iters=40, monitor_residual=1, store_res_history=1, convergence="RELATIVE_INI", tolerance=1e-8, norm="L2")
+    cfg = amgx.Config({"config_version": 2, "determinism_flag": 1, "solver": amg})
+    rsc = amgx.Resources(cfg)
+    A = amgx.Matrix(rsc).upload(rp, ci, va)
+    b = amgx.Vector(rsc).upload(np.ones(n))
+    x = amgx.Vector(rsc).set_zero(n)
+    slv = amgx.Solver(rsc, cfg)
+    try:
+        slv.setup(A)
+        slv.solve(b, x, zero_initial_guess=True)
+        hist = np.array(slv.residual_history()).ravel()
+        cols = [slv.level_coloring(l) for l in range(slv.num_levels())]
+        it, status = slv.iterations_number, slv.status
+    finally:
+        for obj in (slv, x, b, A, rsc, cfg):
+            obj.destroy()
+    oracle.set_coloring_scheme("PARALLEL_GREEDY")
+    oracle.set_uncolored_fraction(0.0)
+    try:
+        o = oracle.AMG(rp, ci, va, max_levels=50, presweeps=0, postsweeps=3, omega=0.75, smoother="MULTICOLOR_DILU")
+    finally:
+        oracle.set_coloring_scheme("MIN_MAX")
+        oracle.set_uncolored_fraction(0.15)
+    assert len(cols) == o.num_levels()
+    for l, (nc, colors) in enumerate(cols):
+        nco, co, _ = oracle.amg_level_dilu(o, l)
+        assert nc == nco and np.array_equal(colors, co), f"level {l} colouring"
+    xo, ito, histo, convo = oracle.amg_solve(o, np.ones(n), tol=1e-8, max_iters=40)
+    assert it == ito and status == "success" and convo
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12

