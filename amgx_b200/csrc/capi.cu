@@ -372,9 +372,14 @@ AMGX_RC AMGX_matrix_replace_coefficients(AMGX_matrix_handle mtx, int n, int nnz,
     rp = A.rsc.get();
     use_device(A.rsc);
     if (!A.initialized) fatal(AMGX_RC_BAD_PARAMETERS, "matrix not initialized");
-    if (A.dist || A.merged_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "replace_coefficients on distributed / merged-diagonal matrices");
+    if (A.merged_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "replace_coefficients on a matrix uploaded with a separate scalar diagonal");
     const int user_nnz = A.nnz;
     if (n != A.n || nnz != user_nnz) fatal(AMGX_RC_BAD_PARAMETERS, "replace_coefficients: size mismatch");
+    if (A.dist) {
+        if (diag_data) fatal(AMGX_RC_NOT_IMPLEMENTED, "replace_coefficients with an external diagonal on a distributed matrix");
+        if (data) dist_replace_values(A, nnz, data);
+        return AMGX_RC_OK;
+    }
     const size_t bs = A.bs(), msz = prec_size(A.mat_prec);
     if (data) AMGXB_CUDA_CHECK(cudaMemcpyAsync(A.values.ptr(), data, (size_t)nnz * bs * msz, cudaMemcpyDefault, A.stream()));
     if (diag_data && A.has_ext_diag)

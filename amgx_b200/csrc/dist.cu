@@ -304,6 +304,41 @@ static void verify_plan(const Matrix &A)
             fatal(AMGX_RC_BAD_PARAMETERS, "distributed matrix is not structurally symmetric across partitions (send/halo size mismatch)");
 }
 
+// AMGX_matrix_replace_coefficients on a row-partitioned matrix: the caller's values come in the caller's row order, the engine keeps
+// rows as [interior | boundary]; entries keep their order inside a row, so row i's segment moves as a block to row perm[i].
+namespace {
+template <class T> __global__ void permute_row_values_kernel(int n, const int *__restrict__ old_rp, const int *__restrict__ perm, const int *__restrict__ new_rp,
+                                                             int bs, const T *__restrict__ src, T *__restrict__ dst)
+{
+    const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const size_t s0 = (size_t)old_rp[i] * bs, len = (size_t)(old_rp[i + 1] - old_rp[i]) * bs, d0 = (size_t)new_rp[perm[i]] * bs;
+        for (size_t k = lane; k < len; k += 32) dst[d0 + k] = src[s0 + k];
+    }
+}
+}  // namespace
+
+void dist_replace_values(Matrix &A, int nnz, const void *data)
+{
+    DistManager &m = *A.dist;
+    if (m.caller_row_ptr.size() != (size_t)A.n + 1) fatal(AMGX_RC_INTERNAL, "distributed matrix without the caller's row pointers");
+    cudaStream_t s = A.stream();
+    const size_t bs = A.bs(), msz = prec_size(A.mat_prec);
+    DevBytes stage;
+    stage.resize(std::max<size_t>((size_t)nnz * bs * msz, 1));
+    if (nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(stage.p, data, (size_t)nnz * bs * msz, cudaMemcpyDefault, s));
+    const int grid = std::max(1, std::min(ceil_div(A.n, 8), 148 * 8));
+    if (A.mat_prec == Prec::F64)
+        permute_row_values_kernel<double><<<grid, 256, 0, s>>>(A.n, m.caller_row_ptr.ptr(), m.perm_old_to_new.ptr(), A.row_ptr.ptr(), (int)bs, (const double *)stage.p,
+                                                                A.values.as<double>());
+    else
+        permute_row_values_kernel<float><<<grid, 256, 0, s>>>(A.n, m.caller_row_ptr.ptr(), m.perm_old_to_new.ptr(), A.row_ptr.ptr(), (int)bs, (const float *)stage.p,
+                                                               A.values.as<float>());
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
 // host arrays: rp[n+1], global cols[nnz], values (mat precision, nnz*bs), optional external diagonal
 void dist_build_matrix(Matrix &A, const int64_t *offsets, int n, int nnz, int bx, int by, const int *rp, const int64_t *cols, const void *vals,
                        const void *diag)
@@ -344,6 +379,7 @@ void dist_build_matrix(Matrix &A, const int64_t *offsets, int n, int nnz, int bx
     if (nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(A.values.ptr(), va2.data(), (size_t)nnz * bs * msz, cudaMemcpyHostToDevice, s));
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
     A.dist = manager_from_plan(A, pl, offsets);
+    A.dist->caller_row_ptr.from_any(rp, (size_t)n + 1, s);
     AMGXB200_partition_plan_free(&pl);
     verify_plan(A);
     A.compute_diag_and_plan();

@@ -22,6 +22,7 @@ struct DistManager {
     DevBuf<int> send_maps;               // B2L maps, concatenated
     DevVec send_buf;                     // packed boundary values (vec precision, * block dim)
     DevBuf<int> perm_old_to_new;         // caller (partition) order -> local order, owned rows
+    DevBuf<int> caller_row_ptr;          // row pointers in the caller's row order (AMGX_matrix_replace_coefficients on a distributed matrix)
     std::vector<int64_t> halo_global;    // global id of each halo column
     int64_t global_offset = 0;           // first global row owned by this rank
     int64_t n_global = 0;
@@ -33,6 +34,7 @@ struct DistManager {
 };
 
 // ---- halo exchange (no-ops on a single GPU) ----
+void dist_replace_values(Matrix &A, int nnz, const void *data);                     // values in the caller's row order -> local row order
 void dist_exchange_halo(const Matrix &A, DevVec &x, cudaStream_t s);
 void dist_exchange_halo_ptr(const Matrix &A, void *x, Prec prec, cudaStream_t s);
 void dist_exchange_halo_coarse(const Matrix &A, const void *xc, cudaStream_t s);   // vector living on the NEXT level
