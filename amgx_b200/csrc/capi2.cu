@@ -31,6 +31,7 @@ static AMGX_RC on_exception(const char *where)
 }
 #define API2_BEGIN try {
 #define API2_END } catch (...) { return on_exception(__func__); } return AMGX_RC_OK;
+#define API2_END_NORETURN } catch (...) { return on_exception(__func__); }
 
 void residual_norm_external(SolverH &h, Matrix &A, Vector &b, Vector &x, std::vector<double> &nrm)
 {
@@ -168,9 +169,295 @@ static void upload_vec(Vector &v, const std::vector<double> &h, int n, int bd)
     v.user_order = true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Partitioned reads: AMGX_read_system_distributed / _global / _maps_one_ring (src/amgx_c.cu:1497-1700, 4069-4430).
+// Every rank reads the whole file and keeps its rows.  Who owns a row: the partition vector if given (num_partitions > ranks:
+// consecutive groups of partitions share a rank, amgx_c.cu:1578-1590), else partition_sizes (contiguous blocks), else equal contiguous
+// blocks (p * n / ranks).  A rank's rows are kept in increasing global id; in the engine's contiguous numbering (the reference's
+// ipartition_map) rank r owns [offsets[r], offsets[r+1]).
+// ---------------------------------------------------------------------------------------------
+struct LocalPart {
+    int n = 0, nnz = 0;
+    std::vector<int64_t> offsets;            // [world+1], contiguous numbering
+    std::vector<int> rows;                   // original global ids of my rows, ascending
+    std::vector<int> rp;
+    std::vector<int64_t> cols_contig, cols_orig;
+    std::vector<double> va, diag, rhs, sol;
+};
+
+static void partition_system(const MMSystem &S, int rank, int world, int num_partitions, const int *partition_sizes, int pv_size, const int *pv_in, LocalPart &L)
+{
+    const int ng = S.n, bsq = S.bx * S.by;
+    std::vector<int> pv(ng);
+    if (pv_in) {
+        if (pv_size != ng) fatal(AMGX_RC_BAD_PARAMETERS, "partition_vector_size does not match the global vector size");
+        int maxp = 0;
+        for (int i = 0; i < ng; i++) { if (pv_in[i] < 0) fatal(AMGX_RC_BAD_PARAMETERS, "negative partition id"); maxp = std::max(maxp, pv_in[i]); }
+        int nparts = num_partitions > 0 ? num_partitions : maxp + 1;
+        if (nparts < maxp + 1) fatal(AMGX_RC_BAD_PARAMETERS, "partition vector names more partitions than num_partitions");
+        if (nparts % world) fatal(AMGX_RC_BAD_PARAMETERS, "the number of partitions must be a multiple of the number of ranks");
+        const int per_rank = nparts / world;
+        for (int i = 0; i < ng; i++) pv[i] = pv_in[i] / per_rank;
+    } else if (partition_sizes) {
+        const int nparts = num_partitions > 0 ? num_partitions : world;
+        if (nparts % world) fatal(AMGX_RC_BAD_PARAMETERS, "the number of partitions must be a multiple of the number of ranks");
+        const int per_rank = nparts / world;
+        long long g = 0;
+        for (int p = 0; p < nparts; p++)
+            for (int k = 0; k < partition_sizes[p]; k++, g++) {
+                if (g >= ng) fatal(AMGX_RC_BAD_PARAMETERS, "partition_sizes add up to more rows than the matrix has");
+                pv[g] = p / per_rank;
+            }
+        if (g != ng) fatal(AMGX_RC_BAD_PARAMETERS, "partition_sizes do not add up to the number of rows");
+    } else {
+        int p = 0;
+        for (int i = 0; i < ng; i++) {
+            while (p + 1 < world && i >= (long long)(p + 1) * ng / world) p++;
+            pv[i] = p;
+        }
+    }
+    L.offsets.assign((size_t)world + 1, 0);
+    std::vector<int64_t> new_global((size_t)std::max(ng, 1));
+    if (!partition_vector_to_contiguous(ng, world, pv.data(), L.offsets.data(), new_global.data()))
+        fatal(AMGX_RC_BAD_PARAMETERS, "partition vector names a rank outside [0, number of ranks)");
+    L.rows.clear();
+    for (int g = 0; g < ng; g++) if (pv[g] == rank) L.rows.push_back(g);
+    L.n = (int)L.rows.size();
+    L.rp.assign((size_t)L.n + 1, 0);
+    for (int i = 0; i < L.n; i++) L.rp[i + 1] = L.rp[i] + (S.rp[L.rows[i] + 1] - S.rp[L.rows[i]]);
+    L.nnz = L.rp[L.n];
+    L.cols_contig.resize((size_t)std::max(L.nnz, 1));
+    L.cols_orig.resize((size_t)std::max(L.nnz, 1));
+    L.va.resize((size_t)L.nnz * bsq);
+    if (S.has_diag) L.diag.resize((size_t)L.n * bsq);
+    if (!S.rhs.empty()) L.rhs.resize((size_t)L.n * S.by);
+    if (!S.sol.empty()) L.sol.resize((size_t)L.n * S.bx);
+    for (int i = 0; i < L.n; i++) {
+        const int g = L.rows[i];
+        for (int k = S.rp[g], o = L.rp[i]; k < S.rp[g + 1]; k++, o++) {
+            L.cols_orig[o] = S.ci[k];
+            L.cols_contig[o] = new_global[S.ci[k]];
+            std::copy(S.va.begin() + (size_t)k * bsq, S.va.begin() + (size_t)(k + 1) * bsq, L.va.begin() + (size_t)o * bsq);
+        }
+        if (S.has_diag) std::copy(S.diag.begin() + (size_t)g * bsq, S.diag.begin() + (size_t)(g + 1) * bsq, L.diag.begin() + (size_t)i * bsq);
+        if (!S.rhs.empty()) std::copy(S.rhs.begin() + (size_t)g * S.by, S.rhs.begin() + (size_t)(g + 1) * S.by, L.rhs.begin() + (size_t)i * S.by);
+        if (!S.sol.empty()) std::copy(S.sol.begin() + (size_t)g * S.bx, S.sol.begin() + (size_t)(g + 1) * S.bx, L.sol.begin() + (size_t)i * S.bx);
+    }
+}
+
+template <class T> static T *c_dup(const std::vector<double> &v)
+{
+    T *p = (T *)malloc(sizeof(T) * std::max<size_t>(v.size(), 1));
+    if (!p) fatal(AMGX_RC_NO_MEMORY, "out of host memory");
+    for (size_t i = 0; i < v.size(); i++) p[i] = (T)v[i];
+    return p;
+}
+static void *c_dup_prec(const std::vector<double> &v, bool f64) { return f64 ? (void *)c_dup<double>(v) : (void *)c_dup<float>(v); }
+template <class T, class U> static T *c_dup_i(const std::vector<U> &v)
+{
+    T *p = (T *)malloc(sizeof(T) * std::max<size_t>(v.size(), 1));
+    if (!p) fatal(AMGX_RC_NO_MEMORY, "out of host memory");
+    for (size_t i = 0; i < v.size(); i++) p[i] = (T)v[i];
+    return p;
+}
+
+// What AMGX_read_system_maps_one_ring hands back (examples/amgx_mpi_capi_agg.c:386-420): rows in their original order, owned columns
+// numbered 0..n-1, halo columns from n on grouped by neighbour (ascending rank) and by ascending global id inside a group; for every
+// neighbour the local rows it needs (send, ascending) and the halo columns its values land in (recv).  Exactly the conventions of
+// the partition planner, whose row renumbering [interior | boundary] is undone here.
+static void maps_one_ring(const MMSystem &S, const LocalPart &L, int rank, int world, std::vector<int> &local_cols, std::vector<int> &neighbors,
+                          std::vector<std::vector<int>> &send, std::vector<std::vector<int>> &recv)
+{
+    AMGXB200_partition_plan pl;
+    memset(&pl, 0, sizeof(pl));
+    partition_plan_create(&pl, rank, world, L.offsets.data(), L.n, L.nnz, L.rp.data(), L.cols_contig.data());
+    std::vector<int> inv((size_t)std::max(L.n, 1));
+    for (int i = 0; i < L.n; i++) inv[pl.perm_old_to_new[i]] = i;
+    local_cols.resize((size_t)std::max(L.nnz, 1));
+    for (int k = 0; k < L.nnz; k++) local_cols[k] = pl.local_cols[k] < L.n ? inv[pl.local_cols[k]] : pl.local_cols[k];
+    neighbors.assign(pl.neighbors, pl.neighbors + pl.num_neighbors);
+    send.assign(pl.num_neighbors, {});
+    recv.assign(pl.num_neighbors, {});
+    for (int q = 0; q < pl.num_neighbors; q++) {
+        for (int k = pl.send_offsets[q]; k < pl.send_offsets[q + 1]; k++) send[q].push_back(inv[pl.send_maps[k]]);
+        for (int k = pl.halo_offsets[q]; k < pl.halo_offsets[q + 1]; k++) recv[q].push_back(L.n + k);
+    }
+    AMGXB200_partition_plan_free(&pl);
+    (void)S;
+}
+
+static AMGX_RC read_maps_impl(int rank, int world, int mode, const char *filename, int num_partitions, const int *partition_sizes, int pv_size, const int *pv,
+                              int *n, int *nnz, int *bx, int *by, int **row_ptrs, int **col_local, int64_t **col_global, void **data, void **diag_data,
+                              void **rhs, void **sol, int *num_neighbors, int **neighbors, int **send_sizes, int ***send_maps, int **recv_sizes,
+                              int ***recv_maps)
+{
+    MMSystem S;
+    read_mm(filename, S);
+    LocalPart L;
+    partition_system(S, rank, world, num_partitions, partition_sizes, pv_size, pv, L);
+    // mode = mem + 16 * vec + 256 * mat + 4096 * ind, 0 = double (include/amgx_config.h:81-124)
+    const bool mat64 = ((mode >> 8) & 15) == 0, vec64 = ((mode >> 4) & 15) == 0;
+    *n = L.n;
+    *nnz = L.nnz;
+    *bx = S.bx;
+    *by = S.by;
+    *row_ptrs = c_dup_i<int>(L.rp);
+    *data = c_dup_prec(L.va, mat64);
+    *diag_data = S.has_diag ? c_dup_prec(L.diag, mat64) : nullptr;
+    std::vector<double> b = L.rhs, x = L.sol;
+    if (b.empty()) b.assign((size_t)L.n * S.by, 1.0);             // no rhs in the file: b = [1,...,1]^T (rhs_from_a = 0)
+    if (x.empty()) x.assign((size_t)L.n * S.bx, 0.0);             // "Initializing solution vector with zeroes..."
+    *rhs = c_dup_prec(b, vec64);
+    *sol = c_dup_prec(x, vec64);
+    if (col_global) *col_global = c_dup_i<int64_t>(L.cols_orig);  // ORIGINAL numbering, to go with the partition vector (amgx_c.cu:4412-4426)
+    if (col_local) {
+        std::vector<int> lc, nb;
+        std::vector<std::vector<int>> sm, rm;
+        maps_one_ring(S, L, rank, world, lc, nb, sm, rm);
+        lc.resize((size_t)L.nnz);
+        *col_local = c_dup_i<int>(lc);
+        const int nn = (int)nb.size();
+        *num_neighbors = nn;
+        *neighbors = c_dup_i<int>(nb);
+        *send_sizes = (int *)malloc(sizeof(int) * std::max(nn, 1));
+        *recv_sizes = (int *)malloc(sizeof(int) * std::max(nn, 1));
+        *send_maps = (int **)malloc(sizeof(int *) * std::max(nn, 1));
+        *recv_maps = (int **)malloc(sizeof(int *) * std::max(nn, 1));
+        for (int q = 0; q < nn; q++) {
+            (*send_sizes)[q] = (int)sm[q].size();
+            (*recv_sizes)[q] = (int)rm[q].size();
+            (*send_maps)[q] = c_dup_i<int>(sm[q]);
+            (*recv_maps)[q] = c_dup_i<int>(rm[q]);
+        }
+    }
+    return AMGX_RC_OK;
+}
+
 }  // namespace amgxb
 
 extern "C" {
+
+AMGX_RC AMGX_read_system_maps_one_ring(int *n, int *nnz, int *block_dimx, int *block_dimy, int **row_ptrs, int **col_indices, void **data, void **diag_data,
+                                       void **rhs, void **sol, int *num_neighbors, int **neighbors, int **send_sizes, int ***send_maps, int **recv_sizes,
+                                       int ***recv_maps, AMGX_resources_handle rsc, AMGX_Mode mode, const char *filename, int allocated_halo_depth,
+                                       int num_partitions, const int *partition_sizes, int partition_vector_size, const int *partition_vector)
+{
+    API2_BEGIN
+    (void)allocated_halo_depth;
+    ResourcesH *r = chk<ResourcesH>(rsc, MAGIC_RSC, "resources");
+    if (!n || !nnz || !block_dimx || !block_dimy || !row_ptrs || !col_indices || !data || !diag_data || !rhs || !sol || !num_neighbors || !neighbors ||
+        !send_sizes || !send_maps || !recv_sizes || !recv_maps)
+        fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_read_system_maps_one_ring: null output pointer");
+    read_maps_impl(r->rsc->rank, r->rsc->world, (int)mode, filename, num_partitions, partition_sizes, partition_vector_size, partition_vector, n, nnz,
+                   block_dimx, block_dimy, row_ptrs, col_indices, nullptr, data, diag_data, rhs, sol, num_neighbors, neighbors, send_sizes, send_maps,
+                   recv_sizes, recv_maps);
+    API2_END
+}
+
+AMGX_RC AMGX_read_system_global(int *n, int *nnz, int *block_dimx, int *block_dimy, int **row_ptrs, void **col_indices_global, void **data, void **diag_data,
+                                void **rhs, void **sol, AMGX_resources_handle rsc, AMGX_Mode mode, const char *filename, int allocated_halo_depth,
+                                int num_partitions, const int *partition_sizes, int partition_vector_size, const int *partition_vector)
+{
+    API2_BEGIN
+    (void)allocated_halo_depth;
+    ResourcesH *r = chk<ResourcesH>(rsc, MAGIC_RSC, "resources");
+    if (!n || !nnz || !block_dimx || !block_dimy || !row_ptrs || !col_indices_global || !data || !diag_data || !rhs || !sol)
+        fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_read_system_global: null output pointer");
+    int64_t *cg = nullptr;
+    read_maps_impl(r->rsc->rank, r->rsc->world, (int)mode, filename, num_partitions, partition_sizes, partition_vector_size, partition_vector, n, nnz,
+                   block_dimx, block_dimy, row_ptrs, nullptr, &cg, data, diag_data, rhs, sol, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    *col_indices_global = cg;
+    API2_END
+}
+
+AMGX_RC AMGX_free_system_maps_one_ring(int *row_ptrs, int *col_indices, void *data, void *diag_data, void *rhs, void *sol, int num_neighbors, int *neighbors,
+                                       int *send_sizes, int **send_maps, int *recv_sizes, int **recv_maps)
+{
+    free(row_ptrs);
+    free(col_indices);
+    free(data);
+    free(diag_data);
+    free(rhs);
+    free(sol);
+    free(neighbors);
+    free(send_sizes);
+    free(recv_sizes);
+    if (send_maps) { for (int q = 0; q < num_neighbors; q++) free(send_maps[q]); free(send_maps); }
+    if (recv_maps) { for (int q = 0; q < num_neighbors; q++) free(recv_maps[q]); free(recv_maps); }
+    return AMGX_RC_OK;
+}
+
+/* Test / tooling hook: AMGX_read_system_maps_one_ring + _global for an explicit (rank, world) pair, no resources handle, no GPU. */
+AMGX_RC AMGXB200_read_system_partition(int rank, int world_size, AMGX_Mode mode, const char *filename, int num_partitions, const int *partition_sizes,
+                                       int partition_vector_size, const int *partition_vector, int *n, int *nnz, int *block_dimx, int *block_dimy,
+                                       int **row_ptrs, int **col_indices_local, int64_t **col_indices_global, void **data, void **diag_data, void **rhs,
+                                       void **sol, int *num_neighbors, int **neighbors, int **send_sizes, int ***send_maps, int **recv_sizes, int ***recv_maps)
+{
+    API2_BEGIN
+    if (rank < 0 || world_size < 1 || rank >= world_size) fatal(AMGX_RC_BAD_PARAMETERS, "bad rank / world size");
+    read_maps_impl(rank, world_size, (int)mode, filename, num_partitions, partition_sizes, partition_vector_size, partition_vector, n, nnz, block_dimx, block_dimy,
+                   row_ptrs, col_indices_local, col_indices_global, data, diag_data, rhs, sol, num_neighbors, neighbors, send_sizes, send_maps, recv_sizes,
+                   recv_maps);
+    API2_END
+}
+
+AMGX_RC AMGX_read_system_distributed(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol, const char *filename, int allocated_halo_depth,
+                                     int num_partitions, const int *partition_sizes, int partition_vector_size, const int *partition_vector)
+{
+    API2_BEGIN
+    (void)allocated_halo_depth;
+    MatrixH *m = mtx ? chk<MatrixH>(mtx, MAGIC_MTX, "matrix") : nullptr;
+    VectorH *b = rhs ? chk<VectorH>(rhs, MAGIC_VEC, "vector") : nullptr;
+    VectorH *x = sol ? chk<VectorH>(sol, MAGIC_VEC, "vector") : nullptr;
+    Resources *rs = m ? m->m->rsc.get() : b ? b->v->rsc.get() : x ? x->v->rsc.get() : nullptr;
+    if (!rs) fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_read_system_distributed: no matrix or vector handle");
+    AMGXB_CUDA_CHECK(cudaSetDevice(rs->device));
+    MMSystem S;
+    read_mm(filename, S);
+    LocalPart L;
+    partition_system(S, rs->rank, rs->world, num_partitions, partition_sizes, partition_vector_size, partition_vector, L);
+    if (m) {
+        Matrix &A = *m->m;
+        const void *vals, *dg = nullptr;
+        std::vector<float> vf, df;
+        if (A.mat_prec == Prec::F64) { vals = L.va.data(); if (S.has_diag) dg = L.diag.data(); }
+        else { vf = convert<float>(L.va); df = convert<float>(L.diag); vals = vf.data(); if (S.has_diag) dg = df.data(); }
+        if (rs->world == 1) {
+            std::vector<int> c32(L.cols_contig.begin(), L.cols_contig.end());
+            upload_matrix(A, L.n, L.nnz, S.bx, S.by, L.rp.data(), c32.data(), vals, dg);
+        } else {
+            dist_build_matrix(A, L.offsets.data(), L.n, L.nnz, S.bx, S.by, L.rp.data(), L.cols_contig.data(), vals, dg);
+        }
+    }
+    auto put = [&](VectorH *vh, const std::vector<double> &h, int bd, bool allow_empty) {
+        if (!vh) return;
+        Vector &v = *vh->v;
+        if (h.empty() && allow_empty) { v.n = 0; v.block_dim = bd; v.data.resize(0, v.prec); return; }
+        upload_vec(v, h, L.n, bd);
+        if (m && m->m->dist) v.dist = m->m->dist;       // bound: the solve permutes from the caller's row order
+    };
+    std::vector<double> hb = L.rhs;
+    if (hb.empty()) hb.assign((size_t)L.n * S.by, 1.0);
+    put(b, hb, S.by, false);
+    put(x, L.sol, S.bx, true);
+    API2_END
+}
+
+/* AMGX_write_system_distributed (src/amgx_c.cu:3557-3600): the partitions are gathered on rank 0 and written as one system.  Here
+ * every rank holds a row-partitioned matrix in the engine's local numbering; the gather is not implemented for more than one rank. */
+AMGX_RC AMGX_write_system_distributed(const AMGX_matrix_handle mtx, const AMGX_vector_handle rhs, const AMGX_vector_handle sol, const char *filename,
+                                      int allocated_halo_depth, int num_partitions, const int *partition_sizes, int partition_vector_size,
+                                      const int *partition_vector)
+{
+    (void)allocated_halo_depth; (void)num_partitions; (void)partition_sizes; (void)partition_vector_size; (void)partition_vector;
+    {
+        API2_BEGIN
+        MatrixH *m = chk<MatrixH>(mtx, MAGIC_MTX, "matrix");
+        if (m->m->dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "AMGX_write_system_distributed: gathering a row-partitioned matrix on rank 0 is not implemented");
+        API2_END_NORETURN
+    }
+    return AMGX_write_system(mtx, rhs, sol, filename);
+}
 
 AMGX_RC AMGX_read_system(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol, const char *filename)
 {

@@ -44,6 +44,8 @@ void dist_download_vector(const Vector &v, void *data);   // local order -> call
 void dist_generate_poisson7(Matrix &A, int nx, int ny, int nz, int px, int py, int pz);
 void dist_upload_global(Matrix &A, int n_global, int n, int nnz, int bx, int by, const int *row_ptrs, const void *cols_global, bool cols32,
                         const void *data, const void *diag_data, int partition_info, const void *partition_data);
+void dist_build_matrix(Matrix &A, const int64_t *offsets, int n, int nnz, int bx, int by, const int *rp, const int64_t *cols, const void *vals,
+                       const void *diag);
 void dist_comm_from_maps_one_ring(Matrix &A, int num_neighbors, const int *neighbors, const int *send_sizes, const int **send_maps,
                                   const int *recv_sizes, const int **recv_maps);
 // pure host partition planner (partition.cpp)

@@ -143,6 +143,23 @@ AMGX_RC AMGX_API AMGX_solver_register_print_callback(AMGX_print_callback func); 
 /* ---- utilities [ref: include/amgx_c.h:440-520] ---- */
 AMGX_RC AMGX_API AMGX_read_system(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol, const char *filename);
 AMGX_RC AMGX_API AMGX_write_system(const AMGX_matrix_handle mtx, const AMGX_vector_handle rhs, const AMGX_vector_handle sol, const char *filename);
+AMGX_RC AMGX_API AMGX_read_system_distributed(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol, const char *filename,
+                                              int allocated_halo_depth, int num_partitions, const int *partition_sizes, int partition_vector_size,
+                                              const int *partition_vector);                                                    /* :441 */
+AMGX_RC AMGX_API AMGX_write_system_distributed(const AMGX_matrix_handle mtx, const AMGX_vector_handle rhs, const AMGX_vector_handle sol, const char *filename,
+                                               int allocated_halo_depth, int num_partitions, const int *partition_sizes, int partition_vector_size,
+                                               const int *partition_vector);                                                   /* :424 */
+AMGX_RC AMGX_API AMGX_read_system_maps_one_ring(int *n, int *nnz, int *block_dimx, int *block_dimy, int **row_ptrs, int **col_indices, void **data,
+                                                void **diag_data, void **rhs, void **sol, int *num_neighbors, int **neighbors, int **send_sizes,
+                                                int ***send_maps, int **recv_sizes, int ***recv_maps, AMGX_resources_handle rsc, AMGX_Mode mode,
+                                                const char *filename, int allocated_halo_depth, int num_partitions, const int *partition_sizes,
+                                                int partition_vector_size, const int *partition_vector);                       /* :452 */
+AMGX_RC AMGX_API AMGX_free_system_maps_one_ring(int *row_ptrs, int *col_indices, void *data, void *diag_data, void *rhs, void *sol, int num_neighbors,
+                                                int *neighbors, int *send_sizes, int **send_maps, int *recv_sizes, int **recv_maps); /* :478 */
+AMGX_RC AMGX_API AMGX_read_system_global(int *n, int *nnz, int *block_dimx, int *block_dimy, int **row_ptrs, void **col_indices_global, void **data,
+                                         void **diag_data, void **rhs, void **sol, AMGX_resources_handle rsc, AMGX_Mode mode, const char *filename,
+                                         int allocated_halo_depth, int num_partitions, const int *partition_sizes, int partition_vector_size,
+                                         const int *partition_vector);                                                         /* :525 */
 AMGX_RC AMGX_API AMGX_generate_distributed_poisson_7pt(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol,
                                                        int allocated_halo_depth, int num_import_rings, int nx, int ny, int nz, int px, int py, int pz);
 AMGX_RC AMGX_API AMGX_write_parameters_description(char *filename, AMGX_GET_PARAMS_DESC_FLAG mode);
@@ -226,6 +243,13 @@ void    AMGX_API AMGXB200_partition_plan_free(AMGXB200_partition_plan *plan);
  * q's first global row).  Pure host code; returns AMGX_RC_BAD_PARAMETERS when the maps do not cover the halo columns. */
 AMGX_RC AMGX_API AMGXB200_comm_maps_to_global_cols(int n, int nnz, const int *local_cols, int64_t my_offset, int num_neighbors, const int *recv_sizes,
                                                    const int *const *recv_maps, const int64_t *const *recv_global, int64_t *cols_out);
+/* AMGX_read_system_maps_one_ring + AMGX_read_system_global for an explicit (rank, world_size) pair: no resources handle, no GPU.  Any of
+ * col_indices_local (with the neighbour / map outputs) and col_indices_global may be NULL.  Free with AMGX_free_system_maps_one_ring (+ free()). */
+AMGX_RC AMGX_API AMGXB200_read_system_partition(int rank, int world_size, AMGX_Mode mode, const char *filename, int num_partitions, const int *partition_sizes,
+                                                int partition_vector_size, const int *partition_vector, int *n, int *nnz, int *block_dimx, int *block_dimy,
+                                                int **row_ptrs, int **col_indices_local, int64_t **col_indices_global, void **data, void **diag_data,
+                                                void **rhs, void **sol, int *num_neighbors, int **neighbors, int **send_sizes, int ***send_maps,
+                                                int **recv_sizes, int ***recv_maps);
 AMGX_RC AMGX_API AMGXB200_partition_vector_to_contiguous(int n_global, int world_size, const int *partition_vector, int64_t *offsets, int64_t *new_global);
 
 #if defined(__cplusplus)

@@ -142,6 +142,55 @@ def partition_vector_section(rank, world, rsc, lib, cfg):
     dist.barrier()
 
 
+def read_distributed_section(rank, world, rsc, lib, cfg):
+    """AMGX_read_system_distributed: every rank reads the MatrixMarket file and keeps the rows a scattered partition vector gives it;
+    the solve must converge to the solution of the global system.  Opt-in until validated on a device."""
+    import ctypes as C
+    import tempfile
+    nx, ny, nz = 9, 8, 3 * world
+    rp, ci, va = gallery.poisson7pt(nx, ny, nz)
+    ng = rp.shape[0] - 1
+    path = os.path.join(tempfile.gettempdir(), f"amgxb_dist_read_{world}.mtx")
+    if rank == 0:
+        with open(path, "w") as f:
+            f.write("%%MatrixMarket matrix coordinate real general\n%%AMGX rhs\n")
+            f.write(f"{ng} {ng} {ci.shape[0]}\n")
+            for i in range(ng):
+                for k in range(rp[i], rp[i + 1]):
+                    f.write(f"{i + 1} {ci[k] + 1} {va[k]!r}\n")
+            for i in range(ng):
+                f.write(f"{1.0 + (i % 7) * 0.25!r}\n")
+    dist.barrier()
+    pv = np.random.default_rng(5).integers(0, world, ng).astype(np.int32)
+    A, b, x = capi.Matrix(rsc), capi.Vector(rsc), capi.Vector(rsc)
+    lib.AMGX_read_system_distributed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rc = lib.AMGX_read_system_distributed(A.h, b.h, x.h, path.encode(), 1, world, None, ng, pv.ctypes.data)
+    assert rc == 0, rc
+    n = int(np.count_nonzero(pv == rank))
+    assert A.get_size()[0] == n and b.get_size()[0] == n
+    x.bind(A)
+    x.set_zero(n)
+    slv = capi.Solver(rsc, cfg)
+    slv.setup(A)
+    slv.solve(b, x)
+    assert slv.status == "success", slv.status
+    counts = [int(np.count_nonzero(pv == r)) for r in range(world)]
+    parts = [torch.zeros(c, dtype=torch.float64, device="cuda") for c in counts]
+    dist.all_gather(parts, torch.from_numpy(x.download()).cuda())
+    xfull = np.zeros(ng)
+    for r in range(world):
+        xfull[pv == r] = parts[r].cpu().numpy()
+    rhs = 1.0 + (np.arange(ng) % 7) * 0.25
+    res = rhs - gallery.to_scipy(rp, ci, va) @ xfull
+    hist = slv.residual_history()
+    assert abs(np.linalg.norm(res) - hist[-1]) <= 1e-9 * hist[0], (np.linalg.norm(res), hist[-1])
+    if rank == 0:
+        print(f"DIST_READ_SYSTEM_OK world={world} iters={slv.iterations_number}", flush=True)
+    for o in (slv, x, b, A):
+        o.destroy()
+    dist.barrier()
+
+
 def comm_maps_section(rank, world, rsc, lib, cfg):
     """AMGX_matrix_comm_from_maps_one_ring + AMGX_matrix_upload_all in LOCAL numbering (examples/amgx_mpi_capi_agg.c:480-485): SpMV
     bit-exact vs the global product, the solve converges to the global solution.  Opt-in until validated on a device."""
@@ -278,6 +327,7 @@ def main():
     if os.environ.get("AMGXB_RUN_UNVALIDATED") == "1":
         partition_vector_section(rank, world, rsc, lib, cfg)
         comm_maps_section(rank, world, rsc, lib, cfg)
+        read_distributed_section(rank, world, rsc, lib, cfg)
     rsc.destroy()
     cfg.destroy()
     capi.finalize()

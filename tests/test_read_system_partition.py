@@ -1,0 +1,110 @@
+"""CPU: AMGX_read_system_maps_one_ring / AMGX_read_system_global semantics through the resource-free hook
+AMGXB200_read_system_partition, against the worked example the reference documents in examples/amgx_mpi_capi_agg.c:367-420
+(12x12 matrix, three partitions [0 0 0 0 1 1 1 1 2 2 2 2]) -- a golden vector from the reference's own sources."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from amgx_b200 import capi
+
+RP = [0, 4, 8, 13, 21, 25, 32, 36, 41, 46, 50, 57, 61]
+CI = [0, 1, 3, 8, 0, 1, 2, 3, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 8, 10, 2, 4, 5, 6, 2, 3, 4, 5, 6, 7, 10, 4, 5, 6, 7, 5, 6, 7, 9, 10, 0, 3, 8, 10, 11,
+      7, 9, 10, 11, 3, 5, 7, 8, 9, 10, 11, 8, 9, 10, 11]
+PV = [0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2]
+# the outputs the reference documents for partitions 0, 1, 2
+EXPECT = {
+    0: dict(n=4, nnz=21, rp=[0, 4, 8, 13, 21], ci=[0, 1, 3, 6, 0, 1, 2, 3, 1, 2, 3, 4, 5, 0, 1, 2, 3, 4, 5, 6, 7], nb=[1, 2],
+            send=[[2, 3], [0, 3]], recv=[[4, 5], [6, 7]]),
+    1: dict(n=4, nnz=20, rp=[0, 4, 11, 15, 20], ci=[4, 0, 1, 2, 4, 5, 0, 1, 2, 3, 7, 0, 1, 2, 3, 1, 2, 3, 6, 7], nb=[0, 2],
+            send=[[0, 1], [1, 3]], recv=[[4, 5], [6, 7]]),
+    2: dict(n=4, nnz=20, rp=[0, 5, 9, 16, 20], ci=[4, 5, 0, 2, 3, 7, 1, 2, 3, 5, 6, 7, 0, 1, 2, 3, 0, 1, 2, 3], nb=[0, 1],
+            send=[[0, 2], [1, 2]], recv=[[4, 5], [6, 7]]),
+}
+
+
+@pytest.fixture(scope="module")
+def mtx_file(tmp_path_factory):
+    p = tmp_path_factory.mktemp("sys") / "example12.mtx"
+    lines = ["%%MatrixMarket matrix coordinate real general", "%%AMGX rhs", f"12 12 {len(CI)}"]
+    for i in range(12):
+        for k in range(RP[i], RP[i + 1]):
+            lines.append(f"{i + 1} {CI[k] + 1} {100 * (i + 1) + CI[k] + 1}")      # value encodes (row, col)
+    lines += [str(float(i + 1)) for i in range(12)]
+    p.write_text("\n".join(lines) + "\n")
+    return str(p)
+
+
+def call(lib, rank, world, filename, pv=None, sizes=None, nparts=0, want_local=True, want_global=True):
+    n, nnz, bx, by, nn = (C.c_int() for _ in range(5))
+    rp, cl, nb, ssz, rsz = (C.POINTER(C.c_int)() for _ in range(5))
+    cg = C.POINTER(C.c_int64)()
+    data, diag, rhs, sol = (C.c_void_p() for _ in range(4))
+    sm, rm = C.POINTER(C.POINTER(C.c_int))(), C.POINTER(C.POINTER(C.c_int))()
+    pva = (C.c_int * len(pv))(*pv) if pv is not None else None
+    sza = (C.c_int * len(sizes))(*sizes) if sizes is not None else None
+    f = lib.AMGXB200_read_system_partition
+    f.restype = C.c_int
+    f.argtypes = None
+    rc = f(rank, world, 8193, filename.encode(), nparts, sza, len(pv) if pv is not None else 0, pva, C.byref(n), C.byref(nnz), C.byref(bx), C.byref(by),
+           C.byref(rp), C.byref(cl) if want_local else None, C.byref(cg) if want_global else None, C.byref(data), C.byref(diag), C.byref(rhs),
+           C.byref(sol), C.byref(nn), C.byref(nb), C.byref(ssz), C.byref(sm), C.byref(rsz), C.byref(rm))
+    if rc != 0:
+        return rc, None
+    out = dict(n=n.value, nnz=nnz.value, bx=bx.value, by=by.value, rp=[rp[i] for i in range(n.value + 1)],
+               data=np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_double)), (max(nnz.value, 1),))[: nnz.value].copy(),
+               rhs=np.ctypeslib.as_array(C.cast(rhs, C.POINTER(C.c_double)), (max(n.value, 1),))[: n.value].copy(),
+               sol=np.ctypeslib.as_array(C.cast(sol, C.POINTER(C.c_double)), (max(n.value, 1),))[: n.value].copy())
+    if want_global:
+        out["cg"] = [cg[i] for i in range(nnz.value)]
+    if want_local:
+        out["ci"] = [cl[i] for i in range(nnz.value)]
+        out["nb"] = [nb[q] for q in range(nn.value)]
+        out["send"] = [[sm[q][k] for k in range(ssz[q])] for q in range(nn.value)]
+        out["recv"] = [[rm[q][k] for k in range(rsz[q])] for q in range(nn.value)]
+        lib.AMGX_free_system_maps_one_ring.argtypes = None
+        lib.AMGX_free_system_maps_one_ring(rp, cl, data, diag, rhs, sol, nn.value, nb, ssz, sm, rsz, rm)
+    return 0, out
+
+
+@pytest.mark.parametrize("rank", [0, 1, 2])
+def test_maps_one_ring_matches_the_reference_worked_example(rank, mtx_file):
+    lib = capi.load_library()
+    rc, o = call(lib, rank, 3, mtx_file, pv=PV)
+    assert rc == 0
+    e = EXPECT[rank]
+    assert (o["n"], o["nnz"], o["bx"], o["by"]) == (e["n"], e["nnz"], 1, 1)
+    assert o["rp"] == e["rp"] and o["ci"] == e["ci"]
+    assert o["nb"] == e["nb"] and o["send"] == e["send"] and o["recv"] == e["recv"]
+    # read_system_global: the same rows with their ORIGINAL global column ids; values / rhs follow the rows
+    lo = 4 * rank
+    assert o["cg"] == CI[RP[lo]:RP[lo + 4]]
+    rows = np.repeat(np.arange(lo, lo + 4), np.diff(RP[lo:lo + 5]))
+    assert np.array_equal(o["data"], 100.0 * (rows + 1) + np.array(o["cg"]) + 1)
+    assert np.array_equal(o["rhs"], np.arange(lo + 1, lo + 5, dtype=float)) and not o["sol"].any()
+
+
+def test_default_and_sized_partitions_and_scattered_vector(mtx_file):
+    lib = capi.load_library()
+    # no partition info: equal contiguous blocks p*n/ranks
+    for r, (lo, hi) in enumerate([(0, 6), (6, 12)]):
+        rc, o = call(lib, r, 2, mtx_file)
+        assert rc == 0 and o["n"] == hi - lo and o["cg"] == CI[RP[lo]:RP[hi]]
+    # partition_sizes: contiguous blocks of the given sizes; 4 partitions on 2 ranks = two consecutive partitions per rank
+    rc, o = call(lib, 1, 2, mtx_file, sizes=[2, 3, 3, 4], nparts=4)
+    assert rc == 0 and o["n"] == 7 and o["cg"] == CI[RP[5]:RP[12]]
+    # scattered vector: rows kept in increasing global id, local numbering consistent with the maps
+    pv = [1, 0, 1, 0, 0, 1, 1, 0, 0, 1, 0, 1]
+    views = [call(lib, r, 2, mtx_file, pv=pv)[1] for r in range(2)]
+    mine = [[g for g in range(12) if pv[g] == r] for r in range(2)]
+    for r in range(2):
+        o, other = views[r], views[1 - r]
+        assert o["n"] == len(mine[r]) and o["nb"] == [1 - r]
+        assert o["cg"] == [c for g in mine[r] for c in CI[RP[g]:RP[g + 1]]]
+        # a halo column's global id = the row the neighbour sends for it
+        halo_gid = {h: mine[1 - r][other["send"][0][k]] for k, h in enumerate(o["recv"][0])}
+        for lc, gc in zip(o["ci"], o["cg"]):
+            assert (mine[r][lc] if lc < o["n"] else halo_gid[lc]) == gc
+    # errors: wrong vector length, sizes that do not add up
+    assert call(lib, 0, 2, mtx_file, pv=[0, 1, 0])[0] != 0
+    assert call(lib, 0, 2, mtx_file, sizes=[5, 5], nparts=2)[0] != 0
