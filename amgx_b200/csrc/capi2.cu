@@ -62,8 +62,63 @@ struct MMSystem {
     bool has_diag = false;
 };
 
+// The reference's binary system file (writer src/matrix_io.cu:267-405, reader src/readers.cu:1676-1960): "%%NVAMGBinary\n", nine
+// uint32 {is_mtx, is_rhs, is_soln, format (0 = CSR), diag, block_dimx, block_dimy, rows, nnz}, int32 row offsets, int32 column
+// indices, float64 values (off-diagonal blocks, then the diagonal blocks when diag), float64 rhs, float64 solution.
+static const char NVAMG_BINARY_HEADER[] = "%%NVAMGBinary\n";
+static bool read_binary(const char *filename, MMSystem &S)
+{
+    FILE *f = fopen(filename, "rb");
+    if (!f) return false;
+    char head[sizeof(NVAMG_BINARY_HEADER)] = {0};
+    const size_t hl = strlen(NVAMG_BINARY_HEADER);
+    if (fread(head, 1, hl, f) != hl || memcmp(head, NVAMG_BINARY_HEADER, hl) != 0) { fclose(f); return false; }
+    auto need = [&](bool ok, const char *what) { if (!ok) { fclose(f); fatal(AMGX_RC_IO_ERROR, std::string("fread failed reading ") + what + ", exiting"); } };
+    uint32_t fl[9];
+    need(fread(fl, sizeof(uint32_t), 9, f) == 9, "the system header");
+    if ((fl[3] & 0xffu) != 0) { fclose(f); fatal(AMGX_RC_IO_ERROR, "binary system file: only the CSR real format is supported"); }
+    S.has_diag = fl[4] != 0;
+    S.bx = (int)fl[5];
+    S.by = (int)fl[6];
+    S.n = (int)fl[7];
+    S.nnz = (int)fl[8];
+    const size_t bsq = (size_t)S.bx * S.by;
+    S.rp.resize((size_t)S.n + 1);
+    S.ci.resize((size_t)S.nnz);
+    S.va.resize((size_t)S.nnz * bsq);
+    need(fread(S.rp.data(), sizeof(int), S.rp.size(), f) == S.rp.size(), "row_offsets");
+    need(S.nnz == 0 || fread(S.ci.data(), sizeof(int), S.ci.size(), f) == S.ci.size(), "column_indices");
+    need(S.va.empty() || fread(S.va.data(), sizeof(double), S.va.size(), f) == S.va.size(), "off-diagonal values");
+    if (S.has_diag) {
+        S.diag.resize((size_t)S.n * bsq);
+        need(fread(S.diag.data(), sizeof(double), S.diag.size(), f) == S.diag.size(), "diagonal values");
+    }
+    if (fl[1]) { S.rhs.resize((size_t)S.n * S.by); need(fread(S.rhs.data(), sizeof(double), S.rhs.size(), f) == S.rhs.size(), "rhs"); }
+    if (fl[2]) { S.sol.resize((size_t)S.n * S.bx); need(fread(S.sol.data(), sizeof(double), S.sol.size(), f) == S.sol.size(), "solution"); }
+    fclose(f);
+    if (S.rp[0] != 0 || S.rp[S.n] != S.nnz) fatal(AMGX_RC_IO_ERROR, "binary system file: inconsistent row offsets");
+    return true;
+}
+
+static void write_binary(const char *filename, int n, int nnz, int bx, int by, const std::vector<int> &rp, const std::vector<int> &ci, const std::vector<double> &va,
+                         bool has_diag, const std::vector<double> &b, const std::vector<double> &x)
+{
+    FILE *f = fopen(filename, "wb");
+    if (!f) fatal(AMGX_RC_BAD_PARAMETERS, "Cannot open output file!11");
+    const uint32_t fl[9] = {1u, (uint32_t)!b.empty(), (uint32_t)!x.empty(), 0u, (uint32_t)has_diag, (uint32_t)bx, (uint32_t)by, (uint32_t)n, (uint32_t)nnz};
+    bool ok = fwrite(NVAMG_BINARY_HEADER, 1, strlen(NVAMG_BINARY_HEADER), f) == strlen(NVAMG_BINARY_HEADER) && fwrite(fl, sizeof(uint32_t), 9, f) == 9;
+    ok = ok && fwrite(rp.data(), sizeof(int), (size_t)n + 1, f) == (size_t)n + 1;
+    ok = ok && (nnz == 0 || fwrite(ci.data(), sizeof(int), (size_t)nnz, f) == (size_t)nnz);
+    ok = ok && (va.empty() || fwrite(va.data(), sizeof(double), va.size(), f) == va.size());
+    ok = ok && (b.empty() || fwrite(b.data(), sizeof(double), b.size(), f) == b.size());
+    ok = ok && (x.empty() || fwrite(x.data(), sizeof(double), x.size(), f) == x.size());
+    fclose(f);
+    if (!ok) fatal(AMGX_RC_IO_ERROR, "error while writing the binary system file");
+}
+
 static void read_mm(const char *filename, MMSystem &S)
 {
+    if (filename && read_binary(filename, S)) return;          // "%%NVAMGBinary" files are detected by their header
     std::ifstream fin(filename);
     if (!fin) fatal(AMGX_RC_IO_ERROR, std::string("Error opening file '") + (filename ? filename : "(null)") + "'");
     std::string line;
@@ -522,6 +577,22 @@ AMGX_RC AMGX_write_system(const AMGX_matrix_handle mtx, const AMGX_vector_handle
     std::vector<double> b, x;
     get_vec(rhs, b);
     get_vec(sol, x);
+    // matrix_writer = matrixmarket (default) | binary, read from the configuration the resources were created with (matrix_io.cu:505-530)
+    std::string writer = "matrixmarket";
+    if (A.rsc->cfg) writer = A.rsc->cfg->get_string("matrix_writer", "default");
+    if (writer == "binary") {
+        f.close();
+        std::vector<double> vall((size_t)(A.nnz + (A.has_ext_diag ? A.n : 0)) * bsq);
+        if (A.mat_prec == Prec::F64) AMGXB_CUDA_CHECK(cudaMemcpy(vall.data(), A.values.ptr(), vall.size() * 8, cudaMemcpyDeviceToHost));
+        else {
+            std::vector<float> vf(vall.size());
+            AMGXB_CUDA_CHECK(cudaMemcpy(vf.data(), A.values.ptr(), vf.size() * 4, cudaMemcpyDeviceToHost));
+            std::copy(vf.begin(), vf.end(), vall.begin());
+        }
+        write_binary(filename, A.n, A.nnz, A.bx, A.by, rp, ci, vall, A.has_ext_diag, b, x);
+        return AMGX_RC_OK;
+    }
+    if (writer != "matrixmarket") fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_writer '" + writer + "' is not supported (matrixmarket, binary)");
     f << "%%MatrixMarket matrix coordinate real general\n";
     f << "%%AMGX " << A.bx << " " << A.by << " sorted" << (b.empty() ? "" : " rhs") << (x.empty() ? "" : " solution") << "\n";
     f << (long long)A.n * A.bx << " " << (long long)A.n * A.by << " " << (long long)A.nnz * bsq << "\n";

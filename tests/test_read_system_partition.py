@@ -108,3 +108,30 @@ def test_default_and_sized_partitions_and_scattered_vector(mtx_file):
     # errors: wrong vector length, sizes that do not add up
     assert call(lib, 0, 2, mtx_file, pv=[0, 1, 0])[0] != 0
     assert call(lib, 0, 2, mtx_file, sizes=[5, 5], nparts=2)[0] != 0
+
+
+def test_binary_system_file_is_detected_and_read(tmp_path):
+    """the reference's "%%NVAMGBinary" layout (src/matrix_io.cu:267-405): header, 9 uint32 flags, int32 offsets / columns, float64 values
+    (+ diagonal blocks), rhs, solution"""
+    import struct
+    lib = capi.load_library()
+    rp = np.array(RP, np.int32)
+    ci = np.array(CI, np.int32)
+    va = np.arange(1, len(CI) + 1, dtype=np.float64) * 0.5
+    rhs = np.linspace(1, 2, 12)
+    sol = np.linspace(-1, 1, 12)
+    p = tmp_path / "sys.bin"
+    with open(p, "wb") as f:
+        f.write(b"%%NVAMGBinary\n")
+        f.write(struct.pack("<9I", 1, 1, 1, 0, 0, 1, 1, 12, len(CI)))
+        f.write(rp.tobytes() + ci.tobytes() + va.tobytes() + rhs.tobytes() + sol.tobytes())
+    rc, o = call(lib, 0, 1, str(p))
+    assert rc == 0 and o["n"] == 12 and o["nnz"] == len(CI) and o["rp"] == RP and o["cg"] == CI and o["ci"] == CI
+    assert np.array_equal(o["data"], va) and np.array_equal(o["rhs"], rhs) and np.array_equal(o["sol"], sol)
+    # partitioned read of the same binary file
+    rc, o1 = call(lib, 1, 3, str(p), pv=PV)
+    assert rc == 0 and o1["ci"] == EXPECT[1]["ci"] and np.array_equal(o1["rhs"], rhs[4:8])
+    # a truncated file fails loudly
+    q = tmp_path / "short.bin"
+    q.write_bytes(p.read_bytes()[:200])
+    assert call(lib, 0, 1, str(q))[0] != 0
