@@ -10,8 +10,8 @@
 //     step, LU staged in shared memory when it fits (n <= 158 in fp64), else read from L2.
 // The arithmetic order is sequential per entry (k ascending), so the CPU restatement reproduces it bit for bit;
 // against cuSOLVER's blocked getrf the results agree to rounding (backward stable either way).
-// Limits: single GPU (a distributed coarsest level would need the reference's block-Jacobi-of-partitions semantics),
-// n = rows * block_dim <= 2048.
+// Row-partitioned matrices: like the reference's default each rank factors the diagonal block it owns (block Jacobi over the partitions);
+// halo values enter only through the right-hand side when the initial guess is not zero.  Limit: n = local rows * block_dim <= 2048.
 #include "solvers.h"
 #include "dist.h"
 
@@ -29,12 +29,32 @@ __global__ void csr_to_dense_kernel(int n_rows, int bdim, const int *__restrict_
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
         for (int k = rp[i]; k < rp[i + 1]; k++) {
             const int j = ci[k];
+            if (j >= n_rows) continue;     // row-partitioned matrix: only the diagonal block this rank owns is factored (dense_lu_solver.cu:893-905)
             for (int r = 0; r < bdim; r++)
                 for (int c = 0; c < bdim; c++) dense[(size_t)(i * bdim + r) + (size_t)(j * bdim + c) * lda] = (T)va[(size_t)k * bs + r * bdim + c];
         }
         if (has_ext_diag)
             for (int r = 0; r < bdim; r++)
                 for (int c = 0; c < bdim; c++) dense[(size_t)(i * bdim + r) + (size_t)(i * bdim + c) * lda] = (T)va[(size_t)(nnz + i) * bs + r * bdim + c];
+    }
+}
+
+// row-partitioned matrix, non-zero initial guess: new_rhs = b - A_halo x (distributed_rhs_mod, dense_lu_solver.cu:148-490): only the
+// entries whose column lives on another rank contribute
+template <class MatT, class T>
+__global__ void halo_rhs_kernel(int n_rows, int bdim, const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va,
+                                const T *__restrict__ x, const T *__restrict__ b, T *out)
+{
+    const int bs = bdim * bdim;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_rows * bdim; t += gridDim.x * blockDim.x) {
+        const int i = t / bdim, r = t % bdim;
+        T acc = b[t];
+        for (int k = rp[i]; k < rp[i + 1]; k++) {
+            const int j = ci[k];
+            if (j < n_rows) continue;
+            for (int c = 0; c < bdim; c++) acc -= (T)va[(size_t)k * bs + r * bdim + c] * x[(size_t)j * bdim + c];
+        }
+        out[t] = acc;
     }
 }
 
@@ -128,7 +148,11 @@ protected:
     void solver_setup(bool) override
     {
         Matrix &A = *A_;
-        if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "DENSE_LU_SOLVER on a distributed coarsest level (use coarse_solver=NOSOLVER)");
+        // A.dist: the reference factors the diagonal block each rank owns -- block Jacobi over the partitions, halo values only enter
+        // through the right-hand side (dense_lu_solver.cu:893-912).  Its all-gathered exact solve (exact_coarse_solve = 1, CLASSICAL only,
+        // dense_lu_solver.cu:667-669) is not provided -- and classical AMG is single-GPU here anyway.
+        if (A.dist && cfg_->get_int("exact_coarse_solve", scope_) != 0 && cfg_->get_string("algorithm", scope_) == "CLASSICAL")
+            fatal(AMGX_RC_NOT_IMPLEMENTED, "DENSE_LU_SOLVER with exact_coarse_solve=1 on a distributed matrix");
         if (A.bx != A.by) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "DENSE_LU_SOLVER needs square blocks");
         n_ = A.n * A.bx;
         if (n_ > LU_MAX_N) fatal(AMGX_RC_NOT_IMPLEMENTED, "DENSE_LU_SOLVER: coarsest level has more than 2048 rows; lower dense_lu_max_rows or use coarse_solver=NOSOLVER");
@@ -154,13 +178,26 @@ protected:
         });
     }
 
-    Status solve_iteration(DevVec &b, DevVec &x, bool) override
+    Status solve_iteration(DevVec &b, DevVec &x, bool xIsZero) override
     {
         if (n_ == 0) return ST_CONVERGED;
         cudaStream_t s = stream();
+        const void *rhs = b.ptr();
+        if (A_->dist && !xIsZero) {
+            Matrix &A = *A_;
+            dist_exchange_halo(A, x, s);
+            dist_wait_halo(A, s);
+            if (rhs_mod_.n != (size_t)n_) rhs_mod_.resize((size_t)n_, A.vec_prec);
+            AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+                halo_rhs_kernel<MatT, VecT><<<std::max(1, ceil_div(n_, 128)), 128, 0, s>>>(A.n, A.bx, A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(),
+                                                                                           x.as<VecT>(), b.as<VecT>(), rhs_mod_.as<VecT>());
+            });
+            count_launch();
+            rhs = rhs_mod_.ptr();
+        }
         AMGXB_DISPATCH_VEC(A_->vec_prec, {
-            if (in_smem_) lu_solve_kernel<VecT, true><<<1, LU_THREADS, smem_full_, s>>>(n_, dense_.as<VecT>(), n_, ipiv_.ptr(), b.as<VecT>(), x.as<VecT>());
-            else lu_solve_kernel<VecT, false><<<1, LU_THREADS, smem_small_, s>>>(n_, dense_.as<VecT>(), n_, ipiv_.ptr(), b.as<VecT>(), x.as<VecT>());
+            if (in_smem_) lu_solve_kernel<VecT, true><<<1, LU_THREADS, smem_full_, s>>>(n_, dense_.as<VecT>(), n_, ipiv_.ptr(), (const VecT *)rhs, x.as<VecT>());
+            else lu_solve_kernel<VecT, false><<<1, LU_THREADS, smem_small_, s>>>(n_, dense_.as<VecT>(), n_, ipiv_.ptr(), (const VecT *)rhs, x.as<VecT>());
         });
         count_launch();
         AMGXB_LAUNCH_CHECK();
@@ -169,6 +206,7 @@ protected:
 
     int n_ = 0;
     DevVec dense_;          // n x n column-major LU factors (vector precision)
+    DevVec rhs_mod_;        // distributed, non-zero initial guess: b - A_halo x
     DevBuf<int> ipiv_;      // n pivots + 1 info word
     size_t smem_small_ = 0, smem_full_ = 0;
     bool in_smem_ = false;

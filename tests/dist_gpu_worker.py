@@ -246,8 +246,23 @@ def comm_maps_section(rank, world, rsc, lib, cfg):
     res = np.ones(ng) - gallery.to_scipy(rp, ci, va) @ torch.cat(parts).cpu().numpy()
     hist = slv.residual_history()
     assert abs(np.linalg.norm(res) - hist[-1]) <= 1e-9 * hist[0]
+    # DENSE_LU_SOLVER on the row-partitioned coarsest level: every rank factors its own diagonal block (block Jacobi over partitions)
+    cfg2 = capi.Config(file=str(ROOT / "amgx_b200" / "configs" / "PCG_AGGREGATION_JACOBI.json"))
+    cfg2.add_parameters("config_version=2, main:tolerance=1e-8, main:max_iters=100, amg:coarse_solver=DENSE_LU_SOLVER, amg:dense_lu_num_rows=64")
+    slv2 = capi.Solver(rsc, cfg2)
+    slv2.setup(A)
+    sol.set_zero(n)
+    slv2.solve(b, sol)
+    assert slv2.status == "success", slv2.status
+    dist.all_gather(parts, torch.from_numpy(sol.download()).cuda())
+    res = np.ones(ng) - gallery.to_scipy(rp, ci, va) @ torch.cat(parts).cpu().numpy()
+    h2 = slv2.residual_history()
+    assert abs(np.linalg.norm(res) - h2[-1]) <= 1e-9 * h2[0]
+    its2 = slv2.iterations_number
+    slv2.destroy()
+    cfg2.destroy()
     if rank == 0:
-        print(f"DIST_COMM_MAPS_OK world={world} iters={slv.iterations_number}", flush=True)
+        print(f"DIST_COMM_MAPS_OK world={world} iters={slv.iterations_number} dense_lu_iters={its2}", flush=True)
     for o in (slv, sol, b, y, x, A):
         o.destroy()
     dist.barrier()
