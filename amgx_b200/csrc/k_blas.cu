@@ -177,6 +177,70 @@ void vec_axpbypcz(const void *x, const void *y, const void *z, void *out, Prec p
     });
 }
 
+// ---- scaling = DIAGONAL_SYMMETRIC (src/scalers/diagonal_symmetric.cu): s_i = 1/sqrt(a_ii); A <- S A S in place (values[jj] *= s_i*s_j),
+// undone by the division; vectors are multiplied / divided entry-wise.  negative[0] is set when a diagonal entry is negative.
+namespace {
+template <class MatT, class VecT> __global__ void diag_inv_sqrt_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va,
+                                                                        VecT *s, int *negative)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        VecT d = 0;
+        for (int k = rp[i]; k < rp[i + 1]; k++) if (ci[k] == i) d = (VecT)va[k];      // grabDiagonalVector: the last match wins
+        if (d < (VecT)0) negative[0] = 1;
+        s[i] = 1. / sqrt(d);
+    }
+}
+template <class MatT, class VecT> __global__ void scale_matrix_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, MatT *va, const VecT *__restrict__ s,
+                                                                       int unscale)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const VecT si = s[i];
+        for (int k = rp[i]; k < rp[i + 1]; k++) {
+            const VecT sj = s[ci[k]];
+            if (unscale) va[k] /= si * sj;
+            else va[k] *= si * sj;
+        }
+    }
+}
+}  // namespace
+
+int diag_sym_scale_setup(const Matrix &A, DevVec &scale, cudaStream_t s)
+{
+    scale.resize((size_t)A.n, A.vec_prec);
+    DevBuf<int> neg;
+    neg.resize(1);
+    neg.zero(s);
+    if (A.n) {
+        const int grid = std::min(ceil_div(A.n, 256), blas_max_grid());
+        AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+            diag_inv_sqrt_kernel<MatT, VecT><<<grid, 256, 0, s>>>(A.n, A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), scale.as<VecT>(), neg.ptr());
+        });
+        count_launch();
+        AMGXB_LAUNCH_CHECK();
+    }
+    return neg.to_host(s)[0];
+}
+
+void diag_sym_scale_matrix(Matrix &A, const DevVec &scale, bool unscale, cudaStream_t s)
+{
+    if (!A.n) return;
+    const int grid = std::min(ceil_div(A.n, 256), blas_max_grid());
+    AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+        scale_matrix_kernel<MatT, VecT><<<grid, 256, 0, s>>>(A.n, A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), scale.as<VecT>(), unscale ? 1 : 0);
+    });
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+}
+
+void vec_scale_entrywise(void *v, const void *d, Prec p, size_t n, bool divide, cudaStream_t s)
+{
+    AMGXB_DISPATCH_VEC(p, {
+        VecT *V = (VecT *)v; const VecT *D = (const VecT *)d;
+        if (divide) launch_map(n, [=] __device__(size_t i) { V[i] /= D[i]; }, s);
+        else launch_map(n, [=] __device__(size_t i) { V[i] *= D[i]; }, s);
+    });
+}
+
 // scale of the coarse-grid correction, error_scaling = 2, 3: out[0] = clamp(scal[nom] / scal[den]) exactly as
 // aggregation_amg_level.cu:797-817 words it (|den| == 0 -> 1; |alpha| < .3 -> sign * .3; |alpha| > 10 -> sign * 10)
 void scalar_error_scale(const double *scal, int slot_nom, int slot_den, double *out, cudaStream_t s)

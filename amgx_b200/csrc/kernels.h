@@ -82,6 +82,10 @@ void vec_axpbypcz(const void *x, const void *y, const void *z, void *out, Prec p
 void vec_scal(void *x, Prec p, size_t n, double a, cudaStream_t s);
 // device-scalar variants: a = sign * scal[slot]
 void vec_axpy_dev(const void *x, void *y, Prec p, size_t n, const double *scal, int slot, double sign, cudaStream_t s);
+// scaling = DIAGONAL_SYMMETRIC (k_blas.cu)
+int  diag_sym_scale_setup(const Matrix &A, DevVec &scale, cudaStream_t s);           // scale_i = 1/sqrt(a_ii); returns 1 if a diagonal entry is negative
+void diag_sym_scale_matrix(Matrix &A, const DevVec &scale, bool unscale, cudaStream_t s);
+void vec_scale_entrywise(void *v, const void *d, Prec p, size_t n, bool divide, cudaStream_t s);
 void scalar_error_scale(const double *scal, int slot_nom, int slot_den, double *out, cudaStream_t s);   // error_scaling 2/3: clamped nom/den
 // fused MGS step: y += sign*scal[slot]*x ; scal[fin_slot] = fin(<z, y>)  (z == nullptr: <y, y>)
 void vec_axpy_dot_dev(const void *x, void *y, const void *z, Prec p, size_t n, const double *scal, int slot, double sign, const ReduceCtx &red, int fin_op,

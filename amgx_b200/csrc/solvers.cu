@@ -164,8 +164,11 @@ Solver::Solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources>
     obtain_timings_ = cfg.get_int("obtain_timings", scope) != 0;
     print_solve_stats_ = cfg.get_int("print_solve_stats", scope) != 0;
     print_grid_stats_ = cfg.get_int("print_grid_stats", scope) != 0;
-    if (cfg.get_string("scaling", scope) != "NONE")
-        fatal(AMGX_RC_BAD_CONFIGURATION, "matrix scaling is outside the solve-phase engine's scope (scaling must be NONE)");
+    {
+        const std::string sc = cfg.get_string("scaling", scope);
+        if (sc == "DIAGONAL_SYMMETRIC") scaling_ = true;
+        else if (sc != "NONE") fatal(AMGX_RC_BAD_CONFIGURATION, "scaling '" + sc + "' is not supported by this engine (NONE, DIAGONAL_SYMMETRIC)");
+    }
     monitor_convergence_ = monitor_residual_;
     if (scope == "default") {   // backward compatibility rule of the reference (solver.cu:52-60)
         // the reference zeroes the print parameters of the default scope after reading the monitoring flags
@@ -226,7 +229,17 @@ void Solver::setup(Matrix &A, bool reuse)
     if (reuse && A_ != &A) fatal(AMGX_RC_UNKNOWN, "Cannot call resetup with a different matrix");
     A_ = &A;
     conv_.fp32 = (A.vec_prec == Prec::F32);
+    if (scaling_) {
+        // src/solvers/solver.cu:440-477: scale the matrix in place, set the solver up on the SCALED matrix, undo the scaling.  (The
+        // reference calls this "very slow" and unfinished; it is reproduced as it is, including the a*s/s round trip of the values.)
+        if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "Diagonal Symmetric scaling not supported for distributed matrices");
+        if (A.bs() != 1 || A.has_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "DIAGONAL_SYMMETRIC scaling: scalar matrices with the diagonal inside the CSR structure");
+        if (diag_sym_scale_setup(A, scale_, stream()))
+            fatal(AMGX_RC_NOT_IMPLEMENTED, "Diagonal symmetric scaling only applies to SPD systems with positive diagonal entries");
+        diag_sym_scale_matrix(A, scale_, false, stream());
+    }
     solver_setup(reuse);
+    if (scaling_) diag_sym_scale_matrix(A, scale_, true, stream());
     if (monitor_residual_ || is_residual_needed()) {
         r_.resize((size_t)A.n_cols * A.by, A.vec_prec);
         r_.zero(stream());
@@ -318,6 +331,24 @@ Status Solver::solve(DevVec &b, DevVec &x, bool xIsZero)
 {
     if (!is_setup_) fatal(AMGX_RC_BAD_CONFIGURATION, "Error, setup must be called before calling solve");
     if (obtain_timings_) AMGXB_CUDA_CHECK(cudaEventRecord(ev_[2], stream()));
+    if (scaling_) {   // solver.cu:667-675: A <- S A S, b <- S b, x <- S^-1 x, all in place; undone before returning
+        diag_sym_scale_matrix(*A_, scale_, false, stream());
+        vec_scale_entrywise(b.ptr(), scale_.ptr(), b.prec, vec_len(), false, stream());
+        vec_scale_entrywise(x.ptr(), scale_.ptr(), x.prec, vec_len(), true, stream());
+    }
+    struct Unscale {   // runs on every way out of solve(), exceptions included
+        Solver *sv; DevVec *b, *x;
+        ~Unscale()
+        {
+            if (!sv->scaling_) return;
+            try {
+                vec_scale_entrywise(x->ptr(), sv->scale_.ptr(), x->prec, sv->vec_len(), false, sv->stream());
+                vec_scale_entrywise(b->ptr(), sv->scale_.ptr(), b->prec, sv->vec_len(), true, sv->stream());
+                diag_sym_scale_matrix(*sv->A_, sv->scale_, true, sv->stream());
+            } catch (...) {   // already unwinding from an error: nothing more to report
+            }
+        }
+    } unscale_guard{this, &b, &x};
     if (monitor_residual_ || is_residual_needed()) {
         if (xIsZero) vec_copy(r_.ptr(), b.ptr(), b.prec, vec_len(), stream());
         else compute_residual(b, x);

@@ -159,6 +159,8 @@ protected:
     std::vector<double> nrm_, nrm_ini_;
     std::vector<std::vector<double>> res_history_;
     ScalarBlock sb_;
+    bool scaling_ = false;      // scaling = DIAGONAL_SYMMETRIC in this solver's scope
+    DevVec scale_;              // s_i = 1 / sqrt(a_ii)
     bool is_setup_ = false;
     double setup_time_ = 0, solve_time_ = 0;
     cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};

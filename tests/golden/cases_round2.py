@@ -107,6 +107,15 @@ def cases():
     yield "poisson16_fgmres_agg_dilu_pgreedy", P(16), _outer("FGMRES", fa, tol=1e-8, max_iters=60, gmres_n_restart=10)
     yield "symbanded3000_fgmres_agg_dilu_pgreedy", sym_banded(3000, 40.0), _outer("FGMRES", fa, tol=1e-8, max_iters=60, gmres_n_restart=10)
     yield "poisson14_amg_gs_pgreedy", P(14), _standalone(_agg(dict(GS(1), matrix_coloring_scheme="PARALLEL_GREEDY"), matrix_coloring_scheme="PARALLEL_GREEDY"))
+    # scaling = DIAGONAL_SYMMETRIC on the main solver (V-cheby-smoother.json): variable-coefficient SPD matrix so that S is not a multiple of I
+    def var_poisson(n):
+        rp, ci, va = gallery.poisson7pt(n)
+        N = rp.shape[0] - 1
+        dd = 1.0 + 0.75 * np.sin(0.37 * np.arange(N)) ** 2
+        rows = np.repeat(np.arange(N), np.diff(rp))
+        return rp, ci, va * dd[rows] * dd[ci]
+    yield "varpoisson12_amg_agg_diagsym", var_poisson(12), _standalone(_agg(scaling="DIAGONAL_SYMMETRIC"))
+    yield "varpoisson12_pcg_agg_diagsym", var_poisson(12), _outer("PCG", _agg(), scaling="DIAGONAL_SYMMETRIC")
     # dense LU coarse solver
     for rows in (32, 128):
         yield f"poisson12_pcg_agg_denselu{rows}", P(12), _outer("PCG", _agg(coarse_solver="DENSE_LU_SOLVER", dense_lu_num_rows=rows))

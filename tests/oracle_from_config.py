@@ -73,6 +73,21 @@ def build_amg(oracle, a, rp, ci, va, determinism=0):
 def run_oracle(oracle, cfg, rp, ci, va, b, x0=None):
     """returns (x, iterations, residual history, converged, amg-or-None)"""
     s = cfg["solver"]
+    if s.get("scaling", "NONE") == "DIAGONAL_SYMMETRIC":
+        # src/solvers/solver.cu:440-477, 667-675, 856-862 + src/scalers/diagonal_symmetric.cu: the solver is set up and run on S A S with
+        # S = diag(1/sqrt(a_ii)), b <- S b, x0 <- S^-1 x0, and the solution is scaled back; norms are those of the scaled system
+        import copy
+        n = rp.shape[0] - 1
+        rows = np.repeat(np.arange(n), np.diff(rp))
+        d = np.zeros(n)
+        d[rows[ci == rows]] = va[ci == rows]
+        sc = 1.0 / np.sqrt(d)
+        vs = va * (sc[rows] * sc[ci])
+        c2 = copy.deepcopy(cfg)
+        c2["solver"]["scaling"] = "NONE"
+        x, it, hist, conv, amg = run_oracle(oracle, c2, rp, ci, vs, b * sc, None if x0 is None else x0 / sc)
+        return x * sc, it, hist, conv, amg
+    assert s.get("scaling", "NONE") == "NONE", s["scaling"]
     det = cfg.get("determinism_flag", 0)
     name = s["solver"]
     tol, mi, norm = _get(s, "tolerance"), _get(s, "max_iters"), _get(s, "norm")

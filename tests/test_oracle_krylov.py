@@ -126,3 +126,20 @@ def test_nonzero_initial_guess_and_immediate_convergence(oracle):
         assert conv and np.linalg.norm(b - A @ x) <= 1.01e-6 * hist[0]
         x, it, hist, conv = oracle.krylov(kind, rp, ci, va, np.zeros_like(b), tol=1e-6, max_iters=10)
         assert it == 0 and conv and not x.any()
+
+
+def test_diagonal_symmetric_scaling_solves_the_original_system(oracle):
+    """scaling = DIAGONAL_SYMMETRIC: the solver works on S A S, S b; the returned x is the solution of A x = b and the reported norms are
+    those of the scaled system (src/solvers/solver.cu:667-675, 856-862)"""
+    from tests.golden.cases_round2 import case_dict
+    from tests.oracle_from_config import run_oracle
+    (rp, ci, va), cfg = case_dict()["varpoisson12_pcg_agg_diagsym"]
+    n = rp.shape[0] - 1
+    A = gallery.to_scipy(rp, ci, va)
+    b = np.random.default_rng(3).standard_normal(n)
+    x, it, hist, conv, amg = run_oracle(oracle, cfg, rp, ci, va, b)
+    assert conv
+    s = 1.0 / np.sqrt(A.diagonal())
+    assert np.isclose(hist[0], np.linalg.norm(s * b), rtol=1e-14)
+    assert np.isclose(hist[-1], np.linalg.norm(s * (b - A @ x)), rtol=1e-6)
+    assert np.linalg.norm(b - A @ x) <= 1e-7 * np.linalg.norm(b)
