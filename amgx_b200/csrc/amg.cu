@@ -88,8 +88,9 @@ void AMGSolver::solver_setup(bool reuse)
 // The level-building loop of AMG_Setup::setup (src/amg.cu:201-418), single-partition form.
 void AMGSolver::setup_aggregation()
 {
-    if (selector_ != "SIZE_2")
-        fatal(AMGX_RC_BAD_CONFIGURATION, "aggregation selector '" + selector_ + "' is not supported by this engine (SIZE_2)");
+    if (selector_ != "SIZE_2" && selector_ != "SIZE_4")
+        fatal(AMGX_RC_BAD_CONFIGURATION, "aggregation selector '" + selector_ + "' is not supported by this engine (SIZE_2, SIZE_4)");
+    if (selector_ == "SIZE_4" && A_->dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "SIZE_4 selector on a distributed matrix (use SIZE_2)");
     cudaStream_t s = stream();
     AggSetupParams prm;
     prm.deterministic = cfg_->get_int("determinism_flag", "default");
@@ -125,7 +126,7 @@ void AMGSolver::setup_aggregation()
             L.aggregates.swap(reuse_aggregates_[li]);       // structure reuse: keep the previous setup's aggregates
             n_agg = reuse_n_coarse_[li];
         } else {
-            n_agg = size2_select(A, prm, L.aggregates, s);
+            n_agg = selector_ == "SIZE_4" ? size4_select(A, prm, L.aggregates, s) : size2_select(A, prm, L.aggregates, s);
         }
         L.n_coarse = n_agg;
         const long long N = dist_allreduce_ll(A, rows, 0) * A.by, nextN = dist_allreduce_ll(A, n_agg, 0) * A.by;

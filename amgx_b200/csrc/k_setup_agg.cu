@@ -241,7 +241,220 @@ template <class MatT> __global__ void extract_diag_kernel(int n, int bsq, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// SIZE_4 selector (src/aggregation/selectors/size4_selector.cu:96-224; kernels include/aggregation/selectors/common_selector.h:178-525):
+// handshake pairs, then handshake pairs of pairs, then the deterministic merge of the leftovers.  In the deterministic flow none
+// of these kernels reads what another thread of the same launch writes, so a launch is a pure function of its inputs.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void s4_find_strongest_nomerge(const int *__restrict__ rp, const int *__restrict__ ci, const float *__restrict__ w, int n,
+                                          const int *__restrict__ partner, int *strongest)
+{
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += gridDim.x * blockDim.x) {
+        if (partner[tid] != -1) continue;
+        float max_w = 0.f;
+        int best = -1;
+        for (int j = rp[tid]; j < rp[tid + 1]; j++) {
+            const int jc = ci[j];
+            if (tid == jc || jc >= n) continue;
+            const float wt = w[j];
+            if (partner[jc] == -1 && (wt > max_w || (wt == max_w && jc > best))) { max_w = wt; best = jc; }
+        }
+        if (best != -1) strongest[tid] = best;      // nothing found: the previous proposal stays (deterministic flow)
+    }
+}
+__global__ void s4_match_edges(int n, int *partner, int *aggregates, const int *__restrict__ strongest)
+{
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += gridDim.x * blockDim.x) {
+        if (partner[tid] != -1) continue;
+        const int pm = strongest[tid];
+        if (pm != -1 && strongest[pm] == tid) {
+            partner[tid] = pm;
+            aggregates[tid] = pm > tid ? tid : pm;
+        }
+    }
+}
+__global__ void s4_count_minus_one(int n, const int *__restrict__ v, int *count)
+{
+    int c = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) c += (v[t] == -1);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+__global__ void s4_assign_unassigned(int n, int *partner)
+{
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += gridDim.x * blockDim.x)
+        if (partner[tid] == -1) partner[tid] = tid;
+}
+__global__ void s4_store_weight(const int *__restrict__ rp, const int *__restrict__ ci, const float *__restrict__ w, int n, const int *__restrict__ aggregated,
+                                const int *__restrict__ aggregates, int *strongest, const int *__restrict__ partner, float *wsn)
+{
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += gridDim.x * blockDim.x) {
+        if (aggregated[tid] != -1) continue;
+        const int p = partner[tid];
+        float max_w = 0.f;
+        int best = -1;
+        for (int j = rp[tid]; j < rp[tid + 1]; j++) {
+            const int jc = ci[j];
+            if (tid == jc || jc >= n) continue;
+            const float wt = w[j];
+            if (aggregated[jc] == -1 && jc != p && (wt > max_w || (wt == max_w && jc > best))) { max_w = wt; best = jc; }
+        }
+        if (best != -1) {
+            wsn[tid] = max_w;
+            strongest[tid] = aggregates[best];
+        }
+    }
+}
+__global__ void s4_agree(int n, int *aggregated, int *strongest, const float *__restrict__ wsn, const int *__restrict__ partner)
+{
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += gridDim.x * blockDim.x) {
+        if (aggregated[tid] != -1) continue;
+        const int p = partner[tid];
+        const float mine = wsn[tid];
+        float theirs = -1;
+        if (p != -1) theirs = wsn[p];
+        if (mine < 0.f && theirs < 0.f) {             // every neighbour is aggregated: the pair stays as it is
+            aggregated[tid] = 1;
+            strongest[tid] = -1;
+        } else if (mine < theirs) {
+            strongest[tid] = strongest[p];            // the weaker half adopts its partner's proposal (the partner does not write: its weight is larger)
+        }
+    }
+}
+__global__ void s4_match_aggregates(int n, int *aggregates, int *aggregated, const int *__restrict__ strongest)
+{
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += gridDim.x * blockDim.x) {
+        if (aggregated[tid] != -1) continue;
+        const int pm = strongest[tid];
+        if (pm == -1) continue;
+        const int mine = aggregates[tid];
+        if (strongest[pm] == mine) {
+            aggregated[tid] = 1;
+            aggregates[tid] = pm > mine ? mine : pm;
+        }
+    }
+}
+__global__ void s4_merge_candidates(const int *__restrict__ rp, const int *__restrict__ ci, const float *__restrict__ w, int n, const int *__restrict__ aggregates,
+                                    const int *__restrict__ aggregated, int *cand)
+{
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += gridDim.x * blockDim.x) {
+        if (aggregated[tid] != -1) continue;
+        float max_w = 0.f;
+        int best = -1;
+        for (int j = rp[tid]; j < rp[tid + 1]; j++) {
+            const int jc = ci[j];
+            if (tid == jc || jc >= n) continue;
+            if (aggregated[jc] != -1) {
+                const float wt = w[j];
+                if (wt > max_w || (wt == max_w && jc > best)) { max_w = wt; best = jc; }
+            }
+        }
+        cand[tid] = best != -1 ? aggregates[best] : tid;
+    }
+}
+__global__ void s4_join(int n, int *aggregates, int *aggregated, const int *__restrict__ cand)
+{
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += gridDim.x * blockDim.x)
+        if (aggregated[tid] == -1 && cand[tid] != -1) { aggregates[tid] = cand[tid]; aggregated[tid] = 1; }
+}
+__global__ void fill_float_kernel(int n, float *v, float x)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) v[t] = x;
+}
+
+// labels (minimum member row ids) -> 0..n_agg-1 in label order (renumberAndCountAggregates, agg_selector.cu:18-43)
+int renumber_aggregates(int n, DevBuf<int> &aggregates, cudaStream_t s)
+{
+    const int g = grid_for(n);
+    DevBuf<int> scratch;
+    scratch.resize(n + 1);
+    scratch.zero(s);
+    mark_kernel<<<g, 256, 0, s>>>(n, aggregates.ptr(), scratch.ptr());
+    count_launch();
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, scratch.ptr(), scratch.ptr(), n + 1, s);
+    DevBytes tmp;
+    tmp.resize(tmp_bytes);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, scratch.ptr(), scratch.ptr(), n + 1, s);
+    relabel_kernel<<<g, 256, 0, s>>>(n, aggregates.ptr(), scratch.ptr());
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    return read_scalar(scratch.ptr() + n, s);
+}
+
 }  // namespace
+
+int size4_select(const Matrix &A, const AggSetupParams &prm, DevBuf<int> &aggregates, cudaStream_t s)
+{
+    const int n = A.n;
+    aggregates.resize(n);
+    if (n == 0) return 0;
+    const int g = grid_for(n);
+    DevBuf<float> w, wsn;
+    DevBuf<int> strongest, partner, aggregated, counter, cand;
+    w.resize(std::max(A.nnz, 1));
+    wsn.resize(n);
+    strongest.resize(n);
+    partner.resize(n);
+    aggregated.resize(n);
+    cand.resize(n);
+    counter.resize(1);
+    iota_kernel<<<g, 256, 0, s>>>(n, aggregates.ptr());
+    fill_int_kernel<<<g, 256, 0, s>>>(n, strongest.ptr(), -1);
+    fill_int_kernel<<<g, 256, 0, s>>>(n, partner.ptr(), -1);
+    count_launch(3);
+    const int bsq = A.bs();
+    const int entry = prm.edge_weight_component * A.bx + prm.edge_weight_component;
+    if (A.mat_prec == Prec::F64)
+        edge_weights_kernel<double><<<g, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.diag_idx.ptr(), A.values.as<double>(), n, bsq, entry, prm.weight_formula, w.ptr());
+    else
+        edge_weights_kernel<float><<<g, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.diag_idx.ptr(), A.values.as<float>(), n, bsq, entry, prm.weight_formula, w.ptr());
+    count_launch();
+    auto count_m1 = [&](const int *v) {
+        counter.zero(s);
+        s4_count_minus_one<<<g, 256, 0, s>>>(n, v, counter.ptr());
+        count_launch();
+        AMGXB_LAUNCH_CHECK();
+        return read_scalar(counter.ptr(), s);
+    };
+    // ---- pairs.  The reference counts -1 over its 3n-entry partner_index array, whose upper 2n entries are still -1 in this phase
+    // (size4_selector.cu:126, 158): the count never reaches 0 nor the tolerance, the loop ends on "no progress" or the iteration cap.
+    int num_unassigned = n, prev = n, icount = 0;
+    do {
+        s4_find_strongest_nomerge<<<g, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), w.ptr(), n, partner.ptr(), strongest.ptr());
+        s4_match_edges<<<g, 256, 0, s>>>(n, partner.ptr(), aggregates.ptr(), strongest.ptr());
+        count_launch(2);
+        prev = num_unassigned;
+        num_unassigned = count_m1(partner.ptr()) + 2 * n;
+        icount++;
+    } while (!(num_unassigned == 0 || icount > prm.max_iterations || 1.0 * num_unassigned / n < prm.max_unassigned || prev == num_unassigned));
+    s4_assign_unassigned<<<g, 256, 0, s>>>(n, partner.ptr());
+    // ---- pairs of pairs
+    fill_float_kernel<<<g, 256, 0, s>>>(n, wsn.ptr(), -1.f);
+    fill_int_kernel<<<g, 256, 0, s>>>(n, aggregated.ptr(), -1);
+    count_launch(3);
+    icount = 0;
+    num_unassigned = prev = n;
+    do {
+        s4_store_weight<<<g, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), w.ptr(), n, aggregated.ptr(), aggregates.ptr(), strongest.ptr(), partner.ptr(), wsn.ptr());
+        s4_agree<<<g, 256, 0, s>>>(n, aggregated.ptr(), strongest.ptr(), wsn.ptr(), partner.ptr());
+        s4_match_aggregates<<<g, 256, 0, s>>>(n, aggregates.ptr(), aggregated.ptr(), strongest.ptr());
+        count_launch(3);
+        prev = num_unassigned;
+        num_unassigned = count_m1(aggregated.ptr());
+        icount++;
+    } while (!(num_unassigned == 0 || icount > prm.max_iterations || 1.0 * num_unassigned / n < prm.max_unassigned || prev == num_unassigned));
+    // ---- leftovers join the aggregate of their strongest aggregated neighbour (deterministic: candidates first, then join)
+    fill_int_kernel<<<g, 256, 0, s>>>(n, cand.ptr(), -1);
+    count_launch();
+    while (num_unassigned != 0) {
+        s4_merge_candidates<<<g, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), w.ptr(), n, aggregates.ptr(), aggregated.ptr(), cand.ptr());
+        s4_join<<<g, 256, 0, s>>>(n, aggregates.ptr(), aggregated.ptr(), cand.ptr());
+        count_launch(2);
+        num_unassigned = count_m1(aggregated.ptr());
+    }
+    return renumber_aggregates(n, aggregates, s);
+}
 
 int size2_select(const Matrix &A, const AggSetupParams &prm, DevBuf<int> &aggregates, cudaStream_t s)
 {

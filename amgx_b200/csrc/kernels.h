@@ -124,6 +124,7 @@ struct AggSetupParams {
 };
 // aggregates[n] (renumbered), returns number of aggregates
 int  size2_select(const Matrix &A, const AggSetupParams &prm, DevBuf<int> &aggregates, cudaStream_t s);
+int  size4_select(const Matrix &A, const AggSetupParams &prm, DevBuf<int> &aggregates, cudaStream_t s);   // pairs of pairs (size4_selector.cu)
 void build_restriction(const DevBuf<int> &aggregates, int n, int n_agg, DevBuf<int> &R_row_offsets, DevBuf<int> &R_col, cudaStream_t s);
 void galerkin_aggregation(const Matrix &A, const DevBuf<int> &aggregates, int n_agg, Matrix &Ac, cudaStream_t s);
 void extract_diagonal(const Matrix &A, DevVec &d, cudaStream_t s);   // d[i] = A(i,i) (mat precision); bs>1: diagonal blocks

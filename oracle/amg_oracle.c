@@ -211,6 +211,111 @@ ORC_API void orc_edge_weights(int n, const int *rp, const int *ci, const double 
     free(diag);
 }
 
+/* SIZE_4: Size4Selector::setAggregates_common_sqblock (src/aggregation/selectors/size4_selector.cu:96-224) with the kernels of
+ * include/aggregation/selectors/common_selector.h:178-525, deterministic flow: handshake pairs (findStrongestNeighbour_NoMerge +
+ * matchEdges), handshake pairs of pairs (_StoreWeight + agreeOnProposal + matchAggregates), candidate/join merge of the leftovers,
+ * renumbering.  No kernel of this flow reads what another thread of the same launch writes, so the loops below may update in
+ * place.  Returns #aggregates.  parity unpinned (no reference golden yet). */
+static int s4_count(int n, const int *v) { int c = 0; for (int i = 0; i < n; i++) c += (v[i] == -1); return c; }
+ORC_API int orc_size4_aggregates(int n, const int *rp, const int *ci, const double *va, int max_iterations, double max_unassigned, int weight_formula, int *agg)
+{
+    if (n == 0) return 0;
+    float *w = (float *)malloc(sizeof(float) * (size_t)(rp[n] > 0 ? rp[n] : 1)), *wsn = (float *)malloc(sizeof(float) * (size_t)n);
+    int *strongest = (int *)malloc(sizeof(int) * (size_t)n), *partner = (int *)malloc(sizeof(int) * (size_t)n);
+    int *aggregated = (int *)malloc(sizeof(int) * (size_t)n), *cand = (int *)malloc(sizeof(int) * (size_t)n);
+    orc_edge_weights(n, rp, ci, va, weight_formula, w);
+    for (int i = 0; i < n; i++) { agg[i] = i; strongest[i] = -1; partner[i] = -1; }
+    int unassigned = n, prev = n, icount = 0;
+    do {                                                   /* ---- pairs ---- */
+        for (int t = 0; t < n; t++) {                      /* findStrongestNeighbourBlockDiaCsr_NoMerge */
+            if (partner[t] != -1) continue;
+            float mw = 0.f; int best = -1;
+            for (int j = rp[t]; j < rp[t + 1]; j++) {
+                const int jc = ci[j];
+                if (t == jc || jc >= n) continue;
+                if (partner[jc] == -1 && (w[j] > mw || (w[j] == mw && jc > best))) { mw = w[j]; best = jc; }
+            }
+            if (best != -1) strongest[t] = best;
+        }
+        for (int t = 0; t < n; t++) {                      /* matchEdges */
+            if (partner[t] != -1) continue;
+            const int pm = strongest[t];
+            if (pm != -1 && strongest[pm] == t) { partner[t] = pm; agg[t] = (pm > t ? t : pm); }     /* each thread writes its own entries only */
+        }
+        prev = unassigned;
+        unassigned = s4_count(n, partner) + 2 * n;         /* the reference counts over its 3n-entry partner_index array */
+        icount++;
+    } while (!(unassigned == 0 || icount > max_iterations || 1.0 * unassigned / n < max_unassigned || prev == unassigned));
+    for (int t = 0; t < n; t++) if (partner[t] == -1) partner[t] = t;      /* assignUnassignedVertices */
+    for (int t = 0; t < n; t++) { wsn[t] = -1.f; aggregated[t] = -1; }
+    icount = 0; unassigned = prev = n;
+    do {                                                   /* ---- pairs of pairs ---- */
+        for (int t = 0; t < n; t++) {                      /* findStrongestNeighbourBlockDiaCsr_StoreWeight */
+            if (aggregated[t] != -1) continue;
+            const int p = partner[t];
+            float mw = 0.f; int best = -1;
+            for (int j = rp[t]; j < rp[t + 1]; j++) {
+                const int jc = ci[j];
+                if (t == jc || jc >= n) continue;
+                if (aggregated[jc] == -1 && jc != p && (w[j] > mw || (w[j] == mw && jc > best))) { mw = w[j]; best = jc; }
+            }
+            if (best != -1) { wsn[t] = mw; strongest[t] = agg[best]; }
+        }
+        {                                                  /* agreeOnProposal: decisions from the launch's inputs */
+            int *sn_in = (int *)malloc(sizeof(int) * (size_t)n);
+            memcpy(sn_in, strongest, sizeof(int) * (size_t)n);
+            for (int t = 0; t < n; t++) {
+                if (aggregated[t] != -1) continue;
+                const int p = partner[t];
+                const float mine = wsn[t], theirs = (p != -1) ? wsn[p] : -1.f;
+                if (mine < 0.f && theirs < 0.f) { aggregated[t] = 1; strongest[t] = -1; }
+                else if (mine < theirs) strongest[t] = sn_in[p];
+            }
+            free(sn_in);
+        }
+        {                                                  /* matchAggregates */
+            int *ag_in = (int *)malloc(sizeof(int) * (size_t)n);
+            memcpy(ag_in, agg, sizeof(int) * (size_t)n);
+            for (int t = 0; t < n; t++) {
+                if (aggregated[t] != -1) continue;
+                const int pm = strongest[t];
+                if (pm == -1) continue;
+                const int mine = ag_in[t];
+                if (strongest[pm] == mine) { aggregated[t] = 1; agg[t] = pm > mine ? mine : pm; }
+            }
+            free(ag_in);
+        }
+        prev = unassigned;
+        unassigned = s4_count(n, aggregated);
+        icount++;
+    } while (!(unassigned == 0 || icount > max_iterations || 1.0 * unassigned / n < max_unassigned || prev == unassigned));
+    for (int t = 0; t < n; t++) cand[t] = -1;
+    while (unassigned != 0) {                              /* mergeWithExistingAggregatesBlockDiaCsr (deterministic) + joinExistingAggregates */
+        for (int t = 0; t < n; t++) {
+            if (aggregated[t] != -1) continue;
+            float mw = 0.f; int best = -1;
+            for (int j = rp[t]; j < rp[t + 1]; j++) {
+                const int jc = ci[j];
+                if (t == jc || jc >= n) continue;
+                if (aggregated[jc] != -1 && (w[j] > mw || (w[j] == mw && jc > best))) { mw = w[j]; best = jc; }
+            }
+            cand[t] = best != -1 ? agg[best] : t;
+        }
+        for (int t = 0; t < n; t++) if (aggregated[t] == -1 && cand[t] != -1) { agg[t] = cand[t]; aggregated[t] = 1; }
+        unassigned = s4_count(n, aggregated);
+    }
+    /* renumberAndCountAggregates */
+    int *mark = (int *)calloc((size_t)n + 1, sizeof(int));
+    for (int i = 0; i < n; i++) mark[agg[i]] = 1;
+    int nagg = 0;
+    for (int i = 0; i <= n; i++) { const int m = mark[i]; mark[i] = nagg; nagg += m; }
+    for (int i = 0; i < n; i++) agg[i] = mark[agg[i]];
+    free(mark); free(w); free(wsn); free(strongest); free(partner); free(aggregated); free(cand);
+    return nagg;
+}
+static int g_agg_selector = 2;       /* 2 SIZE_2, 4 SIZE_4: selector of the NEXT aggregation setups */
+ORC_API void orc_set_aggregation_selector(int size) { g_agg_selector = size; }
+
 /* setAggregates_common_sqblocks (src/aggregation/selectors/size2_selector.cu:736-890), one-phase handshake,
  * deterministic leftover merge, then renumberAndCountAggregates (agg_selector.cu:18-43).  Returns #aggregates. */
 ORC_API int orc_size2_aggregates(int n, const int *rp, const int *ci, const double *va, int max_iterations, double max_unassigned,
@@ -512,7 +617,8 @@ ORC_API orc_amg *orc_amg_setup(int n, const int *rp, const int *ci, const double
             nagg = g_reuse_from->lv[num_levels - 1].nagg;
         } else {
             g_reuse_levels = 0;   /* the chain of reused levels ends at the first rebuilt one */
-            nagg = orc_size2_aggregates(L->n, L->rp, L->ci, L->va, max_iterations, max_unassigned, merge_singletons, weight_formula, L->agg);
+            nagg = g_agg_selector == 4 ? orc_size4_aggregates(L->n, L->rp, L->ci, L->va, max_iterations, max_unassigned, weight_formula, L->agg)
+                                       : orc_size2_aggregates(L->n, L->rp, L->ci, L->va, max_iterations, max_unassigned, merge_singletons, weight_formula, L->agg);
         }
         if ((double)nagg <= coarsen_threshold * (double)L->n && nagg != L->n && nagg >= min_coarse_rows) {
             L->nagg = nagg;

@@ -118,6 +118,19 @@ def size2_aggregates(rp, ci, va, max_iterations=15, max_unassigned=0.05, merge_s
     return agg, nagg
 
 
+def size4_aggregates(rp, ci, va, max_iterations=15, max_unassigned=0.05, weight_formula=0):
+    rp, ci, va = _i(rp), _i(ci), _d(va)
+    n = rp.shape[0] - 1
+    agg = np.empty(n, np.int32)
+    nagg = lib().orc_size4_aggregates(n, _p(rp), _p(ci), _p(va), max_iterations, C.c_double(max_unassigned), weight_formula, _p(agg))
+    return agg, nagg
+
+
+def set_aggregation_selector(name):
+    """selector of the NEXT aggregation setups: "SIZE_2" (default) or "SIZE_4"""
+    lib().orc_set_aggregation_selector({"SIZE_2": 2, "SIZE_4": 4}[name])
+
+
 def restriction(agg, nagg):
     agg = _i(agg)
     n = agg.shape[0]
@@ -152,8 +165,9 @@ class AMG:
 
     def __init__(self, rp, ci, va, max_levels=100, min_coarse_rows=2, coarsen_threshold=1.0, presweeps=1, postsweeps=1, coarsest_sweeps=2,
                  finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, max_iterations=15, max_unassigned=0.05, merge_singletons=1, weight_formula=0,
-                 coarse_solver="NOSOLVER", dense_lu_num_rows=128, reuse_from=None, structure_reuse_levels=0):
+                 coarse_solver="NOSOLVER", dense_lu_num_rows=128, reuse_from=None, structure_reuse_levels=0, selector="SIZE_2"):
         self.rp, self.ci, self.va = _i(rp), _i(ci), _d(va)
+        set_aggregation_selector(selector)
         if reuse_from is not None:                       # AMGX_solver_resetup with structure_reuse_levels
             lib().orc_amg_reuse_structure(reuse_from.h, structure_reuse_levels)
         if coarse_solver == "DENSE_LU_SOLVER":
@@ -163,6 +177,7 @@ class AMG:
         self.h = C.c_void_p(lib().orc_amg_setup(self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold),
                                                 presweeps, postsweeps, coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), max_iterations,
                                                 C.c_double(max_unassigned), merge_singletons, weight_formula))
+        set_aggregation_selector("SIZE_2")
         if coarse_solver == "DENSE_LU_SOLVER":
             lib().orc_amg_enable_dense_lu(self.h)
 

@@ -116,6 +116,12 @@ def cases():
         return rp, ci, va * dd[rows] * dd[ci]
     yield "varpoisson12_amg_agg_diagsym", var_poisson(12), _standalone(_agg(scaling="DIAGONAL_SYMMETRIC"))
     yield "varpoisson12_pcg_agg_diagsym", var_poisson(12), _outer("PCG", _agg(), scaling="DIAGONAL_SYMMETRIC")
+    # SIZE_4 selector; the last one is the shipped AMG_AGGRREGATION_CG.json (SIZE_4, CG cycle, JACOBI_L1, 0 + 2 sweeps)
+    yield "poisson16_pcg_agg_size4", P(16), _outer("PCG", _agg(selector="SIZE_4"))
+    yield "banded3000_fgmres_agg_size4", gallery.random_banded(3000, sigma=40.0), _outer("FGMRES", _agg(selector="SIZE_4"), gmres_n_restart=20)
+    yield "poisson14x12x9_amg_agg_size4_cgcycle", P(14, 12, 9), _standalone(
+        _agg({"scope": "jl1", "solver": "JACOBI_L1", "relaxation_factor": 0.9, "monitor_residual": 0}, selector="SIZE_4", cycle="CG", presweeps=0,
+             postsweeps=2, coarsest_sweeps=2, min_coarse_rows=2), tol=1e-6, max_iters=60)
     # dense LU coarse solver
     for rows in (32, 128):
         yield f"poisson12_pcg_agg_denselu{rows}", P(12), _outer("PCG", _agg(coarse_solver="DENSE_LU_SOLVER", dense_lu_num_rows=rows))

@@ -46,8 +46,8 @@ def build_amg(oracle, a, rp, ci, va, determinism=0):
     oracle.set_coloring_scheme(scheme)
     try:
         if _get(a, "algorithm") == "AGGREGATION":
-            assert a.get("selector", "SIZE_2") == "SIZE_2"
-            amg = oracle.AMG(rp, ci, va, **kw)
+            assert a.get("selector", "SIZE_2") in ("SIZE_2", "SIZE_4")
+            amg = oracle.AMG(rp, ci, va, selector=a.get("selector", "SIZE_2"), **kw)
         else:
             assert _get(a, "selector") in ("PMIS", "HMIS")
             amg = oracle.ClassicalAMG(rp, ci, va, selector=_get(a, "selector"), strength_threshold=_get(a, "strength_threshold"), max_row_sum=_get(a, "max_row_sum"),

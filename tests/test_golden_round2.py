@@ -21,7 +21,8 @@ NOT_CONVERGING = {"poisson9_gmres_one_iteration", "poisson10_amg_agg_cheb2_coars
 # colouring, hence another (equally good) smoother: the golden is compared on convergence and iteration count within 2
 REFERENCE_NONDETERMINISTIC = {"poisson16_fgmres_agg_dilu_pgreedy", "symbanded3000_fgmres_agg_dilu_pgreedy", "poisson14_amg_gs_pgreedy"}
 # host-side dots of nearly cancelling quantities inside the cycle: one digit of slack
-TOL = {"poisson15x12x10_pcgf_agg_CG": 1e-11, "poisson15x12x10_pcgf_agg_CGF": 1e-11, "poisson12_fgmres_agg_CG3": 1e-11, "poisson12_amg_classical_CG": 1e-11}
+TOL = {"poisson15x12x10_pcgf_agg_CG": 1e-11, "poisson15x12x10_pcgf_agg_CGF": 1e-11, "poisson12_fgmres_agg_CG3": 1e-11, "poisson12_amg_classical_CG": 1e-11,
+       "poisson14x12x9_amg_agg_size4_cgcycle": 1e-11}
 
 
 @pytest.mark.parametrize("name", list(CASES))

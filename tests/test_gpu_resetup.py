@@ -50,3 +50,32 @@ def test_resetup_structure_reuse_matches_oracle(amgx, oracle, k):
     finally:
         for obj in (slv, xv, bv, M, rsc, cfg):
             obj.destroy()
+
+
+@pytest.mark.parametrize("mat", ["poisson", "banded"])
+def test_size4_aggregates_bit_exact(amgx, oracle, mat):
+    """integer work: the SIZE_4 aggregates of every level == the restatement's; residual history to 1e-12"""
+    rp, ci, va = gallery.poisson7pt(17, 13, 11) if mat == "poisson" else gallery.random_banded(5000, sigma=45.0)
+    n = rp.shape[0] - 1
+    b = np.ones(n)
+    cfg = amgx.Config(outer_cfg("FGMRES", amg_agg_cfg(selector="SIZE_4"), tol=1e-9, max_iters=80, gmres_n_restart=20))
+    rsc = amgx.Resources(cfg)
+    M = amgx.Matrix(rsc).upload(rp, ci, va)
+    bv = amgx.Vector(rsc).upload(b)
+    xv = amgx.Vector(rsc).set_zero(n)
+    slv = amgx.Solver(rsc, cfg)
+    try:
+        slv.setup(M)
+        slv.solve(bv, xv, zero_initial_guess=True)
+        o = oracle.AMG(rp, ci, va, max_levels=50, presweeps=1, postsweeps=1, omega=0.8, selector="SIZE_4")
+        assert slv.num_levels() == o.num_levels()
+        for l in range(o.num_levels() - 1):
+            agg, _, _ = slv.level_aggregates(l)
+            assert np.array_equal(agg, o.level(l)["aggregates"]), f"aggregates differ on level {l}"
+        xo, ito, histo, convo = oracle.fgmres(rp, ci, va, b, amg=o, tol=1e-9, max_iters=80, restart=20)
+        hist = np.array(slv.residual_history()).ravel()
+        assert convo and slv.status == "success" and slv.iterations_number == ito
+        assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+    finally:
+        for obj in (slv, xv, bv, M, rsc, cfg):
+            obj.destroy()
