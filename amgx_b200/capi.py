@@ -131,6 +131,7 @@ def _declare(lib):
         "AMGXB200_solver_get_last_solve_stats": [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
         "AMGXB200_bench_kernel": [vp, i, i, i, i, C.POINTER(C.c_double)],
         "AMGXB200_partition_plan_create": [C.POINTER(PartitionPlan), i, i, vp, i, i, vp, vp],
+        "AMGXB200_config_check": [vp, i, C.c_char_p, i],
         "AMGXB200_partition_vector_to_contiguous": [i, i, vp, vp, vp],
         "AMGXB200_comm_maps_to_global_cols": [i, i, vp, C.c_int64, i, vp, vp, vp, vp],
     }
@@ -215,6 +216,14 @@ class Config:
         if self.h:
             self.lib.AMGX_config_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def config_check(cfg: "Config", mode: str = "dDDI"):
+    """(supported, message): does the engine provide every component the configuration names?  Pure host code, no GPU needed."""
+    lib = load_library()
+    buf = C.create_string_buffer(1024)
+    rc = lib.AMGXB200_config_check(cfg.h, MODE[mode], buf, 1024)
+    return rc == 0, buf.value.decode(errors="replace")
 
 
 class Resources:

@@ -56,6 +56,32 @@ AMGSolver::AMGSolver(Config &cfg, const std::string &scope, std::shared_ptr<Reso
     } else if (coarse_solver_name_ != "NOSOLVER") {
         coarse_solver_ = Solver::allocate(cfg, scope, "coarse_solver", rsc);
     }
+    validate_config();
+    if (g_dry_run) make_smoother();     // smoothers are otherwise created per level at setup: instantiate one so that its configuration is checked too
+}
+
+// Configuration-only checks of the two hierarchy builders, so that an unsupported option is reported at AMGX_solver_create (and by
+// AMGXB200_config_check) rather than at the first setup.
+void AMGSolver::validate_config()
+{
+    if (algorithm_ == "AGGREGATION") {
+        if (selector_ != "SIZE_2" && selector_ != "SIZE_4")
+            fatal(AMGX_RC_BAD_CONFIGURATION, "aggregation selector '" + selector_ + "' is not supported by this engine (SIZE_2, SIZE_4)");
+        if (cfg_->get_int("handshaking_phases", scope_) == 2 && selector_ == "SIZE_2")
+            fatal(AMGX_RC_NOT_IMPLEMENTED, "SIZE_2 selector: handshaking_phases=2 is not implemented");
+        return;
+    }
+    const std::string strength = cfg_->get_string("strength", scope_), interp = cfg_->get_string("interpolator", scope_);
+    const std::string agg_sel = cfg_->get_string("aggressive_selector", scope_), agg_int = cfg_->get_string("aggressive_interpolator", scope_);
+    if (strength != "AHAT") fatal(AMGX_RC_BAD_CONFIGURATION, "strength '" + strength + "' is not supported by this engine (AHAT)");
+    if (selector_ != "PMIS" && selector_ != "HMIS")
+        fatal(AMGX_RC_BAD_CONFIGURATION, "classical selector '" + selector_ + "' is not supported by this engine (PMIS, HMIS)");
+    if (interp != "D2" && interp != "MULTIPASS") fatal(AMGX_RC_BAD_CONFIGURATION, "interpolator '" + interp + "' is not supported by this engine (D2, MULTIPASS)");
+    if (cfg_->get_int("aggressive_levels", scope_) > 0) {
+        if (agg_sel != "DEFAULT" && agg_sel != "PMIS" && agg_sel != "HMIS")
+            fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_selector '" + agg_sel + "' is not supported (DEFAULT, PMIS, HMIS)");
+        if (agg_int != "MULTIPASS") fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_interpolator '" + agg_int + "' is not supported (MULTIPASS)");
+    }
 }
 
 std::unique_ptr<Solver> AMGSolver::make_smoother() { return Solver::allocate(*cfg_, scope_, "smoother", rsc_); }

@@ -701,6 +701,30 @@ AMGX_RC AMGX_solver_create(AMGX_solver_handle *slv, AMGX_resources_handle rsc, A
     API_END(rp)
 }
 
+/* Does every component this configuration names exist in the engine?  Instantiates the whole solver tree in dry-run mode (the
+ * constructors parse and validate, no device resource is created): AMGX_RC_OK, or the return code AMGX_solver_create would give, with
+ * the message in msg.  Needs no GPU.  What only a matrix can decide (block size, distribution, precision mode) is not covered. */
+AMGX_RC AMGXB200_config_check(const AMGX_config_handle cfg, AMGX_Mode mode, char *msg, int msg_len)
+{
+    if (msg && msg_len > 0) msg[0] = 0;
+    AMGX_RC rc = AMGX_RC_OK;
+    std::string text;
+    g_dry_run = true;
+    try {
+        ConfigH *c = cfgH(cfg);
+        decode_mode((int)mode);
+        auto rsc = std::make_shared<Resources>();
+        rsc->cfg = c->cfg;
+        auto own = std::make_shared<Config>(*c->cfg);
+        std::unique_ptr<Solver> sv = Solver::allocate(*own, "default", "solver", rsc);
+    } catch (const Error &e) { rc = e.rc; text = e.msg; }
+    catch (const std::exception &e) { rc = AMGX_RC_UNKNOWN; text = e.what(); }
+    catch (...) { rc = AMGX_RC_UNKNOWN; text = "unknown exception"; }
+    g_dry_run = false;
+    if (msg && msg_len > 0) { strncpy(msg, text.c_str(), (size_t)msg_len - 1); msg[msg_len - 1] = 0; }
+    return rc;
+}
+
 AMGX_RC AMGX_solver_destroy(AMGX_solver_handle slv)
 {
     API_BEGIN

@@ -135,6 +135,7 @@ static bool dist_fuse()
     return on;
 }
 
+thread_local bool g_dry_run = false;
 static std::atomic<int> g_graph_inhibit{0};
 void GraphInhibit::set() { if (!on) { on = true; g_graph_inhibit++; } }
 GraphInhibit::~GraphInhibit() { if (on) g_graph_inhibit--; }
@@ -188,6 +189,7 @@ Solver::Solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources>
     else if (cv == "COMBINED_REL_INI_ABS") conv_.kind = Convergence::COMBINED_REL_INI_ABS;
     else fatal(AMGX_RC_BAD_CONFIGURATION, "ConvergenceFactory '" + cv + "' has not been registered");
     if (store_res_history_) res_history_.resize(max_iters_ + 1);
+    if (g_dry_run) return;
     sb_.create();
     for (auto &e : ev_) AMGXB_CUDA_CHECK(cudaEventCreate(&e));
 }

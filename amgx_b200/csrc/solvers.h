@@ -74,6 +74,9 @@ struct GraphSegment {
     ~GraphSegment() { reset(); }
 };
 bool graphs_enabled();
+// Dry run (AMGXB200_config_check): constructors parse and validate their configuration but create no device resources, so the
+// whole solver tree of a configuration can be instantiated on a machine without a GPU.
+extern thread_local bool g_dry_run;
 // Solvers that synchronise with the host inside what an enclosing solver would capture (CG / CGF cycles) or whose launch
 // sequence changes from one invocation to the next (reuse_scale) hold one of these for their lifetime.
 struct GraphInhibit {
@@ -296,6 +299,7 @@ protected:
     int cycle_type_ = CYC_V;
     void setup_aggregation();
     void setup_classical();
+    void validate_config();       // everything the setup would reject for configuration reasons alone (called by the constructor)
     void replicate_tail(long long tail_rows);   // distributed hierarchy: assemble the small levels on every rank (amg.cu)
     std::unique_ptr<Solver> make_smoother();
     std::vector<std::unique_ptr<AMGLevel>> levels_;

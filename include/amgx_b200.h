@@ -212,6 +212,10 @@ AMGX_RC AMGX_API AMGXB200_solver_get_level_coloring(AMGX_solver_handle slv, int 
  * of kernels this library launched in it. */
 AMGX_RC AMGX_API AMGXB200_solver_get_last_solve_stats(AMGX_solver_handle slv, double *solve_seconds, long long *kernel_launches);
 
+/* Does the engine provide every component `cfg` names (solvers, smoothers, cycles, selectors, colouring ...)?  AMGX_RC_OK, or the code and
+ * message AMGX_solver_create would produce.  Pure host code: usable without a GPU to vet a configuration before moving to the engine. */
+AMGX_RC AMGX_API AMGXB200_config_check(const AMGX_config_handle cfg, AMGX_Mode mode, char *msg, int msg_len);
+
 /* Hot-kernel micro-benchmarks on an uploaded matrix (device-resident operands).
  * kind: 0 = SpMV y=A*x, 1 = fused Jacobi sweep x' = x + w*(b-A*x)/d, 2 = SpMV fused with dot.
  * Runs `reps` launches on the resource stream, returns average milliseconds per launch measured

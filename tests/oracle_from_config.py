@@ -12,7 +12,7 @@ import numpy as np
 DEFAULTS = dict(max_levels=100, presweeps=1, postsweeps=1, coarsest_sweeps=2, finest_sweeps=-1, cycle="V", cycle_iters=2, error_scaling=0,
                 scaling_smoother_steps=2, reuse_scale=0, coarse_solver="DENSE_LU_SOLVER", dense_lu_num_rows=128, min_coarse_rows=2,
                 relaxation_factor=0.9, symmetric_GS=0, chebyshev_polynomial_order=5, chebyshev_lambda_estimate_mode=0, cheby_max_lambda=1.0,
-                cheby_min_lambda=0.125, strength_threshold=0.25, max_row_sum=1.1, interpolator="D2", aggressive_levels=0,
+                cheby_min_lambda=0.125, strength_threshold=0.25, max_row_sum=1.1, interpolator="D1", aggressive_levels=0,
                 aggressive_interpolator="MULTIPASS", interp_max_elements=-1, gmres_n_restart=20, max_iters=100, tolerance=1e-12, norm="L2",
                 algorithm="CLASSICAL", selector="PMIS", determinism_flag=0, max_uncolored_percentage=0.15)
 

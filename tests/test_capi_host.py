@@ -96,3 +96,51 @@ def test_no_cpu_fallback_in_product():
     for p in list((ROOT / "amgx_b200").rglob("*.py")) + list((ROOT / "amgx_b200" / "csrc").glob("*")):
         if p.is_file() and p.suffix in (".py", ".cu", ".cpp", ".h"):
             assert "oracle" not in p.read_text().replace("oracle/_ref", "").lower() or p.name in (), p
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# AMGXB200_config_check: the whole solver tree of a configuration instantiated in dry-run mode, no GPU
+# ---------------------------------------------------------------------------------------------------------------
+REF_CONFIGS = Path("/root/reference/src/configs")
+# the shipped configurations that name a component the engine does not provide, and the component
+UNSUPPORTED_SHIPPED = {
+    "AGGREGATION_MULTI_PAIRWISE.json": "MULTI_PAIRWISE",
+    "agg_cheb4.json": "SIZE_8",
+    "IDR_DILU.json": "IDR",
+    "IDRMSYNC_DILU.json": "IDRMSYNC",
+}
+
+
+def test_config_check_on_own_configs_and_bad_components(lib):
+    from amgx_b200 import capi
+    cfg = capi.Config(file=str(Path(__file__).resolve().parents[1] / "amgx_b200" / "configs" / "PCG_AGGREGATION_JACOBI.json"))
+    ok, msg = capi.config_check(cfg)
+    assert ok and msg == ""
+    cfg.destroy()
+    for bad, word in [("config_version=2, solver(s)=IDR", "IDR"), ("config_version=2, solver(s)=AMG, s:algorithm=AGGREGATION, s:selector=SIZE_8", "SIZE_8"),
+                      ("config_version=2, solver(s)=AMG, s:interpolator=D2, s:cycle=Q", "Q"), ("config_version=2, solver(s)=AMG, s:interpolator=D1", "D1"),
+                      ("config_version=2, solver(s)=AMG, s:interpolator=D2, s:smoother(m)=MULTICOLOR_DILU, m:matrix_coloring_scheme=ROUND_ROBIN", "ROUND_ROBIN"),
+                      ("config_version=2, solver(s)=AMG, s:interpolator=D2, s:smoother(m)=CHEBYSHEV, m:chebyshev_lambda_estimate_mode=0", "Lanczos"),
+                      ("config_version=2, solver(s)=PCG, s:scaling=BINORMALIZATION", "BINORMALIZATION")]:
+        cfg = capi.Config(bad)
+        ok, msg = capi.config_check(cfg)
+        assert not ok and word in msg, (bad, msg)
+        cfg.destroy()
+
+
+@pytest.mark.skipif(not REF_CONFIGS.is_dir(), reason="the reference's shipped configurations are only present in the build container")
+def test_config_check_on_the_reference_shipped_configs(lib):
+    """58 of the 62 configurations the reference ships name only components the engine provides (README "Status")"""
+    from amgx_b200 import capi
+    files = sorted(REF_CONFIGS.glob("*.json"))
+    assert len(files) == 62
+    unsupported = {}
+    for f in files:
+        cfg = capi.Config(file=str(f))
+        ok, msg = capi.config_check(cfg)
+        cfg.destroy()
+        if not ok:
+            unsupported[f.name] = msg
+    assert set(unsupported) == set(UNSUPPORTED_SHIPPED), unsupported
+    for name, word in UNSUPPORTED_SHIPPED.items():
+        assert word in unsupported[name], (name, unsupported[name])
