@@ -170,11 +170,12 @@ def test_classical_unsupported_options_fail_loudly(amgx):
         cfg = amgx.Config(cfgd)
         rsc = amgx.Resources(cfg)
         A = amgx.Matrix(rsc).upload(rp, ci, va)
-        slv = amgx.Solver(rsc, cfg)
-        with pytest.raises(amgx.AMGXError) as e:
-            slv.setup(A)
+        made = []
+        with pytest.raises(amgx.AMGXError) as e:      # configuration-only checks fire at solver creation, the rest at setup
+            made.append(amgx.Solver(rsc, cfg))
+            made[0].setup(A)
         assert "BAD_CONFIGURATION" in str(e.value), key
-        for o in (slv, A, rsc, cfg):
+        for o in (*made, A, rsc, cfg):
             o.destroy()
 
 
