@@ -56,7 +56,7 @@ def _needs(obj: Path, src: Path, headers_mtime: float) -> bool:
 def build(verbose: bool = False, force: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     inc, libs = _nccl_flags()
-    hdrs = list(CSRC.glob("*.h")) + list((ROOT.parent / "include").glob("*.h"))
+    hdrs = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list((ROOT.parent / "include").glob("*.h"))
     hm = max(h.stat().st_mtime for h in hdrs)
     jobs = []
     for src in sources():

@@ -28,143 +28,7 @@ long long g_kernel_launches = 0;
 
 namespace {
 
-constexpr int PRODUCER_THREADS = 32;
-constexpr int MAX_STAGES = 4;
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    unsigned ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok)
-                     : "r"(smem_u32(bar)), "r"(parity)
-                     : "memory");
-    } while (!ok);
-}
-// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-template <class T> __device__ __forceinline__ T guard_diag(T d);
-template <> __device__ __forceinline__ double guard_diag<double>(double d) { return fabs(d) < 1e-12 ? copysign(1e-12, d) : d; }
-template <> __device__ __forceinline__ float guard_diag<float>(float d) { return fabs((double)d) < 1e-7 ? copysignf((float)1e-7, d) : d; }
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// scalar epilogue executed by one thread of the last CTA
-__device__ void apply_fin(double sum, double *scal, int fin_op, int slot, double *host_mirror, int mirror)
-{
-    double out = sum;
-    switch (fin_op) {
-    case FIN_STORE:
-    case FIN_ABS: scal[slot] = sum; break;
-    case FIN_SQRT: out = sqrt(sum); scal[slot] = out; break;
-    case FIN_ADD: out = scal[slot] + sum; scal[slot] = out; break;
-    case FIN_PCG_ALPHA: {
-        scal[S_DOT] = sum;
-        double a = (sum != 0.0) ? scal[S_RZ] / sum : 0.0;
-        scal[S_ALPHA] = a;
-        scal[S_NEG_ALPHA] = -a;
-        out = a;
-        break;
-    }
-    case FIN_PCG_BETA: {
-        double old = scal[S_RZ];
-        scal[S_RZ_OLD] = old;
-        scal[S_RZ] = sum;
-        double bta = (old != 0.0) ? sum / old : 0.0;
-        scal[S_BETA] = bta;
-        out = sum;
-        break;
-    }
-    }
-    if (mirror && host_mirror) { host_mirror[slot] = out; }
-}
-
-// Block-level deterministic reduction + "last block finalises" pattern.
-// All threads of the CTA must call it; `nthreads` = blockDim.x; smem_red has >= 33 doubles.
-__device__ void block_reduce_finish(double v, double *smem_red, const ReduceCtx &red, int fin_op, int slot, int mirror)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
-    v = warp_sum(v);
-    if (lane == 0) smem_red[warp] = v;
-    __syncthreads();
-    __shared__ bool is_last;
-    if (warp == 0) {
-        double t = (lane < nwarps) ? smem_red[lane] : 0.0;
-        t = warp_sum(t);
-        if (lane == 0) {
-            red.partials[blockIdx.x] = t;
-            __threadfence();
-            unsigned ticket = atomicAdd(red.counter, 1u);
-            is_last = (ticket == gridDim.x - 1);
-        }
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        // fixed order: thread t sums partials t, t+blockDim, ... then a fixed tree
-        double t = 0.0;
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += ((volatile double *)red.partials)[i];
-        t = warp_sum(t);
-        if (lane == 0) smem_red[warp] = t;
-        __syncthreads();
-        if (warp == 0) {
-            double u = (lane < nwarps) ? smem_red[lane] : 0.0;
-            u = warp_sum(u);
-            if (lane == 0) {
-                apply_fin(u, red.scal, fin_op, slot, red.host_mirror, mirror);
-                *red.counter = 0u;
-                __threadfence_system();
-            }
-        }
-    }
-}
-
-template <class MatT, class VecT> struct TileArgs {
-    const int *row_ptr;
-    const int *col;
-    const MatT *val;
-    int n, num_tiles, cap, stages;   // n = end row of the segment
-    int row0;                        // first row of the segment (multiple of 4)
-    const VecT *x;
-    const int *agg;
-    const VecT *b;
-    const MatT *d;
-    VecT *y;
-    double omega;
-    ReduceCtx red;
-    int fin_op, fin_slot, mirror;
-};
-
-template <class VecT, bool AGG> __device__ __forceinline__ VecT gather(const VecT *x, const int *agg, int c)
-{
-    if (AGG) return __ldg(x + __ldg(agg + c));
-    return __ldg(x + c);
-}
+#include "tile_common.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // The tile kernel.  blockDim.x = TILE_ROWS + 32 (last warp = producer).
@@ -457,6 +321,7 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
         if (need <= budget) { p.stages = st; p.smem_bytes = need; p.use_tiles = true; break; }
     }
     A.plan = p;
+    csr_build_colenc(A, s);     // no-op unless AMGXB_COLENC=1
 }
 
 void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int segment)
@@ -467,6 +332,7 @@ void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int
     const int row0 = (segment == 2) ? A.plan.split : 0;
     const int row1 = (segment == 1) ? A.plan.split : A.n;
     if (row1 <= row0) return;
+    if (A.colenc.on && csr_op_enc(A, epi, g, s, segment)) return;
     AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
         TileArgs<MatT, VecT> ta;
         ta.row_ptr = A.row_ptr.ptr();

@@ -1,0 +1,377 @@
+// k_spmv_enc.cu -- EXPERIMENTAL (AMGXB_COLENC=1, default off; written without a device): the CSR tile kernel with a
+// compressed column stream.  Same pipeline, same per-row FMA order and same epilogues as csr_tile_kernel (k_spmv.cu), hence the same
+// bits; what changes is how many bytes of column information a tile moves through TMA:
+//   enc 1  8-bit codes + a per-tile dictionary of the distinct (column - row) offsets (<= 256): 12 -> 9 B per entry
+//          (a 7-point stencil has 7 offsets; the first aggregation levels a few dozen),
+//   enc 2  16-bit offsets from the tile's smallest column (coarser, irregular levels): 12 -> 10 B per entry,
+//   enc 0  the raw 32-bit columns (fallback, identical traffic to the plain kernel).
+// The encoding is chosen per tile by colenc_build_kernel at plan time; it only reads row_ptr / col_idx, so value updates
+// (AMGX_matrix_replace_coefficients) leave it valid.
+// Not used for: distributed matrices (two row segments), the aggregation-fused prolongation gather, the long-row fallback.
+#include "kernels.h"
+#include <climits>
+
+namespace amgxb {
+namespace {
+
+#include "tile_common.cuh"
+
+constexpr int DICT_SLOTS = 256;          // dictionary entries per tile (ints)
+constexpr int HASH_SLOTS = 1024;
+
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+// byte offset of tile `t`'s code segment; sa = first (4-aligned) entry the tile stages.  2 bytes per entry are reserved whatever the
+// encoding, 32 bytes of slack per tile absorb the 16-byte rounding of the copies and the <= 3 entries consecutive tiles share.
+__host__ __device__ inline size_t code_offset(int sa, int t) { return align16((size_t)2 * (size_t)sa) + (size_t)32 * (size_t)t; }
+
+// ---------------------------------------------------------------------------------------------
+// plan: one CTA per tile (grid-stride), TILE_ROWS threads
+// ---------------------------------------------------------------------------------------------
+template <int TILE_ROWS>
+__global__ void __launch_bounds__(TILE_ROWS) colenc_build_kernel(const int *__restrict__ rp, const int *__restrict__ ci, int n, int num_tiles, unsigned char *codes,
+                                                                 int *dict, int *meta, int *stats)
+{
+    __shared__ int keys[HASH_SLOTS];
+    __shared__ int list[DICT_SLOTS], sorted[DICT_SLOTS];
+    __shared__ int s_count, s_min, s_max, s_overflow;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int r0 = tile * TILE_ROWS, r1 = min(r0 + TILE_ROWS, n);
+        const int nz0 = rp[r0], nz1 = rp[r1];
+        const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
+        for (int i = tid; i < HASH_SLOTS; i += TILE_ROWS) keys[i] = INT_MAX;
+        if (tid == 0) { s_count = 0; s_min = INT_MAX; s_max = INT_MIN; s_overflow = 0; }
+        __syncthreads();
+        const int row = r0 + tid;
+        const bool active = row < r1;
+        // ---- pass 1: column range of the tile, set of distinct offsets
+        if (active) {
+            for (int k = rp[row]; k < rp[row + 1]; k++) {
+                const int c = ci[k], delta = c - row;
+                atomicMin(&s_min, c);
+                atomicMax(&s_max, c);
+                if (delta == INT_MAX) { s_overflow = 1; continue; }     // the empty-slot sentinel cannot be a key
+                unsigned h = ((unsigned)delta * 2654435761u) >> 22;      // 10 bits
+                for (int probe = 0; probe < HASH_SLOTS; probe++) {
+                    if (*(volatile int *)&s_overflow) break;
+                    const int old = atomicCAS(&keys[h], INT_MAX, delta);
+                    if (old == INT_MAX) {
+                        if (atomicAdd(&s_count, 1) >= DICT_SLOTS) s_overflow = 1;
+                        break;
+                    }
+                    if (old == delta) break;
+                    h = (h + 1) & (HASH_SLOTS - 1);
+                }
+            }
+        }
+        __syncthreads();
+        const bool use_dict = !s_overflow && s_count <= DICT_SLOTS && nz1 > nz0;
+        const bool use_off16 = !use_dict && nz1 > nz0 && (long long)s_max - (long long)s_min < 65536ll;
+        const int count = s_count;
+        __syncthreads();
+        unsigned char *seg = codes + code_offset(sa, tile);
+        if (use_dict) {
+            // ---- compact the hash set, rank-sort it (ascending: the dictionary, hence the codes, do not depend on insertion order)
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+            for (int i = tid; i < HASH_SLOTS; i += TILE_ROWS)
+                if (keys[i] != INT_MAX) list[atomicAdd(&s_count, 1)] = keys[i];
+            __syncthreads();
+            for (int i = tid; i < count; i += TILE_ROWS) {
+                const int v = list[i];
+                int rank = 0;
+                for (int j = 0; j < count; j++) rank += (list[j] < v);
+                sorted[rank] = v;
+            }
+            __syncthreads();
+            const int padded = (count + 3) & ~3;
+            for (int i = tid; i < padded; i += TILE_ROWS) dict[(size_t)tile * DICT_SLOTS + i] = sorted[min(i, count - 1)];
+            for (int k = sa + tid; k < ea; k += TILE_ROWS)
+                if (k < nz0 || k >= nz1) seg[k - sa] = 0;                 // alignment padding: entries of neighbouring tiles, never decoded
+            if (active) {
+                for (int k = rp[row]; k < rp[row + 1]; k++) {
+                    const int delta = ci[k] - row;
+                    int lo = 0, hi = count - 1;                           // binary search in the sorted dictionary
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sorted[mid] < delta) lo = mid + 1;
+                        else hi = mid;
+                    }
+                    seg[k - sa] = (unsigned char)lo;
+                }
+            }
+            if (tid == 0) { meta[2 * tile] = 1; meta[2 * tile + 1] = padded; atomicAdd(stats + 0, 1); }
+        } else if (use_off16) {
+            const int base = s_min;
+            unsigned short *seg16 = reinterpret_cast<unsigned short *>(seg);
+            for (int i = tid; i < 4; i += TILE_ROWS) dict[(size_t)tile * DICT_SLOTS + i] = base;
+            for (int k = sa + tid; k < ea; k += TILE_ROWS)
+                seg16[k - sa] = (k < nz0 || k >= nz1) ? (unsigned short)0 : (unsigned short)(ci[k] - base);
+            if (tid == 0) { meta[2 * tile] = 2; meta[2 * tile + 1] = 4; atomicAdd(stats + 1, 1); }
+        } else {
+            if (tid == 0) { meta[2 * tile] = 0; meta[2 * tile + 1] = 0; atomicAdd(stats + 2, 1); }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The encoded tile kernel.  blockDim.x = TILE_ROWS + 32 (last warp = producer).
+// per stage: vals[cap] | column stream (cap * 4 bytes: raw columns, or codes) | dict[256] | rp[TILE_ROWS+4]
+// ---------------------------------------------------------------------------------------------
+struct EncArgs {
+    const unsigned char *codes;
+    const int *dict;
+    const int *meta;
+};
+
+template <class MatT, class VecT, int TILE_ROWS, int EPI>
+__global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_kernel(const TileArgs<MatT, VecT> a, const EncArgs e)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + MAX_STAGES;
+    double *smem_red = reinterpret_cast<double *>(smem_raw + 2 * MAX_STAGES * sizeof(uint64_t));
+    unsigned char *stage_base = smem_raw + 512;
+    const size_t vals_bytes = (size_t)a.cap * sizeof(MatT);
+    const size_t cols_bytes = (size_t)a.cap * sizeof(int);
+    const size_t dict_bytes = (size_t)DICT_SLOTS * sizeof(int);
+    const size_t rp_bytes = (size_t)(TILE_ROWS + 4) * sizeof(int);
+    const size_t stage_bytes = vals_bytes + cols_bytes + dict_bytes + rp_bytes;
+    constexpr int CONSUMER_WARPS = TILE_ROWS / 32;
+    constexpr bool HAS_RED = (EPI == EPI_SPMV_DOT || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc = 0.0;
+    const int my_tiles = (a.num_tiles > (int)blockIdx.x) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid >= TILE_ROWS) {
+        // ------------------------------- producer warp -------------------------------
+        if (tid == TILE_ROWS) {
+            for (int it = 0; it < my_tiles; it++) {
+                const int tile = blockIdx.x + it * gridDim.x;
+                const int s = it % a.stages;
+                const unsigned ph = (unsigned)(it / a.stages) & 1u;
+                if (it >= a.stages) mbar_wait(&empty[s], ph ^ 1u);
+                const int r0 = a.row0 + tile * TILE_ROWS;
+                const int r1 = min(r0 + TILE_ROWS, a.n);
+                const int nz0 = __ldg(a.row_ptr + r0), nz1 = __ldg(a.row_ptr + r1);
+                const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
+                const int enc = __ldg(e.meta + 2 * tile), dlen = __ldg(e.meta + 2 * tile + 1);
+                unsigned char *st = stage_base + (size_t)s * stage_bytes;
+                const unsigned rp_copy = (unsigned)(((r1 - r0 + 1 + 3) & ~3) * sizeof(int));
+                const unsigned cnt = (unsigned)(ea - sa);
+                unsigned col_copy = 0;
+                if (cnt) col_copy = enc == 1 ? (unsigned)align16(cnt) : enc == 2 ? (unsigned)align16((size_t)cnt * 2) : cnt * (unsigned)sizeof(int);
+                const unsigned dict_copy = (unsigned)dlen * (unsigned)sizeof(int);
+                mbar_expect_tx(&full[s], rp_copy + cnt * (unsigned)sizeof(MatT) + col_copy + dict_copy);
+                tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes, a.row_ptr + r0, rp_copy, &full[s]);
+                if (cnt) {
+                    tma_bulk_g2s(st, a.val + sa, cnt * (unsigned)sizeof(MatT), &full[s]);
+                    if (enc == 0) tma_bulk_g2s(st + vals_bytes, a.col + sa, col_copy, &full[s]);
+                    else tma_bulk_g2s(st + vals_bytes, e.codes + code_offset(sa, tile), col_copy, &full[s]);
+                }
+                if (dict_copy) tma_bulk_g2s(st + vals_bytes + cols_bytes, e.dict + (size_t)tile * DICT_SLOTS, dict_copy, &full[s]);
+            }
+        }
+    } else {
+        // ------------------------------- consumers: one row per thread -------------------------------
+        for (int it = 0; it < my_tiles; it++) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int s = it % a.stages;
+            const unsigned ph = (unsigned)(it / a.stages) & 1u;
+            const int row = a.row0 + tile * TILE_ROWS + tid;
+            const bool active = row < a.n;
+            const int enc = __ldg(e.meta + 2 * tile);
+            VecT bi = 0, xi = 0;
+            MatT di = 1;
+            if (active) {
+                if (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2 || EPI == EPI_JACOBI_L1 || EPI == EPI_ADD)
+                    bi = __ldg(a.b + row);
+                if (EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_JACOBI_L1) {
+                    di = __ldg(a.d + row);
+                    xi = __ldg(a.x + row);
+                }
+                if (EPI == EPI_SPMV_DOT) xi = __ldg(a.x + row);
+            }
+            const unsigned char *st = stage_base + (size_t)s * stage_bytes;
+            const MatT *vals = reinterpret_cast<const MatT *>(st);
+            const int *cols = reinterpret_cast<const int *>(st + vals_bytes);
+            const unsigned char *c8 = st + vals_bytes;
+            const unsigned short *c16 = reinterpret_cast<const unsigned short *>(st + vals_bytes);
+            const int *dict = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes);
+            const int *rp = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes + dict_bytes);
+            mbar_wait(&full[s], ph);
+            if (active) {
+                const int sa = rp[0] & ~3;
+                int k = rp[tid] - sa;
+                const int kend = rp[tid + 1] - sa;
+                const int base = (enc == 2) ? dict[0] : 0;
+                // the tile's encoding is uniform over the CTA: the branch below does not diverge
+                auto col_at = [&](int kk) -> int {
+                    if (enc == 1) return row + dict[c8[kk]];
+                    if (enc == 2) return base + (int)c16[kk];
+                    return cols[kk];
+                };
+                VecT sum = 0;
+                // 4 gathers in flight per step; FMA chain strictly left to right (as csr_tile_kernel)
+                for (; k + 4 <= kend; k += 4) {
+                    const int c0 = col_at(k), c1 = col_at(k + 1), c2 = col_at(k + 2), c3 = col_at(k + 3);
+                    const VecT x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
+                    sum = fma((VecT)vals[k], x0, sum);
+                    sum = fma((VecT)vals[k + 1], x1, sum);
+                    sum = fma((VecT)vals[k + 2], x2, sum);
+                    sum = fma((VecT)vals[k + 3], x3, sum);
+                }
+                if (k < kend) {
+                    const int c0 = col_at(k);
+                    const int c1 = (k + 1 < kend) ? col_at(k + 1) : c0;
+                    const int c2 = (k + 2 < kend) ? col_at(k + 2) : c0;
+                    const VecT x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2);
+                    sum = fma((VecT)vals[k], x0, sum);
+                    if (k + 1 < kend) sum = fma((VecT)vals[k + 1], x1, sum);
+                    if (k + 2 < kend) sum = fma((VecT)vals[k + 2], x2, sum);
+                }
+                // ---- epilogue (identical to csr_tile_kernel) ----
+                if (EPI == EPI_SPMV) {
+                    a.y[row] = sum;
+                } else if (EPI == EPI_SPMV_DOT) {
+                    a.y[row] = sum;
+                    acc += (double)sum * (double)xi;
+                } else if (EPI == EPI_RESID) {
+                    a.y[row] = bi - sum;
+                } else if (EPI == EPI_ADD) {
+                    a.y[row] = bi + sum;
+                } else if (EPI == EPI_RESID_NRM2) {
+                    const VecT r = bi - sum;
+                    a.y[row] = r;
+                    acc += (double)r * (double)r;
+                } else {
+                    MatT dinv = (MatT)1 / guard_diag<MatT>(di);
+                    VecT t = bi - sum;
+                    t = (VecT)(t * a.omega);
+                    const VecT out = fma(t, (VecT)dinv, xi);
+                    a.y[row] = out;
+                    if (EPI == EPI_JACOBI_DOT) acc += (double)bi * (double)out;
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+        }
+    }
+    if (HAS_RED) block_reduce_finish(acc, smem_red, a.red, a.fin_op, a.fin_slot, a.mirror);
+}
+
+template <class MatT, class VecT, int TILE_ROWS, int EPI>
+void launch_enc(const Matrix &A, const TileArgs<MatT, VecT> &ta, const EncArgs &ea, int grid, cudaStream_t s)
+{
+    const size_t smem = A.colenc.smem_bytes;
+    auto k = csr_tile_enc_kernel<MatT, VecT, TILE_ROWS, EPI>;
+    static size_t attr_bytes = 0;
+    if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+    k<<<grid, TILE_ROWS + PRODUCER_THREADS, smem, s>>>(ta, ea);
+}
+
+template <class MatT, class VecT, int EPI> void launch_enc_epi(const Matrix &A, const TileArgs<MatT, VecT> &ta, const EncArgs &ea, cudaStream_t s)
+{
+    const int grid = std::max(1, std::min(csr_max_grid(A), ta.num_tiles));      // the grid of the plain kernel: same partial sums, same bits
+    if (A.plan.tile_rows == 256) launch_enc<MatT, VecT, 256, EPI>(A, ta, ea, grid, s);
+    else launch_enc<MatT, VecT, 128, EPI>(A, ta, ea, grid, s);
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+bool colenc_requested()
+{
+    static const bool on = getenv("AMGXB_COLENC") ? atoi(getenv("AMGXB_COLENC")) != 0 : false;
+    return on;
+}
+
+// called at the end of csr_build_plan
+void csr_build_colenc(Matrix &A, cudaStream_t s)
+{
+    A.colenc.on = false;
+    if (!colenc_requested() || !A.plan.use_tiles || A.plan.split != 0 || A.dist || A.n == 0 || A.bs() != 1) return;
+    const int T = A.plan.tile_rows, nt = A.plan.num_tiles;
+    const size_t msz = prec_size(A.mat_prec);
+    const size_t smem = 512 + (size_t)A.plan.stages * ((size_t)A.plan.max_tile_nnz * (msz + 4) + (size_t)DICT_SLOTS * 4 + (size_t)(T + 4) * 4);
+    if (smem > (size_t)216 * 1024) return;
+    ColEnc &E = A.colenc;
+    E.codes.resize(align16((size_t)2 * ((size_t)A.nnz + 8)) + (size_t)32 * nt + 64);
+    E.codes.zero(s);
+    E.dict.resize((size_t)nt * DICT_SLOTS);
+    E.dict.zero(s);
+    E.meta.resize((size_t)2 * nt);
+    E.meta.zero(s);
+    DevBuf<int> stats;
+    stats.resize(4);
+    stats.zero(s);
+    const int grid = std::max(1, std::min(nt, 148 * 8));
+    if (T == 256) colenc_build_kernel<256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, nt, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
+    else colenc_build_kernel<128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, nt, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    const std::vector<int> h = stats.to_host(s);
+    E.tiles_dict8 = h[0];
+    E.tiles_off16 = h[1];
+    E.tiles_raw = h[2];
+    E.smem_bytes = smem;
+    E.on = (h[0] + h[1]) > 0;        // nothing to gain when every tile stays raw
+    if (getenv("AMGXB_COLENC_VERBOSE"))
+        fprintf(stderr, "[amgx_b200] colenc level %d: %d tiles of %d rows: dict8 %d, off16 %d, raw %d\n", A.level, nt, T, h[0], h[1], h[2]);
+}
+
+// csr_op entry of the encoded path; returns false when the caller must use the plain kernels
+bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int segment)
+{
+    if (!A.colenc.on || segment != 0 || g.agg) return false;
+    EncArgs ea;
+    ea.codes = A.colenc.codes.ptr();
+    ea.dict = A.colenc.dict.ptr();
+    ea.meta = A.colenc.meta.ptr();
+    AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+        TileArgs<MatT, VecT> ta;
+        ta.row_ptr = A.row_ptr.ptr();
+        ta.col = A.col_idx.ptr();
+        ta.val = A.values.as<MatT>();
+        ta.n = A.n;
+        ta.row0 = 0;
+        ta.num_tiles = A.plan.num_tiles;
+        ta.cap = A.plan.max_tile_nnz;
+        ta.stages = A.plan.stages;
+        ta.x = (const VecT *)g.x;
+        ta.agg = nullptr;
+        ta.b = (const VecT *)g.b;
+        ta.d = (const MatT *)g.d;
+        ta.y = (VecT *)g.y;
+        ta.omega = g.omega;
+        ta.red = g.red;
+        ta.fin_op = g.fin_op;
+        ta.fin_slot = g.fin_slot;
+        ta.mirror = g.mirror;
+        switch (epi) {
+        case EPI_SPMV: launch_enc_epi<MatT, VecT, EPI_SPMV>(A, ta, ea, s); break;
+        case EPI_RESID: launch_enc_epi<MatT, VecT, EPI_RESID>(A, ta, ea, s); break;
+        case EPI_ADD: launch_enc_epi<MatT, VecT, EPI_ADD>(A, ta, ea, s); break;
+        case EPI_JACOBI:
+        case EPI_JACOBI_L1: launch_enc_epi<MatT, VecT, EPI_JACOBI>(A, ta, ea, s); break;
+        case EPI_SPMV_DOT: launch_enc_epi<MatT, VecT, EPI_SPMV_DOT>(A, ta, ea, s); break;
+        case EPI_JACOBI_DOT: launch_enc_epi<MatT, VecT, EPI_JACOBI_DOT>(A, ta, ea, s); break;
+        case EPI_RESID_NRM2: launch_enc_epi<MatT, VecT, EPI_RESID_NRM2>(A, ta, ea, s); break;
+        }
+    });
+    return true;
+}
+
+}  // namespace amgxb

@@ -68,6 +68,9 @@ void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s, 
 // Build diag_idx and the tile plan of A (called once per matrix at upload / level creation).
 void csr_build_plan(Matrix &A, cudaStream_t s);
 int  csr_max_grid(const Matrix &A);     // number of CTAs csr_op launches (partials sizing)
+// experimental compressed column stream (k_spmv_enc.cu; AMGXB_COLENC=1, default off)
+void csr_build_colenc(Matrix &A, cudaStream_t s);                                                     // after csr_build_plan
+bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s, int segment);    // false: use the plain kernels
 
 // -------------------------------------------------------------------------------------------
 // Level-1 kernels (k_blas.cu).  Vectors are VecT arrays of length n; scalars come from device

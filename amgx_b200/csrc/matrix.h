@@ -34,6 +34,17 @@ struct TilePlan {
     int split = 0;              // distributed: first row (multiple of 4) of the segment that reads halo columns
 };
 
+// Optional compressed column stream of the tile kernels (k_spmv_enc.cu, AMGXB_COLENC=1; experimental, default off).  Per tile either
+// 8-bit codes into a dictionary of (column - row) offsets, 16-bit offsets from the tile's smallest column, or the raw 32-bit columns.
+struct ColEnc {
+    bool on = false;
+    DevBuf<unsigned char> codes;    // tile t's code segment starts at byte align16(2 * sa_t) + 32 * t and covers the aligned entry range [sa_t, ea_t)
+    DevBuf<int> dict;               // 256 ints per tile: the sorted offsets (8-bit), or the base column in entry 0 (16-bit)
+    DevBuf<int> meta;               // 2 ints per tile: encoding (0 raw, 1 dict8, 2 off16), dictionary length padded to a multiple of 4
+    size_t smem_bytes = 0;          // dynamic shared memory of the encoded kernel
+    int tiles_dict8 = 0, tiles_off16 = 0, tiles_raw = 0;
+};
+
 struct Matrix {
     std::shared_ptr<Resources> rsc;
     int mode = AMGX_mode_dDDI;
@@ -45,6 +56,7 @@ struct Matrix {
     int bx = 1, by = 1;
     bool has_ext_diag = false;
     bool merged_ext_diag = false;   // scalar matrix uploaded with diag_data: merged into CSR, diagonal first
+    ColEnc colenc;
     bool dist_pending = false;      // comm maps were supplied; the next upload_all is a local distributed upload
     struct CommMaps {               // AMGX_matrix_comm_from_maps[_one_ring]: neighbours, rows to send, halo columns to receive into
         std::vector<int> neighbors;

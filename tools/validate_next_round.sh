@@ -12,6 +12,14 @@ AMGXB_RUN_UNVALIDATED=1 timeout 1200 python -m pytest tests/test_gpu_dense_lu.py
     tests/test_gpu_resetup.py tests/test_golden_round2.py tests/test_gpu_classical.py tests/test_gpu_dist.py -q -m gpu 2>&1 | tail -30 | tee gpurun_out/unvalidated.log
 echo "== reference goldens for the round-2 cases"
 timeout 900 python tests/golden/make_golden.py r2 2>&1 | tail -40 | tee gpurun_out/make_golden_r2.log
+echo "== experimental compressed column stream (csrc/k_spmv_enc.cu): parity suite with AMGXB_COLENC=1, then the bench with and without"
+AMGXB_COLENC=1 AMGXB_COLENC_VERBOSE=1 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/colenc_parity.log
+for E in 0 1; do
+  AMGXB_COLENC=$E timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/colenc_bench_$E.err | grep '^{' | tee gpurun_out/colenc_bench_$E.json | python -c "
+import sys, json
+for l in sys.stdin:
+    d=json.loads(l); r=d['roofline']; print('  COLENC=$E: its/s', round(d['value'],1), 'SpMV ms', round(r['ms_per_launch'],4), 'frac', round(r['frac'],3), 'Jacobi ms', round(r['fused_jacobi_sweep']['ms_per_launch'],4))"
+done
 echo "== replicated tail (partitioned aggregates), 2 GPUs: iterations must equal the tail-off run"
 for T in 0 131072; do
   AMGXB_TAIL_ROWS=$T timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29722 bench.py --gpus 2 --grid 128 --steps 2 --warmup 2 --no-cpu-baseline 2>&1 | grep '^{' | python -c "
