@@ -20,6 +20,11 @@ import sys, json
 for l in sys.stdin:
     d=json.loads(l); r=d['roofline']; print('  COLENC=$E: its/s', round(d['value'],1), 'SpMV ms', round(r['ms_per_launch'],4), 'frac', round(r['frac'],3), 'Jacobi ms', round(r['fused_jacobi_sweep']['ms_per_launch'],4))"
 done
+echo "== config 5 (block 4x4 DILU): MIN_MAX vs PARALLEL_GREEDY colouring"
+timeout 900 python tools/bench_configs.py block_pg 2>&1 | grep '^{' | tee gpurun_out/block_coloring.json | python -c "
+import sys, json
+for l in sys.stdin:
+    d=json.loads(l); print('  ', d['case'], 'colors', d['colors_L0'], 'iters', d['iters'], 'its/s', round(d['iters_per_s'],1), d['status'])"
 echo "== replicated tail (partitioned aggregates), 2 GPUs: iterations must equal the tail-off run"
 for T in 0 131072; do
   AMGXB_TAIL_ROWS=$T timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29722 bench.py --gpus 2 --grid 128 --steps 2 --warmup 2 --no-cpu-baseline 2>&1 | grep '^{' | python -c "
