@@ -1,15 +1,16 @@
 #!/bin/bash
 # First GPU call of the next round: everything that was written after round 1 ran out of GPU minutes.
-#   gpurun --gpus 2 --timeout 1800 -- 'bash tools/validate_next_round.sh'
+#   gpurun --timeout 2400 -- 'bash tools/validate_next_round.sh'                  (ONE GPU: everything but the multi-GPU sections)
+#   gpurun --gpus 2 --timeout 1200 -- 'bash tools/validate_next_round_2gpu.sh'    (charged twice: only what needs two ranks)
 # 1. regular gpu suite (must stay green), 2. the opt-in tests of the unvalidated components, 3. reference goldens for them
 # (tests/golden/cases_round2.py through oracle/_ref/ref_dump) -> copy gpurun_out/golden/r2_*.npz to tests/golden/ and commit,
-# 4. the replicated-tail experiment.
+# 4. the experimental compressed column stream and the colouring comparison.
 mkdir -p gpurun_out
 echo "== full gpu suite (validated components)"
 timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
 echo "== unvalidated: DENSE_LU, W/F/CG/CGF cycles, error_scaling, CG/PCGF/PBICGSTAB/GMRES, MULTICOLOR_GS, CHEBYSHEV(_POLY), resetup, HMIS, partition vectors, comm maps, replicated tail"
 AMGXB_RUN_UNVALIDATED=1 timeout 1200 python -m pytest tests/test_gpu_dense_lu.py tests/test_gpu_cycles.py tests/test_gpu_krylov.py tests/test_gpu_smoothers.py \
-    tests/test_gpu_resetup.py tests/test_golden_round2.py tests/test_gpu_classical.py tests/test_gpu_dist.py -q -m gpu 2>&1 | tail -30 | tee gpurun_out/unvalidated.log
+    tests/test_gpu_resetup.py tests/test_golden_round2.py tests/test_gpu_classical.py -q -m gpu 2>&1 | tail -30 | tee gpurun_out/unvalidated.log
 echo "== reference goldens for the round-2 cases"
 timeout 900 python tests/golden/make_golden.py r2 2>&1 | tail -40 | tee gpurun_out/make_golden_r2.log
 echo "== experimental compressed column stream (csrc/k_spmv_enc.cu): parity suite with AMGXB_COLENC=1, then the bench with and without"
@@ -25,11 +26,3 @@ timeout 900 python tools/bench_configs.py block_pg 2>&1 | grep '^{' | tee gpurun
 import sys, json
 for l in sys.stdin:
     d=json.loads(l); print('  ', d['case'], 'colors', d['colors_L0'], 'iters', d['iters'], 'its/s', round(d['iters_per_s'],1), d['status'])"
-echo "== replicated tail (partitioned aggregates), 2 GPUs: iterations must equal the tail-off run"
-for T in 0 131072; do
-  AMGXB_TAIL_ROWS=$T timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29722 bench.py --gpus 2 --grid 128 --steps 2 --warmup 2 --no-cpu-baseline 2>&1 | grep '^{' | python -c "
-import sys, json
-for l in sys.stdin:
-    d=json.loads(l); print('  tail $T: its', d['config']['iterations_per_step'], d['config']['solve_status'], 'global its/s', round(d['config']['global_iterations_per_sec'],1))"
-done
-echo "== 4 ranks need --gpus 4: AMGXB_TAIL_ROWS=131072 vs 0 at --grid 96 must both give 51 iterations"
