@@ -76,7 +76,8 @@ void AMGSolver::validate_config()
     if (strength != "AHAT") fatal(AMGX_RC_BAD_CONFIGURATION, "strength '" + strength + "' is not supported by this engine (AHAT)");
     if (selector_ != "PMIS" && selector_ != "HMIS")
         fatal(AMGX_RC_BAD_CONFIGURATION, "classical selector '" + selector_ + "' is not supported by this engine (PMIS, HMIS)");
-    if (interp != "D2" && interp != "MULTIPASS") fatal(AMGX_RC_BAD_CONFIGURATION, "interpolator '" + interp + "' is not supported by this engine (D2, MULTIPASS)");
+    if (interp != "D1" && interp != "D2" && interp != "MULTIPASS")
+        fatal(AMGX_RC_BAD_CONFIGURATION, "interpolator '" + interp + "' is not supported by this engine (D1, D2, MULTIPASS)");
     if (cfg_->get_int("aggressive_levels", scope_) > 0) {
         if (agg_sel != "DEFAULT" && agg_sel != "PMIS" && agg_sel != "HMIS")
             fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_selector '" + agg_sel + "' is not supported (DEFAULT, PMIS, HMIS)");

@@ -719,6 +719,159 @@ void interp_d2(const Matrix &A, const int *cf, const u8 *s_con, int nc, Csr &P, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// D1 interpolation -- the reference's DEFAULT interpolator (src/classical/interpolators/distance1.cu:353-867, device flow).  One thread
+// per row, everything sequential inside a row, so the restatement is exact.  For a fine row i with strong coarse set C_i, strong fine
+// set F_i (with or without a common coarse neighbour) and weak fine set W_i:
+//     w_ij = -(a_ij + sum_{k in F_i} a_ik abar_kj / sum_{m in C_i} abar_km) / (a_ii + sum_{W_i} a_ik + sum_{k in F_i, empty denominator} a_ik)
+// where abar keeps only entries whose sign is opposite to a_kk.  Two reference quirks are kept on purpose: a STRONG_FINE row gets one
+// explicit (column 0, value 0) entry, and calculateBKernel's "return" inside its grid-stride loop (4096 x 64 launch) skips row i when
+// some row i - m * 262144 is coarse (B and the D increment of that row stay 0).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int D1_STRONG_COARSE = 1, D1_WEAK_COARSE = 2, D1_STRONG_FINE = 4, D1_STRONG_FINE_NO_COMMON = 8, D1_WEAK_FINE = 16;
+constexpr int D1_REF_THREADS = 262144;
+
+__global__ void d1_count_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ cf, const u8 *__restrict__ s_con, int *nz)
+{
+    ROW_LOOP(i, n) {
+        int cnt = 0;
+        if (cf[i] == FINE) { for (int j = rp[i]; j < rp[i + 1]; j++) if (s_con[j] && cf[ci[j]] >= 0) cnt++; }
+        else cnt = 1;
+        nz[i] = cnt;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) nz[n] = 0;
+}
+__global__ void d1_mark_coarse_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ cf, u8 *mark)
+{
+    ROW_LOOP(i, n) for (int j = rp[i]; j < rp[i + 1]; j++) mark[j] = (ci[j] != i && cf[ci[j]] >= 0) ? 1 : 0;
+}
+__device__ inline bool d1_intersect(const int *__restrict__ ci, const u8 *__restrict__ mark, int b1, int e1, int b2, int e2)
+{
+    int i1 = b1, i2 = b2;
+    if (b1 >= e1 || b2 >= e2) return false;
+    for (;;) {
+        const int c1 = ci[i1], c2 = ci[i2];
+        if (c1 == c2) {
+            if (mark[i1] && mark[i2]) return true;
+            i1++; i2++;
+            if (i1 >= e1 || i2 >= e2) return false;
+        } else if (c1 > c2) { if (++i2 >= e2) return false; }
+        else { if (++i1 >= e1) return false; }
+    }
+}
+__global__ void d1_categorise_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ cf, const u8 *__restrict__ s_con,
+                                     const u8 *__restrict__ mark, int *set)
+{
+    ROW_LOOP(i, n) {
+        const bool coarse_row = cf[i] >= 0;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            int v = 0;
+            const int jc = ci[j];
+            if (!coarse_row && jc != i) {
+                if (cf[jc] >= 0) v = s_con[j] ? D1_STRONG_COARSE : D1_WEAK_COARSE;
+                else if (!s_con[j]) v = D1_WEAK_FINE;
+                else v = d1_intersect(ci, mark, rp[i], rp[i + 1], rp[jc], rp[jc + 1]) ? D1_STRONG_FINE : D1_STRONG_FINE_NO_COMMON;
+            }
+            set[j] = v;
+        }
+    }
+}
+__global__ void d1_B_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va, const double *__restrict__ diag,
+                            const int *__restrict__ set, const int *__restrict__ cf, const int *__restrict__ prp, double *B, double *D)
+{
+    ROW_LOOP(i, n) {
+        bool skipped = false;       // the reference thread owning row i left its loop at an earlier coarse row
+        for (int e = i - D1_REF_THREADS; e >= 0 && !skipped; e -= D1_REF_THREADS) skipped = cf[e] >= 0;
+        if (skipped) continue;
+        if (cf[i] >= 0) { B[prp[i]] = 1; continue; }
+        double dinc = 0;
+        int flag = 0, first_j_loop = 0, local = 0;
+        const double tol = 1e-10;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            if (!(set[j] & D1_STRONG_COARSE)) continue;
+            const int jcol = ci[j];
+            if (flag == 0) { first_j_loop = 1; flag = 1; } else first_j_loop = 0;
+            double sum = 0.0;
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                if (!((set[k] & D1_STRONG_FINE) || (set[k] & D1_STRONG_FINE_NO_COMMON))) continue;
+                const int kcol = ci[k];
+                const double a_ik = va[k];
+                const int sgn = diag[kcol] < 0.0 ? -1 : 1;
+                double top = 0.0, bottom = 0.0;
+                for (int q = rp[kcol]; q < rp[kcol + 1]; q++)
+                    if (ci[q] == jcol && sgn * va[q] < 0) top = a_ik * va[q];
+                for (int m = rp[i]; m < rp[i + 1]; m++) {
+                    if (!(set[m] & D1_STRONG_COARSE)) continue;
+                    const int mcol = ci[m];
+                    for (int q = rp[kcol]; q < rp[kcol + 1]; q++)
+                        if (ci[q] == mcol && sgn * va[q] < 0) bottom += va[q];
+                }
+                if (fabs(bottom) < tol) { if (first_j_loop == 1) dinc += va[k]; }
+                else sum += top / bottom;
+            }
+            B[prp[i] + local] = sum;
+            local++;
+        }
+        D[i] = dinc;
+    }
+}
+__global__ void d1_W_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va, const double *__restrict__ diag,
+                            const int *__restrict__ set, const int *__restrict__ cf, const int *__restrict__ prp, const double *__restrict__ B,
+                            const double *__restrict__ D, int *pc, double *pv)
+{
+    ROW_LOOP(i, n) {
+        if (cf[i] >= 0) { pv[prp[i]] = 1.0; pc[prp[i]] = cf[i]; continue; }
+        double wf = 0;                                   // calculateDKernel: weak-fine entries join the diagonal
+        for (int k = rp[i]; k < rp[i + 1]; k++) if (set[k] & D1_WEAK_FINE) wf += va[k];
+        const double Di = D[i] + wf;
+        int local = 0;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            if (!(set[j] & D1_STRONG_COARSE)) continue;
+            const double bottom = (fabs(diag[i] + Di) < 1e-10) ? 1. : diag[i] + Di;
+            pc[prp[i] + local] = cf[ci[j]];
+            pv[prp[i] + local] = -1.0 / bottom * (va[j] + B[prp[i] + local]);
+            local++;
+        }
+    }
+}
+
+void interp_d1(const Matrix &A, const int *cf, const u8 *s_con, int nc, Csr &P, cudaStream_t s)
+{
+    const int n = A.n;
+    const int *rp = A.row_ptr.ptr(), *ci = A.col_idx.ptr();
+    const double *va = A.values.as<double>();
+    const int g = grid_for(n);
+    DevBuf<int> nz, set;
+    DevBuf<u8> mark;
+    nz.resize((size_t)n + 1);
+    P.n = n;
+    P.nc = nc;
+    P.rp.resize((size_t)n + 1);
+    d1_count_kernel<<<g, 256, 0, s>>>(n, rp, ci, cf, s_con, nz.ptr());
+    exclusive_scan(nz.ptr(), P.rp.ptr(), (size_t)n + 1, s);
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&P.nnz, P.rp.ptr() + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    P.ci.resize((size_t)std::max(P.nnz, 1));
+    P.ci.zero(s);                                        // STRONG_FINE rows keep (column 0, value 0)
+    P.va.resize((size_t)std::max(P.nnz, 1), Prec::F64);
+    P.va.zero(s);
+    mark.resize((size_t)std::max(A.nnz, 1));
+    set.resize((size_t)std::max(A.nnz, 1));
+    DevVec diag, B, D;
+    diag.resize((size_t)std::max(n, 1), Prec::F64);
+    B.resize((size_t)std::max(P.nnz, 1), Prec::F64);
+    D.resize((size_t)std::max(n, 1), Prec::F64);
+    B.zero(s);
+    D.zero(s);
+    diag_value_kernel<<<g, 256, 0, s>>>(n, rp, ci, va, diag.as<double>());
+    d1_mark_coarse_kernel<<<g, 256, 0, s>>>(n, rp, ci, cf, mark.ptr());
+    d1_categorise_kernel<<<g, 256, 0, s>>>(n, rp, ci, cf, s_con, mark.ptr(), set.ptr());
+    d1_B_kernel<<<g, 256, 0, s>>>(n, rp, ci, va, diag.as<double>(), set.ptr(), cf, P.rp.ptr(), B.as<double>(), D.as<double>());
+    d1_W_kernel<<<g, 256, 0, s>>>(n, rp, ci, va, diag.as<double>(), set.ptr(), cf, P.rp.ptr(), B.as<double>(), D.as<double>(), P.ci.ptr(), P.va.as<double>());
+    count_launch(6);
+    AMGXB_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // MULTIPASS interpolation
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void mp_init_assigned_kernel(int n, const int *__restrict__ rp, const int *__restrict__ ci, const u8 *__restrict__ s_con, const int *__restrict__ cf,
@@ -1071,7 +1224,7 @@ std::unique_ptr<Matrix> to_matrix(Csr &C, const Matrix &like, cudaStream_t s)
 struct ClassicalParams {
     double strength_threshold, max_row_sum;
     int max_elmts, aggressive_levels;
-    bool d2, aggressive_multipass, hmis = false, aggressive_hmis = false;
+    bool d2, d1 = false, aggressive_multipass, hmis = false, aggressive_hmis = false;
 };
 
 // createCoarseVertices: strength + C/F splitting; returns the number of coarse points, cf_map renumbered
@@ -1114,7 +1267,8 @@ void AMGSolver::setup_classical()
     if (selector_ != "PMIS" && selector_ != "HMIS")
         fatal(AMGX_RC_BAD_CONFIGURATION, "classical selector '" + selector_ + "' is not supported by this engine (PMIS, HMIS)");
     prm.hmis = (selector_ == "HMIS");
-    if (interp != "D2" && interp != "MULTIPASS") fatal(AMGX_RC_BAD_CONFIGURATION, "interpolator '" + interp + "' is not supported by this engine (D2, MULTIPASS)");
+    if (interp != "D1" && interp != "D2" && interp != "MULTIPASS")
+        fatal(AMGX_RC_BAD_CONFIGURATION, "interpolator '" + interp + "' is not supported by this engine (D1, D2, MULTIPASS)");
     if (prm.aggressive_levels > 0) {
         if (agg_sel != "DEFAULT" && agg_sel != "PMIS" && agg_sel != "HMIS")
             fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_selector '" + agg_sel + "' is not supported (DEFAULT, PMIS, HMIS)");
@@ -1122,6 +1276,7 @@ void AMGSolver::setup_classical()
         if (agg_int != "MULTIPASS") fatal(AMGX_RC_BAD_CONFIGURATION, "aggressive_interpolator '" + agg_int + "' is not supported (MULTIPASS)");
     }
     prm.d2 = (interp == "D2");
+    prm.d1 = (interp == "D1");
     prm.aggressive_multipass = true;
 
     levels_.emplace_back(new AMGLevel);
@@ -1147,7 +1302,8 @@ void AMGSolver::setup_classical()
         bool built_next = false;
         if ((double)nc <= coarsen_threshold_ * (double)rows && nc != rows && nc >= min_coarse_rows_) {
             Csr P, R;
-            if (lvl < prm.aggressive_levels || !prm.d2) interp_multipass(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
+            if (lvl < prm.aggressive_levels || (!prm.d2 && !prm.d1)) interp_multipass(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
+            else if (prm.d1) interp_d1(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
             else interp_d2(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
             s_con.release();
             if (prm.max_elmts > 0 && P.n > 0) truncate_max_elements(P, prm.max_elmts, s);

@@ -682,6 +682,7 @@ ORC_API orc_amg *orc_amg_setup_classical(int n, const int *rp, const int *ci, co
             cla_csr P, R, AP, Ac;
             const int which = (lvl < aggressive_levels) ? aggressive_interp : interp;
             if (which == 1) cla_interp_multipass(L->n, L->rp, L->ci, L->va, cf, s_con, nc, &P);
+            else if (which == 2) cla_interp_d1(L->n, L->rp, L->ci, L->va, cf, s_con, nc, &P);
             else cla_interp_d2(L->n, L->rp, L->ci, L->va, cf, s_con, nc, &P);
             if (max_elmts > 0 && L->n > 0) cla_truncate(&P, max_elmts);
             cla_transpose(&P, &R);

@@ -556,6 +556,121 @@ static void cla_interp_d2(int n, const int *rp, const int *ci, const double *va,
 }
 
 /* Multipass_Interpolator (device) */
+/* Distance1_Interpolator<device>::generateInterpolationMatrix_1x1 (src/classical/interpolators/distance1.cu:353-867), the reference's
+ * DEFAULT interpolator ("D1"): one thread per row, everything sequential inside a row.
+ *   sets (categoriseEdgesKernel :690-745): for a non-coarse row, every off-diagonal entry is strong-coarse (1), weak-coarse (2),
+ *     strong-fine (4: the two rows share a coarse neighbour, found by a two-pointer walk over both rows that assumes ascending
+ *     columns, :645-687), strong-fine-without-common-C (8) or weak-fine (16);
+ *   B_ij (calculateBKernel :426-548) = sum over strong-fine k of a_ik a_kj / sum_{m strong coarse} a_km, only entries of row k whose
+ *     sign is opposite to a_kk count; a k whose denominator vanishes (|.| < 1e-10) goes to the diagonal once (first strong-coarse j);
+ *   D_i (calculateDKernel :400-422) += weak-fine entries;  w_ij = -1 / (a_ii + D_i) * (a_ij + B_ij)  (calculateWKernel :577-612).
+ * Quirks kept: a STRONG_FINE row gets ONE explicit entry (column 0, value 0) because numNonZerosVecKernel counts 1 for every row
+ * that is not FINE (:374-386); calculateBKernel leaves a thread at its first coarse row ("return" inside the grid-stride loop, :448),
+ * so with the reference's launch of 4096 x 64 threads a row i is skipped (B = 0, D not reset) when some row i - m * 262144 is coarse. */
+#define D1_STRONG_COARSE 1
+#define D1_WEAK_COARSE 2
+#define D1_STRONG_FINE 4
+#define D1_STRONG_FINE_NO_COMMON 8
+#define D1_WEAK_FINE 16
+#define D1_REF_THREADS 262144
+static int d1_intersect(const int *ci, const unsigned char *mark, int b1, int e1, int b2, int e2)
+{
+    int i1 = b1, i2 = b2;
+    if (b1 >= e1 || b2 >= e2) return 0;
+    for (;;) {
+        const int c1 = ci[i1], c2 = ci[i2];
+        if (c1 == c2) {
+            if (mark[i1] && mark[i2]) return 1;
+            i1++; i2++;
+            if (i1 >= e1 || i2 >= e2) return 0;
+        } else if (c1 > c2) { if (++i2 >= e2) return 0; }
+        else { if (++i1 >= e1) return 0; }
+    }
+}
+static void cla_interp_d1(int n, const int *rp, const int *ci, const double *va, const int *cf, const unsigned char *s_con, int nc, cla_csr *P)
+{
+    const int nnz = rp[n];
+    double *diag = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    cla_diag(n, rp, ci, va, diag);
+    int *prp = (int *)calloc((size_t)n + 1, sizeof(int));
+    for (int i = 0; i < n; i++) {                                   /* numNonZerosVecKernel + exclusive scan */
+        int cnt = 0;
+        if (cf[i] == CLA_FINE) { for (int j = rp[i]; j < rp[i + 1]; j++) if (s_con[j] && cf[ci[j]] >= 0) cnt++; }
+        else cnt = 1;
+        prp[i + 1] = prp[i] + cnt;
+    }
+    const int pnnz = prp[n];
+    unsigned char *mark = (unsigned char *)calloc((size_t)(nnz > 0 ? nnz : 1), 1);
+    int *set = (int *)calloc((size_t)(nnz > 0 ? nnz : 1), sizeof(int));
+    for (int i = 0; i < n; i++)                                     /* markCoarseEdgesKernel */
+        for (int j = rp[i]; j < rp[i + 1]; j++) if (ci[j] != i && cf[ci[j]] >= 0) mark[j] = 1;
+    for (int i = 0; i < n; i++) {                                   /* categoriseEdgesKernel */
+        if (cf[i] >= 0) continue;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            const int jc = ci[j];
+            if (jc == i) continue;
+            if (cf[jc] >= 0) set[j] |= s_con[j] ? D1_STRONG_COARSE : D1_WEAK_COARSE;
+            else if (!s_con[j]) set[j] |= D1_WEAK_FINE;
+            else set[j] |= d1_intersect(ci, mark, rp[i], rp[i + 1], rp[jc], rp[jc + 1]) ? D1_STRONG_FINE : D1_STRONG_FINE_NO_COMMON;
+        }
+    }
+    int *pc = (int *)calloc((size_t)(pnnz > 0 ? pnnz : 1), sizeof(int));
+    double *pv = (double *)calloc((size_t)(pnnz > 0 ? pnnz : 1), sizeof(double));
+    double *B = (double *)calloc((size_t)(pnnz > 0 ? pnnz : 1), sizeof(double)), *D = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    for (int i = 0; i < n; i++) {                                   /* calculateBKernel */
+        int skipped = 0;                                            /* the thread that owns row i returned at an earlier coarse row */
+        for (int e = i - D1_REF_THREADS; e >= 0 && !skipped; e -= D1_REF_THREADS) skipped = cf[e] >= 0;
+        if (skipped) continue;
+        if (cf[i] >= 0) { B[prp[i]] = 1; continue; }
+        D[i] = 0;
+        int flag = 0, first_j_loop = 0, local = 0;
+        const double tol = 1e-10;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            if (!(set[j] & D1_STRONG_COARSE)) continue;
+            const int jcol = ci[j];
+            if (flag == 0) { first_j_loop = 1; flag = 1; } else first_j_loop = 0;
+            double sum = 0.0;
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                if (!((set[k] & D1_STRONG_FINE) || (set[k] & D1_STRONG_FINE_NO_COMMON))) continue;
+                const int kcol = ci[k];
+                const double a_ik = va[k];
+                const int sgn = diag[kcol] < 0.0 ? -1 : 1;
+                double top = 0.0, bottom = 0.0;
+                for (int q = rp[kcol]; q < rp[kcol + 1]; q++)
+                    if (ci[q] == jcol && sgn * va[q] < 0) top = a_ik * va[q];
+                for (int m = rp[i]; m < rp[i + 1]; m++) {
+                    if (!(set[m] & D1_STRONG_COARSE)) continue;
+                    const int mcol = ci[m];
+                    for (int q = rp[kcol]; q < rp[kcol + 1]; q++)
+                        if (ci[q] == mcol && sgn * va[q] < 0) bottom += va[q];
+                }
+                if (fabs(bottom) < tol) { if (first_j_loop == 1) D[i] += va[k]; }
+                else sum += top / bottom;
+            }
+            B[prp[i] + local] = sum;
+            local++;
+        }
+    }
+    for (int i = 0; i < n; i++) {                                   /* calculateDKernel */
+        double sum = 0;
+        for (int k = rp[i]; k < rp[i + 1]; k++) if (set[k] & D1_WEAK_FINE) sum += va[k];
+        D[i] += sum;
+    }
+    for (int i = 0; i < n; i++) {                                   /* calculateWKernel */
+        if (cf[i] >= 0) { pv[prp[i]] = 1.0; pc[prp[i]] = cf[i]; continue; }
+        int local = 0;
+        for (int j = rp[i]; j < rp[i + 1]; j++) {
+            if (!(set[j] & D1_STRONG_COARSE)) continue;
+            const double bottom = (fabs(diag[i] + D[i]) < 1e-10) ? 1. : diag[i] + D[i];
+            pc[prp[i] + local] = cf[ci[j]];
+            pv[prp[i] + local] = -1.0 / bottom * (va[j] + B[prp[i] + local]);
+            local++;
+        }
+    }
+    P->n = n; P->nc = nc; P->nnz = pnnz; P->rp = prp; P->ci = pc; P->va = pv;
+    free(diag); free(mark); free(set); free(B); free(D);
+}
+
 static void cla_interp_multipass(int n, const int *rp, const int *ci, const double *va, const int *cf, const unsigned char *s_con, int nc, cla_csr *P)
 {
     double *diag = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
@@ -815,6 +930,7 @@ ORC_API orc_cla_matrix *orc_cla_interpolate(int n, const int *rp, const int *ci,
 {
     orc_cla_matrix *h = (orc_cla_matrix *)calloc(1, sizeof(orc_cla_matrix));
     if (interp == 1) cla_interp_multipass(n, rp, ci, va, cf, s_con, nc, &h->m);
+    else if (interp == 2) cla_interp_d1(n, rp, ci, va, cf, s_con, nc, &h->m);
     else cla_interp_d2(n, rp, ci, va, cf, s_con, nc, &h->m);
     if (max_elmts > 0 && n > 0) cla_truncate(&h->m, max_elmts);
     return h;

@@ -457,7 +457,7 @@ def cla_interpolate(rp, ci, va, cf_renumbered, s_con, nc, interpolator="D2", max
     rp, ci, va, cf = _i(rp), _i(ci), _d(va), _i(cf_renumbered)
     s_con = np.ascontiguousarray(s_con, np.uint8)
     n = rp.shape[0] - 1
-    h = C.c_void_p(lib().orc_cla_interpolate(n, _p(rp), _p(ci), _p(va), _p(cf), _p(s_con), nc, {"D2": 0, "MULTIPASS": 1}[interpolator], max_elements))
+    h = C.c_void_p(lib().orc_cla_interpolate(n, _p(rp), _p(ci), _p(va), _p(cf), _p(s_con), nc, {"D2": 0, "MULTIPASS": 1, "D1": 2}[interpolator], max_elements))
     out = _cla_take(h)
     lib().orc_cla_matrix_free(h)
     return out[:3]
@@ -475,7 +475,7 @@ class ClassicalAMG(AMG):
             min_coarse_rows = dense_lu_num_rows
         self.n = self.rp.shape[0] - 1
         sm = SMOOTHERS[smoother]
-        im = {"D2": 0, "MULTIPASS": 1}
+        im = {"D2": 0, "MULTIPASS": 1, "D1": 2}
         set_classical_selector(selector)
         self.h = C.c_void_p(lib().orc_amg_setup_classical(
             self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold), presweeps, postsweeps,

@@ -98,6 +98,13 @@ def cases():
     yield "poisson16x12x9_fgmres_classical_hmis", P(16, 12, 9), _outer("FGMRES", cla(aggressive_levels=0), tol=1e-10, max_iters=60, gmres_n_restart=20)
     yield "banded3000_fgmres_classical_hmis", gallery.random_banded(3000, sigma=40.0), _outer("FGMRES", cla(aggressive_levels=0), tol=1e-10, max_iters=40,
                                                                                                 gmres_n_restart=20)
+    # D1, the default interpolator (the shipped CLASSICAL_* configs that do not name one, e.g. AMG_CLASSICAL_PMIS.json, FGMRES_CLASSICAL_PMIS.json)
+    d1 = lambda **kw: dict(cla(selector="PMIS", interpolator="D1", aggressive_levels=0, interp_max_elements=-1), **kw)
+    yield "poisson14_fgmres_classical_d1", P(14), _outer("FGMRES", d1(), tol=1e-10, max_iters=60, gmres_n_restart=20)
+    yield "poisson16x12x9_fgmres_classical_d1_trunc4", P(16, 12, 9), _outer("FGMRES", d1(interp_max_elements=4), tol=1e-10, max_iters=60, gmres_n_restart=20)
+    yield "banded3000_fgmres_classical_d1", gallery.random_banded(3000, sigma=40.0), _outer("FGMRES", d1(), tol=1e-10, max_iters=40, gmres_n_restart=20)
+    yield "poisson14_fgmres_classical_d1_hmis_aggr", P(14), _outer("FGMRES", d1(selector="HMIS", aggressive_levels=1), tol=1e-10, max_iters=60,
+                                                                  gmres_n_restart=20)
     # PARALLEL_GREEDY colouring: the shipped FGMRES_AGGREGATION.json / FGMRES_AGGREGATION_DILU.json preconditioner (DILU, 0 + 3 sweeps,
     # DENSE_LU coarse solver, min_coarse_rows 32).  The reference's in-place colouring kernel is not reproducible run to run
     # (csrc/coloring.cu), so these goldens are compared loosely: see REFERENCE_NONDETERMINISTIC in tests/test_golden_round2.py

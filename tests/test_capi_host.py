@@ -118,7 +118,7 @@ def test_config_check_on_own_configs_and_bad_components(lib):
     assert ok and msg == ""
     cfg.destroy()
     for bad, word in [("config_version=2, solver(s)=IDR", "IDR"), ("config_version=2, solver(s)=AMG, s:algorithm=AGGREGATION, s:selector=SIZE_8", "SIZE_8"),
-                      ("config_version=2, solver(s)=AMG, s:interpolator=D2, s:cycle=Q", "Q"), ("config_version=2, solver(s)=AMG, s:interpolator=D1", "D1"),
+                      ("config_version=2, solver(s)=AMG, s:interpolator=D2, s:cycle=Q", "Q"), ("config_version=2, solver(s)=AMG, s:interpolator=EM", "EM"),
                       ("config_version=2, solver(s)=AMG, s:interpolator=D2, s:smoother(m)=MULTICOLOR_DILU, m:matrix_coloring_scheme=ROUND_ROBIN", "ROUND_ROBIN"),
                       ("config_version=2, solver(s)=AMG, s:interpolator=D2, s:smoother(m)=CHEBYSHEV, m:chebyshev_lambda_estimate_mode=0", "Lanczos"),
                       ("config_version=2, solver(s)=PCG, s:scaling=BINORMALIZATION", "BINORMALIZATION")]:

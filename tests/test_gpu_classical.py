@@ -165,7 +165,7 @@ def test_classical_full_size_properties(amgx):
 def test_classical_unsupported_options_fail_loudly(amgx):
     rp, ci, va = gallery.poisson7pt(6)
     n = rp.shape[0] - 1
-    for kw, key in ((dict(interpolator="D1"), "interpolator"),):
+    for kw, key in ((dict(interpolator="EM"), "interpolator"),):     # energy-minimisation: registered by the reference, not provided here
         cfgd = cfg_fgmres_classical(**kw)
         cfg = amgx.Config(cfgd)
         rsc = amgx.Resources(cfg)
@@ -205,6 +205,40 @@ def test_hmis_hierarchy_bit_exact_vs_oracle(amgx, oracle, name):
         L, G = o.level(l), g["levels"][l]
         assert np.array_equal(G["cf"], L["cf_map"]), f"level {l} C/F map"
         assert np.array_equal(G["P"][0], L["P_row_offsets"]) and np.array_equal(G["P"][1], L["P_col_indices"]), f"level {l} P pattern"
+        assert np.array_equal(G["A"][2], L["values"]), f"level {l} values (bit-exact)"
+    s = cfgd["solver"]
+    xo, ito, histo, convo = oracle.fgmres(rp, ci, va, np.ones(n), amg=o, tol=s["tolerance"], max_iters=s["max_iters"], restart=s["gmres_n_restart"])
+    assert g["iters"] == ito and g["status"] == "success" and convo
+    assert np.max(np.abs(g["hist"] - histo) / histo[0]) < 1e-12
+
+
+# D1 (the reference's default interpolator): written after round 1's GPU minutes were spent, opt-in until validated
+D1_SYSTEMS = {
+    "poisson14_d1": (lambda: gallery.poisson7pt(14), dict(interpolator="D1", aggressive_levels=0, max_elements=-1)),
+    "poisson20x9x13_d1_trunc4": (lambda: gallery.poisson7pt(20, 9, 13), dict(interpolator="D1", aggressive_levels=0)),
+    "poisson16_d1_aggr1": (lambda: gallery.poisson7pt(16), dict(interpolator="D1", aggressive_levels=1)),
+    "banded4000_d1": (lambda: gallery.random_banded(4000, sigma=40.0, seed=5), dict(interpolator="D1", aggressive_levels=0, max_elements=-1, max_iters=40)),
+}
+
+
+@pytest.mark.parametrize("name", list(D1_SYSTEMS))
+def test_d1_hierarchy_bit_exact_vs_oracle(amgx, oracle, name):
+    import os
+    if os.environ.get("AMGXB_RUN_UNVALIDATED") != "1":
+        pytest.skip("D1 not yet validated on a GPU (AMGXB_RUN_UNVALIDATED=1)")
+    gen, kw = D1_SYSTEMS[name]
+    rp, ci, va = gen()
+    n = rp.shape[0] - 1
+    cfgd = cfg_fgmres_classical(**kw)
+    a = cfgd["solver"]["preconditioner"]
+    g = solve(amgx, cfgd, rp, ci, va, np.ones(n))
+    o = oracle_amg(oracle, rp, ci, va, a)
+    assert g["nl"] == o.num_levels() and g["nl"] >= 3
+    for l in range(g["nl"] - 1):
+        L, G = o.level(l), g["levels"][l]
+        assert np.array_equal(G["cf"], L["cf_map"]), f"level {l} C/F map"
+        assert np.array_equal(G["P"][0], L["P_row_offsets"]) and np.array_equal(G["P"][1], L["P_col_indices"]), f"level {l} P pattern"
+        assert np.array_equal(G["P"][2], L["P_values"]), f"level {l} P values (bit-exact)"
         assert np.array_equal(G["A"][2], L["values"]), f"level {l} values (bit-exact)"
     s = cfgd["solver"]
     xo, ito, histo, convo = oracle.fgmres(rp, ci, va, np.ones(n), amg=o, tol=s["tolerance"], max_iters=s["max_iters"], restart=s["gmres_n_restart"])
