@@ -384,6 +384,7 @@ AMGX_RC AMGX_matrix_replace_coefficients(AMGX_matrix_handle mtx, int n, int nnz,
     if (data) AMGXB_CUDA_CHECK(cudaMemcpyAsync(A.values.ptr(), data, (size_t)nnz * bs * msz, cudaMemcpyDefault, A.stream()));
     if (diag_data && A.has_ext_diag)
         AMGXB_CUDA_CHECK(cudaMemcpyAsync((char *)A.values.ptr() + (size_t)nnz * bs * msz, diag_data, (size_t)n * bs * msz, cudaMemcpyDefault, A.stream()));
+    if (data) csr_values_changed(A, A.stream());
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(A.stream()));
     API_END(rp)
 }

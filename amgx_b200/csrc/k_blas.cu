@@ -230,6 +230,7 @@ void diag_sym_scale_matrix(Matrix &A, const DevVec &scale, bool unscale, cudaStr
     });
     count_launch();
     AMGXB_LAUNCH_CHECK();
+    csr_values_changed(A, s);
 }
 
 void vec_scale_entrywise(void *v, const void *d, Prec p, size_t n, bool divide, cudaStream_t s)

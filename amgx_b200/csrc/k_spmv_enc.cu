@@ -7,6 +7,10 @@
 //   enc 0  the raw 32-bit columns (fallback, identical traffic to the plain kernel).
 // The encoding is chosen per tile by colenc_build_kernel at plan time; it only reads row_ptr / col_idx, so value updates
 // (AMGX_matrix_replace_coefficients) leave it valid.
+// AMGXB_COLENC bit 1 (values 2, 3) adds the same idea for the VALUES ("value indexing"): a tile whose entries take <= 256 distinct bit
+// patterns (stencil matrices and their Galerkin products: 2 on the fine 7-point level, a few dozen below) moves 8-bit codes plus a
+// dictionary of the exact values instead of 8 bytes per entry -- lossless, the FMA operands are bit-identical.  Together: 12 -> 2 B
+// per entry.  The value codes follow the values: csr_values_changed() rebuilds them after replace_coefficients / in-place scaling.
 // Not used for: distributed matrices (two row segments), the aggregation-fused prolongation gather, the long-row fallback.
 #include "kernels.h"
 #include <climits>
@@ -23,6 +27,9 @@ __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t
 // byte offset of tile `t`'s code segment; sa = first (4-aligned) entry the tile stages.  2 bytes per entry are reserved whatever the
 // encoding, 32 bytes of slack per tile absorb the 16-byte rounding of the copies and the <= 3 entries consecutive tiles share.
 __host__ __device__ inline size_t code_offset(int sa, int t) { return align16((size_t)2 * (size_t)sa) + (size_t)32 * (size_t)t; }
+// the same for the value codes (1 byte per entry)
+__host__ __device__ inline size_t vcode_offset(int sa, int t) { return align16((size_t)sa) + (size_t)32 * (size_t)t; }
+constexpr int META = 4;                  // ints per tile: column encoding, column dictionary length, value encoding, value dictionary length
 
 // ---------------------------------------------------------------------------------------------
 // plan: one CTA per tile (grid-stride), TILE_ROWS threads
@@ -100,16 +107,97 @@ __global__ void __launch_bounds__(TILE_ROWS) colenc_build_kernel(const int *__re
                     seg[k - sa] = (unsigned char)lo;
                 }
             }
-            if (tid == 0) { meta[2 * tile] = 1; meta[2 * tile + 1] = padded; atomicAdd(stats + 0, 1); }
+            if (tid == 0) { meta[META * tile] = 1; meta[META * tile + 1] = padded; atomicAdd(stats + 0, 1); }
         } else if (use_off16) {
             const int base = s_min;
             unsigned short *seg16 = reinterpret_cast<unsigned short *>(seg);
             for (int i = tid; i < 4; i += TILE_ROWS) dict[(size_t)tile * DICT_SLOTS + i] = base;
             for (int k = sa + tid; k < ea; k += TILE_ROWS)
                 seg16[k - sa] = (k < nz0 || k >= nz1) ? (unsigned short)0 : (unsigned short)(ci[k] - base);
-            if (tid == 0) { meta[2 * tile] = 2; meta[2 * tile + 1] = 4; atomicAdd(stats + 1, 1); }
+            if (tid == 0) { meta[META * tile] = 2; meta[META * tile + 1] = 4; atomicAdd(stats + 1, 1); }
         } else {
-            if (tid == 0) { meta[2 * tile] = 0; meta[2 * tile + 1] = 0; atomicAdd(stats + 2, 1); }
+            if (tid == 0) { meta[META * tile] = 0; meta[META * tile + 1] = 0; atomicAdd(stats + 2, 1); }
+        }
+        __syncthreads();
+    }
+}
+
+// value dictionary of a tile: the distinct bit patterns of its entries, ascending as unsigned integers
+template <class T> __device__ __forceinline__ unsigned long long val_bits(T v);
+template <> __device__ __forceinline__ unsigned long long val_bits<double>(double v) { return (unsigned long long)__double_as_longlong(v); }
+template <> __device__ __forceinline__ unsigned long long val_bits<float>(float v) { return (unsigned long long)__float_as_uint(v); }
+template <class T> __device__ __forceinline__ T val_from_bits(unsigned long long b);
+template <> __device__ __forceinline__ double val_from_bits<double>(unsigned long long b) { return __longlong_as_double((long long)b); }
+template <> __device__ __forceinline__ float val_from_bits<float>(unsigned long long b) { return __uint_as_float((unsigned)b); }
+
+template <class MatT, int TILE_ROWS>
+__global__ void __launch_bounds__(TILE_ROWS) valenc_build_kernel(const int *__restrict__ rp, const MatT *__restrict__ va, int n, int num_tiles, unsigned char *vcodes,
+                                                                 MatT *vdict, int *meta, int *stats)
+{
+    constexpr unsigned long long EMPTY = ~0ull;
+    __shared__ unsigned long long keys[HASH_SLOTS];
+    __shared__ unsigned long long list[DICT_SLOTS], sorted[DICT_SLOTS];
+    __shared__ int s_count, s_overflow;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int r0 = tile * TILE_ROWS, r1 = min(r0 + TILE_ROWS, n);
+        const int nz0 = rp[r0], nz1 = rp[r1];
+        const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
+        for (int i = tid; i < HASH_SLOTS; i += TILE_ROWS) keys[i] = EMPTY;
+        if (tid == 0) { s_count = 0; s_overflow = 0; }
+        __syncthreads();
+        for (int k = nz0 + tid; k < nz1; k += TILE_ROWS) {
+            if (*(volatile int *)&s_overflow) break;
+            const unsigned long long b = val_bits<MatT>(va[k]);
+            if (b == EMPTY) { s_overflow = 1; break; }                   // the empty-slot sentinel cannot be a key
+            unsigned h = ((unsigned)(b ^ (b >> 32)) * 2654435761u) >> 22;
+            for (int probe = 0; probe < HASH_SLOTS; probe++) {
+                if (*(volatile int *)&s_overflow) break;
+                const unsigned long long old = atomicCAS(&keys[h], EMPTY, b);
+                if (old == EMPTY) {
+                    if (atomicAdd(&s_count, 1) >= DICT_SLOTS) s_overflow = 1;
+                    break;
+                }
+                if (old == b) break;
+                h = (h + 1) & (HASH_SLOTS - 1);
+            }
+        }
+        __syncthreads();
+        const bool use_dict = !s_overflow && s_count <= DICT_SLOTS && nz1 > nz0;
+        const int count = s_count;
+        __syncthreads();
+        if (use_dict) {
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+            for (int i = tid; i < HASH_SLOTS; i += TILE_ROWS)
+                if (keys[i] != EMPTY) list[atomicAdd(&s_count, 1)] = keys[i];
+            __syncthreads();
+            for (int i = tid; i < count; i += TILE_ROWS) {
+                const unsigned long long v = list[i];
+                int rank = 0;
+                for (int j = 0; j < count; j++) rank += (list[j] < v);
+                sorted[rank] = v;
+            }
+            __syncthreads();
+            const int padded = (count + 3) & ~3;
+            for (int i = tid; i < padded; i += TILE_ROWS) vdict[(size_t)tile * DICT_SLOTS + i] = val_from_bits<MatT>(sorted[min(i, count - 1)]);
+            unsigned char *seg = vcodes + vcode_offset(sa, tile);
+            for (int k = sa + tid; k < ea; k += TILE_ROWS) {
+                int lo = 0;
+                if (k >= nz0 && k < nz1) {
+                    const unsigned long long b = val_bits<MatT>(va[k]);
+                    int hi = count - 1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (sorted[mid] < b) lo = mid + 1;
+                        else hi = mid;
+                    }
+                }
+                seg[k - sa] = (unsigned char)lo;                          // alignment padding (entries of neighbouring tiles) gets code 0, never decoded
+            }
+            if (tid == 0) { meta[META * tile + 2] = 1; meta[META * tile + 3] = padded; atomicAdd(stats + 3, 1); }
+        } else {
+            if (tid == 0) { meta[META * tile + 2] = 0; meta[META * tile + 3] = 0; }
         }
         __syncthreads();
     }
@@ -117,12 +205,15 @@ __global__ void __launch_bounds__(TILE_ROWS) colenc_build_kernel(const int *__re
 
 // ---------------------------------------------------------------------------------------------
 // The encoded tile kernel.  blockDim.x = TILE_ROWS + 32 (last warp = producer).
-// per stage: vals[cap] | column stream (cap * 4 bytes: raw columns, or codes) | dict[256] | rp[TILE_ROWS+4]
+// per stage: value stream (cap * sizeof(MatT) bytes: raw values, or codes) | column stream (cap * 4 bytes: raw columns, or codes) |
+//            dict[256] | vdict[256] | rp[TILE_ROWS+4]
 // ---------------------------------------------------------------------------------------------
 struct EncArgs {
     const unsigned char *codes;
     const int *dict;
     const int *meta;
+    const unsigned char *vcodes;
+    const void *vdict;
 };
 
 template <class MatT, class VecT, int TILE_ROWS, int EPI>
@@ -136,8 +227,9 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
     const size_t vals_bytes = (size_t)a.cap * sizeof(MatT);
     const size_t cols_bytes = (size_t)a.cap * sizeof(int);
     const size_t dict_bytes = (size_t)DICT_SLOTS * sizeof(int);
+    const size_t vdict_bytes = (size_t)DICT_SLOTS * sizeof(MatT);
     const size_t rp_bytes = (size_t)(TILE_ROWS + 4) * sizeof(int);
-    const size_t stage_bytes = vals_bytes + cols_bytes + dict_bytes + rp_bytes;
+    const size_t stage_bytes = vals_bytes + cols_bytes + dict_bytes + vdict_bytes + rp_bytes;
     constexpr int CONSUMER_WARPS = TILE_ROWS / 32;
     constexpr bool HAS_RED = (EPI == EPI_SPMV_DOT || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2);
 
@@ -166,21 +258,27 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
                 const int r1 = min(r0 + TILE_ROWS, a.n);
                 const int nz0 = __ldg(a.row_ptr + r0), nz1 = __ldg(a.row_ptr + r1);
                 const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
-                const int enc = __ldg(e.meta + 2 * tile), dlen = __ldg(e.meta + 2 * tile + 1);
+                const int4 m = __ldg(reinterpret_cast<const int4 *>(e.meta) + tile);
+                const int enc = m.x, dlen = m.y, venc = m.z, vdlen = m.w;
                 unsigned char *st = stage_base + (size_t)s * stage_bytes;
                 const unsigned rp_copy = (unsigned)(((r1 - r0 + 1 + 3) & ~3) * sizeof(int));
                 const unsigned cnt = (unsigned)(ea - sa);
-                unsigned col_copy = 0;
+                unsigned col_copy = 0, val_copy = 0;
                 if (cnt) col_copy = enc == 1 ? (unsigned)align16(cnt) : enc == 2 ? (unsigned)align16((size_t)cnt * 2) : cnt * (unsigned)sizeof(int);
+                if (cnt) val_copy = venc == 1 ? (unsigned)align16(cnt) : cnt * (unsigned)sizeof(MatT);
                 const unsigned dict_copy = (unsigned)dlen * (unsigned)sizeof(int);
-                mbar_expect_tx(&full[s], rp_copy + cnt * (unsigned)sizeof(MatT) + col_copy + dict_copy);
-                tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes, a.row_ptr + r0, rp_copy, &full[s]);
+                const unsigned vdict_copy = (unsigned)vdlen * (unsigned)sizeof(MatT);
+                mbar_expect_tx(&full[s], rp_copy + val_copy + col_copy + dict_copy + vdict_copy);
+                tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes + vdict_bytes, a.row_ptr + r0, rp_copy, &full[s]);
                 if (cnt) {
-                    tma_bulk_g2s(st, a.val + sa, cnt * (unsigned)sizeof(MatT), &full[s]);
+                    if (venc == 0) tma_bulk_g2s(st, a.val + sa, val_copy, &full[s]);
+                    else tma_bulk_g2s(st, e.vcodes + vcode_offset(sa, tile), val_copy, &full[s]);
                     if (enc == 0) tma_bulk_g2s(st + vals_bytes, a.col + sa, col_copy, &full[s]);
                     else tma_bulk_g2s(st + vals_bytes, e.codes + code_offset(sa, tile), col_copy, &full[s]);
                 }
                 if (dict_copy) tma_bulk_g2s(st + vals_bytes + cols_bytes, e.dict + (size_t)tile * DICT_SLOTS, dict_copy, &full[s]);
+                if (vdict_copy)
+                    tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes, reinterpret_cast<const MatT *>(e.vdict) + (size_t)tile * DICT_SLOTS, vdict_copy, &full[s]);
             }
         }
     } else {
@@ -191,7 +289,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
             const unsigned ph = (unsigned)(it / a.stages) & 1u;
             const int row = a.row0 + tile * TILE_ROWS + tid;
             const bool active = row < a.n;
-            const int enc = __ldg(e.meta + 2 * tile);
+            const int enc = __ldg(e.meta + META * tile), venc = __ldg(e.meta + META * tile + 2);
             VecT bi = 0, xi = 0;
             MatT di = 1;
             if (active) {
@@ -209,7 +307,9 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
             const unsigned char *c8 = st + vals_bytes;
             const unsigned short *c16 = reinterpret_cast<const unsigned short *>(st + vals_bytes);
             const int *dict = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes);
-            const int *rp = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes + dict_bytes);
+            const unsigned char *v8 = st;
+            const MatT *vdict = reinterpret_cast<const MatT *>(st + vals_bytes + cols_bytes + dict_bytes);
+            const int *rp = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes + dict_bytes + vdict_bytes);
             mbar_wait(&full[s], ph);
             if (active) {
                 const int sa = rp[0] & ~3;
@@ -222,24 +322,25 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
                     if (enc == 2) return base + (int)c16[kk];
                     return cols[kk];
                 };
+                auto val_at = [&](int kk) -> MatT { return venc ? vdict[v8[kk]] : vals[kk]; };
                 VecT sum = 0;
                 // 4 gathers in flight per step; FMA chain strictly left to right (as csr_tile_kernel)
                 for (; k + 4 <= kend; k += 4) {
                     const int c0 = col_at(k), c1 = col_at(k + 1), c2 = col_at(k + 2), c3 = col_at(k + 3);
                     const VecT x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
-                    sum = fma((VecT)vals[k], x0, sum);
-                    sum = fma((VecT)vals[k + 1], x1, sum);
-                    sum = fma((VecT)vals[k + 2], x2, sum);
-                    sum = fma((VecT)vals[k + 3], x3, sum);
+                    sum = fma((VecT)val_at(k), x0, sum);
+                    sum = fma((VecT)val_at(k + 1), x1, sum);
+                    sum = fma((VecT)val_at(k + 2), x2, sum);
+                    sum = fma((VecT)val_at(k + 3), x3, sum);
                 }
                 if (k < kend) {
                     const int c0 = col_at(k);
                     const int c1 = (k + 1 < kend) ? col_at(k + 1) : c0;
                     const int c2 = (k + 2 < kend) ? col_at(k + 2) : c0;
                     const VecT x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2);
-                    sum = fma((VecT)vals[k], x0, sum);
-                    if (k + 1 < kend) sum = fma((VecT)vals[k + 1], x1, sum);
-                    if (k + 2 < kend) sum = fma((VecT)vals[k + 2], x2, sum);
+                    sum = fma((VecT)val_at(k), x0, sum);
+                    if (k + 1 < kend) sum = fma((VecT)val_at(k + 1), x1, sum);
+                    if (k + 2 < kend) sum = fma((VecT)val_at(k + 2), x2, sum);
                 }
                 // ---- epilogue (identical to csr_tile_kernel) ----
                 if (EPI == EPI_SPMV) {
@@ -292,44 +393,98 @@ template <class MatT, class VecT, int EPI> void launch_enc_epi(const Matrix &A, 
 
 }  // namespace
 
-bool colenc_requested()
+// AMGXB_COLENC: bit 0 = compressed columns, bit 1 = value dictionaries (0 / unset: the plain kernels)
+static int colenc_flags()
 {
-    static const bool on = getenv("AMGXB_COLENC") ? atoi(getenv("AMGXB_COLENC")) != 0 : false;
-    return on;
+    static const int f = getenv("AMGXB_COLENC") ? atoi(getenv("AMGXB_COLENC")) & 3 : 0;
+    return f;
+}
+bool colenc_requested() { return colenc_flags() != 0; }
+
+static void build_value_codes(Matrix &A, cudaStream_t s)
+{
+    ColEnc &E = A.colenc;
+    const int T = A.plan.tile_rows, nt = A.plan.num_tiles;
+    DevBuf<int> stats;
+    stats.resize(4);
+    stats.zero(s);
+    const int grid = std::max(1, std::min(nt, 148 * 8));
+    if (A.mat_prec == Prec::F64) {
+        if (T == 256) valenc_build_kernel<double, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.values.as<double>(), A.n, nt, E.vcodes.ptr(), (double *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
+        else valenc_build_kernel<double, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.values.as<double>(), A.n, nt, E.vcodes.ptr(), (double *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
+    } else {
+        if (T == 256) valenc_build_kernel<float, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.values.as<float>(), A.n, nt, E.vcodes.ptr(), (float *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
+        else valenc_build_kernel<float, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.values.as<float>(), A.n, nt, E.vcodes.ptr(), (float *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
+    }
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    E.tiles_val8 = stats.to_host(s)[3];
 }
 
 // called at the end of csr_build_plan
 void csr_build_colenc(Matrix &A, cudaStream_t s)
 {
     A.colenc.on = false;
+    A.colenc.values_encoded = false;
     if (!colenc_requested() || !A.plan.use_tiles || A.plan.split != 0 || A.dist || A.n == 0 || A.bs() != 1) return;
     const int T = A.plan.tile_rows, nt = A.plan.num_tiles;
     const size_t msz = prec_size(A.mat_prec);
-    const size_t smem = 512 + (size_t)A.plan.stages * ((size_t)A.plan.max_tile_nnz * (msz + 4) + (size_t)DICT_SLOTS * 4 + (size_t)(T + 4) * 4);
+    const size_t smem = 512 + (size_t)A.plan.stages * ((size_t)A.plan.max_tile_nnz * (msz + 4) + (size_t)DICT_SLOTS * (4 + msz) + (size_t)(T + 4) * 4);
     if (smem > (size_t)216 * 1024) return;
     ColEnc &E = A.colenc;
-    E.codes.resize(align16((size_t)2 * ((size_t)A.nnz + 8)) + (size_t)32 * nt + 64);
-    E.codes.zero(s);
-    E.dict.resize((size_t)nt * DICT_SLOTS);
-    E.dict.zero(s);
-    E.meta.resize((size_t)2 * nt);
-    E.meta.zero(s);
-    DevBuf<int> stats;
-    stats.resize(4);
-    stats.zero(s);
-    const int grid = std::max(1, std::min(nt, 148 * 8));
-    if (T == 256) colenc_build_kernel<256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, nt, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
-    else colenc_build_kernel<128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, nt, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
-    count_launch();
-    AMGXB_LAUNCH_CHECK();
-    const std::vector<int> h = stats.to_host(s);
-    E.tiles_dict8 = h[0];
-    E.tiles_off16 = h[1];
-    E.tiles_raw = h[2];
+    E.meta.resize((size_t)META * nt);
+    E.meta.zero(s);                                  // encoding 0 everywhere: raw columns, raw values
+    E.tiles_dict8 = E.tiles_off16 = E.tiles_val8 = 0;
+    E.tiles_raw = nt;
+    if (colenc_flags() & 1) {
+        E.codes.resize(align16((size_t)2 * ((size_t)A.nnz + 8)) + (size_t)32 * nt + 64);
+        E.codes.zero(s);
+        E.dict.resize((size_t)nt * DICT_SLOTS);
+        E.dict.zero(s);
+        DevBuf<int> stats;
+        stats.resize(4);
+        stats.zero(s);
+        const int grid = std::max(1, std::min(nt, 148 * 8));
+        if (T == 256) colenc_build_kernel<256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, nt, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
+        else colenc_build_kernel<128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, nt, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
+        count_launch();
+        AMGXB_LAUNCH_CHECK();
+        const std::vector<int> h = stats.to_host(s);
+        E.tiles_dict8 = h[0];
+        E.tiles_off16 = h[1];
+        E.tiles_raw = h[2];
+    } else {
+        E.codes.resize(64);                          // never dereferenced (every tile has column encoding 0); keeps the pointers valid
+        E.dict.resize(64);
+    }
+    if (colenc_flags() & 2) {
+        E.vcodes.resize(align16((size_t)A.nnz + 8) + (size_t)32 * nt + 64);
+        E.vcodes.zero(s);
+        E.vdict.resize((size_t)nt * DICT_SLOTS * msz);
+        E.vdict.zero(s);
+        build_value_codes(A, s);
+        E.values_encoded = true;
+    } else {
+        E.vcodes.resize(64);
+        E.vdict.resize(64);
+    }
     E.smem_bytes = smem;
-    E.on = (h[0] + h[1]) > 0;        // nothing to gain when every tile stays raw
+    E.on = (E.tiles_dict8 + E.tiles_off16 + E.tiles_val8) > 0;        // nothing to gain when every tile stays raw
     if (getenv("AMGXB_COLENC_VERBOSE"))
-        fprintf(stderr, "[amgx_b200] colenc level %d: %d tiles of %d rows: dict8 %d, off16 %d, raw %d\n", A.level, nt, T, h[0], h[1], h[2]);
+        fprintf(stderr, "[amgx_b200] colenc level %d: %d tiles of %d rows: columns dict8 %d, off16 %d, raw %d; values dict8 %d\n", A.level, nt, T, E.tiles_dict8,
+                E.tiles_off16, E.tiles_raw, E.tiles_val8);
+}
+
+// The values of A were changed in place (AMGX_matrix_replace_coefficients, DIAGONAL_SYMMETRIC scaling): the value codes follow them.
+void csr_values_changed(Matrix &A, cudaStream_t s)
+{
+    ColEnc &E = A.colenc;
+    if (!E.values_encoded) return;
+    const int nt = A.plan.num_tiles;
+    // the column half of the per-tile descriptors stays, the value half is rewritten by the build kernel
+    build_value_codes(A, s);
+    E.on = (E.tiles_dict8 + E.tiles_off16 + E.tiles_val8) > 0;
+    (void)nt;
 }
 
 // csr_op entry of the encoded path; returns false when the caller must use the plain kernels
@@ -340,6 +495,8 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
     ea.codes = A.colenc.codes.ptr();
     ea.dict = A.colenc.dict.ptr();
     ea.meta = A.colenc.meta.ptr();
+    ea.vcodes = A.colenc.vcodes.ptr();
+    ea.vdict = A.colenc.vdict.ptr();
     AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
         TileArgs<MatT, VecT> ta;
         ta.row_ptr = A.row_ptr.ptr();

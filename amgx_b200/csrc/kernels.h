@@ -70,6 +70,7 @@ void csr_build_plan(Matrix &A, cudaStream_t s);
 int  csr_max_grid(const Matrix &A);     // number of CTAs csr_op launches (partials sizing)
 // experimental compressed column stream (k_spmv_enc.cu; AMGXB_COLENC=1, default off)
 void csr_build_colenc(Matrix &A, cudaStream_t s);                                                     // after csr_build_plan
+void csr_values_changed(Matrix &A, cudaStream_t s);                                                   // after an in-place change of A.values (no-op unless value codes exist)
 bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s, int segment);    // false: use the plain kernels
 
 // -------------------------------------------------------------------------------------------

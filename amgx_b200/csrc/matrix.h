@@ -40,9 +40,13 @@ struct ColEnc {
     bool on = false;
     DevBuf<unsigned char> codes;    // tile t's code segment starts at byte align16(2 * sa_t) + 32 * t and covers the aligned entry range [sa_t, ea_t)
     DevBuf<int> dict;               // 256 ints per tile: the sorted offsets (8-bit), or the base column in entry 0 (16-bit)
-    DevBuf<int> meta;               // 2 ints per tile: encoding (0 raw, 1 dict8, 2 off16), dictionary length padded to a multiple of 4
+    DevBuf<int> meta;               // 4 ints per tile: column encoding (0 raw, 1 dict8, 2 off16), its dictionary length (padded to a multiple of 4),
+                                    // value encoding (0 raw, 1 dict8), its dictionary length
+    DevBuf<unsigned char> vcodes;   // value codes: tile t's segment starts at byte align16(sa_t) + 32 * t
+    DevBuf<unsigned char> vdict;    // 256 matrix values per tile: the distinct values of the tile, ascending bit patterns
+    bool values_encoded = false;    // the value codes exist and must follow in-place changes of the values (csr_values_changed)
     size_t smem_bytes = 0;          // dynamic shared memory of the encoded kernel
-    int tiles_dict8 = 0, tiles_off16 = 0, tiles_raw = 0;
+    int tiles_dict8 = 0, tiles_off16 = 0, tiles_raw = 0, tiles_val8 = 0;
 };
 
 struct Matrix {

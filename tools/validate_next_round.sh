@@ -13,9 +13,13 @@ AMGXB_RUN_UNVALIDATED=1 timeout 1200 python -m pytest tests/test_gpu_dense_lu.py
     tests/test_gpu_resetup.py tests/test_golden_round2.py tests/test_gpu_classical.py -q -m gpu 2>&1 | tail -30 | tee gpurun_out/unvalidated.log
 echo "== reference goldens for the round-2 cases"
 timeout 900 python tests/golden/make_golden.py r2 2>&1 | tail -40 | tee gpurun_out/make_golden_r2.log
-echo "== experimental compressed column stream (csrc/k_spmv_enc.cu): parity suite with AMGXB_COLENC=1, then the bench with and without"
-AMGXB_COLENC=1 AMGXB_COLENC_VERBOSE=1 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/colenc_parity.log
-for E in 0 1; do
+echo "== experimental compressed matrix streams (csrc/k_spmv_enc.cu): AMGXB_COLENC=1 columns, 3 columns + value dictionaries; parity suite, then the bench"
+for E in 1 3; do
+  AMGXB_COLENC=$E AMGXB_COLENC_VERBOSE=1 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -15 | tee gpurun_out/colenc_parity_$E.log
+done
+# value codes must follow in-place value changes: replace_coefficients + resetup, DIAGONAL_SYMMETRIC scaling
+AMGXB_COLENC=3 AMGXB_RUN_UNVALIDATED=1 timeout 600 python -m pytest tests/test_gpu_resetup.py tests/test_golden_round2.py -q -m gpu -k "resetup or diagsym or replace" 2>&1 | tail -8 | tee gpurun_out/colenc_values_changed.log
+for E in 0 1 3; do
   AMGXB_COLENC=$E timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/colenc_bench_$E.err | grep '^{' | tee gpurun_out/colenc_bench_$E.json | python -c "
 import sys, json
 for l in sys.stdin:
