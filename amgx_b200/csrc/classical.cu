@@ -1253,9 +1253,18 @@ static int classical_select(const Matrix &A, const ClassicalParams &prm, int lev
 void AMGSolver::setup_classical()
 {
     cudaStream_t s = stream();
-    if (A_->dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "classical AMG on a distributed matrix is not implemented (use AGGREGATION)");
+    // Row-partitioned matrix: the hierarchy is built from the assembled global matrix, redundantly on every rank (identical to the
+    // single-GPU hierarchy of the caller's global matrix), then the finest level alone is distributed -- see distribute_finest() below.
+    std::unique_ptr<Matrix> assembled;
+    std::vector<int> g_counts, g_offs;
     if (A_->bs() != 1) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "Unsupported block size for strong connections");   // strength_base.cu:672-681
     if (A_->mat_prec != Prec::F64 || A_->vec_prec != Prec::F64) fatal(AMGX_RC_BAD_MODE, "classical AMG setup needs mode dDDI");
+    if (A_->dist) {
+        if (A_->has_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "classical AMG on a partitioned matrix with an external diagonal");
+        assembled = dist_gather_matrix(*A_, g_counts, g_offs, true);
+        assembled->compute_diag_and_plan();
+    }
+    Matrix *top = assembled ? assembled.get() : A_;
     ClassicalParams prm;
     prm.strength_threshold = cfg_->get_double("strength_threshold", scope_);
     prm.max_row_sum = cfg_->get_double("max_row_sum", scope_);
@@ -1280,7 +1289,7 @@ void AMGSolver::setup_classical()
     prm.aggressive_multipass = true;
 
     levels_.emplace_back(new AMGLevel);
-    levels_[0]->A = A_;
+    levels_[0]->A = top;
     levels_[0]->index = 0;
     int num_levels = 1;
     bool coarse_solver_exists = (bool)coarse_solver_;
@@ -1292,7 +1301,7 @@ void AMGSolver::setup_classical()
         if (num_levels >= max_levels_ || rows <= min_coarse_rows_) {
             if (dense_lu_max_rows_ != 0 && rows > dense_lu_max_rows_) { coarse_solver_.reset(); coarse_solver_exists = false; }
             L.coarsest = true;
-            if (!coarse_solver_exists) { L.smoother = make_smoother(); L.smoother->setup(A, false); }
+            if (!coarse_solver_exists) { L.smoother = make_smoother(); L.smoother->setup(num_levels == 1 ? *A_ : A, false); }
             break;
         }
         DevBuf<u8> s_con;
@@ -1346,11 +1355,83 @@ void AMGSolver::setup_classical()
             L.coarsest = true;
         }
         AMGLevel &Lcur = *levels_[num_levels - 1];
-        if (!Lcur.coarsest || !coarse_solver_exists) { Lcur.smoother = make_smoother(); Lcur.smoother->setup(*Lcur.A, false); }
+        // the smoother of the finest level works on the caller's (possibly partitioned) matrix, not on the assembled copy
+        if (!Lcur.coarsest || !coarse_solver_exists) { Lcur.smoother = make_smoother(); Lcur.smoother->setup(num_levels == 1 ? *A_ : *Lcur.A, false); }
         if (!built_next) break;
         num_levels++;
     }
+    if (assembled) distribute_finest(g_offs);
     if (coarse_solver_) coarse_solver_->setup(*levels_.back()->A, false);
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+namespace {
+__global__ void invert_perm_offset_kernel(int n, const int *__restrict__ perm_old_to_new, int offset, int *global_row_of_local)
+{
+    ROW_LOOP(old, n) global_row_of_local[perm_old_to_new[old]] = offset + old;
+}
+__global__ void gather_rows_count_kernel(int n, const int *__restrict__ rows, const int *__restrict__ rp, int *len)
+{
+    ROW_LOOP(i, n) len[i] = rp[rows[i] + 1] - rp[rows[i]];
+    if (blockIdx.x == 0 && threadIdx.x == 0) len[n] = 0;
+}
+__global__ void gather_rows_fill_kernel(int n, const int *__restrict__ rows, const int *__restrict__ rp, const int *__restrict__ ci, const double *__restrict__ va,
+                                        const int *__restrict__ orp, int *oci, double *ova)
+{
+    ROW_LOOP(i, n) {
+        const int src = rp[rows[i]], len = rp[rows[i] + 1] - src, dst = orp[i];
+        for (int k = 0; k < len; k++) { oci[dst + k] = ci[src + k]; ova[dst + k] = va[src + k]; }
+    }
+}
+}  // namespace
+
+// Classical AMG on a row-partitioned matrix.  Levels >= 1 stay what the loop above built from the assembled matrix: whole, replicated,
+// cycled redundantly by every rank (aggressive coarsening leaves them 6 % of the rows at 512^3; they are latency-, not bandwidth-bound).
+// Level 0 -- where the bytes are -- is distributed: smoothing and residual run on the caller's partitioned matrix with the usual halo
+// exchange; prolongation uses this rank's rows of P (in local row order; columns are global coarse ids, the coarse vector is whole on
+// every rank, so no exchange); restriction applies the transpose of those rows -- this rank's contribution to every coarse residual --
+// and one all-reduce over the coarse vector sums the contributions (the one collective the path adds; it replaces the reference's
+// reverse halo exchange of R's halo rows, classical_amg_level.cu:590-644).  Same operators as the single-GPU hierarchy of the global
+// matrix; the restricted residual differs from it only by the association of that sum.
+void AMGSolver::distribute_finest(const std::vector<int> &g_offs)
+{
+    cudaStream_t s = stream();
+    AMGLevel &L = *levels_[0];
+    const Matrix &A = *A_;
+    DistManager &m = *A.dist;
+    L.A = A_;
+    A_->level = 0;
+    L.cf_map.release();
+    if (L.coarsest) return;                   // a single level: nothing to transfer
+    const int n = A.n, nc = L.P->n_cols;
+    DevBuf<int> rows, len;
+    rows.resize((size_t)std::max(n, 1));
+    len.resize((size_t)n + 1);
+    const int g = grid_for(n);
+    invert_perm_offset_kernel<<<g, 256, 0, s>>>(n, m.perm_old_to_new.ptr(), g_offs[m.rank], rows.ptr());
+    Csr Pl, Rl;
+    Pl.n = n;
+    Pl.nc = nc;
+    Pl.rp.resize((size_t)n + 1);
+    gather_rows_count_kernel<<<g, 256, 0, s>>>(n, rows.ptr(), L.P->row_ptr.ptr(), len.ptr());
+    exclusive_scan(len.ptr(), Pl.rp.ptr(), (size_t)n + 1, s);
+    AMGXB_CUDA_CHECK(cudaMemcpyAsync(&Pl.nnz, Pl.rp.ptr() + n, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    Pl.ci.resize((size_t)std::max(Pl.nnz, 1));
+    Pl.va.resize((size_t)std::max(Pl.nnz, 1), Prec::F64);
+    gather_rows_fill_kernel<<<g, 256, 0, s>>>(n, rows.ptr(), L.P->row_ptr.ptr(), L.P->col_idx.ptr(), L.P->values.as<double>(), Pl.rp.ptr(), Pl.ci.ptr(),
+                                              Pl.va.as<double>());
+    count_launch(3);
+    AMGXB_LAUNCH_CHECK();
+    transpose_csr(Pl, Rl, s);
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));      // the assembled P and R are released next
+    L.P = to_matrix(Pl, A, s);
+    L.R = to_matrix(Rl, A, s);
+    csr_build_plan(*L.P, s);
+    csr_build_plan(*L.R, s);
+    L.cla_reduce_over = A_;
+    L.r.resize((size_t)A.n_cols, A.vec_prec);
+    L.r.zero(s);
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
@@ -1361,6 +1442,7 @@ void classical_restrict(AMGLevel &L, const DevVec &r, cudaStream_t s)
     g.x = r.ptr();
     g.y = L.bc.ptr();
     csr_op(*L.R, EPI_SPMV, g, s, 0);
+    if (L.cla_reduce_over) dist_allreduce_vec(*L.cla_reduce_over, L.bc.ptr(), L.bc.prec, (size_t)L.R->n, s);
 }
 // xout = x + P e  (prolongateAndApplyCorrection: multiply(P, e, tmp); axpby(x, tmp, x, 1, 1); classical_amg_level.cu:851-913)
 void classical_prolong_add(AMGLevel &L, const void *x, void *xout, cudaStream_t s)

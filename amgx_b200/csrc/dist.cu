@@ -720,7 +720,10 @@ namespace {
 __global__ void iota_off_kernel(int n, int off, int *v) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = off + i; }
 }
 
-std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &counts, std::vector<int> &offs)
+// caller_order = false: rank r's rows appear at offs[r] + (local row index), the order the distributed vectors have (replicated coarse tail);
+// caller_order = true: at offs[r] + (row index in the caller's upload order), i.e. the assembled matrix IS the caller's global matrix, entry
+// order included, when the ranks own contiguous blocks (classical AMG on a partitioned matrix builds its hierarchy from it).
+std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &counts, std::vector<int> &offs, bool caller_order)
 {
     DistManager &m = *A.dist;
     cudaStream_t s = A.stream();
@@ -751,25 +754,49 @@ std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &co
     // global ids of the local columns (owned: offset + local index; halo: asked from the owner)
     DevBuf<int> gid;
     gid.resize((size_t)std::max(A.n_cols, 1));
-    iota_off_kernel<<<std::max(1, std::min(ceil_div(A.n_cols, 256), 1024)), 256, 0, s>>>(A.n_cols, offs[rank], gid.ptr());
-    count_launch();
+    std::vector<int> h_perm;        // caller_order: position in the caller's order -> local row
+    if (caller_order) {
+        h_perm = m.perm_old_to_new.to_host(s);
+        std::vector<int> g0((size_t)std::max(A.n_cols, 1), 0);
+        for (int old = 0; old < A.n; old++) g0[h_perm[old]] = offs[rank] + old;
+        gid.from_any(g0.data(), g0.size(), s);
+    } else {
+        iota_off_kernel<<<std::max(1, std::min(ceil_div(A.n_cols, 256), 1024)), 256, 0, s>>>(A.n_cols, offs[rank], gid.ptr());
+        count_launch();
+    }
     dist_exchange_int(A, gid.ptr(), s);
     std::vector<int> h_gid = gid.to_host(s), h_rp = A.row_ptr.to_host(s), h_ci = A.col_idx.to_host(s);
     // padded all-gather of row lengths, global columns and values
     std::vector<int> len_pad((size_t)std::max(n_max, 1), 0), col_pad((size_t)std::max(nnz_max, 1), 0);
-    for (int i = 0; i < A.n; i++) len_pad[i] = h_rp[i + 1] - h_rp[i];
-    for (int k = 0; k < A.nnz; k++) col_pad[k] = h_gid[h_ci[k]];
     DevBuf<int> d_len, d_col, r_len, r_col;
     DevBytes d_val, r_val;
-    d_len.from_any(len_pad.data(), len_pad.size(), s);
-    d_col.from_any(col_pad.data(), col_pad.size(), s);
-    r_len.resize(len_pad.size() * world);
-    r_col.resize(col_pad.size() * world);
     const size_t val_pad = (size_t)std::max(nnz_max, 1) * bs * msz;
     d_val.resize(val_pad);
     r_val.resize(val_pad * world);
     AMGXB_CUDA_CHECK(cudaMemsetAsync(d_val.p, 0, val_pad, s));
-    if (A.nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(d_val.p, A.values.ptr(), (size_t)A.nnz * bs * msz, cudaMemcpyDeviceToDevice, s));
+    if (!caller_order) {
+        for (int i = 0; i < A.n; i++) len_pad[i] = h_rp[i + 1] - h_rp[i];
+        for (int k = 0; k < A.nnz; k++) col_pad[k] = h_gid[h_ci[k]];
+        if (A.nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(d_val.p, A.values.ptr(), (size_t)A.nnz * bs * msz, cudaMemcpyDeviceToDevice, s));
+    } else {
+        std::vector<char> v_loc((size_t)std::max(A.nnz, 1) * bs * msz), v_out((size_t)std::max(A.nnz, 1) * bs * msz);
+        if (A.nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(v_loc.data(), A.values.ptr(), (size_t)A.nnz * bs * msz, cudaMemcpyDeviceToHost, s));
+        AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+        size_t k = 0;
+        for (int old = 0; old < A.n; old++) {
+            const int i = h_perm[old], len = h_rp[i + 1] - h_rp[i];
+            len_pad[old] = len;
+            for (int kk = h_rp[i]; kk < h_rp[i + 1]; kk++) col_pad[k + (size_t)(kk - h_rp[i])] = h_gid[h_ci[kk]];
+            if (len) memcpy(&v_out[k * bs * msz], &v_loc[(size_t)h_rp[i] * bs * msz], (size_t)len * bs * msz);
+            k += (size_t)len;
+        }
+        if (A.nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(d_val.p, v_out.data(), (size_t)A.nnz * bs * msz, cudaMemcpyHostToDevice, s));
+        AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));      // v_out goes out of scope below
+    }
+    d_len.from_any(len_pad.data(), len_pad.size(), s);
+    d_col.from_any(col_pad.data(), col_pad.size(), s);
+    r_len.resize(len_pad.size() * world);
+    r_col.resize(col_pad.size() * world);
     AMGXB_NCCL_CHECK(ncclGroupStart());
     AMGXB_NCCL_CHECK(ncclAllGather(d_len.ptr(), r_len.ptr(), len_pad.size(), ncclInt32, comm_of(A), s));
     AMGXB_NCCL_CHECK(ncclAllGather(d_col.ptr(), r_col.ptr(), col_pad.size(), ncclInt32, comm_of(A), s));
@@ -796,7 +823,7 @@ std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &co
     G->mat_prec = A.mat_prec;
     G->vec_prec = A.vec_prec;
     upload_matrix(*G, N, (int)NNZ, A.bx, A.by, g_rp.data(), g_ci.data(), g_va.data(), nullptr);
-    if (getenv("AMGXB_TAIL_CHECK") && bs == 1 && A.vec_prec == Prec::F64) {
+    if (getenv("AMGXB_TAIL_CHECK") && !caller_order && bs == 1 && A.vec_prec == Prec::F64) {
         // self-check: y = A x through the distributed operator must equal the owned slice of G x for x(g) = sin(1 + 0.37 g);
         // and an all-gather of the owned global ids must reproduce 0..N-1
         std::vector<double> xg((size_t)N), xl((size_t)A.n_cols);
@@ -850,6 +877,12 @@ std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &co
                 rank, world, N, NNZ, A.n, m.n_halo, (int)m.neighbors.size(), md, mx, asym, bad, cks);
     }
     return G;
+}
+
+void dist_allreduce_vec(const Matrix &A, void *v, Prec prec, size_t n, cudaStream_t s)
+{
+    if (!A.dist || n == 0) return;
+    AMGXB_NCCL_CHECK(ncclAllReduce(v, v, n, prec == Prec::F64 ? ncclDouble : ncclFloat, ncclSum, comm_of(A), s));
 }
 
 void dist_allgatherv_int_inplace(const Matrix &A, int *v, const std::vector<int> &counts, const std::vector<int> &offs, cudaStream_t s)

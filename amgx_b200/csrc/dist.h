@@ -42,7 +42,8 @@ void dist_wait_halo(const Matrix &A, cudaStream_t s);                           
 void dist_exchange_int(const Matrix &A, int *x, cudaStream_t s);                   // blocking (stream-ordered) int exchange, x has n_cols entries
 long long dist_allreduce_ll(const Matrix &A, long long v, int op);                 // host value, op: 0 sum, 1 min, 2 max
 // replicated coarse tail
-std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &counts, std::vector<int> &offs);
+std::unique_ptr<Matrix> dist_gather_matrix(const Matrix &A, std::vector<int> &counts, std::vector<int> &offs, bool caller_order = false);
+void dist_allreduce_vec(const Matrix &A, void *v, Prec prec, size_t n, cudaStream_t s);   // in-place sum over the ranks, on stream s
 void dist_allgatherv_int_inplace(const Matrix &A, int *v, const std::vector<int> &counts, const std::vector<int> &offs, cudaStream_t s);
 void dist_allgatherv_inplace(const Matrix &A, void *v, Prec prec, int bsize, const std::vector<int> &counts, const std::vector<int> &offs, cudaStream_t s);
 std::shared_ptr<DistManager> dist_coarsen(const Matrix &A, DevBuf<int> &aggregates, int n_agg, int *n_interior_c);

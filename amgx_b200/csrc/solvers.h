@@ -260,6 +260,7 @@ struct AMGLevel {
     // classical
     std::unique_ptr<Matrix> P, R;
     DevBuf<int> cf_map;
+    const Matrix *cla_reduce_over = nullptr;   // partitioned finest level: R holds this rank's columns only, the restricted residual is summed over the ranks of this matrix
     // cycle work vectors (sized for the NEXT level: bc, xc) and residual of this level
     DevVec bc, xc, r;
     bool init_cycle = false;
@@ -299,6 +300,7 @@ protected:
     int cycle_type_ = CYC_V;
     void setup_aggregation();
     void setup_classical();
+    void distribute_finest(const std::vector<int> &g_offs);   // classical.cu: classical AMG on a row-partitioned matrix
     void validate_config();       // everything the setup would reject for configuration reasons alone (called by the constructor)
     void replicate_tail(long long tail_rows);   // distributed hierarchy: assemble the small levels on every rank (amg.cu)
     std::unique_ptr<Solver> make_smoother();

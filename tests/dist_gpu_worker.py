@@ -268,6 +268,63 @@ def comm_maps_section(rank, world, rsc, lib, cfg):
     dist.barrier()
 
 
+def classical_section(rank, world, rsc, lib):
+    """FGMRES + classical AMG (BASELINE config 3 style) on a row-partitioned matrix: the hierarchy is the single-GPU hierarchy of the global
+    matrix (levels >= 1 replicated, level 0 distributed, one all-reduce per restriction), so level sizes and the iteration count must equal
+    the CPU oracle's run on the global system and the residual history may differ only by the association of the restriction sum and of
+    the dot products.  Opt-in (AMGXB_RUN_UNVALIDATED=1) until validated on a device."""
+    import ctypes as C
+    sys.path.insert(0, str(ROOT / "tests"))
+    from golden.make_golden import cfg_fgmres_classical
+    for name, (nx, ny, nzl), kw in (("aggr_multipass_d2", (14, 12, 7), dict()), ("d2_only", (12, 10, 6), dict(aggressive_levels=0)),
+                                    ("d1", (12, 10, 6), dict(interpolator="D1", aggressive_levels=0, max_elements=-1))):
+        rp, ci, va = gallery.poisson7pt(nx, ny, nzl * world)
+        ng = rp.shape[0] - 1
+        offsets = np.array([nx * ny * nzl * r for r in range(world + 1)], np.int64)
+        lo, hi = int(offsets[rank]), int(offsets[rank + 1])
+        lrp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+        lci = ci[rp[lo]:rp[hi]].astype(np.int64)
+        lva = np.ascontiguousarray(va[rp[lo]:rp[hi]])
+        cfgd = cfg_fgmres_classical(**kw)
+        a = cfgd["solver"]["preconditioner"]
+        cfg = capi.Config(cfgd)
+        A = capi.Matrix(rsc)
+        dh = C.c_void_p()
+        assert lib.AMGX_distribution_create(C.byref(dh), cfg.h) == 0
+        assert lib.AMGX_distribution_set_partition_data(dh, 1, offsets.ctypes.data) == 0
+        rc = lib.AMGX_matrix_upload_distributed(A.h, ng, hi - lo, lci.shape[0], 1, 1, lrp.ctypes.data, lci.ctypes.data, lva.ctypes.data, None, dh)
+        assert rc == 0, rc
+        lib.AMGX_distribution_destroy(dh)
+        b, sol = capi.Vector(rsc), capi.Vector(rsc)
+        b.bind(A)
+        sol.bind(A)
+        b.upload(np.ones(hi - lo))
+        sol.set_zero(hi - lo)
+        slv = capi.Solver(rsc, cfg)
+        slv.setup(A)
+        slv.solve(b, sol)
+        assert slv.status == "success", (name, slv.status)
+        hist = np.asarray(slv.residual_history()).ravel()
+        o = orc.ClassicalAMG(rp, ci, va, selector="PMIS", max_levels=a["max_levels"], min_coarse_rows=a["min_coarse_rows"], presweeps=a["presweeps"],
+                             postsweeps=a["postsweeps"], coarsest_sweeps=a["coarsest_sweeps"], smoother=a["smoother"]["solver"],
+                             omega=a["smoother"]["relaxation_factor"], strength_threshold=a["strength_threshold"], max_row_sum=a["max_row_sum"],
+                             interpolator=a["interpolator"], aggressive_levels=a["aggressive_levels"], interp_max_elements=a["interp_max_elements"])
+        sc = cfgd["solver"]
+        xo, ito, histo, convo = orc.fgmres(rp, ci, va, np.ones(ng), amg=o, tol=sc["tolerance"], max_iters=sc["max_iters"], restart=sc["gmres_n_restart"])
+        assert slv.num_levels() == o.num_levels(), (name, slv.num_levels(), o.num_levels())
+        assert slv.iterations_number == ito and convo, (name, slv.iterations_number, ito)
+        assert np.max(np.abs(hist - histo) / histo[0]) < 1e-9, (name, np.max(np.abs(hist - histo) / histo[0]))
+        parts = [torch.zeros(int(offsets[r + 1] - offsets[r]), dtype=torch.float64, device="cuda") for r in range(world)]
+        dist.all_gather(parts, torch.from_numpy(sol.download()).cuda())
+        xfull = torch.cat(parts).cpu().numpy()
+        assert np.max(np.abs(xfull - xo)) <= 1e-8 * np.max(np.abs(xo)), name
+        if rank == 0:
+            print(f"DIST_CLASSICAL_OK world={world} case={name} levels={slv.num_levels()} iters={ito} max_hist_dev={np.max(np.abs(hist - histo) / histo[0]):.2e}", flush=True)
+        for ob in (slv, sol, b, A, cfg):
+            ob.destroy()
+    dist.barrier()
+
+
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -343,6 +400,7 @@ def main():
         partition_vector_section(rank, world, rsc, lib, cfg)
         comm_maps_section(rank, world, rsc, lib, cfg)
         read_distributed_section(rank, world, rsc, lib, cfg)
+        classical_section(rank, world, rsc, lib)
     rsc.destroy()
     cfg.destroy()
     capi.finalize()
