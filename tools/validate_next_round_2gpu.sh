@@ -14,3 +14,6 @@ for l in sys.stdin:
     d=json.loads(l); print('  tail $T: its', d['config']['iterations_per_step'], d['config']['solve_status'], 'global its/s', round(d['config']['global_iterations_per_sec'],1))"
 done
 echo "== 4 ranks need --gpus 4: AMGXB_TAIL_ROWS=131072 vs 0 at --grid 96 must both give 51 iterations"
+echo "== config 3 (FGMRES + classical AMG) on 1 and 2 GPUs, same global 128^3 problem: same iteration count expected"
+timeout 300 python tools/bench_classical_dist.py 128 2>&1 | grep '^{' | tee gpurun_out/cla_dist_1.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29731 tools/bench_classical_dist.py 128 2>&1 | grep '^{' | tee gpurun_out/cla_dist_2.json
