@@ -435,7 +435,7 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse,
     if (n_post > 0) sm->smooth(b, x, false, n_post, have_fuse ? &f : nullptr, in_alt);
 }
 
-double AMGSolver::host_dot(const DevVec &x, const DevVec &y, size_t n)
+double AMGSolver::host_dot(const DevVec &x, const DevVec &y, size_t n, const Matrix *over)
 {
     cudaStream_t s = stream();
     ReduceCtx red = red_ctx();
@@ -443,6 +443,7 @@ double AMGSolver::host_dot(const DevVec &x, const DevVec &y, size_t n)
     double h = 0;
     AMGXB_CUDA_CHECK(cudaMemcpyAsync(&h, red.scal + S_TMP0, sizeof(double), cudaMemcpyDeviceToHost, s));
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (over && over->dist) dist_allreduce_host(*over, &h, 1, 0);      // owned rows of every rank
     return h;
 }
 
@@ -454,7 +455,6 @@ void AMGSolver::cg_cycle_dispatch(int lvl, DevVec &b, DevVec &x, bool flex)
     cudaStream_t s = stream();
     AMGLevel &L = *levels_[lvl];
     Matrix &A = *L.A;
-    if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "CG / CGF cycles on a distributed matrix");
     const size_t n = (size_t)A.n * A.by, N = (size_t)A.n_cols * A.by;
     const Prec vp = A.vec_prec;
     const int type = flex ? CYC_CGF : CYC_CG;
@@ -462,6 +462,7 @@ void AMGSolver::cg_cycle_dispatch(int lvl, DevVec &b, DevVec &x, bool flex)
         if (v->n != N) { v->resize(N, vp); v->zero(s); }
     DevVec &y = L.cg_y, &z = L.cg_z, &r = L.cg_r, &p = L.cg_p, &d = L.cg_d;
     auto apply = [&](DevVec &in, DevVec &out) {
+        dist_exchange_halo(A, in, s);
         CsrOpArgs g;
         g.x = in.ptr();
         g.y = out.ptr();
@@ -476,12 +477,12 @@ void AMGSolver::cg_cycle_dispatch(int lvl, DevVec &b, DevVec &x, bool flex)
     L.init_cycle = true;
     cycle(lvl, r, z, nullptr, type);                               // z = M r
     vec_copy(p.ptr(), z.ptr(), vp, n, s);
-    double rz = flex ? 0.0 : host_dot(r, z, n);
+    double rz = flex ? 0.0 : host_dot(r, z, n, &A);
     int k = 0;
     while (true) {
         apply(p, y);
-        if (flex) rz = host_dot(r, z, n);
-        const double alpha = rz / host_dot(y, p, n);
+        if (flex) rz = host_dot(r, z, n, &A);
+        const double alpha = rz / host_dot(y, p, n, &A);
         vec_axpy(p.ptr(), x.ptr(), vp, n, alpha, s);
         if (++k == cycle_iters_) break;
         if (flex) vec_copy(d.ptr(), r.ptr(), vp, n, s);
@@ -490,10 +491,10 @@ void AMGSolver::cg_cycle_dispatch(int lvl, DevVec &b, DevVec &x, bool flex)
         L.init_cycle = true;
         cycle(lvl, r, z, nullptr, type);
         double beta;
-        if (flex) beta = host_dot(z, d, n) / rz;
+        if (flex) beta = host_dot(z, d, n, &A) / rz;
         else {
             const double rz_old = rz;
-            rz = host_dot(r, z, n);
+            rz = host_dot(r, z, n, &A);
             beta = rz / rz_old;
         }
         vec_axpby(z.ptr(), p.ptr(), p.ptr(), vp, n, 1.0, beta, s);

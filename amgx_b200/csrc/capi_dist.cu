@@ -189,8 +189,10 @@ AMGX_RC AMGX_matrix_comm_from_maps(AMGX_matrix_handle mtx, int allocated_halo_de
 {
     API3_BEGIN
     MatrixH *m = chk<MatrixH>(mtx, MAGIC_MTX, "matrix");
-    (void)allocated_halo_depth;
-    if (num_import_rings > 1) fatal(AMGX_RC_NOT_IMPLEMENTED, "AMGX_matrix_comm_from_maps with more than one import ring");
+    // the reference's own limits (src/amgx_c.cu:1871-1887)
+    if (allocated_halo_depth > 1) fatal(AMGX_RC_BAD_PARAMETERS, "Allocated_halo_depth > 1 currently not supported");
+    if (num_import_rings > 1) fatal(AMGX_RC_BAD_PARAMETERS, "num_import_rings > 1 currently not supported");
+    if (allocated_halo_depth != num_import_rings) fatal(AMGX_RC_BAD_PARAMETERS, "num_import_rings != allocated_halo_depth currently not supported");
     if (max_num_neighbors < 0 || (max_num_neighbors > 0 && (!neighbors || !send_ptrs || !send_maps || !recv_ptrs || !recv_maps)))
         fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_matrix_comm_from_maps: null map arrays");
     std::vector<int> ssz(max_num_neighbors), rsz(max_num_neighbors);

@@ -291,7 +291,7 @@ protected:
     enum CycleType { CYC_V = 0, CYC_W = 1, CYC_F = 2, CYC_CG = 3, CYC_CGF = 4 };
     void cg_cycle_dispatch(int lvl, DevVec &b, DevVec &x, bool flex);               // CG(F)_CycleDispatcher::dispatch
     void scaled_correction(AMGLevel &L, const DevVec &rf, DevVec &x);              // x += lambda * smoothed(P xc)
-    double host_dot(const DevVec &x, const DevVec &y, size_t n);
+    double host_dot(const DevVec &x, const DevVec &y, size_t n, const Matrix *over = nullptr);   // over: all-reduce across the ranks of this matrix
     int cycle_iters_ = 2, scaling_smoother_steps_ = 2, reuse_scale_ = 0;
     GraphInhibit inhibit_;
     std::vector<DevBuf<int>> reuse_aggregates_;     // resetup with structure_reuse_levels: aggregates carried over, per level
