@@ -92,6 +92,9 @@ void AMGSolver::solver_setup(bool reuse)
     // AMGX_solver_resetup with structure_reuse_levels = k: the aggregates (hence R and P) of the first k-1 coarsenings are
     // kept and only the Galerkin values, the smoothers and everything below are recomputed (src/amg.cu:229-272: a level is
     // rebuilt when structure_reuse_levels <= its 1-based index; -1 keeps the structure of every level).
+    seg_cycle_.reset();          // captured cycles refer to the buffers of the previous hierarchy
+    seg_cycle_zero_.reset();
+    seg_coarse_.reset();
     reuse_aggregates_.clear();
     reuse_n_coarse_.clear();
     const int reuse_levels = cfg_->get_int("structure_reuse_levels", scope_);
@@ -385,7 +388,20 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse,
     // next level is the coarsest a single fixed cycle is launched whatever the type (fixed_cycle.cu:169-179).  The second
     // visit continues from the xc the first one left (its init flag has been cleared).
     levels_[lvl + 1]->init_cycle = true;
-    if (type == CYC_V || levels_[lvl + 1]->coarsest) {
+    // AMGXB_GRAPH_COARSE=1 (experimental, default off): when the cycle is a preconditioner whose caller cannot capture it (FGMRES hands in a
+    // different vector pair every iteration), everything below the finest level still works on fixed buffers (bc, xc of level 0) and
+    // is replayed as one CUDA graph: the launch-latency-bound tail of the hierarchy costs one graph launch.
+    static const bool graph_coarse = getenv("AMGXB_GRAPH_COARSE") ? atoi(getenv("AMGXB_GRAPH_COARSE")) != 0 : false;
+    bool capturing = false;
+    if (graph_coarse && finest && type == CYC_V) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); st = cudaStreamCaptureStatusActive; }
+        capturing = (st != cudaStreamCaptureStatusNone);
+    }
+    if (graph_coarse && finest && type == CYC_V && !capturing && !levels_[1]->A->dist) {
+        run_segment(seg_coarse_, L.bc.ptr(), L.xc.ptr(), [&] { levels_[1]->init_cycle = true; cycle(1, L.bc, L.xc, nullptr, CYC_V); });
+        levels_[1]->init_cycle = false;
+    } else if (type == CYC_V || levels_[lvl + 1]->coarsest) {
         cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_V);
     } else if (type == CYC_W) {
         cycle(lvl + 1, L.bc, L.xc, nullptr, CYC_W);

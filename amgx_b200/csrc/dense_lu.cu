@@ -150,7 +150,8 @@ protected:
         Matrix &A = *A_;
         // A.dist: the reference factors the diagonal block each rank owns -- block Jacobi over the partitions, halo values only enter
         // through the right-hand side (dense_lu_solver.cu:893-912).  Its all-gathered exact solve (exact_coarse_solve = 1, CLASSICAL only,
-        // dense_lu_solver.cu:667-669) is not provided -- and classical AMG is single-GPU here anyway.
+        // dense_lu_solver.cu:667-669) is not provided as such; classical AMG on a partitioned matrix keeps its coarse levels whole on
+        // every rank (classical.cu: distribute_finest), so its coarsest solve is exact without it.
         if (A.dist && cfg_->get_int("exact_coarse_solve", scope_) != 0 && cfg_->get_string("algorithm", scope_) == "CLASSICAL")
             fatal(AMGX_RC_NOT_IMPLEMENTED, "DENSE_LU_SOLVER with exact_coarse_solve=1 on a distributed matrix");
         if (A.bx != A.by) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "DENSE_LU_SOLVER needs square blocks");

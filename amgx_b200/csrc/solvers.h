@@ -311,6 +311,7 @@ protected:
     double coarsen_threshold_ = 1.0;
     std::unique_ptr<Solver> coarse_solver_;
     GraphSegment seg_cycle_, seg_cycle_zero_;   // stand-alone AMG solver: the V-cycle between two convergence checks
+    GraphSegment seg_coarse_;                   // AMGXB_GRAPH_COARSE=1: levels >= 1 of a V-cycle used as a preconditioner (fixed bc / xc buffers)
 };
 
 template <class F> void Solver::run_segment(GraphSegment &g, const void *k0, const void *k1, F &&body)

@@ -30,3 +30,11 @@ timeout 900 python tools/bench_configs.py block_pg 2>&1 | grep '^{' | tee gpurun
 import sys, json
 for l in sys.stdin:
     d=json.loads(l); print('  ', d['case'], 'colors', d['colors_L0'], 'iters', d['iters'], 'its/s', round(d['iters_per_s'],1), d['status'])"
+echo "== config 3: coarse levels of the preconditioner V-cycle replayed as one CUDA graph (AMGXB_GRAPH_COARSE=1): parity, then 128^3 / 256^3 with and without"
+AMGXB_GRAPH_COARSE=1 timeout 600 python -m pytest tests/test_gpu_classical.py -x -q -m gpu 2>&1 | tail -4 | tee gpurun_out/graph_coarse_parity.log
+for G in 0 1; do
+  AMGXB_GRAPH_COARSE=$G timeout 900 python tools/bench_classical.py 128 256 2>&1 | grep '"engine": "ours"' | tee gpurun_out/graph_coarse_$G.json | python -c "
+import sys, json
+for l in sys.stdin:
+    d=json.loads(l); print('  GRAPH_COARSE=$G nx', d['nx'], 'iters', d['iters'], 'its/s', round(d['iters_per_s'],1), 'launches', d['launches'])"
+done
