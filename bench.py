@@ -290,10 +290,11 @@ def main():
         # a number taken under a profiler is not a bench value, but the byte counters are deterministic for a given grid)
         traffic = None
         tf = ROOT / "profiles" / f"r01_ncu_traffic_spmv_{nx}.json"
-        if tf.exists():
+        enc = os.environ.get("AMGXB_COLENC", "0")
+        if tf.exists() and enc in ("", "0"):      # the capture is of the plain kernel; an experimental encoded stream moves fewer bytes
             traffic = json.loads(tf.read_text())["traffic_bytes_per_launch"]
         roof = {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": byt / ms / 1e6 / peak, "traffic": traffic,
-                "kernel": "csr_tile_kernel<EPI_SPMV> (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt, "peak_source": peak_src,
+                "kernel": "csr_tile_kernel<EPI_SPMV> (fine level)" if enc in ("", "0") else f"csr_tile_enc_kernel<EPI_SPMV> (fine level, AMGXB_COLENC={enc})", "ms_per_launch": ms, "algorithmic_bytes": byt, "peak_source": peak_src,
                 "fused_jacobi_sweep": {"ms_per_launch": ms_j, "algorithmic_bytes": byt + 4 * n * 8, "achieved": (byt + 4 * n * 8) / ms_j / 1e6,
                                        "frac": (byt + 4 * n * 8) / ms_j / 1e6 / peak}}
     cpu = None
