@@ -97,6 +97,9 @@ void AMGSolver::solver_setup(bool reuse)
     seg_coarse_.reset();
     reuse_aggregates_.clear();
     reuse_n_coarse_.clear();
+    reuse_P_.clear();
+    reuse_R_.clear();
+    reuse_cf_.clear();
     const int reuse_levels = cfg_->get_int("structure_reuse_levels", scope_);
     if (reuse && reuse_levels != 0 && algorithm_ == "AGGREGATION" && !levels_.empty() && !A_->dist) {
         for (size_t l = 0; l + 1 < levels_.size(); l++) {
@@ -106,8 +109,17 @@ void AMGSolver::solver_setup(bool reuse)
             reuse_aggregates_.back().swap(levels_[l]->aggregates);
             reuse_n_coarse_.push_back(levels_[l]->n_coarse);
         }
-    } else if (reuse && reuse_levels != 0 && algorithm_ != "AGGREGATION") {
-        amgx_printf("Warning: structure_reuse_levels is honoured for AGGREGATION hierarchies only; the classical hierarchy is rebuilt\n");
+    } else if (reuse && reuse_levels != 0 && algorithm_ == "CLASSICAL" && !levels_.empty() && !A_->dist) {
+        // classical levels keep P and R whole -- pattern AND values -- and only A_c = R A P is recomputed (classical_amg_level.cu:274-291)
+        for (size_t l = 0; l + 1 < levels_.size(); l++) {
+            if (reuse_levels != -1 && reuse_levels <= (int)l + 1) break;
+            if (!levels_[l]->P || !levels_[l]->R || (l == 0 && levels_[0]->A->n != A_->n)) break;
+            reuse_P_.push_back(std::move(levels_[l]->P));
+            reuse_R_.push_back(std::move(levels_[l]->R));
+            reuse_cf_.emplace_back();
+            reuse_cf_.back().swap(levels_[l]->cf_map);
+            reuse_n_coarse_.push_back(levels_[l]->n_coarse);
+        }
     }
     levels_.clear();
     if (dense_lu_num_rows_ > 0) min_coarse_rows_ = dense_lu_num_rows_ / A_->by;   // src/amg.cu:1154-1157

@@ -1259,6 +1259,8 @@ void AMGSolver::setup_classical()
     std::vector<int> g_counts, g_offs;
     if (A_->bs() != 1) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "Unsupported block size for strong connections");   // strength_base.cu:672-681
     if (A_->mat_prec != Prec::F64 || A_->vec_prec != Prec::F64) fatal(AMGX_RC_BAD_MODE, "classical AMG setup needs mode dDDI");
+    if (A_->dist && cfg_->get_string("interpolator", scope_) == "D1")      // classical_amg_level.cu:268-273
+        fatal(AMGX_RC_NOT_IMPLEMENTED, "D1 interpolation is not supported in distributed settings");
     if (A_->dist) {
         if (A_->has_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "classical AMG on a partitioned matrix with an external diagonal");
         assembled = dist_gather_matrix(*A_, g_counts, g_offs, true);
@@ -1306,22 +1308,40 @@ void AMGSolver::setup_classical()
         }
         DevBuf<u8> s_con;
         const int lvl = num_levels - 1;
-        const int nc = classical_select(A, prm, lvl, s_con, L.cf_map, s);
+        // AMGX_solver_resetup with structure_reuse_levels: P and R of the previous setup stand, only the Galerkin product follows the new values
+        const bool reused = (size_t)lvl < reuse_P_.size() && reuse_P_[lvl] && reuse_P_[lvl]->n == rows;
+        if (!reused) { reuse_P_.resize(std::min(reuse_P_.size(), (size_t)lvl)); reuse_R_.resize(reuse_P_.size()); }   // the chain ends at the first rebuilt level
+        int nc;
+        if (reused) {
+            L.cf_map.swap(reuse_cf_[lvl]);
+            nc = reuse_n_coarse_[lvl];
+        } else {
+            nc = classical_select(A, prm, lvl, s_con, L.cf_map, s);
+        }
         L.n_coarse = nc;
         bool built_next = false;
         if ((double)nc <= coarsen_threshold_ * (double)rows && nc != rows && nc >= min_coarse_rows_) {
             Csr P, R;
-            if (lvl < prm.aggressive_levels || (!prm.d2 && !prm.d1)) interp_multipass(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
-            else if (prm.d1) interp_d1(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
-            else interp_d2(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
-            s_con.release();
-            if (prm.max_elmts > 0 && P.n > 0) truncate_max_elements(P, prm.max_elmts, s);
-            transpose_csr(P, R, s);
+            if (reused) {
+                L.P = std::move(reuse_P_[lvl]);
+                L.R = std::move(reuse_R_[lvl]);
+            } else {
+                if (lvl < prm.aggressive_levels || (!prm.d2 && !prm.d1)) interp_multipass(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
+                else if (prm.d1) interp_d1(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
+                else interp_d2(A, L.cf_map.ptr(), s_con.ptr(), nc, P, s);
+                s_con.release();
+                if (prm.max_elmts > 0 && P.n > 0) truncate_max_elements(P, prm.max_elmts, s);
+                transpose_csr(P, R, s);
+                L.P = to_matrix(P, A, s);
+                L.R = to_matrix(R, A, s);
+                csr_build_plan(*L.P, s);
+                csr_build_plan(*L.R, s);
+            }
             // A_c = R (A P)
             Csr AP;
             AP.n = rows;
             AP.nc = nc;
-            spgemm_csr(rows, A.row_ptr, A.col_idx, A.values, P.rp, P.ci, P.va, AP.rp, AP.ci, AP.va, &AP.nnz, s);
+            spgemm_csr(rows, A.row_ptr, A.col_idx, A.values, L.P->row_ptr, L.P->col_idx, L.P->values, AP.rp, AP.ci, AP.va, &AP.nnz, s);
             std::unique_ptr<AMGLevel> next(new AMGLevel);
             next->owned_A.reset(new Matrix);
             Matrix &Ac = *next->owned_A;
@@ -1331,14 +1351,10 @@ void AMGSolver::setup_classical()
             Ac.vec_prec = A.vec_prec;
             Ac.n = nc;
             Ac.n_cols = nc;
-            spgemm_csr(nc, R.rp, R.ci, R.va, AP.rp, AP.ci, AP.va, Ac.row_ptr, Ac.col_idx, Ac.values, &Ac.nnz, s);
+            spgemm_csr(nc, L.R->row_ptr, L.R->col_idx, L.R->values, AP.rp, AP.ci, AP.va, Ac.row_ptr, Ac.col_idx, Ac.values, &Ac.nnz, s);
             Ac.values.n = (size_t)Ac.nnz;
             AP.rp.release(); AP.ci.release(); AP.va.b.release();
             Ac.compute_diag_and_plan();
-            L.P = to_matrix(P, A, s);
-            L.R = to_matrix(R, A, s);
-            csr_build_plan(*L.P, s);
-            csr_build_plan(*L.R, s);
             next->A = next->owned_A.get();
             next->index = num_levels;
             L.bc.resize((size_t)nc, A.vec_prec);

@@ -296,6 +296,8 @@ protected:
     GraphInhibit inhibit_;
     std::vector<DevBuf<int>> reuse_aggregates_;     // resetup with structure_reuse_levels: aggregates carried over, per level
     std::vector<int> reuse_n_coarse_;
+    std::vector<std::unique_ptr<Matrix>> reuse_P_, reuse_R_;   // classical: P and R carried over whole
+    std::vector<DevBuf<int>> reuse_cf_;
     void cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse, int type = -1);   // type -1: the configured cycle
     int cycle_type_ = CYC_V;
     void setup_aggregation();

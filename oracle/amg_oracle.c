@@ -669,6 +669,39 @@ ORC_API orc_amg *orc_amg_setup_classical(int n, const int *rp, const int *ci, co
         L->tmp = (double *)malloc(sizeof(double) * (size_t)(L->n > 0 ? L->n : 1));
         if (num_levels >= max_levels || L->n <= min_coarse_rows) { L->coarsest = 1; break; }
         const int lvl = num_levels - 1;
+        /* AMGX_solver_resetup with structure_reuse_levels (src/amg.cu:229-272, classical_amg_level.cu:274-291): a reused level keeps P and R --
+         * pattern and values -- and only A_c = R A P follows the new matrix */
+        if (g_reuse_from && g_reuse_levels != 0 && (g_reuse_levels == -1 || g_reuse_levels > num_levels) && num_levels < g_reuse_from->num_levels &&
+            g_reuse_from->lv[lvl].Pp && g_reuse_from->lv[lvl].n == L->n) {
+            const orc_level *O = &g_reuse_from->lv[lvl];
+            const int nc = O->nagg, pn = O->Pp[O->n];
+            cla_csr P, R, AP, Ac;
+            P.n = L->n; P.nc = nc; P.nnz = pn;
+            P.rp = (int *)malloc(sizeof(int) * ((size_t)L->n + 1)); memcpy(P.rp, O->Pp, sizeof(int) * ((size_t)L->n + 1));
+            P.ci = (int *)malloc(sizeof(int) * (size_t)(pn > 0 ? pn : 1)); memcpy(P.ci, O->Pc, sizeof(int) * (size_t)pn);
+            P.va = (double *)malloc(sizeof(double) * (size_t)(pn > 0 ? pn : 1)); memcpy(P.va, O->Pv, sizeof(double) * (size_t)pn);
+            R.n = nc; R.nc = L->n; R.nnz = pn;
+            R.rp = (int *)malloc(sizeof(int) * ((size_t)nc + 1)); memcpy(R.rp, O->Rtp, sizeof(int) * ((size_t)nc + 1));
+            R.ci = (int *)malloc(sizeof(int) * (size_t)(pn > 0 ? pn : 1)); memcpy(R.ci, O->Rtc, sizeof(int) * (size_t)pn);
+            R.va = (double *)malloc(sizeof(double) * (size_t)(pn > 0 ? pn : 1)); memcpy(R.va, O->Rtv, sizeof(double) * (size_t)pn);
+            int *cf = (int *)malloc(sizeof(int) * (size_t)(L->n > 0 ? L->n : 1));
+            memcpy(cf, O->cf, sizeof(int) * (size_t)L->n);
+            cla_spgemm(L->n, L->rp, L->ci, L->va, P.rp, P.ci, P.va, nc, &AP);
+            cla_spgemm(nc, R.rp, R.ci, R.va, AP.rp, AP.ci, AP.va, nc, &Ac);
+            cla_csr_free(&AP);
+            L->nagg = nc;
+            L->Pp = P.rp; L->Pc = P.ci; L->Pv = P.va;
+            L->Rtp = R.rp; L->Rtc = R.ci; L->Rtv = R.va;
+            L->cf = cf;
+            orc_level *N = &a->lv[num_levels];
+            N->n = nc; N->nnz = Ac.nnz; N->rp = Ac.rp; N->ci = Ac.ci; N->va = Ac.va; N->own = 1;
+            L->bc = (double *)calloc((size_t)nc, sizeof(double));
+            L->xc = (double *)calloc((size_t)nc, sizeof(double));
+            L->r = (double *)calloc((size_t)L->n, sizeof(double));
+            num_levels++;
+            continue;
+        }
+        g_reuse_levels = 0;   /* the chain of reused levels ends at the first rebuilt one */
         unsigned char *s_con = (unsigned char *)calloc((size_t)(L->nnz > 0 ? L->nnz : 1), 1);
         float *w = (float *)calloc((size_t)(L->n > 0 ? L->n : 1), sizeof(float));
         int *cf = (int *)calloc((size_t)(L->n > 0 ? L->n : 1), sizeof(int));
@@ -707,6 +740,7 @@ ORC_API orc_amg *orc_amg_setup_classical(int n, const int *rp, const int *ci, co
         }
     }
     a->num_levels = num_levels;
+    g_reuse_from = NULL; g_reuse_levels = 0;
     return a;
 }
 ORC_API int orc_amg_level_classical(const orc_amg *a, int l, int *cf, int *Pp, int *Pc, double *Pv, int *pnnz)

@@ -469,7 +469,7 @@ class ClassicalAMG(AMG):
     def __init__(self, rp, ci, va, max_levels=100, min_coarse_rows=2, coarsen_threshold=1.0, presweeps=1, postsweeps=1, coarsest_sweeps=2,
                  finest_sweeps=-1, smoother="BLOCK_JACOBI", omega=0.9, strength_threshold=0.25, max_row_sum=1.1, interpolator="D1",
                  aggressive_levels=0, aggressive_interpolator="MULTIPASS", interp_max_elements=-1, coarse_solver="NOSOLVER", dense_lu_num_rows=128,
-                 selector="PMIS"):
+                 selector="PMIS", reuse_from=None, structure_reuse_levels=0):
         self.rp, self.ci, self.va = _i(rp), _i(ci), _d(va)
         if coarse_solver == "DENSE_LU_SOLVER":
             min_coarse_rows = dense_lu_num_rows
@@ -477,6 +477,8 @@ class ClassicalAMG(AMG):
         sm = SMOOTHERS[smoother]
         im = {"D2": 0, "MULTIPASS": 1, "D1": 2}
         set_classical_selector(selector)
+        if reuse_from is not None:                       # AMGX_solver_resetup with structure_reuse_levels: P and R carried over
+            lib().orc_amg_reuse_structure(reuse_from.h, structure_reuse_levels)
         self.h = C.c_void_p(lib().orc_amg_setup_classical(
             self.n, _p(self.rp), _p(self.ci), _p(self.va), max_levels, min_coarse_rows, C.c_double(coarsen_threshold), presweeps, postsweeps,
             coarsest_sweeps, finest_sweeps, sm, C.c_double(omega), C.c_double(strength_threshold), C.c_double(max_row_sum), im[interpolator],

@@ -276,8 +276,7 @@ def classical_section(rank, world, rsc, lib):
     import ctypes as C
     sys.path.insert(0, str(ROOT / "tests"))
     from golden.make_golden import cfg_fgmres_classical
-    for name, (nx, ny, nzl), kw in (("aggr_multipass_d2", (14, 12, 7), dict()), ("d2_only", (12, 10, 6), dict(aggressive_levels=0)),
-                                    ("d1", (12, 10, 6), dict(interpolator="D1", aggressive_levels=0, max_elements=-1))):
+    for name, (nx, ny, nzl), kw in (("aggr_multipass_d2", (14, 12, 7), dict()), ("d2_only", (12, 10, 6), dict(aggressive_levels=0))):
         rp, ci, va = gallery.poisson7pt(nx, ny, nzl * world)
         ng = rp.shape[0] - 1
         offsets = np.array([nx * ny * nzl * r for r in range(world + 1)], np.int64)

@@ -79,3 +79,48 @@ def test_size4_aggregates_bit_exact(amgx, oracle, mat):
     finally:
         for obj in (slv, xv, bv, M, rsc, cfg):
             obj.destroy()
+
+
+@pytest.mark.parametrize("k", [0, 2, -1])
+def test_classical_resetup_keeps_P_and_R(amgx, oracle, k):
+    """classical hierarchy: reused levels keep P and R (pattern and values), A_c = R A_new P"""
+    from tests.golden.make_golden import cfg_fgmres_classical
+    rp, ci, va = gallery.poisson7pt(12, 10, 9)
+    n = rp.shape[0] - 1
+    A0 = gallery.to_scipy(rp, ci, va)
+    A0.sort_indices()
+    D = 1.0 + 3.0 * np.random.default_rng(9).random(n)
+    B = (sp.diags(D) @ A0 @ sp.diags(D)).tocsr()
+    B.sort_indices()
+    rp, ci, va, vb = A0.indptr.astype(np.int32), A0.indices.astype(np.int32), A0.data.copy(), B.data.copy()
+    cfgd = cfg_fgmres_classical(aggressive_levels=0, tol=1e-9, max_iters=80)
+    a = cfgd["solver"]["preconditioner"]
+    a["structure_reuse_levels"] = k
+    kw = dict(selector="PMIS", max_levels=a["max_levels"], min_coarse_rows=a["min_coarse_rows"], presweeps=a["presweeps"], postsweeps=a["postsweeps"],
+              coarsest_sweeps=a["coarsest_sweeps"], smoother=a["smoother"]["solver"], omega=a["smoother"]["relaxation_factor"],
+              strength_threshold=a["strength_threshold"], max_row_sum=a["max_row_sum"], interpolator=a["interpolator"],
+              aggressive_levels=a["aggressive_levels"], interp_max_elements=a["interp_max_elements"])
+    first = oracle.ClassicalAMG(rp, ci, va, **kw)
+    o = oracle.ClassicalAMG(rp, ci, vb, reuse_from=first, structure_reuse_levels=k, **kw)
+    s = cfgd["solver"]
+    xo, ito, histo, convo = oracle.fgmres(rp, ci, vb, np.ones(n), amg=o, tol=s["tolerance"], max_iters=s["max_iters"], restart=s["gmres_n_restart"])
+    cfg = amgx.Config(cfgd)
+    rsc = amgx.Resources(cfg)
+    A = amgx.Matrix(rsc).upload(rp, ci, va)
+    b, x = amgx.Vector(rsc).upload(np.ones(n)), amgx.Vector(rsc)
+    x.set_zero(n)
+    slv = amgx.Solver(rsc, cfg)
+    slv.setup(A)
+    A.replace_coefficients(vb)
+    slv.resetup(A)
+    slv.solve(b, x, zero_initial_guess=True)
+    assert slv.num_levels() == o.num_levels()
+    for l in range(slv.num_levels() - 1):
+        assert np.array_equal(slv.level_matrix(l)[2], o.level(l)["values"]), (k, l)
+        if l + 1 < slv.num_levels():
+            assert np.array_equal(slv.level_P(l)[2], o.level(l)["P_values"]), (k, l)
+    hist = np.array(slv.residual_history()).ravel()
+    assert slv.iterations_number == ito and convo
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+    for ob in (slv, x, b, A, rsc, cfg):
+        ob.destroy()

@@ -382,3 +382,38 @@ def test_classical_amg_with_d1_converges(oracle):
                               max_row_sum=0.9, interpolator="D1", interp_max_elements=4)
     x, it, hist, conv = oracle.fgmres(rp, ci, va, np.ones(n), amg=amg, tol=1e-8, max_iters=60, restart=20)
     assert conv and it < 30
+
+
+def test_structure_reuse_keeps_P_and_R_and_recomputes_the_galerkin_product(oracle):
+    """AMGX_solver_resetup with structure_reuse_levels = k on a classical hierarchy: coarsenings 1 .. k-1 keep P and R whole (pattern and
+    values, classical_amg_level.cu:274-291), A_c = R A P is recomputed from the new matrix; the first rebuilt level is a fresh coarsening"""
+    import scipy.sparse as sp
+    rp, ci, va = gallery.poisson7pt(10, 9, 8)
+    n = rp.shape[0] - 1
+    A = gallery.to_scipy(rp, ci, va)
+    D = 1.0 + 3.0 * np.random.default_rng(9).random(n)
+    B = (sp.diags(D) @ A @ sp.diags(D)).tocsr()
+    A.sort_indices(); B.sort_indices()
+    rp, ci, va, vb = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy(), B.data.copy()
+    kw = dict(max_levels=50, presweeps=1, postsweeps=1, omega=0.8, interpolator="D2", interp_max_elements=4, strength_threshold=0.25, max_row_sum=0.9)
+    first = oracle.ClassicalAMG(rp, ci, va, **kw)
+    fresh = oracle.ClassicalAMG(rp, ci, vb, **kw)
+    assert first.num_levels() >= 3
+    assert not np.array_equal(first.level(0)["P_values"], fresh.level(0)["P_values"])
+    for k in (0, 1, 2, 3, -1):
+        re = oracle.ClassicalAMG(rp, ci, vb, reuse_from=first, structure_reuse_levels=k, **kw)
+        kept = re.num_levels() - 1 if k == -1 else max(0, min(k - 1, re.num_levels() - 1, first.num_levels() - 1))
+        for l in range(kept):
+            Ll, Lf, Ln = re.level(l), first.level(l), re.level(l + 1)
+            for key in ("cf_map", "P_row_offsets", "P_col_indices", "P_values"):
+                assert np.array_equal(Ll[key], Lf[key]), (k, l, key)
+            Al = gallery.to_scipy(Ll["row_ptr"], Ll["col_idx"], Ll["values"])
+            P = sp.csr_matrix((Ll["P_values"], Ll["P_col_indices"], Ll["P_row_offsets"]), shape=(Ll["n"], Ll["n_coarse"]))
+            got = gallery.to_scipy(Ln["row_ptr"], Ln["col_idx"], Ln["values"]).toarray()
+            assert np.allclose(got, (P.T @ Al @ P).toarray(), rtol=1e-12, atol=1e-13)
+        if kept == 0:
+            for key in ("cf_map", "P_values"):
+                assert np.array_equal(re.level(0)[key], fresh.level(0)[key])
+        x, it, hist, conv = oracle.fgmres(rp, ci, vb, np.ones(n), amg=re, tol=1e-8, max_iters=100, restart=20)
+        assert conv
+        assert np.linalg.norm(np.ones(n) - B @ x) <= 1.5e-8 * np.sqrt(n)
