@@ -1332,16 +1332,17 @@ void AMGSolver::setup_classical()
                 s_con.release();
                 if (prm.max_elmts > 0 && P.n > 0) truncate_max_elements(P, prm.max_elmts, s);
                 transpose_csr(P, R, s);
-                L.P = to_matrix(P, A, s);
-                L.R = to_matrix(R, A, s);
-                csr_build_plan(*L.P, s);
-                csr_build_plan(*L.R, s);
             }
+            // the operands of the Galerkin product: the carried-over matrices, or the fresh P / R (turned into matrices further down)
+            const DevBuf<int> &p_rp = reused ? L.P->row_ptr : P.rp, &p_ci = reused ? L.P->col_idx : P.ci;
+            const DevVec &p_va = reused ? L.P->values : P.va;
+            const DevBuf<int> &r_rp = reused ? L.R->row_ptr : R.rp, &r_ci = reused ? L.R->col_idx : R.ci;
+            const DevVec &r_va = reused ? L.R->values : R.va;
             // A_c = R (A P)
             Csr AP;
             AP.n = rows;
             AP.nc = nc;
-            spgemm_csr(rows, A.row_ptr, A.col_idx, A.values, L.P->row_ptr, L.P->col_idx, L.P->values, AP.rp, AP.ci, AP.va, &AP.nnz, s);
+            spgemm_csr(rows, A.row_ptr, A.col_idx, A.values, p_rp, p_ci, p_va, AP.rp, AP.ci, AP.va, &AP.nnz, s);
             std::unique_ptr<AMGLevel> next(new AMGLevel);
             next->owned_A.reset(new Matrix);
             Matrix &Ac = *next->owned_A;
@@ -1351,10 +1352,16 @@ void AMGSolver::setup_classical()
             Ac.vec_prec = A.vec_prec;
             Ac.n = nc;
             Ac.n_cols = nc;
-            spgemm_csr(nc, L.R->row_ptr, L.R->col_idx, L.R->values, AP.rp, AP.ci, AP.va, Ac.row_ptr, Ac.col_idx, Ac.values, &Ac.nnz, s);
+            spgemm_csr(nc, r_rp, r_ci, r_va, AP.rp, AP.ci, AP.va, Ac.row_ptr, Ac.col_idx, Ac.values, &Ac.nnz, s);
             Ac.values.n = (size_t)Ac.nnz;
             AP.rp.release(); AP.ci.release(); AP.va.b.release();
             Ac.compute_diag_and_plan();
+            if (!reused) {
+                L.P = to_matrix(P, A, s);
+                L.R = to_matrix(R, A, s);
+                csr_build_plan(*L.P, s);
+                csr_build_plan(*L.R, s);
+            }
             next->A = next->owned_A.get();
             next->index = num_levels;
             L.bc.resize((size_t)nc, A.vec_prec);
