@@ -1,0 +1,56 @@
+"""GPU: degenerate inputs through the C-ABI against the oracle (same shapes as tests/test_oracle_edge_cases.py).  Written after round 1's
+GPU minutes were spent: opt-in until validated on a device."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from amgx_b200 import gallery
+from tests._gpu_util import UNVALIDATED, amg_agg_cfg, outer_cfg, run_engine
+
+pytestmark = [pytest.mark.gpu, UNVALIDATED]
+
+
+def test_one_by_one_system(amgx):
+    rp, ci, va = np.array([0, 1], np.int32), np.array([0], np.int32), np.array([4.0])
+    x, it, status, hist = run_engine(amgx, outer_cfg("PCG", amg_agg_cfg(), tol=1e-10, max_iters=5), rp, ci, va, np.array([2.0]))
+    assert status == "success" and it == 1 and x[0] == 0.5
+
+
+def test_diagonal_matrix_single_level(amgx, oracle):
+    n = 50
+    D = sp.diags(np.arange(1, n + 1, dtype=float)).tocsr()
+    rp, ci, va = D.indptr.astype(np.int32), D.indices.astype(np.int32), D.data
+    x, it, status, hist = run_engine(amgx, outer_cfg("PCG", amg_agg_cfg(omega=1.0), tol=1e-10, max_iters=20), rp, ci, va, np.ones(n))
+    a = oracle.AMG(rp, ci, va, max_levels=50, presweeps=1, postsweeps=1, omega=1.0)
+    xo, ito, histo, convo = oracle.pcg(rp, ci, va, np.ones(n), amg=a, tol=1e-10, max_iters=20)
+    assert status == "success" and it == ito == 1 and np.array_equal(x, xo)
+
+
+def test_zero_right_hand_side(amgx):
+    rp, ci, va = gallery.poisson7pt(5)
+    n = rp.shape[0] - 1
+    for outer in ("PCG", "FGMRES"):
+        x, it, status, hist = run_engine(amgx, outer_cfg(outer, amg_agg_cfg(), tol=1e-8, max_iters=10), rp, ci, va, np.zeros(n))
+        assert status == "success" and it == 0 and not x.any()
+
+
+def test_rows_without_off_diagonal_entries(amgx, oracle):
+    """a few isolated rows inside a Poisson matrix: singleton aggregates, STRONG_FINE points for the classical selector"""
+    rp, ci, va = gallery.poisson7pt(8)
+    n = rp.shape[0] - 1
+    A = gallery.to_scipy(rp, ci, va).tolil()
+    for i in (0, 100, 101, 300, n - 1):
+        for j in list(A.rows[i]):
+            if j != i:
+                A[i, j] = 0.0
+                A[j, i] = 0.0
+    A = A.tocsr()
+    A.eliminate_zeros()
+    A.sort_indices()
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+    b = np.ones(n)
+    x, it, status, hist = run_engine(amgx, outer_cfg("PCG", amg_agg_cfg(), tol=1e-9, max_iters=60), rp, ci, va, b)
+    a = oracle.AMG(rp, ci, va, max_levels=50, presweeps=1, postsweeps=1, omega=0.8)
+    xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, amg=a, tol=1e-9, max_iters=60)
+    assert status == "success" and convo and it == ito
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12

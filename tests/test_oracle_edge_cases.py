@@ -1,0 +1,54 @@
+"""CPU: degenerate inputs through the oracle (the engine's GPU parity tests use the same shapes): a 1 x 1 system, a diagonal matrix
+(no edges: every aggregate is a singleton, coarsening stalls on the first level, src/amg.cu:365-389), a zero right-hand side, a
+matrix with an empty row block structure that forces size-1 and size-3 aggregates."""
+import numpy as np
+import scipy.sparse as sp
+
+from amgx_b200 import gallery
+
+
+def test_one_by_one_system(oracle):
+    rp, ci, va = np.array([0, 1], np.int32), np.array([0], np.int32), np.array([4.0])
+    x, it, hist, conv = oracle.pcg(rp, ci, va, np.array([2.0]), tol=1e-10, max_iters=5)
+    assert conv and it == 1 and x[0] == 0.5 and hist[-1] == 0.0
+    assert oracle.AMG(rp, ci, va, max_levels=10).num_levels() == 1
+    assert oracle.ClassicalAMG(rp, ci, va, max_levels=10, interpolator="D2").num_levels() == 1
+
+
+def test_diagonal_matrix_does_not_coarsen(oracle):
+    n = 50
+    D = sp.diags(np.arange(1, n + 1, dtype=float)).tocsr()
+    rp, ci, va = D.indptr.astype(np.int32), D.indices.astype(np.int32), D.data
+    a = oracle.AMG(rp, ci, va, max_levels=10, presweeps=1, postsweeps=1, omega=1.0)
+    assert a.num_levels() == 1
+    x, it, hist, conv = oracle.pcg(rp, ci, va, np.ones(n), amg=a, tol=1e-10, max_iters=20)
+    assert conv and it == 1 and np.allclose(x, 1 / np.arange(1, n + 1), rtol=1e-15)
+    c = oracle.ClassicalAMG(rp, ci, va, max_levels=10, interpolator="D2")
+    assert c.num_levels() == 1
+    for interp in ("D1", "D2", "MULTIPASS"):
+        assert oracle.ClassicalAMG(rp, ci, va, max_levels=10, interpolator=interp).num_levels() == 1
+
+
+def test_zero_right_hand_side_converges_immediately(oracle):
+    rp, ci, va = gallery.poisson7pt(5)
+    n = rp.shape[0] - 1
+    a = oracle.AMG(rp, ci, va, max_levels=10)
+    x, it, hist, conv = oracle.pcg(rp, ci, va, np.zeros(n), amg=a, tol=1e-8, max_iters=10)
+    assert conv and it == 0 and not x.any()
+    x, it, hist, conv = oracle.fgmres(rp, ci, va, np.zeros(n), amg=a, tol=1e-8, max_iters=10, restart=5)
+    assert conv and it == 0 and not x.any()
+
+
+def test_path_graph_gives_odd_sized_aggregates(oracle):
+    """a 1-D chain of 7 rows: pairs by handshake, the leftover joins a neighbour's aggregate (size 3), ids ordered by first member"""
+    n = 7
+    A = sp.diags([-np.ones(n - 1), 2.0 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1]).tocsr()
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data
+    agg, nagg = oracle.size2_aggregates(rp, ci, va)[:2]
+    sizes = np.bincount(agg)
+    assert sizes.sum() == n and sizes.min() >= 1 and sizes.max() <= 3 and nagg == len(sizes)
+    first = [int(np.nonzero(agg == a)[0][0]) for a in range(nagg)]
+    assert first == sorted(first)
+    for a in range(nagg):               # aggregates are connected pieces of the chain
+        m = np.nonzero(agg == a)[0]
+        assert m.max() - m.min() == len(m) - 1
