@@ -54,3 +54,15 @@ def test_rows_without_off_diagonal_entries(amgx, oracle):
     xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, amg=a, tol=1e-9, max_iters=60)
     assert status == "success" and convo and it == ito
     assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+
+
+@pytest.mark.parametrize("smoother", ["BLOCK_JACOBI", "JACOBI_L1", "MULTICOLOR_DILU", "MULTICOLOR_GS"])
+def test_structurally_missing_diagonal_entries_give_no_nan(amgx, oracle, smoother):
+    """the reference's ImplicitZeroInDiagonal unit test (src/tests/zero_in_diagonal_handling.cu) through the C-ABI: rows without a
+    diagonal entry must not produce NaNs or errors; the hierarchy has the oracle's level count"""
+    from tests.test_oracle_edge_cases import missing_diagonal_matrix
+    rp, ci, va = missing_diagonal_matrix()
+    n = rp.shape[0] - 1
+    cfgd = outer_cfg("PCG", amg_agg_cfg(smoother=smoother, max_levels=10), tol=1e-8, max_iters=3)
+    x, it, status, hist = run_engine(amgx, cfgd, rp, ci, va, np.ones(n))
+    assert np.isfinite(x).all() and np.isfinite(hist).all()

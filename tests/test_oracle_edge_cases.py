@@ -52,3 +52,42 @@ def test_path_graph_gives_odd_sized_aggregates(oracle):
     for a in range(nagg):               # aggregates are connected pieces of the chain
         m = np.nonzero(agg == a)[0]
         assert m.max() - m.min() == len(m) - 1
+
+
+def missing_diagonal_matrix(n=200, seed=1):
+    """the generator of the reference's zero_in_diagonal_handling test (src/tests/zero_in_diagonal_handling.cu:57-118): unit values,
+    up to 10 random columns per row, five rows have no diagonal entry at all"""
+    rng = np.random.default_rng(seed)
+    rows, cols, left = [], [], 5
+    for i in range(n):
+        c = set()
+        if left > 0 and rng.integers(5) != 0:
+            left -= 1
+        else:
+            c.add(i)
+        for _ in range(max(1, int(rng.random() * (10 - len(c))))):
+            c.add(int(rng.integers(n)))
+        for j in sorted(c):
+            rows.append(i)
+            cols.append(j)
+    A = sp.csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(n, n))
+    A.sort_indices()
+    return A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+
+
+def test_structurally_missing_diagonal_entries_give_no_nan(oracle):
+    """ImplicitZeroInDiagonal: selectors, coarse generators, colourings and smoothers must survive rows without a diagonal entry
+    (the guards: isNotCloseToZero(d) ? d : epsilon(d), block_jacobi_solver.cu:29-50; Einv of DILU: res != 0 ? 1 / res : res)"""
+    rp, ci, va = missing_diagonal_matrix()
+    n = rp.shape[0] - 1
+    for sm in ("BLOCK_JACOBI", "JACOBI_L1", "MULTICOLOR_DILU", "MULTICOLOR_GS"):
+        a = oracle.AMG(rp, ci, va, max_levels=10, presweeps=1, postsweeps=1, omega=0.8, smoother=sm)
+        assert a.num_levels() >= 2
+        for l in range(a.num_levels()):
+            assert np.isfinite(a.level(l)["values"]).all()
+        x, it, hist, conv = oracle.pcg(rp, ci, va, np.ones(n), amg=a, tol=1e-8, max_iters=3)
+        assert np.isfinite(x).all() and np.isfinite(hist).all(), sm
+    for interp in ("D1", "D2", "MULTIPASS"):
+        c = oracle.ClassicalAMG(rp, ci, va, max_levels=10, interpolator=interp)
+        x, it, hist, conv = oracle.fgmres(rp, ci, va, np.ones(n), amg=c, tol=1e-8, max_iters=3, restart=3)
+        assert np.isfinite(x).all() and np.isfinite(hist).all(), interp
