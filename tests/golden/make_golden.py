@@ -141,7 +141,11 @@ def main():
         sysf, cfgf, outf = OUT / f"{name}.sys", OUT / f"{name}.json", OUT / f"{name}.bin"
         write_system(sysf, rp, ci, va, rhs, block=(bs, bs))
         cfgf.write_text(json.dumps(cfg, indent=1))
-        r = subprocess.run([str(REF), str(sysf), str(cfgf), str(outf), mode], capture_output=True, text=True, env=env)
+        try:
+            r = subprocess.run([str(REF), str(sysf), str(cfgf), str(outf), mode], capture_output=True, text=True, env=env, timeout=180)
+        except subprocess.TimeoutExpired:
+            print(f"[{name}] ref_dump TIMED OUT after 180 s")
+            continue
         if r.returncode != 0:
             print(f"[{name}] ref_dump FAILED rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
             continue
