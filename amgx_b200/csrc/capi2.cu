@@ -498,20 +498,133 @@ AMGX_RC AMGX_read_system_distributed(AMGX_matrix_handle mtx, AMGX_vector_handle 
     API2_END
 }
 
-/* AMGX_write_system_distributed (src/amgx_c.cu:3557-3600): the partitions are gathered on rank 0 and written as one system.  Here
- * every rank holds a row-partitioned matrix in the engine's local numbering; the gather is not implemented for more than one rank. */
+// matrix_writer = matrixmarket (default) | binary, read from the configuration the resources were created with (matrix_io.cu:505-530).
+// va holds nnz blocks, followed by n diagonal blocks when ext_diag (written by the binary format only).
+static void write_host_system(const char *filename, const std::string &writer, int n, int nnz, int bx, int by, const std::vector<int> &rp, const std::vector<int> &ci,
+                              const std::vector<double> &va, bool ext_diag, const std::vector<double> &b, const std::vector<double> &x)
+{
+    const int bsq = bx * by;
+    if (writer == "binary") {
+        write_binary(filename, n, nnz, bx, by, rp, ci, va, ext_diag, b, x);
+        return;
+    }
+    if (writer != "matrixmarket") fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_writer '" + writer + "' is not supported (matrixmarket, binary)");
+    std::ofstream f(filename);
+    if (!f) fatal(AMGX_RC_IO_ERROR, "cannot open output file");
+    f << "%%MatrixMarket matrix coordinate real general\n";
+    f << "%%AMGX " << bx << " " << by << " sorted" << (b.empty() ? "" : " rhs") << (x.empty() ? "" : " solution") << "\n";
+    f << (long long)n * bx << " " << (long long)n * by << " " << (long long)nnz * bsq << "\n";
+    f.precision(17);
+    for (int i = 0; i < n; i++)
+        for (int k = rp[i]; k < rp[i + 1]; k++)
+            for (int r = 0; r < bx; r++)
+                for (int c = 0; c < by; c++)
+                    f << (long long)i * bx + r + 1 << " " << (long long)ci[k] * by + c + 1 << " " << va[(size_t)k * bsq + r * by + c] << "\n";
+    for (double v : b) f << v << "\n";
+    for (double v : x) f << v << "\n";
+}
+
+/* AMGX_write_system_distributed (src/amgx_c.cu:1406-1491, 3557-3600): the partitions are gathered and rank 0 writes ONE global system.
+ * Every rank assembles the global matrix in the callers' row order (dist_gather_matrix) and the vectors with one all-gather; when the
+ * matrix was uploaded through a partition vector, passing the same vector here restores the original global numbering (the reference's
+ * construct_global_matrix); without it the rows appear in the contiguous per-rank numbering.  Collective: every rank must call it. */
 AMGX_RC AMGX_write_system_distributed(const AMGX_matrix_handle mtx, const AMGX_vector_handle rhs, const AMGX_vector_handle sol, const char *filename,
                                       int allocated_halo_depth, int num_partitions, const int *partition_sizes, int partition_vector_size,
                                       const int *partition_vector)
 {
-    (void)allocated_halo_depth; (void)num_partitions; (void)partition_sizes; (void)partition_vector_size; (void)partition_vector;
+    (void)allocated_halo_depth; (void)num_partitions; (void)partition_sizes;
+    bool is_dist = false;
     {
         API2_BEGIN
         MatrixH *m = chk<MatrixH>(mtx, MAGIC_MTX, "matrix");
-        if (m->m->dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "AMGX_write_system_distributed: gathering a row-partitioned matrix on rank 0 is not implemented");
+        is_dist = (bool)m->m->dist;
         API2_END_NORETURN
     }
-    return AMGX_write_system(mtx, rhs, sol, filename);
+    if (!is_dist) return AMGX_write_system(mtx, rhs, sol, filename);
+    API2_BEGIN
+    if (!filename) fatal(AMGX_RC_BAD_PARAMETERS, "null file name");
+    MatrixH *m = chk<MatrixH>(mtx, MAGIC_MTX, "matrix");
+    Matrix &A = *m->m;
+    AMGXB_CUDA_CHECK(cudaSetDevice(A.rsc->device));
+    if (A.has_ext_diag) fatal(AMGX_RC_NOT_IMPLEMENTED, "AMGX_write_system_distributed with an external diagonal");
+    cudaStream_t s = A.stream();
+    const int rank = A.rsc->rank, world = A.rsc->world;
+    std::vector<int> counts, offs;
+    std::unique_ptr<Matrix> G = dist_gather_matrix(A, counts, offs, true);
+    const int N = G->n, NNZ = G->nnz, bsq = A.bs();
+    auto gather_vec = [&](AMGX_vector_handle vh, std::vector<double> &out) {
+        if (!vh) return;
+        VectorH *v = chk<VectorH>(vh, MAGIC_VEC, "vector");
+        const int bd = v->v->block_dim;
+        if (v->v->n != A.n) fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_write_system_distributed: vector and matrix sizes differ");
+        const size_t len = (size_t)A.n * bd;
+        std::vector<double> mine(len);
+        if (len) {
+            if (v->v->prec == Prec::F64) {
+                if (v->v->dist && !v->v->user_order) dist_download_vector(*v->v, mine.data());
+                else AMGXB_CUDA_CHECK(cudaMemcpy(mine.data(), v->v->data.ptr(), len * 8, cudaMemcpyDeviceToHost));
+            } else {
+                std::vector<float> t(len);
+                if (v->v->dist && !v->v->user_order) dist_download_vector(*v->v, t.data());
+                else AMGXB_CUDA_CHECK(cudaMemcpy(t.data(), v->v->data.ptr(), len * 4, cudaMemcpyDeviceToHost));
+                std::copy(t.begin(), t.end(), mine.begin());
+            }
+        }
+        DevVec g;
+        g.resize((size_t)N * bd, Prec::F64);
+        g.zero(s);
+        if (len) AMGXB_CUDA_CHECK(cudaMemcpyAsync((double *)g.ptr() + (size_t)offs[rank] * bd, mine.data(), len * 8, cudaMemcpyHostToDevice, s));
+        dist_allgatherv_inplace(A, g.ptr(), Prec::F64, bd, counts, offs, s);
+        out.resize((size_t)N * bd);
+        if (!out.empty()) AMGXB_CUDA_CHECK(cudaMemcpyAsync(out.data(), g.ptr(), out.size() * 8, cudaMemcpyDeviceToHost, s));
+        AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+    };
+    std::vector<double> b, x;
+    gather_vec(rhs, b);
+    gather_vec(sol, x);
+    if (rank != 0) return AMGX_RC_OK;
+    std::vector<int> rp = G->row_ptr.to_host(s), ci = G->col_idx.to_host(s);
+    std::vector<double> va((size_t)NNZ * bsq);
+    if (NNZ) {
+        if (A.mat_prec == Prec::F64) AMGXB_CUDA_CHECK(cudaMemcpy(va.data(), G->values.ptr(), va.size() * 8, cudaMemcpyDeviceToHost));
+        else {
+            std::vector<float> vf(va.size());
+            AMGXB_CUDA_CHECK(cudaMemcpy(vf.data(), G->values.ptr(), vf.size() * 4, cudaMemcpyDeviceToHost));
+            std::copy(vf.begin(), vf.end(), va.begin());
+        }
+    }
+    if (partition_vector) {
+        // contiguous id (what the ranks hold) -> original global id
+        if (partition_vector_size != N) fatal(AMGX_RC_BAD_PARAMETERS, "AMGX_write_system_distributed: partition vector size != global number of rows");
+        std::vector<int64_t> off((size_t)world + 1), newg((size_t)std::max(N, 1));
+        if (!partition_vector_to_contiguous(N, world, partition_vector, off.data(), newg.data()))
+            fatal(AMGX_RC_BAD_PARAMETERS, "partition vector names a rank outside [0, number of ranks)");
+        std::vector<int> orig((size_t)std::max(N, 1));
+        for (int g = 0; g < N; g++) orig[(size_t)newg[g]] = g;
+        std::vector<int> rp2((size_t)N + 1, 0), ci2(ci.size());
+        std::vector<double> va2(va.size());
+        for (int i = 0; i < N; i++) rp2[(size_t)orig[i] + 1] = rp[i + 1] - rp[i];
+        for (int i = 0; i < N; i++) rp2[i + 1] += rp2[i];
+        for (int i = 0; i < N; i++) {
+            const int d = rp2[orig[i]];
+            for (int k = rp[i]; k < rp[i + 1]; k++) {
+                ci2[(size_t)d + (k - rp[i])] = orig[ci[k]];
+                std::copy(va.begin() + (size_t)k * bsq, va.begin() + (size_t)(k + 1) * bsq, va2.begin() + (size_t)(d + (k - rp[i])) * bsq);
+            }
+        }
+        rp.swap(rp2); ci.swap(ci2); va.swap(va2);
+        auto unpermute = [&](std::vector<double> &v) {
+            if (v.empty()) return;
+            const size_t bd = v.size() / (size_t)N;
+            std::vector<double> t(v.size());
+            for (int i = 0; i < N; i++) std::copy(v.begin() + (size_t)i * bd, v.begin() + (size_t)(i + 1) * bd, t.begin() + (size_t)orig[i] * bd);
+            v.swap(t);
+        };
+        unpermute(b);
+        unpermute(x);
+    }
+    write_host_system(filename, A.rsc->cfg ? A.rsc->cfg->get_string("matrix_writer", "default") : std::string("matrixmarket"), N, NNZ, A.bx, A.by, rp, ci, va, false, b, x);
+    API2_END
 }
 
 AMGX_RC AMGX_read_system(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol, const char *filename)
@@ -577,33 +690,19 @@ AMGX_RC AMGX_write_system(const AMGX_matrix_handle mtx, const AMGX_vector_handle
     std::vector<double> b, x;
     get_vec(rhs, b);
     get_vec(sol, x);
-    // matrix_writer = matrixmarket (default) | binary, read from the configuration the resources were created with (matrix_io.cu:505-530)
-    std::string writer = "matrixmarket";
-    if (A.rsc->cfg) writer = A.rsc->cfg->get_string("matrix_writer", "default");
-    if (writer == "binary") {
-        f.close();
-        std::vector<double> vall((size_t)(A.nnz + (A.has_ext_diag ? A.n : 0)) * bsq);
+    std::vector<double> vall;
+    if (A.has_ext_diag) {
+        vall.resize((size_t)(A.nnz + A.n) * bsq);
         if (A.mat_prec == Prec::F64) AMGXB_CUDA_CHECK(cudaMemcpy(vall.data(), A.values.ptr(), vall.size() * 8, cudaMemcpyDeviceToHost));
         else {
             std::vector<float> vf(vall.size());
             AMGXB_CUDA_CHECK(cudaMemcpy(vf.data(), A.values.ptr(), vf.size() * 4, cudaMemcpyDeviceToHost));
             std::copy(vf.begin(), vf.end(), vall.begin());
         }
-        write_binary(filename, A.n, A.nnz, A.bx, A.by, rp, ci, vall, A.has_ext_diag, b, x);
-        return AMGX_RC_OK;
     }
-    if (writer != "matrixmarket") fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_writer '" + writer + "' is not supported (matrixmarket, binary)");
-    f << "%%MatrixMarket matrix coordinate real general\n";
-    f << "%%AMGX " << A.bx << " " << A.by << " sorted" << (b.empty() ? "" : " rhs") << (x.empty() ? "" : " solution") << "\n";
-    f << (long long)A.n * A.bx << " " << (long long)A.n * A.by << " " << (long long)A.nnz * bsq << "\n";
-    f.precision(17);
-    for (int i = 0; i < A.n; i++)
-        for (int k = rp[i]; k < rp[i + 1]; k++)
-            for (int r = 0; r < A.bx; r++)
-                for (int c = 0; c < A.by; c++)
-                    f << (long long)i * A.bx + r + 1 << " " << (long long)ci[k] * A.by + c + 1 << " " << va[(size_t)k * bsq + r * A.by + c] << "\n";
-    for (double v : b) f << v << "\n";
-    for (double v : x) f << v << "\n";
+    f.close();
+    write_host_system(filename, A.rsc->cfg ? A.rsc->cfg->get_string("matrix_writer", "default") : std::string("matrixmarket"), A.n, A.nnz, A.bx, A.by, rp, ci,
+                      A.has_ext_diag ? vall : va, A.has_ext_diag, b, x);
     API2_END
 }
 

@@ -184,8 +184,24 @@ def read_distributed_section(rank, world, rsc, lib, cfg):
     res = rhs - gallery.to_scipy(rp, ci, va) @ xfull
     hist = slv.residual_history()
     assert abs(np.linalg.norm(res) - hist[-1]) <= 1e-9 * hist[0], (np.linalg.norm(res), hist[-1])
+    # AMGX_write_system_distributed: the partitions are gathered, rank 0 writes the global system in the ORIGINAL numbering
+    out = os.path.join(tempfile.gettempdir(), f"amgxb_dist_write_{world}.mtx")
+    lib.AMGX_write_system_distributed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    assert lib.AMGX_write_system_distributed(A.h, b.h, x.h, out.encode(), 1, world, None, ng, pv.ctypes.data) == 0
+    dist.barrier()
     if rank == 0:
-        print(f"DIST_READ_SYSTEM_OK world={world} iters={slv.iterations_number}", flush=True)
+        import scipy.sparse as sp
+        with open(out) as f:
+            lines = [l for l in f if not l.startswith("%")]
+        nr, ncol, nnz = (int(t) for t in lines[0].split())
+        assert (nr, ncol, nnz) == (ng, ng, ci.shape[0])
+        ent = np.array([l.split() for l in lines[1:1 + nnz]], dtype=float)
+        W = sp.csr_matrix((ent[:, 2], (ent[:, 0].astype(int) - 1, ent[:, 1].astype(int) - 1)), shape=(ng, ng))
+        assert abs(W - gallery.to_scipy(rp, ci, va)).max() == 0.0, "written matrix differs from the global one"
+        tail = np.array([float(l) for l in lines[1 + nnz:]])
+        assert tail.shape[0] == 2 * ng and np.array_equal(tail[:ng], rhs) and np.array_equal(tail[ng:], xfull)
+    if rank == 0:
+        print(f"DIST_READ_SYSTEM_OK world={world} iters={slv.iterations_number} write_gathered=ok", flush=True)
     for o in (slv, x, b, A):
         o.destroy()
     dist.barrier()
