@@ -118,9 +118,10 @@ static void write_binary(const char *filename, int n, int nnz, int bx, int by, c
 
 static void read_mm(const char *filename, MMSystem &S)
 {
-    if (filename && read_binary(filename, S)) return;          // "%%NVAMGBinary" files are detected by their header
+    if (!filename) fatal(AMGX_RC_IO_ERROR, "Error opening file '(null)'");
+    if (read_binary(filename, S)) return;          // "%%NVAMGBinary" files are detected by their header
     std::ifstream fin(filename);
-    if (!fin) fatal(AMGX_RC_IO_ERROR, std::string("Error opening file '") + (filename ? filename : "(null)") + "'");
+    if (!fin) fatal(AMGX_RC_IO_ERROR, std::string("Error opening file '") + filename + "'");
     std::string line;
     bool symmetric = false, skew = false, pattern = false, has_rhs = false, has_sol = false, base0 = false, sorted_hint = false;
     (void)sorted_hint;
@@ -659,10 +660,11 @@ AMGX_RC AMGX_read_system(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_ve
 AMGX_RC AMGX_write_system(const AMGX_matrix_handle mtx, const AMGX_vector_handle rhs, const AMGX_vector_handle sol, const char *filename)
 {
     API2_BEGIN
+    if (!filename) fatal(AMGX_RC_BAD_PARAMETERS, "null file name");
     MatrixH *m = chk<MatrixH>(mtx, MAGIC_MTX, "matrix");
     Matrix &A = *m->m;
     AMGXB_CUDA_CHECK(cudaSetDevice(A.rsc->device));
-    if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "write_system of a distributed matrix");
+    if (A.dist) fatal(AMGX_RC_NOT_IMPLEMENTED, "write_system of a distributed matrix: use AMGX_write_system_distributed");
     std::ofstream f(filename);
     if (!f) fatal(AMGX_RC_IO_ERROR, "cannot open output file");
     std::vector<int> rp = A.row_ptr.to_host(A.stream()), ci = A.col_idx.to_host(A.stream());
