@@ -66,3 +66,17 @@ def test_structurally_missing_diagonal_entries_give_no_nan(amgx, oracle, smoothe
     cfgd = outer_cfg("PCG", amg_agg_cfg(smoother=smoother, max_levels=10), tol=1e-8, max_iters=3)
     x, it, status, hist = run_engine(amgx, cfgd, rp, ci, va, np.ones(n))
     assert np.isfinite(x).all() and np.isfinite(hist).all()
+
+
+def test_fgmres_convergence_poisson(amgx):
+    """the reference's FGMRESConvergencePoisson unit test with its own legacy configuration string, through the C-ABI"""
+    from tests.test_oracle_edge_cases import poisson2d
+    for size in (5, 7, 10):
+        for points in (5, 9):
+            A = poisson2d(points, size, size)
+            rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+            n = rp.shape[0] - 1
+            cfg = (f"config_version=2, solver(s1)=FGMRES, s1:preconditioner(jacobi)=BLOCK_JACOBI, jacobi:max_iters=1, s1:max_iters={n},s1:norm=L2, "
+                   f"determinism_flag=1, s1:tolerance=1e-14, s1:gmres_n_restart={n}, s1:convergence=RELATIVE_INI_CORE, s1:monitor_residual=1, s1:print_solve_stats=1")
+            x, it, status, hist = run_engine(amgx, cfg, rp, ci, va, np.ones(n))
+            assert np.linalg.norm(np.ones(n) - A @ x) / np.sqrt(n) < 1e-5, (points, size)

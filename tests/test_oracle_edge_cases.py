@@ -91,3 +91,65 @@ def test_structurally_missing_diagonal_entries_give_no_nan(oracle):
         c = oracle.ClassicalAMG(rp, ci, va, max_levels=10, interpolator=interp)
         x, it, hist, conv = oracle.fgmres(rp, ci, va, np.ones(n), amg=c, tol=1e-8, max_iters=3, restart=3)
         assert np.isfinite(x).all() and np.isfinite(hist).all(), interp
+
+
+def poisson27(nx, ny, nz):
+    """27-point stencil, centre 26, the 26 neighbours -1 (cusp::gallery::poisson27pt, what generatePoissonForTest(..., 27, ...) builds)"""
+    idx = np.arange(nx * ny * nz).reshape(nz, ny, nx)
+    rows, cols, vals = [], [], []
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                src = idx[max(0, -dz):nz - max(0, dz), max(0, -dy):ny - max(0, dy), max(0, -dx):nx - max(0, dx)]
+                dst = idx[max(0, dz):nz - max(0, -dz), max(0, dy):ny - max(0, -dy), max(0, dx):nx - max(0, -dx)]
+                rows.append(src.ravel())
+                cols.append(dst.ravel())
+                vals.append(np.full(src.size, 26.0 if (dx, dy, dz) == (0, 0, 0) else -1.0))
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(idx.size, idx.size))
+    A.sort_indices()
+    return A
+
+
+def test_aggregates_coarsening_factor(oracle):
+    """the reference's AggregatesCoarseningFactor unit test (src/tests/aggregates_coarsening_factor.cu): on a 20^3 27-point Poisson matrix
+    with values perturbed by up to 1/50, max_unassigned_percentage = 0.1, deterministic: SIZE_2 leaves < 1.1 / 2 of the rows,
+    SIZE_4 < 1.1 / 4; every row gets a valid aggregate id"""
+    A = poisson27(20, 20, 20)
+    A.data += np.random.default_rng(30).random(A.nnz) / 50.0
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+    n = rp.shape[0] - 1
+    for fn, bound in ((oracle.size2_aggregates, 1.1 / 2), (oracle.size4_aggregates, 1.1 / 4)):
+        agg, nagg = fn(rp, ci, va, max_unassigned=0.1)[:2]
+        assert nagg / n < bound, (fn.__name__, nagg / n)
+        assert agg.min() == 0 and agg.max() == nagg - 1 and np.unique(agg).shape[0] == nagg
+
+
+def poisson2d(points, nx, ny):
+    """cusp::gallery::poisson5pt / poisson9pt: centre 4 (8), neighbours -1"""
+    idx = np.arange(nx * ny).reshape(ny, nx)
+    rows, cols, vals = [], [], []
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            if points == 5 and dx != 0 and dy != 0:
+                continue
+            src = idx[max(0, -dy):ny - max(0, dy), max(0, -dx):nx - max(0, dx)]
+            dst = idx[max(0, dy):ny - max(0, -dy), max(0, dx):nx - max(0, -dx)]
+            rows.append(src.ravel())
+            cols.append(dst.ravel())
+            vals.append(np.full(src.size, float(points - 1) if (dx, dy) == (0, 0) else -1.0))
+    A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(idx.size, idx.size))
+    A.sort_indices()
+    return A
+
+
+def test_fgmres_convergence_poisson(oracle):
+    """the reference's FGMRESConvergencePoisson unit test (src/tests/fgmres_convergence_poisson.cu): FGMRES with a full-length restart and
+    one BLOCK_JACOBI sweep as preconditioner on 5- and 9-point Poisson grids 5x5 .. 10x10, tolerance 1e-14: true relative residual < 1e-5"""
+    for size in range(5, 11):
+        for points in (5, 9):
+            A = poisson2d(points, size, size)
+            rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+            n = rp.shape[0] - 1
+            b = np.ones(n)
+            x, it, hist, conv = oracle.fgmres(rp, ci, va, b, jacobi_omega=0.9, tol=1e-14, max_iters=n, restart=n)
+            assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) < 1e-5, (points, size)
