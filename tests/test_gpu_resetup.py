@@ -124,3 +124,42 @@ def test_classical_resetup_keeps_P_and_R(amgx, oracle, k):
     assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
     for ob in (slv, x, b, A, rsc, cfg):
         ob.destroy()
+
+
+def test_amg_levels_reuse_reference_unit_test(amgx):
+    """the reference's AmgLevelsReuse unit test (src/tests/amg_levels_reuse.cu) with its own configuration string: 27-point Poisson, set up,
+    solve, replace the coefficients, set up again (and, beyond the reference test, resetup), solve from the previous iterate -- the final x
+    must not depend on structure_reuse_levels (1e-8)"""
+    from tests.test_oracle_edge_cases import poisson27
+    A = poisson27(24, 24, 24)
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+    n = rp.shape[0] - 1
+    rng = np.random.default_rng(1)
+    b0, x0 = 1.0 + rng.random(n), 1.0 + np.random.default_rng(2).random(n)
+    base = ("config_version=2, solver(main_solver)=AMG, main_solver:algorithm=AGGREGATION, main_solver:coarseAgenerator=LOW_DEG,main_solver:coloring_level=1,"
+            "main_solver:convergence=RELATIVE_MAX,main_solver:cycle=V,main_solver:matrix_coloring_scheme=MIN_MAX,main_solver:max_levels=21,main_solver:norm=L1,"
+            "main_solver:postsweeps=3,main_solver:presweeps=0,main_solver:selector=SIZE_2,main_solver:smoother=BLOCK_JACOBI,main_solver:tolerance=0.1,")
+    tail = (",main_solver:max_iters=2,main_solver:monitor_residual=1,determinism_flag=1,max_uncolored_percentage=0.,main_solver:store_res_history=1,"
+            "main_solver:obtain_timings=1")
+    for use_resetup in (False, True):
+        ref = None
+        for k in range(0, 10, 3):
+            cfg = amgx.Config(base + f", main_solver:structure_reuse_levels={k}, " + tail)
+            rsc = amgx.Resources(cfg)
+            M = amgx.Matrix(rsc).upload(rp, ci, va)
+            bv, xv = amgx.Vector(rsc).upload(b0), amgx.Vector(rsc).upload(x0)
+            slv = amgx.Solver(rsc, cfg)
+            slv.setup(M)
+            slv.solve(bv, xv)
+            x1 = xv.download()
+            M.replace_coefficients(va)
+            (slv.resetup if use_resetup else slv.setup)(M)
+            xv.upload(x1)
+            slv.solve(bv, xv)
+            x2 = xv.download()
+            if ref is None:
+                ref = x2
+            else:
+                assert np.max(np.abs(x2 - ref)) <= 1e-8 * max(1.0, np.max(np.abs(ref))), (use_resetup, k)
+            for ob in (slv, xv, bv, M, rsc, cfg):
+                ob.destroy()
