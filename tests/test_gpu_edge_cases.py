@@ -80,3 +80,12 @@ def test_fgmres_convergence_poisson(amgx):
                    f"determinism_flag=1, s1:tolerance=1e-14, s1:gmres_n_restart={n}, s1:convergence=RELATIVE_INI_CORE, s1:monitor_residual=1, s1:print_solve_stats=1")
             x, it, status, hist = run_engine(amgx, cfg, rp, ci, va, np.ones(n))
             assert np.linalg.norm(np.ones(n) - A @ x) / np.sqrt(n) < 1e-5, (points, size)
+
+
+def test_fgmres_zero_initial_residual(amgx):
+    """the reference's FGMRESZeroInitialResidual unit test, its configuration string included"""
+    rp, ci, va = np.array([0, 1, 2], np.int32), np.array([0, 1], np.int32), np.array([2.0, 4.0])
+    cfg = ("config_version=2, solver(s1)=FGMRES, s1:preconditioner(jacobi)=BLOCK_JACOBI, jacobi:max_iters=1, s1:max_iters=2,s1:norm=L2, determinism_flag=1, "
+           "s1:tolerance=1e-14, s1:gmres_n_restart=2, s1:convergence=RELATIVE_INI_CORE, s1:monitor_residual=1, s1:print_solve_stats=1")
+    x, it, status, hist = run_engine(amgx, cfg, rp, ci, va, np.zeros(2), x0=np.zeros(2))
+    assert status == "success" and it == 0 and not x.any()

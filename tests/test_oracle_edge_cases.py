@@ -153,3 +153,10 @@ def test_fgmres_convergence_poisson(oracle):
             b = np.ones(n)
             x, it, hist, conv = oracle.fgmres(rp, ci, va, b, jacobi_omega=0.9, tol=1e-14, max_iters=n, restart=n)
             assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) < 1e-5, (points, size)
+
+
+def test_fgmres_zero_initial_residual(oracle):
+    """the reference's FGMRESZeroInitialResidual unit test: A = diag(2, 4), b = 0, x = 0 -- convergence is reported without an iteration"""
+    rp, ci, va = np.array([0, 1, 2], np.int32), np.array([0, 1], np.int32), np.array([2.0, 4.0])
+    x, it, hist, conv = oracle.fgmres(rp, ci, va, np.zeros(2), jacobi_omega=0.9, tol=1e-14, max_iters=2, restart=2)
+    assert conv and it == 0 and not x.any() and np.isfinite(hist).all()
