@@ -89,3 +89,18 @@ def test_fgmres_zero_initial_residual(amgx):
            "s1:tolerance=1e-14, s1:gmres_n_restart=2, s1:convergence=RELATIVE_INI_CORE, s1:monitor_residual=1, s1:print_solve_stats=1")
     x, it, status, hist = run_engine(amgx, cfg, rp, ci, va, np.zeros(2), x0=np.zeros(2))
     assert status == "success" and it == 0 and not x.any()
+
+
+@pytest.mark.parametrize("smoother", ["BLOCK_JACOBI", "MULTICOLOR_DILU", "MULTICOLOR_GS"])
+def test_scalar_smoothers_poisson(amgx, smoother):
+    """the reference's ScalarSmootherPoisson unit test with its own (config_version 1) strings: the smoother as the solver, 1000 iterations"""
+    from tests.test_oracle_edge_cases import poisson2d
+    A = poisson2d(9, 10, 10)
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+    n = rp.shape[0] - 1
+    extra = ",symmetric_GS=1" if smoother == "MULTICOLOR_GS" else ""
+    cfg = (f"determinism_flag=1, solver={smoother}, coloring_level=1, matrix_coloring_scheme=MIN_MAX, max_uncolored_percentage=0.0, smoother_weight=1.0, "
+           f"max_iters=1000, monitor_residual=0{extra}")
+    x, it, status, hist = run_engine(amgx, cfg, rp, ci, va, np.ones(n), x0=np.zeros(n))
+    r = np.linalg.norm(np.ones(n) - A @ x)
+    assert r < np.sqrt(n) and r < 1e-5, (smoother, r)
