@@ -11,7 +11,7 @@
 // The arithmetic order is sequential per entry (k ascending), so the CPU restatement reproduces it bit for bit;
 // against cuSOLVER's blocked getrf the results agree to rounding (backward stable either way).
 // Row-partitioned matrices: like the reference's default each rank factors the diagonal block it owns (block Jacobi over the partitions);
-// halo values enter only through the right-hand side when the initial guess is not zero.  Limit: n = local rows * block_dim <= 2048.
+// halo values enter only through the right-hand side when the initial guess is not zero.  Limit: n = local rows * block_dim <= 8192.
 #include "solvers.h"
 #include "dist.h"
 
@@ -19,7 +19,7 @@ namespace amgxb {
 namespace {
 
 constexpr int LU_THREADS = 1024;
-constexpr int LU_MAX_N = 2048;
+constexpr int LU_MAX_N = 8192;      // 512 MB of factors in fp64; the reference's own unit test factors 4096 rows (src/tests/dense_lu.cu:232)
 
 template <class MatT, class T>
 __global__ void csr_to_dense_kernel(int n_rows, int bdim, const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, int nnz,
@@ -156,7 +156,7 @@ protected:
             fatal(AMGX_RC_NOT_IMPLEMENTED, "DENSE_LU_SOLVER with exact_coarse_solve=1 on a distributed matrix");
         if (A.bx != A.by) fatal(AMGX_RC_NOT_SUPPORTED_BLOCKSIZE, "DENSE_LU_SOLVER needs square blocks");
         n_ = A.n * A.bx;
-        if (n_ > LU_MAX_N) fatal(AMGX_RC_NOT_IMPLEMENTED, "DENSE_LU_SOLVER: coarsest level has more than 2048 rows; lower dense_lu_max_rows or use coarse_solver=NOSOLVER");
+        if (n_ > LU_MAX_N) fatal(AMGX_RC_NOT_IMPLEMENTED, "DENSE_LU_SOLVER: coarsest level has more than 8192 rows; lower dense_lu_max_rows or use coarse_solver=NOSOLVER");
         cudaStream_t s = stream();
         dense_.resize((size_t)std::max(n_, 1) * std::max(n_, 1), A.vec_prec);
         dense_.zero(s);

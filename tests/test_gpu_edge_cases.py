@@ -104,3 +104,14 @@ def test_scalar_smoothers_poisson(amgx, smoother):
     x, it, status, hist = run_engine(amgx, cfg, rp, ci, va, np.ones(n), x0=np.zeros(n))
     r = np.linalg.norm(np.ones(n) - A @ x)
     assert r < np.sqrt(n) and r < 1e-5, (smoother, r)
+
+
+def test_dense_lu_solve_poisson3d(amgx):
+    """the reference's DenseLUSolverTest_Solve_Poisson3D unit test: DENSE_LU_SOLVER as the solver on the 16^3 27-point Poisson matrix
+    (4096 rows), b = 1: residual norm < 1e-12"""
+    from tests.test_oracle_edge_cases import poisson27
+    A = poisson27(16, 16, 16)
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+    n = rp.shape[0] - 1
+    x, it, status, hist = run_engine(amgx, "solver=DENSE_LU_SOLVER, monitor_residual=1, dense_lu_max_rows=0", rp, ci, va, np.ones(n), x0=np.zeros(n))
+    assert np.linalg.norm(np.ones(n) - A @ x) < 1e-12

@@ -181,3 +181,12 @@ def test_scalar_smoothers_poisson(oracle):
             assert r < np.linalg.norm(b) and r < 1e-5, (sm, r)
     finally:
         oracle.set_uncolored_fraction(0.15)
+
+
+def test_dense_lu_solve_poisson3d(oracle):
+    """the reference's DenseLUSolverTest_Solve_Poisson3D unit test (src/tests/dense_lu.cu:215-258; 27-point Poisson, b = 1, residual norm
+    < 1e-12) on the restatement of the coarse solver; 10^3 rows here, the opt-in GPU test runs the reference's 16^3"""
+    A = poisson27(10, 10, 10)
+    n = A.shape[0]
+    x, lu, ipiv = oracle.dense_lu_solve(A.toarray(), np.ones(n))
+    assert np.linalg.norm(np.ones(n) - A @ x) < 1e-12
