@@ -176,6 +176,8 @@ protected:
         in_smem_ = smem_full_ <= (size_t)200 * 1024;
         AMGXB_DISPATCH_VEC(A.vec_prec, {
             if (in_smem_) AMGXB_CUDA_CHECK(cudaFuncSetAttribute(lu_solve_kernel<VecT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full_));
+            else if (smem_small_ > (size_t)48 * 1024)
+                AMGXB_CUDA_CHECK(cudaFuncSetAttribute(lu_solve_kernel<VecT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small_));
         });
     }
 
