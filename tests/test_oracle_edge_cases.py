@@ -190,3 +190,25 @@ def test_dense_lu_solve_poisson3d(oracle):
     n = A.shape[0]
     x, lu, ipiv = oracle.dense_lu_solve(A.toarray(), np.ones(n))
     assert np.linalg.norm(np.ones(n) - A @ x) < 1e-12
+
+
+def test_valid_coloring_on_random_symmetric_structures(oracle):
+    """the reference's MinMaxColoringTest unit test (src/tests/valid_coloring.cu), coloring_level 1, max_uncolored_percentage 0: on random
+    structurally symmetric matrices no two neighbouring coloured rows share a colour -- for MIN_MAX and for PARALLEL_GREEDY"""
+    rng = np.random.default_rng(10125)
+    for trial in range(10):
+        n = int(rng.integers(1, 10000))
+        per_row = max(int(rng.integers(0, 10)), 1)
+        r = np.repeat(np.arange(n), per_row)
+        c = rng.integers(0, n, r.shape[0])
+        S = sp.coo_matrix((np.ones(r.shape[0]), (r, c)), shape=(n, n)).tocsr()
+        S = (S + S.T + sp.identity(n)).tocsr()
+        S.sort_indices()
+        rp, ci = S.indptr.astype(np.int32), S.indices.astype(np.int32)
+        rows = np.repeat(np.arange(n), np.diff(rp))
+        off = rows != ci
+        for fn in (oracle.color_min_max, oracle.color_parallel_greedy):
+            nc, colors, srows, offs = fn(rp, ci, 0.0)
+            both = off & (colors[rows] != 0) & (colors[ci] != 0)
+            assert not np.any(colors[rows][both] == colors[ci][both]), (fn.__name__, trial)
+            assert np.array_equal(np.sort(srows), np.arange(n)) and offs[0] == 0 and offs[-1] == n
