@@ -115,3 +115,20 @@ def test_dense_lu_solve_poisson3d(amgx):
     n = rp.shape[0] - 1
     x, it, status, hist = run_engine(amgx, "solver=DENSE_LU_SOLVER, monitor_residual=1, dense_lu_max_rows=0", rp, ci, va, np.ones(n), x0=np.zeros(n))
     assert np.linalg.norm(np.ones(n) - A @ x) < 1e-12
+
+
+@pytest.mark.parametrize("algo", ["SIZE_2", "SIZE_4", "PMIS_D2", "PMIS_D1", "HMIS_MULTIPASS"])
+def test_explicit_zero_values_and_unsymmetric_structure_give_no_nan(amgx, algo):
+    """the reference's ExplicitZeroValues unit test (src/tests/zero_values_handling.cu) through the C-ABI"""
+    from tests.test_oracle_edge_cases import random_unsymmetric_with_a_zero
+    rp, ci, va = random_unsymmetric_with_a_zero()
+    n = rp.shape[0] - 1
+    for smoother in ("BLOCK_JACOBI", "JACOBI_L1", "MULTICOLOR_DILU"):
+        if algo.startswith("SIZE"):
+            amg = amg_agg_cfg(smoother=smoother, max_levels=10, selector=algo)
+        else:
+            sel, interp = algo.split("_")
+            amg = amg_agg_cfg(smoother=smoother, max_levels=10)
+            amg.update(algorithm="CLASSICAL", selector=sel, interpolator=interp)
+        x, it, status, hist = run_engine(amgx, outer_cfg("FGMRES", amg, tol=1e-8, max_iters=2, gmres_n_restart=2), rp, ci, va, np.ones(n))
+        assert np.isfinite(x).all() and np.isfinite(hist).all(), (algo, smoother)

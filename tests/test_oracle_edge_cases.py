@@ -212,3 +212,43 @@ def test_valid_coloring_on_random_symmetric_structures(oracle):
             both = off & (colors[rows] != 0) & (colors[ci] != 0)
             assert not np.any(colors[rows][both] == colors[ci][both]), (fn.__name__, trial)
             assert np.array_equal(np.sort(srows), np.arange(n)) and offs[0] == 0 and offs[-1] == n
+
+
+def random_unsymmetric_with_a_zero(n=100, seed=31):
+    """generateMatrixRandomStruct + random_fill + random_add_zeros of the reference's zero_values_handling test: random, structurally
+    unsymmetric rows (diagonal included), positive random values, the first off-diagonal value of one row replaced by an explicit zero"""
+    rng = np.random.default_rng(seed)
+    rows, cols = [], []
+    for i in range(n):
+        c = {i}
+        for _ in range(int(rng.integers(1, 10))):
+            c.add(int(rng.integers(n)))
+        for j in sorted(c):
+            rows.append(i)
+            cols.append(j)
+    A = sp.csr_matrix((rng.random(len(rows)) + 0.1, (rows, cols)), shape=(n, n))
+    A.sort_indices()
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.copy()
+    while True:
+        r = int(rng.integers(n - 1))
+        if ci[rp[r]] != r:
+            va[rp[r]] = 0.0
+            return rp, ci, va
+
+
+def test_explicit_zero_values_and_unsymmetric_structure_give_no_nan(oracle):
+    """ExplicitZeroValues (src/tests/zero_values_handling.cu): every selector, coarse generator, colouring, smoother, strength,
+    classical selector and interpolator must get through such a matrix without NaNs or errors"""
+    for seed in (31, 32, 33):
+        rp, ci, va = random_unsymmetric_with_a_zero(seed=seed)
+        n = rp.shape[0] - 1
+        for sel in ("SIZE_2", "SIZE_4"):
+            for sm in ("BLOCK_JACOBI", "JACOBI_L1", "MULTICOLOR_DILU", "MULTICOLOR_GS"):
+                a = oracle.AMG(rp, ci, va, max_levels=10, min_coarse_rows=2, smoother=sm, selector=sel)
+                x, it, hist, conv = oracle.pcg(rp, ci, va, np.ones(n), amg=a, tol=1e-8, max_iters=2)
+                assert np.isfinite(x).all() and np.isfinite(hist).all(), (seed, sel, sm)
+        for s in ("PMIS", "HMIS"):
+            for interp in ("D1", "D2", "MULTIPASS"):
+                c = oracle.ClassicalAMG(rp, ci, va, max_levels=10, interpolator=interp, selector=s)
+                x, it, hist, conv = oracle.fgmres(rp, ci, va, np.ones(n), amg=c, tol=1e-8, max_iters=2, restart=2)
+                assert np.isfinite(x).all() and np.isfinite(hist).all(), (seed, s, interp)
