@@ -132,3 +132,34 @@ def test_explicit_zero_values_and_unsymmetric_structure_give_no_nan(amgx, algo):
             amg.update(algorithm="CLASSICAL", selector=sel, interpolator=interp)
         x, it, status, hist = run_engine(amgx, outer_cfg("FGMRES", amg, tol=1e-8, max_iters=2, gmres_n_restart=2), rp, ci, va, np.ones(n))
         assert np.isfinite(x).all() and np.isfinite(hist).all(), (algo, smoother)
+
+
+@pytest.mark.parametrize("writer", ["matrixmarket", "binary"])
+@pytest.mark.parametrize("block", [1, 4])
+def test_generated_matrix_io_round_trip(amgx, tmp_path, writer, block):
+    """the reference's generated_matrix_io unit test: write a system with AMGX_write_system (MatrixMarket with the %%AMGX header, or the
+    %%NVAMGBinary format), read it back with AMGX_read_system: matrix, right-hand side and solution survive bit for bit"""
+    import ctypes as C
+    lib = amgx.load_library()
+    if block == 1:
+        rp, ci, va = gallery.random_banded(500, sigma=12.0, seed=4)
+    else:
+        rp, ci, va = gallery.block_elasticity(5, 4, 3)
+    n = rp.shape[0] - 1
+    cfg = amgx.Config(f"matrix_writer={writer}")
+    rsc = amgx.Resources(cfg)
+    va = np.ascontiguousarray(np.asarray(va, np.float64).ravel())
+    A = amgx.Matrix(rsc).upload(rp, ci, va, block_dims=(block, block))
+    rng = np.random.default_rng(8)
+    bh, xh = rng.standard_normal(n * block), rng.standard_normal(n * block)
+    b = amgx.Vector(rsc).upload(bh, block_dim=block)
+    x = amgx.Vector(rsc).upload(xh, block_dim=block)
+    fn = str(tmp_path / f"sys_{writer}_{block}.dat").encode()
+    assert lib.AMGX_write_system(A.h, b.h, x.h, fn) == 0
+    A2, b2, x2 = amgx.Matrix(rsc), amgx.Vector(rsc), amgx.Vector(rsc)
+    assert lib.AMGX_read_system(A2.h, b2.h, x2.h, fn) == 0
+    rp2, ci2, va2, _ = A2.download()
+    assert np.array_equal(rp2, rp) and np.array_equal(ci2, ci) and np.array_equal(va2, va)
+    assert np.array_equal(b2.download(), bh) and np.array_equal(x2.download(), xh)
+    for ob in (x2, b2, A2, x, b, A, rsc, cfg):
+        ob.destroy()

@@ -27,7 +27,7 @@ fi
 if [ "$STAGE" = unvalidated ] || [ "$STAGE" = all ]; then
   echo "== unvalidated: DENSE_LU, W/F/CG/CGF cycles, error_scaling, CG/PCGF/PBICGSTAB/GMRES, MULTICOLOR_GS, CHEBYSHEV(_POLY), resetup (aggregation + classical), HMIS, D1, SIZE_4"
   AMGXB_RUN_UNVALIDATED=1 timeout 1500 $PT tests/test_gpu_dense_lu.py tests/test_gpu_cycles.py tests/test_gpu_krylov.py tests/test_gpu_smoothers.py \
-      tests/test_gpu_resetup.py tests/test_gpu_classical.py tests/test_gpu_edge_cases.py tests/test_golden_round2.py 2>&1 | tail -40 | tee gpurun_out/unvalidated.log
+      tests/test_gpu_resetup.py tests/test_gpu_classical.py tests/test_gpu_edge_cases.py tests/test_capi_graceful_failure.py tests/test_golden_round2.py 2>&1 | tail -40 | tee gpurun_out/unvalidated.log
 fi
 
 if [ "$STAGE" = goldens ] || [ "$STAGE" = all ]; then
