@@ -184,27 +184,43 @@ static void read_mm(const char *filename, MMSystem &S)
         put(i, j, v);
         if (symmetric && i != j) put(j, i, skew ? -v : v);
     }
+    // What follows the entries in the reference's format (writer src/matrix_io.cu:222-258, reader src/readers.cu:1290-1406): with
+    // "diagonal" one line of block_size values per row (the diagonal blocks, which are then NOT among the entries); with "rhs" /
+    // "solution" a line holding the vector length, then the values.  Files without the length lines, and files that carry the diagonal
+    // inline as (i, i) entries, are accepted too: the layout is told apart by the number of values left in the file.
+    std::vector<double> tail;
+    for (double v; fin >> v;) tail.push_back(v);
+    const size_t need_b = has_rhs ? (size_t)n * S.by : 0, need_x = has_sol ? (size_t)n * S.bx : 0, L = (size_t)has_rhs + (size_t)has_sol;
+    const size_t D = S.has_diag ? (size_t)n * bsq : 0;
+    bool diag_section = false, lengths = false;
+    if (S.has_diag && tail.size() == D + need_b + need_x + L) { diag_section = true; lengths = L > 0; }
+    else if (S.has_diag && tail.size() == D + need_b + need_x) diag_section = true;
+    else if (tail.size() == need_b + need_x + L) lengths = L > 0;
+    else if (tail.size() != need_b + need_x) fatal(AMGX_RC_IO_ERROR, "MatrixMarket: unexpected number of values after the matrix entries (diagonal / rhs / solution sections)");
     S.n = n;
     S.rp.assign(n + 1, 0);
     if (S.has_diag) S.diag.assign((size_t)n * bsq, 0.0);
     for (int i = 0; i < n; i++) {
         for (auto &kv : rowsmap[i]) {
-            if (S.has_diag && kv.first == i) { std::copy(kv.second.begin(), kv.second.end(), S.diag.begin() + (size_t)i * bsq); continue; }
+            if (S.has_diag && !diag_section && kv.first == i) { std::copy(kv.second.begin(), kv.second.end(), S.diag.begin() + (size_t)i * bsq); continue; }
             S.ci.push_back(kv.first);
             S.va.insert(S.va.end(), kv.second.begin(), kv.second.end());
         }
         S.rp[i + 1] = (int)S.ci.size();
     }
     S.nnz = (int)S.ci.size();
-    auto read_vec = [&](std::vector<double> &v, size_t len) {
-        v.resize(len);
-        for (size_t k = 0; k < len; k++) {
-            fin >> v[k];
-            if (!fin) fatal(AMGX_RC_IO_ERROR, "MatrixMarket: unexpected end of file in rhs/solution");
+    size_t pos = 0;
+    if (diag_section) { std::copy(tail.begin(), tail.begin() + (long)D, S.diag.begin()); pos = D; }
+    auto take = [&](std::vector<double> &v, size_t len) {
+        if (lengths) {
+            if ((size_t)tail[pos] != len) fatal(AMGX_RC_IO_ERROR, "MatrixMarket: rhs / solution length line does not match the matrix size");
+            pos++;
         }
+        v.assign(tail.begin() + (long)pos, tail.begin() + (long)(pos + len));
+        pos += len;
     };
-    if (has_rhs) read_vec(S.rhs, (size_t)n * S.by);
-    if (has_sol) read_vec(S.sol, (size_t)n * S.bx);
+    if (has_rhs) take(S.rhs, need_b);
+    if (has_sol) take(S.sol, need_x);
 }
 
 template <class T> static std::vector<T> convert(const std::vector<double> &v)
@@ -512,17 +528,26 @@ static void write_host_system(const char *filename, const std::string &writer, i
     if (writer != "matrixmarket") fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_writer '" + writer + "' is not supported (matrixmarket, binary)");
     std::ofstream f(filename);
     if (!f) fatal(AMGX_RC_IO_ERROR, "cannot open output file");
+    // the reference's writer, src/matrix_io.cu:120-258: "%%NVAMG bx by [diagonal] [rhs] [solution]" (no "sorted": the columns need not be),
+    // entries, the diagonal blocks one per line when they are stored outside the CSR structure, then length + values of rhs and solution;
+    // 17 significant digits instead of the reference's 16 so that a round trip is exact
     f << "%%MatrixMarket matrix coordinate real general\n";
-    f << "%%AMGX " << bx << " " << by << " sorted" << (b.empty() ? "" : " rhs") << (x.empty() ? "" : " solution") << "\n";
+    f << "%%NVAMG " << bx << " " << by << (ext_diag ? " diagonal" : "") << (b.empty() ? "" : " rhs") << (x.empty() ? "" : " solution") << "\n";
     f << (long long)n * bx << " " << (long long)n * by << " " << (long long)nnz * bsq << "\n";
     f.precision(17);
+    f << std::scientific;
     for (int i = 0; i < n; i++)
         for (int k = rp[i]; k < rp[i + 1]; k++)
             for (int r = 0; r < bx; r++)
                 for (int c = 0; c < by; c++)
                     f << (long long)i * bx + r + 1 << " " << (long long)ci[k] * by + c + 1 << " " << va[(size_t)k * bsq + r * by + c] << "\n";
-    for (double v : b) f << v << "\n";
-    for (double v : x) f << v << "\n";
+    if (ext_diag)
+        for (int i = 0; i < n; i++) {
+            for (int k = 0; k < bsq; k++) f << va[((size_t)nnz + i) * bsq + k] << " ";
+            f << "\n";
+        }
+    if (!b.empty()) { f << b.size() << "\n"; for (double v : b) f << v << "\n"; }
+    if (!x.empty()) { f << x.size() << "\n"; for (double v : x) f << v << "\n"; }
 }
 
 /* AMGX_write_system_distributed (src/amgx_c.cu:1406-1491, 3557-3600): the partitions are gathered and rank 0 writes ONE global system.

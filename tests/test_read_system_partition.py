@@ -135,3 +135,37 @@ def test_binary_system_file_is_detected_and_read(tmp_path):
     q = tmp_path / "short.bin"
     q.write_bytes(p.read_bytes()[:200])
     assert call(lib, 0, 1, str(q))[0] != 0
+
+
+def _write(path, header, entries, tail_lines):
+    path.write_text("\n".join(["%%MatrixMarket matrix coordinate real general", header, f"12 12 {len(entries)}"] + entries + tail_lines) + "\n")
+    return str(path)
+
+
+@pytest.mark.parametrize("with_lengths", [True, False])
+def test_reference_file_format_sections(tmp_path, with_lengths):
+    """What the reference's own writer emits after the entries (src/matrix_io.cu:222-258) and its reader expects (src/readers.cu:1290-1406):
+    with "diagonal" one line per row holding the diagonal block (which is then not among the entries), and a LENGTH line in front of
+    the rhs and of the solution.  Files without the length lines (older files of this engine, hand-written ones) still read the same."""
+    lib = capi.load_library()
+    off = [(i, CI[k]) for i in range(12) for k in range(RP[i], RP[i + 1]) if CI[k] != i]
+    entries = [f"{i + 1} {j + 1} {100 * (i + 1) + j + 1}" for i, j in off]
+    diag = [f"{1000.0 + i!r} " for i in range(12)]
+    rhs, sol = [str(float(i + 1)) for i in range(12)], [str(0.5 * i) for i in range(12)]
+    tail = diag + (["12"] if with_lengths else []) + rhs + (["12"] if with_lengths else []) + sol
+    fn = _write(tmp_path / "ref_format.mtx", "%%NVAMG 1 1 diagonal rhs solution", entries, tail)
+    rc, got = call(lib, 0, 1, fn, want_local=False)
+    assert rc == 0
+    assert got["n"] == 12 and np.array_equal(got["rhs"], np.arange(1.0, 13.0)) and np.array_equal(got["sol"], 0.5 * np.arange(12))
+    # the external diagonal is handed back separately or merged, depending on the hook; either way every value must be found once
+    vals = sorted(got["data"].tolist())
+    assert vals[: len(off)] == sorted(100.0 * (i + 1) + j + 1 for i, j in off)
+    # the same system with the diagonal INLINE (no "diagonal" keyword) and no solution section
+    inline = [f"{i + 1} {CI[k] + 1} {100 * (i + 1) + CI[k] + 1}" for i in range(12) for k in range(RP[i], RP[i + 1])]
+    fn2 = _write(tmp_path / "inline.mtx", "%%AMGX rhs", inline, (["12"] if with_lengths else []) + rhs)
+    rc, got2 = call(lib, 0, 1, fn2, want_local=False)
+    assert rc == 0 and got2["nnz"] == len(CI) and np.array_equal(got2["rhs"], np.arange(1.0, 13.0))
+    # a wrong number of trailing values is an error, not a silent misread
+    fn3 = _write(tmp_path / "short.mtx", "%%AMGX rhs", inline, rhs[:-2])
+    rc, _ = call(lib, 0, 1, fn3, want_local=False)
+    assert rc != 0
