@@ -163,3 +163,37 @@ def test_generated_matrix_io_round_trip(amgx, tmp_path, writer, block):
     assert np.array_equal(b2.download(), bh) and np.array_equal(x2.download(), xh)
     for ob in (x2, b2, A2, x, b, A, rsc, cfg):
         ob.destroy()
+
+
+@pytest.mark.parametrize("where", ["device", "pinned", "pageable"])
+def test_capi_upload_distributed_from_any_memory(amgx, where):
+    """the reference's CAPIUpload* unit tests (src/tests/capi_upload_tests.cu): AMGX_matrix_upload_distributed on one GPU with 32-bit
+    column indices and a NULL partition vector accepts device, pinned and pageable arrays; the matrix arrives intact"""
+    import ctypes as C
+    import torch
+    lib = amgx.load_library()
+    n = 10
+    rp = np.arange(0, n * n + 1, n, dtype=np.int32)
+    ci = np.tile(np.arange(n, dtype=np.int32), n)
+    va = np.random.default_rng(2).standard_normal(n * n) + np.repeat(np.eye(n).ravel() * 20, 1)
+    cfg = amgx.Config("config_version=2, solver(slv)=PCG, slv:preconditioner(amg)=NOSOLVER, slv:max_iters=100, slv:monitor_residual=1, "
+                      "slv:convergence=ABSOLUTE, slv:tolerance=1e-07, slv:norm=L2")
+    rsc = amgx.Resources(cfg)
+    A = amgx.Matrix(rsc)
+    dh = C.c_void_p()
+    assert lib.AMGX_distribution_create(C.byref(dh), cfg.h) == 0
+    assert lib.AMGX_distribution_set_32bit_colindices(dh, 1) == 0
+    assert lib.AMGX_distribution_set_partition_data(dh, 0, None) == 0          # AMGX_DIST_PARTITION_VECTOR, default partition
+    ts = [torch.from_numpy(a) for a in (rp, ci, va)]
+    if where == "device":
+        ts = [t.cuda() for t in ts]
+    elif where == "pinned":
+        ts = [t.pin_memory() for t in ts]
+    lib.AMGX_matrix_upload_distributed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib.AMGX_matrix_upload_distributed(A.h, n, n, n * n, 1, 1, ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), None, dh)
+    assert rc == 0, rc
+    lib.AMGX_distribution_destroy(dh)
+    rp2, ci2, va2, _ = A.download()
+    assert np.array_equal(rp2, rp) and np.array_equal(ci2, ci) and np.array_equal(va2, va)
+    for ob in (A, rsc, cfg):
+        ob.destroy()
