@@ -511,7 +511,9 @@ AMGX_RC AMGX_read_system_distributed(AMGX_matrix_handle mtx, AMGX_vector_handle 
     std::vector<double> hb = L.rhs;
     if (hb.empty()) hb.assign((size_t)L.n * S.by, 1.0);
     put(b, hb, S.by, false);
-    put(x, L.sol, S.bx, true);
+    std::vector<double> hx = L.sol;
+    if (hx.empty()) hx.assign((size_t)L.n * S.bx, 0.0);         // no solution section: zeros, as in AMGX_read_system
+    put(x, hx, S.bx, false);
     API2_END
 }
 
@@ -676,8 +678,10 @@ AMGX_RC AMGX_read_system(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_ve
     }
     if (sol) {
         VectorH *x = chk<VectorH>(sol, MAGIC_VEC, "vector");
-        if (!S.sol.empty()) upload_vec(*x->v, S.sol, S.n, S.bx);
-        else { x->v->n = 0; x->v->block_dim = S.bx; x->v->data.resize(0, x->v->prec); }
+        // no solution section: x = [0, ..., 0]^T of the matrix size, as the reference's reader leaves it (src/readers.cu:1392-1412)
+        std::vector<double> h = S.sol;
+        if (h.empty()) h.assign((size_t)S.n * S.bx, 0.0);
+        upload_vec(*x->v, h, S.n, S.bx);
     }
     API2_END
 }
