@@ -673,7 +673,23 @@ AMGX_RC AMGX_read_system(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_ve
     if (rhs) {
         VectorH *b = chk<VectorH>(rhs, MAGIC_VEC, "vector");
         std::vector<double> h = S.rhs;
-        if (h.empty()) h.assign((size_t)S.n * S.by, 1.0);   // rhs_from_a = 0: b = [1,...,1]^T
+        if (h.empty()) {
+            // no rhs in the file (src/readers.cu:1364-1388): b = [1,...,1]^T, or b = A e with e = [1,...,1]^T when rhs_from_a = 1
+            const bool from_a = b->v->rsc && b->v->rsc->cfg && b->v->rsc->cfg->get_int("rhs_from_a", "default") == 1;
+            if (!from_a) h.assign((size_t)S.n * S.by, 1.0);
+            else {
+                h.assign((size_t)S.n * S.by, 0.0);
+                const int bsq = S.bx * S.by;
+                for (int i = 0; i < S.n; i++) {
+                    for (int k = S.rp[i]; k < S.rp[i + 1]; k++)
+                        for (int r = 0; r < S.bx; r++)
+                            for (int c = 0; c < S.by; c++) h[(size_t)i * S.by + r] += S.va[(size_t)k * bsq + r * S.by + c];
+                    if (S.has_diag)
+                        for (int r = 0; r < S.bx; r++)
+                            for (int c = 0; c < S.by; c++) h[(size_t)i * S.by + r] += S.diag[(size_t)i * bsq + r * S.by + c];
+                }
+            }
+        }
         upload_vec(*b->v, h, S.n, S.by);
     }
     if (sol) {
