@@ -552,6 +552,21 @@ static void write_host_system(const char *filename, const std::string &writer, i
     if (!x.empty()) { f << x.size() << "\n"; for (double v : x) f << v << "\n"; }
 }
 
+AMGX_RC AMGXB200_write_system_host(const char *filename, const char *writer, int n, int nnz, int block_dimx, int block_dimy, const int *row_ptrs,
+                                   const int *col_indices, const double *values, int ext_diag, const double *rhs, const double *sol)
+{
+    API2_BEGIN
+    if (!filename || !writer || n < 0 || nnz < 0 || block_dimx < 1 || block_dimy < 1 || !row_ptrs || (nnz > 0 && (!col_indices || !values)))
+        fatal(AMGX_RC_BAD_PARAMETERS, "AMGXB200_write_system_host: bad arguments");
+    const size_t bsq = (size_t)block_dimx * block_dimy;
+    std::vector<int> rp(row_ptrs, row_ptrs + n + 1), ci(col_indices, col_indices + nnz);
+    std::vector<double> va(values, values + ((size_t)nnz + (ext_diag ? (size_t)n : 0)) * bsq), b, x;
+    if (rhs) b.assign(rhs, rhs + (size_t)n * block_dimy);
+    if (sol) x.assign(sol, sol + (size_t)n * block_dimx);
+    write_host_system(filename, writer, n, nnz, block_dimx, block_dimy, rp, ci, va, ext_diag != 0, b, x);
+    API2_END
+}
+
 /* AMGX_write_system_distributed (src/amgx_c.cu:1406-1491, 3557-3600): the partitions are gathered and rank 0 writes ONE global system.
  * Every rank assembles the global matrix in the callers' row order (dist_gather_matrix) and the vectors with one all-gather; when the
  * matrix was uploaded through a partition vector, passing the same vector here restores the original global numbering (the reference's

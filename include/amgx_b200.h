@@ -255,6 +255,11 @@ AMGX_RC AMGX_API AMGXB200_read_system_partition(int rank, int world_size, AMGX_M
                                                 void **rhs, void **sol, int *num_neighbors, int **neighbors, int **send_sizes, int ***send_maps,
                                                 int **recv_sizes, int ***recv_maps);
 AMGX_RC AMGX_API AMGXB200_partition_vector_to_contiguous(int n_global, int world_size, const int *partition_vector, int64_t *offsets, int64_t *new_global);
+/* The file writer behind AMGX_write_system[_distributed] for host arrays (fp64): writer = "matrixmarket" (the reference's layout,
+ * src/matrix_io.cu:120-258) or "binary" (%%NVAMGBinary).  values holds nnz blocks followed by n diagonal blocks when ext_diag != 0;
+ * rhs / sol may be NULL.  Pure host code, no GPU: lets the writer / reader pair be tested without a device. */
+AMGX_RC AMGX_API AMGXB200_write_system_host(const char *filename, const char *writer, int n, int nnz, int block_dimx, int block_dimy, const int *row_ptrs,
+                                            const int *col_indices, const double *values, int ext_diag, const double *rhs, const double *sol);
 
 #if defined(__cplusplus)
 }
