@@ -48,7 +48,7 @@ def test_oracle_matches_reference_golden(oracle, name):
         return
     assert it == int(d["iterations"][0]) and conv == (int(d["status"][0]) == 0)
     assert np.max(np.abs(hist - href) / href[0]) < TOL.get(name, 1e-12)
-    if amg is not None:
+    if amg is not None and "num_levels" in d:      # ref_dump finds the hierarchy only under PCG / FGMRES / AMG-as-main-solver
         assert amg.num_levels() == int(d["num_levels"][0])
 
 
