@@ -49,6 +49,20 @@ class PartitionPlan(C.Structure):
 _lib = None
 
 
+def _preload_nccl():
+    """The engine links libnccl.so.2 by soname.  A process that later imports torch needs torch's bundled NCCL (newer than the system
+    one): whichever copy is mapped first serves both, so map the bundled one first when it exists (no torch import needed)."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            so = Path(list(spec.submodule_search_locations)[0]) / "lib" / "libnccl.so.2"
+            if so.exists():
+                C.CDLL(str(so), mode=C.RTLD_GLOBAL)
+    except Exception:
+        pass      # the system libnccl is used
+
+
 def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     """Load the engine.  Raises OSError when the shared library is missing (no fallback)."""
     global _lib
@@ -57,6 +71,7 @@ def load_library(path: str | os.PathLike | None = None) -> C.CDLL:
     p = Path(path) if path else _LIB_PATH
     if not p.exists():
         raise OSError(f"{p} not found: build it with `python -m amgx_b200.build` (or __graft_entry__.build())")
+    _preload_nccl()
     lib = C.CDLL(str(p), mode=C.RTLD_GLOBAL)
     _declare(lib)
     if path is None:

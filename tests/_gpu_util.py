@@ -4,8 +4,7 @@ import os
 import numpy as np
 import pytest
 
-UNVALIDATED = pytest.mark.skipif(os.environ.get("AMGXB_RUN_UNVALIDATED") != "1",
-                                 reason="component not yet validated on a GPU (set AMGXB_RUN_UNVALIDATED=1; tools/validate_next_round.sh)")
+UNVALIDATED = pytest.mark.validated_r2   # was an opt-in gate in round 1; every single-GPU suite ran on a B200 in round 2 (gpurun_out/r2/unvalidated.log)
 
 
 def run_engine(amgx, cfgd, rp, ci, va, b, x0=None, mode="dDDI", block=1):
@@ -25,7 +24,10 @@ def run_engine(amgx, cfgd, rp, ci, va, b, x0=None, mode="dDDI", block=1):
         slv.setup(A)
         slv.solve(bv, xv, zero_initial_guess=x0 is None)
         x = xv.download()
-        hist = np.array(slv.residual_history()).ravel()
+        try:
+            hist = np.array(slv.residual_history()).ravel()
+        except amgx.AMGXError:      # store_res_history off (the reference's own unit-test configurations): no history to read, as in the reference
+            hist = np.zeros(0)
         return x, slv.iterations_number, slv.status, hist
     finally:
         for obj in (slv, xv, bv, A, rsc, cfg):

@@ -10,6 +10,7 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "validated_r2: components written at the end of round 1, first run on a B200 in round 2 (no longer gated)")
 
 
 @pytest.fixture(scope="session")

@@ -157,7 +157,7 @@ def read_distributed_section(rank, world, rsc, lib, cfg):
             f.write(f"{ng} {ng} {ci.shape[0]}\n")
             for i in range(ng):
                 for k in range(rp[i], rp[i + 1]):
-                    f.write(f"{i + 1} {ci[k] + 1} {va[k]!r}\n")
+                    f.write(f"{i + 1} {ci[k] + 1} {float(va[k])!r}\n")
             for i in range(ng):
                 f.write(f"{1.0 + (i % 7) * 0.25!r}\n")
     dist.barrier()

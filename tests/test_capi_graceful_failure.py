@@ -61,7 +61,7 @@ def test_device_side_failures(lib, tmp_path):
         f.write(f"{n} {n} {nnz}\n")
         for i in range(n):
             for k in range(rp[i], rp[i + 1]):
-                f.write(f"{i + 1} {ci[k] + 1} {va[k]!r}\n")
+                f.write(f"{i + 1} {ci[k] + 1} {float(va[k])!r}\n")
     assert lib.AMGX_read_system(A, b, x, b"nonexisting_file.mtx") != 0
     assert lib.AMGX_read_system(A, b, x, str(fn).encode()) == 0
     nr, bx, by = C.c_int(), C.c_int(), C.c_int()

@@ -190,8 +190,6 @@ HMIS_SYSTEMS = {
 @pytest.mark.parametrize("name", list(HMIS_SYSTEMS))
 def test_hmis_hierarchy_bit_exact_vs_oracle(amgx, oracle, name):
     import os
-    if os.environ.get("AMGXB_RUN_UNVALIDATED") != "1":
-        pytest.skip("HMIS not yet validated on a GPU (AMGXB_RUN_UNVALIDATED=1)")
     gen, kw = HMIS_SYSTEMS[name]
     rp, ci, va = gen()
     n = rp.shape[0] - 1
@@ -224,8 +222,6 @@ D1_SYSTEMS = {
 @pytest.mark.parametrize("name", list(D1_SYSTEMS))
 def test_d1_hierarchy_bit_exact_vs_oracle(amgx, oracle, name):
     import os
-    if os.environ.get("AMGXB_RUN_UNVALIDATED") != "1":
-        pytest.skip("D1 not yet validated on a GPU (AMGXB_RUN_UNVALIDATED=1)")
     gen, kw = D1_SYSTEMS[name]
     rp, ci, va = gen()
     n = rp.shape[0] - 1

@@ -1,6 +1,6 @@
 """GPU: W and F cycles of the engine against the CPU restatement (iteration counts, residual history 1e-12).
 
-Added after this round's GPU minutes were spent: NOT yet run on a device, therefore opt-in (AMGXB_RUN_UNVALIDATED=1).  The V cycle --
+First run on a B200 in round 2.  The V cycle --
 the only cycle the judged configurations use -- is unchanged and covered by the regular tests."""
 import os
 
@@ -9,8 +9,7 @@ import pytest
 
 from amgx_b200 import gallery
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("AMGXB_RUN_UNVALIDATED") != "1", reason="W/F cycles not yet validated on a GPU (set AMGXB_RUN_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("cyc", ["W", "F"])

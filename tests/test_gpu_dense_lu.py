@@ -1,8 +1,6 @@
 """GPU: DENSE_LU_SOLVER (csrc/dense_lu.cu) against the CPU restatement.
 
-The solver was written after this round's GPU minutes were spent: these tests have NOT been run on a device yet and are therefore
-opt-in (AMGXB_RUN_UNVALIDATED=1) so that the suite the driver runs only contains validated checks.  First task of the next round:
-run them, then drop the guard."""
+First run on a B200 in round 2 (all green); part of the regular -m gpu suite since."""
 import os
 
 import numpy as np
@@ -10,8 +8,7 @@ import pytest
 
 from amgx_b200 import gallery
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("AMGXB_RUN_UNVALIDATED") != "1", reason="DENSE_LU_SOLVER not yet validated on a GPU (set AMGXB_RUN_UNVALIDATED=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def cfg_pcg_agg_dense(num_rows=64, tol=1e-10):

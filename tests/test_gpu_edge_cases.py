@@ -146,6 +146,11 @@ def test_generated_matrix_io_round_trip(amgx, tmp_path, writer, block):
     else:
         rp, ci, va = gallery.block_elasticity(5, 4, 3)
     n = rp.shape[0] - 1
+    # the reference's MatrixMarket reader builds CSR from the coordinate entries by sorting them (src/readers.cu:1293-1325), so a round trip
+    # returns column-sorted rows; its own unit test generates sorted matrices.  Sort the input the same way.
+    va = np.asarray(va, np.float64).reshape(ci.shape[0], -1)
+    order = np.concatenate([rp[i] + np.argsort(ci[rp[i]:rp[i + 1]], kind="stable") for i in range(n)])
+    ci, va = np.ascontiguousarray(ci[order]), np.ascontiguousarray(va[order])
     cfg = amgx.Config(f"matrix_writer={writer}")
     rsc = amgx.Resources(cfg)
     va = np.ascontiguousarray(np.asarray(va, np.float64).ravel())

@@ -80,14 +80,15 @@ def test_amg_chebyshev_matches_oracle(amgx, oracle, precond, order, mode):
     rp, ci, va = gallery.poisson7pt(15, 13, 10)
     n = rp.shape[0] - 1
     b = np.ones(n)
-    amg = _cheb_amg(precond, order, mode, cheby_max_lambda=0.95, cheby_min_lambda=0.1)
+    # mode 3 (BLOCK_JACOBI(0.9)-preconditioned): the spectrum of 0.9 D^-1 A reaches 1.8, so the user bounds must cover it (0.95 stagnates, also in the oracle)
+    amg = _cheb_amg(precond, order, mode, cheby_max_lambda=1.9, cheby_min_lambda=0.2)
     x, it, status, hist = run_engine(amgx, outer_cfg("PCG", amg, tol=1e-9, max_iters=80), rp, ci, va, b)
     oracle.set_chebyshev_precond(precond)
     try:
         o = oracle.AMG(rp, ci, va, max_levels=50, presweeps=0, postsweeps=1, coarsest_sweeps=0, smoother="CHEBYSHEV")
     finally:
         oracle.set_chebyshev_precond(None)
-    o.set_chebyshev(order=order, mode=mode, precond=precond, inner_omega=0.9, user_max=0.95, user_min=0.1).set_error_scaling(3)
+    o.set_chebyshev(order=order, mode=mode, precond=precond, inner_omega=0.9, user_max=1.9, user_min=0.2).set_error_scaling(3)
     xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, amg=o, tol=1e-9, max_iters=80)
     assert convo and status == "success" and it == ito
     assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
@@ -135,7 +136,9 @@ def test_parallel_greedy_colouring_bit_exact(amgx, oracle, mat):
     n = rp.shape[0] - 1
     amg = amg_agg_cfg(pre=0, post=3, omega=0.75, smoother="MULTICOLOR_DILU", matrix_coloring_scheme="PARALLEL_GREEDY")
     amg["smoother"]["matrix_coloring_scheme"] = "PARALLEL_GREEDY"
-    amg.update(scope="main", max_iters=40, monitor_residual=1, store_res_history=1, convergence="RELATIVE_INI", tolerance=1e-8, norm="L2")
+    # the stand-alone AMG iteration diverges on the banded matrix (also in the oracle): there only the first sweeps are compared
+    mi = 60 if mat == "poisson" else 4
+    amg.update(scope="main", max_iters=mi, monitor_residual=1, store_res_history=1, convergence="RELATIVE_INI", tolerance=1e-8, norm="L2")
     cfg = amgx.Config({"config_version": 2, "determinism_flag": 1, "solver": amg})
     rsc = amgx.Resources(cfg)
     A = amgx.Matrix(rsc).upload(rp, ci, va)
@@ -162,6 +165,8 @@ def test_parallel_greedy_colouring_bit_exact(amgx, oracle, mat):
     for l, (nc, colors) in enumerate(cols):
         nco, co, _ = oracle.amg_level_dilu(o, l)
         assert nc == nco and np.array_equal(colors, co), f"level {l} colouring"
-    xo, ito, histo, convo = oracle.amg_solve(o, np.ones(n), tol=1e-8, max_iters=40)
-    assert it == ito and status == "success" and convo
-    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+    xo, ito, histo, convo = oracle.amg_solve(o, np.ones(n), tol=1e-8, max_iters=mi)
+    assert it == ito and (status == "success") == bool(convo)
+    if mat == "poisson":
+        assert convo
+    assert np.max(np.abs(hist - histo) / np.maximum(histo, histo[0])) < 1e-12
