@@ -10,6 +10,7 @@
 // Each shortcut produces bit-identical vectors to the unfused sequence (0 + e == e, b - A*0 == b).
 #include "solvers.h"
 #include "dist.h"
+#include "p2p.h"
 #include <sstream>
 #include <iomanip>
 
@@ -186,6 +187,10 @@ void AMGSolver::setup_aggregation()
                 next->owned_A->dist = cdist;
                 next->owned_A->n_cols = n_agg + cdist->n_halo;
                 next->owned_A->split_row = n_int_c;
+                next->owned_A->rsc = A.rsc;
+                next->owned_A->bx = A.bx;
+                next->owned_A->by = A.by;
+                p2p_manager_setup(*next->owned_A);      // peer-memory receive window of the coarse level (collective)
             }
             next->owned_A->compute_diag_and_plan();
             next->A = next->owned_A.get();

@@ -6,6 +6,7 @@
 #include "dist.h"
 #include <cmath>
 #include "capi_internal.h"
+#include "p2p.h"
 #include <nccl.h>
 #include <algorithm>
 #include <numeric>
@@ -46,10 +47,12 @@ void dist_init_comm(Resources *rsc, const AMGXB200_comm *comm)
     rsc->nccl_comm = c;
     rsc->rank = comm->rank;
     rsc->world = comm->world_size;
+    p2p_init(rsc);      // NVLink peer-memory windows (CUDA IPC); falls back to NCCL send/recv when unavailable
 }
 
 void dist_destroy_comm(Resources *rsc)
 {
+    p2p_shutdown(rsc);
     if (rsc->nccl_comm) {
         ncclCommDestroy((ncclComm_t)rsc->nccl_comm);
         rsc->nccl_comm = nullptr;
@@ -161,6 +164,10 @@ void dist_exchange_halo_ptr(const Matrix &A, void *x, Prec prec, cudaStream_t s)
     if (!A.dist) return;
     if (A.dist->exchange_pending) dist_wait_halo(A, s);
     const int bsize = A.bx;
+    if (p2p_exchange_start(A, x, prec, bsize, s)) {      // one kernel stores my boundary values into the neighbours' windows
+        A.dist->exchange_pending = !A.dist->neighbors.empty();
+        return;
+    }
     if (prec == Prec::F64) exchange_typed<double>(A, (double *)x, bsize, s, ncclDouble);
     else exchange_typed<float>(A, (float *)x, bsize, s, ncclFloat);
 }
@@ -170,6 +177,11 @@ void dist_exchange_halo(const Matrix &A, DevVec &x, cudaStream_t s) { dist_excha
 void dist_wait_halo(const Matrix &A, cudaStream_t s)
 {
     if (!A.dist || !A.dist->exchange_pending) return;
+    if (A.dist->p2p_pending_x) {
+        p2p_exchange_wait(A, s);
+        A.dist->exchange_pending = false;
+        return;
+    }
     AMGXB_CUDA_CHECK(cudaStreamWaitEvent(s, A.dist->ev_done, 0));
     A.dist->exchange_pending = false;
 }
@@ -193,6 +205,7 @@ ReduceCtx dist_wrap_reduce(const Matrix &, const ReduceCtx &red) { return red; }
 void dist_allreduce_scalar_fin(const Matrix &A, const ReduceCtx &red, int slot, int fin_op, cudaStream_t s)
 {
     if (!A.dist) return;
+    if (p2p_allreduce_scalar(A, red, slot, 0, 0, fin_op, 0, false, s)) return;
     AMGXB_NCCL_CHECK(ncclAllReduce(red.scal + slot, red.scal + slot, 1, ncclDouble, ncclSum, comm_of(A), s));
     if (fin_op != FIN_STORE) {
         fin_kernel<<<1, 1, 0, s>>>(red.scal, slot, fin_op);
@@ -205,6 +218,7 @@ void dist_allreduce_scalar_fin(const Matrix &A, const ReduceCtx &red, int slot, 
 void dist_allreduce_norm(const Matrix &A, const ReduceCtx &red, int slot, int norm_type, cudaStream_t s)
 {
     if (!A.dist) return;
+    if (p2p_allreduce_scalar(A, red, slot, norm_type == 2 ? 2 : 0, 1, FIN_STORE, norm_type == 1, true, s)) return;
     AMGXB_NCCL_CHECK(ncclAllReduce(red.scal + slot, red.scal + slot, 1, ncclDouble, norm_type == 2 ? ncclMax : ncclSum, comm_of(A), s));
     sqrt_mirror_kernel<<<1, 1, 0, s>>>(red.scal, slot, norm_type == 1, red.host_mirror);
     count_launch();
@@ -382,6 +396,7 @@ void dist_build_matrix(Matrix &A, const int64_t *offsets, int n, int nnz, int bx
     A.dist->caller_row_ptr.from_any(rp, (size_t)n + 1, s);
     AMGXB200_partition_plan_free(&pl);
     verify_plan(A);
+    p2p_manager_setup(A);
     A.compute_diag_and_plan();
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
 }

@@ -30,6 +30,38 @@ namespace {
 
 #include "tile_common.cuh"
 
+// One row's dot product from the staged tile: U column loads, then U gathers of x in flight, then the FMA chain in storage order
+// (the per-row order of the reference's csrmv: y = a*x + y, amgx_cusparse.cu:1004-1012).  Slots past the end of the row re-read
+// the row's first column (an L1 hit) and are not accumulated.
+template <class MatT, class VecT, bool AGG, int U>
+__device__ __forceinline__ VecT row_dot(const MatT *__restrict__ vals, const int *__restrict__ cols, int k, const int kend, const VecT *__restrict__ x,
+                                        const int *__restrict__ agg)
+{
+    VecT sum = 0;
+    for (; k + U <= kend; k += U) {
+        int c[U];
+        VecT xv[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) c[j] = cols[k + j];
+#pragma unroll
+        for (int j = 0; j < U; j++) xv[j] = gather<VecT, AGG>(x, agg, c[j]);
+#pragma unroll
+        for (int j = 0; j < U; j++) sum = fma((VecT)vals[k + j], xv[j], sum);
+    }
+    if (k < kend) {
+        int c[U - 1];
+        VecT xv[U - 1];
+#pragma unroll
+        for (int j = 0; j < U - 1; j++) c[j] = cols[(k + j < kend) ? k + j : k];
+#pragma unroll
+        for (int j = 0; j < U - 1; j++) xv[j] = gather<VecT, AGG>(x, agg, c[j]);
+#pragma unroll
+        for (int j = 0; j < U - 1; j++)
+            if (k + j < kend) sum = fma((VecT)vals[k + j], xv[j], sum);
+    }
+    return sum;
+}
+
 // ---------------------------------------------------------------------------------------------
 // The tile kernel.  blockDim.x = TILE_ROWS + 32 (last warp = producer).
 // shared memory layout: [stages x full mbarrier][stages x empty mbarrier][red scratch 40 doubles]
@@ -116,26 +148,10 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
                 int k = rp[tid] - sa;
                 const int kend = rp[tid + 1] - sa;
                 VecT sum = 0;
-                // 4 gathers in flight per step; FMA chain strictly left to right
-                for (; k + 4 <= kend; k += 4) {
-                    const int c0 = cols[k], c1 = cols[k + 1], c2 = cols[k + 2], c3 = cols[k + 3];
-                    const VecT x0 = gather<VecT, AGG>(a.x, a.agg, c0), x1 = gather<VecT, AGG>(a.x, a.agg, c1),
-                               x2 = gather<VecT, AGG>(a.x, a.agg, c2), x3 = gather<VecT, AGG>(a.x, a.agg, c3);
-                    sum = fma((VecT)vals[k], x0, sum);
-                    sum = fma((VecT)vals[k + 1], x1, sum);
-                    sum = fma((VecT)vals[k + 2], x2, sum);
-                    sum = fma((VecT)vals[k + 3], x3, sum);
-                }
-                if (k < kend) {
-                    const int c0 = cols[k];
-                    const int c1 = (k + 1 < kend) ? cols[k + 1] : c0;
-                    const int c2 = (k + 2 < kend) ? cols[k + 2] : c0;
-                    const VecT x0 = gather<VecT, AGG>(a.x, a.agg, c0), x1 = gather<VecT, AGG>(a.x, a.agg, c1),
-                               x2 = gather<VecT, AGG>(a.x, a.agg, c2);
-                    sum = fma((VecT)vals[k], x0, sum);
-                    if (k + 1 < kend) sum = fma((VecT)vals[k + 1], x1, sum);
-                    if (k + 2 < kend) sum = fma((VecT)vals[k + 2], x2, sum);
-                }
+                // U gathers in flight per step (U = 8 when the plan says so: rows of a 7-point stencil then take ONE dependent
+                // LDS -> gather -> FMA round instead of two); the FMA chain runs strictly left to right either way
+                if (a.unroll == 8) sum = row_dot<MatT, VecT, AGG, 8>(vals, cols, k, kend, a.x, a.agg);
+                else sum = row_dot<MatT, VecT, AGG, 4>(vals, cols, k, kend, a.x, a.agg);
                 // ---- epilogue ----
                 if (EPI == EPI_SPMV) {
                     a.y[row] = sum;
@@ -279,7 +295,8 @@ int csr_max_grid(const Matrix &A)
     const int sms = A.rsc ? A.rsc->num_sms : 148;
     if (A.plan.use_tiles) {
         int per_sm = (int)std::min<size_t>(227 * 1024 / std::max<size_t>(A.plan.smem_bytes, 1), (size_t)(2048 / (A.plan.tile_rows + PRODUCER_THREADS)));
-        per_sm = std::max(1, std::min(per_sm, 4));
+        static const int env_ctas = getenv("AMGXB_TILE_CTAS") ? atoi(getenv("AMGXB_TILE_CTAS")) : 0;
+        per_sm = std::max(1, std::min(per_sm, env_ctas > 0 ? env_ctas : 4));
         return std::max(1, std::min(A.plan.num_tiles, sms * per_sm));
     }
     return std::max(1, std::min(ceil_div(A.n, 8), sms * 8));
@@ -314,7 +331,12 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
     p.max_tile_nnz = std::max(4, h[0]);
     const size_t msz = prec_size(A.mat_prec);
     p.use_tiles = false;
-    for (int st = MAX_STAGES; st >= 2; st--) {
+    p.max_row_nnz = h[1];
+    // tuning knobs (defaults chosen from the r02 sweeps in profiles/): pipeline depth, CTAs per SM, gathers in flight per step
+    static const int env_stages = getenv("AMGXB_TILE_STAGES") ? atoi(getenv("AMGXB_TILE_STAGES")) : 0;
+    static const int env_unroll = getenv("AMGXB_TILE_UNROLL") ? atoi(getenv("AMGXB_TILE_UNROLL")) : 0;
+    p.unroll = (env_unroll == 4 || env_unroll == 8) ? env_unroll : 4;
+    for (int st = (env_stages >= 2 && env_stages <= MAX_STAGES) ? env_stages : MAX_STAGES; st >= 2; st--) {
         size_t need = tile_smem_bytes(p.max_tile_nnz, st, p.tile_rows, msz);
         // prefer >= 2 CTAs per SM at full depth, accept 1 CTA per SM at depth 2
         size_t budget = (st > 2) ? (size_t)110 * 1024 : (size_t)216 * 1024;
@@ -343,6 +365,7 @@ void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int
         ta.num_tiles = ceil_div(row1 - row0, std::max(1, A.plan.tile_rows));
         ta.cap = A.plan.max_tile_nnz;
         ta.stages = A.plan.stages;
+        ta.unroll = A.plan.unroll;
         ta.x = (const VecT *)g.x;
         ta.agg = g.agg;
         ta.b = (const VecT *)g.b;

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(TILE_ROWS) colenc_build_kernel(const int *__re
                     seg[k - sa] = (unsigned char)lo;
                 }
             }
-            if (tid == 0) { meta[META * tile] = 1; meta[META * tile + 1] = padded; atomicAdd(stats + 0, 1); }
+            if (tid == 0) { meta[META * tile] = 1; meta[META * tile + 1] = padded; atomicAdd(stats + 0, 1); atomicMax(stats + 4, padded); }
         } else if (use_off16) {
             const int base = s_min;
             unsigned short *seg16 = reinterpret_cast<unsigned short *>(seg);
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(TILE_ROWS) valenc_build_kernel(const int *__re
                 }
                 seg[k - sa] = (unsigned char)lo;                          // alignment padding (entries of neighbouring tiles) gets code 0, never decoded
             }
-            if (tid == 0) { meta[META * tile + 2] = 1; meta[META * tile + 3] = padded; atomicAdd(stats + 3, 1); }
+            if (tid == 0) { meta[META * tile + 2] = 1; meta[META * tile + 3] = padded; atomicAdd(stats + 3, 1); atomicMax(stats + 5, padded); }
         } else {
             if (tid == 0) { meta[META * tile + 2] = 0; meta[META * tile + 3] = 0; }
         }
@@ -205,8 +205,11 @@ __global__ void __launch_bounds__(TILE_ROWS) valenc_build_kernel(const int *__re
 
 // ---------------------------------------------------------------------------------------------
 // The encoded tile kernel.  blockDim.x = TILE_ROWS + 32 (last warp = producer).
-// per stage: value stream (cap * sizeof(MatT) bytes: raw values, or codes) | column stream (cap * 4 bytes: raw columns, or codes) |
-//            dict[256] | vdict[256] | rp[TILE_ROWS+4]
+// Stage layout, sized PER LEVEL from what its tiles actually use (a level whose tiles are all coded stages 2 bytes per entry, so
+// many more CTAs fit an SM -- the consumers are latency-bound, occupancy is what buys bandwidth here):
+//   value stream  cap * val_w bytes (val_w = 1 when every tile has a value dictionary, else sizeof(MatT))
+//   column stream cap * col_w bytes (col_w = 1: all dict8; 2: dict8 / off16; 4: some tile keeps raw columns)
+//   dict[dict_cap] ints | vdict[vdict_cap] MatT | rp[TILE_ROWS+4]
 // ---------------------------------------------------------------------------------------------
 struct EncArgs {
     const unsigned char *codes;
@@ -214,7 +217,49 @@ struct EncArgs {
     const int *meta;
     const unsigned char *vcodes;
     const void *vdict;
+    int val_w, col_w, dict_cap, vdict_cap;
 };
+
+// one row of an encoded tile: 8 code loads, 8 dictionary look-ups, 8 gathers of x in flight, FMA chain in storage order
+template <class MatT, class VecT, int ENC, int VENC>
+__device__ __forceinline__ VecT row_dot_enc(const unsigned char *__restrict__ vstream, const unsigned char *__restrict__ cstream, const int *__restrict__ dict,
+                                            const MatT *__restrict__ vdict, int k, const int kend, const int row, const VecT *__restrict__ x)
+{
+    constexpr int U = 8;
+    const int base = (ENC == 2) ? dict[0] : row;
+    auto col_at = [&](int kk) -> int {
+        if (ENC == 1) return base + dict[cstream[kk]];
+        if (ENC == 2) return base + (int)reinterpret_cast<const unsigned short *>(cstream)[kk];
+        return reinterpret_cast<const int *>(cstream)[kk];
+    };
+    auto val_at = [&](int kk) -> MatT {
+        if (VENC) return vdict[vstream[kk]];
+        return reinterpret_cast<const MatT *>(vstream)[kk];
+    };
+    VecT sum = 0;
+    for (; k + U <= kend; k += U) {
+        int c[U];
+        VecT xv[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) c[j] = col_at(k + j);
+#pragma unroll
+        for (int j = 0; j < U; j++) xv[j] = __ldg(x + c[j]);
+#pragma unroll
+        for (int j = 0; j < U; j++) sum = fma((VecT)val_at(k + j), xv[j], sum);
+    }
+    if (k < kend) {
+        int c[U - 1];
+        VecT xv[U - 1];
+#pragma unroll
+        for (int j = 0; j < U - 1; j++) c[j] = col_at((k + j < kend) ? k + j : k);
+#pragma unroll
+        for (int j = 0; j < U - 1; j++) xv[j] = __ldg(x + c[j]);
+#pragma unroll
+        for (int j = 0; j < U - 1; j++)
+            if (k + j < kend) sum = fma((VecT)val_at(k + j), xv[j], sum);
+    }
+    return sum;
+}
 
 template <class MatT, class VecT, int TILE_ROWS, int EPI>
 __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_kernel(const TileArgs<MatT, VecT> a, const EncArgs e)
@@ -224,10 +269,10 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
     uint64_t *empty = full + MAX_STAGES;
     double *smem_red = reinterpret_cast<double *>(smem_raw + 2 * MAX_STAGES * sizeof(uint64_t));
     unsigned char *stage_base = smem_raw + 512;
-    const size_t vals_bytes = (size_t)a.cap * sizeof(MatT);
-    const size_t cols_bytes = (size_t)a.cap * sizeof(int);
-    const size_t dict_bytes = (size_t)DICT_SLOTS * sizeof(int);
-    const size_t vdict_bytes = (size_t)DICT_SLOTS * sizeof(MatT);
+    const size_t vals_bytes = align16((size_t)a.cap * e.val_w);
+    const size_t cols_bytes = align16((size_t)a.cap * e.col_w);
+    const size_t dict_bytes = (size_t)e.dict_cap * sizeof(int);
+    const size_t vdict_bytes = align16((size_t)e.vdict_cap * sizeof(MatT));
     const size_t rp_bytes = (size_t)(TILE_ROWS + 4) * sizeof(int);
     const size_t stage_bytes = vals_bytes + cols_bytes + dict_bytes + vdict_bytes + rp_bytes;
     constexpr int CONSUMER_WARPS = TILE_ROWS / 32;
@@ -267,7 +312,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
                 if (cnt) col_copy = enc == 1 ? (unsigned)align16(cnt) : enc == 2 ? (unsigned)align16((size_t)cnt * 2) : cnt * (unsigned)sizeof(int);
                 if (cnt) val_copy = venc == 1 ? (unsigned)align16(cnt) : cnt * (unsigned)sizeof(MatT);
                 const unsigned dict_copy = (unsigned)dlen * (unsigned)sizeof(int);
-                const unsigned vdict_copy = (unsigned)vdlen * (unsigned)sizeof(MatT);
+                const unsigned vdict_copy = (unsigned)align16((size_t)vdlen * sizeof(MatT));
                 mbar_expect_tx(&full[s], rp_copy + val_copy + col_copy + dict_copy + vdict_copy);
                 tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes + vdict_bytes, a.row_ptr + r0, rp_copy, &full[s]);
                 if (cnt) {
@@ -302,45 +347,24 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
                 if (EPI == EPI_SPMV_DOT) xi = __ldg(a.x + row);
             }
             const unsigned char *st = stage_base + (size_t)s * stage_bytes;
-            const MatT *vals = reinterpret_cast<const MatT *>(st);
-            const int *cols = reinterpret_cast<const int *>(st + vals_bytes);
-            const unsigned char *c8 = st + vals_bytes;
-            const unsigned short *c16 = reinterpret_cast<const unsigned short *>(st + vals_bytes);
+            const unsigned char *vstream = st;
+            const unsigned char *cstream = st + vals_bytes;
             const int *dict = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes);
-            const unsigned char *v8 = st;
             const MatT *vdict = reinterpret_cast<const MatT *>(st + vals_bytes + cols_bytes + dict_bytes);
             const int *rp = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes + dict_bytes + vdict_bytes);
             mbar_wait(&full[s], ph);
             if (active) {
                 const int sa = rp[0] & ~3;
-                int k = rp[tid] - sa;
-                const int kend = rp[tid + 1] - sa;
-                const int base = (enc == 2) ? dict[0] : 0;
-                // the tile's encoding is uniform over the CTA: the branch below does not diverge
-                auto col_at = [&](int kk) -> int {
-                    if (enc == 1) return row + dict[c8[kk]];
-                    if (enc == 2) return base + (int)c16[kk];
-                    return cols[kk];
-                };
-                auto val_at = [&](int kk) -> MatT { return venc ? vdict[v8[kk]] : vals[kk]; };
-                VecT sum = 0;
-                // 4 gathers in flight per step; FMA chain strictly left to right (as csr_tile_kernel)
-                for (; k + 4 <= kend; k += 4) {
-                    const int c0 = col_at(k), c1 = col_at(k + 1), c2 = col_at(k + 2), c3 = col_at(k + 3);
-                    const VecT x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2), x3 = __ldg(a.x + c3);
-                    sum = fma((VecT)val_at(k), x0, sum);
-                    sum = fma((VecT)val_at(k + 1), x1, sum);
-                    sum = fma((VecT)val_at(k + 2), x2, sum);
-                    sum = fma((VecT)val_at(k + 3), x3, sum);
-                }
-                if (k < kend) {
-                    const int c0 = col_at(k);
-                    const int c1 = (k + 1 < kend) ? col_at(k + 1) : c0;
-                    const int c2 = (k + 2 < kend) ? col_at(k + 2) : c0;
-                    const VecT x0 = __ldg(a.x + c0), x1 = __ldg(a.x + c1), x2 = __ldg(a.x + c2);
-                    sum = fma((VecT)val_at(k), x0, sum);
-                    if (k + 1 < kend) sum = fma((VecT)val_at(k + 1), x1, sum);
-                    if (k + 2 < kend) sum = fma((VecT)val_at(k + 2), x2, sum);
+                const int k = rp[tid] - sa, kend = rp[tid + 1] - sa;
+                // the tile's encoding is uniform over the CTA: the switch does not diverge
+                VecT sum;
+                switch (enc * 2 + venc) {
+                case 3: sum = row_dot_enc<MatT, VecT, 1, 1>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
+                case 2: sum = row_dot_enc<MatT, VecT, 1, 0>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
+                case 5: sum = row_dot_enc<MatT, VecT, 2, 1>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
+                case 4: sum = row_dot_enc<MatT, VecT, 2, 0>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
+                case 1: sum = row_dot_enc<MatT, VecT, 0, 1>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
+                default: sum = row_dot_enc<MatT, VecT, 0, 0>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
                 }
                 // ---- epilogue (identical to csr_tile_kernel) ----
                 if (EPI == EPI_SPMV) {
@@ -384,7 +408,8 @@ void launch_enc(const Matrix &A, const TileArgs<MatT, VecT> &ta, const EncArgs &
 
 template <class MatT, class VecT, int EPI> void launch_enc_epi(const Matrix &A, const TileArgs<MatT, VecT> &ta, const EncArgs &ea, cudaStream_t s)
 {
-    const int grid = std::max(1, std::min(csr_max_grid(A), ta.num_tiles));      // the grid of the plain kernel: same partial sums, same bits
+    const int sms = A.rsc ? A.rsc->num_sms : 148;
+    const int grid = std::max(1, std::min(sms * A.colenc.ctas_per_sm, ta.num_tiles));
     if (A.plan.tile_rows == 256) launch_enc<MatT, VecT, 256, EPI>(A, ta, ea, grid, s);
     else launch_enc<MatT, VecT, 128, EPI>(A, ta, ea, grid, s);
     count_launch();
@@ -406,7 +431,7 @@ static void build_value_codes(Matrix &A, cudaStream_t s)
     ColEnc &E = A.colenc;
     const int T = A.plan.tile_rows, nt = A.plan.num_tiles;
     DevBuf<int> stats;
-    stats.resize(4);
+    stats.resize(8);
     stats.zero(s);
     const int grid = std::max(1, std::min(nt, 148 * 8));
     if (A.mat_prec == Prec::F64) {
@@ -418,7 +443,40 @@ static void build_value_codes(Matrix &A, cudaStream_t s)
     }
     count_launch();
     AMGXB_LAUNCH_CHECK();
-    E.tiles_val8 = stats.to_host(s)[3];
+    const std::vector<int> h = stats.to_host(s);
+    E.tiles_val8 = h[3];
+    E.max_vdlen = h[5];
+}
+
+// Stage layout and occupancy of the encoded kernel for this level, from what its tiles use (see the kernel's header comment).
+static void finalize_layout(Matrix &A)
+{
+    ColEnc &E = A.colenc;
+    const int T = A.plan.tile_rows, nt = A.plan.num_tiles;
+    const size_t msz = prec_size(A.mat_prec);
+    E.col_w = E.tiles_raw > 0 ? 4 : (E.tiles_off16 > 0 ? 2 : 1);
+    E.val_w = (E.tiles_val8 == nt) ? 1 : (int)msz;
+    E.dict_cap = std::max(E.max_dlen, E.tiles_off16 > 0 ? 4 : 0);
+    E.vdict_cap = E.max_vdlen;
+    const size_t cap = (size_t)A.plan.max_tile_nnz;
+    const size_t stage = align16(cap * E.val_w) + align16(cap * E.col_w) + (size_t)E.dict_cap * 4 + align16((size_t)E.vdict_cap * msz) + (size_t)(T + 4) * 4;
+    static const int env_stages = getenv("AMGXB_ENC_STAGES") ? atoi(getenv("AMGXB_ENC_STAGES")) : 0;
+    static const int env_ctas = getenv("AMGXB_ENC_CTAS") ? atoi(getenv("AMGXB_ENC_CTAS")) : 0;
+    const int by_threads = std::min(2048 / (T + PRODUCER_THREADS), 65536 / ((T + PRODUCER_THREADS) * 40));   // threads and registers (40 per thread, -Xptxas -v)
+    E.on = false;
+    int best_st = 0, best_ctas = 0;
+    for (int st = (env_stages >= 2 && env_stages <= MAX_STAGES) ? env_stages : MAX_STAGES; st >= 2; st--) {
+        const size_t smem = 512 + (size_t)st * stage;
+        if (smem > (size_t)216 * 1024) continue;
+        const int ctas = std::max(1, std::min(by_threads, (int)((size_t)227 * 1024 / (smem + 1024))));
+        if (ctas > best_ctas) { best_ctas = ctas; best_st = st; }
+        if (ctas >= 4) break;
+    }
+    if (!best_st) return;
+    E.stages = best_st;
+    E.ctas_per_sm = env_ctas > 0 ? std::min(env_ctas, best_ctas) : best_ctas;
+    E.smem_bytes = 512 + (size_t)best_st * stage;
+    E.on = (E.tiles_dict8 + E.tiles_off16 + E.tiles_val8) > 0;        // nothing to gain when every tile stays raw
 }
 
 // called at the end of csr_build_plan
@@ -429,12 +487,11 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
     if (!colenc_requested() || !A.plan.use_tiles || A.plan.split != 0 || A.dist || A.n == 0 || A.bs() != 1) return;
     const int T = A.plan.tile_rows, nt = A.plan.num_tiles;
     const size_t msz = prec_size(A.mat_prec);
-    const size_t smem = 512 + (size_t)A.plan.stages * ((size_t)A.plan.max_tile_nnz * (msz + 4) + (size_t)DICT_SLOTS * (4 + msz) + (size_t)(T + 4) * 4);
-    if (smem > (size_t)216 * 1024) return;
     ColEnc &E = A.colenc;
     E.meta.resize((size_t)META * nt);
     E.meta.zero(s);                                  // encoding 0 everywhere: raw columns, raw values
     E.tiles_dict8 = E.tiles_off16 = E.tiles_val8 = 0;
+    E.max_dlen = E.max_vdlen = 0;
     E.tiles_raw = nt;
     if (colenc_flags() & 1) {
         E.codes.resize(align16((size_t)2 * ((size_t)A.nnz + 8)) + (size_t)32 * nt + 64);
@@ -442,7 +499,7 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
         E.dict.resize((size_t)nt * DICT_SLOTS);
         E.dict.zero(s);
         DevBuf<int> stats;
-        stats.resize(4);
+        stats.resize(8);
         stats.zero(s);
         const int grid = std::max(1, std::min(nt, 148 * 8));
         if (T == 256) colenc_build_kernel<256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, nt, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
@@ -453,6 +510,7 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
         E.tiles_dict8 = h[0];
         E.tiles_off16 = h[1];
         E.tiles_raw = h[2];
+        E.max_dlen = h[4];
     } else {
         E.codes.resize(64);                          // never dereferenced (every tile has column encoding 0); keeps the pointers valid
         E.dict.resize(64);
@@ -468,11 +526,11 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
         E.vcodes.resize(64);
         E.vdict.resize(64);
     }
-    E.smem_bytes = smem;
-    E.on = (E.tiles_dict8 + E.tiles_off16 + E.tiles_val8) > 0;        // nothing to gain when every tile stays raw
+    finalize_layout(A);
     if (getenv("AMGXB_COLENC_VERBOSE"))
-        fprintf(stderr, "[amgx_b200] colenc level %d: %d tiles of %d rows: columns dict8 %d, off16 %d, raw %d; values dict8 %d\n", A.level, nt, T, E.tiles_dict8,
-                E.tiles_off16, E.tiles_raw, E.tiles_val8);
+        fprintf(stderr, "[amgx_b200] colenc level %d: %d tiles of %d rows: columns dict8 %d, off16 %d, raw %d; values dict8 %d | stage widths col %d val %d B, dict %d / %d, "
+                        "%d stages, %zu B smem, %d CTAs/SM%s\n", A.level, nt, T, E.tiles_dict8, E.tiles_off16, E.tiles_raw, E.tiles_val8, E.col_w, E.val_w, E.dict_cap,
+                E.vdict_cap, E.stages, E.smem_bytes, E.ctas_per_sm, E.on ? "" : " (off)");
 }
 
 // The values of A were changed in place (AMGX_matrix_replace_coefficients, DIAGONAL_SYMMETRIC scaling): the value codes follow them.
@@ -483,7 +541,7 @@ void csr_values_changed(Matrix &A, cudaStream_t s)
     const int nt = A.plan.num_tiles;
     // the column half of the per-tile descriptors stays, the value half is rewritten by the build kernel
     build_value_codes(A, s);
-    E.on = (E.tiles_dict8 + E.tiles_off16 + E.tiles_val8) > 0;
+    finalize_layout(A);
     (void)nt;
 }
 
@@ -497,6 +555,10 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
     ea.meta = A.colenc.meta.ptr();
     ea.vcodes = A.colenc.vcodes.ptr();
     ea.vdict = A.colenc.vdict.ptr();
+    ea.val_w = A.colenc.val_w;
+    ea.col_w = A.colenc.col_w;
+    ea.dict_cap = A.colenc.dict_cap;
+    ea.vdict_cap = A.colenc.vdict_cap;
     AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
         TileArgs<MatT, VecT> ta;
         ta.row_ptr = A.row_ptr.ptr();
@@ -506,7 +568,8 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
         ta.row0 = 0;
         ta.num_tiles = A.plan.num_tiles;
         ta.cap = A.plan.max_tile_nnz;
-        ta.stages = A.plan.stages;
+        ta.stages = A.colenc.stages;
+        ta.unroll = 8;
         ta.x = (const VecT *)g.x;
         ta.agg = nullptr;
         ta.b = (const VecT *)g.b;

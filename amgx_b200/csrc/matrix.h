@@ -19,6 +19,7 @@ struct Resources {
     int num_sms = 148;
     int rank = 0, world = 1;
     void *nccl_comm = nullptr;           // ncclComm_t when world > 1
+    void *p2p = nullptr;                 // PeerWindow (p2p.cu): CUDA-IPC mapped windows of all ranks, null -> NCCL send/recv path
     ~Resources();
 };
 
@@ -32,6 +33,8 @@ struct TilePlan {
     size_t smem_bytes = 0;      // dynamic shared memory per CTA
     bool use_tiles = false;     // false -> generic warp-per-row kernel
     int split = 0;              // distributed: first row (multiple of 4) of the segment that reads halo columns
+    int unroll = 4;             // gathers in flight per consumer step (4 or 8)
+    int max_row_nnz = 0;
 };
 
 // Optional compressed column stream of the tile kernels (k_spmv_enc.cu, AMGXB_COLENC=1; experimental, default off).  Per tile either
@@ -47,6 +50,9 @@ struct ColEnc {
     bool values_encoded = false;    // the value codes exist and must follow in-place changes of the values (csr_values_changed)
     size_t smem_bytes = 0;          // dynamic shared memory of the encoded kernel
     int tiles_dict8 = 0, tiles_off16 = 0, tiles_raw = 0, tiles_val8 = 0;
+    int max_dlen = 0, max_vdlen = 0;               // longest (padded) dictionaries of the level
+    int col_w = 4, val_w = 8, dict_cap = 0, vdict_cap = 0;   // stage layout of the level (finalize_layout)
+    int stages = 2, ctas_per_sm = 1;
 };
 
 struct Matrix {

@@ -125,6 +125,7 @@ template <class MatT, class VecT> struct TileArgs {
     const MatT *val;
     int n, num_tiles, cap, stages;   // n = end row of the segment
     int row0;                        // first row of the segment (multiple of 4)
+    int unroll;                      // gathers in flight per consumer step: 4 or 8
     const VecT *x;
     const int *agg;
     const VecT *b;
