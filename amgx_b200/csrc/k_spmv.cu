@@ -294,9 +294,7 @@ int csr_max_grid(const Matrix &A)
 {
     const int sms = A.rsc ? A.rsc->num_sms : 148;
     if (A.plan.use_tiles) {
-        int per_sm = (int)std::min<size_t>(227 * 1024 / std::max<size_t>(A.plan.smem_bytes, 1), (size_t)(2048 / (A.plan.tile_rows + PRODUCER_THREADS)));
-        static const int env_ctas = getenv("AMGXB_TILE_CTAS") ? atoi(getenv("AMGXB_TILE_CTAS")) : 0;
-        per_sm = std::max(1, std::min(per_sm, env_ctas > 0 ? env_ctas : 4));
+        const int per_sm = std::max(1, A.plan.ctas_per_sm);
         return std::max(1, std::min(A.plan.num_tiles, sms * per_sm));
     }
     return std::max(1, std::min(ceil_div(A.n, 8), sms * 8));
@@ -336,12 +334,20 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
     static const int env_stages = getenv("AMGXB_TILE_STAGES") ? atoi(getenv("AMGXB_TILE_STAGES")) : 0;
     static const int env_unroll = getenv("AMGXB_TILE_UNROLL") ? atoi(getenv("AMGXB_TILE_UNROLL")) : 0;
     p.unroll = (env_unroll == 4 || env_unroll == 8) ? env_unroll : 4;
+    // The consumers are latency-bound (one row per thread, dependent LDS -> gather -> FMA rounds), so resident consumer warps are what
+    // buys bandwidth: pick the pipeline depth that lets the most CTAs share an SM (ties: the deeper pipeline).  r02 sweep on 256^3 / 512^3
+    // 7-point Poisson (profiles/r02_tile_sweep.md): 4 stages x 2 CTAs/SM 0.300 ms, 2 stages x 3 CTAs 0.291 ms, 2 stages x 4 CTAs 0.250 ms.
+    static const int env_ctas = getenv("AMGXB_TILE_CTAS") ? atoi(getenv("AMGXB_TILE_CTAS")) : 0;
+    const int by_threads = std::min(2048 / (p.tile_rows + PRODUCER_THREADS), 65536 / ((p.tile_rows + PRODUCER_THREADS) * 40));   // threads, registers (40 / thread)
+    int best_ctas = 0;
     for (int st = (env_stages >= 2 && env_stages <= MAX_STAGES) ? env_stages : MAX_STAGES; st >= 2; st--) {
-        size_t need = tile_smem_bytes(p.max_tile_nnz, st, p.tile_rows, msz);
-        // prefer >= 2 CTAs per SM at full depth, accept 1 CTA per SM at depth 2
-        size_t budget = (st > 2) ? (size_t)110 * 1024 : (size_t)216 * 1024;
-        if (need <= budget) { p.stages = st; p.smem_bytes = need; p.use_tiles = true; break; }
+        const size_t need = tile_smem_bytes(p.max_tile_nnz, st, p.tile_rows, msz);
+        if (need > (size_t)216 * 1024) continue;
+        const int ctas = std::max(1, std::min(by_threads, (int)((size_t)227 * 1024 / (need + 1024))));
+        if (ctas > best_ctas) { best_ctas = ctas; p.stages = st; p.smem_bytes = need; p.use_tiles = true; }
+        if (env_stages) break;
     }
+    p.ctas_per_sm = env_ctas > 0 ? std::min(env_ctas, std::max(best_ctas, 1)) : std::max(best_ctas, 1);
     A.plan = p;
     csr_build_colenc(A, s);     // no-op unless AMGXB_COLENC=1
 }

@@ -34,6 +34,7 @@ struct TilePlan {
     bool use_tiles = false;     // false -> generic warp-per-row kernel
     int split = 0;              // distributed: first row (multiple of 4) of the segment that reads halo columns
     int unroll = 4;             // gathers in flight per consumer step (4 or 8)
+    int ctas_per_sm = 1;        // resident CTAs per SM the grid is sized for
     int max_row_nnz = 0;
 };
 

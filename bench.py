@@ -1,31 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- solve-phase benchmark of the B200 AMG engine (contract: see README / DESIGN.md).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n NX]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload poisson|banded|block] [--grid NX] [--strong]
 
-Workload (BASELINE.json configs[1]): 3-D 7-point Poisson 256^3, fp64, aggregation AMG (SIZE_2) V-cycle
-preconditioned CG, BLOCK_JACOBI(0.8) 0+3 sweeps -- the reference's PCG_AGGREGATION_JACOBI.json.
-A "step" is one AMGX_solver_solve (zero initial guess, b = 1, RELATIVE_INI 1e-6, max 100 iterations);
-metric = outer Krylov iterations (one V-cycle each) per second, whole job.
-  value : solves with b/x already resident in HBM, timed by CUDA events recorded by the library on its
-          solve stream (AMGXB200_solver_get_last_solve_stats), max over ranks.
-  e2e   : the same solve through the C-ABI with HOST buffers: AMGX_vector_upload(rhs) from pinned host
-          memory + AMGX_vector_set_zero + AMGX_solver_solve + AMGX_vector_download(sol), wall clock
-          around the synchronous calls.
-  roofline : fine-level CSR SpMV kernel (the kernel family every sweep / residual / Krylov product runs),
-          algorithmic bytes nnz*(8+4)+rows*4 per launch / CUDA-event time per launch, against the
-          measured HBM copy peak in MEASURED_PEAKS.json.
-  cpu_baseline / --impl reference : the CPU oracle port of the reference algorithm (the reference's
-          own host path has no SIZE_2 aggregation: src/aggregation/selectors/size2_selector.cu:630-643
-          throws) on all host threads, on a bounded sample of the same workload.
-N > 1: the matrix is row-partitioned (z-slabs) over the ranks, one process per GPU, NCCL halo exchange;
-weak scaling (each rank owns an NX^3 / 1 slab: global grid NX x NX x (NX*N)).
+Default workload (BASELINE.json configs[1]): 3-D 7-point Poisson 256^3, fp64, aggregation AMG (SIZE_2) V-cycle preconditioned CG,
+BLOCK_JACOBI(0.8) 0+3 sweeps -- the reference's PCG_AGGREGATION_JACOBI.json.  A "step" is one AMGX_solver_solve (zero initial guess,
+b = 1, RELATIVE_INI 1e-6, max 100 iterations); metric = outer Krylov iterations (one V-cycle each) per second, whole job.
+  value : solves with b / x already resident in HBM, timed by CUDA events the library records on its solve stream
+          (AMGXB200_solver_get_last_solve_stats), max over ranks.
+  e2e   : the same solve through the C-ABI with HOST buffers: AMGX_vector_upload(rhs) from pinned host memory + AMGX_vector_set_zero
+          + AMGX_solver_solve + AMGX_vector_download(sol), wall clock around the synchronous calls.
+  roofline : the DOMINANT kernel of the iteration = the fused Jacobi sweep on the fine level (csr_tile_kernel<EPI_JACOBI>, ~70 % of an
+          iteration: profiles/r01_launches_solve_256.md); algorithmic bytes nnz*(8+4) + rows*4 + 4*rows*8 per launch / CUDA-event time
+          per launch, against the measured HBM copy peak (MEASURED_PEAKS.json).  roofline.spmv carries the plain fine-level SpMV
+          (north-star bytes nnz*12 + rows*4), roofline.iteration the whole outer iteration.
+  reference_gpu : the UNMODIFIED reference (oracle/_ref, its own sm_100 GPU build) on the same matrix and configuration, timed in
+          this run by its own harness (oracle/ref_build/ref_dump.cu, cudaEvents around AMGX_solver_solve).  Context, not the target.
+  cpu_baseline / --impl reference : the CPU oracle port of the reference algorithm (the reference's own host path has no SIZE_2
+          aggregation: src/aggregation/selectors/size2_selector.cu:630-643 throws) at the REAL problem size, on an explicit
+          thread count, bounded in iterations.
+N > 1 (one process per GPU, row partition in z-slabs, peer-memory / NCCL halo exchange):
+  default  weak scaling: every rank owns an NX^3 box, global grid NX x NX x (NX*N); value = global iterations/s x N (see
+           config.value_definition), config.global_iterations_per_sec is the raw rate.
+  --strong the global grid stays NX^3 (BASELINE configs[3] with --grid 512): value = global iterations/s, scaling "strong".
+  parity   object: the same distributed code path on a reduced global problem against a single-rank solve of the assembled matrix.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -40,6 +45,12 @@ sys.path.insert(0, str(ROOT))
 CONFIG = ROOT / "amgx_b200" / "configs" / "PCG_AGGREGATION_JACOBI.json"
 METRIC = "solve_phase_vcycle_iterations_per_sec"
 UNIT = "iterations/s"
+
+BLOCK_CFG = {"config_version": 2, "solver": {
+    "scope": "main", "solver": "AMG", "algorithm": "AGGREGATION", "selector": "SIZE_2", "cycle": "V", "max_levels": 50,
+    "matrix_coloring_scheme": "MIN_MAX", "max_uncolored_percentage": 0.15, "smoother": "MULTICOLOR_DILU", "relaxation_factor": 0.9,
+    "presweeps": 1, "postsweeps": 1, "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER", "max_iters": 100,
+    "monitor_residual": 1, "store_res_history": 1, "convergence": "RELATIVE_INI", "tolerance": 1e-6, "norm": "L2"}}
 
 
 def measured_peak():
@@ -102,62 +113,190 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def oracle_baseline(nx_sample: int, nx_full: int, iters: int):
-    """CPU port (oracle) of the same solver on the host cores, bounded sample.  The thread count is calibrated first
-    (1, 4, 8, ... all cores; two iterations each): OpenMP over every core of a large box is slower than a few threads
-    for these memory-bound loops, and the baseline should be the best the port can do."""
+# ------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores, at the real size of the workload, bounded in iterations
+# ------------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Explicit thread count of the CPU arm: the cores this process may run on, capped at 32 (these memory-bound loops lose beyond
+    that).  torchrun's OMP_NUM_THREADS=1 is deliberately ignored: the baseline gets the cores of the box whatever launched it."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    return max(1, min(avail, 32)), avail
+
+
+def oracle_baseline(nx, ny, nz, iters):
+    """PCG + aggregation-AMG of the oracle on the nx x ny x nz Poisson problem: `iters` iterations, timed; setup untimed."""
     from amgx_b200 import gallery
     from oracle import oracle as orc
-    all_cores = orc.num_threads()
-    rp, ci, va = gallery.poisson7pt(nx_sample)
+    cores, avail = host_threads()
+    orc.set_num_threads(cores)
+    rp, ci, va = gallery.poisson7pt(nx, ny, nz)
     n = rp.shape[0] - 1
     t0 = time.time()
     amg = orc.AMG(rp, ci, va, max_levels=50, presweeps=0, postsweeps=3, omega=0.8)
     t_setup = time.time() - t0
-    best_t, cores = None, 1
-    for th in (1, 4, 8, 16, 32):   # more threads than that only lose on these memory-bound loops (measured: 128 threads 70x slower than 8)
-        if th > all_cores:
-            continue
-        orc.set_num_threads(th)
-        t0 = time.time()
-        orc.pcg(rp, ci, va, np.ones(n), amg=amg, tol=1e-30, max_iters=2)
-        dt = time.time() - t0
-        if best_t is None or dt < best_t:
-            best_t, cores = dt, th
-    orc.set_num_threads(cores)
+    orc.pcg(rp, ci, va, np.ones(n), amg=amg, tol=1e-30, max_iters=1)          # touch every level once (page faults, thread pool)
     t0 = time.time()
     _, it, hist, _ = orc.pcg(rp, ci, va, np.ones(n), amg=amg, tol=1e-30, max_iters=iters)
     dt = time.time() - t0
-    orc.set_num_threads(all_cores)
-    scale = (nx_sample ** 3) / float(nx_full ** 3)
-    return {"value": it / dt * scale, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"oracle PCG+aggregation-AMG on 7-pt Poisson {nx_sample}^3 ({n} rows), {it} iterations in {dt:.2f} s on {cores} of "
-                      f"{all_cores} host threads (best of a 1..all calibration; setup {t_setup:.1f} s untimed); iterations/s scaled by rows ratio "
-                      f"{scale:.4g} to {nx_full}^3",
-            "measured_iters_per_s_on_sample": it / dt}
+    return {"value": it / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle PCG + aggregation-AMG on the full 7-pt Poisson {nx}x{ny}x{nz} ({n} rows, {amg.num_levels()} levels): {it} iterations in {dt:.2f} s on "
+                      f"{cores} OpenMP threads ({avail} host cores visible); setup {t_setup:.1f} s untimed; no extrapolation"}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the reference has no CPU SIZE_2), same config."""
     if rank != 0:
         return
-    nx_sample = min(args.n, 128)
-    per_step_iters = 10
-    for _ in range(args.warmup):
-        pass  # the oracle is deterministic CPU code: warm-up would only repeat the sample
-    vals = []
-    base = None
-    for _ in range(max(1, min(args.steps, 3))):
-        base = oracle_baseline(nx_sample, args.n, per_step_iters)
+    nx = args.n
+    nz = nx if (args.strong or world == 1) else nx * world
+    note = None
+    if world > 2 and not args.strong:
+        # the 8x problem needs > 60 GB of host arrays in numpy: bound the sample to two slabs and say so
+        nz = nx * 2
+        note = f"sample = 2 of the {world} slabs (host memory bound); iterations/s scaled by rows ratio 2/{world}"
+    iters = 5 if nx <= 256 else 2
+    vals, base = [], None
+    for _ in range(max(1, min(args.steps, 2))):
+        base = oracle_baseline(nx, nx, nz, iters)
         vals.append(base["value"])
     v = float(np.median(vals))
+    if note:
+        v *= 2.0 / world
+        base["sample"] += "; " + note
+    if not args.strong:
+        v *= world          # same normalisation as the engine's line: N=1-sized sub-problems advanced per second
     base["value"] = v
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"7-pt Poisson {args.n}^3 fp64, PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI)", "grid": args.n},
+           "ms_per_step": None, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, world),
            "cpu_baseline": base,
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "note": "reference has no CPU implementation of SIZE_2 aggregation (size2_selector.cu:630-643 throws); this is the oracle port"}
     print(json.dumps(out), flush=True)
+
+
+def workload_config(args, world):
+    nx = args.n
+    if args.workload == "poisson":
+        if args.strong:
+            w = f"7-pt Poisson {nx}^3 fp64 row-partitioned over {world} GPU(s), PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI.json)"
+        else:
+            w = f"7-pt Poisson {nx}x{nx}x{nx * world} fp64, PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI.json)"
+    elif args.workload == "banded":
+        w = f"SuiteSparse-shaped banded-random CSR, {args.rows} rows, row length 3+Poisson(12), sigma 2000, fp64, PCG + aggregation-AMG V-cycle"
+    else:
+        w = f"block 4x4 elasticity-like {nx}^3 block rows, {args.mode}, AMG V-cycle + MULTICOLOR_DILU (AGGREGATION_DILU)"
+    return {"workload": w, "grid": nx}
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# reference GPU build beside it (context): oracle/_ref/ref_dump on the same generated matrix and configuration
+# ------------------------------------------------------------------------------------------------------------------------
+def reference_gpu(nx, reps=2):
+    exe = ROOT / "oracle" / "_ref" / "ref_dump"
+    if not exe.exists():
+        return {"unavailable": "oracle/_ref/ref_dump not built (oracle/ref_build/Makefile, needs /root/reference)"}
+    try:
+        env = dict(os.environ, REFDUMP_NO_LEVELS="1", LD_LIBRARY_PATH=str(exe.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        r = subprocess.run([str(exe), f"poisson:{nx}", str(CONFIG), "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=900, env=env)
+        m = re.search(r"ref_dump: status (\d+) iterations (\d+) setup ([0-9.eE+-]+) s solve ([0-9.eE+-]+) s", r.stdout)
+        if not m:
+            return {"unavailable": "ref_dump gave no timing line", "tail": (r.stdout + r.stderr)[-300:]}
+        st, it, ts, tsol = int(m.group(1)), int(m.group(2)), float(m.group(3)), float(m.group(4))
+        return {"value": it / tsol, "unit": UNIT, "iterations": it, "solve_seconds": tsol, "setup_seconds": ts, "status": st,
+                "how": f"unmodified reference (sm_100 build, oracle/_ref/libamgx_ref.so) through its own C API, best of {reps} AMGX_solver_solve calls timed with "
+                       f"cudaEvents by oracle/ref_build/ref_dump.cu on the same GPU after this engine's timed region"}
+    except Exception as e:      # never let the context figure cost the bench line
+        return {"unavailable": repr(e)}
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# N > 1: parity of the distributed path against a single-rank solve of the assembled matrix (reduced size)
+# ------------------------------------------------------------------------------------------------------------------------
+def distributed_parity(capi, dist, torch, rsc, rank, world, local_rank):
+    """Global grid g x g x (g*world), g = 48.  (a) distributed SpMV == single-rank SpMV of the assembled matrix, bit for bit;
+    (b) PCG + BLOCK_JACOBI (no hierarchy: only reduction order differs): residual histories to 1e-12;
+    (c) PCG + aggregation AMG: the hierarchy is built per slab (aggregates never cross partitions, as in the reference), so it is
+        a different preconditioner than the single-rank one: iteration counts of both and the final true residual are reported."""
+    from amgx_b200 import gallery
+    g = 48
+    nzg = g * world
+    out = {"grid": [g, g, nzg]}
+    jac = {"config_version": 2, "determinism_flag": 1, "solver": {"scope": "main", "solver": "PCG", "max_iters": 40, "monitor_residual": 1, "store_res_history": 1,
+           "convergence": "RELATIVE_INI", "tolerance": 1e-10, "norm": "L2",
+           "preconditioner": {"scope": "jac", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "max_iters": 1, "monitor_residual": 0}}}
+    xg = np.random.default_rng(7).standard_normal(g * g * nzg)
+    nloc = g * g * g
+    res = {}
+    for name, cfgobj in (("jacobi", capi.Config(jac)), ("amg", capi.Config(file=str(CONFIG)))):
+        A, b, x, y = capi.Matrix(rsc), capi.Vector(rsc), capi.Vector(rsc), capi.Vector(rsc)
+        A.generate_poisson7(b, x, g, g, g, 1, 1, world)
+        b.bind(A)
+        x.bind(A)
+        y.bind(A)
+        if name == "jacobi":
+            x.upload(xg[rank * nloc:(rank + 1) * nloc])
+            y.set_zero(nloc)
+            A.multiply(x, y)
+            yl = y.download()
+            x.set_zero(nloc)
+        slv = capi.Solver(rsc, cfgobj)
+        slv.setup(A)
+        slv.solve(b, x, zero_initial_guess=True)
+        hist = np.array(slv.residual_history())
+        xl = x.download()
+        parts = [torch.zeros(nloc, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(xl).cuda())
+        xfull = torch.cat(parts).cpu().numpy()
+        if name == "jacobi":
+            parts = [torch.zeros(nloc, dtype=torch.float64, device="cuda") for _ in range(world)]
+            dist.all_gather(parts, torch.from_numpy(yl).cuda())
+            yfull = torch.cat(parts).cpu().numpy()
+        res[name] = (hist, slv.iterations_number, slv.status, xfull)
+        for o in (slv, y, x, b, A, cfgobj):
+            o.destroy()
+    if rank == 0:
+        cfg1 = capi.Config(jac)
+        rsc1 = capi.Resources(cfg1, device=local_rank)
+        rp, ci, va = gallery.poisson7pt(g, g, nzg)
+        ng = rp.shape[0] - 1
+        for name, cfgobj in (("jacobi", cfg1), ("amg", capi.Config(file=str(CONFIG)))):
+            A = capi.Matrix(rsc1).upload(rp, ci, va)
+            b = capi.Vector(rsc1).upload(np.ones(ng))
+            x = capi.Vector(rsc1)
+            if name == "jacobi":
+                x.upload(xg)
+                y = capi.Vector(rsc1).set_zero(ng)
+                A.multiply(x, y)
+                out["spmv_bit_exact"] = bool(np.array_equal(y.download(), yfull))
+                y.destroy()
+            x.set_zero(ng)
+            slv = capi.Solver(rsc1, cfgobj)
+            slv.setup(A)
+            slv.solve(b, x, zero_initial_guess=True)
+            h1 = np.array(slv.residual_history())
+            hist, it, status, xfull = res[name]
+            m = min(len(h1), len(hist))
+            import scipy.sparse as sp
+            true_res = float(np.linalg.norm(np.ones(ng) - sp.csr_matrix((va, ci, rp), shape=(ng, ng)) @ xfull))
+            out[name] = {"iterations_distributed": int(it), "iterations_single_rank": int(slv.iterations_number), "status": status,
+                         "max_rel_history_deviation": float(np.max(np.abs(h1[:m] - hist[:m]) / h1[0])),
+                         "true_residual_of_distributed_solution_rel": true_res / float(h1[0]), "reported_final_residual_rel": float(hist[-1] / hist[0])}
+            for o in (slv, x, b, A):
+                o.destroy()
+            if cfgobj is not cfg1:
+                cfgobj.destroy()
+        rsc1.destroy()
+        cfg1.destroy()
+        j = out.get("jacobi", {})
+        out["green"] = bool(out.get("spmv_bit_exact") and j.get("max_rel_history_deviation", 1) < 1e-12 and
+                            j.get("iterations_distributed") == j.get("iterations_single_rank") and out["amg"]["status"] == "success" and
+                            abs(out["amg"]["true_residual_of_distributed_solution_rel"] - out["amg"]["reported_final_residual_rel"]) < 1e-9)
+    dist.barrier()
+    return out
 
 
 def main():
@@ -166,14 +305,25 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", dest="n", type=int, default=256, help="grid points per dimension (per rank for --gpus > 1)")
+    ap.add_argument("--workload", default="poisson", choices=["poisson", "banded", "block"])
+    ap.add_argument("--grid", dest="n", type=int, default=None, help="grid points per dimension (poisson: per rank unless --strong; block: block rows per dimension)")
+    ap.add_argument("--rows", type=int, default=4_000_000, help="banded workload: number of rows")
+    ap.add_argument("--mode", default="dDFI", choices=["dDDI", "dDFI", "dFFI"], help="block workload: AMGX mode")
+    ap.add_argument("--strong", action="store_true", help="N > 1: keep the global grid at --grid^3 (BASELINE configs[3] with --grid 512)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
+    if args.n is None:
+        args.n = 160 if args.workload == "block" else 256
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        if args.workload != "poisson":
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU arm exists for the poisson workload (BASELINE configs[1])"}), flush=True)
+            return
+        run_reference(args, rank, world)
         return
 
     import torch
@@ -184,13 +334,20 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
     distributed = world > 1
+    if distributed and args.workload != "poisson":
+        raise SystemExit("multi-GPU bench lines exist for the poisson workload; see tools/bench_block_dist.py for the block configuration")
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     capi.initialize()
     capi.register_print_callback(None)
-    cfg = capi.Config(file=str(CONFIG))
+    mode = "dDDI"
+    if args.workload == "block":
+        mode = args.mode
+        cfg = capi.Config(BLOCK_CFG)
+    else:
+        cfg = capi.Config(file=str(CONFIG))
     comm = None
     if distributed:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -199,13 +356,33 @@ def main():
         dist.broadcast(idt, 0)
         comm = capi.AMGXB200_comm(rank, world, bytes(idt.cpu().numpy().tobytes()))
     rsc = capi.Resources(cfg, device=local_rank, comm=comm) if (distributed or local_rank) else capi.Resources(cfg)
-    A, b, x = capi.Matrix(rsc), capi.Vector(rsc), capi.Vector(rsc)
+    A, b, x = capi.Matrix(rsc, mode), capi.Vector(rsc, mode), capi.Vector(rsc, mode)
     nx = args.n
+    bd = 1
     t0 = time.time()
-    A.generate_poisson7(b, x, nx, nx, nx, 1, 1, world)     # z-slabs: global grid nx * nx * (nx*world)
+    if args.workload == "poisson":
+        if args.strong:
+            if nx % world:
+                raise SystemExit("--strong needs --grid divisible by the number of ranks")
+            A.generate_poisson7(b, x, nx, nx, nx // world, 1, 1, world)      # z-slabs of the fixed nx^3 grid
+        else:
+            A.generate_poisson7(b, x, nx, nx, nx, 1, 1, world)               # z-slabs: global grid nx * nx * (nx*world)
+    elif args.workload == "banded":
+        from amgx_b200 import gallery
+        rp, ci, va = gallery.random_banded(args.rows)
+        A.upload(rp, ci, va)
+        b.upload(np.ones(rp.shape[0] - 1))
+        del rp, ci, va
+    else:
+        from amgx_b200 import gallery
+        bd = 4
+        rp, ci, va = gallery.block_elasticity(nx, nx, nx, dtype=np.float32 if mode[2] == "F" else np.float64)
+        A.upload(rp, ci, va, block_dims=(4, 4))
+        b.upload(np.ones((rp.shape[0] - 1) * 4), block_dim=4)
+        del rp, ci, va
     n, _, _ = A.get_size()
     nnz = A.get_nnz()
-    slv = capi.Solver(rsc, cfg)
+    slv = capi.Solver(rsc, cfg, mode)
     slv.setup(A)
     t_setup = time.time() - t0
     if distributed:
@@ -220,7 +397,7 @@ def main():
 
     # ---- device-resident timing ----
     def one_solve():
-        x.set_zero(n)
+        x.set_zero(n, bd)
         slv.solve(b, x, zero_initial_guess=True)
         s, k = slv.last_solve_stats()
         return s, k, slv.iterations_number
@@ -242,24 +419,25 @@ def main():
         t = torch.tensor([tot_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot_s = float(t.item())
-    # whole-job aggregate: every rank owns one N=1 workload (weak scaling), so the job advances `world` N=1-sized
-    # problems by one V-cycle iteration per outer iteration: value = iterations/s x world.  The raw outer
-    # iterations/s of the (world x larger) global problem is reported as config.global_iterations_per_sec.
+    # weak scaling: every rank owns one N=1 workload, so the job advances `world` N=1-sized problems by one V-cycle iteration per outer
+    # iteration: value = iterations/s x world; the raw rate of the (world x larger) global problem is config.global_iterations_per_sec.
+    # strong scaling: the global problem is the N=1 problem: value = raw rate.
     raw_its = tot_it / tot_s
-    value = raw_its * world
+    value = raw_its if (args.strong or not distributed) else raw_its * world
     status = slv.status
-    hist = slv.residual_history() if rank == 0 else []
+    hist = np.array(slv.residual_history()).ravel() if rank == 0 else None
 
     # ---- end to end through the C-ABI with host buffers ----
-    hb = np.ones(n)
-    hx = np.zeros(n)
+    dt_v = np.float64 if mode[1] == "D" else np.float32
+    hb = np.ones(n * bd, dtype=dt_v)
+    hx = np.zeros(n * bd, dtype=dt_v)
     lib = capi.load_library()
     lib.AMGX_pin_memory(hb.ctypes.data, hb.nbytes)
     lib.AMGX_pin_memory(hx.ctypes.data, hx.nbytes)
 
     def one_e2e():
-        b.upload(hb)
-        x.set_zero(n)
+        b.upload(hb, block_dim=bd)
+        x.set_zero(n, bd)
         slv.solve(b, x, zero_initial_guess=True)
         x.download(hx)
         return slv.iterations_number
@@ -278,67 +456,97 @@ def main():
         e_dt = float(t.item())
     lib.AMGX_unpin_memory(hb.ctypes.data)
     lib.AMGX_unpin_memory(hx.ctypes.data)
+    e2e_value = e_it / e_dt * (1 if (args.strong or not distributed) else world)
 
-    # ---- roofline of the dominant kernel (fine-level CSR SpMV) ----
+    # ---- roofline of the dominant kernel ----
     roof = None
     if not distributed:
         peak, peak_src = measured_peak()
-        ms = A.bench_kernel(0, warmup=3, reps=20, flush_l2=False)      # operands (1.47 GB at 256^3) >> 126 MB L2
-        ms_j = A.bench_kernel(1, warmup=3, reps=20, flush_l2=False)
-        byt = nnz * 12 + n * 4
-        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of the same workload (never measured here:
-        # a number taken under a profiler is not a bench value, but the byte counters are deterministic for a given grid)
-        traffic = None
-        tf = ROOT / "profiles" / f"r01_ncu_traffic_spmv_{nx}.json"
-        enc = os.environ.get("AMGXB_COLENC", "0")
-        if tf.exists() and enc in ("", "0"):      # the capture is of the plain kernel; an experimental encoded stream moves fewer bytes
-            traffic = json.loads(tf.read_text())["traffic_bytes_per_launch"]
-        roof = {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": byt / ms / 1e6 / peak, "traffic": traffic,
-                "kernel": "csr_tile_kernel<EPI_SPMV> (fine level)" if enc in ("", "0") else f"csr_tile_enc_kernel<EPI_SPMV> (fine level, AMGXB_COLENC={enc})", "ms_per_launch": ms, "algorithmic_bytes": byt, "peak_source": peak_src,
-                "fused_jacobi_sweep": {"ms_per_launch": ms_j, "algorithmic_bytes": byt + 4 * n * 8, "achieved": (byt + 4 * n * 8) / ms_j / 1e6,
-                                       "frac": (byt + 4 * n * 8) / ms_j / 1e6 / peak}}
+        msz = 8 if mode[2] == "D" else 4
+        vsz = 8 if mode[1] == "D" else 4
+        ms = A.bench_kernel(0, warmup=3, reps=20, flush_l2=False)      # operands (>= 1.4 GB) >> 126 MB L2
+        byt = nnz * (msz * bd * bd + 4) + n * 4
+        enc = os.environ.get("AMGXB_COLENC", "")
+        spmv = {"kernel": ("csr_tile_kernel<EPI_SPMV>" if bd == 1 else "block4_kernel<SPMV>") + " (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt,
+                "achieved": byt / ms / 1e6, "frac": byt / ms / 1e6 / peak}
+        if bd == 1:
+            ms_j = A.bench_kernel(1, warmup=3, reps=20, flush_l2=False)
+            byt_j = byt + 4 * n * vsz
+            traffic = None
+            tf = ROOT / "profiles" / f"r02_ncu_traffic_jacobi_{nx}.json"
+            if tf.exists() and args.workload == "poisson":
+                traffic = json.loads(tf.read_text()).get("traffic_bytes_per_launch")
+            roof = {"bound": "hbm", "achieved": byt_j / ms_j / 1e6, "peak": peak, "unit": "GB/s", "frac": byt_j / ms_j / 1e6 / peak, "traffic": traffic,
+                    "kernel": "fused Jacobi sweep, fine level: " + ("csr_tile_enc_kernel<EPI_JACOBI> (coded column / value streams)" if A_uses_enc(enc) else "csr_tile_kernel<EPI_JACOBI>"),
+                    "ms_per_launch": ms_j, "algorithmic_bytes": byt_j, "peak_source": peak_src, "share_of_iteration": "~70 % (profiles/r02_launches_solve_256.md)",
+                    "spmv": spmv}
+        else:
+            roof = {"bound": "hbm", "achieved": spmv["achieved"], "peak": peak, "unit": "GB/s", "frac": spmv["frac"], "traffic": None, "kernel": spmv["kernel"],
+                    "ms_per_launch": ms, "algorithmic_bytes": byt, "peak_source": peak_src}
         # whole outer iteration against the same peak: SURVEY 8(d)'s per-unit figures summed over the hierarchy the setup actually built
         # (PCG outside M^-1: M(A_0) + 12 N 8; per level: 3 fused post-sweeps M(A_l) + 4 n_l 8 each, restriction and prolongation
         # n_l (4 + 8) + n_{l+1} 8 each; presweeps = 0 and a zero initial guess leave no residual pass; coarsest: a zero-guess sweep + a full one)
+        if args.workload != "block":
+            try:
+                lv = [slv.level_info(l) for l in range(slv.num_levels())]
+                M = lambda i: i["nnz"] * 12 + i["n"] * 4
+                it_bytes = M(lv[0]) + 12 * lv[0]["n"] * 8
+                for l, i in enumerate(lv):
+                    if l + 1 < len(lv):
+                        it_bytes += 3 * (M(i) + 4 * i["n"] * 8) + 2 * (i["n"] * 12 + lv[l + 1]["n"] * 8)
+                    else:
+                        it_bytes += 3 * i["n"] * 8 + (M(i) + 4 * i["n"] * 8)
+                ms_it = tot_s / max(tot_it, 1) * 1e3
+                roof["iteration"] = {"algorithmic_bytes": int(it_bytes), "levels": len(lv), "ms_at_peak": it_bytes / peak / 1e6, "ms_measured": ms_it,
+                                     "achieved": it_bytes / ms_it / 1e6, "frac": it_bytes / ms_it / 1e6 / peak,
+                                     "operator_complexity": sum(i["nnz"] for i in lv) / lv[0]["nnz"]}
+            except Exception as e:      # never let the extra figure cost the bench line
+                roof["iteration"] = {"error": repr(e)}
+
+    parity = None
+    if distributed and not args.no_parity:
         try:
-            lv = [slv.level_info(l) for l in range(slv.num_levels())]
-            M = lambda i: i["nnz"] * 12 + i["n"] * 4
-            it_bytes = M(lv[0]) + 12 * lv[0]["n"] * 8
-            for l, i in enumerate(lv):
-                if l + 1 < len(lv):
-                    it_bytes += 3 * (M(i) + 4 * i["n"] * 8) + 2 * (i["n"] * 12 + lv[l + 1]["n"] * 8)
-                else:
-                    it_bytes += 3 * i["n"] * 8 + (M(i) + 4 * i["n"] * 8)
-            ms_it = tot_s / max(tot_it, 1) * 1e3
-            roof["iteration"] = {"algorithmic_bytes": int(it_bytes), "levels": len(lv), "ms_at_peak": it_bytes / peak / 1e6, "ms_measured": ms_it,
-                                 "achieved": it_bytes / ms_it / 1e6, "frac": it_bytes / ms_it / 1e6 / peak,
-                                 "operator_complexity": sum(i["nnz"] for i in lv) / lv[0]["nnz"]}
-        except Exception as e:      # never let the extra figure cost the bench line
-            roof["iteration"] = {"error": repr(e)}
+            parity = distributed_parity(capi, dist, torch, rsc, rank, world, local_rank)
+        except Exception as e:
+            parity = {"error": repr(e)}
+
+    for o in (slv, x, b, A):
+        o.destroy()
+    refgpu = None
+    if rank == 0 and not distributed and args.workload == "poisson" and not args.no_reference_gpu:
+        torch.cuda.empty_cache()
+        refgpu = reference_gpu(nx)
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline and not distributed:
-        cpu = oracle_baseline(min(nx, 128), nx, 10)
+    if rank == 0 and not args.no_cpu_baseline and not distributed and args.workload == "poisson":
+        cpu = oracle_baseline(nx, nx, nx, 5 if nx <= 256 else 2)
 
     if rank == 0:
+        cfgd = workload_config(args, world)
+        cfgd.update({"rows": n * world, "nnz_per_rank": nnz, "iterations_per_step": tot_it / args.steps, "solve_status": status,
+                     "global_iterations_per_sec": raw_its,
+                     "value_definition": ("outer iterations (one V-cycle each) per second of the fixed global problem" if (args.strong or not distributed) else
+                                          "outer PCG iterations (one V-cycle each) per second x number of N=1-sized sub-problems (= n_gpus)"),
+                     "l2": "inputs larger than L2 (matrix alone %.2f GB per rank)" % (nnz * (12 if bd == 1 else 16 * (8 if mode[2] == 'D' else 4) + 4) / 1e9),
+                     "setup_seconds": t_setup, "parallelism": f"row-partition x{world}" if distributed else "single GPU",
+                     "exchange": ("peer-memory stores over NVLink (CUDA IPC)" if os.environ.get("AMGXB_P2P", "1") != "0" else "NCCL send/recv") if distributed else None})
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic",
-               "config": {"workload": f"7-pt Poisson {nx}x{nx}x{nx * world} fp64, PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI.json)",
-                          "rows": n * world, "nnz_per_rank": nnz, "iterations_per_step": tot_it / args.steps, "solve_status": status,
-                          "global_iterations_per_sec": raw_its,
-                          "value_definition": "outer PCG iterations (one V-cycle each) per second x number of N=1-sized sub-problems (= n_gpus)",
-                          "l2": "inputs larger than L2 (matrix alone %.2f GB per rank)" % (nnz * 12 / 1e9), "setup_seconds": t_setup,
-                          "parallelism": f"row-partition x{world}" if distributed else "single GPU"},
-               "e2e": {"value": e_it / e_dt * world, "unit": UNIT, "h2d_bytes_per_step": int(hb.nbytes), "d2h_bytes_per_step": int(hx.nbytes),
+               "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+               "dtype": "f64" if mode == "dDDI" else ("f32 matrix / f64 vectors" if mode == "dDFI" else "f32"), "data": "synthetic",
+               "config": cfgd,
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hb.nbytes), "d2h_bytes_per_step": int(hx.nbytes),
                        "ms_per_step": e_dt / args.steps * 1e3},
-               "gpu_launches": int(tot_k), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-               "final_relative_residual": (hist[-1] / hist[0]) if hist else None}
+               "gpu_launches": int(tot_k), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": refgpu, "parity": parity,
+               "final_relative_residual": float(hist[-1] / hist[0]) if hist is not None and len(hist) else None}
         print(json.dumps(out), flush=True)
-    for o in (slv, x, b, A, rsc, cfg):
+    for o in (rsc, cfg):
         o.destroy()
     capi.finalize()
     if distributed:
         dist.destroy_process_group()
+
+
+def A_uses_enc(enc: str) -> bool:
+    return enc not in ("", "0")
 
 
 if __name__ == "__main__":
