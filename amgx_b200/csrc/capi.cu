@@ -773,8 +773,9 @@ static AMGX_RC solver_solve_impl(AMGX_solver_handle slv, AMGX_vector_handle rhs,
     if (b->v->block_dim != A.by) fatal(AMGX_RC_BAD_PARAMETERS, "Block sizes do not match");
     if (b->v->n != A.n) fatal(AMGX_RC_BAD_PARAMETERS, "rhs size does not match the matrix");
     const size_t need = (size_t)A.n_cols * A.by;
-    if (x->v->n != A.n || x->v->data.n < (size_t)A.n * A.by) {
-        if (!xIsZero && x->v->n != A.n) fatal(AMGX_RC_BAD_PARAMETERS, "solution size does not match the matrix");
+    if (!xIsZero) {     // a non-zero initial guess is read: it must have the matrix's shape (a block_dim-1 upload for a 4x4 system must not pass)
+        if (x->v->n != A.n) fatal(AMGX_RC_BAD_PARAMETERS, "solution size does not match the matrix");
+        if (x->v->block_dim != A.bx || x->v->data.n < (size_t)A.n * A.bx) fatal(AMGX_RC_BAD_PARAMETERS, "Block sizes do not match");
     }
     dist_prepare_vector(A, *b->v);
     if (xIsZero && (x->v->n != A.n || x->v->data.n < need)) {

@@ -170,6 +170,12 @@ protected:
         });
         count_launch(2);
         AMGXB_LAUNCH_CHECK();
+        {   // a zero pivot is a setup error, as in the reference (dense_lu_solver.cu:542-560), not inf / NaN at solve time
+            int info = 0;
+            AMGXB_CUDA_CHECK(cudaMemcpyAsync(&info, ipiv_.ptr() + n_, sizeof(int), cudaMemcpyDeviceToHost, s));
+            AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
+            if (info != 0) fatal(AMGX_RC_INTERNAL, "Dense LU factorization failed due to a singular matrix");
+        }
         const size_t esz = prec_size(A.vec_prec);
         smem_small_ = (size_t)((n_ + 1) & ~1) * esz;
         smem_full_ = smem_small_ + (size_t)n_ * n_ * esz;

@@ -56,6 +56,56 @@ __global__ void dilu_setup_1x1(const int *__restrict__ rp, const int *__restrict
     }
 }
 
+// Loads of the vectors a sweep updates (x, delta, Delta).  The per-colour kernels see them through L1 (kernel boundaries
+// invalidate it); the fused level kernel below runs all colours in ONE launch across the CTAs of a cluster, where another SM's
+// L1 may hold a stale line: there the loads go to L2 (ld.global.cg).
+template <bool CG, class T> __device__ __forceinline__ T ldv(const T *p) { return CG ? __ldcg(p) : *p; }
+
+// one row of the forward sweep, 8 lanes per row (lane l of the row group); identical for every caller, so the sums associate alike
+template <class MatT, class VecT, bool CG>
+__device__ __forceinline__ void dilu_fwd_row_1x1(const bool act, const int i, const int l, const int *__restrict__ rp, const int *__restrict__ ci,
+                                                 const MatT *__restrict__ va, const VecT *x, const VecT *__restrict__ b, VecT *delta, int color,
+                                                 const int *__restrict__ colors, const MatT *__restrict__ Einv, int n_owned)
+{
+    VecT acc = 0;
+    if (act && l == 0) acc = b[i];
+    if (act) {
+        const int k1 = rp[i + 1];
+        for (int k = rp[i] + l; k < k1; k += NTPR) {
+            const int j = ci[k];
+            VecT xx = ldv<CG>(x + j);
+            if (color != 0 && j < n_owned && colors[j] < color) xx += ldv<CG>(delta + j);
+            acc -= (VecT)va[k] * xx;
+        }
+    }
+#pragma unroll
+    for (int m = NTPR / 2; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (act && l == 0) delta[i] = (VecT)Einv[i] * acc;
+}
+
+template <class MatT, class VecT, bool CG>
+__device__ __forceinline__ void dilu_bwd_row_1x1(const bool act, const int i, const int l, const int *__restrict__ rp, const int *__restrict__ ci,
+                                                 const MatT *__restrict__ va, VecT *x, double weight, const int *__restrict__ colors,
+                                                 const MatT *__restrict__ Einv, const VecT *delta, VecT *Delta, int color, int n_owned)
+{
+    VecT acc = 0;
+    if (act) {
+        const int k1 = rp[i + 1];
+        for (int k = rp[i] + l; k < k1; k += NTPR) {
+            const int j = ci[k];
+            const bool valid = color != 0 && j < n_owned && colors[j] > color;
+            if (valid) acc += (VecT)va[k] * ldv<CG>(Delta + j);
+        }
+    }
+#pragma unroll
+    for (int m = NTPR / 2; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (act && l == 0) {
+        const VecT v = ldv<CG>(delta + i) - (VecT)Einv[i] * acc;
+        x[i] = ldv<CG>(x + i) + (VecT)(weight * v);
+        Delta[i] = v;
+    }
+}
+
 template <class MatT, class VecT>
 __global__ void dilu_forward_1x1(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, const VecT *x,
                                  const VecT *__restrict__ b, VecT *delta, const int *__restrict__ rows, int nrows, int color,
@@ -65,21 +115,7 @@ __global__ void dilu_forward_1x1(const int *__restrict__ rp, const int *__restri
     const int rows_per_grid = gridDim.x * (blockDim.x / NTPR);
     for (int it = blockIdx.x * (blockDim.x / NTPR) + threadIdx.x / NTPR; __any_sync(0xffffffffu, it < nrows); it += rows_per_grid) {
         const bool act = it < nrows;
-        const int i = act ? rows[it] : 0;
-        VecT acc = 0;
-        if (act && l == 0) acc = b[i];
-        if (act) {
-            const int k1 = rp[i + 1];
-            for (int k = rp[i] + l; k < k1; k += NTPR) {
-                const int j = ci[k];
-                VecT xx = x[j];
-                if (color != 0 && j < n_owned && colors[j] < color) xx += delta[j];
-                acc -= (VecT)va[k] * xx;
-            }
-        }
-#pragma unroll
-        for (int m = NTPR / 2; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-        if (act && l == 0) delta[i] = (VecT)Einv[i] * acc;
+        dilu_fwd_row_1x1<MatT, VecT, false>(act, act ? rows[it] : 0, l, rp, ci, va, x, b, delta, color, colors, Einv, n_owned);
     }
 }
 
@@ -92,23 +128,7 @@ __global__ void dilu_backward_1x1(const int *__restrict__ rp, const int *__restr
     const int rows_per_grid = gridDim.x * (blockDim.x / NTPR);
     for (int it = blockIdx.x * (blockDim.x / NTPR) + threadIdx.x / NTPR; __any_sync(0xffffffffu, it < nrows); it += rows_per_grid) {
         const bool act = it < nrows;
-        const int i = act ? rows[it] : 0;
-        VecT acc = 0;
-        if (act) {
-            const int k1 = rp[i + 1];
-            for (int k = rp[i] + l; k < k1; k += NTPR) {
-                const int j = ci[k];
-                const bool valid = color != 0 && j < n_owned && colors[j] > color;
-                if (valid) acc += (VecT)va[k] * Delta[j];
-            }
-        }
-#pragma unroll
-        for (int m = NTPR / 2; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-        if (act && l == 0) {
-            const VecT v = delta[i] - (VecT)Einv[i] * acc;
-            x[i] += (VecT)(weight * v);
-            Delta[i] = v;
-        }
+        dilu_bwd_row_1x1<MatT, VecT, false>(act, act ? rows[it] : 0, l, rp, ci, va, x, weight, colors, Einv, delta, Delta, color, n_owned);
     }
 }
 
@@ -179,55 +199,149 @@ __global__ void dilu_setup_4x4(const int *__restrict__ rp, const int *__restrict
 // One warp per block row: quad q (lanes 4q..4q+3) takes the blocks q, q+8, ... of the row, thread r of a quad owns
 // component r; the eight partial 4-vectors are combined with an xor butterfly over the quads.  (A single quad walking
 // a 30..60-block coarse row serially is a pure latency chain: ~0.5 us per block.)
+template <class MatT, class VecT, bool BACKWARD, bool CG>
+__device__ __forceinline__ void dilu_row_4x4(const int i, const int lane, const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, VecT *x,
+                                             const VecT *__restrict__ b, VecT *delta, VecT *Delta, double weight, int color, const int *__restrict__ colors,
+                                             const MatT *__restrict__ Einv, int n_owned)
+{
+    const int r = lane & 3, q = lane >> 2;
+    VecT acc = 0;
+    if (!BACKWARD && q == 0) acc = b[(size_t)i * 4 + r];
+    const int k1 = rp[i + 1];
+    for (int k = rp[i] + q; k < k1; k += 8) {
+        const int j = ci[k];
+        const MatT *a = va + (size_t)k * 16 + r * 4;
+        if (!BACKWARD) {
+            const bool valid = color != 0 && j < n_owned && colors[j] < color;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                VecT xx = ldv<CG>(x + (size_t)j * 4 + m);
+                if (valid) xx += ldv<CG>(delta + (size_t)j * 4 + m);
+                acc -= (VecT)a[m] * xx;
+            }
+        } else {
+            const bool valid = color != 0 && j < n_owned && colors[j] > color;
+            if (valid) {
+#pragma unroll
+                for (int m = 0; m < 4; m++) acc += (VecT)a[m] * ldv<CG>(Delta + (size_t)j * 4 + m);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    // y = Einv_i * acc (4x4 mat-vec inside quad 0; every quad holds the full acc)
+    VecT y = 0;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const VecT am = __shfl_sync(0xffffffffu, acc, m);
+        y += (VecT)Einv[(size_t)i * 16 + r * 4 + m] * am;
+    }
+    if (q == 0) {
+        const size_t idx = (size_t)i * 4 + r;
+        if (!BACKWARD) delta[idx] = y;
+        else {
+            const VecT v = ldv<CG>(delta + idx) - y;
+            x[idx] = ldv<CG>(x + idx) + (VecT)(weight * v);
+            Delta[idx] = v;
+        }
+    }
+}
+
 template <class MatT, class VecT, bool BACKWARD>
 __global__ void __launch_bounds__(128) dilu_sweep_4x4(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, VecT *x,
                                                       const VecT *__restrict__ b, VecT *delta, VecT *Delta, double weight, const int *__restrict__ rows, int nrows,
                                                       int color, const int *__restrict__ colors, const MatT *__restrict__ Einv, int n_owned)
 {
     const int lane = threadIdx.x & 31;
-    const int r = lane & 3, q = lane >> 2;
     const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
-    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nrows; it += warps_per_grid) {
-        const int i = rows[it];
-        VecT acc = 0;
-        if (!BACKWARD && q == 0) acc = b[(size_t)i * 4 + r];
-        const int k1 = rp[i + 1];
-        for (int k = rp[i] + q; k < k1; k += 8) {
-            const int j = ci[k];
-            const MatT *a = va + (size_t)k * 16 + r * 4;
-            if (!BACKWARD) {
-                const bool valid = color != 0 && j < n_owned && colors[j] < color;
-#pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    VecT xx = x[(size_t)j * 4 + m];
-                    if (valid) xx += delta[(size_t)j * 4 + m];
-                    acc -= (VecT)a[m] * xx;
+    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nrows; it += warps_per_grid)
+        dilu_row_4x4<MatT, VecT, BACKWARD, false>(rows[it], lane, rp, ci, va, x, b, delta, Delta, weight, color, colors, Einv, n_owned);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused level kernel: ALL colours of a forward + backward sweep (and all `sweeps` sweeps of a smooth call) in one launch by one
+// thread-block CLUSTER; colours are separated by cluster barriers (barrier.cluster, hardware-supported on sm_90+/sm_100) instead of
+// kernel boundaries.  For the levels of the hierarchy whose colours hold fewer rows than the machine has warps -- on a 20-level
+// block hierarchy that is 12 levels x 2 x (9..40) colours x 2 sweeps of 15 us latency-bound launches (profiles/r02_block.md).
+// Same per-row functions as the per-colour kernels => the same bits.  Mutable vectors are read through L2 (see ldv).
+// ---------------------------------------------------------------------------------------------
+struct DiluLevelArgs {
+    const int *rp, *ci, *colors, *sorted_rows, *color_offsets;   // color_offsets: device copy, [num_colors + 1]
+    const void *va, *Einv, *b;
+    void *x, *delta, *Delta;
+    double weight;
+    int n, n_owned, num_colors, sweeps, zero_first, bs;
+};
+
+__device__ __forceinline__ void cluster_barrier()
+{
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+
+template <class MatT, class VecT, int BS>
+__global__ void __launch_bounds__(1024) dilu_level_kernel(const DiluLevelArgs a)
+{
+    const int *__restrict__ rp = a.rp, *__restrict__ ci = a.ci, *__restrict__ colors = a.colors, *__restrict__ rows = a.sorted_rows;
+    const MatT *__restrict__ va = (const MatT *)a.va, *__restrict__ Einv = (const MatT *)a.Einv;
+    const VecT *__restrict__ b = (const VecT *)a.b;
+    VecT *x = (VecT *)a.x, *delta = (VecT *)a.delta, *Delta = (VecT *)a.Delta;
+    const int lane = threadIdx.x & 31;
+    const int nthreads = (int)(cluster_nctarank() * blockDim.x), tid = (int)(cluster_ctarank() * blockDim.x + threadIdx.x);
+    const int nc = a.num_colors;
+    for (int sw = 0; sw < a.sweeps; sw++) {
+        if (sw == 0 && a.zero_first) {
+            for (long long t = tid; t < (long long)a.n * BS; t += nthreads) x[t] = 0;
+            cluster_barrier();
+        }
+        for (int c = 0; c < nc; c++) {          // forward, colours ascending
+            const int off = a.color_offsets[c], cnt = a.color_offsets[c + 1] - off;
+            if (cnt == 0) continue;
+            if (BS == 1) {
+                const int l = threadIdx.x % NTPR;
+                for (int it = tid / NTPR; __any_sync(0xffffffffu, it < cnt); it += nthreads / NTPR) {
+                    const bool act = it < cnt;
+                    dilu_fwd_row_1x1<MatT, VecT, true>(act, act ? rows[off + it] : 0, l, rp, ci, va, x, b, delta, c, colors, Einv, a.n_owned);
                 }
             } else {
-                const bool valid = color != 0 && j < n_owned && colors[j] > color;
-                if (valid) {
-#pragma unroll
-                    for (int m = 0; m < 4; m++) acc += (VecT)a[m] * Delta[(size_t)j * 4 + m];
+                for (int it = tid >> 5; it < cnt; it += nthreads >> 5)
+                    dilu_row_4x4<MatT, VecT, false, true>(rows[off + it], lane, rp, ci, va, x, b, delta, Delta, a.weight, c, colors, Einv, a.n_owned);
+            }
+            cluster_barrier();
+        }
+        for (int c = nc - 1; c >= 0; c--) {     // backward, colours descending
+            const int off = a.color_offsets[c], cnt = a.color_offsets[c + 1] - off;
+            if (cnt == 0) continue;
+            if (c == nc - 1) {                  // last colour: Delta = delta (dilu_backward_skip)
+                for (long long t = tid; t < (long long)cnt * BS; t += nthreads) {
+                    const size_t idx = (size_t)rows[off + (int)(t / BS)] * BS + (size_t)(t % BS);
+                    const VecT v = __ldcg(delta + idx);
+                    x[idx] = __ldcg(x + idx) + (VecT)(a.weight * v);
+                    Delta[idx] = v;
                 }
+            } else if (BS == 1) {
+                const int l = threadIdx.x % NTPR;
+                for (int it = tid / NTPR; __any_sync(0xffffffffu, it < cnt); it += nthreads / NTPR) {
+                    const bool act = it < cnt;
+                    dilu_bwd_row_1x1<MatT, VecT, true>(act, act ? rows[off + it] : 0, l, rp, ci, va, x, a.weight, colors, Einv, delta, Delta, c, a.n_owned);
+                }
+            } else {
+                for (int it = tid >> 5; it < cnt; it += nthreads >> 5)
+                    dilu_row_4x4<MatT, VecT, true, true>(rows[off + it], lane, rp, ci, va, x, b, delta, Delta, a.weight, c, colors, Einv, a.n_owned);
             }
-        }
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        // y = Einv_i * acc (4x4 mat-vec inside quad 0; every quad holds the full acc)
-        VecT y = 0;
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-            const VecT am = __shfl_sync(0xffffffffu, acc, m);
-            y += (VecT)Einv[(size_t)i * 16 + r * 4 + m] * am;
-        }
-        if (q == 0) {
-            const size_t idx = (size_t)i * 4 + r;
-            if (!BACKWARD) delta[idx] = y;
-            else {
-                const VecT v = delta[idx] - y;
-                x[idx] += (VecT)(weight * v);
-                Delta[idx] = v;
-            }
+            cluster_barrier();
         }
     }
 }
@@ -256,6 +370,7 @@ public:
     void smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const SmoothFuse *fuse, bool input_in_alt = false) override
     {
         if (input_in_alt || (fuse && (fuse->agg || fuse->dot_b_x))) fatal(AMGX_RC_INTERNAL, "DILU does not support fused sweeps");
+        if (fused_level_ && !A_->dist && sweeps > 0) { level_sweeps(b, x, xIsZero, sweeps); return; }     // all colours, all sweeps: one launch
         for (int it = 0; it < sweeps; it++) sweep(b, x, xIsZero && it == 0);
     }
 
@@ -292,6 +407,59 @@ protected:
             count_launch();
             AMGXB_LAUNCH_CHECK();
         }
+        // levels whose colours are smaller than the machine: the fused cluster kernel (dilu_level_kernel)
+        static const int fused_rows = getenv("AMGXB_DILU_FUSED_ROWS") ? atoi(getenv("AMGXB_DILU_FUSED_ROWS")) : 32768;
+        fused_level_ = A.n > 0 && A.n <= fused_rows && A.num_colors > 0;
+        if (fused_level_) {
+            d_color_offsets_.from_any(A.color_offsets.data(), A.color_offsets.size(), s);
+            // one CTA up to 2048 rows, a cluster of 8 CTAs (the portable maximum) above
+            cluster_size_ = A.n <= 2048 ? 1 : 8;
+        }
+    }
+
+    // forward + backward over all colours, `sweeps` times, in ONE launch (one thread-block cluster)
+    void level_sweeps(DevVec &b, DevVec &x, bool xIsZero, int sweeps)
+    {
+        Matrix &A = *A_;
+        cudaStream_t s = stream();
+        DiluLevelArgs a;
+        a.rp = A.row_ptr.ptr();
+        a.ci = A.col_idx.ptr();
+        a.colors = A.row_colors.ptr();
+        a.sorted_rows = A.sorted_rows_by_color.ptr();
+        a.color_offsets = d_color_offsets_.ptr();
+        a.va = A.values.ptr();
+        a.Einv = Einv_.ptr();
+        a.b = b.ptr();
+        a.x = x.ptr();
+        a.delta = delta_.ptr();
+        a.Delta = Delta_.ptr();
+        a.weight = weight_;
+        a.n = A.n;
+        a.n_owned = A.n;
+        a.num_colors = A.num_colors;
+        a.sweeps = sweeps;
+        a.zero_first = xIsZero ? 1 : 0;
+        a.bs = A.bs();
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)cluster_size_, 1, 1);
+        cfg.blockDim = dim3(1024, 1, 1);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cluster_size_;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+            if (A.bs() == 1) AMGXB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dilu_level_kernel<MatT, VecT, 1>, a));
+            else AMGXB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dilu_level_kernel<MatT, VecT, 4>, a));
+        });
+        count_launch();
+        AMGXB_LAUNCH_CHECK();
     }
 
     void sweep(DevVec &b, DevVec &x, bool xIsZero)
@@ -357,6 +525,9 @@ protected:
     double weight_ = 0.9, uncolored_fraction_ = 0.15;
     std::string scheme_ = "MIN_MAX";
     DevVec Einv_, delta_, Delta_;
+    bool fused_level_ = false;
+    int cluster_size_ = 1;
+    DevBuf<int> d_color_offsets_;
 };
 
 std::unique_ptr<Solver> make_dilu_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc)

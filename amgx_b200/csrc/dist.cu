@@ -164,6 +164,9 @@ void dist_exchange_halo_ptr(const Matrix &A, void *x, Prec prec, cudaStream_t s)
     if (!A.dist) return;
     if (A.dist->exchange_pending) dist_wait_halo(A, s);
     const int bsize = A.bx;
+    // peer-memory path.  Matrices applied as a whole (no interior / boundary split: small levels, block matrices) exchange in ONE kernel;
+    // split matrices push now and wait in front of the boundary rows, the interior rows run in between.
+    if (A.plan.split == 0 && p2p_exchange_blocking(A, x, prec, bsize, s)) { A.dist->exchange_pending = false; return; }
     if (p2p_exchange_start(A, x, prec, bsize, s)) {      // one kernel stores my boundary values into the neighbours' windows
         A.dist->exchange_pending = !A.dist->neighbors.empty();
         return;

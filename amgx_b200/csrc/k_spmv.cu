@@ -319,6 +319,10 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
     tile_stats_kernel<<<std::min(ceil_div(A.n, 256), 1024), 256, 0, s>>>(A.row_ptr.ptr(), 0, A.n, p.tile_rows, p.num_tiles, stats.ptr(), stats.ptr() + 1);
     count_launch();
     p.split = (A.split_row / 4) * 4;   // distributed: rows [0, split) never touch halo columns
+    // The split buys overlap of the halo exchange with the interior rows; below AMGXB_SPLIT_ROWS rows an interior kernel is shorter than
+    // the two extra launches the split costs, so small levels exchange first (one kernel on the peer-memory path) and run as a whole.
+    static const int split_rows = getenv("AMGXB_SPLIT_ROWS") ? atoi(getenv("AMGXB_SPLIT_ROWS")) : (1 << 20);
+    if (A.n < split_rows) p.split = 0;
     if (p.split > 0 && p.split < A.n) {
         tile_stats_kernel<<<std::min(ceil_div(A.n, 256), 1024), 256, 0, s>>>(A.row_ptr.ptr(), 0, p.split, p.tile_rows, ceil_div(p.split, p.tile_rows), stats.ptr(), stats.ptr() + 1);
         tile_stats_kernel<<<std::min(ceil_div(A.n, 256), 1024), 256, 0, s>>>(A.row_ptr.ptr(), p.split, A.n, p.tile_rows, ceil_div(A.n - p.split, p.tile_rows), stats.ptr(), stats.ptr() + 1);

@@ -35,15 +35,16 @@ constexpr int META = 4;                  // ints per tile: column encoding, colu
 // plan: one CTA per tile (grid-stride), TILE_ROWS threads
 // ---------------------------------------------------------------------------------------------
 template <int TILE_ROWS>
-__global__ void __launch_bounds__(TILE_ROWS) colenc_build_kernel(const int *__restrict__ rp, const int *__restrict__ ci, int n, int num_tiles, unsigned char *codes,
-                                                                 int *dict, int *meta, int *stats)
+__global__ void __launch_bounds__(TILE_ROWS) colenc_build_kernel(const int *__restrict__ rp, const int *__restrict__ ci, int row0, int n, int num_tiles, int tile_base,
+                                                                 unsigned char *codes, int *dict, int *meta, int *stats)
 {
     __shared__ int keys[HASH_SLOTS];
     __shared__ int list[DICT_SLOTS], sorted[DICT_SLOTS];
     __shared__ int s_count, s_min, s_max, s_overflow;
     const int tid = threadIdx.x;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int r0 = tile * TILE_ROWS, r1 = min(r0 + TILE_ROWS, n);
+    for (int ltile = blockIdx.x; ltile < num_tiles; ltile += gridDim.x) {
+        const int tile = tile_base + ltile;             // tiles are numbered over the row segments of the matrix: [0, split) then [split, n)
+        const int r0 = row0 + ltile * TILE_ROWS, r1 = min(r0 + TILE_ROWS, n);
         const int nz0 = rp[r0], nz1 = rp[r1];
         const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
         for (int i = tid; i < HASH_SLOTS; i += TILE_ROWS) keys[i] = INT_MAX;
@@ -131,16 +132,17 @@ template <> __device__ __forceinline__ double val_from_bits<double>(unsigned lon
 template <> __device__ __forceinline__ float val_from_bits<float>(unsigned long long b) { return __uint_as_float((unsigned)b); }
 
 template <class MatT, int TILE_ROWS>
-__global__ void __launch_bounds__(TILE_ROWS) valenc_build_kernel(const int *__restrict__ rp, const MatT *__restrict__ va, int n, int num_tiles, unsigned char *vcodes,
-                                                                 MatT *vdict, int *meta, int *stats)
+__global__ void __launch_bounds__(TILE_ROWS) valenc_build_kernel(const int *__restrict__ rp, const MatT *__restrict__ va, int row0, int n, int num_tiles, int tile_base,
+                                                                 unsigned char *vcodes, MatT *vdict, int *meta, int *stats)
 {
     constexpr unsigned long long EMPTY = ~0ull;
     __shared__ unsigned long long keys[HASH_SLOTS];
     __shared__ unsigned long long list[DICT_SLOTS], sorted[DICT_SLOTS];
     __shared__ int s_count, s_overflow;
     const int tid = threadIdx.x;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int r0 = tile * TILE_ROWS, r1 = min(r0 + TILE_ROWS, n);
+    for (int ltile = blockIdx.x; ltile < num_tiles; ltile += gridDim.x) {
+        const int tile = tile_base + ltile;
+        const int r0 = row0 + ltile * TILE_ROWS, r1 = min(r0 + TILE_ROWS, n);
         const int nz0 = rp[r0], nz1 = rp[r1];
         const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
         for (int i = tid; i < HASH_SLOTS; i += TILE_ROWS) keys[i] = EMPTY;
@@ -218,6 +220,7 @@ struct EncArgs {
     const unsigned char *vcodes;
     const void *vdict;
     int val_w, col_w, dict_cap, vdict_cap;
+    int tile_base;      // global index of the segment's first tile (meta / dictionaries / code segments are numbered over all segments)
 };
 
 // one row of an encoded tile: 8 code loads, 8 dictionary look-ups, 8 gathers of x in flight, FMA chain in storage order
@@ -303,7 +306,8 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
                 const int r1 = min(r0 + TILE_ROWS, a.n);
                 const int nz0 = __ldg(a.row_ptr + r0), nz1 = __ldg(a.row_ptr + r1);
                 const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
-                const int4 m = __ldg(reinterpret_cast<const int4 *>(e.meta) + tile);
+                const int gtile = e.tile_base + tile;
+                const int4 m = __ldg(reinterpret_cast<const int4 *>(e.meta) + gtile);
                 const int enc = m.x, dlen = m.y, venc = m.z, vdlen = m.w;
                 unsigned char *st = stage_base + (size_t)s * stage_bytes;
                 const unsigned rp_copy = (unsigned)(((r1 - r0 + 1 + 3) & ~3) * sizeof(int));
@@ -317,13 +321,13 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
                 tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes + vdict_bytes, a.row_ptr + r0, rp_copy, &full[s]);
                 if (cnt) {
                     if (venc == 0) tma_bulk_g2s(st, a.val + sa, val_copy, &full[s]);
-                    else tma_bulk_g2s(st, e.vcodes + vcode_offset(sa, tile), val_copy, &full[s]);
+                    else tma_bulk_g2s(st, e.vcodes + vcode_offset(sa, gtile), val_copy, &full[s]);
                     if (enc == 0) tma_bulk_g2s(st + vals_bytes, a.col + sa, col_copy, &full[s]);
-                    else tma_bulk_g2s(st + vals_bytes, e.codes + code_offset(sa, tile), col_copy, &full[s]);
+                    else tma_bulk_g2s(st + vals_bytes, e.codes + code_offset(sa, gtile), col_copy, &full[s]);
                 }
-                if (dict_copy) tma_bulk_g2s(st + vals_bytes + cols_bytes, e.dict + (size_t)tile * DICT_SLOTS, dict_copy, &full[s]);
+                if (dict_copy) tma_bulk_g2s(st + vals_bytes + cols_bytes, e.dict + (size_t)gtile * DICT_SLOTS, dict_copy, &full[s]);
                 if (vdict_copy)
-                    tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes, reinterpret_cast<const MatT *>(e.vdict) + (size_t)tile * DICT_SLOTS, vdict_copy, &full[s]);
+                    tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes, reinterpret_cast<const MatT *>(e.vdict) + (size_t)gtile * DICT_SLOTS, vdict_copy, &full[s]);
             }
         }
     } else {
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
             const unsigned ph = (unsigned)(it / a.stages) & 1u;
             const int row = a.row0 + tile * TILE_ROWS + tid;
             const bool active = row < a.n;
-            const int enc = __ldg(e.meta + META * tile), venc = __ldg(e.meta + META * tile + 2);
+            const int enc = __ldg(e.meta + META * (e.tile_base + tile)), venc = __ldg(e.meta + META * (e.tile_base + tile) + 2);
             VecT bi = 0, xi = 0;
             MatT di = 1;
             if (active) {
@@ -426,6 +430,21 @@ static int colenc_flags()
 }
 bool colenc_requested() { return colenc_flags() != 0; }
 
+// Row segments the tile kernels run over: the whole matrix, or (row-partitioned matrices) the interior rows [0, split) and the rows
+// [split, n) that read halo columns.  Tiles are numbered over the segments in this order.
+struct EncSeg { int row0, row1, tiles, base; };
+static int enc_segments(const Matrix &A, EncSeg seg[2])
+{
+    const int T = A.plan.tile_rows;
+    if (A.plan.split > 0 && A.plan.split < A.n) {
+        seg[0] = EncSeg{0, A.plan.split, ceil_div(A.plan.split, T), 0};
+        seg[1] = EncSeg{A.plan.split, A.n, ceil_div(A.n - A.plan.split, T), seg[0].tiles};
+        return 2;
+    }
+    seg[0] = EncSeg{0, A.n, ceil_div(A.n, T), 0};
+    return 1;
+}
+
 static void build_value_codes(Matrix &A, cudaStream_t s)
 {
     ColEnc &E = A.colenc;
@@ -433,15 +452,20 @@ static void build_value_codes(Matrix &A, cudaStream_t s)
     DevBuf<int> stats;
     stats.resize(8);
     stats.zero(s);
-    const int grid = std::max(1, std::min(nt, 148 * 8));
-    if (A.mat_prec == Prec::F64) {
-        if (T == 256) valenc_build_kernel<double, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.values.as<double>(), A.n, nt, E.vcodes.ptr(), (double *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
-        else valenc_build_kernel<double, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.values.as<double>(), A.n, nt, E.vcodes.ptr(), (double *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
-    } else {
-        if (T == 256) valenc_build_kernel<float, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.values.as<float>(), A.n, nt, E.vcodes.ptr(), (float *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
-        else valenc_build_kernel<float, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.values.as<float>(), A.n, nt, E.vcodes.ptr(), (float *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
+    EncSeg seg[2];
+    const int nseg = enc_segments(A, seg);
+    for (int g = 0; g < nseg; g++) {
+        const int grid = std::max(1, std::min(seg[g].tiles, 148 * 8));
+        if (A.mat_prec == Prec::F64) {
+            if (T == 256) valenc_build_kernel<double, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.values.as<double>(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.vcodes.ptr(), (double *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
+            else valenc_build_kernel<double, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.values.as<double>(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.vcodes.ptr(), (double *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
+        } else {
+            if (T == 256) valenc_build_kernel<float, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.values.as<float>(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.vcodes.ptr(), (float *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
+            else valenc_build_kernel<float, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.values.as<float>(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.vcodes.ptr(), (float *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
+        }
+        count_launch();
     }
-    count_launch();
+    (void)nt;
     AMGXB_LAUNCH_CHECK();
     const std::vector<int> h = stats.to_host(s);
     E.tiles_val8 = h[3];
@@ -452,7 +476,7 @@ static void build_value_codes(Matrix &A, cudaStream_t s)
 static void finalize_layout(Matrix &A)
 {
     ColEnc &E = A.colenc;
-    const int T = A.plan.tile_rows, nt = A.plan.num_tiles;
+    const int T = A.plan.tile_rows, nt = E.num_tiles;
     const size_t msz = prec_size(A.mat_prec);
     E.col_w = E.tiles_raw > 0 ? 4 : (E.tiles_off16 > 0 ? 2 : 1);
     E.val_w = (E.tiles_val8 == nt) ? 1 : (int)msz;
@@ -484,10 +508,13 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
 {
     A.colenc.on = false;
     A.colenc.values_encoded = false;
-    if (!colenc_requested() || !A.plan.use_tiles || A.plan.split != 0 || A.dist || A.n == 0 || A.bs() != 1) return;
-    const int T = A.plan.tile_rows, nt = A.plan.num_tiles;
+    if (!colenc_requested() || !A.plan.use_tiles || A.n == 0 || A.bs() != 1) return;
+    EncSeg seg[2];
+    const int nseg = enc_segments(A, seg);
+    const int T = A.plan.tile_rows, nt = seg[nseg - 1].base + seg[nseg - 1].tiles;
     const size_t msz = prec_size(A.mat_prec);
     ColEnc &E = A.colenc;
+    E.num_tiles = nt;
     E.meta.resize((size_t)META * nt);
     E.meta.zero(s);                                  // encoding 0 everywhere: raw columns, raw values
     E.tiles_dict8 = E.tiles_off16 = E.tiles_val8 = 0;
@@ -501,10 +528,12 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
         DevBuf<int> stats;
         stats.resize(8);
         stats.zero(s);
-        const int grid = std::max(1, std::min(nt, 148 * 8));
-        if (T == 256) colenc_build_kernel<256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, nt, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
-        else colenc_build_kernel<128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, nt, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
-        count_launch();
+        for (int g = 0; g < nseg; g++) {
+            const int grid = std::max(1, std::min(seg[g].tiles, 148 * 8));
+            if (T == 256) colenc_build_kernel<256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
+            else colenc_build_kernel<128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
+            count_launch();
+        }
         AMGXB_LAUNCH_CHECK();
         const std::vector<int> h = stats.to_host(s);
         E.tiles_dict8 = h[0];
@@ -548,8 +577,13 @@ void csr_values_changed(Matrix &A, cudaStream_t s)
 // csr_op entry of the encoded path; returns false when the caller must use the plain kernels
 bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int segment)
 {
-    if (!A.colenc.on || segment != 0 || g.agg) return false;
+    if (!A.colenc.on || g.agg) return false;
+    EncSeg seg[2];
+    const int nseg = enc_segments(A, seg);
+    if ((nseg == 1) != (segment == 0)) return false;      // a split matrix applied as a whole (or the reverse): the plain kernels
+    const EncSeg &sg = seg[segment == 2 ? 1 : 0];
     EncArgs ea;
+    ea.tile_base = sg.base;
     ea.codes = A.colenc.codes.ptr();
     ea.dict = A.colenc.dict.ptr();
     ea.meta = A.colenc.meta.ptr();
@@ -564,9 +598,9 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
         ta.row_ptr = A.row_ptr.ptr();
         ta.col = A.col_idx.ptr();
         ta.val = A.values.as<MatT>();
-        ta.n = A.n;
-        ta.row0 = 0;
-        ta.num_tiles = A.plan.num_tiles;
+        ta.n = sg.row1;
+        ta.row0 = sg.row0;
+        ta.num_tiles = sg.tiles;
         ta.cap = A.plan.max_tile_nnz;
         ta.stages = A.colenc.stages;
         ta.unroll = 8;

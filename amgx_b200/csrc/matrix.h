@@ -54,6 +54,7 @@ struct ColEnc {
     int max_dlen = 0, max_vdlen = 0;               // longest (padded) dictionaries of the level
     int col_w = 4, val_w = 8, dict_cap = 0, vdict_cap = 0;   // stage layout of the level (finalize_layout)
     int stages = 2, ctas_per_sm = 1;
+    int num_tiles = 0;                             // tiles over all row segments ([0, split) then [split, n) on a row-partitioned matrix)
 };
 
 struct Matrix {

@@ -109,6 +109,45 @@ template <class T> __global__ void __launch_bounds__(256) p2p_wait_unpack_kernel
     if (is_last && threadIdx.x == 0) { d->recv_epoch = e; d->counter_wait = 0; }
 }
 
+// Fused exchange for the levels where there is nothing worth overlapping (below AMGXB_SPLIT_ROWS rows the interior kernel is shorter than a
+// launch): push my boundary values, release the flags (last CTA to finish its stores), acquire the neighbours' flags, unpack -- ONE kernel
+// per exchange, and the matrix is then applied by ONE kernel over all its rows.  No intra-grid barrier is needed: what a CTA waits for comes
+// from the neighbours' grids.  The grid is small (<= 32 CTAs) so that it is always fully resident (two grids spinning on each other's
+// flags must both be able to finish their pushes).
+template <class T> __global__ void __launch_bounds__(256) p2p_exchange_kernel(LinkDev *d, const int *__restrict__ map, T *x, int bsize, long long halo_count, long long halo_first)
+{
+    const u64 e = *(volatile u64 *)&d->send_epoch + 1;      // send and receive epochs advance together on this path
+    const int nn = d->nn;
+    for (int q = 0; q < nn; q++) {
+        T *dst = reinterpret_cast<T *>(d->peer_data[q] + (e & 1) * d->peer_parity_stride[q]);
+        const int b0 = d->send_begin[q];
+        const long long total = (long long)(d->send_end[q] - b0) * bsize;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+            const int k = (int)(t / bsize), c = (int)(t % bsize);
+            dst[t] = x[(size_t)map[b0 + k] * bsize + c];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) is_last = (atomicAdd(&d->counter_push, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence_system();
+        if ((int)threadIdx.x < nn) st_release_sys(d->peer_flag[threadIdx.x], e);
+    }
+    if ((int)threadIdx.x < nn) wait_flag(d->flags + threadIdx.x, e);
+    __syncthreads();
+    const T *src = reinterpret_cast<const T *>(d->stage + (e & 1) * d->stage_stride);
+    T *x_halo = x + halo_first;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < halo_count; t += (long long)gridDim.x * blockDim.x) x_halo[t] = __ldcg(src + t);
+    __syncthreads();
+    __shared__ bool is_last2;
+    if (threadIdx.x == 0) is_last2 = (atomicAdd(&d->counter_wait, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last2 && threadIdx.x == 0) { d->send_epoch = e; d->recv_epoch = e; d->counter_push = 0; d->counter_wait = 0; }
+}
+
 // per-resources device state of the scalar all-reduce
 struct RedDev {
     int world, rank;
@@ -424,6 +463,23 @@ void p2p_exchange_wait(const Matrix &A, cudaStream_t s)
     count_launch();
     AMGXB_LAUNCH_CHECK();
     m.p2p_pending_x = nullptr;
+}
+
+// whole exchange in one kernel (see p2p_exchange_kernel): on return (stream order) the halo tail of x is filled
+bool p2p_exchange_blocking(const Matrix &A, void *x, Prec prec, int bsize, cudaStream_t s)
+{
+    DistManager &m = *A.dist;
+    if (!m.p2p || bsize != m.p2p->bsize) return false;
+    if (m.neighbors.empty()) return true;
+    const int nn = (int)m.neighbors.size();
+    const long long work = std::max<long long>((long long)m.send_offsets[nn], (long long)m.n_halo) * bsize;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((work + 2047) / 2048, 32));
+    const long long halo_count = (long long)m.n_halo * bsize, halo_first = (long long)m.n_owned * bsize;
+    if (prec == Prec::F64) p2p_exchange_kernel<double><<<grid, 256, 0, s>>>(m.p2p->dev, m.send_maps.ptr(), (double *)x, bsize, halo_count, halo_first);
+    else p2p_exchange_kernel<float><<<grid, 256, 0, s>>>(m.p2p->dev, m.send_maps.ptr(), (float *)x, bsize, halo_count, halo_first);
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    return true;
 }
 
 // scal[slot] <- op over the ranks of scal[slot], then the scalar epilogue; one 32-thread kernel.  Returns false without a window.

@@ -454,14 +454,21 @@ void Solver::smooth(DevVec &b, DevVec &x, bool xIsZero, int sweeps, const Smooth
 {
     if (input_in_alt) fatal(AMGX_RC_INTERNAL, "smoother has no alternate input buffer");
     if (fuse && (fuse->agg || fuse->dot_b_x)) fatal(AMGX_RC_INTERNAL, "smoother does not support fused sweeps");
-    const int saved = max_iters_;
-    const bool mr = monitor_residual_, mc = monitor_convergence_;
+    // the smoother's own settings come back on every path, a throwing solve included (graceful-failure recovery: CAPIFailure)
+    struct Restore {
+        Solver &s;
+        int max_iters;
+        bool mr, mc, tol_override;
+        double tol_value, conv_tol;
+        ~Restore()
+        {
+            s.max_iters_ = max_iters; s.monitor_residual_ = mr; s.monitor_convergence_ = mc;
+            s.tol_override_ = tol_override; s.tol_value_ = tol_value; s.conv_.tolerance = conv_tol;
+        }
+    } restore{*this, max_iters_, monitor_residual_, monitor_convergence_, tol_override_, tol_value_, conv_.tolerance};
     set_max_iters(sweeps);
     set_tolerance(0.0);
     solve(b, x, xIsZero);
-    max_iters_ = saved;
-    monitor_residual_ = mr;
-    monitor_convergence_ = mc;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -242,7 +242,7 @@ def distributed_parity(capi, dist, torch, rsc, rank, world, local_rank):
             y.set_zero(nloc)
             A.multiply(x, y)
             yl = y.download()
-            x.set_zero(nloc)
+        x.set_zero(nloc)            # a zero initial guess is a PROMISE to the solver (as in the reference): the generator filled x with ones
         slv = capi.Solver(rsc, cfgobj)
         slv.setup(A)
         slv.solve(b, x, zero_initial_guess=True)

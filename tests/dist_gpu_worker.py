@@ -199,7 +199,9 @@ def read_distributed_section(rank, world, rsc, lib, cfg):
         W = sp.csr_matrix((ent[:, 2], (ent[:, 0].astype(int) - 1, ent[:, 1].astype(int) - 1)), shape=(ng, ng))
         assert abs(W - gallery.to_scipy(rp, ci, va)).max() == 0.0, "written matrix differs from the global one"
         tail = np.array([float(l) for l in lines[1 + nnz:]])
-        assert tail.shape[0] == 2 * ng and np.array_equal(tail[:ng], rhs) and np.array_equal(tail[ng:], xfull)
+        # the reference's layout (src/matrix_io.cu:222-258): a line with the vector length in front of the rhs and of the solution
+        assert tail.shape[0] == 2 * ng + 2 and tail[0] == ng and tail[ng + 1] == ng
+        assert np.array_equal(tail[1:ng + 1], rhs) and np.array_equal(tail[ng + 2:], xfull)
     if rank == 0:
         print(f"DIST_READ_SYSTEM_OK world={world} iters={slv.iterations_number} write_gathered=ok", flush=True)
     for o in (slv, x, b, A):
