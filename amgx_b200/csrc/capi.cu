@@ -377,7 +377,11 @@ AMGX_RC AMGX_matrix_replace_coefficients(AMGX_matrix_handle mtx, int n, int nnz,
     if (n != A.n || nnz != user_nnz) fatal(AMGX_RC_BAD_PARAMETERS, "replace_coefficients: size mismatch");
     if (A.dist) {
         if (diag_data) fatal(AMGX_RC_NOT_IMPLEMENTED, "replace_coefficients with an external diagonal on a distributed matrix");
-        if (data) dist_replace_values(A, nnz, data);
+        if (data) {
+            dist_replace_values(A, nnz, data);
+            csr_values_changed(A, A.stream());      // the value codes of the tile kernels follow the values
+            AMGXB_CUDA_CHECK(cudaStreamSynchronize(A.stream()));
+        }
         return AMGX_RC_OK;
     }
     const size_t bs = A.bs(), msz = prec_size(A.mat_prec);

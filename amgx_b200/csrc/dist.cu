@@ -164,12 +164,24 @@ void dist_exchange_halo_ptr(const Matrix &A, void *x, Prec prec, cudaStream_t s)
     if (!A.dist) return;
     if (A.dist->exchange_pending) dist_wait_halo(A, s);
     const int bsize = A.bx;
-    // peer-memory path.  Matrices applied as a whole (no interior / boundary split: small levels, block matrices) exchange in ONE kernel;
-    // split matrices push now and wait in front of the boundary rows, the interior rows run in between.
-    if (A.plan.split == 0 && p2p_exchange_blocking(A, x, prec, bsize, s)) { A.dist->exchange_pending = false; return; }
-    if (p2p_exchange_start(A, x, prec, bsize, s)) {      // one kernel stores my boundary values into the neighbours' windows
-        A.dist->exchange_pending = !A.dist->neighbors.empty();
-        return;
+    // Peer-memory path: the whole exchange is ONE kernel (p2p.cu).  Matrices applied as a whole (small levels, block matrices) run it on
+    // the compute stream; split matrices run it on the side stream while the interior rows are processed, and the boundary rows wait
+    // for its event -- the structure of the NCCL path without the pack kernel and the NCCL launch.
+    if (A.dist->p2p) {
+        DistManager &m = *A.dist;
+        if (A.plan.split == 0) {
+            if (p2p_exchange_blocking(A, x, prec, bsize, s)) { m.exchange_pending = false; return; }
+        } else if (!m.neighbors.empty()) {
+            ensure_scratch(m);
+            cudaStream_t side = A.rsc->side_stream;
+            AMGXB_CUDA_CHECK(cudaEventRecord(m.ev_pack, s));
+            AMGXB_CUDA_CHECK(cudaStreamWaitEvent(side, m.ev_pack, 0));
+            if (p2p_exchange_blocking(A, x, prec, bsize, side)) {
+                AMGXB_CUDA_CHECK(cudaEventRecord(m.ev_done, side));
+                m.exchange_pending = true;
+                return;
+            }
+        } else return;
     }
     if (prec == Prec::F64) exchange_typed<double>(A, (double *)x, bsize, s, ncclDouble);
     else exchange_typed<float>(A, (float *)x, bsize, s, ncclFloat);
@@ -180,11 +192,6 @@ void dist_exchange_halo(const Matrix &A, DevVec &x, cudaStream_t s) { dist_excha
 void dist_wait_halo(const Matrix &A, cudaStream_t s)
 {
     if (!A.dist || !A.dist->exchange_pending) return;
-    if (A.dist->p2p_pending_x) {
-        p2p_exchange_wait(A, s);
-        A.dist->exchange_pending = false;
-        return;
-    }
     AMGXB_CUDA_CHECK(cudaStreamWaitEvent(s, A.dist->ev_done, 0));
     A.dist->exchange_pending = false;
 }

@@ -32,9 +32,6 @@ struct DistManager {
     bool exchange_pending = false;       // a halo exchange is in flight on the side stream
     DevBuf<int> halo_int;                // scratch for integer halo exchanges
     std::shared_ptr<P2PLink> p2p;        // peer-memory link of this manager (p2p.cu); null -> NCCL send/recv
-    void *p2p_pending_x = nullptr;       // vector whose halo tail the pending peer-memory exchange fills
-    Prec p2p_pending_prec = Prec::F64;
-    int p2p_pending_bsize = 1;
     ~DistManager();
 };
 

@@ -50,9 +50,10 @@ __device__ __forceinline__ u64 ld_acquire_sys(const u64 *p)
 __device__ __forceinline__ void wait_flag(const u64 *flag, u64 e)
 {
     const long long t0 = clock64();
+    int spins = 0;
     while (ld_acquire_sys(flag) < e) {
-        __nanosleep(64);
-        if (clock64() - t0 > 60000000000ll) { printf("[amgx_b200] peer-memory wait timed out (flag %p, epoch %llu)\n", (const void *)flag, e); __trap(); }
+        if (++spins > 4096) __nanosleep(128);      // the common case completes within a few microseconds: poll hot first
+        if ((spins & 1023) == 0 && clock64() - t0 > 60000000000ll) { printf("[amgx_b200] peer-memory wait timed out (flag %p, epoch %llu)\n", (const void *)flag, e); __trap(); }
     }
 }
 
@@ -70,7 +71,13 @@ struct LinkDev {
     unsigned counter_push, counter_wait;
 };
 
-template <class T> __global__ void __launch_bounds__(256) p2p_push_kernel(LinkDev *d, const int *__restrict__ map, const T *__restrict__ x, int bsize)
+// The exchange: push my boundary values into the neighbours' windows, release the epoch flags (last CTA to finish its stores), acquire
+// the neighbours' flags, copy my window into the halo tail of x -- ONE kernel.  No intra-grid barrier is needed: what a CTA waits for
+// comes from the neighbours' grids.  The grid is small (<= 32 CTAs) so that it is always fully resident (two grids spinning on each
+// other's flags must both be able to finish their pushes).  Ordering: a CTA's peer stores are made visible at system scope by ONE
+// fence of its thread 0 after the CTA barrier (cumulativity), before its ticket; whoever draws the last ticket therefore knows every
+// CTA's data has been performed at system scope and only has to keep its own release stores of the flags behind that observation.
+template <class T> __global__ void __launch_bounds__(256) p2p_exchange_kernel(LinkDev *d, const int *__restrict__ map, T *x, int bsize, long long halo_count, long long halo_first)
 {
     const u64 e = *(volatile u64 *)&d->send_epoch + 1;
     const int nn = d->nn;
@@ -83,69 +90,25 @@ template <class T> __global__ void __launch_bounds__(256) p2p_push_kernel(LinkDe
             dst[t] = x[(size_t)map[b0 + k] * bsize + c];
         }
     }
-    __threadfence_system();
     __syncthreads();
     __shared__ bool is_last;
-    if (threadIdx.x == 0) is_last = (atomicAdd(&d->counter_push, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (is_last) {
+    if (threadIdx.x == 0) {
         __threadfence_system();
-        if ((int)threadIdx.x < nn) st_release_sys(d->peer_flag[threadIdx.x], e);
-        if (threadIdx.x == 0) { d->send_epoch = e; d->counter_push = 0; }
+        is_last = (gridDim.x == 1) || (atomicAdd(&d->counter_push, 1u) == gridDim.x - 1);
+        __threadfence();
     }
-}
-
-template <class T> __global__ void __launch_bounds__(256) p2p_wait_unpack_kernel(LinkDev *d, T *__restrict__ x_halo, long long count)
-{
-    const u64 e = *(volatile u64 *)&d->recv_epoch + 1;
-    if ((int)threadIdx.x < d->nn) wait_flag(d->flags + threadIdx.x, e);
     __syncthreads();
-    const T *src = reinterpret_cast<const T *>(d->stage + (e & 1) * d->stage_stride);
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (long long)gridDim.x * blockDim.x) x_halo[t] = __ldcg(src + t);
-    __syncthreads();
-    __shared__ bool is_last;
-    if (threadIdx.x == 0) is_last = (atomicAdd(&d->counter_wait, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (is_last && threadIdx.x == 0) { d->recv_epoch = e; d->counter_wait = 0; }
-}
-
-// Fused exchange for the levels where there is nothing worth overlapping (below AMGXB_SPLIT_ROWS rows the interior kernel is shorter than a
-// launch): push my boundary values, release the flags (last CTA to finish its stores), acquire the neighbours' flags, unpack -- ONE kernel
-// per exchange, and the matrix is then applied by ONE kernel over all its rows.  No intra-grid barrier is needed: what a CTA waits for comes
-// from the neighbours' grids.  The grid is small (<= 32 CTAs) so that it is always fully resident (two grids spinning on each other's
-// flags must both be able to finish their pushes).
-template <class T> __global__ void __launch_bounds__(256) p2p_exchange_kernel(LinkDev *d, const int *__restrict__ map, T *x, int bsize, long long halo_count, long long halo_first)
-{
-    const u64 e = *(volatile u64 *)&d->send_epoch + 1;      // send and receive epochs advance together on this path
-    const int nn = d->nn;
-    for (int q = 0; q < nn; q++) {
-        T *dst = reinterpret_cast<T *>(d->peer_data[q] + (e & 1) * d->peer_parity_stride[q]);
-        const int b0 = d->send_begin[q];
-        const long long total = (long long)(d->send_end[q] - b0) * bsize;
-        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-            const int k = (int)(t / bsize), c = (int)(t % bsize);
-            dst[t] = x[(size_t)map[b0 + k] * bsize + c];
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    __shared__ bool is_last;
-    if (threadIdx.x == 0) is_last = (atomicAdd(&d->counter_push, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (is_last) {
-        __threadfence_system();
-        if ((int)threadIdx.x < nn) st_release_sys(d->peer_flag[threadIdx.x], e);
-    }
+    if (is_last && (int)threadIdx.x < nn) st_release_sys(d->peer_flag[threadIdx.x], e);
     if ((int)threadIdx.x < nn) wait_flag(d->flags + threadIdx.x, e);
     __syncthreads();
     const T *src = reinterpret_cast<const T *>(d->stage + (e & 1) * d->stage_stride);
     T *x_halo = x + halo_first;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < halo_count; t += (long long)gridDim.x * blockDim.x) x_halo[t] = __ldcg(src + t);
     __syncthreads();
-    __shared__ bool is_last2;
-    if (threadIdx.x == 0) is_last2 = (atomicAdd(&d->counter_wait, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (is_last2 && threadIdx.x == 0) { d->send_epoch = e; d->recv_epoch = e; d->counter_push = 0; d->counter_wait = 0; }
+    if (threadIdx.x == 0) {
+        const bool last2 = (gridDim.x == 1) || (atomicAdd(&d->counter_wait, 1u) == gridDim.x - 1);
+        if (last2) { d->send_epoch = e; d->recv_epoch = e; d->counter_push = 0; d->counter_wait = 0; }
+    }
 }
 
 // per-resources device state of the scalar all-reduce
@@ -423,49 +386,8 @@ void p2p_manager_setup(const Matrix &A)
     m.p2p = link;
 }
 
-template <class T> static void push_typed(const Matrix &A, const T *x, int bsize, cudaStream_t s)
-{
-    DistManager &m = *A.dist;
-    const int nn = (int)m.neighbors.size();
-    const long long total = (long long)m.send_offsets[nn] * bsize;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 2047) / 2048, 64));
-    p2p_push_kernel<T><<<grid, 256, 0, s>>>(m.p2p->dev, m.send_maps.ptr(), x, bsize);
-    count_launch();
-    AMGXB_LAUNCH_CHECK();
-}
-
-// start: values of my boundary rows -> the neighbours' windows.  Returns false when this manager has no peer-memory link
-// (element size > 8 bytes never happens; ints use the NCCL path at setup time).
-bool p2p_exchange_start(const Matrix &A, void *x, Prec prec, int bsize, cudaStream_t s)
-{
-    DistManager &m = *A.dist;
-    if (!m.p2p || bsize != m.p2p->bsize) return false;
-    if (m.neighbors.empty()) return true;
-    if (prec == Prec::F64) push_typed<double>(A, (const double *)x, bsize, s);
-    else push_typed<float>(A, (const float *)x, bsize, s);
-    m.p2p_pending_x = x;
-    m.p2p_pending_prec = prec;
-    m.p2p_pending_bsize = bsize;
-    return true;
-}
-
-// wait: acquire the neighbours' flags, copy my window into the halo tail of the vector the exchange was started on
-void p2p_exchange_wait(const Matrix &A, cudaStream_t s)
-{
-    DistManager &m = *A.dist;
-    if (!m.p2p || !m.p2p_pending_x) return;
-    const long long count = (long long)m.n_halo * m.p2p_pending_bsize;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((count + 2047) / 2048, 64));
-    if (m.p2p_pending_prec == Prec::F64)
-        p2p_wait_unpack_kernel<double><<<grid, 256, 0, s>>>(m.p2p->dev, (double *)m.p2p_pending_x + (size_t)m.n_owned * m.p2p_pending_bsize, count);
-    else
-        p2p_wait_unpack_kernel<float><<<grid, 256, 0, s>>>(m.p2p->dev, (float *)m.p2p_pending_x + (size_t)m.n_owned * m.p2p_pending_bsize, count);
-    count_launch();
-    AMGXB_LAUNCH_CHECK();
-    m.p2p_pending_x = nullptr;
-}
-
-// whole exchange in one kernel (see p2p_exchange_kernel): on return (stream order) the halo tail of x is filled
+// the whole exchange as one kernel on stream s (see p2p_exchange_kernel): in stream order, the halo tail of x is filled afterwards.
+// Returns false when this manager has no peer-memory link (the caller then takes the NCCL path).
 bool p2p_exchange_blocking(const Matrix &A, void *x, Prec prec, int bsize, cudaStream_t s)
 {
     DistManager &m = *A.dist;

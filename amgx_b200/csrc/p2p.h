@@ -15,9 +15,7 @@ void p2p_init(Resources *rsc);                      // collective, after the NCC
 void p2p_shutdown(Resources *rsc);
 bool p2p_available(const Resources *rsc);
 void p2p_manager_setup(const Matrix &A);            // collective: receive window of A.dist, addresses exchanged with the neighbours
-bool p2p_exchange_start(const Matrix &A, void *x, Prec prec, int bsize, cudaStream_t s);
-void p2p_exchange_wait(const Matrix &A, cudaStream_t s);
-bool p2p_exchange_blocking(const Matrix &A, void *x, Prec prec, int bsize, cudaStream_t s);   // push + wait + unpack in one kernel
+bool p2p_exchange_blocking(const Matrix &A, void *x, Prec prec, int bsize, cudaStream_t s);   // push + flags + wait + unpack: one kernel on stream s
 // op 0 sum / 2 max; post 0: FinOp epilogue, post 1: norm epilogue (sqrt when do_sqrt; host mirror when mirror)
 bool p2p_allreduce_scalar(const Matrix &A, const ReduceCtx &red, int slot, int op, int post, int fin_op, int do_sqrt, bool mirror, cudaStream_t s);
 
