@@ -303,29 +303,70 @@ static std::shared_ptr<DistManager> manager_from_plan(Matrix &A, const AMGXB200_
     return m;
 }
 
-// verify the structural-symmetry assumption of the planner: what I send to q must be what q expects
-static void verify_plan(const Matrix &A)
+// The planner (partition.cpp) derives the send side locally, which is only right when the pattern is structurally symmetric across the
+// cut (row i references a column of q <=> q references row i).  The reference accepts any pattern: its B2L maps are built from what the
+// RECEIVERS ask for (createOneRingB2Lmaps, src/distributed/distributed_manager.cu).  Do the same: every rank learns how many of its rows
+// each other rank needs (all-gather of the need counts), the receivers send the global ids of their halo columns to the owners, and the
+// send maps are rebuilt from what arrives.  Neighbour lists become symmetric (a neighbour one only sends to, or only receives from,
+// has an empty range on the other side), so every grouped send/recv and every peer-memory flag has its partner.  On a structurally
+// symmetric pattern this reproduces the planner's maps exactly (same rows, ascending global id).
+static void reconcile_plan(Matrix &A)
 {
     DistManager &m = *A.dist;
-    const int nn = (int)m.neighbors.size();
-    if (nn == 0) return;
-    ensure_scratch(m);
+    const int world = m.world, rank = m.rank;
     cudaStream_t s = A.stream();
-    DevBuf<int> sendc, recvc;
-    std::vector<int> hs(nn), hr(nn, -1);
-    for (int q = 0; q < nn; q++) hs[q] = m.send_offsets[q + 1] - m.send_offsets[q];
-    sendc.from_any(hs.data(), nn, s);
-    recvc.resize(nn);
+    ensure_scratch(m);
+    const int nn0 = (int)m.neighbors.size();
+    // need[r * world + q] = number of halo columns rank r reads from rank q
+    std::vector<int> mine(world, 0);
+    for (int q = 0; q < nn0; q++) mine[m.neighbors[q]] = m.halo_offsets[q + 1] - m.halo_offsets[q];
+    DevBuf<int> d_mine, d_all;
+    d_mine.from_any(mine.data(), (size_t)world, s);
+    d_all.resize((size_t)world * world);
+    AMGXB_NCCL_CHECK(ncclAllGather(d_mine.ptr(), d_all.ptr(), (size_t)world, ncclInt32, comm_of(A), s));
+    const std::vector<int> need = d_all.to_host(s);
+    // symmetric neighbour list, ascending rank; halo ranges keep the planner's order (ascending owner)
+    std::vector<int> nbrs, halo_off{0}, send_cnt;
+    std::vector<int> old_index(world, -1);
+    for (int q = 0; q < nn0; q++) old_index[m.neighbors[q]] = q;
+    for (int q = 0; q < world; q++) {
+        if (q == rank) continue;
+        const int i_need = need[(size_t)rank * world + q], q_needs = need[(size_t)q * world + rank];
+        if (i_need == 0 && q_needs == 0) continue;
+        nbrs.push_back(q);
+        halo_off.push_back(halo_off.back() + i_need);
+        send_cnt.push_back(q_needs);
+    }
+    const int nn = (int)nbrs.size();
+    if (halo_off.back() != m.n_halo) fatal(AMGX_RC_INTERNAL, "reconcile_plan: halo ranges do not add up");
+    // ids I need -> owners; ids the others need from me <- requesters
+    std::vector<long long> ask((size_t)std::max(m.n_halo, 1));
+    for (int k = 0; k < m.n_halo; k++) ask[k] = (long long)m.halo_global[k];
+    std::vector<int> send_off(nn + 1, 0);
+    for (int q = 0; q < nn; q++) send_off[q + 1] = send_off[q] + send_cnt[q];
+    DevBuf<long long> d_ask, d_req;
+    d_ask.from_any(ask.data(), ask.size(), s);
+    d_req.resize((size_t)std::max(send_off[nn], 1));
     AMGXB_NCCL_CHECK(ncclGroupStart());
     for (int q = 0; q < nn; q++) {
-        AMGXB_NCCL_CHECK(ncclSend(sendc.ptr() + q, 1, ncclInt32, m.neighbors[q], comm_of(A), s));
-        AMGXB_NCCL_CHECK(ncclRecv(recvc.ptr() + q, 1, ncclInt32, m.neighbors[q], comm_of(A), s));
+        const int hc = halo_off[q + 1] - halo_off[q];
+        if (hc) AMGXB_NCCL_CHECK(ncclSend(d_ask.ptr() + halo_off[q], (size_t)hc, ncclInt64, nbrs[q], comm_of(A), s));
+        if (send_cnt[q]) AMGXB_NCCL_CHECK(ncclRecv(d_req.ptr() + send_off[q], (size_t)send_cnt[q], ncclInt64, nbrs[q], comm_of(A), s));
     }
     AMGXB_NCCL_CHECK(ncclGroupEnd());
-    hr = recvc.to_host(s);
-    for (int q = 0; q < nn; q++)
-        if (hr[q] != m.halo_offsets[q + 1] - m.halo_offsets[q])
-            fatal(AMGX_RC_BAD_PARAMETERS, "distributed matrix is not structurally symmetric across partitions (send/halo size mismatch)");
+    const std::vector<long long> req = d_req.to_host(s);
+    const std::vector<int> perm = m.perm_old_to_new.to_host(s);
+    std::vector<int> smap((size_t)std::max(send_off[nn], 1));
+    for (int k = 0; k < send_off[nn]; k++) {
+        const long long g = req[k] - (long long)m.global_offset;
+        if (g < 0 || g >= m.n_owned) fatal(AMGX_RC_BAD_PARAMETERS, "distributed matrix: a neighbour asks for a row this rank does not own (inconsistent partition offsets)");
+        smap[k] = perm[(size_t)g];
+    }
+    m.neighbors = nbrs;
+    m.halo_offsets = halo_off;
+    m.send_offsets = send_off;
+    m.send_maps.from_any(smap.data(), (size_t)send_off[nn], s);
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
 // AMGX_matrix_replace_coefficients on a row-partitioned matrix: the caller's values come in the caller's row order, the engine keeps
@@ -405,7 +446,7 @@ void dist_build_matrix(Matrix &A, const int64_t *offsets, int n, int nnz, int bx
     A.dist = manager_from_plan(A, pl, offsets);
     A.dist->caller_row_ptr.from_any(rp, (size_t)n + 1, s);
     AMGXB200_partition_plan_free(&pl);
-    verify_plan(A);
+    reconcile_plan(A);      // send side from what the receivers ask for (any pattern, not only structurally symmetric ones)
     p2p_manager_setup(A);
     A.compute_diag_and_plan();
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));

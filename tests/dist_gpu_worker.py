@@ -77,6 +77,52 @@ def block_dilu_section(rank, world, rsc, lib):
     dist.barrier()
 
 
+def nonsymmetric_section(rank, world, rsc, lib, cfg):
+    """A pattern that is NOT structurally symmetric across the cut: rank r's rows reference columns of rank r+1 that do not
+    reference them back, and one rank pair is coupled in one direction only.  The send maps are derived from what the receivers ask for
+    (dist.cu: reconcile_plan), so the distributed SpMV must equal the global one bit for bit."""
+    import scipy.sparse as sp
+    nloc = 40
+    ng = nloc * world
+    rng = np.random.default_rng(21)
+    A = sp.lil_matrix((ng, ng))
+    for i in range(ng):
+        A[i, i] = 4.0 + (i % 3)
+        if i + 1 < ng and (i + 1) // nloc == i // nloc:
+            A[i, i + 1] = -1.0
+            A[i + 1, i] = -0.5
+    for r in range(world - 1):          # one-directional coupling r -> r+1: rows of r read columns of r+1, never the reverse
+        for k in range(12):
+            i = r * nloc + int(rng.integers(0, nloc))
+            j = (r + 1) * nloc + int(rng.integers(0, nloc))
+            A[i, j] = -0.25 - 0.01 * k
+    A = A.tocsr()
+    A.sort_indices()
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+    lo, hi = rank * nloc, (rank + 1) * nloc
+    lrp = (rp[lo:hi + 1] - rp[lo]).astype(np.int32)
+    lci = ci[rp[lo]:rp[hi]].astype(np.int64)
+    lva = va[rp[lo]:rp[hi]].copy()
+    pv = np.repeat(np.arange(world), nloc).astype(np.int32)
+    M = capi.Matrix(rsc)
+    rc = lib.AMGX_matrix_upload_all_global(M.h, ng, nloc, lci.shape[0], 1, 1, lrp.ctypes.data, lci.ctypes.data, lva.ctypes.data, None, 1, 1, pv.ctypes.data)
+    assert rc == 0, rc
+    xg = rng.standard_normal(ng)
+    x, y = capi.Vector(rsc), capi.Vector(rsc)
+    x.bind(M)
+    y.bind(M)
+    x.upload(xg[lo:hi])
+    y.set_zero(nloc)
+    for _ in range(3):                  # repeated exchanges: epochs / double buffering of the peer-memory path
+        M.multiply(x, y)
+    assert np.array_equal(y.download(), orc.spmv(rp, ci, va, xg)[lo:hi]), "nonsymmetric partition: distributed SpMV differs from the global one"
+    if rank == 0:
+        print(f"DIST_NONSYMMETRIC_OK world={world}", flush=True)
+    for o in (y, x, M):
+        o.destroy()
+    dist.barrier()
+
+
 def partition_vector_section(rank, world, rsc, lib, cfg):
     """AMGX_matrix_upload_all_global with a scattered (non-contiguous) partition vector: SpMV bit-exact vs the global product and the
     solve converges to the global solution.  Opt-in (AMGXB_RUN_UNVALIDATED=1) until validated on a device."""
@@ -459,6 +505,7 @@ def main():
     for o in (slv, sol, b, y, x, A):
         o.destroy()
     block_dilu_section(rank, world, rsc, lib)
+    nonsymmetric_section(rank, world, rsc, lib, cfg)
     if os.environ.get("AMGXB_RUN_UNVALIDATED") == "1":
         partition_vector_section(rank, world, rsc, lib, cfg)
         comm_maps_section(rank, world, rsc, lib, cfg)

@@ -34,5 +34,6 @@ def test_distributed_spmv_and_solve(world, tail_rows):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DIST_GPU_OK" in r.stdout
     assert r.stdout.count("DIST_BLOCK_DILU_OK") == 4, r.stdout[-3000:]
+    assert "DIST_NONSYMMETRIC_OK" in r.stdout, r.stdout[-3000:]
     if os.environ.get("AMGXB_RUN_UNVALIDATED") == "1":
         assert all(t in r.stdout for t in ("DIST_PARTITION_VECTOR_OK", "DIST_COMM_MAPS_OK", "DIST_READ_SYSTEM_OK")), r.stdout[-3000:]
