@@ -405,10 +405,10 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse,
     // next level is the coarsest a single fixed cycle is launched whatever the type (fixed_cycle.cu:169-179).  The second
     // visit continues from the xc the first one left (its init flag has been cleared).
     levels_[lvl + 1]->init_cycle = true;
-    // AMGXB_GRAPH_COARSE=1 (experimental, default off): when the cycle is a preconditioner whose caller cannot capture it (FGMRES hands in a
+    // AMGXB_GRAPH_COARSE (default on since r02): when the cycle is a preconditioner whose caller cannot capture it (FGMRES hands in a
     // different vector pair every iteration), everything below the finest level still works on fixed buffers (bc, xc of level 0) and
     // is replayed as one CUDA graph: the launch-latency-bound tail of the hierarchy costs one graph launch.
-    static const bool graph_coarse = getenv("AMGXB_GRAPH_COARSE") ? atoi(getenv("AMGXB_GRAPH_COARSE")) != 0 : false;
+    static const bool graph_coarse = getenv("AMGXB_GRAPH_COARSE") ? atoi(getenv("AMGXB_GRAPH_COARSE")) != 0 : true;      // r02: parity green (33 tests), +2 % at 256^3, +10 % at 128^3 on config 3
     bool capturing = false;
     if (graph_coarse && finest && type == CYC_V) {
         cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;

@@ -407,13 +407,17 @@ protected:
             count_launch();
             AMGXB_LAUNCH_CHECK();
         }
-        // levels whose colours are smaller than the machine: the fused cluster kernel (dilu_level_kernel)
-        static const int fused_rows = getenv("AMGXB_DILU_FUSED_ROWS") ? atoi(getenv("AMGXB_DILU_FUSED_ROWS")) : 32768;
-        fused_level_ = A.n > 0 && A.n <= fused_rows && A.num_colors > 0;
+        // Levels whose LARGEST colour fits the warps of one cluster in a single pass take the fused kernel (dilu_level_kernel): there a
+        // colour costs one barrier instead of one launch.  Larger colours need the whole machine: a cluster has 8 x 32 warps, a per-colour
+        // launch up to 148 x 64 (r02: fusing levels of up to 32768 rows made config 5 slower, 53 -> 46 it/s).
+        static const int fused_on = getenv("AMGXB_DILU_FUSED") ? atoi(getenv("AMGXB_DILU_FUSED")) : 1;
+        int max_color = 0;
+        for (int c = 0; c < A.num_colors; c++) max_color = std::max(max_color, A.color_offsets[c + 1] - A.color_offsets[c]);
+        const int rows_per_warp = (bs == 1) ? 32 / NTPR : 1;
+        fused_level_ = fused_on && A.n > 0 && A.num_colors > 0 && max_color <= 8 * 32 * rows_per_warp;
         if (fused_level_) {
             d_color_offsets_.from_any(A.color_offsets.data(), A.color_offsets.size(), s);
-            // one CTA up to 2048 rows, a cluster of 8 CTAs (the portable maximum) above
-            cluster_size_ = A.n <= 2048 ? 1 : 8;
+            cluster_size_ = max_color <= 32 * rows_per_warp ? 1 : 8;     // one CTA, or a cluster of 8 (the portable maximum)
         }
     }
 

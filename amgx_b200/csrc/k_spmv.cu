@@ -124,7 +124,10 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
             const int tile = blockIdx.x + it * gridDim.x;
             const int s = it % a.stages;
             const unsigned ph = (unsigned)(it / a.stages) & 1u;
-            const int row = a.row0 + tile * TILE_ROWS + tid;
+            // which row of the tile this thread takes: its own, or (irregular matrices) the tid-th longest, so that the rows of a warp
+            // have similar lengths and the warp is not paced by its longest row.  A row is still summed left to right by ONE thread.
+            const int lrow = a.perm ? (int)__ldg(a.perm + (size_t)(a.tile_base + tile) * TILE_ROWS + tid) : tid;
+            const int row = a.row0 + tile * TILE_ROWS + lrow;
             const bool active = row < a.n;
             // operands that do not depend on the staged tile: issue their loads before waiting
             VecT bi = 0, xi = 0;
@@ -145,8 +148,8 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
             mbar_wait(&full[s], ph);
             if (active) {
                 const int sa = rp[0] & ~3;
-                int k = rp[tid] - sa;
-                const int kend = rp[tid + 1] - sa;
+                int k = rp[lrow] - sa;
+                const int kend = rp[lrow + 1] - sa;
                 VecT sum = 0;
                 // U gathers in flight per step (U = 8 when the plan says so: rows of a 7-point stencil then take ONE dependent
                 // LDS -> gather -> FMA round instead of two); the FMA chain runs strictly left to right either way
@@ -252,6 +255,28 @@ __global__ void tile_stats_kernel(const int *row_ptr, int row0, int n, int tile_
         atomicMax(max_row_nnz, row_ptr[i + 1] - row_ptr[i]);
 }
 
+// thread -> row map of every tile: rows sorted by (length descending, index ascending); rows past the end of the segment come last.
+// One CTA per tile, rank sort in shared memory (setup time).
+template <int TILE_ROWS>
+__global__ void __launch_bounds__(TILE_ROWS) tile_perm_kernel(const int *__restrict__ rp, int row0, int n, int num_tiles, int tile_base, unsigned char *perm)
+{
+    __shared__ int len[TILE_ROWS];
+    const int tid = threadIdx.x;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int row = row0 + t * TILE_ROWS + tid;
+        const int mine = row < n ? rp[row + 1] - rp[row] : -1;
+        len[tid] = mine;
+        __syncthreads();
+        int rank = 0;
+        for (int j = 0; j < TILE_ROWS; j++) {
+            const int o = len[j];
+            rank += (o > mine) || (o == mine && j < tid);
+        }
+        perm[(size_t)(tile_base + t) * TILE_ROWS + rank] = (unsigned char)tid;
+        __syncthreads();
+    }
+}
+
 size_t tile_smem_bytes(int cap, int stages, int tile_rows, size_t mat_size)
 {
     return 512 + (size_t)stages * ((size_t)cap * (mat_size + 4) + (size_t)(tile_rows + 4) * 4);
@@ -352,6 +377,26 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
         if (env_stages) break;
     }
     p.ctas_per_sm = env_ctas > 0 ? std::min(env_ctas, std::max(best_ctas, 1)) : std::max(best_ctas, 1);
+    // irregular rows: hand the rows of a tile to the threads sorted by length, and keep 8 gathers in flight per step
+    {
+        static const int env_perm = getenv("AMGXB_TILE_PERM") ? atoi(getenv("AMGXB_TILE_PERM")) : -1;
+        const double mean = (double)A.nnz / std::max(A.n, 1);
+        p.use_perm = p.use_tiles && (env_perm >= 0 ? env_perm != 0 : (double)p.max_row_nnz >= mean + 2.0);
+        if (!env_unroll && mean > 8.0) p.unroll = 8;
+        if (p.use_perm) {
+            const int T = p.tile_rows;
+            int nseg = 1, r0[2] = {0, 0}, r1[2] = {A.n, 0}, nt[2] = {ceil_div(A.n, T), 0};
+            if (p.split > 0 && p.split < A.n) { nseg = 2; r1[0] = p.split; nt[0] = ceil_div(p.split, T); r0[1] = p.split; r1[1] = A.n; nt[1] = ceil_div(A.n - p.split, T); }
+            A.tile_perm.resize((size_t)(nt[0] + nt[1]) * T);
+            for (int g = 0, base = 0; g < nseg; base += nt[g], g++) {
+                const int grid = std::max(1, std::min(nt[g], sms * 8));
+                if (T == 256) tile_perm_kernel<256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), r0[g], r1[g], nt[g], base, A.tile_perm.ptr());
+                else tile_perm_kernel<128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), r0[g], r1[g], nt[g], base, A.tile_perm.ptr());
+                count_launch();
+            }
+            AMGXB_LAUNCH_CHECK();
+        }
+    }
     A.plan = p;
     csr_build_colenc(A, s);     // no-op unless AMGXB_COLENC=1
 }
@@ -376,6 +421,9 @@ void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int
         ta.cap = A.plan.max_tile_nnz;
         ta.stages = A.plan.stages;
         ta.unroll = A.plan.unroll;
+        // (a split matrix applied as a whole has another tiling than its two segments: no map then)
+        ta.perm = (A.plan.use_perm && !(A.plan.split > 0 && segment == 0)) ? A.tile_perm.ptr() : nullptr;
+        ta.tile_base = (segment == 2) ? ceil_div(A.plan.split, std::max(1, A.plan.tile_rows)) : 0;
         ta.x = (const VecT *)g.x;
         ta.agg = g.agg;
         ta.b = (const VecT *)g.b;

@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
             const int tile = blockIdx.x + it * gridDim.x;
             const int s = it % a.stages;
             const unsigned ph = (unsigned)(it / a.stages) & 1u;
-            const int row = a.row0 + tile * TILE_ROWS + tid;
+            const int lrow = a.perm ? (int)__ldg(a.perm + (size_t)(e.tile_base + tile) * TILE_ROWS + tid) : tid;      // length-sorted rows (k_spmv.cu)
+            const int row = a.row0 + tile * TILE_ROWS + lrow;
             const bool active = row < a.n;
             const int enc = __ldg(e.meta + META * (e.tile_base + tile)), venc = __ldg(e.meta + META * (e.tile_base + tile) + 2);
             VecT bi = 0, xi = 0;
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
             mbar_wait(&full[s], ph);
             if (active) {
                 const int sa = rp[0] & ~3;
-                const int k = rp[tid] - sa, kend = rp[tid + 1] - sa;
+                const int k = rp[lrow] - sa, kend = rp[lrow + 1] - sa;
                 // the tile's encoding is uniform over the CTA: the switch does not diverge
                 VecT sum;
                 switch (enc * 2 + venc) {
@@ -604,6 +605,8 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
         ta.cap = A.plan.max_tile_nnz;
         ta.stages = A.colenc.stages;
         ta.unroll = 8;
+        ta.perm = A.plan.use_perm ? A.tile_perm.ptr() : nullptr;
+        ta.tile_base = sg.base;
         ta.x = (const VecT *)g.x;
         ta.agg = nullptr;
         ta.b = (const VecT *)g.b;

@@ -35,6 +35,7 @@ struct TilePlan {
     int split = 0;              // distributed: first row (multiple of 4) of the segment that reads halo columns
     int unroll = 4;             // gathers in flight per consumer step (4 or 8)
     int ctas_per_sm = 1;        // resident CTAs per SM the grid is sized for
+    bool use_perm = false;      // rows of a tile are handed to the threads sorted by length (Matrix::tile_perm)
     int max_row_nnz = 0;
 };
 
@@ -81,6 +82,7 @@ struct Matrix {
     DevBuf<int> row_ptr, col_idx, diag_idx;
     DevVec values;        // (nnz [+ n if ext diag]) * bx*by scalars of mat_prec
     TilePlan plan;
+    DevBuf<unsigned char> tile_perm;   // plan.use_perm: for every tile (numbered over the row segments) and thread, the row of the tile it takes
 
     std::shared_ptr<DistManager> dist;   // null on a single GPU
 

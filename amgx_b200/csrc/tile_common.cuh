@@ -126,6 +126,8 @@ template <class MatT, class VecT> struct TileArgs {
     int n, num_tiles, cap, stages;   // n = end row of the segment
     int row0;                        // first row of the segment (multiple of 4)
     int unroll;                      // gathers in flight per consumer step: 4 or 8
+    const unsigned char *perm;       // length-sorted thread -> row map of every tile (null: thread t takes row t), see tile_perm_kernel
+    int tile_base;                   // index of the segment's first tile in `perm` (tiles are numbered over the row segments)
     const VecT *x;
     const int *agg;
     const VecT *b;

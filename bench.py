@@ -53,6 +53,15 @@ BLOCK_CFG = {"config_version": 2, "solver": {
     "monitor_residual": 1, "store_res_history": 1, "convergence": "RELATIVE_INI", "tolerance": 1e-6, "norm": "L2"}}
 
 
+# SuiteSparse-shaped CSR is not symmetric: FGMRES outside, the same aggregation-AMG V-cycle (BLOCK_JACOBI 0.8, 0 + 3 sweeps) inside
+BANDED_CFG = {"config_version": 2, "determinism_flag": 1, "solver": {
+    "scope": "main", "solver": "FGMRES", "max_iters": 100, "gmres_n_restart": 20, "monitor_residual": 1, "store_res_history": 1,
+    "convergence": "RELATIVE_INI", "tolerance": 1e-6, "norm": "L2",
+    "preconditioner": {"scope": "amg", "solver": "AMG", "algorithm": "AGGREGATION", "selector": "SIZE_2", "cycle": "V", "max_levels": 50,
+                       "presweeps": 0, "postsweeps": 3, "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER", "max_iters": 1, "monitor_residual": 0,
+                       "smoother": {"scope": "jacobi", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "monitor_residual": 0}}}}
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -186,7 +195,7 @@ def workload_config(args, world):
         else:
             w = f"7-pt Poisson {nx}x{nx}x{nx * world} fp64, PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI.json)"
     elif args.workload == "banded":
-        w = f"SuiteSparse-shaped banded-random CSR, {args.rows} rows, row length 3+Poisson(12), sigma 2000, fp64, PCG + aggregation-AMG V-cycle"
+        w = f"SuiteSparse-shaped banded-random CSR (nonsymmetric), {args.rows} rows, row length 3+Poisson(12), sigma 2000, fp64, FGMRES(20) + aggregation-AMG V-cycle"
     else:
         w = f"block 4x4 elasticity-like {nx}^3 block rows, {args.mode}, AMG V-cycle + MULTICOLOR_DILU (AGGREGATION_DILU)"
     return {"workload": w, "grid": nx}
@@ -346,6 +355,8 @@ def main():
     if args.workload == "block":
         mode = args.mode
         cfg = capi.Config(BLOCK_CFG)
+    elif args.workload == "banded":
+        cfg = capi.Config(BANDED_CFG)
     else:
         cfg = capi.Config(file=str(CONFIG))
     comm = None
@@ -486,7 +497,7 @@ def main():
         # whole outer iteration against the same peak: SURVEY 8(d)'s per-unit figures summed over the hierarchy the setup actually built
         # (PCG outside M^-1: M(A_0) + 12 N 8; per level: 3 fused post-sweeps M(A_l) + 4 n_l 8 each, restriction and prolongation
         # n_l (4 + 8) + n_{l+1} 8 each; presweeps = 0 and a zero initial guess leave no residual pass; coarsest: a zero-guess sweep + a full one)
-        if args.workload != "block":
+        if args.workload == "poisson":
             try:
                 lv = [slv.level_info(l) for l in range(slv.num_levels())]
                 M = lambda i: i["nnz"] * 12 + i["n"] * 4
@@ -546,7 +557,7 @@ def main():
 
 
 def A_uses_enc(enc: str) -> bool:
-    return enc not in ("", "0")
+    return enc != "0"          # AMGXB_COLENC defaults to 3 (coded column and value streams) since r02
 
 
 if __name__ == "__main__":
