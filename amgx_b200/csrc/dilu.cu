@@ -199,34 +199,53 @@ __global__ void dilu_setup_4x4(const int *__restrict__ rp, const int *__restrict
 // One warp per block row: quad q (lanes 4q..4q+3) takes the blocks q, q+8, ... of the row, thread r of a quad owns
 // component r; the eight partial 4-vectors are combined with an xor butterfly over the quads.  (A single quad walking
 // a 30..60-block coarse row serially is a pure latency chain: ~0.5 us per block.)
-template <class MatT, class VecT, bool BACKWARD, bool CG>
-__device__ __forceinline__ void dilu_row_4x4(const int i, const int lane, const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, VecT *x,
+// 4 consecutive scalars with 16-byte loads (a block row of the matrix, a block of a vector); CG: through L2 (see ldv)
+template <bool CG> __device__ __forceinline__ void ld4v(const double *p, double (&o)[4])
+{
+    const double2 a = CG ? __ldcg(reinterpret_cast<const double2 *>(p)) : *reinterpret_cast<const double2 *>(p);
+    const double2 b = CG ? __ldcg(reinterpret_cast<const double2 *>(p) + 1) : *(reinterpret_cast<const double2 *>(p) + 1);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+template <bool CG> __device__ __forceinline__ void ld4v(const float *p, float (&o)[4])
+{
+    const float4 a = CG ? __ldcg(reinterpret_cast<const float4 *>(p)) : *reinterpret_cast<const float4 *>(p);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+
+template <class MatT, class VecT, bool BACKWARD, bool CG, class Mid>
+__device__ __forceinline__ void dilu_row_4x4(const int i, const int k0, const int k1, const int lane, const int *__restrict__ ci, const MatT *__restrict__ va, VecT *x,
                                              const VecT *__restrict__ b, VecT *delta, VecT *Delta, double weight, int color, const int *__restrict__ colors,
-                                             const MatT *__restrict__ Einv, int n_owned)
+                                             const MatT *__restrict__ Einv, int n_owned, Mid mid)
 {
     const int r = lane & 3, q = lane >> 2;
     VecT acc = 0;
     if (!BACKWARD && q == 0) acc = b[(size_t)i * 4 + r];
-    const int k1 = rp[i + 1];
-    for (int k = rp[i] + q; k < k1; k += 8) {
+    for (int k = k0 + q; k < k1; k += 8) {
         const int j = ci[k];
-        const MatT *a = va + (size_t)k * 16 + r * 4;
+        MatT a[4];
+        ld4v<false>(va + (size_t)k * 16 + r * 4, a);
         if (!BACKWARD) {
             const bool valid = color != 0 && j < n_owned && colors[j] < color;
+            VecT xv[4], dv[4] = {0, 0, 0, 0};
+            ld4v<CG>(x + (size_t)j * 4, xv);
+            if (valid) ld4v<CG>(delta + (size_t)j * 4, dv);
 #pragma unroll
             for (int m = 0; m < 4; m++) {
-                VecT xx = ldv<CG>(x + (size_t)j * 4 + m);
-                if (valid) xx += ldv<CG>(delta + (size_t)j * 4 + m);
+                VecT xx = xv[m];
+                if (valid) xx += dv[m];
                 acc -= (VecT)a[m] * xx;
             }
         } else {
             const bool valid = color != 0 && j < n_owned && colors[j] > color;
             if (valid) {
+                VecT Dv[4];
+                ld4v<CG>(Delta + (size_t)j * 4, Dv);
 #pragma unroll
-                for (int m = 0; m < 4; m++) acc += (VecT)a[m] * ldv<CG>(Delta + (size_t)j * 4 + m);
+                for (int m = 0; m < 4; m++) acc += (VecT)a[m] * Dv[m];
             }
         }
     }
+    mid();      // the caller's prefetch of the NEXT row's extent goes here: behind this row's gathers, in front of its reduction
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     // y = Einv_i * acc (4x4 mat-vec inside quad 0; every quad holds the full acc)
@@ -247,6 +266,8 @@ __device__ __forceinline__ void dilu_row_4x4(const int i, const int lane, const 
     }
 }
 
+// One colour of a sweep.  A warp walks its rows with the NEXT row's index and extent already in flight (a row is a chain of dependent
+// loads: sorted_rows -> row_ptr -> col -> x; prefetching the first two halves it: r02 ncu, 25 % of the DRAM peak and latency-bound).
 template <class MatT, class VecT, bool BACKWARD>
 __global__ void __launch_bounds__(128) dilu_sweep_4x4(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, VecT *x,
                                                       const VecT *__restrict__ b, VecT *delta, VecT *Delta, double weight, const int *__restrict__ rows, int nrows,
@@ -254,8 +275,19 @@ __global__ void __launch_bounds__(128) dilu_sweep_4x4(const int *__restrict__ rp
 {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
-    for (int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nrows; it += warps_per_grid)
-        dilu_row_4x4<MatT, VecT, BACKWARD, false>(rows[it], lane, rp, ci, va, x, b, delta, Delta, weight, color, colors, Einv, n_owned);
+    int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (it >= nrows) return;
+    int i = rows[it];
+    int k0 = rp[i], k1 = rp[i + 1];
+    while (true) {
+        const int itn = it + warps_per_grid;
+        const int in = itn < nrows ? __ldg(rows + itn) : -1;
+        int k0n = 0, k1n = 0;
+        dilu_row_4x4<MatT, VecT, BACKWARD, false>(i, k0, k1, lane, ci, va, x, b, delta, Delta, weight, color, colors, Einv, n_owned,
+                                                  [&] { if (in >= 0) { k0n = __ldg(rp + in); k1n = __ldg(rp + in + 1); } });
+        if (in < 0) break;
+        it = itn; i = in; k0 = k0n; k1 = k1n;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -317,7 +349,7 @@ __global__ void __launch_bounds__(1024) dilu_level_kernel(const DiluLevelArgs a)
                 }
             } else {
                 for (int it = tid >> 5; it < cnt; it += nthreads >> 5)
-                    dilu_row_4x4<MatT, VecT, false, true>(rows[off + it], lane, rp, ci, va, x, b, delta, Delta, a.weight, c, colors, Einv, a.n_owned);
+                    { const int i = rows[off + it]; dilu_row_4x4<MatT, VecT, false, true>(i, rp[i], rp[i + 1], lane, ci, va, x, b, delta, Delta, a.weight, c, colors, Einv, a.n_owned, [] {}); }
             }
             cluster_barrier();
         }
@@ -339,7 +371,7 @@ __global__ void __launch_bounds__(1024) dilu_level_kernel(const DiluLevelArgs a)
                 }
             } else {
                 for (int it = tid >> 5; it < cnt; it += nthreads >> 5)
-                    dilu_row_4x4<MatT, VecT, true, true>(rows[off + it], lane, rp, ci, va, x, b, delta, Delta, a.weight, c, colors, Einv, a.n_owned);
+                    { const int i = rows[off + it]; dilu_row_4x4<MatT, VecT, true, true>(i, rp[i], rp[i + 1], lane, ci, va, x, b, delta, Delta, a.weight, c, colors, Einv, a.n_owned, [] {}); }
             }
             cluster_barrier();
         }
