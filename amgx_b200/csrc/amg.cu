@@ -373,6 +373,7 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse,
             x.zero(s);
         }
         if (coarse_solver_) coarse_solver_->solve(b, x, x_is_zero && n_pre == 0);
+        phase_mark("coarsest", lvl, s);
         return;
     }
     bool x_virtual_zero = false;   // x holds no data yet and is mathematically zero
@@ -400,6 +401,7 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse,
         classical_restrict(L, *rsrc, s);
     }
 
+    phase_mark("down: pre-smooth, residual, restrict", lvl, s);
     // ---- coarse-grid correction ----
     // V: one cycle on the next level; W: two W cycles; F: a W cycle then a V cycle (src/cycles/{v,w,f}_cycle.cu).  When the
     // next level is the coarsest a single fixed cycle is launched whatever the type (fixed_cycle.cu:169-179).  The second
@@ -466,6 +468,7 @@ void AMGSolver::cycle(int lvl, DevVec &b, DevVec &x, const SmoothFuse *top_fuse,
         classical_prolong_add(L, x_virtual_zero ? nullptr : x.ptr(), xin, s);   // xin = x + P xc  (0 + P xc == P xc exactly)
     }
     if (n_post > 0) sm->smooth(b, x, false, n_post, have_fuse ? &f : nullptr, in_alt);
+    phase_mark("up: prolong, post-smooth", lvl, s);
 }
 
 double AMGSolver::host_dot(const DevVec &x, const DevVec &y, size_t n, const Matrix *over)

@@ -807,6 +807,7 @@ static AMGX_RC solver_solve_impl(AMGX_solver_handle slv, AMGX_vector_handle rhs,
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     h->last_solve_seconds = ms * 1e-3;
+    phase_report(h->rsc->stream, h->solver->get_num_iters());      // AMGXB_PHASE_TIMING=1 only
     h->last_solve_launches = g_kernel_launches - launches0;
     h->last_status = st;
     API_END(rp)

@@ -140,10 +140,53 @@ static std::atomic<int> g_graph_inhibit{0};
 void GraphInhibit::set() { if (!on) { on = true; g_graph_inhibit++; } }
 GraphInhibit::~GraphInhibit() { if (on) g_graph_inhibit--; }
 
+bool phase_timing_on()
+{
+    static const bool on = getenv("AMGXB_PHASE_TIMING") ? atoi(getenv("AMGXB_PHASE_TIMING")) != 0 : false;
+    return on;
+}
+namespace {
+struct PhaseMark { cudaEvent_t ev; std::string label; };
+std::vector<PhaseMark> g_marks;
+std::vector<cudaEvent_t> g_mark_pool;
+}
+void phase_mark(const char *label, int level, cudaStream_t s)
+{
+    if (!phase_timing_on() || g_marks.size() > 200000) return;
+    cudaEvent_t e;
+    if (!g_mark_pool.empty()) { e = g_mark_pool.back(); g_mark_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    char buf[96];
+    if (level >= 0) snprintf(buf, sizeof(buf), "L%02d %s", level, label);
+    else snprintf(buf, sizeof(buf), "%s", label);
+    g_marks.push_back(PhaseMark{e, buf});
+}
+void phase_report(cudaStream_t s, int iterations)
+{
+    if (!phase_timing_on() || g_marks.size() < 2) return;
+    cudaStreamSynchronize(s);
+    std::map<std::string, std::pair<double, int>> acc;
+    double total = 0;
+    for (size_t i = 1; i < g_marks.size(); i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, g_marks[i - 1].ev, g_marks[i].ev) != cudaSuccess) { cudaGetLastError(); continue; }
+        acc[g_marks[i].label].first += ms;
+        acc[g_marks[i].label].second++;
+        total += ms;
+    }
+    const int it = std::max(iterations, 1);
+    fprintf(stderr, "[amgx_b200 phase timing] %d iterations, %.3f ms marked, %.3f ms / iteration (time since the previous mark, per label)\n", iterations, total, total / it);
+    for (auto &kv : acc)
+        fprintf(stderr, "  %-28s %9.3f ms total  %8.1f us / iteration  (%d marks)\n", kv.first.c_str(), kv.second.first, kv.second.first / it * 1e3, kv.second.second);
+    for (auto &m : g_marks) g_mark_pool.push_back(m.ev);
+    g_marks.clear();
+}
+
 bool graphs_enabled()
 {
     static const bool on = getenv("AMGXB_GRAPHS") ? atoi(getenv("AMGXB_GRAPHS")) != 0 : true;
-    return on && g_graph_inhibit.load() == 0;
+    return on && g_graph_inhibit.load() == 0 && !phase_timing_on();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -681,7 +724,9 @@ void PCGSolver::enqueue_B()
 Status PCGSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
 {
     Status conv_stat = ST_NOT_CONVERGED;
+    phase_mark("pcg: begin iteration", -1, stream());
     run_segment(segA_, x.ptr(), r_.ptr(), [&] { enqueue_A(x); });
+    phase_mark("pcg: A p, alpha, x/r update, norm", -1, stream());
     if (monitor_convergence_) {
         const bool scalar_norm = use_scalar_norm_ || A_->by == 1;
         if (scalar_norm) read_norm(nrm_);
@@ -691,6 +736,7 @@ Status PCGSolver::solve_iteration(DevVec &b, DevVec &x, bool xIsZero)
     }
     if (is_last_iter()) return monitor_convergence_ ? ST_NOT_CONVERGED : ST_CONVERGED;
     run_segment(segB_, z_.ptr(), r_.ptr(), [&] { enqueue_B(); });
+    phase_mark("pcg: beta, p update (after V-cycle)", -1, stream());
     return monitor_convergence_ ? ST_NOT_CONVERGED : ST_CONVERGED;
 }
 

@@ -43,6 +43,12 @@ struct ScalarBlock {
     void destroy();
 };
 
+// AMGXB_PHASE_TIMING=1: cudaEvent marks along the solve (graphs off), summed per label and printed to stderr when the outer solve ends.
+// A diagnostic for where an iteration's time goes (per level, per phase); not used in timed runs.
+bool phase_timing_on();
+void phase_mark(const char *label, int level, cudaStream_t s);
+void phase_report(cudaStream_t s, int iterations);
+
 struct ReduceScratch {           // one per Resources (kernels on one stream run in order)
     DevBuf<double> partials;
     DevBuf<unsigned> counter;
