@@ -377,12 +377,15 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
         if (env_stages) break;
     }
     p.ctas_per_sm = env_ctas > 0 ? std::min(env_ctas, std::max(best_ctas, 1)) : std::max(best_ctas, 1);
-    // irregular rows: hand the rows of a tile to the threads sorted by length, and keep 8 gathers in flight per step
+    // irregular rows (opt-in, AMGXB_TILE_PERM=1): hand the rows of a tile to the threads sorted by length
     {
         static const int env_perm = getenv("AMGXB_TILE_PERM") ? atoi(getenv("AMGXB_TILE_PERM")) : -1;
         const double mean = (double)A.nnz / std::max(A.n, 1);
-        p.use_perm = p.use_tiles && (env_perm >= 0 ? env_perm != 0 : (double)p.max_row_nnz >= mean + 2.0);
-        if (!env_unroll && mean > 8.0) p.unroll = 8;
+        // r02 A/B on B200: OFF by default.  On the Poisson hierarchy (coarse levels: mean 8-15, max ~2x) the sorted assignment costs 8 % of the
+        // solve (311 vs 336 it/s): the vectors of a tile (b, d, x, y) are then touched in a scattered order by each warp; on the 4 M-row
+        // banded matrix it is neutral (SpMV 0.45 vs 0.43 of peak): that kernel is bound by the L2 sectors of the random gathers, not by imbalance.
+        p.use_perm = p.use_tiles && env_perm > 0;
+        (void)mean;
         if (p.use_perm) {
             const int T = p.tile_rows;
             int nseg = 1, r0[2] = {0, 0}, r1[2] = {A.n, 0}, nt[2] = {ceil_div(A.n, T), 0};
