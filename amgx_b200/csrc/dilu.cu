@@ -12,12 +12,15 @@
 // reduction; setup: 32 lanes per row) so that their sums associate exactly like the reference's.
 #include "solvers.h"
 #include "dist.h"
+#include <cub/cub.cuh>
 
 namespace amgxb {
 
 void color_matrix(Matrix &A, const std::string &scheme, double max_uncolored_fraction, cudaStream_t s);   // coloring.cu
 
 namespace {
+
+#include "tile_common.cuh"
 
 constexpr int NTPR = 8;   // lanes per row in the 1x1 sweeps
 
@@ -378,6 +381,194 @@ __global__ void __launch_bounds__(1024) dilu_level_kernel(const DiluLevelArgs a)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Colour-sorted DILU for 4x4 blocks on the LARGE levels (r02).  The per-colour kernels above walk rows in colour order through the
+// sorted_rows indirection: every row is a chain of dependent loads and the matrix arrives in scattered 64-byte requests -- 25 % of the
+// DRAM peak (ncu, profiles/r02_ncu_kernels.md).  Here the smoother keeps its own copy of the matrix with the ROWS SORTED BY COLOUR
+// (the reference's reorder idea, src/matrix.cu:749-812, applied to the rows): a colour is then a contiguous row range, staged tile by
+// tile with TMA bulk copies exactly like the block SpMV (k_block.cu: block4_tile_kernel), a quad per block row consuming from shared
+// memory.  The two colour predicates of the sweeps are decided once at setup and travel in the top bits of the column index:
+//   bit 30: the column has a LOWER colour than the row (forward: add delta_j to x_j)         [colors[j] < colors[i], j owned]
+//   bit 31: the column has a HIGHER colour than the row and the row's colour is not 0        [the reference's `c != 0` guard]
+// Summation order inside a row: storage order, one quad (the 8-quad butterfly of dilu_row_4x4 associates differently: results agree
+// to rounding, as they do with the reference's own half-warp kernel).
+// ---------------------------------------------------------------------------------------------
+constexpr int DT_ROWS = 32, DT_CONSUMERS = DT_ROWS * 4, DT_STAGES = 2;
+constexpr unsigned CS_LOWER = 0x40000000u, CS_HIGHER = 0x80000000u, CS_MASK = 0x3fffffffu;
+
+struct DiluTileArgs {
+    const int *rp, *ci, *rows;        // colour-sorted row pointers / flagged columns; original row id of every sorted row
+    const void *va, *Einv, *b;
+    void *x, *delta, *Delta;
+    double weight;
+    int row0, row1, num_tiles, cap;   // sorted-row range of the colour
+};
+
+__global__ void cs_lengths_kernel(const int *__restrict__ rp, const int *__restrict__ rows, int n, int *len)
+{
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) { const int i = rows[p]; len[p] = rp[i + 1] - rp[i]; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) len[n] = 0;
+}
+
+template <class MatT>
+__global__ void cs_permute_kernel(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ va, const int *__restrict__ rows,
+                                  const int *__restrict__ colors, const int *__restrict__ cs_rp, int n, int n_owned, int *cs_ci, MatT *cs_va)
+{
+    const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n; p += warps) {
+        const int i = rows[p], k0 = rp[i], len = rp[i + 1] - k0, d0 = cs_rp[p], ci_color = colors[i];
+        for (int k = lane; k < len; k += 32) {
+            const int j = ci[k0 + k];
+            unsigned c = (unsigned)j;
+            if (j < n_owned && j != i) {
+                const int cj = colors[j];
+                if (cj < ci_color) c |= CS_LOWER;
+                else if (cj > ci_color && ci_color != 0) c |= CS_HIGHER;
+            }
+            cs_ci[d0 + k] = (int)c;
+        }
+        const size_t s0 = (size_t)k0 * 16, t0 = (size_t)d0 * 16, total = (size_t)len * 16;
+        for (size_t t = lane; t < total; t += 32) cs_va[t0 + t] = va[s0 + t];
+    }
+}
+
+__global__ void cs_tile_stats_kernel(const int *rp, int row0, int row1, int num_tiles, int *max_tile_nnz)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < num_tiles; t += gridDim.x * blockDim.x) {
+        const int r0 = row0 + t * DT_ROWS, r1 = min(r0 + DT_ROWS, row1);
+        atomicMax(max_tile_nnz, ((rp[r1] + 3) & ~3) - (rp[r0] & ~3));
+    }
+}
+
+template <class MatT, class VecT, bool BACKWARD>
+__global__ void __launch_bounds__(DT_CONSUMERS + PRODUCER_THREADS) dilu_tile_kernel(const DiluTileArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + MAX_STAGES;
+    unsigned char *stage_base = smem_raw + 128;
+    const size_t vals_bytes = (size_t)a.cap * 16 * sizeof(MatT);
+    const size_t cols_bytes = (size_t)a.cap * sizeof(int);
+    const size_t rp_bytes = (size_t)(DT_ROWS + 4) * sizeof(int);
+    const size_t stage_bytes = vals_bytes + cols_bytes + rp_bytes;
+    const MatT *__restrict__ va = (const MatT *)a.va;
+    const MatT *__restrict__ Einv = (const MatT *)a.Einv;
+    VecT *x = (VecT *)a.x, *delta = (VecT *)a.delta, *Delta = (VecT *)a.Delta;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < DT_STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], DT_CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int my_tiles = (a.num_tiles > (int)blockIdx.x) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (tid >= DT_CONSUMERS) {
+        if (tid == DT_CONSUMERS) {
+            for (int it = 0; it < my_tiles; it++) {
+                const int tile = blockIdx.x + it * gridDim.x;
+                const int s = it % DT_STAGES;
+                const unsigned ph = (unsigned)(it / DT_STAGES) & 1u;
+                if (it >= DT_STAGES) mbar_wait(&empty[s], ph ^ 1u);
+                const int r0 = a.row0 + tile * DT_ROWS, r1 = min(r0 + DT_ROWS, a.row1);
+                const int nz0 = __ldg(a.rp + r0), nz1 = __ldg(a.rp + r1);
+                const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
+                unsigned char *st = stage_base + (size_t)s * stage_bytes;
+                // the row_ptr slice starts at an arbitrary sorted row: copy from the 16-byte aligned address below it
+                const int ra = r0 & ~3;
+                const unsigned rp_copy = (unsigned)(((r1 - ra + 1 + 3) & ~3) * sizeof(int));
+                const unsigned cnt = (unsigned)(ea - sa);
+                mbar_expect_tx(&full[s], rp_copy + cnt * (unsigned)(16 * sizeof(MatT) + sizeof(int)));
+                tma_bulk_g2s(st + vals_bytes + cols_bytes, a.rp + ra, rp_copy, &full[s]);
+                if (cnt) {
+                    tma_bulk_g2s(st, va + (size_t)sa * 16, cnt * (unsigned)(16 * sizeof(MatT)), &full[s]);
+                    tma_bulk_g2s(st + vals_bytes, a.ci + sa, cnt * (unsigned)sizeof(int), &full[s]);
+                }
+            }
+        }
+    } else {
+        const int r = tid & 3, lane = tid & 31, qbase = lane & ~3, q = tid >> 2;
+        for (int it = 0; it < my_tiles; it++) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int s = it % DT_STAGES;
+            const unsigned ph = (unsigned)(it / DT_STAGES) & 1u;
+            const int r0 = a.row0 + tile * DT_ROWS;
+            const int p = r0 + q;
+            const bool act = p < a.row1;
+            const int i = act ? __ldg(a.rows + p) : 0;
+            VecT acc = 0;
+            if (act && !BACKWARD) acc = ((const VecT *)a.b)[(size_t)i * 4 + r];
+            const unsigned char *st = stage_base + (size_t)s * stage_bytes;
+            const MatT *vals = reinterpret_cast<const MatT *>(st);
+            const unsigned *cols = reinterpret_cast<const unsigned *>(st + vals_bytes);
+            const int *rp = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes) + (r0 & 3);
+            mbar_wait(&full[s], ph);
+            if (act) {
+                const int sa = rp[0] & ~3;
+                const int k0 = rp[q] - sa, kend = rp[q + 1] - sa;
+                if (!BACKWARD) {
+                    for (int k = k0; k < kend; k++) {
+                        const unsigned c = cols[k];
+                        const int j = (int)(c & CS_MASK);
+                        MatT av[4];
+                        VecT xv[4];
+                        ld4v<false>(vals + (size_t)k * 16 + r * 4, av);
+                        ld4v<false>(x + (size_t)j * 4, xv);
+                        if (c & CS_LOWER) {
+                            VecT dv[4];
+                            ld4v<false>(delta + (size_t)j * 4, dv);
+#pragma unroll
+                            for (int m = 0; m < 4; m++) xv[m] += dv[m];
+                        }
+#pragma unroll
+                        for (int m = 0; m < 4; m++) acc -= (VecT)av[m] * xv[m];
+                    }
+                } else {
+                    for (int k = k0; k < kend; k++) {
+                        const unsigned c = cols[k];
+                        if (!(c & CS_HIGHER)) continue;
+                        const int j = (int)(c & CS_MASK);
+                        MatT av[4];
+                        VecT Dv[4];
+                        ld4v<false>(vals + (size_t)k * 16 + r * 4, av);
+                        ld4v<false>(Delta + (size_t)j * 4, Dv);
+#pragma unroll
+                        for (int m = 0; m < 4; m++) acc += (VecT)av[m] * Dv[m];
+                    }
+                }
+            }
+            // y = Einv_i * acc inside the quad
+            VecT y = 0;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const VecT am = __shfl_sync(0xffffffffu, acc, qbase + m);
+                if (act) y += (VecT)Einv[(size_t)i * 16 + r * 4 + m] * am;
+            }
+            if (act) {
+                const size_t idx = (size_t)i * 4 + r;
+                if (!BACKWARD) delta[idx] = y;
+                else {
+                    const VecT v = delta[idx] - y;
+                    x[idx] = x[idx] + (VecT)(a.weight * v);
+                    Delta[idx] = v;
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+        }
+    }
+}
+
+template <class MatT, class VecT, bool BACKWARD> void launch_dilu_tile(const DiluTileArgs &ta, int grid, size_t smem, cudaStream_t s)
+{
+    auto k = dilu_tile_kernel<MatT, VecT, BACKWARD>;
+    static size_t attr_bytes = 0;
+    if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+    k<<<grid, DT_CONSUMERS + PRODUCER_THREADS, smem, s>>>(ta);
+}
+
 }  // namespace
 
 class MulticolorDILUSolver : public Solver {
@@ -451,6 +642,84 @@ protected:
             d_color_offsets_.from_any(A.color_offsets.data(), A.color_offsets.size(), s);
             cluster_size_ = max_color <= 32 * rows_per_warp ? 1 : 8;     // one CTA, or a cluster of 8 (the portable maximum)
         }
+        build_color_sorted();
+    }
+
+    // colour-sorted copy of a 4x4 block matrix for the tile kernels (large levels only: the fused level kernel takes the small ones)
+    void build_color_sorted()
+    {
+        Matrix &A = *A_;
+        cudaStream_t s = stream();
+        cs_ready_ = false;
+        static const int tiles_on = getenv("AMGXB_DILU_TILES") ? atoi(getenv("AMGXB_DILU_TILES")) : 1;
+        if (!tiles_on || fused_level_ || A.bs() != 16 || A.n == 0 || (long long)A.n_cols >= (1ll << 30)) return;
+        const int n = A.n;
+        DevBuf<int> len;
+        len.resize((size_t)n + 1);
+        cs_lengths_kernel<<<std::max(1, std::min(ceil_div(n, 256), 2048)), 256, 0, s>>>(A.row_ptr.ptr(), A.sorted_rows_by_color.ptr(), n, len.ptr());
+        cs_rp_.resize((size_t)n + 1);
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len.ptr(), cs_rp_.ptr(), n + 1, s);
+        DevBytes tmp;
+        tmp.resize(tmp_bytes);
+        cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, len.ptr(), cs_rp_.ptr(), n + 1, s);
+        cs_ci_.resize((size_t)std::max(A.nnz, 1) + 8);
+        cs_va_.resize(((size_t)std::max(A.nnz, 1) + 8) * 16, A.mat_prec);
+        const int grid = std::max(1, std::min(ceil_div(n, 8), 148 * 16));
+        if (A.mat_prec == Prec::F64)
+            cs_permute_kernel<double><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<double>(), A.sorted_rows_by_color.ptr(), A.row_colors.ptr(),
+                                                           cs_rp_.ptr(), n, A.n, cs_ci_.ptr(), cs_va_.as<double>());
+        else
+            cs_permute_kernel<float><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<float>(), A.sorted_rows_by_color.ptr(), A.row_colors.ptr(),
+                                                          cs_rp_.ptr(), n, A.n, cs_ci_.ptr(), cs_va_.as<float>());
+        count_launch(4);
+        // stage capacity: the largest tile of any colour
+        DevBuf<int> st;
+        st.resize(1);
+        st.zero(s);
+        for (int c = 0; c < A.num_colors; c++) {
+            const int off = A.color_offsets[c], cnt = A.color_offsets[c + 1] - off;
+            if (cnt == 0) continue;
+            const int nt = ceil_div(cnt, DT_ROWS);
+            cs_tile_stats_kernel<<<std::max(1, std::min(ceil_div(nt, 256), 1024)), 256, 0, s>>>(cs_rp_.ptr(), off, off + cnt, nt, st.ptr());
+            count_launch();
+        }
+        AMGXB_LAUNCH_CHECK();
+        cs_cap_ = std::max(4, st.to_host(s)[0]);
+        cs_smem_ = 128 + (size_t)DT_STAGES * ((size_t)cs_cap_ * (16 * prec_size(A.mat_prec) + 4) + (size_t)(DT_ROWS + 4) * 4);
+        if (cs_smem_ > (size_t)200 * 1024) { cs_rp_.release(); cs_ci_.release(); return; }
+        const int by_threads = std::min(2048 / (DT_CONSUMERS + PRODUCER_THREADS), 65536 / ((DT_CONSUMERS + PRODUCER_THREADS) * 48));
+        cs_ctas_ = std::max(1, std::min(by_threads, (int)((size_t)227 * 1024 / (cs_smem_ + 1024))));
+        cs_ready_ = true;
+    }
+
+    // one colour of a sweep through the colour-sorted copy
+    void tile_color(DevVec &b, DevVec &x, int c, bool backward)
+    {
+        Matrix &A = *A_;
+        cudaStream_t s = stream();
+        const int off = A.color_offsets[c], cnt = A.color_offsets[c + 1] - off;
+        DiluTileArgs ta;
+        ta.rp = cs_rp_.ptr();
+        ta.ci = cs_ci_.ptr();
+        ta.rows = A.sorted_rows_by_color.ptr();
+        ta.va = cs_va_.ptr();
+        ta.Einv = Einv_.ptr();
+        ta.b = b.ptr();
+        ta.x = x.ptr();
+        ta.delta = delta_.ptr();
+        ta.Delta = Delta_.ptr();
+        ta.weight = weight_;
+        ta.row0 = off;
+        ta.row1 = off + cnt;
+        ta.num_tiles = ceil_div(cnt, DT_ROWS);
+        ta.cap = cs_cap_;
+        const int grid = std::max(1, std::min(ta.num_tiles, (A.rsc ? A.rsc->num_sms : 148) * cs_ctas_));
+        AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+            if (backward) launch_dilu_tile<MatT, VecT, true>(ta, grid, cs_smem_, s);
+            else launch_dilu_tile<MatT, VecT, false>(ta, grid, cs_smem_, s);
+        });
+        count_launch();
     }
 
     // forward + backward over all colours, `sweeps` times, in ONE launch (one thread-block cluster)
@@ -521,6 +790,9 @@ protected:
                     const int grid = std::min(4096, ceil_div(cnt, 128 / NTPR));
                     dilu_forward_1x1<MatT, VecT><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
                                                                       A.sorted_rows_by_color.ptr() + off, cnt, c, A.row_colors.ptr(), Einv_.as<MatT>(), A.n);
+                } else if (cs_ready_) {
+                    tile_color(b, x, c, false);
+                    continue;
                 } else {
                     const int grid = std::min(148 * 16, ceil_div(cnt, 4));
                     dilu_sweep_4x4<MatT, VecT, false><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
@@ -540,6 +812,9 @@ protected:
                     dilu_backward_1x1<MatT, VecT><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), weight_,
                                                                        A.sorted_rows_by_color.ptr() + off, A.row_colors.ptr(), Einv_.as<MatT>(), delta_.as<VecT>(),
                                                                        Delta_.as<VecT>(), cnt, c, A.n);
+                } else if (cs_ready_) {
+                    tile_color(b, x, c, true);
+                    continue;
                 } else {
                     const int grid = std::min(148 * 16, ceil_div(cnt, 4));
                     dilu_sweep_4x4<MatT, VecT, true><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
@@ -564,6 +839,12 @@ protected:
     bool fused_level_ = false;
     int cluster_size_ = 1;
     DevBuf<int> d_color_offsets_;
+    // colour-sorted copy for the tile kernels
+    bool cs_ready_ = false;
+    DevBuf<int> cs_rp_, cs_ci_;
+    DevVec cs_va_;
+    int cs_cap_ = 0, cs_ctas_ = 1;
+    size_t cs_smem_ = 0;
 };
 
 std::unique_ptr<Solver> make_dilu_solver(Config &cfg, const std::string &scope, std::shared_ptr<Resources> rsc)
