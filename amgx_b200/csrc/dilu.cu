@@ -508,34 +508,51 @@ __global__ void __launch_bounds__(DT_CONSUMERS + PRODUCER_THREADS) dilu_tile_ker
             if (act) {
                 const int sa = rp[0] & ~3;
                 const int k0 = rp[q] - sa, kend = rp[q + 1] - sa;
+                // four blocks per step: their gathers of x (and delta / Delta) are in flight together -- a quad walking its row one block
+                // at a time is a chain of L2 round trips (r02: 2.0 ms per sweep on 4.1 M rows that way)
                 if (!BACKWARD) {
-                    for (int k = k0; k < kend; k++) {
-                        const unsigned c = cols[k];
-                        const int j = (int)(c & CS_MASK);
-                        MatT av[4];
-                        VecT xv[4];
-                        ld4v<false>(vals + (size_t)k * 16 + r * 4, av);
-                        ld4v<false>(x + (size_t)j * 4, xv);
-                        if (c & CS_LOWER) {
-                            VecT dv[4];
-                            ld4v<false>(delta + (size_t)j * 4, dv);
+                    for (int k = k0; k < kend; k += 4) {
+                        unsigned c[4];
+                        VecT xv[4][4], dv[4][4];
 #pragma unroll
-                            for (int m = 0; m < 4; m++) xv[m] += dv[m];
+                        for (int u = 0; u < 4; u++) c[u] = cols[(k + u < kend) ? k + u : k0];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) ld4v<false>(x + (size_t)(c[u] & CS_MASK) * 4, xv[u]);
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (k + u < kend && (c[u] & CS_LOWER)) ld4v<false>(delta + (size_t)(c[u] & CS_MASK) * 4, dv[u]);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (k + u < kend) {
+                                MatT av[4];
+                                ld4v<false>(vals + (size_t)(k + u) * 16 + r * 4, av);
+                                if (c[u] & CS_LOWER) {
+#pragma unroll
+                                    for (int m = 0; m < 4; m++) xv[u][m] += dv[u][m];
+                                }
+#pragma unroll
+                                for (int m = 0; m < 4; m++) acc -= (VecT)av[m] * xv[u][m];
+                            }
                         }
-#pragma unroll
-                        for (int m = 0; m < 4; m++) acc -= (VecT)av[m] * xv[m];
                     }
                 } else {
-                    for (int k = k0; k < kend; k++) {
-                        const unsigned c = cols[k];
-                        if (!(c & CS_HIGHER)) continue;
-                        const int j = (int)(c & CS_MASK);
-                        MatT av[4];
-                        VecT Dv[4];
-                        ld4v<false>(vals + (size_t)k * 16 + r * 4, av);
-                        ld4v<false>(Delta + (size_t)j * 4, Dv);
+                    for (int k = k0; k < kend; k += 4) {
+                        unsigned c[4];
+                        VecT Dv[4][4];
 #pragma unroll
-                        for (int m = 0; m < 4; m++) acc += (VecT)av[m] * Dv[m];
+                        for (int u = 0; u < 4; u++) c[u] = (k + u < kend) ? cols[k + u] : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (c[u] & CS_HIGHER) ld4v<false>(Delta + (size_t)(c[u] & CS_MASK) * 4, Dv[u]);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (c[u] & CS_HIGHER) {
+                                MatT av[4];
+                                ld4v<false>(vals + (size_t)(k + u) * 16 + r * 4, av);
+#pragma unroll
+                                for (int m = 0; m < 4; m++) acc += (VecT)av[m] * Dv[u][m];
+                            }
+                        }
                     }
                 }
             }
@@ -652,7 +669,8 @@ protected:
         cudaStream_t s = stream();
         cs_ready_ = false;
         static const int tiles_on = getenv("AMGXB_DILU_TILES") ? atoi(getenv("AMGXB_DILU_TILES")) : 1;
-        if (!tiles_on || fused_level_ || A.bs() != 16 || A.n == 0 || (long long)A.n_cols >= (1ll << 30)) return;
+        // short rows only: a quad walks its row alone here; the 30-60-block rows of the coarse levels keep the 8-quads-per-row kernel
+        if (!tiles_on || fused_level_ || A.bs() != 16 || A.n == 0 || (long long)A.n_cols >= (1ll << 30) || (double)A.nnz > 12.0 * A.n) return;
         const int n = A.n;
         DevBuf<int> len;
         len.resize((size_t)n + 1);
@@ -688,7 +706,8 @@ protected:
         cs_cap_ = std::max(4, st.to_host(s)[0]);
         cs_smem_ = 128 + (size_t)DT_STAGES * ((size_t)cs_cap_ * (16 * prec_size(A.mat_prec) + 4) + (size_t)(DT_ROWS + 4) * 4);
         if (cs_smem_ > (size_t)200 * 1024) { cs_rp_.release(); cs_ci_.release(); return; }
-        const int by_threads = std::min(2048 / (DT_CONSUMERS + PRODUCER_THREADS), 65536 / ((DT_CONSUMERS + PRODUCER_THREADS) * 48));
+        const int regs = (A.mat_prec == Prec::F64) ? 96 : 64;      // cuobjdump -res-usage, forward kernel (four blocks of gathers in flight)
+        const int by_threads = std::min(2048 / (DT_CONSUMERS + PRODUCER_THREADS), 65536 / ((DT_CONSUMERS + PRODUCER_THREADS) * regs));
         cs_ctas_ = std::max(1, std::min(by_threads, (int)((size_t)227 * 1024 / (cs_smem_ + 1024))));
         cs_ready_ = true;
     }

@@ -205,6 +205,98 @@ __global__ void __launch_bounds__(TILE_ROWS) valenc_build_kernel(const int *__re
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Pair dictionary (r02): a tile whose columns AND values are dictionary-coded and whose entries take <= 256 distinct
+// (column code, value code) combinations gets ONE code byte per entry into a per-tile table of (column offset, value) pairs
+// (7 pairs on a 7-point level, tens to ~150 on the first aggregation level).  The consumer then needs one byte load and one
+// 16-byte look-up per entry instead of two byte loads and two look-ups: the coded kernels are bound by the SM's load/store
+// wavefronts, not by HBM (ncu: 46 % DRAM, 64 % SM), so this is where their time is.  Built after the column and value codes;
+// the pair flag lives beside them (pmeta), so value changes simply rebuild value codes and pairs.
+// ---------------------------------------------------------------------------------------------
+template <class MatT> struct EncPair;
+template <> struct __align__(16) EncPair<double> { int off; int pad; double val; };
+template <> struct __align__(8) EncPair<float> { int off; float val; };
+
+template <class MatT, int TILE_ROWS>
+__global__ void __launch_bounds__(TILE_ROWS) pairenc_build_kernel(const int *__restrict__ rp, int row0, int n, int num_tiles, int tile_base, const unsigned char *__restrict__ codes,
+                                                                  const unsigned char *__restrict__ vcodes, const int *__restrict__ dict, const MatT *__restrict__ vdict,
+                                                                  const int *__restrict__ meta, unsigned char *pcodes, EncPair<MatT> *pdict, int *pmeta, int *stats)
+{
+    __shared__ unsigned bitmap[2048];         // one bit per (column code, value code) combination
+    __shared__ int wprefix[2048];
+    __shared__ int part[TILE_ROWS];
+    const int tid = threadIdx.x;
+    for (int ltile = blockIdx.x; ltile < num_tiles; ltile += gridDim.x) {
+        const int tile = tile_base + ltile;
+        const int r0 = row0 + ltile * TILE_ROWS, r1 = min(r0 + TILE_ROWS, n);
+        const int nz0 = rp[r0], nz1 = rp[r1];
+        const int sa = nz0 & ~3, ea = (nz1 + 3) & ~3;
+        if (meta[META * tile] != 1 || meta[META * tile + 2] != 1 || nz1 == nz0) {
+            if (tid == 0) pmeta[tile] = 0;
+            continue;                                                     // uniform over the CTA
+        }
+        const unsigned char *cseg = codes + code_offset(sa, tile), *vseg = vcodes + vcode_offset(sa, tile);
+        for (int i = tid; i < 2048; i += TILE_ROWS) bitmap[i] = 0u;
+        __syncthreads();
+        for (int k = nz0 + tid; k < nz1; k += TILE_ROWS) {
+            const unsigned key = ((unsigned)cseg[k - sa] << 8) | (unsigned)vseg[k - sa];
+            atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+        }
+        __syncthreads();
+        // exclusive prefix of the per-word popcounts: each thread owns 2048 / TILE_ROWS consecutive words
+        constexpr int WPT = 2048 / TILE_ROWS;
+        int local = 0;
+        for (int w = 0; w < WPT; w++) local += __popc(bitmap[tid * WPT + w]);
+        part[tid] = local;
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int t = 0; t < TILE_ROWS; t++) { const int v = part[t]; part[t] = run; run += v; }
+            wprefix[0] = run;                                             // total, parked until everybody has read its partial
+        }
+        __syncthreads();
+        const int count = wprefix[0];
+        __syncthreads();
+        int run = part[tid];
+        for (int w = 0; w < WPT; w++) { wprefix[tid * WPT + w] = run; run += __popc(bitmap[tid * WPT + w]); }
+        __syncthreads();
+        if (count <= DICT_SLOTS) {
+            unsigned char *pseg = pcodes + vcode_offset(sa, tile);
+            for (int k = sa + tid; k < ea; k += TILE_ROWS) {
+                int code = 0;
+                if (k >= nz0 && k < nz1) {
+                    const unsigned key = ((unsigned)cseg[k - sa] << 8) | (unsigned)vseg[k - sa];
+                    code = wprefix[key >> 5] + __popc(bitmap[key >> 5] & ((1u << (key & 31)) - 1u));
+                }
+                pseg[k - sa] = (unsigned char)code;
+            }
+            const int *dt = dict + (size_t)tile * DICT_SLOTS;
+            const MatT *vt = vdict + (size_t)tile * DICT_SLOTS;
+            EncPair<MatT> *pt = pdict + (size_t)tile * DICT_SLOTS;
+            for (int w = tid; w < 2048; w += TILE_ROWS) {
+                unsigned bits = bitmap[w];
+                int rank = wprefix[w];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const unsigned key = ((unsigned)w << 5) | (unsigned)b;
+                    EncPair<MatT> pr;
+                    memset(&pr, 0, sizeof(pr));
+                    pr.off = dt[key >> 8];
+                    pr.val = vt[key & 255u];
+                    pt[rank++] = pr;
+                }
+            }
+            const int padded = (count + 3) & ~3;
+            __syncthreads();
+            for (int i = count + tid; i < padded; i += TILE_ROWS) pt[i] = pt[count - 1];
+            if (tid == 0) { pmeta[tile] = padded; atomicAdd(stats + 6, 1); atomicMax(stats + 7, padded); }
+        } else if (tid == 0) pmeta[tile] = 0;
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The encoded tile kernel.  blockDim.x = TILE_ROWS + 32 (last warp = producer).
 // Stage layout, sized PER LEVEL from what its tiles actually use (a level whose tiles are all coded stages 2 bytes per entry, so
@@ -219,7 +311,10 @@ struct EncArgs {
     const int *meta;
     const unsigned char *vcodes;
     const void *vdict;
-    int val_w, col_w, dict_cap, vdict_cap;
+    const unsigned char *pcodes;   // pair codes (1 byte per entry) and pair tables of the tiles with pmeta[tile] > 0
+    const void *pdict;
+    const int *pmeta;
+    int val_w, col_w, dict_cap, vdict_cap;   // vdict_cap counts BYTES of the value / pair dictionary region
     int tile_base;      // global index of the segment's first tile (meta / dictionaries / code segments are numbered over all segments)
 };
 
@@ -264,6 +359,37 @@ __device__ __forceinline__ VecT row_dot_enc(const unsigned char *__restrict__ vs
     return sum;
 }
 
+// one row of a pair-coded tile: one byte load + one 16-byte look-up per entry
+template <class MatT, class VecT>
+__device__ __forceinline__ VecT row_dot_pair(const unsigned char *__restrict__ cstream, const EncPair<MatT> *__restrict__ pdict, int k, const int kend, const int row,
+                                             const VecT *__restrict__ x)
+{
+    constexpr int U = 8;
+    VecT sum = 0;
+    for (; k + U <= kend; k += U) {
+        EncPair<MatT> p[U];
+        VecT xv[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) p[j] = pdict[cstream[k + j]];
+#pragma unroll
+        for (int j = 0; j < U; j++) xv[j] = __ldg(x + row + p[j].off);
+#pragma unroll
+        for (int j = 0; j < U; j++) sum = fma((VecT)p[j].val, xv[j], sum);
+    }
+    if (k < kend) {
+        EncPair<MatT> p[U - 1];
+        VecT xv[U - 1];
+#pragma unroll
+        for (int j = 0; j < U - 1; j++) p[j] = pdict[cstream[(k + j < kend) ? k + j : k]];
+#pragma unroll
+        for (int j = 0; j < U - 1; j++) xv[j] = __ldg(x + row + p[j].off);
+#pragma unroll
+        for (int j = 0; j < U - 1; j++)
+            if (k + j < kend) sum = fma((VecT)p[j].val, xv[j], sum);
+    }
+    return sum;
+}
+
 template <class MatT, class VecT, int TILE_ROWS, int EPI>
 __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_kernel(const TileArgs<MatT, VecT> a, const EncArgs e)
 {
@@ -275,7 +401,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
     const size_t vals_bytes = align16((size_t)a.cap * e.val_w);
     const size_t cols_bytes = align16((size_t)a.cap * e.col_w);
     const size_t dict_bytes = (size_t)e.dict_cap * sizeof(int);
-    const size_t vdict_bytes = align16((size_t)e.vdict_cap * sizeof(MatT));
+    const size_t vdict_bytes = align16((size_t)e.vdict_cap);
     const size_t rp_bytes = (size_t)(TILE_ROWS + 4) * sizeof(int);
     const size_t stage_bytes = vals_bytes + cols_bytes + dict_bytes + vdict_bytes + rp_bytes;
     constexpr int CONSUMER_WARPS = TILE_ROWS / 32;
@@ -309,9 +435,18 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
                 const int gtile = e.tile_base + tile;
                 const int4 m = __ldg(reinterpret_cast<const int4 *>(e.meta) + gtile);
                 const int enc = m.x, dlen = m.y, venc = m.z, vdlen = m.w;
+                const int pdlen = __ldg(e.pmeta + gtile);
                 unsigned char *st = stage_base + (size_t)s * stage_bytes;
                 const unsigned rp_copy = (unsigned)(((r1 - r0 + 1 + 3) & ~3) * sizeof(int));
                 const unsigned cnt = (unsigned)(ea - sa);
+                if (pdlen > 0) {      // pair-coded tile: code bytes into the column stream, the pair table into the value-dictionary region
+                    const unsigned pc_copy = (unsigned)align16(cnt), pd_copy = (unsigned)align16((size_t)pdlen * sizeof(EncPair<MatT>));
+                    mbar_expect_tx(&full[s], rp_copy + pc_copy + pd_copy);
+                    tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes + vdict_bytes, a.row_ptr + r0, rp_copy, &full[s]);
+                    tma_bulk_g2s(st + vals_bytes, e.pcodes + vcode_offset(sa, gtile), pc_copy, &full[s]);
+                    tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes, reinterpret_cast<const EncPair<MatT> *>(e.pdict) + (size_t)gtile * DICT_SLOTS, pd_copy, &full[s]);
+                    continue;
+                }
                 unsigned col_copy = 0, val_copy = 0;
                 if (cnt) col_copy = enc == 1 ? (unsigned)align16(cnt) : enc == 2 ? (unsigned)align16((size_t)cnt * 2) : cnt * (unsigned)sizeof(int);
                 if (cnt) val_copy = venc == 1 ? (unsigned)align16(cnt) : cnt * (unsigned)sizeof(MatT);
@@ -340,6 +475,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
             const int row = a.row0 + tile * TILE_ROWS + lrow;
             const bool active = row < a.n;
             const int enc = __ldg(e.meta + META * (e.tile_base + tile)), venc = __ldg(e.meta + META * (e.tile_base + tile) + 2);
+            const int pd = __ldg(e.pmeta + e.tile_base + tile);
             VecT bi = 0, xi = 0;
             MatT di = 1;
             if (active) {
@@ -363,7 +499,8 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_ker
                 const int k = rp[lrow] - sa, kend = rp[lrow + 1] - sa;
                 // the tile's encoding is uniform over the CTA: the switch does not diverge
                 VecT sum;
-                switch (enc * 2 + venc) {
+                if (pd > 0) sum = row_dot_pair<MatT, VecT>(cstream, reinterpret_cast<const EncPair<MatT> *>(vdict), k, kend, row, a.x);
+                else switch (enc * 2 + venc) {
                 case 3: sum = row_dot_enc<MatT, VecT, 1, 1>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
                 case 2: sum = row_dot_enc<MatT, VecT, 1, 0>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
                 case 5: sum = row_dot_enc<MatT, VecT, 2, 1>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
@@ -473,18 +610,67 @@ static void build_value_codes(Matrix &A, cudaStream_t s)
     E.max_vdlen = h[5];
 }
 
+// pair tables of the tiles whose columns and values are both dictionary-coded (pairenc_build_kernel); off with AMGXB_ENC_PAIRS=0
+static void build_pair_codes(Matrix &A, cudaStream_t s)
+{
+    ColEnc &E = A.colenc;
+    const int T = A.plan.tile_rows, nt = E.num_tiles;
+    static const int pairs_on = getenv("AMGXB_ENC_PAIRS") ? atoi(getenv("AMGXB_ENC_PAIRS")) : 1;
+    E.tiles_pair = 0;
+    E.max_pdlen = 0;
+    E.pmeta.resize((size_t)std::max(nt, 1));
+    E.pmeta.zero(s);
+    if (!pairs_on || !E.values_encoded || E.tiles_dict8 == 0 || E.tiles_val8 == 0) { if (E.pcodes.size() == 0) { E.pcodes.resize(64); E.pdict.resize(64); } return; }
+    const size_t msz = prec_size(A.mat_prec), psz = msz == 8 ? 16 : 8;
+    E.pcodes.resize(align16((size_t)A.nnz + 8) + (size_t)32 * nt + 64);
+    E.pdict.resize((size_t)nt * DICT_SLOTS * psz);
+    DevBuf<int> stats;
+    stats.resize(8);
+    stats.zero(s);
+    EncSeg seg[2];
+    const int nseg = enc_segments(A, seg);
+    for (int g = 0; g < nseg; g++) {
+        const int grid = std::max(1, std::min(seg[g].tiles, 148 * 8));
+        if (A.mat_prec == Prec::F64) {
+            if (T == 256) pairenc_build_kernel<double, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.vcodes.ptr(), E.dict.ptr(), (const double *)E.vdict.ptr(), E.meta.ptr(), E.pcodes.ptr(), (EncPair<double> *)E.pdict.ptr(), E.pmeta.ptr(), stats.ptr());
+            else pairenc_build_kernel<double, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.vcodes.ptr(), E.dict.ptr(), (const double *)E.vdict.ptr(), E.meta.ptr(), E.pcodes.ptr(), (EncPair<double> *)E.pdict.ptr(), E.pmeta.ptr(), stats.ptr());
+        } else {
+            if (T == 256) pairenc_build_kernel<float, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.vcodes.ptr(), E.dict.ptr(), (const float *)E.vdict.ptr(), E.meta.ptr(), E.pcodes.ptr(), (EncPair<float> *)E.pdict.ptr(), E.pmeta.ptr(), stats.ptr());
+            else pairenc_build_kernel<float, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.vcodes.ptr(), E.dict.ptr(), (const float *)E.vdict.ptr(), E.meta.ptr(), E.pcodes.ptr(), (EncPair<float> *)E.pdict.ptr(), E.pmeta.ptr(), stats.ptr());
+        }
+        count_launch();
+    }
+    AMGXB_LAUNCH_CHECK();
+    const std::vector<int> h = stats.to_host(s);
+    E.tiles_pair = h[6];
+    E.max_pdlen = h[7];
+}
+
 // Stage layout and occupancy of the encoded kernel for this level, from what its tiles use (see the kernel's header comment).
-static void finalize_layout(Matrix &A)
+static void finalize_layout(Matrix &A, cudaStream_t s)
 {
     ColEnc &E = A.colenc;
     const int T = A.plan.tile_rows, nt = E.num_tiles;
     const size_t msz = prec_size(A.mat_prec);
-    E.col_w = E.tiles_raw > 0 ? 4 : (E.tiles_off16 > 0 ? 2 : 1);
-    E.val_w = (E.tiles_val8 == nt) ? 1 : (int)msz;
+    // what the tiles that are NOT pair-coded need (pair-coded tiles stage one code byte per entry and their table, no value stream)
+    int raw_c = E.tiles_raw, off16 = E.tiles_off16, val_raw = nt - E.tiles_val8, val8 = E.tiles_val8;
+    if (E.tiles_pair > 0) {
+        const std::vector<int> hm = E.meta.to_host(s), hp = E.pmeta.to_host(s);
+        raw_c = off16 = val_raw = val8 = 0;
+        for (int t = 0; t < nt; t++) {
+            if (hp[t] > 0) continue;
+            raw_c += hm[(size_t)META * t] == 0;
+            off16 += hm[(size_t)META * t] == 2;
+            val_raw += hm[(size_t)META * t + 2] == 0;
+            val8 += hm[(size_t)META * t + 2] == 1;
+        }
+    }
+    E.col_w = raw_c > 0 ? 4 : (off16 > 0 ? 2 : 1);
+    E.val_w = val_raw > 0 ? (int)msz : (val8 > 0 ? 1 : 0);
     E.dict_cap = std::max(E.max_dlen, E.tiles_off16 > 0 ? 4 : 0);
-    E.vdict_cap = E.max_vdlen;
+    E.vdict_cap = (int)std::max((size_t)E.max_vdlen * msz, (size_t)E.max_pdlen * (msz == 8 ? 16 : 8));      // bytes
     const size_t cap = (size_t)A.plan.max_tile_nnz;
-    const size_t stage = align16(cap * E.val_w) + align16(cap * E.col_w) + (size_t)E.dict_cap * 4 + align16((size_t)E.vdict_cap * msz) + (size_t)(T + 4) * 4;
+    const size_t stage = align16(cap * E.val_w) + align16(cap * E.col_w) + (size_t)E.dict_cap * 4 + align16((size_t)E.vdict_cap) + (size_t)(T + 4) * 4;
     static const int env_stages = getenv("AMGXB_ENC_STAGES") ? atoi(getenv("AMGXB_ENC_STAGES")) : 0;
     static const int env_ctas = getenv("AMGXB_ENC_CTAS") ? atoi(getenv("AMGXB_ENC_CTAS")) : 0;
     const int by_threads = std::min(2048 / (T + PRODUCER_THREADS), 65536 / ((T + PRODUCER_THREADS) * 40));   // threads and registers (40 per thread, -Xptxas -v)
@@ -556,10 +742,11 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
         E.vcodes.resize(64);
         E.vdict.resize(64);
     }
-    finalize_layout(A);
+    build_pair_codes(A, s);
+    finalize_layout(A, s);
     if (getenv("AMGXB_COLENC_VERBOSE"))
-        fprintf(stderr, "[amgx_b200] colenc level %d: %d tiles of %d rows: columns dict8 %d, off16 %d, raw %d; values dict8 %d | stage widths col %d val %d B, dict %d / %d, "
-                        "%d stages, %zu B smem, %d CTAs/SM%s\n", A.level, nt, T, E.tiles_dict8, E.tiles_off16, E.tiles_raw, E.tiles_val8, E.col_w, E.val_w, E.dict_cap,
+        fprintf(stderr, "[amgx_b200] colenc level %d: %d tiles of %d rows: columns dict8 %d, off16 %d, raw %d; values dict8 %d; pair-coded %d | stage widths col %d val %d B, dict %d / %d B, "
+                        "%d stages, %zu B smem, %d CTAs/SM%s\n", A.level, nt, T, E.tiles_dict8, E.tiles_off16, E.tiles_raw, E.tiles_val8, E.tiles_pair, E.col_w, E.val_w, E.dict_cap,
                 E.vdict_cap, E.stages, E.smem_bytes, E.ctas_per_sm, E.on ? "" : " (off)");
 }
 
@@ -571,7 +758,8 @@ void csr_values_changed(Matrix &A, cudaStream_t s)
     const int nt = A.plan.num_tiles;
     // the column half of the per-tile descriptors stays, the value half is rewritten by the build kernel
     build_value_codes(A, s);
-    finalize_layout(A);
+    build_pair_codes(A, s);
+    finalize_layout(A, s);
     (void)nt;
 }
 
@@ -590,6 +778,9 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
     ea.meta = A.colenc.meta.ptr();
     ea.vcodes = A.colenc.vcodes.ptr();
     ea.vdict = A.colenc.vdict.ptr();
+    ea.pcodes = A.colenc.pcodes.ptr();
+    ea.pdict = A.colenc.pdict.ptr();
+    ea.pmeta = A.colenc.pmeta.ptr();
     ea.val_w = A.colenc.val_w;
     ea.col_w = A.colenc.col_w;
     ea.dict_cap = A.colenc.dict_cap;

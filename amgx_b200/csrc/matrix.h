@@ -53,6 +53,10 @@ struct ColEnc {
     size_t smem_bytes = 0;          // dynamic shared memory of the encoded kernel
     int tiles_dict8 = 0, tiles_off16 = 0, tiles_raw = 0, tiles_val8 = 0;
     int max_dlen = 0, max_vdlen = 0;               // longest (padded) dictionaries of the level
+    DevBuf<unsigned char> pcodes;   // pair codes: one byte per entry into the tile's (column offset, value) table (tiles with pmeta > 0)
+    DevBuf<unsigned char> pdict;    // 256 pairs per tile
+    DevBuf<int> pmeta;              // per tile: (padded) length of its pair table, 0 = not pair-coded
+    int tiles_pair = 0, max_pdlen = 0;
     int col_w = 4, val_w = 8, dict_cap = 0, vdict_cap = 0;   // stage layout of the level (finalize_layout)
     int stages = 2, ctas_per_sm = 1;
     int num_tiles = 0;                             // tiles over all row segments ([0, split) then [split, n) on a row-partitioned matrix)
