@@ -359,33 +359,55 @@ __device__ __forceinline__ VecT row_dot_enc(const unsigned char *__restrict__ vs
     return sum;
 }
 
-// one row of a pair-coded tile: one byte load + one 16-byte look-up per entry
+// one row of a pair-coded tile: one byte load + one 16-byte look-up per entry.  The coded kernels are bound by instruction ISSUE (ncu r02:
+// smsp__issue_active 68 %, 295 thread instructions per 7-entry row with the predicated 8-wide loop), so rows are dispatched on their exact
+// length to straight-line code: N code loads, N look-ups, N gathers in flight, N FMAs in storage order, no predicates.
+// one table entry with ONE shared-memory load (LDS.128 / LDS.64) instead of one per member
+__device__ __forceinline__ void ld_pair(const EncPair<double> *p, int &off, double &val)
+{
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    off = (int)v.x;
+    val = __hiloint2double((int)v.w, (int)v.z);
+}
+__device__ __forceinline__ void ld_pair(const EncPair<float> *p, int &off, float &val)
+{
+    const uint2 v = *reinterpret_cast<const uint2 *>(p);
+    off = (int)v.x;
+    val = __uint_as_float(v.y);
+}
+
+template <class MatT, class VecT, int N>
+__device__ __forceinline__ VecT row_pair_fixed(const unsigned char *__restrict__ cs, const EncPair<MatT> *__restrict__ pdict, const VecT *__restrict__ x, const int row, VecT sum)
+{
+    int off[N];
+    MatT val[N];
+    VecT xv[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) ld_pair(pdict + cs[j], off[j], val[j]);
+#pragma unroll
+    for (int j = 0; j < N; j++) xv[j] = __ldg(x + (row + off[j]));      // 32-bit column, then one scaled 64-bit add
+#pragma unroll
+    for (int j = 0; j < N; j++) sum = fma((VecT)val[j], xv[j], sum);
+    return sum;
+}
+
 template <class MatT, class VecT>
 __device__ __forceinline__ VecT row_dot_pair(const unsigned char *__restrict__ cstream, const EncPair<MatT> *__restrict__ pdict, int k, const int kend, const int row,
                                              const VecT *__restrict__ x)
 {
-    constexpr int U = 8;
+    const unsigned char *cs = cstream + k;
+    int len = kend - k;
     VecT sum = 0;
-    for (; k + U <= kend; k += U) {
-        EncPair<MatT> p[U];
-        VecT xv[U];
-#pragma unroll
-        for (int j = 0; j < U; j++) p[j] = pdict[cstream[k + j]];
-#pragma unroll
-        for (int j = 0; j < U; j++) xv[j] = __ldg(x + row + p[j].off);
-#pragma unroll
-        for (int j = 0; j < U; j++) sum = fma((VecT)p[j].val, xv[j], sum);
-    }
-    if (k < kend) {
-        EncPair<MatT> p[U - 1];
-        VecT xv[U - 1];
-#pragma unroll
-        for (int j = 0; j < U - 1; j++) p[j] = pdict[cstream[(k + j < kend) ? k + j : k]];
-#pragma unroll
-        for (int j = 0; j < U - 1; j++) xv[j] = __ldg(x + row + p[j].off);
-#pragma unroll
-        for (int j = 0; j < U - 1; j++)
-            if (k + j < kend) sum = fma((VecT)p[j].val, xv[j], sum);
+    for (; len >= 8; len -= 8, cs += 8) sum = row_pair_fixed<MatT, VecT, 8>(cs, pdict, x, row, sum);
+    switch (len) {
+    case 7: sum = row_pair_fixed<MatT, VecT, 7>(cs, pdict, x, row, sum); break;
+    case 6: sum = row_pair_fixed<MatT, VecT, 6>(cs, pdict, x, row, sum); break;
+    case 5: sum = row_pair_fixed<MatT, VecT, 5>(cs, pdict, x, row, sum); break;
+    case 4: sum = row_pair_fixed<MatT, VecT, 4>(cs, pdict, x, row, sum); break;
+    case 3: sum = row_pair_fixed<MatT, VecT, 3>(cs, pdict, x, row, sum); break;
+    case 2: sum = row_pair_fixed<MatT, VecT, 2>(cs, pdict, x, row, sum); break;
+    case 1: sum = row_pair_fixed<MatT, VecT, 1>(cs, pdict, x, row, sum); break;
+    default: break;
     }
     return sum;
 }
