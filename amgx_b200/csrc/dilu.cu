@@ -670,7 +670,9 @@ protected:
         cs_ready_ = false;
         static const int tiles_on = getenv("AMGXB_DILU_TILES") ? atoi(getenv("AMGXB_DILU_TILES")) : 1;
         // short rows only: a quad walks its row alone here; the 30-60-block rows of the coarse levels keep the 8-quads-per-row kernel
-        if (!tiles_on || fused_level_ || A.bs() != 16 || A.n == 0 || (long long)A.n_cols >= (1ll << 30) || (double)A.nnz > 12.0 * A.n) return;
+        // ... and fp32 blocks only: with 128-byte blocks three CTAs fit an SM and the tile form loses to form 1 (r02: 45.0 vs 47.6 it/s in dDDI,
+        // 63.6 vs 60.2 in dDFI on the 160^3 problem)
+        if (!tiles_on || fused_level_ || A.bs() != 16 || A.n == 0 || (long long)A.n_cols >= (1ll << 30) || (double)A.nnz > 12.0 * A.n || A.mat_prec != Prec::F32) return;
         const int n = A.n;
         DevBuf<int> len;
         len.resize((size_t)n + 1);

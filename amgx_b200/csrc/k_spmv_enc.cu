@@ -14,6 +14,7 @@
 // Not used for: distributed matrices (two row segments), the aggregation-fused prolongation gather, the long-row fallback.
 #include "kernels.h"
 #include <climits>
+#include <map>
 
 namespace amgxb {
 namespace {
@@ -413,7 +414,7 @@ __device__ __forceinline__ VecT row_dot_pair(const unsigned char *__restrict__ c
 }
 
 template <class MatT, class VecT, int TILE_ROWS, int EPI>
-__global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_enc_kernel(const TileArgs<MatT, VecT> a, const EncArgs e)
+__global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 256 ? 5 : 9)) csr_tile_enc_kernel(const TileArgs<MatT, VecT> a, const EncArgs e)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
@@ -567,6 +568,17 @@ void launch_enc(const Matrix &A, const TileArgs<MatT, VecT> &ta, const EncArgs &
     auto k = csr_tile_enc_kernel<MatT, VecT, TILE_ROWS, EPI>;
     static size_t attr_bytes = 0;
     if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+    // the persistent grid must not exceed what is RESIDENT for this instantiation (registers differ per epilogue): a CTA that waits for a
+    // slot runs its tiles after everybody else's (r02: 52 registers -> 4 resident of 5 launched per SM cost 50 % on the Jacobi sweep)
+    static std::map<size_t, int> occ_by_smem;
+    auto it = occ_by_smem.find(smem);
+    if (it == occ_by_smem.end()) {
+        int occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, TILE_ROWS + PRODUCER_THREADS, smem) != cudaSuccess) { cudaGetLastError(); occ = 1; }
+        it = occ_by_smem.emplace(smem, std::max(occ, 1)).first;
+    }
+    const int sms = A.rsc ? A.rsc->num_sms : 148;
+    grid = std::max(1, std::min(grid, sms * it->second));
     k<<<grid, TILE_ROWS + PRODUCER_THREADS, smem, s>>>(ta, ea);
 }
 
