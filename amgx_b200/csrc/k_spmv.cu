@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
     if (tid >= TILE_ROWS) {
         // ------------------------------- producer warp -------------------------------
         if (tid == TILE_ROWS) {
-            for (int it = 0; it < my_tiles; it++) {
+            int s = 0;             // stage and mbarrier phase advance by counting: no runtime division per tile
+            unsigned ph = 0u;
+            for (int it = 0; it < my_tiles; it++, s = (s + 1 == a.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
                 const int tile = blockIdx.x + it * gridDim.x;
-                const int s = it % a.stages;
-                const unsigned ph = (unsigned)(it / a.stages) & 1u;
                 if (it >= a.stages) mbar_wait(&empty[s], ph ^ 1u);
                 const int r0 = a.row0 + tile * TILE_ROWS;
                 const int r1 = min(r0 + TILE_ROWS, a.n);
@@ -120,10 +120,10 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
         }
     } else {
         // ------------------------------- consumers: one row per thread -------------------------------
-        for (int it = 0; it < my_tiles; it++) {
+        int s = 0;
+        unsigned ph = 0u;
+        for (int it = 0; it < my_tiles; it++, s = (s + 1 == a.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
             const int tile = blockIdx.x + it * gridDim.x;
-            const int s = it % a.stages;
-            const unsigned ph = (unsigned)(it / a.stages) & 1u;
             // which row of the tile this thread takes: its own, or (irregular matrices) the tid-th longest, so that the rows of a warp
             // have similar lengths and the warp is not paced by its longest row.  A row is still summed left to right by ONE thread.
             const int lrow = a.perm ? (int)__ldg(a.perm + (size_t)(a.tile_base + tile) * TILE_ROWS + tid) : tid;

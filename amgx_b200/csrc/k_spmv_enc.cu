@@ -319,50 +319,51 @@ struct EncArgs {
     int tile_base;      // global index of the segment's first tile (meta / dictionaries / code segments are numbered over all segments)
 };
 
-// one row of an encoded tile: 8 code loads, 8 dictionary look-ups, 8 gathers of x in flight, FMA chain in storage order
-template <class MatT, class VecT, int ENC, int VENC>
-__device__ __forceinline__ VecT row_dot_enc(const unsigned char *__restrict__ vstream, const unsigned char *__restrict__ cstream, const int *__restrict__ dict,
-                                            const MatT *__restrict__ vdict, int k, const int kend, const int row, const VecT *__restrict__ x)
+// one row of an encoded tile (separate column / value codes): rows are dispatched on their exact length to straight-line code (N code loads,
+// N dictionary look-ups, N gathers of x in flight, N FMAs in storage order, no predicates) -- the coded kernels are bound by instruction issue
+template <class MatT, class VecT, int ENC, int VENC, int N>
+__device__ __forceinline__ VecT row_enc_fixed(const unsigned char *__restrict__ vstream, const unsigned char *__restrict__ cstream, const int *__restrict__ dict,
+                                              const MatT *__restrict__ vdict, const int k, const int base, const VecT *__restrict__ x, VecT sum)
 {
-    constexpr int U = 8;
-    const int base = (ENC == 2) ? dict[0] : row;
-    auto col_at = [&](int kk) -> int {
-        if (ENC == 1) return base + dict[cstream[kk]];
-        if (ENC == 2) return base + (int)reinterpret_cast<const unsigned short *>(cstream)[kk];
-        return reinterpret_cast<const int *>(cstream)[kk];
-    };
-    auto val_at = [&](int kk) -> MatT {
-        if (VENC) return vdict[vstream[kk]];
-        return reinterpret_cast<const MatT *>(vstream)[kk];
-    };
-    VecT sum = 0;
-    for (; k + U <= kend; k += U) {
-        int c[U];
-        VecT xv[U];
+    int c[N];
+    VecT xv[N];
 #pragma unroll
-        for (int j = 0; j < U; j++) c[j] = col_at(k + j);
-#pragma unroll
-        for (int j = 0; j < U; j++) xv[j] = __ldg(x + c[j]);
-#pragma unroll
-        for (int j = 0; j < U; j++) sum = fma((VecT)val_at(k + j), xv[j], sum);
+    for (int j = 0; j < N; j++) {
+        if (ENC == 1) c[j] = base + dict[cstream[k + j]];
+        else if (ENC == 2) c[j] = base + (int)reinterpret_cast<const unsigned short *>(cstream)[k + j];
+        else c[j] = reinterpret_cast<const int *>(cstream)[k + j];
     }
-    if (k < kend) {
-        int c[U - 1];
-        VecT xv[U - 1];
 #pragma unroll
-        for (int j = 0; j < U - 1; j++) c[j] = col_at((k + j < kend) ? k + j : k);
+    for (int j = 0; j < N; j++) xv[j] = __ldg(x + c[j]);
 #pragma unroll
-        for (int j = 0; j < U - 1; j++) xv[j] = __ldg(x + c[j]);
-#pragma unroll
-        for (int j = 0; j < U - 1; j++)
-            if (k + j < kend) sum = fma((VecT)val_at(k + j), xv[j], sum);
+    for (int j = 0; j < N; j++) {
+        const MatT v = VENC ? vdict[vstream[k + j]] : reinterpret_cast<const MatT *>(vstream)[k + j];
+        sum = fma((VecT)v, xv[j], sum);
     }
     return sum;
 }
 
-// one row of a pair-coded tile: one byte load + one 16-byte look-up per entry.  The coded kernels are bound by instruction ISSUE (ncu r02:
-// smsp__issue_active 68 %, 295 thread instructions per 7-entry row with the predicated 8-wide loop), so rows are dispatched on their exact
-// length to straight-line code: N code loads, N look-ups, N gathers in flight, N FMAs in storage order, no predicates.
+template <class MatT, class VecT, int ENC, int VENC>
+__device__ __forceinline__ VecT row_dot_enc(const unsigned char *__restrict__ vstream, const unsigned char *__restrict__ cstream, const int *__restrict__ dict,
+                                            const MatT *__restrict__ vdict, int k, const int kend, const int row, const VecT *__restrict__ x)
+{
+    const int base = (ENC == 2) ? dict[0] : row;
+    int len = kend - k;
+    VecT sum = 0;
+    for (; len >= 8; len -= 8, k += 8) sum = row_enc_fixed<MatT, VecT, ENC, VENC, 8>(vstream, cstream, dict, vdict, k, base, x, sum);
+    switch (len) {
+    case 7: sum = row_enc_fixed<MatT, VecT, ENC, VENC, 7>(vstream, cstream, dict, vdict, k, base, x, sum); break;
+    case 6: sum = row_enc_fixed<MatT, VecT, ENC, VENC, 6>(vstream, cstream, dict, vdict, k, base, x, sum); break;
+    case 5: sum = row_enc_fixed<MatT, VecT, ENC, VENC, 5>(vstream, cstream, dict, vdict, k, base, x, sum); break;
+    case 4: sum = row_enc_fixed<MatT, VecT, ENC, VENC, 4>(vstream, cstream, dict, vdict, k, base, x, sum); break;
+    case 3: sum = row_enc_fixed<MatT, VecT, ENC, VENC, 3>(vstream, cstream, dict, vdict, k, base, x, sum); break;
+    case 2: sum = row_enc_fixed<MatT, VecT, ENC, VENC, 2>(vstream, cstream, dict, vdict, k, base, x, sum); break;
+    case 1: sum = row_enc_fixed<MatT, VecT, ENC, VENC, 1>(vstream, cstream, dict, vdict, k, base, x, sum); break;
+    default: break;
+    }
+    return sum;
+}
+
 // one table entry with ONE shared-memory load (LDS.128 / LDS.64) instead of one per member
 __device__ __forceinline__ void ld_pair(const EncPair<double> *p, int &off, double &val)
 {
@@ -426,7 +427,8 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 25
     const size_t dict_bytes = (size_t)e.dict_cap * sizeof(int);
     const size_t vdict_bytes = align16((size_t)e.vdict_cap);
     const size_t rp_bytes = (size_t)(TILE_ROWS + 4) * sizeof(int);
-    const size_t stage_bytes = vals_bytes + cols_bytes + dict_bytes + vdict_bytes + rp_bytes;
+    const size_t hdr_off = vals_bytes + cols_bytes + dict_bytes + vdict_bytes + rp_bytes;      // 16-byte tile header: what the producer read from meta / pmeta
+    const size_t stage_bytes = hdr_off + 16;
     constexpr int CONSUMER_WARPS = TILE_ROWS / 32;
     constexpr bool HAS_RED = (EPI == EPI_SPMV_DOT || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2);
 
@@ -446,10 +448,10 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 25
     if (tid >= TILE_ROWS) {
         // ------------------------------- producer warp -------------------------------
         if (tid == TILE_ROWS) {
-            for (int it = 0; it < my_tiles; it++) {
+            int s = 0;             // stage and mbarrier phase advance by counting: no runtime division per tile
+            unsigned ph = 0u;
+            for (int it = 0; it < my_tiles; it++, s = (s + 1 == a.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
                 const int tile = blockIdx.x + it * gridDim.x;
-                const int s = it % a.stages;
-                const unsigned ph = (unsigned)(it / a.stages) & 1u;
                 if (it >= a.stages) mbar_wait(&empty[s], ph ^ 1u);
                 const int r0 = a.row0 + tile * TILE_ROWS;
                 const int r1 = min(r0 + TILE_ROWS, a.n);
@@ -462,6 +464,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 25
                 unsigned char *st = stage_base + (size_t)s * stage_bytes;
                 const unsigned rp_copy = (unsigned)(((r1 - r0 + 1 + 3) & ~3) * sizeof(int));
                 const unsigned cnt = (unsigned)(ea - sa);
+                *reinterpret_cast<int4 *>(st + hdr_off) = make_int4(enc, venc, pdlen, 0);       // released to the consumers by the arrive below
                 if (pdlen > 0) {      // pair-coded tile: code bytes into the column stream, the pair table into the value-dictionary region
                     const unsigned pc_copy = (unsigned)align16(cnt), pd_copy = (unsigned)align16((size_t)pdlen * sizeof(EncPair<MatT>));
                     mbar_expect_tx(&full[s], rp_copy + pc_copy + pd_copy);
@@ -490,15 +493,13 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 25
         }
     } else {
         // ------------------------------- consumers: one row per thread -------------------------------
-        for (int it = 0; it < my_tiles; it++) {
+        int s = 0;
+        unsigned ph = 0u;
+        for (int it = 0; it < my_tiles; it++, s = (s + 1 == a.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
             const int tile = blockIdx.x + it * gridDim.x;
-            const int s = it % a.stages;
-            const unsigned ph = (unsigned)(it / a.stages) & 1u;
             const int lrow = a.perm ? (int)__ldg(a.perm + (size_t)(e.tile_base + tile) * TILE_ROWS + tid) : tid;      // length-sorted rows (k_spmv.cu)
             const int row = a.row0 + tile * TILE_ROWS + lrow;
             const bool active = row < a.n;
-            const int enc = __ldg(e.meta + META * (e.tile_base + tile)), venc = __ldg(e.meta + META * (e.tile_base + tile) + 2);
-            const int pd = __ldg(e.pmeta + e.tile_base + tile);
             VecT bi = 0, xi = 0;
             MatT di = 1;
             if (active) {
@@ -517,6 +518,8 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 25
             const MatT *vdict = reinterpret_cast<const MatT *>(st + vals_bytes + cols_bytes + dict_bytes);
             const int *rp = reinterpret_cast<const int *>(st + vals_bytes + cols_bytes + dict_bytes + vdict_bytes);
             mbar_wait(&full[s], ph);
+            const int4 hdr = *reinterpret_cast<const int4 *>(st + hdr_off);      // the tile's encoding, uniform over the CTA
+            const int enc = hdr.x, venc = hdr.y, pd = hdr.z;
             if (active) {
                 const int sa = rp[0] & ~3;
                 const int k = rp[lrow] - sa, kend = rp[lrow + 1] - sa;
@@ -704,7 +707,7 @@ static void finalize_layout(Matrix &A, cudaStream_t s)
     E.dict_cap = std::max(E.max_dlen, E.tiles_off16 > 0 ? 4 : 0);
     E.vdict_cap = (int)std::max((size_t)E.max_vdlen * msz, (size_t)E.max_pdlen * (msz == 8 ? 16 : 8));      // bytes
     const size_t cap = (size_t)A.plan.max_tile_nnz;
-    const size_t stage = align16(cap * E.val_w) + align16(cap * E.col_w) + (size_t)E.dict_cap * 4 + align16((size_t)E.vdict_cap) + (size_t)(T + 4) * 4;
+    const size_t stage = align16(cap * E.val_w) + align16(cap * E.col_w) + (size_t)E.dict_cap * 4 + align16((size_t)E.vdict_cap) + (size_t)(T + 4) * 4 + 16;
     static const int env_stages = getenv("AMGXB_ENC_STAGES") ? atoi(getenv("AMGXB_ENC_STAGES")) : 0;
     static const int env_ctas = getenv("AMGXB_ENC_CTAS") ? atoi(getenv("AMGXB_ENC_CTAS")) : 0;
     const int by_threads = std::min(2048 / (T + PRODUCER_THREADS), 65536 / ((T + PRODUCER_THREADS) * 40));   // threads and registers (40 per thread, -Xptxas -v)

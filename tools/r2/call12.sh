@@ -2,6 +2,7 @@
 # round-2 GPU call 12 (2 GPUs): where does an iteration's time go at N = 2 (phase timing, graphs off) + coding statistics of the partitioned levels
 mkdir -p gpurun_out/r2
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+timeout 600 python -m pytest -q -m gpu --timeout=300 tests/test_gpu_parity.py tests/test_gpu_classical.py tests/test_gpu_dist.py -k "not 4-" 2>&1 | tail -2 | cut -c1-300
 for T in 0 131072; do
 AMGXB_PHASE_TIMING=1 AMGXB_COLENC_VERBOSE=1 AMGXB_TAIL_ROWS=$T timeout 600 $TR --master-port 29761 bench.py --gpus 2 --steps 1 --warmup 1 --no-cpu-baseline --no-parity > /dev/null 2> gpurun_out/r2/phase_n2_tail$T.txt
 echo "== N=2 tail=$T"; grep "colenc level" gpurun_out/r2/phase_n2_tail$T.txt | head -12 | cut -c1-260; grep -A58 "phase timing\]" gpurun_out/r2/phase_n2_tail$T.txt | head -60 | cut -c1-160
