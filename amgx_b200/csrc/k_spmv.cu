@@ -346,7 +346,10 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
     p.split = (A.split_row / 4) * 4;   // distributed: rows [0, split) never touch halo columns
     // The split buys overlap of the halo exchange with the interior rows; below AMGXB_SPLIT_ROWS rows an interior kernel is shorter than
     // the two extra launches the split costs, so small levels exchange first (one kernel on the peer-memory path) and run as a whole.
-    static const int split_rows = getenv("AMGXB_SPLIT_ROWS") ? atoi(getenv("AMGXB_SPLIT_ROWS")) : (1 << 20);
+    // With the peer-memory exchange (one ~10 us kernel, p2p.cu) even the fine level gains nothing from the overlap that the two extra
+    // launches and the cross-stream edges cost (r02, N = 2: 283 it/s split at 2^20 rows, 288 never split), so the split is for the NCCL path.
+    static const int env_split = getenv("AMGXB_SPLIT_ROWS") ? atoi(getenv("AMGXB_SPLIT_ROWS")) : -1;
+    const int split_rows = env_split >= 0 ? env_split : ((A.rsc && A.rsc->p2p) ? (1 << 30) : (1 << 20));
     if (A.n < split_rows) p.split = 0;
     if (p.split > 0 && p.split < A.n) {
         tile_stats_kernel<<<std::min(ceil_div(A.n, 256), 1024), 256, 0, s>>>(A.row_ptr.ptr(), 0, p.split, p.tile_rows, ceil_div(p.split, p.tile_rows), stats.ptr(), stats.ptr() + 1);

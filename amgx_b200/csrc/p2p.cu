@@ -395,7 +395,7 @@ bool p2p_exchange_blocking(const Matrix &A, void *x, Prec prec, int bsize, cudaS
     if (m.neighbors.empty()) return true;
     const int nn = (int)m.neighbors.size();
     const long long work = std::max<long long>((long long)m.send_offsets[nn], (long long)m.n_halo) * bsize;
-    static const int max_ctas = getenv("AMGXB_P2P_CTAS") ? std::max(1, std::min(32, atoi(getenv("AMGXB_P2P_CTAS")))) : 8;
+    static const int max_ctas = getenv("AMGXB_P2P_CTAS") ? std::max(1, std::min(32, atoi(getenv("AMGXB_P2P_CTAS")))) : 32;     // r02, N = 2: 2 CTAs 223, 8 CTAs 272, 32 CTAs 283 global it/s
     const int grid = (int)std::max<long long>(1, std::min<long long>((work + 2047) / 2048, max_ctas));
     const long long halo_count = (long long)m.n_halo * bsize, halo_first = (long long)m.n_owned * bsize;
     if (prec == Prec::F64) p2p_exchange_kernel<double><<<grid, 256, 0, s>>>(m.p2p->dev, m.send_maps.ptr(), (double *)x, bsize, halo_count, halo_first);
