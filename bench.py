@@ -11,7 +11,7 @@ b = 1, RELATIVE_INI 1e-6, max 100 iterations); metric = outer Krylov iterations 
   e2e   : the same solve through the C-ABI with HOST buffers: AMGX_vector_upload(rhs) from pinned host memory + AMGX_vector_set_zero
           + AMGX_solver_solve + AMGX_vector_download(sol), wall clock around the synchronous calls.
   roofline : the DOMINANT kernel of the iteration = the fused Jacobi sweep on the fine level (csr_tile_kernel<EPI_JACOBI>, ~70 % of an
-          iteration: profiles/r01_launches_solve_256.md); algorithmic bytes nnz*(8+4) + rows*4 + 4*rows*8 per launch / CUDA-event time
+          iteration: profiles/r02_launches_solve_256.md); algorithmic bytes nnz*(8+4) + rows*4 + 4*rows*8 per launch / CUDA-event time
           per launch, against the measured HBM copy peak (MEASURED_PEAKS.json).  roofline.spmv carries the plain fine-level SpMV
           (north-star bytes nnz*12 + rows*4), roofline.iteration the whole outer iteration.
   reference_gpu : the UNMODIFIED reference (oracle/_ref, its own sm_100 GPU build) on the same matrix and configuration, timed in
@@ -478,7 +478,7 @@ def main():
         ms = A.bench_kernel(0, warmup=3, reps=20, flush_l2=False)      # operands (>= 1.4 GB) >> 126 MB L2
         byt = nnz * (msz * bd * bd + 4) + n * 4
         enc = os.environ.get("AMGXB_COLENC", "")
-        spmv = {"kernel": ("csr_tile_kernel<EPI_SPMV>" if bd == 1 else "block4_kernel<SPMV>") + " (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt,
+        spmv = {"kernel": ("csr_tile_kernel<EPI_SPMV>" if bd == 1 else "block4_tile_kernel<SPMV> (TMA-staged 4x4 blocks)") + " (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt,
                 "achieved": byt / ms / 1e6, "frac": byt / ms / 1e6 / peak}
         if bd == 1:
             ms_j = A.bench_kernel(1, warmup=3, reps=20, flush_l2=False)

@@ -54,17 +54,58 @@ def ncu_table(rep, title, note=""):
     return o + [""]
 
 doc = ["# r02 -- ncu `--set full` captures, per kernel (B200, 7-point Poisson 256^3 unless noted)", "",
-       "Raw reports stay in gpurun_out/r2/ncu (scratch, 8-14 MB each); this file holds the judged metrics per launch.",
-       "traffic = DRAM read + DRAM write; compare with the algorithmic bytes in DESIGN 3.1 / 3.8.", ""]
+       "Raw reports stay in gpurun_out/r2/ncu (scratch, 8-15 MB each); this file holds the judged metrics per launch.",
+       "traffic = DRAM read + DRAM write; compare with the algorithmic bytes in DESIGN 3.1 / 3.8 / 3.9.", ""]
 doc += ncu_table(SRC / "ncu" / "plain_256.ncu-rep", "csr_tile_kernel<EPI_SPMV> -- plain CSR streams (AMGXB_COLENC=0), occupancy plan (2 stages x 4 CTAs/SM)",
                  "Algorithmic bytes 1.4717 GB (+ 0.268 GB of vectors the formula leaves out).")
-doc += ncu_table(SRC / "ncu" / "enc_256.ncu-rep", "csr_tile_enc_kernel<EPI_SPMV> -- coded column + value streams (default)", "Same SpMV, 2 B per entry + dictionaries.")
-doc += ncu_table(SRC / "ncu" / "enc_jacobi_256.ncu-rep", "csr_tile_enc_kernel<EPI_JACOBI> -- the dominant kernel of the iteration (fused Jacobi sweep, coded streams)")
-doc += ncu_table(SRC / "ncu" / "level1_256.ncu-rep", "level-1 and transfer kernels inside a solve (vec_dot, pcg_update_xr, restrict, prolong)")
-doc += ncu_table(SRC / "ncu" / "block_96b.ncu-rep", "block 4x4 (dDFI, 96^3 block rows): TMA-staged block tile kernel, DILU colour sweeps, fused DILU level kernel")
-if not (SRC / "ncu" / "block_96b.ncu-rep").exists():
-    doc += ncu_table(SRC / "ncu" / "block_96.ncu-rep", "block 4x4 (dDFI, 96^3): DILU colour sweeps before the prefetch")
+doc += ncu_table(SRC / "ncu" / "enc_spmv_256_final.ncu-rep", "csr_tile_enc_kernel<EPI_SPMV> -- coded streams with pair tables (final default)", "1 code byte per entry + the tile's pair table.")
+doc += ncu_table(SRC / "ncu" / "enc_jacobi_256_final.ncu-rep", "csr_tile_enc_kernel<EPI_JACOBI> -- the dominant kernel of the iteration (fused Jacobi sweep, final default)")
+doc += ncu_table(SRC / "ncu" / "enc_256.ncu-rep", "history: csr_tile_enc_kernel<EPI_SPMV> before the pair tables (separate column / value codes, predicated 8-wide decode)")
+doc += ncu_table(SRC / "ncu" / "enc_jacobi_256.ncu-rep", "history: csr_tile_enc_kernel<EPI_JACOBI> before the pair tables (issue-bound: smsp__issue_active 68 %)")
+doc += ncu_table(SRC / "ncu" / "level1_256.ncu-rep", "level-1 and transfer kernels inside a solve (vec_dot, restrict)")
+doc += ncu_table(SRC / "ncu" / "level1b_256.ncu-rep", "level-1 and transfer kernels inside a solve (pcg_update_xr, prolong_set, vec_axpby_dev)")
+doc += ncu_table(SRC / "ncu" / "block_160.ncu-rep", "block 4x4 (dDFI, 160^3 = 4.1 M block rows): TMA-staged block tile kernel, colour-sorted DILU tile kernels, fused DILU level kernel")
+doc += ncu_table(SRC / "ncu" / "block_96b.ncu-rep", "block 4x4 (dDFI, 96^3): per-colour DILU sweeps (8 quads per row, next-row prefetch)")
 (DST / "r02_ncu_kernels.md").write_text("\n".join(doc) + "\n")
+
+# ---- final bench lines
+fin = SRC / "final"
+if fin.exists():
+    rows = ["# r02 -- final bench lines (one B200; raw JSON lines beside this file as r02_bench_*.json)", "",
+            "| workload | it/s (device-resident) | e2e it/s (host buffers) | iterations | status | dominant kernel: ms, fraction of 6575 GB/s | reference GPU build it/s | CPU port it/s (threads) |", "|---|---|---|---|---|---|---|---|"]
+    for f in sorted(fin.glob("bench_*.json")):
+        d = last_json(f)
+        if not d:
+            continue
+        (DST / f"r02_{f.name}").write_text(json.dumps(d) + "\n")
+        r = d.get("roofline") or {}
+        ref = (d.get("reference_gpu") or {}).get("value")
+        cpu = d.get("cpu_baseline") or {}
+        rows.append(f"| {d.get('config', {}).get('workload', f.name)[:90]} | {d['value']:.1f} | {d['e2e']['value']:.1f} | {d.get('config', {}).get('iterations_per_step')} | "
+                    f"{d.get('config', {}).get('solve_status')} | {(r.get('kernel') or '')[:50]}: {r.get('ms_per_launch') and round(r['ms_per_launch'], 4)} ms, {r.get('frac') and round(r['frac'], 3)} | "
+                    f"{ref and round(ref, 1)} | {cpu.get('value') and round(cpu['value'], 2)} ({cpu.get('cores')}) |")
+    cl = fin / "classical.jsonl"
+    if cl.exists():
+        rows += ["", "Config 3 (FGMRES + classical AMG, `tools/bench_classical.py`):", "", "| engine | grid | iterations | solve s | it/s | setup s |", "|---|---|---|---|---|---|"]
+        for l in open(cl):
+            if l.startswith("{"):
+                d = json.loads(l)
+                rows.append(f"| {d['engine']} | {d['nx']}^3 | {d['iters']} | {d['solve_s']:.4f} | {d['iters_per_s']:.1f} | {d['setup_s']:.2f} |")
+    sc = sorted(fin.glob("scale_*.json"))
+    if sc:
+        rows += ["", "Multi-GPU (`bench.py --gpus N`, one process per GPU):", "", "| run | N | value | global it/s | iterations | launches / iteration | e2e | parity object green |", "|---|---|---|---|---|---|---|---|"]
+        for f in sc:
+            d = last_json(f)
+            if not d:
+                continue
+            (DST / f"r02_{f.name}").write_text(json.dumps(d) + "\n")
+            c = d["config"]
+            rows.append(f"| {f.stem} ({d['scaling']}, {c.get('exchange')}) | {d['n_gpus']} | {d['value']:.1f} | {c['global_iterations_per_sec']:.1f} | {c['iterations_per_step']} | "
+                        f"{round(d['gpu_launches'] / d['steps'] / c['iterations_per_step'])} | {d['e2e']['value']:.1f} | {(d.get('parity') or {}).get('green')} |")
+    (DST / "r02_configs.md").write_text("\n".join(rows) + "\n")
+    for f in ("launches_solve_256_final.csv", "launches_solve_256_final.md"):
+        if (SRC / "ncu" / f).exists():
+            (DST / ("r02_" + f.replace("_final", ""))).write_text((SRC / "ncu" / f).read_text())
 
 # ---- launch list
 for f in ("launches_solve_256.csv", "launches_solve_256.md"):
