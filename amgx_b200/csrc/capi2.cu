@@ -192,11 +192,28 @@ static void read_mm(const char *filename, MMSystem &S)
     for (double v; fin >> v;) tail.push_back(v);
     const size_t need_b = has_rhs ? (size_t)n * S.by : 0, need_x = has_sol ? (size_t)n * S.bx : 0, L = (size_t)has_rhs + (size_t)has_sol;
     const size_t D = S.has_diag ? (size_t)n * bsq : 0;
-    bool diag_section = false, lengths = false;
-    if (S.has_diag && tail.size() == D + need_b + need_x + L) { diag_section = true; lengths = L > 0; }
-    else if (S.has_diag && tail.size() == D + need_b + need_x) diag_section = true;
-    else if (tail.size() == need_b + need_x + L) lengths = L > 0;
-    else if (tail.size() != need_b + need_x) fatal(AMGX_RC_IO_ERROR, "MatrixMarket: unexpected number of values after the matrix entries (diagonal / rhs / solution sections)");
+    // Candidate layouts in the reference's order of preference (its own writer first); a candidate is accepted when the value count fits
+    // AND, where it claims length lines, those tokens really hold the vector lengths -- the count alone is ambiguous for 1- and 2-row
+    // systems (n * block size can equal the number of length lines).
+    bool diag_section = false, lengths = false, found = false;
+    auto fits = [&](bool ds, bool ln) -> bool {
+        const size_t d = ds ? D : 0, l = ln ? L : 0;
+        if (tail.size() != d + need_b + need_x + l) return false;
+        if (ln) {
+            size_t pos = d;
+            if (has_rhs) { if ((size_t)tail[pos] != need_b || tail[pos] != (double)need_b) return false; pos += 1 + need_b; }
+            if (has_sol) { if ((size_t)tail[pos] != need_x || tail[pos] != (double)need_x) return false; }
+        }
+        return true;
+    };
+    const bool cand[4][2] = {{true, true}, {true, false}, {false, true}, {false, false}};
+    for (int c = 0; c < 4 && !found; c++) {
+        const bool ds = cand[c][0], ln = cand[c][1] && L > 0;
+        if (ds && !S.has_diag) continue;
+        if (cand[c][1] && L == 0) continue;
+        if (fits(ds, ln)) { diag_section = ds; lengths = ln; found = true; }
+    }
+    if (!found) fatal(AMGX_RC_IO_ERROR, "MatrixMarket: unexpected number of values after the matrix entries (diagonal / rhs / solution sections)");
     S.n = n;
     S.rp.assign(n + 1, 0);
     if (S.has_diag) S.diag.assign((size_t)n * bsq, 0.0);

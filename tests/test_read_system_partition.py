@@ -211,3 +211,21 @@ def test_writer_reader_round_trip_on_the_host(tmp_path, writer, block, ext_diag)
     if ext_diag:
         assert diag.value and np.array_equal(arr(diag, n * bsq), va[len(rows) * bsq:])
     assert np.array_equal(arr(rhs, n * block), b) and np.array_equal(arr(sol, n * block), x)
+
+
+def test_one_row_system_with_diagonal_section_is_not_misread(tmp_path):
+    """with n * block size == number of length lines the value COUNT cannot tell the layouts apart (1-row system, 'diagonal' +
+    'rhs': diagonal section + rhs without a length line has as many values as inline diagonal + length line + rhs).  The reader checks that
+    a claimed length line really holds the vector length."""
+    lib = capi.load_library()
+    base = ["%%MatrixMarket matrix coordinate real general"]
+    # reference layout: no entries, one diagonal line, a length line, the rhs
+    p1 = tmp_path / "one_ref.mtx"
+    p1.write_text("\n".join(base + ["%%NVAMG 1 1 diagonal rhs", "1 1 0", "7.5", "1", "3.25"]) + "\n")
+    rc, got = call(lib, 0, 1, str(p1), want_local=False)
+    assert rc == 0 and got["n"] == 1 and got["rhs"][0] == 3.25
+    # legacy layout: diagonal section + rhs WITHOUT the length line; the rhs value 1.0 must not be taken for a length line
+    p2 = tmp_path / "one_legacy.mtx"
+    p2.write_text("\n".join(base + ["%%NVAMG 1 1 diagonal rhs", "1 1 0", "7.5", "4.0"]) + "\n")
+    rc, got = call(lib, 0, 1, str(p2), want_local=False)
+    assert rc == 0 and got["rhs"][0] == 4.0
