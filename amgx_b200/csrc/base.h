@@ -162,6 +162,10 @@ struct DevVec {
     size_t nbytes() const { return n * prec_size(prec); }
 };
 
+// Grid-stride kernels cap their grids at a small multiple of the SM count of the ONE target of this library (sm_100a, B200: 148 SMs on two
+// dies); the persistent tile kernels size their grids from Resources::num_sms (the device's own count) and the occupancy of the instantiation.
+constexpr int B200_SMS = 148;
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace amgxb

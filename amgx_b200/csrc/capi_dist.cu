@@ -80,7 +80,7 @@ AMGX_RC AMGX_generate_distributed_poisson_7pt(AMGX_matrix_handle mtx, AMGX_vecto
         A.dist.reset();
         A.row_ptr.resize(n + 1);
         A.row_ptr.zero(s);
-        const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+        const int grid = (int)std::min<long long>((n + 255) / 256, B200_SMS * 16);
         poisson7_count_kernel<<<grid, 256, 0, s>>>(nx, ny, nz, A.row_ptr.ptr());
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, A.row_ptr.ptr(), A.row_ptr.ptr(), (int)n + 1, s);

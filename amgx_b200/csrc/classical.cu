@@ -29,7 +29,7 @@ constexpr int COARSE = -1, FINE = -2, STRONG_FINE = -3, UNASSIGNED = -4;
 typedef unsigned char u8;
 typedef long long i64;
 
-inline int grid_for(i64 n) { return (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, 148 * 16)); }
+inline int grid_for(i64 n) { return (int)std::max<i64>(1, std::min<i64>((n + 255) / 256, B200_SMS * 16)); }
 #define ROW_LOOP(i, n) for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += gridDim.x * blockDim.x)
 
 __host__ __device__ inline float cla_hash(int i)   // ourHash, strength_base.cu:41-55

@@ -96,7 +96,7 @@ __global__ void offsets_k(int n, const int *__restrict__ keys, int n_keys, int *
     }
 }
 
-inline int grid_for(long long n) { return std::max(1, std::min(ceil_div(n, 256), 148 * 16)); }
+inline int grid_for(long long n) { return std::max(1, std::min(ceil_div(n, 256), B200_SMS * 16)); }
 
 void build_color_arrays(Matrix &A, cudaStream_t s)
 {

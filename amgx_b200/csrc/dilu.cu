@@ -685,7 +685,7 @@ protected:
         cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, len.ptr(), cs_rp_.ptr(), n + 1, s);
         cs_ci_.resize((size_t)std::max(A.nnz, 1) + 8);
         cs_va_.resize(((size_t)std::max(A.nnz, 1) + 8) * 16, A.mat_prec);
-        const int grid = std::max(1, std::min(ceil_div(n, 8), 148 * 16));
+        const int grid = std::max(1, std::min(ceil_div(n, 8), B200_SMS * 16));
         if (A.mat_prec == Prec::F64)
             cs_permute_kernel<double><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<double>(), A.sorted_rows_by_color.ptr(), A.row_colors.ptr(),
                                                            cs_rp_.ptr(), n, A.n, cs_ci_.ptr(), cs_va_.as<double>());
@@ -815,7 +815,7 @@ protected:
                     tile_color(b, x, c, false);
                     continue;
                 } else {
-                    const int grid = std::min(148 * 16, ceil_div(cnt, 4));
+                    const int grid = std::min(B200_SMS * 16, ceil_div(cnt, 4));
                     dilu_sweep_4x4<MatT, VecT, false><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
                                                                            Delta_.as<VecT>(), weight_, A.sorted_rows_by_color.ptr() + off, cnt, c, A.row_colors.ptr(),
                                                                            Einv_.as<MatT>(), A.n);
@@ -837,7 +837,7 @@ protected:
                     tile_color(b, x, c, true);
                     continue;
                 } else {
-                    const int grid = std::min(148 * 16, ceil_div(cnt, 4));
+                    const int grid = std::min(B200_SMS * 16, ceil_div(cnt, 4));
                     dilu_sweep_4x4<MatT, VecT, true><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), x.as<VecT>(), b.as<VecT>(), delta_.as<VecT>(),
                                                                           Delta_.as<VecT>(), weight_, A.sorted_rows_by_color.ptr() + off, cnt, c, A.row_colors.ptr(),
                                                                           Einv_.as<MatT>(), A.n);

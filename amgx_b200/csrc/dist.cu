@@ -140,7 +140,7 @@ template <class T> static void exchange_typed(const Matrix &A, T *x, int bsize, 
     if (m.send_buf.b.bytes < need) m.send_buf.b.resize(need);
     T *buf = (T *)m.send_buf.b.p;
     if (total_send) {
-        const int grid = std::min(ceil_div((long long)total_send * bsize, 256), 148 * 8);
+        const int grid = std::min(ceil_div((long long)total_send * bsize, 256), B200_SMS * 8);
         pack_kernel<T><<<grid, 256, 0, s>>>(m.send_maps.ptr(), total_send, bsize, x, buf);
         count_launch();
         AMGXB_LAUNCH_CHECK();
@@ -392,7 +392,7 @@ void dist_replace_values(Matrix &A, int nnz, const void *data)
     DevBytes stage;
     stage.resize(std::max<size_t>((size_t)nnz * bs * msz, 1));
     if (nnz) AMGXB_CUDA_CHECK(cudaMemcpyAsync(stage.p, data, (size_t)nnz * bs * msz, cudaMemcpyDefault, s));
-    const int grid = std::max(1, std::min(ceil_div(A.n, 8), 148 * 8));
+    const int grid = std::max(1, std::min(ceil_div(A.n, 8), B200_SMS * 8));
     if (A.mat_prec == Prec::F64)
         permute_row_values_kernel<double><<<grid, 256, 0, s>>>(A.n, m.caller_row_ptr.ptr(), m.perm_old_to_new.ptr(), A.row_ptr.ptr(), (int)bs, (const double *)stage.p,
                                                                 A.values.as<double>());
@@ -672,7 +672,7 @@ void dist_prepare_vector(const Matrix &A, Vector &v)
         DevVec nv;
         nv.resize(need, v.prec);
         nv.zero(s);
-        const int grid = std::min(ceil_div((long long)m.n_owned * bd, 256), 148 * 8);
+        const int grid = std::min(ceil_div((long long)m.n_owned * bd, 256), B200_SMS * 8);
         if (v.prec == Prec::F64) permute_kernel<double><<<grid, 256, 0, s>>>(m.perm_old_to_new.ptr(), m.n_owned, bd, v.data.as<double>(), nv.as<double>(), 1);
         else permute_kernel<float><<<grid, 256, 0, s>>>(m.perm_old_to_new.ptr(), m.n_owned, bd, v.data.as<float>(), nv.as<float>(), 1);
         count_launch();
@@ -698,7 +698,7 @@ void dist_download_vector(const Vector &v, void *data)
     cudaStream_t s = v.rsc->stream;
     DevVec tmp;
     tmp.resize((size_t)m.n_owned * bd, v.prec);
-    const int grid = std::min(ceil_div((long long)m.n_owned * bd, 256), 148 * 8);
+    const int grid = std::min(ceil_div((long long)m.n_owned * bd, 256), B200_SMS * 8);
     if (v.prec == Prec::F64) permute_kernel<double><<<grid, 256, 0, s>>>(m.perm_old_to_new.ptr(), m.n_owned, bd, v.data.as<double>(), tmp.as<double>(), 0);
     else permute_kernel<float><<<grid, 256, 0, s>>>(m.perm_old_to_new.ptr(), m.n_owned, bd, v.data.as<float>(), tmp.as<float>(), 0);
     count_launch();

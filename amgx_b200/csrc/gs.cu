@@ -93,7 +93,7 @@ protected:
     template <class MatT, class VecT, int NPR> void launch_color(DevVec &b, DevVec &x, int off, int cnt)
     {
         Matrix &A = *A_;
-        const int grid = std::min(148 * 8, ceil_div(cnt, 256 / NPR));
+        const int grid = std::min(B200_SMS * 8, ceil_div(cnt, 256 / NPR));
         gs_color_sweep<MatT, VecT, NPR><<<grid, 256, 0, stream()>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.diag_idx.ptr(), A.values.as<MatT>(), b.as<VecT>(),
                                                                    x.as<VecT>(), (VecT)weight_, A.sorted_rows_by_color.ptr() + off, cnt);
         count_launch();

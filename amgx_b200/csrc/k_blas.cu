@@ -130,7 +130,7 @@ template <bool IS_MAX, class F> void launch_reduce(size_t n, F f, const ReduceCt
 
 }  // namespace
 
-int blas_max_grid() { return 148 * 8; }
+int blas_max_grid() { return B200_SMS * 8; }
 
 void vec_fill(void *x, Prec p, size_t n, double v, cudaStream_t s)
 {

@@ -433,7 +433,7 @@ void block_jacobi_setup(const Matrix &A, DevVec &dinv, cudaStream_t s)
 void block_jacobi_zero(const Matrix &A, const DevVec &dinv, const DevVec &b, void *x, double omega, cudaStream_t s)
 {
     if (A.n == 0) return;
-    const int grid = std::max(1, std::min(ceil_div(A.n, 64), 148 * 8));
+    const int grid = std::max(1, std::min(ceil_div(A.n, 64), B200_SMS * 8));
     AMGXB_DISPATCH(A.mat_prec, A.vec_prec, { block4_jacobi_zero<MatT, VecT><<<grid, 256, 0, s>>>(A.n, dinv.as<MatT>(), b.as<VecT>(), (VecT *)x, omega); });
     count_launch();
     AMGXB_LAUNCH_CHECK();

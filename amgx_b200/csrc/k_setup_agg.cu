@@ -176,7 +176,7 @@ __global__ void offsets_from_sorted_kernel(int n, const int *__restrict__ keys, 
     }
 }
 
-inline int grid_for(long long n) { return std::max(1, std::min(ceil_div(n, 256), 148 * 16)); }
+inline int grid_for(long long n) { return std::max(1, std::min(ceil_div(n, 256), B200_SMS * 16)); }
 
 template <class T> T read_scalar(const T *dptr, cudaStream_t s)
 {

@@ -630,7 +630,7 @@ static void build_value_codes(Matrix &A, cudaStream_t s)
     EncSeg seg[2];
     const int nseg = enc_segments(A, seg);
     for (int g = 0; g < nseg; g++) {
-        const int grid = std::max(1, std::min(seg[g].tiles, 148 * 8));
+        const int grid = std::max(1, std::min(seg[g].tiles, B200_SMS * 8));
         if (A.mat_prec == Prec::F64) {
             if (T == 256) valenc_build_kernel<double, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.values.as<double>(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.vcodes.ptr(), (double *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
             else valenc_build_kernel<double, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.values.as<double>(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.vcodes.ptr(), (double *)E.vdict.ptr(), E.meta.ptr(), stats.ptr());
@@ -667,7 +667,7 @@ static void build_pair_codes(Matrix &A, cudaStream_t s)
     EncSeg seg[2];
     const int nseg = enc_segments(A, seg);
     for (int g = 0; g < nseg; g++) {
-        const int grid = std::max(1, std::min(seg[g].tiles, 148 * 8));
+        const int grid = std::max(1, std::min(seg[g].tiles, B200_SMS * 8));
         if (A.mat_prec == Prec::F64) {
             if (T == 256) pairenc_build_kernel<double, 256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.vcodes.ptr(), E.dict.ptr(), (const double *)E.vdict.ptr(), E.meta.ptr(), E.pcodes.ptr(), (EncPair<double> *)E.pdict.ptr(), E.pmeta.ptr(), stats.ptr());
             else pairenc_build_kernel<double, 128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.vcodes.ptr(), E.dict.ptr(), (const double *)E.vdict.ptr(), E.meta.ptr(), E.pcodes.ptr(), (EncPair<double> *)E.pdict.ptr(), E.pmeta.ptr(), stats.ptr());
@@ -753,7 +753,7 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
         stats.resize(8);
         stats.zero(s);
         for (int g = 0; g < nseg; g++) {
-            const int grid = std::max(1, std::min(seg[g].tiles, 148 * 8));
+            const int grid = std::max(1, std::min(seg[g].tiles, B200_SMS * 8));
             if (T == 256) colenc_build_kernel<256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
             else colenc_build_kernel<128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.codes.ptr(), E.dict.ptr(), E.meta.ptr(), stats.ptr());
             count_launch();

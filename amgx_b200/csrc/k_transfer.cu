@@ -55,7 +55,7 @@ void agg_prolong_set(const int *aggregates, const void *e, void *x, Prec p, int 
 {
     if (n == 0) return;
     AMGXB_DISPATCH_VEC(p, {
-        int grid = std::min(ceil_div((long long)n * bsize, 256), 148 * 16);
+        int grid = std::min(ceil_div((long long)n * bsize, 256), B200_SMS * 16);
         prolong_set_kernel<VecT><<<grid, 256, 0, s>>>(aggregates, (const VecT *)e, (VecT *)x, n, bsize);
     });
     count_launch();
@@ -67,10 +67,10 @@ void agg_restrict(const int *Rp, const int *Rc, const void *r, void *rc, Prec p,
     if (n_agg == 0) return;
     AMGXB_DISPATCH_VEC(p, {
         if (bsize == 1) {
-            int grid = std::min(ceil_div(n_agg, 256), 148 * 16);
+            int grid = std::min(ceil_div(n_agg, 256), B200_SMS * 16);
             restrict_kernel<VecT><<<grid, 256, 0, s>>>(Rp, Rc, (const VecT *)r, (VecT *)rc, n_agg);
         } else {
-            int grid = std::min(ceil_div((long long)n_agg * bsize, 256), 148 * 16);
+            int grid = std::min(ceil_div((long long)n_agg * bsize, 256), B200_SMS * 16);
             restrict_block_kernel<VecT><<<grid, 256, 0, s>>>(Rp, Rc, (const VecT *)r, (VecT *)rc, n_agg, bsize);
         }
     });
@@ -82,7 +82,7 @@ void agg_prolong_add(const int *aggregates, const void *e, const void *x, void *
 {
     if (n == 0) return;
     AMGXB_DISPATCH_VEC(p, {
-        int grid = std::min(ceil_div((long long)n * bsize, 256), 148 * 16);
+        int grid = std::min(ceil_div((long long)n * bsize, 256), B200_SMS * 16);
         prolong_kernel<VecT><<<grid, 256, 0, s>>>(aggregates, (const VecT *)e, (const VecT *)x, (VecT *)xout, n, bsize);
     });
     count_launch();

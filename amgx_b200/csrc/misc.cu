@@ -68,7 +68,7 @@ void l1_row_norms(const Matrix &A, DevVec &d, cudaStream_t s)
 {
     d.resize((size_t)A.n, A.mat_prec);
     if (A.n == 0) return;
-    const int grid = std::min(ceil_div(A.n, 256), 148 * 16);
+    const int grid = std::min(ceil_div(A.n, 256), B200_SMS * 16);
     AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
         l1_kernel<MatT, VecT><<<grid, 256, 0, s>>>(A.n, A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<MatT>(), d.as<MatT>());
     });

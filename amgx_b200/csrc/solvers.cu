@@ -92,7 +92,7 @@ void ScalarBlock::destroy()
 
 void ReduceScratch::ensure(cudaStream_t s)
 {
-    const size_t need = 148 * 16 + 64;
+    const size_t need = B200_SMS * 16 + 64;
     if (partials.size() < need) {
         partials.resize(need);
         counter.resize(1);

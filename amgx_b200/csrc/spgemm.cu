@@ -134,7 +134,7 @@ template <int TABLE> void run_symbolic(int m, const int *rows, const int *arp, c
     const size_t smem = per_warp * wpb;
     auto k = spgemm_symbolic_kernel<TABLE>;
     AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<warps_grid(m, wpb, 148 * 16), wpb * 32, smem, s>>>(m, rows, arp, aci, brp, bci, row_nnz, fail_list, fail_count);
+    k<<<warps_grid(m, wpb, B200_SMS * 16), wpb * 32, smem, s>>>(m, rows, arp, aci, brp, bci, row_nnz, fail_list, fail_count);
     count_launch();
     AMGXB_LAUNCH_CHECK();
 }
@@ -148,7 +148,7 @@ template <class T, int TABLE> void run_numeric(int m, const int *arp, const int 
     const size_t smem = per_warp * wpb;
     auto k = spgemm_numeric_kernel<T, TABLE>;
     AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<warps_grid(m, wpb, 148 * 16), wpb * 32, smem, s>>>(m, arp, aci, ava, brp, bci, bva, crp, cci, cva, lo, LIMIT);
+    k<<<warps_grid(m, wpb, B200_SMS * 16), wpb * 32, smem, s>>>(m, arp, aci, ava, brp, bci, bva, crp, cci, cva, lo, LIMIT);
     count_launch();
     AMGXB_LAUNCH_CHECK();
 }
