@@ -298,6 +298,130 @@ __global__ void __launch_bounds__(TILE_ROWS) pairenc_build_kernel(const int *__r
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row patterns (r02): on a stencil level most rows of a tile are the SAME sequence of (offset, value) pairs -- all interior rows of a
+// 7-point tile are one pattern.  A pair-coded tile whose rows have <= 7 entries and take <= 64 distinct sequences of pair codes moves
+// ONE byte per ROW: the row's pattern id into a per-tile table of patterns (7 pair-code bytes + length).  The consumer loads its pattern
+// with one 16-byte look-up and peels the pair codes out of a register -- no per-entry code loads, no row_ptr slice.  HBM per row:
+// 1 byte + the vectors.  Built after the pair tables (rowpat_build_kernel); value changes rebuild pairs and patterns.
+// ---------------------------------------------------------------------------------------------
+constexpr int RP_SLOTS = 64;             // patterns per tile
+constexpr int RP_MAX_LEN = 7;            // entries per row: 7 code bytes + the length in the top byte of the 64-bit pattern key
+struct __align__(16) RowPattern { unsigned long long codes; int len; int pad; };
+
+template <int TILE_ROWS>
+__global__ void __launch_bounds__(TILE_ROWS) rowpat_build_kernel(const int *__restrict__ rp, int row0, int n, int num_tiles, int tile_base, const unsigned char *__restrict__ pcodes,
+                                                                 const int *__restrict__ pmeta, unsigned char *rowcodes, RowPattern *rpat, int *rmeta, int *stats)
+{
+    constexpr int HS = 256;
+    constexpr unsigned long long EMPTY = ~0ull;
+    __shared__ unsigned long long hkey[HS];           // open addressing; a key is its own length tag (top byte), so one 64-bit CAS claims or matches a slot
+    __shared__ unsigned long long lkey[RP_SLOTS];
+    __shared__ int srank[RP_SLOTS];
+    __shared__ int s_count, s_bad;
+    const int tid = threadIdx.x;
+    for (int ltile = blockIdx.x; ltile < num_tiles; ltile += gridDim.x) {
+        const int tile = tile_base + ltile;
+        const int r0 = row0 + ltile * TILE_ROWS, r1 = min(r0 + TILE_ROWS, n);
+        if (pmeta[tile] <= 0) {
+            if (tid == 0) rmeta[tile] = 0;
+            continue;
+        }
+        const int nz0 = rp[r0], sa = nz0 & ~3;
+        const unsigned char *pseg = pcodes + vcode_offset(sa, tile);
+        for (int i = tid; i < HS; i += TILE_ROWS) hkey[i] = EMPTY;
+        if (tid == 0) { s_count = 0; s_bad = 0; }
+        __syncthreads();
+        const int row = r0 + tid;
+        unsigned long long key = 0ull;                 // rows past the end of the segment: the empty pattern
+        if (row < r1) {
+            const int k0 = rp[row], len = rp[row + 1] - k0;
+            if (len > RP_MAX_LEN) s_bad = 1;
+            else {
+                for (int j = 0; j < len; j++) key |= (unsigned long long)pseg[k0 + j - sa] << (8 * j);
+                key |= (unsigned long long)len << 56;
+            }
+        }
+        __syncthreads();
+        if (!s_bad) {
+            unsigned h = (unsigned)(((key ^ (key >> 29)) * 0xff51afd7ed558ccdull) >> 56) & (HS - 1);
+            for (int probe = 0; probe < HS; probe++) {
+                const unsigned long long old = atomicCAS(&hkey[h], EMPTY, key);
+                if (old == EMPTY) { if (atomicAdd(&s_count, 1) >= RP_SLOTS) s_bad = 1; break; }
+                if (old == key) break;
+                h = (h + 1) & (HS - 1);
+            }
+        }
+        __syncthreads();
+        const int count = s_count;
+        const bool ok = !s_bad && count <= RP_SLOTS;
+        __syncthreads();
+        if (ok) {
+            // compact + rank (ascending key, i.e. by length then codes: the table, hence the row codes, do not depend on insertion order)
+            if (tid == 0) s_count = 0;
+            __syncthreads();
+            for (int i = tid; i < HS; i += TILE_ROWS)
+                if (hkey[i] != EMPTY) lkey[atomicAdd(&s_count, 1)] = hkey[i];
+            __syncthreads();
+            for (int i = tid; i < count; i += TILE_ROWS) {
+                int rank = 0;
+                for (int j = 0; j < count; j++) rank += lkey[j] < lkey[i];
+                srank[i] = rank;
+                RowPattern pt;
+                pt.codes = lkey[i];
+                pt.len = (int)(lkey[i] >> 56);
+                pt.pad = 0;
+                rpat[(size_t)tile * RP_SLOTS + rank] = pt;
+            }
+            __syncthreads();
+            int code = 0;
+            for (int i = 0; i < count; i++)
+                if (lkey[i] == key) { code = srank[i]; break; }
+            rowcodes[(size_t)tile * TILE_ROWS + tid] = (unsigned char)code;
+            if (tid == 0) { rmeta[tile] = count; atomicAdd(stats + 0, 1); atomicMax(stats + 1, count); }
+        } else if (tid == 0) rmeta[tile] = 0;
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void ld_pair(const EncPair<double> *p, int &off, double &val);
+__device__ __forceinline__ void ld_pair(const EncPair<float> *p, int &off, float &val);
+
+// one row of a row-pattern tile: the pair codes come out of a register
+template <class MatT, class VecT, int N>
+__device__ __forceinline__ VecT row_pat_fixed(const unsigned long long codes, const EncPair<MatT> *__restrict__ pdict, const VecT *__restrict__ x, const int row)
+{
+    int off[N];
+    MatT val[N];
+    VecT xv[N];
+    VecT sum = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) ld_pair(pdict + (unsigned)((codes >> (8 * j)) & 0xffull), off[j], val[j]);
+#pragma unroll
+    for (int j = 0; j < N; j++) xv[j] = __ldg(x + (row + off[j]));
+#pragma unroll
+    for (int j = 0; j < N; j++) sum = fma((VecT)val[j], xv[j], sum);
+    return sum;
+}
+template <class MatT, class VecT>
+__device__ __forceinline__ VecT row_dot_pattern(const RowPattern *__restrict__ rpat, const unsigned char code, const EncPair<MatT> *__restrict__ pdict, const int row,
+                                                const VecT *__restrict__ x)
+{
+    const uint4 v = *reinterpret_cast<const uint4 *>(rpat + code);
+    const unsigned long long codes = ((unsigned long long)v.y << 32) | v.x;
+    switch ((int)v.z) {
+    case 7: return row_pat_fixed<MatT, VecT, 7>(codes, pdict, x, row);
+    case 6: return row_pat_fixed<MatT, VecT, 6>(codes, pdict, x, row);
+    case 5: return row_pat_fixed<MatT, VecT, 5>(codes, pdict, x, row);
+    case 4: return row_pat_fixed<MatT, VecT, 4>(codes, pdict, x, row);
+    case 3: return row_pat_fixed<MatT, VecT, 3>(codes, pdict, x, row);
+    case 2: return row_pat_fixed<MatT, VecT, 2>(codes, pdict, x, row);
+    case 1: return row_pat_fixed<MatT, VecT, 1>(codes, pdict, x, row);
+    default: return (VecT)0;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The encoded tile kernel.  blockDim.x = TILE_ROWS + 32 (last warp = producer).
 // Stage layout, sized PER LEVEL from what its tiles actually use (a level whose tiles are all coded stages 2 bytes per entry, so
@@ -315,6 +439,9 @@ struct EncArgs {
     const unsigned char *pcodes;   // pair codes (1 byte per entry) and pair tables of the tiles with pmeta[tile] > 0
     const void *pdict;
     const int *pmeta;
+    const unsigned char *rowcodes; // row-pattern ids (1 byte per row) and pattern tables of the tiles with rmeta[tile] > 0
+    const RowPattern *rpat;
+    const int *rmeta;
     int val_w, col_w, dict_cap, vdict_cap;   // vdict_cap counts BYTES of the value / pair dictionary region
     int tile_base;      // global index of the segment's first tile (meta / dictionaries / code segments are numbered over all segments)
 };
@@ -414,6 +541,37 @@ __device__ __forceinline__ VecT row_dot_pair(const unsigned char *__restrict__ c
     return sum;
 }
 
+// what a consumer does with its row's dot product (identical to csr_tile_kernel); returns the row's contribution to the fused reduction
+template <class MatT, class VecT, int EPI>
+__device__ __forceinline__ double tile_epilogue(const TileArgs<MatT, VecT> &a, const int row, const VecT sum, const VecT bi, const MatT di, const VecT xi)
+{
+    if (EPI == EPI_SPMV) {
+        a.y[row] = sum;
+        return 0.0;
+    } else if (EPI == EPI_SPMV_DOT) {
+        a.y[row] = sum;
+        return (double)sum * (double)xi;
+    } else if (EPI == EPI_RESID) {
+        a.y[row] = bi - sum;
+        return 0.0;
+    } else if (EPI == EPI_ADD) {
+        a.y[row] = bi + sum;
+        return 0.0;
+    } else if (EPI == EPI_RESID_NRM2) {
+        const VecT r = bi - sum;
+        a.y[row] = r;
+        return (double)r * (double)r;
+    } else {
+        // x + ((b - Ax) * w) * (1/d): d = 1/d; b -= y; b *= w; b*d + x  (one FMA)
+        MatT dinv = (MatT)1 / guard_diag<MatT>(di);
+        VecT t = bi - sum;
+        t = (VecT)(t * a.omega);
+        const VecT out = fma(t, (VecT)dinv, xi);
+        a.y[row] = out;
+        return (EPI == EPI_JACOBI_DOT) ? (double)bi * (double)out : 0.0;
+    }
+}
+
 template <class MatT, class VecT, int TILE_ROWS, int EPI>
 __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 256 ? 5 : 9)) csr_tile_enc_kernel(const TileArgs<MatT, VecT> a, const EncArgs e)
 {
@@ -464,7 +622,17 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 25
                 unsigned char *st = stage_base + (size_t)s * stage_bytes;
                 const unsigned rp_copy = (unsigned)(((r1 - r0 + 1 + 3) & ~3) * sizeof(int));
                 const unsigned cnt = (unsigned)(ea - sa);
-                *reinterpret_cast<int4 *>(st + hdr_off) = make_int4(enc, venc, pdlen, 0);       // released to the consumers by the arrive below
+                const int rplen = pdlen > 0 ? __ldg(e.rmeta + gtile) : 0;
+                *reinterpret_cast<int4 *>(st + hdr_off) = make_int4(enc, venc, pdlen, rplen);   // released to the consumers by the arrive below
+                if (rplen > 0) {      // row-pattern tile: one byte per ROW into the column stream, patterns into the dictionary region, pairs beside them
+                    const unsigned rc_copy = (unsigned)TILE_ROWS, rp2_copy = (unsigned)rplen * (unsigned)sizeof(RowPattern),
+                                   pd_copy = (unsigned)align16((size_t)pdlen * sizeof(EncPair<MatT>));
+                    mbar_expect_tx(&full[s], rc_copy + rp2_copy + pd_copy);
+                    tma_bulk_g2s(st + vals_bytes, e.rowcodes + (size_t)gtile * TILE_ROWS, rc_copy, &full[s]);
+                    tma_bulk_g2s(st + vals_bytes + cols_bytes, e.rpat + (size_t)gtile * RP_SLOTS, rp2_copy, &full[s]);
+                    tma_bulk_g2s(st + vals_bytes + cols_bytes + dict_bytes, reinterpret_cast<const EncPair<MatT> *>(e.pdict) + (size_t)gtile * DICT_SLOTS, pd_copy, &full[s]);
+                    continue;
+                }
                 if (pdlen > 0) {      // pair-coded tile: code bytes into the column stream, the pair table into the value-dictionary region
                     const unsigned pc_copy = (unsigned)align16(cnt), pd_copy = (unsigned)align16((size_t)pdlen * sizeof(EncPair<MatT>));
                     mbar_expect_tx(&full[s], rp_copy + pc_copy + pd_copy);
@@ -520,6 +688,13 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 25
             mbar_wait(&full[s], ph);
             const int4 hdr = *reinterpret_cast<const int4 *>(st + hdr_off);      // the tile's encoding, uniform over the CTA
             const int enc = hdr.x, venc = hdr.y, pd = hdr.z;
+            if (hdr.w > 0) {
+                // row-pattern tile: no row_ptr slice, no per-entry codes
+                if (active) {
+                    const VecT sum = row_dot_pattern<MatT, VecT>(reinterpret_cast<const RowPattern *>(dict), cstream[lrow], reinterpret_cast<const EncPair<MatT> *>(vdict), row, a.x);
+                    acc += tile_epilogue<MatT, VecT, EPI>(a, row, sum, bi, di, xi);
+                }
+            } else
             if (active) {
                 const int sa = rp[0] & ~3;
                 const int k = rp[lrow] - sa, kend = rp[lrow + 1] - sa;
@@ -534,28 +709,7 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 25
                 case 1: sum = row_dot_enc<MatT, VecT, 0, 1>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
                 default: sum = row_dot_enc<MatT, VecT, 0, 0>(vstream, cstream, dict, vdict, k, kend, row, a.x); break;
                 }
-                // ---- epilogue (identical to csr_tile_kernel) ----
-                if (EPI == EPI_SPMV) {
-                    a.y[row] = sum;
-                } else if (EPI == EPI_SPMV_DOT) {
-                    a.y[row] = sum;
-                    acc += (double)sum * (double)xi;
-                } else if (EPI == EPI_RESID) {
-                    a.y[row] = bi - sum;
-                } else if (EPI == EPI_ADD) {
-                    a.y[row] = bi + sum;
-                } else if (EPI == EPI_RESID_NRM2) {
-                    const VecT r = bi - sum;
-                    a.y[row] = r;
-                    acc += (double)r * (double)r;
-                } else {
-                    MatT dinv = (MatT)1 / guard_diag<MatT>(di);
-                    VecT t = bi - sum;
-                    t = (VecT)(t * a.omega);
-                    const VecT out = fma(t, (VecT)dinv, xi);
-                    a.y[row] = out;
-                    if (EPI == EPI_JACOBI_DOT) acc += (double)bi * (double)out;
-                }
+                acc += tile_epilogue<MatT, VecT, EPI>(a, row, sum, bi, di, xi);
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[s]);
@@ -683,6 +837,37 @@ static void build_pair_codes(Matrix &A, cudaStream_t s)
     E.max_pdlen = h[7];
 }
 
+// row patterns of the pair-coded tiles (rowpat_build_kernel); off with AMGXB_ENC_ROWPAT=0
+static void build_row_patterns(Matrix &A, cudaStream_t s)
+{
+    ColEnc &E = A.colenc;
+    const int T = A.plan.tile_rows, nt = E.num_tiles;
+    static const int on = getenv("AMGXB_ENC_ROWPAT") ? atoi(getenv("AMGXB_ENC_ROWPAT")) : 1;
+    E.tiles_rowpat = 0;
+    E.max_rplen = 0;
+    E.rmeta.resize((size_t)std::max(nt, 1));
+    E.rmeta.zero(s);
+    // the T row codes travel in the tile's column-stream region: it must hold them (cap * col_w >= cap >= T)
+    if (!on || E.tiles_pair == 0 || A.plan.max_tile_nnz < T) { if (E.rowcodes.size() == 0) { E.rowcodes.resize(64); E.rpat.resize(64); } return; }
+    E.rowcodes.resize((size_t)nt * T + 64);
+    E.rpat.resize((size_t)nt * RP_SLOTS * sizeof(RowPattern));
+    DevBuf<int> stats;
+    stats.resize(8);
+    stats.zero(s);
+    EncSeg seg[2];
+    const int nseg = enc_segments(A, seg);
+    for (int g = 0; g < nseg; g++) {
+        const int grid = std::max(1, std::min(seg[g].tiles, B200_SMS * 8));
+        if (T == 256) rowpat_build_kernel<256><<<grid, 256, 0, s>>>(A.row_ptr.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.pcodes.ptr(), E.pmeta.ptr(), E.rowcodes.ptr(), (RowPattern *)E.rpat.ptr(), E.rmeta.ptr(), stats.ptr());
+        else rowpat_build_kernel<128><<<grid, 128, 0, s>>>(A.row_ptr.ptr(), seg[g].row0, seg[g].row1, seg[g].tiles, seg[g].base, E.pcodes.ptr(), E.pmeta.ptr(), E.rowcodes.ptr(), (RowPattern *)E.rpat.ptr(), E.rmeta.ptr(), stats.ptr());
+        count_launch();
+    }
+    AMGXB_LAUNCH_CHECK();
+    const std::vector<int> h = stats.to_host(s);
+    E.tiles_rowpat = h[0];
+    E.max_rplen = h[1];
+}
+
 // Stage layout and occupancy of the encoded kernel for this level, from what its tiles use (see the kernel's header comment).
 static void finalize_layout(Matrix &A, cudaStream_t s)
 {
@@ -704,7 +889,7 @@ static void finalize_layout(Matrix &A, cudaStream_t s)
     }
     E.col_w = raw_c > 0 ? 4 : (off16 > 0 ? 2 : 1);
     E.val_w = val_raw > 0 ? (int)msz : (val8 > 0 ? 1 : 0);
-    E.dict_cap = std::max(E.max_dlen, E.tiles_off16 > 0 ? 4 : 0);
+    E.dict_cap = std::max(std::max(E.max_dlen, E.tiles_off16 > 0 ? 4 : 0), E.max_rplen * (int)(sizeof(RowPattern) / 4));      // ints; the region also holds a tile's row patterns
     E.vdict_cap = (int)std::max((size_t)E.max_vdlen * msz, (size_t)E.max_pdlen * (msz == 8 ? 16 : 8));      // bytes
     const size_t cap = (size_t)A.plan.max_tile_nnz;
     const size_t stage = align16(cap * E.val_w) + align16(cap * E.col_w) + (size_t)E.dict_cap * 4 + align16((size_t)E.vdict_cap) + (size_t)(T + 4) * 4 + 16;
@@ -780,10 +965,11 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
         E.vdict.resize(64);
     }
     build_pair_codes(A, s);
+    build_row_patterns(A, s);
     finalize_layout(A, s);
     if (getenv("AMGXB_COLENC_VERBOSE"))
-        fprintf(stderr, "[amgx_b200] colenc level %d: %d tiles of %d rows: columns dict8 %d, off16 %d, raw %d; values dict8 %d; pair-coded %d | stage widths col %d val %d B, dict %d / %d B, "
-                        "%d stages, %zu B smem, %d CTAs/SM%s\n", A.level, nt, T, E.tiles_dict8, E.tiles_off16, E.tiles_raw, E.tiles_val8, E.tiles_pair, E.col_w, E.val_w, E.dict_cap,
+        fprintf(stderr, "[amgx_b200] colenc level %d: %d tiles of %d rows: columns dict8 %d, off16 %d, raw %d; values dict8 %d; pair-coded %d, row patterns %d | stage widths col %d val %d B, dict %d / %d B, "
+                        "%d stages, %zu B smem, %d CTAs/SM%s\n", A.level, nt, T, E.tiles_dict8, E.tiles_off16, E.tiles_raw, E.tiles_val8, E.tiles_pair, E.tiles_rowpat, E.col_w, E.val_w, E.dict_cap,
                 E.vdict_cap, E.stages, E.smem_bytes, E.ctas_per_sm, E.on ? "" : " (off)");
 }
 
@@ -796,6 +982,7 @@ void csr_values_changed(Matrix &A, cudaStream_t s)
     // the column half of the per-tile descriptors stays, the value half is rewritten by the build kernel
     build_value_codes(A, s);
     build_pair_codes(A, s);
+    build_row_patterns(A, s);
     finalize_layout(A, s);
     (void)nt;
 }
@@ -818,6 +1005,9 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
     ea.pcodes = A.colenc.pcodes.ptr();
     ea.pdict = A.colenc.pdict.ptr();
     ea.pmeta = A.colenc.pmeta.ptr();
+    ea.rowcodes = A.colenc.rowcodes.ptr();
+    ea.rpat = (const RowPattern *)A.colenc.rpat.ptr();
+    ea.rmeta = A.colenc.rmeta.ptr();
     ea.val_w = A.colenc.val_w;
     ea.col_w = A.colenc.col_w;
     ea.dict_cap = A.colenc.dict_cap;

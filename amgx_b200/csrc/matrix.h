@@ -57,6 +57,10 @@ struct ColEnc {
     DevBuf<unsigned char> pdict;    // 256 pairs per tile
     DevBuf<int> pmeta;              // per tile: (padded) length of its pair table, 0 = not pair-coded
     int tiles_pair = 0, max_pdlen = 0;
+    DevBuf<unsigned char> rowcodes; // row-pattern ids: one byte per row (tiles with rmeta > 0)
+    DevBuf<unsigned char> rpat;     // 64 patterns of 16 bytes per tile (7 pair codes + length)
+    DevBuf<int> rmeta;              // per tile: number of row patterns, 0 = rows keep their per-entry pair codes
+    int tiles_rowpat = 0, max_rplen = 0;
     int col_w = 4, val_w = 8, dict_cap = 0, vdict_cap = 0;   // stage layout of the level (finalize_layout)
     int stages = 2, ctas_per_sm = 1;
     int num_tiles = 0;                             // tiles over all row segments ([0, split) then [split, n) on a row-partitioned matrix)
