@@ -145,6 +145,7 @@ def _declare(lib):
         "AMGXB200_solver_get_level_coloring": [vp, i, ip, vp],
         "AMGXB200_solver_get_last_solve_stats": [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
         "AMGXB200_bench_kernel": [vp, i, i, i, i, C.POINTER(C.c_double)],
+        "AMGXB200_matrix_get_kernel_plan": [vp] + [C.POINTER(C.c_int)] * 5,
         "AMGXB200_partition_plan_create": [C.POINTER(PartitionPlan), i, i, vp, i, i, vp, vp],
         "AMGXB200_config_check": [vp, i, C.c_char_p, i],
         "AMGXB200_partition_vector_to_contiguous": [i, i, vp, vp, vp],
@@ -329,6 +330,11 @@ class Matrix:
     def generate_poisson7(self, rhs: "Vector", sol: "Vector", nx, ny, nz, px=1, py=1, pz=1, rings=1):
         _ck(self.lib.AMGX_generate_distributed_poisson_7pt(self.h, rhs.h if rhs else None, sol.h if sol else None, 1, rings, nx, ny, nz, px, py, pz),
             "AMGX_generate_distributed_poisson_7pt")
+
+    def kernel_info(self) -> dict:
+        v = [C.c_int() for _ in range(5)]
+        _ck(self.lib.AMGXB200_matrix_get_kernel_plan(self.h, *[C.byref(t) for t in v]), "AMGXB200_matrix_get_kernel_plan")
+        return dict(zip(("tile_rows", "coded_tiles", "pair_tiles", "row_pattern_tiles", "window"), (t.value for t in v)))
 
     def bench_kernel(self, kind: int, warmup=3, reps=20, flush_l2=False) -> float:
         ms = C.c_double()

@@ -793,6 +793,21 @@ AMGX_RC AMGXB200_get_nccl_unique_id(char *id128)
     API2_END
 }
 
+// which scalar CSR kernel family the matrix was planned for (tests assert that the path they mean to cover is the one that runs)
+AMGX_RC AMGXB200_matrix_get_kernel_plan(AMGX_matrix_handle mtx, int *tile_rows, int *coded_tiles, int *pair_tiles, int *row_pattern_tiles, int *window)
+{
+    API2_BEGIN
+    MatrixH *m = chk<MatrixH>(mtx, MAGIC_MTX, "matrix");
+    const Matrix &A = *m->m;
+    if (!A.initialized) fatal(AMGX_RC_BAD_PARAMETERS, "matrix not uploaded");
+    if (tile_rows) *tile_rows = A.plan.use_tiles ? A.plan.tile_rows : 0;
+    if (coded_tiles) *coded_tiles = A.colenc.on ? A.colenc.tiles_dict8 + A.colenc.tiles_off16 : 0;
+    if (pair_tiles) *pair_tiles = A.colenc.on ? A.colenc.tiles_pair : 0;
+    if (row_pattern_tiles) *row_pattern_tiles = A.colenc.on ? A.colenc.tiles_rowpat : 0;
+    if (window) *window = A.win.on ? A.win.ring : 0;
+    API2_END
+}
+
 // kind: 0 SpMV, 1 fused Jacobi sweep, 2 SpMV+dot
 AMGX_RC AMGXB200_bench_kernel(AMGX_matrix_handle mtx, int kind, int warmup, int reps, int flush_l2, double *avg_ms)
 {

@@ -116,6 +116,11 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS) csr_tile_kernel(
                     tma_bulk_g2s(st, a.val + sa, cnt * (unsigned)sizeof(MatT), &full[s]);
                     tma_bulk_g2s(st + vals_bytes, a.col + sa, cnt * (unsigned)sizeof(int), &full[s]);
                 }
+                if (a.l2pf) {      // the consumers' per-row vector loads of this tile, `stages` tiles ahead of them (tile_common.cuh)
+                    if (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2 || EPI == EPI_JACOBI_L1 || EPI == EPI_ADD)
+                        l2_prefetch_span(a.b + r0, r1 - r0);
+                    if (EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_JACOBI_L1) l2_prefetch_span(a.d + r0, r1 - r0);
+                }
             }
         }
     } else {
@@ -405,6 +410,7 @@ void csr_build_plan(Matrix &A, cudaStream_t s)
     }
     A.plan = p;
     csr_build_colenc(A, s);     // no-op unless AMGXB_COLENC=1
+    csr_build_window(A, s);     // banded irregular levels only
 }
 
 void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int segment)
@@ -415,6 +421,7 @@ void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int
     const int row0 = (segment == 2) ? A.plan.split : 0;
     const int row1 = (segment == 1) ? A.plan.split : A.n;
     if (row1 <= row0) return;
+    if (A.win.on && csr_op_win(A, epi, g, s, segment)) return;
     if (A.colenc.on && csr_op_enc(A, epi, g, s, segment)) return;
     AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
         TileArgs<MatT, VecT> ta;
@@ -430,6 +437,7 @@ void csr_op(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int
         // (a split matrix applied as a whole has another tiling than its two segments: no map then)
         ta.perm = (A.plan.use_perm && !(A.plan.split > 0 && segment == 0)) ? A.tile_perm.ptr() : nullptr;
         ta.tile_base = (segment == 2) ? ceil_div(A.plan.split, std::max(1, A.plan.tile_rows)) : 0;
+        ta.l2pf = (l2_prefetch_flags() & 1) != 0;
         ta.x = (const VecT *)g.x;
         ta.agg = g.agg;
         ta.b = (const VecT *)g.b;

@@ -299,6 +299,21 @@ __global__ void __launch_bounds__(TILE_ROWS) pairenc_build_kernel(const int *__r
 }
 
 
+// x rows worth prefetching for a tile (see l2_prefetch_span): on a dictionary-coded tile the k-th neighbours of consecutive rows are
+// consecutive in x, and the neighbour at the largest offset is the first reader of its x rows -- a DRAM miss on the consumers' critical
+// path unless the producer asks for those rows ahead of time.  Tiles with other column codings (no such structure) get 0.
+__global__ void xahead_kernel(const int *__restrict__ meta, const int *__restrict__ dict, int num_tiles, int *__restrict__ xahead)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    int best = 0;
+    if (meta[META * t] == 1) {
+        const int dlen = meta[META * t + 1];
+        for (int i = 0; i < dlen; i++) best = max(best, dict[(size_t)t * DICT_SLOTS + i]);
+    }
+    xahead[t] = best;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Row patterns (r02): on a stencil level most rows of a tile are the SAME sequence of (offset, value) pairs -- all interior rows of a
 // 7-point tile are one pattern.  A pair-coded tile whose rows have <= 7 entries and take <= 64 distinct sequences of pair codes moves
@@ -442,8 +457,10 @@ struct EncArgs {
     const unsigned char *rowcodes; // row-pattern ids (1 byte per row) and pattern tables of the tiles with rmeta[tile] > 0
     const RowPattern *rpat;
     const int *rmeta;
+    const int *xahead;             // per tile: the largest column offset of a dictionary-coded (stencil-like) tile, 0 = none: x rows to prefetch into L2
     int val_w, col_w, dict_cap, vdict_cap;   // vdict_cap counts BYTES of the value / pair dictionary region
     int tile_base;      // global index of the segment's first tile (meta / dictionaries / code segments are numbered over all segments)
+    int x_len;          // entries of x a column may address (rows + halo)
 };
 
 // one row of an encoded tile (separate column / value codes): rows are dispatched on their exact length to straight-line code (N code loads,
@@ -541,37 +558,6 @@ __device__ __forceinline__ VecT row_dot_pair(const unsigned char *__restrict__ c
     return sum;
 }
 
-// what a consumer does with its row's dot product (identical to csr_tile_kernel); returns the row's contribution to the fused reduction
-template <class MatT, class VecT, int EPI>
-__device__ __forceinline__ double tile_epilogue(const TileArgs<MatT, VecT> &a, const int row, const VecT sum, const VecT bi, const MatT di, const VecT xi)
-{
-    if (EPI == EPI_SPMV) {
-        a.y[row] = sum;
-        return 0.0;
-    } else if (EPI == EPI_SPMV_DOT) {
-        a.y[row] = sum;
-        return (double)sum * (double)xi;
-    } else if (EPI == EPI_RESID) {
-        a.y[row] = bi - sum;
-        return 0.0;
-    } else if (EPI == EPI_ADD) {
-        a.y[row] = bi + sum;
-        return 0.0;
-    } else if (EPI == EPI_RESID_NRM2) {
-        const VecT r = bi - sum;
-        a.y[row] = r;
-        return (double)r * (double)r;
-    } else {
-        // x + ((b - Ax) * w) * (1/d): d = 1/d; b -= y; b *= w; b*d + x  (one FMA)
-        MatT dinv = (MatT)1 / guard_diag<MatT>(di);
-        VecT t = bi - sum;
-        t = (VecT)(t * a.omega);
-        const VecT out = fma(t, (VecT)dinv, xi);
-        a.y[row] = out;
-        return (EPI == EPI_JACOBI_DOT) ? (double)bi * (double)out : 0.0;
-    }
-}
-
 template <class MatT, class VecT, int TILE_ROWS, int EPI>
 __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 256 ? 5 : 9)) csr_tile_enc_kernel(const TileArgs<MatT, VecT> a, const EncArgs e)
 {
@@ -624,6 +610,13 @@ __global__ void __launch_bounds__(TILE_ROWS + PRODUCER_THREADS, (TILE_ROWS == 25
                 const unsigned cnt = (unsigned)(ea - sa);
                 const int rplen = pdlen > 0 ? __ldg(e.rmeta + gtile) : 0;
                 *reinterpret_cast<int4 *>(st + hdr_off) = make_int4(enc, venc, pdlen, rplen);   // released to the consumers by the arrive below
+                if (a.l2pf) {     // `stages` tiles ahead of the consumers: their per-row vector loads, and the x rows only this tile's furthest neighbour has reached
+                    if (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2 || EPI == EPI_JACOBI_L1 || EPI == EPI_ADD)
+                        l2_prefetch_span(a.b + r0, r1 - r0);
+                    if (EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_JACOBI_L1) l2_prefetch_span(a.d + r0, r1 - r0);
+                    const int ahead = __ldg(e.xahead + gtile);
+                    if (ahead > 0) l2_prefetch_span(a.x + (size_t)r0 + ahead, min(r1 - r0, e.x_len - r0 - ahead));
+                }
                 if (rplen > 0) {      // row-pattern tile: one byte per ROW into the column stream, patterns into the dictionary region, pairs beside them
                     const unsigned rc_copy = (unsigned)TILE_ROWS, rp2_copy = (unsigned)rplen * (unsigned)sizeof(RowPattern),
                                    pd_copy = (unsigned)align16((size_t)pdlen * sizeof(EncPair<MatT>));
@@ -964,6 +957,12 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
         E.vcodes.resize(64);
         E.vdict.resize(64);
     }
+    E.xahead.resize((size_t)std::max(nt, 1));
+    if (colenc_flags() & 1) {
+        xahead_kernel<<<ceil_div(nt, 256), 256, 0, s>>>(E.meta.ptr(), E.dict.ptr(), nt, E.xahead.ptr());
+        count_launch();
+        AMGXB_LAUNCH_CHECK();
+    } else E.xahead.zero(s);
     build_pair_codes(A, s);
     build_row_patterns(A, s);
     finalize_layout(A, s);
@@ -977,6 +976,7 @@ void csr_build_colenc(Matrix &A, cudaStream_t s)
 void csr_values_changed(Matrix &A, cudaStream_t s)
 {
     ColEnc &E = A.colenc;
+    csr_window_values_changed(A, s);
     if (!E.values_encoded) return;
     const int nt = A.plan.num_tiles;
     // the column half of the per-tile descriptors stays, the value half is rewritten by the build kernel
@@ -997,6 +997,7 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
     const EncSeg &sg = seg[segment == 2 ? 1 : 0];
     EncArgs ea;
     ea.tile_base = sg.base;
+    ea.x_len = A.n;
     ea.codes = A.colenc.codes.ptr();
     ea.dict = A.colenc.dict.ptr();
     ea.meta = A.colenc.meta.ptr();
@@ -1008,6 +1009,7 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
     ea.rowcodes = A.colenc.rowcodes.ptr();
     ea.rpat = (const RowPattern *)A.colenc.rpat.ptr();
     ea.rmeta = A.colenc.rmeta.ptr();
+    ea.xahead = A.colenc.xahead.ptr();
     ea.val_w = A.colenc.val_w;
     ea.col_w = A.colenc.col_w;
     ea.dict_cap = A.colenc.dict_cap;
@@ -1025,6 +1027,7 @@ bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
         ta.unroll = 8;
         ta.perm = A.plan.use_perm ? A.tile_perm.ptr() : nullptr;
         ta.tile_base = sg.base;
+        ta.l2pf = (l2_prefetch_flags() & 2) != 0;
         ta.x = (const VecT *)g.x;
         ta.agg = nullptr;
         ta.b = (const VecT *)g.b;

@@ -1,0 +1,432 @@
+// k_spmv_win.cu -- the CSR tile kernel for BANDED irregular matrices (SuiteSparse-shaped: random columns within a few thousand rows of
+// the diagonal): a sliding window of x lives in shared memory.
+//
+// Why: on such a matrix every entry gathers 8 bytes of x from a different 32-byte sector.  The matrix streams through TMA at 10-12 B per
+// entry, but the gathers pull 32 B per entry through L2 -> L1 (r02: 0.27 ms per SpMV on the 4 M-row matrix = 0.45 of the copy peak by the
+// 12 B/entry count, with DRAM far from saturated).  The columns of a row tile, however, fall into [r0 - W, r0 + T + W) for a W of a few
+// sigma -- and that window moves by only T rows from one tile to the next.  So:
+//   * a CTA owns a CONTIGUOUS range of tiles (one CTA per SM) and keeps x[r0 - W, r0 + S*T + W) in a ring buffer in shared memory
+//     (index = column & (R - 1)); advancing one tile costs ONE 2 KB bulk copy of the T new entries -- x is read from L2 / DRAM once per CTA
+//     range instead of once per entry;
+//   * the columns travel as 16-bit (column - row) offsets (2 B per entry; an offset that does not fit, or a column outside the window,
+//     falls back to the 32-bit column / a global gather of x -- the window is a cache, never a restriction);
+//   * values and offsets are stored a second time in SLICED-ELL order (per 256-row tile the rows sorted by length, 32-row slices stored
+//     entry-major, SELL-32-256): a thread still owns one row and sums it left to right with FMA -- the same bits as every other CSR kernel
+//     here -- but the 32 lanes of a warp now read 32 consecutive shared-memory words per step.  First version (CSR order in shared
+//     memory, lanes one row length apart): 27 shared-memory wavefronts per warp step, l1tex LSU pipe 70 % busy, 0.271 ms (ncu r02);
+//   * the consumers read values, offsets and x from shared memory only.
+// Ring safety: the producer runs at most S tiles ahead, tile p's chunk x[r_p + W, r_p + T + W) overwrites the slots of
+// x[r_p + W - R, ...), which the oldest tile still being consumed (p - S + 1) no longer addresses iff S*T + 2W <= R.
+// Chosen per level at plan time from the matrix's own offset statistics (csr_build_window); AMGXB_WINDOW=0 disables it.
+#include "kernels.h"
+#include <map>
+
+namespace amgxb {
+namespace {
+
+#include "tile_common.cuh"
+
+constexpr int WIN_T = 256;
+constexpr short WIN_FAR = -32768;        // "read the 32-bit column": the offset does not fit 16 bits
+
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+struct WinArgs {
+    const void *sv;             // values in sliced-ELL order (MatT)
+    const short *so;            // column - row in the same order (WIN_FAR: read the 32-bit column of the CSR copy)
+    const unsigned char *perm;  // sorted position -> local row of every tile
+    const long long *tbase;     // first entry of every tile in sv / so (num_tiles + 1)
+    const int *sbase;           // first entry of every 32-row slice, relative to its tile
+    int ring;                   // R: entries of the ring buffer, a power of two and a multiple of WIN_T
+    int w;                      // W: half-width of the window, a multiple of WIN_T
+    int x_len;                  // entries of x that may be staged (whole 16-byte units of the owned rows)
+    int tiles_per_cta;
+};
+
+// plan 1: how many entries two candidate windows would hold
+__global__ void win_stats_kernel(const int *__restrict__ rp, const int *__restrict__ ci, int n, int w1, int w2, unsigned long long *stats)
+{
+    unsigned long long in1 = 0, in2 = 0;
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+        const int k1 = rp[row + 1];
+        for (int k = rp[row]; k < k1; k++) {
+            const int d = ci[k] - row;
+            const int ad = d < 0 ? -d : d;
+            in1 += ad <= w1;
+            in2 += ad <= w2;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        in1 += __shfl_xor_sync(0xffffffffu, in1, o);
+        in2 += __shfl_xor_sync(0xffffffffu, in2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(stats + 0, in1);
+        atomicAdd(stats + 1, in2);
+    }
+}
+
+// plan 2: per tile, the rows sorted by length (descending, ties by index) -> sorted position p is handled by thread p; the 32 rows of a
+// slice (= a consumer warp) then have nearly equal lengths, and a slice is stored entry-major: entry j of lane l at slice + 32 j + l.
+// A slice is as long as its first row; the few positions past a shorter row's end are padding that is never read.
+__global__ void __launch_bounds__(WIN_T) sell_plan_kernel(const int *__restrict__ rp, int n, int num_tiles, unsigned char *perm, int *sbase, int *tlen)
+{
+    __shared__ int len[WIN_T];
+    __shared__ int slen[WIN_T / 32];
+    const int tid = threadIdx.x;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int row = t * WIN_T + tid;
+        const int mine = row < n ? rp[row + 1] - rp[row] : -1;       // rows past the end sort last
+        len[tid] = mine;
+        __syncthreads();
+        int rank = 0;
+        for (int j = 0; j < WIN_T; j++) rank += (len[j] > mine) || (len[j] == mine && j < tid);
+        perm[(size_t)t * WIN_T + rank] = (unsigned char)tid;
+        if ((rank & 31) == 0) slen[rank >> 5] = max(mine, 0);
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int sl = 0; sl < WIN_T / 32; sl++) { sbase[(size_t)t * (WIN_T / 32) + sl] = run; run += 32 * slen[sl]; }
+            tlen[t] = run;
+        }
+        __syncthreads();
+    }
+}
+
+// plan 3 (and after every in-place change of the values, so == nullptr): CSR -> sliced-ELL copy
+template <class MatT>
+__global__ void __launch_bounds__(WIN_T) sell_fill_kernel(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ val, int n, int num_tiles,
+                                                          const unsigned char *__restrict__ perm, const long long *__restrict__ tbase, const int *__restrict__ sbase, MatT *sv, short *so)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int row = t * WIN_T + (int)perm[(size_t)t * WIN_T + tid];
+        const int k0 = row < n ? rp[row] : 0, len = row < n ? rp[row + 1] - k0 : 0;
+        const int L = __shfl_sync(0xffffffffu, len, 0);
+        const long long base = tbase[t] + sbase[(size_t)t * (WIN_T / 32) + warp] + lane;
+        for (int j = 0; j < L; j++) {
+            const long long dst = base + (long long)j * 32;
+            if (j < len) {
+                sv[dst] = val[k0 + j];
+                if (so) {
+                    const int d = ci[k0 + j] - row;
+                    so[dst] = (d > -32768 && d < 32768) ? (short)d : WIN_FAR;
+                }
+            } else {
+                sv[dst] = (MatT)0;
+                if (so) so[dst] = 0;
+            }
+        }
+    }
+}
+
+// up to N entries of one row, `rem` of them present: offsets -> columns, x from the ring (outside the window: from global memory), FMAs in
+// storage order.  vals / offs point at the lane's first entry of the step, consecutive entries of a row are 32 apart.
+template <class MatT, class VecT, int N, bool FULL>
+__device__ __forceinline__ VecT row_sell_step(const MatT *__restrict__ vals, const short *__restrict__ offs, const int *__restrict__ gcol, const int rem,
+                                              const VecT *__restrict__ ring, const unsigned mask, const int lo, const unsigned span, const int row, const VecT *__restrict__ x, VecT sum)
+{
+    int c[N];
+    MatT v[N];
+    VecT xv[N];
+#pragma unroll
+    for (int u = 0; u < N; u++)
+        if (FULL || u < rem) {
+            const int o = offs[u * 32];
+            v[u] = vals[u * 32];
+            c[u] = row + o;
+            if (o == (int)WIN_FAR) c[u] = __ldg(gcol + u);
+        }
+#pragma unroll
+    for (int u = 0; u < N; u++)
+        if (FULL || u < rem) {
+            if ((unsigned)(c[u] - lo) < span) xv[u] = ring[(unsigned)c[u] & mask];
+            else xv[u] = __ldg(x + c[u]);
+        }
+#pragma unroll
+    for (int u = 0; u < N; u++)
+        if (FULL || u < rem) sum = fma((VecT)v[u], xv[u], sum);
+    return sum;
+}
+
+// blockDim.x = WIN_T + 32 (last warp = producer), one CTA per SM.
+// smem: barriers + reduction scratch (512 B) | ring[R] | stages x { values cap | offsets cap | row_ptr slice T + 4 | row order T | slice offsets | header 16 B }
+template <class MatT, class VecT, int EPI>
+__global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel(const TileArgs<MatT, VecT> a, const WinArgs w)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *empty = full + MAX_STAGES;
+    double *smem_red = reinterpret_cast<double *>(smem_raw + 2 * MAX_STAGES * sizeof(uint64_t));
+    VecT *ring = reinterpret_cast<VecT *>(smem_raw + 512);
+    unsigned char *stage_base = smem_raw + 512 + (size_t)w.ring * sizeof(VecT);
+    const size_t vals_bytes = align16((size_t)a.cap * sizeof(MatT));
+    const size_t offs_bytes = align16((size_t)a.cap * sizeof(short));
+    constexpr int CONSUMER_WARPS = WIN_T / 32;
+    const size_t rp_bytes = (size_t)(WIN_T + 4) * sizeof(int);
+    const size_t perm_off = vals_bytes + offs_bytes + rp_bytes;           // the tile's row order and slice offsets travel with it: nothing the consumers
+    const size_t sbase_off = perm_off + WIN_T;                            // need before their first FMA comes from global memory
+    const size_t hdr_off = sbase_off + CONSUMER_WARPS * sizeof(int);
+    const size_t stage_bytes = hdr_off + 16;
+    constexpr bool HAS_RED = (EPI == EPI_SPMV_DOT || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2);
+    constexpr bool NEED_B = (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2 || EPI == EPI_JACOBI_L1 || EPI == EPI_ADD);
+    constexpr bool NEED_D = (EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_JACOBI_L1);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < a.stages; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc = 0.0;
+    const int t_begin = (int)blockIdx.x * w.tiles_per_cta;
+    const int my_tiles = max(0, min(a.num_tiles, t_begin + w.tiles_per_cta) - t_begin);
+    const unsigned mask = (unsigned)w.ring - 1u;
+
+    if (tid >= WIN_T) {
+        // ------------------------------- producer warp -------------------------------
+        if (tid == WIN_T) {
+            int s = 0;
+            unsigned ph = 0u;
+            for (int it = 0; it < my_tiles; it++, s = (s + 1 == a.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
+                const int tile = t_begin + it;
+                if (it >= a.stages) mbar_wait(&empty[s], ph ^ 1u);
+                const int r0 = tile * WIN_T;
+                const int r1 = min(r0 + WIN_T, a.n);
+                const long long tb0 = __ldg(w.tbase + tile);
+                const unsigned cnt = (unsigned)(__ldg(w.tbase + tile + 1) - tb0);       // a multiple of 32 entries
+                unsigned char *st = stage_base + (size_t)s * stage_bytes;
+                const unsigned rp_copy = (unsigned)(((r1 - r0 + 1 + 3) & ~3) * sizeof(int));
+                const unsigned val_copy = cnt * (unsigned)sizeof(MatT), off_copy = cnt * (unsigned)sizeof(short);
+                // the part of x this tile adds to the ring: everything for the CTA's first tile, the T entries at the far end afterwards
+                const int win_lo = max(0, r0 - w.w), win_hi = min(w.x_len, r0 + WIN_T + w.w);
+                const int x0 = (it == 0) ? win_lo : min(w.x_len, r0 + w.w);
+                const unsigned x_copy = win_hi > x0 ? (unsigned)(win_hi - x0) * (unsigned)sizeof(VecT) : 0u;
+                *reinterpret_cast<int4 *>(st + hdr_off) = make_int4(win_lo, win_hi > win_lo ? win_hi - win_lo : 0, 0, 0);   // released to the consumers by the arrive below
+                mbar_expect_tx(&full[s], rp_copy + val_copy + off_copy + x_copy + (unsigned)WIN_T + (unsigned)(CONSUMER_WARPS * sizeof(int)));
+                tma_bulk_g2s(st + vals_bytes + offs_bytes, a.row_ptr + r0, rp_copy, &full[s]);
+                tma_bulk_g2s(st + perm_off, w.perm + (size_t)tile * WIN_T, (unsigned)WIN_T, &full[s]);
+                tma_bulk_g2s(st + sbase_off, w.sbase + (size_t)tile * CONSUMER_WARPS, (unsigned)(CONSUMER_WARPS * sizeof(int)), &full[s]);
+                if (cnt) {
+                    tma_bulk_g2s(st, reinterpret_cast<const MatT *>(w.sv) + tb0, val_copy, &full[s]);
+                    tma_bulk_g2s(st + vals_bytes, w.so + tb0, off_copy, &full[s]);
+                }
+                for (int p = x0; p < win_hi;) {                           // pieces that do not cross the end of the ring (one, or two for the first tile)
+                    const int e = min(win_hi, (int)(((unsigned)p | mask) + 1u));
+                    tma_bulk_g2s(ring + ((unsigned)p & mask), a.x + p, (unsigned)(e - p) * (unsigned)sizeof(VecT), &full[s]);
+                    p = e;
+                }
+                if (a.l2pf) {
+                    if (NEED_B) l2_prefetch_span(a.b + r0, r1 - r0);
+                    if (NEED_D) l2_prefetch_span(a.d + r0, r1 - r0);
+                }
+            }
+        }
+    } else {
+        // ------------------------------- consumers: one row per thread, a warp = one slice -------------------------------
+        const int lane = tid & 31, warp = tid >> 5;
+        int s = 0;
+        unsigned ph = 0u;
+        for (int it = 0; it < my_tiles; it++, s = (s + 1 == a.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
+            const int tile = t_begin + it;
+            const unsigned char *st = stage_base + (size_t)s * stage_bytes;
+            const int *rp = reinterpret_cast<const int *>(st + vals_bytes + offs_bytes);
+            mbar_wait(&full[s], ph);
+            const int4 hdr = *reinterpret_cast<const int4 *>(st + hdr_off);
+            const int lrow = (int)st[perm_off + tid];
+            const int sb = reinterpret_cast<const int *>(st + sbase_off)[warp];
+            const int row = tile * WIN_T + lrow;
+            const bool active = row < a.n;
+            // the row's vector operands: needed by the epilogue only, their latency (L2: the producer asked for these lines when it issued
+            // the tile) hides behind the row's dot product
+            VecT bi = 0, xi = 0;
+            MatT di = 1;
+            if (active) {
+                if (NEED_B) bi = __ldg(a.b + row);
+                if (NEED_D) di = __ldg(a.d + row);
+                if (NEED_D || EPI == EPI_SPMV_DOT) xi = ((unsigned)(row - hdr.x) < (unsigned)hdr.y) ? ring[(unsigned)row & mask] : __ldg(a.x + row);      // the row's own x sits in the window
+            }
+            const MatT *vals = reinterpret_cast<const MatT *>(st) + sb + lane;
+            const short *offs = reinterpret_cast<const short *>(st + vals_bytes) + sb + lane;
+            const int k0 = active ? rp[lrow] : 0;
+            const int len = active ? rp[lrow + 1] - k0 : 0;
+            const int L = __shfl_sync(0xffffffffu, len, 0);              // the slice's first row is its longest
+            const int *gcol = a.col + k0;
+            VecT sum = 0;
+            for (int j = 0; j < L; j += 8) {
+                const int rem = len - j;
+                if (rem >= 8) sum = row_sell_step<MatT, VecT, 8, true>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, row, a.x, sum);
+                else if (rem > 0) sum = row_sell_step<MatT, VecT, 8, false>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, row, a.x, sum);
+            }
+            if (active) acc += tile_epilogue<MatT, VecT, EPI>(a, row, sum, bi, di, xi);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+    }
+    if (HAS_RED) block_reduce_finish(acc, smem_red, a.red, a.fin_op, a.fin_slot, a.mirror);
+}
+
+template <class MatT, class VecT, int EPI> void launch_win(const Matrix &A, const TileArgs<MatT, VecT> &ta, const WinArgs &wa, cudaStream_t s)
+{
+    const size_t smem = A.win.smem_bytes;
+    auto k = csr_window_kernel<MatT, VecT, EPI>;
+    static size_t attr_bytes = 0;
+    if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+    k<<<A.win.grid, WIN_T + PRODUCER_THREADS, smem, s>>>(ta, wa);
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+static void sell_fill(Matrix &A, bool with_offsets, cudaStream_t s)
+{
+    WinPlan &P = A.win;
+    const int sms = A.rsc ? A.rsc->num_sms : B200_SMS;
+    const int grid = std::max(1, std::min(A.plan.num_tiles, sms * 8));
+    short *so = with_offsets ? P.so.ptr() : nullptr;
+    if (A.mat_prec == Prec::F64)
+        sell_fill_kernel<double><<<grid, WIN_T, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<double>(), A.n, A.plan.num_tiles, P.perm.ptr(), P.tbase.ptr(), P.sbase.ptr(),
+                                                        (double *)P.sv.ptr(), so);
+    else
+        sell_fill_kernel<float><<<grid, WIN_T, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<float>(), A.n, A.plan.num_tiles, P.perm.ptr(), P.tbase.ptr(), P.sbase.ptr(),
+                                                       (float *)P.sv.ptr(), so);
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+}
+
+// called at the end of csr_build_plan (after the coded streams: a level they pair-code is a stencil level and stays with them)
+void csr_build_window(Matrix &A, cudaStream_t s)
+{
+    WinPlan &P = A.win;
+    P.on = false;
+    static const int env_on = getenv("AMGXB_WINDOW") ? atoi(getenv("AMGXB_WINDOW")) : 1;
+    static const double env_min = getenv("AMGXB_WINDOW_MIN_INSIDE") ? atof(getenv("AMGXB_WINDOW_MIN_INSIDE")) : 0.85;
+    const int sms = A.rsc ? A.rsc->num_sms : B200_SMS;
+    if (!env_on || A.bs() != 1 || !A.plan.use_tiles || A.plan.tile_rows != WIN_T || A.plan.split != 0 || A.plan.use_perm) return;
+    if (A.n_cols > A.n) return;                                    // halo columns live behind the owned rows: the plain / coded kernels
+    const int nt = A.plan.num_tiles;
+    if (nt < sms * 8) return;                                      // a CTA's first tile loads the whole window: needs a range of tiles to pay for it
+    if ((double)A.nnz < 8.0 * (double)A.n) return;                 // short rows: the vectors dominate, nothing to gain
+    if (A.colenc.on && 2 * A.colenc.tiles_pair > A.colenc.num_tiles) return;
+    const size_t msz = prec_size(A.mat_prec), vsz = prec_size(A.vec_prec);
+    struct Cand { int ring, stages, w; } cand[2] = {{16384, 2, 0}, {8192, 3, 0}};
+    for (Cand &c : cand) c.w = ((c.ring - c.stages * WIN_T) / 2 / WIN_T) * WIN_T;
+    DevBuf<unsigned long long> stats;
+    stats.resize(2);
+    stats.zero(s);
+    win_stats_kernel<<<std::min(ceil_div(A.n, 256), sms * 16), 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, cand[0].w, cand[1].w, stats.ptr());
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    const std::vector<unsigned long long> h = stats.to_host(s);
+    const double inside[2] = {(double)h[0] / (double)std::max(A.nnz, 1), (double)h[1] / (double)std::max(A.nnz, 1)};
+    const bool verbose = getenv("AMGXB_WINDOW_VERBOSE") != nullptr;
+    if (std::max(inside[0], inside[1]) < env_min) {
+        if (verbose) fprintf(stderr, "[amgx_b200] window level %d: %d rows, inside +-%d: %.3f, +-%d: %.3f -> off\n", A.level, A.n, cand[0].w, inside[0], cand[1].w, inside[1]);
+        return;
+    }
+    // sliced-ELL plan: sorted rows, slice and tile offsets
+    P.perm.resize((size_t)nt * WIN_T);
+    P.sbase.resize((size_t)nt * (WIN_T / 32));
+    DevBuf<int> tlen;
+    tlen.resize((size_t)nt);
+    sell_plan_kernel<<<std::max(1, std::min(nt, sms * 8)), WIN_T, 0, s>>>(A.row_ptr.ptr(), A.n, nt, P.perm.ptr(), P.sbase.ptr(), tlen.ptr());
+    count_launch();
+    AMGXB_LAUNCH_CHECK();
+    const std::vector<int> hl = tlen.to_host(s);
+    std::vector<long long> hb((size_t)nt + 1, 0);
+    int cap = 32;
+    for (int t = 0; t < nt; t++) { hb[t + 1] = hb[t] + hl[t]; cap = std::max(cap, hl[t]); }
+    const size_t stage = align16((size_t)cap * msz) + align16((size_t)cap * sizeof(short)) + (size_t)(WIN_T + 4) * sizeof(int) + WIN_T + (WIN_T / 32) * sizeof(int) + 16;
+    int best = -1;
+    for (int i = 0; i < 2; i++) {
+        const size_t smem = 512 + (size_t)cand[i].ring * vsz + (size_t)cand[i].stages * stage;
+        if (smem > (size_t)226 * 1024 || inside[i] < env_min) continue;
+        if (best < 0 || inside[i] > inside[best] + 0.02) best = i;       // the wider window when it fits; the narrower one must hold clearly more to win
+    }
+    if (verbose)
+        fprintf(stderr, "[amgx_b200] window level %d: %d rows, %.1f entries per row (sliced-ELL padding %.1f %%, longest tile %d); inside +-%d: %.3f, +-%d: %.3f -> %s\n", A.level, A.n,
+                (double)A.nnz / A.n, 100.0 * ((double)hb[nt] / std::max(A.nnz, 1) - 1.0), cap, cand[0].w, inside[0], cand[1].w, inside[1],
+                best < 0 ? "off (shared memory)" : (best == 0 ? "ring 16384 x 2 stages" : "ring 8192 x 3 stages"));
+    if (best < 0 || (double)hb[nt] > 1.25 * (double)A.nnz) { P.perm.release(); P.sbase.release(); return; }
+    P.tbase.from_any(hb.data(), hb.size(), s);
+    AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));                     // hb is a local
+    P.sv.resize((size_t)hb[nt] * msz + 64);
+    P.so.resize((size_t)hb[nt] + 64);
+    P.cap = cap;
+    P.ring = cand[best].ring;
+    P.w = cand[best].w;
+    P.stages = cand[best].stages;
+    P.smem_bytes = 512 + (size_t)P.ring * vsz + (size_t)P.stages * stage;
+    P.inside = inside[best];
+    sell_fill(A, true, s);
+    const int ctas = std::min(sms, nt);
+    P.tiles_per_cta = ceil_div(nt, ctas);
+    P.grid = ceil_div(nt, P.tiles_per_cta);
+    P.on = true;
+}
+
+// the values of A changed in place: the sliced-ELL copy follows them (called from csr_values_changed)
+void csr_window_values_changed(Matrix &A, cudaStream_t s)
+{
+    if (A.win.on) sell_fill(A, false, s);
+}
+
+// csr_op entry of the window path; false: the caller goes on to the coded / plain kernels
+bool csr_op_win(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s, int segment)
+{
+    if (!A.win.on || g.agg || segment != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(g.x) & 15u) != 0) return false;          // the ring is filled by 16-byte bulk copies of x
+    WinArgs wa;
+    wa.sv = A.win.sv.ptr();
+    wa.so = A.win.so.ptr();
+    wa.perm = A.win.perm.ptr();
+    wa.tbase = A.win.tbase.ptr();
+    wa.sbase = A.win.sbase.ptr();
+    wa.ring = A.win.ring;
+    wa.w = A.win.w;
+    wa.tiles_per_cta = A.win.tiles_per_cta;
+    AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
+        wa.x_len = A.n & ~(int)(16 / sizeof(VecT) - 1);
+        TileArgs<MatT, VecT> ta;
+        ta.row_ptr = A.row_ptr.ptr();
+        ta.col = A.col_idx.ptr();
+        ta.val = A.values.as<MatT>();
+        ta.n = A.n;
+        ta.row0 = 0;
+        ta.num_tiles = A.plan.num_tiles;
+        ta.cap = A.win.cap;
+        ta.stages = A.win.stages;
+        ta.unroll = 8;
+        ta.perm = nullptr;
+        ta.tile_base = 0;
+        ta.l2pf = (l2_prefetch_flags() & 1) != 0;
+        ta.x = (const VecT *)g.x;
+        ta.agg = nullptr;
+        ta.b = (const VecT *)g.b;
+        ta.d = (const MatT *)g.d;
+        ta.y = (VecT *)g.y;
+        ta.omega = g.omega;
+        ta.red = g.red;
+        ta.fin_op = g.fin_op;
+        ta.fin_slot = g.fin_slot;
+        ta.mirror = g.mirror;
+        switch (epi) {
+        case EPI_SPMV: launch_win<MatT, VecT, EPI_SPMV>(A, ta, wa, s); break;
+        case EPI_RESID: launch_win<MatT, VecT, EPI_RESID>(A, ta, wa, s); break;
+        case EPI_ADD: launch_win<MatT, VecT, EPI_ADD>(A, ta, wa, s); break;
+        case EPI_JACOBI:
+        case EPI_JACOBI_L1: launch_win<MatT, VecT, EPI_JACOBI>(A, ta, wa, s); break;
+        case EPI_SPMV_DOT: launch_win<MatT, VecT, EPI_SPMV_DOT>(A, ta, wa, s); break;
+        case EPI_JACOBI_DOT: launch_win<MatT, VecT, EPI_JACOBI_DOT>(A, ta, wa, s); break;
+        case EPI_RESID_NRM2: launch_win<MatT, VecT, EPI_RESID_NRM2>(A, ta, wa, s); break;
+        }
+    });
+    return true;
+}
+
+}  // namespace amgxb

@@ -72,6 +72,10 @@ int  csr_max_grid(const Matrix &A);     // number of CTAs csr_op launches (parti
 void csr_build_colenc(Matrix &A, cudaStream_t s);                                                     // after csr_build_plan
 void csr_values_changed(Matrix &A, cudaStream_t s);                                                   // after an in-place change of A.values (no-op unless value codes exist)
 bool csr_op_enc(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s, int segment);    // false: use the plain kernels
+// sliding x window in shared memory for banded irregular matrices (k_spmv_win.cu; AMGXB_WINDOW=0 disables)
+void csr_build_window(Matrix &A, cudaStream_t s);                                                     // after csr_build_colenc
+bool csr_op_win(const Matrix &A, CsrEpi epi, const CsrOpArgs &args, cudaStream_t s, int segment);    // false: use the coded / plain kernels
+void csr_window_values_changed(Matrix &A, cudaStream_t s);                                            // its sliced-ELL copy of the values follows in-place changes
 
 // -------------------------------------------------------------------------------------------
 // Level-1 kernels (k_blas.cu).  Vectors are VecT arrays of length n; scalars come from device

@@ -39,6 +39,20 @@ struct TilePlan {
     int max_row_nnz = 0;
 };
 
+// Sliding-window plan of the banded-matrix kernel (k_spmv_win.cu): x[r0 - w, r0 + stages * T + w) of a CTA's tile range in a shared-memory ring
+struct WinPlan {
+    bool on = false;
+    DevBuf<unsigned char> sv;   // values in sliced-ELL order (per tile: rows sorted by length, 32-row slices stored entry-major)
+    DevBuf<short> so;           // column - row in the same order (-32768: use the 32-bit column of the CSR arrays)
+    DevBuf<unsigned char> perm; // sorted position -> local row, per tile
+    DevBuf<long long> tbase;    // first entry of every tile (num_tiles + 1)
+    DevBuf<int> sbase;          // first entry of every slice relative to its tile
+    int cap = 0;                // entries of the longest tile
+    int ring = 0, w = 0, stages = 0, tiles_per_cta = 0, grid = 0;
+    size_t smem_bytes = 0;
+    double inside = 0.0;        // fraction of the entries whose column lies within +-w of the row
+};
+
 // Optional compressed column stream of the tile kernels (k_spmv_enc.cu, AMGXB_COLENC=1; experimental, default off).  Per tile either
 // 8-bit codes into a dictionary of (column - row) offsets, 16-bit offsets from the tile's smallest column, or the raw 32-bit columns.
 struct ColEnc {
@@ -61,6 +75,7 @@ struct ColEnc {
     DevBuf<unsigned char> rpat;     // 64 patterns of 16 bytes per tile (7 pair codes + length)
     DevBuf<int> rmeta;              // per tile: number of row patterns, 0 = rows keep their per-entry pair codes
     int tiles_rowpat = 0, max_rplen = 0;
+    DevBuf<int> xahead;             // per tile: largest column offset of a dictionary-coded tile (x rows the producer prefetches into L2), else 0
     int col_w = 4, val_w = 8, dict_cap = 0, vdict_cap = 0;   // stage layout of the level (finalize_layout)
     int stages = 2, ctas_per_sm = 1;
     int num_tiles = 0;                             // tiles over all row segments ([0, split) then [split, n) on a row-partitioned matrix)
@@ -78,6 +93,7 @@ struct Matrix {
     bool has_ext_diag = false;
     bool merged_ext_diag = false;   // scalar matrix uploaded with diag_data: merged into CSR, diagonal first
     ColEnc colenc;
+    WinPlan win;
     bool dist_pending = false;      // comm maps were supplied; the next upload_all is a local distributed upload
     struct CommMaps {               // AMGX_matrix_comm_from_maps[_one_ring]: neighbours, rows to send, halo columns to receive into
         std::vector<int> neighbors;

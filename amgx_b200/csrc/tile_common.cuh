@@ -119,6 +119,26 @@ __device__ void block_reduce_finish(double v, double *smem_red, const ReduceCtx 
     }
 }
 
+// Pull `count` elements at `ptr` towards L2 ahead of their consumers (UBLKPF.L2): the producer warp runs `stages` tiles ahead, so the
+// per-row vector loads and the furthest-ahead gathers of a tile find their lines in L2 instead of paying a DRAM round trip on the
+// consumers' critical path (one row per thread = one dependent chain per tile).  Rounded inwards to 16 bytes: never reads outside.
+template <class T> __device__ __forceinline__ void l2_prefetch_span(const T *ptr, int count)
+{
+    if (count <= 0) return;
+    const unsigned long long a0 = (reinterpret_cast<unsigned long long>(ptr) + 15ull) & ~15ull;
+    const unsigned long long a1 = (reinterpret_cast<unsigned long long>(ptr + count)) & ~15ull;
+    if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
+}
+
+// AMGXB_L2_PREFETCH: bit 0 = the plain tile kernel (b / d slices), bit 1 = the coded kernel (b / d and the x rows ahead).  r02 A/B at 256^3:
+// plain fused Jacobi 0.297 -> 0.289 ms (solve 260 -> 265 it/s), coded kernels 0.159 -> 0.170 ms (their consumers are bound by the SM's
+// load/store path, not by DRAM latency, and the extra requests only add to it): default 1.
+inline int l2_prefetch_flags()
+{
+    static const int on = getenv("AMGXB_L2_PREFETCH") ? atoi(getenv("AMGXB_L2_PREFETCH")) : 1;
+    return on;
+}
+
 template <class MatT, class VecT> struct TileArgs {
     const int *row_ptr;
     const int *col;
@@ -128,6 +148,7 @@ template <class MatT, class VecT> struct TileArgs {
     int unroll;                      // gathers in flight per consumer step: 4 or 8
     const unsigned char *perm;       // length-sorted thread -> row map of every tile (null: thread t takes row t), see tile_perm_kernel
     int tile_base;                   // index of the segment's first tile in `perm` (tiles are numbered over the row segments)
+    int l2pf;                        // producer prefetches the tile's b / d slices (and, coded stencil tiles, the x rows its furthest neighbour reads) into L2
     const VecT *x;
     const int *agg;
     const VecT *b;
@@ -142,4 +163,35 @@ template <class VecT, bool AGG> __device__ __forceinline__ VecT gather(const Vec
 {
     if (AGG) return __ldg(x + __ldg(agg + c));
     return __ldg(x + c);
+}
+
+// what a consumer does with its row's dot product (identical to csr_tile_kernel); returns the row's contribution to the fused reduction
+template <class MatT, class VecT, int EPI>
+__device__ __forceinline__ double tile_epilogue(const TileArgs<MatT, VecT> &a, const int row, const VecT sum, const VecT bi, const MatT di, const VecT xi)
+{
+    if (EPI == EPI_SPMV) {
+        a.y[row] = sum;
+        return 0.0;
+    } else if (EPI == EPI_SPMV_DOT) {
+        a.y[row] = sum;
+        return (double)sum * (double)xi;
+    } else if (EPI == EPI_RESID) {
+        a.y[row] = bi - sum;
+        return 0.0;
+    } else if (EPI == EPI_ADD) {
+        a.y[row] = bi + sum;
+        return 0.0;
+    } else if (EPI == EPI_RESID_NRM2) {
+        const VecT r = bi - sum;
+        a.y[row] = r;
+        return (double)r * (double)r;
+    } else {
+        // x + ((b - Ax) * w) * (1/d): d = 1/d; b -= y; b *= w; b*d + x  (one FMA)
+        MatT dinv = (MatT)1 / guard_diag<MatT>(di);
+        VecT t = bi - sum;
+        t = (VecT)(t * a.omega);
+        const VecT out = fma(t, (VecT)dinv, xi);
+        a.y[row] = out;
+        return (EPI == EPI_JACOBI_DOT) ? (double)bi * (double)out : 0.0;
+    }
 }

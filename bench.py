@@ -478,7 +478,15 @@ def main():
         ms = A.bench_kernel(0, warmup=3, reps=20, flush_l2=False)      # operands (>= 1.4 GB) >> 126 MB L2
         byt = nnz * (msz * bd * bd + 4) + n * 4
         enc = os.environ.get("AMGXB_COLENC", "")
-        spmv = {"kernel": ("csr_tile_kernel<EPI_SPMV>" if bd == 1 else "block4_tile_kernel<SPMV> (TMA-staged 4x4 blocks)") + " (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt,
+        kinfo = A.kernel_info() if bd == 1 else {}
+        if kinfo.get("window"):
+            family = "csr_window_kernel<%s> (x window of %d entries in shared memory, 16-bit column offsets)"
+            family = family.replace("%d", str(kinfo["window"]))
+        elif kinfo.get("coded_tiles"):
+            family = "csr_tile_enc_kernel<%s> (coded column / value streams)"
+        else:
+            family = "csr_tile_kernel<%s>"
+        spmv = {"kernel": (family % "EPI_SPMV" if bd == 1 else "block4_tile_kernel<SPMV> (TMA-staged 4x4 blocks)") + " (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt,
                 "achieved": byt / ms / 1e6, "frac": byt / ms / 1e6 / peak}
         if bd == 1:
             ms_j = A.bench_kernel(1, warmup=3, reps=20, flush_l2=False)
@@ -488,7 +496,7 @@ def main():
             if tf.exists() and args.workload == "poisson":
                 traffic = json.loads(tf.read_text()).get("traffic_bytes_per_launch")
             roof = {"bound": "hbm", "achieved": byt_j / ms_j / 1e6, "peak": peak, "unit": "GB/s", "frac": byt_j / ms_j / 1e6 / peak, "traffic": traffic,
-                    "kernel": "fused Jacobi sweep, fine level: " + ("csr_tile_enc_kernel<EPI_JACOBI> (coded column / value streams)" if A_uses_enc(enc) else "csr_tile_kernel<EPI_JACOBI>"),
+                    "kernel": "fused Jacobi sweep, fine level: " + family % "EPI_JACOBI", "kernel_plan": kinfo,
                     "ms_per_launch": ms_j, "algorithmic_bytes": byt_j, "peak_source": peak_src, "share_of_iteration": "~70 % (profiles/r02_launches_solve_256.md)",
                     "spmv": spmv}
         else:
@@ -554,10 +562,6 @@ def main():
     capi.finalize()
     if distributed:
         dist.destroy_process_group()
-
-
-def A_uses_enc(enc: str) -> bool:
-    return enc != "0"          # AMGXB_COLENC defaults to 3 (coded column and value streams) since r02
 
 
 if __name__ == "__main__":

@@ -222,6 +222,11 @@ AMGX_RC AMGX_API AMGXB200_config_check(const AMGX_config_handle cfg, AMGX_Mode m
  * with CUDA events on that stream, after `warmup` untimed launches. */
 AMGX_RC AMGX_API AMGXB200_bench_kernel(AMGX_matrix_handle mtx, int kind, int warmup, int reps, int flush_l2, double *avg_ms);
 
+/* Which scalar CSR kernel family an uploaded matrix was planned for: rows per tile of the TMA tile kernels (0: the fallback kernels),
+ * tiles with coded column streams, with pair tables, with row patterns (k_spmv_enc.cu), and the ring size of the sliding x window of the
+ * banded-matrix kernel (k_spmv_win.cu; 0 = not used).  Any pointer may be NULL.  Extension: the reference exposes no such query. */
+AMGX_RC AMGX_API AMGXB200_matrix_get_kernel_plan(AMGX_matrix_handle mtx, int *tile_rows, int *coded_tiles, int *pair_tiles, int *row_pattern_tiles, int *window);
+
 /* Partition planner (pure host code, needs no GPU): given this rank's rows of a global CSR
  * (global column ids, contiguous row partition by offsets[world+1]) computes the local
  * renumbering [interior | boundary | halo], the per-neighbour send maps (B2L) and the halo
