@@ -27,13 +27,14 @@ namespace {
 #include "tile_common.cuh"
 
 constexpr int WIN_T = 256;
-constexpr short WIN_FAR = -32768;        // "read the 32-bit column": the offset does not fit 16 bits
+constexpr int WIN_BIAS = 32768;          // offsets are stored biased (unsigned 16 bits: one LDS.U16, no sign extension)
+constexpr unsigned short WIN_FAR = 0;    // "read the 32-bit column": column - row does not fit (lands below the window by construction)
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 struct WinArgs {
     const void *sv;             // values in sliced-ELL order (MatT)
-    const short *so;            // column - row in the same order (WIN_FAR: read the 32-bit column of the CSR copy)
+    const unsigned short *so;            // column - row in the same order (WIN_FAR: read the 32-bit column of the CSR copy)
     const unsigned char *perm;  // sorted position -> local row of every tile
     const long long *tbase;     // first entry of every tile in sv / so (num_tiles + 1)
     const int *sbase;           // first entry of every 32-row slice, relative to its tile
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(WIN_T) sell_plan_kernel(const int *__restrict_
 // plan 3 (and after every in-place change of the values, so == nullptr): CSR -> sliced-ELL copy
 template <class MatT>
 __global__ void __launch_bounds__(WIN_T) sell_fill_kernel(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ val, int n, int num_tiles,
-                                                          const unsigned char *__restrict__ perm, const long long *__restrict__ tbase, const int *__restrict__ sbase, MatT *sv, short *so)
+                                                          const unsigned char *__restrict__ perm, const long long *__restrict__ tbase, const int *__restrict__ sbase, MatT *sv, unsigned short *so)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(WIN_T) sell_fill_kernel(const int *__restrict_
                 sv[dst] = val[k0 + j];
                 if (so) {
                     const int d = ci[k0 + j] - row;
-                    so[dst] = (d > -32768 && d < 32768) ? (short)d : WIN_FAR;
+                    so[dst] = (d > -WIN_BIAS && d < WIN_BIAS) ? (unsigned short)(d + WIN_BIAS) : WIN_FAR;
                 }
             } else {
                 sv[dst] = (MatT)0;
@@ -120,29 +121,40 @@ __global__ void __launch_bounds__(WIN_T) sell_fill_kernel(const int *__restrict_
     }
 }
 
-// up to N entries of one row, `rem` of them present: offsets -> columns, x from the ring (outside the window: from global memory), FMAs in
-// storage order.  vals / offs point at the lane's first entry of the step, consecutive entries of a row are 32 apart.
+// up to N entries of one row, `rem` of them present: offsets -> columns, x from the ring, FMAs in storage order.  vals / offs point at the
+// lane's first entry of the step, consecutive entries of a row are 32 apart.  The common case (every column inside the window) is
+// straight-line code: N offset / value loads, N ring loads, N FMAs; a thread with a column outside the window (or a 16-bit overflow:
+// WIN_FAR lands below the window by construction) takes the per-entry path with the global gather.
 template <class MatT, class VecT, int N, bool FULL>
-__device__ __forceinline__ VecT row_sell_step(const MatT *__restrict__ vals, const short *__restrict__ offs, const int *__restrict__ gcol, const int rem,
+__device__ __forceinline__ VecT row_sell_step(const MatT *__restrict__ vals, const unsigned short *__restrict__ offs, const int *__restrict__ gcol, const int rem,
                                               const VecT *__restrict__ ring, const unsigned mask, const int lo, const unsigned span, const int row, const VecT *__restrict__ x, VecT sum)
 {
     int c[N];
     MatT v[N];
     VecT xv[N];
+    bool inside = true;
 #pragma unroll
     for (int u = 0; u < N; u++)
         if (FULL || u < rem) {
-            const int o = offs[u * 32];
+            c[u] = row + (int)offs[u * 32];      // row arrives with the bias already subtracted
             v[u] = vals[u * 32];
-            c[u] = row + o;
-            if (o == (int)WIN_FAR) c[u] = __ldg(gcol + u);
+            inside = inside && ((unsigned)(c[u] - lo) < span);
         }
+    if (inside) {
 #pragma unroll
-    for (int u = 0; u < N; u++)
-        if (FULL || u < rem) {
-            if ((unsigned)(c[u] - lo) < span) xv[u] = ring[(unsigned)c[u] & mask];
-            else xv[u] = __ldg(x + c[u]);
-        }
+        for (int u = 0; u < N; u++)
+            if (FULL || u < rem) xv[u] = ring[(unsigned)c[u] & mask];
+    } else {
+#pragma unroll
+        for (int u = 0; u < N; u++)
+            if (FULL || u < rem) {
+                if ((unsigned)(c[u] - lo) < span) xv[u] = ring[(unsigned)c[u] & mask];
+                else {
+                    if (offs[u * 32] == WIN_FAR) c[u] = __ldg(gcol + u);
+                    xv[u] = __ldg(x + c[u]);
+                }
+            }
+    }
 #pragma unroll
     for (int u = 0; u < N; u++)
         if (FULL || u < rem) sum = fma((VecT)v[u], xv[u], sum);
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel
                 if (NEED_D || EPI == EPI_SPMV_DOT) xi = ((unsigned)(row - hdr.x) < (unsigned)hdr.y) ? ring[(unsigned)row & mask] : __ldg(a.x + row);      // the row's own x sits in the window
             }
             const MatT *vals = reinterpret_cast<const MatT *>(st) + sb + lane;
-            const short *offs = reinterpret_cast<const short *>(st + vals_bytes) + sb + lane;
+            const unsigned short *offs = reinterpret_cast<const unsigned short *>(st + vals_bytes) + sb + lane;
             const int k0 = active ? rp[lrow] : 0;
             const int len = active ? rp[lrow + 1] - k0 : 0;
             const int L = __shfl_sync(0xffffffffu, len, 0);              // the slice's first row is its longest
@@ -259,8 +271,8 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel
             VecT sum = 0;
             for (int j = 0; j < L; j += 8) {
                 const int rem = len - j;
-                if (rem >= 8) sum = row_sell_step<MatT, VecT, 8, true>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, row, a.x, sum);
-                else if (rem > 0) sum = row_sell_step<MatT, VecT, 8, false>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, row, a.x, sum);
+                if (rem >= 8) sum = row_sell_step<MatT, VecT, 8, true>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, row - WIN_BIAS, a.x, sum);
+                else if (rem > 0) sum = row_sell_step<MatT, VecT, 8, false>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, row - WIN_BIAS, a.x, sum);
             }
             if (active) acc += tile_epilogue<MatT, VecT, EPI>(a, row, sum, bi, di, xi);
             __syncwarp();
@@ -288,7 +300,7 @@ static void sell_fill(Matrix &A, bool with_offsets, cudaStream_t s)
     WinPlan &P = A.win;
     const int sms = A.rsc ? A.rsc->num_sms : B200_SMS;
     const int grid = std::max(1, std::min(A.plan.num_tiles, sms * 8));
-    short *so = with_offsets ? P.so.ptr() : nullptr;
+    unsigned short *so = with_offsets ? P.so.ptr() : nullptr;
     if (A.mat_prec == Prec::F64)
         sell_fill_kernel<double><<<grid, WIN_T, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<double>(), A.n, A.plan.num_tiles, P.perm.ptr(), P.tbase.ptr(), P.sbase.ptr(),
                                                         (double *)P.sv.ptr(), so);

@@ -43,7 +43,7 @@ struct TilePlan {
 struct WinPlan {
     bool on = false;
     DevBuf<unsigned char> sv;   // values in sliced-ELL order (per tile: rows sorted by length, 32-row slices stored entry-major)
-    DevBuf<short> so;           // column - row in the same order (-32768: use the 32-bit column of the CSR arrays)
+    DevBuf<unsigned short> so;  // column - row + 32768 in the same order (0: use the 32-bit column of the CSR arrays)
     DevBuf<unsigned char> perm; // sorted position -> local row, per tile
     DevBuf<long long> tbase;    // first entry of every tile (num_tiles + 1)
     DevBuf<int> sbase;          // first entry of every slice relative to its tile
