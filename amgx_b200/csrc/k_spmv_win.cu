@@ -269,11 +269,14 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel
             const int L = __shfl_sync(0xffffffffu, len, 0);              // the slice's first row is its longest
             const int *gcol = a.col + k0;
             VecT sum = 0;
-            for (int j = 0; j < L; j += 8) {
+            const int rowb = row - WIN_BIAS;
+            auto step8 = [&](const int j) {
                 const int rem = len - j;
-                if (rem >= 8) sum = row_sell_step<MatT, VecT, 8, true>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, row - WIN_BIAS, a.x, sum);
-                else if (rem > 0) sum = row_sell_step<MatT, VecT, 8, false>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, row - WIN_BIAS, a.x, sum);
-            }
+                if (rem >= 8) sum = row_sell_step<MatT, VecT, 8, true>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, rowb, a.x, sum);
+                else if (rem > 0) sum = row_sell_step<MatT, VecT, 8, false>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, rowb, a.x, sum);
+            };
+            int j = 0;
+            for (; j < L; j += 8) step8(j);
             if (active) acc += tile_epilogue<MatT, VecT, EPI>(a, row, sum, bi, di, xi);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
@@ -317,7 +320,8 @@ void csr_build_window(Matrix &A, cudaStream_t s)
     WinPlan &P = A.win;
     P.on = false;
     static const int env_on = getenv("AMGXB_WINDOW") ? atoi(getenv("AMGXB_WINDOW")) : 1;
-    static const double env_min = getenv("AMGXB_WINDOW_MIN_INSIDE") ? atof(getenv("AMGXB_WINDOW_MIN_INSIDE")) : 0.85;
+    static const double env_min = getenv("AMGXB_WINDOW_MIN_INSIDE") ? atof(getenv("AMGXB_WINDOW_MIN_INSIDE")) : 0.97;     // a column outside the window costs a global gather inside the FMA chain: r02, 7 % outside = 2.8x slower
+    static const int env_ring = getenv("AMGXB_WINDOW_RING") ? atoi(getenv("AMGXB_WINDOW_RING")) : 0;      // experiments: force 16384 (2 stages) or 8192 (3 stages)
     const int sms = A.rsc ? A.rsc->num_sms : B200_SMS;
     if (!env_on || A.bs() != 1 || !A.plan.use_tiles || A.plan.tile_rows != WIN_T || A.plan.split != 0 || A.plan.use_perm) return;
     if (A.n_cols > A.n) return;                                    // halo columns live behind the owned rows: the plain / coded kernels
@@ -358,6 +362,7 @@ void csr_build_window(Matrix &A, cudaStream_t s)
     for (int i = 0; i < 2; i++) {
         const size_t smem = 512 + (size_t)cand[i].ring * vsz + (size_t)cand[i].stages * stage;
         if (smem > (size_t)226 * 1024 || inside[i] < env_min) continue;
+        if (env_ring > 0 && cand[i].ring != env_ring) continue;
         if (best < 0 || inside[i] > inside[best] + 0.02) best = i;       // the wider window when it fits; the narrower one must hold clearly more to win
     }
     if (verbose)
