@@ -42,6 +42,9 @@ struct WinArgs {
     int w;                      // W: half-width of the window, a multiple of WIN_T
     int x_len;                  // entries of x that may be staged (whole 16-byte units of the owned rows)
     int tiles_per_cta;
+    const unsigned short *smeta; // streaming kernel: local row | length << 8 of every sorted position
+    const int *slens;            // streaming kernel: entries per row of every slice
+    const int *row_ptr;
 };
 
 // plan 1: how many entries two candidate windows would hold
@@ -70,7 +73,7 @@ __global__ void win_stats_kernel(const int *__restrict__ rp, const int *__restri
 // plan 2: per tile, the rows sorted by length (descending, ties by index) -> sorted position p is handled by thread p; the 32 rows of a
 // slice (= a consumer warp) then have nearly equal lengths, and a slice is stored entry-major: entry j of lane l at slice + 32 j + l.
 // A slice is as long as its first row; the few positions past a shorter row's end are padding that is never read.
-__global__ void __launch_bounds__(WIN_T) sell_plan_kernel(const int *__restrict__ rp, int n, int num_tiles, unsigned char *perm, int *sbase, int *tlen)
+__global__ void __launch_bounds__(WIN_T) sell_plan_kernel(const int *__restrict__ rp, int n, int num_tiles, unsigned char *perm, int *sbase, int *tlen, unsigned short *smeta, int *slens)
 {
     __shared__ int len[WIN_T];
     __shared__ int slen[WIN_T / 32];
@@ -83,11 +86,12 @@ __global__ void __launch_bounds__(WIN_T) sell_plan_kernel(const int *__restrict_
         int rank = 0;
         for (int j = 0; j < WIN_T; j++) rank += (len[j] > mine) || (len[j] == mine && j < tid);
         perm[(size_t)t * WIN_T + rank] = (unsigned char)tid;
+        smeta[(size_t)t * WIN_T + rank] = (unsigned short)(tid | (min(max(mine, 0), 255) << 8));      // local row and length of sorted position `rank` (streaming kernel)
         if ((rank & 31) == 0) slen[rank >> 5] = max(mine, 0);
         __syncthreads();
         if (tid == 0) {
             int run = 0;
-            for (int sl = 0; sl < WIN_T / 32; sl++) { sbase[(size_t)t * (WIN_T / 32) + sl] = run; run += 32 * slen[sl]; }
+            for (int sl = 0; sl < WIN_T / 32; sl++) { sbase[(size_t)t * (WIN_T / 32) + sl] = run; slens[(size_t)t * (WIN_T / 32) + sl] = slen[sl]; run += 32 * slen[sl]; }
             tlen[t] = run;
         }
         __syncthreads();
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(WIN_T) sell_fill_kernel(const int *__restrict_
 // straight-line code: N offset / value loads, N ring loads, N FMAs; a thread with a column outside the window (or a 16-bit overflow:
 // WIN_FAR lands below the window by construction) takes the per-entry path with the global gather.
 template <class MatT, class VecT, int N, bool FULL>
-__device__ __forceinline__ VecT row_sell_step(const MatT *__restrict__ vals, const unsigned short *__restrict__ offs, const int *__restrict__ gcol, const int rem,
+__device__ __forceinline__ VecT row_sell_step(const MatT *__restrict__ vals, const unsigned short *__restrict__ offs, const int *__restrict__ col, const int *__restrict__ rpp, const int j0, const int rem,
                                               const VecT *__restrict__ ring, const unsigned mask, const int lo, const unsigned span, const int row, const VecT *__restrict__ x, VecT sum)
 {
     int c[N];
@@ -150,7 +154,7 @@ __device__ __forceinline__ VecT row_sell_step(const MatT *__restrict__ vals, con
             if (FULL || u < rem) {
                 if ((unsigned)(c[u] - lo) < span) xv[u] = ring[(unsigned)c[u] & mask];
                 else {
-                    if (offs[u * 32] == WIN_FAR) c[u] = __ldg(gcol + u);
+                    if (offs[u * 32] == WIN_FAR) c[u] = __ldg(col + (__ldg(rpp) + j0 + u));      // rare: the CSR copy's 32-bit column
                     xv[u] = __ldg(x + c[u]);
                 }
             }
@@ -267,13 +271,12 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel
             const int k0 = active ? rp[lrow] : 0;
             const int len = active ? rp[lrow + 1] - k0 : 0;
             const int L = __shfl_sync(0xffffffffu, len, 0);              // the slice's first row is its longest
-            const int *gcol = a.col + k0;
             VecT sum = 0;
             const int rowb = row - WIN_BIAS;
             auto step8 = [&](const int j) {
                 const int rem = len - j;
-                if (rem >= 8) sum = row_sell_step<MatT, VecT, 8, true>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, rowb, a.x, sum);
-                else if (rem > 0) sum = row_sell_step<MatT, VecT, 8, false>(vals + j * 32, offs + j * 32, gcol + j, rem, ring, mask, hdr.x, (unsigned)hdr.y, rowb, a.x, sum);
+                if (rem >= 8) sum = row_sell_step<MatT, VecT, 8, true>(vals + j * 32, offs + j * 32, a.col, a.row_ptr + row, j, rem, ring, mask, hdr.x, (unsigned)hdr.y, rowb, a.x, sum);
+                else if (rem > 0) sum = row_sell_step<MatT, VecT, 8, false>(vals + j * 32, offs + j * 32, a.col, a.row_ptr + row, j, rem, ring, mask, hdr.x, (unsigned)hdr.y, rowb, a.x, sum);
             };
             int j = 0;
             for (; j < L; j += 8) step8(j);
@@ -285,13 +288,195 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel
     if (HAS_RED) block_reduce_finish(acc, smem_red, a.red, a.fin_op, a.fin_slot, a.mirror);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming form (AMGXB_WINDOW_STREAM=1, opt-in: measured SLOWER than the whole-tile form, kept as the record of the experiment): the same
+// ring, the same sliced-ELL data, but no whole-tile stages.  Motivation: with whole tiles the 8 consumer warps meet at every tile -- the
+// warp holding the tile's longest slice (28 entries per row against 17 on average) sets the pace, and the next 48 KB load starts only
+// when the slowest warp is done (ncu r02: consumers waiting for data 35-40 % of the time at 56 % DRAM throughput).  Here every consumer
+// warp has its own queue of SQ small buffers; a slice travels as chunks of <= 8 entry-rows (2.5 KB), and slice s of tile t goes to warp
+// (s + t) mod 8, so long and short slices rotate over the warps.  A warp refills its own queue: after consuming a chunk its lane 0
+// issues the bulk copy of the chunk SQ ahead into the same buffer (first attempt: 8 lanes of a producer warp, one per queue -- UBLKCP
+// from divergent lanes is serialised by the uniform datapath and the producer became the bottleneck: 0.35 ms).  A separate thread feeds
+// the ring; the only coupling left is the ring: x of tile t may be overwritten once all 8 warps are done with tile t - SK + 1 (rempty,
+// count 8), i.e. SK * T + 2 W <= R.  Result on the 4 M-row banded matrix: SpMV 0.208 ms against 0.167 ms for the whole-tile form -- the
+// data waits shrink to 13 % of the samples, but the per-chunk bookkeeping (76 M warp instructions against 45 M) costs more than they
+// did with only two warps per scheduler to hide it.
+// ---------------------------------------------------------------------------------------------
+constexpr int SQ = 4;        // chunk buffers per consumer warp
+constexpr int SCH = 8;       // entry-rows per chunk
+constexpr int SK = 2;        // tiles whose part of x may be in use at the same time
+
+template <class MatT, class VecT, int EPI>
+__global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_stream_kernel(const TileArgs<MatT, VecT> a, const WinArgs w)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int CONSUMER_WARPS = WIN_T / 32;
+    constexpr unsigned CHUNK_VALS = SCH * 32 * sizeof(MatT), CHUNK_BYTES = CHUNK_VALS + SCH * 32 * sizeof(unsigned short);
+    uint64_t *cfull = reinterpret_cast<uint64_t *>(smem_raw);                 // [warp][slot]
+    uint64_t *rfull = cfull + CONSUMER_WARPS * SQ;                             // [SK]
+    uint64_t *rempty = rfull + SK;
+    double *smem_red = reinterpret_cast<double *>(smem_raw + 640);
+    VecT *ring = reinterpret_cast<VecT *>(smem_raw + 1024);
+    unsigned char *chunk_base = smem_raw + 1024 + (size_t)w.ring * sizeof(VecT);
+    constexpr bool HAS_RED = (EPI == EPI_SPMV_DOT || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2);
+    constexpr bool NEED_B = (EPI == EPI_RESID || EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2 || EPI == EPI_JACOBI_L1 || EPI == EPI_ADD);
+    constexpr bool NEED_D = (EPI == EPI_JACOBI || EPI == EPI_JACOBI_DOT || EPI == EPI_JACOBI_L1);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < CONSUMER_WARPS * SQ; i++) {
+            mbar_init(&cfull[i], 1);
+        }
+        for (int i = 0; i < SK; i++) {
+            mbar_init(&rfull[i], 1);
+            mbar_init(&rempty[i], CONSUMER_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc = 0.0;
+    const int t_begin = (int)blockIdx.x * w.tiles_per_cta;
+    const int my_tiles = max(0, min(a.num_tiles, t_begin + w.tiles_per_cta) - t_begin);
+    const unsigned mask = (unsigned)w.ring - 1u;
+
+    if (tid >= WIN_T) {
+        // ------------------------------- ring warp: one thread keeps x[r0 - W, r0 + SK * T + W) of the CTA's tile range in the ring -------------------------------
+        if (tid == WIN_T) {
+            if (my_tiles > 0) {            // the CTA's slice descriptors and row maps: small, read by every warp a little ahead of use -- pull them into L2 now
+                l2_prefetch_span(w.tbase + t_begin, my_tiles + 1);
+                l2_prefetch_span(w.sbase + (size_t)t_begin * CONSUMER_WARPS, my_tiles * CONSUMER_WARPS);
+                l2_prefetch_span(w.slens + (size_t)t_begin * CONSUMER_WARPS, my_tiles * CONSUMER_WARPS);
+                l2_prefetch_span(w.smeta + (size_t)t_begin * WIN_T, my_tiles * WIN_T);
+            }
+            for (int it = 0; it < my_tiles; it++) {
+                const int slot = it & (SK - 1);
+                if (it >= SK) mbar_wait(&rempty[slot], ((unsigned)(it / SK) - 1u) & 1u);
+                const int tile = t_begin + it;
+                const int r0 = tile * WIN_T, r1 = min(r0 + WIN_T, a.n);
+                const int win_lo = max(0, r0 - w.w), win_hi = min(w.x_len, r0 + WIN_T + w.w);
+                const int x0 = (it == 0) ? win_lo : min(w.x_len, r0 + w.w);
+                const unsigned x_copy = win_hi > x0 ? (unsigned)(win_hi - x0) * (unsigned)sizeof(VecT) : 0u;
+                mbar_expect_tx(&rfull[slot], x_copy);
+                for (int p = x0; p < win_hi;) {
+                    const int e = min(win_hi, (int)(((unsigned)p | mask) + 1u));
+                    tma_bulk_g2s(ring + ((unsigned)p & mask), a.x + p, (unsigned)(e - p) * (unsigned)sizeof(VecT), &rfull[slot]);
+                    p = e;
+                }
+                if (a.l2pf) {
+                    if (NEED_B) l2_prefetch_span(a.b + r0, r1 - r0);
+                    if (NEED_D) l2_prefetch_span(a.d + r0, r1 - r0);
+                }
+            }
+        }
+    } else {
+        // ------------------------------- consumers: a warp = one slice at a time; it refills its own queue -------------------------------
+        const int lane = tid & 31, wq = tid >> 5;
+        // load cursor (warp-uniform): the chunk that goes into the buffer the warp frees next.  Chunks of a slice are contiguous, so the cursor
+        // is two running pointers; the descriptors of the next two slices are already in registers (their lines were pulled into L2 by the
+        // ring thread when the kernel started).
+        const MatT *p_v = nullptr;
+        const unsigned short *p_o = nullptr;
+        int p_it = -1, p_rem = 0;          // tile of the cursor, entry-rows left in its slice
+        int n1_L = 0, n2_L = 0;
+        long long n1_base = 0, n2_base = 0;
+        unsigned gi = 0;                   // chunks issued
+        auto load_desc = [&](const int itn, long long &base, int &L) {
+            base = 0;
+            L = 0;
+            if (itn < my_tiles) {
+                const int tn = t_begin + itn, sn = (wq - itn) & 7;
+                base = __ldg(w.tbase + tn) + __ldg(w.sbase + (size_t)tn * CONSUMER_WARPS + sn);
+                L = __ldg(w.slens + (size_t)tn * CONSUMER_WARPS + sn);
+            }
+        };
+        load_desc(0, n1_base, n1_L);
+        load_desc(1, n2_base, n2_L);
+        auto issue = [&]() {
+            while (p_rem <= 0 && p_it < my_tiles) {        // slice exhausted (or empty): on to the next tile's slice
+                p_it++;
+                p_v = reinterpret_cast<const MatT *>(w.sv) + n1_base;
+                p_o = w.so + n1_base;
+                p_rem = n1_L;
+                n1_base = n2_base;
+                n1_L = n2_L;
+                load_desc(p_it + 2, n2_base, n2_L);
+            }
+            if (p_it >= my_tiles) return;
+            if (lane == 0) {
+                const unsigned q = gi & (SQ - 1);
+                const unsigned ne = (unsigned)min(SCH, p_rem);
+                unsigned char *buf = chunk_base + (size_t)(wq * SQ + q) * CHUNK_BYTES;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the warp's reads of this buffer precede the bulk copy that refills it
+                mbar_expect_tx(&cfull[wq * SQ + q], ne * 32u * (unsigned)(sizeof(MatT) + sizeof(unsigned short)));
+                tma_bulk_g2s(buf, p_v, ne * 32u * (unsigned)sizeof(MatT), &cfull[wq * SQ + q]);
+                tma_bulk_g2s(buf + CHUNK_VALS, p_o, ne * 32u * (unsigned)sizeof(unsigned short), &cfull[wq * SQ + q]);
+            }
+            p_v += SCH * 32;
+            p_o += SCH * 32;
+            p_rem -= SCH;
+            gi++;
+        };
+        for (int i = 0; i < SQ; i++) issue();
+        unsigned g = 0;
+        unsigned meta_next = my_tiles > 0 ? (unsigned)__ldg(w.smeta + (size_t)t_begin * WIN_T + (wq & 7) * 32 + lane) : 0u;
+        for (int it = 0; it < my_tiles; it++) {
+            const int tile = t_begin + it;
+            const unsigned meta = meta_next;
+            if (it + 1 < my_tiles) meta_next = (unsigned)__ldg(w.smeta + (size_t)(tile + 1) * WIN_T + ((wq - it - 1) & 7) * 32 + lane);
+            const int lrow = (int)(meta & 255u), len = (int)(meta >> 8);
+            const int row = tile * WIN_T + lrow;
+            const bool active = row < a.n;
+            VecT bi = 0, xi = 0;
+            MatT di = 1;
+            if (active) {
+                if (NEED_B) bi = __ldg(a.b + row);
+                if (NEED_D) di = __ldg(a.d + row);
+            }
+            const int L = __shfl_sync(0xffffffffu, len, 0);
+            const int r0 = tile * WIN_T;
+            const int win_lo = max(0, r0 - w.w), win_hi = min(w.x_len, r0 + WIN_T + w.w);
+            const unsigned span = win_hi > win_lo ? (unsigned)(win_hi - win_lo) : 0u;
+            const int slot = it & (SK - 1);
+            mbar_wait(&rfull[slot], (unsigned)(it / SK) & 1u);
+            if (active && (NEED_D || EPI == EPI_SPMV_DOT)) xi = ((unsigned)(row - win_lo) < span) ? ring[(unsigned)row & mask] : __ldg(a.x + row);
+            const int rowb = row - WIN_BIAS;
+            VecT sum = 0;
+            for (int c0 = 0; c0 < L; c0 += SCH, g++) {
+                const unsigned q = g & (SQ - 1);
+                mbar_wait(&cfull[wq * SQ + q], (g / SQ) & 1u);
+                const unsigned char *buf = chunk_base + (size_t)(wq * SQ + q) * CHUNK_BYTES;
+                const MatT *vals = reinterpret_cast<const MatT *>(buf) + lane;
+                const unsigned short *offs = reinterpret_cast<const unsigned short *>(buf + CHUNK_VALS) + lane;
+                const int rem = len - c0;
+                if (rem >= SCH) sum = row_sell_step<MatT, VecT, SCH, true>(vals, offs, a.col, w.row_ptr + row, c0, rem, ring, mask, win_lo, span, rowb, a.x, sum);
+                else if (rem > 0) sum = row_sell_step<MatT, VecT, SCH, false>(vals, offs, a.col, w.row_ptr + row, c0, rem, ring, mask, win_lo, span, rowb, a.x, sum);
+                __syncwarp();
+                issue();                   // refill the buffer just consumed with the chunk SQ ahead
+            }
+            if (active) acc += tile_epilogue<MatT, VecT, EPI>(a, row, sum, bi, di, xi);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rempty[slot]);
+        }
+    }
+    if (HAS_RED) block_reduce_finish(acc, smem_red, a.red, a.fin_op, a.fin_slot, a.mirror);
+}
+
 template <class MatT, class VecT, int EPI> void launch_win(const Matrix &A, const TileArgs<MatT, VecT> &ta, const WinArgs &wa, cudaStream_t s)
 {
-    const size_t smem = A.win.smem_bytes;
-    auto k = csr_window_kernel<MatT, VecT, EPI>;
-    static size_t attr_bytes = 0;
-    if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
-    k<<<A.win.grid, WIN_T + PRODUCER_THREADS, smem, s>>>(ta, wa);
+    if (A.win.stream) {
+        const size_t smem = A.win.stream_smem_bytes;
+        auto k = csr_stream_kernel<MatT, VecT, EPI>;
+        static size_t attr_bytes = 0;
+        if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+        k<<<A.win.grid, WIN_T + PRODUCER_THREADS, smem, s>>>(ta, wa);
+    } else {
+        const size_t smem = A.win.smem_bytes;
+        auto k = csr_window_kernel<MatT, VecT, EPI>;
+        static size_t attr_bytes = 0;
+        if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+        k<<<A.win.grid, WIN_T + PRODUCER_THREADS, smem, s>>>(ta, wa);
+    }
     count_launch();
     AMGXB_LAUNCH_CHECK();
 }
@@ -350,7 +535,9 @@ void csr_build_window(Matrix &A, cudaStream_t s)
     P.sbase.resize((size_t)nt * (WIN_T / 32));
     DevBuf<int> tlen;
     tlen.resize((size_t)nt);
-    sell_plan_kernel<<<std::max(1, std::min(nt, sms * 8)), WIN_T, 0, s>>>(A.row_ptr.ptr(), A.n, nt, P.perm.ptr(), P.sbase.ptr(), tlen.ptr());
+    P.smeta.resize((size_t)nt * WIN_T);
+    P.slens.resize((size_t)nt * (WIN_T / 32));
+    sell_plan_kernel<<<std::max(1, std::min(nt, sms * 8)), WIN_T, 0, s>>>(A.row_ptr.ptr(), A.n, nt, P.perm.ptr(), P.sbase.ptr(), tlen.ptr(), P.smeta.ptr(), P.slens.ptr());
     count_launch();
     AMGXB_LAUNCH_CHECK();
     const std::vector<int> hl = tlen.to_host(s);
@@ -369,7 +556,7 @@ void csr_build_window(Matrix &A, cudaStream_t s)
         fprintf(stderr, "[amgx_b200] window level %d: %d rows, %.1f entries per row (sliced-ELL padding %.1f %%, longest tile %d); inside +-%d: %.3f, +-%d: %.3f -> %s\n", A.level, A.n,
                 (double)A.nnz / A.n, 100.0 * ((double)hb[nt] / std::max(A.nnz, 1) - 1.0), cap, cand[0].w, inside[0], cand[1].w, inside[1],
                 best < 0 ? "off (shared memory)" : (best == 0 ? "ring 16384 x 2 stages" : "ring 8192 x 3 stages"));
-    if (best < 0 || (double)hb[nt] > 1.25 * (double)A.nnz) { P.perm.release(); P.sbase.release(); return; }
+    if (best < 0 || (double)hb[nt] > 1.25 * (double)A.nnz) { P.perm.release(); P.sbase.release(); P.smeta.release(); P.slens.release(); return; }
     P.tbase.from_any(hb.data(), hb.size(), s);
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));                     // hb is a local
     P.sv.resize((size_t)hb[nt] * msz + 64);
@@ -380,6 +567,10 @@ void csr_build_window(Matrix &A, cudaStream_t s)
     P.stages = cand[best].stages;
     P.smem_bytes = 512 + (size_t)P.ring * vsz + (size_t)P.stages * stage;
     P.inside = inside[best];
+    static const int env_stream = getenv("AMGXB_WINDOW_STREAM") ? atoi(getenv("AMGXB_WINDOW_STREAM")) : 0;      // opt-in, see the streaming form's header comment
+    P.stream_smem_bytes = 1024 + (size_t)P.ring * vsz + (size_t)(WIN_T / 32) * SQ * SCH * 32 * (msz + sizeof(unsigned short));
+    // streaming form: lengths travel in 8 bits, SK tiles of x in use at once need SK * T + 2 W <= R (the plan's W satisfies it for stages >= SK)
+    P.stream = env_stream != 0 && A.plan.max_row_nnz <= 255 && P.stages >= SK && P.stream_smem_bytes <= (size_t)226 * 1024;
     sell_fill(A, true, s);
     const int ctas = std::min(sms, nt);
     P.tiles_per_cta = ceil_div(nt, ctas);
@@ -407,6 +598,9 @@ bool csr_op_win(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
     wa.ring = A.win.ring;
     wa.w = A.win.w;
     wa.tiles_per_cta = A.win.tiles_per_cta;
+    wa.smeta = A.win.smeta.ptr();
+    wa.slens = A.win.slens.ptr();
+    wa.row_ptr = A.row_ptr.ptr();
     AMGXB_DISPATCH(A.mat_prec, A.vec_prec, {
         wa.x_len = A.n & ~(int)(16 / sizeof(VecT) - 1);
         TileArgs<MatT, VecT> ta;

@@ -47,9 +47,12 @@ struct WinPlan {
     DevBuf<unsigned char> perm; // sorted position -> local row, per tile
     DevBuf<long long> tbase;    // first entry of every tile (num_tiles + 1)
     DevBuf<int> sbase;          // first entry of every slice relative to its tile
+    DevBuf<unsigned short> smeta; // local row | length << 8 of every sorted position (streaming form of the kernel)
+    DevBuf<int> slens;          // entries per row of every slice
+    bool stream = false;        // per-warp chunk queues instead of whole-tile stages
     int cap = 0;                // entries of the longest tile
     int ring = 0, w = 0, stages = 0, tiles_per_cta = 0, grid = 0;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0, stream_smem_bytes = 0;
     double inside = 0.0;        // fraction of the entries whose column lies within +-w of the row
 };
 

@@ -30,6 +30,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
                      : "memory");
     } while (!ok);
 }
+// non-blocking probe of a phase (polling loops that serve several barriers)
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
 {
