@@ -109,3 +109,17 @@ def test_window_fgmres_jacobi_vs_oracle(amgx, oracle, system):
     m = min(len(hist), len(histo))
     assert m >= 2 and np.max(np.abs(hist[:m] - np.asarray(histo)[:m])) <= 1e-12 * hist[0]
     assert np.max(np.abs(x - xo)) <= 1e-11 * np.max(np.abs(xo))
+
+
+def test_window_streaming_form_in_subprocess():
+    """the opt-in streaming form (AMGXB_WINDOW_STREAM=1: per-warp chunk queues) through the same bit-exact checks; the switch is read once per
+    process, hence the subprocess"""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    env = dict(os.environ, AMGXB_WINDOW_STREAM="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", str(root / "tests" / "test_gpu_window.py"), "-k",
+                        "spmv_bit_exact or jacobi_sweeps or replace_coefficients"], capture_output=True, text=True, timeout=600, cwd=str(root), env=env)
+    assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
