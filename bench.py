@@ -492,8 +492,8 @@ def main():
             ms_j = A.bench_kernel(1, warmup=3, reps=20, flush_l2=False)
             byt_j = byt + 4 * n * vsz
             traffic = None
-            tf = ROOT / "profiles" / f"r02_ncu_traffic_jacobi_{nx}.json"
-            if tf.exists() and args.workload == "poisson":
+            tf = ROOT / "profiles" / (f"r02_ncu_traffic_jacobi_{nx}.json" if args.workload == "poisson" else "r02_ncu_traffic_jacobi_banded.json")
+            if tf.exists() and (args.workload == "poisson" or (args.workload == "banded" and kinfo.get("window"))):
                 traffic = json.loads(tf.read_text()).get("traffic_bytes_per_launch")
             roof = {"bound": "hbm", "achieved": byt_j / ms_j / 1e6, "peak": peak, "unit": "GB/s", "frac": byt_j / ms_j / 1e6 / peak, "traffic": traffic,
                     "kernel": "fused Jacobi sweep, fine level: " + family % "EPI_JACOBI", "kernel_plan": kinfo,

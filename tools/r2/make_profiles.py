@@ -58,8 +58,11 @@ doc = ["# r02 -- ncu `--set full` captures, per kernel (B200, 7-point Poisson 25
        "traffic = DRAM read + DRAM write; compare with the algorithmic bytes in DESIGN 3.1 / 3.8 / 3.9.", ""]
 doc += ncu_table(SRC / "ncu" / "plain_256.ncu-rep", "csr_tile_kernel<EPI_SPMV> -- plain CSR streams (AMGXB_COLENC=0), occupancy plan (2 stages x 4 CTAs/SM)",
                  "Algorithmic bytes 1.4717 GB (+ 0.268 GB of vectors the formula leaves out).")
-doc += ncu_table(SRC / "ncu" / "enc_spmv_256_final.ncu-rep", "csr_tile_enc_kernel<EPI_SPMV> -- coded streams with pair tables (final default)", "1 code byte per entry + the tile's pair table.")
+doc += ncu_table(SRC / "ncu" / "enc_spmv_256_final.ncu-rep", "csr_tile_enc_kernel<EPI_SPMV> -- coded streams with pair tables and row patterns (final default)", "1 code byte per ROW + the tile's pattern and pair tables.")
 doc += ncu_table(SRC / "ncu" / "enc_jacobi_256_final.ncu-rep", "csr_tile_enc_kernel<EPI_JACOBI> -- the dominant kernel of the iteration (fused Jacobi sweep, final default)")
+doc += ncu_table(SRC / "ncu" / "window_banded_final.ncu-rep", "csr_window_kernel<EPI_SPMV> x 2, <EPI_JACOBI> -- SuiteSparse-shaped banded matrix (4 M rows, 63.9 M entries): x ring in shared memory, sliced-ELL copy (final default)",
+                 "Stored bytes: 69.1 M entries x 10 B + vectors; x read once per CTA range.")
+doc += ncu_table(SRC / "ncu" / "stream_banded.ncu-rep", "csr_stream_kernel<EPI_SPMV> -- the opt-in streaming form of the window kernel (per-warp chunk queues; slower, DESIGN 3.10)")
 doc += ncu_table(SRC / "ncu" / "enc_256.ncu-rep", "history: csr_tile_enc_kernel<EPI_SPMV> before the pair tables (separate column / value codes, predicated 8-wide decode)")
 doc += ncu_table(SRC / "ncu" / "enc_jacobi_256.ncu-rep", "history: csr_tile_enc_kernel<EPI_JACOBI> before the pair tables (issue-bound: smsp__issue_active 68 %)")
 doc += ncu_table(SRC / "ncu" / "level1_256.ncu-rep", "level-1 and transfer kernels inside a solve (vec_dot, restrict)")
