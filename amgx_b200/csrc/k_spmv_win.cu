@@ -48,12 +48,14 @@ struct WinArgs {
 };
 
 // plan 1: how many entries two candidate windows would hold
-__global__ void win_stats_kernel(const int *__restrict__ rp, const int *__restrict__ ci, int n, int w1, int w2, unsigned long long *stats)
+__global__ void win_stats_kernel(const int *__restrict__ rp, const int *__restrict__ ci, int n, int w1, int w2, int lmax, unsigned long long *stats)
 {
-    unsigned long long in1 = 0, in2 = 0;
+    unsigned long long in1 = 0, in2 = 0, reg = 0, nlong = 0;
     for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
-        const int k1 = rp[row + 1];
-        for (int k = rp[row]; k < k1; k++) {
+        const int k0 = rp[row], k1 = rp[row + 1];
+        if (k1 - k0 > lmax) { nlong++; continue; }          // long rows go to the warp-per-row side kernel: not part of the window's business
+        reg += (unsigned long long)(k1 - k0);
+        for (int k = k0; k < k1; k++) {
             const int d = ci[k] - row;
             const int ad = d < 0 ? -d : d;
             in1 += ad <= w1;
@@ -63,30 +65,38 @@ __global__ void win_stats_kernel(const int *__restrict__ rp, const int *__restri
     for (int o = 16; o > 0; o >>= 1) {
         in1 += __shfl_xor_sync(0xffffffffu, in1, o);
         in2 += __shfl_xor_sync(0xffffffffu, in2, o);
+        reg += __shfl_xor_sync(0xffffffffu, reg, o);
+        nlong += __shfl_xor_sync(0xffffffffu, nlong, o);
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(stats + 0, in1);
         atomicAdd(stats + 1, in2);
+        atomicAdd(stats + 2, reg);
+        atomicAdd(stats + 3, nlong);
     }
 }
 
 // plan 2: per tile, the rows sorted by length (descending, ties by index) -> sorted position p is handled by thread p; the 32 rows of a
 // slice (= a consumer warp) then have nearly equal lengths, and a slice is stored entry-major: entry j of lane l at slice + 32 j + l.
 // A slice is as long as its first row; the few positions past a shorter row's end are padding that is never read.
-__global__ void __launch_bounds__(WIN_T) sell_plan_kernel(const int *__restrict__ rp, int n, int num_tiles, unsigned char *perm, int *sbase, int *tlen, unsigned short *smeta, int *slens)
+__global__ void __launch_bounds__(WIN_T) sell_plan_kernel(const int *__restrict__ rp, int n, int num_tiles, int lmax, unsigned char *perm, int *sbase, int *tlen, unsigned short *smeta, int *slens,
+                                                          int *long_rows, int *long_count)
 {
     __shared__ int len[WIN_T];
     __shared__ int slen[WIN_T / 32];
     const int tid = threadIdx.x;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int row = t * WIN_T + tid;
-        const int mine = row < n ? rp[row + 1] - rp[row] : -1;       // rows past the end sort last
+        const int true_len = row < n ? rp[row + 1] - rp[row] : -1;
+        const bool is_long = true_len > lmax;                          // summed by the side kernel (csr_long_rows_kernel); stored with length 0 here
+        const int mine = is_long ? 0 : true_len;                      // rows past the end (-1) sort last
+        if (is_long) long_rows[atomicAdd(long_count, 1)] = row;
         len[tid] = mine;
         __syncthreads();
         int rank = 0;
         for (int j = 0; j < WIN_T; j++) rank += (len[j] > mine) || (len[j] == mine && j < tid);
         perm[(size_t)t * WIN_T + rank] = (unsigned char)tid;
-        smeta[(size_t)t * WIN_T + rank] = (unsigned short)(tid | (min(max(mine, 0), 255) << 8));      // local row and length of sorted position `rank` (streaming kernel)
+        smeta[(size_t)t * WIN_T + rank] = (unsigned short)(tid | ((is_long ? 255 : max(mine, 0)) << 8));      // local row and length of sorted position `rank`; 255 = long row
         if ((rank & 31) == 0) slen[rank >> 5] = max(mine, 0);
         __syncthreads();
         if (tid == 0) {
@@ -101,12 +111,15 @@ __global__ void __launch_bounds__(WIN_T) sell_plan_kernel(const int *__restrict_
 // plan 3 (and after every in-place change of the values, so == nullptr): CSR -> sliced-ELL copy
 template <class MatT>
 __global__ void __launch_bounds__(WIN_T) sell_fill_kernel(const int *__restrict__ rp, const int *__restrict__ ci, const MatT *__restrict__ val, int n, int num_tiles,
-                                                          const unsigned char *__restrict__ perm, const long long *__restrict__ tbase, const int *__restrict__ sbase, MatT *sv, unsigned short *so)
+                                                          const unsigned char *__restrict__ perm, const unsigned short *__restrict__ smeta, const long long *__restrict__ tbase, const int *__restrict__ sbase, MatT *sv,
+                                                          unsigned short *so)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int row = t * WIN_T + (int)perm[(size_t)t * WIN_T + tid];
-        const int k0 = row < n ? rp[row] : 0, len = row < n ? rp[row + 1] - k0 : 0;
+        const int k0 = row < n ? rp[row] : 0;
+        const int lenb = (int)(smeta[(size_t)t * WIN_T + tid] >> 8);
+        const int len = (row < n && lenb != 255) ? lenb : 0;            // long rows are not stored
         const int L = __shfl_sync(0xffffffffu, len, 0);
         const long long base = tbase[t] + sbase[(size_t)t * (WIN_T / 32) + warp] + lane;
         for (int j = 0; j < L; j++) {
@@ -165,8 +178,29 @@ __device__ __forceinline__ VecT row_sell_step(const MatT *__restrict__ vals, con
     return sum;
 }
 
+// Rows longer than the plan's lmax (hub rows of aggregated levels: 2 % of the rows, a third of the entries on level 1 of the banded
+// hierarchy) would force whole slices to their length.  They are left out of the sliced-ELL copy and summed here, a warp per row over the CSR
+// arrays, in exactly the order of csr_vector_kernel (lane-strided FMAs, xor-shuffle tree) -- the kernel those levels ran before, so these
+// rows keep their bits.  The dot product is parked in y[row]; the window kernel picks it up and applies the epilogue / reduction as for
+// any other row.  (The caller guarantees y aliases neither b nor x.)
+template <class MatT, class VecT>
+__global__ void __launch_bounds__(256) csr_long_rows_kernel(const int *__restrict__ row_ptr, const int *__restrict__ col, const MatT *__restrict__ val, const VecT *__restrict__ x,
+                                                            VecT *__restrict__ y, const int *__restrict__ long_rows, int num_long)
+{
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < num_long; i += gridDim.x * wpb) {
+        const int row = __ldg(long_rows + i);
+        const int k0 = __ldg(row_ptr + row), k1 = __ldg(row_ptr + row + 1);
+        VecT sum = 0;
+        for (int k = k0 + lane; k < k1; k += 32) sum = fma((VecT)__ldg(val + k), __ldg(x + __ldg(col + k)), sum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) y[row] = sum;
+    }
+}
+
 // blockDim.x = WIN_T + 32 (last warp = producer), one CTA per SM.
-// smem: barriers + reduction scratch (512 B) | ring[R] | stages x { values cap | offsets cap | row_ptr slice T + 4 | row order T | slice offsets | header 16 B }
+// smem: barriers + reduction scratch (512 B) | ring[R] | stages x { values cap | offsets cap | row map T x 2 B | slice offsets | header 16 B }
 template <class MatT, class VecT, int EPI>
 __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel(const TileArgs<MatT, VecT> a, const WinArgs w)
 {
@@ -179,9 +213,8 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel
     const size_t vals_bytes = align16((size_t)a.cap * sizeof(MatT));
     const size_t offs_bytes = align16((size_t)a.cap * sizeof(short));
     constexpr int CONSUMER_WARPS = WIN_T / 32;
-    const size_t rp_bytes = (size_t)(WIN_T + 4) * sizeof(int);
-    const size_t perm_off = vals_bytes + offs_bytes + rp_bytes;           // the tile's row order and slice offsets travel with it: nothing the consumers
-    const size_t sbase_off = perm_off + WIN_T;                            // need before their first FMA comes from global memory
+    const size_t meta_off = vals_bytes + offs_bytes;                       // the tile's row map (local row | length << 8 per sorted position) and slice offsets
+    const size_t sbase_off = meta_off + WIN_T * sizeof(unsigned short);   // travel with it: nothing the consumers need before their first FMA comes from global memory
     const size_t hdr_off = sbase_off + CONSUMER_WARPS * sizeof(int);
     const size_t stage_bytes = hdr_off + 16;
     constexpr bool HAS_RED = (EPI == EPI_SPMV_DOT || EPI == EPI_JACOBI_DOT || EPI == EPI_RESID_NRM2);
@@ -216,16 +249,14 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel
                 const long long tb0 = __ldg(w.tbase + tile);
                 const unsigned cnt = (unsigned)(__ldg(w.tbase + tile + 1) - tb0);       // a multiple of 32 entries
                 unsigned char *st = stage_base + (size_t)s * stage_bytes;
-                const unsigned rp_copy = (unsigned)(((r1 - r0 + 1 + 3) & ~3) * sizeof(int));
                 const unsigned val_copy = cnt * (unsigned)sizeof(MatT), off_copy = cnt * (unsigned)sizeof(short);
                 // the part of x this tile adds to the ring: everything for the CTA's first tile, the T entries at the far end afterwards
                 const int win_lo = max(0, r0 - w.w), win_hi = min(w.x_len, r0 + WIN_T + w.w);
                 const int x0 = (it == 0) ? win_lo : min(w.x_len, r0 + w.w);
                 const unsigned x_copy = win_hi > x0 ? (unsigned)(win_hi - x0) * (unsigned)sizeof(VecT) : 0u;
                 *reinterpret_cast<int4 *>(st + hdr_off) = make_int4(win_lo, win_hi > win_lo ? win_hi - win_lo : 0, 0, 0);   // released to the consumers by the arrive below
-                mbar_expect_tx(&full[s], rp_copy + val_copy + off_copy + x_copy + (unsigned)WIN_T + (unsigned)(CONSUMER_WARPS * sizeof(int)));
-                tma_bulk_g2s(st + vals_bytes + offs_bytes, a.row_ptr + r0, rp_copy, &full[s]);
-                tma_bulk_g2s(st + perm_off, w.perm + (size_t)tile * WIN_T, (unsigned)WIN_T, &full[s]);
+                mbar_expect_tx(&full[s], val_copy + off_copy + x_copy + (unsigned)(WIN_T * sizeof(unsigned short)) + (unsigned)(CONSUMER_WARPS * sizeof(int)));
+                tma_bulk_g2s(st + meta_off, w.smeta + (size_t)tile * WIN_T, (unsigned)(WIN_T * sizeof(unsigned short)), &full[s]);
                 tma_bulk_g2s(st + sbase_off, w.sbase + (size_t)tile * CONSUMER_WARPS, (unsigned)(CONSUMER_WARPS * sizeof(int)), &full[s]);
                 if (cnt) {
                     tma_bulk_g2s(st, reinterpret_cast<const MatT *>(w.sv) + tb0, val_copy, &full[s]);
@@ -250,10 +281,11 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel
         for (int it = 0; it < my_tiles; it++, s = (s + 1 == a.stages) ? 0 : s + 1, ph ^= (s == 0) ? 1u : 0u) {
             const int tile = t_begin + it;
             const unsigned char *st = stage_base + (size_t)s * stage_bytes;
-            const int *rp = reinterpret_cast<const int *>(st + vals_bytes + offs_bytes);
             mbar_wait(&full[s], ph);
             const int4 hdr = *reinterpret_cast<const int4 *>(st + hdr_off);
-            const int lrow = (int)st[perm_off + tid];
+            const unsigned meta = reinterpret_cast<const unsigned short *>(st + meta_off)[tid];
+            const int lrow = (int)(meta & 255u);
+            const bool is_long = (meta >> 8) == 255u;                    // its dot product was left in y[row] by csr_long_rows_kernel
             const int sb = reinterpret_cast<const int *>(st + sbase_off)[warp];
             const int row = tile * WIN_T + lrow;
             const bool active = row < a.n;
@@ -268,10 +300,9 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_window_kernel
             }
             const MatT *vals = reinterpret_cast<const MatT *>(st) + sb + lane;
             const unsigned short *offs = reinterpret_cast<const unsigned short *>(st + vals_bytes) + sb + lane;
-            const int k0 = active ? rp[lrow] : 0;
-            const int len = active ? rp[lrow + 1] - k0 : 0;
+            const int len = (active && !is_long) ? (int)(meta >> 8) : 0;
             const int L = __shfl_sync(0xffffffffu, len, 0);              // the slice's first row is its longest
-            VecT sum = 0;
+            VecT sum = (active && is_long) ? a.y[row] : (VecT)0;
             const int rowb = row - WIN_BIAS;
             auto step8 = [&](const int j) {
                 const int rem = len - j;
@@ -424,7 +455,9 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_stream_kernel
             const int tile = t_begin + it;
             const unsigned meta = meta_next;
             if (it + 1 < my_tiles) meta_next = (unsigned)__ldg(w.smeta + (size_t)(tile + 1) * WIN_T + ((wq - it - 1) & 7) * 32 + lane);
-            const int lrow = (int)(meta & 255u), len = (int)(meta >> 8);
+            const int lrow = (int)(meta & 255u);
+            const bool is_long = (meta >> 8) == 255u;                    // summed by csr_long_rows_kernel, parked in y[row]
+            const int len = is_long ? 0 : (int)(meta >> 8);
             const int row = tile * WIN_T + lrow;
             const bool active = row < a.n;
             VecT bi = 0, xi = 0;
@@ -441,7 +474,7 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_stream_kernel
             mbar_wait(&rfull[slot], (unsigned)(it / SK) & 1u);
             if (active && (NEED_D || EPI == EPI_SPMV_DOT)) xi = ((unsigned)(row - win_lo) < span) ? ring[(unsigned)row & mask] : __ldg(a.x + row);
             const int rowb = row - WIN_BIAS;
-            VecT sum = 0;
+            VecT sum = (active && is_long) ? a.y[row] : (VecT)0;
             for (int c0 = 0; c0 < L; c0 += SCH, g++) {
                 const unsigned q = g & (SQ - 1);
                 mbar_wait(&cfull[wq * SQ + q], (g / SQ) & 1u);
@@ -464,6 +497,11 @@ __global__ void __launch_bounds__(WIN_T + PRODUCER_THREADS, 1) csr_stream_kernel
 
 template <class MatT, class VecT, int EPI> void launch_win(const Matrix &A, const TileArgs<MatT, VecT> &ta, const WinArgs &wa, cudaStream_t s)
 {
+    if (A.win.num_long > 0) {
+        const int sms = A.rsc ? A.rsc->num_sms : B200_SMS;
+        csr_long_rows_kernel<MatT, VecT><<<std::max(1, std::min(ceil_div(A.win.num_long, 8), sms * 8)), 256, 0, s>>>(ta.row_ptr, ta.col, ta.val, ta.x, ta.y, A.win.long_rows.ptr(), A.win.num_long);
+        count_launch();
+    }
     if (A.win.stream) {
         const size_t smem = A.win.stream_smem_bytes;
         auto k = csr_stream_kernel<MatT, VecT, EPI>;
@@ -490,11 +528,11 @@ static void sell_fill(Matrix &A, bool with_offsets, cudaStream_t s)
     const int grid = std::max(1, std::min(A.plan.num_tiles, sms * 8));
     unsigned short *so = with_offsets ? P.so.ptr() : nullptr;
     if (A.mat_prec == Prec::F64)
-        sell_fill_kernel<double><<<grid, WIN_T, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<double>(), A.n, A.plan.num_tiles, P.perm.ptr(), P.tbase.ptr(), P.sbase.ptr(),
-                                                        (double *)P.sv.ptr(), so);
+        sell_fill_kernel<double><<<grid, WIN_T, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<double>(), A.n, A.plan.num_tiles, P.perm.ptr(), P.smeta.ptr(), P.tbase.ptr(),
+                                                        P.sbase.ptr(), (double *)P.sv.ptr(), so);
     else
-        sell_fill_kernel<float><<<grid, WIN_T, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<float>(), A.n, A.plan.num_tiles, P.perm.ptr(), P.tbase.ptr(), P.sbase.ptr(),
-                                                       (float *)P.sv.ptr(), so);
+        sell_fill_kernel<float><<<grid, WIN_T, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.values.as<float>(), A.n, A.plan.num_tiles, P.perm.ptr(), P.smeta.ptr(), P.tbase.ptr(),
+                                                       P.sbase.ptr(), (float *)P.sv.ptr(), so);
     count_launch();
     AMGXB_LAUNCH_CHECK();
 }
@@ -508,7 +546,8 @@ void csr_build_window(Matrix &A, cudaStream_t s)
     static const double env_min = getenv("AMGXB_WINDOW_MIN_INSIDE") ? atof(getenv("AMGXB_WINDOW_MIN_INSIDE")) : 0.97;     // a column outside the window costs a global gather inside the FMA chain: r02, 7 % outside = 2.8x slower
     static const int env_ring = getenv("AMGXB_WINDOW_RING") ? atoi(getenv("AMGXB_WINDOW_RING")) : 0;      // experiments: force 16384 (2 stages) or 8192 (3 stages)
     const int sms = A.rsc ? A.rsc->num_sms : B200_SMS;
-    if (!env_on || A.bs() != 1 || !A.plan.use_tiles || A.plan.tile_rows != WIN_T || A.plan.split != 0 || A.plan.use_perm) return;
+    // (a level whose plain tile plan failed because a few hub rows blow up a tile -- plan.use_tiles false -- is exactly what the long-row split is for)
+    if (!env_on || A.bs() != 1 || A.plan.tile_rows != WIN_T || A.plan.split != 0 || A.plan.use_perm) return;
     if (A.n_cols > A.n) return;                                    // halo columns live behind the owned rows: the plain / coded kernels
     const int nt = A.plan.num_tiles;
     if (nt < sms * 8) return;                                      // a CTA's first tile loads the whole window: needs a range of tiles to pay for it
@@ -517,14 +556,22 @@ void csr_build_window(Matrix &A, cudaStream_t s)
     const size_t msz = prec_size(A.mat_prec), vsz = prec_size(A.vec_prec);
     struct Cand { int ring, stages, w; } cand[2] = {{16384, 2, 0}, {8192, 3, 0}};
     for (Cand &c : cand) c.w = ((c.ring - c.stages * WIN_T) / 2 / WIN_T) * WIN_T;
+    // rows longer than lmax leave the sliced-ELL copy (one of them would stretch its whole slice): 3 x the mean, at least 48 and at most what
+    // 8 bits hold -- no row of the 4 M-row banded matrix (mean 16, longest 34), the hub rows of its first aggregated level (mean 23; 2.4 % of
+    // the rows hold 330-2600 entries each, a third of all entries)
+    static const int env_lmax = getenv("AMGXB_WINDOW_LMAX") ? atoi(getenv("AMGXB_WINDOW_LMAX")) : 0;
+    const int lmax = env_lmax > 0 ? std::min(env_lmax, 254) : std::max(48, std::min(254, (int)(3.0 * (double)A.nnz / (double)std::max(A.n, 1))));
     DevBuf<unsigned long long> stats;
-    stats.resize(2);
+    stats.resize(4);
     stats.zero(s);
-    win_stats_kernel<<<std::min(ceil_div(A.n, 256), sms * 16), 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, cand[0].w, cand[1].w, stats.ptr());
+    win_stats_kernel<<<std::min(ceil_div(A.n, 256), sms * 16), 256, 0, s>>>(A.row_ptr.ptr(), A.col_idx.ptr(), A.n, cand[0].w, cand[1].w, lmax, stats.ptr());
     count_launch();
     AMGXB_LAUNCH_CHECK();
     const std::vector<unsigned long long> h = stats.to_host(s);
-    const double inside[2] = {(double)h[0] / (double)std::max(A.nnz, 1), (double)h[1] / (double)std::max(A.nnz, 1)};
+    const long long nnz_reg = (long long)h[2];
+    const int num_long = (int)h[3];
+    if (nnz_reg < 4 * (long long)A.n) return;                     // what is left after the long rows is too thin to be worth a second copy
+    const double inside[2] = {(double)h[0] / (double)std::max(nnz_reg, 1LL), (double)h[1] / (double)std::max(nnz_reg, 1LL)};
     const bool verbose = getenv("AMGXB_WINDOW_VERBOSE") != nullptr;
     if (std::max(inside[0], inside[1]) < env_min) {
         if (verbose) fprintf(stderr, "[amgx_b200] window level %d: %d rows, inside +-%d: %.3f, +-%d: %.3f -> off\n", A.level, A.n, cand[0].w, inside[0], cand[1].w, inside[1]);
@@ -537,14 +584,19 @@ void csr_build_window(Matrix &A, cudaStream_t s)
     tlen.resize((size_t)nt);
     P.smeta.resize((size_t)nt * WIN_T);
     P.slens.resize((size_t)nt * (WIN_T / 32));
-    sell_plan_kernel<<<std::max(1, std::min(nt, sms * 8)), WIN_T, 0, s>>>(A.row_ptr.ptr(), A.n, nt, P.perm.ptr(), P.sbase.ptr(), tlen.ptr(), P.smeta.ptr(), P.slens.ptr());
+    P.long_rows.resize((size_t)std::max(num_long, 1));
+    DevBuf<int> long_count;
+    long_count.resize(1);
+    long_count.zero(s);
+    sell_plan_kernel<<<std::max(1, std::min(nt, sms * 8)), WIN_T, 0, s>>>(A.row_ptr.ptr(), A.n, nt, lmax, P.perm.ptr(), P.sbase.ptr(), tlen.ptr(), P.smeta.ptr(), P.slens.ptr(), P.long_rows.ptr(),
+                                                                          long_count.ptr());
     count_launch();
     AMGXB_LAUNCH_CHECK();
     const std::vector<int> hl = tlen.to_host(s);
     std::vector<long long> hb((size_t)nt + 1, 0);
     int cap = 32;
     for (int t = 0; t < nt; t++) { hb[t + 1] = hb[t] + hl[t]; cap = std::max(cap, hl[t]); }
-    const size_t stage = align16((size_t)cap * msz) + align16((size_t)cap * sizeof(short)) + (size_t)(WIN_T + 4) * sizeof(int) + WIN_T + (WIN_T / 32) * sizeof(int) + 16;
+    const size_t stage = align16((size_t)cap * msz) + align16((size_t)cap * sizeof(short)) + WIN_T * sizeof(unsigned short) + (WIN_T / 32) * sizeof(int) + 16;
     int best = -1;
     for (int i = 0; i < 2; i++) {
         const size_t smem = 512 + (size_t)cand[i].ring * vsz + (size_t)cand[i].stages * stage;
@@ -553,10 +605,13 @@ void csr_build_window(Matrix &A, cudaStream_t s)
         if (best < 0 || inside[i] > inside[best] + 0.02) best = i;       // the wider window when it fits; the narrower one must hold clearly more to win
     }
     if (verbose)
-        fprintf(stderr, "[amgx_b200] window level %d: %d rows, %.1f entries per row (sliced-ELL padding %.1f %%, longest tile %d); inside +-%d: %.3f, +-%d: %.3f -> %s\n", A.level, A.n,
-                (double)A.nnz / A.n, 100.0 * ((double)hb[nt] / std::max(A.nnz, 1) - 1.0), cap, cand[0].w, inside[0], cand[1].w, inside[1],
+        fprintf(stderr, "[amgx_b200] window level %d: %d rows, %.1f entries per row; %d rows longer than %d (%.1f %% of the entries) go to the warp-per-row kernel; sliced-ELL padding %.1f %%, "
+                        "longest tile %d; inside +-%d: %.3f, +-%d: %.3f -> %s\n", A.level, A.n, (double)A.nnz / A.n, num_long, lmax, 100.0 * (1.0 - (double)nnz_reg / std::max(A.nnz, 1)),
+                100.0 * ((double)hb[nt] / (double)std::max(nnz_reg, 1LL) - 1.0), cap, cand[0].w, inside[0], cand[1].w, inside[1],
                 best < 0 ? "off (shared memory)" : (best == 0 ? "ring 16384 x 2 stages" : "ring 8192 x 3 stages"));
-    if (best < 0 || (double)hb[nt] > 1.25 * (double)A.nnz) { P.perm.release(); P.sbase.release(); P.smeta.release(); P.slens.release(); return; }
+    if (best < 0 || (double)hb[nt] > 1.25 * (double)nnz_reg) { P.perm.release(); P.sbase.release(); P.smeta.release(); P.slens.release(); P.long_rows.release(); return; }
+    P.num_long = num_long;
+    P.lmax = lmax;
     P.tbase.from_any(hb.data(), hb.size(), s);
     AMGXB_CUDA_CHECK(cudaStreamSynchronize(s));                     // hb is a local
     P.sv.resize((size_t)hb[nt] * msz + 64);
@@ -570,7 +625,7 @@ void csr_build_window(Matrix &A, cudaStream_t s)
     static const int env_stream = getenv("AMGXB_WINDOW_STREAM") ? atoi(getenv("AMGXB_WINDOW_STREAM")) : 0;      // opt-in, see the streaming form's header comment
     P.stream_smem_bytes = 1024 + (size_t)P.ring * vsz + (size_t)(WIN_T / 32) * SQ * SCH * 32 * (msz + sizeof(unsigned short));
     // streaming form: lengths travel in 8 bits, SK tiles of x in use at once need SK * T + 2 W <= R (the plan's W satisfies it for stages >= SK)
-    P.stream = env_stream != 0 && A.plan.max_row_nnz <= 255 && P.stages >= SK && P.stream_smem_bytes <= (size_t)226 * 1024;
+    P.stream = env_stream != 0 && P.stages >= SK && P.stream_smem_bytes <= (size_t)226 * 1024;
     sell_fill(A, true, s);
     const int ctas = std::min(sms, nt);
     P.tiles_per_cta = ceil_div(nt, ctas);
@@ -589,6 +644,7 @@ bool csr_op_win(const Matrix &A, CsrEpi epi, const CsrOpArgs &g, cudaStream_t s,
 {
     if (!A.win.on || g.agg || segment != 0) return false;
     if ((reinterpret_cast<uintptr_t>(g.x) & 15u) != 0) return false;          // the ring is filled by 16-byte bulk copies of x
+    if (A.win.num_long > 0 && (g.y == g.b || g.y == g.x)) return false;         // the long rows' dot products are parked in y before b and x are read
     WinArgs wa;
     wa.sv = A.win.sv.ptr();
     wa.so = A.win.so.ptr();

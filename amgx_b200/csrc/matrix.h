@@ -50,6 +50,8 @@ struct WinPlan {
     DevBuf<unsigned short> smeta; // local row | length << 8 of every sorted position (streaming form of the kernel)
     DevBuf<int> slens;          // entries per row of every slice
     bool stream = false;        // per-warp chunk queues instead of whole-tile stages
+    DevBuf<int> long_rows;      // rows longer than lmax: left out of the sliced-ELL copy, summed by the warp-per-row side kernel
+    int num_long = 0, lmax = 0;
     int cap = 0;                // entries of the longest tile
     int ring = 0, w = 0, stages = 0, tiles_per_cta = 0, grid = 0;
     size_t smem_bytes = 0, stream_smem_bytes = 0;

@@ -123,3 +123,67 @@ def test_window_streaming_form_in_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", str(root / "tests" / "test_gpu_window.py"), "-k",
                         "spmv_bit_exact or jacobi_sweeps or replace_coefficients"], capture_output=True, text=True, timeout=600, cwd=str(root), env=env)
     assert r.returncode == 0 and "3 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def banded_with_hub_rows(n, sigma, seed=21, hubs=900, hub_len=400):
+    """the shape of the first aggregated level of the banded hierarchy: most rows short, ~1 % hub rows with hundreds of entries inside the band"""
+    rp, ci, va = gallery.random_banded(n, seed=seed, sigma=sigma)
+    rng = np.random.default_rng(seed + 1)
+    hub = np.sort(rng.choice(np.arange(5000, n - 5000), hubs, replace=False))
+    lens = np.diff(rp).astype(np.int64)
+    new_lens = lens.copy()
+    new_lens[hub] = hub_len
+    rp2 = np.zeros(n + 1, np.int64)
+    np.cumsum(new_lens, out=rp2[1:])
+    ci2 = np.empty(rp2[-1], np.int32)
+    va2 = np.empty(rp2[-1], np.float64)
+    keep = np.ones(n, bool)
+    keep[hub] = False
+    # ordinary rows keep their entries
+    src = np.repeat(rp[:-1][keep], lens[keep]) + (np.arange(lens[keep].sum()) - np.repeat(np.cumsum(lens[keep]) - lens[keep], lens[keep]))
+    dst = np.repeat(rp2[:-1][keep], lens[keep]) + (np.arange(lens[keep].sum()) - np.repeat(np.cumsum(lens[keep]) - lens[keep], lens[keep]))
+    ci2[dst] = ci[src]
+    va2[dst] = va[src]
+    for h in hub:                                            # hub rows: diagonal first, then distinct columns within +-4000
+        cols = h + rng.choice(np.arange(-4000, 4001), hub_len - 1, replace=False)
+        cols = cols[cols != h][:hub_len - 1]
+        cols = np.concatenate([[h], cols, np.full(hub_len - 1 - cols.shape[0], h + 4001)])
+        v = -rng.random(hub_len)
+        v[0] = 1.05 * np.abs(v[1:]).sum() + 1e-3
+        ci2[rp2[h]:rp2[h + 1]] = cols
+        va2[rp2[h]:rp2[h + 1]] = v
+    return rp2.astype(np.int32), ci2, va2
+
+
+def test_window_long_rows_side_kernel(amgx, oracle):
+    """hub rows leave the sliced-ELL copy and are summed by the warp-per-row side kernel (another summation order: tolerance); every other row
+    stays bit-exact; the fused Jacobi sweep and the residual pick the parked dot products up"""
+    rp, ci, va = banded_with_hub_rows(400_000, 1500.0)
+    n = rp.shape[0] - 1
+    lens = np.diff(rp)
+    cfg = amgx.Config("config_version=2, solver(main)=NOSOLVER")
+    rsc = amgx.Resources(cfg)
+    A = amgx.Matrix(rsc).upload(rp, ci, va)
+    xv, yv = amgx.Vector(rsc), amgx.Vector(rsc)
+    try:
+        assert A.kernel_info()["window"] > 0
+        x = np.random.default_rng(5).standard_normal(n)
+        xv.upload(x)
+        yv.set_zero(n)
+        A.multiply(xv, yv)
+        y, ref = yv.download(), oracle.spmv(rp, ci, va, x)
+        short = lens <= 64
+        assert np.array_equal(y[short], ref[short])
+        assert np.max(np.abs(y - ref)) <= 1e-13 * np.max(np.abs(ref))
+    finally:
+        for o in (yv, xv, A, rsc, cfg):
+            o.destroy()
+    rng = np.random.default_rng(6)
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    jc = {"config_version": 2, "solver": {"scope": "main", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "max_iters": 2, "monitor_residual": 0}}
+    xj, it, status, hist = run_engine(amgx, jc, rp, ci, va, b, x0=x0)
+    d = oracle.extract_diag(rp, ci, va)
+    xo = x0
+    for _ in range(2):
+        xo = oracle.jacobi_sweep(rp, ci, va, d, b, xo, 0.8)
+    assert np.max(np.abs(xj - xo)) <= 1e-13 * np.max(np.abs(xo))

@@ -5,8 +5,8 @@ import re, subprocess, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[2]
 OBJ = ROOT / "amgx_b200" / "_build"
-units = ["k_spmv", "k_spmv_enc", "k_blas", "k_transfer", "k_block", "dilu", "p2p", "fgmres", "dist"]
-pats = {"UBLKCP": r"\bUBLKCP", "SYNCS (mbarrier)": r"\bSYNCS", "UTMALDG": r"UTMALDG", "UCGABAR (cluster barrier)": r"UCGABAR", "LDG/STG .STRONG.SYS": r"(LDG|STG)\.E[.0-9A-Z]*\.STRONG\.SYS",
+units = ["k_spmv", "k_spmv_enc", "k_spmv_win", "k_blas", "k_transfer", "k_block", "dilu", "p2p", "fgmres", "dist"]
+pats = {"UBLKCP": r"\bUBLKCP", "UBLKPF.L2 (bulk L2 prefetch)": r"\bUBLKPF", "SYNCS (mbarrier)": r"\bSYNCS", "UTMALDG": r"UTMALDG", "UCGABAR (cluster barrier)": r"UCGABAR", "LDG/STG .STRONG.SYS": r"(LDG|STG)\.E[.0-9A-Z]*\.STRONG\.SYS",
         "DFMA": r"\bDFMA", "FFMA": r"\bFFMA", "LDS": r"\bLDS", "SHFL": r"\bSHFL", "HMMA (legacy tensor)": r"\bHMMA", "UTC*MMA (tcgen05)": r"UTC[A-Z]*MMA"}
 out = ["# r02 -- SASS evidence of the shipped sm_100a objects (`cuobjdump -sass amgx_b200/_build/*.o`, tools/r2/sass_evidence.py)\n",
        "No tensor-core instructions are expected: every hot kernel is an HBM-bound sparse / level-1 op (DESIGN 3).  TMA here is the 1-D bulk copy",
@@ -39,6 +39,7 @@ def excerpt(unit, func_pat, line_pat, before=3, after=6, title=""):
 
 excerpt("k_spmv", "csr_tile_kernelIddLi256ELi2ELb0", r"UBLKCP", 6, 14, "producer warp of the CSR tile kernel (fused Jacobi): expect_tx on the stage's mbarrier, three bulk copies (row_ptr slice, values, columns)")
 excerpt("k_spmv_enc", "csr_tile_enc_kernelIddLi256ELi2E", r"UBLKCP", 4, 20, "producer of the coded-stream tile kernel: code streams + dictionaries by bulk copy")
+excerpt("k_spmv_win", "csr_window_kernelIddLi2E", r"UBLKCP", 4, 26, "producer of the sliding-window kernel (fused Jacobi): sliced-ELL values and 16-bit offsets, row map, slice offsets and the x ring chunk by bulk copy; UBLKPF.L2 = prefetch of the b / d slices")
 excerpt("k_spmv", "csr_tile_kernelIddLi256ELi2ELb0", r"SYNCS\.PHASECHK|SYNCS\.ARRIVE", 2, 6, "consumer side: mbarrier phase check / arrive")
 excerpt("dilu", "dilu_level_kernelIfdLi4", r"UCGABAR_ARV", 4, 6, "fused DILU level kernel: colour boundary = cluster barrier (barrier.cluster.arrive.release / wait.acquire)")
 excerpt("p2p", "p2p_exchange_kernelId", r"STG\.E\.64\.STRONG\.SYS", 6, 8, "peer-memory exchange kernel: release store of the epoch flag into the neighbour's window")
