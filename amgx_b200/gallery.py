@@ -68,8 +68,10 @@ def block_elasticity_slab(nx: int, ny: int, nz: int, k0: int, k1: int, dtype=np.
     I4 = np.eye(4)
     off = -(I4 + 0.1 * S)
     dia = 6.6 * I4 + 0.6 * S
-    vals = np.where((val > 0)[:, None, None], dia[None], off[None]).astype(dtype)
-    return rp, col, np.ascontiguousarray(vals.reshape(-1))
+    vals = np.empty((val.shape[0], 4, 4), dtype)          # filled in the target type: no fp64 temporary of nnz x 16
+    vals[:] = off.astype(dtype)
+    vals[val > 0] = dia.astype(dtype)
+    return rp, col, vals.reshape(-1)
 
 
 def poisson7pt_sorted(nx: int, ny: int | None = None, nz: int | None = None, dtype=np.float64):
@@ -91,7 +93,13 @@ def _unique_sorted(key: np.ndarray) -> np.ndarray:
                 return torch.unique(torch.from_numpy(key).cuda()).cpu().numpy()
         except Exception:
             pass
-    return np.unique(key)
+    key = np.sort(key)                      # (np.unique on 60 M int64 keys takes minutes with numpy 2.3; sort + neighbour mask: seconds)
+    if key.shape[0] == 0:
+        return key
+    first = np.empty(key.shape[0], dtype=bool)
+    first[0] = True
+    np.not_equal(key[1:], key[:-1], out=first[1:])
+    return key[first]
 
 
 def random_banded(n: int = 4_000_000, seed: int = 12345, lam: float = 12.0, sigma: float = 2000.0, dtype=np.float64):
@@ -134,8 +142,10 @@ def block_elasticity(nx: int, ny: int, nz: int, dtype=np.float64):
     I4 = np.eye(4)
     off = -(I4 + 0.1 * S)
     dia = 6.6 * I4 + 0.6 * S
-    vals = np.where((val > 0)[:, None, None], dia[None], off[None]).astype(dtype)
-    return rp, col, np.ascontiguousarray(vals.reshape(-1))
+    vals = np.empty((val.shape[0], 4, 4), dtype)          # filled in the target type: no fp64 temporary of nnz x 16
+    vals[:] = off.astype(dtype)
+    vals[val > 0] = dia.astype(dtype)
+    return rp, col, vals.reshape(-1)
 
 
 def to_scipy(rp, col, val, n=None):
