@@ -24,6 +24,11 @@ N > 1 (one process per GPU, row partition in z-slabs, peer-memory / NCCL halo ex
            config.value_definition), config.global_iterations_per_sec is the raw rate.
   --strong the global grid stays NX^3 (BASELINE configs[3] with --grid 512): value = global iterations/s, scaling "strong".
   parity   object: the same distributed code path on a reduced global problem against a single-rank solve of the assembled matrix.
+  strong_512 object (default weak run, N divides 512): BASELINE configs[3] as stated -- the 512^3 grid row-partitioned over the N ranks,
+           same solver, device-timed like `value`; its N=1 counterpart is other_workloads.poisson512 of the N=1 line.
+Default N=1 line only: other_workloads = the other BASELINE workloads (512^3 Poisson = the north star's target size, the 4 M-row
+  SuiteSparse-shaped matrix, the 4x4 block configuration), each measured by THIS script in a child process after the main line's
+  numbers are final (`python bench.py --workload ... --no-extras`), under a common time budget; --no-extras skips them.
 """
 from __future__ import annotations
 
@@ -308,6 +313,131 @@ def distributed_parity(capi, dist, torch, rsc, rank, world, local_rank):
     return out
 
 
+# ------------------------------------------------------------------------------------------------------------------------
+# the other BASELINE workloads beside the default line (N = 1): child processes of this script, bounded in time
+# ------------------------------------------------------------------------------------------------------------------------
+EXTRA_WORKLOADS = [
+    ("poisson512", ["--workload", "poisson", "--grid", "512", "--steps", "2", "--warmup", "3"]),        # north star: >= 70 % of the roofline at 512^3
+    ("banded4m", ["--workload", "banded", "--steps", "3", "--warmup", "3"]),                              # SURVEY 8(d) input 2
+    ("block160_dDFI", ["--workload", "block", "--mode", "dDFI", "--steps", "3", "--warmup", "3"]),        # BASELINE configs[4] at 160^3 block rows
+]
+
+
+def other_workloads(budget_s=270.0, per_run_s=150.0, workloads=None, script=None):
+    """Runs `bench.py <flags> --no-cpu-baseline --no-reference-gpu --no-extras` once per extra workload and returns their JSON lines
+    (None-valued keys dropped).  A child that fails, prints no line or runs out of time costs only its own entry."""
+    out = {}
+    t_end = time.time() + budget_s
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK")}
+    for name, flags in (EXTRA_WORKLOADS if workloads is None else workloads):
+        left = t_end - time.time()
+        if left < 40.0:
+            out[name] = {"skipped": "time budget of the extra workloads spent"}
+            continue
+        cmd = [sys.executable, str(script or (ROOT / "bench.py")), *flags, "--no-cpu-baseline", "--no-reference-gpu", "--no-extras"]
+        t0 = time.time()
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=min(left, per_run_s), env=env, cwd=str(ROOT))
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if not lines:
+                out[name] = {"error": "no JSON line", "returncode": r.returncode, "tail": (r.stderr or r.stdout)[-300:]}
+                continue
+            d = json.loads(lines[-1])
+            d = {k: v for k, v in d.items() if v is not None}
+            d["wall_seconds_of_the_child"] = time.time() - t0
+            out[name] = d
+        except subprocess.TimeoutExpired:
+            out[name] = {"error": "timed out after %.0f s" % (time.time() - t0)}
+        except Exception as e:      # never let an extra cost the bench line
+            out[name] = {"error": repr(e)}
+    return out
+
+
+class LineGuard:
+    """Holds rank 0's JSON line while the context objects of a multi-GPU run (parity, strong_512) are computed.  Those run collectives;
+    should one of them hang, the guard prints the line as it stands -- its headline numbers are final before the guard is armed --
+    and ends the process, on every rank, instead of leaving the launcher waiting."""
+
+    def __init__(self, out, armed, limit_s):
+        self.out = out
+        self.lock = threading.Lock()
+        self.done = False
+        self.timer = None
+        if armed:
+            self.timer = threading.Timer(limit_s, self._expire)
+            self.timer.daemon = True
+            self.timer.start()
+        self.limit_s = limit_s
+
+    def _emit(self, note=None):
+        with self.lock:
+            if self.done:
+                return False
+            self.done = True
+        if self.out is not None:
+            if note:
+                self.out["note"] = note
+            print(json.dumps(self.out, default=str), flush=True)
+        return True
+
+    def _expire(self):
+        if self._emit("context objects (parity / strong_512) did not finish within %.0f s: line printed without them" % self.limit_s):
+            sys.stdout.flush()
+            os._exit(0)
+
+    def finish(self):
+        if self.timer is not None:
+            self.timer.cancel()
+        self._emit()
+
+
+def strong_512(capi, dist, torch, rsc, cfg, world, steps, warmup, grid=512):
+    """BASELINE configs[3] as stated: the grid^3 Poisson problem row-partitioned over the ranks (z-slabs of grid / world planes), PCG +
+    aggregation AMG, zero initial guess; timed like the main line (the library's CUDA events on its solve stream, max over ranks)."""
+    t0 = time.time()
+    A, b, x = capi.Matrix(rsc), capi.Vector(rsc), capi.Vector(rsc)
+    A.generate_poisson7(b, x, grid, grid, grid // world, 1, 1, world)
+    n, _, _ = A.get_size()
+    slv = capi.Solver(rsc, cfg)
+    slv.setup(A)
+    b.bind(A)
+    x.bind(A)
+    t_setup = time.time() - t0
+
+    def one():
+        x.set_zero(n, 1)
+        slv.solve(b, x, zero_initial_guess=True)
+        s, k = slv.last_solve_stats()
+        return s, k, slv.iterations_number
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    tot_s, tot_k, tot_it = 0.0, 0, 0
+    for _ in range(steps):
+        s, k, it = one()
+        tot_s += s
+        tot_k += k
+        tot_it += it
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([tot_s], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_s = float(t.item())
+    status = slv.status
+    hist = np.array(slv.residual_history()).ravel()
+    res = {"workload": f"7-pt Poisson {grid}^3 fp64 row-partitioned over {world} GPUs (z-slabs of {grid // world} planes), PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI.json)",
+           "value": tot_it / tot_s, "unit": UNIT, "scaling": "strong", "steps": steps, "warmup": warmup, "ms_per_step": tot_s / steps * 1e3,
+           "iterations_per_step": tot_it / steps, "solve_status": status, "rows": n * world, "setup_seconds": t_setup, "gpu_launches": int(tot_k),
+           "final_relative_residual": float(hist[-1] / hist[0]) if len(hist) else None,
+           "n1_counterpart": "other_workloads.poisson512.value of the N=1 line (same grid, same solver, one GPU)"}
+    for o in (slv, x, b, A):
+        o.destroy()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -322,6 +452,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_workloads (N = 1) and strong_512 (N > 1)")
     args = ap.parse_args()
     if args.n is None:
         args.n = 160 if args.workload == "block" else 256
@@ -522,23 +653,8 @@ def main():
             except Exception as e:      # never let the extra figure cost the bench line
                 roof["iteration"] = {"error": repr(e)}
 
-    parity = None
-    if distributed and not args.no_parity:
-        try:
-            parity = distributed_parity(capi, dist, torch, rsc, rank, world, local_rank)
-        except Exception as e:
-            parity = {"error": repr(e)}
-
-    for o in (slv, x, b, A):
-        o.destroy()
-    refgpu = None
-    if rank == 0 and not distributed and args.workload == "poisson" and not args.no_reference_gpu:
-        torch.cuda.empty_cache()
-        refgpu = reference_gpu(nx)
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline and not distributed and args.workload == "poisson":
-        cpu = oracle_baseline(nx, nx, nx, 5 if nx <= 256 else 2)
-
+    # ---- the line: value, e2e, roofline and clocks are final here; what follows only adds context objects to it ----
+    out = None
     if rank == 0:
         cfgd = workload_config(args, world)
         cfgd.update({"rows": n * world, "nnz_per_rank": nnz, "iterations_per_step": tot_it / args.steps, "solve_status": status,
@@ -554,9 +670,39 @@ def main():
                "config": cfgd,
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hb.nbytes), "d2h_bytes_per_step": int(hx.nbytes),
                        "ms_per_step": e_dt / args.steps * 1e3},
-               "gpu_launches": int(tot_k), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "reference_gpu": refgpu, "parity": parity,
+               "gpu_launches": int(tot_k), "clocks": clocks, "roofline": roof, "cpu_baseline": None, "reference_gpu": None, "parity": None,
                "final_relative_residual": float(hist[-1] / hist[0]) if hist is not None and len(hist) else None}
-        print(json.dumps(out), flush=True)
+    guard = LineGuard(out, armed=distributed, limit_s=float(os.environ.get("AMGXB_BENCH_GUARD_S", "300")))      # parity and strong_512 run collectives: a hang there must not cost the line
+
+    if distributed and not args.no_parity:
+        try:
+            parity = distributed_parity(capi, dist, torch, rsc, rank, world, local_rank)
+        except Exception as e:
+            parity = {"error": repr(e)}
+        if out is not None:
+            out["parity"] = parity
+
+    for o in (slv, x, b, A):
+        o.destroy()
+
+    if distributed and not args.no_extras and args.workload == "poisson" and not args.strong and nx == 256 and 512 % world == 0:
+        try:
+            torch.cuda.empty_cache()
+            st = strong_512(capi, dist, torch, rsc, cfg, world, steps=3, warmup=3)
+        except Exception as e:
+            st = {"error": repr(e)}
+        if out is not None:
+            out["strong_512"] = st
+
+    if rank == 0 and not distributed and args.workload == "poisson":
+        if not args.no_reference_gpu:
+            torch.cuda.empty_cache()
+            out["reference_gpu"] = reference_gpu(nx)
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = oracle_baseline(nx, nx, nx, 5 if nx <= 256 else 2)
+        if not args.no_extras and nx == 256:
+            out["other_workloads"] = other_workloads()
+    guard.finish()
     for o in (rsc, cfg):
         o.destroy()
     capi.finalize()

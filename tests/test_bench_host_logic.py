@@ -1,0 +1,91 @@
+"""Host logic of bench.py without a GPU: the engine is replaced by a stand-in (tests/bench_dryrun_worker.py), so these tests say
+nothing about kernels -- they pin how the JSON line is assembled, that a failing / slow context object never costs the line, and that
+the multi-GPU flow (run here over gloo, world size 2) ends even when a collective context object hangs."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+WORKER = ROOT / "tests" / "bench_dryrun_worker.py"
+sys.path.insert(0, str(ROOT))
+
+CONTRACT_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                 "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "reference_gpu", "parity", "final_relative_residual"]
+
+
+def _line(stdout):
+    lines = [ln for ln in stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, stdout[-2000:]          # ONE JSON line
+    return json.loads(lines[0])
+
+
+def test_other_workloads_children(tmp_path):
+    """Every extra workload is a child `bench.py <flags> --no-cpu-baseline --no-reference-gpu --no-extras`; a child that prints no line,
+    fails or overruns its time costs only its own entry."""
+    import bench
+    small = [("poisson_small", ["--workload", "poisson", "--grid", "16", "--steps", "2", "--warmup", "1"]),
+             ("banded_small", ["--workload", "banded", "--rows", "20000", "--steps", "2", "--warmup", "1"]),
+             ("block_small", ["--workload", "block", "--grid", "8", "--mode", "dDFI", "--steps", "2", "--warmup", "1"])]
+    out = bench.other_workloads(budget_s=200, per_run_s=100, workloads=small, script=WORKER)
+    for name, _ in small:
+        assert "error" not in out[name] and "skipped" not in out[name], out[name]
+        assert out[name]["metric"] == bench.METRIC and out[name]["value"] > 0 and out[name]["n_gpus"] == 1
+        assert "other_workloads" not in out[name] and "cpu_baseline" not in out[name]           # --no-extras reached the child; None-valued keys dropped
+    assert "SuiteSparse-shaped" in out["banded_small"]["config"]["workload"] and "20000 rows" in out["banded_small"]["config"]["workload"]
+    assert out["block_small"]["dtype"] == "f32 matrix / f64 vectors" and "block4" in out["block_small"]["roofline"]["kernel"]
+    # the flags of the real list parse
+    for _, flags in bench.EXTRA_WORKLOADS:
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), *flags, "--no-cpu-baseline", "--no-reference-gpu", "--no-extras", "--help"], capture_output=True, text=True)
+        assert r.returncode == 0
+
+    bad = tmp_path / "bad.py"
+    bad.write_text("import sys, time\nif '--grid' in sys.argv:\n    time.sleep(60)\nprint('no json here'); sys.exit(3)\n")
+    out = bench.other_workloads(budget_s=42.5, per_run_s=3, workloads=[("fails", []), ("slow", ["--grid", "1"]), ("late", [])], script=bad)
+    assert "timed out" in out["slow"]["error"]
+    assert out["fails"]["error"] == "no JSON line" and out["fails"]["returncode"] == 3
+    assert "skipped" in out["late"]                                                              # fewer than 40 s of the budget left
+
+
+def test_single_gpu_line_survives_failing_extras():
+    """N = 1 default flow: the children (the real bench.py) stop at once without a device -- the line is printed all the same."""
+    r = subprocess.run([sys.executable, str(WORKER), "--steps", "2", "--warmup", "1", "--no-cpu-baseline", "--no-reference-gpu"], capture_output=True, text=True, timeout=600)
+    d = _line(r.stdout)
+    for k in CONTRACT_KEYS:
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["config"]["workload"].startswith("7-pt Poisson 256x256x256")
+    assert d["roofline"]["bound"] == "hbm" and d["roofline"]["spmv"]["frac"] > 0 and d["roofline"]["iteration"]["levels"] == 3
+    assert set(d["other_workloads"]) == {"poisson512", "banded4m", "block160_dDFI"}
+    assert all("error" in v for v in d["other_workloads"].values())
+    assert "strong_512" not in d
+
+
+def _torchrun(port, extra_env=None, args=()):
+    env = dict(os.environ, **(extra_env or {}))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           str(WORKER), "--gpus", "2", "--steps", "2", "--warmup", "1", "--no-parity", *args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+
+
+def test_two_rank_line_has_strong_512():
+    r = _torchrun(29541)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = _line(r.stdout)
+    assert d["n_gpus"] == 2 and d["value"] == 2 * d["config"]["global_iterations_per_sec"] and d["roofline"] is None
+    s = d["strong_512"]
+    assert s["scaling"] == "strong" and s["rows"] == 512 ** 3 and "z-slabs of 256 planes" in s["workload"] and s["warmup"] >= 3
+    assert "other_workloads" not in d and "note" not in d
+    d = _line(_torchrun(29542, args=("--no-extras",)).stdout)
+    assert "strong_512" not in d
+    d = _line(_torchrun(29543, args=("--strong", "--grid", "512")).stdout)
+    assert "strong_512" not in d and d["scaling"] == "strong" and d["value"] == d["config"]["global_iterations_per_sec"]
+
+
+def test_two_rank_line_is_printed_when_a_context_object_hangs():
+    """Rank 1 never returns from its first solve of the strong_512 problem: after AMGXB_BENCH_GUARD_S seconds rank 0 prints the line
+    without the object and every rank ends."""
+    r = _torchrun(29544, extra_env={"BENCH_DRYRUN_HANG": "strong", "AMGXB_BENCH_GUARD_S": "5"})
+    d = _line(r.stdout)
+    assert d["n_gpus"] == 2 and d["value"] > 0 and "strong_512" not in d
+    assert "did not finish" in d["note"]
