@@ -43,6 +43,10 @@ struct Error : public std::exception {
 void amgx_output(const char *msg, int len);
 void amgx_printf(const char *fmt, ...);
 
+// Opt a kernel in to `smem` bytes of dynamic shared memory.  The attribute belongs to the (function, device) pair, so what has been
+// granted is remembered per device: a process that drives several GPUs opts in on each of them (misc.cu).
+void smem_opt_in(const void *kernel, size_t smem);
+
 // Global launch counter (our kernels only): incremented by every launcher in k_*.cu.
 extern long long g_kernel_launches;
 inline void count_launch(int n = 1) { g_kernel_launches += n; }

@@ -581,8 +581,7 @@ __global__ void __launch_bounds__(DT_CONSUMERS + PRODUCER_THREADS) dilu_tile_ker
 template <class MatT, class VecT, bool BACKWARD> void launch_dilu_tile(const DiluTileArgs &ta, int grid, size_t smem, cudaStream_t s)
 {
     auto k = dilu_tile_kernel<MatT, VecT, BACKWARD>;
-    static size_t attr_bytes = 0;
-    if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+    smem_opt_in(reinterpret_cast<const void *>(k), smem);      // exactly what this kernel needs, once per size and device
     k<<<grid, DT_CONSUMERS + PRODUCER_THREADS, smem, s>>>(ta);
 }
 

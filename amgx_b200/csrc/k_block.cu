@@ -261,8 +261,7 @@ __global__ void __launch_bounds__(BT_CONSUMERS + PRODUCER_THREADS) block4_tile_k
 template <class MatT, class VecT, int MODE> void launch_block_tile(const BlockTileArgs &ta, int grid, size_t smem, cudaStream_t s)
 {
     auto k = block4_tile_kernel<MatT, VecT, MODE>;
-    static size_t attr_bytes = 0;       // opt in to the dynamic shared memory this kernel needs, once per size
-    if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+    smem_opt_in(reinterpret_cast<const void *>(k), smem);      // exactly what this kernel needs, once per size and device
     k<<<grid, BT_CONSUMERS + PRODUCER_THREADS, smem, s>>>(ta);
 }
 

@@ -292,13 +292,11 @@ template <class MatT, class VecT, int TILE_ROWS, int EPI> void launch_tile(const
     const size_t smem = A.plan.smem_bytes;
     if (ta.agg) {
         auto k = csr_tile_kernel<MatT, VecT, TILE_ROWS, EPI, true>;
-        static size_t attr_bytes = 0;   // opt in to exactly what this kernel needs (static smem counts against the 227 KB cap)
-        if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+        smem_opt_in(reinterpret_cast<const void *>(k), smem);      // exactly what this kernel needs, once per size and device
         k<<<grid, TILE_ROWS + PRODUCER_THREADS, smem, s>>>(ta);
     } else {
         auto k = csr_tile_kernel<MatT, VecT, TILE_ROWS, EPI, false>;
-        static size_t attr_bytes = 0;   // opt in to exactly what this kernel needs (static smem counts against the 227 KB cap)
-        if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+        smem_opt_in(reinterpret_cast<const void *>(k), smem);      // exactly what this kernel needs, once per size and device
         k<<<grid, TILE_ROWS + PRODUCER_THREADS, smem, s>>>(ta);
     }
 }

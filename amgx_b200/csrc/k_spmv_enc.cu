@@ -716,8 +716,7 @@ void launch_enc(const Matrix &A, const TileArgs<MatT, VecT> &ta, const EncArgs &
 {
     const size_t smem = A.colenc.smem_bytes;
     auto k = csr_tile_enc_kernel<MatT, VecT, TILE_ROWS, EPI>;
-    static size_t attr_bytes = 0;
-    if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+    smem_opt_in(reinterpret_cast<const void *>(k), smem);      // exactly what this kernel needs, once per size and device
     // the persistent grid must not exceed what is RESIDENT for this instantiation (registers differ per epilogue): a CTA that waits for a
     // slot runs its tiles after everybody else's (r02: 52 registers -> 4 resident of 5 launched per SM cost 50 % on the Jacobi sweep)
     static std::map<size_t, int> occ_by_smem;

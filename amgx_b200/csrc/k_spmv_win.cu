@@ -505,14 +505,12 @@ template <class MatT, class VecT, int EPI> void launch_win(const Matrix &A, cons
     if (A.win.stream) {
         const size_t smem = A.win.stream_smem_bytes;
         auto k = csr_stream_kernel<MatT, VecT, EPI>;
-        static size_t attr_bytes = 0;
-        if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+        smem_opt_in(reinterpret_cast<const void *>(k), smem);      // exactly what this kernel needs, once per size and device
         k<<<A.win.grid, WIN_T + PRODUCER_THREADS, smem, s>>>(ta, wa);
     } else {
         const size_t smem = A.win.smem_bytes;
         auto k = csr_window_kernel<MatT, VecT, EPI>;
-        static size_t attr_bytes = 0;
-        if (smem > attr_bytes) { AMGXB_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_bytes = smem; }
+        smem_opt_in(reinterpret_cast<const void *>(k), smem);      // exactly what this kernel needs, once per size and device
         k<<<A.win.grid, WIN_T + PRODUCER_THREADS, smem, s>>>(ta, wa);
     }
     count_launch();

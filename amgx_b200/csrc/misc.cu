@@ -2,6 +2,8 @@
 #include "solvers.h"
 #include "dist.h"
 #include <cstdarg>
+#include <map>
+#include <utility>
 
 namespace amgxb {
 
@@ -22,6 +24,18 @@ void amgx_printf(const char *fmt, ...)
     int n = vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
     if (n > 0) amgx_output(buf, std::min(n, (int)sizeof(buf) - 1));
+}
+
+void smem_opt_in(const void *kernel, size_t smem)
+{
+    static std::map<std::pair<const void *, int>, size_t> granted;      // (kernel, device) -> bytes; host threads do not share handles (as in the reference)
+    int dev = 0;
+    AMGXB_CUDA_CHECK(cudaGetDevice(&dev));
+    size_t &have = granted[std::make_pair(kernel, dev)];
+    if (smem > have) {
+        AMGXB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
 }
 
 double device_mem_used_gb()
