@@ -215,7 +215,7 @@ def reference_gpu(nx, reps=2):
         return {"unavailable": "oracle/_ref/ref_dump not built (oracle/ref_build/Makefile, needs /root/reference)"}
     try:
         env = dict(os.environ, REFDUMP_NO_LEVELS="1", LD_LIBRARY_PATH=str(exe.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-        r = subprocess.run([str(exe), f"poisson:{nx}", str(CONFIG), "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=900, env=env)
+        r = subprocess.run([str(exe), f"poisson:{nx}", str(CONFIG), "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=300, env=env)
         m = re.search(r"ref_dump: status (\d+) iterations (\d+) setup ([0-9.eE+-]+) s solve ([0-9.eE+-]+) s", r.stdout)
         if not m:
             return {"unavailable": "ref_dump gave no timing line", "tail": (r.stdout + r.stderr)[-300:]}
@@ -323,7 +323,7 @@ EXTRA_WORKLOADS = [
 ]
 
 
-def other_workloads(budget_s=270.0, per_run_s=150.0, workloads=None, script=None):
+def other_workloads(budget_s=240.0, per_run_s=110.0, workloads=None, script=None):
     """Runs `bench.py <flags> --no-cpu-baseline --no-reference-gpu --no-extras` once per extra workload and returns their JSON lines
     (None-valued keys dropped).  A child that fails, prints no line or runs out of time costs only its own entry."""
     out = {}
