@@ -247,6 +247,10 @@ protected:
     double beta_ = 0;
     size_t krylov_len_ = 0;
     bool update_x_every_iteration_ = false, update_r_every_iteration_ = false;
+    bool trunc_ = false;                // gmres_krylov_dim < restart: the truncated variant (rings of krylov_dim + 2 / + 1 vectors)
+    DevVec resid_;                      // truncated variant: the recursively updated residual vector whose norm is monitored
+    DevVec &Vr(int i) { return V_[(size_t)i % V_.size()]; }
+    DevVec &Zr(int i) { return Z_[(size_t)i % Z_.size()]; }
     double &H(int i, int j) { return H_[(size_t)i * (R_ + 1) + j]; }   // (R+2) x (R+1) storage
     double *hs_dev_ = nullptr, *hs_host_ = nullptr, *hs_host_dev_ = nullptr;   // Hessenberg column on device + pinned mirror
 };

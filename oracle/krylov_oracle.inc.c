@@ -205,3 +205,93 @@ fin:
     free(r); free(c.dj);
     return it;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* FGMRES with gmres_krylov_dim < gmres_n_restart: the reference's truncated variant ("DQGMRES"). */
+/*   KrylovSubspaceBuffer          src/solvers/fgmres_solver.cu:17-211: rings of K+2 V- and K+1 Z-vectors (max_dimension = K + 1),        */
+/*                                 get_smallest_m() = max(m - K, 0)                                                                       */
+/*   solver_setup                  :284-298: update_x_every_iteration = update_r_every_iteration = (K < R) (with monitoring)              */
+/*   solve_iteration               :406-569: truncated modified Gram-Schmidt over V(smallest..m); ALL Givens rotations of the cycle are   */
+/*                                 applied to the new column (rows below `smallest` hold whatever the previous cycle left there: m_H is   */
+/*                                 allocated once and never cleared -- kept here on purpose); p_m = (z_m - sum_{i>=smallest} h_im p_i) /  */
+/*                                 h_mm, x += s_m p_m every iteration; the residual VECTOR follows the recursion of :520-533 and its L2    */
+/*                                 norm (not |s[m+1]|) drives the convergence check (checkConvergenceGMRES :348-398).                      */
+/* Same conventions as orc_fgmres above.  parity unpinned: no reference golden was generated for this variant (no shipped configuration  */
+/* sets gmres_krylov_dim); the restatement is checked against an independent numpy formulation (tests/test_oracle_krylov.py).             */
+/* ------------------------------------------------------------------------------------------- */
+ORC_API int orc_fgmres_trunc(int n, const int *rp, const int *ci, const double *va, const orc_amg *amg, int precond, double jac_omega, const double *b,
+                             double *x, int x_is_zero, double tol, int max_iters, int restart, int krylov_dim, double *res_hist, int *converged_out)
+{
+    const int R = restart;
+    int K = max_iters < R ? max_iters : R;
+    if (krylov_dim > 0 && krylov_dim < K) K = krylov_dim;
+    const int NV = K + 2, NZ = K + 1;
+    const size_t nn = (size_t)(n > 0 ? n : 1), nb = sizeof(double) * nn;
+    kry_ctx c = {n, precond, rp, ci, va, amg, jac_omega, NULL};
+    if (precond == 2) { c.dj = (double *)malloc(nb); orc_extract_diag(n, rp, ci, va, c.dj); }
+    double **V = (double **)malloc(sizeof(double *) * (size_t)NV), **Z = (double **)malloc(sizeof(double *) * (size_t)NZ);
+    for (int i = 0; i < NV; i++) V[i] = (double *)calloc(nn, sizeof(double));
+    for (int i = 0; i < NZ; i++) Z[i] = (double *)calloc(nn, sizeof(double));
+    double *H = (double *)calloc((size_t)(R + 2) * (size_t)(R + 1), sizeof(double));
+    double *s = (double *)calloc((size_t)R + 2, sizeof(double)), *cs = (double *)calloc((size_t)R + 1, sizeof(double)), *sn = (double *)calloc((size_t)R + 1, sizeof(double));
+    double *gamma = (double *)calloc((size_t)R + 2, sizeof(double));
+    double *r = (double *)malloc(nb), *resid = (double *)calloc(nn, sizeof(double));
+#define HH(i, j) H[(size_t)(i) * (size_t)(R + 1) + (size_t)(j)]
+#define VV(i) V[(i) % NV]
+#define ZZ(i) Z[(i) % NZ]
+    if (x_is_zero) memcpy(r, b, nb);
+    else orc_residual(n, rp, ci, va, x, b, r);
+    double nrm = orc_nrm2(n, r), nrm_ini = nrm;
+    res_hist[0] = nrm;
+    int done = conv_relative_ini(nrm, nrm_ini, tol), it = 0, conv = done;
+    if (max_iters == 0) { conv = 0; goto fin; }
+    for (it = 0; it < max_iters && !done; it++) {
+        const int m = it % R;
+        if (m == 0) {
+            orc_residual(n, rp, ci, va, x, b, VV(0));
+            const double beta = orc_nrm2(n, VV(0));
+            if (it == 0 && conv_relative_ini(beta, nrm_ini, tol)) { res_hist[it + 1] = beta; conv = 1; it++; break; }
+            { const double a = 1.0 / beta; double *v0 = VV(0); for (int i = 0; i < n; i++) v0[i] = v0[i] * a; }
+            for (int i = 0; i < R + 2; i++) s[i] = 0.0;
+            s[0] = beta;
+        }
+        double *vm1 = VV(m + 1), *zm = ZZ(m);
+        kry_precond(&c, VV(m), zm);
+        orc_spmv(n, rp, ci, va, zm, vm1);
+        const int sm = m > K ? m - K : 0;
+        for (int i = sm; i <= m; i++) {
+            const double h = orc_dot(n, VV(i), vm1);
+            HH(i, m) = h;
+            kry_axpy(n, VV(i), vm1, -h);
+        }
+        HH(m + 1, m) = orc_nrm2(n, vm1);
+        { const double a = 1.0 / HH(m + 1, m); for (int k = 0; k < n; k++) vm1[k] = vm1[k] * a; }
+        gamma[m] = s[m];
+        for (int k = 0; k < m; k++) {
+            const double t = cs[k] * HH(k, m) + sn[k] * HH(k + 1, m);
+            HH(k + 1, m) = -sn[k] * HH(k, m) + cs[k] * HH(k + 1, m);
+            HH(k, m) = t;
+        }
+        gen_rot(HH(m, m), HH(m + 1, m), &cs[m], &sn[m]);
+        HH(m, m) = cs[m] * HH(m, m) + sn[m] * HH(m + 1, m);
+        HH(m + 1, m) = 0.0;
+        { const double t = cs[m] * s[m]; s[m + 1] = -sn[m] * s[m]; s[m] = t; }
+        for (int i = sm; i < m; i++) kry_axpy(n, ZZ(i), zm, -HH(i, m));
+        { const double a = 1.0 / HH(m, m); for (int k = 0; k < n; k++) zm[k] = zm[k] * a; }
+        kry_axpy(n, zm, x, s[m]);
+        if (m == 0) kry_axpby(n, VV(1), VV(0), resid, s[1] * cs[0], -1.0 * s[1] * sn[0]);
+        else kry_axpby(n, vm1, resid, resid, s[m + 1] * cs[m], -1.0 * s[m + 1] * sn[m] / gamma[m]);
+        nrm = orc_nrm2(n, resid);
+        res_hist[it + 1] = nrm;
+        if (conv_relative_ini(nrm, nrm_ini, tol)) { conv = 1; done = 1; it++; break; }
+    }
+fin:
+    if (converged_out) *converged_out = conv;
+    for (int i = 0; i < NV; i++) free(V[i]);
+    for (int i = 0; i < NZ; i++) free(Z[i]);
+    free(V); free(Z); free(H); free(s); free(cs); free(sn); free(gamma); free(r); free(resid); free(c.dj);
+#undef HH
+#undef VV
+#undef ZZ
+    return it;
+}

@@ -256,7 +256,8 @@ def pcg(rp, ci, va, b, amg: AMG | None = None, jacobi_omega: float | None = None
     return x, it, hist[: it + 1].copy(), bool(conv.value)
 
 
-def fgmres(rp, ci, va, b, amg: AMG | None = None, jacobi_omega: float | None = None, x0=None, tol=1e-6, max_iters=100, restart=20):
+def fgmres(rp, ci, va, b, amg: AMG | None = None, jacobi_omega: float | None = None, x0=None, tol=1e-6, max_iters=100, restart=20, krylov_dim=0):
+    """krylov_dim (gmres_krylov_dim) smaller than min(max_iters, restart): the reference's truncated variant (orc_fgmres_trunc)"""
     rp, ci, va, b = _i(rp), _i(ci), _d(va), _d(b)
     n = rp.shape[0] - 1
     zero = x0 is None
@@ -264,6 +265,10 @@ def fgmres(rp, ci, va, b, amg: AMG | None = None, jacobi_omega: float | None = N
     hist = np.zeros(max_iters + 1)
     conv = C.c_int()
     precond = 1 if amg is not None else (2 if jacobi_omega is not None else 0)
+    if 0 < krylov_dim < min(max_iters, restart):
+        it = lib().orc_fgmres_trunc(n, _p(rp), _p(ci), _p(va), amg.h if amg is not None else None, precond, C.c_double(jacobi_omega or 0.0), _p(b), _p(x),
+                                    int(zero), C.c_double(tol), max_iters, restart, int(krylov_dim), _p(hist), C.byref(conv))
+        return x, it, hist[: it + 1].copy(), bool(conv.value)
     it = lib().orc_fgmres(n, _p(rp), _p(ci), _p(va), amg.h if amg is not None else None, precond, C.c_double(jacobi_omega or 0.0), _p(b), _p(x),
                           int(zero), C.c_double(tol), max_iters, restart, _p(hist), C.byref(conv))
     return x, it, hist[: it + 1].copy(), bool(conv.value)
