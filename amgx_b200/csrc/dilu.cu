@@ -600,8 +600,11 @@ public:
         if (scheme_ != "MIN_MAX" && scheme_ != "PARALLEL_GREEDY")
             fatal(AMGX_RC_BAD_CONFIGURATION, "matrix_coloring_scheme '" + scheme_ + "' is not supported by this engine (MIN_MAX, PARALLEL_GREEDY, or AMGX_matrix_attach_coloring)");
         if (cfg.get_int("coloring_level", scope) != 1) fatal(AMGX_RC_BAD_CONFIGURATION, "MULTICOLOR_DILU: coloring_level must be 1");
-        if (cfg.get_int("reorder_cols_by_color", scope) != 0 || cfg.get_int("insert_diag_while_reordering", scope) != 0)
-            fatal(AMGX_RC_NOT_IMPLEMENTED, "reorder_cols_by_color / insert_diag_while_reordering");
+        // reorder_cols_by_color / insert_diag_while_reordering (src/matrix.cu:749-812): the reference sorts the entries of every row by the colour of
+        // their column so that its sweeps can split a row into "earlier colours | later colours" without reading the colour array.  A memory
+        // layout, not an algorithm: the sweeps here look up the colour of every column (or work on their own colour-sorted copy), whatever the
+        // caller's entry order is, so the two
+        // switches are accepted and change nothing (the caller's matrix is not permuted; sums differ from the reference's by their rounding only).
         uncolored_fraction_ = cfg.get_int("determinism_flag", "default") ? 0.0 : cfg.get_double("max_uncolored_percentage", scope);
     }
     bool is_coloring_needed() const override { return true; }

@@ -128,6 +128,19 @@ def test_config_check_on_own_configs_and_bad_components(lib):
         cfg.destroy()
 
 
+def test_config_check_accepts_layout_hints_and_truncated_fgmres(lib):
+    """reorder_cols_by_color / insert_diag_while_reordering are memory-layout switches of the reference's colour sweeps (src/matrix.cu:749-812):
+    accepted, they change nothing here; gmres_krylov_dim below the restart length selects the truncated FGMRES variant"""
+    from amgx_b200 import capi
+    for good in ["config_version=2, solver(s)=AMG, s:algorithm=AGGREGATION, s:selector=SIZE_2, s:smoother(m)=MULTICOLOR_DILU, m:reorder_cols_by_color=1, m:insert_diag_while_reordering=1",
+                 "config_version=2, solver(s)=AMG, s:algorithm=AGGREGATION, s:selector=SIZE_2, s:smoother(m)=MULTICOLOR_GS, m:reorder_cols_by_color=1",
+                 "config_version=2, solver(s)=FGMRES, s:gmres_n_restart=20, s:gmres_krylov_dim=4, s:preconditioner(p)=BLOCK_JACOBI"]:
+        cfg = capi.Config(good)
+        ok, msg = capi.config_check(cfg)
+        assert ok and msg == "", (good, msg)
+        cfg.destroy()
+
+
 @pytest.mark.skipif(not REF_CONFIGS.is_dir(), reason="the reference's shipped configurations are only present in the build container")
 def test_config_check_on_the_reference_shipped_configs(lib):
     """58 of the 62 configurations the reference ships name only components the engine provides (README "Status")"""
