@@ -427,7 +427,7 @@ def strong_512(capi, dist, torch, rsc, cfg, world, steps, warmup, grid=512):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tot_s = float(t.item())
     status = slv.status
-    hist = np.array(slv.residual_history()).ravel()
+    hist = np.array(slv.residual_history()).ravel() if dist.get_rank() == 0 else np.zeros(0)      # read where the main line reads it
     res = {"workload": f"7-pt Poisson {grid}^3 fp64 row-partitioned over {world} GPUs (z-slabs of {grid // world} planes), PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI.json)",
            "value": tot_it / tot_s, "unit": UNIT, "scaling": "strong", "steps": steps, "warmup": warmup, "ms_per_step": tot_s / steps * 1e3,
            "iterations_per_step": tot_it / steps, "solve_status": status, "rows": n * world, "setup_seconds": t_setup, "gpu_launches": int(tot_k),
