@@ -107,7 +107,7 @@ def run_oracle(oracle, cfg, rp, ci, va, b, x0=None):
     if name == "PCG":
         x, it, hist, conv = oracle.pcg(rp, ci, va, b, x0=x0, tol=tol, max_iters=mi, norm=norm, **kw)
     elif name == "FGMRES":
-        x, it, hist, conv = oracle.fgmres(rp, ci, va, b, x0=x0, tol=tol, max_iters=mi, restart=_get(s, "gmres_n_restart"), **kw)
+        x, it, hist, conv = oracle.fgmres(rp, ci, va, b, x0=x0, tol=tol, max_iters=mi, restart=_get(s, "gmres_n_restart"), krylov_dim=s.get("gmres_krylov_dim", 0), **kw)
     else:
         x, it, hist, conv = oracle.krylov(name, rp, ci, va, b, x0=x0, tol=tol, max_iters=mi, restart=_get(s, "gmres_n_restart"), norm=norm, **kw)
     return x, it, hist, conv, amg
