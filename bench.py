@@ -29,6 +29,8 @@ N > 1 (one process per GPU, row partition in z-slabs, peer-memory / NCCL halo ex
 Default N=1 line only: other_workloads = the other BASELINE workloads (512^3 Poisson = the north star's target size, the 4 M-row
   SuiteSparse-shaped matrix, the 4x4 block configuration), each measured by THIS script in a child process after the main line's
   numbers are final (`python bench.py --workload ... --no-extras`), under a common time budget; --no-extras skips them.
+  reference_host_path = the reference's own host implementation (mode hDDI, PCG + BLOCK_JACOBI: the solver family it has on the CPU),
+  timed on the host cores beside this engine on the same configuration.
 """
 from __future__ import annotations
 
@@ -225,6 +227,62 @@ def reference_gpu(nx, reps=2):
                        f"cudaEvents by oracle/ref_build/ref_dump.cu on the same GPU after this engine's timed region"}
     except Exception as e:      # never let the context figure cost the bench line
         return {"unavailable": repr(e)}
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# the reference's OWN CPU path beside the engine: the one solver family it implements completely on the host
+# ------------------------------------------------------------------------------------------------------------------------
+HOST_PATH_CFG = {"config_version": 2, "determinism_flag": 1, "solver": {
+    "scope": "main", "solver": "PCG", "max_iters": 10, "monitor_residual": 1, "store_res_history": 1, "convergence": "RELATIVE_INI", "tolerance": 1e-30, "norm": "L2",
+    "preconditioner": {"scope": "jac", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "max_iters": 1, "monitor_residual": 0}}}
+
+
+def reference_host_path(capi, rsc, nx):
+    """BASELINE configs[0]'s solver (PCG + BLOCK_JACOBI) is the one whose every component the reference implements on the host
+    (src/multiply.cu:753-852, src/solvers/block_jacobi_solver.cu:1256-1332; aggregation SIZE_2 and DILU have no host path).
+    Here: that solver, 10 iterations, on the nx^3 Poisson matrix -- (a) the UNMODIFIED reference in its host mode hDDI through
+    oracle/_ref/ref_dump (single-threaded C++ loops: cores = 1), (b) this engine on the same configuration and matrix.
+    First written after round 2's GPU minutes were spent: the reference side reports `unavailable` with the reason if its host mode fails."""
+    out = {"config": f"PCG + BLOCK_JACOBI(0.8), {HOST_PATH_CFG['solver']['max_iters']} iterations, 7-pt Poisson {nx}^3 fp64, b = 1, x0 = 0", "unit": UNIT}
+    try:
+        cfg = capi.Config(HOST_PATH_CFG)
+        A, b, x = capi.Matrix(rsc), capi.Vector(rsc), capi.Vector(rsc)
+        A.generate_poisson7(b, x, nx, nx, nx, 1, 1, 1)
+        n, _, _ = A.get_size()
+        slv = capi.Solver(rsc, cfg)
+        slv.setup(A)
+        tot_s, tot_it = 0.0, 0
+        for i in range(6):                                  # 3 warm-up solves, 3 timed
+            x.set_zero(n, 1)
+            slv.solve(b, x, zero_initial_guess=True)
+            if i >= 3:
+                tot_s += slv.last_solve_stats()[0]
+                tot_it += slv.iterations_number
+        out["engine"] = {"value": tot_it / tot_s, "iterations": tot_it // 3, "how": "this engine, device-timed like `value`"}
+        for o in (slv, x, b, A, cfg):
+            o.destroy()
+    except Exception as e:      # never let a context figure cost the bench line
+        out["engine"] = {"unavailable": repr(e)}
+    exe = ROOT / "oracle" / "_ref" / "ref_dump"
+    if not exe.exists():
+        out["reference_cpu"] = {"unavailable": "oracle/_ref/ref_dump not built"}
+        return out
+    try:
+        cfg_path = "/tmp/amgxb_host_path_cfg.json"
+        Path(cfg_path).write_text(json.dumps(HOST_PATH_CFG))
+        env = dict(os.environ, REFDUMP_NO_LEVELS="1", LD_LIBRARY_PATH=str(exe.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        r = subprocess.run([str(exe), f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump_host.bin", "hDDI", "1"], capture_output=True, text=True, timeout=240, env=env)
+        m = re.search(r"ref_dump: status (\d+) iterations (\d+) setup ([0-9.eE+-]+) s solve ([0-9.eE+-]+) s", r.stdout)
+        if not m:
+            out["reference_cpu"] = {"unavailable": "ref_dump (hDDI) gave no timing line", "tail": (r.stdout + r.stderr)[-300:]}
+        else:
+            it, ts, tsol = int(m.group(2)), float(m.group(3)), float(m.group(4))
+            out["reference_cpu"] = {"value": it / tsol, "kind": "reference", "cores": 1, "iterations": it, "solve_seconds": tsol, "setup_seconds": ts,
+                                    "how": "unmodified reference (oracle/_ref/libamgx_ref.so), mode hDDI = its own host implementation (single-threaded), one "
+                                           "AMGX_solver_solve timed by oracle/ref_build/ref_dump.cu"}
+    except Exception as e:
+        out["reference_cpu"] = {"unavailable": repr(e)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------------
@@ -700,6 +758,8 @@ def main():
             out["reference_gpu"] = reference_gpu(nx)
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = oracle_baseline(nx, nx, nx, 5 if nx <= 256 else 2)
+        if not args.no_extras and not args.no_reference_gpu and not args.no_cpu_baseline and nx == 256:
+            out["reference_host_path"] = reference_host_path(capi, rsc, nx)
         if not args.no_extras and nx == 256:
             out["other_workloads"] = other_workloads()
     guard.finish()
