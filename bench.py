@@ -26,6 +26,8 @@ N > 1 (one process per GPU, row partition in z-slabs, peer-memory / NCCL halo ex
   parity   object: the same distributed code path on a reduced global problem against a single-rank solve of the assembled matrix.
   strong_512 object (default weak run, N divides 512): BASELINE configs[3] as stated -- the 512^3 grid row-partitioned over the N ranks,
            same solver, device-timed like `value`; its N=1 counterpart is other_workloads.poisson512 of the N=1 line.
+  block_weak object (same runs): BASELINE configs[4]-style weak scaling, 160^3 4x4 block rows per GPU, AMG + MULTICOLOR_DILU, dDFI;
+           N=1 counterpart other_workloads.block160_dDFI.
 Default N=1 line only: other_workloads = the other BASELINE workloads (512^3 Poisson = the north star's target size, the 4 M-row
   SuiteSparse-shaped matrix, the 4x4 block configuration), each measured by THIS script in a child process after the main line's
   numbers are final (`python bench.py --workload ... --no-extras`), under a common time budget; --no-extras skips them.
@@ -439,7 +441,7 @@ class LineGuard:
         return True
 
     def _expire(self):
-        if self._emit("context objects (parity / strong_512) did not finish within %.0f s: line printed without them" % self.limit_s):
+        if self._emit("context objects (parity / strong_512 / block_weak) did not finish within %.0f s: line printed without what was missing" % self.limit_s):
             sys.stdout.flush()
             os._exit(0)
 
@@ -492,6 +494,69 @@ def strong_512(capi, dist, torch, rsc, cfg, world, steps, warmup, grid=512):
            "final_relative_residual": float(hist[-1] / hist[0]) if len(hist) else None,
            "n1_counterpart": "other_workloads.poisson512.value of the N=1 line (same grid, same solver, one GPU)"}
     for o in (slv, x, b, A):
+        o.destroy()
+    return res
+
+
+def block_weak(capi, dist, torch, rsc, rank, world, nx=160, mode="dDFI", steps=3, warmup=3):
+    """BASELINE configs[4]-style weak scaling: nx^3 4x4 block rows per GPU (z-slabs of the nx x nx x (nx * N) grid), AMG V-cycle +
+    MULTICOLOR_DILU, fp32 matrix / fp64 vectors, uploaded through AMGX_matrix_upload_distributed (partition offsets) as an application
+    would; timed like the main line.  The N = 1 counterpart is other_workloads.block160_dDFI of the N = 1 line."""
+    import ctypes as C
+    from amgx_b200 import gallery
+    t0 = time.time()
+    cfg = capi.Config(BLOCK_CFG)
+    nz = nx * world
+    lrp, lci, lva = gallery.block_elasticity_slab(nx, nx, nz, nx * rank, nx * (rank + 1), dtype=np.float32 if mode[2] == "F" else np.float64)
+    n = lrp.shape[0] - 1
+    lib = capi.load_library()
+    A = capi.Matrix(rsc, mode)
+    offsets = np.array([nx * nx * nx * r for r in range(world + 1)], np.int64)
+    dh = C.c_void_p()
+    if lib.AMGX_distribution_create(C.byref(dh), cfg.h) != 0 or lib.AMGX_distribution_set_partition_data(dh, 1, offsets.ctypes.data) != 0:
+        raise RuntimeError("AMGX_distribution_create / set_partition_data failed")
+    rc = lib.AMGX_matrix_upload_distributed(A.h, nx * nx * nz, n, lci.shape[0], 4, 4, lrp.ctypes.data, lci.ctypes.data, lva.ctypes.data, None, dh)
+    lib.AMGX_distribution_destroy(dh)
+    if rc != 0:
+        raise RuntimeError(f"AMGX_matrix_upload_distributed returned {rc}")
+    del lva, lci
+    b, x = capi.Vector(rsc, mode), capi.Vector(rsc, mode)
+    b.bind(A)
+    x.bind(A)
+    b.upload(np.ones(n * 4), block_dim=4)
+    x.set_zero(n, 4)
+    slv = capi.Solver(rsc, cfg, mode)
+    slv.setup(A)
+    t_setup = time.time() - t0
+
+    def one():
+        x.set_zero(n, 4)
+        slv.solve(b, x, zero_initial_guess=True)
+        s, k = slv.last_solve_stats()
+        return s, k, slv.iterations_number
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    tot_s, tot_k, tot_it = 0.0, 0, 0
+    for _ in range(steps):
+        s, k, it = one()
+        tot_s += s
+        tot_k += k
+        tot_it += it
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([tot_s], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_s = float(t.item())
+    res = {"workload": f"block 4x4 elasticity-like, {nx}^3 block rows per GPU x {world} GPUs, {mode}, AMG V-cycle + MULTICOLOR_DILU (AGGREGATION_DILU), AMGX_matrix_upload_distributed",
+           "value": tot_it / tot_s * world, "unit": UNIT, "scaling": "weak", "global_iterations_per_sec": tot_it / tot_s, "steps": steps, "warmup": warmup,
+           "ms_per_step": tot_s / steps * 1e3, "iterations_per_step": tot_it / steps, "solve_status": slv.status, "block_rows_global": nx * nx * nz,
+           "generate_upload_setup_seconds": t_setup, "gpu_launches": int(tot_k),
+           "n1_counterpart": "other_workloads.block160_dDFI.value of the N=1 line (same rows per GPU, same solver)"}
+    for o in (slv, x, b, A, cfg):
         o.destroy()
     return res
 
@@ -754,6 +819,12 @@ def main():
             st = {"error": repr(e)}
         if out is not None:
             out["strong_512"] = st
+        try:
+            bw = block_weak(capi, dist, torch, rsc, rank, world, nx=int(os.environ.get("AMGXB_BENCH_BLOCK_NX", "160")))
+        except Exception as e:
+            bw = {"error": repr(e)}
+        if out is not None:
+            out["block_weak"] = bw
 
     if rank == 0 and not distributed and args.workload == "poisson":
         if not args.no_reference_gpu:

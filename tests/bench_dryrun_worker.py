@@ -61,6 +61,8 @@ class _Obj:
 
 
 class Config(_Obj):
+    h = 1
+
     def __init__(self, options=None, file=None):
         assert options is not None or Path(file).exists()
 
@@ -71,8 +73,11 @@ class Resources(_Obj):
 
 
 class Matrix(_Obj):
+    h = 2
+
     def __init__(self, rsc, mode="dDDI"):
         self.rsc, self.n, self.nnz, self.bd = rsc, 0, 0, 1
+        self.index = 0
 
     def generate_poisson7(self, rhs, sol, nx, ny, nz, px=1, py=1, pz=1, rings=1):
         STATE["matrices"] += 1
@@ -152,6 +157,19 @@ class _Lib:
         return 0
 
     def AMGX_unpin_memory(self, ptr):
+        return 0
+
+    def AMGX_distribution_create(self, dh, cfg):
+        return 0
+
+    def AMGX_distribution_set_partition_data(self, dh, kind, ptr):
+        return 0
+
+    def AMGX_distribution_destroy(self, dh):
+        return 0
+
+    def AMGX_matrix_upload_distributed(self, A, n_global, n, nnz, bx, by, rp, ci, va, diag, dh):
+        assert n_global > n > 0 and nnz > 0 and bx == by == 4
         return 0
 
 

@@ -62,7 +62,7 @@ def test_single_gpu_line_survives_failing_extras():
 
 
 def _torchrun(port, extra_env=None, args=()):
-    env = dict(os.environ, **(extra_env or {}))
+    env = dict(os.environ, AMGXB_BENCH_BLOCK_NX="10", **(extra_env or {}))      # block_weak generates its slab in numpy: keep it small here
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
            str(WORKER), "--gpus", "2", "--steps", "2", "--warmup", "1", "--no-parity", *args]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
@@ -75,11 +75,13 @@ def test_two_rank_line_has_strong_512():
     assert d["n_gpus"] == 2 and d["value"] == 2 * d["config"]["global_iterations_per_sec"] and d["roofline"] is None
     s = d["strong_512"]
     assert s["scaling"] == "strong" and s["rows"] == 512 ** 3 and "z-slabs of 256 planes" in s["workload"] and s["warmup"] >= 3
+    w = d["block_weak"]
+    assert w["scaling"] == "weak" and w["block_rows_global"] == 2 * 10 ** 3 and w["value"] == 2 * w["global_iterations_per_sec"] and "dDFI" in w["workload"]
     assert "other_workloads" not in d and "note" not in d
     d = _line(_torchrun(29542, args=("--no-extras",)).stdout)
-    assert "strong_512" not in d
+    assert "strong_512" not in d and "block_weak" not in d
     d = _line(_torchrun(29543, args=("--strong", "--grid", "512")).stdout)
-    assert "strong_512" not in d and d["scaling"] == "strong" and d["value"] == d["config"]["global_iterations_per_sec"]
+    assert "strong_512" not in d and "block_weak" not in d and d["scaling"] == "strong" and d["value"] == d["config"]["global_iterations_per_sec"]
 
 
 def test_two_rank_line_is_printed_when_a_context_object_hangs():
