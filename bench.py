@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- solve-phase benchmark of the B200 AMG engine (contract: see README / DESIGN.md).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload poisson|banded|block] [--grid NX] [--strong]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload poisson|classical|banded|block] [--grid NX] [--strong]
 
 Default workload (BASELINE.json configs[1]): 3-D 7-point Poisson 256^3, fp64, aggregation AMG (SIZE_2) V-cycle preconditioned CG,
 BLOCK_JACOBI(0.8) 0+3 sweeps -- the reference's PCG_AGGREGATION_JACOBI.json.  A "step" is one AMGX_solver_solve (zero initial guess,
@@ -69,6 +69,18 @@ BANDED_CFG = {"config_version": 2, "determinism_flag": 1, "solver": {
     "preconditioner": {"scope": "amg", "solver": "AMG", "algorithm": "AGGREGATION", "selector": "SIZE_2", "cycle": "V", "max_levels": 50,
                        "presweeps": 0, "postsweeps": 3, "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER", "max_iters": 1, "monitor_residual": 0,
                        "smoother": {"scope": "jacobi", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "monitor_residual": 0}}}}
+
+
+# BASELINE configs[2]: the reference's FGMRES_CLASSICAL_AGGRESSIVE_PMIS.json (PMIS, aggressive level 0 with MULTIPASS, D2 below, interp_max_elements 4,
+# JACOBI_L1 2 + 2 sweeps) with gmres_n_restart 20 (100 Krylov vectors of 512^3 rows would not fit beside the hierarchy)
+CLASSICAL_CFG = {"config_version": 2, "solver": {
+    "scope": "main", "solver": "FGMRES", "max_iters": 100, "gmres_n_restart": 20, "monitor_residual": 1, "store_res_history": 1,
+    "convergence": "RELATIVE_INI", "tolerance": 1e-6, "norm": "L2",
+    "preconditioner": {"scope": "amg_solver", "solver": "AMG", "algorithm": "CLASSICAL", "selector": "PMIS", "interpolator": "D2", "aggressive_levels": 1,
+                       "interp_max_elements": 4, "max_row_sum": 0.9, "strength_threshold": 0.25, "cycle": "V", "max_levels": 50, "min_coarse_rows": 2,
+                       "presweeps": 2, "postsweeps": 2, "coarsest_sweeps": 2, "coarse_solver": "NOSOLVER", "max_iters": 1, "monitor_residual": 0,
+                       "print_grid_stats": 0,
+                       "smoother": {"scope": "jacobi", "solver": "JACOBI_L1", "relaxation_factor": 1, "monitor_residual": 0}}}}
 
 
 def measured_peak():
@@ -203,6 +215,8 @@ def workload_config(args, world):
             w = f"7-pt Poisson {nx}^3 fp64 row-partitioned over {world} GPU(s), PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI.json)"
         else:
             w = f"7-pt Poisson {nx}x{nx}x{nx * world} fp64, PCG + aggregation-AMG V-cycle (PCG_AGGREGATION_JACOBI.json)"
+    elif args.workload == "classical":
+        w = f"7-pt Poisson {nx}^3 fp64, FGMRES(20) + classical AMG V-cycle (FGMRES_CLASSICAL_AGGRESSIVE_PMIS.json: PMIS, aggressive level 0, D2, JACOBI_L1 2 + 2)"
     elif args.workload == "banded":
         w = f"SuiteSparse-shaped banded-random CSR (nonsymmetric), {args.rows} rows, row length 3+Poisson(12), sigma 2000, fp64, FGMRES(20) + aggregation-AMG V-cycle"
     else:
@@ -213,13 +227,18 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------------------------------
 # reference GPU build beside it (context): oracle/_ref/ref_dump on the same generated matrix and configuration
 # ------------------------------------------------------------------------------------------------------------------------
-def reference_gpu(nx, reps=2):
+def reference_gpu(nx, reps=2, config=None):
+    """config: a configuration dictionary (written to a file for the harness); default = PCG_AGGREGATION_JACOBI.json"""
     exe = ROOT / "oracle" / "_ref" / "ref_dump"
     if not exe.exists():
         return {"unavailable": "oracle/_ref/ref_dump not built (oracle/ref_build/Makefile, needs /root/reference)"}
     try:
+        cfg_path = str(CONFIG)
+        if config is not None:
+            cfg_path = "/tmp/amgxb_refgpu_cfg.json"
+            Path(cfg_path).write_text(json.dumps(config))
         env = dict(os.environ, REFDUMP_NO_LEVELS="1", LD_LIBRARY_PATH=str(exe.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-        r = subprocess.run([str(exe), f"poisson:{nx}", str(CONFIG), "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=300, env=env)
+        r = subprocess.run([str(exe), f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=300, env=env)
         m = re.search(r"ref_dump: status (\d+) iterations (\d+) setup ([0-9.eE+-]+) s solve ([0-9.eE+-]+) s", r.stdout)
         if not m:
             return {"unavailable": "ref_dump gave no timing line", "tail": (r.stdout + r.stderr)[-300:]}
@@ -378,6 +397,7 @@ def distributed_parity(capi, dist, torch, rsc, rank, world, local_rank):
 # ------------------------------------------------------------------------------------------------------------------------
 EXTRA_WORKLOADS = [
     ("poisson512", ["--workload", "poisson", "--grid", "512", "--steps", "2", "--warmup", "3"]),        # north star: >= 70 % of the roofline at 512^3
+    ("classical512", ["--workload", "classical", "--grid", "512", "--steps", "2", "--warmup", "3"]),      # BASELINE configs[2]
     ("banded4m", ["--workload", "banded", "--steps", "3", "--warmup", "3"]),                              # SURVEY 8(d) input 2
     ("block160_dDFI", ["--workload", "block", "--mode", "dDFI", "--steps", "3", "--warmup", "3"]),        # BASELINE configs[4] at 160^3 block rows
 ]
@@ -567,7 +587,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="poisson", choices=["poisson", "banded", "block"])
+    ap.add_argument("--workload", default="poisson", choices=["poisson", "classical", "banded", "block"])
     ap.add_argument("--grid", dest="n", type=int, default=None, help="grid points per dimension (poisson: per rank unless --strong; block: block rows per dimension)")
     ap.add_argument("--rows", type=int, default=4_000_000, help="banded workload: number of rows")
     ap.add_argument("--mode", default="dDFI", choices=["dDDI", "dDFI", "dFFI"], help="block workload: AMGX mode")
@@ -611,6 +631,8 @@ def main():
         cfg = capi.Config(BLOCK_CFG)
     elif args.workload == "banded":
         cfg = capi.Config(BANDED_CFG)
+    elif args.workload == "classical":
+        cfg = capi.Config(CLASSICAL_CFG)
     else:
         cfg = capi.Config(file=str(CONFIG))
     comm = None
@@ -625,7 +647,9 @@ def main():
     nx = args.n
     bd = 1
     t0 = time.time()
-    if args.workload == "poisson":
+    if args.workload == "classical":
+        A.generate_poisson7(b, x, nx, nx, nx, 1, 1, 1)
+    elif args.workload == "poisson":
         if args.strong:
             if nx % world:
                 raise SystemExit("--strong needs --grid divisible by the number of ranks")
@@ -751,7 +775,8 @@ def main():
                 traffic = json.loads(tf.read_text()).get("traffic_bytes_per_launch")
             roof = {"bound": "hbm", "achieved": byt_j / ms_j / 1e6, "peak": peak, "unit": "GB/s", "frac": byt_j / ms_j / 1e6 / peak, "traffic": traffic,
                     "kernel": "fused Jacobi sweep, fine level: " + family % "EPI_JACOBI", "kernel_plan": kinfo,
-                    "ms_per_launch": ms_j, "algorithmic_bytes": byt_j, "peak_source": peak_src, "share_of_iteration": "~70 % (profiles/r02_launches_solve_256.md)",
+                    "ms_per_launch": ms_j, "algorithmic_bytes": byt_j, "peak_source": peak_src,
+                    "share_of_iteration": "~70 % (profiles/r02_launches_solve_256.md)" if args.workload == "poisson" else None,
                     "spmv": spmv}
             if traffic:     # the same launch by the bytes that actually crossed the HBM interface (ncu dram__bytes_read + write, committed capture)
                 roof["dram"] = {"bytes_per_launch": traffic, "achieved": traffic / ms_j / 1e6, "frac": traffic / ms_j / 1e6 / peak,
@@ -826,6 +851,9 @@ def main():
         if out is not None:
             out["block_weak"] = bw
 
+    if rank == 0 and not distributed and args.workload == "classical" and not args.no_reference_gpu:
+        torch.cuda.empty_cache()
+        out["reference_gpu"] = reference_gpu(nx, config=CLASSICAL_CFG)
     if rank == 0 and not distributed and args.workload == "poisson":
         if not args.no_reference_gpu:
             torch.cuda.empty_cache()

@@ -26,6 +26,7 @@ def test_other_workloads_children(tmp_path):
     fails or overruns its time costs only its own entry."""
     import bench
     small = [("poisson_small", ["--workload", "poisson", "--grid", "16", "--steps", "2", "--warmup", "1"]),
+             ("classical_small", ["--workload", "classical", "--grid", "16", "--steps", "2", "--warmup", "1"]),
              ("banded_small", ["--workload", "banded", "--rows", "20000", "--steps", "2", "--warmup", "1"]),
              ("block_small", ["--workload", "block", "--grid", "8", "--mode", "dDFI", "--steps", "2", "--warmup", "1"])]
     out = bench.other_workloads(budget_s=200, per_run_s=100, workloads=small, script=WORKER)
@@ -34,6 +35,7 @@ def test_other_workloads_children(tmp_path):
         assert out[name]["metric"] == bench.METRIC and out[name]["value"] > 0 and out[name]["n_gpus"] == 1
         assert "other_workloads" not in out[name] and "cpu_baseline" not in out[name]           # --no-extras reached the child; None-valued keys dropped
     assert "SuiteSparse-shaped" in out["banded_small"]["config"]["workload"] and "20000 rows" in out["banded_small"]["config"]["workload"]
+    assert "classical AMG" in out["classical_small"]["config"]["workload"] and "iteration" not in out["classical_small"]["roofline"]
     assert out["block_small"]["dtype"] == "f32 matrix / f64 vectors" and "block4" in out["block_small"]["roofline"]["kernel"]
     # the flags of the real list parse
     for _, flags in bench.EXTRA_WORKLOADS:
@@ -56,7 +58,7 @@ def test_single_gpu_line_survives_failing_extras():
         assert k in d, k
     assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["config"]["workload"].startswith("7-pt Poisson 256x256x256")
     assert d["roofline"]["bound"] == "hbm" and d["roofline"]["spmv"]["frac"] > 0 and d["roofline"]["iteration"]["levels"] == 3
-    assert set(d["other_workloads"]) == {"poisson512", "banded4m", "block160_dDFI"}
+    assert set(d["other_workloads"]) == {"poisson512", "classical512", "banded4m", "block160_dDFI"}
     assert all("error" in v for v in d["other_workloads"].values())
     assert "strong_512" not in d
 
@@ -91,3 +93,15 @@ def test_two_rank_line_is_printed_when_a_context_object_hangs():
     d = _line(r.stdout)
     assert d["n_gpus"] == 2 and d["value"] > 0 and "strong_512" not in d
     assert "did not finish" in d["note"]
+
+
+def test_bench_configurations_pass_config_check():
+    """every configuration dictionary bench.py hands to the engine names only components the engine provides (no GPU needed)"""
+    import bench
+    from amgx_b200 import capi
+    capi.load_library()
+    for name in ("CLASSICAL_CFG", "BLOCK_CFG", "BANDED_CFG", "HOST_PATH_CFG"):
+        cfg = capi.Config(getattr(bench, name))
+        ok, msg = capi.config_check(cfg)
+        cfg.destroy()
+        assert ok, (name, msg)
