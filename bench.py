@@ -750,59 +750,62 @@ def main():
     # ---- roofline of the dominant kernel ----
     roof = None
     if not distributed:
-        peak, peak_src = measured_peak()
-        msz = 8 if mode[2] == "D" else 4
-        vsz = 8 if mode[1] == "D" else 4
-        ms = A.bench_kernel(0, warmup=3, reps=20, flush_l2=False)      # operands (>= 1.4 GB) >> 126 MB L2
-        byt = nnz * (msz * bd * bd + 4) + n * 4
-        enc = os.environ.get("AMGXB_COLENC", "")
-        kinfo = A.kernel_info() if bd == 1 else {}
-        if kinfo.get("window"):
-            family = "csr_window_kernel<%s> (x window of %d entries in shared memory, 16-bit column offsets)"
-            family = family.replace("%d", str(kinfo["window"]))
-        elif kinfo.get("coded_tiles"):
-            family = "csr_tile_enc_kernel<%s> (coded column / value streams)"
-        else:
-            family = "csr_tile_kernel<%s>"
-        spmv = {"kernel": (family % "EPI_SPMV" if bd == 1 else "block4_tile_kernel<SPMV> (TMA-staged 4x4 blocks)") + " (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt,
-                "achieved": byt / ms / 1e6, "frac": byt / ms / 1e6 / peak}
-        if bd == 1:
-            ms_j = A.bench_kernel(1, warmup=3, reps=20, flush_l2=False)
-            byt_j = byt + 4 * n * vsz
-            traffic = None
-            tf = ROOT / "profiles" / (f"r02_ncu_traffic_jacobi_{nx}.json" if args.workload == "poisson" else "r02_ncu_traffic_jacobi_banded.json")
-            if tf.exists() and (args.workload == "poisson" or (args.workload == "banded" and kinfo.get("window"))):
-                traffic = json.loads(tf.read_text()).get("traffic_bytes_per_launch")
-            roof = {"bound": "hbm", "achieved": byt_j / ms_j / 1e6, "peak": peak, "unit": "GB/s", "frac": byt_j / ms_j / 1e6 / peak, "traffic": traffic,
-                    "kernel": "fused Jacobi sweep, fine level: " + family % "EPI_JACOBI", "kernel_plan": kinfo,
-                    "ms_per_launch": ms_j, "algorithmic_bytes": byt_j, "peak_source": peak_src,
-                    "share_of_iteration": "~70 % (profiles/r02_launches_solve_256.md)" if args.workload == "poisson" else None,
-                    "spmv": spmv}
-            if traffic:     # the same launch by the bytes that actually crossed the HBM interface (ncu dram__bytes_read + write, committed capture)
-                roof["dram"] = {"bytes_per_launch": traffic, "achieved": traffic / ms_j / 1e6, "frac": traffic / ms_j / 1e6 / peak,
-                                "note": "coded matrix streams move fewer bytes than the north-star formula charges, so `frac` above can exceed 1; this is the DRAM-side view of the same time"}
-        else:
-            roof = {"bound": "hbm", "achieved": spmv["achieved"], "peak": peak, "unit": "GB/s", "frac": spmv["frac"], "traffic": None, "kernel": spmv["kernel"],
-                    "ms_per_launch": ms, "algorithmic_bytes": byt, "peak_source": peak_src}
-        # whole outer iteration against the same peak: SURVEY 8(d)'s per-unit figures summed over the hierarchy the setup actually built
-        # (PCG outside M^-1: M(A_0) + 12 N 8; per level: 3 fused post-sweeps M(A_l) + 4 n_l 8 each, restriction and prolongation
-        # n_l (4 + 8) + n_{l+1} 8 each; presweeps = 0 and a zero initial guess leave no residual pass; coarsest: a zero-guess sweep + a full one)
-        if args.workload == "poisson":
-            try:
-                lv = [slv.level_info(l) for l in range(slv.num_levels())]
-                M = lambda i: i["nnz"] * 12 + i["n"] * 4
-                it_bytes = M(lv[0]) + 12 * lv[0]["n"] * 8
-                for l, i in enumerate(lv):
-                    if l + 1 < len(lv):
-                        it_bytes += 3 * (M(i) + 4 * i["n"] * 8) + 2 * (i["n"] * 12 + lv[l + 1]["n"] * 8)
-                    else:
-                        it_bytes += 3 * i["n"] * 8 + (M(i) + 4 * i["n"] * 8)
-                ms_it = tot_s / max(tot_it, 1) * 1e3
-                roof["iteration"] = {"algorithmic_bytes": int(it_bytes), "levels": len(lv), "ms_at_peak": it_bytes / peak / 1e6, "ms_measured": ms_it,
-                                     "achieved": it_bytes / ms_it / 1e6, "frac": it_bytes / ms_it / 1e6 / peak,
-                                     "operator_complexity": sum(i["nnz"] for i in lv) / lv[0]["nnz"]}
-            except Exception as e:      # never let the extra figure cost the bench line
-                roof["iteration"] = {"error": repr(e)}
+        try:
+            peak, peak_src = measured_peak()
+            msz = 8 if mode[2] == "D" else 4
+            vsz = 8 if mode[1] == "D" else 4
+            ms = A.bench_kernel(0, warmup=3, reps=20, flush_l2=False)      # operands (>= 1.4 GB) >> 126 MB L2
+            byt = nnz * (msz * bd * bd + 4) + n * 4
+            enc = os.environ.get("AMGXB_COLENC", "")
+            kinfo = A.kernel_info() if bd == 1 else {}
+            if kinfo.get("window"):
+                family = "csr_window_kernel<%s> (x window of %d entries in shared memory, 16-bit column offsets)"
+                family = family.replace("%d", str(kinfo["window"]))
+            elif kinfo.get("coded_tiles"):
+                family = "csr_tile_enc_kernel<%s> (coded column / value streams)"
+            else:
+                family = "csr_tile_kernel<%s>"
+            spmv = {"kernel": (family % "EPI_SPMV" if bd == 1 else "block4_tile_kernel<SPMV> (TMA-staged 4x4 blocks)") + " (fine level)", "ms_per_launch": ms, "algorithmic_bytes": byt,
+                    "achieved": byt / ms / 1e6, "frac": byt / ms / 1e6 / peak}
+            if bd == 1:
+                ms_j = A.bench_kernel(1, warmup=3, reps=20, flush_l2=False)
+                byt_j = byt + 4 * n * vsz
+                traffic = None
+                tf = ROOT / "profiles" / (f"r02_ncu_traffic_jacobi_{nx}.json" if args.workload == "poisson" else "r02_ncu_traffic_jacobi_banded.json")
+                if tf.exists() and (args.workload == "poisson" or (args.workload == "banded" and kinfo.get("window"))):
+                    traffic = json.loads(tf.read_text()).get("traffic_bytes_per_launch")
+                roof = {"bound": "hbm", "achieved": byt_j / ms_j / 1e6, "peak": peak, "unit": "GB/s", "frac": byt_j / ms_j / 1e6 / peak, "traffic": traffic,
+                        "kernel": "fused Jacobi sweep, fine level: " + family % "EPI_JACOBI", "kernel_plan": kinfo,
+                        "ms_per_launch": ms_j, "algorithmic_bytes": byt_j, "peak_source": peak_src,
+                        "share_of_iteration": "~70 % (profiles/r02_launches_solve_256.md)" if args.workload == "poisson" else None,
+                        "spmv": spmv}
+                if traffic:     # the same launch by the bytes that actually crossed the HBM interface (ncu dram__bytes_read + write, committed capture)
+                    roof["dram"] = {"bytes_per_launch": traffic, "achieved": traffic / ms_j / 1e6, "frac": traffic / ms_j / 1e6 / peak,
+                                    "note": "coded matrix streams move fewer bytes than the north-star formula charges, so `frac` above can exceed 1; this is the DRAM-side view of the same time"}
+            else:
+                roof = {"bound": "hbm", "achieved": spmv["achieved"], "peak": peak, "unit": "GB/s", "frac": spmv["frac"], "traffic": None, "kernel": spmv["kernel"],
+                        "ms_per_launch": ms, "algorithmic_bytes": byt, "peak_source": peak_src}
+            # whole outer iteration against the same peak: SURVEY 8(d)'s per-unit figures summed over the hierarchy the setup actually built
+            # (PCG outside M^-1: M(A_0) + 12 N 8; per level: 3 fused post-sweeps M(A_l) + 4 n_l 8 each, restriction and prolongation
+            # n_l (4 + 8) + n_{l+1} 8 each; presweeps = 0 and a zero initial guess leave no residual pass; coarsest: a zero-guess sweep + a full one)
+            if args.workload == "poisson":
+                try:
+                    lv = [slv.level_info(l) for l in range(slv.num_levels())]
+                    M = lambda i: i["nnz"] * 12 + i["n"] * 4
+                    it_bytes = M(lv[0]) + 12 * lv[0]["n"] * 8
+                    for l, i in enumerate(lv):
+                        if l + 1 < len(lv):
+                            it_bytes += 3 * (M(i) + 4 * i["n"] * 8) + 2 * (i["n"] * 12 + lv[l + 1]["n"] * 8)
+                        else:
+                            it_bytes += 3 * i["n"] * 8 + (M(i) + 4 * i["n"] * 8)
+                    ms_it = tot_s / max(tot_it, 1) * 1e3
+                    roof["iteration"] = {"algorithmic_bytes": int(it_bytes), "levels": len(lv), "ms_at_peak": it_bytes / peak / 1e6, "ms_measured": ms_it,
+                                         "achieved": it_bytes / ms_it / 1e6, "frac": it_bytes / ms_it / 1e6 / peak,
+                                         "operator_complexity": sum(i["nnz"] for i in lv) / lv[0]["nnz"]}
+                except Exception as e:      # never let the extra figure cost the bench line
+                    roof["iteration"] = {"error": repr(e)}
+        except Exception as e:      # a kernel-level figure must not cost the line its solve-level numbers
+            roof = {"error": repr(e)}
 
     # ---- the line: value, e2e, roofline and clocks are final here; what follows only adds context objects to it ----
     out = None
