@@ -63,119 +63,119 @@ typedef struct AMGX_vector_handle_struct       *AMGX_vector_handle;
 typedef struct AMGX_solver_handle_struct       *AMGX_solver_handle;
 typedef struct AMGX_distribution_handle_struct *AMGX_distribution_handle;
 
-/* ---- build / init / system [ref: include/amgx_c.h:149-196] ---- */
-AMGX_RC AMGX_API AMGX_get_api_version(int *major, int *minor);                         /* :149 */
-AMGX_RC AMGX_API AMGX_get_build_info_strings(char **version, char **date, char **time);/* :153 */
-AMGX_RC AMGX_API AMGX_get_error_string(AMGX_RC err, char *buf, int buf_len);           /* :158 */
-AMGX_RC AMGX_API AMGX_initialize(void);                                                /* :164 */
-AMGX_RC AMGX_API AMGX_initialize_plugins(void);                                        /* :166 */
-AMGX_RC AMGX_API AMGX_finalize(void);                                                  /* :168 */
-AMGX_RC AMGX_API AMGX_finalize_plugins(void);                                          /* :170 */
-void    AMGX_API AMGX_abort(AMGX_resources_handle rsrc, int err);                      /* :172 */
-AMGX_RC AMGX_API AMGX_pin_memory(void *ptr, unsigned int bytes);                       /* :177 */
-AMGX_RC AMGX_API AMGX_unpin_memory(void *ptr);                                         /* :181 */
-AMGX_RC AMGX_API AMGX_install_signal_handler(void);                                    /* :184 */
-AMGX_RC AMGX_API AMGX_reset_signal_handler(void);                                      /* :186 */
-AMGX_RC AMGX_API AMGX_register_print_callback(AMGX_print_callback func);               /* :188 */
+/* ---- build / init / system [ref: include/amgx_c.h:150-190] ---- */
+AMGX_RC AMGX_API AMGX_get_api_version(int *major, int *minor);   /* :150 */
+AMGX_RC AMGX_API AMGX_get_build_info_strings(char **version, char **date, char **time);   /* :154 */
+AMGX_RC AMGX_API AMGX_get_error_string(AMGX_RC err, char *buf, int buf_len);   /* :159 */
+AMGX_RC AMGX_API AMGX_initialize(void);   /* :165 */
+AMGX_RC AMGX_API AMGX_initialize_plugins(void);   /* :167 */
+AMGX_RC AMGX_API AMGX_finalize(void);   /* :169 */
+AMGX_RC AMGX_API AMGX_finalize_plugins(void);   /* :171 */
+void    AMGX_API AMGX_abort(AMGX_resources_handle rsrc, int err);   /* :173 */
+AMGX_RC AMGX_API AMGX_pin_memory(void *ptr, unsigned int bytes);   /* :178 */
+AMGX_RC AMGX_API AMGX_unpin_memory(void *ptr);   /* :182 */
+AMGX_RC AMGX_API AMGX_install_signal_handler(void);   /* :185 */
+AMGX_RC AMGX_API AMGX_reset_signal_handler(void);   /* :187 */
+AMGX_RC AMGX_API AMGX_register_print_callback(AMGX_print_callback func);   /* :189 */
 
-/* ---- config [ref: include/amgx_c.h:192-215] ---- */
-AMGX_RC AMGX_API AMGX_config_create(AMGX_config_handle *cfg, const char *options);
-AMGX_RC AMGX_API AMGX_config_add_parameters(AMGX_config_handle *cfg, const char *options);
-AMGX_RC AMGX_API AMGX_config_create_from_file(AMGX_config_handle *cfg, const char *param_file);
-AMGX_RC AMGX_API AMGX_config_create_from_file_and_string(AMGX_config_handle *cfg, const char *param_file, const char *options);
-AMGX_RC AMGX_API AMGX_config_get_default_number_of_rings(AMGX_config_handle cfg, int *num_import_rings);
-AMGX_RC AMGX_API AMGX_config_destroy(AMGX_config_handle cfg);
+/* ---- config [ref: include/amgx_c.h:193-215] ---- */
+AMGX_RC AMGX_API AMGX_config_create(AMGX_config_handle *cfg, const char *options);   /* :193 */
+AMGX_RC AMGX_API AMGX_config_add_parameters(AMGX_config_handle *cfg, const char *options);   /* :197 */
+AMGX_RC AMGX_API AMGX_config_create_from_file(AMGX_config_handle *cfg, const char *param_file);   /* :201 */
+AMGX_RC AMGX_API AMGX_config_create_from_file_and_string(AMGX_config_handle *cfg, const char *param_file, const char *options);   /* :205 */
+AMGX_RC AMGX_API AMGX_config_get_default_number_of_rings(AMGX_config_handle cfg, int *num_import_rings);   /* :210 */
+AMGX_RC AMGX_API AMGX_config_destroy(AMGX_config_handle cfg);   /* :214 */
 
-/* ---- resources [ref: include/amgx_c.h:218-231].
+/* ---- resources [ref: include/amgx_c.h:218-230].
  * `comm`: the reference dereferences it as MPI_Comm*.  This image has no MPI; here `comm` is
  * NULL (single process, single GPU) or a pointer to an AMGXB200_comm (below): rank, world
  * size and an ncclUniqueId obtained with AMGXB200_get_nccl_unique_id on rank 0 and
  * broadcast by the launcher (torch.distributed in bench.py / tests). ---- */
-AMGX_RC AMGX_API AMGX_resources_create(AMGX_resources_handle *rsc, AMGX_config_handle cfg, void *comm, int device_num, const int *devices);
-AMGX_RC AMGX_API AMGX_resources_create_simple(AMGX_resources_handle *rsc, AMGX_config_handle cfg);
-AMGX_RC AMGX_API AMGX_resources_destroy(AMGX_resources_handle rsc);
+AMGX_RC AMGX_API AMGX_resources_create(AMGX_resources_handle *rsc, AMGX_config_handle cfg, void *comm, int device_num, const int *devices);   /* :218 */
+AMGX_RC AMGX_API AMGX_resources_create_simple(AMGX_resources_handle *rsc, AMGX_config_handle cfg);   /* :225 */
+AMGX_RC AMGX_API AMGX_resources_destroy(AMGX_resources_handle rsc);   /* :229 */
 
-/* ---- distribution [ref: include/amgx_c.h:236-264] ---- */
-AMGX_RC AMGX_API AMGX_distribution_create(AMGX_distribution_handle *dist, AMGX_config_handle cfg);
-AMGX_RC AMGX_API AMGX_distribution_destroy(AMGX_distribution_handle dist);
-AMGX_RC AMGX_API AMGX_distribution_set_partition_data(AMGX_distribution_handle dist, AMGX_DIST_PARTITION_INFO info, const void *partition_data);
-AMGX_RC AMGX_API AMGX_distribution_set_32bit_colindices(AMGX_distribution_handle dist, int use32bit);
+/* ---- distribution [ref: include/amgx_c.h:235-259] ---- */
+AMGX_RC AMGX_API AMGX_distribution_create(AMGX_distribution_handle *dist, AMGX_config_handle cfg);   /* :235 */
+AMGX_RC AMGX_API AMGX_distribution_destroy(AMGX_distribution_handle dist);   /* :238 */
+AMGX_RC AMGX_API AMGX_distribution_set_partition_data(AMGX_distribution_handle dist, AMGX_DIST_PARTITION_INFO info, const void *partition_data);   /* :251 */
+AMGX_RC AMGX_API AMGX_distribution_set_32bit_colindices(AMGX_distribution_handle dist, int use32bit);   /* :258 */
 
-/* ---- matrix [ref: include/amgx_c.h:267-343] ---- */
-AMGX_RC AMGX_API AMGX_matrix_create(AMGX_matrix_handle *mtx, AMGX_resources_handle rsc, AMGX_Mode mode);
-AMGX_RC AMGX_API AMGX_matrix_destroy(AMGX_matrix_handle mtx);
+/* ---- matrix [ref: include/amgx_c.h:262-333] ---- */
+AMGX_RC AMGX_API AMGX_matrix_create(AMGX_matrix_handle *mtx, AMGX_resources_handle rsc, AMGX_Mode mode);   /* :262 */
+AMGX_RC AMGX_API AMGX_matrix_destroy(AMGX_matrix_handle mtx);   /* :267 */
 AMGX_RC AMGX_API AMGX_matrix_upload_all(AMGX_matrix_handle mtx, int n, int nnz, int block_dimx, int block_dimy,
-                                        const int *row_ptrs, const int *col_indices, const void *data, const void *diag_data);
-AMGX_RC AMGX_API AMGX_matrix_replace_coefficients(AMGX_matrix_handle mtx, int n, int nnz, const void *data, const void *diag_data);
-AMGX_RC AMGX_API AMGX_matrix_get_size(const AMGX_matrix_handle mtx, int *n, int *block_dimx, int *block_dimy);
-AMGX_RC AMGX_API AMGX_matrix_get_nnz(const AMGX_matrix_handle mtx, int *nnz);
-AMGX_RC AMGX_API AMGX_matrix_download_all(const AMGX_matrix_handle mtx, int *row_ptrs, int *col_indices, void *data, void **diag_data);
-AMGX_RC AMGX_API AMGX_matrix_vector_multiply(AMGX_matrix_handle mtx, AMGX_vector_handle x, AMGX_vector_handle y);
-AMGX_RC AMGX_API AMGX_matrix_set_boundary_separation(AMGX_matrix_handle mtx, int boundary_separation);
+                                        const int *row_ptrs, const int *col_indices, const void *data, const void *diag_data);   /* :270 */
+AMGX_RC AMGX_API AMGX_matrix_replace_coefficients(AMGX_matrix_handle mtx, int n, int nnz, const void *data, const void *diag_data);   /* :281 */
+AMGX_RC AMGX_API AMGX_matrix_get_size(const AMGX_matrix_handle mtx, int *n, int *block_dimx, int *block_dimy);   /* :288 */
+AMGX_RC AMGX_API AMGX_matrix_get_nnz(const AMGX_matrix_handle mtx, int *nnz);   /* :294 */
+AMGX_RC AMGX_API AMGX_matrix_download_all(const AMGX_matrix_handle mtx, int *row_ptrs, int *col_indices, void *data, void **diag_data);   /* :298 */
+AMGX_RC AMGX_API AMGX_matrix_vector_multiply(AMGX_matrix_handle mtx, AMGX_vector_handle x, AMGX_vector_handle y);   /* :305 */
+AMGX_RC AMGX_API AMGX_matrix_set_boundary_separation(AMGX_matrix_handle mtx, int boundary_separation);   /* :310 */
 AMGX_RC AMGX_API AMGX_matrix_comm_from_maps(AMGX_matrix_handle mtx, int allocated_halo_depth, int num_import_rings, int max_num_neighbors,
-                                            const int *neighbors, const int *send_ptrs, const int *send_maps, const int *recv_ptrs, const int *recv_maps);
+                                            const int *neighbors, const int *send_ptrs, const int *send_maps, const int *recv_ptrs, const int *recv_maps);   /* :314 */
 AMGX_RC AMGX_API AMGX_matrix_comm_from_maps_one_ring(AMGX_matrix_handle mtx, int allocated_halo_depth, int num_neighbors, const int *neighbors,
-                                                     const int *send_sizes, const int **send_maps, const int *recv_sizes, const int **recv_maps);
+                                                     const int *send_sizes, const int **send_maps, const int *recv_sizes, const int **recv_maps);   /* :325 */
 
-/* ---- vector [ref: include/amgx_c.h:346-386] ---- */
-AMGX_RC AMGX_API AMGX_vector_create(AMGX_vector_handle *vec, AMGX_resources_handle rsc, AMGX_Mode mode);
-AMGX_RC AMGX_API AMGX_vector_destroy(AMGX_vector_handle vec);
-AMGX_RC AMGX_API AMGX_vector_upload(AMGX_vector_handle vec, int n, int block_dim, const void *data);
-AMGX_RC AMGX_API AMGX_vector_set_zero(AMGX_vector_handle vec, int n, int block_dim);
-AMGX_RC AMGX_API AMGX_vector_set_random(AMGX_vector_handle vec, int n);
-AMGX_RC AMGX_API AMGX_vector_download(const AMGX_vector_handle vec, void *data);
-AMGX_RC AMGX_API AMGX_vector_get_size(const AMGX_vector_handle vec, int *n, int *block_dim);
-AMGX_RC AMGX_API AMGX_vector_bind(AMGX_vector_handle vec, const AMGX_matrix_handle mtx);
+/* ---- vector [ref: include/amgx_c.h:336-370] ---- */
+AMGX_RC AMGX_API AMGX_vector_create(AMGX_vector_handle *vec, AMGX_resources_handle rsc, AMGX_Mode mode);   /* :336 */
+AMGX_RC AMGX_API AMGX_vector_destroy(AMGX_vector_handle vec);   /* :341 */
+AMGX_RC AMGX_API AMGX_vector_upload(AMGX_vector_handle vec, int n, int block_dim, const void *data);   /* :344 */
+AMGX_RC AMGX_API AMGX_vector_set_zero(AMGX_vector_handle vec, int n, int block_dim);   /* :350 */
+AMGX_RC AMGX_API AMGX_vector_set_random(AMGX_vector_handle vec, int n);   /* :355 */
+AMGX_RC AMGX_API AMGX_vector_download(const AMGX_vector_handle vec, void *data);   /* :359 */
+AMGX_RC AMGX_API AMGX_vector_get_size(const AMGX_vector_handle vec, int *n, int *block_dim);   /* :363 */
+AMGX_RC AMGX_API AMGX_vector_bind(AMGX_vector_handle vec, const AMGX_matrix_handle mtx);   /* :368 */
 
-/* ---- solver [ref: include/amgx_c.h:389-437] ---- */
-AMGX_RC AMGX_API AMGX_solver_create(AMGX_solver_handle *slv, AMGX_resources_handle rsc, AMGX_Mode mode, const AMGX_config_handle cfg_solver);
-AMGX_RC AMGX_API AMGX_solver_destroy(AMGX_solver_handle slv);
-AMGX_RC AMGX_API AMGX_solver_setup(AMGX_solver_handle slv, AMGX_matrix_handle mtx);                                  /* :398 */
-AMGX_RC AMGX_API AMGX_solver_solve(AMGX_solver_handle slv, AMGX_vector_handle rhs, AMGX_vector_handle sol);          /* :402 */
-AMGX_RC AMGX_API AMGX_solver_solve_with_0_initial_guess(AMGX_solver_handle slv, AMGX_vector_handle rhs, AMGX_vector_handle sol);
-AMGX_RC AMGX_API AMGX_solver_get_iterations_number(AMGX_solver_handle slv, int *n);
-AMGX_RC AMGX_API AMGX_solver_get_iteration_residual(AMGX_solver_handle slv, int it, int idx, double *res);
-AMGX_RC AMGX_API AMGX_solver_get_status(AMGX_solver_handle slv, AMGX_SOLVE_STATUS *st);
-AMGX_RC AMGX_API AMGX_solver_calculate_residual_norm(AMGX_solver_handle solver, AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle x, void *norm_vector);
-AMGX_RC AMGX_API AMGX_solver_resetup(AMGX_solver_handle slv, AMGX_matrix_handle mtx);                                /* :602 */
-AMGX_RC AMGX_API AMGX_solver_register_print_callback(AMGX_print_callback func);                                       /* :599 */
+/* ---- solver [ref: include/amgx_c.h:373-605] ---- */
+AMGX_RC AMGX_API AMGX_solver_create(AMGX_solver_handle *slv, AMGX_resources_handle rsc, AMGX_Mode mode, const AMGX_config_handle cfg_solver);   /* :373 */
+AMGX_RC AMGX_API AMGX_solver_destroy(AMGX_solver_handle slv);   /* :379 */
+AMGX_RC AMGX_API AMGX_solver_setup(AMGX_solver_handle slv, AMGX_matrix_handle mtx);   /* :382 */
+AMGX_RC AMGX_API AMGX_solver_solve(AMGX_solver_handle slv, AMGX_vector_handle rhs, AMGX_vector_handle sol);   /* :386 */
+AMGX_RC AMGX_API AMGX_solver_solve_with_0_initial_guess(AMGX_solver_handle slv, AMGX_vector_handle rhs, AMGX_vector_handle sol);   /* :391 */
+AMGX_RC AMGX_API AMGX_solver_get_iterations_number(AMGX_solver_handle slv, int *n);   /* :396 */
+AMGX_RC AMGX_API AMGX_solver_get_iteration_residual(AMGX_solver_handle slv, int it, int idx, double *res);   /* :400 */
+AMGX_RC AMGX_API AMGX_solver_get_status(AMGX_solver_handle slv, AMGX_SOLVE_STATUS *st);   /* :406 */
+AMGX_RC AMGX_API AMGX_solver_calculate_residual_norm(AMGX_solver_handle solver, AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle x, void *norm_vector);   /* :410 */
+AMGX_RC AMGX_API AMGX_solver_resetup(AMGX_solver_handle slv, AMGX_matrix_handle mtx);   /* :603 */
+AMGX_RC AMGX_API AMGX_solver_register_print_callback(AMGX_print_callback func);   /* :600 */
 
-/* ---- utilities [ref: include/amgx_c.h:440-520] ---- */
-AMGX_RC AMGX_API AMGX_read_system(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol, const char *filename);
-AMGX_RC AMGX_API AMGX_write_system(const AMGX_matrix_handle mtx, const AMGX_vector_handle rhs, const AMGX_vector_handle sol, const char *filename);
+/* ---- utilities [ref: include/amgx_c.h:418-595] ---- */
+AMGX_RC AMGX_API AMGX_read_system(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol, const char *filename);   /* :435 */
+AMGX_RC AMGX_API AMGX_write_system(const AMGX_matrix_handle mtx, const AMGX_vector_handle rhs, const AMGX_vector_handle sol, const char *filename);   /* :418 */
 AMGX_RC AMGX_API AMGX_read_system_distributed(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol, const char *filename,
                                               int allocated_halo_depth, int num_partitions, const int *partition_sizes, int partition_vector_size,
-                                              const int *partition_vector);                                                    /* :441 */
+                                              const int *partition_vector);   /* :441 */
 AMGX_RC AMGX_API AMGX_write_system_distributed(const AMGX_matrix_handle mtx, const AMGX_vector_handle rhs, const AMGX_vector_handle sol, const char *filename,
                                                int allocated_halo_depth, int num_partitions, const int *partition_sizes, int partition_vector_size,
-                                               const int *partition_vector);                                                   /* :424 */
+                                               const int *partition_vector);   /* :424 */
 AMGX_RC AMGX_API AMGX_read_system_maps_one_ring(int *n, int *nnz, int *block_dimx, int *block_dimy, int **row_ptrs, int **col_indices, void **data,
                                                 void **diag_data, void **rhs, void **sol, int *num_neighbors, int **neighbors, int **send_sizes,
                                                 int ***send_maps, int **recv_sizes, int ***recv_maps, AMGX_resources_handle rsc, AMGX_Mode mode,
                                                 const char *filename, int allocated_halo_depth, int num_partitions, const int *partition_sizes,
-                                                int partition_vector_size, const int *partition_vector);                       /* :452 */
+                                                int partition_vector_size, const int *partition_vector);   /* :452 */
 AMGX_RC AMGX_API AMGX_free_system_maps_one_ring(int *row_ptrs, int *col_indices, void *data, void *diag_data, void *rhs, void *sol, int num_neighbors,
-                                                int *neighbors, int *send_sizes, int **send_maps, int *recv_sizes, int **recv_maps); /* :478 */
+                                                int *neighbors, int *send_sizes, int **send_maps, int *recv_sizes, int **recv_maps);   /* :478 */
 AMGX_RC AMGX_API AMGX_read_system_global(int *n, int *nnz, int *block_dimx, int *block_dimy, int **row_ptrs, void **col_indices_global, void **data,
                                          void **diag_data, void **rhs, void **sol, AMGX_resources_handle rsc, AMGX_Mode mode, const char *filename,
                                          int allocated_halo_depth, int num_partitions, const int *partition_sizes, int partition_vector_size,
-                                         const int *partition_vector);                                                         /* :525 */
+                                         const int *partition_vector);   /* :525 */
 AMGX_RC AMGX_API AMGX_generate_distributed_poisson_7pt(AMGX_matrix_handle mtx, AMGX_vector_handle rhs, AMGX_vector_handle sol,
-                                                       int allocated_halo_depth, int num_import_rings, int nx, int ny, int nz, int px, int py, int pz);
-AMGX_RC AMGX_API AMGX_write_parameters_description(char *filename, AMGX_GET_PARAMS_DESC_FLAG mode);
-AMGX_RC AMGX_API AMGX_matrix_attach_coloring(AMGX_matrix_handle mtx, int *row_coloring, int num_rows, int num_colors);
-AMGX_RC AMGX_API AMGX_matrix_attach_geometry(AMGX_matrix_handle mtx, double *geox, double *geoy, double *geoz, int n);
+                                                       int allocated_halo_depth, int num_import_rings, int nx, int ny, int nz, int px, int py, int pz);   /* :492 */
+AMGX_RC AMGX_API AMGX_write_parameters_description(char *filename, AMGX_GET_PARAMS_DESC_FLAG mode);   /* :505 */
+AMGX_RC AMGX_API AMGX_matrix_attach_coloring(AMGX_matrix_handle mtx, int *row_coloring, int num_rows, int num_colors);   /* :512 */
+AMGX_RC AMGX_API AMGX_matrix_attach_geometry(AMGX_matrix_handle mtx, double *geox, double *geoy, double *geoz, int n);   /* :518 */
 AMGX_RC AMGX_API AMGX_matrix_upload_all_global(AMGX_matrix_handle mtx, int n_global, int n, int nnz, int block_dimx, int block_dimy,
                                                const int *row_ptrs, const void *col_indices_global, const void *data, const void *diag_data,
-                                               int allocated_halo_depth, int num_import_rings, const int *partition_vector);
+                                               int allocated_halo_depth, int num_import_rings, const int *partition_vector);   /* :545 */
 AMGX_RC AMGX_API AMGX_matrix_upload_all_global_32(AMGX_matrix_handle mtx, int n_global, int n, int nnz, int block_dimx, int block_dimy,
                                                   const int *row_ptrs, const void *col_indices_global, const void *data, const void *diag_data,
-                                                  int allocated_halo_depth, int num_import_rings, const int *partition_vector);
+                                                  int allocated_halo_depth, int num_import_rings, const int *partition_vector);   /* :560 */
 AMGX_RC AMGX_API AMGX_matrix_upload_distributed(AMGX_matrix_handle mtx, int n_global, int n, int nnz, int block_dimx, int block_dimy,
                                                 const int *row_ptrs, const void *col_indices_global, const void *data, const void *diag_data,
-                                                AMGX_distribution_handle distribution);
-AMGX_RC AMGX_API AMGX_matrix_check_symmetry(AMGX_matrix_handle mtx, int *structurally_symmetric, int *symmetric);
-AMGX_RC AMGX_API AMGX_matrix_check_diag_dominant(const AMGX_matrix_handle mtx, int *diag_dominant);
+                                                AMGX_distribution_handle distribution);   /* :575 */
+AMGX_RC AMGX_API AMGX_matrix_check_symmetry(AMGX_matrix_handle mtx, int *structurally_symmetric, int *symmetric);   /* :588 */
+AMGX_RC AMGX_API AMGX_matrix_check_diag_dominant(const AMGX_matrix_handle mtx, int *diag_dominant);   /* :593 */
 
 /* =====================================================================================
  * Extensions of this library (not in the reference).
