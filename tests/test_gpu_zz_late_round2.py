@@ -4,6 +4,8 @@ with `pytest -m gpu` like everything else; the file name sorts last so that with
   * FGMRES with gmres_krylov_dim < min(max_iters, gmres_n_restart): the reference's truncated variant (csrc/fgmres.cu, header) against its
     CPU restatement (oracle/krylov_oracle.inc.c orc_fgmres_trunc): same iteration count, residual history to 1e-12 relative.  No
     reference golden exists for this variant (no shipped configuration sets gmres_krylov_dim): parity unpinned beyond the restatement.
+  * PCG monitored in the L1 / L2 / LMAX norm against the oracle (the reference's norm_tests.cu, through the residual history); the kernels
+    behind it ran in round 2 (L1 through the block DILU suite, L2 everywhere) -- only this direct comparison is new.
 """
 import numpy as np
 import pytest
@@ -59,3 +61,18 @@ def test_fgmres_krylov_dim_at_or_above_the_restart_is_the_standard_solver(amgx, 
     x3, it3, st3, h3 = run_engine(amgx, outer_cfg("FGMRES", JACOBI, tol=1e-9, max_iters=80, gmres_n_restart=10, gmres_krylov_dim=25), rp, ci, va, b)
     assert it1 == it2 == it3 and st1 == st2 == st3 == "success"
     assert np.array_equal(h1, h2) and np.array_equal(h1, h3) and np.array_equal(x1, x2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# norm_tests.cu of the reference (L1 / L2 / LMAX of device vectors against host values, type-epsilon x size): here through the solve
+# monitor -- PCG with each norm type against the oracle: the residual history IS the sequence of norms (src/norm.cu:34-90, src/blas.cu:814-917)
+# ---------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("norm", ["L1", "L2", "LMAX"])
+def test_pcg_residual_norm_types_match_oracle(amgx, oracle, norm):
+    rp, ci, va = gallery.poisson7pt(17, 13, 11)
+    n = rp.shape[0] - 1
+    b = np.random.default_rng(21).standard_normal(n)
+    x, it, status, hist = run_engine(amgx, outer_cfg("PCG", JACOBI, tol=1e-7, max_iters=200, norm=norm), rp, ci, va, b)
+    xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, jacobi_omega=0.8, tol=1e-7, max_iters=200, norm=norm)
+    assert convo and status == "success" and it == ito
+    assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12

@@ -252,3 +252,26 @@ def test_explicit_zero_values_and_unsymmetric_structure_give_no_nan(oracle):
                 c = oracle.ClassicalAMG(rp, ci, va, max_levels=10, interpolator=interp, selector=s)
                 x, it, hist, conv = oracle.fgmres(rp, ci, va, np.ones(n), amg=c, tol=1e-8, max_iters=2, restart=2)
                 assert np.isfinite(x).all() and np.isfinite(hist).all(), (seed, s, interp)
+
+
+def test_norms_against_numpy(oracle):
+    """norm_tests.cu of the reference: L1 / L2 / LMAX against host values within type-epsilon x size; here the oracle's norm functions
+    (the checker of every residual history) against numpy, and through the PCG monitor: history entry 0 is the norm of b"""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    lib = oracle.lib()
+    for n in (1, 7, 1000, 65537):
+        v = np.ascontiguousarray(rng.standard_normal(n) * 10.0 ** rng.integers(-3, 4, n))
+        p = v.ctypes.data_as(C.c_void_p)
+        eps = np.finfo(np.float64).eps * n
+        assert abs(lib.orc_nrm1(n, p) - np.abs(v).sum()) <= eps * np.abs(v).sum()
+        assert abs(lib.orc_nrm2(n, p) - np.linalg.norm(v)) <= eps * np.linalg.norm(v)
+        assert lib.orc_nrmmax(n, p) == np.abs(v).max()
+    from amgx_b200 import gallery
+    rp, ci, va = gallery.poisson7pt(6)
+    b = rng.standard_normal(rp.shape[0] - 1)
+    for norm, f in (("L1", lambda r: np.abs(r).sum()), ("L2", np.linalg.norm), ("LMAX", lambda r: np.abs(r).max())):
+        x, it, hist, conv = oracle.pcg(rp, ci, va, b, jacobi_omega=0.8, tol=1e-8, max_iters=100, norm=norm)
+        assert conv and abs(hist[0] - f(b)) <= 1e-14 * f(b)
+        r = b - gallery.to_scipy(rp, ci, va) @ x
+        assert f(r) <= 1.0001e-8 * f(b) + 1e-15
