@@ -227,7 +227,7 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------------------------------
 # reference GPU build beside it (context): oracle/_ref/ref_dump on the same generated matrix and configuration
 # ------------------------------------------------------------------------------------------------------------------------
-def reference_gpu(nx, reps=2, config=None):
+def reference_gpu(nx, reps=2, config=None, timeout=300.0):
     """config: a configuration dictionary (written to a file for the harness); default = PCG_AGGREGATION_JACOBI.json"""
     exe = ROOT / "oracle" / "_ref" / "ref_dump"
     if not exe.exists():
@@ -238,7 +238,7 @@ def reference_gpu(nx, reps=2, config=None):
             cfg_path = "/tmp/amgxb_refgpu_cfg.json"
             Path(cfg_path).write_text(json.dumps(config))
         env = dict(os.environ, REFDUMP_NO_LEVELS="1", LD_LIBRARY_PATH=str(exe.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-        r = subprocess.run([str(exe), f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=300, env=env)
+        r = subprocess.run([str(exe), f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=timeout, env=env)
         m = re.search(r"ref_dump: status (\d+) iterations (\d+) setup ([0-9.eE+-]+) s solve ([0-9.eE+-]+) s", r.stdout)
         if not m:
             return {"unavailable": "ref_dump gave no timing line", "tail": (r.stdout + r.stderr)[-300:]}
@@ -258,7 +258,7 @@ HOST_PATH_CFG = {"config_version": 2, "determinism_flag": 1, "solver": {
     "preconditioner": {"scope": "jac", "solver": "BLOCK_JACOBI", "relaxation_factor": 0.8, "max_iters": 1, "monitor_residual": 0}}}
 
 
-def reference_host_path(capi, rsc, nx):
+def reference_host_path(capi, rsc, nx, timeout=240.0):
     """BASELINE configs[0]'s solver (PCG + BLOCK_JACOBI) is the one whose every component the reference implements on the host
     (src/multiply.cu:753-852, src/solvers/block_jacobi_solver.cu:1256-1332; aggregation SIZE_2 and DILU have no host path).
     Here: that solver, 10 iterations, on the nx^3 Poisson matrix -- (a) the UNMODIFIED reference in its host mode hDDI through
@@ -292,7 +292,7 @@ def reference_host_path(capi, rsc, nx):
         cfg_path = "/tmp/amgxb_host_path_cfg.json"
         Path(cfg_path).write_text(json.dumps(HOST_PATH_CFG))
         env = dict(os.environ, REFDUMP_NO_LEVELS="1", LD_LIBRARY_PATH=str(exe.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-        r = subprocess.run([str(exe), f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump_host.bin", "hDDI", "1"], capture_output=True, text=True, timeout=240, env=env)
+        r = subprocess.run([str(exe), f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump_host.bin", "hDDI", "1"], capture_output=True, text=True, timeout=timeout, env=env)
         m = re.search(r"ref_dump: status (\d+) iterations (\d+) setup ([0-9.eE+-]+) s solve ([0-9.eE+-]+) s", r.stdout)
         if not m:
             out["reference_cpu"] = {"unavailable": "ref_dump (hDDI) gave no timing line", "tail": (r.stdout + r.stderr)[-300:]}
@@ -827,6 +827,15 @@ def main():
                "gpu_launches": int(tot_k), "clocks": clocks, "roofline": roof, "cpu_baseline": None, "reference_gpu": None, "parity": None,
                "final_relative_residual": float(hist[-1] / hist[0]) if hist is not None and len(hist) else None}
     guard = LineGuard(out, armed=distributed, limit_s=float(os.environ.get("AMGXB_BENCH_GUARD_S", "300")))      # parity and strong_512 run collectives: a hang there must not cost the line
+    # the context objects of the N = 1 line are child processes with their own time limits; together they get AMGXB_BENCH_CONTEXT_S seconds,
+    # and a SIGTERM from whoever launched the bench prints the line as it stands instead of losing it
+    ctx_deadline = time.time() + float(os.environ.get("AMGXB_BENCH_CONTEXT_S", "360"))
+    ctx_left = lambda cap: max(5.0, min(cap, ctx_deadline - time.time()))
+    try:
+        import signal
+        signal.signal(signal.SIGTERM, lambda *_a: (guard._emit("terminated from outside while the context objects were running: line printed as it stood"), os._exit(0)))
+    except Exception:
+        pass
 
     if distributed and not args.no_parity:
         try:
@@ -856,17 +865,17 @@ def main():
 
     if rank == 0 and not distributed and args.workload == "classical" and not args.no_reference_gpu:
         torch.cuda.empty_cache()
-        out["reference_gpu"] = reference_gpu(nx, config=CLASSICAL_CFG)
+        out["reference_gpu"] = reference_gpu(nx, config=CLASSICAL_CFG, timeout=ctx_left(300.0))
     if rank == 0 and not distributed and args.workload == "poisson":
         if not args.no_reference_gpu:
             torch.cuda.empty_cache()
-            out["reference_gpu"] = reference_gpu(nx)
+            out["reference_gpu"] = reference_gpu(nx, timeout=ctx_left(300.0))
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = oracle_baseline(nx, nx, nx, 5 if nx <= 256 else 2)
         if not args.no_extras and not args.no_reference_gpu and not args.no_cpu_baseline and nx == 256:
-            out["reference_host_path"] = reference_host_path(capi, rsc, nx)
+            out["reference_host_path"] = reference_host_path(capi, rsc, nx, timeout=ctx_left(240.0))
         if not args.no_extras and nx == 256:
-            out["other_workloads"] = other_workloads()
+            out["other_workloads"] = other_workloads(budget_s=ctx_left(240.0))
     guard.finish()
     for o in (rsc, cfg):
         o.destroy()

@@ -105,3 +105,26 @@ def test_bench_configurations_pass_config_check():
         ok, msg = capi.config_check(cfg)
         cfg.destroy()
         assert ok, (name, msg)
+
+
+def test_sigterm_during_the_context_objects_prints_the_line():
+    """whoever launched the bench may end it while the context objects run (they can take minutes): the line, whose headline numbers
+    are final by then, is printed as it stands"""
+    import signal
+    import time
+    code = ("import sys, time; sys.argv = ['bench.py', '--steps', '2', '--warmup', '1', '--no-cpu-baseline', '--no-reference-gpu']\n"
+            "import tests.bench_dryrun_worker as w\n"
+            "def slow(**k):\n    print('CONTEXT_STARTED', file=sys.stderr, flush=True); time.sleep(200)\n"
+            "w.bench.other_workloads = slow\n"
+            "w.bench.main()\n")
+    p = subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(ROOT))
+    t0 = time.time()
+    for ln in p.stderr:                      # wait until the context phase has begun
+        if "CONTEXT_STARTED" in ln or time.time() - t0 > 120:
+            break
+    time.sleep(0.5)
+    p.send_signal(signal.SIGTERM)
+    out, _ = p.communicate(timeout=60)
+    d = _line(out)
+    assert p.returncode == 0 and d["value"] > 0 and "other_workloads" not in d
+    assert "terminated from outside" in d["note"]
