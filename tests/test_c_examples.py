@@ -30,6 +30,15 @@ def test_own_example_is_strict_c_and_links(built_lib, tmp_path):
     assert "warning" not in r.stderr, r.stderr      # the header is consumable from C without a single diagnostic
 
 
+def test_distributed_example_is_strict_c_and_links(built_lib, tmp_path):
+    """examples/poisson_dist_capi.c: the multi-GPU bootstrap (AMGXB200_comm instead of MPI_Comm*) from plain C, one process per GPU"""
+    r = _cc(ROOT / "examples" / "poisson_dist_capi.c", tmp_path / "poisson_dist_capi", ROOT / "include")
+    assert r.returncode == 0, r.stderr
+    assert "warning" not in r.stderr, r.stderr
+    run = subprocess.run([str(tmp_path / "poisson_dist_capi"), "4"], capture_output=True, text=True, cwd=str(ROOT), env={"WORLD_SIZE": "2", "RANK": "1", "PATH": "/usr/bin"})
+    assert run.returncode == 1 and "AMGXB_ID_FILE" in run.stderr          # refuses to start a multi-rank run without a way to share the id
+
+
 @pytest.mark.skipif(not (REF / "examples" / "amgx_capi.c").exists(), reason="reference tree not present on this box")
 def test_reference_example_links_against_our_library(built_lib, tmp_path):
     r = _cc(REF / "examples" / "amgx_capi.c", tmp_path / "amgx_capi_ref", REF / "include")

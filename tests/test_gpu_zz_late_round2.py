@@ -76,3 +76,29 @@ def test_pcg_residual_norm_types_match_oracle(amgx, oracle, norm):
     xo, ito, histo, convo = oracle.pcg(rp, ci, va, b, jacobi_omega=0.8, tol=1e-7, max_iters=200, norm=norm)
     assert convo and status == "success" and it == ito
     assert np.max(np.abs(hist - histo) / histo[0]) < 1e-12
+
+
+def test_plain_c_two_process_example(tmp_path):
+    """examples/poisson_dist_capi.c: two processes, one GPU each, the communicator id shared through a file -- no MPI, no Python in the
+    loop.  Same global problem as a single-rank solve of 24 x 24 x 48: converges, and the residual histories agree to the reduction order."""
+    import os
+    import subprocess
+    from pathlib import Path
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = Path(__file__).resolve().parents[1]
+    exe = tmp_path / "poisson_dist_capi"
+    r = subprocess.run(["gcc", "-std=c99", str(root / "examples" / "poisson_dist_capi.c"), f"-I{root / 'include'}", f"-L{root / 'amgx_b200'}", "-lamgxsh",
+                        f"-Wl,-rpath,{root / 'amgx_b200'}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    idf = tmp_path / "id.bin"
+    procs = []
+    for rank in (0, 1):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), AMGXB_ID_FILE=str(idf))
+        procs.append(subprocess.Popen([str(exe), "24", str(root / "amgx_b200" / "configs" / "PCG_AGGREGATION_JACOBI.json")], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                      text=True, env=env, cwd=str(root)))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    head = outs[0][0].splitlines()[0]
+    assert head.startswith("ranks 2 local rows 13824 status 0"), head
