@@ -621,6 +621,10 @@ def main():
         raise SystemExit("multi-GPU bench lines exist for the poisson workload; see tools/bench_block_dist.py for the block configuration")
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the peer-memory receive window is bump-allocated per Resources and never shrinks: the main problem, the parity problems, strong_512
+        # and block_weak all carve their levels out of it (about 30 MB together; default window 64 MB) -- leave room so that none of them
+        # falls back to the NCCL path half way
+        os.environ.setdefault("AMGXB_P2P_WINDOW_MB", "256")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     capi.initialize()
