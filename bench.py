@@ -28,8 +28,8 @@ N > 1 (one process per GPU, row partition in z-slabs, peer-memory / NCCL halo ex
            same solver, device-timed like `value`; its N=1 counterpart is other_workloads.poisson512 of the N=1 line.
   block_weak object (same runs): BASELINE configs[4]-style weak scaling, 160^3 4x4 block rows per GPU, AMG + MULTICOLOR_DILU, dDFI;
            N=1 counterpart other_workloads.block160_dDFI.
-Default N=1 line only: other_workloads = the other BASELINE workloads (512^3 Poisson = the north star's target size, the 4 M-row
-  SuiteSparse-shaped matrix, the 4x4 block configuration), each measured by THIS script in a child process after the main line's
+Default N=1 line only: other_workloads = the other BASELINE workloads (512^3 Poisson = the north star's target size, FGMRES + classical AMG at
+  512^3 = configs[2], the 4 M-row SuiteSparse-shaped matrix, the 4x4 block configuration), each measured by THIS script in a child process after the main line's
   numbers are final (`python bench.py --workload ... --no-extras`), under a common time budget; --no-extras skips them.
   reference_host_path = the reference's own host implementation (mode hDDI, PCG + BLOCK_JACOBI: the solver family it has on the CPU),
   timed on the host cores beside this engine on the same configuration.
@@ -595,7 +595,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip other_workloads (N = 1) and strong_512 (N > 1)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the context runs: other_workloads and reference_host_path (N = 1), strong_512 and block_weak (N > 1)")
     args = ap.parse_args()
     if args.n is None:
         args.n = 160 if args.workload == "block" else 256
