@@ -6,6 +6,9 @@ with `pytest -m gpu` like everything else; the file name sorts last so that with
     reference golden exists for this variant (no shipped configuration sets gmres_krylov_dim): parity unpinned beyond the restatement.
   * PCG monitored in the L1 / L2 / LMAX norm against the oracle (the reference's norm_tests.cu, through the residual history); the kernels
     behind it ran in round 2 (L1 through the block DILU suite, L2 everywhere) -- only this direct comparison is new.
+  * examples/poisson_dist_capi.c as two processes (needs two GPUs).
+  * BASELINE.json's full sizes 256^3 and 512^3 through size-independent properties (linearity, exact row sums, true vs reported residual,
+    bit-reproducible second solve; 71 iterations at 256^3): validated entry points, new only in size.
 """
 import numpy as np
 import pytest
@@ -102,3 +105,66 @@ def test_plain_c_two_process_example(tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
     head = outs[0][0].splitlines()[0]
     assert head.startswith("ranks 2 local rows 13824 status 0"), head
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# BASELINE.json's FULL sizes (256^3 = configs[1], 512^3 = configs[2] / [3]) through size-independent properties: the oracle needs minutes
+# there, the properties do not.  Same checks as tests/test_gpu_parity.py::test_full_size_properties (128^3); every entry point used here
+# ran in round 2 -- new is only the size, i.e. the coded / row-pattern kernels on exactly the matrices the bench measures.
+# ---------------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nx", [256, 512])
+def test_baseline_full_size_properties(amgx, nx):
+    from pathlib import Path
+    cfg = amgx.Config(file=str(Path(__file__).resolve().parents[1] / "amgx_b200" / "configs" / "PCG_AGGREGATION_JACOBI.json"))
+    rsc = amgx.Resources(cfg)
+    A, bv, xv = amgx.Matrix(rsc), amgx.Vector(rsc), amgx.Vector(rsc)
+    objs = [A, bv, xv]
+    try:
+        A.generate_poisson7(bv, xv, nx, nx, nx)
+        n = nx ** 3
+        assert A.get_size()[0] == n and A.get_nnz() == 7 * n - 6 * nx * nx
+        rng = np.random.default_rng(0)
+        u, v = rng.standard_normal(n), rng.standard_normal(n)
+        uv, y = amgx.Vector(rsc), amgx.Vector(rsc)
+        objs += [uv, y]
+        y.set_zero(n)
+        # linearity: A (2u - 3v) = 2 A u - 3 A v
+        uv.upload(u)
+        A.multiply(uv, y)
+        lin = 2.0 * y.download()
+        uv.upload(v)
+        A.multiply(uv, y)
+        lin -= 3.0 * y.download()
+        uv.upload(2.0 * u - 3.0 * v)
+        A.multiply(uv, y)
+        assert np.max(np.abs(y.download() - lin)) <= 1e-12 * np.max(np.abs(lin))
+        del u, v, lin
+        # row sums: A 1 = number of missing neighbours (0 inside, 6 nx^2 in total), exactly
+        uv.upload(np.ones(n))
+        A.multiply(uv, y)
+        s = y.download().reshape(nx, nx, nx)
+        assert s[1:-1, 1:-1, 1:-1].max() == 0.0 and s[1:-1, 1:-1, 1:-1].min() == 0.0 and s.sum() == 6.0 * nx * nx
+        del s
+        # the solve: the reported last residual norm is the true one; 256^3 converges in the 71 iterations the reference needs
+        slv = amgx.Solver(rsc, cfg)
+        objs.append(slv)
+        slv.setup(A)
+        xv.set_zero(n)
+        slv.solve(bv, xv, zero_initial_guess=True)
+        hist = np.array(slv.residual_history())
+        if nx == 256:
+            assert slv.status == "success" and slv.iterations_number == 71
+        assert hist[-1] < 1e-4 * hist[0] and np.all(np.isfinite(hist))
+        A.multiply(xv, y)
+        r = 1.0 - y.download()
+        assert abs(np.linalg.norm(r) - hist[-1]) <= 1e-9 * hist[0]
+        # a second solve reproduces the first bit for bit
+        x1 = xv.download()
+        xv.set_zero(n)
+        slv.solve(bv, xv, zero_initial_guess=True)
+        assert np.array_equal(x1, xv.download()) and np.array_equal(hist, np.array(slv.residual_history()))
+    finally:
+        for o in reversed(objs):
+            o.destroy()
+        rsc.destroy()
+        cfg.destroy()
