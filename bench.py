@@ -52,6 +52,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 CONFIG = ROOT / "amgx_b200" / "configs" / "PCG_AGGREGATION_JACOBI.json"
+REF_SYSTEM = "/tmp/amgxb_ref_system.bin"
 METRIC = "solve_phase_vcycle_iterations_per_sec"
 UNIT = "iterations/s"
 
@@ -227,8 +228,17 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------------------------------
 # reference GPU build beside it (context): oracle/_ref/ref_dump on the same generated matrix and configuration
 # ------------------------------------------------------------------------------------------------------------------------
-def reference_gpu(nx, reps=2, config=None, timeout=300.0):
-    """config: a configuration dictionary (written to a file for the harness); default = PCG_AGGREGATION_JACOBI.json"""
+def write_ref_system(path, rp, ci, va, rhs):
+    """a scalar CSR system in the input format of oracle/ref_build/ref_dump.cu (header n, nnz, bx, by, has_diag, has_x0; then the arrays)"""
+    with open(path, "wb") as f:
+        f.write(np.array([rp.shape[0] - 1, ci.shape[0], 1, 1, 0, 0], np.int32).tobytes())
+        for a, t in ((rp, np.int32), (ci, np.int32), (va, np.float64), (rhs, np.float64)):
+            f.write(np.ascontiguousarray(a, t).tobytes())
+
+
+def reference_gpu(nx, reps=2, config=None, timeout=300.0, system=None):
+    """config: a configuration dictionary (written to a file for the harness); default = PCG_AGGREGATION_JACOBI.json.
+    system: a file written by write_ref_system instead of the generated nx^3 Poisson matrix."""
     exe = ROOT / "oracle" / "_ref" / "ref_dump"
     if not exe.exists():
         return {"unavailable": "oracle/_ref/ref_dump not built (oracle/ref_build/Makefile, needs /root/reference)"}
@@ -238,7 +248,7 @@ def reference_gpu(nx, reps=2, config=None, timeout=300.0):
             cfg_path = "/tmp/amgxb_refgpu_cfg.json"
             Path(cfg_path).write_text(json.dumps(config))
         env = dict(os.environ, REFDUMP_NO_LEVELS="1", LD_LIBRARY_PATH=str(exe.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-        r = subprocess.run([str(exe), f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=timeout, env=env)
+        r = subprocess.run([str(exe), system or f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=timeout, env=env)
         m = re.search(r"ref_dump: status (\d+) iterations (\d+) setup ([0-9.eE+-]+) s solve ([0-9.eE+-]+) s", r.stdout)
         if not m:
             return {"unavailable": "ref_dump gave no timing line", "tail": (r.stdout + r.stderr)[-300:]}
@@ -398,13 +408,13 @@ def distributed_parity(capi, dist, torch, rsc, rank, world, local_rank):
 EXTRA_WORKLOADS = [
     ("poisson512", ["--workload", "poisson", "--grid", "512", "--steps", "2", "--warmup", "3"]),        # north star: >= 70 % of the roofline at 512^3
     ("classical512", ["--workload", "classical", "--grid", "512", "--steps", "2", "--warmup", "3"]),      # BASELINE configs[2]
-    ("banded4m", ["--workload", "banded", "--steps", "3", "--warmup", "3"]),                              # SURVEY 8(d) input 2
+    ("banded4m", ["--workload", "banded", "--steps", "3", "--warmup", "3", "+reference-gpu"]),            # SURVEY 8(d) input 2; with the reference GPU build on the same matrix
     ("block160_dDFI", ["--workload", "block", "--mode", "dDFI", "--steps", "3", "--warmup", "3"]),        # BASELINE configs[4] at 160^3 block rows
 ]
 
 
 def other_workloads(budget_s=240.0, per_run_s=110.0, workloads=None, script=None):
-    """Runs `bench.py <flags> --no-cpu-baseline --no-reference-gpu --no-extras` once per extra workload and returns their JSON lines
+    """Runs `bench.py <flags> --no-cpu-baseline [--no-reference-gpu] --no-extras` once per extra workload and returns their JSON lines
     (None-valued keys dropped).  A child that fails, prints no line or runs out of time costs only its own entry."""
     out = {}
     t_end = time.time() + budget_s
@@ -414,7 +424,9 @@ def other_workloads(budget_s=240.0, per_run_s=110.0, workloads=None, script=None
         if left < 40.0:
             out[name] = {"skipped": "time budget of the extra workloads spent"}
             continue
-        cmd = [sys.executable, str(script or (ROOT / "bench.py")), *flags, "--no-cpu-baseline", "--no-reference-gpu", "--no-extras"]
+        cmd = [sys.executable, str(script or (ROOT / "bench.py")), *[f for f in flags if f != "+reference-gpu"], "--no-cpu-baseline", "--no-extras"]
+        if "+reference-gpu" not in flags:
+            cmd.append("--no-reference-gpu")
         t0 = time.time()
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=min(left, per_run_s), env=env, cwd=str(ROOT))
@@ -665,6 +677,11 @@ def main():
         rp, ci, va = gallery.random_banded(args.rows)
         A.upload(rp, ci, va)
         b.upload(np.ones(rp.shape[0] - 1))
+        if rank == 0 and not args.no_reference_gpu:      # the same matrix for the reference GPU build, run after this engine's timed region
+            try:
+                write_ref_system(REF_SYSTEM, rp, ci, va, np.ones(rp.shape[0] - 1))
+            except Exception:
+                pass
         del rp, ci, va
     else:
         from amgx_b200 import gallery
@@ -870,6 +887,14 @@ def main():
     if rank == 0 and not distributed and args.workload == "classical" and not args.no_reference_gpu:
         torch.cuda.empty_cache()
         out["reference_gpu"] = reference_gpu(nx, config=CLASSICAL_CFG, timeout=ctx_left(300.0))
+    if rank == 0 and not distributed and args.workload == "banded" and not args.no_reference_gpu:
+        torch.cuda.empty_cache()
+        out["reference_gpu"] = reference_gpu(0, config=BANDED_CFG, timeout=ctx_left(300.0), system=REF_SYSTEM) if os.path.exists(REF_SYSTEM) else \
+            {"unavailable": "the system file for the reference could not be written"}
+        try:
+            os.remove(REF_SYSTEM)
+        except OSError:
+            pass
     if rank == 0 and not distributed and args.workload == "poisson":
         if not args.no_reference_gpu:
             torch.cuda.empty_cache()
