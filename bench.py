@@ -405,15 +405,29 @@ def distributed_parity(capi, dist, torch, rsc, rank, world, local_rank):
 # ------------------------------------------------------------------------------------------------------------------------
 # the other BASELINE workloads beside the default line (N = 1): child processes of this script, bounded in time
 # ------------------------------------------------------------------------------------------------------------------------
+_CURRENT_CHILD = [None]        # process group of the context child that is running (ended with the bench if the bench is terminated)
+
+
+def _end_current_child():
+    pg = _CURRENT_CHILD[0]
+    if pg:
+        try:
+            os.killpg(pg, 9)
+        except OSError:
+            pass
+    _CURRENT_CHILD[0] = None
+
+
 EXTRA_WORKLOADS = [
-    ("poisson512", ["--workload", "poisson", "--grid", "512", "--steps", "2", "--warmup", "3"]),        # north star: >= 70 % of the roofline at 512^3
-    ("classical512", ["--workload", "classical", "--grid", "512", "--steps", "2", "--warmup", "3"]),      # BASELINE configs[2]
+    # "+reference-gpu": the child also times the unmodified reference GPU build on the same matrix and configuration (its reference_gpu object)
+    ("poisson512", ["--workload", "poisson", "--grid", "512", "--steps", "2", "--warmup", "3", "+reference-gpu"]),        # north star: >= 70 % of the roofline at 512^3
+    ("classical512", ["--workload", "classical", "--grid", "512", "--steps", "2", "--warmup", "3", "+reference-gpu"]),      # BASELINE configs[2]
     ("banded4m", ["--workload", "banded", "--steps", "3", "--warmup", "3", "+reference-gpu"]),            # SURVEY 8(d) input 2; with the reference GPU build on the same matrix
     ("block160_dDFI", ["--workload", "block", "--mode", "dDFI", "--steps", "3", "--warmup", "3"]),        # BASELINE configs[4] at 160^3 block rows
 ]
 
 
-def other_workloads(budget_s=240.0, per_run_s=110.0, workloads=None, script=None):
+def other_workloads(budget_s=270.0, per_run_s=120.0, workloads=None, script=None):
     """Runs `bench.py <flags> --no-cpu-baseline [--no-reference-gpu] --no-extras` once per extra workload and returns their JSON lines
     (None-valued keys dropped).  A child that fails, prints no line or runs out of time costs only its own entry."""
     out = {}
@@ -429,10 +443,21 @@ def other_workloads(budget_s=240.0, per_run_s=110.0, workloads=None, script=None
             cmd.append("--no-reference-gpu")
         t0 = time.time()
         try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=min(left, per_run_s), env=env, cwd=str(ROOT))
-            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            # own session: a child that overruns is ended together with whatever it started (the reference harness), so that nothing of it
+            # is still on the GPU when the next child is timed
+            proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=str(ROOT), start_new_session=True)
+            _CURRENT_CHILD[0] = proc.pid
+            try:
+                c_out, c_err = proc.communicate(timeout=min(left, per_run_s))
+            except subprocess.TimeoutExpired:
+                _end_current_child()
+                proc.communicate()
+                raise
+            finally:
+                _CURRENT_CHILD[0] = None
+            lines = [ln for ln in c_out.splitlines() if ln.startswith("{")]
             if not lines:
-                out[name] = {"error": "no JSON line", "returncode": r.returncode, "tail": (r.stderr or r.stdout)[-300:]}
+                out[name] = {"error": "no JSON line", "returncode": proc.returncode, "tail": (c_err or c_out)[-300:]}
                 continue
             d = json.loads(lines[-1])
             d = {k: v for k, v in d.items() if v is not None}
@@ -850,11 +875,11 @@ def main():
     guard = LineGuard(out, armed=distributed, limit_s=float(os.environ.get("AMGXB_BENCH_GUARD_S", "300")))      # parity and strong_512 run collectives: a hang there must not cost the line
     # the context objects of the N = 1 line are child processes with their own time limits; together they get AMGXB_BENCH_CONTEXT_S seconds,
     # and a SIGTERM from whoever launched the bench prints the line as it stands instead of losing it
-    ctx_deadline = time.time() + float(os.environ.get("AMGXB_BENCH_CONTEXT_S", "360"))
+    ctx_deadline = time.time() + float(os.environ.get("AMGXB_BENCH_CONTEXT_S", "400"))
     ctx_left = lambda cap: max(5.0, min(cap, ctx_deadline - time.time()))
     try:
         import signal
-        signal.signal(signal.SIGTERM, lambda *_a: (guard._emit("terminated from outside while the context objects were running: line printed as it stood"), os._exit(0)))
+        signal.signal(signal.SIGTERM, lambda *_a: (_end_current_child(), guard._emit("terminated from outside while the context objects were running: line printed as it stood"), os._exit(0)))
     except Exception:
         pass
 
@@ -904,7 +929,7 @@ def main():
         if not args.no_extras and not args.no_reference_gpu and not args.no_cpu_baseline and nx == 256:
             out["reference_host_path"] = reference_host_path(capi, rsc, nx, timeout=ctx_left(240.0))
         if not args.no_extras and nx == 256:
-            out["other_workloads"] = other_workloads(budget_s=ctx_left(240.0))
+            out["other_workloads"] = other_workloads(budget_s=ctx_left(270.0))
     guard.finish()
     for o in (rsc, cfg):
         o.destroy()
