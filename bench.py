@@ -228,15 +228,16 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------------------------------
 # reference GPU build beside it (context): oracle/_ref/ref_dump on the same generated matrix and configuration
 # ------------------------------------------------------------------------------------------------------------------------
-def write_ref_system(path, rp, ci, va, rhs):
-    """a scalar CSR system in the input format of oracle/ref_build/ref_dump.cu (header n, nnz, bx, by, has_diag, has_x0; then the arrays)"""
+def write_ref_system(path, rp, ci, va, rhs, block=1):
+    """a (block-)CSR system in the input format of oracle/ref_build/ref_dump.cu (header n, nnz, bx, by, has_diag, has_x0; then the arrays,
+    values and vectors as doubles: the harness converts to the mode's precisions itself)"""
     with open(path, "wb") as f:
-        f.write(np.array([rp.shape[0] - 1, ci.shape[0], 1, 1, 0, 0], np.int32).tobytes())
+        f.write(np.array([rp.shape[0] - 1, ci.shape[0], block, block, 0, 0], np.int32).tobytes())
         for a, t in ((rp, np.int32), (ci, np.int32), (va, np.float64), (rhs, np.float64)):
             f.write(np.ascontiguousarray(a, t).tobytes())
 
 
-def reference_gpu(nx, reps=2, config=None, timeout=300.0, system=None):
+def reference_gpu(nx, reps=2, config=None, timeout=300.0, system=None, mode="dDDI"):
     """config: a configuration dictionary (written to a file for the harness); default = PCG_AGGREGATION_JACOBI.json.
     system: a file written by write_ref_system instead of the generated nx^3 Poisson matrix."""
     exe = ROOT / "oracle" / "_ref" / "ref_dump"
@@ -248,7 +249,7 @@ def reference_gpu(nx, reps=2, config=None, timeout=300.0, system=None):
             cfg_path = "/tmp/amgxb_refgpu_cfg.json"
             Path(cfg_path).write_text(json.dumps(config))
         env = dict(os.environ, REFDUMP_NO_LEVELS="1", LD_LIBRARY_PATH=str(exe.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-        r = subprocess.run([str(exe), system or f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump.bin", "dDDI", str(reps)], capture_output=True, text=True, timeout=timeout, env=env)
+        r = subprocess.run([str(exe), system or f"poisson:{nx}", cfg_path, "/tmp/amgxb_refdump.bin", mode, str(reps)], capture_output=True, text=True, timeout=timeout, env=env)
         m = re.search(r"ref_dump: status (\d+) iterations (\d+) setup ([0-9.eE+-]+) s solve ([0-9.eE+-]+) s", r.stdout)
         if not m:
             return {"unavailable": "ref_dump gave no timing line", "tail": (r.stdout + r.stderr)[-300:]}
@@ -423,7 +424,7 @@ EXTRA_WORKLOADS = [
     ("poisson512", ["--workload", "poisson", "--grid", "512", "--steps", "2", "--warmup", "3", "+reference-gpu"]),        # north star: >= 70 % of the roofline at 512^3
     ("classical512", ["--workload", "classical", "--grid", "512", "--steps", "2", "--warmup", "3", "+reference-gpu"]),      # BASELINE configs[2]
     ("banded4m", ["--workload", "banded", "--steps", "3", "--warmup", "3", "+reference-gpu"]),            # SURVEY 8(d) input 2; with the reference GPU build on the same matrix
-    ("block160_dDFI", ["--workload", "block", "--mode", "dDFI", "--steps", "3", "--warmup", "3"]),        # BASELINE configs[4] at 160^3 block rows
+    ("block160_dDFI", ["--workload", "block", "--mode", "dDFI", "--steps", "3", "--warmup", "3", "+reference-gpu"]),        # BASELINE configs[4] at 160^3 block rows
 ]
 
 
@@ -714,6 +715,14 @@ def main():
         rp, ci, va = gallery.block_elasticity(nx, nx, nx, dtype=np.float32 if mode[2] == "F" else np.float64)
         A.upload(rp, ci, va, block_dims=(4, 4))
         b.upload(np.ones((rp.shape[0] - 1) * 4), block_dim=4)
+        if rank == 0 and not args.no_reference_gpu:      # the same matrix for the reference GPU build (3.7 GB of doubles at 160^3), run after this engine's timed region
+            try:
+                write_ref_system(REF_SYSTEM, rp, ci, va, np.ones((rp.shape[0] - 1) * 4), block=4)
+            except Exception:
+                try:
+                    os.remove(REF_SYSTEM)
+                except OSError:
+                    pass
         del rp, ci, va
     n, _, _ = A.get_size()
     nnz = A.get_nnz()
@@ -912,10 +921,10 @@ def main():
     if rank == 0 and not distributed and args.workload == "classical" and not args.no_reference_gpu:
         torch.cuda.empty_cache()
         out["reference_gpu"] = reference_gpu(nx, config=CLASSICAL_CFG, timeout=ctx_left(300.0))
-    if rank == 0 and not distributed and args.workload == "banded" and not args.no_reference_gpu:
+    if rank == 0 and not distributed and args.workload in ("banded", "block") and not args.no_reference_gpu:
         torch.cuda.empty_cache()
-        out["reference_gpu"] = reference_gpu(0, config=BANDED_CFG, timeout=ctx_left(300.0), system=REF_SYSTEM) if os.path.exists(REF_SYSTEM) else \
-            {"unavailable": "the system file for the reference could not be written"}
+        out["reference_gpu"] = reference_gpu(0, config=BANDED_CFG if args.workload == "banded" else BLOCK_CFG, timeout=ctx_left(300.0), system=REF_SYSTEM, mode=mode) \
+            if os.path.exists(REF_SYSTEM) else {"unavailable": "the system file for the reference could not be written"}
         try:
             os.remove(REF_SYSTEM)
         except OSError:

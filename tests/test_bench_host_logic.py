@@ -28,7 +28,7 @@ def test_other_workloads_children(tmp_path):
     small = [("poisson_small", ["--workload", "poisson", "--grid", "16", "--steps", "2", "--warmup", "1"]),
              ("classical_small", ["--workload", "classical", "--grid", "16", "--steps", "2", "--warmup", "1"]),
              ("banded_small", ["--workload", "banded", "--rows", "20000", "--steps", "2", "--warmup", "1", "+reference-gpu"]),
-             ("block_small", ["--workload", "block", "--grid", "8", "--mode", "dDFI", "--steps", "2", "--warmup", "1"])]
+             ("block_small", ["--workload", "block", "--grid", "8", "--mode", "dDFI", "--steps", "2", "--warmup", "1", "+reference-gpu"])]
     out = bench.other_workloads(budget_s=200, per_run_s=100, workloads=small, script=WORKER)
     for name, _ in small:
         assert "error" not in out[name] and "skipped" not in out[name], out[name]
@@ -37,6 +37,7 @@ def test_other_workloads_children(tmp_path):
     assert "unavailable" in out["banded_small"]["reference_gpu"] and "reference_gpu" not in out["poisson_small"]        # the harness ran (and found no GPU) for that one only
     assert "SuiteSparse-shaped" in out["banded_small"]["config"]["workload"] and "20000 rows" in out["banded_small"]["config"]["workload"]
     assert "classical AMG" in out["classical_small"]["config"]["workload"] and "iteration" not in out["classical_small"]["roofline"]
+    assert "unavailable" in out["block_small"]["reference_gpu"]
     assert out["block_small"]["dtype"] == "f32 matrix / f64 vectors" and "block4" in out["block_small"]["roofline"]["kernel"]
     # the flags of the real list parse
     for _, flags in bench.EXTRA_WORKLOADS:
