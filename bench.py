@@ -428,9 +428,6 @@ EXTRA_WORKLOADS = [
     ("classical512", ["--workload", "classical", "--grid", "512", "--steps", "2", "--warmup", "3", "+reference-gpu"]),              # BASELINE configs[2]
     ("block160_dDFI", ["--workload", "block", "--mode", "dDFI", "--steps", "3", "--warmup", "3", "+reference-gpu"]),                # BASELINE configs[4] at 160^3 block rows
 ]
-    ("banded4m", ["--workload", "banded", "--steps", "3", "--warmup", "3", "+reference-gpu"]),            # SURVEY 8(d) input 2; with the reference GPU build on the same matrix
-    ("block160_dDFI", ["--workload", "block", "--mode", "dDFI", "--steps", "3", "--warmup", "3", "+reference-gpu"]),        # BASELINE configs[4] at 160^3 block rows
-]
 
 
 def other_workloads(budget_s=240.0, per_run_s=110.0, workloads=None, script=None):
