@@ -942,6 +942,10 @@ def main():
         if not args.no_extras and nx == 256:
             out["other_workloads"] = other_workloads(budget_s=ctx_left(240.0))
     guard.finish()
+    # the line is out; a teardown that hangs (a communicator left in a bad state by a failed context object) must not keep the launcher waiting
+    t_exit = threading.Timer(90.0, lambda: os._exit(0))
+    t_exit.daemon = True
+    t_exit.start()
     for o in (rsc, cfg):
         o.destroy()
     capi.finalize()
